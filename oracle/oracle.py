@@ -1,0 +1,197 @@
+"""ctypes front-end of the CPU oracle (TEST INFRASTRUCTURE — see oracle/oracle.h).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class Config(C.Structure):
+    """Mirror of orc::Config (oracle/oracle.h) — field order and types must match."""
+    _fields_ = [
+        ("nang", C.c_int), ("nfre", C.c_int), ("nfre_red", C.c_int), ("ifre1", C.c_int), ("fr1", C.c_double),
+        ("iphys", C.c_int), ("isnonlin", C.c_int), ("idamping", C.c_int), ("irefra", C.c_int), ("icase", C.c_int),
+        ("ipropags", C.c_int), ("llgcbz0", C.c_int), ("llnormagam", C.c_int), ("llcapchnk", C.c_int),
+        ("lbiwbk", C.c_int), ("licerun", C.c_int), ("lmaskice", C.c_int), ("lwamrsetci", C.c_int),
+        ("lciwa1", C.c_int), ("lciwa2", C.c_int), ("lciwa3", C.c_int), ("lciscal", C.c_int), ("lwflux", C.c_int),
+        ("lwfluxout", C.c_int), ("lwnemocou", C.c_int), ("lwvflx_snl", C.c_int), ("lwcouast", C.c_int),
+        ("lwcou", C.c_int), ("icode", C.c_int), ("idelt", C.c_double), ("idelpro", C.c_double),
+        ("delpro_lf", C.c_double), ("ifrelfmax", C.c_int), ("ximp", C.c_double), ("rnu", C.c_double),
+        ("rnum", C.c_double), ("wspmin", C.c_double), ("cithrsh", C.c_double), ("cithrsh_tail", C.c_double),
+        ("ciblock", C.c_double), ("flmin", C.c_double), ("zalpfacx", C.c_double), ("bathymax", C.c_double),
+        ("deptha", C.c_double), ("nproma", C.c_int), ("npr", C.c_int), ("ll1d", C.c_int),
+        ("store_all_weights", C.c_int), ("nthreads", C.c_int),
+    ]
+
+
+def default_config(**kw) -> Config:
+    c = Config(nang=12, nfre=36, nfre_red=25, ifre1=3, fr1=4.177248e-02, iphys=1, isnonlin=0, idamping=1, irefra=0,
+               icase=1, ipropags=2, llgcbz0=0, llnormagam=0, llcapchnk=1, lbiwbk=1, licerun=1, lmaskice=1,
+               lwamrsetci=1, lciwa1=0, lciwa2=0, lciwa3=0, lciscal=0, lwflux=0, lwfluxout=1, lwnemocou=0,
+               lwvflx_snl=1, lwcouast=0, lwcou=0, icode=3, idelt=900.0, idelpro=900.0, delpro_lf=900.0, ifrelfmax=0,
+               ximp=1.0, rnu=1.5e-5, rnum=0.11 * 1.5e-5, wspmin=1.0, cithrsh=0.3, cithrsh_tail=0.3, ciblock=0.0,
+               flmin=1e-5, zalpfacx=1.0, bathymax=998.999, deptha=2.0, nproma=32, npr=1, ll1d=0,
+               store_all_weights=0, nthreads=1)
+    for k, v in kw.items():
+        if not hasattr(c, k):
+            raise KeyError(k)
+        setattr(c, k, v)
+    c.ifre1 = 1 if c.nfre_red == 25 else 3
+    return c
+
+
+def build(fast: bool = False) -> str:
+    name = "liboracle_fast.so" if fast else "liboracle.so"
+    path = os.path.join(_HERE, name)
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h"))]
+    if not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, name], stdout=subprocess.DEVNULL)
+    return path
+
+
+_libs = {}
+
+
+def _lib(fast=False):
+    if fast not in _libs:
+        lib = C.CDLL(build(fast))
+        lib.orc_create.restype = C.c_void_p
+        lib.orc_create.argtypes = [C.POINTER(Config), C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+        lib.orc_destroy.argtypes = [C.c_void_p]
+        lib.orc_niblo.argtypes = [C.c_void_p]
+        for f in ("orc_get_table",):
+            getattr(lib, f).restype = C.c_long
+            getattr(lib, f).argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long]
+        for f in ("orc_get_itable", "orc_get_rank_double"):
+            getattr(lib, f).restype = C.c_long
+            getattr(lib, f).argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_long]
+        for f in ("orc_set_field", "orc_get_field", "orc_get_field3"):
+            getattr(lib, f).argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        for f in ("orc_set_fl1", "orc_get_fl1", "orc_get_xllws"):
+            getattr(lib, f).argtypes = [C.c_void_p, C.c_void_p]
+        lib.orc_get_hs_fm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.orc_propag.argtypes = [C.c_void_p]
+        lib.orc_implsch.argtypes = [C.c_void_p]
+        assert lib.orc_config_size() == C.sizeof(Config), "oracle Config layout mismatch"
+        _libs[fast] = lib
+    return _libs[fast]
+
+
+class Oracle:
+    def __init__(self, cfg: Config, grid, fast: bool = False):
+        """grid: ecwam_b200.synth.SynthGrid (or anything with ngy/nlonrgg/amosop/amonop/mask/depth)."""
+        self.lib = _lib(fast)
+        self.cfg = cfg
+        nl = np.ascontiguousarray(grid.nlonrgg, dtype=np.int32)
+        mk = np.ascontiguousarray(grid.mask, dtype=np.uint8)
+        dp = np.ascontiguousarray(grid.depth, dtype=np.float64)
+        self.h = self.lib.orc_create(C.byref(cfg), int(grid.ngy), nl.ctypes.data, float(grid.amosop), float(grid.amonop),
+                                     mk.ctypes.data, dp.ctypes.data)
+        if not self.h:
+            raise RuntimeError("orc_create failed")
+        self.niblo = self.lib.orc_niblo(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.orc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- tables
+    def table(self, name, cap=1 << 16):
+        buf = np.empty(cap, dtype=np.float64)
+        n = self.lib.orc_get_table(self.h, name.encode(), buf.ctypes.data, cap)
+        if n < 0:
+            return self.table(name, -n)
+        if n == 0:
+            raise KeyError(name)
+        return buf[:n].copy()
+
+    def itable(self, name, rank=0, cap=1 << 16):
+        buf = np.empty(cap, dtype=np.int32)
+        n = self.lib.orc_get_itable(self.h, name.encode(), rank, buf.ctypes.data, cap)
+        if n < 0:
+            return self.itable(name, rank, -n)
+        if n == 0:
+            raise KeyError(name)
+        return buf[:n].copy()
+
+    def iscalar(self, name, rank=0):
+        return int(self.itable(name, rank, 4)[0])
+
+    def rank_double(self, name, rank=0, cap=1 << 20):
+        buf = np.empty(cap, dtype=np.float64)
+        n = self.lib.orc_get_rank_double(self.h, name.encode(), rank, buf.ctypes.data, cap)
+        if n < 0:
+            return self.rank_double(name, rank, -n)
+        if n == 0:
+            raise KeyError(name)
+        return buf[:n].copy()
+
+    # ---- per-point fields (original global order)
+    def set_field(self, name, v):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        assert v.shape == (self.niblo,)
+        if self.lib.orc_set_field(self.h, name.encode(), v.ctypes.data) != 0:
+            raise KeyError(name)
+
+    def get_field(self, name):
+        v = np.empty(self.niblo)
+        if self.lib.orc_get_field(self.h, name.encode(), v.ctypes.data) != 0:
+            raise KeyError(name)
+        return v
+
+    def get_field3(self, name):
+        v = np.empty((self.cfg.nfre, self.niblo))
+        if self.lib.orc_get_field3(self.h, name.encode(), v.ctypes.data) != 0:
+            raise KeyError(name)
+        return v
+
+    def set_fl1(self, fl):
+        fl = np.ascontiguousarray(fl, dtype=np.float64)
+        assert fl.shape == (self.cfg.nfre, self.cfg.nang, self.niblo)
+        self.lib.orc_set_fl1(self.h, fl.ctypes.data)
+
+    def get_fl1(self):
+        fl = np.empty((self.cfg.nfre, self.cfg.nang, self.niblo))
+        self.lib.orc_get_fl1(self.h, fl.ctypes.data)
+        return fl
+
+    def get_xllws(self):
+        fl = np.empty((self.cfg.nfre, self.cfg.nang, self.niblo))
+        self.lib.orc_get_xllws(self.h, fl.ctypes.data)
+        return fl
+
+    def hs_fm(self):
+        hs = np.empty(self.niblo)
+        fm = np.empty(self.niblo)
+        self.lib.orc_get_hs_fm(self.h, hs.ctypes.data, fm.ctypes.data)
+        return hs, fm
+
+    # ---- hot path
+    def propag(self) -> int:
+        rc = self.lib.orc_propag(self.h)
+        if rc < 0:
+            raise RuntimeError("orc_propag failed")
+        return rc
+
+    def implsch(self):
+        if self.lib.orc_implsch(self.h) != 0:
+            raise RuntimeError("orc_implsch failed")
+
+    def step(self):
+        """One WAMINTGR sub-step with IDELPRO == IDELT (wamintgr.F90:94-146)."""
+        cfl = self.propag()
+        self.implsch()
+        return cfl

@@ -1,0 +1,245 @@
+// ORACLE (test infrastructure) — C API used by tests/, smoke() and bench.py's CPU-baseline legs through ctypes.
+// All per-point arrays cross this API in the ORIGINAL global sea-point order (south->north, west->east,
+// mblock.F90:126-135), independent of the emulated decomposition; spectra as [m][k][ij] (ij fastest).
+#include "oracle.h"
+#include <cstring>
+#include <map>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace orc;
+
+static ArrD* field2d(Fields& f, const std::string& n) {
+  static const std::map<std::string, ArrD Fields::*> mp = {
+      {"DEPTH", &Fields::DEPTH}, {"EMAXDPT", &Fields::EMAXDPT}, {"DELLAM1", &Fields::DELLAM1},
+      {"COSPHM1", &Fields::COSPHM1}, {"UCUR", &Fields::UCUR}, {"VCUR", &Fields::VCUR}, {"AIRD", &Fields::AIRD},
+      {"WDWAVE", &Fields::WDWAVE}, {"CICOVER", &Fields::CICOVER}, {"WSWAVE", &Fields::WSWAVE},
+      {"WSTAR", &Fields::WSTAR}, {"USTRA", &Fields::USTRA}, {"VSTRA", &Fields::VSTRA}, {"UFRIC", &Fields::UFRIC},
+      {"TAUW", &Fields::TAUW}, {"TAUWDIR", &Fields::TAUWDIR}, {"Z0M", &Fields::Z0M}, {"Z0B", &Fields::Z0B},
+      {"CHRNCK", &Fields::CHRNCK}, {"CITHICK", &Fields::CITHICK}, {"WSEMEAN", &Fields::WSEMEAN},
+      {"WSFMEAN", &Fields::WSFMEAN}, {"USTOKES", &Fields::USTOKES}, {"VSTOKES", &Fields::VSTOKES},
+      {"STRNMS", &Fields::STRNMS}, {"TAUXD", &Fields::TAUXD}, {"TAUYD", &Fields::TAUYD},
+      {"TAUOCXD", &Fields::TAUOCXD}, {"TAUOCYD", &Fields::TAUOCYD}, {"TAUOC", &Fields::TAUOC},
+      {"TAUICX", &Fields::TAUICX}, {"TAUICY", &Fields::TAUICY}, {"PHIOCD", &Fields::PHIOCD},
+      {"PHIEPS", &Fields::PHIEPS}, {"PHIAW", &Fields::PHIAW}};
+  auto it = mp.find(n);
+  return it == mp.end() ? nullptr : &(f.*(it->second));
+}
+static ArrD* field3d(Fields& f, const std::string& n) {
+  static const std::map<std::string, ArrD Fields::*> mp = {
+      {"WAVNUM", &Fields::WAVNUM}, {"CINV", &Fields::CINV}, {"CGROUP", &Fields::CGROUP}, {"XK2CG", &Fields::XK2CG},
+      {"OMOSNH2KD", &Fields::OMOSNH2KD}, {"STOKFAC", &Fields::STOKFAC}, {"CIWA", &Fields::CIWA}};
+  auto it = mp.find(n);
+  return it == mp.end() ? nullptr : &(f.*(it->second));
+}
+
+template <class T>
+static long copy_out(const std::vector<T>& v, T* out, long cap) {
+  if ((long)v.size() > cap) return -(long)v.size();
+  std::memcpy(out, v.data(), v.size() * sizeof(T));
+  return (long)v.size();
+}
+
+extern "C" {
+
+void* orc_create(const Config* cfg, int ngy, const int* nlonrgg, double amosop, double amonop,
+                 const unsigned char* maskflat, const double* depth_sea) {
+  try {
+    Model* m = new Model();
+    m->cfg = *cfg;
+#ifdef _OPENMP
+    omp_set_num_threads(std::max(1, cfg->nthreads));
+#endif
+    init_tables(m->cfg, m->tab);
+    build_grid(m->cfg, m->grid, ngy, nlonrgg, amosop, amonop, maskflat);
+    m->depth0.assign(depth_sea, depth_sea + m->grid.NIBLO);
+    mpdecomp(m->cfg, m->tab, m->grid, m->ranks);
+    alloc_fields(*m);
+    return m;
+  } catch (std::exception& e) {
+    fprintf(stderr, "orc_create: %s\n", e.what());
+    return nullptr;
+  }
+}
+void orc_destroy(void* h) { delete (Model*)h; }
+int orc_niblo(void* h) { return ((Model*)h)->grid.NIBLO; }
+int orc_config_size() { return (int)sizeof(Config); }
+
+// named scalar / small-table getters ------------------------------------------------------------------
+long orc_get_table(void* h, const char* name, double* out, long cap) {
+  Model* m = (Model*)h;
+  Tables& t = m->tab;
+  std::string n(name);
+  std::map<std::string, ArrD*> mp = {
+      {"FR", &t.FR}, {"DFIM", &t.DFIM}, {"TH", &t.TH}, {"COSTH", &t.COSTH}, {"SINTH", &t.SINTH},
+      {"DFIMOFR", &t.DFIMOFR}, {"DFIMFR", &t.DFIMFR}, {"ZPIFR", &t.ZPIFR}, {"FR5", &t.FR5}, {"COFRM4", &t.COFRM4},
+      {"FLMAX", &t.FLMAX}, {"RHOWG_DFIM", &t.RHOWG_DFIM}, {"DFIM_SIM", &t.DFIM_SIM}, {"SATWEIGHTS", &t.SATWEIGHTS},
+      {"SWELLFT", &t.SWELLFT}, {"WTAUHF", &t.WTAUHF}, {"AF11", &t.AF11}, {"FKLAP", &t.FKLAP}, {"FKLAP1", &t.FKLAP1},
+      {"FKLAM", &t.FKLAM}, {"FKLAM1", &t.FKLAM1}, {"FRH", &t.FRH}, {"RNLCOEF", &t.RNLCOEF}, {"FTRF", &t.FTRF},
+      {"ZDELLO", &m->grid.ZDELLO}, {"COSPH", &m->grid.COSPH}, {"SINPH", &m->grid.SINPH}, {"DELLAM", &m->grid.DELLAM}};
+  auto it = mp.find(n);
+  if (it != mp.end()) return copy_out(it->second->d, out, cap);
+  std::map<std::string, double> sc = {
+      {"X0TAUHF", t.X0TAUHF}, {"DELTH", t.DELTH}, {"FLOGSPRDM1", t.FLOGSPRDM1}, {"BETAMAXOXKAPPA2", t.BETAMAXOXKAPPA2},
+      {"DAL1", t.DAL1}, {"DAL2", t.DAL2}, {"ACL1", t.ACL1}, {"ACL2", t.ACL2}, {"CL11", t.CL11}, {"CL21", t.CL21},
+      {"XDELLA", m->grid.XDELLA}, {"R", t.R}, {"ZPI", t.ZPI}, {"TAUWSHELTER", t.TAUWSHELTER}, {"BETAMAX", t.BETAMAX}};
+  auto is = sc.find(n);
+  if (is != sc.end()) { if (cap < 1) return -1; out[0] = is->second; return 1; }
+  return 0;
+}
+long orc_get_itable(void* h, const char* name, int rank, int* out, long cap) {
+  Model* m = (Model*)h;
+  Tables& t = m->tab;
+  RankDecomp& r = m->ranks[rank];
+  std::string n(name);
+  std::map<std::string, ArrI*> mp = {
+      {"INDICESSAT", &t.INDICESSAT}, {"IKP", &t.IKP}, {"IKP1", &t.IKP1}, {"IKM", &t.IKM}, {"IKM1", &t.IKM1},
+      {"K1W", &t.K1W}, {"K2W", &t.K2W}, {"K11W", &t.K11W}, {"K21W", &t.K21W}, {"INLCOEF", &t.INLCOEF},
+      {"KLAT", &r.KLAT}, {"KLON", &r.KLON}, {"KCOR", &r.KCOR}, {"NFROMPE", &r.NFROMPE}, {"NTOPE", &r.NTOPE},
+      {"NIJSTART", &r.NIJSTART}, {"IJTOPE", &r.IJTOPE}, {"NTOPELST", &r.NTOPELST}, {"NFROMPELST", &r.NFROMPELST},
+      {"KIJL4CHNK", &r.KIJL4CHNK}, {"IJFROMCHNK", &r.IJFROMCHNK}, {"MPM", &r.MPM}, {"KPM", &r.KPM}, {"JXO", &r.JXO},
+      {"JYO", &r.JYO}, {"KCR", &r.KCR}, {"NSTART", &m->grid.NSTART}, {"NEND", &m->grid.NEND},
+      {"NEWIJ2IJ", &m->grid.NEWIJ2IJ}, {"IJ2NEWIJ", &m->grid.IJ2NEWIJ}, {"IXLG", &m->grid.IXLG}, {"KXLT", &m->grid.KXLT},
+      {"KLENBOT", &m->grid.KLENBOT}, {"KLENTOP", &m->grid.KLENTOP}};
+  auto it = mp.find(n);
+  if (it != mp.end()) return copy_out(it->second->d, out, cap);
+  std::map<std::string, int> sc = {
+      {"NINF", r.NINF}, {"NSUP", r.NSUP}, {"IJS", r.IJS}, {"IJL", r.IJL}, {"NPROMA", r.NPROMA}, {"NCHNK", r.NCHNK},
+      {"NTOPEMAX", r.NTOPEMAX}, {"NFROMPEMAX", r.NFROMPEMAX}, {"NGBTOPE", r.NGBTOPE}, {"NGBFROMPE", r.NGBFROMPE},
+      {"NSDSNTH", t.NSDSNTH}, {"MFRSTLW", t.MFRSTLW}, {"MLSTHG", t.MLSTHG}, {"KFRH", t.KFRH}, {"NFRE_ODD", t.NFRE_ODD},
+      {"CFL_FAIL", r.cfl_fail}, {"NIBLO", m->grid.NIBLO}};
+  auto is = sc.find(n);
+  if (is != sc.end()) { if (cap < 1) return -1; out[0] = is->second; return 1; }
+  return 0;
+}
+long orc_get_rank_double(void* h, const char* name, int rank, double* out, long cap) {
+  Model* m = (Model*)h;
+  RankDecomp& r = m->ranks[rank];
+  std::string n(name);
+  std::map<std::string, ArrD*> mp = {{"WLAT", &r.WLAT}, {"WCOR", &r.WCOR}, {"W8", &r.W8}, {"SUMWN", &r.SUMWN},
+                                     {"WLATN", &r.WLATN}, {"WLONN", &r.WLONN}, {"WCORN", &r.WCORN}, {"WKPMN", &r.WKPMN}};
+  auto it = mp.find(n);
+  if (it != mp.end()) return copy_out(it->second->d, out, cap);
+  return 0;
+}
+
+// per-point fields in original global order ------------------------------------------------------------
+static inline void locate(Model* m, int ij0 /*1-based original*/, int& ir, int& ip, int& ic) {
+  int nij = m->grid.IJ2NEWIJ(ij0);
+  ir = 0;
+  while (nij > m->grid.NEND(ir + 1)) ++ir;
+  RankDecomp& r = m->ranks[ir];
+  int l = nij - r.IJS;
+  ic = l / r.NPROMA + 1;
+  ip = l % r.NPROMA + 1;
+}
+// after setting real points, replicate point 1 of the last chunk into its padding lanes (mpdecomp.F90:1443-1456)
+static void pad2d(Model* m, ArrD Fields::*mem) {
+  for (int ir = 0; ir < m->cfg.npr; ++ir) {
+    RankDecomp& r = m->ranks[ir];
+    ArrD& a = m->fld[ir].*mem;
+    int C = r.NCHNK;
+    for (int j = r.KIJL4CHNK(C) + 1; j <= r.NPROMA; ++j) a(j, C) = a(1, C);
+  }
+}
+int orc_set_field(void* h, const char* name, const double* v) {
+  Model* m = (Model*)h;
+  std::string n(name);
+  if (!field2d(m->fld[0], n)) return -1;
+  for (int ij = 1; ij <= m->grid.NIBLO; ++ij) {
+    int ir, ip, ic; locate(m, ij, ir, ip, ic);
+    (*field2d(m->fld[ir], n))(ip, ic) = v[ij - 1];
+  }
+  for (int ir = 0; ir < m->cfg.npr; ++ir) {
+    RankDecomp& r = m->ranks[ir];
+    ArrD& a = *field2d(m->fld[ir], n);
+    int C = r.NCHNK;
+    for (int j = r.KIJL4CHNK(C) + 1; j <= r.NPROMA; ++j) a(j, C) = a(1, C);
+  }
+  (void)pad2d;
+  return 0;
+}
+int orc_get_field(void* h, const char* name, double* v) {
+  Model* m = (Model*)h;
+  std::string n(name);
+  if (n == "MIJ") {
+    for (int ij = 1; ij <= m->grid.NIBLO; ++ij) { int ir, ip, ic; locate(m, ij, ir, ip, ic); v[ij - 1] = m->fld[ir].MIJ(ip, ic); }
+    return 0;
+  }
+  if (!field2d(m->fld[0], n)) return -1;
+  for (int ij = 1; ij <= m->grid.NIBLO; ++ij) {
+    int ir, ip, ic; locate(m, ij, ir, ip, ic);
+    v[ij - 1] = (*field2d(m->fld[ir], n))(ip, ic);
+  }
+  return 0;
+}
+// (NFRE, NIBLO) arrays as [m][ij]
+int orc_get_field3(void* h, const char* name, double* v) {
+  Model* m = (Model*)h;
+  std::string n(name);
+  if (!field3d(m->fld[0], n)) return -1;
+  const long N = m->grid.NIBLO;
+  for (int ij = 1; ij <= N; ++ij) {
+    int ir, ip, ic; locate(m, ij, ir, ip, ic);
+    ArrD& a = *field3d(m->fld[ir], n);
+    for (int M = 1; M <= m->cfg.nfre; ++M) v[(M - 1) * N + ij - 1] = a(ip, M, ic);
+  }
+  return 0;
+}
+static int spec_io(Model* m, bool xllws, double* v, bool set) {
+  const long N = m->grid.NIBLO;
+  const int A = m->cfg.nang, F = m->cfg.nfre;
+  for (int ij = 1; ij <= N; ++ij) {
+    int ir, ip, ic; locate(m, ij, ir, ip, ic);
+    ArrD& a = xllws ? m->fld[ir].XLLWS : m->fld[ir].FL1;
+    for (int M = 1; M <= F; ++M)
+      for (int K = 1; K <= A; ++K) {
+        size_t o = ((size_t)(M - 1) * A + (K - 1)) * N + ij - 1;
+        if (set) a(ip, K, M, ic) = v[o]; else v[o] = a(ip, K, M, ic);
+      }
+  }
+  if (set)
+    for (int ir = 0; ir < m->cfg.npr; ++ir) {
+      RankDecomp& r = m->ranks[ir];
+      ArrD& a = m->fld[ir].FL1;
+      int C = r.NCHNK;
+      for (int M = 1; M <= F; ++M)
+        for (int K = 1; K <= A; ++K)
+          for (int j = r.KIJL4CHNK(C) + 1; j <= r.NPROMA; ++j) a(j, K, M, C) = a(1, K, M, C);
+    }
+  return 0;
+}
+int orc_set_fl1(void* h, const double* v) { return spec_io((Model*)h, false, const_cast<double*>(v), true); }
+int orc_get_fl1(void* h, double* v) { return spec_io((Model*)h, false, v, false); }
+int orc_get_xllws(void* h, double* v) { return spec_io((Model*)h, true, v, false); }
+
+// the hot path ---------------------------------------------------------------------------------------
+int orc_propag(void* h) {
+  try { propag_wam(*(Model*)h); } catch (std::exception& e) { fprintf(stderr, "orc_propag: %s\n", e.what()); return -1; }
+  int cfl = 0;
+  for (auto& r : ((Model*)h)->ranks) cfl += r.cfl_fail;
+  return cfl;
+}
+int orc_implsch(void* h) {
+  try { implsch_all(*(Model*)h); } catch (std::exception& e) { fprintf(stderr, "orc_implsch: %s\n", e.what()); return -1; }
+  return 0;
+}
+// Hs = 4 sqrt(EM), mean frequency FM (femean.F90, outblock.F90:223-244) in original order
+int orc_get_hs_fm(void* h, double* hs, double* fm) {
+  Model* m = (Model*)h;
+  const int A = m->cfg.nang, F = m->cfg.nfre;
+  std::vector<double> spec((size_t)A * F);
+  for (int ij = 1; ij <= m->grid.NIBLO; ++ij) {
+    int ir, ip, ic; locate(m, ij, ir, ip, ic);
+    ArrD& a = m->fld[ir].FL1;
+    for (int M = 1; M <= F; ++M) for (int K = 1; K <= A; ++K) spec[(M - 1) * A + K - 1] = a(ip, K, M, ic);
+    double EM, FM;
+    femean(m->tab, m->cfg, 1, spec.data(), &EM, &FM);
+    hs[ij - 1] = 4.0 * std::sqrt(EM);
+    fm[ij - 1] = FM;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,1066 @@
+// ORACLE (test infrastructure) — IMPLSCH and its call tree, restated loop by loop from the reference.
+// Branches exercised by the BASELINE configs only: LLGCBZ0=F, LLNORMAGAM=F, ISNONLIN=0,
+// LCIWA*=F, LWNEMOCOU*=F, ICODE_WND=3; IPHYS=0 and 1.  Off-by-default branches throw.
+#include "oracle.h"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace orc {
+
+namespace {
+// 1-based views on column-major storage
+struct V1 { double* p; inline double& operator()(int i) const { return p[i - 1]; } };
+struct V2 { double* p; int n0; inline double& operator()(int i, int j) const { return p[(i - 1) + (size_t)n0 * (j - 1)]; } };
+struct V3 { double* p; int n0, n1; inline double& operator()(int i, int j, int k) const { return p[(i - 1) + (size_t)n0 * ((j - 1) + (size_t)n1 * (k - 1))]; } };
+struct I1 { int* p; inline int& operator()(int i) const { return p[i - 1]; } };
+struct L1 { std::vector<double> v; V1 view() { return V1{v.data()}; } L1(int n) : v(n, 0.0) {} };
+inline double sq(double x) { return x * x; }
+inline double p4(double x) { double y = x * x; return y * y; }
+
+struct Ctx {
+  const Config& c; const Tables& t; int KIJS, KIJL, NANG, NFRE;
+};
+
+// semean.F90:60-124
+void SEMEAN(const Ctx& x, V3 FL1, V1 EM, bool LLEPSMIN) {
+  const Tables& t = x.t;
+  std::vector<double> TEMP(x.KIJL + 1);
+  for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) EM(IJ) = LLEPSMIN ? t.EPSMIN : 0.0;
+  for (int M = 1; M <= x.NFRE; ++M) {
+    for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) TEMP[IJ] = FL1(IJ, 1, M);
+    for (int K = 2; K <= x.NANG; ++K) for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) TEMP[IJ] = TEMP[IJ] + FL1(IJ, K, M);
+    for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) EM(IJ) = EM(IJ) + t.DFIM(M) * TEMP[IJ];
+  }
+  double DELT25 = t.WETAIL * t.FR(x.NFRE) * t.DELTH;
+  for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) EM(IJ) = EM(IJ) + DELT25 * TEMP[IJ];
+}
+
+// sdepthlim.F90:50-82
+void SDEPTHLIM(const Ctx& x, V1 EMAXDPT, V3 FL1) {
+  L1 EMs(x.KIJL); V1 EM = EMs.view();
+  SEMEAN(x, FL1, EM, true);
+  for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) EM(IJ) = std::min(EMAXDPT(IJ) / EM(IJ), 1.0);
+  for (int M = 1; M <= x.NFRE; ++M) for (int K = 1; K <= x.NANG; ++K) for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ)
+    FL1(IJ, K, M) = std::max(FL1(IJ, K, M) * EM(IJ), x.t.EPSMIN);
+}
+
+// fkmean.F90:60-154
+void FKMEAN(const Ctx& x, V3 FL1, V2 WAVNUM, V1 EM, V1 FM1, V1 F1, V1 AK, V1 XK) {
+  const Tables& t = x.t;
+  std::vector<double> TEMPA(x.KIJL + 1), TEMPX(x.KIJL + 1), TEMP2(x.KIJL + 1);
+  for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) { EM(IJ) = t.EPSMIN; FM1(IJ) = t.EPSMIN; F1(IJ) = t.EPSMIN; AK(IJ) = t.EPSMIN; XK(IJ) = t.EPSMIN; }
+  double DELT25 = t.WETAIL * t.FR(x.NFRE) * t.DELTH;
+  double COEFM1 = t.FRTAIL * t.DELTH;
+  double COEF1 = t.WP1TAIL * t.DELTH * sq(t.FR(x.NFRE));
+  double COEFA = COEFM1 * std::sqrt(t.G) / t.ZPI;
+  double COEFX = COEF1 * (t.ZPI / std::sqrt(t.G));
+  for (int M = 1; M <= x.NFRE; ++M) {
+    for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) {
+      double SQRTK = std::sqrt(WAVNUM(IJ, M));
+      TEMPA[IJ] = t.DFIM(M) / SQRTK;
+      TEMPX[IJ] = SQRTK * t.DFIM(M);
+    }
+    for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) TEMP2[IJ] = FL1(IJ, 1, M);
+    for (int K = 2; K <= x.NANG; ++K) for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) TEMP2[IJ] = TEMP2[IJ] + FL1(IJ, K, M);
+    for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) {
+      EM(IJ) = EM(IJ) + t.DFIM(M) * TEMP2[IJ];
+      FM1(IJ) = FM1(IJ) + t.DFIMOFR(M) * TEMP2[IJ];
+      F1(IJ) = F1(IJ) + t.DFIMFR(M) * TEMP2[IJ];
+      AK(IJ) = AK(IJ) + TEMPA[IJ] * TEMP2[IJ];
+      XK(IJ) = XK(IJ) + TEMPX[IJ] * TEMP2[IJ];
+    }
+  }
+  for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) {
+    EM(IJ) = EM(IJ) + DELT25 * TEMP2[IJ];
+    FM1(IJ) = FM1(IJ) + COEFM1 * TEMP2[IJ];
+    FM1(IJ) = EM(IJ) / FM1(IJ);
+    F1(IJ) = F1(IJ) + COEF1 * TEMP2[IJ];
+    F1(IJ) = F1(IJ) / EM(IJ);
+    AK(IJ) = AK(IJ) + COEFA * TEMP2[IJ];
+    AK(IJ) = sq(EM(IJ) / AK(IJ));
+    XK(IJ) = XK(IJ) + COEFX * TEMP2[IJ];
+    XK(IJ) = sq(XK(IJ) / EM(IJ));
+  }
+}
+
+// femeanws.F90:50-127
+void FEMEANWS(const Ctx& x, V3 FL1, V3 XLLWS, V1 FM, double* EMout) {
+  const Tables& t = x.t;
+  std::vector<double> TEMP2(x.KIJL + 1), EM_LOC(x.KIJL + 1);
+  for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) { EM_LOC[IJ] = t.EPSMIN; FM(IJ) = t.EPSMIN; }
+  double DELT25 = t.WETAIL * t.FR(x.NFRE) * t.DELTH;
+  double DELT2 = t.FRTAIL * t.DELTH;
+  for (int M = 1; M <= x.NFRE; ++M) {
+    for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) TEMP2[IJ] = 0.0;
+    for (int K = 1; K <= x.NANG; ++K) for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) TEMP2[IJ] = TEMP2[IJ] + XLLWS(IJ, K, M) * FL1(IJ, K, M);
+    for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) { EM_LOC[IJ] = EM_LOC[IJ] + t.DFIM(M) * TEMP2[IJ]; FM(IJ) = FM(IJ) + t.DFIMOFR(M) * TEMP2[IJ]; }
+  }
+  for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) {
+    EM_LOC[IJ] = EM_LOC[IJ] + DELT25 * TEMP2[IJ];
+    FM(IJ) = FM(IJ) + DELT2 * TEMP2[IJ];
+    FM(IJ) = EM_LOC[IJ] / FM(IJ);
+  }
+  if (EMout) for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) EMout[IJ - 1] = EM_LOC[IJ];
+}
+
+// frcutindex.F90:84-108
+void FRCUTINDEX(const Ctx& x, V1 FM, V1 FMWS, V1 UFRIC, V1 CICOVER, I1 MIJ, V2 RHOWGDFTH) {
+  const Tables& t = x.t;
+  const double FRIC = 28.0;  // yowfred.F90
+  double FPMH = t.TAILFACTOR / t.FR(1);
+  double FPPM = t.TAILFACTOR_PM * t.G / (FRIC * t.ZPIFR(1));
+  for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) {
+    if (CICOVER(IJ) <= x.c.cithrsh_tail) {
+      double FM2 = std::max(FMWS(IJ), FM(IJ)) * FPMH;
+      double FPM = FPPM / std::max(UFRIC(IJ), t.EPSMIN);
+      double FPM4 = std::max(FM2, FPM);
+      MIJ(IJ) = (int)nint(std::log10(FPM4) * t.FLOGSPRDM1) + 1;
+      MIJ(IJ) = std::min(std::max(1, MIJ(IJ)), x.NFRE);
+    } else {
+      MIJ(IJ) = x.NFRE;
+    }
+  }
+  for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) {
+    for (int M = 1; M <= MIJ(IJ); ++M) RHOWGDFTH(IJ, M) = t.RHOWG_DFIM(M);
+    if (MIJ(IJ) != x.NFRE) RHOWGDFTH(IJ, MIJ(IJ)) = 0.5 * RHOWGDFTH(IJ, MIJ(IJ));
+    for (int M = MIJ(IJ) + 1; M <= x.NFRE; ++M) RHOWGDFTH(IJ, M) = 0.0;
+  }
+}
+
+// chnkmin.F90
+double CHNKMIN(const Tables& t, double U10) { return t.ALPHAMIN + (t.ALPHA - t.ALPHAMIN) * 0.5 * (1.0 - std::tanh(U10 - t.CHNKMIN_U)); }
+
+// taut_z0.F90:281-341 (LLGCBZ0 = .FALSE. branch) via airsea.F90 ICODE_WND == 3
+void TAUT_Z0(const Ctx& x, int IUSFG, V1 UTOP, V1 UDIR, V1 TAUW, V1 TAUWDIR, V1 USTAR, V1 Z0, V1 Z0B, V1 CHRNCK) {
+  const Tables& t = x.t;
+  const Config& c = x.c;
+  if (c.llgcbz0) throw std::runtime_error("TAUT_Z0: LLGCBZ0 branch not restated (SURVEY 8f)");
+  const int NITER = 18;
+  const double TWOXMP1 = 3.0;
+  double XLOGXL = std::log(t.XNLEV);
+  double US2TOTAUW = 1.0 + t.EPS1;
+  std::vector<double> TAUWACT(x.KIJL + 1), TAUWEFF(x.KIJL + 1), XMIN(x.KIJL + 1), ALPHAOG(x.KIJL + 1);
+  for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) {
+    double COSDIFF = std::cos(UDIR(IJ) - TAUWDIR(IJ));
+    TAUWACT[IJ] = std::max(TAUW(IJ) * COSDIFF, t.EPSMIN);
+  }
+  for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) TAUWEFF[IJ] = TAUWACT[IJ] * US2TOTAUW;
+  if (c.llcapchnk) {
+    for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) {
+      double CHARNOCK_MIN = CHNKMIN(t, UTOP(IJ));
+      XMIN[IJ] = 0.15 * (t.ALPHA - CHARNOCK_MIN);
+      ALPHAOG[IJ] = CHARNOCK_MIN * t.GM1;
+    }
+  } else {
+    for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) { XMIN[IJ] = 0.0; ALPHAOG[IJ] = t.ALPHA * t.GM1; }
+  }
+  for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) {
+    double XKUTOP = t.XKAPPA * UTOP(IJ);
+    double USTOLD = (1 - IUSFG) * UTOP(IJ) * std::sqrt(std::min(t.ACD + t.BCD * UTOP(IJ), t.CDMAX)) + IUSFG * USTAR(IJ);
+    double TAUOLD = std::max(sq(USTOLD), TAUWEFF[IJ]);
+    USTAR(IJ) = std::sqrt(TAUOLD);
+    double USTM1 = 1.0 / std::max(USTAR(IJ), t.EPSUS);
+    double Z0CH = 0.0, Z0VIS, Z0TOT, X, XOLOGZ0, F, ZZ, DELF, TAUNEW;
+    for (int ITER = 1; ITER <= NITER; ++ITER) {
+      X = std::max(TAUWACT[IJ] / TAUOLD, XMIN[IJ]);
+      Z0CH = ALPHAOG[IJ] * TAUOLD / std::sqrt(1.0 - X);
+      Z0VIS = c.rnum * USTM1;
+      Z0TOT = Z0CH + Z0VIS;
+      XOLOGZ0 = 1.0 / (XLOGXL - std::log(Z0TOT));
+      F = USTAR(IJ) - XKUTOP * XOLOGZ0;
+      ZZ = USTM1 * (Z0CH * (2.0 - TWOXMP1 * X) / (1.0 - X) - Z0VIS) / Z0TOT;
+      DELF = 1.0 - XKUTOP * sq(XOLOGZ0) * ZZ;
+      if (DELF != 0.0) USTAR(IJ) = USTAR(IJ) - F / DELF;
+      TAUNEW = std::max(sq(USTAR(IJ)), TAUWEFF[IJ]);
+      USTAR(IJ) = std::sqrt(TAUNEW);
+      if (TAUNEW == TAUOLD) break;
+      USTM1 = 1.0 / std::max(USTAR(IJ), t.EPSUS);
+      TAUOLD = TAUNEW;
+    }
+    Z0(IJ) = Z0CH;
+    Z0B(IJ) = ALPHAOG[IJ] * TAUOLD;
+    CHRNCK(IJ) = std::max(t.G * Z0(IJ) * sq(USTM1), t.ALPHAMIN);
+  }
+}
+
+// wsigstar.F90:105-129 (LLGCBZ0=LLNORMAGAM=F branch)
+void WSIGSTAR(const Ctx& x, V1 WSWAVE, V1 UFRIC, V1 Z0M, V1 WSTAR, V1 SIG_N) {
+  const Tables& t = x.t;
+  if (x.c.llgcbz0 || x.c.llnormagam) throw std::runtime_error("WSIGSTAR: GC branch not restated");
+  const double BG_GUST = 0.0, ONETHIRD = 1.0 / 3.0, SIG_NMAX = 0.9, C1 = 1.03e-3, C2 = 0.04e-3, P1 = 1.48, P2 = -0.21;
+  double XKAPPAD = 1.0 / t.XKAPPA;
+  for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) {
+    double U10 = UFRIC(IJ) * XKAPPAD * (std::log(10.0) - std::log(Z0M(IJ)));
+    U10 = std::max(U10, x.c.wspmin);
+    double U10M1 = 1.0 / U10;
+    double C2U10P1 = C2 * std::pow(U10, P1);
+    double U10P2 = std::pow(U10, P2);
+    double C_D = (C1 + C2U10P1) * U10P2;
+    double DC_DDU = (P2 * C1 + (P1 + P2) * C2U10P1) * U10P2 * U10M1;
+    double SIG_CONV = 1.0 + 0.5 * U10 / C_D * DC_DDU;
+    SIG_N(IJ) = std::min(SIG_NMAX, SIG_CONV * U10M1 * std::pow(BG_GUST * UFRIC(IJ) * UFRIC(IJ) * UFRIC(IJ) + 0.5 * t.XKAPPA * WSTAR(IJ) * WSTAR(IJ) * WSTAR(IJ), ONETHIRD));
+  }
+}
+
+// sinput_ard.F90:149-524
+void SINPUT_ARD(const Ctx& x, int NGST, bool LLSNEG, V3 FL1, V2 WAVNUM, V2 CINV, V2 XK2CG, V1 WDWAVE, V1 WSWAVE,
+                V1 UFRIC, V1 Z0M, V2 COSWDIF, V2 SINWDIF2, V1 RAORW, V1 WSTAR, V3 FLD, V3 SL, V3 SPOS, V3 XLLWS) {
+  (void)XK2CG; (void)SINWDIF2;
+  const Tables& t = x.t;
+  const Config& c = x.c;
+  const int KIJS = x.KIJS, KIJL = x.KIJL, NANG = x.NANG, NFRE = x.NFRE;
+  if (c.llnormagam) throw std::runtime_error("SINPUT_ARD: LLNORMAGAM branch not restated");
+  const int n = KIJL + 1;
+  std::vector<double> CONSTF(n), Z0VIS(n), Z0NOZ(n), FWW(n), PVISC(n), PTURB(n), ZCN(n), SIG_Ns(n), UORBT(n), AORB(n),
+      TEMP(n), RE(n), RE_C(n), ZORB(n), CNSN(n), FLP_AVG(n), SLP_AVG(n), ROGOROAIR(n), AIRD_PVISC(n), USG2(n), FLP(n),
+      SLP(n), DSTAB1(n), TEMP1(n), TEMP2(n), CONST11(n), CONST22(n);
+  std::vector<double> XSTRESS(2 * n), YSTRESS(2 * n), TAUX(2 * n), TAUY(2 * n), USTP(2 * n), USTPM1(2 * n), USDIRP(2 * n),
+      UCN(2 * n), UCNZALPD(2 * n), GAMNORMA(2 * n, 1.0);
+  auto i2 = [n](int ij, int ig) { return ij + n * (ig - 1); };
+  std::vector<double> GAM0((size_t)n * NANG * 2), DSTAB((size_t)n * NANG * 2, 0.0), COSLP((size_t)n * NANG);
+  auto i3 = [n, NANG](int ij, int k, int ig) { return ij + (size_t)n * ((k - 1) + (size_t)NANG * (ig - 1)); };
+  auto ik = [n](int ij, int k) { return ij + (size_t)n * (k - 1); };
+
+  double AVG_GST = 1.0 / NGST;
+  double CONST1 = t.BETAMAXOXKAPPA2;
+  double ABS_TAUWSHELTER = std::fabs(t.TAUWSHELTER);
+  bool LTAUWSHELTER = ABS_TAUWSHELTER != 0.0;
+  if (NGST > 1) WSIGSTAR(x, WSWAVE, UFRIC, Z0M, WSTAR, V1{SIG_Ns.data() + 1});
+  double NU_AIR = 0, FACM1_NU_AIR = 0, FAC_NU_AIR = 0, FU = 0, FUD = 0, DELABM1 = 0;
+  if (LLSNEG) {
+    NU_AIR = c.rnu;
+    FACM1_NU_AIR = 4.0 / NU_AIR;
+    FAC_NU_AIR = c.rnum;
+    FU = std::fabs(t.SWELLF3);
+    FUD = t.SWELLF2;
+    DELABM1 = (double)t.IAB / (t.ABMAX - t.ABMIN);
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) { UORBT[IJ] = t.EPSMIN; AORB[IJ] = t.EPSMIN; }
+    for (int M = 1; M <= NFRE; ++M) {
+      double SIG = t.ZPIFR(M), SIG2 = SIG * SIG, DFIM_SIG2 = t.DFIM(M) * SIG2;
+      for (int IJ = KIJS; IJ <= KIJL; ++IJ) TEMP[IJ] = FL1(IJ, 1, M);
+      for (int K = 2; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) TEMP[IJ] = TEMP[IJ] + FL1(IJ, K, M);
+      for (int IJ = KIJS; IJ <= KIJL; ++IJ) { UORBT[IJ] = UORBT[IJ] + DFIM_SIG2 * TEMP[IJ]; AORB[IJ] = AORB[IJ] + t.DFIM(M) * TEMP[IJ]; }
+    }
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      UORBT[IJ] = 2.0 * std::sqrt(UORBT[IJ]);
+      AORB[IJ] = 2.0 * std::sqrt(AORB[IJ]);
+      RE[IJ] = FACM1_NU_AIR * UORBT[IJ] * AORB[IJ];
+      Z0VIS[IJ] = FAC_NU_AIR / std::max(UFRIC(IJ), 0.0001);
+      double Z0TUB = t.Z0RAT * std::min(t.Z0TUBMAX, Z0M(IJ));
+      Z0NOZ[IJ] = std::max(Z0VIS[IJ], Z0TUB);
+      ZORB[IJ] = AORB[IJ] / Z0NOZ[IJ];
+      double XI = (std::log10(std::max(ZORB[IJ], 3.0)) - t.ABMIN) * DELABM1;
+      int IND = std::min(t.IAB - 1, (int)XI);
+      double DELI1 = std::min(1.0, XI - (double)IND);
+      double DELI2 = 1.0 - DELI1;
+      FWW[IJ] = t.SWELLFT(IND) * DELI2 + t.SWELLFT(IND + 1) * DELI1;
+      TEMP2[IJ] = FWW[IJ] * UORBT[IJ];
+    }
+    if (t.SWELLF6 == 1.0) { for (int IJ = KIJS; IJ <= KIJL; ++IJ) RE_C[IJ] = t.SWELLF4; }
+    else { double H = 1.0 - t.SWELLF6; for (int IJ = KIJS; IJ <= KIJL; ++IJ) RE_C[IJ] = t.SWELLF4 * std::pow(2.0 / AORB[IJ], H); }
+    if (t.SWELLF7 > 0.0) {
+      for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+        double SMOOTH = 0.5 * std::tanh((RE[IJ] - RE_C[IJ]) * t.SWELLF7M1);
+        PTURB[IJ] = 0.5 + SMOOTH; PVISC[IJ] = 0.5 - SMOOTH;
+      }
+    } else {
+      for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+        if (RE[IJ] <= RE_C[IJ]) { PTURB[IJ] = 0.0; PVISC[IJ] = 0.5; } else { PTURB[IJ] = 0.5; PVISC[IJ] = 0.0; }
+      }
+    }
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) AIRD_PVISC[IJ] = PVISC[IJ] * RAORW(IJ);
+  }
+  if (NGST == 1) { for (int IJ = KIJS; IJ <= KIJL; ++IJ) USTP[i2(IJ, 1)] = UFRIC(IJ); }
+  else if (NGST == 2) {
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) { USTP[i2(IJ, 1)] = UFRIC(IJ) * (1.0 + SIG_Ns[IJ]); USTP[i2(IJ, 2)] = UFRIC(IJ) * (1.0 - SIG_Ns[IJ]); }
+  } else throw std::runtime_error("SINPUT_ARD: NGST > 2");
+  for (int IGST = 1; IGST <= NGST; ++IGST) for (int IJ = KIJS; IJ <= KIJL; ++IJ) USTPM1[i2(IJ, IGST)] = 1.0 / std::max(USTP[i2(IJ, IGST)], t.EPSUS);
+  if (LTAUWSHELTER) {
+    for (int IGST = 1; IGST <= NGST; ++IGST)
+      for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+        XSTRESS[i2(IJ, IGST)] = 0.0; YSTRESS[i2(IJ, IGST)] = 0.0;
+        USG2[IJ] = sq(USTP[i2(IJ, IGST)]);
+        TAUX[i2(IJ, IGST)] = USG2[IJ] * std::sin(WDWAVE(IJ));
+        TAUY[i2(IJ, IGST)] = USG2[IJ] * std::cos(WDWAVE(IJ));
+      }
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) ROGOROAIR[IJ] = t.G / RAORW(IJ);
+  } else {
+    for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) COSLP[ik(IJ, K)] = COSWDIF(IJ, K);
+  }
+  double COEF = 0, COEF5 = 0;
+  for (int M = 1; M <= NFRE; ++M) {
+    double SIG = t.ZPIFR(M), SIG2 = SIG * SIG, CONST = SIG * CONST1;
+    if (LLSNEG) { COEF = -t.SWELLF * 16. * SIG2 / t.G; COEF5 = -t.SWELLF5 * 2. * std::sqrt(2. * NU_AIR * SIG); }
+    if (LTAUWSHELTER) {
+      for (int IGST = 1; IGST <= NGST; ++IGST)
+        for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+          double TAUPX = TAUX[i2(IJ, IGST)] - ABS_TAUWSHELTER * XSTRESS[i2(IJ, IGST)];
+          double TAUPY = TAUY[i2(IJ, IGST)] - ABS_TAUWSHELTER * YSTRESS[i2(IJ, IGST)];
+          USDIRP[i2(IJ, IGST)] = std::atan2(TAUPX, TAUPY);
+          USTP[i2(IJ, IGST)] = std::pow(TAUPX * TAUPX + TAUPY * TAUPY, 0.25);
+          USTPM1[i2(IJ, IGST)] = 1.0 / std::max(USTP[i2(IJ, IGST)], t.EPSUS);
+        }
+      for (int IJ = KIJS; IJ <= KIJL; ++IJ) CONSTF[IJ] = ROGOROAIR[IJ] * CINV(IJ, M) * t.DFIM(M);
+    }
+    for (int IGST = 1; IGST <= NGST; ++IGST)
+      for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+        UCN[i2(IJ, IGST)] = USTP[i2(IJ, IGST)] * CINV(IJ, M);
+        UCNZALPD[i2(IJ, IGST)] = t.XKAPPA / (UCN[i2(IJ, IGST)] + t.ZALP);
+      }
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) { ZCN[IJ] = std::log(WAVNUM(IJ, M) * Z0M(IJ)); CNSN[IJ] = CONST * RAORW(IJ); }
+    for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) XLLWS(IJ, K, M) = 0.0;
+    if (LLSNEG) for (int IJ = KIJS; IJ <= KIJL; ++IJ) { DSTAB1[IJ] = COEF5 * AIRD_PVISC[IJ] * WAVNUM(IJ, M); TEMP1[IJ] = COEF * RAORW(IJ); }
+    for (int IGST = 1; IGST <= NGST; ++IGST) {
+      for (int K = 1; K <= NANG; ++K) {
+        if (LTAUWSHELTER) for (int IJ = KIJS; IJ <= KIJL; ++IJ) COSLP[ik(IJ, K)] = std::cos(t.TH(K) - USDIRP[i2(IJ, IGST)]);
+        for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+          GAM0[i3(IJ, K, IGST)] = 0.0;
+          if (COSLP[ik(IJ, K)] > 0.01) {
+            double X = COSLP[ik(IJ, K)] * UCN[i2(IJ, IGST)];
+            double ZLOG = ZCN[IJ] + UCNZALPD[i2(IJ, IGST)] / COSLP[ik(IJ, K)];
+            if (ZLOG < 0.0) {
+              double ZLOG2X = ZLOG * ZLOG * X;
+              GAM0[i3(IJ, K, IGST)] = std::exp(ZLOG) * ZLOG2X * ZLOG2X * CNSN[IJ];
+              XLLWS(IJ, K, M) = 1.0;
+            }
+          }
+        }
+      }
+      if (LLSNEG)
+        for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+          double DSTAB2 = TEMP1[IJ] * (TEMP2[IJ] + (FU + FUD * COSLP[ik(IJ, K)]) * USTP[i2(IJ, IGST)]);
+          DSTAB[i3(IJ, K, IGST)] = DSTAB1[IJ] + PTURB[IJ] * DSTAB2;
+        }
+    }
+    for (int K = 1; K <= NANG; ++K) {
+      for (int IGST = 1; IGST <= NGST; ++IGST) {
+        for (int IJ = KIJS; IJ <= KIJL; ++IJ) { SLP[IJ] = GAM0[i3(IJ, K, IGST)] * GAMNORMA[i2(IJ, IGST)]; FLP[IJ] = SLP[IJ] + DSTAB[i3(IJ, K, IGST)]; }
+        for (int IJ = KIJS; IJ <= KIJL; ++IJ) SLP[IJ] = SLP[IJ] * FL1(IJ, K, M);
+        if (LTAUWSHELTER) {
+          for (int IJ = KIJS; IJ <= KIJL; ++IJ) { CONST11[IJ] = CONSTF[IJ] * t.SINTH(K); CONST22[IJ] = CONSTF[IJ] * t.COSTH(K); }
+          for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+            XSTRESS[i2(IJ, IGST)] = XSTRESS[i2(IJ, IGST)] + SLP[IJ] * CONST11[IJ];
+            YSTRESS[i2(IJ, IGST)] = YSTRESS[i2(IJ, IGST)] + SLP[IJ] * CONST22[IJ];
+          }
+        }
+        if (IGST == 1) { for (int IJ = KIJS; IJ <= KIJL; ++IJ) { SLP_AVG[IJ] = SLP[IJ]; FLP_AVG[IJ] = FLP[IJ]; } }
+        else { for (int IJ = KIJS; IJ <= KIJL; ++IJ) { SLP_AVG[IJ] = SLP_AVG[IJ] + SLP[IJ]; FLP_AVG[IJ] = FLP_AVG[IJ] + FLP[IJ]; } }
+      }
+      for (int IJ = KIJS; IJ <= KIJL; ++IJ) SPOS(IJ, K, M) = AVG_GST * SLP_AVG[IJ];
+      for (int IJ = KIJS; IJ <= KIJL; ++IJ) { FLD(IJ, K, M) = AVG_GST * FLP_AVG[IJ]; SL(IJ, K, M) = FLD(IJ, K, M) * FL1(IJ, K, M); }
+    }
+  }
+}
+
+// sinput_jan.F90:150-400
+void SINPUT_JAN(const Ctx& x, int NGST, bool LLSNEG, V3 FL1, V2 WAVNUM, V2 CINV, V2 XK2CG, V1 WSWAVE, V1 UFRIC, V1 Z0M,
+                V2 COSWDIF, V2 SINWDIF2, V1 RAORW, V1 WSTAR, V3 FLD, V3 SL, V3 SPOS, V3 XLLWS) {
+  (void)XK2CG; (void)SINWDIF2;
+  const Tables& t = x.t;
+  const Config& c = x.c;
+  const int KIJS = x.KIJS, KIJL = x.KIJL, NANG = x.NANG, NFRE = x.NFRE;
+  if (c.llnormagam) throw std::runtime_error("SINPUT_JAN: LLNORMAGAM branch not restated");
+  const int n = KIJL + 1;
+  auto i2 = [n](int ij, int ig) { return ij + n * (ig - 1); };
+  auto i3 = [n, NANG](int ij, int k, int ig) { return ij + (size_t)n * ((k - 1) + (size_t)NANG * (ig - 1)); };
+  auto ik = [n](int ij, int k) { return ij + (size_t)n * (k - 1); };
+  std::vector<double> ZTANHKD(n), SIG_Ns(n), CNSN(n), UFAC1(n), UFAC2(n);
+  std::vector<double> SIGDEV(2 * n), US(2 * n), Z0(2 * n), UCN(2 * n), ZCN(2 * n), USTPM1(2 * n), XVD(2 * n), UCND(2 * n),
+      CONST3_UCN2(2 * n), GAMNORMA(2 * n, 1.0);
+  std::vector<double> GAM0((size_t)n * NANG * 2);
+  std::vector<char> LZ((size_t)n * NANG);
+  double WSIN[3] = {0, 0, 0};
+  double CONST1 = t.BETAMAXOXKAPPA2;
+  double CONST3 = 2.0 * t.XKAPPA / CONST1;
+  double XKAPPAD = 1.E0 / t.XKAPPA;
+  CONST3 = c.idamping * CONST3;
+  if (NGST > 1) WSIGSTAR(x, WSWAVE, UFRIC, Z0M, WSTAR, V1{SIG_Ns.data() + 1});
+  for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) LZ[ik(IJ, K)] = COSWDIF(IJ, K) > 0.01;
+  if (NGST == 1) { WSIN[1] = 1.0; for (int IJ = KIJS; IJ <= KIJL; ++IJ) SIGDEV[i2(IJ, 1)] = 1.0; }
+  else if (NGST == 2) {
+    WSIN[1] = 0.5; WSIN[2] = 0.5;
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) { SIGDEV[i2(IJ, 1)] = 1.0 - SIG_Ns[IJ]; SIGDEV[i2(IJ, 2)] = 1.0 + SIG_Ns[IJ]; }
+  } else throw std::runtime_error("SINPUT_JAN: NGST > 2");
+  if (NGST == 1) { for (int IJ = KIJS; IJ <= KIJL; ++IJ) { US[i2(IJ, 1)] = UFRIC(IJ); Z0[i2(IJ, 1)] = Z0M(IJ); } }
+  else for (int IGST = 1; IGST <= NGST; ++IGST) for (int IJ = KIJS; IJ <= KIJL; ++IJ) { US[i2(IJ, IGST)] = UFRIC(IJ) * SIGDEV[i2(IJ, IGST)]; Z0[i2(IJ, IGST)] = Z0M(IJ); }
+  for (int IGST = 1; IGST <= NGST; ++IGST) for (int IJ = KIJS; IJ <= KIJL; ++IJ) USTPM1[i2(IJ, IGST)] = 1.0 / std::max(US[i2(IJ, IGST)], t.EPSUS);
+  for (int M = 1; M <= NFRE; ++M) {
+    double CONST = t.ZPIFR(M) * CONST1;
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) ZTANHKD[IJ] = sq(t.ZPIFR(M)) / (t.G * WAVNUM(IJ, M));
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) CNSN[IJ] = CONST * ZTANHKD[IJ] * RAORW(IJ);
+    for (int IGST = 1; IGST <= NGST; ++IGST)
+      for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+        UCN[i2(IJ, IGST)] = US[i2(IJ, IGST)] * CINV(IJ, M) + t.ZALP;
+        CONST3_UCN2[i2(IJ, IGST)] = CONST3 * sq(UCN[i2(IJ, IGST)]);
+        UCND[i2(IJ, IGST)] = 1.0 / UCN[i2(IJ, IGST)];
+        ZCN[i2(IJ, IGST)] = std::log(WAVNUM(IJ, M) * Z0[i2(IJ, IGST)]);
+        XVD[i2(IJ, IGST)] = 1.0 / (-US[i2(IJ, IGST)] * XKAPPAD * ZCN[i2(IJ, IGST)] * CINV(IJ, M));
+      }
+    for (int K = 1; K <= NANG; ++K) {
+      for (int IJ = KIJS; IJ <= KIJL; ++IJ) XLLWS(IJ, K, M) = 0.0;
+      for (int IGST = 1; IGST <= NGST; ++IGST)
+        for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+          if (LZ[ik(IJ, K)]) {
+            double ZLOG = ZCN[i2(IJ, IGST)] + t.XKAPPA / COSWDIF(IJ, K) * UCND[i2(IJ, IGST)];
+            if (ZLOG < 0.0) {
+              double X = COSWDIF(IJ, K) * UCN[i2(IJ, IGST)];
+              double ZLOG2X = ZLOG * ZLOG * X;
+              GAM0[i3(IJ, K, IGST)] = ZLOG2X * ZLOG2X * std::exp(ZLOG) * CNSN[IJ];
+              XLLWS(IJ, K, M) = 1.0;
+            } else GAM0[i3(IJ, K, IGST)] = 0.0;
+          } else GAM0[i3(IJ, K, IGST)] = 0.0;
+        }
+    }
+    for (int K = 1; K <= NANG; ++K) {
+      for (int IJ = KIJS; IJ <= KIJL; ++IJ) UFAC1[IJ] = WSIN[1] * GAM0[i3(IJ, K, 1)] * GAMNORMA[i2(IJ, 1)];
+      if (NGST == 2) for (int IJ = KIJS; IJ <= KIJL; ++IJ) UFAC1[IJ] = UFAC1[IJ] + WSIN[2] * GAM0[i3(IJ, K, 2)] * GAMNORMA[i2(IJ, 2)];
+      if (LLSNEG) {
+        for (int IJ = KIJS; IJ <= KIJL; ++IJ) { double ZBETA = CONST3_UCN2[i2(IJ, 1)] * (COSWDIF(IJ, K) - XVD[i2(IJ, 1)]); UFAC2[IJ] = WSIN[1] * ZBETA; }
+        if (NGST == 2) for (int IJ = KIJS; IJ <= KIJL; ++IJ) { double ZBETA = CONST3_UCN2[i2(IJ, 2)] * (COSWDIF(IJ, K) - XVD[i2(IJ, 2)]); UFAC2[IJ] = UFAC2[IJ] + WSIN[2] * ZBETA; }
+      } else for (int IJ = KIJS; IJ <= KIJL; ++IJ) UFAC2[IJ] = 0.0;
+      for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+        FLD(IJ, K, M) = UFAC1[IJ] + UFAC2[IJ] * CNSN[IJ];
+        SPOS(IJ, K, M) = UFAC1[IJ] * FL1(IJ, K, M);
+        SL(IJ, K, M) = FLD(IJ, K, M) * FL1(IJ, K, M);
+      }
+    }
+  }
+}
+
+// tau_phi_hf.F90:111-305 (LLGCBZ0=F, LLNORMAGAM=F)
+void TAU_PHI_HF(const Ctx& x, I1 MIJ, bool LTAUWSHELTER, V1 UFRIC, V1 Z0M, V3 FL1, V1 AIRD, V2 COSWDIF, V2 SINWDIF2,
+                V1 UST, V1 TAUHF, V1 PHIHF, bool LLPHIHF) {
+  (void)UFRIC;
+  const Tables& t = x.t;
+  const int KIJS = x.KIJS, KIJL = x.KIJL, NANG = x.NANG;
+  const int n = KIJL + 1;
+  const double ZSUPMAX = 0.0;
+  std::vector<double> SQRTZ0OG(n), ZSUP(n), ZINF(n), DELZ(n), TAUL(n), XLOGGZ0(n), SQRTGZ0(n), USTPH(n), CONST1(n, 0.0),
+      CONST2(n, 0.0), CONSTTAU(n), CONSTPHI(n), F1DCOS2(n), F1DCOS3(n), F1D(n), F1DSIN2(n);
+  double X0G = t.X0TAUHF * t.G;
+  if (LLPHIHF) for (int IJ = KIJS; IJ <= KIJL; ++IJ) USTPH[IJ] = UST(IJ);
+  for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+    XLOGGZ0[IJ] = std::log(t.G * Z0M(IJ));
+    double OMEGACC = std::max(t.ZPIFR(MIJ(IJ)), X0G / UST(IJ));
+    SQRTZ0OG[IJ] = std::sqrt(Z0M(IJ) * t.GM1);
+    SQRTGZ0[IJ] = 1.0 / SQRTZ0OG[IJ];
+    double YC = OMEGACC * SQRTZ0OG[IJ];
+    ZINF[IJ] = std::log(YC);
+  }
+  for (int IJ = KIJS; IJ <= KIJL; ++IJ) CONSTTAU[IJ] = t.ZPI4GM2 * t.FR5(MIJ(IJ));
+  for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+    double COSW = std::max(COSWDIF(IJ, 1), 0.0);
+    double FCOSW2 = FL1(IJ, 1, MIJ(IJ)) * COSW * COSW;
+    F1DCOS3[IJ] = FCOSW2 * COSW; F1DCOS2[IJ] = FCOSW2;
+    F1DSIN2[IJ] = FL1(IJ, 1, MIJ(IJ)) * SINWDIF2(IJ, 1);
+    F1D[IJ] = FL1(IJ, 1, MIJ(IJ));
+  }
+  for (int K = 2; K <= NANG; ++K)
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      double COSW = std::max(COSWDIF(IJ, K), 0.0);
+      double FCOSW2 = FL1(IJ, K, MIJ(IJ)) * COSW * COSW;
+      F1DCOS3[IJ] = F1DCOS3[IJ] + FCOSW2 * COSW;
+      F1DCOS2[IJ] = F1DCOS2[IJ] + FCOSW2;
+      F1DSIN2[IJ] = F1DSIN2[IJ] + FL1(IJ, K, MIJ(IJ)) * SINWDIF2(IJ, K);
+      F1D[IJ] = F1D[IJ] + FL1(IJ, K, MIJ(IJ));
+    }
+  for (int IJ = KIJS; IJ <= KIJL; ++IJ) { F1DCOS3[IJ] = t.DELTH * F1DCOS3[IJ]; F1DCOS2[IJ] = t.DELTH * F1DCOS2[IJ]; F1DSIN2[IJ] = t.DELTH * F1DSIN2[IJ]; F1D[IJ] = t.DELTH * F1D[IJ]; }
+  for (int IJ = KIJS; IJ <= KIJL; ++IJ) ZSUP[IJ] = ZSUPMAX;
+  for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+    TAUL[IJ] = sq(UST(IJ));
+    DELZ[IJ] = std::max((ZSUP[IJ] - ZINF[IJ]) / (double)(t.JTOT_TAUHF - 1), 0.0);
+    TAUHF(IJ) = 0.0;
+  }
+  if (LTAUWSHELTER) {
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ)
+      for (int J = 1; J <= t.JTOT_TAUHF; ++J) {
+        double Y = std::exp(ZINF[IJ] + (double)(J - 1) * DELZ[IJ]);
+        double OMEGA = Y * SQRTGZ0[IJ];
+        double CM1 = OMEGA * t.GM1;
+        double ZX = UST(IJ) * CM1 + t.ZALP;
+        double ZARG = t.XKAPPA / ZX;
+        double ZLOG = XLOGGZ0[IJ] + 2.0 * std::log(CM1) + ZARG;
+        ZLOG = std::min(ZLOG, 0.0);
+        double ZBETA = p4(ZLOG) * std::exp(ZLOG);
+        double ZNZ = ZBETA * UST(IJ) * Y;
+        double GAMNORMA = (1.0 + CONST1[IJ] * ZNZ) / (1.0 + CONST2[IJ] * ZNZ);
+        double FNC2 = F1DCOS3[IJ] * CONSTTAU[IJ] * ZBETA * TAUL[IJ] * t.WTAUHF(J) * DELZ[IJ] * GAMNORMA;
+        TAUL[IJ] = std::max(TAUL[IJ] - t.TAUWSHELTER * FNC2, 0.0);
+        UST(IJ) = std::sqrt(TAUL[IJ]);
+        TAUHF(IJ) = TAUHF(IJ) + FNC2;
+      }
+  } else {
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      for (int J = 1; J <= t.JTOT_TAUHF; ++J) {
+        double Y = std::exp(ZINF[IJ] + (double)(J - 1) * DELZ[IJ]);
+        double OMEGA = Y * SQRTGZ0[IJ];
+        double CM1 = OMEGA * t.GM1;
+        double ZX = UST(IJ) * CM1 + t.ZALP;
+        double ZARG = t.XKAPPA / ZX;
+        double ZLOG = XLOGGZ0[IJ] + 2.0 * std::log(CM1) + ZARG;
+        ZLOG = std::min(ZLOG, 0.0);
+        double ZBETA = p4(ZLOG) * std::exp(ZLOG);
+        double FNC2 = ZBETA * t.WTAUHF(J);
+        double ZNZ = ZBETA * UST(IJ) * Y;
+        double GAMNORMA = (1.0 + CONST1[IJ] * ZNZ) / (1.0 + CONST2[IJ] * ZNZ);
+        TAUHF(IJ) = TAUHF(IJ) + FNC2 * GAMNORMA;
+      }
+      TAUHF(IJ) = F1DCOS3[IJ] * CONSTTAU[IJ] * TAUL[IJ] * TAUHF(IJ) * DELZ[IJ];
+    }
+  }
+  for (int IJ = KIJS; IJ <= KIJL; ++IJ) PHIHF(IJ) = 0.0;
+  if (LLPHIHF) {
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      TAUL[IJ] = sq(USTPH[IJ]);
+      ZSUP[IJ] = ZSUPMAX;
+      DELZ[IJ] = std::max((ZSUP[IJ] - ZINF[IJ]) / (double)(t.JTOT_TAUHF - 1), 0.0);
+    }
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) CONSTPHI[IJ] = AIRD(IJ) * t.ZPI4GM1 * t.FR5(MIJ(IJ));
+    if (LTAUWSHELTER) {
+      for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+        for (int J = 1; J <= t.JTOT_TAUHF; ++J) {
+          double Y = std::exp(ZINF[IJ] + (double)(J - 1) * DELZ[IJ]);
+          double OMEGA = Y * SQRTGZ0[IJ];
+          double CM1 = OMEGA * t.GM1;
+          double ZX = USTPH[IJ] * CM1 + t.ZALP;
+          double ZARG = t.XKAPPA / ZX;
+          double ZLOG = XLOGGZ0[IJ] + 2.0 * std::log(CM1) + ZARG;
+          ZLOG = std::min(ZLOG, 0.0);
+          double ZBETA = p4(ZLOG) * std::exp(ZLOG);
+          double ZNZ = ZBETA * UST(IJ) * Y;
+          double GAMNORMA = (1.0 + CONST1[IJ] * ZNZ) / (1.0 + CONST2[IJ] * ZNZ);
+          double FNC2 = ZBETA * TAUL[IJ] * t.WTAUHF(J) * DELZ[IJ] * GAMNORMA;
+          TAUL[IJ] = std::max(TAUL[IJ] - t.TAUWSHELTER * F1DCOS3[IJ] * CONSTTAU[IJ] * FNC2, 0.0);
+          USTPH[IJ] = std::sqrt(TAUL[IJ]);
+          PHIHF(IJ) = PHIHF(IJ) + FNC2 / Y;
+        }
+        PHIHF(IJ) = F1DCOS2[IJ] * CONSTPHI[IJ] * SQRTZ0OG[IJ] * PHIHF(IJ);
+      }
+    } else {
+      for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+        for (int J = 1; J <= t.JTOT_TAUHF; ++J) {
+          double Y = std::exp(ZINF[IJ] + (double)(J - 1) * DELZ[IJ]);
+          double OMEGA = Y * SQRTGZ0[IJ];
+          double CM1 = OMEGA * t.GM1;
+          double ZX = USTPH[IJ] * CM1 + t.ZALP;
+          double ZARG = t.XKAPPA / ZX;
+          double ZLOG = XLOGGZ0[IJ] + 2.0 * std::log(CM1) + ZARG;
+          ZLOG = std::min(ZLOG, 0.0);
+          double ZBETA = p4(ZLOG) * std::exp(ZLOG);
+          double ZNZ = ZBETA * UST(IJ) * Y;
+          double GAMNORMA = (1.0 + CONST1[IJ] * ZNZ) / (1.0 + CONST2[IJ] * ZNZ);
+          double FNC2 = ZBETA * t.WTAUHF(J) * GAMNORMA;
+          PHIHF(IJ) = PHIHF(IJ) + FNC2 / Y;
+        }
+        PHIHF(IJ) = F1DCOS2[IJ] * CONSTPHI[IJ] * SQRTZ0OG[IJ] * TAUL[IJ] * PHIHF(IJ) * DELZ[IJ];
+      }
+    }
+  }
+}
+
+// stresso.F90:120-233
+void STRESSO(const Ctx& x, I1 MIJ, V2 RHOWGDFTH, V3 FL1, V3 SL, V3 SPOS, V2 CINV, V1 WDWAVE, V1 UFRIC, V1 Z0M, V1 AIRD,
+             V2 COSWDIF, V2 SINWDIF2, V1 TAUW, V1 TAUWDIR, V1 PHIWA, bool LLPHIWA) {
+  const Tables& t = x.t;
+  const int KIJS = x.KIJS, KIJL = x.KIJL, NANG = x.NANG, NFRE = x.NFRE;
+  const int n = KIJL + 1;
+  std::vector<double> XSTRESS(n), YSTRESS(n), TAUHF(n), PHIHF(n), USDIRP(n), UST(n), SUMT(n), SUMX(n), SUMY(n);
+  for (int IJ = KIJS; IJ <= KIJL; ++IJ) { PHIWA(IJ) = 0.0; XSTRESS[IJ] = 0.0; YSTRESS[IJ] = 0.0; }
+  if (LLPHIWA)
+    for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ)
+      PHIWA(IJ) = PHIWA(IJ) + (SL(IJ, K, M) - SPOS(IJ, K, M)) * t.RHOWG_DFIM(M);
+  for (int M = 1; M <= NFRE; ++M) {
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) { SUMX[IJ] = SPOS(IJ, 1, M) * t.SINTH(1); SUMY[IJ] = SPOS(IJ, 1, M) * t.COSTH(1); SUMT[IJ] = SPOS(IJ, 1, M); }
+    for (int K = 2; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      SUMX[IJ] = SUMX[IJ] + SPOS(IJ, K, M) * t.SINTH(K);
+      SUMY[IJ] = SUMY[IJ] + SPOS(IJ, K, M) * t.COSTH(K);
+      SUMT[IJ] = SUMT[IJ] + SPOS(IJ, K, M);
+    }
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      double CMRHOWGDFTH = RHOWGDFTH(IJ, M) * CINV(IJ, M);
+      XSTRESS[IJ] = XSTRESS[IJ] + CMRHOWGDFTH * SUMX[IJ];
+      YSTRESS[IJ] = YSTRESS[IJ] + CMRHOWGDFTH * SUMY[IJ];
+    }
+    if (LLPHIWA) for (int IJ = KIJS; IJ <= KIJL; ++IJ) PHIWA(IJ) = PHIWA(IJ) + RHOWGDFTH(IJ, M) * SUMT[IJ];
+  }
+  for (int IJ = KIJS; IJ <= KIJL; ++IJ) { XSTRESS[IJ] = XSTRESS[IJ] / std::max(AIRD(IJ), 1.0); YSTRESS[IJ] = YSTRESS[IJ] / std::max(AIRD(IJ), 1.0); }
+  bool LTAUWSHELTER;
+  if (x.c.iphys == 0 || t.TAUWSHELTER == 0.0) {
+    LTAUWSHELTER = false;
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) { USDIRP[IJ] = WDWAVE(IJ); UST[IJ] = UFRIC(IJ); }
+  } else {
+    LTAUWSHELTER = true;
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      double TAUX = sq(UFRIC(IJ)) * std::sin(WDWAVE(IJ));
+      double TAUY = sq(UFRIC(IJ)) * std::cos(WDWAVE(IJ));
+      double TAUPX = TAUX - t.TAUWSHELTER * XSTRESS[IJ];
+      double TAUPY = TAUY - t.TAUWSHELTER * YSTRESS[IJ];
+      USDIRP[IJ] = std::atan2(TAUPX, TAUPY);
+      UST[IJ] = std::pow(TAUPX * TAUPX + TAUPY * TAUPY, 0.25);
+    }
+  }
+  TAU_PHI_HF(x, MIJ, LTAUWSHELTER, UFRIC, Z0M, FL1, AIRD, COSWDIF, SINWDIF2, V1{UST.data() + 1}, V1{TAUHF.data() + 1},
+             V1{PHIHF.data() + 1}, LLPHIWA);
+  for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+    XSTRESS[IJ] = XSTRESS[IJ] + TAUHF[IJ] * std::sin(USDIRP[IJ]);
+    YSTRESS[IJ] = YSTRESS[IJ] + TAUHF[IJ] * std::cos(USDIRP[IJ]);
+    TAUW(IJ) = std::sqrt(sq(XSTRESS[IJ]) + sq(YSTRESS[IJ]));
+    TAUW(IJ) = std::max(TAUW(IJ), 0.0);
+    TAUWDIR(IJ) = std::atan2(XSTRESS[IJ], YSTRESS[IJ]);
+  }
+  if (!x.c.llgcbz0) {
+    double TAUTOUS2 = 1.0 / (1.0 + t.EPS1);
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) TAUW(IJ) = std::min(TAUW(IJ), sq(UFRIC(IJ)) * TAUTOUS2);
+  }
+  if (LLPHIWA) for (int IJ = KIJS; IJ <= KIJL; ++IJ) PHIWA(IJ) = PHIWA(IJ) + PHIHF[IJ];
+}
+
+// sdissip_ard.F90:131-318 (SSDSC3 = 0 and SSDSC5 = 0: cumulative and turbulence terms are dead, setwavphys.F90:152,177)
+void SDISSIP_ARD(const Ctx& x, V3 FL1, V3 FLD, V3 SL, V2 WAVNUM, V2 CGROUP, V2 XK2CG, V1 UFRIC, V2 COSWDIF, V1 RAORW) {
+  (void)CGROUP; (void)UFRIC; (void)COSWDIF; (void)RAORW;
+  const Tables& t = x.t;
+  const int KIJS = x.KIJS, KIJL = x.KIJL, NANG = x.NANG, NFRE = x.NFRE;
+  if (t.SSDSC3 != 0.0 || t.SSDSC5 != 0.0) throw std::runtime_error("SDISSIP_ARD: SSDSC3/SSDSC5 terms not restated");
+  const int n = KIJL;
+  std::vector<double> FACSAT((size_t)n * NFRE), BTH0((size_t)n * NFRE, 0.0), BTH((size_t)n * NANG * NFRE, 0.0), D((size_t)n * NANG * NFRE);
+  V2 vFACSAT{FACSAT.data(), n}, vBTH0{BTH0.data(), n};
+  V3 vBTH{BTH.data(), n, NANG}, vD{D.data(), n, NANG};
+  double TPIINV = 1.0 / t.ZPI;
+  double TMP03 = 1.0 / (t.SDSBR * t.MICHE);
+  double SSDSC6M1 = 1. - t.SSDSC6;
+  for (int M = 1; M <= NFRE; ++M) for (int IJ = KIJS; IJ <= KIJL; ++IJ) vFACSAT(IJ, M) = WAVNUM(IJ, M) * TPIINV * XK2CG(IJ, M);
+  for (int M = 1; M <= NFRE; ++M)
+    for (int K = 1; K <= NANG; ++K) {
+      for (int K2 = 1; K2 <= t.NSDSNTH * 2 + 1; ++K2) {
+        int KK = t.INDICESSAT(K, K2);
+        for (int IJ = KIJS; IJ <= KIJL; ++IJ) vBTH(IJ, K, M) = vBTH(IJ, K, M) + t.SATWEIGHTS(K, K2) * FL1(IJ, KK, M);
+      }
+      for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+        vBTH(IJ, K, M) = vBTH(IJ, K, M) * vFACSAT(IJ, M);
+        vBTH0(IJ, M) = std::max(vBTH0(IJ, M), vBTH(IJ, K, M));
+      }
+    }
+  for (int M = 1; M <= NFRE; ++M) {
+    double SSDSC2_SIG = t.SSDSC2 * t.ZPIFR(M);
+    double ZCOEF = SSDSC2_SIG * t.SSDSC6;
+    double ZCOEFM1 = SSDSC2_SIG * SSDSC6M1;
+    for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ)
+      vD(IJ, K, M) = ZCOEF * sq(std::max(0., vBTH0(IJ, M) * TMP03 - t.SSDSC4)) + ZCOEFM1 * sq(std::max(0., vBTH(IJ, K, M) * TMP03 - t.SSDSC4));  // **IPSAT, IPSAT=2
+  }
+  for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+    SL(IJ, K, M) = SL(IJ, K, M) + vD(IJ, K, M) * FL1(IJ, K, M);
+    FLD(IJ, K, M) = FLD(IJ, K, M) + vD(IJ, K, M);
+  }
+}
+
+// sdissip_jan.F90:96-132
+void SDISSIP_JAN(const Ctx& x, V3 FL1, V3 FLD, V3 SL, V2 WAVNUM, V1 EMEAN, V1 F1MEAN, V1 XKMEAN) {
+  const Tables& t = x.t;
+  const int KIJS = x.KIJS, KIJL = x.KIJL, NANG = x.NANG, NFRE = x.NFRE;
+  const int n = KIJL + 1;
+  std::vector<double> TEMP1(n), SDS(n), X(n), XK2(n);
+  double DELTA_SDISM1 = 1.0 - t.DELTA_SDIS;
+  double CONSS = t.CDIS * t.ZPI;
+  for (int IJ = KIJS; IJ <= KIJL; ++IJ) SDS[IJ] = CONSS * F1MEAN(IJ) * sq(EMEAN(IJ)) * p4(XKMEAN(IJ));
+  for (int M = 1; M <= NFRE; ++M) {
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) { X[IJ] = WAVNUM(IJ, M) / XKMEAN(IJ); XK2[IJ] = sq(WAVNUM(IJ, M)); }
+    double CVIS = x.c.rnu * t.CDISVIS;
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) TEMP1[IJ] = SDS[IJ] * X[IJ] * (DELTA_SDISM1 + t.DELTA_SDIS * X[IJ]) + CVIS * XK2[IJ];
+    for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      FLD(IJ, K, M) = FLD(IJ, K, M) + TEMP1[IJ];
+      SL(IJ, K, M) = SL(IJ, K, M) + TEMP1[IJ] * FL1(IJ, K, M);
+    }
+  }
+}
+
+// snonlin.F90:116-498 (ISNONLIN = 0)
+void SNONLIN(const Ctx& x, V3 FL1, V3 FLD, V3 SL, V2 WAVNUM, V1 DEPTH, V1 AKMEAN) {
+  (void)WAVNUM;
+  const Tables& t = x.t;
+  const int KIJS = x.KIJS, KIJL = x.KIJL, NANG = x.NANG, NFRE = x.NFRE;
+  if (x.c.isnonlin != 0) throw std::runtime_error("SNONLIN: ISNONLIN != 0 not restated");
+  const int n = KIJL + 1;
+  std::vector<double> FTEMP(n), AD(n), DELAD(n), DELAP(n), DELAM(n), ENHFR(n);
+  std::vector<double> ENH((size_t)n * t.MLSTHG);
+  auto enh = [&](int ij, int mc) -> double& { return ENH[ij + (size_t)n * (mc - 1)]; };
+  for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+    ENHFR[IJ] = std::max(0.75 * DEPTH(IJ) * AKMEAN(IJ), 0.5);
+    ENHFR[IJ] = 1.0 + (5.5 / ENHFR[IJ]) * (1.0 - .833 * ENHFR[IJ]) * std::exp(-1.25 * ENHFR[IJ]);
+  }
+  for (int MC = 1; MC <= t.MLSTHG; ++MC) for (int IJ = KIJS; IJ <= KIJL; ++IJ) enh(IJ, MC) = ENHFR[IJ];
+  int MFR1STFR = -t.MFRSTLW + 1;
+  int MFRLSTFR = NFRE - t.KFRH + MFR1STFR;
+  for (int MC = 1; MC <= t.MLSTHG; ++MC) {
+    int MP = t.IKP(MC), MP1 = t.IKP1(MC), MM = t.IKM(MC), MM1 = t.IKM1(MC);
+    int IC = t.INLCOEF(1, MC), IP = t.INLCOEF(2, MC), IP1 = t.INLCOEF(3, MC), IM = t.INLCOEF(4, MC), IM1 = t.INLCOEF(5, MC);
+    double FTAIL = t.RNLCOEF(1, MC);
+    double GW1 = t.RNLCOEF(2, MC), GW2 = t.RNLCOEF(3, MC), GW3 = t.RNLCOEF(4, MC), GW4 = t.RNLCOEF(5, MC);
+    double FKLAMPA = t.RNLCOEF(6, MC), FKLAMPB = t.RNLCOEF(7, MC), FKLAMP2 = t.RNLCOEF(8, MC), FKLAMP1 = t.RNLCOEF(9, MC);
+    double FKLAPA2 = t.RNLCOEF(10, MC), FKLAPB2 = t.RNLCOEF(11, MC), FKLAP12 = t.RNLCOEF(12, MC), FKLAP22 = t.RNLCOEF(13, MC);
+    double GW5 = t.RNLCOEF(14, MC), GW6 = t.RNLCOEF(15, MC), GW7 = t.RNLCOEF(16, MC), GW8 = t.RNLCOEF(17, MC);
+    double FKLAMMA = t.RNLCOEF(18, MC), FKLAMMB = t.RNLCOEF(19, MC), FKLAMM2 = t.RNLCOEF(20, MC), FKLAMM1 = t.RNLCOEF(21, MC);
+    double FKLAMA2 = t.RNLCOEF(22, MC), FKLAMB2 = t.RNLCOEF(23, MC), FKLAM12 = t.RNLCOEF(24, MC), FKLAM22 = t.RNLCOEF(25, MC);
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) FTEMP[IJ] = t.AF11(MC) * enh(IJ, MC);
+    const int branch = (MC > MFR1STFR && MC < MFRLSTFR) ? 0 : (MC >= MFRLSTFR ? 1 : 2);
+    for (int KH = 1; KH <= 2; ++KH) {
+      for (int K = 1; K <= NANG; ++K) {
+        int K1 = t.K1W(K, KH), K2 = t.K2W(K, KH), K11 = t.K11W(K, KH), K21 = t.K21W(K, KH);
+        for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+          double SAP = GW1 * FL1(IJ, K1, IP) + GW2 * FL1(IJ, K11, IP) + GW3 * FL1(IJ, K1, IP1) + GW4 * FL1(IJ, K11, IP1);
+          double SAM = GW5 * FL1(IJ, K2, IM) + GW6 * FL1(IJ, K21, IM) + GW7 * FL1(IJ, K2, IM1) + GW8 * FL1(IJ, K21, IM1);
+          double FIJ = (branch == 0) ? FL1(IJ, K, IC) : FL1(IJ, K, IC) * FTAIL;
+          double FAD1 = FIJ * (SAP + SAM);
+          double FAD2 = FAD1 - 2.0 * SAP * SAM;
+          FAD1 = FAD1 + FAD2;
+          double FCEN = FTEMP[IJ] * FIJ;
+          AD[IJ] = FAD2 * FCEN;
+          DELAD[IJ] = FAD1 * FTEMP[IJ];
+          DELAP[IJ] = (FIJ - 2.0 * SAM) * t.DAL1 * FCEN;
+          DELAM[IJ] = (FIJ - 2.0 * SAP) * t.DAL2 * FCEN;
+        }
+        auto centre = [&]() { for (int IJ = KIJS; IJ <= KIJL; ++IJ) { SL(IJ, K, MC) = SL(IJ, K, MC) - 2.0 * AD[IJ]; FLD(IJ, K, MC) = FLD(IJ, K, MC) - 2.0 * DELAD[IJ]; } };
+        auto mm = [&]() { for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+          SL(IJ, K2, MM) = SL(IJ, K2, MM) + AD[IJ] * FKLAMM1; FLD(IJ, K2, MM) = FLD(IJ, K2, MM) + DELAM[IJ] * FKLAM12;
+          SL(IJ, K21, MM) = SL(IJ, K21, MM) + AD[IJ] * FKLAMM2; FLD(IJ, K21, MM) = FLD(IJ, K21, MM) + DELAM[IJ] * FKLAM22; } };
+        auto mm1 = [&]() { for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+          SL(IJ, K2, MM1) = SL(IJ, K2, MM1) + AD[IJ] * FKLAMMA; FLD(IJ, K2, MM1) = FLD(IJ, K2, MM1) + DELAM[IJ] * FKLAMA2;
+          SL(IJ, K21, MM1) = SL(IJ, K21, MM1) + AD[IJ] * FKLAMMB; FLD(IJ, K21, MM1) = FLD(IJ, K21, MM1) + DELAM[IJ] * FKLAMB2; } };
+        auto mp = [&]() { for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+          SL(IJ, K1, MP) = SL(IJ, K1, MP) + AD[IJ] * FKLAMP1; FLD(IJ, K1, MP) = FLD(IJ, K1, MP) + DELAP[IJ] * FKLAP12;
+          SL(IJ, K11, MP) = SL(IJ, K11, MP) + AD[IJ] * FKLAMP2; FLD(IJ, K11, MP) = FLD(IJ, K11, MP) + DELAP[IJ] * FKLAP22; } };
+        auto mp1 = [&]() { for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+          SL(IJ, K1, MP1) = SL(IJ, K1, MP1) + AD[IJ] * FKLAMPA; FLD(IJ, K1, MP1) = FLD(IJ, K1, MP1) + DELAP[IJ] * FKLAPA2;
+          SL(IJ, K11, MP1) = SL(IJ, K11, MP1) + AD[IJ] * FKLAMPB; FLD(IJ, K11, MP1) = FLD(IJ, K11, MP1) + DELAP[IJ] * FKLAPB2; } };
+        if (branch == 0) {          // :253-308
+          centre(); mm(); mm1(); mp(); mp1();
+        } else if (branch == 1) {   // :312-410
+          mm();
+          if (MM1 <= NFRE) {
+            mm1();
+            if (MC <= NFRE) {
+              centre();
+              if (MP <= NFRE) { mp(); if (MP1 <= NFRE) mp1(); }
+            }
+          }
+        } else {                    // :414-490
+          if (MM1 >= 1) mm1();
+          centre(); mp(); mp1();
+        }
+      }
+    }
+  }
+}
+
+// sdiwbk.F90:69-117
+void SDIWBK(const Ctx& x, V3 FL1, V3 FLD, V3 SL, V1 DEPTH, V1 EMAXDPT, V1 EMEAN, V1 F1MEAN) {
+  if (!x.c.lbiwbk) return;
+  const int KIJS = x.KIJS, KIJL = x.KIJL;
+  const double ALPH_B_J = 1.0, COEF_B_J = 2 * ALPH_B_J, DEPTHTRS = 50.0;
+  std::vector<double> SDS(KIJL + 1, 0.0);
+  for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+    if (DEPTH(IJ) < DEPTHTRS) {
+      double ALPH = 2.0 * EMAXDPT(IJ) / EMEAN(IJ);
+      double ARG = std::min(ALPH, 50.0);
+      double Q_OLD = std::exp(-ARG), Q = Q_OLD;
+      for (int IC = 1; IC <= 15; ++IC) {
+        double EXPQ = std::exp(-ARG * (1.0 - Q_OLD));
+        Q = Q_OLD - (EXPQ - Q_OLD) / (ARG * EXPQ - 1.0);
+        double REL_ERR = std::fabs(Q - Q_OLD) / Q_OLD;
+        if (REL_ERR < 0.00001) break;
+        Q_OLD = Q;
+      }
+      Q = std::min(Q, 1.0);
+      SDS[IJ] = COEF_B_J * ALPH * Q * F1MEAN(IJ);
+    }
+  }
+  for (int M = 1; M <= x.c.nfre_red; ++M) for (int K = 1; K <= x.NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ)
+    if (DEPTH(IJ) < DEPTHTRS) { SL(IJ, K, M) = SL(IJ, K, M) - SDS[IJ] * FL1(IJ, K, M); FLD(IJ, K, M) = FLD(IJ, K, M) - SDS[IJ]; }
+}
+
+// sbottom.F90:76-97
+void SBOTTOM(const Ctx& x, V3 FL1, V3 FLD, V3 SL, V2 WAVNUM, V1 DEPTH) {
+  const int KIJS = x.KIJS, KIJL = x.KIJL;
+  double CONST = -2.0 * 0.038 * x.t.GM1;
+  std::vector<double> SBO(KIJL + 1);
+  for (int M = 1; M <= x.c.nfre_red; ++M) {
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      if (DEPTH(IJ) < x.c.bathymax) {
+        double ARG = 2.0 * DEPTH(IJ) * WAVNUM(IJ, M);
+        ARG = std::min(ARG, 50.0);
+        SBO[IJ] = CONST * WAVNUM(IJ, M) / std::sinh(ARG);
+      } else SBO[IJ] = 0.0;
+    }
+    for (int K = 1; K <= x.NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) { SL(IJ, K, M) = SL(IJ, K, M) + SBO[IJ] * FL1(IJ, K, M); FLD(IJ, K, M) = FLD(IJ, K, M) + SBO[IJ]; }
+  }
+}
+
+// wnfluxes.F90:163-331 (LWNEMOCOU=F, LWNEMOCOUWRS=F, LCIWA*=F)
+void WNFLUXES(const Ctx& x, I1 MIJ, V2 RHOWGDFTH, V2 CINV, V3 SSURF, V1 CICOVER, V1 PHIWA, V1 EM, V1 F1, V1 WSWAVE,
+              V1 WDWAVE, V1 USTRA, V1 VSTRA, V1 UFRIC, V1 AIRD, V1 TAUXD, V1 TAUYD, V1 TAUOCXD, V1 TAUOCYD, V1 TAUOC,
+              V1 TAUICX, V1 TAUICY, V1 PHIOCD, V1 PHIEPS, V1 PHIAW) {
+  (void)MIJ;
+  const Tables& t = x.t;
+  const Config& c = x.c;
+  const int KIJS = x.KIJS, KIJL = x.KIJL, NANG = x.NANG, NFRE = x.NFRE;
+  const int n = KIJL + 1;
+  const double PHIOC_ICE = -3.75, PHIAW_ICE = 3.75, C1 = 1.03e-3, C2 = 0.04e-3, P1 = 1.48, P2 = -0.21, CDMAX_LOC = 0.003,
+               EFD_MIN = 0.0625, EFD_MAX = 6.25;
+  std::vector<double> XSTRESS(n, 0.0), YSTRESS(n, 0.0), USTAR(n), PHILF(n, 0.0), OOVAL(n), EM_OC(n), F1_OC(n), SUMT(n), SUMX(n), SUMY(n);
+  double EPSUS3 = t.EPSUS * std::sqrt(t.EPSUS);
+  double ZCITHRS = c.ciblock, CITHRSH_INV = 1. / std::max(c.cithrsh, 0.01), ZMAXEXP = 10.;
+  double EFD_FAC = 4.0 * t.EGRCRV / (t.G * t.G);
+  double FFD_FAC = std::pow(t.EGRCRV / t.AFCRV, 1.0 / t.BFCRV) * t.G;
+  for (int M = 1; M <= NFRE; ++M) {
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) { SUMT[IJ] = SSURF(IJ, 1, M); SUMX[IJ] = t.SINTH(1) * SSURF(IJ, 1, M); SUMY[IJ] = t.COSTH(1) * SSURF(IJ, 1, M); }
+    for (int K = 2; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      SUMT[IJ] = SUMT[IJ] + SSURF(IJ, K, M);
+      SUMX[IJ] = SUMX[IJ] + t.SINTH(K) * SSURF(IJ, K, M);
+      SUMY[IJ] = SUMY[IJ] + t.COSTH(K) * SSURF(IJ, K, M);
+    }
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      PHILF[IJ] = PHILF[IJ] + SUMT[IJ] * RHOWGDFTH(IJ, M);
+      double CMRHOWGDFTH = CINV(IJ, M) * RHOWGDFTH(IJ, M);
+      XSTRESS[IJ] = XSTRESS[IJ] + SUMX[IJ] * CMRHOWGDFTH;
+      YSTRESS[IJ] = YSTRESS[IJ] + SUMY[IJ] * CMRHOWGDFTH;
+    }
+  }
+  if (c.licerun && c.lwamrsetci) {
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      if (CICOVER(IJ) > ZCITHRS) {
+        OOVAL[IJ] = std::exp(-std::min(p4(CICOVER(IJ) * CITHRSH_INV), ZMAXEXP));
+        double U10P = std::max(WSWAVE(IJ), t.EPSU10);
+        double CD_BULK = std::min((C1 + C2 * std::pow(U10P, P1)) * std::pow(U10P, P2), CDMAX_LOC);
+        double CD_WAVE = sq(UFRIC(IJ) / U10P);
+        double CD_ICE = OOVAL[IJ] * CD_WAVE + (1.0 - OOVAL[IJ]) * CD_BULK;
+        USTAR[IJ] = std::max(std::sqrt(CD_ICE) * U10P, t.EPSUS);
+        double EFD = std::min(EFD_FAC * p4(USTAR[IJ]), EFD_MAX);
+        EM_OC[IJ] = std::max(OOVAL[IJ] * EM(IJ) + (1.0 - OOVAL[IJ]) * EFD, EFD_MIN);
+        double FFD = FFD_FAC / USTAR[IJ];
+        F1_OC[IJ] = OOVAL[IJ] * F1(IJ) + (1.0 - OOVAL[IJ]) * FFD;
+        F1_OC[IJ] = std::min(std::max(F1_OC[IJ], t.FR(2)), t.FR(NFRE));
+      } else { OOVAL[IJ] = 1.0; USTAR[IJ] = UFRIC(IJ); EM_OC[IJ] = EM(IJ); F1_OC[IJ] = F1(IJ); }
+    }
+  } else {
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) { OOVAL[IJ] = 1.0; USTAR[IJ] = UFRIC(IJ); EM_OC[IJ] = EM(IJ); F1_OC[IJ] = F1(IJ); }
+  }
+  for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+    double TAU = AIRD(IJ) * std::max(sq(USTAR[IJ]), t.EPSUS);
+    TAUXD(IJ) = TAU * std::sin(WDWAVE(IJ));
+    TAUYD(IJ) = TAU * std::cos(WDWAVE(IJ));
+    TAUOCXD(IJ) = TAUXD(IJ) - OOVAL[IJ] * XSTRESS[IJ];
+    TAUOCYD(IJ) = TAUYD(IJ) - OOVAL[IJ] * YSTRESS[IJ];
+    double TAUO = std::sqrt(sq(TAUOCXD(IJ)) + sq(TAUOCYD(IJ)));
+    TAUOC(IJ) = std::min(std::max(TAUO / TAU, t.TAUOCMIN), t.TAUOCMAX);
+  }
+  for (int IJ = KIJS; IJ <= KIJL; ++IJ) { TAUICX(IJ) = 0.0; TAUICY(IJ) = 0.0; }
+  if (c.lwcouast)
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ)
+      if (USTRA(IJ) != 0.0 || VSTRA(IJ) != 0.0) {
+        TAUXD(IJ) = USTRA(IJ); TAUOCXD(IJ) = USTRA(IJ) * TAUOC(IJ); TAUYD(IJ) = VSTRA(IJ); TAUOCYD(IJ) = VSTRA(IJ) * TAUOC(IJ);
+      }
+  for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+    double XN = AIRD(IJ) * std::max(USTAR[IJ] * USTAR[IJ] * USTAR[IJ], EPSUS3);
+    PHIOCD(IJ) = OOVAL[IJ] * (PHILF[IJ] - PHIWA(IJ)) + (1.0 - OOVAL[IJ]) * PHIOC_ICE * XN;
+    PHIEPS(IJ) = PHIOCD(IJ) / XN;
+    PHIEPS(IJ) = std::min(std::max(PHIEPS(IJ), t.PHIEPSMIN), t.PHIEPSMAX);
+    PHIOCD(IJ) = PHIEPS(IJ) * XN;
+    PHIAW(IJ) = PHIWA(IJ) / XN;
+    PHIAW(IJ) = OOVAL[IJ] * PHIWA(IJ) / XN + (1.0 - OOVAL[IJ]) * PHIAW_ICE;
+  }
+  (void)EM_OC; (void)F1_OC;
+}
+
+// imphftail.F90:71-87
+void IMPHFTAIL(const Ctx& x, I1 MIJ, V2 FLM, V2 WAVNUM, V2 XK2CG, V3 FL1) {
+  for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) {
+    double TEMP1 = 1.0 / XK2CG(IJ, MIJ(IJ)) / WAVNUM(IJ, MIJ(IJ));
+    for (int M = MIJ(IJ) + 1; M <= x.NFRE; ++M) {
+      double TEMP2 = 1.0 / XK2CG(IJ, M) / WAVNUM(IJ, M);
+      TEMP2 = TEMP2 / TEMP1;
+      for (int K = 1; K <= x.NANG; ++K) { double TFAC = FL1(IJ, K, MIJ(IJ)); FL1(IJ, K, M) = std::max(TEMP2 * TFAC, FLM(IJ, K)); }
+    }
+  }
+}
+
+// setice.F90:64-86
+void SETICE(const Ctx& x, V3 FL1, V1 CICOVER, V2 COSWDIF) {
+  const int n = x.KIJL + 1;
+  std::vector<double> CIREDUC(n), TEMP(n), ICEFREE(n);
+  for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) {
+    if (CICOVER(IJ) > x.c.cithrsh) { CIREDUC[IJ] = std::max(x.t.EPSMIN, (1.0 - CICOVER(IJ))); ICEFREE[IJ] = 0.0; }
+    else { CIREDUC[IJ] = 0.0; ICEFREE[IJ] = 1.0; }
+  }
+  for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) TEMP[IJ] = CIREDUC[IJ] * x.c.flmin;
+  for (int M = 1; M <= x.NFRE; ++M) for (int K = 1; K <= x.NANG; ++K) for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ)
+    FL1(IJ, K, M) = FL1(IJ, K, M) * ICEFREE[IJ] + TEMP[IJ] * sq(std::max(0.0, COSWDIF(IJ, K)));
+}
+
+// stokesdrift.F90:84-142
+void STOKESDRIFT(const Ctx& x, V3 FL1, V2 STOKFAC, V1 WSWAVE, V1 WDWAVE, V1 CICOVER, V1 USTOKES, V1 VSTOKES) {
+  const Tables& t = x.t;
+  const double STMAX = 1.5;
+  std::vector<double> STFAC(x.KIJL + 1);
+  double CONST = 2.0 * t.DELTH * t.ZPI * t.ZPI * t.ZPI / t.G * p4(t.FR(t.NFRE_ODD));
+  for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) { USTOKES(IJ) = 0.0; VSTOKES(IJ) = 0.0; }
+  for (int M = 1; M <= t.NFRE_ODD; ++M) {
+    for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) STFAC[IJ] = STOKFAC(IJ, M) * t.DFIM_SIM(M);
+    for (int K = 1; K <= x.NANG; ++K) for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) {
+      double FAC3 = STFAC[IJ] * FL1(IJ, K, M);
+      USTOKES(IJ) = USTOKES(IJ) + FAC3 * t.SINTH(K);
+      VSTOKES(IJ) = VSTOKES(IJ) + FAC3 * t.COSTH(K);
+    }
+  }
+  for (int K = 1; K <= x.NANG; ++K) {
+    double FAC1 = CONST * t.SINTH(K), FAC2 = CONST * t.COSTH(K);
+    for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) { USTOKES(IJ) = USTOKES(IJ) + FAC1 * FL1(IJ, K, t.NFRE_ODD); VSTOKES(IJ) = VSTOKES(IJ) + FAC2 * FL1(IJ, K, t.NFRE_ODD); }
+  }
+  if (x.c.licerun && x.c.lwamrsetci)
+    for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ)
+      if (CICOVER(IJ) > x.c.cithrsh) {
+        USTOKES(IJ) = 0.016 * WSWAVE(IJ) * std::sin(WDWAVE(IJ)) * (1.0 - CICOVER(IJ));
+        VSTOKES(IJ) = 0.016 * WSWAVE(IJ) * std::cos(WDWAVE(IJ)) * (1.0 - CICOVER(IJ));
+      }
+  for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) {
+    USTOKES(IJ) = std::min(std::max(USTOKES(IJ), -STMAX), STMAX);
+    VSTOKES(IJ) = std::min(std::max(VSTOKES(IJ), -STMAX), STMAX);
+  }
+}
+
+}  // namespace
+
+// femean.F90 (outblock.F90:223-244 uses it for Hs / mean period)
+void femean(const Tables& t, const Config& c, int KIJL, const double* Fp, double* EM, double* FM) {
+  V3 F{const_cast<double*>(Fp), KIJL, c.nang};
+  std::vector<double> TEMP2(KIJL + 1);
+  for (int IJ = 1; IJ <= KIJL; ++IJ) { EM[IJ - 1] = t.EPSMIN; FM[IJ - 1] = t.EPSMIN; }
+  double DELT25 = t.WETAIL * t.FR(c.nfre) * t.DELTH;
+  double DELT2 = t.FRTAIL * t.DELTH;
+  for (int M = 1; M <= c.nfre; ++M) {
+    for (int IJ = 1; IJ <= KIJL; ++IJ) TEMP2[IJ] = std::max(F(IJ, 1, M), t.EPSMIN);
+    for (int K = 2; K <= c.nang; ++K) for (int IJ = 1; IJ <= KIJL; ++IJ) TEMP2[IJ] = TEMP2[IJ] + std::max(F(IJ, K, M), t.EPSMIN);
+    for (int IJ = 1; IJ <= KIJL; ++IJ) { EM[IJ - 1] = EM[IJ - 1] + TEMP2[IJ] * t.DFIM(M); FM[IJ - 1] = FM[IJ - 1] + t.DFIMOFR(M) * TEMP2[IJ]; }
+  }
+  for (int IJ = 1; IJ <= KIJL; ++IJ) {
+    EM[IJ - 1] = EM[IJ - 1] + DELT25 * TEMP2[IJ];
+    FM[IJ - 1] = FM[IJ - 1] + DELT2 * TEMP2[IJ];
+    FM[IJ - 1] = EM[IJ - 1] / FM[IJ - 1];
+    FM[IJ - 1] = std::max(FM[IJ - 1], t.FR(1));
+  }
+}
+
+// implsch.F90:177-465 for one NPROMA chunk, with sinflx.F90:101-185 inlined as a lambda
+void implsch_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK) {
+  const int NANG = c.nang, NFRE = c.nfre, KIJS = 1;
+  Ctx x{c, t, KIJS, KIJL, NANG, NFRE};
+  const int P = KIJL;
+  auto s3 = [&](ArrD& a) { return V3{&a(1, 1, 1, ICHNK), P, NANG}; };
+  auto s2 = [&](ArrD& a) { return V2{&a(1, 1, ICHNK), P}; };
+  auto s1 = [&](ArrD& a) { return V1{&a(1, ICHNK)}; };
+  V3 FL1 = s3(f.FL1), XLLWS = s3(f.XLLWS);
+  V2 WAVNUM = s2(f.WAVNUM), CGROUP = s2(f.CGROUP), CINV = s2(f.CINV), XK2CG = s2(f.XK2CG), STOKFAC = s2(f.STOKFAC);
+  V1 EMAXDPT = s1(f.EMAXDPT), DEPTH = s1(f.DEPTH), AIRD = s1(f.AIRD), WDWAVE = s1(f.WDWAVE), CICOVER = s1(f.CICOVER),
+     WSWAVE = s1(f.WSWAVE), WSTAR = s1(f.WSTAR), USTRA = s1(f.USTRA), VSTRA = s1(f.VSTRA), UFRIC = s1(f.UFRIC),
+     TAUW = s1(f.TAUW), TAUWDIR = s1(f.TAUWDIR), Z0M = s1(f.Z0M), Z0B = s1(f.Z0B), CHRNCK = s1(f.CHRNCK),
+     WSEMEAN = s1(f.WSEMEAN), WSFMEAN = s1(f.WSFMEAN), USTOKES = s1(f.USTOKES), VSTOKES = s1(f.VSTOKES),
+     TAUXD = s1(f.TAUXD), TAUYD = s1(f.TAUYD), TAUOCXD = s1(f.TAUOCXD), TAUOCYD = s1(f.TAUOCYD), TAUOC = s1(f.TAUOC),
+     TAUICX = s1(f.TAUICX), TAUICY = s1(f.TAUICY), PHIOCD = s1(f.PHIOCD), PHIEPS = s1(f.PHIEPS), PHIAW = s1(f.PHIAW);
+  I1 MIJ{&f.MIJ(1, ICHNK)};
+
+  const size_t n3 = (size_t)P * NANG * NFRE;
+  std::vector<double> sFLD(n3), sSL(n3), sSPOS(n3), sSSOURCE(n3, 0.0);
+  V3 FLD{sFLD.data(), P, NANG}, SL{sSL.data(), P, NANG}, SPOS{sSPOS.data(), P, NANG}, SSOURCE{sSSOURCE.data(), P, NANG};
+  std::vector<double> sFLM((size_t)P * NANG), sCOSWDIF((size_t)P * NANG), sSINWDIF2((size_t)P * NANG), sTEMP((size_t)P * NFRE), sRHOWGDFTH((size_t)P * NFRE);
+  V2 FLM{sFLM.data(), P}, COSWDIF{sCOSWDIF.data(), P}, SINWDIF2{sSINWDIF2.data(), P}, TEMP{sTEMP.data(), P}, RHOWGDFTH{sRHOWGDFTH.data(), P};
+  L1 lRAORW(P), lEMEAN(P), lFMEAN(P), lHALP(P), lEMEANWS(P), lFMEANWS(P), lUSFM(P), lF1MEAN(P), lAKMEAN(P), lXKMEAN(P), lPHIWA(P);
+  V1 RAORW = lRAORW.view(), EMEAN = lEMEAN.view(), FMEAN = lFMEAN.view(), HALP = lHALP.view(), FMEANWS = lFMEANWS.view(),
+     USFM = lUSFM.view(), F1MEAN = lF1MEAN.view(), AKMEAN = lAKMEAN.view(), XKMEAN = lXKMEAN.view(), PHIWA = lPHIWA.view();
+  std::vector<double> DELFL(NFRE + 1);
+
+  double DELT = c.idelt, DELTM = 1.0 / DELT, DELT5 = c.ximp * DELT;
+  bool LCFLX = c.lwflux || c.lwfluxout || c.lwnemocou;
+  for (int IJ = KIJS; IJ <= KIJL; ++IJ) RAORW(IJ) = std::max(AIRD(IJ), 1.0) * t.ROWATERM1;
+  for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+    COSWDIF(IJ, K) = std::cos(t.TH(K) - WDWAVE(IJ));
+    SINWDIF2(IJ, K) = sq(std::sin(t.TH(K) - WDWAVE(IJ)));
+  }
+  if (c.lbiwbk) SDEPTHLIM(x, EMAXDPT, FL1);
+  FKMEAN(x, FL1, WAVNUM, EMEAN, FMEAN, F1MEAN, AKMEAN, XKMEAN);
+  for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ)
+    FLM(IJ, K) = (1. - 0.9 * std::min(CICOVER(IJ), 0.99)) * c.flmin * sq(std::max(0.0, COSWDIF(IJ, K)));
+
+  // ---- SINFLX x2 (sinflx.F90)
+  const int NCALL = 2;
+  for (int ICALL = 1; ICALL <= NCALL; ++ICALL) {
+    int IUSFG, ICODE_WND;
+    if (ICALL == 1) { IUSFG = 0; ICODE_WND = c.icode; } else { IUSFG = 1; ICODE_WND = 3; }
+    if (ICODE_WND != 3) throw std::runtime_error("AIRSEA: only ICODE_WND=3 restated");
+    if (ICALL == 1) {
+      for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) FL1(IJ, K, NFRE) = std::max(FL1(IJ, K, NFRE), FLM(IJ, K));
+      if (c.llgcbz0) throw std::runtime_error("HALPHAP not restated");
+      for (int IJ = KIJS; IJ <= KIJL; ++IJ) HALP(IJ) = 0.0;
+    }
+    TAUT_Z0(x, IUSFG, WSWAVE, WDWAVE, TAUW, TAUWDIR, UFRIC, Z0M, Z0B, CHRNCK);
+    int NGST; bool LLPHIWA, LLSNEG;
+    if (ICALL < NCALL) { NGST = 1; LLPHIWA = false; LLSNEG = false; } else { NGST = 2; LLPHIWA = true; LLSNEG = true; }
+    if (c.iphys == 0) SINPUT_JAN(x, NGST, LLSNEG, FL1, WAVNUM, CINV, XK2CG, WSWAVE, UFRIC, Z0M, COSWDIF, SINWDIF2, RAORW, WSTAR, FLD, SL, SPOS, XLLWS);
+    else SINPUT_ARD(x, NGST, LLSNEG, FL1, WAVNUM, CINV, XK2CG, WDWAVE, WSWAVE, UFRIC, Z0M, COSWDIF, SINWDIF2, RAORW, WSTAR, FLD, SL, SPOS, XLLWS);
+    FEMEANWS(x, FL1, XLLWS, FMEANWS, nullptr);
+    FRCUTINDEX(x, FMEAN, FMEANWS, UFRIC, CICOVER, MIJ, RHOWGDFTH);
+    STRESSO(x, MIJ, RHOWGDFTH, FL1, SL, SPOS, CINV, WDWAVE, UFRIC, Z0M, AIRD, COSWDIF, SINWDIF2, TAUW, TAUWDIR, PHIWA, LLPHIWA);
+  }
+  if (c.iphys == 0) SDISSIP_JAN(x, FL1, FLD, SL, WAVNUM, EMEAN, F1MEAN, XKMEAN);
+  else SDISSIP_ARD(x, FL1, FLD, SL, WAVNUM, CGROUP, XK2CG, UFRIC, COSWDIF, RAORW);
+  if (LCFLX && !c.lwvflx_snl) for (size_t i = 0; i < n3; ++i) sSSOURCE[i] = sSL[i];
+  SNONLIN(x, FL1, FLD, SL, WAVNUM, DEPTH, AKMEAN);
+  if (LCFLX && c.lwvflx_snl)
+    for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      double GTEMP1 = std::max((1.0 - DELT5 * FLD(IJ, K, M)), 1.0);
+      SSOURCE(IJ, K, M) = SL(IJ, K, M) / GTEMP1;
+    }
+  SDIWBK(x, FL1, FLD, SL, DEPTH, EMAXDPT, EMEAN, F1MEAN);
+  if (c.licerun) {
+    if (c.lciscal || c.lciwa1 || c.lciwa2 || c.lciwa3) throw std::runtime_error("sea-ice attenuation branches not restated (SURVEY 8f)");
+  }
+  SBOTTOM(x, FL1, FLD, SL, WAVNUM, DEPTH);
+  // ---- 2.4 new spectra (implsch.F90:352-395)
+  for (int M = 1; M <= NFRE; ++M) DELFL[M] = t.COFRM4(M) * DELT;
+  for (int IJ = KIJS; IJ <= KIJL; ++IJ) USFM(IJ) = UFRIC(IJ) * std::max(FMEANWS(IJ), FMEAN(IJ));
+  for (int M = 1; M <= NFRE; ++M) for (int IJ = KIJS; IJ <= KIJL; ++IJ) TEMP(IJ, M) = USFM(IJ) * DELFL[M];
+  for (int K = 1; K <= NANG; ++K) for (int M = 1; M <= NFRE; ++M) for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+    double GTEMP1 = std::max((1.0 - DELT5 * FLD(IJ, K, M)), 1.0);
+    double GTEMP2 = DELT * SL(IJ, K, M) / GTEMP1;
+    double FLHAB = std::fabs(GTEMP2);
+    FLHAB = std::min(FLHAB, TEMP(IJ, M));
+    FL1(IJ, K, M) = FL1(IJ, K, M) + sign(FLHAB, GTEMP2);
+    FL1(IJ, K, M) = std::max(FL1(IJ, K, M), FLM(IJ, K));
+    SSOURCE(IJ, K, M) = SSOURCE(IJ, K, M) + DELTM * std::min(t.FLMAX(M) - FL1(IJ, K, M), 0.0);
+    FL1(IJ, K, M) = std::min(FL1(IJ, K, M), t.FLMAX(M));
+  }
+  if (LCFLX)
+    WNFLUXES(x, MIJ, RHOWGDFTH, CINV, SSOURCE, CICOVER, PHIWA, EMEAN, F1MEAN, WSWAVE, WDWAVE, USTRA, VSTRA, UFRIC, AIRD,
+             TAUXD, TAUYD, TAUOCXD, TAUOCYD, TAUOC, TAUICX, TAUICY, PHIOCD, PHIEPS, PHIAW);
+  // ---- 2.5 tail
+  FKMEAN(x, FL1, WAVNUM, EMEAN, FMEAN, F1MEAN, AKMEAN, XKMEAN);
+  FEMEANWS(x, FL1, XLLWS, FMEANWS, lEMEANWS.v.data());
+  IMPHFTAIL(x, MIJ, FLM, WAVNUM, XK2CG, FL1);
+  if (c.lwflux)
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      if (lEMEANWS.v[IJ - 1] < t.WSEMEAN_MIN) { WSEMEAN(IJ) = t.WSEMEAN_MIN; WSFMEAN(IJ) = 2. * t.FR(NFRE); }
+      else { WSEMEAN(IJ) = lEMEANWS.v[IJ - 1]; WSFMEAN(IJ) = FMEANWS(IJ); }
+    }
+  if (c.licerun && c.lmaskice) SETICE(x, FL1, CICOVER, COSWDIF);
+  STOKESDRIFT(x, FL1, STOKFAC, WSWAVE, WDWAVE, CICOVER, USTOKES, VSTOKES);  // stokestrn.F90:76 (no NEMO coupling)
+}
+
+// wamintgr.F90:117-146
+void implsch_all(Model& m) {
+  for (int ir = 0; ir < m.cfg.npr; ++ir) {
+    RankDecomp& r = m.ranks[ir];
+    Fields& f = m.fld[ir];
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int ICHNK = 1; ICHNK <= r.NCHNK; ++ICHNK) implsch_chunk(m.cfg, m.tab, f, r.NPROMA, ICHNK);
+  }
+}
+
+}  // namespace orc
