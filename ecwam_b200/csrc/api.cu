@@ -1,0 +1,653 @@
+// C ABI of libecwam_b200.so (include/ecwam_b200.h): per-rank handle, device tables, NCCL halo plan,
+// PROPAG_WAM / IMPLSCH / WAMINTGR entry points.
+#include "internal.h"
+#include <nccl.h>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+static thread_local char g_err[1024] = "";
+void ew_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+#define EW_FAIL(code, ...) do { ew_set_error(__VA_ARGS__); return (code); } while (0)
+#define EW_FAIL_H(h, code, ...) do { ew_set_error(__VA_ARGS__); delete (h); return (code); } while (0)
+#define EW_NCCL_CHECK(call)                                                                  \
+  do {                                                                                       \
+    ncclResult_t r_ = (call);                                                                \
+    if (r_ != ncclSuccess) EW_FAIL(ECWAM_B200_ENCCL, "%s:%d: %s: %s", __FILE__, __LINE__, #call, ncclGetErrorString(r_)); \
+  } while (0)
+
+using namespace ew;
+
+namespace {
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  int alloc(size_t cnt) {
+    free();
+    n = cnt;
+    if (cnt == 0) return 0;
+    cudaError_t e = cudaMalloc((void**)&p, cnt * sizeof(T));
+    if (e != cudaSuccess) { ew_set_error("cudaMalloc(%zu bytes): %s", cnt * sizeof(T), cudaGetErrorString(e)); p = nullptr; return ECWAM_B200_ECUDA; }
+    return 0;
+  }
+  int upload(const std::vector<T>& v, cudaStream_t st) {
+    int rc = alloc(v.size());
+    if (rc) return rc;
+    if (v.empty()) return 0;
+    EW_CUDA_CHECK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    EW_CUDA_CHECK(cudaStreamSynchronize(st));
+    return 0;
+  }
+  void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct TimingClass { double total_ms = 0; long long count = 0; std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending; };
+}  // namespace
+
+struct ecwam_b200_handle_s {
+  ecwam_b200_params par;
+  DevConst dc;
+  PropConst pc;
+  cudaStream_t st = nullptr;
+  ncclComm_t comm = nullptr;
+  int nproc = 1, irank0 = 0;
+  // propagation
+  PropDev pd;
+  DBuf<int> nbr, halo_off, halo_str, send_l, send_pre, send_peer_of, recv_pre, recv_peer_of, recv_e, flag, count;
+  DBuf<double> wl, pt, cgext, halo, sendbuf, fl3, cosph_m, cosph_p, land_cg, cgrecv;
+  std::vector<int> h_spre, h_rpre;   // per peer prefix sums (size nproc+1)
+  int nsend = 0, nrecv = 0;
+  int msplit = 0;
+  bool weights_dirty = true;
+  // implsch
+  DBuf<double> scr, satw, swellft;
+  DBuf<int> kw, isat;
+  DevTabPtr tab;
+  // fields
+  ecwam_b200_fields dev;
+  bool bound = false;
+  // host-call mirrors
+  ecwam_b200_fields mir;
+  bool mir_alloc = false, mir_static_done = false;
+  std::vector<void*> mir_bufs;
+  // stats
+  long long nlaunch = 0;
+  bool timing = false;
+  std::map<std::string, TimingClass> tm;
+};
+typedef ecwam_b200_handle_s H;
+
+static H* g_const_owner = nullptr;
+static int ensure_const(H* h) {
+  if (g_const_owner == h) return 0;
+  int rc = upload_dev_const(h->dc, h->st);
+  if (rc) return rc;
+  rc = upload_prop_const(h->pc, h->st);
+  if (rc) return rc;
+  g_const_owner = h;
+  return 0;
+}
+
+namespace {
+struct ScopedTimer {
+  H* h; TimingClass* tc = nullptr; cudaEvent_t a = nullptr, b = nullptr;
+  ScopedTimer(H* h_, const char* name) : h(h_) {
+    if (!h->timing) return;
+    tc = &h->tm[name];
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, h->st);
+  }
+  ~ScopedTimer() {
+    if (!tc) return;
+    cudaEventRecord(b, h->st);
+    tc->pending.push_back({a, b});
+  }
+};
+void drain_timing(H* h) {
+  for (auto& kv : h->tm) {
+    for (auto& pr : kv.second.pending) {
+      cudaEventSynchronize(pr.second);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, pr.first, pr.second);
+      kv.second.total_ms += ms; kv.second.count++;
+      cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+    }
+    kv.second.pending.clear();
+  }
+}
+inline long nint_l(double x) { return std::lround(x); }
+}  // namespace
+
+extern "C" {
+
+const char* ecwam_b200_last_error(void) { return g_err; }
+int ecwam_b200_version(void) { return 100; }
+
+int ecwam_b200_nccl_unique_id(char id_out[128]) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  EW_NCCL_CHECK(ncclGetUniqueId(&id));
+  memcpy(id_out, &id, 128);
+  return 0;
+}
+int ecwam_b200_nccl_comm_init(const char id[128], int nranks, int rank, void** comm_out) {
+  ncclUniqueId uid;
+  memcpy(&uid, id, 128);
+  ncclComm_t c;
+  EW_NCCL_CHECK(ncclCommInitRank(&c, nranks, uid, rank));
+  *comm_out = (void*)c;
+  return 0;
+}
+int ecwam_b200_nccl_comm_destroy(void* comm) {
+  if (comm) EW_NCCL_CHECK(ncclCommDestroy((ncclComm_t)comm));
+  return 0;
+}
+
+static int fill_dev_const(const ecwam_b200_params& p, const ecwam_b200_tables& t, DevConst& c) {
+  memset(&c, 0, sizeof(c));
+  if (p.nang < 4 || p.nang > EW_MAXA || p.nfre < 2 || p.nfre > EW_MAXF || p.nfre_red < 1 || p.nfre_red > p.nfre)
+    EW_FAIL(ECWAM_B200_EINVAL, "unsupported spectral dimensions NANG=%d NFRE=%d NFRE_RED=%d", p.nang, p.nfre, p.nfre_red);
+  if (p.irefra != 0 || p.icase != 1) EW_FAIL(ECWAM_B200_EINVAL, "only IREFRA=0, ICASE=1 is implemented (SURVEY 8f rank 3)");
+  if (p.isnonlin != 0) EW_FAIL(ECWAM_B200_EINVAL, "only ISNONLIN=0 is implemented");
+  if (p.llgcbz0 || p.llnormagam) EW_FAIL(ECWAM_B200_EINVAL, "LLGCBZ0 / LLNORMAGAM branches are not implemented (SURVEY 8f rank 2)");
+  if (p.lciwa) EW_FAIL(ECWAM_B200_EINVAL, "LCIWA* / LCISCAL sea-ice attenuation is not implemented (SURVEY 8f rank 2)");
+  if (p.lwnemocou) EW_FAIL(ECWAM_B200_EINVAL, "NEMO coupling accumulators are not implemented");
+  if (p.icode_wnd != 3) EW_FAIL(ECWAM_B200_EINVAL, "only ICODE_WND=3 (10 m wind forcing) is implemented");
+  if ((p.lwflux || p.lwfluxout) && !p.lwvflx_snl) EW_FAIL(ECWAM_B200_EINVAL, "LWVFLX_SNL=F is not implemented");
+  if (p.iphys != 0 && p.iphys != 1) EW_FAIL(ECWAM_B200_EINVAL, "IPHYS must be 0 or 1");
+  if (t.mlsthg > EW_MAXMC || t.mlsthg < 1 || t.mfrstlw > 1) EW_FAIL(ECWAM_B200_EINVAL, "bad MLSTHG/MFRSTLW");
+  if (t.jtot_tauhf > EW_MAXJT) EW_FAIL(ECWAM_B200_EINVAL, "JTOT_TAUHF too large");
+  if (p.iphys == 1 && (2 * t.nsdsnth + 1 > EW_MAXSAT)) EW_FAIL(ECWAM_B200_EINVAL, "NSDSNTH too large");
+  if (p.iphys == 1 && (t.ssdsc3 != 0.0 || t.ssdsc5 != 0.0))
+    EW_FAIL(ECWAM_B200_EINVAL, "SDISSIP_ARD cumulative (SSDSC3) / turbulence (SSDSC5) terms are not implemented");
+  c.A = p.nang; c.F = p.nfre; c.Fr = p.nfre_red; c.iphys = p.iphys; c.idamping = p.idamping; c.llcapchnk = p.llcapchnk;
+  c.lbiwbk = p.lbiwbk; c.licerun = p.licerun; c.lmaskice = p.lmaskice; c.lwamrsetci = p.lwamrsetci; c.lwflux = p.lwflux;
+  c.lcflx = (p.lwflux || p.lwfluxout || p.lwnemocou) ? 1 : 0;   // implsch.F90:187
+  c.lwvflx_snl = p.lwvflx_snl; c.lwcouast = p.lwcouast;
+  c.delt = p.idelt; c.ximp = p.ximp; c.rnu = p.rnu; c.rnum = p.rnum; c.wspmin = p.wspmin; c.cithrsh = p.cithrsh;
+  c.cithrsh_tail = p.cithrsh_tail; c.ciblock = p.ciblock; c.flmin = p.flmin; c.bathymax = p.bathymax;
+  c.G = t.g; c.GM1 = t.gm1; c.ZPI = t.zpi; c.ZPI4GM1 = t.zpi4gm1; c.ZPI4GM2 = t.zpi4gm2; c.ROWATERM1 = t.rowaterm1;
+  c.EPSMIN = t.epsmin; c.EPSUS = t.epsus; c.EPSU10 = t.epsu10; c.ACD = t.acd; c.BCD = t.bcd; c.CDMAX = t.cdmax;
+  c.TAUOCMIN = t.tauocmin; c.TAUOCMAX = t.tauocmax; c.PHIEPSMIN = t.phiepsmin; c.PHIEPSMAX = t.phiepsmax;
+  c.WSEMEAN_MIN = t.wsemean_min;
+  c.FRATIO = t.fratio; c.WETAIL = t.wetail; c.FRTAIL = t.frtail; c.WP1TAIL = t.wp1tail; c.DELTH = t.delth;
+  c.FLOGSPRDM1 = t.flogsprdm1; c.NFRE_ODD = t.nfre_odd;
+  for (int m = 0; m < p.nfre; ++m) {
+    c.FR[m] = t.fr[m]; c.DFIM[m] = t.dfim[m]; c.DFIMOFR[m] = t.dfimofr[m]; c.DFIMFR[m] = t.dfimfr[m];
+    c.ZPIFR[m] = t.zpifr[m]; c.FR5[m] = t.fr5[m]; c.COFRM4[m] = t.cofrm4[m]; c.FLMAX[m] = t.flmax[m];
+    c.RHOWG_DFIM[m] = t.rhowg_dfim[m]; c.DFIM_SIM[m] = t.dfim_sim[m];
+  }
+  for (int k = 0; k < p.nang; ++k) { c.TH[k] = t.th[k]; c.COSTH[k] = t.costh[k]; c.SINTH[k] = t.sinth[k]; }
+  c.XKAPPA = t.xkappa; c.XNLEV = t.xnlev; c.ALPHA = t.alpha; c.ALPHAMIN = t.alphamin; c.CHNKMIN_U = t.chnkmin_u;
+  c.ZALP = t.zalp; c.BETAMAXOXKAPPA2 = t.betamaxoxkappa2; c.TAUWSHELTER = t.tauwshelter; c.TAILFACTOR = t.tailfactor;
+  c.TAILFACTOR_PM = t.tailfactor_pm; c.SWELLF = t.swellf; c.SWELLF2 = t.swellf2; c.SWELLF3 = t.swellf3;
+  c.SWELLF4 = t.swellf4; c.SWELLF5 = t.swellf5; c.SWELLF6 = t.swellf6; c.SWELLF7 = t.swellf7; c.SWELLF7M1 = t.swellf7m1;
+  c.Z0RAT = t.z0rat; c.Z0TUBMAX = t.z0tubmax; c.ABMIN = t.abmin; c.ABMAX = t.abmax; c.CDIS = t.cdis;
+  c.DELTA_SDIS = t.delta_sdis; c.CDISVIS = t.cdisvis; c.SDSBR = t.sdsbr; c.SSDSC2 = t.ssdsc2; c.SSDSC3 = t.ssdsc3;
+  c.SSDSC4 = t.ssdsc4; c.SSDSC5 = t.ssdsc5; c.SSDSC6 = t.ssdsc6; c.MICHE = t.miche; c.EGRCRV = t.egrcrv;
+  c.AFCRV = t.afcrv; c.BFCRV = t.bfcrv; c.NSDSNTH = t.nsdsnth;
+  c.IAB = t.iab; c.JTOT = t.jtot_tauhf; c.EPS1 = t.eps1; c.X0TAUHF = t.x0tauhf;
+  for (int j = 0; j < t.jtot_tauhf; ++j) c.WTAUHF[j] = t.wtauhf[j];
+  c.MLSTHG = t.mlsthg; c.MFRSTLW = t.mfrstlw; c.KFRH = t.kfrh; c.DAL1 = t.dal1; c.DAL2 = t.dal2;
+  const int off = 1 - t.mfrstlw;   // index of MC=1 inside the (MFRSTLW:MLSTHG) arrays
+  for (int mc = 0; mc < t.mlsthg; ++mc) {
+    c.IKP[mc] = t.ikp[off + mc]; c.IKP1[mc] = t.ikp1[off + mc]; c.IKM[mc] = t.ikm[off + mc]; c.IKM1[mc] = t.ikm1[off + mc];
+    c.AF11[mc] = t.af11[off + mc];
+    for (int j = 0; j < 5; ++j) c.INLCOEF[mc][j] = t.inlcoef[j + 5 * mc];
+    for (int j = 0; j < 25; ++j) c.RNLCOEF[mc][j] = t.rnlcoef[j + 25 * mc];
+  }
+  return 0;
+}
+
+int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* tables, const ecwam_b200_decomp* dec,
+                      void* nccl_comm, void* cuda_stream, ecwam_b200_handle* out) {
+  if (!params || !tables || !dec || !out) EW_FAIL(ECWAM_B200_EINVAL, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    EW_FAIL(ECWAM_B200_ECUDA, "no CUDA device: the WAMINTGR hot path has no CPU fallback");
+  H* h = new H();
+  h->par = *params;
+  h->st = (cudaStream_t)cuda_stream;
+  h->comm = (ncclComm_t)nccl_comm;
+  h->nproc = dec->nproc; h->irank0 = dec->irank - 1;
+  if (h->nproc > 1 && !h->comm) { EW_FAIL_H(h, ECWAM_B200_EINVAL, "nproc > 1 needs an NCCL communicator"); }
+  int rc = fill_dev_const(*params, *tables, h->dc);
+  if (rc) { delete h; return rc; }
+  const ecwam_b200_params& p = h->par;
+  const int A = p.nang, F = p.nfre, Fr = p.nfre_red, P = p.nproma;
+  const int nloc = dec->ijl - dec->ijs + 1;
+  const int nbot = dec->ijs - dec->ninf, ntop = dec->nsup - dec->ijl;
+  const int next = nbot + nloc + ntop + 1;
+  if (nloc <= 0 || P <= 0 || (long long)P * p.nchnk < nloc || (long long)P * (p.nchnk - 1) >= nloc) {
+    EW_FAIL_H(h, ECWAM_B200_EINVAL, "NPROMA=%d NCHNK=%d do not cover %d own points (mchunk.F90:64-75)", P, p.nchnk, nloc);
+  }
+  // ---- direction tables (ctuwupdt.F90:111-161, ctuw.F90:404-431)
+  PropConst& pc = h->pc;
+  memset(&pc, 0, sizeof(pc));
+  for (int k = 0; k < A; ++k) {
+    const double cs = tables->costh[k], sn = tables->sinth[k];
+    pc.quad[k] = (cs >= 0.0 ? 0 : 2) + (sn >= 0.0 ? 0 : 1);
+    pc.kpm_m[k] = (k - 1 < 0) ? A - 1 : k - 1;
+    pc.kpm_p[k] = (k + 1 >= A) ? 0 : k + 1;
+    pc.sinth[k] = sn; pc.costh[k] = cs;
+  }
+  pc.delpro[0] = p.delpro_lf; pc.delpro[1] = p.idelpro;
+  for (int v = 0; v < 2; ++v) {
+    const double delth0 = 0.25 * pc.delpro[v] / tables->delth;
+    for (int k = 0; k < A; ++k) {
+      pc.sp[v][k] = delth0 * (tables->sinth[k] + tables->sinth[pc.kpm_p[k]]) / tables->r_earth;
+      pc.sm[v][k] = delth0 * (tables->sinth[k] + tables->sinth[pc.kpm_m[k]]) / tables->r_earth;
+    }
+  }
+  pc.cmtodeg = 360.0 / tables->circ;
+  pc.xdella = dec->xdella;
+  h->msplit = (p.ifrelfmax > 0) ? std::min(p.ifrelfmax, Fr) : 0;   // ctuwupdt.F90:193-235
+
+  // ---- per-point tables
+  const int NLAND = dec->nsup + 1;
+  auto ext = [&](int ij) { return ij - dec->ninf; };
+  std::vector<int> nbr((size_t)14 * nloc);
+  std::vector<double> wl((size_t)6 * nloc), pt((size_t)5 * nloc, 0.0), cpm(nloc), cpp(nloc);
+  for (int l = 0; l < nloc; ++l) {
+    int klat[2][2], kcor[4][2];
+    for (int ic = 0; ic < 2; ++ic) nbr[(size_t)ic * nloc + l] = ext(dec->klon[l + (size_t)nloc * ic]);
+    for (int icl = 0; icl < 2; ++icl)
+      for (int ic = 0; ic < 2; ++ic) {
+        klat[ic][icl] = dec->klat[l + (size_t)nloc * (ic + 2 * icl)];
+        nbr[(size_t)(2 + ic + 2 * icl) * nloc + l] = ext(klat[ic][icl]);
+      }
+    for (int icl = 0; icl < 2; ++icl)
+      for (int icr = 0; icr < 4; ++icr) {
+        kcor[icr][icl] = dec->kcor[l + (size_t)nloc * (icr + 4 * icl)];
+        nbr[(size_t)(6 + icr + 4 * icl) * nloc + l] = ext(kcor[icr][icl]);
+      }
+    // CTUWINI's edit of WLAT/WCOR next to land (ctuwini.F90:61-99)
+    for (int ic = 0; ic < 2; ++ic) {
+      double w = dec->wlat[l + (size_t)nloc * ic];
+      if (klat[ic][0] < NLAND && klat[ic][1] < NLAND) {}
+      else if (klat[ic][0] == NLAND) { if (w <= 0.75) w = 0.0; }
+      else { if (w >= 0.5) w = 1.0; }
+      wl[(size_t)ic * nloc + l] = w;
+    }
+    for (int icr = 0; icr < 4; ++icr) {
+      double w = dec->wcor[l + (size_t)nloc * icr];
+      if (kcor[icr][0] < NLAND && kcor[icr][1] < NLAND) {}
+      else if (kcor[icr][0] == NLAND) { if (w <= 0.75) w = 0.0; }
+      else { if (w > 0.5) w = 1.0; }
+      wl[(size_t)(2 + icr) * nloc + l] = w;
+    }
+    const int ky = dec->kxlt[l];   // 1-based row
+    if (ky < 1 || ky > dec->ngy) { EW_FAIL_H(h, ECWAM_B200_EINVAL, "KXLT out of range"); }
+    const int km = std::max(1, std::min(ky - 1, dec->ngy)), kp = std::max(1, std::min(ky + 1, dec->ngy));
+    cpm[l] = dec->cosph[km - 1];
+    cpp[l] = dec->cosph[kp - 1];
+    pt[(size_t)3 * nloc + l] = dec->zdello[ky - 1];
+    pt[(size_t)4 * nloc + l] = dec->sinph[ky - 1] / dec->cosph[ky - 1];
+  }
+  for (size_t i = 0; i < nbr.size(); ++i)
+    if (nbr[i] < 0 || nbr[i] >= next) { EW_FAIL_H(h, ECWAM_B200_EINVAL, "neighbour index outside NINF..NSUP+1"); }
+
+  // ---- halo plan (mpdecomp.F90:966-1176, mpexchng.F90:120-249)
+  const int np = h->nproc;
+  h->h_spre.assign(np + 1, 0); h->h_rpre.assign(np + 1, 0);
+  for (int q = 0; q < np; ++q) {
+    h->h_spre[q + 1] = h->h_spre[q] + (np > 1 ? dec->ntope[q] : 0);
+    h->h_rpre[q + 1] = h->h_rpre[q] + (np > 1 ? dec->nfrompe[q] : 0);
+  }
+  h->nsend = h->h_spre[np]; h->nrecv = h->h_rpre[np];
+  if (h->nrecv != nbot + ntop) { EW_FAIL_H(h, ECWAM_B200_EINVAL, "sum(NFROMPE)=%d != halo size %d", h->nrecv, nbot + ntop); }
+  std::vector<int> send_l(h->nsend), send_peer(h->nsend), recv_e(h->nrecv), recv_peer(h->nrecv);
+  std::vector<int> halo_off(nbot + ntop + 1, 0), halo_str(nbot + ntop + 1, 0);
+  const size_t halo_elems = (size_t)h->nrecv * A * Fr;
+  if (halo_elems + 1 > 0x7fffffffull) { EW_FAIL_H(h, ECWAM_B200_EINVAL, "halo too large"); }
+  for (int q = 0; q < np && np > 1; ++q) {
+    for (int ih = 0; ih < dec->ntope[q]; ++ih) {
+      const int ij = dec->ijtope[ih + (size_t)dec->ntopemax * q];
+      if (ij < dec->ijs || ij > dec->ijl) { EW_FAIL_H(h, ECWAM_B200_EINVAL, "IJTOPE outside own range"); }
+      send_l[h->h_spre[q] + ih] = ij - dec->ijs;
+      send_peer[h->h_spre[q] + ih] = q;
+    }
+    const int nr = dec->nfrompe[q];
+    for (int ih = 0; ih < nr; ++ih) {
+      const int e = ext(dec->nijstart[q] + ih);
+      if (e < 0 || e >= next - 1 || (e >= nbot && e < nbot + nloc)) { EW_FAIL_H(h, ECWAM_B200_EINVAL, "NIJSTART outside halo"); }
+      recv_e[h->h_rpre[q] + ih] = e;
+      recv_peer[h->h_rpre[q] + ih] = q;
+      const int hh = (e < nbot) ? e : e - nloc;
+      halo_off[hh] = (int)((size_t)h->h_rpre[q] * A * Fr + ih);
+      halo_str[hh] = nr;
+    }
+  }
+  halo_off[nbot + ntop] = (int)halo_elems;   // land: one zero element, stride 0
+  halo_str[nbot + ntop] = 0;
+
+  cudaStream_t st = h->st;
+  bool ok = true;
+  ok = ok && !h->nbr.upload(nbr, st) && !h->wl.upload(wl, st) && !h->pt.upload(pt, st) && !h->cosph_m.upload(cpm, st) &&
+       !h->cosph_p.upload(cpp, st) && !h->halo_off.upload(halo_off, st) && !h->halo_str.upload(halo_str, st) &&
+       !h->send_l.upload(send_l, st) && !h->send_peer_of.upload(send_peer, st) && !h->send_pre.upload(h->h_spre, st) &&
+       !h->recv_pre.upload(h->h_rpre, st) && !h->recv_peer_of.upload(recv_peer, st) && !h->recv_e.upload(recv_e, st);
+  std::vector<double> landcg(Fr, 0.0);
+  if (dec->land_cgroup) for (int m = 0; m < Fr; ++m) landcg[m] = dec->land_cgroup[m];
+  ok = ok && !h->land_cg.upload(landcg, st);
+  ok = ok && !h->cgext.alloc((size_t)Fr * next) && !h->halo.alloc(halo_elems + 1) &&
+       !h->sendbuf.alloc((size_t)h->nsend * A * Fr) && !h->cgrecv.alloc((size_t)h->nrecv * Fr) &&
+       !h->fl3.alloc((size_t)P * A * Fr * p.nchnk) && !h->flag.alloc(nloc) && !h->count.alloc(1);
+  // IMPLSCH tables
+  std::vector<int> kw((size_t)8 * A);
+  for (int kh = 0; kh < 2; ++kh)
+    for (int k = 0; k < A; ++k) {
+      kw[(size_t)(0 + kh) * A + k] = tables->k1w[k + A * kh] - 1;
+      kw[(size_t)(2 + kh) * A + k] = tables->k2w[k + A * kh] - 1;
+      kw[(size_t)(4 + kh) * A + k] = tables->k11w[k + A * kh] - 1;
+      kw[(size_t)(6 + kh) * A + k] = tables->k21w[k + A * kh] - 1;
+    }
+  for (int v : kw) if (v < 0 || v >= A) { ok = false; ew_set_error("K1W/K2W/K11W/K21W out of range"); }
+  ok = ok && !h->kw.upload(kw, st);
+  if (p.iphys == 1) {
+    const int ns = 2 * tables->nsdsnth + 1;
+    std::vector<int> isat((size_t)ns * A);
+    std::vector<double> satw((size_t)ns * A);
+    for (int j = 0; j < ns; ++j)
+      for (int k = 0; k < A; ++k) { isat[(size_t)j * A + k] = tables->indicessat[k + A * j] - 1; satw[(size_t)j * A + k] = tables->satweights[k + A * j]; }
+    ok = ok && !h->isat.upload(isat, st) && !h->satw.upload(satw, st);
+  }
+  std::vector<double> sw(tables->swellft, tables->swellft + tables->iab);
+  ok = ok && !h->swellft.upload(sw, st);
+  const long long npts = (long long)P * p.nchnk;
+  ok = ok && !h->scr.alloc(implsch_scratch_doubles(npts));
+  if (!ok) { ecwam_b200_destroy(h); return ECWAM_B200_ECUDA; }
+  cudaMemsetAsync(h->halo.p, 0, (halo_elems + 1) * sizeof(double), st);
+  cudaMemsetAsync(h->fl3.p, 0, h->fl3.n * sizeof(double), st);
+  cudaMemsetAsync(h->cgext.p, 0, h->cgext.n * sizeof(double), st);
+  cudaMemsetAsync(h->scr.p, 0, h->scr.n * sizeof(double), st);
+
+  PropDev& d = h->pd;
+  d.nloc = nloc; d.nbot = nbot; d.ntop = ntop; d.next = next; d.P = P; d.A = A; d.F = F; d.Fr = Fr; d.nchnk = p.nchnk;
+  d.nbr = h->nbr.p; d.wl = h->wl.p; d.pt = h->pt.p; d.cgext = h->cgext.p; d.halo_off = h->halo_off.p;
+  d.halo_str = h->halo_str.p; d.halo = h->halo.p;
+  h->tab.k1w = h->kw.p; h->tab.k2w = h->kw.p + 2 * A; h->tab.k11w = h->kw.p + 4 * A; h->tab.k21w = h->kw.p + 6 * A;
+  h->tab.indicessat = h->isat.p; h->tab.satweights = h->satw.p; h->tab.swellft = h->swellft.p;
+  memset(&h->dev, 0, sizeof(h->dev));
+  memset(&h->mir, 0, sizeof(h->mir));
+  if (cudaStreamSynchronize(st) != cudaSuccess) { ecwam_b200_destroy(h); EW_FAIL(ECWAM_B200_ECUDA, "create: stream sync failed"); }
+  *out = h;
+  return 0;
+}
+
+int ecwam_b200_destroy(ecwam_b200_handle h) {
+  if (!h) return 0;
+  cudaStreamSynchronize(h->st);
+  drain_timing(h);
+  if (g_const_owner == h) g_const_owner = nullptr;
+  h->nbr.free(); h->halo_off.free(); h->halo_str.free(); h->send_l.free(); h->send_pre.free(); h->send_peer_of.free();
+  h->recv_pre.free(); h->recv_peer_of.free(); h->recv_e.free(); h->flag.free(); h->count.free(); h->wl.free(); h->pt.free();
+  h->cgext.free(); h->halo.free(); h->sendbuf.free(); h->fl3.free(); h->cosph_m.free(); h->cosph_p.free();
+  h->land_cg.free(); h->cgrecv.free(); h->scr.free(); h->satw.free(); h->swellft.free(); h->kw.free(); h->isat.free();
+  for (void* b : h->mir_bufs) cudaFree(b);
+  delete h;
+  return 0;
+}
+
+int ecwam_b200_bind_fields(ecwam_b200_handle h, const ecwam_b200_fields* dev) {
+  if (!h || !dev) EW_FAIL(ECWAM_B200_EINVAL, "null argument");
+  if (!dev->fl1 || !dev->xllws || !dev->wavnum || !dev->cinv || !dev->cgroup || !dev->xk2cg || !dev->stokfac || !dev->depth ||
+      !dev->emaxdpt || !dev->cosphm1 || !dev->aird || !dev->wdwave || !dev->cicover || !dev->wswave || !dev->wstar ||
+      !dev->ufric || !dev->tauw || !dev->tauwdir || !dev->z0m || !dev->z0b || !dev->chrnck || !dev->ustokes || !dev->vstokes ||
+      !dev->tauxd || !dev->tauyd || !dev->tauocxd || !dev->tauocyd || !dev->tauoc || !dev->tauicx || !dev->tauicy ||
+      !dev->phiocd || !dev->phieps || !dev->phiaw || !dev->mij || !dev->wsemean || !dev->wsfmean || !dev->ustra || !dev->vstra)
+    EW_FAIL(ECWAM_B200_EINVAL, "bind_fields: a required field pointer is NULL");
+  h->dev = *dev;
+  h->bound = true;
+  h->weights_dirty = true;
+  return 0;
+}
+
+int ecwam_b200_invalidate_weights(ecwam_b200_handle h) {
+  if (!h) EW_FAIL(ECWAM_B200_EINVAL, "null handle");
+  h->weights_dirty = true;
+  return 0;
+}
+
+// MPEXCHNG (mpexchng.F90:164-206) over NCCL: one grouped send/recv per neighbouring rank.
+static int exchange(H* h, const double* sendbuf, double* recvbuf, size_t per_point_full, size_t per_point_now) {
+  if (h->nproc <= 1) return 0;
+  EW_NCCL_CHECK(ncclGroupStart());
+  for (int q = 0; q < h->nproc; ++q) {
+    const int ns = h->h_spre[q + 1] - h->h_spre[q], nr = h->h_rpre[q + 1] - h->h_rpre[q];
+    if (ns > 0) EW_NCCL_CHECK(ncclSend(sendbuf + (size_t)h->h_spre[q] * per_point_full, (size_t)ns * per_point_now, ncclDouble, q, h->comm, h->st));
+    if (nr > 0) EW_NCCL_CHECK(ncclRecv(recvbuf + (size_t)h->h_rpre[q] * per_point_full, (size_t)nr * per_point_now, ncclDouble, q, h->comm, h->st));
+  }
+  EW_NCCL_CHECK(ncclGroupEnd());
+  return 0;
+}
+
+// halo exchange of the spectrum held in `src` (chunked layout with srcF frequencies), frequencies [0, nm)
+static int halo_spectrum(H* h, const double* src, int srcF, int nm) {
+  if (h->nproc <= 1) return 0;
+  ScopedTimer t(h, "halo");
+  const PropDev& d = h->pd;
+  launch_pack(d, src, srcF, nullptr, 0, d.A, nm, d.Fr, h->send_l.p, h->send_pre.p, h->send_peer_of.p, h->nsend, h->sendbuf.p, h->st);
+  h->nlaunch += (h->nsend > 0);
+  return exchange(h, h->sendbuf.p, h->halo.p, (size_t)d.A * d.Fr, (size_t)d.A * nm);
+}
+
+// CTUWUPDT equivalent: PROENVHALO of the group velocity + per-point set-up + CFL scan (propag_wam.F90:221-236)
+static int update_weights(H* h, int* cfl) {
+  const PropDev& d = h->pd;
+  launch_setup_points(d, h->dev.cosphm1, h->cosph_m.p, h->cosph_p.p, h->pt.p, h->st);
+  launch_fill_cgext(d, h->dev.cgroup, h->cgext.p, h->land_cg.p, h->st);
+  h->nlaunch += 3;
+  if (h->nproc > 1) {
+    launch_pack(d, nullptr, 0, h->cgext.p, 1, 1, d.Fr, d.Fr, h->send_l.p, h->send_pre.p, h->send_peer_of.p, h->nsend,
+                h->sendbuf.p, h->st);
+    int rc = exchange(h, h->sendbuf.p, h->cgrecv.p, (size_t)d.Fr, (size_t)d.Fr);
+    if (rc) return rc;
+    launch_unpack_cg(d, h->cgrecv.p, h->recv_pre.p, h->recv_peer_of.p, h->recv_e.p, h->nrecv, d.Fr, h->cgext.p, h->st);
+    h->nlaunch += 2;
+  }
+  launch_ctu_check(d, 0, d.Fr, h->msplit, h->flag.p, h->count.p, h->st);
+  h->nlaunch += 2;
+  int cnt = 0;
+  EW_CUDA_CHECK(cudaMemcpyAsync(&cnt, h->count.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  EW_CUDA_CHECK(cudaStreamSynchronize(h->st));
+  *cfl = cnt;
+  h->weights_dirty = false;
+  return 0;
+}
+
+// returns CFL count (>=0) or error (<0); leaves m>=msplit results in FL3 and tells where the fast-wave
+// frequencies ended up (in_fl3)
+static int propag_core(H* h, bool* lf_in_fl3) {
+  if (!h->bound) EW_FAIL(ECWAM_B200_ESTATE, "fields not bound");
+  int rc = ensure_const(h);
+  if (rc) return rc;
+  const PropDev& d = h->pd;
+  const ecwam_b200_params& p = h->par;
+  int cfl = 0;
+  if (h->weights_dirty) {
+    rc = update_weights(h, &cfl);
+    if (rc) return rc;
+    if (cfl > 0) { ew_set_error("CTUW: CFL / weight-range check failed at %d grid points (ctuwdrv.F90:127-146)", cfl); h->weights_dirty = true; return cfl; }
+  }
+  rc = halo_spectrum(h, h->dev.fl1, d.F, d.Fr);   // propag_wam.F90:166
+  if (rc) return rc;
+  {
+    ScopedTimer t(h, "propags2");
+    launch_propags2(d, h->dev.fl1, d.F, h->fl3.p, d.Fr, 0, d.Fr, h->msplit, h->st);   // propag_wam.F90:245-251
+    h->nlaunch++;
+  }
+  *lf_in_fl3 = true;
+  if (p.ifrelfmax > 0 && p.ifrelfmax < d.Fr) {   // propag_wam.F90:257-313
+    const int nstep = (int)nint_l(p.idelpro / p.delpro_lf);
+    for (int isub = 2; isub <= nstep; ++isub) {
+      const double* src = *lf_in_fl3 ? h->fl3.p : h->dev.fl1;
+      double* dst = *lf_in_fl3 ? h->dev.fl1 : h->fl3.p;
+      const int sF = *lf_in_fl3 ? d.Fr : d.F, dF = *lf_in_fl3 ? d.F : d.Fr;
+      rc = halo_spectrum(h, src, sF, p.ifrelfmax);
+      if (rc) return rc;
+      ScopedTimer t(h, "propags2");
+      launch_propags2(d, src, sF, dst, dF, 0, p.ifrelfmax, h->msplit, h->st);
+      h->nlaunch++;
+      *lf_in_fl3 = !*lf_in_fl3;
+    }
+  }
+  return 0;
+}
+
+int ecwam_b200_propag(ecwam_b200_handle h) {
+  if (!h) EW_FAIL(ECWAM_B200_EINVAL, "null handle");
+  bool lf_in_fl3 = true;
+  int rc = propag_core(h, &lf_in_fl3);
+  if (rc) return rc;
+  const PropDev& d = h->pd;
+  const int ms = (h->par.ifrelfmax > 0 && h->par.ifrelfmax < d.Fr) ? h->par.ifrelfmax : 0;
+  ScopedTimer t(h, "copyback");
+  if (lf_in_fl3) {
+    launch_copyback(d, h->fl3.p, h->dev.fl1, 0, d.Fr, h->st);
+    h->nlaunch++;
+  } else {
+    launch_copyback(d, h->fl3.p, h->dev.fl1, ms, d.Fr, h->st);
+    launch_pad(d, h->dev.fl1, 0, ms, h->st);
+    h->nlaunch += 2;
+  }
+  EW_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+static ImplDev make_impl(H* h, bool from_fl3) {
+  ImplDev d;
+  d.P = h->par.nproma; d.A = h->par.nang; d.F = h->par.nfre; d.Fr = h->par.nfre_red; d.nchnk = h->par.nchnk;
+  d.npts = (long long)d.P * d.nchnk;
+  d.f = h->dev;
+  d.fl_lo = from_fl3 ? h->fl3.p : h->dev.fl1;
+  d.lo_F = from_fl3 ? d.Fr : d.F;
+  d.scr = h->scr.p;
+  d.tab = h->tab;
+  return d;
+}
+
+int ecwam_b200_implsch(ecwam_b200_handle h, int ichnk0, int nchnk) {
+  if (!h) EW_FAIL(ECWAM_B200_EINVAL, "null handle");
+  if (!h->bound) EW_FAIL(ECWAM_B200_ESTATE, "fields not bound");
+  if (ichnk0 < 1 || nchnk < 1 || ichnk0 + nchnk - 1 > h->par.nchnk) EW_FAIL(ECWAM_B200_EINVAL, "chunk range out of bounds");
+  int rc = ensure_const(h);
+  if (rc) return rc;
+  ImplDev d = make_impl(h, false);
+  ScopedTimer t(h, "implsch");
+  rc = launch_implsch(d, (long long)(ichnk0 - 1) * d.P, (long long)nchnk * d.P, h->st, &h->nlaunch);
+  if (rc) return rc;
+  EW_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+int ecwam_b200_implsch_all(ecwam_b200_handle h) {
+  if (!h) EW_FAIL(ECWAM_B200_EINVAL, "null handle");
+  return ecwam_b200_implsch(h, 1, h->par.nchnk);
+}
+
+int ecwam_b200_wamintgr(ecwam_b200_handle h) {
+  if (!h) EW_FAIL(ECWAM_B200_EINVAL, "null handle");
+  int rc = ecwam_b200_propag(h);
+  if (rc) return rc;
+  return ecwam_b200_implsch_all(h);
+}
+
+int ecwam_b200_synchronize(ecwam_b200_handle h) {
+  if (!h) EW_FAIL(ECWAM_B200_EINVAL, "null handle");
+  EW_CUDA_CHECK(cudaStreamSynchronize(h->st));
+  EW_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+long long ecwam_b200_launch_count(ecwam_b200_handle h) { return h ? h->nlaunch : 0; }
+int ecwam_b200_timing_enable(ecwam_b200_handle h, int on) { if (!h) return ECWAM_B200_EINVAL; h->timing = on != 0; return 0; }
+int ecwam_b200_timing_get(ecwam_b200_handle h, const char* name, double* total_ms, long long* count) {
+  if (!h || !name) EW_FAIL(ECWAM_B200_EINVAL, "null argument");
+  drain_timing(h);
+  auto it = h->tm.find(name);
+  if (total_ms) *total_ms = it == h->tm.end() ? 0.0 : it->second.total_ms;
+  if (count) *count = it == h->tm.end() ? 0 : it->second.count;
+  return 0;
+}
+int ecwam_b200_timing_reset(ecwam_b200_handle h) {
+  if (!h) return ECWAM_B200_EINVAL;
+  drain_timing(h);
+  h->tm.clear();
+  return 0;
+}
+
+// ---- host-buffer entry point ----------------------------------------------------------------------------
+namespace {
+struct FieldDesc { size_t off; int kind; /* 0: (P,A,F,C) 1: (P,F,C) 2: (P,C) double 3: (P,C) int */ int dir; /* 1 in(static) 2 in(per step) 4 out */ };
+#define FD(member, kind, dir) {offsetof(ecwam_b200_fields, member), kind, dir}
+const FieldDesc kFields[] = {
+    FD(fl1, 0, 2 | 4), FD(xllws, 0, 8),
+    FD(wavnum, 1, 1), FD(cinv, 1, 1), FD(cgroup, 1, 1), FD(xk2cg, 1, 1), FD(omosnh2kd, 1, 1), FD(stokfac, 1, 1), FD(ciwa, 1, 1),
+    FD(depth, 2, 1), FD(emaxdpt, 2, 1), FD(dellam1, 2, 1), FD(cosphm1, 2, 1), FD(ucur, 2, 1), FD(vcur, 2, 1),
+    FD(aird, 2, 2), FD(wdwave, 2, 2), FD(cicover, 2, 2), FD(wswave, 2, 2), FD(wstar, 2, 2), FD(ustra, 2, 2), FD(vstra, 2, 2),
+    FD(ufric, 2, 2 | 4), FD(tauw, 2, 2 | 4), FD(tauwdir, 2, 2 | 4), FD(z0m, 2, 2 | 4), FD(z0b, 2, 2 | 4), FD(chrnck, 2, 2 | 4),
+    FD(cithick, 2, 2),
+    FD(wsemean, 2, 4), FD(wsfmean, 2, 4), FD(ustokes, 2, 4), FD(vstokes, 2, 4), FD(strnms, 2, 0), FD(tauxd, 2, 4), FD(tauyd, 2, 4),
+    FD(tauocxd, 2, 4), FD(tauocyd, 2, 4), FD(tauoc, 2, 4), FD(tauicx, 2, 4), FD(tauicy, 2, 4), FD(phiocd, 2, 4), FD(phieps, 2, 4),
+    FD(phiaw, 2, 4), FD(mij, 3, 4)};
+#undef FD
+inline void*& fptr(ecwam_b200_fields& f, size_t off) { return *(void**)((char*)&f + off); }
+inline void* fptr_c(const ecwam_b200_fields& f, size_t off) { return *(void* const*)((const char*)&f + off); }
+}  // namespace
+
+int ecwam_b200_wamintgr_host(ecwam_b200_handle h, const ecwam_b200_fields* host, int with_xllws, long long* h2d_bytes,
+                             long long* d2h_bytes) {
+  if (!h || !host) EW_FAIL(ECWAM_B200_EINVAL, "null argument");
+  const ecwam_b200_params& p = h->par;
+  const size_t npts = (size_t)p.nproma * p.nchnk;
+  auto bytes_of = [&](int kind) -> size_t {
+    switch (kind) { case 0: return npts * p.nang * p.nfre * 8; case 1: return npts * p.nfre * 8; case 2: return npts * 8; default: return npts * 4; }
+  };
+  if (!h->mir_alloc) {
+    for (const FieldDesc& fd : kFields) {
+      void* b = nullptr;
+      EW_CUDA_CHECK(cudaMalloc(&b, bytes_of(fd.kind)));
+      EW_CUDA_CHECK(cudaMemsetAsync(b, 0, bytes_of(fd.kind), h->st));
+      h->mir_bufs.push_back(b);
+      fptr(h->mir, fd.off) = b;
+    }
+    h->mir_alloc = true;
+    int rc = ecwam_b200_bind_fields(h, &h->mir);
+    if (rc) return rc;
+  }
+  long long nin = 0, nout = 0;
+  for (const FieldDesc& fd : kFields) {
+    const void* src = fptr_c(*host, fd.off);
+    const bool is_static = (fd.dir & 1) != 0, per_step = (fd.dir & 2) != 0;
+    if (!src) continue;
+    if ((is_static && !h->mir_static_done) || per_step) {
+      EW_CUDA_CHECK(cudaMemcpyAsync(fptr(h->mir, fd.off), src, bytes_of(fd.kind), cudaMemcpyHostToDevice, h->st));
+      nin += (long long)bytes_of(fd.kind);
+    }
+  }
+  h->mir_static_done = true;
+  int rc = ecwam_b200_wamintgr(h);
+  if (rc) return rc;
+  for (const FieldDesc& fd : kFields) {
+    void* dst = fptr_c(*host, fd.off);
+    if (!dst) continue;
+    if ((fd.dir & 4) || ((fd.dir & 8) && with_xllws)) {
+      EW_CUDA_CHECK(cudaMemcpyAsync(dst, fptr(h->mir, fd.off), bytes_of(fd.kind), cudaMemcpyDeviceToHost, h->st));
+      nout += (long long)bytes_of(fd.kind);
+    }
+  }
+  EW_CUDA_CHECK(cudaStreamSynchronize(h->st));
+  if (h2d_bytes) *h2d_bytes = nin;
+  if (d2h_bytes) *d2h_bytes = nout;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,66 @@
+// Shared device-side declarations of the B200-native WAMINTGR hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+#define EW_MAXF 40     // >= NFRE
+#define EW_MAXA 48     // >= NANG
+#define EW_MAXMC 48    // >= MLSTHG
+#define EW_MAXSAT 25   // >= 2*NSDSNTH+1
+#define EW_MAXJT 24    // >= JTOT_TAUHF
+
+// Small read-only tables (YOWFRED/YOWPHYS/YOWINDN/... module state) held in __constant__ memory.
+// Filled from ecwam_b200_tables + ecwam_b200_params at ecwam_b200_create.
+struct DevConst {
+  // dimensions / switches (ecwam_b200_params)
+  int A, F, Fr, iphys, idamping, llcapchnk, lbiwbk, licerun, lmaskice, lwamrsetci, lwflux, lcflx, lwvflx_snl,
+      lwcouast;
+  double delt, ximp, rnu, rnum, wspmin, cithrsh, cithrsh_tail, ciblock, flmin, bathymax;
+  // YOWPCONS
+  double G, GM1, ZPI, ZPI4GM1, ZPI4GM2, ROWATERM1, EPSMIN, EPSUS, EPSU10, ACD, BCD, CDMAX, TAUOCMIN, TAUOCMAX,
+      PHIEPSMIN, PHIEPSMAX, WSEMEAN_MIN;
+  // YOWFRED
+  double FRATIO, WETAIL, FRTAIL, WP1TAIL, DELTH, FLOGSPRDM1;
+  int NFRE_ODD;
+  double FR[EW_MAXF], DFIM[EW_MAXF], DFIMOFR[EW_MAXF], DFIMFR[EW_MAXF], ZPIFR[EW_MAXF], FR5[EW_MAXF],
+      COFRM4[EW_MAXF], FLMAX[EW_MAXF], RHOWG_DFIM[EW_MAXF], DFIM_SIM[EW_MAXF];
+  double TH[EW_MAXA], COSTH[EW_MAXA], SINTH[EW_MAXA];
+  // YOWPHYS
+  double XKAPPA, XNLEV, ALPHA, ALPHAMIN, CHNKMIN_U, ZALP, BETAMAXOXKAPPA2, TAUWSHELTER, TAILFACTOR, TAILFACTOR_PM,
+      SWELLF, SWELLF2, SWELLF3, SWELLF4, SWELLF5, SWELLF6, SWELLF7, SWELLF7M1, Z0RAT, Z0TUBMAX, ABMIN, ABMAX, CDIS,
+      DELTA_SDIS, CDISVIS, SDSBR, SSDSC2, SSDSC3, SSDSC4, SSDSC5, SSDSC6, MICHE, EGRCRV, AFCRV, BFCRV;
+  int NSDSNTH;
+  // YOWTABL / YOWCOUP
+  int IAB, JTOT;
+  double EPS1, X0TAUHF, WTAUHF[EW_MAXJT];
+  // YOWINDN: per-MC interaction tables (0-based MC index = MC-1), frequency indices are 1-based as in Fortran
+  int MLSTHG, MFRSTLW, KFRH;
+  double DAL1, DAL2;
+  int IKP[EW_MAXMC], IKP1[EW_MAXMC], IKM[EW_MAXMC], IKM1[EW_MAXMC];
+  int INLCOEF[EW_MAXMC][5];
+  double RNLCOEF[EW_MAXMC][25];
+  double AF11[EW_MAXMC];
+};
+
+// tables too irregular / large for constant memory (per-lane indexed)
+struct DevTabPtr {
+  const int* k1w;         // [2][A] 0-based direction indices
+  const int* k2w;
+  const int* k11w;
+  const int* k21w;
+  const int* indicessat;  // [2N+1][A] 0-based
+  const double* satweights;  // [2N+1][A]
+  const double* swellft;  // [IAB]
+};
+
+#define EW_CUDA_CHECK(call)                                                              \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      ew_set_error("%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      return ECWAM_B200_ECUDA;                                                           \
+    }                                                                                    \
+  } while (0)
+
+void ew_set_error(const char* fmt, ...);

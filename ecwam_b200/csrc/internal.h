@@ -1,0 +1,64 @@
+// Internal declarations shared by the translation units of libecwam_b200.so.
+#pragma once
+#include "../../include/ecwam_b200.h"
+#include "dev_common.cuh"
+
+namespace ew {
+
+// Device view of one rank's propagation tables (built once at ecwam_b200_create).
+// Extended 0-based index e = IJ - NINF: halo-below [0,nbot), own [nbot,nbot+nloc), halo-above, land = next-1.
+struct PropDev {
+  int nloc, nbot, ntop, next;   // next = nbot+nloc+ntop+1
+  int P, A, F, Fr, nchnk;
+  const int* nbr;        // [14][nloc]: KLON(1..2), KLAT(ic,icl) at 2+(ic-1)+2(icl-1), KCOR(icr,icl) at 6+(icr-1)+4(icl-1)
+  const double* wl;      // [6][nloc]: WLAT(1..2), WCOR(1..4) after CTUWINI's land edit (ctuwini.F90:61-99)
+  const double* pt;      // [5][nloc]: COSPHM1, DP(1), DP(2), ZDELLO(ky), TANPH(ky)
+  const double* cgext;   // [Fr][next] group velocity incl. halo and land slot (proenvhalo.F90)
+  const int* halo_off;   // [nbot+ntop+1] offset of (k=0,m=0) of a halo point in `halo`; land -> a zero element
+  const int* halo_str;   // [nbot+ntop+1] direction stride (= points received from that peer); land -> 0
+  const double* halo;    // received spectra, per peer block [m][k][ih]
+};
+
+// per-direction tables of the CTU scheme (ctuwupdt.F90:111-161), constant memory
+struct PropConst {
+  int quad[EW_MAXA];        // 0: cos>=0,sin>=0  1: cos>=0,sin<0  2: cos<0,sin>=0  3: cos<0,sin<0
+  int kpm_m[EW_MAXA];       // KPM(K,-1) 0-based
+  int kpm_p[EW_MAXA];       // KPM(K,+1)
+  double sinth[EW_MAXA], costh[EW_MAXA];
+  double sp[2][EW_MAXA];    // DELTH0*(SINTH(K)+SINTH(KP1))/R for the two DELPRO values (ctuw.F90:423-431)
+  double sm[2][EW_MAXA];
+  double delpro[2];
+  double cmtodeg;           // 360/CIRC
+  double xdella;
+};
+int upload_prop_const(const PropConst& h, cudaStream_t st);
+
+void launch_propags2(const PropDev& d, const double* src, int srcF, double* dst, int dstF, int m0, int m1, int msplit,
+                     cudaStream_t st);
+void launch_ctu_check(const PropDev& d, int m0, int m1, int msplit, int* flag, int* count, cudaStream_t st);
+void launch_setup_points(const PropDev& d, const double* cosphm1_fld, const double* cosph_m, const double* cosph_p,
+                         double* pt, cudaStream_t st);
+void launch_fill_cgext(const PropDev& d, const double* cgroup, double* cgext, const double* land_cg, cudaStream_t st);
+void launch_pack(const PropDev& d, const double* src, int srcF, const double* cgext, int mode, int nk, int nm, int nfull,
+                 const int* send_l, const int* send_pre, const int* send_peer_of, int ntot, double* out, cudaStream_t st);
+void launch_unpack_cg(const PropDev& d, const double* in, const int* recv_pre, const int* recv_peer_of, const int* recv_e,
+                      int ntot, int nfull, double* cgext, cudaStream_t st);
+void launch_copyback(const PropDev& d, const double* fl3, double* fl1, int m0, int m1, cudaStream_t st);
+void launch_pad(const PropDev& d, double* fl1, int m0, int m1, cudaStream_t st);
+
+// ---- IMPLSCH -----------------------------------------------------------------------------------------------
+struct ImplDev {
+  int P, A, F, Fr, nchnk;
+  long long npts;          // P*nchnk (padded lanes included, as the reference: KIJL = NPROMA_WAM, wamintgr.F90:120)
+  ecwam_b200_fields f;     // device pointers
+  const double* fl_lo;     // source of FL1 for m < lo_nf: either f.fl1 (lo_F = F) or the propagation scratch (lo_F = Fr)
+  int lo_F;
+  double* scr;             // [NSCR][npts] scalar scratch between the kernels
+  DevTabPtr tab;
+};
+int upload_dev_const(const DevConst& h, cudaStream_t st);
+// launches the IMPLSCH kernel sequence for points [p0, p0+np)
+int launch_implsch(const ImplDev& d, long long p0, long long np, cudaStream_t st, long long* nlaunch);
+size_t implsch_scratch_doubles(long long npts);
+
+}  // namespace ew

@@ -1,0 +1,371 @@
+// PROPAG_WAM / PROPAGS2 (IPROPAGS=2, IREFRA=0, ICASE=1) for sm_100a.
+//
+// What the reference does per advection step (src/ecwam/propag_wam.F90:105-405):
+//   FL1 chunks -> FL1_EXT block copy, MPEXCHNG halo, PROPAGS2 reading 8 STORED weight arrays per (ij,k,m)
+//   (src/ecwam/propags2.F90:99-121; weights from src/ecwam/ctuw.F90:160-275,404-501), block -> chunk copy.
+// The stored weights are 150 KB per grid point at 36x29 (ctuwupdt.F90:171-178) and would not fit one B200
+// at O640, so this kernel RECOMPUTES them per (ij,k,m) from ~150 B of per-point tables and the group
+// velocity of the 7-point neighbourhood, and gathers straight from the caller's NPROMA-chunked FL1
+// (no FL1_EXT copy).  HBM traffic per bin: one 8-byte read + one 8-byte write (+ L2-served neighbours).
+//
+// This translation unit is compiled with -fmad=false and the weight arithmetic keeps the reference's
+// operation order, so the result is bit-identical to the reference's stored-weight formulation.
+#include "internal.h"
+
+namespace ew {
+
+// per-direction tables of the CTU scheme (ctuwupdt.F90:111-161): struct PropConst in internal.h
+__constant__ PropConst c_prop;
+
+int upload_prop_const(const PropConst& h, cudaStream_t st) {
+  EW_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_prop, &h, sizeof(PropConst), 0, cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+// ---- addressing --------------------------------------------------------------------------------------
+struct SpecSrc {
+  const double* base;   // spectrum in the NPROMA-chunked layout (P, A, nF, C)
+  long long cstride;    // P*A*nF
+};
+
+__device__ __forceinline__ void nbr_base(const PropDev& d, const SpecSrc& s, int e, int m, const double*& p, int& kstr) {
+  const int l = e - d.nbot;
+  if ((unsigned)l < (unsigned)d.nloc) {
+    const int c = l / d.P;
+    const int i = l - c * d.P;
+    p = s.base + i + (long long)c * s.cstride + (long long)m * d.P * d.A;
+    kstr = d.P;
+  } else {
+    const int h = (e < d.nbot) ? e : e - d.nloc;
+    const int st = __ldg(d.halo_str + h);
+    p = d.halo + __ldg(d.halo_off + h) + (long long)m * d.A * st;
+    kstr = st;
+  }
+}
+
+// ---- the CTU weights + update for one direction, one quadrant (compile-time upwind selectors) ---------
+// JX1/JY1: upwind longitude / latitude neighbour (1|2), KC: upwind corner (1..4) = JXO(K,1), JYO(K,1), KCR(K,1)
+struct PointM {            // k-independent quantities of one (point, frequency)
+  double hx[2], hy[2];     // 0.5*(CG+CG_lon(ic)), 0.5*(CG+DP(ic)*CGYP(ic))      (ctuw.F90:160-171,199-210)
+  double cg, tanph, cosphm1, zdello, gam1, wlat[2], wlatm1[2], wcor[4], wcorm1[4];
+};
+
+template <int JX1, int JY1, int KC>
+__device__ __forceinline__ double ctu_update(const PointM& q, int k, int idp, double f0, double flon, double flat1,
+                                             double flat2, double fc1, double fc2, double fkm, double fkp) {
+  constexpr int JX2 = 3 - JX1, JY2 = 3 - JY1;
+  const double snk = c_prop.sinth[k], csk = c_prop.costh[k];
+  const double mdel = -c_prop.delpro[idp];
+  // displacements through the four interfaces (ctuw.F90:172-235); ISSU=ISSV=1 when IREFRA=0
+  const double dxu1 = fabs(mdel * (q.hx[JX1 - 1] * snk * q.cosphm1) * c_prop.cmtodeg);
+  const double dxu2 = fabs(mdel * (q.hx[JX2 - 1] * snk * q.cosphm1) * c_prop.cmtodeg);
+  const double dyu1 = fabs(mdel * (q.hy[JY1 - 1] * csk) * c_prop.cmtodeg);
+  const double dyu2 = fabs(mdel * (q.hy[JY2 - 1] * csk) * c_prop.cmtodeg);
+  const double dxx = q.zdello - dxu2;           // - DXDW(JXO(K,1)) = 0
+  const double dyy = c_prop.xdella - dyu2;
+  const double wl = dxx * dyu1 * q.gam1;        // WEIGHT(JYO(K,1))      (ctuw.F90:243)
+  const double wlatn1 = q.wlat[JY1 - 1] * wl;
+  const double wlatn2 = q.wlatm1[JY1 - 1] * wl;
+  const double wlonn = dyy * dxu1 * q.gam1;     // WLONN(..,JXO(K,1))     (ctuw.F90:253)
+  const double wc = dxu1 * dyu1 * q.gam1;       // WEIGHT(1)              (ctuw.F90:258)
+  const double wcorn1 = q.wcor[KC - 1] * wc;
+  const double wcorn2 = q.wcorm1[KC - 1] * wc;
+  double sumwn = (q.zdello * dyu2 + c_prop.xdella * dxu2 - dxu2 * dyu2) * q.gam1;   // (ctuw.F90:268-274)
+  // great-circle turning (ctuw.F90:404-501, IREFRA=0: DRCP=DRCM=0)
+  const double dthp = q.tanph * c_prop.sp[idp][k] * q.cg;
+  const double dthm = q.tanph * c_prop.sm[idp][k] * q.cg;
+  const double w0 = (dthp + fabs(dthp)) + (fabs(dthm) - dthm);
+  const double wp = -dthp + fabs(dthp);
+  const double wm = dthm + fabs(dthm);
+  sumwn = sumwn + w0;                           // (ctuw.F90:608)
+  // propags2.F90:106-116, left-to-right
+  return (1.0 - sumwn) * f0 + wlonn * flon + wlatn1 * flat1 + wlatn2 * flat2 + wcorn1 * fc1 + wcorn2 * fc2 + wm * fkm +
+         wp * fkp;
+}
+
+// One thread = one own grid point x one group of MG frequencies; loops the directions.
+// grid = (ceil(nloc/blockDim), ngroups): blockIdx.x (points) varies fastest so that the rows north and south
+// of the running row stay L2-resident for one frequency group at a time.
+__global__ void __launch_bounds__(128) propags2_kernel(PropDev d, SpecSrc src, double* __restrict__ dst, long long dcstride,
+                                                       int m0, int m1, int MG, int msplit) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= d.nloc) return;
+  const int mb = m0 + blockIdx.y * MG;
+  const int me = min(mb + MG, m1);
+  const int nl = d.nloc;
+  int nb[14];
+#pragma unroll
+  for (int j = 0; j < 14; ++j) nb[j] = __ldg(d.nbr + (size_t)j * nl + l);
+  PointM q;
+  q.wlat[0] = __ldg(d.wl + l);
+  q.wlat[1] = __ldg(d.wl + nl + l);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) q.wcor[j] = __ldg(d.wl + (size_t)(2 + j) * nl + l);
+  q.wlatm1[0] = 1.0 - q.wlat[0];
+  q.wlatm1[1] = 1.0 - q.wlat[1];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) q.wcorm1[j] = 1.0 - q.wcor[j];
+  q.cosphm1 = __ldg(d.pt + l);
+  const double dp1 = __ldg(d.pt + nl + l), dp2 = __ldg(d.pt + 2 * (size_t)nl + l);
+  q.zdello = __ldg(d.pt + 3 * (size_t)nl + l);
+  q.tanph = __ldg(d.pt + 4 * (size_t)nl + l);
+  q.gam1 = 1.0 / (q.zdello * c_prop.xdella);
+  const int e0 = d.nbot + l;
+  const int c = l / d.P, i = l - c * d.P;
+  const int A = d.A;
+  for (int m = mb; m < me; ++m) {
+    const int idp = (m < msplit) ? 0 : 1;
+    const double* cgm = d.cgext + (size_t)m * d.next;
+    q.cg = __ldg(cgm + e0);
+    q.hx[0] = 0.5 * (q.cg + __ldg(cgm + nb[0]));
+    q.hx[1] = 0.5 * (q.cg + __ldg(cgm + nb[1]));
+    {
+      const double cgyp1 = q.wlat[0] * __ldg(cgm + nb[2]) + (1.0 - q.wlat[0]) * __ldg(cgm + nb[4]);
+      const double cgyp2 = q.wlat[1] * __ldg(cgm + nb[3]) + (1.0 - q.wlat[1]) * __ldg(cgm + nb[5]);
+      q.hy[0] = 0.5 * (q.cg + dp1 * cgyp1);
+      q.hy[1] = 0.5 * (q.cg + dp2 * cgyp2);
+    }
+    const double* ps = src.base + i + (long long)c * src.cstride + (long long)m * d.P * A;
+    double* pd = dst + i + (long long)c * dcstride + (long long)m * d.P * A;
+    const int P = d.P;
+    // neighbour bases for this frequency: lon(1,2), lat(ic,icl), cor(icr,icl)
+    const double* pb[14];
+    int ks[14];
+#pragma unroll
+    for (int j = 0; j < 14; ++j) nbr_base(d, src, nb[j], m, pb[j], ks[j]);
+    for (int k = 0; k < A; ++k) {
+      const double f0 = ps[(size_t)k * P];
+      const double fkm = ps[(size_t)c_prop.kpm_m[k] * P];
+      const double fkp = ps[(size_t)c_prop.kpm_p[k] * P];
+      double r;
+#define LD(j) __ldg(pb[j] + (size_t)k * ks[j])
+      switch (c_prop.quad[k]) {
+        case 0:  // JX1=1 JY1=1 KCR=3 : west, south, SW
+          r = ctu_update<1, 1, 3>(q, k, idp, f0, LD(0), LD(2), LD(4), LD(6 + 2), LD(10 + 2), fkm, fkp);
+          break;
+        case 1:  // JX1=2 JY1=1 KCR=2 : east, south, SE
+          r = ctu_update<2, 1, 2>(q, k, idp, f0, LD(1), LD(2), LD(4), LD(6 + 1), LD(10 + 1), fkm, fkp);
+          break;
+        case 2:  // JX1=1 JY1=2 KCR=4 : west, north, NW
+          r = ctu_update<1, 2, 4>(q, k, idp, f0, LD(0), LD(3), LD(5), LD(6 + 3), LD(10 + 3), fkm, fkp);
+          break;
+        default:  // JX1=2 JY1=2 KCR=1 : east, north, NE
+          r = ctu_update<2, 2, 1>(q, k, idp, f0, LD(1), LD(3), LD(5), LD(6 + 0), LD(10 + 0), fkm, fkp);
+          break;
+      }
+#undef LD
+      pd[(size_t)k * P] = r;
+    }
+  }
+}
+
+// ---- first-call CFL / weight-range scan (ctuw.F90:282-358, 536-690) -> flag per own point ----------------
+__global__ void __launch_bounds__(128) ctu_check_kernel(PropDev d, int m0, int m1, int msplit, int* __restrict__ flag) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= d.nloc) return;
+  const int nl = d.nloc;
+  int nb[6];
+  for (int j = 0; j < 6; ++j) nb[j] = __ldg(d.nbr + (size_t)j * nl + l);
+  double wlat[2], wcor[4];
+  wlat[0] = d.wl[l];
+  wlat[1] = d.wl[nl + l];
+  for (int j = 0; j < 4; ++j) wcor[j] = d.wl[(size_t)(2 + j) * nl + l];
+  const double cosphm1 = d.pt[l], dp1 = d.pt[nl + l], dp2 = d.pt[2 * (size_t)nl + l], zdello = d.pt[3 * (size_t)nl + l],
+               tanph = d.pt[4 * (size_t)nl + l];
+  const double xdella = c_prop.xdella, gam1 = 1.0 / (zdello * xdella);
+  const int e0 = d.nbot + l;
+  bool bad = false;
+  auto chk = [&](double w) { if (w > 1.0 || w < 0.0) bad = true; };
+  for (int m = m0 + blockIdx.y; m < m1; m += gridDim.y) {
+    const int idp = (m < msplit) ? 0 : 1;
+    const double* cgm = d.cgext + (size_t)m * d.next;
+    const double cg = cgm[e0];
+    double hx[2], hy[2];
+    hx[0] = 0.5 * (cg + cgm[nb[0]]);
+    hx[1] = 0.5 * (cg + cgm[nb[1]]);
+    hy[0] = 0.5 * (cg + dp1 * (wlat[0] * cgm[nb[2]] + (1.0 - wlat[0]) * cgm[nb[4]]));
+    hy[1] = 0.5 * (cg + dp2 * (wlat[1] * cgm[nb[3]] + (1.0 - wlat[1]) * cgm[nb[5]]));
+    const double mdel = -c_prop.delpro[idp];
+    for (int k = 0; k < d.A; ++k) {
+      const int qd = c_prop.quad[k];
+      const int jx1 = (qd & 1) ? 1 : 0, jx2 = 1 - jx1, jy1 = (qd & 2) ? 1 : 0, jy2 = 1 - jy1;   // 0-based
+      // KCR(K,1..4) (ctuwupdt.F90:124-160), 0-based corner ids
+      int kcr[4];
+      if (qd == 0) { kcr[0] = 2; kcr[1] = 1; kcr[2] = 3; kcr[3] = 0; }
+      else if (qd == 1) { kcr[0] = 1; kcr[1] = 2; kcr[2] = 0; kcr[3] = 3; }
+      else if (qd == 2) { kcr[0] = 3; kcr[1] = 0; kcr[2] = 2; kcr[3] = 1; }
+      else { kcr[0] = 0; kcr[1] = 3; kcr[2] = 1; kcr[3] = 2; }
+      double dxu[2], dyu[2];
+      for (int ic = 0; ic < 2; ++ic) {
+        dxu[ic] = fabs(mdel * (hx[ic] * c_prop.sinth[k] * cosphm1) * c_prop.cmtodeg);
+        dyu[ic] = fabs(mdel * (hy[ic] * c_prop.costh[k]) * c_prop.cmtodeg);
+        if (dxu[ic] > zdello || dyu[ic] > xdella) bad = true;
+      }
+      const double dxx = zdello - dxu[jx2], dyy = xdella - dyu[jy2];
+      double wgt[2];
+      wgt[jy1] = dxx * dyu[jy1] * gam1;
+      wgt[jy2] = dxx * 0.0 * gam1;
+      for (int ic = 0; ic < 2; ++ic) { chk(wlat[ic] * wgt[ic]); chk((1.0 - wlat[ic]) * wgt[ic]); }
+      chk(dyy * dxu[jx1] * gam1);
+      chk(dyy * 0.0 * gam1);
+      double w4[4] = {dxu[jx1] * dyu[jy1] * gam1, 0.0 * dyu[jy1] * gam1, dxu[jx1] * 0.0 * gam1, 0.0};
+      for (int icr = 0; icr < 4; ++icr) { chk(wcor[kcr[icr]] * w4[icr]); chk((1.0 - wcor[kcr[icr]]) * w4[icr]); }
+      double sumwn = (zdello * dyu[jy2] + xdella * dxu[jx2] - dxu[jx2] * dyu[jy2]) * gam1;
+      const double dthp = tanph * c_prop.sp[idp][k] * cg, dthm = tanph * c_prop.sm[idp][k] * cg;
+      const double w0 = (dthp + fabs(dthp)) + (fabs(dthm) - dthm), wp = -dthp + fabs(dthp), wm = dthm + fabs(dthm);
+      chk(w0); chk(wp); chk(wm);
+      sumwn = sumwn + w0;
+      chk(sumwn);
+    }
+  }
+  if (bad) flag[l] = 1;
+}
+
+__global__ void count_flags_kernel(const int* __restrict__ flag, int n, int* __restrict__ out) {
+  int s = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += flag[i] != 0;
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+// ---- set-up kernels (PROENVHALO / CTUWINI equivalents, once per weight update) ------------------------------
+// pt[0]=COSPHM1_EXT(ij) (from the caller's field), pt[1..2]=DP(ij,1..2)=COSPH(ky-+1)*COSPHM1 (ctuwini.F90:150-163)
+__global__ void setup_points_kernel(PropDev d, const double* __restrict__ cosphm1_fld, const double* __restrict__ cosph_m,
+                                    const double* __restrict__ cosph_p, double* __restrict__ pt) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= d.nloc) return;
+  const int c = l / d.P, i = l - c * d.P;
+  const double cm1 = cosphm1_fld[(size_t)c * d.P + i];
+  pt[l] = cm1;
+  pt[(size_t)d.nloc + l] = cosph_m[l] * cm1;
+  pt[2 * (size_t)d.nloc + l] = cosph_p[l] * cm1;
+}
+
+// CGROUP(P,F,C) -> CG_EXT[m][nbot + l]   (proenvhalo.F90:67-83, group velocity only)
+__global__ void fill_cgext_kernel(PropDev d, const double* __restrict__ cgroup, double* __restrict__ cgext) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (l >= d.nloc) return;
+  const int c = l / d.P, i = l - c * d.P;
+  cgext[(size_t)m * d.next + d.nbot + l] = cgroup[i + (size_t)d.P * (m + (size_t)d.F * c)];
+}
+
+// gather a (points, nk, nm) message block for every peer: out[peerblock + ih + ns*(k + nk*m)]
+// mode 0: spectrum from the chunked layout; mode 1: CG_EXT (nk = 1)
+__global__ void pack_kernel(PropDev d, SpecSrc src, const double* __restrict__ cgext, int mode, int nk, int nm, int nfull,
+                            const int* __restrict__ send_l, const int* __restrict__ send_pre, const int* __restrict__ send_peer_of,
+                            int ntot, double* __restrict__ out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= ntot) return;
+  const int km = blockIdx.y;      // k + nk*m
+  const int m = km / nk, k = km - m * nk;
+  const int q = send_peer_of[s];
+  const int pre = send_pre[q], ns = send_pre[q + 1] - pre;
+  const int ih = s - pre;
+  const int l = send_l[s];
+  double v;
+  if (mode == 0) {
+    const int c = l / d.P, i = l - c * d.P;
+    v = src.base[i + (long long)c * src.cstride + ((long long)m * d.A + k) * d.P];
+  } else {
+    v = cgext[(size_t)m * d.next + d.nbot + l];
+  }
+  out[(size_t)pre * nk * nfull + ih + (size_t)ns * km] = v;
+}
+
+// received CG blocks -> CG_EXT halo slots; land slot <- WVPRPT_LAND%CGROUP (proenvhalo.F90:98-106)
+__global__ void unpack_cg_kernel(PropDev d, const double* __restrict__ in, const int* __restrict__ recv_pre,
+                                 const int* __restrict__ recv_peer_of, const int* __restrict__ recv_e, int ntot, int nfull,
+                                 double* __restrict__ cgext) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (s >= ntot) return;
+  const int q = recv_peer_of[s];
+  const int pre = recv_pre[q], nr = recv_pre[q + 1] - pre;
+  cgext[(size_t)m * d.next + recv_e[s]] = in[(size_t)pre * nfull + (s - pre) + (size_t)nr * m];
+}
+__global__ void land_cg_kernel(PropDev d, const double* __restrict__ land_cg, double* __restrict__ cgext) {
+  const int m = threadIdx.x;
+  if (m < d.Fr) cgext[(size_t)m * d.next + d.next - 1] = land_cg[m];
+}
+
+// FL3 (P,A,Fr,C) -> FL1 (P,A,F,C) for m in [m0,m1) + refresh of the padded lanes of the last chunk
+// (propag_wam.F90:368-405).  One thread per (lane, k, m, chunk) element; lane fastest.
+__global__ void copyback_kernel(PropDev d, const double* __restrict__ fl3, double* __restrict__ fl1, int m0, int m1) {
+  const long long n = (long long)d.P * d.A * (m1 - m0);
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (idx >= n) return;
+  const int i = (int)(idx % d.P);
+  const long long km = idx / d.P + (long long)m0 * d.A;
+  const int kijl = min(d.P, d.nloc - c * d.P);
+  const int is = (i < kijl) ? i : 0;
+  fl1[i + d.P * (km + (long long)d.A * d.F * c)] = fl3[is + d.P * (km + (long long)d.A * d.Fr * c)];
+}
+// padded lanes only (used when the last sub-step already wrote FL1 directly)
+__global__ void pad_kernel(PropDev d, double* __restrict__ fl1, int m0, int m1) {
+  const int c = d.nchnk - 1;
+  const int kijl = d.nloc - c * d.P;
+  const int npad = d.P - kijl;
+  const long long n = (long long)npad * d.A * (m1 - m0);
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int i = kijl + (int)(idx % npad);
+  const long long km = idx / npad + (long long)m0 * d.A;
+  double* p = fl1 + d.P * (km + (long long)d.A * d.F * c);
+  p[i] = p[0];
+}
+
+// ---- host launchers --------------------------------------------------------------------------------------
+void launch_propags2(const PropDev& d, const double* src, int srcF, double* dst, int dstF, int m0, int m1, int msplit,
+                     cudaStream_t st) {
+  if (m1 <= m0 || d.nloc <= 0) return;
+  const int MG = 8;
+  SpecSrc s{src, (long long)d.P * d.A * srcF};
+  dim3 grid((d.nloc + 127) / 128, (m1 - m0 + MG - 1) / MG);
+  propags2_kernel<<<grid, 128, 0, st>>>(d, s, dst, (long long)d.P * d.A * dstF, m0, m1, MG, msplit);
+}
+void launch_ctu_check(const PropDev& d, int m0, int m1, int msplit, int* flag, int* count, cudaStream_t st) {
+  cudaMemsetAsync(flag, 0, sizeof(int) * d.nloc, st);
+  cudaMemsetAsync(count, 0, sizeof(int), st);
+  dim3 grid((d.nloc + 127) / 128, min(m1 - m0, 8));
+  ctu_check_kernel<<<grid, 128, 0, st>>>(d, m0, m1, msplit, flag);
+  count_flags_kernel<<<148, 256, 0, st>>>(flag, d.nloc, count);
+}
+void launch_setup_points(const PropDev& d, const double* cosphm1_fld, const double* cosph_m, const double* cosph_p,
+                         double* pt, cudaStream_t st) {
+  setup_points_kernel<<<(d.nloc + 255) / 256, 256, 0, st>>>(d, cosphm1_fld, cosph_m, cosph_p, pt);
+}
+void launch_fill_cgext(const PropDev& d, const double* cgroup, double* cgext, const double* land_cg, cudaStream_t st) {
+  dim3 grid((d.nloc + 255) / 256, d.Fr);
+  fill_cgext_kernel<<<grid, 256, 0, st>>>(d, cgroup, cgext);
+  land_cg_kernel<<<1, 64, 0, st>>>(d, land_cg, cgext);
+}
+void launch_pack(const PropDev& d, const double* src, int srcF, const double* cgext, int mode, int nk, int nm, int nfull,
+                 const int* send_l, const int* send_pre, const int* send_peer_of, int ntot, double* out, cudaStream_t st) {
+  if (ntot <= 0) return;
+  SpecSrc s{src, (long long)d.P * d.A * srcF};
+  dim3 grid((ntot + 127) / 128, nk * nm);
+  pack_kernel<<<grid, 128, 0, st>>>(d, s, cgext, mode, nk, nm, nfull, send_l, send_pre, send_peer_of, ntot, out);
+}
+void launch_unpack_cg(const PropDev& d, const double* in, const int* recv_pre, const int* recv_peer_of, const int* recv_e,
+                      int ntot, int nfull, double* cgext, cudaStream_t st) {
+  if (ntot <= 0) return;
+  dim3 grid((ntot + 127) / 128, d.Fr);
+  unpack_cg_kernel<<<grid, 128, 0, st>>>(d, in, recv_pre, recv_peer_of, recv_e, ntot, nfull, cgext);
+}
+void launch_copyback(const PropDev& d, const double* fl3, double* fl1, int m0, int m1, cudaStream_t st) {
+  if (m1 <= m0) return;
+  const long long n = (long long)d.P * d.A * (m1 - m0);
+  dim3 grid((unsigned)((n + 255) / 256), d.nchnk);
+  copyback_kernel<<<grid, 256, 0, st>>>(d, fl3, fl1, m0, m1);
+}
+void launch_pad(const PropDev& d, double* fl1, int m0, int m1, cudaStream_t st) {
+  const int kijl = d.nloc - (d.nchnk - 1) * d.P;
+  const int npad = d.P - kijl;
+  if (npad <= 0 || m1 <= m0) return;
+  const long long n = (long long)npad * d.A * (m1 - m0);
+  pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, fl1, m0, m1);
+}
+
+}  // namespace ew

@@ -1,0 +1,278 @@
+"""Host-side mirror of the WAMINTGR call sequence (src/ecwam/wamintgr.F90:94-146) on top of the C ABI.
+
+`WamSetup` does what INITMDL / MPDECOMP do once (tables, decomposition, neighbour tables — host C++ inside the
+library), `WamIntgr` owns one rank's NPROMA-chunked fields on one GPU (torch tensors = device memory only) and calls
+PROPAG_WAM / IMPLSCH through the library.  Per-point data cross this module in the ORIGINAL global sea-point
+order (rows south->north, west->east), exactly like oracle/oracle.py, so the parity tests can feed both sides
+the same arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import numpy as np
+
+from . import lib as L
+
+# the members of ecwam_b200_fields by shape class
+F4 = ("fl1", "xllws")
+F3 = ("wavnum", "cinv", "cgroup", "xk2cg", "omosnh2kd", "stokfac", "ciwa")
+F2 = ("depth", "emaxdpt", "dellam1", "cosphm1", "ucur", "vcur", "aird", "wdwave", "cicover", "wswave", "wstar", "ustra",
+      "vstra", "ufric", "tauw", "tauwdir", "z0m", "z0b", "chrnck", "cithick", "wsemean", "wsfmean", "ustokes", "vstokes",
+      "strnms", "tauxd", "tauyd", "tauocxd", "tauocyd", "tauoc", "tauicx", "tauicy", "phiocd", "phieps", "phiaw")
+FI = ("mij",)
+
+
+def default_params(**kw) -> L.Params:
+    """Namelist values of the reference's test configurations."""
+    p = L.Params(nang=12, nfre=36, nfre_red=25, iphys=1, isnonlin=0, idamping=1, irefra=0, icase=1, llgcbz0=0, llnormagam=0,
+                 llcapchnk=1, lbiwbk=1, licerun=1, lmaskice=1, lwamrsetci=1, lciwa=0, lwflux=0, lwfluxout=1, lwnemocou=0,
+                 lwvflx_snl=1, lwcouast=0, icode_wnd=3, ifrelfmax=0, nproma=32, nchnk=0, idelt=900.0, idelpro=900.0,
+                 delpro_lf=900.0, ximp=1.0, rnu=1.5e-5, rnum=0.11 * 1.5e-5, wspmin=1.0, cithrsh=0.3, cithrsh_tail=0.3,
+                 ciblock=0.0, flmin=1e-5, bathymax=998.999)
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise KeyError(k)
+        setattr(p, k, v)
+    return p
+
+
+def _np(ptr, n, dtype):
+    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+
+
+class WamSetup:
+    """Tables + grid + decomposition for `nproc` ranks (host only; no GPU needed)."""
+
+    def __init__(self, grid, nproc: int = 1, ll1d: bool = False, **params):
+        self.lib = L.load()
+        self.grid = grid
+        self.nproc = nproc
+        self.par = default_params(**params)
+        self.ifre1 = 1 if self.par.nfre_red == 25 else 3      # share/ecwam/scripts/ecwam_configure.sh:52-57
+        self.fr1 = 4.177248e-02
+        h = C.c_void_p()
+        L.check(self.lib.ecwam_b200_host_tables_create(C.byref(self.par), self.ifre1, self.fr1, C.byref(h)), "host_tables_create")
+        self._ht = h
+        self.tables = self.lib.ecwam_b200_host_tables_get(h).contents
+        nl = np.ascontiguousarray(grid.nlonrgg, dtype=np.int32)
+        mk = np.ascontiguousarray(grid.mask, dtype=np.uint8)
+        g = C.c_void_p()
+        L.check(self.lib.ecwam_b200_host_grid_create(int(grid.ngy), nl.ctypes.data_as(C.POINTER(C.c_int)), float(grid.amosop),
+                                                     float(grid.amonop), mk.tobytes(), nproc, int(ll1d), C.byref(g)),
+                "host_grid_create")
+        self._hg = g
+        self.niblo = self.lib.ecwam_b200_host_grid_niblo(g)
+        assert self.niblo == grid.niblo
+        self.ij2new = _np(self.lib.ecwam_b200_host_grid_ij2newij(g), self.niblo + 1, np.int64)
+        self.new2ij = _np(self.lib.ecwam_b200_host_grid_newij2ij(g), self.niblo + 1, np.int64)
+        self.kxlt = _np(self.lib.ecwam_b200_host_grid_kxlt(g), self.niblo, np.int64)
+        self.nstart = _np(self.lib.ecwam_b200_host_grid_nstart(g), nproc, np.int64)
+        self.nend = _np(self.lib.ecwam_b200_host_grid_nend(g), nproc, np.int64)
+        # land-point group velocity = deep-water value at BATHYMAX (initdpthflds.F90:80-88)
+        deep = np.array([self.par.bathymax])
+        cg = np.empty(self.par.nfre)
+        dpp = C.POINTER(C.c_double)
+        L.check(self.lib.ecwam_b200_host_depthprpt(C.byref(self.tables), self.par.nfre, 1, deep.ctypes.data_as(dpp), None, None,
+                                                   cg.ctypes.data_as(dpp), None, None, None), "depthprpt")
+        self.land_cgroup = np.ascontiguousarray(cg[: self.par.nfre_red])
+
+    def table(self, name, n):
+        return _np(getattr(self.tables, name), n, np.float64)
+
+    def itable(self, name, n):
+        return _np(getattr(self.tables, name), n, np.int32)
+
+    def decomp(self, rank: int) -> L.Decomp:
+        """Decomposition tables of 0-based `rank` (a copy of the struct with land_cgroup filled in)."""
+        d = self.lib.ecwam_b200_host_grid_decomp(self._hg, rank + 1).contents
+        out = L.Decomp()
+        C.memmove(C.byref(out), C.byref(d), C.sizeof(L.Decomp))
+        out.land_cgroup = self.land_cgroup.ctypes.data_as(C.POINTER(C.c_double))
+        return out
+
+    def decomp_arrays(self, rank: int):
+        d = self.decomp(rank)
+        n = d.ijl - d.ijs + 1
+        return dict(ijs=d.ijs, ijl=d.ijl, ninf=d.ninf, nsup=d.nsup, ntopemax=d.ntopemax,
+                    klat=_np(d.klat, 4 * n, np.int32), klon=_np(d.klon, 2 * n, np.int32), kcor=_np(d.kcor, 8 * n, np.int32),
+                    wlat=_np(d.wlat, 2 * n, np.float64), wcor=_np(d.wcor, 4 * n, np.float64),
+                    nfrompe=_np(d.nfrompe, self.nproc, np.int32), ntope=_np(d.ntope, self.nproc, np.int32),
+                    nijstart=_np(d.nijstart, self.nproc, np.int32), ijtope=_np(d.ijtope, d.ntopemax * self.nproc, np.int32))
+
+    def close(self):
+        if getattr(self, "_ht", None):
+            self.lib.ecwam_b200_host_tables_free(self._ht)
+            self._ht = None
+        if getattr(self, "_hg", None):
+            self.lib.ecwam_b200_host_grid_free(self._hg)
+            self._hg = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class WamIntgr:
+    """One rank of the WAMINTGR hot path on one GPU."""
+
+    def __init__(self, setup: WamSetup, rank: int = 0, device="cuda:0", nccl_comm=None, alloc_fields=True):
+        import torch
+        self.torch = torch
+        self.s = setup
+        self.lib = setup.lib
+        self.rank = rank
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.EcwamError("the WAMINTGR hot path is CUDA only (no CPU fallback)")
+        torch.cuda.set_device(self.device)
+        self.ijs, self.ijl = int(setup.nstart[rank]), int(setup.nend[rank])
+        self.nloc = self.ijl - self.ijs + 1
+        P = min(setup.par.nproma, self.nloc)                  # mpdecomp.F90:1343-1356
+        self.P = P
+        self.C = (self.nloc + P - 1) // P                     # mchunk.F90:33-75
+        self.par = L.Params()
+        C.memmove(C.byref(self.par), C.byref(setup.par), C.sizeof(L.Params))
+        self.par.nproma, self.par.nchnk = P, self.C
+        self.A, self.F, self.Fr = self.par.nang, self.par.nfre, self.par.nfre_red
+        # chunk slot -> original global sea-point index (padded lanes of the last chunk copy its first point)
+        slot = np.arange(P * self.C)
+        slot = np.where(slot < self.nloc, slot, (slot // P) * P)
+        self.src = setup.new2ij[self.ijs + slot] - 1            # 0-based original index per slot
+        self.own = setup.new2ij[self.ijs + np.arange(self.nloc)] - 1
+        self.comm = nccl_comm
+        self._dec = setup.decomp(rank)
+        h = C.c_void_p()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        L.check(self.lib.ecwam_b200_create(C.byref(self.par), C.byref(setup.tables), C.byref(self._dec),
+                                           C.c_void_p(nccl_comm) if nccl_comm else None, C.c_void_p(stream), C.byref(h)), "create")
+        self.h = h
+        self.t = {}
+        if alloc_fields:
+            self._alloc()
+
+    # ---- field storage (device memory through torch)
+    def _alloc(self):
+        torch = self.torch
+        P, Cn, A, F = self.P, self.C, self.A, self.F
+        dev = self.device
+        for n in F4:
+            self.t[n] = torch.zeros((Cn, F, A, P), dtype=torch.float64, device=dev)
+        for n in F3:
+            self.t[n] = torch.zeros((Cn, F, P), dtype=torch.float64, device=dev)
+        for n in F2:
+            self.t[n] = torch.zeros((Cn, P), dtype=torch.float64, device=dev)
+        self.t["mij"] = torch.full((Cn, P), F, dtype=torch.int32, device=dev)
+        self.t["ciwa"].fill_(1.0)
+        self.bind()
+
+    def bind(self):
+        f = L.Fields()
+        for n, _ in L.Fields._fields_:
+            ptr = self.t[n].data_ptr()
+            setattr(f, n, C.cast(ptr, C.POINTER(C.c_int if n == "mij" else C.c_double)))
+        self.fields = f
+        L.check(self.lib.ecwam_b200_bind_fields(self.h, C.byref(f)), "bind_fields")
+
+    def set_static(self, depth_global: np.ndarray):
+        """Depth-derived fields: DEPTH, EMAXDPT, DELLAM1, COSPHM1 and DEPTHPRPT (initdpthflds.F90:57-88)."""
+        torch = self.torch
+        s = self.s
+        d = np.ascontiguousarray(depth_global[self.src])
+        ky = s.kxlt[self.ijs - 1 + np.where(np.arange(self.P * self.C) < self.nloc, np.arange(self.P * self.C),
+                                           (np.arange(self.P * self.C) // self.P) * self.P)]
+        zd = s.table_grid("zdello")[ky - 1]
+        cosph = s.table_grid("cosph")[ky - 1]
+        circ = s.tables.circ
+        gam = np.where(d < 4.0, 0.8 * d / 4.0, 0.8)
+        vals = dict(depth=d, emaxdpt=0.0625 * (gam * d) * (gam * d), cosphm1=1.0 / cosph, dellam1=1.0 / (zd * circ / 360.0))
+        for k, v in vals.items():
+            self.t[k].copy_(torch.from_numpy(np.ascontiguousarray(v)).view(self.C, self.P))
+        n = self.P * self.C
+        out = {k: np.empty((self.F, n)) for k in ("wavnum", "cinv", "cgroup", "xk2cg", "omosnh2kd", "stokfac")}
+        dpp = C.POINTER(C.c_double)
+        L.check(self.lib.ecwam_b200_host_depthprpt(C.byref(s.tables), self.F, n, d.ctypes.data_as(dpp),
+                                                   *[out[k].ctypes.data_as(dpp) for k in
+                                                     ("wavnum", "cinv", "cgroup", "xk2cg", "omosnh2kd", "stokfac")]), "depthprpt")
+        for k, v in out.items():
+            # (F, C*P) -> (C, F, P)
+            self.t[k].copy_(torch.from_numpy(v).view(self.F, self.C, self.P).permute(1, 0, 2))
+
+    def set_field(self, name: str, v_global: np.ndarray):
+        self.t[name.lower()].copy_(self.torch.from_numpy(np.ascontiguousarray(v_global[self.src])).view(self.C, self.P))
+
+    def get_field(self, name: str) -> np.ndarray:
+        """Own points only, in slot order (use .own for their original global indices)."""
+        return self.t[name.lower()].reshape(-1)[: self.nloc].cpu().numpy()
+
+    def get_field3(self, name: str) -> np.ndarray:
+        return self.t[name.lower()].permute(1, 0, 2).reshape(self.F, -1)[:, : self.nloc].cpu().numpy()
+
+    def set_fl1(self, fl_global: np.ndarray):
+        """fl_global[m, k, ij] in original global order."""
+        torch = self.torch
+        x = torch.from_numpy(np.ascontiguousarray(fl_global[:, :, self.src]))      # (F, A, C*P)
+        self.t["fl1"].copy_(x.view(self.F, self.A, self.C, self.P).permute(2, 0, 1, 3))
+
+    def get_spec(self, name="fl1") -> np.ndarray:
+        """[m, k, own point] of FL1 or XLLWS."""
+        x = self.t[name].permute(1, 2, 0, 3).reshape(self.F, self.A, -1)[:, :, : self.nloc]
+        return x.cpu().numpy()
+
+    # ---- the hot path
+    def propag(self) -> int:
+        return L.check(self.lib.ecwam_b200_propag(self.h), "propag")
+
+    def implsch(self):
+        L.check(self.lib.ecwam_b200_implsch_all(self.h), "implsch_all")
+
+    def step(self) -> int:
+        """One WAMINTGR sub-step with IDELPRO == IDELT."""
+        return L.check(self.lib.ecwam_b200_wamintgr(self.h), "wamintgr")
+
+    def synchronize(self):
+        L.check(self.lib.ecwam_b200_synchronize(self.h), "synchronize")
+
+    def launch_count(self) -> int:
+        return int(self.lib.ecwam_b200_launch_count(self.h))
+
+    def timing(self, name: str):
+        tot, cnt = C.c_double(), C.c_longlong()
+        self.lib.ecwam_b200_timing_get(self.h, name.encode(), C.byref(tot), C.byref(cnt))
+        return tot.value, cnt.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ecwam_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _table_grid(self, name):
+    d = self.lib.ecwam_b200_host_grid_decomp(self._hg, 1).contents
+    return _np(getattr(d, name), d.ngy, np.float64)
+
+
+WamSetup.table_grid = _table_grid
+
+
+def hs_fm(setup: WamSetup, fl: np.ndarray):
+    """Hs = 4 sqrt(EM) and mean frequency FM of spectra fl[m,k,n] (femean.F90, outblock.F90:223-244) — numpy, for
+    diagnostics and parity metrics only."""
+    F = setup.par.nfre
+    dfim = setup.table("dfim", F)
+    dfimofr = setup.table("dfimofr", F)
+    fr = setup.table("fr", F)
+    delth = setup.tables.delth
+    eps = setup.tables.epsmin
+    t2 = np.maximum(fl, eps).sum(axis=1)                       # (F, n)
+    em = eps + (t2 * dfim[:, None]).sum(axis=0) + setup.tables.wetail * fr[-1] * delth * t2[-1]
+    fm = eps + (t2 * dfimofr[:, None]).sum(axis=0) + setup.tables.frtail * delth * t2[-1]
+    fm = np.maximum(em / fm, fr[0])
+    return 4.0 * np.sqrt(em), fm

@@ -1,0 +1,361 @@
+/* ecwam_b200.h — C ABI of the B200-native WAMINTGR hot path (PROPAG_WAM/PROPAGS2 + IMPLSCH).
+ *
+ * This is the drop-in boundary: a Fortran ecWAM build binds these entry points with ISO_C_BINDING and keeps
+ * the reference signatures of IMPLSCH (src/ecwam/implsch.F90:10-23) and PROPAG_WAM (src/ecwam/propag_wam.F90:10-11)
+ * as thin shims (INTEGRATION.md shows the shim).  Plain pointers and sizes only, no torch / C++ types.
+ *
+ * All paths below are relative to the reference tree (/root/reference).
+ *
+ * Conventions
+ *   - reals are IEEE double (JWRB in a dp build, src/ecwam/parkind_wave.F90:23-35), integers are 32-bit (JWIM);
+ *   - arrays keep the reference's column-major NPROMA-blocked layouts (src/ecwam/yowdrvtype_config.yml:12-56):
+ *       FL1, XLLWS        (NPROMA, NANG, NFRE, NCHNK)
+ *       WAVNUM ... CIWA   (NPROMA, NFRE, NCHNK)
+ *       1-D fields        (NPROMA, NCHNK)
+ *     the library never re-orders or frees caller memory;
+ *   - every function returns 0 on success, a negative ECWAM_B200_E* code on failure
+ *     (ecwam_b200_propag returns the number of CFL-violating grid points, >0, where the reference would
+ *     call ABORT1 in src/ecwam/ctuwdrv.F90:127-146); ecwam_b200_last_error() gives the message;
+ *   - one handle per MPI rank / GPU, driven from one host thread (SURVEY.md 8b "Threading").
+ *
+ * NOTE for ecwam_b200/lib.py: the struct bodies are parsed to build the ctypes mirrors — keep ONE member
+ * per line, of the forms `int x;`, `double x;`, `const double* x;`, `const int* x;`, `double* x;`, `int* x;`.
+ */
+#ifndef ECWAM_B200_H
+#define ECWAM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECWAM_B200_EINVAL (-1)   /* bad argument / unsupported configuration            */
+#define ECWAM_B200_ECUDA (-2)    /* CUDA runtime error                                  */
+#define ECWAM_B200_ENCCL (-3)    /* NCCL error                                          */
+#define ECWAM_B200_ESTATE (-4)   /* call out of order (e.g. fields not bound)           */
+
+/* ---------------------------------------------------------------------------------------------------
+ * Run parameters = the NALINE namelist values the hot path reads (src/ecwam/mpuserin.F90:180-260,
+ * defaults :540-800; values written by share/ecwam/scripts/ecwam_run_model.sh:211-269).               */
+typedef struct ecwam_b200_params {
+  int nang;        /* YOWPARAM NANG                                                    */
+  int nfre;        /* YOWPARAM NFRE   (physics frequencies, 36)                         */
+  int nfre_red;    /* YOWPARAM NFRE_RED (propagated frequencies)                        */
+  int iphys;       /* YOWSTAT IPHYS: 0 = Janssen/WAM4, 1 = Ardhuin et al. 2010          */
+  int isnonlin;    /* YOWSTAT ISNONLIN (0 only)                                         */
+  int idamping;    /* YOWSTAT IDAMPING (SINPUT_JAN)                                     */
+  int irefra;      /* YOWSTAT IREFRA (0 only)                                           */
+  int icase;       /* YOWSTAT ICASE (1 = spherical, only)                               */
+  int llgcbz0;     /* YOWCOUP LLGCBZ0 (0 only)                                          */
+  int llnormagam;  /* YOWCOUP LLNORMAGAM (0 only)                                       */
+  int llcapchnk;   /* YOWCOUP LLCAPCHNK                                                 */
+  int lbiwbk;      /* YOWSTAT LBIWBK                                                    */
+  int licerun;     /* YOWICE LICERUN                                                    */
+  int lmaskice;    /* YOWICE LMASKICE                                                   */
+  int lwamrsetci;  /* YOWICE LWAMRSETCI                                                 */
+  int lciwa;       /* LCIWA1|LCIWA2|LCIWA3|LCISCAL (must be 0)                          */
+  int lwflux;      /* YOWCOUP LWFLUX                                                    */
+  int lwfluxout;   /* YOWCOUP LWFLUXOUT (userin.F90:470 sets it .TRUE.)                 */
+  int lwnemocou;   /* YOWCOUP LWNEMOCOU (0 only)                                        */
+  int lwvflx_snl;  /* YOWCOUP LWVFLX_SNL                                                */
+  int lwcouast;    /* YOWCOUP LWCOUAST                                                  */
+  int icode_wnd;   /* YOWWNDG ICODE (3 = 10 m wind, only)                               */
+  int ifrelfmax;   /* YOWSTAT IFRELFMAX (fast-wave sub-stepping, O1280)                 */
+  int nproma;      /* YOWPARAM NPROMA_WAM                                               */
+  int nchnk;       /* YOWPARAM NCHNK                                                    */
+  double idelt;    /* YOWSTAT IDELT   [s]                                               */
+  double idelpro;  /* YOWSTAT IDELPRO [s]                                               */
+  double delpro_lf;/* YOWSTAT DELPRO_LF [s]                                             */
+  double ximp;     /* YOWSTAT XIMP                                                      */
+  double rnu;      /* YOWPHYS RNU                                                       */
+  double rnum;     /* YOWPHYS RNUM                                                      */
+  double wspmin;   /* YOWWIND WSPMIN                                                    */
+  double cithrsh;  /* YOWICE CITHRSH                                                    */
+  double cithrsh_tail; /* YOWICE CITHRSH_TAIL                                           */
+  double ciblock;  /* YOWICE CIBLOCK                                                    */
+  double flmin;    /* YOWICE FLMIN                                                      */
+  double bathymax; /* YOWSHAL BATHYMAX                                                  */
+} ecwam_b200_params;
+
+/* ---------------------------------------------------------------------------------------------------
+ * Small read-only tables = module variables of YOWPCONS, YOWFRED, YOWPHYS, YOWTABL, YOWCOUP, YOWINDN
+ * (SURVEY.md 8b "Global state consumed").  Host pointers; copied at ecwam_b200_create.
+ * ecwam_b200_host_tables() fills one from `params` alone (stand-alone / synthetic runs).              */
+typedef struct ecwam_b200_tables {
+  /* YOWPCONS (src/ecwam/yowpcons.F90:19-79, iniwcst.F90) */
+  double g;
+  double gm1;
+  double zpi;
+  double zpi4gm1;
+  double zpi4gm2;
+  double circ;
+  double r_earth;
+  double rowaterm1;
+  double epsmin;
+  double epsus;
+  double epsu10;
+  double acd;
+  double bcd;
+  double cdmax;
+  double tauocmin;
+  double tauocmax;
+  double phiepsmin;
+  double phiepsmax;
+  double wsemean_min;
+  /* YOWFRED (src/ecwam/yowfred.F90:20-120, mfredir.F90, initmdl.F90:437-503) */
+  double fratio;
+  double wetail;
+  double frtail;
+  double wp1tail;
+  double delth;
+  double flogsprdm1;
+  int nfre_odd;
+  const double* fr;          /* (NFRE) */
+  const double* dfim;        /* (NFRE) */
+  const double* dfimofr;     /* (NFRE) */
+  const double* dfimfr;      /* (NFRE) */
+  const double* zpifr;       /* (NFRE) */
+  const double* fr5;         /* (NFRE) */
+  const double* cofrm4;      /* (NFRE) */
+  const double* flmax;       /* (NFRE) */
+  const double* rhowg_dfim;  /* (NFRE) */
+  const double* dfim_sim;    /* (NFRE) */
+  const double* th;          /* (NANG) */
+  const double* costh;       /* (NANG) */
+  const double* sinth;       /* (NANG) */
+  /* YOWPHYS (src/ecwam/yowphys.F90, setwavphys.F90:46-205) */
+  double xkappa;
+  double xnlev;
+  double alpha;
+  double alphamin;
+  double chnkmin_u;
+  double zalp;
+  double betamaxoxkappa2;
+  double tauwshelter;
+  double tailfactor;
+  double tailfactor_pm;
+  double swellf;
+  double swellf2;
+  double swellf3;
+  double swellf4;
+  double swellf5;
+  double swellf6;
+  double swellf7;
+  double swellf7m1;
+  double z0rat;
+  double z0tubmax;
+  double abmin;
+  double abmax;
+  double cdis;
+  double delta_sdis;
+  double cdisvis;
+  double sdsbr;
+  double ssdsc2;
+  double ssdsc3;
+  double ssdsc4;
+  double ssdsc5;
+  double ssdsc6;
+  double miche;
+  double egrcrv;
+  double afcrv;
+  double bfcrv;
+  int nsdsnth;
+  const int* indicessat;     /* (NANG, 2*NSDSNTH+1), 1-based direction indices (init_sdiss_ardh.F90:69-96) */
+  const double* satweights;  /* (NANG, 2*NSDSNTH+1) */
+  /* YOWTABL / YOWCOUP (tabu_swellft.F90:64-83, init_x0tauhf.F90:65-100) */
+  int iab;
+  double eps1;
+  const double* swellft;     /* (IAB) */
+  int jtot_tauhf;
+  double x0tauhf;
+  const double* wtauhf;      /* (JTOT_TAUHF) */
+  /* YOWINDN (nlweigt.F90:94-262, inisnonlin.F90:89-270) */
+  int mfrstlw;
+  int mlsthg;
+  int kfrh;
+  double dal1;
+  double dal2;
+  const int* ikp;            /* (MFRSTLW:MLSTHG) */
+  const int* ikp1;           /* (MFRSTLW:MLSTHG) */
+  const int* ikm;            /* (MFRSTLW:MLSTHG) */
+  const int* ikm1;           /* (MFRSTLW:MLSTHG) */
+  const int* k1w;            /* (NANG,2) 1-based */
+  const int* k2w;            /* (NANG,2) */
+  const int* k11w;           /* (NANG,2) */
+  const int* k21w;           /* (NANG,2) */
+  const int* inlcoef;        /* (5, MLSTHG) */
+  const double* rnlcoef;     /* (25, MLSTHG) */
+  const double* af11;        /* (MFRSTLW:MLSTHG) */
+} ecwam_b200_tables;
+
+/* ---------------------------------------------------------------------------------------------------
+ * Per-rank grid / decomposition tables = YOWMAP, YOWUBUF, YOWSPEC, YOWMPP after MPDECOMP
+ * (src/ecwam/mpdecomp.F90:690-1296, propconnect.F90, yowubuf.F90:59-96, yowspec.F90:17-33).
+ * Indices keep the reference's 1-based extended numbering: own points IJS..IJL, halo NINF..IJS-1 and
+ * IJL+1..NSUP, land = NSUP+1.  Host pointers; copied at ecwam_b200_create.                            */
+typedef struct ecwam_b200_decomp {
+  int irank;                 /* 1-based rank (YOWMPP IRANK) */
+  int nproc;                 /* YOWMPP NPROC */
+  int ijs;                   /* NSTART(IRANK) */
+  int ijl;                   /* NEND(IRANK) */
+  int ninf;                  /* YOWMPP NINF */
+  int nsup;                  /* YOWMPP NSUP */
+  int ngy;                   /* YOWPARAM NGY */
+  double xdella;             /* YOWMAP XDELLA [deg] */
+  const double* zdello;      /* (NGY) YOWMAP ZDELLO [deg] */
+  const double* cosph;       /* (NGY) YOWMAP COSPH */
+  const double* sinph;       /* (NGY) YOWMAP SINPH */
+  const int* kxlt;           /* (IJS:IJL) BLK2GLO%KXLT latitude row of each own point */
+  const int* klat;           /* (IJS:IJL,2,2) */
+  const int* klon;           /* (IJS:IJL,2)   */
+  const int* kcor;           /* (IJS:IJL,4,2) */
+  const double* wlat;        /* (IJS:IJL,2)  as left by PROPCONNECT (CTUWINI's edit is applied internally) */
+  const double* wcor;        /* (IJS:IJL,4)   */
+  const int* nfrompe;        /* (NPROC) */
+  const int* ntope;          /* (NPROC) */
+  const int* nijstart;       /* (NPROC) */
+  int ntopemax;
+  const int* ijtope;         /* (NTOPEMAX, NPROC) */
+  const double* land_cgroup; /* (NFRE_RED) WVPRPT_LAND%CGROUP (initdpthflds.F90:80-88) */
+} ecwam_b200_decomp;
+
+/* ---------------------------------------------------------------------------------------------------
+ * Model fields (device pointers, or host pointers for ecwam_b200_wamintgr_host) = the arguments of
+ * IMPLSCH (implsch.F90:117-143) and PROPAG_WAM (propag_wam.F90:74-77) over ALL chunks.                */
+typedef struct ecwam_b200_fields {
+  double* fl1;               /* (P,A,F,C) inout */
+  double* xllws;             /* (P,A,F,C) out   */
+  const double* wavnum;      /* (P,F,C) */
+  const double* cinv;
+  const double* cgroup;
+  const double* xk2cg;
+  const double* omosnh2kd;   /* PROPAG_WAM only (IREFRA/=0; unused) */
+  const double* stokfac;
+  const double* ciwa;        /* unused (LCIWA*=F) */
+  const double* depth;       /* (P,C) */
+  const double* emaxdpt;
+  const double* dellam1;
+  const double* cosphm1;
+  const double* ucur;        /* unused (IREFRA=0) */
+  const double* vcur;
+  double* aird;
+  double* wdwave;
+  double* cicover;
+  double* wswave;
+  double* wstar;
+  double* ustra;
+  double* vstra;
+  double* ufric;
+  double* tauw;
+  double* tauwdir;
+  double* z0m;
+  double* z0b;
+  double* chrnck;
+  double* cithick;
+  double* wsemean;
+  double* wsfmean;
+  double* ustokes;
+  double* vstokes;
+  double* strnms;
+  double* tauxd;
+  double* tauyd;
+  double* tauocxd;
+  double* tauocyd;
+  double* tauoc;
+  double* tauicx;
+  double* tauicy;
+  double* phiocd;
+  double* phieps;
+  double* phiaw;
+  int* mij;                  /* (P,C) out */
+} ecwam_b200_fields;
+
+typedef struct ecwam_b200_handle_s* ecwam_b200_handle;
+
+/* Create the per-rank state: uploads tables, builds the device neighbour tables and halo plan.
+ * nccl_comm: an ncclComm_t (or NULL when nproc==1); cuda_stream: a cudaStream_t (NULL = default stream).
+ * Replaces the one-off set-up the reference does in INITMDL/MPDECOMP/CTUWUPDT index helpers
+ * (src/ecwam/ctuwupdt.F90:93-166).                                                                     */
+int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* tables,
+                      const ecwam_b200_decomp* decomp, void* nccl_comm, void* cuda_stream,
+                      ecwam_b200_handle* out);
+int ecwam_b200_destroy(ecwam_b200_handle h);
+
+/* NCCL bootstrap helpers so that a host without its own NCCL binding (Fortran, ctypes) can build the
+ * communicator: rank 0 calls _nccl_unique_id, broadcasts the 128 bytes by any means (MPL_BROADCAST in
+ * ecWAM), every rank calls _nccl_comm_init.                                                            */
+int ecwam_b200_nccl_unique_id(char id_out[128]);
+int ecwam_b200_nccl_comm_init(const char id[128], int nranks, int rank, void** comm_out);
+int ecwam_b200_nccl_comm_destroy(void* comm);
+
+/* Bind DEVICE pointers of the model fields (FIELD_API GET_DEVICE_DATA_* + C_LOC on the Fortran side,
+ * src/ecwam/wamintgr_loki_gpu.F90:141-157).                                                            */
+int ecwam_b200_bind_fields(ecwam_b200_handle h, const ecwam_b200_fields* dev);
+
+/* PROPAG_WAM over the whole local block (src/ecwam/propag_wam.F90:10-419, IPROPAGS=2, IREFRA=0):
+ * halo exchange of FL1 (MPEXCHNG -> NCCL), first-call CTU weight set-up + CFL check (CTUWUPDT),
+ * PROPAGS2 (+ fast-wave sub-steps), result back in FL1 with padded lanes refreshed.
+ * Returns the number of own grid points that violate the CFL / weight-range checks (0 = ok).           */
+int ecwam_b200_propag(ecwam_b200_handle h);
+/* Force the CTU set-up to be redone at the next ecwam_b200_propag (LUPDTWGHT, getcurr.F90:289).        */
+int ecwam_b200_invalidate_weights(ecwam_b200_handle h);
+
+/* IMPLSCH for all NCHNK chunks in one go = the chunk loop of WAMINTGR (src/ecwam/wamintgr.F90:117-146). */
+int ecwam_b200_implsch_all(ecwam_b200_handle h);
+/* IMPLSCH for chunks ichnk0 .. ichnk0+nchnk-1 (1-based): the single-chunk reference call is nchnk=1.   */
+int ecwam_b200_implsch(ecwam_b200_handle h, int ichnk0, int nchnk);
+
+/* One WAMINTGR sub-step with IDELPRO == IDELT: PROPAG_WAM then IMPLSCH (wamintgr.F90:94-146) with the
+ * block->chunk copy of PROPAG_WAM fused into IMPLSCH's load.  Same results as _propag + _implsch_all.  */
+int ecwam_b200_wamintgr(ecwam_b200_handle h);
+
+/* Same step for callers whose fields live in HOST memory (pinned or pageable): copies the IMPLSCH /
+ * PROPAG_WAM inputs host->device, runs the step, copies FL1, XLLWS(optional) and the 1-D outputs back.
+ * `host` uses the same struct with host pointers; with_xllws != 0 also returns XLLWS.
+ * h2d_bytes / d2h_bytes (optional) receive the bytes moved.                                            */
+int ecwam_b200_wamintgr_host(ecwam_b200_handle h, const ecwam_b200_fields* host, int with_xllws,
+                             long long* h2d_bytes, long long* d2h_bytes);
+
+int ecwam_b200_synchronize(ecwam_b200_handle h);
+/* Kernel launch counter (all kernels launched through this handle since creation). */
+long long ecwam_b200_launch_count(ecwam_b200_handle h);
+/* Average device time [ms] of the named kernel class since the last reset ("propags2", "implsch_main", ...),
+ * measured with CUDA events on the handle's stream when timing is enabled.                             */
+int ecwam_b200_timing_enable(ecwam_b200_handle h, int on);
+int ecwam_b200_timing_get(ecwam_b200_handle h, const char* name, double* total_ms, long long* count);
+int ecwam_b200_timing_reset(ecwam_b200_handle h);
+const char* ecwam_b200_last_error(void);
+int ecwam_b200_version(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Host-side builders (C++; one-off, init only) for callers that do not bring ecWAM's module state:
+ * the equivalents of MFREDIR/INITMDL/SETWAVPHYS/INISNONLIN/... and of PROPCONNECT/MPDECOMP/MCHUNK.
+ * The returned objects own their arrays; *_free releases them.                                         */
+typedef struct ecwam_b200_host_tables_s* ecwam_b200_host_tables_t;
+int ecwam_b200_host_tables_create(const ecwam_b200_params* params, int ifre1, double fr1,
+                                  ecwam_b200_host_tables_t* out);
+const ecwam_b200_tables* ecwam_b200_host_tables_get(ecwam_b200_host_tables_t t);
+int ecwam_b200_host_tables_free(ecwam_b200_host_tables_t t);
+
+typedef struct ecwam_b200_host_grid_s* ecwam_b200_host_grid_t;
+/* Reduced grid + sea mask -> sea-point order, MPDECOMP for nproc ranks, PROPCONNECT, halo lists.
+ * nlonrgg (NGY) points per row south->north; mask: one byte per grid cell, row-major south->north.      */
+int ecwam_b200_host_grid_create(int ngy, const int* nlonrgg, double amosop, double amonop,
+                                const unsigned char* mask, int nproc, int ll1d, ecwam_b200_host_grid_t* out);
+int ecwam_b200_host_grid_niblo(ecwam_b200_host_grid_t g);
+/* decomp of 1-based rank `irank`; land_cgroup must be supplied by the caller before ecwam_b200_create. */
+const ecwam_b200_decomp* ecwam_b200_host_grid_decomp(ecwam_b200_host_grid_t g, int irank);
+/* maps between the original global sea-point order (1..NIBLO) and the relabelled order (mpdecomp.F90:667-686) */
+const int* ecwam_b200_host_grid_ij2newij(ecwam_b200_host_grid_t g);   /* (0:NIBLO) */
+const int* ecwam_b200_host_grid_newij2ij(ecwam_b200_host_grid_t g);   /* (0:NIBLO) */
+const int* ecwam_b200_host_grid_kxlt(ecwam_b200_host_grid_t g);       /* (NIBLO) relabelled order */
+const int* ecwam_b200_host_grid_nstart(ecwam_b200_host_grid_t g);     /* (NPROC) */
+const int* ecwam_b200_host_grid_nend(ecwam_b200_host_grid_t g);       /* (NPROC) */
+int ecwam_b200_host_grid_free(ecwam_b200_host_grid_t g);
+/* DEPTHPRPT/AKI (depthprpt.F90:60-81, aki.F90:71-91): dispersion fields for n points, arrays (n,NFRE). */
+int ecwam_b200_host_depthprpt(const ecwam_b200_tables* t, int nfre, long long n, const double* depth, double* wavnum,
+                              double* cinv, double* cgroup, double* xk2cg, double* omosnh2kd, double* stokfac);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECWAM_B200_H */
