@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Benchmark of the WAMINTGR hot path (PROPAG_WAM/PROPAGS2 + IMPLSCH) — BASELINE.json's metric:
+grid-point spectra/s per timestep at O640 (36 directions x 29 propagated / 36 physics frequencies, FP64).
+
+  python bench.py --gpus N --steps K --warmup W            this repo's CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W    the CPU restatement of the reference (oracle/) on the host cores
+
+One "step" = one WAMINTGR sub-step (one PROPAG_WAM + one IMPLSCH over every grid point).  Synthetic wind / ice /
+bathymetry and a JONSWAP cold start (the GRIB forcing and ETOPO1 are not available offline).  The grid is partitioned
+over the N GPUs with ecWAM's MPDECOMP decomposition (total work fixed: strong scaling); the MPEXCHNG halo is an NCCL
+grouped send/recv.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "grid-point spectra/s per timestep (IMPLSCH+PROPAGS2)"
+UNIT = "spectra/s"
+
+
+def workload_cfg(name):
+    from ecwam_b200 import synth
+    c = dict(synth.CONFIGS[name])
+    nproma = {"O48": 32, "O320": 64, "O640": 32, "O1280": 32}[name]
+    return c, nproma
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(workload, steps, warmup, sample_N=None, quiet=True):
+    """Times the CPU restatement of the reference (oracle/, -O3 build, OpenMP over NPROMA chunks as
+    wamintgr.F90:117) on a bounded sample of the workload: same spectral resolution, physics and time step, on a
+    smaller octahedral grid with the same synthetic-continent recipe.  Returns (spectra/s, ms/step, cores, sample)."""
+    from ecwam_b200 import synth
+    from oracle import oracle as O
+    cfgw, _ = workload_cfg(workload)
+    cores = os.cpu_count() or 1
+    if sample_N is None:
+        # ~0.3 ms per point per step per core at 36x36: keep one step near 3 s
+        sample_N = 96 if cores >= 16 else 64
+        if cfgw["N"] < sample_N:
+            sample_N = cfgw["N"]
+    g = synth.make_grid(sample_N, "continents")
+    cfg = O.default_config(nang=cfgw["nang"], nfre_red=cfgw["nfre_red"], nproma=24, npr=1, iphys=1, idelt=cfgw["idelt"],
+                           idelpro=cfgw["idelpro"], delpro_lf=cfgw["delpro_lf"], ifrelfmax=cfgw["ifrelfmax"], nthreads=cores)
+    o = O.Oracle(cfg, g, fast=True)
+    f = synth.make_forcing(g)
+    for k, v in f.items():
+        o.set_field(k, v)
+    o.set_fl1(synth.jonswap_cold_start(f["WSWAVE"], f["WDWAVE"], cfgw["nang"], 36, cfgw["nfre_red"]))
+    for _ in range(warmup):
+        o.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.step()
+    dt = time.perf_counter() - t0
+    sample = "O%d synthetic-continent grid, %d sea points, %dx%d(%d) spectrum, %d timed steps, OpenMP %d threads" % (
+        sample_N, g.niblo, cfgw["nang"], 36, cfgw["nfre_red"], steps, cores)
+    return g.niblo * steps / dt, dt / steps * 1e3, cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    warm = max(0, min(args.warmup, 1))
+    val, ms, cores, sample = cpu_reference_run(args.workload, min(steps, 3), warm)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": min(steps, 3),
+            "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": args.workload + " (bounded CPU sample: " + sample + ")"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------------------
+def make_case(workload, world, rank, device, mask="continents"):
+    """Set-up (not timed): grid, MPDECOMP for `world` ranks, tables, this rank's fields on its GPU."""
+    from ecwam_b200 import synth, model as M, lib as L
+    import torch
+    cfgw, nproma = workload_cfg(workload)
+    g = synth.make_grid(cfgw["N"], mask)
+    s = M.WamSetup(g, nproc=world, nang=cfgw["nang"], nfre_red=cfgw["nfre_red"], iphys=1, nproma=nproma, idelt=cfgw["idelt"],
+                   idelpro=cfgw["idelpro"], delpro_lf=cfgw["delpro_lf"], ifrelfmax=cfgw["ifrelfmax"])
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+        lib = L.load()
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            L.check(lib.ecwam_b200_nccl_unique_id(buf), "nccl_unique_id")
+        t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone().to(device)
+        dist.broadcast(t, 0)
+        idb = bytes(t.cpu().numpy().tobytes())
+        cm = C.c_void_p()
+        L.check(lib.ecwam_b200_nccl_comm_init(idb, world, rank, C.byref(cm)), "nccl_comm_init")
+        comm = cm.value
+    w = M.WamIntgr(s, rank, device=device, nccl_comm=comm)
+    w.set_static(g.depth)
+    f = synth.make_forcing(g)
+    for k, v in f.items():
+        w.set_field(k, v)
+    synth.jonswap_cold_start_device(w, f["WSWAVE"], f["WDWAVE"])
+    return g, s, w, f
+
+
+def run_gpu(args):
+    import torch
+    from ecwam_b200 import lib as L
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the WAMINTGR hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    g, s, w, forcing = make_case(args.workload, world, rank, device)
+    lib = w.lib
+    npts_total = g.niblo
+    K, W = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---- device-resident timing ------------------------------------------------------------------------------
+    for _ in range(W):
+        cfl = w.step()
+        if cfl:
+            raise SystemExit("CFL violated in the synthetic case: %d points" % cfl)
+    L.check(lib.ecwam_b200_timing_reset(w.h), "timing_reset")
+    lib.ecwam_b200_timing_enable(w.h, 1)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    n0 = w.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        w.step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    launches = w.launch_count() - n0
+    kern = {}
+    for nm in ("propags2", "halo", "copyback", "implsch_airsea1", "implsch_spec1", "implsch_scalar2", "implsch_spec2", "implsch_scalar4"):
+        tot, cnt = w.timing(nm)
+        if cnt:
+            kern[nm] = tot / cnt
+    lib.ecwam_b200_timing_enable(w.h, 0)
+    value = npts_total * K / (ms_total * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        from ecwam_b200 import model as M
+        host = {}
+        hf = L.Fields()
+        for n, _ in L.Fields._fields_:
+            if n == "xllws":          # not returned per step (with_xllws=0): no pinned copy needed
+                continue
+            t = w.t[n]
+            ht = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            ht.copy_(t)
+            host[n] = ht
+            setattr(hf, n, C.cast(ht.data_ptr(), C.POINTER(C.c_int if n == "mij" else C.c_double)))
+        hin, hout = C.c_longlong(), C.c_longlong()
+        Ke = max(1, min(K, args.e2e_steps))
+        # first call allocates the library's device mirrors and uploads the static fields: warm-up, untimed
+        L.check(lib.ecwam_b200_wamintgr_host(w.h, C.byref(hf), 0, C.byref(hin), C.byref(hout)), "wamintgr_host")
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            L.check(lib.ecwam_b200_wamintgr_host(w.h, C.byref(hf), 0, C.byref(hin), C.byref(hout)), "wamintgr_host")
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        bts = torch.tensor([hin.value, hout.value], dtype=torch.float64, device=device)
+        if dist is not None:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(bts, op=dist.ReduceOp.SUM)
+        e2e = {"value": npts_total * Ke / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(bts[0].item()),
+               "d2h_bytes_per_step": int(bts[1].item()), "steps": Ke,
+               "what": "ecwam_b200_wamintgr_host: FL1 + forcing + stress state host->device from pinned buffers, step, "
+                       "FL1 + all 1-D outputs + MIJ device->host, every step"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------------
+    A, F, Fr = w.A, w.F, w.Fr
+    alg = {"implsch_spec2": (2 * A * F * 8 + A * F * 8 + 5 * F * 8 + 30 * 8), "implsch_spec1": (A * F * 8 + 3 * F * 8 + 20 * 8),
+           "propags2": (2 * A * Fr * 8 + 14 * 4 + 11 * 8 + Fr * 8), "copyback": 2 * A * Fr * 8}
+    dom = max((k for k in kern if k in alg), key=lambda k: kern[k]) if kern else None
+    peak, peak_src = peaks()
+    roof = None
+    if dom:
+        pts_rank = w.P * w.C if dom.startswith("implsch") else w.nloc
+        ach = alg[dom] * pts_rank / (kern[dom] * 1e-3) / 1e9
+        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_point": alg[dom], "points_per_launch": pts_rank,
+                "ms_per_launch": kern[dom],
+                "note": "IMPLSCH kernels are FP64-pipe bound (SURVEY 8d): HBM fraction reported as the contract asks; "
+                        "FP64-pipe utilisation is in profiles/"}
+    cpu = None
+    if not args.no_cpu:
+        v, msc, cores, sample = cpu_reference_run(args.workload, 2, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_step_sample": msc}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s octahedral grid, synthetic continents (%d sea points), %dx%d spectrum (%d propagated), "
+                                   "IPHYS=1, NPROMA=%d, dt=%gs" % (args.workload, npts_total, A, F, Fr, w.par.nproma, w.par.idelt),
+                       "parallelism": "mpdecomp%d" % world, "l2": "inputs larger than L2 (FL1 %.1f GB per GPU)" % (w.t["fl1"].numel() * 8 / 1e9)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "kernel_ms": kern, "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="O640", choices=["O48", "O320", "O640", "O1280"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -543,9 +543,14 @@ int ecwam_b200_implsch(ecwam_b200_handle h, int ichnk0, int nchnk) {
   int rc = ensure_const(h);
   if (rc) return rc;
   ImplDev d = make_impl(h, false);
-  ScopedTimer t(h, "implsch");
-  rc = launch_implsch(d, (long long)(ichnk0 - 1) * d.P, (long long)nchnk * d.P, h->st, &h->nlaunch);
-  if (rc) return rc;
+  static const char* kStage[EW_IMPLSCH_NSTAGE] = {"implsch_airsea1", "implsch_spec1", "implsch_scalar2", "implsch_spec2",
+                                                   "implsch_scalar4"};
+  for (int s = 0; s < EW_IMPLSCH_NSTAGE; ++s) {
+    ScopedTimer t(h, kStage[s]);
+    rc = launch_implsch_stage(d, (long long)(ichnk0 - 1) * d.P, (long long)nchnk * d.P, s, h->st);
+    if (rc) return rc;
+    h->nlaunch++;
+  }
   EW_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -989,7 +989,7 @@ __global__ void __launch_bounds__(PASS == 1 ? 256 : 192) k_spec(ImplDev d, long 
   }
 }
 
-int launch_implsch(const ImplDev& d, long long p0, long long np, cudaStream_t st, long long* nlaunch) {
+int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage, cudaStream_t st) {
   if (np <= 0) return 0;
   const int A = d.A, F = d.F, AF = A * F;
   if (A > 32 * KPL) { ew_set_error("NANG too large for the warp mapping"); return ECWAM_B200_EINVAL; }
@@ -1003,12 +1003,14 @@ int launch_implsch(const ImplDev& d, long long p0, long long np, cudaStream_t st
     attr_done = true;
   }
   if (sm1 > 227 * 1024 || sm2 > 227 * 1024) { ew_set_error("spectrum too large for shared memory"); return ECWAM_B200_EINVAL; }
-  k_airsea1<<<gs, 128, 0, st>>>(d, p0, np);
-  k_spec<1><<<(unsigned)((np + 7) / 8), 256, sm1, st>>>(d, p0, np);
-  k_scalar2<<<gs, 128, 0, st>>>(d, p0, np);
-  k_spec<2><<<(unsigned)((np + 5) / 6), 192, sm2, st>>>(d, p0, np);
-  k_scalar4<<<gs, 128, 0, st>>>(d, p0, np);
-  if (nlaunch) *nlaunch += 5;
+  switch (stage) {
+    case 0: k_airsea1<<<gs, 128, 0, st>>>(d, p0, np); break;
+    case 1: k_spec<1><<<(unsigned)((np + 7) / 8), 256, sm1, st>>>(d, p0, np); break;
+    case 2: k_scalar2<<<gs, 128, 0, st>>>(d, p0, np); break;
+    case 3: k_spec<2><<<(unsigned)((np + 5) / 6), 192, sm2, st>>>(d, p0, np); break;
+    case 4: k_scalar4<<<gs, 128, 0, st>>>(d, p0, np); break;
+    default: return ECWAM_B200_EINVAL;
+  }
   return 0;
 }
 

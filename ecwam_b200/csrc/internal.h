@@ -57,8 +57,10 @@ struct ImplDev {
   DevTabPtr tab;
 };
 int upload_dev_const(const DevConst& h, cudaStream_t st);
-// launches the IMPLSCH kernel sequence for points [p0, p0+np)
-int launch_implsch(const ImplDev& d, long long p0, long long np, cudaStream_t st, long long* nlaunch);
+// launches stage 0..4 of the IMPLSCH kernel sequence (k_airsea1, k_spec<1>, k_scalar2, k_spec<2>, k_scalar4)
+// for points [p0, p0+np)
+#define EW_IMPLSCH_NSTAGE 5
+int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage, cudaStream_t st);
 size_t implsch_scratch_doubles(long long npts);
 
 }  // namespace ew

@@ -162,3 +162,48 @@ def jonswap_cold_start(wswave, wdwave, nang, nfre, nfre_red, fetch=50000.0, fm=0
     for m in range(nfre_red, nfre):
         fl[m] = fl[nfre_red - 1] * (fr5[nfre_red - 1] / fr5[m])
     return fl
+
+
+def jonswap_cold_start_device(w, wswave, wdwave, fetch=50000.0, fm=0.2, alfa=0.018, gamma=3.0, sa=0.07, sb=0.09):
+    """Same cold start as `jonswap_cold_start`, evaluated on the GPU straight into the NPROMA-chunked FL1 of the
+    WamIntgr `w` (for grids whose (NFRE, NANG, NIBLO) host array would be tens of GB).  wswave/wdwave: numpy arrays in
+    the original global order."""
+    torch = w.torch
+    dev = w.device
+    A, F, Fr, P, C = w.A, w.F, w.Fr, w.P, w.C
+    G = 9.806
+    zpi = 2 * np.pi
+    zpi4gm2 = zpi ** 4 / G ** 2
+    fr, _, _ = frequencies(F, Fr)
+    th = torch.tensor((np.arange(A) + 0.5) * zpi / A, dtype=torch.float64, device=dev)
+    u10 = torch.from_numpy(np.ascontiguousarray(wswave[w.src])).to(dev)
+    thes = torch.from_numpy(np.ascontiguousarray(wdwave[w.src])).to(dev)
+    ok = u10 > 0.1e-08
+    us = torch.where(ok, u10, torch.ones_like(u10))
+    gxu = G * fetch / (us * us)
+    ug = G / us
+    fp = 2.84 * gxu ** (-3.0 / 10.0)
+    fp = torch.clamp(fp, min=0.13)
+    fp = torch.minimum(fp, fm / ug)
+    alphaj = torch.clamp(0.033 * fp ** (2.0 / 3.0), min=0.0081)
+    fp = torch.where(ok, fp * ug, torch.zeros_like(fp))
+    alphaj = torch.where(ok, alphaj, torch.zeros_like(alphaj))
+    st = torch.cos(th[:, None] - thes[None, :])
+    st = torch.where(st > 0.0, (2.0 / np.pi) * st * st, torch.zeros_like(st))
+    st = torch.where(st < 0.1e-08, torch.zeros_like(st), st)
+    good = (alphaj != 0.0) & (fp != 0.0)
+    fps = torch.where(good, fp, torch.ones_like(fp))
+    fl1 = w.t["fl1"]                                     # (C, F, A, P)
+    fr5 = fr ** 5
+    for m in range(F):
+        mm = min(m, Fr - 1)
+        frh = float(fr[mm])
+        sigma = torch.where(frh > fps, torch.full_like(fps, sb), torch.full_like(fps, sa))
+        earg = torch.clamp(0.5 * ((frh - fps) / (sigma * fps)) ** 2, max=50.0)
+        fjon = gamma ** torch.exp(-earg)
+        fmpf = torch.clamp(1.25 * (fps / frh) ** 4, max=50.0)
+        et = torch.where(good, alphaj * (1.0 / (frh ** 5 * zpi4gm2)) * torch.exp(-fmpf) * fjon, torch.zeros_like(fps))
+        x = et[None, :] * st                              # (A, C*P)
+        if m >= Fr:
+            x = x * float(fr5[Fr - 1] / fr5[m])
+        fl1[:, m] = x.view(A, C, P).permute(1, 0, 2)
