@@ -225,7 +225,7 @@ def run_gpu(args):
     ms_total = float(ms.item())
     launches = w.launch_count() - n0
     kern = {}
-    for nm in ("propags2", "halo", "copyback", "implsch_airsea1", "implsch_spec1", "implsch_scalar2", "implsch_spec2", "implsch_scalar4"):
+    for nm in ("propags2", "halo", "copyback", "implsch_point", "implsch_stencil"):
         tot, cnt = w.timing(nm)
         if cnt:
             kern[nm] = tot / cnt
@@ -271,7 +271,9 @@ def run_gpu(args):
         return
     # ---- roofline of the dominant kernel ------------------------------------------------------------------------
     A, F, Fr = w.A, w.F, w.Fr
-    alg = {"implsch_spec2": (2 * A * F * 8 + A * F * 8 + 5 * F * 8 + 30 * 8), "implsch_spec1": (A * F * 8 + 3 * F * 8 + 20 * 8),
+    # algorithmic bytes per grid point and launch (DESIGN.md "Kernels"): k_point reads FL1 once and writes XLLWS and the
+    # wind-input scratch; k_stencil reads FL1 + scratch and writes FL1; PROPAGS2 reads and writes the propagated part
+    alg = {"implsch_point": (3 * A * F * 8 + 2 * F * 8 + 30 * 8), "implsch_stencil": (3 * A * F * 8 + 4 * F * 8 + 30 * 8),
            "propags2": (2 * A * Fr * 8 + 14 * 4 + 11 * 8 + Fr * 8), "copyback": 2 * A * Fr * 8}
     dom = max((k for k in kern if k in alg), key=lambda k: kern[k]) if kern else None
     peak, peak_src = peaks()

@@ -69,7 +69,7 @@ struct ecwam_b200_handle_s {
   int msplit = 0;
   bool weights_dirty = true;
   // implsch
-  DBuf<double> scr, satw, swellft;
+  DBuf<double> scr, satw, swellft, fldin;
   DBuf<int> kw, isat;
   DevTabPtr tab;
   // fields
@@ -343,7 +343,7 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
        !h->sendbuf.alloc((size_t)h->nsend * A * Fr) && !h->cgrecv.alloc((size_t)h->nrecv * Fr) &&
        !h->fl3.alloc((size_t)P * A * Fr * p.nchnk) && !h->flag.alloc(nloc) && !h->count.alloc(1);
   // IMPLSCH tables
-  std::vector<int> kw((size_t)8 * A);
+  std::vector<int> kw((size_t)16 * A, -1);
   for (int kh = 0; kh < 2; ++kh)
     for (int k = 0; k < A; ++k) {
       kw[(size_t)(0 + kh) * A + k] = tables->k1w[k + A * kh] - 1;
@@ -351,7 +351,19 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
       kw[(size_t)(4 + kh) * A + k] = tables->k11w[k + A * kh] - 1;
       kw[(size_t)(6 + kh) * A + k] = tables->k21w[k + A * kh] - 1;
     }
-  for (int v : kw) if (v < 0 || v >= A) { ok = false; ew_set_error("K1W/K2W/K11W/K21W out of range"); }
+  for (size_t i = 0; i < (size_t)8 * A; ++i) if (kw[i] < 0 || kw[i] >= A) { ok = false; ew_set_error("K1W/K2W/K11W/K21W out of range"); }
+  // inverse direction maps for the gather form of SNONLIN: each of K1W..K21W(.,KH) is a cyclic shift (jafu.F90)
+  for (int tb = 0; tb < 4 && ok; ++tb)
+    for (int kh = 0; kh < 2; ++kh) {
+      for (int k = 0; k < A; ++k) kw[(size_t)(8 + 2 * tb + kh) * A + kw[(size_t)(2 * tb + kh) * A + k]] = k;
+      for (int k = 0; k < A; ++k) if (kw[(size_t)(8 + 2 * tb + kh) * A + k] < 0) { ok = false; ew_set_error("K1W/K2W/K11W/K21W is not a permutation"); }
+    }
+  // the frequency sweep of k_stencil relies on the DIA offsets of FRATIO=1.1, lambda=0.25 (nlweigt.F90:94-103)
+  for (int mc = 1; mc <= tables->mlsthg && ok; ++mc) {
+    const int o = mc - tables->mfrstlw;
+    if (tables->ikp[o] != mc + 2 || tables->ikp1[o] != mc + 3 || tables->ikm[o] != mc - 4 || tables->ikm1[o] != mc - 3 ||
+        tables->mlsthg != F + 4) { ok = false; ew_set_error("unsupported DIA frequency offsets (need IKP=M+2, IKM=M-4, MLSTHG=NFRE+4)"); }
+  }
   ok = ok && !h->kw.upload(kw, st);
   if (p.iphys == 1) {
     const int ns = 2 * tables->nsdsnth + 1;
@@ -364,7 +376,7 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
   std::vector<double> sw(tables->swellft, tables->swellft + tables->iab);
   ok = ok && !h->swellft.upload(sw, st);
   const long long npts = (long long)P * p.nchnk;
-  ok = ok && !h->scr.alloc(implsch_scratch_doubles(npts));
+  ok = ok && !h->scr.alloc(implsch_scratch_doubles(npts)) && !h->fldin.alloc((size_t)npts * A * F);
   if (!ok) { ecwam_b200_destroy(h); return ECWAM_B200_ECUDA; }
   cudaMemsetAsync(h->halo.p, 0, (halo_elems + 1) * sizeof(double), st);
   cudaMemsetAsync(h->fl3.p, 0, h->fl3.n * sizeof(double), st);
@@ -376,6 +388,7 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
   d.nbr = h->nbr.p; d.wl = h->wl.p; d.pt = h->pt.p; d.cgext = h->cgext.p; d.halo_off = h->halo_off.p;
   d.halo_str = h->halo_str.p; d.halo = h->halo.p;
   h->tab.k1w = h->kw.p; h->tab.k2w = h->kw.p + 2 * A; h->tab.k11w = h->kw.p + 4 * A; h->tab.k21w = h->kw.p + 6 * A;
+  h->tab.ik1w = h->kw.p + 8 * A; h->tab.ik2w = h->kw.p + 10 * A; h->tab.ik11w = h->kw.p + 12 * A; h->tab.ik21w = h->kw.p + 14 * A;
   h->tab.indicessat = h->isat.p; h->tab.satweights = h->satw.p; h->tab.swellft = h->swellft.p;
   memset(&h->dev, 0, sizeof(h->dev));
   memset(&h->mir, 0, sizeof(h->mir));
@@ -392,7 +405,7 @@ int ecwam_b200_destroy(ecwam_b200_handle h) {
   h->nbr.free(); h->halo_off.free(); h->halo_str.free(); h->send_l.free(); h->send_pre.free(); h->send_peer_of.free();
   h->recv_pre.free(); h->recv_peer_of.free(); h->recv_e.free(); h->flag.free(); h->count.free(); h->wl.free(); h->pt.free();
   h->cgext.free(); h->halo.free(); h->sendbuf.free(); h->fl3.free(); h->cosph_m.free(); h->cosph_p.free();
-  h->land_cg.free(); h->cgrecv.free(); h->scr.free(); h->satw.free(); h->swellft.free(); h->kw.free(); h->isat.free();
+  h->land_cg.free(); h->cgrecv.free(); h->scr.free(); h->fldin.free(); h->satw.free(); h->swellft.free(); h->kw.free(); h->isat.free();
   for (void* b : h->mir_bufs) cudaFree(b);
   delete h;
   return 0;
@@ -532,6 +545,8 @@ static ImplDev make_impl(H* h, bool from_fl3) {
   d.fl_lo = from_fl3 ? h->fl3.p : h->dev.fl1;
   d.lo_F = from_fl3 ? d.Fr : d.F;
   d.scr = h->scr.p;
+  d.fldin = h->fldin.p;
+  d.nloc = h->pd.nloc;
   d.tab = h->tab;
   return d;
 }
@@ -543,8 +558,7 @@ int ecwam_b200_implsch(ecwam_b200_handle h, int ichnk0, int nchnk) {
   int rc = ensure_const(h);
   if (rc) return rc;
   ImplDev d = make_impl(h, false);
-  static const char* kStage[EW_IMPLSCH_NSTAGE] = {"implsch_airsea1", "implsch_spec1", "implsch_scalar2", "implsch_spec2",
-                                                   "implsch_scalar4"};
+  static const char* kStage[EW_IMPLSCH_NSTAGE] = {"implsch_point", "implsch_stencil"};
   for (int s = 0; s < EW_IMPLSCH_NSTAGE; ++s) {
     ScopedTimer t(h, kStage[s]);
     rc = launch_implsch_stage(d, (long long)(ichnk0 - 1) * d.P, (long long)nchnk * d.P, s, h->st);

@@ -49,6 +49,10 @@ struct DevTabPtr {
   const int* k2w;
   const int* k11w;
   const int* k21w;
+  const int* ik1w;        // inverse maps: ik1w[kh][k] = K with K1W(K,kh) = k  (gather form of SNONLIN)
+  const int* ik2w;
+  const int* ik11w;
+  const int* ik21w;
   const int* indicessat;  // [2N+1][A] 0-based
   const double* satweights;  // [2N+1][A]
   const double* swellft;  // [IAB]

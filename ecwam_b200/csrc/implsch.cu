@@ -1,16 +1,12 @@
 // IMPLSCH (src/ecwam/implsch.F90:10-468) for sm_100a: the implicit source-term step of WAMINTGR.
 //
 // The reference runs the whole call tree per NPROMA chunk with every (IJ,K,M) temporary in memory
-// (implsch.F90:152-170).  Here the step is five kernels:
-//   k_airsea1   lane = grid point   AIRSEA/TAUT_Z0, first call           (sinflx.F90 ICALL=1; taut_z0.F90:281-341)
-//   k_spec<1>   warp = grid point   SDEPTHLIM, FKMEAN, SINPUT (NGST=1), FEMEANWS, FRCUTINDEX, STRESSO sums
-//   k_scalar2   lane = grid point   TAU_PHI_HF, TAUW, TAUT_Z0 (2nd call), WSIGSTAR, swell-friction scalars, SDIWBK Q
-//   k_spec<2>   warp = grid point   SINPUT (NGST=2, LLSNEG), FEMEANWS, FRCUTINDEX, STRESSO sums, SDISSIP, SNONLIN,
-//                                   SDIWBK, SBOTTOM, implicit update, WNFLUXES sums, IMPHFTAIL, SETICE, STOKESDRIFT
-//   k_scalar4   lane = grid point   TAU_PHI_HF (stress + PHI), TAUW/TAUWDIR/PHIWA, WNFLUXES closure
-// In the warp-per-point kernels the NANG x NFRE spectrum of the point lives in shared memory, lane = direction,
-// the per-frequency direction sums are warp-shuffle reductions, and nothing but FL1, XLLWS and the 1-D outputs
-// goes back to HBM.  The serial per-point solvers (Newton loops, the 19-point HF integral) run one point per lane.
+// (implsch.F90:152-170).  Here the step is two kernels:
+//   k_point    lane = grid point: the parts that stream over the spectrum with per-point state (SDEPTHLIM, FKMEAN, both
+//              SINFLX calls with AIRSEA/TAUT_Z0, SINPUT, FEMEANWS, FRCUTINDEX, STRESSO/TAU_PHI_HF, WSIGSTAR, SDIWBK's Q)
+//   k_stencil  CTA = 8 grid points x NANG threads: the parts that couple spectral bins (SDISSIP saturation window, SNONLIN
+//              DIA quadruplets) fused with SDIWBK, SBOTTOM, the implicit update, WNFLUXES, IMPHFTAIL, SETICE, STOKESDRIFT
+// Nothing but FL1, XLLWS, the 1-D outputs and one scratch array (the wind-input linearisation) touches HBM.
 #include "internal.h"
 
 namespace ew {
@@ -28,7 +24,7 @@ enum {
   S_UORBT, S_AORB, S_SIGN, S_TEMP2, S_PTURB, S_PVISC,    // SINPUT_ARD swell-dissipation scalars, WSIGSTAR
   S_SDS,                                                  // SDIWBK
   S_PHILF, S_XSTROC, S_YSTROC,                            // WNFLUXES sums
-  S_MIJ, S_USTOLD,
+  S_MIJ, S_USTOLD, S_FAC, S_USFM,
   NSCR
 };
 size_t implsch_scratch_doubles(long long npts) { return (size_t)NSCR * (size_t)npts; }
@@ -104,14 +100,6 @@ __device__ void taut_z0(int iusfg, double utop, double udir, double tauw, double
   z0 = z0ch;
   z0b = alphaog * tauold;
   chrnck = fmax(c_dc.G * z0 * sq(ustm1), c_dc.ALPHAMIN);
-}
-
-__global__ void __launch_bounds__(128) k_airsea1(ImplDev d, long long p0, long long np) {
-  const long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= p0 + np) return;
-  double ustar = d.f.ufric[p], z0, z0b, ch;
-  taut_z0(0, d.f.wswave[p], d.f.wdwave[p], d.f.tauw[p], d.f.tauwdir[p], ustar, z0, z0b, ch);
-  d.f.ufric[p] = ustar; d.f.z0m[p] = z0; d.f.z0b[p] = z0b; d.f.chrnck[p] = ch;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -198,35 +186,6 @@ __device__ void tau_phi_hf(int mij, bool shelter, double z0m, double aird, doubl
   }
 }
 
-// stresso.F90:187-233: closure of the wave stress from the low-frequency sums + HF tail
-__device__ void stresso_close(const ImplDev& d, long long p, bool llphiwa, double& tauw, double& tauwdir, double& phiwa) {
-  const double* s = d.scr;
-  const long long n = d.npts;
-  const double aird = d.f.aird[p], ufric = d.f.ufric[p], wdwave = d.f.wdwave[p], z0m = d.f.z0m[p];
-  const double am = fmax(aird, 1.0);
-  double xstress = s[S_XSTR * n + p] / am, ystress = s[S_YSTR * n + p] / am;
-  const int mij = (int)s[S_MIJ * n + p];
-  bool shelter;
-  double usdirp, ust;
-  if (c_dc.iphys == 0 || c_dc.TAUWSHELTER == 0.0) {
-    shelter = false; usdirp = wdwave; ust = ufric;
-  } else {
-    shelter = true;
-    const double taux = sq(ufric) * sin(wdwave), tauy = sq(ufric) * cos(wdwave);
-    const double taupx = taux - c_dc.TAUWSHELTER * xstress, taupy = tauy - c_dc.TAUWSHELTER * ystress;
-    usdirp = atan2(taupx, taupy);
-    ust = sqrt(sqrt(taupx * taupx + taupy * taupy));
-  }
-  double tauhf, phihf;
-  tau_phi_hf(mij, shelter, z0m, aird, s[S_F1DCOS3 * n + p], s[S_F1DCOS2 * n + p], ust, tauhf, phihf, llphiwa);
-  xstress = xstress + tauhf * sin(usdirp);
-  ystress = ystress + tauhf * cos(usdirp);
-  tauw = fmax(sqrt(sq(xstress) + sq(ystress)), 0.0);
-  tauwdir = atan2(xstress, ystress);
-  tauw = fmin(tauw, sq(ufric) * (1.0 / (1.0 + c_dc.EPS1)));   // .NOT. LLGCBZ0 (stresso.F90:218-223)
-  phiwa = llphiwa ? s[S_PHIWA * n + p] + phihf : 0.0;
-}
-
 // wsigstar.F90:105-129
 __device__ double wsigstar(double ufric, double z0m, double wstar) {
   const double ONETHIRD = 1.0 / 3.0, SIG_NMAX = 0.9, C1 = 1.03e-3, C2 = 0.04e-3, P1 = 1.48, P2 = -0.21;
@@ -242,127 +201,6 @@ __device__ double wsigstar(double ufric, double z0m, double wstar) {
   return fmin(SIG_NMAX, sig_conv * u10m1 * pow(0.0 * ufric * ufric * ufric + 0.5 * c_dc.XKAPPA * wstar * wstar * wstar, ONETHIRD));
 }
 
-__global__ void __launch_bounds__(128) k_scalar2(ImplDev d, long long p0, long long np) {
-  const long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= p0 + np) return;
-  double* s = d.scr;
-  const long long n = d.npts;
-  // STRESSO closure of SINFLX call 1 (LLPHIWA = F)
-  double tauw, tauwdir, phiwa;
-  stresso_close(d, p, false, tauw, tauwdir, phiwa);
-  d.f.tauw[p] = tauw; d.f.tauwdir[p] = tauwdir;
-  // SINFLX call 2: AIRSEA with IUSFG=1
-  double ustar = d.f.ufric[p], z0, z0b, ch;
-  taut_z0(1, d.f.wswave[p], d.f.wdwave[p], tauw, tauwdir, ustar, z0, z0b, ch);
-  d.f.ufric[p] = ustar; d.f.z0m[p] = z0; d.f.z0b[p] = z0b; d.f.chrnck[p] = ch;
-  // WSIGSTAR for NGST=2
-  s[S_SIGN * n + p] = wsigstar(ustar, z0, d.f.wstar[p]);
-  // swell-dissipation scalars of SINPUT_ARD (sinput_ard.F90:179-271), LLSNEG
-  if (c_dc.iphys == 1) {
-    const double raorw = fmax(d.f.aird[p], 1.0) * c_dc.ROWATERM1;
-    const double uorbt = 2.0 * sqrt(s[S_UORBT * n + p]);
-    const double aorb = 2.0 * sqrt(s[S_AORB * n + p]);
-    const double re = (4.0 / c_dc.rnu) * uorbt * aorb;
-    const double z0vis = c_dc.rnum / fmax(ustar, 0.0001);
-    const double z0tub = c_dc.Z0RAT * fmin(c_dc.Z0TUBMAX, z0);
-    const double z0noz = fmax(z0vis, z0tub);
-    const double zorb = aorb / z0noz;
-    const double delabm1 = (double)c_dc.IAB / (c_dc.ABMAX - c_dc.ABMIN);
-    const double xi = (log10(fmax(zorb, 3.0)) - c_dc.ABMIN) * delabm1;
-    const int ind = min(c_dc.IAB - 1, (int)xi);
-    const double deli1 = fmin(1.0, xi - (double)ind);
-    const double deli2 = 1.0 - deli1;
-    const double fww = d.tab.swellft[ind - 1] * deli2 + d.tab.swellft[ind] * deli1;
-    s[S_TEMP2 * n + p] = fww * uorbt;
-    double re_c;
-    if (c_dc.SWELLF6 == 1.0) re_c = c_dc.SWELLF4;
-    else re_c = c_dc.SWELLF4 * pow(2.0 / aorb, 1.0 - c_dc.SWELLF6);
-    double pturb, pvisc;
-    if (c_dc.SWELLF7 > 0.0) {
-      const double smooth = 0.5 * tanh((re - re_c) * c_dc.SWELLF7M1);
-      pturb = 0.5 + smooth; pvisc = 0.5 - smooth;
-    } else if (re <= re_c) { pturb = 0.0; pvisc = 0.5; }
-    else { pturb = 0.5; pvisc = 0.0; }
-    s[S_PTURB * n + p] = pturb;
-    s[S_PVISC * n + p] = pvisc * raorw;   // AIRD_PVISC
-  }
-  // SDIWBK (sdiwbk.F90:69-104): Battjes-Janssen fraction of breaking waves
-  double sds = 0.0;
-  if (c_dc.lbiwbk && d.f.depth[p] < 50.0) {
-    const double alph = 2.0 * d.f.emaxdpt[p] / s[S_EMEAN * n + p];
-    const double arg = fmin(alph, 50.0);
-    double q_old = exp(-arg), q = q_old;
-    for (int ic = 1; ic <= 15; ++ic) {
-      const double expq = exp(-arg * (1.0 - q_old));
-      q = q_old - (expq - q_old) / (arg * expq - 1.0);
-      const double rel_err = fabs(q - q_old) / q_old;
-      if (rel_err < 0.00001) break;
-      q_old = q;
-    }
-    q = fmin(q, 1.0);
-    sds = 2.0 * alph * q * s[S_F1MEAN * n + p];
-  }
-  s[S_SDS * n + p] = sds;
-}
-
-// wnfluxes.F90:222-331 (LWNEMOCOU=F) after the spectral sums
-__global__ void __launch_bounds__(128) k_scalar4(ImplDev d, long long p0, long long np) {
-  const long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= p0 + np) return;
-  const double* s = d.scr;
-  const long long n = d.npts;
-  double tauw, tauwdir, phiwa;
-  stresso_close(d, p, true, tauw, tauwdir, phiwa);
-  d.f.tauw[p] = tauw; d.f.tauwdir[p] = tauwdir;
-  if (!c_dc.lcflx) return;
-  const double PHIOC_ICE = -3.75, PHIAW_ICE = 3.75, C1 = 1.03e-3, C2 = 0.04e-3, P1 = 1.48, P2 = -0.21, CDMAX_LOC = 0.003;
-  const double epsus3 = c_dc.EPSUS * sqrt(c_dc.EPSUS);
-  const double cithrsh_inv = 1.0 / fmax(c_dc.cithrsh, 0.01);
-  const double cicover = d.f.cicover[p], ufric = d.f.ufric[p], aird = d.f.aird[p], wdwave = d.f.wdwave[p];
-  double ooval = 1.0, ustar = ufric;
-  if (c_dc.licerun && c_dc.lwamrsetci && cicover > c_dc.ciblock) {
-    ooval = exp(-fmin(p4(cicover * cithrsh_inv), 10.0));
-    const double u10p = fmax(d.f.wswave[p], c_dc.EPSU10);
-    const double cd_bulk = fmin((C1 + C2 * pow(u10p, P1)) * pow(u10p, P2), CDMAX_LOC);
-    const double cd_wave = sq(ufric / u10p);
-    const double cd_ice = ooval * cd_wave + (1.0 - ooval) * cd_bulk;
-    ustar = fmax(sqrt(cd_ice) * u10p, c_dc.EPSUS);
-  }
-  const double xstress = s[S_XSTROC * n + p], ystress = s[S_YSTROC * n + p], philf = s[S_PHILF * n + p];
-  const double tau = aird * fmax(sq(ustar), c_dc.EPSUS);
-  double tauxd = tau * sin(wdwave), tauyd = tau * cos(wdwave);
-  double tauocxd = tauxd - ooval * xstress, tauocyd = tauyd - ooval * ystress;
-  const double tauo = sqrt(sq(tauocxd) + sq(tauocyd));
-  const double tauoc = fmin(fmax(tauo / tau, c_dc.TAUOCMIN), c_dc.TAUOCMAX);
-  if (c_dc.lwcouast) {
-    const double us = d.f.ustra[p], vs = d.f.vstra[p];
-    if (us != 0.0 || vs != 0.0) { tauxd = us; tauocxd = us * tauoc; tauyd = vs; tauocyd = vs * tauoc; }
-  }
-  d.f.tauxd[p] = tauxd; d.f.tauyd[p] = tauyd; d.f.tauocxd[p] = tauocxd; d.f.tauocyd[p] = tauocyd; d.f.tauoc[p] = tauoc;
-  d.f.tauicx[p] = 0.0; d.f.tauicy[p] = 0.0;
-  const double xn = aird * fmax(ustar * ustar * ustar, epsus3);
-  double phiocd = ooval * (philf - phiwa) + (1.0 - ooval) * PHIOC_ICE * xn;
-  double phieps = phiocd / xn;
-  phieps = fmin(fmax(phieps, c_dc.PHIEPSMIN), c_dc.PHIEPSMAX);
-  phiocd = phieps * xn;
-  const double phiaw = ooval * phiwa / xn + (1.0 - ooval) * PHIAW_ICE;
-  d.f.phiocd[p] = phiocd; d.f.phieps[p] = phieps; d.f.phiaw[p] = phiaw;
-}
-
-// =========================================================================================================
-// Warp-per-point spectral kernels
-// =========================================================================================================
-#define KPL 2   // directions per lane: k = lane, lane + 32  (NANG <= 64)
-
-struct WarpPt {
-  double* fl;    // [F][A] spectrum of this point (shared memory)
-  double* fld;   // [F][A] (pass 2)
-  double* sl;    // [F][A] (pass 2)
-  double* tb;    // per-frequency tables [NTB][EW_MAXF]
-  unsigned char* xl;   // [F][A] XLLWS flags (pass 2)
-};
-enum { TB_WAVNUM = 0, TB_CINV, TB_XK2CG, TB_ZCN, TB_A, TB_B, NTB };
-
 // RHOWGDFTH(IJ,M) of frcutindex.F90:99-108 (m 0-based)
 __device__ __forceinline__ double rhowgdfth(int m, int mij) {
   if (m + 1 > mij) return 0.0;
@@ -371,188 +209,83 @@ __device__ __forceinline__ double rhowgdfth(int m, int mij) {
   return r;
 }
 
-template <int PASS>
-__global__ void __launch_bounds__(PASS == 1 ? 256 : 192) k_spec(ImplDev d, long long p0, long long np) {
-  constexpr int WPB = (PASS == 1) ? 8 : 6;
-  extern __shared__ double smem[];
-  const int A = c_dc.A, F = c_dc.F, AF = A * F;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const long long pb = p0 + (long long)blockIdx.x * WPB;
-  const long long pend = p0 + np;
-  const int nptb = (int)min((long long)WPB, pend - pb);
-  // ---- shared memory carve-up
-  const int per_pt = (PASS == 1 ? 1 : 3) * AF + NTB * EW_MAXF + (PASS == 2 ? (AF + 7) / 8 : 0);
-  WarpPt W;
-  {
-    double* base = smem + (size_t)w * per_pt;
-    W.fl = base;
-    W.fld = (PASS == 2) ? base + AF : nullptr;
-    W.sl = (PASS == 2) ? base + 2 * AF : nullptr;
-    W.tb = base + (PASS == 1 ? 1 : 3) * AF;
-    W.xl = (PASS == 2) ? (unsigned char*)(W.tb + NTB * EW_MAXF) : nullptr;
-  }
-  // ---- cooperative load of the FL1 tile: consecutive threads read consecutive grid points (lane dimension of
-  //      the NPROMA-chunked layout) so that every 32-byte sector fetched is fully used
-  {
-    const int tot = nptb * AF;
-    for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
-      const int i = idx % nptb, bin = idx / nptb;
-      const long long p = pb + i;
-      const long long c = p / d.P;
-      const int ln = (int)(p - c * d.P);
-      const int m = bin / A;
-      double v;
-      if (m < d.Fr && d.lo_F != d.F) {
-        // reading the propagation scratch (P,A,Fr,C): padded lanes of the last chunk take lane 0 (propag_wam.F90:388-398)
-        v = d.fl_lo[(size_t)ln + (size_t)d.P * ((size_t)bin + (size_t)A * d.lo_F * (size_t)c)];
-      } else {
-        v = d.f.fl1[(size_t)ln + (size_t)d.P * ((size_t)bin + (size_t)AF * (size_t)c)];
-      }
-      smem[(size_t)i * per_pt + bin] = v;
-    }
-  }
-  __syncthreads();
-  const bool active = w < nptb;
-  const long long p = active ? pb + w : pb;   // inactive warps shadow point pb but never store
-  const long long n = d.npts;
-  double* s = d.scr;
+// =========================================================================================================
+// k_point: lane = grid point.  Everything of IMPLSCH that is a stream over the spectrum with per-point state:
+//   SDEPTHLIM/SEMEAN, FKMEAN, both SINFLX calls (AIRSEA/TAUT_Z0, SINPUT with its sheltering recurrence over
+//   frequency, FEMEANWS, FRCUTINDEX, STRESSO + TAU_PHI_HF), WSIGSTAR, the swell-friction scalars and SDIWBK's Q.
+// The 32 lanes of a warp are 32 consecutive grid points, so every FL1(ij,k,m) access is one coalesced 256-byte
+// row of the NPROMA-chunked array, all per-point scalars are thread-private (no redundant work, no shuffles),
+// and the direction tables come out of constant memory with a warp-uniform index.  Writes: the wind-input
+// linearisation FLD (scratch, same layout as FL1), XLLWS (final), MIJ and the 1-D stress fields.
+// =========================================================================================================
+struct PointSrc {
+  const double* lo;   // frequencies [0, mlo): propagation scratch or FL1 itself
+  const double* hi;   // FL1
+  int mlo;
+  size_t kstr;        // P
+};
 
-  // ---- per-point scalars
-  const double aird = d.f.aird[p], wdwave = d.f.wdwave[p], cicover = d.f.cicover[p];
-  const double ufric = d.f.ufric[p], z0m = d.f.z0m[p], depth = d.f.depth[p];
-  const double raorw = fmax(aird, 1.0) * c_dc.ROWATERM1;
-  double* fl = W.fl;
-  // per-frequency tables: lane m loads frequency m
-  for (int m = lane; m < F; m += 32) {
-    const size_t o = idx3(d, p, m);
-    const double wn = d.f.wavnum[o];
-    W.tb[TB_WAVNUM * EW_MAXF + m] = wn;
-    W.tb[TB_CINV * EW_MAXF + m] = d.f.cinv[o];
-    W.tb[TB_XK2CG * EW_MAXF + m] = d.f.xk2cg[o];
-    W.tb[TB_ZCN * EW_MAXF + m] = log(wn * z0m);
-    const double sqk = sqrt(wn);
-    W.tb[TB_A * EW_MAXF + m] = c_dc.DFIM[m] / sqk;   // FKMEAN TEMPA
-    W.tb[TB_B * EW_MAXF + m] = sqk * c_dc.DFIM[m];   // FKMEAN TEMPX
-  }
-  // per-lane direction data
-  double coswdif[KPL], sinwdif2[KPL], sinth[KPL], costh[KPL], flm[KPL];
-  bool kv[KPL];
-#pragma unroll
-  for (int j = 0; j < KPL; ++j) {
-    const int k = lane + 32 * j;
-    kv[j] = k < A;
-    const int kk = kv[j] ? k : 0;
-    coswdif[j] = cos(c_dc.TH[kk] - wdwave);
-    sinwdif2[j] = sq(sin(c_dc.TH[kk] - wdwave));
-    sinth[j] = c_dc.SINTH[kk];
-    costh[j] = c_dc.COSTH[kk];
-    flm[j] = (1. - 0.9 * fmin(cicover, 0.99)) * c_dc.flmin * sq(fmax(0.0, coswdif[j]));   // implsch.F90:237-242
-  }
-  __syncwarp();
-  const double DELT25 = c_dc.WETAIL * c_dc.FR[F - 1] * c_dc.DELTH;
-
-  // ---- SDEPTHLIM (sdepthlim.F90:50-82 with SEMEAN)
-  if (c_dc.lbiwbk) {
-    double acc = 0.0, last = 0.0;
-    for (int m = 0; m < F; ++m) {
-      double t = 0.0;
-#pragma unroll
-      for (int j = 0; j < KPL; ++j) if (kv[j]) t += fl[m * A + lane + 32 * j];
-      acc += c_dc.DFIM[m] * t;
-      last = t;
-    }
-    const double em = c_dc.EPSMIN + wsum(acc) + DELT25 * wsum(last);
-    const double fac = fmin(d.f.emaxdpt[p] / em, 1.0);
-    for (int m = 0; m < F; ++m)
-#pragma unroll
-      for (int j = 0; j < KPL; ++j) if (kv[j]) { const int o = m * A + lane + 32 * j; fl[o] = fmax(fl[o] * fac, c_dc.EPSMIN); }
-  }
-  // ---- FKMEAN (fkmean.F90:60-154), first call only; pass 2 re-reads the scalars
-  double emean, fmean, f1mean, akmean, xkmean;
-  if (PASS == 1) {
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, last = 0;
-    for (int m = 0; m < F; ++m) {
-      double t = 0.0;
-#pragma unroll
-      for (int j = 0; j < KPL; ++j) if (kv[j]) t += fl[m * A + lane + 32 * j];
-      a0 += c_dc.DFIM[m] * t; a1 += c_dc.DFIMOFR[m] * t; a2 += c_dc.DFIMFR[m] * t;
-      a3 += W.tb[TB_A * EW_MAXF + m] * t; a4 += W.tb[TB_B * EW_MAXF + m] * t;
-      last = t;
-    }
-    a0 = wsum(a0); a1 = wsum(a1); a2 = wsum(a2); a3 = wsum(a3); a4 = wsum(a4); last = wsum(last);
-    const double COEFM1 = c_dc.FRTAIL * c_dc.DELTH;
-    const double COEF1 = c_dc.WP1TAIL * c_dc.DELTH * sq(c_dc.FR[F - 1]);
-    const double COEFA = COEFM1 * sqrt(c_dc.G) / c_dc.ZPI;
-    const double COEFX = COEF1 * (c_dc.ZPI / sqrt(c_dc.G));
-    emean = c_dc.EPSMIN + a0 + DELT25 * last;
-    fmean = emean / (c_dc.EPSMIN + a1 + COEFM1 * last);
-    f1mean = (c_dc.EPSMIN + a2 + COEF1 * last) / emean;
-    akmean = sq(emean / (c_dc.EPSMIN + a3 + COEFA * last));
-    xkmean = sq((c_dc.EPSMIN + a4 + COEFX * last) / emean);
-    if (active && lane == 0) {
-      s[S_EMEAN * n + p] = emean; s[S_FMEAN * n + p] = fmean; s[S_F1MEAN * n + p] = f1mean;
-      s[S_AKMEAN * n + p] = akmean; s[S_XKMEAN * n + p] = xkmean;
-    }
-  } else {
-    emean = s[S_EMEAN * n + p]; fmean = s[S_FMEAN * n + p]; f1mean = s[S_F1MEAN * n + p];
-    akmean = s[S_AKMEAN * n + p]; xkmean = s[S_XKMEAN * n + p];
-  }
-  // ---- SINFLX, first call: FL1(:,:,NFRE) = MAX(FL1, FLM) (sinflx.F90:126-129)
-#pragma unroll
-  for (int j = 0; j < KPL; ++j) if (kv[j]) { const int o = (F - 1) * A + lane + 32 * j; fl[o] = fmax(fl[o], flm[j]); }
-  __syncwarp();
-
-  // ---- SINPUT
-  constexpr int NGST = (PASS == 1) ? 1 : 2;
-  constexpr bool LLSNEG = (PASS == 2);
-  double sig_n = 0.0, temp2_sw = 0.0, pturb = 0.0, aird_pvisc = 0.0;
-  if (PASS == 2) {
-    sig_n = s[S_SIGN * n + p];
-    if (c_dc.iphys == 1) { temp2_sw = s[S_TEMP2 * n + p]; pturb = s[S_PTURB * n + p]; aird_pvisc = s[S_PVISC * n + p]; }
-  }
-  // lane-distributed per-frequency sums (lane m%32 keeps frequency m): SPOS moments for STRESSO
-  double dsumx[2] = {0, 0}, dsumy[2] = {0, 0}, dsumt[2] = {0, 0};
-  // lane-accumulated sums
-  double ws_em = 0.0, ws_fm = 0.0, ws_last = 0.0;   // FEMEANWS
-  double phiwa_acc = 0.0;                            // sum (SL-SPOS)*RHOWG_DFIM
-  double uorbt_acc = 0.0, aorb_acc = 0.0;            // pass 1: orbital velocity / amplitude sums for pass 2
+template <int NGST, bool LLSNEG, bool STORE>
+__device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d, long long p, double fac, double flmc,
+                                             double snw, double csw, double ufric, double z0m, double raorw, double sig_n,
+                                             double temp2_sw, double pturb, double aird_pvisc, double* __restrict__ fld_out,
+                                             double* __restrict__ xl_out, double* sumx, double* sumy, double* sumt,
+                                             double& ws_em, double& ws_fm, double& ws_last, double& phiwa_acc,
+                                             double& uorbt_acc, double& aorb_acc, double* mom) {
+  const int A = c_dc.A, F = c_dc.F;
   const double CONST1 = c_dc.BETAMAXOXKAPPA2;
-  if (c_dc.iphys == 1) {
-    // ================= SINPUT_ARD (sinput_ard.F90:149-524) =================
-    const double abs_shelter = fabs(c_dc.TAUWSHELTER);
-    const bool ltauwshelter = abs_shelter != 0.0;
-    double ustp[NGST], xstress[NGST], ystress[NGST], taux[NGST], tauy[NGST];
+  const size_t kstr = S.kstr;
+  ws_em = 0.0; ws_fm = 0.0; ws_last = 0.0; phiwa_acc = 0.0; uorbt_acc = 0.0; aorb_acc = 0.0;
+  const bool ard = c_dc.iphys == 1;
+  const double abs_shelter = fabs(c_dc.TAUWSHELTER);
+  const bool ltauwshelter = ard && abs_shelter != 0.0;
+  double ustp[NGST], xstress[NGST], ystress[NGST], taux[NGST], tauy[NGST], wsin[NGST];
+  if (ard) {
     if (NGST == 1) ustp[0] = ufric;
     else { ustp[0] = ufric * (1.0 + sig_n); ustp[NGST - 1] = ufric * (1.0 - sig_n); }
-    const double snw = sin(wdwave), csw = cos(wdwave);
+  } else {
+    if (NGST == 1) ustp[0] = ufric;
+    else { ustp[0] = ufric * (1.0 - sig_n); ustp[NGST - 1] = ufric * (1.0 + sig_n); }
+  }
 #pragma unroll
-    for (int g = 0; g < NGST; ++g) {
-      xstress[g] = 0.0; ystress[g] = 0.0;
-      const double usg2 = sq(ustp[g]);
-      taux[g] = usg2 * snw; tauy[g] = usg2 * csw;
-    }
-    const double rogoroair = c_dc.G / raorw;
-    const double FU = fabs(c_dc.SWELLF3), FUD = c_dc.SWELLF2;
-    for (int m = 0; m < F; ++m) {
-      const double sig = c_dc.ZPIFR[m], sig2 = sig * sig;
-      const double cinv = W.tb[TB_CINV * EW_MAXF + m], wavnum = W.tb[TB_WAVNUM * EW_MAXF + m];
-      const double zcn = W.tb[TB_ZCN * EW_MAXF + m];
-      const double cnsn = sig * CONST1 * raorw;
-      const double constf = rogoroair * cinv * c_dc.DFIM[m];
-      double coef = 0.0, coef5 = 0.0, dstab1 = 0.0, temp1 = 0.0;
+  for (int g = 0; g < NGST; ++g) {
+    xstress[g] = 0.0; ystress[g] = 0.0;
+    const double usg2 = sq(ustp[g]);
+    taux[g] = usg2 * snw; tauy[g] = usg2 * csw;
+    wsin[g] = 1.0 / NGST;
+  }
+  const double rogoroair = c_dc.G / raorw;
+  const double FU = fabs(c_dc.SWELLF3), FUD = c_dc.SWELLF2;
+  const double CONST3 = c_dc.idamping * (2.0 * c_dc.XKAPPA / CONST1);
+  const double xkappad = 1.0 / c_dc.XKAPPA;
+  const double avg = 1.0 / NGST;
+  for (int m = 0; m < F; ++m) {
+    const size_t o3 = idx3(d, p, m);
+    const double wavnum = d.f.wavnum[o3], cinv = d.f.cinv[o3];
+    const double sig = c_dc.ZPIFR[m], sig2 = sig * sig;
+    const double zcn = log(wavnum * z0m);
+    const double dfim = c_dc.DFIM[m], dfimofr = c_dc.DFIMOFR[m], rhowg = c_dc.RHOWG_DFIM[m];
+    const double* fsrc = (m < S.mlo ? S.lo + (size_t)m * A * kstr * 1 : S.hi + (size_t)m * A * kstr);
+    double* fo = STORE ? fld_out + (size_t)m * A * kstr : nullptr;
+    double* xo = STORE ? xl_out + (size_t)m * A * kstr : nullptr;
+    const bool lastm = (m == F - 1);
+    double cnsn, constf = 0.0, dstab1 = 0.0, temp1 = 0.0;
+    double cosu[NGST], sinu[NGST], ucn[NGST], ucnzalpd[NGST], const3_ucn2[NGST], xvd[NGST];
+    if (ard) {
+      cnsn = sig * CONST1 * raorw;
+      constf = rogoroair * cinv * dfim;
       if (LLSNEG) {
-        coef = -c_dc.SWELLF * 16. * sig2 / c_dc.G;
-        coef5 = -c_dc.SWELLF5 * 2. * sqrt(2. * c_dc.rnu * sig);
+        const double coef = -c_dc.SWELLF * 16. * sig2 / c_dc.G;
+        const double coef5 = -c_dc.SWELLF5 * 2. * sqrt(2. * c_dc.rnu * sig);
         dstab1 = coef5 * aird_pvisc * wavnum;
         temp1 = coef * raorw;
       }
-      double cosu[NGST], sinu[NGST], ucn[NGST], ucnzalpd[NGST];
 #pragma unroll
       for (int g = 0; g < NGST; ++g) {
         if (ltauwshelter) {
           const double taupx = taux[g] - abs_shelter * xstress[g];
           const double taupy = tauy[g] - abs_shelter * ystress[g];
-          // USDIRP = ATAN2(TAUPX,TAUPY); only cos(TH-USDIRP) is needed: use the unit vector instead of the angle
+          // USDIRP = ATAN2(TAUPX,TAUPY) is only used as cos(TH-USDIRP): keep the unit vector instead of the angle
           const double t2 = taupx * taupx + taupy * taupy;
           const double rt = sqrt(t2);
           ustp[g] = sqrt(rt);
@@ -562,20 +295,36 @@ __global__ void __launch_bounds__(PASS == 1 ? 256 : 192) k_spec(ImplDev d, long 
         ucn[g] = ustp[g] * cinv;
         ucnzalpd[g] = c_dc.XKAPPA / (ucn[g] + c_dc.ZALP);
       }
-      double sx[NGST], sy[NGST], st = 0.0;
+    } else {
+      const double ztanhkd = sig2 / (c_dc.G * wavnum);
+      cnsn = sig * CONST1 * ztanhkd * raorw;
 #pragma unroll
-      for (int g = 0; g < NGST; ++g) { sx[g] = 0.0; sy[g] = 0.0; }
+      for (int g = 0; g < NGST; ++g) {
+        ucn[g] = ustp[g] * cinv + c_dc.ZALP;
+        const3_ucn2[g] = CONST3 * sq(ucn[g]);
+        ucnzalpd[g] = 1.0 / ucn[g];                    // UCND
+        xvd[g] = 1.0 / (-ustp[g] * xkappad * zcn * cinv);
+        cosu[g] = csw; sinu[g] = snw;
+      }
+    }
+    double sx[NGST], sy[NGST], st = 0.0, tsum = 0.0, traw = 0.0;
 #pragma unroll
-      for (int j = 0; j < KPL; ++j) {
-        if (!kv[j]) continue;
-        const int o = m * A + lane + 32 * j;
-        const double f = fl[o];
-        double slp_avg = 0.0, flp_avg = 0.0;
-        bool xll = false;
+    for (int g = 0; g < NGST; ++g) { sx[g] = 0.0; sy[g] = 0.0; }
+#pragma unroll 2
+    for (int k = 0; k < A; ++k) {
+      double f = fmax(__ldg(fsrc + (size_t)k * kstr) * fac, c_dc.EPSMIN);      // SDEPTHLIM applied on the fly
+      const double snk = c_dc.SINTH[k], csk = c_dc.COSTH[k];
+      const double cwd = csk * csw + snk * snw;                                  // COSWDIF(K)
+      traw += f;                                                                 // FKMEAN sees the spectrum before the floor
+      if (lastm) f = fmax(f, flmc * sq(fmax(0.0, cwd)));                         // sinflx.F90:126-129
+      tsum += f;
+      double slp_avg = 0.0, flp_avg = 0.0, ufac2 = 0.0;
+      bool xll = false;
 #pragma unroll
-        for (int g = 0; g < NGST; ++g) {
-          const double coslp = ltauwshelter ? (costh[j] * cosu[g] + sinth[j] * sinu[g]) : coswdif[j];
-          double gam0 = 0.0;
+      for (int g = 0; g < NGST; ++g) {
+        double gam0 = 0.0;
+        if (ard) {
+          const double coslp = ltauwshelter ? (csk * cosu[g] + snk * sinu[g]) : cwd;
           if (coslp > 0.01) {
             const double x = coslp * ucn[g];
             const double zlog = zcn + ucnzalpd[g] / coslp;
@@ -586,431 +335,569 @@ __global__ void __launch_bounds__(PASS == 1 ? 256 : 192) k_spec(ImplDev d, long 
             }
           }
           double dstab = 0.0;
-          if (LLSNEG) {
-            const double dstab2 = temp1 * (temp2_sw + (FU + FUD * coslp) * ustp[g]);
-            dstab = dstab1 + pturb * dstab2;
-          }
-          double slp = gam0;              // GAMNORMA = 1
-          const double flp = slp + dstab;
-          slp = slp * f;
-          sx[g] += slp * sinth[j];
-          sy[g] += slp * costh[j];
-          slp_avg += slp; flp_avg += flp;
-        }
-        const double avg = 1.0 / NGST;
-        const double spos = avg * slp_avg;
-        const double fldv = avg * flp_avg;
-        const double slv = fldv * f;
-        st += spos;
-        if (PASS == 2) { W.fld[o] = fldv; W.sl[o] = slv; W.xl[o] = xll ? 1 : 0; phiwa_acc += (slv - spos) * c_dc.RHOWG_DFIM[m]; }
-        const double xf = xll ? f : 0.0;
-        ws_em += c_dc.DFIM[m] * xf; ws_fm += c_dc.DFIMOFR[m] * xf;
-        if (m == F - 1) ws_last += xf;
-        if (PASS == 1) { uorbt_acc += c_dc.DFIM[m] * sig2 * f; aorb_acc += c_dc.DFIM[m] * f; }
-      }
-      double sxa = 0.0, sya = 0.0;
-#pragma unroll
-      for (int g = 0; g < NGST; ++g) {
-        sx[g] = wsum(sx[g]); sy[g] = wsum(sy[g]);
-        xstress[g] += constf * sx[g];      // XSTRESS = XSTRESS + SLP*CONSTF*SINTH(K), summed over K
-        ystress[g] += constf * sy[g];
-        sxa += sx[g]; sya += sy[g];
-      }
-      if (PASS == 2) st = wsum(st);
-      if (lane == (m & 31)) { dsumx[m >> 5] = sxa * (1.0 / NGST); dsumy[m >> 5] = sya * (1.0 / NGST); dsumt[m >> 5] = st; }
-    }
-  } else {
-    // ================= SINPUT_JAN (sinput_jan.F90:150-400) =================
-    const double CONST3 = c_dc.idamping * (2.0 * c_dc.XKAPPA / CONST1);
-    const double xkappad = 1.0 / c_dc.XKAPPA;
-    double us[NGST], wsin[NGST];
-    if (NGST == 1) { us[0] = ufric; wsin[0] = 1.0; }
-    else { us[0] = ufric * (1.0 - sig_n); us[NGST - 1] = ufric * (1.0 + sig_n); wsin[0] = 0.5; wsin[NGST - 1] = 0.5; }
-    for (int m = 0; m < F; ++m) {
-      const double sig = c_dc.ZPIFR[m], sig2 = sig * sig;
-      const double cinv = W.tb[TB_CINV * EW_MAXF + m], wavnum = W.tb[TB_WAVNUM * EW_MAXF + m];
-      const double ztanhkd = sig2 / (c_dc.G * wavnum);
-      const double cnsn = sig * CONST1 * ztanhkd * raorw;
-      const double zcn = W.tb[TB_ZCN * EW_MAXF + m];
-      double ucn[NGST], const3_ucn2[NGST], ucnd[NGST], xvd[NGST];
-#pragma unroll
-      for (int g = 0; g < NGST; ++g) {
-        ucn[g] = us[g] * cinv + c_dc.ZALP;
-        const3_ucn2[g] = CONST3 * sq(ucn[g]);
-        ucnd[g] = 1.0 / ucn[g];
-        xvd[g] = 1.0 / (-us[g] * xkappad * zcn * cinv);
-      }
-      double sx = 0.0, sy = 0.0, st = 0.0;
-#pragma unroll
-      for (int j = 0; j < KPL; ++j) {
-        if (!kv[j]) continue;
-        const int o = m * A + lane + 32 * j;
-        const double f = fl[o];
-        double ufac1 = 0.0, ufac2 = 0.0;
-        bool xll = false;
-#pragma unroll
-        for (int g = 0; g < NGST; ++g) {
-          double gam0 = 0.0;
-          if (coswdif[j] > 0.01) {
-            const double zlog = zcn + c_dc.XKAPPA / coswdif[j] * ucnd[g];
+          if (LLSNEG) dstab = dstab1 + pturb * (temp1 * (temp2_sw + (FU + FUD * coslp) * ustp[g]));
+          const double slp = gam0 * f;
+          sx[g] += slp * snk; sy[g] += slp * csk;
+          slp_avg += slp; flp_avg += gam0 + dstab;
+        } else {
+          if (cwd > 0.01) {
+            const double zlog = zcn + c_dc.XKAPPA / cwd * ucnzalpd[g];
             if (zlog < 0.0) {
-              const double x = coswdif[j] * ucn[g];
+              const double x = cwd * ucn[g];
               const double zlog2x = zlog * zlog * x;
               gam0 = zlog2x * zlog2x * exp(zlog) * cnsn;
               xll = true;
             }
           }
-          ufac1 += wsin[g] * gam0;
-          if (LLSNEG) ufac2 += wsin[g] * (const3_ucn2[g] * (coswdif[j] - xvd[g]));
+          slp_avg += wsin[g] * gam0;                   // UFAC1
+          if (LLSNEG) ufac2 += wsin[g] * (const3_ucn2[g] * (cwd - xvd[g]));
         }
-        const double fldv = ufac1 + ufac2 * cnsn;
-        const double spos = ufac1 * f;
-        const double slv = fldv * f;
-        sx += spos * sinth[j]; sy += spos * costh[j]; st += spos;
-        if (PASS == 2) { W.fld[o] = fldv; W.sl[o] = slv; W.xl[o] = xll ? 1 : 0; phiwa_acc += (slv - spos) * c_dc.RHOWG_DFIM[m]; }
-        const double xf = xll ? f : 0.0;
-        ws_em += c_dc.DFIM[m] * xf; ws_fm += c_dc.DFIMOFR[m] * xf;
-        if (m == F - 1) ws_last += xf;
       }
-      sx = wsum(sx); sy = wsum(sy);
-      if (PASS == 2) st = wsum(st);
-      if (lane == (m & 31)) { dsumx[m >> 5] = sx; dsumy[m >> 5] = sy; dsumt[m >> 5] = st; }
+      double spos, fldv;
+      if (ard) { spos = avg * slp_avg; fldv = avg * flp_avg; }
+      else { fldv = slp_avg + ufac2 * cnsn; spos = slp_avg * f; sx[0] += spos * snk; sy[0] += spos * csk; }
+      const double slv = fldv * f;
+      st += spos;
+      if (STORE) {
+        fo[(size_t)k * kstr] = fldv;
+        xo[(size_t)k * kstr] = xll ? 1.0 : 0.0;
+        phiwa_acc += (slv - spos) * rhowg;
+      }
+      if (xll) { ws_em += dfim * f; ws_fm += dfimofr * f; if (lastm) ws_last += f; }
     }
+    // moments of the (depth-limited, floored) spectrum
+    if (!STORE) {
+      const double sqk = sqrt(wavnum);
+      mom[0] += dfim * traw; mom[1] += dfimofr * traw; mom[2] += c_dc.DFIMFR[m] * traw;
+      mom[3] += (dfim / sqk) * traw; mom[4] += (sqk * dfim) * traw; mom[5] = traw;
+      uorbt_acc += dfim * sig2 * tsum; aorb_acc += dfim * tsum;
+    }
+    double sxa = 0.0, sya = 0.0;
+    if (ard) {
+#pragma unroll
+      for (int g = 0; g < NGST; ++g) {
+        xstress[g] += constf * sx[g];
+        ystress[g] += constf * sy[g];
+        sxa += sx[g]; sya += sy[g];
+      }
+      sxa *= avg; sya *= avg;
+    } else { sxa = sx[0]; sya = sy[0]; }
+    sumx[m] = sxa; sumy[m] = sya; sumt[m] = st;
   }
-  // ---- FEMEANWS (femeanws.F90:50-127)
-  ws_em = wsum(ws_em); ws_fm = wsum(ws_fm); ws_last = wsum(ws_last);
-  const double emeanws = c_dc.EPSMIN + ws_em + DELT25 * ws_last;
-  const double fmeanws = emeanws / (c_dc.EPSMIN + ws_fm + c_dc.FRTAIL * c_dc.DELTH * ws_last);
-  // ---- FRCUTINDEX (frcutindex.F90:84-97)
-  int mij;
-  if (cicover <= c_dc.cithrsh_tail) {
+}
+
+__global__ void __launch_bounds__(128) k_point(ImplDev d, long long p0, long long np) {
+  const long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= p0 + np) return;
+  const int A = c_dc.A, F = c_dc.F;
+  const long long n = d.npts;
+  double* s = d.scr;
+  const long long c = p / d.P;
+  const int i = (int)(p - c * d.P);
+  PointSrc S;
+  S.kstr = (size_t)d.P;
+  S.hi = d.f.fl1 + (size_t)i + (size_t)d.P * A * F * (size_t)c;
+  if (d.lo_F != d.F) {
+    // propagation scratch (P,A,Fr,C): padded lanes of the last chunk take the chunk's first point (propag_wam.F90:388-398)
+    const int il = (p < d.nloc) ? i : 0;
+    S.lo = d.fl_lo + (size_t)il + (size_t)d.P * A * d.lo_F * (size_t)c;
+    S.mlo = d.Fr;
+  } else { S.lo = S.hi; S.mlo = 0; }
+  const double aird = d.f.aird[p], wdwave = d.f.wdwave[p], cicover = d.f.cicover[p], wswave = d.f.wswave[p];
+  const double raorw = fmax(aird, 1.0) * c_dc.ROWATERM1;
+  double snw, csw;
+  sincos(wdwave, &snw, &csw);
+  const double flmc = (1. - 0.9 * fmin(cicover, 0.99)) * c_dc.flmin;      // FLM(K) = flmc*max(0,COSWDIF)**2
+  const double DELT25 = c_dc.WETAIL * c_dc.FR[F - 1] * c_dc.DELTH;
+  // ---- SDEPTHLIM (sdepthlim.F90:50-82): EM of the incoming spectrum -> limiting factor
+  double fac = 1.0;
+  if (c_dc.lbiwbk) {
+    double em = c_dc.EPSMIN, last = 0.0;
+    for (int m = 0; m < F; ++m) {
+      const double* fsrc = (m < S.mlo ? S.lo : S.hi) + (size_t)m * A * S.kstr;
+      double t = 0.0;
+#pragma unroll 4
+      for (int k = 0; k < A; ++k) t += __ldg(fsrc + (size_t)k * S.kstr);
+      em += c_dc.DFIM[m] * t;
+      last = t;
+    }
+    em += DELT25 * last;
+    fac = fmin(d.f.emaxdpt[p] / em, 1.0);
+  }
+  // ---- SINFLX call 1: AIRSEA (IUSFG=0), SINPUT (NGST=1), FEMEANWS, FRCUTINDEX, STRESSO
+  double ustar = d.f.ufric[p], z0, z0b, ch;
+  double tauw = d.f.tauw[p], tauwdir = d.f.tauwdir[p];
+  taut_z0(0, wswave, wdwave, tauw, tauwdir, ustar, z0, z0b, ch);
+  double sumx[EW_MAXF], sumy[EW_MAXF], sumt[EW_MAXF];
+  double ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc;
+  double mom[6] = {0, 0, 0, 0, 0, 0};
+  sinput_point<1, false, false>(S, d, p, fac, flmc, snw, csw, ustar, z0, raorw, 0.0, 0.0, 0.0, 0.0, nullptr, nullptr, sumx, sumy,
+                                sumt, ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc, mom);
+  // FKMEAN (fkmean.F90:60-154)
+  const double COEFM1 = c_dc.FRTAIL * c_dc.DELTH;
+  const double COEF1 = c_dc.WP1TAIL * c_dc.DELTH * sq(c_dc.FR[F - 1]);
+  const double COEFA = COEFM1 * sqrt(c_dc.G) / c_dc.ZPI;
+  const double COEFX = COEF1 * (c_dc.ZPI / sqrt(c_dc.G));
+  const double emean = c_dc.EPSMIN + mom[0] + DELT25 * mom[5];
+  const double fmean = emean / (c_dc.EPSMIN + mom[1] + COEFM1 * mom[5]);
+  const double f1mean = (c_dc.EPSMIN + mom[2] + COEF1 * mom[5]) / emean;
+  const double akmean = sq(emean / (c_dc.EPSMIN + mom[3] + COEFA * mom[5]));
+  const double xkmean = sq((c_dc.EPSMIN + mom[4] + COEFX * mom[5]) / emean);
+  s[S_EMEAN * n + p] = emean; s[S_FMEAN * n + p] = fmean; s[S_F1MEAN * n + p] = f1mean;
+  s[S_AKMEAN * n + p] = akmean; s[S_XKMEAN * n + p] = xkmean;
+  s[S_FAC * n + p] = fac;
+
+  auto frcut = [&](double fmeanws, double ust) -> int {   // frcutindex.F90:84-97
+    if (cicover > c_dc.cithrsh_tail) return F;
     const double fpmh = c_dc.TAILFACTOR / c_dc.FR[0];
     const double fppm = c_dc.TAILFACTOR_PM * c_dc.G / (28.0 * c_dc.ZPIFR[0]);
     const double fm2 = fmax(fmeanws, fmean) * fpmh;
-    const double fpm = fppm / fmax(ufric, c_dc.EPSMIN);
+    const double fpm = fppm / fmax(ust, c_dc.EPSMIN);
     const double fpm4 = fmax(fm2, fpm);
-    const double xr = log10(fpm4) * c_dc.FLOGSPRDM1;
-    mij = (int)lround(xr) + 1;     // NINT
-    mij = min(max(1, mij), F);
-  } else mij = F;
-  // ---- STRESSO low-frequency sums (stresso.F90:120-186)
-  {
-    double xs = 0.0, ys = 0.0, pw = 0.0;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int m = lane + 32 * h;
-      if (m < F) {
-        const double r = rhowgdfth(m, mij);
-        const double cm = r * W.tb[TB_CINV * EW_MAXF + m];
-        xs += cm * dsumx[h]; ys += cm * dsumy[h]; pw += r * dsumt[h];
-      }
-    }
-    xs = wsum(xs); ys = wsum(ys);
-    double f3 = 0.0, f2 = 0.0;
-#pragma unroll
-    for (int j = 0; j < KPL; ++j) if (kv[j]) {
-      const double cw = fmax(coswdif[j], 0.0);
-      const double fc2 = fl[(mij - 1) * A + lane + 32 * j] * cw * cw;
-      f3 += fc2 * cw; f2 += fc2;
-    }
-    f3 = c_dc.DELTH * wsum(f3);
-    f2 = c_dc.DELTH * wsum(f2);
-    if (PASS == 2) { pw = wsum(pw) + wsum(phiwa_acc); }
-    if (active && lane == 0) {
-      s[S_XSTR * n + p] = xs; s[S_YSTR * n + p] = ys; s[S_F1DCOS3 * n + p] = f3; s[S_F1DCOS2 * n + p] = f2;
-      s[S_MIJ * n + p] = (double)mij;
-      if (PASS == 2) s[S_PHIWA * n + p] = pw;
-    }
-  }
-  if (PASS == 1) {
-    uorbt_acc = wsum(uorbt_acc); aorb_acc = wsum(aorb_acc);
-    if (active && lane == 0) { s[S_UORBT * n + p] = c_dc.EPSMIN + uorbt_acc; s[S_AORB * n + p] = c_dc.EPSMIN + aorb_acc; }
-    return;
-  }
-
-  if (PASS == 2) {
-    double* fld = W.fld;
-    double* sl = W.sl;
-    __syncwarp();
-    // ---- SDISSIP
-    if (c_dc.iphys == 1) {
-      // SDISSIP_ARD (sdissip_ard.F90:131-318), saturation-based part only (SSDSC3 = SSDSC5 = 0)
-      const double tpiinv = 1.0 / c_dc.ZPI;
-      const double tmp03 = 1.0 / (c_dc.SDSBR * c_dc.MICHE);
-      const double ssdsc6m1 = 1. - c_dc.SSDSC6;
-      const int ns = 2 * c_dc.NSDSNTH + 1;
-      for (int m = 0; m < F; ++m) {
-        const double facsat = W.tb[TB_WAVNUM * EW_MAXF + m] * tpiinv * W.tb[TB_XK2CG * EW_MAXF + m];
-        double bth[KPL], bmax = 0.0;
-#pragma unroll
-        for (int j = 0; j < KPL; ++j) {
-          bth[j] = 0.0;
-          if (!kv[j]) continue;
-          const int k = lane + 32 * j;
-          double b = 0.0;
-          for (int k2 = 0; k2 < ns; ++k2) b += __ldg(d.tab.satweights + k2 * A + k) * fl[m * A + __ldg(d.tab.indicessat + k2 * A + k)];
-          bth[j] = b * facsat;
-          bmax = fmax(bmax, bth[j]);
-        }
-        const double bth0 = wmax(bmax);
-        const double ssdsc2_sig = c_dc.SSDSC2 * c_dc.ZPIFR[m];
-        const double zcoef = ssdsc2_sig * c_dc.SSDSC6, zcoefm1 = ssdsc2_sig * ssdsc6m1;
-#pragma unroll
-        for (int j = 0; j < KPL; ++j) if (kv[j]) {
-          const int o = m * A + lane + 32 * j;
-          const double dd = zcoef * sq(fmax(0., bth0 * tmp03 - c_dc.SSDSC4)) + zcoefm1 * sq(fmax(0., bth[j] * tmp03 - c_dc.SSDSC4));
-          sl[o] = sl[o] + dd * fl[o];
-          fld[o] = fld[o] + dd;
-        }
-      }
-    } else {
-      // SDISSIP_JAN (sdissip_jan.F90:96-132)
-      const double sds = c_dc.CDIS * c_dc.ZPI * f1mean * sq(emean) * p4(xkmean);
-      const double cvis = c_dc.rnu * c_dc.CDISVIS;
-      for (int m = 0; m < F; ++m) {
-        const double wn = W.tb[TB_WAVNUM * EW_MAXF + m];
-        const double x = wn / xkmean;
-        const double temp1 = sds * x * ((1.0 - c_dc.DELTA_SDIS) + c_dc.DELTA_SDIS * x) + cvis * sq(wn);
-#pragma unroll
-        for (int j = 0; j < KPL; ++j) if (kv[j]) {
-          const int o = m * A + lane + 32 * j;
-          fld[o] = fld[o] + temp1;
-          sl[o] = sl[o] + temp1 * fl[o];
-        }
-      }
-    }
-    __syncwarp();
-    // ---- SNONLIN (snonlin.F90:116-498, ISNONLIN=0): DIA quadruplets, scatter form with warp-synchronous steps
-    {
-      double enhfr = fmax(0.75 * depth * akmean, 0.5);
-      enhfr = 1.0 + (5.5 / enhfr) * (1.0 - .833 * enhfr) * exp(-1.25 * enhfr);
-      const int MFR1STFR = -c_dc.MFRSTLW + 1;
-      const int MFRLSTFR = F - c_dc.KFRH + MFR1STFR;
-      for (int mc = 1; mc <= c_dc.MLSTHG; ++mc) {
-        const int MP = c_dc.IKP[mc - 1], MP1 = c_dc.IKP1[mc - 1], MM = c_dc.IKM[mc - 1], MM1 = c_dc.IKM1[mc - 1];
-        const int IC = c_dc.INLCOEF[mc - 1][0], IP = c_dc.INLCOEF[mc - 1][1], IP1 = c_dc.INLCOEF[mc - 1][2],
-                  IM = c_dc.INLCOEF[mc - 1][3], IM1 = c_dc.INLCOEF[mc - 1][4];
-        const double* R = c_dc.RNLCOEF[mc - 1];
-        const double FTAIL = R[0], GW1 = R[1], GW2 = R[2], GW3 = R[3], GW4 = R[4];
-        const double FKLAMPA = R[5], FKLAMPB = R[6], FKLAMP2 = R[7], FKLAMP1 = R[8];
-        const double FKLAPA2 = R[9], FKLAPB2 = R[10], FKLAP12 = R[11], FKLAP22 = R[12];
-        const double GW5 = R[13], GW6 = R[14], GW7 = R[15], GW8 = R[16];
-        const double FKLAMMA = R[17], FKLAMMB = R[18], FKLAMM2 = R[19], FKLAMM1 = R[20];
-        const double FKLAMA2 = R[21], FKLAMB2 = R[22], FKLAM12 = R[23], FKLAM22 = R[24];
-        const double ftemp = c_dc.AF11[mc - 1] * enhfr;
-        const int branch = (mc > MFR1STFR && mc < MFRLSTFR) ? 0 : (mc >= MFRLSTFR ? 1 : 2);
-        bool do_c, do_mm, do_mm1, do_mp, do_mp1;
-        if (branch == 0) { do_c = do_mm = do_mm1 = do_mp = do_mp1 = true; }
-        else if (branch == 1) {
-          do_mm = true; do_mm1 = MM1 <= F; do_c = do_mm1 && mc <= F; do_mp = do_c && MP <= F; do_mp1 = do_mp && MP1 <= F;
-        } else { do_mm = false; do_mm1 = MM1 >= 1; do_c = true; do_mp = true; do_mp1 = true; }
-        const double* fIP = fl + (IP - 1) * A; const double* fIP1 = fl + (IP1 - 1) * A;
-        const double* fIM = fl + (IM - 1) * A; const double* fIM1 = fl + (IM1 - 1) * A;
-        const double* fIC = fl + (IC - 1) * A;
-        for (int kh = 0; kh < 2; ++kh) {
-#pragma unroll
-          for (int j = 0; j < KPL; ++j) {
-            // all lanes run the step sequence (warp-synchronous); lanes without a direction contribute nothing
-            const int k = lane + 32 * j;
-            const bool v = k < A;
-            if (j > 0 && A <= 32) break;
-            const int kk = v ? k : 0;
-            const int K1 = __ldg(d.tab.k1w + kh * A + kk), K2 = __ldg(d.tab.k2w + kh * A + kk);
-            const int K11 = __ldg(d.tab.k11w + kh * A + kk), K21 = __ldg(d.tab.k21w + kh * A + kk);
-            const double sap = GW1 * fIP[K1] + GW2 * fIP[K11] + GW3 * fIP1[K1] + GW4 * fIP1[K11];
-            const double sam = GW5 * fIM[K2] + GW6 * fIM[K21] + GW7 * fIM1[K2] + GW8 * fIM1[K21];
-            const double fij = (branch == 0) ? fIC[kk] : fIC[kk] * FTAIL;
-            double fad1 = fij * (sap + sam);
-            const double fad2 = fad1 - 2.0 * sap * sam;
-            fad1 = fad1 + fad2;
-            const double fcen = ftemp * fij;
-            const double ad = fad2 * fcen;
-            const double delad = fad1 * ftemp;
-            const double delap = (fij - 2.0 * sam) * c_dc.DAL1 * fcen;
-            const double delam = (fij - 2.0 * sap) * c_dc.DAL2 * fcen;
-            // the nine updates; within one step every lane hits a distinct (direction, frequency) bin
-            if (do_c) { if (v) { const int o = (mc - 1) * A + kk; sl[o] -= 2.0 * ad; fld[o] -= 2.0 * delad; } __syncwarp(); }
-            if (do_mm) {
-              if (v) { const int o = (MM - 1) * A + K2; sl[o] += ad * FKLAMM1; fld[o] += delam * FKLAM12; } __syncwarp();
-              if (v) { const int o = (MM - 1) * A + K21; sl[o] += ad * FKLAMM2; fld[o] += delam * FKLAM22; } __syncwarp();
-            }
-            if (do_mm1) {
-              if (v) { const int o = (MM1 - 1) * A + K2; sl[o] += ad * FKLAMMA; fld[o] += delam * FKLAMA2; } __syncwarp();
-              if (v) { const int o = (MM1 - 1) * A + K21; sl[o] += ad * FKLAMMB; fld[o] += delam * FKLAMB2; } __syncwarp();
-            }
-            if (do_mp) {
-              if (v) { const int o = (MP - 1) * A + K1; sl[o] += ad * FKLAMP1; fld[o] += delap * FKLAP12; } __syncwarp();
-              if (v) { const int o = (MP - 1) * A + K11; sl[o] += ad * FKLAMP2; fld[o] += delap * FKLAP22; } __syncwarp();
-            }
-            if (do_mp1) {
-              if (v) { const int o = (MP1 - 1) * A + K1; sl[o] += ad * FKLAMPA; fld[o] += delap * FKLAPA2; } __syncwarp();
-              if (v) { const int o = (MP1 - 1) * A + K11; sl[o] += ad * FKLAMPB; fld[o] += delap * FKLAPB2; } __syncwarp();
-            }
-          }
-        }
-      }
-    }
-    __syncwarp();
-    // ---- SSOURCE capture, SDIWBK, SBOTTOM, implicit update (implsch.F90:294-395), WNFLUXES sums
-    const double delt = c_dc.delt, deltm = 1.0 / delt, delt5 = c_dc.ximp * delt;
-    const double usfm = ufric * fmax(fmeanws, fmean);
-    const double sds_bk = s[S_SDS * n + p];
-    const bool brk = c_dc.lbiwbk && depth < 50.0;
-    double philf = 0.0, xsoc = 0.0, ysoc = 0.0;
-    const double sbo_const = -2.0 * 0.038 * c_dc.GM1;
-    for (int m = 0; m < F; ++m) {
-      const double tempm = usfm * (c_dc.COFRM4[m] * delt);
-      double sbo = 0.0;
-      if (m < c_dc.Fr && depth < c_dc.bathymax) {
-        const double wn = W.tb[TB_WAVNUM * EW_MAXF + m];
-        const double arg = fmin(2.0 * depth * wn, 50.0);
-        sbo = sbo_const * wn / sinh(arg);
-      }
+    int mij = (int)lround(log10(fpm4) * c_dc.FLOGSPRDM1) + 1;
+    return min(max(1, mij), F);
+  };
+  // STRESSO (stresso.F90:120-233) from the per-frequency SPOS moments; returns TAUW, TAUWDIR, PHIWA
+  auto stresso = [&](int mij, double ust_in, double z0m, bool llphiwa, double phiwa_lf, double& tw, double& twd, double& phiwa) {
+    double xs = 0.0, ys = 0.0, pw = phiwa_lf;
+    for (int m = 0; m < mij; ++m) {
       const double r = rhowgdfth(m, mij);
-      const double cmr = W.tb[TB_CINV * EW_MAXF + m] * r;
-      double sumt = 0.0, sumx = 0.0, sumy = 0.0;
+      const double cm = r * d.f.cinv[idx3(d, p, m)];
+      xs += cm * sumx[m]; ys += cm * sumy[m]; pw += r * sumt[m];
+    }
+    const double am = fmax(aird, 1.0);
+    xs = xs / am; ys = ys / am;
+    // directional moments of the spectrum at the cut-off frequency (tau_phi_hf.F90:150-178)
+    double f3 = 0.0, f2 = 0.0;
+    {
+      const int m = mij - 1;
+      const double* fsrc = (m < S.mlo ? S.lo : S.hi) + (size_t)m * A * S.kstr;
+      for (int k = 0; k < A; ++k) {
+        double f = fmax(__ldg(fsrc + (size_t)k * S.kstr) * fac, c_dc.EPSMIN);
+        const double cwd = c_dc.COSTH[k] * csw + c_dc.SINTH[k] * snw;
+        if (m == F - 1) f = fmax(f, flmc * sq(fmax(0.0, cwd)));
+        const double cw = fmax(cwd, 0.0);
+        const double fc2 = f * cw * cw;
+        f3 += fc2 * cw; f2 += fc2;
+      }
+      f3 *= c_dc.DELTH; f2 *= c_dc.DELTH;
+    }
+    bool shelter;
+    double usdirp_s, usdirp_c, ust;
+    if (c_dc.iphys == 0 || c_dc.TAUWSHELTER == 0.0) { shelter = false; usdirp_s = snw; usdirp_c = csw; ust = ust_in; }
+    else {
+      shelter = true;
+      const double taupx = sq(ust_in) * snw - c_dc.TAUWSHELTER * xs, taupy = sq(ust_in) * csw - c_dc.TAUWSHELTER * ys;
+      const double rt = sqrt(taupx * taupx + taupy * taupy);
+      ust = sqrt(rt);
+      if (rt > 0.0) { usdirp_s = taupx / rt; usdirp_c = taupy / rt; } else { usdirp_s = 0.0; usdirp_c = 1.0; }
+    }
+    double tauhf, phihf;
+    tau_phi_hf(mij, shelter, z0m, aird, f3, f2, ust, tauhf, phihf, llphiwa);
+    xs = xs + tauhf * usdirp_s;
+    ys = ys + tauhf * usdirp_c;
+    tw = fmax(sqrt(sq(xs) + sq(ys)), 0.0);
+    twd = atan2(xs, ys);
+    tw = fmin(tw, sq(ust_in) * (1.0 / (1.0 + c_dc.EPS1)));
+    phiwa = llphiwa ? pw + phihf : 0.0;
+  };
+  {
+    const double emeanws = c_dc.EPSMIN + ws_em + DELT25 * ws_last;
+    const double fmeanws = emeanws / (c_dc.EPSMIN + ws_fm + c_dc.FRTAIL * c_dc.DELTH * ws_last);
+    const int mij1 = frcut(fmeanws, ustar);
+    double ph;
+    stresso(mij1, ustar, z0, false, 0.0, tauw, tauwdir, ph);
+  }
+  // ---- SINFLX call 2: AIRSEA (IUSFG=1), SINPUT (NGST=2, LLSNEG), FEMEANWS, FRCUTINDEX, STRESSO (LLPHIWA)
+  taut_z0(1, wswave, wdwave, tauw, tauwdir, ustar, z0, z0b, ch);
+  d.f.ufric[p] = ustar; d.f.z0m[p] = z0; d.f.z0b[p] = z0b; d.f.chrnck[p] = ch;
+  const double sig_n = wsigstar(ustar, z0, d.f.wstar[p]);
+  double temp2_sw = 0.0, pturb = 0.0, aird_pvisc = 0.0;
+  if (c_dc.iphys == 1) {   // sinput_ard.F90:179-271
+    const double uorbt = 2.0 * sqrt(c_dc.EPSMIN + uorbt_acc), aorb = 2.0 * sqrt(c_dc.EPSMIN + aorb_acc);
+    const double re = (4.0 / c_dc.rnu) * uorbt * aorb;
+    const double z0vis = c_dc.rnum / fmax(ustar, 0.0001);
+    const double z0tub = c_dc.Z0RAT * fmin(c_dc.Z0TUBMAX, z0);
+    const double zorb = aorb / fmax(z0vis, z0tub);
+    const double delabm1 = (double)c_dc.IAB / (c_dc.ABMAX - c_dc.ABMIN);
+    const double xi = (log10(fmax(zorb, 3.0)) - c_dc.ABMIN) * delabm1;
+    const int ind = min(c_dc.IAB - 1, (int)xi);
+    const double deli1 = fmin(1.0, xi - (double)ind), deli2 = 1.0 - deli1;
+    const double fww = __ldg(d.tab.swellft + ind - 1) * deli2 + __ldg(d.tab.swellft + ind) * deli1;
+    temp2_sw = fww * uorbt;
+    const double re_c = (c_dc.SWELLF6 == 1.0) ? c_dc.SWELLF4 : c_dc.SWELLF4 * pow(2.0 / aorb, 1.0 - c_dc.SWELLF6);
+    double pvisc;
+    if (c_dc.SWELLF7 > 0.0) { const double sm = 0.5 * tanh((re - re_c) * c_dc.SWELLF7M1); pturb = 0.5 + sm; pvisc = 0.5 - sm; }
+    else if (re <= re_c) { pturb = 0.0; pvisc = 0.5; }
+    else { pturb = 0.5; pvisc = 0.0; }
+    aird_pvisc = pvisc * raorw;
+  }
+  double* fld_out = d.fldin + (size_t)i + (size_t)d.P * A * F * (size_t)c;
+  double* xl_out = d.f.xllws + (size_t)i + (size_t)d.P * A * F * (size_t)c;
+  double dum[6];
+  sinput_point<2, true, true>(S, d, p, fac, flmc, snw, csw, ustar, z0, raorw, sig_n, temp2_sw, pturb, aird_pvisc, fld_out, xl_out,
+                              sumx, sumy, sumt, ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc, dum);
+  const double emeanws = c_dc.EPSMIN + ws_em + DELT25 * ws_last;
+  const double fmeanws = emeanws / (c_dc.EPSMIN + ws_fm + c_dc.FRTAIL * c_dc.DELTH * ws_last);
+  const int mij = frcut(fmeanws, ustar);
+  double phiwa;
+  stresso(mij, ustar, z0, true, phiwa_acc, tauw, tauwdir, phiwa);
+  d.f.tauw[p] = tauw; d.f.tauwdir[p] = tauwdir; d.f.mij[p] = mij;
+  s[S_PHIWA * n + p] = phiwa;
+  s[S_MIJ * n + p] = (double)mij;
+  s[S_USFM * n + p] = ustar * fmax(fmeanws, fmean);
+  // ---- SDIWBK (sdiwbk.F90:69-104)
+  double sds = 0.0;
+  if (c_dc.lbiwbk && d.f.depth[p] < 50.0) {
+    const double alph = 2.0 * d.f.emaxdpt[p] / emean;
+    const double arg = fmin(alph, 50.0);
+    double q_old = exp(-arg), q = q_old;
+    for (int ic = 1; ic <= 15; ++ic) {
+      const double expq = exp(-arg * (1.0 - q_old));
+      q = q_old - (expq - q_old) / (arg * expq - 1.0);
+      const double rel_err = fabs(q - q_old) / q_old;
+      if (rel_err < 0.00001) break;
+      q_old = q;
+    }
+    q = fmin(q, 1.0);
+    sds = 2.0 * alph * q * f1mean;
+  }
+  s[S_SDS * n + p] = sds;
+}
+
+
+// =========================================================================================================
+// k_stencil: CTA = 8 consecutive grid points x NANG threads (thread = (point, direction)).
+// SDISSIP, SNONLIN, SDIWBK, SBOTTOM, the implicit update, WNFLUXES, IMPHFTAIL, SETICE and STOKESDRIFT as ONE sweep
+// over frequency.  The DIA quadruplets of "centre" frequency MC only touch the frequencies MC-4 .. MC+3
+// (nlweigt.F90: IKM=MC-4, IKM1=MC-3, IKP=MC+2, IKP1=MC+3 for FRATIO=1.1), so the sweep keeps
+//   * an 8-row ring of the spectrum in shared memory (rows stream in from HBM one per step, already
+//     depth-limited and floored),
+//   * the 8 pending rows of the SNONLIN sums SL/FLD of the thread's own direction in registers,
+// and, at step MC, finishes row MC-4: it receives its last DIA contribution, gets the dissipation, breaking and
+// bottom terms, is advanced in time and leaves for HBM.  The reference's scatter of each quadruplet into 9 bins
+// (snonlin.F90:253-308) becomes a gather through the inverse direction tables: no atomics, fixed summation order.
+// =========================================================================================================
+#define ST_NPT 8
+
+__global__ void __launch_bounds__(ST_NPT * EW_MAXA) k_stencil(ImplDev d, long long p0, long long np) {
+  extern __shared__ double smem[];
+  const int A = c_dc.A, F = c_dc.F, NPT = ST_NPT;
+  const int NS = 2 * c_dc.NSDSNTH + 1;
+  double* ring = smem;                               // [8][NPT][A]
+  double* cur = ring + 8 * NPT * A;                  // [6][NPT][A]
+  double* sin_ = cur + 6 * NPT * A;                  // [NPT][A]
+  double* sout = sin_ + NPT * A;                     // [NPT][A]
+  double* satw = sout + NPT * A;                     // [NS][A]
+  double* rowsc = satw + EW_MAXSAT * A;              // [NPT][8]
+  unsigned long long* bth0 = (unsigned long long*)(rowsc + NPT * 8);   // [4][NPT]
+  const int t = threadIdx.x;
+  const int p = t / A, k = t - p * A;                // compute role
+  const int kt = t / NPT, pt = t - kt * NPT;         // transfer role (grid point fastest -> 64-byte segments)
+  const long long pbase = p0 + (long long)blockIdx.x * NPT;
+  const long long plast = p0 + np - 1;
+  const bool pvalid = pbase + p <= plast, tvalid = pbase + pt <= plast;
+  const long long pp = min(pbase + p, plast), tp = min(pbase + pt, plast);
+  const long long n = d.npts;
+  const double* s = d.scr;
+  // ---- transfer-role constants
+  const long long tc = tp / d.P;
+  const int ti = (int)(tp - tc * d.P);
+  const size_t P = (size_t)d.P;
+  const double* g_hi = d.f.fl1 + (size_t)ti + P * A * F * (size_t)tc + P * (size_t)kt;
+  const double* g_lo = g_hi;
+  int mlo = 0;
+  if (d.lo_F != d.F) {
+    const int il = (tp < d.nloc) ? ti : 0;
+    g_lo = d.fl_lo + (size_t)il + P * A * d.lo_F * (size_t)tc + P * (size_t)kt;
+    mlo = d.Fr;
+  }
+  const double* g_fld = d.fldin + (size_t)ti + P * A * F * (size_t)tc + P * (size_t)kt;
+  double* g_out = d.f.fl1 + (size_t)ti + P * A * F * (size_t)tc + P * (size_t)kt;
+  const size_t rstr = P * A;                          // row (frequency) stride in the chunked layout
+  double t_fac, t_floor;
+  {
+    const double wd = d.f.wdwave[tp], ci = d.f.cicover[tp];
+    const double cwd = c_dc.COSTH[kt] * cos(wd) + c_dc.SINTH[kt] * sin(wd);
+    t_fac = s[S_FAC * n + tp];
+    t_floor = (1. - 0.9 * fmin(ci, 0.99)) * c_dc.flmin * sq(fmax(0.0, cwd));
+  }
+  auto load_row = [&](int r) -> double {             // depth-limited (+ floored at NFRE) spectrum row r of (pt, kt)
+    double v = __ldg((r < mlo ? g_lo : g_hi) + (size_t)r * rstr);
+    v = fmax(v * t_fac, c_dc.EPSMIN);
+    if (r == F - 1) v = fmax(v, t_floor);
+    return v;
+  };
+  // ---- compute-role constants
+  const double wdwave = d.f.wdwave[pp], cicover = d.f.cicover[pp], depth = d.f.depth[pp];
+  double snw, csw;
+  sincos(wdwave, &snw, &csw);
+  const double sinth = c_dc.SINTH[k], costh = c_dc.COSTH[k];
+  const double coswdif = costh * csw + sinth * snw;
+  const double flm = (1. - 0.9 * fmin(cicover, 0.99)) * c_dc.flmin * sq(fmax(0.0, coswdif));
+  const int mij = (int)s[S_MIJ * n + pp];
+  const double usfm = s[S_USFM * n + pp], sds_bk = s[S_SDS * n + pp];
+  const double emean = s[S_EMEAN * n + pp], f1mean = s[S_F1MEAN * n + pp], akmean = s[S_AKMEAN * n + pp],
+               xkmean = s[S_XKMEAN * n + pp];
+  const bool brk = c_dc.lbiwbk && depth < 50.0;
+  double enhfr = fmax(0.75 * depth * akmean, 0.5);
+  enhfr = 1.0 + (5.5 / enhfr) * (1.0 - .833 * enhfr) * exp(-1.25 * enhfr);
+  int ik1[2], ik11[2], ik2[2], ik21[2], k1[2], k11[2], k2[2], k21[2];
 #pragma unroll
-      for (int j = 0; j < KPL; ++j) if (kv[j]) {
-        const int o = m * A + lane + 32 * j;
-        double slv = sl[o], fldv = fld[o];
-        const double f0 = fl[o];
+  for (int kh = 0; kh < 2; ++kh) {
+    k1[kh] = __ldg(d.tab.k1w + kh * A + k); k11[kh] = __ldg(d.tab.k11w + kh * A + k);
+    k2[kh] = __ldg(d.tab.k2w + kh * A + k); k21[kh] = __ldg(d.tab.k21w + kh * A + k);
+    ik1[kh] = __ldg(d.tab.ik1w + kh * A + k); ik11[kh] = __ldg(d.tab.ik11w + kh * A + k);
+    ik2[kh] = __ldg(d.tab.ik2w + kh * A + k); ik21[kh] = __ldg(d.tab.ik21w + kh * A + k);
+  }
+  const long long pc = pp / d.P;
+  const double* g_xl = d.f.xllws + (size_t)(pp - pc * d.P) + P * A * F * (size_t)pc + P * (size_t)k;
+  double cireduc = 0.0, icefree = 1.0;
+  if (c_dc.licerun && c_dc.lmaskice && cicover > c_dc.cithrsh) { cireduc = fmax(c_dc.EPSMIN, 1.0 - cicover); icefree = 0.0; }
+  const double ice_add = cireduc * c_dc.flmin * sq(fmax(0.0, coswdif));
+  const bool setice = c_dc.licerun && c_dc.lmaskice;
+  const double delt = c_dc.delt, deltm = 1.0 / delt, delt5 = c_dc.ximp * delt;
+  const double tpiinv = 1.0 / c_dc.ZPI, tmp03 = 1.0 / (c_dc.SDSBR * c_dc.MICHE), ssdsc6m1 = 1. - c_dc.SSDSC6;
+  const double sbo_const = -2.0 * 0.038 * c_dc.GM1;
+  const double sds_jan = c_dc.CDIS * c_dc.ZPI * f1mean * sq(emean) * p4(xkmean);
+  const bool ard = c_dc.iphys == 1;
+  const int MFR1STFR = -c_dc.MFRSTLW + 1, MFRLSTFR = F - c_dc.KFRH + MFR1STFR, MLSTHG = c_dc.MLSTHG;
+  // ---- prologue: saturation weights, first 4 rows of the ring, zero the BTH0 slots
+  if (ard) for (int x = t; x < NS * A; x += blockDim.x) satw[x] = __ldg(d.tab.satweights + x);
+  if (t < 4 * NPT) bth0[t] = 0ull;
+  for (int r = 0; r < 4 && r < F; ++r) ring[((r & 7) * NPT + pt) * A + kt] = load_row(r);
+  double acc_sl[8], acc_fld[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc_sl[j] = 0.0; acc_fld[j] = 0.0; }
+  double b_prev = 0.0, fmij = 0.0;
+  double a_philf = 0.0, a_xs = 0.0, a_ys = 0.0, a_us = 0.0, a_vs = 0.0, a_e1 = 0.0, a_e2 = 0.0, a_el = 0.0;
+  __syncthreads();
+
+  for (int mc0 = 0; mc0 < MLSTHG; mc0 += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int MC0 = mc0 + j;
+      if (MC0 >= MLSTHG) break;
+      // ================= phase A =================
+      const int rin = MC0 + 4, rfin = MC0 - 4, rb = MC0 - 3, rout = MC0 - 5;
+      double xF = 0.0, xI = 0.0;
+      if (rin < F) xF = load_row(rin);
+      if (rfin >= 0 && rfin < F) xI = __ldg(g_fld + (size_t)rfin * rstr);
+      if (rout >= 0 && tvalid) g_out[(size_t)rout * rstr] = sout[pt * A + kt];
+      // DIA interaction values of centre frequency MC = MC0+1 (snonlin.F90:225-250)
+      const int IC = c_dc.INLCOEF[MC0][0], IP = c_dc.INLCOEF[MC0][1], IP1 = c_dc.INLCOEF[MC0][2], IM = c_dc.INLCOEF[MC0][3],
+                IM1 = c_dc.INLCOEF[MC0][4];
+      const double* R = c_dc.RNLCOEF[MC0];
+      const double ftemp = c_dc.AF11[MC0] * enhfr;
+      const int MC = MC0 + 1;
+      const int branch = (MC > MFR1STFR && MC < MFRLSTFR) ? 0 : (MC >= MFRLSTFR ? 1 : 2);
+      bool do_c, do_mm, do_mm1, do_mp, do_mp1;
+      {
+        const int MP = c_dc.IKP[MC0], MP1 = c_dc.IKP1[MC0], MM1 = c_dc.IKM1[MC0];
+        if (branch == 0) { do_c = do_mm = do_mm1 = do_mp = do_mp1 = true; }
+        else if (branch == 1) { do_mm = true; do_mm1 = MM1 <= F; do_c = do_mm1 && MC <= F; do_mp = do_c && MP <= F; do_mp1 = do_mp && MP1 <= F; }
+        else { do_mm = false; do_mm1 = MM1 >= 1; do_c = true; do_mp = true; do_mp1 = true; }
+      }
+      const double* rIP = ring + (((IP - 1) & 7) * NPT + p) * A;
+      const double* rIP1 = ring + (((IP1 - 1) & 7) * NPT + p) * A;
+      const double* rIM = ring + (((IM - 1) & 7) * NPT + p) * A;
+      const double* rIM1 = ring + (((IM1 - 1) & 7) * NPT + p) * A;
+      const double* rIC = ring + (((IC - 1) & 7) * NPT + p) * A;
+      double ad[2], delad[2];
+      {
+        const double fc = rIC[k];
+        const double fij = (branch == 0) ? fc : fc * R[0];
+        const double fcen = ftemp * fij;
+#pragma unroll
+        for (int kh = 0; kh < 2; ++kh) {
+          const double sap = R[1] * rIP[k1[kh]] + R[2] * rIP[k11[kh]] + R[3] * rIP1[k1[kh]] + R[4] * rIP1[k11[kh]];
+          const double sam = R[13] * rIM[k2[kh]] + R[14] * rIM[k21[kh]] + R[15] * rIM1[k2[kh]] + R[16] * rIM1[k21[kh]];
+          double fad1 = fij * (sap + sam);
+          const double fad2 = fad1 - 2.0 * sap * sam;
+          fad1 = fad1 + fad2;
+          ad[kh] = fad2 * fcen;
+          delad[kh] = fad1 * ftemp;
+          cur[((0 + kh) * NPT + p) * A + k] = ad[kh];
+          cur[((2 + kh) * NPT + p) * A + k] = (fij - 2.0 * sam) * c_dc.DAL1 * fcen;   // DELAP
+          cur[((4 + kh) * NPT + p) * A + k] = (fij - 2.0 * sap) * c_dc.DAL2 * fcen;   // DELAM
+        }
+      }
+      const double fold = (rfin >= 0) ? ring[((rfin & 7) * NPT + p) * A + k] : 0.0;
+      // saturation spectrum of row rb for SDISSIP_ARD (sdissip_ard.F90:142-160)
+      double b_next = 0.0;
+      if (ard && rb >= 0 && rb < F) {
+        const size_t o3 = idx3(d, pp, rb);
+        const double facsat = d.f.wavnum[o3] * tpiinv * d.f.xk2cg[o3];
+        const double* rr = ring + ((rb & 7) * NPT + p) * A;
+        double b = 0.0;
+        for (int x = 0; x < NS; ++x) b += satw[x * A + k] * rr[__ldg(d.tab.indicessat + x * A + k)];
+        b_next = b * facsat;
+        atomicMax(&bth0[(rb & 3) * NPT + p], (unsigned long long)__double_as_longlong(fmax(b_next, 0.0)));
+      }
+      if (k == 0) {
+        bth0[((rb + 1) & 3) * NPT + p] = 0ull;
+        if (rfin >= 0) {   // per-row scalars of the row finished in this step
+          const int r = rfin;
+          const size_t o3 = idx3(d, pp, r);
+          const double wn = d.f.wavnum[o3], ci = d.f.cinv[o3], xk = d.f.xk2cg[o3];
+          double* rs = rowsc + p * 8;
+          rs[0] = usfm * (c_dc.COFRM4[r] * delt);
+          double sbo = 0.0;
+          if (r < c_dc.Fr && depth < c_dc.bathymax) sbo = sbo_const * wn / sinh(fmin(2.0 * depth * wn, 50.0));
+          rs[1] = sbo;
+          const double rr = rhowgdfth(r, mij);
+          rs[2] = rr; rs[3] = ci * rr;
+          rs[4] = 1.0 / xk / wn;                                      // IMPHFTAIL 1/(k^3 cg)
+          rs[5] = (r < c_dc.NFRE_ODD) ? d.f.stokfac[o3] * c_dc.DFIM_SIM[r] : 0.0;
+          if (!ard) { const double x = wn / xkmean; rs[6] = sds_jan * x * ((1.0 - c_dc.DELTA_SDIS) + c_dc.DELTA_SDIS * x) + c_dc.rnu * c_dc.CDISVIS * sq(wn); }
+        }
+      }
+      sin_[pt * A + kt] = xI;
+      __syncthreads();
+      // ================= phase B =================
+      // gather the quadruplet contributions of MC into the pending rows (snonlin.F90:253-308, :333-410, :446-490)
+      {
+        double sl_mm = 0, fl_mm = 0, sl_mm1 = 0, fl_mm1 = 0, sl_mp = 0, fl_mp = 0, sl_mp1 = 0, fl_mp1 = 0;
+#pragma unroll
+        for (int kh = 0; kh < 2; ++kh) {
+          const double* cA = cur + ((0 + kh) * NPT + p) * A;
+          const double* cP = cur + ((2 + kh) * NPT + p) * A;
+          const double* cM = cur + ((4 + kh) * NPT + p) * A;
+          const double a2 = cA[ik2[kh]], a21 = cA[ik21[kh]], m2 = cM[ik2[kh]], m21 = cM[ik21[kh]];
+          const double a1 = cA[ik1[kh]], a11 = cA[ik11[kh]], q1 = cP[ik1[kh]], q11 = cP[ik11[kh]];
+          sl_mm += a2 * R[20] + a21 * R[19];   fl_mm += m2 * R[23] + m21 * R[24];     // FKLAMM1, FKLAMM2 | FKLAM12, FKLAM22
+          sl_mm1 += a2 * R[17] + a21 * R[18];  fl_mm1 += m2 * R[21] + m21 * R[22];    // FKLAMMA, FKLAMMB | FKLAMA2, FKLAMB2
+          sl_mp += a1 * R[8] + a11 * R[7];     fl_mp += q1 * R[11] + q11 * R[12];     // FKLAMP1, FKLAMP2 | FKLAP12, FKLAP22
+          sl_mp1 += a1 * R[5] + a11 * R[6];    fl_mp1 += q1 * R[9] + q11 * R[10];     // FKLAMPA, FKLAMPB | FKLAPA2, FKLAPB2
+        }
+        if (do_c) { acc_sl[j] -= 2.0 * (ad[0] + ad[1]); acc_fld[j] -= 2.0 * (delad[0] + delad[1]); }
+        if (do_mm) { acc_sl[(j + 4) & 7] += sl_mm; acc_fld[(j + 4) & 7] += fl_mm; }
+        if (do_mm1) { acc_sl[(j + 5) & 7] += sl_mm1; acc_fld[(j + 5) & 7] += fl_mm1; }
+        if (do_mp) { acc_sl[(j + 2) & 7] += sl_mp; acc_fld[(j + 2) & 7] += fl_mp; }
+        if (do_mp1) { acc_sl[(j + 3) & 7] += sl_mp1; acc_fld[(j + 3) & 7] += fl_mp1; }
+      }
+      // finish row rfin (implsch.F90:276-395 for this bin)
+      if (rfin >= 0) {
+        const int r = rfin;
+        const double* rs = rowsc + p * 8;
+        const double f0 = fold;
+        double fldv = sin_[p * A + k];                 // wind input (SINPUT, second SINFLX call)
+        double slv = fldv * f0;
+        double dd;
+        if (ard) {
+          const double b0 = __longlong_as_double((long long)bth0[(r & 3) * NPT + p]);
+          const double ssdsc2_sig = c_dc.SSDSC2 * c_dc.ZPIFR[r];
+          dd = ssdsc2_sig * c_dc.SSDSC6 * sq(fmax(0., b0 * tmp03 - c_dc.SSDSC4)) +
+               ssdsc2_sig * ssdsc6m1 * sq(fmax(0., b_prev * tmp03 - c_dc.SSDSC4));
+        } else dd = rs[6];
+        slv = slv + dd * f0; fldv = fldv + dd;         // SDISSIP
+        slv = slv + acc_sl[(j + 4) & 7]; fldv = fldv + acc_fld[(j + 4) & 7];   // SNONLIN
+        acc_sl[(j + 4) & 7] = 0.0; acc_fld[(j + 4) & 7] = 0.0;
         double ssource = 0.0;
         if (c_dc.lcflx && c_dc.lwvflx_snl) ssource = slv / fmax(1.0 - delt5 * fldv, 1.0);
-        if (m < c_dc.Fr) {
-          if (brk) { slv = slv - sds_bk * f0; fldv = fldv - sds_bk; }   // SDIWBK
-          slv = slv + sbo * f0; fldv = fldv + sbo;                      // SBOTTOM
+        if (r < c_dc.Fr) {
+          if (brk) { slv = slv - sds_bk * f0; fldv = fldv - sds_bk; }          // SDIWBK
+          slv = slv + rs[1] * f0; fldv = fldv + rs[1];                         // SBOTTOM
         }
         const double gtemp1 = fmax(1.0 - delt5 * fldv, 1.0);
         const double gtemp2 = delt * slv / gtemp1;
-        const double flhab = fmin(fabs(gtemp2), tempm);
+        const double flhab = fmin(fabs(gtemp2), rs[0]);
         double fn = f0 + copysign(flhab, gtemp2);
-        fn = fmax(fn, flm[j]);
-        ssource = ssource + deltm * fmin(c_dc.FLMAX[m] - fn, 0.0);
-        fn = fmin(fn, c_dc.FLMAX[m]);
-        fld[o] = fn;    // new spectrum parked in FLD (old FL1 no longer needed below, but keep fl intact until all read)
-        sumt += ssource; sumx += sinth[j] * ssource; sumy += costh[j] * ssource;
-      }
-      philf += sumt * r; xsoc += sumx * cmr; ysoc += sumy * cmr;
-    }
-    __syncwarp();
-    if (c_dc.lcflx) {
-      philf = wsum(philf); xsoc = wsum(xsoc); ysoc = wsum(ysoc);
-      if (active && lane == 0) { s[S_PHILF * n + p] = philf; s[S_XSTROC * n + p] = xsoc; s[S_YSTROC * n + p] = ysoc; }
-    }
-    // from here FLD holds the new FL1
-    double* fn = fld;
-    // ---- FEMEANWS on the new spectrum for WSEMEAN/WSFMEAN (implsch.F90:424-446), LWFLUX only
-    if (c_dc.lwflux) {
-      double e1 = 0.0, e2 = 0.0, el = 0.0;
-      for (int m = 0; m < F; ++m)
-#pragma unroll
-        for (int j = 0; j < KPL; ++j) if (kv[j]) {
-          const int o = m * A + lane + 32 * j;
-          const double xf = W.xl[o] ? fn[o] : 0.0;
-          e1 += c_dc.DFIM[m] * xf; e2 += c_dc.DFIMOFR[m] * xf;
-          if (m == F - 1) el += xf;
+        fn = fmax(fn, flm);
+        ssource = ssource + deltm * fmin(c_dc.FLMAX[r] - fn, 0.0);
+        fn = fmin(fn, c_dc.FLMAX[r]);
+        a_philf += ssource * rs[2]; a_xs += sinth * ssource * rs[3]; a_ys += costh * ssource * rs[3];   // WNFLUXES
+        if (c_dc.lwflux) {   // FEMEANWS on the new spectrum (before the tail is imposed)
+          const double xf = (g_xl[(size_t)r * rstr] != 0.0) ? fn : 0.0;
+          a_e1 += c_dc.DFIM[r] * xf; a_e2 += c_dc.DFIMOFR[r] * xf;
+          if (r == F - 1) a_el += xf;
         }
-      e1 = wsum(e1); e2 = wsum(e2); el = wsum(el);
-      const double em2 = c_dc.EPSMIN + e1 + DELT25 * el;
-      const double fm2 = em2 / (c_dc.EPSMIN + e2 + c_dc.FRTAIL * c_dc.DELTH * el);
-      if (active && lane == 0) {
-        if (em2 < c_dc.WSEMEAN_MIN) { d.f.wsemean[p] = c_dc.WSEMEAN_MIN; d.f.wsfmean[p] = 2. * c_dc.FR[F - 1]; }
-        else { d.f.wsemean[p] = em2; d.f.wsfmean[p] = fm2; }
-      }
-    }
-    // ---- IMPHFTAIL (imphftail.F90:71-87)
-    {
-      const double temp1 = 1.0 / W.tb[TB_XK2CG * EW_MAXF + mij - 1] / W.tb[TB_WAVNUM * EW_MAXF + mij - 1];
-      for (int m = mij; m < F; ++m) {
-        double temp2 = 1.0 / W.tb[TB_XK2CG * EW_MAXF + m] / W.tb[TB_WAVNUM * EW_MAXF + m];
-        temp2 = temp2 / temp1;
-#pragma unroll
-        for (int j = 0; j < KPL; ++j) if (kv[j]) {
-          const int k = lane + 32 * j;
-          fn[m * A + k] = fmax(temp2 * fn[(mij - 1) * A + k], flm[j]);
+        if (r == mij - 1) { fmij = fn; rowsc[p * 8 + 7] = rs[4]; }               // IMPHFTAIL reference row
+        if (r > mij - 1) fn = fmax((rs[4] / rowsc[p * 8 + 7]) * fmij, flm);
+        if (setice) fn = fn * icefree + ice_add;                                 // SETICE
+        a_us += rs[5] * fn * sinth; a_vs += rs[5] * fn * costh;                  // STOKESDRIFT
+        if (r == c_dc.NFRE_ODD - 1) {
+          const double cst = 2.0 * c_dc.DELTH * c_dc.ZPI * c_dc.ZPI * c_dc.ZPI / c_dc.G * p4(c_dc.FR[c_dc.NFRE_ODD - 1]);
+          a_us += cst * sinth * fn; a_vs += cst * costh * fn;
         }
+        sout[p * A + k] = fn;
       }
+      if (rin < F) ring[((rin & 7) * NPT + pt) * A + kt] = xF;
+      b_prev = b_next;
+      __syncthreads();
     }
-    // ---- SETICE (setice.F90:64-86)
-    if (c_dc.licerun && c_dc.lmaskice) {
-      double cireduc, icefree;
-      if (cicover > c_dc.cithrsh) { cireduc = fmax(c_dc.EPSMIN, 1.0 - cicover); icefree = 0.0; }
-      else { cireduc = 0.0; icefree = 1.0; }
-      const double temp = cireduc * c_dc.flmin;
-      for (int m = 0; m < F; ++m)
+  }
+  // last finished row -> HBM
+  if (tvalid) g_out[(size_t)(F - 1) * rstr] = sout[pt * A + kt];
+  // ---- per-point sums over direction, then the scalar closures (thread k == 0 of every point)
+  double* red = cur;   // [8 quantities][NPT][A]  (cur is free now: 6*NPT*A >= 8*NPT*A? no -> use ring as well)
+  red = ring;          // 8*NPT*A doubles
+  red[(0 * NPT + p) * A + k] = a_philf; red[(1 * NPT + p) * A + k] = a_xs; red[(2 * NPT + p) * A + k] = a_ys;
+  red[(3 * NPT + p) * A + k] = a_us; red[(4 * NPT + p) * A + k] = a_vs; red[(5 * NPT + p) * A + k] = a_e1;
+  red[(6 * NPT + p) * A + k] = a_e2; red[(7 * NPT + p) * A + k] = a_el;
+  __syncthreads();
+  if (k == 0 && pvalid) {
+    double q[8];
 #pragma unroll
-        for (int j = 0; j < KPL; ++j) if (kv[j]) {
-          const int o = m * A + lane + 32 * j;
-          fn[o] = fn[o] * icefree + temp * sq(fmax(0.0, coswdif[j]));
-        }
+    for (int x = 0; x < 8; ++x) { double v = 0.0; for (int kk = 0; kk < A; ++kk) v += red[(x * NPT + p) * A + kk]; q[x] = v; }
+    const double ufric = d.f.ufric[pp], aird = d.f.aird[pp], wsw = d.f.wswave[pp];
+    // STOKESDRIFT closure (stokesdrift.F90:118-142)
+    double us = q[3], vs = q[4];
+    if (c_dc.licerun && c_dc.lwamrsetci && cicover > c_dc.cithrsh) { us = 0.016 * wsw * snw * (1.0 - cicover); vs = 0.016 * wsw * csw * (1.0 - cicover); }
+    d.f.ustokes[pp] = fmin(fmax(us, -1.5), 1.5); d.f.vstokes[pp] = fmin(fmax(vs, -1.5), 1.5);
+    if (c_dc.lwflux) {   // implsch.F90:435-446
+      const double DELT25 = c_dc.WETAIL * c_dc.FR[F - 1] * c_dc.DELTH;
+      const double em2 = c_dc.EPSMIN + q[5] + DELT25 * q[7];
+      const double fm2 = em2 / (c_dc.EPSMIN + q[6] + c_dc.FRTAIL * c_dc.DELTH * q[7]);
+      if (em2 < c_dc.WSEMEAN_MIN) { d.f.wsemean[pp] = c_dc.WSEMEAN_MIN; d.f.wsfmean[pp] = 2. * c_dc.FR[F - 1]; }
+      else { d.f.wsemean[pp] = em2; d.f.wsfmean[pp] = fm2; }
     }
-    // ---- STOKESDRIFT (stokesdrift.F90:84-142)
-    {
-      double us = 0.0, vs = 0.0;
-      for (int m = 0; m < c_dc.NFRE_ODD; ++m) {
-        const double stfac = d.f.stokfac[idx3(d, p, m)] * c_dc.DFIM_SIM[m];
-#pragma unroll
-        for (int j = 0; j < KPL; ++j) if (kv[j]) {
-          const double fac3 = stfac * fn[m * A + lane + 32 * j];
-          us += fac3 * sinth[j]; vs += fac3 * costh[j];
-        }
+    if (c_dc.lcflx) {    // WNFLUXES closure (wnfluxes.F90:222-331, LWNEMOCOU=F)
+      const double PHIOC_ICE = -3.75, PHIAW_ICE = 3.75, C1 = 1.03e-3, C2 = 0.04e-3, P1 = 1.48, P2 = -0.21, CDMAX_LOC = 0.003;
+      const double epsus3 = c_dc.EPSUS * sqrt(c_dc.EPSUS);
+      const double cithrsh_inv = 1.0 / fmax(c_dc.cithrsh, 0.01);
+      const double phiwa = s[S_PHIWA * n + pp];
+      double ooval = 1.0, ustar = ufric;
+      if (c_dc.licerun && c_dc.lwamrsetci && cicover > c_dc.ciblock) {
+        ooval = exp(-fmin(p4(cicover * cithrsh_inv), 10.0));
+        const double u10p = fmax(wsw, c_dc.EPSU10);
+        const double cd_bulk = fmin((C1 + C2 * pow(u10p, P1)) * pow(u10p, P2), CDMAX_LOC);
+        const double cd_wave = sq(ufric / u10p);
+        ustar = fmax(sqrt(ooval * cd_wave + (1.0 - ooval) * cd_bulk) * u10p, c_dc.EPSUS);
       }
-      const double cst = 2.0 * c_dc.DELTH * c_dc.ZPI * c_dc.ZPI * c_dc.ZPI / c_dc.G * p4(c_dc.FR[c_dc.NFRE_ODD - 1]);
-#pragma unroll
-      for (int j = 0; j < KPL; ++j) if (kv[j]) {
-        const double ff = fn[(c_dc.NFRE_ODD - 1) * A + lane + 32 * j];
-        us += cst * sinth[j] * ff; vs += cst * costh[j] * ff;
+      const double tau = aird * fmax(sq(ustar), c_dc.EPSUS);
+      double tauxd = tau * snw, tauyd = tau * csw;
+      double tauocxd = tauxd - ooval * q[1], tauocyd = tauyd - ooval * q[2];
+      const double tauoc = fmin(fmax(sqrt(sq(tauocxd) + sq(tauocyd)) / tau, c_dc.TAUOCMIN), c_dc.TAUOCMAX);
+      if (c_dc.lwcouast) {
+        const double ua = d.f.ustra[pp], va = d.f.vstra[pp];
+        if (ua != 0.0 || va != 0.0) { tauxd = ua; tauocxd = ua * tauoc; tauyd = va; tauocyd = va * tauoc; }
       }
-      us = wsum(us); vs = wsum(vs);
-      if (c_dc.licerun && c_dc.lwamrsetci && cicover > c_dc.cithrsh) {
-        const double wsw = d.f.wswave[p];
-        us = 0.016 * wsw * sin(wdwave) * (1.0 - cicover);
-        vs = 0.016 * wsw * cos(wdwave) * (1.0 - cicover);
-      }
-      us = fmin(fmax(us, -1.5), 1.5); vs = fmin(fmax(vs, -1.5), 1.5);
-      if (active && lane == 0) { d.f.ustokes[p] = us; d.f.vstokes[p] = vs; d.f.mij[p] = mij; }
-    }
-    __syncthreads();
-    // ---- cooperative store of FL1 and XLLWS (grid-point index fastest)
-    {
-      const int tot = nptb * AF;
-      for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
-        const int i = idx % nptb, bin = idx / nptb;
-        const long long pp = pb + i;
-        const long long c = pp / d.P;
-        const int ln = (int)(pp - c * d.P);
-        const double* base = smem + (size_t)i * per_pt;
-        const size_t go = (size_t)ln + (size_t)d.P * ((size_t)bin + (size_t)AF * (size_t)c);
-        d.f.fl1[go] = base[AF + bin];
-        const unsigned char* xl = (const unsigned char*)(base + 3 * AF + NTB * EW_MAXF);
-        d.f.xllws[go] = xl[bin] ? 1.0 : 0.0;
-      }
+      d.f.tauxd[pp] = tauxd; d.f.tauyd[pp] = tauyd; d.f.tauocxd[pp] = tauocxd; d.f.tauocyd[pp] = tauocyd; d.f.tauoc[pp] = tauoc;
+      d.f.tauicx[pp] = 0.0; d.f.tauicy[pp] = 0.0;
+      const double xn = aird * fmax(ustar * ustar * ustar, epsus3);
+      double phiocd = ooval * (q[0] - phiwa) + (1.0 - ooval) * PHIOC_ICE * xn;
+      const double phieps = fmin(fmax(phiocd / xn, c_dc.PHIEPSMIN), c_dc.PHIEPSMAX);
+      phiocd = phieps * xn;
+      d.f.phiocd[pp] = phiocd; d.f.phieps[pp] = phieps; d.f.phiaw[pp] = ooval * phiwa / xn + (1.0 - ooval) * PHIAW_ICE;
     }
   }
 }
 
 int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage, cudaStream_t st) {
   if (np <= 0) return 0;
-  const int A = d.A, F = d.F, AF = A * F;
-  if (A > 32 * KPL) { ew_set_error("NANG too large for the warp mapping"); return ECWAM_B200_EINVAL; }
-  const unsigned gs = (unsigned)((np + 127) / 128);
-  const size_t sm1 = (size_t)8 * ((size_t)AF + NTB * EW_MAXF) * sizeof(double);
-  const size_t sm2 = (size_t)6 * ((size_t)3 * AF + NTB * EW_MAXF + (AF + 7) / 8) * sizeof(double);
-  static bool attr_done = false;
-  if (!attr_done) {
-    EW_CUDA_CHECK(cudaFuncSetAttribute(k_spec<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    EW_CUDA_CHECK(cudaFuncSetAttribute(k_spec<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done = true;
-  }
-  if (sm1 > 227 * 1024 || sm2 > 227 * 1024) { ew_set_error("spectrum too large for shared memory"); return ECWAM_B200_EINVAL; }
-  switch (stage) {
-    case 0: k_airsea1<<<gs, 128, 0, st>>>(d, p0, np); break;
-    case 1: k_spec<1><<<(unsigned)((np + 7) / 8), 256, sm1, st>>>(d, p0, np); break;
-    case 2: k_scalar2<<<gs, 128, 0, st>>>(d, p0, np); break;
-    case 3: k_spec<2><<<(unsigned)((np + 5) / 6), 192, sm2, st>>>(d, p0, np); break;
-    case 4: k_scalar4<<<gs, 128, 0, st>>>(d, p0, np); break;
-    default: return ECWAM_B200_EINVAL;
-  }
+  const int A = d.A;
+  if (stage == 0) {
+    k_point<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(d, p0, np);
+  } else if (stage == 1) {
+    const size_t sm = ((size_t)16 * ST_NPT * A + (size_t)EW_MAXSAT * A + ST_NPT * 8 + 4 * ST_NPT) * sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) {
+      EW_CUDA_CHECK(cudaFuncSetAttribute(k_stencil, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      attr_done = true;
+    }
+    k_stencil<<<(unsigned)((np + ST_NPT - 1) / ST_NPT), ST_NPT * A, sm, st>>>(d, p0, np);
+  } else return ECWAM_B200_EINVAL;
   return 0;
 }
 

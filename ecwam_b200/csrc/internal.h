@@ -54,12 +54,13 @@ struct ImplDev {
   const double* fl_lo;     // source of FL1 for m < lo_nf: either f.fl1 (lo_F = F) or the propagation scratch (lo_F = Fr)
   int lo_F;
   double* scr;             // [NSCR][npts] scalar scratch between the kernels
+  double* fldin;           // (P,A,F,C) wind-input linearisation FLD handed from k_point to the stencil kernel
+  long long nloc;          // own points (slots >= nloc of the last chunk are padding)
   DevTabPtr tab;
 };
 int upload_dev_const(const DevConst& h, cudaStream_t st);
-// launches stage 0..4 of the IMPLSCH kernel sequence (k_airsea1, k_spec<1>, k_scalar2, k_spec<2>, k_scalar4)
-// for points [p0, p0+np)
-#define EW_IMPLSCH_NSTAGE 5
+// launches stage 0..1 of the IMPLSCH kernel sequence (k_point, k_stencil) for points [p0, p0+np)
+#define EW_IMPLSCH_NSTAGE 2
 int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage, cudaStream_t st);
 size_t implsch_scratch_doubles(long long npts);
 
