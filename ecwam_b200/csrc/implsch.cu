@@ -386,7 +386,7 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
   }
 }
 
-__global__ void __launch_bounds__(128) k_point(ImplDev d, long long p0, long long np) {
+__global__ void __launch_bounds__(128, 4) k_point(ImplDev d, long long p0, long long np) {
   const long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= p0 + np) return;
   const int A = c_dc.A, F = c_dc.F;
@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(128) k_point(ImplDev d, long long p0, long lon
 // =========================================================================================================
 #define ST_NPT 8
 
-__global__ void __launch_bounds__(ST_NPT * EW_MAXA) k_stencil(ImplDev d, long long p0, long long np) {
+__global__ void __launch_bounds__(ST_NPT * 36, 2) k_stencil(ImplDev d, long long p0, long long np) {
   extern __shared__ double smem[];
   const int A = c_dc.A, F = c_dc.F, NPT = ST_NPT;
   const int NS = 2 * c_dc.NSDSNTH + 1;
@@ -590,7 +590,8 @@ __global__ void __launch_bounds__(ST_NPT * EW_MAXA) k_stencil(ImplDev d, long lo
   double* sout = sin_ + NPT * A;                     // [NPT][A]
   double* satw = sout + NPT * A;                     // [NS][A]
   double* rowsc = satw + EW_MAXSAT * A;              // [NPT][8]
-  unsigned long long* bth0 = (unsigned long long*)(rowsc + NPT * 8);   // [4][NPT]
+  double* bthv = rowsc + NPT * 8;                    // [NPT][A] saturation spectrum of the row being prepared
+  double* bth0 = bthv + NPT * A;                     // [4 row slots][NPT][4 partial maxima]
   const int t = threadIdx.x;
   const int p = t / A, k = t - p * A;                // compute role
   const int kt = t / NPT, pt = t - kt * NPT;         // transfer role (grid point fastest -> 64-byte segments)
@@ -664,7 +665,6 @@ __global__ void __launch_bounds__(ST_NPT * EW_MAXA) k_stencil(ImplDev d, long lo
   const int MFR1STFR = -c_dc.MFRSTLW + 1, MFRLSTFR = F - c_dc.KFRH + MFR1STFR, MLSTHG = c_dc.MLSTHG;
   // ---- prologue: saturation weights, first 4 rows of the ring, zero the BTH0 slots
   if (ard) for (int x = t; x < NS * A; x += blockDim.x) satw[x] = __ldg(d.tab.satweights + x);
-  if (t < 4 * NPT) bth0[t] = 0ull;
   for (int r = 0; r < 4 && r < F; ++r) ring[((r & 7) * NPT + pt) * A + kt] = load_row(r);
   double acc_sl[8], acc_fld[8];
 #pragma unroll
@@ -673,11 +673,10 @@ __global__ void __launch_bounds__(ST_NPT * EW_MAXA) k_stencil(ImplDev d, long lo
   double a_philf = 0.0, a_xs = 0.0, a_ys = 0.0, a_us = 0.0, a_vs = 0.0, a_e1 = 0.0, a_e2 = 0.0, a_el = 0.0;
   __syncthreads();
 
-  for (int mc0 = 0; mc0 < MLSTHG; mc0 += 8) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int MC0 = mc0 + j;
-      if (MC0 >= MLSTHG) break;
+  // acc_*[i] = pending SNONLIN sums of row MC0-4+i (the window slides by one row per step)
+  {
+#pragma unroll 1
+    for (int MC0 = 0; MC0 < MLSTHG; ++MC0) {
       // ================= phase A =================
       const int rin = MC0 + 4, rfin = MC0 - 4, rb = MC0 - 3, rout = MC0 - 5;
       double xF = 0.0, xI = 0.0;
@@ -732,10 +731,9 @@ __global__ void __launch_bounds__(ST_NPT * EW_MAXA) k_stencil(ImplDev d, long lo
         double b = 0.0;
         for (int x = 0; x < NS; ++x) b += satw[x * A + k] * rr[__ldg(d.tab.indicessat + x * A + k)];
         b_next = b * facsat;
-        atomicMax(&bth0[(rb & 3) * NPT + p], (unsigned long long)__double_as_longlong(fmax(b_next, 0.0)));
+        bthv[p * A + k] = b_next;
       }
       if (k == 0) {
-        bth0[((rb + 1) & 3) * NPT + p] = 0ull;
         if (rfin >= 0) {   // per-row scalars of the row finished in this step
           const int r = rfin;
           const size_t o3 = idx3(d, pp, r);
@@ -770,11 +768,11 @@ __global__ void __launch_bounds__(ST_NPT * EW_MAXA) k_stencil(ImplDev d, long lo
           sl_mp += a1 * R[8] + a11 * R[7];     fl_mp += q1 * R[11] + q11 * R[12];     // FKLAMP1, FKLAMP2 | FKLAP12, FKLAP22
           sl_mp1 += a1 * R[5] + a11 * R[6];    fl_mp1 += q1 * R[9] + q11 * R[10];     // FKLAMPA, FKLAMPB | FKLAPA2, FKLAPB2
         }
-        if (do_c) { acc_sl[j] -= 2.0 * (ad[0] + ad[1]); acc_fld[j] -= 2.0 * (delad[0] + delad[1]); }
-        if (do_mm) { acc_sl[(j + 4) & 7] += sl_mm; acc_fld[(j + 4) & 7] += fl_mm; }
-        if (do_mm1) { acc_sl[(j + 5) & 7] += sl_mm1; acc_fld[(j + 5) & 7] += fl_mm1; }
-        if (do_mp) { acc_sl[(j + 2) & 7] += sl_mp; acc_fld[(j + 2) & 7] += fl_mp; }
-        if (do_mp1) { acc_sl[(j + 3) & 7] += sl_mp1; acc_fld[(j + 3) & 7] += fl_mp1; }
+        if (do_c) { acc_sl[4] -= 2.0 * (ad[0] + ad[1]); acc_fld[4] -= 2.0 * (delad[0] + delad[1]); }
+        if (do_mm) { acc_sl[0] += sl_mm; acc_fld[0] += fl_mm; }
+        if (do_mm1) { acc_sl[1] += sl_mm1; acc_fld[1] += fl_mm1; }
+        if (do_mp) { acc_sl[6] += sl_mp; acc_fld[6] += fl_mp; }
+        if (do_mp1) { acc_sl[7] += sl_mp1; acc_fld[7] += fl_mp1; }
       }
       // finish row rfin (implsch.F90:276-395 for this bin)
       if (rfin >= 0) {
@@ -785,14 +783,14 @@ __global__ void __launch_bounds__(ST_NPT * EW_MAXA) k_stencil(ImplDev d, long lo
         double slv = fldv * f0;
         double dd;
         if (ard) {
-          const double b0 = __longlong_as_double((long long)bth0[(r & 3) * NPT + p]);
+          const double* bp = bth0 + ((r & 3) * NPT + p) * 4;
+          const double b0 = fmax(fmax(bp[0], bp[1]), fmax(bp[2], bp[3]));
           const double ssdsc2_sig = c_dc.SSDSC2 * c_dc.ZPIFR[r];
           dd = ssdsc2_sig * c_dc.SSDSC6 * sq(fmax(0., b0 * tmp03 - c_dc.SSDSC4)) +
                ssdsc2_sig * ssdsc6m1 * sq(fmax(0., b_prev * tmp03 - c_dc.SSDSC4));
         } else dd = rs[6];
         slv = slv + dd * f0; fldv = fldv + dd;         // SDISSIP
-        slv = slv + acc_sl[(j + 4) & 7]; fldv = fldv + acc_fld[(j + 4) & 7];   // SNONLIN
-        acc_sl[(j + 4) & 7] = 0.0; acc_fld[(j + 4) & 7] = 0.0;
+        slv = slv + acc_sl[0]; fldv = fldv + acc_fld[0];   // SNONLIN
         double ssource = 0.0;
         if (c_dc.lcflx && c_dc.lwvflx_snl) ssource = slv / fmax(1.0 - delt5 * fldv, 1.0);
         if (r < c_dc.Fr) {
@@ -823,7 +821,15 @@ __global__ void __launch_bounds__(ST_NPT * EW_MAXA) k_stencil(ImplDev d, long lo
         sout[p * A + k] = fn;
       }
       if (rin < F) ring[((rin & 7) * NPT + pt) * A + kt] = xF;
+      if (ard && k < 4 && rb >= 0 && rb < F) {   // BTH0 = max over direction, as 4 partial maxima per point
+        double mx = 0.0;
+        for (int kk = k; kk < A; kk += 4) mx = fmax(mx, bthv[p * A + kk]);
+        bth0[((rb & 3) * NPT + p) * 4 + k] = mx;
+      }
       b_prev = b_next;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) { acc_sl[i] = acc_sl[i + 1]; acc_fld[i] = acc_fld[i + 1]; }
+      acc_sl[7] = 0.0; acc_fld[7] = 0.0;
       __syncthreads();
     }
   }
@@ -887,10 +893,11 @@ __global__ void __launch_bounds__(ST_NPT * EW_MAXA) k_stencil(ImplDev d, long lo
 int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage, cudaStream_t st) {
   if (np <= 0) return 0;
   const int A = d.A;
+  if (A > 36) { ew_set_error("k_stencil is built for NANG <= 36"); return ECWAM_B200_EINVAL; }
   if (stage == 0) {
     k_point<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(d, p0, np);
   } else if (stage == 1) {
-    const size_t sm = ((size_t)16 * ST_NPT * A + (size_t)EW_MAXSAT * A + ST_NPT * 8 + 4 * ST_NPT) * sizeof(double);
+    const size_t sm = ((size_t)17 * ST_NPT * A + (size_t)EW_MAXSAT * A + ST_NPT * 8 + 16 * ST_NPT) * sizeof(double);
     static bool attr_done = false;
     if (!attr_done) {
       EW_CUDA_CHECK(cudaFuncSetAttribute(k_stencil, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
