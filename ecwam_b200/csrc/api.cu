@@ -547,6 +547,7 @@ static ImplDev make_impl(H* h, bool from_fl3) {
   d.scr = h->scr.p;
   d.fldin = h->fldin.p;
   d.nloc = h->pd.nloc;
+  d.lwflux = h->par.lwflux;
   d.tab = h->tab;
   return d;
 }

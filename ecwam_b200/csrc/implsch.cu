@@ -218,12 +218,30 @@ __device__ __forceinline__ double rhowgdfth(int m, int mij) {
 // and the direction tables come out of constant memory with a warp-uniform index.  Writes: the wind-input
 // linearisation FLD (scratch, same layout as FL1), XLLWS (final), MIJ and the 1-D stress fields.
 // =========================================================================================================
+#define KP_NTH 128    // threads per block of k_point
 struct PointSrc {
   const double* lo;   // frequencies [0, mlo): propagation scratch or FL1 itself
   const double* hi;   // FL1
   int mlo;
   size_t kstr;        // P
+  double* stage;      // shared memory: [2 stages][A][KP_NTH], this thread's column = + threadIdx.x
 };
+// Row pipeline: the NANG values of frequency m of this thread's grid point go HBM -> shared memory with cp.async
+// (8 bytes per lane = one coalesced 256-byte row segment per warp and direction) one whole row ahead of the arithmetic,
+// so that ~NANG loads per thread are in flight instead of one.
+__device__ __forceinline__ void row_issue(const PointSrc& S, int m, int A) {
+  const double* g = (m < S.mlo ? S.lo : S.hi) + (size_t)m * A * S.kstr;
+  unsigned sa = (unsigned)__cvta_generic_to_shared(S.stage + (size_t)(m & 1) * A * KP_NTH);
+  for (int k = 0; k < A; ++k) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(g));
+    sa += KP_NTH * 8;
+    g += S.kstr;
+  }
+  asm volatile("cp.async.commit_group;\n" ::);
+}
+template <int N>
+__device__ __forceinline__ void row_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ const double* row_ptr(const PointSrc& S, int m, int A) { return S.stage + (size_t)(m & 1) * A * KP_NTH; }
 
 template <int NGST, bool LLSNEG, bool STORE>
 __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d, long long p, double fac, double flmc,
@@ -231,7 +249,7 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
                                              double temp2_sw, double pturb, double aird_pvisc, double* __restrict__ fld_out,
                                              double* __restrict__ xl_out, double* sumx, double* sumy, double* sumt,
                                              double& ws_em, double& ws_fm, double& ws_last, double& phiwa_acc,
-                                             double& uorbt_acc, double& aorb_acc, double* mom) {
+                                             double& uorbt_acc, double& aorb_acc, double* mom, bool dostore) {
   const int A = c_dc.A, F = c_dc.F;
   const double CONST1 = c_dc.BETAMAXOXKAPPA2;
   const size_t kstr = S.kstr;
@@ -259,13 +277,15 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
   const double CONST3 = c_dc.idamping * (2.0 * c_dc.XKAPPA / CONST1);
   const double xkappad = 1.0 / c_dc.XKAPPA;
   const double avg = 1.0 / NGST;
+  row_issue(S, 0, A);
   for (int m = 0; m < F; ++m) {
+    if (m + 1 < F) { row_issue(S, m + 1, A); row_wait<1>(); } else row_wait<0>();
     const size_t o3 = idx3(d, p, m);
     const double wavnum = d.f.wavnum[o3], cinv = d.f.cinv[o3];
     const double sig = c_dc.ZPIFR[m], sig2 = sig * sig;
     const double zcn = log(wavnum * z0m);
     const double dfim = c_dc.DFIM[m], dfimofr = c_dc.DFIMOFR[m], rhowg = c_dc.RHOWG_DFIM[m];
-    const double* fsrc = (m < S.mlo ? S.lo + (size_t)m * A * kstr * 1 : S.hi + (size_t)m * A * kstr);
+    const double* fsrc = row_ptr(S, m, A);
     double* fo = STORE ? fld_out + (size_t)m * A * kstr : nullptr;
     double* xo = STORE ? xl_out + (size_t)m * A * kstr : nullptr;
     const bool lastm = (m == F - 1);
@@ -312,7 +332,7 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
     for (int g = 0; g < NGST; ++g) { sx[g] = 0.0; sy[g] = 0.0; }
 #pragma unroll 2
     for (int k = 0; k < A; ++k) {
-      double f = fmax(__ldg(fsrc + (size_t)k * kstr) * fac, c_dc.EPSMIN);      // SDEPTHLIM applied on the fly
+      double f = fmax(fsrc[k * KP_NTH] * fac, c_dc.EPSMIN);                      // SDEPTHLIM applied on the fly
       const double snk = c_dc.SINTH[k], csk = c_dc.COSTH[k];
       const double cwd = csk * csw + snk * snw;                                  // COSWDIF(K)
       traw += f;                                                                 // FKMEAN sees the spectrum before the floor
@@ -359,8 +379,10 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
       const double slv = fldv * f;
       st += spos;
       if (STORE) {
-        fo[(size_t)k * kstr] = fldv;
-        xo[(size_t)k * kstr] = xll ? 1.0 : 0.0;
+        if (dostore) {
+          fo[(size_t)k * kstr] = fldv;
+          xo[(size_t)k * kstr] = xll ? 1.0 : 0.0;
+        }
         phiwa_acc += (slv - spos) * rhowg;
       }
       if (xll) { ws_em += dfim * f; ws_fm += dfimofr * f; if (lastm) ws_last += f; }
@@ -386,15 +408,18 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
   }
 }
 
-__global__ void __launch_bounds__(128, 4) k_point(ImplDev d, long long p0, long long np) {
-  const long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= p0 + np) return;
+__global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, long long np) {
+  extern __shared__ double smem[];
+  long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = p < p0 + np;
+  if (!valid) p = p0 + np - 1;      // tail threads shadow the last point (they keep the cp.async pipeline uniform) and never store
   const int A = c_dc.A, F = c_dc.F;
   const long long n = d.npts;
   double* s = d.scr;
   const long long c = p / d.P;
   const int i = (int)(p - c * d.P);
   PointSrc S;
+  S.stage = smem + threadIdx.x;
   S.kstr = (size_t)d.P;
   S.hi = d.f.fl1 + (size_t)i + (size_t)d.P * A * F * (size_t)c;
   if (d.lo_F != d.F) {
@@ -413,11 +438,13 @@ __global__ void __launch_bounds__(128, 4) k_point(ImplDev d, long long p0, long 
   double fac = 1.0;
   if (c_dc.lbiwbk) {
     double em = c_dc.EPSMIN, last = 0.0;
+    row_issue(S, 0, A);
     for (int m = 0; m < F; ++m) {
-      const double* fsrc = (m < S.mlo ? S.lo : S.hi) + (size_t)m * A * S.kstr;
+      if (m + 1 < F) { row_issue(S, m + 1, A); row_wait<1>(); } else row_wait<0>();
+      const double* fsrc = row_ptr(S, m, A);
       double t = 0.0;
 #pragma unroll 4
-      for (int k = 0; k < A; ++k) t += __ldg(fsrc + (size_t)k * S.kstr);
+      for (int k = 0; k < A; ++k) t += fsrc[k * KP_NTH];
       em += c_dc.DFIM[m] * t;
       last = t;
     }
@@ -432,7 +459,7 @@ __global__ void __launch_bounds__(128, 4) k_point(ImplDev d, long long p0, long 
   double ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc;
   double mom[6] = {0, 0, 0, 0, 0, 0};
   sinput_point<1, false, false>(S, d, p, fac, flmc, snw, csw, ustar, z0, raorw, 0.0, 0.0, 0.0, 0.0, nullptr, nullptr, sumx, sumy,
-                                sumt, ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc, mom);
+                                sumt, ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc, mom, false);
   // FKMEAN (fkmean.F90:60-154)
   const double COEFM1 = c_dc.FRTAIL * c_dc.DELTH;
   const double COEF1 = c_dc.WP1TAIL * c_dc.DELTH * sq(c_dc.FR[F - 1]);
@@ -443,9 +470,11 @@ __global__ void __launch_bounds__(128, 4) k_point(ImplDev d, long long p0, long 
   const double f1mean = (c_dc.EPSMIN + mom[2] + COEF1 * mom[5]) / emean;
   const double akmean = sq(emean / (c_dc.EPSMIN + mom[3] + COEFA * mom[5]));
   const double xkmean = sq((c_dc.EPSMIN + mom[4] + COEFX * mom[5]) / emean);
-  s[S_EMEAN * n + p] = emean; s[S_FMEAN * n + p] = fmean; s[S_F1MEAN * n + p] = f1mean;
-  s[S_AKMEAN * n + p] = akmean; s[S_XKMEAN * n + p] = xkmean;
-  s[S_FAC * n + p] = fac;
+  if (valid) {
+    s[S_EMEAN * n + p] = emean; s[S_FMEAN * n + p] = fmean; s[S_F1MEAN * n + p] = f1mean;
+    s[S_AKMEAN * n + p] = akmean; s[S_XKMEAN * n + p] = xkmean;
+    s[S_FAC * n + p] = fac;
+  }
 
   auto frcut = [&](double fmeanws, double ust) -> int {   // frcutindex.F90:84-97
     if (cicover > c_dc.cithrsh_tail) return F;
@@ -510,7 +539,7 @@ __global__ void __launch_bounds__(128, 4) k_point(ImplDev d, long long p0, long 
   }
   // ---- SINFLX call 2: AIRSEA (IUSFG=1), SINPUT (NGST=2, LLSNEG), FEMEANWS, FRCUTINDEX, STRESSO (LLPHIWA)
   taut_z0(1, wswave, wdwave, tauw, tauwdir, ustar, z0, z0b, ch);
-  d.f.ufric[p] = ustar; d.f.z0m[p] = z0; d.f.z0b[p] = z0b; d.f.chrnck[p] = ch;
+  if (valid) { d.f.ufric[p] = ustar; d.f.z0m[p] = z0; d.f.z0b[p] = z0b; d.f.chrnck[p] = ch; }
   const double sig_n = wsigstar(ustar, z0, d.f.wstar[p]);
   double temp2_sw = 0.0, pturb = 0.0, aird_pvisc = 0.0;
   if (c_dc.iphys == 1) {   // sinput_ard.F90:179-271
@@ -536,16 +565,18 @@ __global__ void __launch_bounds__(128, 4) k_point(ImplDev d, long long p0, long 
   double* xl_out = d.f.xllws + (size_t)i + (size_t)d.P * A * F * (size_t)c;
   double dum[6];
   sinput_point<2, true, true>(S, d, p, fac, flmc, snw, csw, ustar, z0, raorw, sig_n, temp2_sw, pturb, aird_pvisc, fld_out, xl_out,
-                              sumx, sumy, sumt, ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc, dum);
+                              sumx, sumy, sumt, ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc, dum, valid);
   const double emeanws = c_dc.EPSMIN + ws_em + DELT25 * ws_last;
   const double fmeanws = emeanws / (c_dc.EPSMIN + ws_fm + c_dc.FRTAIL * c_dc.DELTH * ws_last);
   const int mij = frcut(fmeanws, ustar);
   double phiwa;
   stresso(mij, ustar, z0, true, phiwa_acc, tauw, tauwdir, phiwa);
-  d.f.tauw[p] = tauw; d.f.tauwdir[p] = tauwdir; d.f.mij[p] = mij;
-  s[S_PHIWA * n + p] = phiwa;
-  s[S_MIJ * n + p] = (double)mij;
-  s[S_USFM * n + p] = ustar * fmax(fmeanws, fmean);
+  if (valid) {
+    d.f.tauw[p] = tauw; d.f.tauwdir[p] = tauwdir; d.f.mij[p] = mij;
+    s[S_PHIWA * n + p] = phiwa;
+    s[S_MIJ * n + p] = (double)mij;
+    s[S_USFM * n + p] = ustar * fmax(fmeanws, fmean);
+  }
   // ---- SDIWBK (sdiwbk.F90:69-104)
   double sds = 0.0;
   if (c_dc.lbiwbk && d.f.depth[p] < 50.0) {
@@ -562,7 +593,7 @@ __global__ void __launch_bounds__(128, 4) k_point(ImplDev d, long long p0, long 
     q = fmin(q, 1.0);
     sds = 2.0 * alph * q * f1mean;
   }
-  s[S_SDS * n + p] = sds;
+  if (valid) s[S_SDS * n + p] = sds;
 }
 
 
@@ -579,43 +610,45 @@ __global__ void __launch_bounds__(128, 4) k_point(ImplDev d, long long p0, long 
 // (snonlin.F90:253-308) becomes a gather through the inverse direction tables: no atomics, fixed summation order.
 // =========================================================================================================
 #define ST_NPT 8
+enum { TQ_FACSAT = 0, TQ_SBO, TQ_CINV, TQ_TAIL, TQ_STF, TQ_JAN, TQ_N };
 
-__global__ void __launch_bounds__(ST_NPT * 36, 2) k_stencil(ImplDev d, long long p0, long long np) {
+template <bool LWFLUX>
+__global__ void __maxnreg__(112) k_stencil(ImplDev d, long long p0, long long np) {
   extern __shared__ double smem[];
   const int A = c_dc.A, F = c_dc.F, NPT = ST_NPT;
-  const int NS = 2 * c_dc.NSDSNTH + 1;
-  double* ring = smem;                               // [8][NPT][A]
-  double* cur = ring + 8 * NPT * A;                  // [6][NPT][A]
-  double* sin_ = cur + 6 * NPT * A;                  // [NPT][A]
-  double* sout = sin_ + NPT * A;                     // [NPT][A]
-  double* satw = sout + NPT * A;                     // [NS][A]
-  double* rowsc = satw + EW_MAXSAT * A;              // [NPT][8]
-  double* bthv = rowsc + NPT * 8;                    // [NPT][A] saturation spectrum of the row being prepared
-  double* bth0 = bthv + NPT * A;                     // [4 row slots][NPT][4 partial maxima]
+  const int PS = NPT * A;                            // one (point, direction) plane
+  const int NSD = c_dc.NSDSNTH, NS = 2 * NSD + 1;
+  double* ring = smem;                               // [8][PS]  spectrum rows (frequencies) r with slot r&7
+  double* cur = ring + 8 * PS;                       // [6][PS]  AD(kh), DELAP(kh), DELAM(kh) of the current MC
+  double* sin_ = cur + 6 * PS;                       // [PS]     wind-input FLD of the row being finished
+  double* sout = sin_ + PS;                          // [PS]     finished row on its way out
+  double* bthv = sout + PS;                          // [PS]     saturation spectrum of the row being prepared
+  double* satw = bthv + PS;                          // [NS][A]
+  double* tb = satw + EW_MAXSAT * A;                 // [TQ_N][F][NPT] per-(point, frequency) scalars
+  double* bth0 = tb + TQ_N * F * NPT;                // [4 row slots][NPT][4 partial maxima]
   const int t = threadIdx.x;
   const int p = t / A, k = t - p * A;                // compute role
   const int kt = t / NPT, pt = t - kt * NPT;         // transfer role (grid point fastest -> 64-byte segments)
+  const int me = p * A + k, mt = pt * A + kt;
   const long long pbase = p0 + (long long)blockIdx.x * NPT;
   const long long plast = p0 + np - 1;
   const bool pvalid = pbase + p <= plast, tvalid = pbase + pt <= plast;
   const long long pp = min(pbase + p, plast), tp = min(pbase + pt, plast);
   const long long n = d.npts;
   const double* s = d.scr;
-  // ---- transfer-role constants
+  const size_t P = (size_t)d.P;
+  const size_t rstr = P * A;                          // row (frequency) stride in the chunked layout
+  // ---- transfer-role pointers (advance by one row per step)
   const long long tc = tp / d.P;
   const int ti = (int)(tp - tc * d.P);
-  const size_t P = (size_t)d.P;
-  const double* g_hi = d.f.fl1 + (size_t)ti + P * A * F * (size_t)tc + P * (size_t)kt;
-  const double* g_lo = g_hi;
+  const size_t off_hi = (size_t)ti + P * A * F * (size_t)tc + P * (size_t)kt;     // element (ti, kt, 0, tc) of a (P,A,F,C) array
+  size_t off_lo = off_hi;
   int mlo = 0;
   if (d.lo_F != d.F) {
     const int il = (tp < d.nloc) ? ti : 0;
-    g_lo = d.fl_lo + (size_t)il + P * A * d.lo_F * (size_t)tc + P * (size_t)kt;
+    off_lo = (size_t)il + P * A * d.lo_F * (size_t)tc + P * (size_t)kt;
     mlo = d.Fr;
   }
-  const double* g_fld = d.fldin + (size_t)ti + P * A * F * (size_t)tc + P * (size_t)kt;
-  double* g_out = d.f.fl1 + (size_t)ti + P * A * F * (size_t)tc + P * (size_t)kt;
-  const size_t rstr = P * A;                          // row (frequency) stride in the chunked layout
   double t_fac, t_floor;
   {
     const double wd = d.f.wdwave[tp], ci = d.f.cicover[tp];
@@ -624,7 +657,7 @@ __global__ void __launch_bounds__(ST_NPT * 36, 2) k_stencil(ImplDev d, long long
     t_floor = (1. - 0.9 * fmin(ci, 0.99)) * c_dc.flmin * sq(fmax(0.0, cwd));
   }
   auto load_row = [&](int r) -> double {             // depth-limited (+ floored at NFRE) spectrum row r of (pt, kt)
-    double v = __ldg((r < mlo ? g_lo : g_hi) + (size_t)r * rstr);
+    double v = __ldg((r < mlo ? d.fl_lo + off_lo : d.f.fl1 + off_hi) + (size_t)r * rstr);
     v = fmax(v * t_fac, c_dc.EPSMIN);
     if (r == F - 1) v = fmax(v, t_floor);
     return v;
@@ -637,221 +670,234 @@ __global__ void __launch_bounds__(ST_NPT * 36, 2) k_stencil(ImplDev d, long long
   const double coswdif = costh * csw + sinth * snw;
   const double flm = (1. - 0.9 * fmin(cicover, 0.99)) * c_dc.flmin * sq(fmax(0.0, coswdif));
   const int mij = (int)s[S_MIJ * n + pp];
-  const double usfm = s[S_USFM * n + pp], sds_bk = s[S_SDS * n + pp];
-  const double emean = s[S_EMEAN * n + pp], f1mean = s[S_F1MEAN * n + pp], akmean = s[S_AKMEAN * n + pp],
-               xkmean = s[S_XKMEAN * n + pp];
+  const double usfm_delt = s[S_USFM * n + pp] * c_dc.delt, sds_bk = s[S_SDS * n + pp];
   const bool brk = c_dc.lbiwbk && depth < 50.0;
-  double enhfr = fmax(0.75 * depth * akmean, 0.5);
-  enhfr = 1.0 + (5.5 / enhfr) * (1.0 - .833 * enhfr) * exp(-1.25 * enhfr);
-  int ik1[2], ik11[2], ik2[2], ik21[2], k1[2], k11[2], k2[2], k21[2];
+  const bool ard = c_dc.iphys == 1;
+  double enhfr;
+  {
+    const double akmean = s[S_AKMEAN * n + pp];
+    enhfr = fmax(0.75 * depth * akmean, 0.5);
+    enhfr = 1.0 + (5.5 / enhfr) * (1.0 - .833 * enhfr) * exp(-1.25 * enhfr);
+  }
+  // element offsets inside a plane: interaction partners (K1W..K21W) and their inverses for the gather
+  // (two 16-bit offsets per register: lo = first table, hi = second)
+  unsigned o1p[2], o2p[2], g1p[2], g2p[2];
 #pragma unroll
   for (int kh = 0; kh < 2; ++kh) {
-    k1[kh] = __ldg(d.tab.k1w + kh * A + k); k11[kh] = __ldg(d.tab.k11w + kh * A + k);
-    k2[kh] = __ldg(d.tab.k2w + kh * A + k); k21[kh] = __ldg(d.tab.k21w + kh * A + k);
-    ik1[kh] = __ldg(d.tab.ik1w + kh * A + k); ik11[kh] = __ldg(d.tab.ik11w + kh * A + k);
-    ik2[kh] = __ldg(d.tab.ik2w + kh * A + k); ik21[kh] = __ldg(d.tab.ik21w + kh * A + k);
+    o1p[kh] = (unsigned)(p * A + __ldg(d.tab.k1w + kh * A + k)) | ((unsigned)(p * A + __ldg(d.tab.k11w + kh * A + k)) << 16);
+    o2p[kh] = (unsigned)(p * A + __ldg(d.tab.k2w + kh * A + k)) | ((unsigned)(p * A + __ldg(d.tab.k21w + kh * A + k)) << 16);
+    g1p[kh] = (unsigned)(p * A + __ldg(d.tab.ik1w + kh * A + k)) | ((unsigned)(p * A + __ldg(d.tab.ik11w + kh * A + k)) << 16);
+    g2p[kh] = (unsigned)(p * A + __ldg(d.tab.ik2w + kh * A + k)) | ((unsigned)(p * A + __ldg(d.tab.ik21w + kh * A + k)) << 16);
   }
-  const long long pc = pp / d.P;
-  const double* g_xl = d.f.xllws + (size_t)(pp - pc * d.P) + P * A * F * (size_t)pc + P * (size_t)k;
-  double cireduc = 0.0, icefree = 1.0;
-  if (c_dc.licerun && c_dc.lmaskice && cicover > c_dc.cithrsh) { cireduc = fmax(c_dc.EPSMIN, 1.0 - cicover); icefree = 0.0; }
-  const double ice_add = cireduc * c_dc.flmin * sq(fmax(0.0, coswdif));
+  double icefree = 1.0, ice_add = 0.0;
   const bool setice = c_dc.licerun && c_dc.lmaskice;
+  if (setice && cicover > c_dc.cithrsh) { icefree = 0.0; ice_add = fmax(c_dc.EPSMIN, 1.0 - cicover) * c_dc.flmin * sq(fmax(0.0, coswdif)); }
   const double delt = c_dc.delt, deltm = 1.0 / delt, delt5 = c_dc.ximp * delt;
-  const double tpiinv = 1.0 / c_dc.ZPI, tmp03 = 1.0 / (c_dc.SDSBR * c_dc.MICHE), ssdsc6m1 = 1. - c_dc.SSDSC6;
-  const double sbo_const = -2.0 * 0.038 * c_dc.GM1;
-  const double sds_jan = c_dc.CDIS * c_dc.ZPI * f1mean * sq(emean) * p4(xkmean);
-  const bool ard = c_dc.iphys == 1;
+  const double tmp03 = 1.0 / (c_dc.SDSBR * c_dc.MICHE);
   const int MFR1STFR = -c_dc.MFRSTLW + 1, MFRLSTFR = F - c_dc.KFRH + MFR1STFR, MLSTHG = c_dc.MLSTHG;
-  // ---- prologue: saturation weights, first 4 rows of the ring, zero the BTH0 slots
+  // ---- prologue: per-(point, frequency) scalars, saturation weights, first 4 rows of the ring
+  for (int x = t; x < F * NPT; x += blockDim.x) {
+    const int m = x / NPT, q = x - m * NPT;
+    const long long qp = min(pbase + q, plast);
+    const long long qc = qp / d.P;
+    const size_t o3 = (size_t)(qp - qc * d.P) + P * ((size_t)m + (size_t)F * (size_t)qc);
+    const double wn = d.f.wavnum[o3], ci = d.f.cinv[o3], xk = d.f.xk2cg[o3], dep = d.f.depth[qp];
+    tb[(TQ_FACSAT * F + m) * NPT + q] = wn * (1.0 / c_dc.ZPI) * xk;
+    double sbo = 0.0;
+    if (m < c_dc.Fr && dep < c_dc.bathymax) sbo = (-2.0 * 0.038 * c_dc.GM1) * wn / sinh(fmin(2.0 * dep * wn, 50.0));   // sbottom.F90:76-97
+    tb[(TQ_SBO * F + m) * NPT + q] = sbo;
+    tb[(TQ_CINV * F + m) * NPT + q] = ci;
+    tb[(TQ_TAIL * F + m) * NPT + q] = 1.0 / xk / wn;                                    // imphftail.F90:73-81
+    tb[(TQ_STF * F + m) * NPT + q] = (m < c_dc.NFRE_ODD) ? d.f.stokfac[o3] * c_dc.DFIM_SIM[m] : 0.0;
+    double tj = 0.0;
+    if (!ard) {   // SDISSIP_JAN (sdissip_jan.F90:96-132)
+      const double emean = s[S_EMEAN * n + qp], f1mean = s[S_F1MEAN * n + qp], xkmean = s[S_XKMEAN * n + qp];
+      const double sds = c_dc.CDIS * c_dc.ZPI * f1mean * sq(emean) * p4(xkmean);
+      const double xx = wn / xkmean;
+      tj = sds * xx * ((1.0 - c_dc.DELTA_SDIS) + c_dc.DELTA_SDIS * xx) + c_dc.rnu * c_dc.CDISVIS * sq(wn);
+    }
+    tb[(TQ_JAN * F + m) * NPT + q] = tj;
+  }
   if (ard) for (int x = t; x < NS * A; x += blockDim.x) satw[x] = __ldg(d.tab.satweights + x);
-  for (int r = 0; r < 4 && r < F; ++r) ring[((r & 7) * NPT + pt) * A + kt] = load_row(r);
-  double acc_sl[8], acc_fld[8];
+  for (int r = 0; r < 4 && r < F; ++r) ring[(r & 7) * PS + mt] = load_row(r);
+  double acc_sl[8], acc_fld[8];   // pending SNONLIN sums of rows MC0-4 .. MC0+3 (window slides one row per step)
 #pragma unroll
   for (int j = 0; j < 8; ++j) { acc_sl[j] = 0.0; acc_fld[j] = 0.0; }
   double b_prev = 0.0, fmij = 0.0;
   double a_philf = 0.0, a_xs = 0.0, a_ys = 0.0, a_us = 0.0, a_vs = 0.0, a_e1 = 0.0, a_e2 = 0.0, a_el = 0.0;
+  size_t off_xl = 0;
+  if (LWFLUX) { const long long pc = pp / d.P; off_xl = (size_t)(pp - pc * d.P) + P * A * F * (size_t)pc + P * (size_t)k; }
+  int ksat0 = k - NSD;
+  if (ksat0 < 0) ksat0 += A;
   __syncthreads();
+  const double tail_mij = tb[(TQ_TAIL * F + (mij - 1)) * NPT + p];
 
-  // acc_*[i] = pending SNONLIN sums of row MC0-4+i (the window slides by one row per step)
-  {
 #pragma unroll 1
-    for (int MC0 = 0; MC0 < MLSTHG; ++MC0) {
-      // ================= phase A =================
-      const int rin = MC0 + 4, rfin = MC0 - 4, rb = MC0 - 3, rout = MC0 - 5;
-      double xF = 0.0, xI = 0.0;
-      if (rin < F) xF = load_row(rin);
-      if (rfin >= 0 && rfin < F) xI = __ldg(g_fld + (size_t)rfin * rstr);
-      if (rout >= 0 && tvalid) g_out[(size_t)rout * rstr] = sout[pt * A + kt];
-      // DIA interaction values of centre frequency MC = MC0+1 (snonlin.F90:225-250)
-      const int IC = c_dc.INLCOEF[MC0][0], IP = c_dc.INLCOEF[MC0][1], IP1 = c_dc.INLCOEF[MC0][2], IM = c_dc.INLCOEF[MC0][3],
-                IM1 = c_dc.INLCOEF[MC0][4];
-      const double* R = c_dc.RNLCOEF[MC0];
-      const double ftemp = c_dc.AF11[MC0] * enhfr;
-      const int MC = MC0 + 1;
-      const int branch = (MC > MFR1STFR && MC < MFRLSTFR) ? 0 : (MC >= MFRLSTFR ? 1 : 2);
-      bool do_c, do_mm, do_mm1, do_mp, do_mp1;
-      {
-        const int MP = c_dc.IKP[MC0], MP1 = c_dc.IKP1[MC0], MM1 = c_dc.IKM1[MC0];
-        if (branch == 0) { do_c = do_mm = do_mm1 = do_mp = do_mp1 = true; }
-        else if (branch == 1) { do_mm = true; do_mm1 = MM1 <= F; do_c = do_mm1 && MC <= F; do_mp = do_c && MP <= F; do_mp1 = do_mp && MP1 <= F; }
-        else { do_mm = false; do_mm1 = MM1 >= 1; do_c = true; do_mp = true; do_mp1 = true; }
-      }
-      const double* rIP = ring + (((IP - 1) & 7) * NPT + p) * A;
-      const double* rIP1 = ring + (((IP1 - 1) & 7) * NPT + p) * A;
-      const double* rIM = ring + (((IM - 1) & 7) * NPT + p) * A;
-      const double* rIM1 = ring + (((IM1 - 1) & 7) * NPT + p) * A;
-      const double* rIC = ring + (((IC - 1) & 7) * NPT + p) * A;
-      double ad[2], delad[2];
-      {
-        const double fc = rIC[k];
-        const double fij = (branch == 0) ? fc : fc * R[0];
-        const double fcen = ftemp * fij;
-#pragma unroll
-        for (int kh = 0; kh < 2; ++kh) {
-          const double sap = R[1] * rIP[k1[kh]] + R[2] * rIP[k11[kh]] + R[3] * rIP1[k1[kh]] + R[4] * rIP1[k11[kh]];
-          const double sam = R[13] * rIM[k2[kh]] + R[14] * rIM[k21[kh]] + R[15] * rIM1[k2[kh]] + R[16] * rIM1[k21[kh]];
-          double fad1 = fij * (sap + sam);
-          const double fad2 = fad1 - 2.0 * sap * sam;
-          fad1 = fad1 + fad2;
-          ad[kh] = fad2 * fcen;
-          delad[kh] = fad1 * ftemp;
-          cur[((0 + kh) * NPT + p) * A + k] = ad[kh];
-          cur[((2 + kh) * NPT + p) * A + k] = (fij - 2.0 * sam) * c_dc.DAL1 * fcen;   // DELAP
-          cur[((4 + kh) * NPT + p) * A + k] = (fij - 2.0 * sap) * c_dc.DAL2 * fcen;   // DELAM
-        }
-      }
-      const double fold = (rfin >= 0) ? ring[((rfin & 7) * NPT + p) * A + k] : 0.0;
-      // saturation spectrum of row rb for SDISSIP_ARD (sdissip_ard.F90:142-160)
-      double b_next = 0.0;
-      if (ard && rb >= 0 && rb < F) {
-        const size_t o3 = idx3(d, pp, rb);
-        const double facsat = d.f.wavnum[o3] * tpiinv * d.f.xk2cg[o3];
-        const double* rr = ring + ((rb & 7) * NPT + p) * A;
-        double b = 0.0;
-        for (int x = 0; x < NS; ++x) b += satw[x * A + k] * rr[__ldg(d.tab.indicessat + x * A + k)];
-        b_next = b * facsat;
-        bthv[p * A + k] = b_next;
-      }
-      if (k == 0) {
-        if (rfin >= 0) {   // per-row scalars of the row finished in this step
-          const int r = rfin;
-          const size_t o3 = idx3(d, pp, r);
-          const double wn = d.f.wavnum[o3], ci = d.f.cinv[o3], xk = d.f.xk2cg[o3];
-          double* rs = rowsc + p * 8;
-          rs[0] = usfm * (c_dc.COFRM4[r] * delt);
-          double sbo = 0.0;
-          if (r < c_dc.Fr && depth < c_dc.bathymax) sbo = sbo_const * wn / sinh(fmin(2.0 * depth * wn, 50.0));
-          rs[1] = sbo;
-          const double rr = rhowgdfth(r, mij);
-          rs[2] = rr; rs[3] = ci * rr;
-          rs[4] = 1.0 / xk / wn;                                      // IMPHFTAIL 1/(k^3 cg)
-          rs[5] = (r < c_dc.NFRE_ODD) ? d.f.stokfac[o3] * c_dc.DFIM_SIM[r] : 0.0;
-          if (!ard) { const double x = wn / xkmean; rs[6] = sds_jan * x * ((1.0 - c_dc.DELTA_SDIS) + c_dc.DELTA_SDIS * x) + c_dc.rnu * c_dc.CDISVIS * sq(wn); }
-        }
-      }
-      sin_[pt * A + kt] = xI;
-      __syncthreads();
-      // ================= phase B =================
-      // gather the quadruplet contributions of MC into the pending rows (snonlin.F90:253-308, :333-410, :446-490)
-      {
-        double sl_mm = 0, fl_mm = 0, sl_mm1 = 0, fl_mm1 = 0, sl_mp = 0, fl_mp = 0, sl_mp1 = 0, fl_mp1 = 0;
-#pragma unroll
-        for (int kh = 0; kh < 2; ++kh) {
-          const double* cA = cur + ((0 + kh) * NPT + p) * A;
-          const double* cP = cur + ((2 + kh) * NPT + p) * A;
-          const double* cM = cur + ((4 + kh) * NPT + p) * A;
-          const double a2 = cA[ik2[kh]], a21 = cA[ik21[kh]], m2 = cM[ik2[kh]], m21 = cM[ik21[kh]];
-          const double a1 = cA[ik1[kh]], a11 = cA[ik11[kh]], q1 = cP[ik1[kh]], q11 = cP[ik11[kh]];
-          sl_mm += a2 * R[20] + a21 * R[19];   fl_mm += m2 * R[23] + m21 * R[24];     // FKLAMM1, FKLAMM2 | FKLAM12, FKLAM22
-          sl_mm1 += a2 * R[17] + a21 * R[18];  fl_mm1 += m2 * R[21] + m21 * R[22];    // FKLAMMA, FKLAMMB | FKLAMA2, FKLAMB2
-          sl_mp += a1 * R[8] + a11 * R[7];     fl_mp += q1 * R[11] + q11 * R[12];     // FKLAMP1, FKLAMP2 | FKLAP12, FKLAP22
-          sl_mp1 += a1 * R[5] + a11 * R[6];    fl_mp1 += q1 * R[9] + q11 * R[10];     // FKLAMPA, FKLAMPB | FKLAPA2, FKLAPB2
-        }
-        if (do_c) { acc_sl[4] -= 2.0 * (ad[0] + ad[1]); acc_fld[4] -= 2.0 * (delad[0] + delad[1]); }
-        if (do_mm) { acc_sl[0] += sl_mm; acc_fld[0] += fl_mm; }
-        if (do_mm1) { acc_sl[1] += sl_mm1; acc_fld[1] += fl_mm1; }
-        if (do_mp) { acc_sl[6] += sl_mp; acc_fld[6] += fl_mp; }
-        if (do_mp1) { acc_sl[7] += sl_mp1; acc_fld[7] += fl_mp1; }
-      }
-      // finish row rfin (implsch.F90:276-395 for this bin)
-      if (rfin >= 0) {
-        const int r = rfin;
-        const double* rs = rowsc + p * 8;
-        const double f0 = fold;
-        double fldv = sin_[p * A + k];                 // wind input (SINPUT, second SINFLX call)
-        double slv = fldv * f0;
-        double dd;
-        if (ard) {
-          const double* bp = bth0 + ((r & 3) * NPT + p) * 4;
-          const double b0 = fmax(fmax(bp[0], bp[1]), fmax(bp[2], bp[3]));
-          const double ssdsc2_sig = c_dc.SSDSC2 * c_dc.ZPIFR[r];
-          dd = ssdsc2_sig * c_dc.SSDSC6 * sq(fmax(0., b0 * tmp03 - c_dc.SSDSC4)) +
-               ssdsc2_sig * ssdsc6m1 * sq(fmax(0., b_prev * tmp03 - c_dc.SSDSC4));
-        } else dd = rs[6];
-        slv = slv + dd * f0; fldv = fldv + dd;         // SDISSIP
-        slv = slv + acc_sl[0]; fldv = fldv + acc_fld[0];   // SNONLIN
-        double ssource = 0.0;
-        if (c_dc.lcflx && c_dc.lwvflx_snl) ssource = slv / fmax(1.0 - delt5 * fldv, 1.0);
-        if (r < c_dc.Fr) {
-          if (brk) { slv = slv - sds_bk * f0; fldv = fldv - sds_bk; }          // SDIWBK
-          slv = slv + rs[1] * f0; fldv = fldv + rs[1];                         // SBOTTOM
-        }
-        const double gtemp1 = fmax(1.0 - delt5 * fldv, 1.0);
-        const double gtemp2 = delt * slv / gtemp1;
-        const double flhab = fmin(fabs(gtemp2), rs[0]);
-        double fn = f0 + copysign(flhab, gtemp2);
-        fn = fmax(fn, flm);
-        ssource = ssource + deltm * fmin(c_dc.FLMAX[r] - fn, 0.0);
-        fn = fmin(fn, c_dc.FLMAX[r]);
-        a_philf += ssource * rs[2]; a_xs += sinth * ssource * rs[3]; a_ys += costh * ssource * rs[3];   // WNFLUXES
-        if (c_dc.lwflux) {   // FEMEANWS on the new spectrum (before the tail is imposed)
-          const double xf = (g_xl[(size_t)r * rstr] != 0.0) ? fn : 0.0;
-          a_e1 += c_dc.DFIM[r] * xf; a_e2 += c_dc.DFIMOFR[r] * xf;
-          if (r == F - 1) a_el += xf;
-        }
-        if (r == mij - 1) { fmij = fn; rowsc[p * 8 + 7] = rs[4]; }               // IMPHFTAIL reference row
-        if (r > mij - 1) fn = fmax((rs[4] / rowsc[p * 8 + 7]) * fmij, flm);
-        if (setice) fn = fn * icefree + ice_add;                                 // SETICE
-        a_us += rs[5] * fn * sinth; a_vs += rs[5] * fn * costh;                  // STOKESDRIFT
-        if (r == c_dc.NFRE_ODD - 1) {
-          const double cst = 2.0 * c_dc.DELTH * c_dc.ZPI * c_dc.ZPI * c_dc.ZPI / c_dc.G * p4(c_dc.FR[c_dc.NFRE_ODD - 1]);
-          a_us += cst * sinth * fn; a_vs += cst * costh * fn;
-        }
-        sout[p * A + k] = fn;
-      }
-      if (rin < F) ring[((rin & 7) * NPT + pt) * A + kt] = xF;
-      if (ard && k < 4 && rb >= 0 && rb < F) {   // BTH0 = max over direction, as 4 partial maxima per point
-        double mx = 0.0;
-        for (int kk = k; kk < A; kk += 4) mx = fmax(mx, bthv[p * A + kk]);
-        bth0[((rb & 3) * NPT + p) * 4 + k] = mx;
-      }
-      b_prev = b_next;
-#pragma unroll
-      for (int i = 0; i < 7; ++i) { acc_sl[i] = acc_sl[i + 1]; acc_fld[i] = acc_fld[i + 1]; }
-      acc_sl[7] = 0.0; acc_fld[7] = 0.0;
-      __syncthreads();
+  for (int MC0 = 0; MC0 < MLSTHG; ++MC0) {
+    // ================= phase A =================
+    const int rin = MC0 + 4, rfin = MC0 - 4, rb = MC0 - 3, rout = MC0 - 5;
+    double xF = 0.0, xI = 0.0;
+    if (rin < F) xF = load_row(rin);
+    if (rfin >= 0) xI = __ldg(d.fldin + off_hi + (size_t)rfin * rstr);
+    if (rout >= 0 && tvalid) d.f.fl1[off_hi + (size_t)rout * rstr] = sout[mt];
+    // DIA interaction values of centre frequency MC = MC0+1 (snonlin.F90:225-250)
+    const double* R = c_dc.RNLCOEF[MC0];
+    const double ftemp = c_dc.AF11[MC0] * enhfr;
+    const int MC = MC0 + 1;
+    const int branch = (MC > MFR1STFR && MC < MFRLSTFR) ? 0 : (MC >= MFRLSTFR ? 1 : 2);
+    bool do_c, do_mm, do_mm1, do_mp, do_mp1;
+    {
+      const int MP = MC + 2, MP1 = MC + 3, MM1 = MC - 3;
+      if (branch == 0) { do_c = do_mm = do_mm1 = do_mp = do_mp1 = true; }
+      else if (branch == 1) { do_mm = true; do_mm1 = MM1 <= F; do_c = do_mm1 && MC <= F; do_mp = do_c && MP <= F; do_mp1 = do_mp && MP1 <= F; }
+      else { do_mm = false; do_mm1 = MM1 >= 1; do_c = true; do_mp = true; do_mp1 = true; }
     }
+    double ad[2], delad[2];
+    {
+      const double* rIP = ring + ((c_dc.INLCOEF[MC0][1] - 1) & 7) * PS;
+      const double* rIP1 = ring + ((c_dc.INLCOEF[MC0][2] - 1) & 7) * PS;
+      const double* rIM = ring + ((c_dc.INLCOEF[MC0][3] - 1) & 7) * PS;
+      const double* rIM1 = ring + ((c_dc.INLCOEF[MC0][4] - 1) & 7) * PS;
+      const double fc = ring[((c_dc.INLCOEF[MC0][0] - 1) & 7) * PS + me];
+      const double fij = (branch == 0) ? fc : fc * R[0];
+      const double fcen = ftemp * fij;
+#pragma unroll
+      for (int kh = 0; kh < 2; ++kh) {
+        const int o1 = o1p[kh] & 0xffff, o11 = o1p[kh] >> 16, o2 = o2p[kh] & 0xffff, o21 = o2p[kh] >> 16;
+        const double sap = R[1] * rIP[o1] + R[2] * rIP[o11] + R[3] * rIP1[o1] + R[4] * rIP1[o11];
+        const double sam = R[13] * rIM[o2] + R[14] * rIM[o21] + R[15] * rIM1[o2] + R[16] * rIM1[o21];
+        double fad1 = fij * (sap + sam);
+        const double fad2 = fad1 - 2.0 * sap * sam;
+        fad1 = fad1 + fad2;
+        ad[kh] = fad2 * fcen;
+        delad[kh] = fad1 * ftemp;
+        cur[(0 + kh) * PS + me] = ad[kh];
+        cur[(2 + kh) * PS + me] = (fij - 2.0 * sam) * c_dc.DAL1 * fcen;   // DELAP
+        cur[(4 + kh) * PS + me] = (fij - 2.0 * sap) * c_dc.DAL2 * fcen;   // DELAM
+      }
+    }
+    const double fold = (rfin >= 0) ? ring[(rfin & 7) * PS + me] : 0.0;
+    // saturation spectrum of row rb for SDISSIP_ARD (sdissip_ard.F90:142-160): cyclic window of 2*NSDSNTH+1 directions
+    double b_next = 0.0;
+    if (ard && rb >= 0 && rb < F) {
+      const double* rr = ring + (rb & 7) * PS + p * A;
+      const double* ws = satw + k;
+      int kk = ksat0;
+      double b = 0.0;
+      for (int x = 0; x < NS; ++x) {
+        b += ws[0] * rr[kk];
+        ws += A;
+        kk = (kk + 1 == A) ? 0 : kk + 1;
+      }
+      b_next = b * tb[(TQ_FACSAT * F + rb) * NPT + p];
+      bthv[me] = b_next;
+    }
+    sin_[mt] = xI;
+    __syncthreads();
+    // ================= phase B =================
+    // gather the quadruplet contributions of MC into the pending rows (snonlin.F90:253-308, :333-410, :446-490)
+    {
+      double sl_mm = 0, fl_mm = 0, sl_mm1 = 0, fl_mm1 = 0, sl_mp = 0, fl_mp = 0, sl_mp1 = 0, fl_mp1 = 0;
+#pragma unroll
+      for (int kh = 0; kh < 2; ++kh) {
+        const double* cA = cur + (0 + kh) * PS;
+        const double* cP = cur + (2 + kh) * PS;
+        const double* cM = cur + (4 + kh) * PS;
+        const int g1 = g1p[kh] & 0xffff, g11 = g1p[kh] >> 16, g2 = g2p[kh] & 0xffff, g21 = g2p[kh] >> 16;
+        const double a2 = cA[g2], a21 = cA[g21], m2 = cM[g2], m21 = cM[g21];
+        const double a1 = cA[g1], a11 = cA[g11], q1 = cP[g1], q11 = cP[g11];
+        sl_mm += a2 * R[20] + a21 * R[19];   fl_mm += m2 * R[23] + m21 * R[24];     // FKLAMM1, FKLAMM2 | FKLAM12, FKLAM22
+        sl_mm1 += a2 * R[17] + a21 * R[18];  fl_mm1 += m2 * R[21] + m21 * R[22];    // FKLAMMA, FKLAMMB | FKLAMA2, FKLAMB2
+        sl_mp += a1 * R[8] + a11 * R[7];     fl_mp += q1 * R[11] + q11 * R[12];     // FKLAMP1, FKLAMP2 | FKLAP12, FKLAP22
+        sl_mp1 += a1 * R[5] + a11 * R[6];    fl_mp1 += q1 * R[9] + q11 * R[10];     // FKLAMPA, FKLAMPB | FKLAPA2, FKLAPB2
+      }
+      if (do_c) { acc_sl[4] -= 2.0 * (ad[0] + ad[1]); acc_fld[4] -= 2.0 * (delad[0] + delad[1]); }
+      if (do_mm) { acc_sl[0] += sl_mm; acc_fld[0] += fl_mm; }
+      if (do_mm1) { acc_sl[1] += sl_mm1; acc_fld[1] += fl_mm1; }
+      if (do_mp) { acc_sl[6] += sl_mp; acc_fld[6] += fl_mp; }
+      if (do_mp1) { acc_sl[7] += sl_mp1; acc_fld[7] += fl_mp1; }
+    }
+    // finish row rfin (implsch.F90:276-395 for this bin)
+    if (rfin >= 0) {
+      const int r = rfin;
+      const double f0 = fold;
+      double fldv = sin_[me];                          // wind input (SINPUT, second SINFLX call)
+      double slv = fldv * f0;
+      double dd;
+      if (ard) {
+        const double* bp = bth0 + ((r & 3) * NPT + p) * 4;
+        const double b0 = fmax(fmax(bp[0], bp[1]), fmax(bp[2], bp[3]));
+        const double ssdsc2_sig = c_dc.SSDSC2 * c_dc.ZPIFR[r];
+        dd = ssdsc2_sig * c_dc.SSDSC6 * sq(fmax(0., b0 * tmp03 - c_dc.SSDSC4)) +
+             ssdsc2_sig * (1. - c_dc.SSDSC6) * sq(fmax(0., b_prev * tmp03 - c_dc.SSDSC4));
+      } else dd = tb[(TQ_JAN * F + r) * NPT + p];
+      slv = slv + dd * f0; fldv = fldv + dd;           // SDISSIP
+      slv = slv + acc_sl[0]; fldv = fldv + acc_fld[0]; // SNONLIN
+      double ssource = 0.0;
+      if (c_dc.lcflx && c_dc.lwvflx_snl) ssource = slv / fmax(1.0 - delt5 * fldv, 1.0);
+      if (r < c_dc.Fr) {
+        if (brk) { slv = slv - sds_bk * f0; fldv = fldv - sds_bk; }              // SDIWBK
+        const double sbo = tb[(TQ_SBO * F + r) * NPT + p];
+        slv = slv + sbo * f0; fldv = fldv + sbo;                                 // SBOTTOM
+      }
+      const double gtemp1 = fmax(1.0 - delt5 * fldv, 1.0);
+      const double gtemp2 = delt * slv / gtemp1;
+      const double flhab = fmin(fabs(gtemp2), usfm_delt * c_dc.COFRM4[r]);
+      double fn = f0 + copysign(flhab, gtemp2);
+      fn = fmax(fn, flm);
+      ssource = ssource + deltm * fmin(c_dc.FLMAX[r] - fn, 0.0);
+      fn = fmin(fn, c_dc.FLMAX[r]);
+      {   // WNFLUXES sums (wnfluxes.F90:200-220)
+        const double rr = rhowgdfth(r, mij);
+        const double cmr = tb[(TQ_CINV * F + r) * NPT + p] * rr;
+        a_philf += ssource * rr; a_xs += sinth * ssource * cmr; a_ys += costh * ssource * cmr;
+      }
+      if (LWFLUX) {   // FEMEANWS on the new spectrum (before the tail is imposed)
+        const double xf = (d.f.xllws[off_xl + (size_t)r * rstr] != 0.0) ? fn : 0.0;
+        a_e1 += c_dc.DFIM[r] * xf; a_e2 += c_dc.DFIMOFR[r] * xf;
+        if (r == F - 1) a_el += xf;
+      }
+      if (r == mij - 1) fmij = fn;                                               // IMPHFTAIL reference row
+      if (r > mij - 1) fn = fmax((tb[(TQ_TAIL * F + r) * NPT + p] / tail_mij) * fmij, flm);
+      if (setice) fn = fn * icefree + ice_add;                                   // SETICE
+      const double stf = tb[(TQ_STF * F + r) * NPT + p];
+      a_us += stf * fn * sinth; a_vs += stf * fn * costh;                        // STOKESDRIFT
+      if (r == c_dc.NFRE_ODD - 1) {
+        const double cst = 2.0 * c_dc.DELTH * c_dc.ZPI * c_dc.ZPI * c_dc.ZPI / c_dc.G * p4(c_dc.FR[c_dc.NFRE_ODD - 1]);
+        a_us += cst * sinth * fn; a_vs += cst * costh * fn;
+      }
+      sout[me] = fn;
+    }
+    if (rin < F) ring[(rin & 7) * PS + mt] = xF;
+    if (ard && t < 4 * NPT && rb >= 0 && rb < F) {   // BTH0 = max over direction, as 4 partial maxima per point (warp 0)
+      const int q = t >> 2, part = t & 3;
+      double mx = 0.0;
+      for (int kk = part; kk < A; kk += 4) mx = fmax(mx, bthv[q * A + kk]);
+      bth0[((rb & 3) * NPT + q) * 4 + part] = mx;
+    }
+    b_prev = b_next;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) { acc_sl[i] = acc_sl[i + 1]; acc_fld[i] = acc_fld[i + 1]; }
+    acc_sl[7] = 0.0; acc_fld[7] = 0.0;
+    __syncthreads();
   }
   // last finished row -> HBM
-  if (tvalid) g_out[(size_t)(F - 1) * rstr] = sout[pt * A + kt];
-  // ---- per-point sums over direction, then the scalar closures (thread k == 0 of every point)
-  double* red = cur;   // [8 quantities][NPT][A]  (cur is free now: 6*NPT*A >= 8*NPT*A? no -> use ring as well)
-  red = ring;          // 8*NPT*A doubles
-  red[(0 * NPT + p) * A + k] = a_philf; red[(1 * NPT + p) * A + k] = a_xs; red[(2 * NPT + p) * A + k] = a_ys;
-  red[(3 * NPT + p) * A + k] = a_us; red[(4 * NPT + p) * A + k] = a_vs; red[(5 * NPT + p) * A + k] = a_e1;
-  red[(6 * NPT + p) * A + k] = a_e2; red[(7 * NPT + p) * A + k] = a_el;
+  if (tvalid) d.f.fl1[off_hi + (size_t)(F - 1) * rstr] = sout[mt];
+  // ---- per-point sums over direction, then the scalar closures (one thread per point)
+  double* red = ring;          // 8 planes
+  red[0 * PS + me] = a_philf; red[1 * PS + me] = a_xs; red[2 * PS + me] = a_ys; red[3 * PS + me] = a_us;
+  red[4 * PS + me] = a_vs; red[5 * PS + me] = a_e1; red[6 * PS + me] = a_e2; red[7 * PS + me] = a_el;
   __syncthreads();
   if (k == 0 && pvalid) {
     double q[8];
 #pragma unroll
-    for (int x = 0; x < 8; ++x) { double v = 0.0; for (int kk = 0; kk < A; ++kk) v += red[(x * NPT + p) * A + kk]; q[x] = v; }
+    for (int x = 0; x < 8; ++x) { double v = 0.0; for (int kk = 0; kk < A; ++kk) v += red[x * PS + p * A + kk]; q[x] = v; }
     const double ufric = d.f.ufric[pp], aird = d.f.aird[pp], wsw = d.f.wswave[pp];
     // STOKESDRIFT closure (stokesdrift.F90:118-142)
     double us = q[3], vs = q[4];
     if (c_dc.licerun && c_dc.lwamrsetci && cicover > c_dc.cithrsh) { us = 0.016 * wsw * snw * (1.0 - cicover); vs = 0.016 * wsw * csw * (1.0 - cicover); }
     d.f.ustokes[pp] = fmin(fmax(us, -1.5), 1.5); d.f.vstokes[pp] = fmin(fmax(vs, -1.5), 1.5);
-    if (c_dc.lwflux) {   // implsch.F90:435-446
+    if (LWFLUX) {   // implsch.F90:435-446
       const double DELT25 = c_dc.WETAIL * c_dc.FR[F - 1] * c_dc.DELTH;
       const double em2 = c_dc.EPSMIN + q[5] + DELT25 * q[7];
       const double fm2 = em2 / (c_dc.EPSMIN + q[6] + c_dc.FRTAIL * c_dc.DELTH * q[7]);
@@ -895,15 +941,20 @@ int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage
   const int A = d.A;
   if (A > 36) { ew_set_error("k_stencil is built for NANG <= 36"); return ECWAM_B200_EINVAL; }
   if (stage == 0) {
-    k_point<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(d, p0, np);
+    const size_t smp = (size_t)2 * A * KP_NTH * sizeof(double);
+    static bool attr_p = false;
+    if (!attr_p) { EW_CUDA_CHECK(cudaFuncSetAttribute(k_point, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_p = true; }
+    k_point<<<(unsigned)((np + KP_NTH - 1) / KP_NTH), KP_NTH, smp, st>>>(d, p0, np);
   } else if (stage == 1) {
-    const size_t sm = ((size_t)17 * ST_NPT * A + (size_t)EW_MAXSAT * A + ST_NPT * 8 + 16 * ST_NPT) * sizeof(double);
+    const size_t sm = ((size_t)17 * ST_NPT * A + (size_t)EW_MAXSAT * A + (size_t)TQ_N * d.F * ST_NPT + 16 * ST_NPT) * sizeof(double);
     static bool attr_done = false;
     if (!attr_done) {
-      EW_CUDA_CHECK(cudaFuncSetAttribute(k_stencil, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      EW_CUDA_CHECK(cudaFuncSetAttribute(k_stencil<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      EW_CUDA_CHECK(cudaFuncSetAttribute(k_stencil<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       attr_done = true;
     }
-    k_stencil<<<(unsigned)((np + ST_NPT - 1) / ST_NPT), ST_NPT * A, sm, st>>>(d, p0, np);
+    if (d.lwflux) k_stencil<true><<<(unsigned)((np + ST_NPT - 1) / ST_NPT), ST_NPT * A, sm, st>>>(d, p0, np);
+    else k_stencil<false><<<(unsigned)((np + ST_NPT - 1) / ST_NPT), ST_NPT * A, sm, st>>>(d, p0, np);
   } else return ECWAM_B200_EINVAL;
   return 0;
 }

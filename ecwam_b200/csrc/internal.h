@@ -55,6 +55,7 @@ struct ImplDev {
   int lo_F;
   double* scr;             // [NSCR][npts] scalar scratch between the kernels
   double* fldin;           // (P,A,F,C) wind-input linearisation FLD handed from k_point to the stencil kernel
+  int lwflux;              // YOWCOUP LWFLUX (selects the k_stencil instance that also forms WSEMEAN/WSFMEAN)
   long long nloc;          // own points (slots >= nloc of the last chunk are padding)
   DevTabPtr tab;
 };
