@@ -240,6 +240,13 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
     pc.kpm_p[k] = (k + 1 >= A) ? 0 : k + 1;
     pc.sinth[k] = sn; pc.costh[k] = cs;
   }
+  {  // the quadrants must be contiguous direction ranges in the order quad = 0, 2, 3, 1 (TH(K) increasing from DELTH/2)
+    static const int order[4] = {0, 2, 3, 1};
+    int k = 0;
+    for (int j = 0; j < 4; ++j) { pc.kq[j] = k; while (k < A && pc.quad[k] == order[j]) ++k; }
+    pc.kq[4] = k;
+    if (k != A) EW_FAIL_H(h, ECWAM_B200_EINVAL, "directions are not ordered by compass quadrant (TH must increase from DELTH/2)");
+  }
   pc.delpro[0] = p.delpro_lf; pc.delpro[1] = p.idelpro;
   for (int v = 0; v < 2; ++v) {
     const double delth0 = 0.25 * pc.delpro[v] / tables->delth;
@@ -544,6 +551,7 @@ static ImplDev make_impl(H* h, bool from_fl3) {
   d.f = h->dev;
   d.fl_lo = from_fl3 ? h->fl3.p : h->dev.fl1;
   d.lo_F = from_fl3 ? d.Fr : d.F;
+  d.lo_on = from_fl3 ? 1 : 0;
   d.scr = h->scr.p;
   d.fldin = h->fldin.p;
   d.nloc = h->pd.nloc;
@@ -552,13 +560,12 @@ static ImplDev make_impl(H* h, bool from_fl3) {
   return d;
 }
 
-int ecwam_b200_implsch(ecwam_b200_handle h, int ichnk0, int nchnk) {
-  if (!h) EW_FAIL(ECWAM_B200_EINVAL, "null handle");
+static int implsch_range(H* h, int ichnk0, int nchnk, bool from_fl3) {
   if (!h->bound) EW_FAIL(ECWAM_B200_ESTATE, "fields not bound");
   if (ichnk0 < 1 || nchnk < 1 || ichnk0 + nchnk - 1 > h->par.nchnk) EW_FAIL(ECWAM_B200_EINVAL, "chunk range out of bounds");
   int rc = ensure_const(h);
   if (rc) return rc;
-  ImplDev d = make_impl(h, false);
+  ImplDev d = make_impl(h, from_fl3);
   static const char* kStage[EW_IMPLSCH_NSTAGE] = {"implsch_point", "implsch_stencil"};
   for (int s = 0; s < EW_IMPLSCH_NSTAGE; ++s) {
     ScopedTimer t(h, kStage[s]);
@@ -569,16 +576,30 @@ int ecwam_b200_implsch(ecwam_b200_handle h, int ichnk0, int nchnk) {
   EW_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
+int ecwam_b200_implsch(ecwam_b200_handle h, int ichnk0, int nchnk) {
+  if (!h) EW_FAIL(ECWAM_B200_EINVAL, "null handle");
+  return implsch_range(h, ichnk0, nchnk, false);
+}
 int ecwam_b200_implsch_all(ecwam_b200_handle h) {
   if (!h) EW_FAIL(ECWAM_B200_EINVAL, "null handle");
-  return ecwam_b200_implsch(h, 1, h->par.nchnk);
+  return implsch_range(h, 1, h->par.nchnk, false);
 }
 
+// PROPAG_WAM + IMPLSCH with the block->chunk copy of PROPAG_WAM (propag_wam.F90:368-405) folded into IMPLSCH's loads:
+// the IMPLSCH kernels read the propagated frequencies straight from the propagation scratch and write FL1.
 int ecwam_b200_wamintgr(ecwam_b200_handle h) {
   if (!h) EW_FAIL(ECWAM_B200_EINVAL, "null handle");
-  int rc = ecwam_b200_propag(h);
+  bool lf_in_fl3 = true;
+  int rc = propag_core(h, &lf_in_fl3);
   if (rc) return rc;
-  return ecwam_b200_implsch_all(h);
+  if (!lf_in_fl3) {   // odd number of fast-wave sub-steps left the low frequencies in FL1: finish PROPAG_WAM the plain way
+    const PropDev& d = h->pd;
+    launch_copyback(d, h->fl3.p, h->dev.fl1, h->par.ifrelfmax, d.Fr, h->st);
+    launch_pad(d, h->dev.fl1, 0, h->par.ifrelfmax, h->st);
+    h->nlaunch += 2;
+    return implsch_range(h, 1, h->par.nchnk, false);
+  }
+  return implsch_range(h, 1, h->par.nchnk, true);
 }
 
 int ecwam_b200_synchronize(ecwam_b200_handle h) {

@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
   S.stage = smem + threadIdx.x;
   S.kstr = (size_t)d.P;
   S.hi = d.f.fl1 + (size_t)i + (size_t)d.P * A * F * (size_t)c;
-  if (d.lo_F != d.F) {
+  if (d.lo_on) {
     // propagation scratch (P,A,Fr,C): padded lanes of the last chunk take the chunk's first point (propag_wam.F90:388-398)
     const int il = (p < d.nloc) ? i : 0;
     S.lo = d.fl_lo + (size_t)il + (size_t)d.P * A * d.lo_F * (size_t)c;
@@ -644,7 +644,7 @@ __global__ void __maxnreg__(112) k_stencil(ImplDev d, long long p0, long long np
   const size_t off_hi = (size_t)ti + P * A * F * (size_t)tc + P * (size_t)kt;     // element (ti, kt, 0, tc) of a (P,A,F,C) array
   size_t off_lo = off_hi;
   int mlo = 0;
-  if (d.lo_F != d.F) {
+  if (d.lo_on) {
     const int il = (tp < d.nloc) ? ti : 0;
     off_lo = (size_t)il + P * A * d.lo_F * (size_t)tc + P * (size_t)kt;
     mlo = d.Fr;
@@ -943,7 +943,11 @@ int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage
   if (stage == 0) {
     const size_t smp = (size_t)2 * A * KP_NTH * sizeof(double);
     static bool attr_p = false;
-    if (!attr_p) { EW_CUDA_CHECK(cudaFuncSetAttribute(k_point, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_p = true; }
+    if (!attr_p) {
+      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      attr_p = true;
+    }
     k_point<<<(unsigned)((np + KP_NTH - 1) / KP_NTH), KP_NTH, smp, st>>>(d, p0, np);
   } else if (stage == 1) {
     const size_t sm = ((size_t)17 * ST_NPT * A + (size_t)EW_MAXSAT * A + (size_t)TQ_N * d.F * ST_NPT + 16 * ST_NPT) * sizeof(double);
@@ -951,6 +955,8 @@ int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage
     if (!attr_done) {
       EW_CUDA_CHECK(cudaFuncSetAttribute(k_stencil<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       EW_CUDA_CHECK(cudaFuncSetAttribute(k_stencil<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      EW_CUDA_CHECK(cudaFuncSetAttribute(k_stencil<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      EW_CUDA_CHECK(cudaFuncSetAttribute(k_stencil<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       attr_done = true;
     }
     if (d.lwflux) k_stencil<true><<<(unsigned)((np + ST_NPT - 1) / ST_NPT), ST_NPT * A, sm, st>>>(d, p0, np);

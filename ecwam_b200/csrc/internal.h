@@ -22,6 +22,7 @@ struct PropDev {
 // per-direction tables of the CTU scheme (ctuwupdt.F90:111-161), constant memory
 struct PropConst {
   int quad[EW_MAXA];        // 0: cos>=0,sin>=0  1: cos>=0,sin<0  2: cos<0,sin>=0  3: cos<0,sin<0
+  int kq[5];                // directions [kq[j],kq[j+1]) form compass quadrant j: quad = 0, 2, 3, 1 (TH increasing)
   int kpm_m[EW_MAXA];       // KPM(K,-1) 0-based
   int kpm_p[EW_MAXA];       // KPM(K,+1)
   double sinth[EW_MAXA], costh[EW_MAXA];
@@ -53,6 +54,7 @@ struct ImplDev {
   ecwam_b200_fields f;     // device pointers
   const double* fl_lo;     // source of FL1 for m < lo_nf: either f.fl1 (lo_F = F) or the propagation scratch (lo_F = Fr)
   int lo_F;
+  int lo_on;               // 1: frequencies < Fr are read from fl_lo (layout (P,A,lo_F,C)), padded lanes from lane 0
   double* scr;             // [NSCR][npts] scalar scratch between the kernels
   double* fldin;           // (P,A,F,C) wind-input linearisation FLD handed from k_point to the stencil kernel
   int lwflux;              // YOWCOUP LWFLUX (selects the k_stencil instance that also forms WSEMEAN/WSFMEAN)

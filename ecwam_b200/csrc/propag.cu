@@ -83,28 +83,72 @@ __device__ __forceinline__ double ctu_update(const PointM& q, int k, int idp, do
          wp * fkp;
 }
 
-// One thread = one own grid point x one group of MG frequencies; loops the directions.
+// One thread = one own grid point x one group of MG frequencies.  For every frequency the directions are walked
+// quadrant by quadrant (the upwind selectors JXO/JYO/KCR of ctuwupdt.F90:111-161 are constant inside a quadrant of
+// the compass), so only the five upwind neighbours of the running quadrant are addressed, and two directions are
+// in flight per iteration (12 independent gathers).
 // grid = (ceil(nloc/blockDim), ngroups): blockIdx.x (points) varies fastest so that the rows north and south
 // of the running row stay L2-resident for one frequency group at a time.
-__global__ void __launch_bounds__(128) propags2_kernel(PropDev d, SpecSrc src, double* __restrict__ dst, long long dcstride,
-                                                       int m0, int m1, int MG, int msplit) {
+template <int JX1, int JY1, int KC>
+__device__ __forceinline__ void ctu_quadrant(const PropDev& d, const SpecSrc& src, PointM& q, int l, int m, int idp, int k0, int k1,
+                                             const double* __restrict__ ps, double* __restrict__ pd) {
+  if (k0 >= k1) return;
+  const int nl = d.nloc;
+  // upwind neighbours of this quadrant: longitude JX1, latitude JY1 (closest, second closest), corner KC (ditto)
+  const int e_lon = __ldg(d.nbr + (size_t)(JX1 - 1) * nl + l);
+  const int e_la1 = __ldg(d.nbr + (size_t)(2 + (JY1 - 1)) * nl + l);
+  const int e_la2 = __ldg(d.nbr + (size_t)(4 + (JY1 - 1)) * nl + l);
+  const int e_c1 = __ldg(d.nbr + (size_t)(6 + (KC - 1)) * nl + l);
+  const int e_c2 = __ldg(d.nbr + (size_t)(10 + (KC - 1)) * nl + l);
+  const double *p_lon, *p_la1, *p_la2, *p_c1, *p_c2;
+  int s_lon, s_la1, s_la2, s_c1, s_c2;
+  nbr_base(d, src, e_lon, m, p_lon, s_lon);
+  nbr_base(d, src, e_la1, m, p_la1, s_la1);
+  nbr_base(d, src, e_la2, m, p_la2, s_la2);
+  nbr_base(d, src, e_c1, m, p_c1, s_c1);
+  nbr_base(d, src, e_c2, m, p_c2, s_c2);
+  q.wlat[JY1 - 1] = __ldg(d.wl + (size_t)(JY1 - 1) * nl + l);
+  q.wlatm1[JY1 - 1] = 1.0 - q.wlat[JY1 - 1];
+  q.wcor[KC - 1] = __ldg(d.wl + (size_t)(2 + KC - 1) * nl + l);
+  q.wcorm1[KC - 1] = 1.0 - q.wcor[KC - 1];
+  const int P = d.P;
+  int k = k0;
+  for (; k + 1 < k1; k += 2) {
+    const int ka = k, kb = k + 1;
+    const double a0 = ps[(size_t)ka * P], b0 = ps[(size_t)kb * P];
+    const double am = ps[(size_t)c_prop.kpm_m[ka] * P], bp = ps[(size_t)c_prop.kpm_p[kb] * P];
+    const double a1 = __ldg(p_lon + (size_t)ka * s_lon), b1 = __ldg(p_lon + (size_t)kb * s_lon);
+    const double a2 = __ldg(p_la1 + (size_t)ka * s_la1), b2 = __ldg(p_la1 + (size_t)kb * s_la1);
+    const double a3 = __ldg(p_la2 + (size_t)ka * s_la2), b3 = __ldg(p_la2 + (size_t)kb * s_la2);
+    const double a4 = __ldg(p_c1 + (size_t)ka * s_c1), b4 = __ldg(p_c1 + (size_t)kb * s_c1);
+    const double a5 = __ldg(p_c2 + (size_t)ka * s_c2), b5 = __ldg(p_c2 + (size_t)kb * s_c2);
+    // KPM(ka,+1) = kb and KPM(kb,-1) = ka inside a quadrant
+    const double ra = ctu_update<JX1, JY1, KC>(q, ka, idp, a0, a1, a2, a3, a4, a5, am, b0);
+    const double rb = ctu_update<JX1, JY1, KC>(q, kb, idp, b0, b1, b2, b3, b4, b5, a0, bp);
+    pd[(size_t)ka * P] = ra;
+    pd[(size_t)kb * P] = rb;
+  }
+  for (; k < k1; ++k) {
+    const double f0 = ps[(size_t)k * P];
+    const double fkm = ps[(size_t)c_prop.kpm_m[k] * P], fkp = ps[(size_t)c_prop.kpm_p[k] * P];
+    pd[(size_t)k * P] = ctu_update<JX1, JY1, KC>(q, k, idp, f0, __ldg(p_lon + (size_t)k * s_lon), __ldg(p_la1 + (size_t)k * s_la1),
+                                                 __ldg(p_la2 + (size_t)k * s_la2), __ldg(p_c1 + (size_t)k * s_c1),
+                                                 __ldg(p_c2 + (size_t)k * s_c2), fkm, fkp);
+  }
+}
+
+__global__ void __launch_bounds__(128, 4) propags2_kernel(PropDev d, SpecSrc src, double* __restrict__ dst, long long dcstride,
+                                                          int m0, int m1, int MG, int msplit) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= d.nloc) return;
   const int mb = m0 + blockIdx.y * MG;
   const int me = min(mb + MG, m1);
   const int nl = d.nloc;
-  int nb[14];
+  int nb[6];
 #pragma unroll
-  for (int j = 0; j < 14; ++j) nb[j] = __ldg(d.nbr + (size_t)j * nl + l);
+  for (int j = 0; j < 6; ++j) nb[j] = __ldg(d.nbr + (size_t)j * nl + l);
   PointM q;
-  q.wlat[0] = __ldg(d.wl + l);
-  q.wlat[1] = __ldg(d.wl + nl + l);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) q.wcor[j] = __ldg(d.wl + (size_t)(2 + j) * nl + l);
-  q.wlatm1[0] = 1.0 - q.wlat[0];
-  q.wlatm1[1] = 1.0 - q.wlat[1];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) q.wcorm1[j] = 1.0 - q.wcor[j];
+  const double wlat0 = __ldg(d.wl + l), wlat1 = __ldg(d.wl + nl + l);
   q.cosphm1 = __ldg(d.pt + l);
   const double dp1 = __ldg(d.pt + nl + l), dp2 = __ldg(d.pt + 2 * (size_t)nl + l);
   q.zdello = __ldg(d.pt + 3 * (size_t)nl + l);
@@ -120,42 +164,18 @@ __global__ void __launch_bounds__(128) propags2_kernel(PropDev d, SpecSrc src, d
     q.hx[0] = 0.5 * (q.cg + __ldg(cgm + nb[0]));
     q.hx[1] = 0.5 * (q.cg + __ldg(cgm + nb[1]));
     {
-      const double cgyp1 = q.wlat[0] * __ldg(cgm + nb[2]) + (1.0 - q.wlat[0]) * __ldg(cgm + nb[4]);
-      const double cgyp2 = q.wlat[1] * __ldg(cgm + nb[3]) + (1.0 - q.wlat[1]) * __ldg(cgm + nb[5]);
+      const double cgyp1 = wlat0 * __ldg(cgm + nb[2]) + (1.0 - wlat0) * __ldg(cgm + nb[4]);
+      const double cgyp2 = wlat1 * __ldg(cgm + nb[3]) + (1.0 - wlat1) * __ldg(cgm + nb[5]);
       q.hy[0] = 0.5 * (q.cg + dp1 * cgyp1);
       q.hy[1] = 0.5 * (q.cg + dp2 * cgyp2);
     }
     const double* ps = src.base + i + (long long)c * src.cstride + (long long)m * d.P * A;
     double* pd = dst + i + (long long)c * dcstride + (long long)m * d.P * A;
-    const int P = d.P;
-    // neighbour bases for this frequency: lon(1,2), lat(ic,icl), cor(icr,icl)
-    const double* pb[14];
-    int ks[14];
-#pragma unroll
-    for (int j = 0; j < 14; ++j) nbr_base(d, src, nb[j], m, pb[j], ks[j]);
-    for (int k = 0; k < A; ++k) {
-      const double f0 = ps[(size_t)k * P];
-      const double fkm = ps[(size_t)c_prop.kpm_m[k] * P];
-      const double fkp = ps[(size_t)c_prop.kpm_p[k] * P];
-      double r;
-#define LD(j) __ldg(pb[j] + (size_t)k * ks[j])
-      switch (c_prop.quad[k]) {
-        case 0:  // JX1=1 JY1=1 KCR=3 : west, south, SW
-          r = ctu_update<1, 1, 3>(q, k, idp, f0, LD(0), LD(2), LD(4), LD(6 + 2), LD(10 + 2), fkm, fkp);
-          break;
-        case 1:  // JX1=2 JY1=1 KCR=2 : east, south, SE
-          r = ctu_update<2, 1, 2>(q, k, idp, f0, LD(1), LD(2), LD(4), LD(6 + 1), LD(10 + 1), fkm, fkp);
-          break;
-        case 2:  // JX1=1 JY1=2 KCR=4 : west, north, NW
-          r = ctu_update<1, 2, 4>(q, k, idp, f0, LD(0), LD(3), LD(5), LD(6 + 3), LD(10 + 3), fkm, fkp);
-          break;
-        default:  // JX1=2 JY1=2 KCR=1 : east, north, NE
-          r = ctu_update<2, 2, 1>(q, k, idp, f0, LD(1), LD(3), LD(5), LD(6 + 0), LD(10 + 0), fkm, fkp);
-          break;
-      }
-#undef LD
-      pd[(size_t)k * P] = r;
-    }
+    // quadrant k-ranges [kq[j], kq[j+1]) in the order: (sin>=0,cos>=0) (sin>=0,cos<0) (sin<0,cos<0) (sin<0,cos>=0)
+    ctu_quadrant<1, 1, 3>(d, src, q, l, m, idp, c_prop.kq[0], c_prop.kq[1], ps, pd);   // west, south, SW
+    ctu_quadrant<1, 2, 4>(d, src, q, l, m, idp, c_prop.kq[1], c_prop.kq[2], ps, pd);   // west, north, NW
+    ctu_quadrant<2, 2, 1>(d, src, q, l, m, idp, c_prop.kq[2], c_prop.kq[3], ps, pd);   // east, north, NE
+    ctu_quadrant<2, 1, 2>(d, src, q, l, m, idp, c_prop.kq[3], c_prop.kq[4], ps, pd);   // east, south, SE
   }
 }
 

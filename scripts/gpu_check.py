@@ -8,7 +8,7 @@ from ecwam_b200 import synth, model as M
 def relerr(a, b, floor=1e-300):
     return np.abs(a - b).max() / max(np.abs(b).max(), floor)
 
-def run(N, A, Fr, mk, iphys, nsteps, nproma=32, idelt=900.0):
+def run(N, A, Fr, mk, iphys, nsteps, nproma=32, idelt=900.0, fused=False):
     g = synth.make_grid(N, mk)
     cfg = O.default_config(nang=A, nfre_red=Fr, nproma=nproma, npr=1, iphys=iphys, idelt=idelt, idelpro=idelt, delpro_lf=idelt)
     o = O.Oracle(cfg, g)
@@ -27,11 +27,14 @@ def run(N, A, Fr, mk, iphys, nsteps, nproma=32, idelt=900.0):
     for nm in ('DEPTH', 'EMAXDPT', 'COSPHM1'):
         print('  static', nm, np.abs(w.get_field(nm) - o.get_field(nm)[w.own]).max())
     for step in range(nsteps):
-        cfl_o = o.propag(); cfl_g = w.propag(); w.synchronize()
-        a = w.get_spec('fl1'); b = o.get_fl1()[:, :, w.own]
-        nbad = (a != b).sum()
-        print(f' step {step} propag: cfl {cfl_o}/{cfl_g} bitwise-different bins {nbad} of {a.size} rel {relerr(a,b):.3e}')
-        o.implsch(); w.implsch(); w.synchronize()
+        if fused:
+            o.step(); w.step(); w.synchronize()
+        else:
+            cfl_o = o.propag(); cfl_g = w.propag(); w.synchronize()
+            a = w.get_spec('fl1'); b = o.get_fl1()[:, :, w.own]
+            nbad = (a != b).sum()
+            print(f' step {step} propag: cfl {cfl_o}/{cfl_g} bitwise-different bins {nbad} of {a.size} rel {relerr(a,b):.3e}')
+            o.implsch(); w.implsch(); w.synchronize()
         a = w.get_spec('fl1'); b = o.get_fl1()[:, :, w.own]
         big = b > 1e-8 * b.max()
         print(f' step {step} implsch: FL1 rel(max) {relerr(a,b):.3e} relbins {np.abs(a-b)[big].max() and (np.abs(a-b)[big]/b[big]).max():.3e} nan {np.isnan(a).sum()}')
@@ -50,5 +53,5 @@ if __name__ == '__main__':
     import torch
     print(torch.cuda.get_device_name(0))
     run(48, 12, 25, 'continents', 1, 3)
-    run(24, 36, 29, 'continents', 1, 2, nproma=24, idelt=450.0)
+    run(24, 36, 29, 'continents', 1, 2, nproma=24, idelt=450.0, fused=True)
     run(32, 24, 29, 'continents', 0, 2, nproma=64)
