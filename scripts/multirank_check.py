@@ -1,0 +1,63 @@
+"""Run under torchrun: N ranks (one GPU each) propagate + integrate with the NCCL halo and every rank compares its own points
+with the 1-rank CPU oracle.  PROPAGS2 must be bit-identical to the 1-rank result (it is order-independent per point)."""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from common import CASES, make_oracle, relerr
+from ecwam_b200 import lib as L, model as M, synth
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = L.load()
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        L.check(lib.ecwam_b200_nccl_unique_id(buf), "uid")
+    t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone().cuda()
+    dist.broadcast(t, 0)
+    cm = C.c_void_p()
+    L.check(lib.ecwam_b200_nccl_comm_init(bytes(t.cpu().numpy().tobytes()), world, rank, C.byref(cm)), "comm_init")
+    ok = True
+    for case, extra in (("o48like", {}), ("o640like", dict(ifrelfmax=5, delpro_lf=225.0))):
+        CASES["_mr"] = dict(CASES[case], N=28)
+        g, o, f, fl = make_oracle("_mr", **extra)
+        c = CASES["_mr"]
+        s = M.WamSetup(g, nproc=world, nang=c["A"], nfre_red=c["Fr"], iphys=c["iphys"], nproma=c["nproma"], idelt=c["dt"],
+                       idelpro=c["dt"], delpro_lf=extra.get("delpro_lf", c["dt"]), ifrelfmax=extra.get("ifrelfmax", 0))
+        w = M.WamIntgr(s, rank, device="cuda:%d" % local, nccl_comm=cm.value)
+        w.set_static(g.depth)
+        for k, v in f.items():
+            w.set_field(k, v)
+        w.set_fl1(fl)
+        assert o.propag() == 0 and w.propag() == 0
+        w.synchronize()
+        same = np.array_equal(w.get_spec("fl1"), o.get_fl1()[:, :, w.own])
+        o.implsch(); w.implsch()
+        for _ in range(2):
+            o.step(); w.step()
+        w.synchronize()
+        e = relerr(w.get_spec("fl1"), o.get_fl1()[:, :, w.own])
+        mij_ok = bool((w.get_field("mij") == o.get_field("MIJ")[w.own]).all())
+        print("rank %d %s: propag bit-exact %s, FL1 rel err after 3 steps %.2e, MIJ exact %s" % (rank, case, same, e, mij_ok), flush=True)
+        ok = ok and same and e < 1e-12 and mij_ok
+        w.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0 and flag.item() == 1:
+        print("MULTIRANK OK")
+    L.check(lib.ecwam_b200_nccl_comm_destroy(cm), "comm_destroy")
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,206 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
+inputs, against the committed golden outputs, and through size-independent properties.
+
+Tolerances (BASELINE.json north_star: "integer tables and cut-off indices bit-exact; spectra and integrated parameters
+within a stated relative tolerance"):
+  * PROPAGS2 from identical inputs ............ bit-exact (propag.cu keeps the reference's operation order, -fmad=false)
+  * MIJ, XLLWS ................................ exact
+  * FL1 after IMPLSCH / WAMINTGR steps ........ max |a-b| / max|b| <= 1e-12  and, per bin above 1e-8*max, relative 1e-10
+  * UFRIC, TAUW, Z0M, stresses, fluxes, Hs .... relative 1e-10
+(FMA contraction, the fixed-order gather of the DIA terms and the unit-vector form of cos(TH-USDIRP) are the sources of
+the ~1e-15 differences.)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from common import CASES, OUT_FIELDS, make_gpu, make_oracle, relerr
+from ecwam_b200 import lib as L, model as M
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL_SPEC, RTOL_BIN, RTOL_FIELD = 1e-12, 1e-10, 1e-10
+
+
+def check_state(w, o, fields=True):
+    a, b = w.get_spec("fl1"), o.get_fl1()[:, :, w.own]
+    assert np.isfinite(a).all()
+    assert relerr(a, b) <= RTOL_SPEC
+    big = b > 1e-8 * b.max()
+    assert (np.abs(a - b)[big] / b[big]).max() <= RTOL_BIN
+    assert (w.get_spec("xllws") == o.get_xllws()[:, :, w.own]).all()
+    assert (w.get_field("mij") == o.get_field("MIJ")[w.own]).all()          # cut-off index: exact
+    if fields:
+        for nm in OUT_FIELDS:
+            assert relerr(w.get_field(nm), o.get_field(nm)[w.own]) <= RTOL_FIELD, nm
+
+
+@pytest.mark.parametrize("case", ["o48like", "o320like", "o640like", "aqua"])
+def test_propags2_bit_exact(built, case):
+    g, o, f, fl = make_oracle(case)
+    _, s, w = make_gpu(case)
+    assert o.propag() == 0 and w.propag() == 0
+    w.synchronize()
+    np.testing.assert_array_equal(w.get_spec("fl1"), o.get_fl1()[:, :, w.own])
+    # padded lanes of the last chunk repeat its first point (propag_wam.F90:388-398)
+    t = w.t["fl1"]
+    npad = w.P * w.C - w.nloc
+    if npad:
+        last = t[-1]                                    # (F, A, P)
+        assert (last[: w.Fr, :, w.P - npad:] == last[: w.Fr, :, :1]).all()
+
+
+@pytest.mark.parametrize("case", ["o48like", "o48_iphys0", "o320like", "o640like"])
+def test_implsch_matches_oracle(built, case):
+    g, o, f, fl = make_oracle(case)
+    _, s, w = make_gpu(case)
+    o.implsch()
+    w.implsch()
+    w.synchronize()
+    check_state(w, o)
+
+
+@pytest.mark.parametrize("case", ["o48like", "o48_iphys0", "o640like"])
+def test_wamintgr_steps_match_oracle(built, case):
+    g, o, f, fl = make_oracle(case)
+    _, s, w = make_gpu(case)
+    for _ in range(4):
+        assert o.step() == 0 and w.step() == 0        # fused PROPAG_WAM + IMPLSCH entry point
+    w.synchronize()
+    check_state(w, o)
+    hs_o, fm_o = o.hs_fm()
+    hs_g, fm_g = M.hs_fm(s, w.get_spec("fl1"))
+    assert relerr(hs_g, hs_o[w.own]) <= RTOL_FIELD and relerr(fm_g, fm_o[w.own]) <= RTOL_FIELD
+    # the statistics.log norms (mpminmaxavg.F90:129-147): plain mean / min / max over the sea points
+    for red in (np.mean, np.min, np.max):
+        assert abs(red(hs_g) - red(hs_o[w.own])) <= 1e-12 * abs(red(hs_o))
+
+
+def test_fused_step_equals_separate_calls(built):
+    _, s, w1 = make_gpu("o640like")
+    _, _, w2 = make_gpu("o640like")
+    for _ in range(2):
+        w1.step()
+        w2.propag()
+        w2.implsch()
+    w1.synchronize(); w2.synchronize()
+    np.testing.assert_array_equal(w1.get_spec("fl1"), w2.get_spec("fl1"))
+    np.testing.assert_array_equal(w1.get_field("tauw"), w2.get_field("tauw"))
+
+
+def test_single_chunk_implsch_equals_all_chunks(built):
+    """IMPLSCH(KIJS,KIJL,...) per chunk, as wamintgr.F90:117-146 calls it, == one launch over all chunks."""
+    _, s, w1 = make_gpu("o48like")
+    _, _, w2 = make_gpu("o48like")
+    w1.implsch()
+    for ic in range(1, w2.C + 1, 3):
+        L.check(w2.lib.ecwam_b200_implsch(w2.h, ic, min(3, w2.C - ic + 1)), "implsch")
+    w1.synchronize(); w2.synchronize()
+    np.testing.assert_array_equal(w1.get_spec("fl1"), w2.get_spec("fl1"))
+    np.testing.assert_array_equal(w1.get_field("ufric"), w2.get_field("ufric"))
+
+
+def test_fast_wave_substeps_bit_exact(built):
+    g, o, f, fl = make_oracle("o640like", ifrelfmax=5, delpro_lf=225.0)
+    _, s, w = make_gpu("o640like", ifrelfmax=5, delpro_lf=225.0)
+    assert o.propag() == 0 and w.propag() == 0
+    w.synchronize()
+    np.testing.assert_array_equal(w.get_spec("fl1"), o.get_fl1()[:, :, w.own])
+    o.implsch(); o.step()
+    w.implsch(); w.step()
+    w.synchronize()
+    check_state(w, o)
+
+
+@pytest.mark.parametrize("name", ["g_iphys1", "g_iphys0", "g_a36"])
+def test_against_golden(built, name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    CASES["_gold"] = dict(CASES[str(z["case"])], N=int(z["N"]))
+    _, s, w = make_gpu("_gold")
+    for _ in range(int(z["nsteps"])):
+        assert w.step() == 0
+    w.synchronize()
+    inv = np.argsort(w.own)                     # own -> original order (1 rank: a permutation of all points)
+    a = w.get_spec("fl1")[:, :, inv]
+    assert relerr(a, z["fl"]) <= RTOL_SPEC
+    np.testing.assert_array_equal(w.get_field("mij")[inv], z["mij"])
+    np.testing.assert_array_equal(np.packbits(w.get_spec("xllws")[:, :, inv].astype(np.uint8).ravel()), z["xllws"])
+    for nm in OUT_FIELDS:
+        assert relerr(w.get_field(nm)[inv], z[nm]) <= RTOL_FIELD, nm
+
+
+def test_cfl_violation_is_reported(built):
+    """a 10x too long advection step must come back as a positive count (the reference aborts, ctuwdrv.F90:127-146)."""
+    g, o, f, fl = make_oracle("o48like", idelpro=20000.0, delpro_lf=20000.0)
+    _, s, w = make_gpu("o48like", idelpro=20000.0, delpro_lf=20000.0)
+    n_o = o.propag()
+    n_g = w.lib.ecwam_b200_propag(w.h)
+    assert n_o > 0 and n_g == n_o
+
+
+def test_unsupported_switches_are_rejected(built):
+    from ecwam_b200 import synth
+    g = synth.make_grid(8, "aqua")
+    for kw in (dict(irefra=2), dict(llgcbz0=1), dict(isnonlin=1), dict(lciwa=1)):
+        s = M.WamSetup(g, nproc=1, **kw)
+        with pytest.raises(L.EcwamError):
+            M.WamIntgr(s, 0)
+
+
+def test_host_buffer_entry_point(built):
+    """ecwam_b200_wamintgr_host: fields in host memory, copies inside the call; same result as the device-resident path."""
+    import torch
+    _, s, w1 = make_gpu("o48like")
+    _, _, w2 = make_gpu("o48like")
+    host = {n: w2.t[n].cpu().pin_memory() for n, _ in L.Fields._fields_}
+    hf = L.Fields()
+    for n, _ in L.Fields._fields_:
+        setattr(hf, n, C.cast(host[n].data_ptr(), C.POINTER(C.c_int if n == "mij" else C.c_double)))
+    hin, hout = C.c_longlong(), C.c_longlong()
+    for _ in range(2):
+        w1.step()
+        L.check(w2.lib.ecwam_b200_wamintgr_host(w2.h, C.byref(hf), 1, C.byref(hin), C.byref(hout)), "wamintgr_host")
+    w1.synchronize()
+    assert hin.value > 0 and hout.value > 0
+    np.testing.assert_array_equal(host["fl1"].numpy(), w1.t["fl1"].cpu().numpy())
+    np.testing.assert_array_equal(host["xllws"].numpy(), w1.t["xllws"].cpu().numpy())
+    np.testing.assert_array_equal(host["ufric"].numpy(), w1.t["ufric"].cpu().numpy())
+    np.testing.assert_array_equal(host["mij"].numpy(), w1.t["mij"].cpu().numpy())
+
+
+def test_full_size_properties_o320(built):
+    """BASELINE config 3 at full size (O320, 24x29, ~278k sea points): size-independent properties instead of the oracle:
+    finite, non-negative, bounded by FLMAX, padded lanes consistent, and re-running from the same state is deterministic."""
+    import torch
+    from ecwam_b200 import synth
+    g = synth.make_grid(320, "continents")
+    s = M.WamSetup(g, nproc=1, nang=24, nfre_red=29, nproma=64)
+    w = M.WamIntgr(s, 0)
+    w.set_static(g.depth)
+    f = synth.make_forcing(g)
+    for k, v in f.items():
+        w.set_field(k, v)
+    synth.jonswap_cold_start_device(w, f["WSWAVE"], f["WDWAVE"])
+    snap = {k: v.clone() for k, v in w.t.items()}
+    for _ in range(2):
+        assert w.step() == 0
+    w.synchronize()
+    fl = w.t["fl1"]
+    assert torch.isfinite(fl).all() and fl.min().item() >= 0.0
+    flmax = torch.tensor(s.table("flmax", 36), device=fl.device).view(1, 36, 1, 1)
+    assert (fl <= flmax * (1 + 1e-15)).all()
+    mij = w.t["mij"]
+    assert mij.min().item() >= 1 and mij.max().item() <= 36
+    x = w.t["xllws"]
+    assert ((x == 0) | (x == 1)).all()
+    first = fl.clone()
+    for k, v in snap.items():
+        w.t[k].copy_(v)
+    for _ in range(2):
+        w.step()
+    w.synchronize()
+    assert torch.equal(first, w.t["fl1"])            # deterministic: no atomics, fixed summation order
+    hs, fm = M.hs_fm(s, w.get_spec("fl1")[:, :, ::37])
+    assert 0.0 < hs.mean() < 5.0 and hs.max() < 20.0
