@@ -69,7 +69,9 @@ struct ecwam_b200_handle_s {
   int msplit = 0;
   bool weights_dirty = true;
   // implsch
-  DBuf<double> scr, satw, swellft, fldin;
+  DBuf<double> scr, satw, swellft, fldin, tbg;
+  int dsh[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  int halo_r = 0, halo_c = 0;
   DBuf<int> kw, isat;
   DevTabPtr tab;
   // fields
@@ -371,6 +373,23 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
     if (tables->ikp[o] != mc + 2 || tables->ikp1[o] != mc + 3 || tables->ikm[o] != mc - 4 || tables->ikm1[o] != mc - 3 ||
         tables->mlsthg != F + 4) { ok = false; ew_set_error("unsupported DIA frequency offsets (need IKP=M+2, IKM=M-4, MLSTHG=NFRE+4)"); }
   }
+  // K1W, K11W, K2W, K21W(.,KH) as signed cyclic shifts (jafu.F90): k_stencil addresses partners as own bin + shift
+  {
+    static const int order[4] = {0, 2, 1, 3};   // kw blocks are K1W, K2W, K11W, K21W
+    int maxsh = 0;
+    for (int kh = 0; kh < 2 && ok; ++kh)
+      for (int q = 0; q < 4 && ok; ++q) {
+        const int* tbl = &kw[(size_t)(2 * order[q] + kh) * A];
+        int sh = tbl[0];
+        if (sh > A / 2) sh -= A;
+        for (int k = 0; k < A; ++k) if (tbl[k] != ((k + sh) % A + A) % A) { ok = false; ew_set_error("K1W/K2W/K11W/K21W is not a cyclic shift"); }
+        h->dsh[kh][q] = sh;
+        maxsh = std::max(maxsh, std::abs(sh));
+      }
+    h->halo_c = maxsh;
+    h->halo_r = std::max(maxsh, p.iphys == 1 ? tables->nsdsnth : 0);
+    if (ok && (2 * h->halo_r > A || (p.iphys == 1 && 2 * tables->nsdsnth + 1 > 17))) { ok = false; ew_set_error("direction halo %d too wide for NANG=%d", h->halo_r, A); }
+  }
   ok = ok && !h->kw.upload(kw, st);
   if (p.iphys == 1) {
     const int ns = 2 * tables->nsdsnth + 1;
@@ -383,7 +402,8 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
   std::vector<double> sw(tables->swellft, tables->swellft + tables->iab);
   ok = ok && !h->swellft.upload(sw, st);
   const long long npts = (long long)P * p.nchnk;
-  ok = ok && !h->scr.alloc(implsch_scratch_doubles(npts)) && !h->fldin.alloc((size_t)npts * A * F);
+  ok = ok && !h->scr.alloc(implsch_scratch_doubles(npts)) && !h->fldin.alloc((size_t)npts * A * F) &&
+       !h->tbg.alloc((size_t)EW_TQ_N * F * npts);
   if (!ok) { ecwam_b200_destroy(h); return ECWAM_B200_ECUDA; }
   cudaMemsetAsync(h->halo.p, 0, (halo_elems + 1) * sizeof(double), st);
   cudaMemsetAsync(h->fl3.p, 0, h->fl3.n * sizeof(double), st);
@@ -412,7 +432,7 @@ int ecwam_b200_destroy(ecwam_b200_handle h) {
   h->nbr.free(); h->halo_off.free(); h->halo_str.free(); h->send_l.free(); h->send_pre.free(); h->send_peer_of.free();
   h->recv_pre.free(); h->recv_peer_of.free(); h->recv_e.free(); h->flag.free(); h->count.free(); h->wl.free(); h->pt.free();
   h->cgext.free(); h->halo.free(); h->sendbuf.free(); h->fl3.free(); h->cosph_m.free(); h->cosph_p.free();
-  h->land_cg.free(); h->cgrecv.free(); h->scr.free(); h->fldin.free(); h->satw.free(); h->swellft.free(); h->kw.free(); h->isat.free();
+  h->land_cg.free(); h->cgrecv.free(); h->scr.free(); h->fldin.free(); h->tbg.free(); h->satw.free(); h->swellft.free(); h->kw.free(); h->isat.free();
   for (void* b : h->mir_bufs) cudaFree(b);
   delete h;
   return 0;
@@ -537,7 +557,7 @@ int ecwam_b200_propag(ecwam_b200_handle h) {
     h->nlaunch++;
   } else {
     launch_copyback(d, h->fl3.p, h->dev.fl1, ms, d.Fr, h->st);
-    launch_pad(d, h->dev.fl1, 0, ms, h->st);
+    launch_pad(d, h->dev.fl1, d.F, 0, ms, h->st);
     h->nlaunch += 2;
   }
   EW_CUDA_CHECK(cudaGetLastError());
@@ -557,6 +577,9 @@ static ImplDev make_impl(H* h, bool from_fl3) {
   d.nloc = h->pd.nloc;
   d.lwflux = h->par.lwflux;
   d.tab = h->tab;
+  d.tbg = h->tbg.p;
+  memcpy(d.dsh, h->dsh, sizeof(d.dsh));
+  d.halo_r = h->halo_r; d.halo_c = h->halo_c;
   return d;
 }
 
@@ -595,10 +618,11 @@ int ecwam_b200_wamintgr(ecwam_b200_handle h) {
   if (!lf_in_fl3) {   // odd number of fast-wave sub-steps left the low frequencies in FL1: finish PROPAG_WAM the plain way
     const PropDev& d = h->pd;
     launch_copyback(d, h->fl3.p, h->dev.fl1, h->par.ifrelfmax, d.Fr, h->st);
-    launch_pad(d, h->dev.fl1, 0, h->par.ifrelfmax, h->st);
+    launch_pad(d, h->dev.fl1, d.F, 0, h->par.ifrelfmax, h->st);
     h->nlaunch += 2;
     return implsch_range(h, 1, h->par.nchnk, false);
   }
+  launch_pad(h->pd, h->fl3.p, h->pd.Fr, 0, h->pd.Fr, h->st);   // padded lanes of the last chunk (propag_wam.F90:388-398)
   return implsch_range(h, 1, h->par.nchnk, true);
 }
 

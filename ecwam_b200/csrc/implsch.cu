@@ -28,6 +28,9 @@ enum {
   NSCR
 };
 size_t implsch_scratch_doubles(long long npts) { return (size_t)NSCR * (size_t)npts; }
+// planes of ImplDev::tbg [TQ_N][F][npts]: per-(point, frequency) scalars that k_point derives once for k_stencil
+enum { TQ_FACSAT = 0, TQ_SBO, TQ_CINV, TQ_TAIL, TQ_STF, TQ_JAN, TQ_N };
+static_assert(TQ_N == EW_TQ_N, "tbg planes");
 
 #define FULLMASK 0xffffffffu
 __device__ __forceinline__ double wsum(double v) {
@@ -249,7 +252,8 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
                                              double temp2_sw, double pturb, double aird_pvisc, double* __restrict__ fld_out,
                                              double* __restrict__ xl_out, double* sumx, double* sumy, double* sumt,
                                              double& ws_em, double& ws_fm, double& ws_last, double& phiwa_acc,
-                                             double& uorbt_acc, double& aorb_acc, double* mom, bool dostore) {
+                                             double& uorbt_acc, double& aorb_acc, double* mom, bool dostore,
+                                             double depth = 0.0, double jan_sds = 0.0, double xkmean = 1.0) {
   const int A = c_dc.A, F = c_dc.F;
   const double CONST1 = c_dc.BETAMAXOXKAPPA2;
   const size_t kstr = S.kstr;
@@ -285,6 +289,26 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
     const double sig = c_dc.ZPIFR[m], sig2 = sig * sig;
     const double zcn = log(wavnum * z0m);
     const double dfim = c_dc.DFIM[m], dfimofr = c_dc.DFIMOFR[m], rhowg = c_dc.RHOWG_DFIM[m];
+    if (STORE) {
+      if (dostore) {   // per-(point, frequency) scalars of the frequency sweep in k_stencil
+        const size_t n = (size_t)d.npts, qs = (size_t)F * n;
+        double* tg = d.tbg + (size_t)m * n + (size_t)p;
+        const double xk = d.f.xk2cg[o3];
+        tg[TQ_FACSAT * qs] = wavnum * (1.0 / c_dc.ZPI) * xk;                                        // sdissip_ard.F90:142-160
+        double sbo = 0.0;
+        if (m < c_dc.Fr && depth < c_dc.bathymax) sbo = (-2.0 * 0.038 * c_dc.GM1) * wavnum / sinh(fmin(2.0 * depth * wavnum, 50.0));   // sbottom.F90:76-97
+        tg[TQ_SBO * qs] = sbo;
+        tg[TQ_CINV * qs] = cinv;
+        tg[TQ_TAIL * qs] = 1.0 / xk / wavnum;                                                       // imphftail.F90:73-81
+        tg[TQ_STF * qs] = (m < c_dc.NFRE_ODD) ? d.f.stokfac[o3] * c_dc.DFIM_SIM[m] : 0.0;          // stokesdrift.F90:100-116
+        double tj = 0.0;
+        if (!ard) {   // SDISSIP_JAN (sdissip_jan.F90:96-132)
+          const double xx = wavnum / xkmean;
+          tj = jan_sds * xx * ((1.0 - c_dc.DELTA_SDIS) + c_dc.DELTA_SDIS * xx) + c_dc.rnu * c_dc.CDISVIS * sq(wavnum);
+        }
+        tg[TQ_JAN * qs] = tj;
+      }
+    }
     const double* fsrc = row_ptr(S, m, A);
     double* fo = STORE ? fld_out + (size_t)m * A * kstr : nullptr;
     double* xo = STORE ? xl_out + (size_t)m * A * kstr : nullptr;
@@ -565,7 +589,8 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
   double* xl_out = d.f.xllws + (size_t)i + (size_t)d.P * A * F * (size_t)c;
   double dum[6];
   sinput_point<2, true, true>(S, d, p, fac, flmc, snw, csw, ustar, z0, raorw, sig_n, temp2_sw, pturb, aird_pvisc, fld_out, xl_out,
-                              sumx, sumy, sumt, ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc, dum, valid);
+                              sumx, sumy, sumt, ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc, dum, valid, d.f.depth[p],
+                              c_dc.CDIS * c_dc.ZPI * f1mean * sq(emean) * p4(xkmean), xkmean);
   const double emeanws = c_dc.EPSMIN + ws_em + DELT25 * ws_last;
   const double fmeanws = emeanws / (c_dc.EPSMIN + ws_fm + c_dc.FRTAIL * c_dc.DELTH * ws_last);
   const int mij = frcut(fmeanws, ustar);
@@ -598,300 +623,465 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
 
 
 // =========================================================================================================
-// k_stencil: CTA = 8 consecutive grid points x NANG threads (thread = (point, direction)).
+// k_stencil: CTA = 8 consecutive grid points x NANG directions; thread = (direction k, group of NP consecutive points).
 // SDISSIP, SNONLIN, SDIWBK, SBOTTOM, the implicit update, WNFLUXES, IMPHFTAIL, SETICE and STOKESDRIFT as ONE sweep
-// over frequency.  The DIA quadruplets of "centre" frequency MC only touch the frequencies MC-4 .. MC+3
-// (nlweigt.F90: IKM=MC-4, IKM1=MC-3, IKP=MC+2, IKP1=MC+3 for FRATIO=1.1), so the sweep keeps
-//   * an 8-row ring of the spectrum in shared memory (rows stream in from HBM one per step, already
-//     depth-limited and floored),
-//   * the 8 pending rows of the SNONLIN sums SL/FLD of the thread's own direction in registers,
+// over frequency with ONE barrier per step.  The DIA quadruplets of "centre" frequency MC only touch the frequencies
+// MC-4 .. MC+3 (nlweigt.F90: IKM=MC-4, IKM1=MC-3, IKP=MC+2, IKP1=MC+3 for FRATIO=1.1), so the sweep keeps
+//   * a 9-row ring of the spectrum in shared memory, [row][direction + halo][point]: rows stream in from HBM one per
+//     step (already depth-limited and floored); the cyclic direction halo turns every partner / window access into
+//     "own address + uniform offset" (K1W..K21W are cyclic shifts, jafu.F90) -> no per-load address arithmetic,
+//     and with NP=2 every shared-memory access is one 16-byte LDS/STS serving two grid points,
+//   * the 8 pending rows of the SNONLIN sums SL/FLD of the thread's own bins in registers,
 // and, at step MC, finishes row MC-4: it receives its last DIA contribution, gets the dissipation, breaking and
-// bottom terms, is advanced in time and leaves for HBM.  The reference's scatter of each quadruplet into 9 bins
-// (snonlin.F90:253-308) becomes a gather through the inverse direction tables: no atomics, fixed summation order.
+// bottom terms, is advanced in time and goes straight from registers to HBM (the thread that computes a bin also
+// loads and stores it: 8 points x 8 B = 64-byte segments).  The reference's scatter of each quadruplet into 9 bins
+// (snonlin.F90:253-308) is a gather through the inverse shifts: no atomics, fixed summation order.
+// Hazards: row s+4 is written in phase A of step s into the slot of row s-5 (last read in step s-1, phase A);
+// the interaction planes, the per-warp saturation maxima and BTH0 are double-buffered by the parity of s.
 // =========================================================================================================
 #define ST_NPT 8
-enum { TQ_FACSAT = 0, TQ_SBO, TQ_CINV, TQ_TAIL, TQ_STF, TQ_JAN, TQ_N };
+#define ST_RING 9
+#define ST_NSMAX 17   // 2*NSDSNTH+1 <= 17 (NANG <= 36, init_sdiss_ardh.F90:72)
+enum { PC_FAC = 0, PC_ENH, PC_USFMDELT, PC_SDSBK, PC_RTAIL, PC_FLMC, PC_ICEADD, PC_ICEFREE, PC_SNW, PC_CSW, PC_N };
 
-template <bool LWFLUX>
-__global__ void __maxnreg__(112) k_stencil(ImplDev d, long long p0, long long np) {
-  extern __shared__ double smem[];
-  const int A = c_dc.A, F = c_dc.F, NPT = ST_NPT;
-  const int PS = NPT * A;                            // one (point, direction) plane
+template <int NP> struct Vd;
+template <> struct Vd<1> { double v[1]; };
+template <> struct __align__(16) Vd<2> { double v[2]; };
+template <int NP> __device__ __forceinline__ Vd<NP> lds(const char* sm, unsigned off) { return *reinterpret_cast<const Vd<NP>*>(sm + off); }
+template <int NP> __device__ __forceinline__ void sts(char* sm, unsigned off, const Vd<NP>& x) { *reinterpret_cast<Vd<NP>*>(sm + off) = x; }
+template <int NP> __device__ __forceinline__ Vd<NP> ldg(const double* p) { return __ldg(reinterpret_cast<const Vd<NP>*>(p)); }
+template <> __device__ __forceinline__ Vd<1> ldg<1>(const double* p) { Vd<1> r; r.v[0] = __ldg(p); return r; }
+template <> __device__ __forceinline__ Vd<2> ldg<2>(const double* p) {
+  const double2 t = __ldg(reinterpret_cast<const double2*>(p));
+  Vd<2> r; r.v[0] = t.x; r.v[1] = t.y; return r;
+}
+template <int NP> __device__ __forceinline__ void stg(double* p, const Vd<NP>& x) { *reinterpret_cast<Vd<NP>*>(p) = x; }
+// a / b for b >= 1 (no overflow / denormal paths needed): reciprocal seed + 2 Newton steps + residual correction
+__device__ __forceinline__ double div_ge1(double a, double b) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  double e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  const double q = a * r;
+  return fma(fma(-b, q, a), r, q);
+}
+__device__ __forceinline__ unsigned slot9(int r) { return (unsigned)(r % ST_RING); }
+
+struct StencilSmem {   // byte offsets into dynamic shared memory
+  unsigned ring, cur, satw, tbs, pc, part, bth0, total, RSB, PSB;
+};
+__host__ __device__ inline StencilSmem stencil_smem(int A, int halo_r, int halo_c, int nwarp) {
+  StencilSmem s;
+  s.RSB = (unsigned)(A + 2 * halo_r) * ST_NPT * 8;
+  s.PSB = (unsigned)(A + 2 * halo_c) * ST_NPT * 8;
+  unsigned o = 0;
+  s.ring = o; o += ST_RING * s.RSB;
+  s.cur = o; o += 2 * 6 * s.PSB;
+  s.satw = o; o += (unsigned)A * EW_MAXSAT * 8; o = (o + 15u) & ~15u;
+  s.tbs = o; o += 4 * TQ_N * ST_NPT * 8;
+  s.pc = o; o += PC_N * ST_NPT * 8;
+  s.part = o; o += 2u * (unsigned)nwarp * ST_NPT * 8;
+  s.bth0 = o; o += 2 * ST_NPT * 8;
+  s.total = o;
+  return s;
+}
+
+template <int NP, bool LWFLUX>
+__global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? 3 : 2) k_stencil(ImplDev d, long long p0, long long np) {
+  extern __shared__ __align__(16) char sm[];
+  typedef Vd<NP> V;
+  const int A = c_dc.A, F = c_dc.F;
+  constexpr int NG = ST_NPT / NP;                    // point groups per CTA
   const int NSD = c_dc.NSDSNTH, NS = 2 * NSD + 1;
-  double* ring = smem;                               // [8][PS]  spectrum rows (frequencies) r with slot r&7
-  double* cur = ring + 8 * PS;                       // [6][PS]  AD(kh), DELAP(kh), DELAM(kh) of the current MC
-  double* sin_ = cur + 6 * PS;                       // [PS]     wind-input FLD of the row being finished
-  double* sout = sin_ + PS;                          // [PS]     finished row on its way out
-  double* bthv = sout + PS;                          // [PS]     saturation spectrum of the row being prepared
-  double* satw = bthv + PS;                          // [NS][A]
-  double* tb = satw + EW_MAXSAT * A;                 // [TQ_N][F][NPT] per-(point, frequency) scalars
-  double* bth0 = tb + TQ_N * F * NPT;                // [4 row slots][NPT][4 partial maxima]
+  const bool ard = c_dc.iphys == 1;
+  const int H = d.halo_r, HC = d.halo_c;
+  const int nwarp = (int)(blockDim.x >> 5);
+  const StencilSmem L = stencil_smem(A, H, HC, nwarp);
+  const unsigned RSB = L.RSB, PSB = L.PSB;
   const int t = threadIdx.x;
-  const int p = t / A, k = t - p * A;                // compute role
-  const int kt = t / NPT, pt = t - kt * NPT;         // transfer role (grid point fastest -> 64-byte segments)
-  const int me = p * A + k, mt = pt * A + kt;
-  const long long pbase = p0 + (long long)blockIdx.x * NPT;
+  int k = t / NG;
+  const int j = t - k * NG;
+  const bool act = k < A;                            // threads beyond NANG*NG shadow the last direction and never store
+  if (!act) k = A - 1;
+  const unsigned jo = (unsigned)(j * NP * 8);
+  const unsigned me_r = (unsigned)(k + H) * (ST_NPT * 8) + jo;     // own bin inside a ring row
+  const unsigned me_c = (unsigned)(k + HC) * (ST_NPT * 8) + jo;    // own bin inside an interaction plane
+  // ---- points
+  const long long pbase = p0 + (long long)blockIdx.x * ST_NPT;
   const long long plast = p0 + np - 1;
-  const bool pvalid = pbase + p <= plast, tvalid = pbase + pt <= plast;
-  const long long pp = min(pbase + p, plast), tp = min(pbase + pt, plast);
+  long long pq = pbase + (long long)j * NP;          // first point of the group
+  const bool pvalid = pq + (NP - 1) <= plast;
+  if (!pvalid) pq = plast - (NP - 1);
+  const bool dost = act && pvalid;
   const long long n = d.npts;
   const double* s = d.scr;
   const size_t P = (size_t)d.P;
-  const size_t rstr = P * A;                          // row (frequency) stride in the chunked layout
-  // ---- transfer-role pointers (advance by one row per step)
-  const long long tc = tp / d.P;
-  const int ti = (int)(tp - tc * d.P);
-  const size_t off_hi = (size_t)ti + P * A * F * (size_t)tc + P * (size_t)kt;     // element (ti, kt, 0, tc) of a (P,A,F,C) array
-  size_t off_lo = off_hi;
+  const size_t rstr = P * A;                         // row (frequency) stride of the chunked layout
+  const long long pc_ = pq / d.P;
+  const int pi_ = (int)(pq - pc_ * d.P);
+  const size_t off_hi = (size_t)pi_ + P * A * F * (size_t)pc_ + P * (size_t)k;    // element (pi, k, 0, pc) of a (P,A,F,C) array
+  const double* src_lo = d.f.fl1 + off_hi;
+  size_t rstr_dummy = 0; (void)rstr_dummy;
   int mlo = 0;
-  if (d.lo_on) {
-    const int il = (tp < d.nloc) ? ti : 0;
-    off_lo = (size_t)il + P * A * d.lo_F * (size_t)tc + P * (size_t)kt;
+  if (d.lo_on) {   // propagated frequencies come from the propagation scratch (P,A,Fr,C); its padded lanes are filled (launch_pad)
+    src_lo = d.fl_lo + (size_t)pi_ + P * A * d.lo_F * (size_t)pc_ + P * (size_t)k;
     mlo = d.Fr;
   }
-  double t_fac, t_floor;
-  {
-    const double wd = d.f.wdwave[tp], ci = d.f.cicover[tp];
-    const double cwd = c_dc.COSTH[kt] * cos(wd) + c_dc.SINTH[kt] * sin(wd);
-    t_fac = s[S_FAC * n + tp];
-    t_floor = (1. - 0.9 * fmin(ci, 0.99)) * c_dc.flmin * sq(fmax(0.0, cwd));
-  }
-  auto load_row = [&](int r) -> double {             // depth-limited (+ floored at NFRE) spectrum row r of (pt, kt)
-    double v = __ldg((r < mlo ? d.fl_lo + off_lo : d.f.fl1 + off_hi) + (size_t)r * rstr);
-    v = fmax(v * t_fac, c_dc.EPSMIN);
-    if (r == F - 1) v = fmax(v, t_floor);
-    return v;
-  };
-  // ---- compute-role constants
-  const double wdwave = d.f.wdwave[pp], cicover = d.f.cicover[pp], depth = d.f.depth[pp];
-  double snw, csw;
-  sincos(wdwave, &snw, &csw);
-  const double sinth = c_dc.SINTH[k], costh = c_dc.COSTH[k];
-  const double coswdif = costh * csw + sinth * snw;
-  const double flm = (1. - 0.9 * fmin(cicover, 0.99)) * c_dc.flmin * sq(fmax(0.0, coswdif));
-  const int mij = (int)s[S_MIJ * n + pp];
-  const double usfm_delt = s[S_USFM * n + pp] * c_dc.delt, sds_bk = s[S_SDS * n + pp];
-  const bool brk = c_dc.lbiwbk && depth < 50.0;
-  const bool ard = c_dc.iphys == 1;
-  double enhfr;
-  {
-    const double akmean = s[S_AKMEAN * n + pp];
-    enhfr = fmax(0.75 * depth * akmean, 0.5);
+  const double* src_hi = d.f.fl1 + off_hi;
+  double* dst = d.f.fl1 + off_hi;
+  const double* src_in = d.fldin + off_hi;
+  const double* src_xl = d.f.xllws + off_hi;
+
+  // ---- prologue: per-point constants, saturation weights
+  if (t < ST_NPT) {
+    const long long qp = min(pbase + t, plast);
+    double* pcv = reinterpret_cast<double*>(sm + L.pc) + t;
+    const double wd = d.f.wdwave[qp], ci = d.f.cicover[qp], dep = d.f.depth[qp];
+    double snw, csw;
+    sincos(wd, &snw, &csw);
+    double enhfr = fmax(0.75 * dep * s[S_AKMEAN * n + qp], 0.5);
     enhfr = 1.0 + (5.5 / enhfr) * (1.0 - .833 * enhfr) * exp(-1.25 * enhfr);
+    const int mijq = (int)s[S_MIJ * n + qp];
+    const bool seticeq = c_dc.licerun && c_dc.lmaskice && ci > c_dc.cithrsh;
+    pcv[PC_FAC * ST_NPT] = s[S_FAC * n + qp];
+    pcv[PC_ENH * ST_NPT] = enhfr;
+    pcv[PC_USFMDELT * ST_NPT] = s[S_USFM * n + qp] * c_dc.delt;
+    pcv[PC_SDSBK * ST_NPT] = (c_dc.lbiwbk && dep < 50.0) ? s[S_SDS * n + qp] : 0.0;
+    pcv[PC_RTAIL * ST_NPT] = 1.0 / d.tbg[((size_t)TQ_TAIL * F + (mijq - 1)) * n + qp];
+    pcv[PC_FLMC * ST_NPT] = (1. - 0.9 * fmin(ci, 0.99)) * c_dc.flmin;
+    pcv[PC_ICEADD * ST_NPT] = seticeq ? fmax(c_dc.EPSMIN, 1.0 - ci) * c_dc.flmin : 0.0;
+    pcv[PC_ICEFREE * ST_NPT] = seticeq ? 0.0 : 1.0;
+    pcv[PC_SNW * ST_NPT] = snw;
+    pcv[PC_CSW * ST_NPT] = csw;
   }
-  // element offsets inside a plane: interaction partners (K1W..K21W) and their inverses for the gather
-  // (two 16-bit offsets per register: lo = first table, hi = second)
-  unsigned o1p[2], o2p[2], g1p[2], g2p[2];
+  if (ard) for (int x = t; x < NS * A; x += blockDim.x) {   // (x, kk) -> [kk][x]
+    const int xs = x / A, kk = x - xs * A;
+    reinterpret_cast<double*>(sm + L.satw)[kk * EW_MAXSAT + xs] = __ldg(d.tab.satweights + x);
+  }
+  __syncthreads();
+  const double sinth = c_dc.SINTH[k], costh = c_dc.COSTH[k];
+  V flm, iceadd;
+  int mij[NP];
+  {
+    const V snw = lds<NP>(sm, L.pc + PC_SNW * 64 + jo), csw = lds<NP>(sm, L.pc + PC_CSW * 64 + jo);
+    const V flmc = lds<NP>(sm, L.pc + PC_FLMC * 64 + jo), ia = lds<NP>(sm, L.pc + PC_ICEADD * 64 + jo);
 #pragma unroll
-  for (int kh = 0; kh < 2; ++kh) {
-    o1p[kh] = (unsigned)(p * A + __ldg(d.tab.k1w + kh * A + k)) | ((unsigned)(p * A + __ldg(d.tab.k11w + kh * A + k)) << 16);
-    o2p[kh] = (unsigned)(p * A + __ldg(d.tab.k2w + kh * A + k)) | ((unsigned)(p * A + __ldg(d.tab.k21w + kh * A + k)) << 16);
-    g1p[kh] = (unsigned)(p * A + __ldg(d.tab.ik1w + kh * A + k)) | ((unsigned)(p * A + __ldg(d.tab.ik11w + kh * A + k)) << 16);
-    g2p[kh] = (unsigned)(p * A + __ldg(d.tab.ik2w + kh * A + k)) | ((unsigned)(p * A + __ldg(d.tab.ik21w + kh * A + k)) << 16);
+    for (int i = 0; i < NP; ++i) {
+      const double cw2 = sq(fmax(0.0, costh * csw.v[i] + sinth * snw.v[i]));
+      flm.v[i] = flmc.v[i] * cw2;
+      iceadd.v[i] = ia.v[i] * cw2;
+      mij[i] = (int)s[S_MIJ * n + pq + i];
+    }
   }
-  double icefree = 1.0, ice_add = 0.0;
   const bool setice = c_dc.licerun && c_dc.lmaskice;
-  if (setice && cicover > c_dc.cithrsh) { icefree = 0.0; ice_add = fmax(c_dc.EPSMIN, 1.0 - cicover) * c_dc.flmin * sq(fmax(0.0, coswdif)); }
   const double delt = c_dc.delt, deltm = 1.0 / delt, delt5 = c_dc.ximp * delt;
   const double tmp03 = 1.0 / (c_dc.SDSBR * c_dc.MICHE);
   const int MFR1STFR = -c_dc.MFRSTLW + 1, MFRLSTFR = F - c_dc.KFRH + MFR1STFR, MLSTHG = c_dc.MLSTHG;
-  // ---- prologue: per-(point, frequency) scalars, saturation weights, first 4 rows of the ring
-  for (int x = t; x < F * NPT; x += blockDim.x) {
-    const int m = x / NPT, q = x - m * NPT;
-    const long long qp = min(pbase + q, plast);
-    const long long qc = qp / d.P;
-    const size_t o3 = (size_t)(qp - qc * d.P) + P * ((size_t)m + (size_t)F * (size_t)qc);
-    const double wn = d.f.wavnum[o3], ci = d.f.cinv[o3], xk = d.f.xk2cg[o3], dep = d.f.depth[qp];
-    tb[(TQ_FACSAT * F + m) * NPT + q] = wn * (1.0 / c_dc.ZPI) * xk;
-    double sbo = 0.0;
-    if (m < c_dc.Fr && dep < c_dc.bathymax) sbo = (-2.0 * 0.038 * c_dc.GM1) * wn / sinh(fmin(2.0 * dep * wn, 50.0));   // sbottom.F90:76-97
-    tb[(TQ_SBO * F + m) * NPT + q] = sbo;
-    tb[(TQ_CINV * F + m) * NPT + q] = ci;
-    tb[(TQ_TAIL * F + m) * NPT + q] = 1.0 / xk / wn;                                    // imphftail.F90:73-81
-    tb[(TQ_STF * F + m) * NPT + q] = (m < c_dc.NFRE_ODD) ? d.f.stokfac[o3] * c_dc.DFIM_SIM[m] : 0.0;
-    double tj = 0.0;
-    if (!ard) {   // SDISSIP_JAN (sdissip_jan.F90:96-132)
-      const double emean = s[S_EMEAN * n + qp], f1mean = s[S_F1MEAN * n + qp], xkmean = s[S_XKMEAN * n + qp];
-      const double sds = c_dc.CDIS * c_dc.ZPI * f1mean * sq(emean) * p4(xkmean);
-      const double xx = wn / xkmean;
-      tj = sds * xx * ((1.0 - c_dc.DELTA_SDIS) + c_dc.DELTA_SDIS * xx) + c_dc.rnu * c_dc.CDISVIS * sq(wn);
-    }
-    tb[(TQ_JAN * F + m) * NPT + q] = tj;
-  }
-  if (ard) for (int x = t; x < NS * A; x += blockDim.x) satw[x] = __ldg(d.tab.satweights + x);
-  for (int r = 0; r < 4 && r < F; ++r) ring[(r & 7) * PS + mt] = load_row(r);
-  double acc_sl[8], acc_fld[8];   // pending SNONLIN sums of rows MC0-4 .. MC0+3 (window slides one row per step)
+  const bool lssource = c_dc.lcflx && c_dc.lwvflx_snl;
+  // uniform shared-memory offsets of the interaction partners (bytes)
+  int so[2][4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { acc_sl[j] = 0.0; acc_fld[j] = 0.0; }
-  double b_prev = 0.0, fmij = 0.0;
-  double a_philf = 0.0, a_xs = 0.0, a_ys = 0.0, a_us = 0.0, a_vs = 0.0, a_e1 = 0.0, a_e2 = 0.0, a_el = 0.0;
-  size_t off_xl = 0;
-  if (LWFLUX) { const long long pc = pp / d.P; off_xl = (size_t)(pp - pc * d.P) + P * A * F * (size_t)pc + P * (size_t)k; }
-  int ksat0 = k - NSD;
-  if (ksat0 < 0) ksat0 += A;
-  __syncthreads();
-  const double tail_mij = tb[(TQ_TAIL * F + (mij - 1)) * NPT + p];
+  for (int kh = 0; kh < 2; ++kh)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) so[kh][q] = d.dsh[kh][q] * (ST_NPT * 8);
+
+  double asl[8][NP], afl[8][NP];   // pending SNONLIN sums of rows s-4 .. s+3 (window slides one row per step)
+#pragma unroll
+  for (int x = 0; x < 8; ++x)
+#pragma unroll
+    for (int i = 0; i < NP; ++i) { asl[x][i] = 0.0; afl[x][i] = 0.0; }
+  V b_prev, fmij, a_philf, a_ts, a_tu, a_e1, a_e2, a_el;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) { b_prev.v[i] = 0.0; fmij.v[i] = 0.0; a_philf.v[i] = 0.0; a_ts.v[i] = 0.0; a_tu.v[i] = 0.0; a_e1.v[i] = 0.0; a_e2.v[i] = 0.0; a_el.v[i] = 0.0; }
+  const unsigned satw_me = L.satw + (unsigned)k * (EW_MAXSAT * 8);
+  const unsigned lane = (unsigned)t & 31u;
 
 #pragma unroll 1
-  for (int MC0 = 0; MC0 < MLSTHG; ++MC0) {
+  for (int st = -4; st < MLSTHG; ++st) {
     // ================= phase A =================
-    const int rin = MC0 + 4, rfin = MC0 - 4, rb = MC0 - 3, rout = MC0 - 5;
-    double xF = 0.0, xI = 0.0;
-    if (rin < F) xF = load_row(rin);
-    if (rfin >= 0) xI = __ldg(d.fldin + off_hi + (size_t)rfin * rstr);
-    if (rout >= 0 && tvalid) d.f.fl1[off_hi + (size_t)rout * rstr] = sout[mt];
-    // DIA interaction values of centre frequency MC = MC0+1 (snonlin.F90:225-250)
-    const double* R = c_dc.RNLCOEF[MC0];
-    const double ftemp = c_dc.AF11[MC0] * enhfr;
-    const int MC = MC0 + 1;
-    const int branch = (MC > MFR1STFR && MC < MFRLSTFR) ? 0 : (MC >= MFRLSTFR ? 1 : 2);
-    bool do_c, do_mm, do_mm1, do_mp, do_mp1;
-    {
-      const int MP = MC + 2, MP1 = MC + 3, MM1 = MC - 3;
-      if (branch == 0) { do_c = do_mm = do_mm1 = do_mp = do_mp1 = true; }
-      else if (branch == 1) { do_mm = true; do_mm1 = MM1 <= F; do_c = do_mm1 && MC <= F; do_mp = do_c && MP <= F; do_mp1 = do_mp && MP1 <= F; }
-      else { do_mm = false; do_mm1 = MM1 >= 1; do_c = true; do_mp = true; do_mp1 = true; }
+    const int rin = st + 4, rfin = st - 4, rb = st - 3, rtb = st - 2;
+    const unsigned par = (unsigned)st & 1u;
+    V xF, xI, xL, fold, b_next;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) { xF.v[i] = 0.0; xI.v[i] = 0.0; xL.v[i] = 0.0; fold.v[i] = 0.0; b_next.v[i] = 0.0; }
+    if (rin < F) xF = ldg<NP>((rin < mlo ? src_lo : src_hi) + (size_t)rin * rstr);
+    if (rfin >= 0) {
+      xI = ldg<NP>(src_in + (size_t)rfin * rstr);
+      if (LWFLUX) xL = ldg<NP>(src_xl + (size_t)rfin * rstr);
     }
-    double ad[2], delad[2];
-    {
-      const double* rIP = ring + ((c_dc.INLCOEF[MC0][1] - 1) & 7) * PS;
-      const double* rIP1 = ring + ((c_dc.INLCOEF[MC0][2] - 1) & 7) * PS;
-      const double* rIM = ring + ((c_dc.INLCOEF[MC0][3] - 1) & 7) * PS;
-      const double* rIM1 = ring + ((c_dc.INLCOEF[MC0][4] - 1) & 7) * PS;
-      const double fc = ring[((c_dc.INLCOEF[MC0][0] - 1) & 7) * PS + me];
-      const double fij = (branch == 0) ? fc : fc * R[0];
-      const double fcen = ftemp * fij;
+    if (rtb >= 0 && rtb < F && t < TQ_N * ST_NPT) {   // per-(point, frequency) scalars of row rtb (used from the next step on)
+      const int q = t >> 3, pt = t & 7;
+      const double* g = d.tbg + ((size_t)q * F + rtb) * n + min(pbase + pt, plast);
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(sm + L.tbs + (unsigned)(((rtb & 3) * TQ_N + q) * 64 + pt * 8));
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(g));
+    }
+    if (st >= 0) {
+      // DIA interaction values of centre frequency MC = st+1 (snonlin.F90:225-250)
+      const int MC0 = st, MC = st + 1;
+      const double* R = c_dc.RNLCOEF[MC0];
+      const int branch = (MC > MFR1STFR && MC < MFRLSTFR) ? 0 : (MC >= MFRLSTFR ? 1 : 2);
+      bool do_c;
+      {
+        const int MM1 = MC - 3;
+        if (branch == 0) do_c = true;
+        else if (branch == 1) do_c = (MM1 <= F) && MC <= F;
+        else do_c = true;
+      }
+      const unsigned bIC = L.ring + slot9(c_dc.INLCOEF[MC0][0] - 1) * RSB + me_r;
+      const unsigned bIP = L.ring + slot9(c_dc.INLCOEF[MC0][1] - 1) * RSB + me_r;
+      const unsigned bIP1 = L.ring + slot9(c_dc.INLCOEF[MC0][2] - 1) * RSB + me_r;
+      const unsigned bIM = L.ring + slot9(c_dc.INLCOEF[MC0][3] - 1) * RSB + me_r;
+      const unsigned bIM1 = L.ring + slot9(c_dc.INLCOEF[MC0][4] - 1) * RSB + me_r;
+      const unsigned cb = L.cur + par * 6u * PSB + me_c;
+      const V fc = lds<NP>(sm, bIC);
+      const V enh = lds<NP>(sm, L.pc + PC_ENH * 64 + jo);
+      const double af11 = c_dc.AF11[MC0];
+      V fij, fcen, ftemp;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        ftemp.v[i] = af11 * enh.v[i];
+        fij.v[i] = (branch == 0) ? fc.v[i] : fc.v[i] * R[0];
+        fcen.v[i] = ftemp.v[i] * fij.v[i];
+      }
+      V csl, cfl;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) { csl.v[i] = 0.0; cfl.v[i] = 0.0; }
 #pragma unroll
       for (int kh = 0; kh < 2; ++kh) {
-        const int o1 = o1p[kh] & 0xffff, o11 = o1p[kh] >> 16, o2 = o2p[kh] & 0xffff, o21 = o2p[kh] >> 16;
-        const double sap = R[1] * rIP[o1] + R[2] * rIP[o11] + R[3] * rIP1[o1] + R[4] * rIP1[o11];
-        const double sam = R[13] * rIM[o2] + R[14] * rIM[o21] + R[15] * rIM1[o2] + R[16] * rIM1[o21];
-        double fad1 = fij * (sap + sam);
-        const double fad2 = fad1 - 2.0 * sap * sam;
-        fad1 = fad1 + fad2;
-        ad[kh] = fad2 * fcen;
-        delad[kh] = fad1 * ftemp;
-        cur[(0 + kh) * PS + me] = ad[kh];
-        cur[(2 + kh) * PS + me] = (fij - 2.0 * sam) * c_dc.DAL1 * fcen;   // DELAP
-        cur[(4 + kh) * PS + me] = (fij - 2.0 * sap) * c_dc.DAL2 * fcen;   // DELAM
+        const V p1 = lds<NP>(sm, bIP + so[kh][0]), p11 = lds<NP>(sm, bIP + so[kh][1]);
+        const V q1 = lds<NP>(sm, bIP1 + so[kh][0]), q11 = lds<NP>(sm, bIP1 + so[kh][1]);
+        const V m2 = lds<NP>(sm, bIM + so[kh][2]), m21 = lds<NP>(sm, bIM + so[kh][3]);
+        const V n2 = lds<NP>(sm, bIM1 + so[kh][2]), n21 = lds<NP>(sm, bIM1 + so[kh][3]);
+        V vad, vdp, vdm;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          const double sap = R[1] * p1.v[i] + R[2] * p11.v[i] + R[3] * q1.v[i] + R[4] * q11.v[i];
+          const double sam = R[13] * m2.v[i] + R[14] * m21.v[i] + R[15] * n2.v[i] + R[16] * n21.v[i];
+          double fad1 = fij.v[i] * (sap + sam);
+          const double fad2 = fad1 - 2.0 * sap * sam;
+          fad1 = fad1 + fad2;
+          vad.v[i] = fad2 * fcen.v[i];
+          csl.v[i] += vad.v[i];
+          cfl.v[i] += fad1 * ftemp.v[i];
+          vdp.v[i] = (fij.v[i] - 2.0 * sam) * c_dc.DAL1 * fcen.v[i];   // DELAP
+          vdm.v[i] = (fij.v[i] - 2.0 * sap) * c_dc.DAL2 * fcen.v[i];   // DELAM
+        }
+        if (act) {
+          sts<NP>(sm, cb + (0 + kh) * PSB, vad);
+          sts<NP>(sm, cb + (2 + kh) * PSB, vdp);
+          sts<NP>(sm, cb + (4 + kh) * PSB, vdm);
+          if (k < HC) {
+            sts<NP>(sm, cb + (0 + kh) * PSB + (unsigned)A * 64u, vad);
+            sts<NP>(sm, cb + (2 + kh) * PSB + (unsigned)A * 64u, vdp);
+            sts<NP>(sm, cb + (4 + kh) * PSB + (unsigned)A * 64u, vdm);
+          }
+          if (k >= A - HC) {
+            sts<NP>(sm, cb + (0 + kh) * PSB - (unsigned)A * 64u, vad);
+            sts<NP>(sm, cb + (2 + kh) * PSB - (unsigned)A * 64u, vdp);
+            sts<NP>(sm, cb + (4 + kh) * PSB - (unsigned)A * 64u, vdm);
+          }
+        }
+      }
+      if (do_c) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) { asl[4][i] -= 2.0 * csl.v[i]; afl[4][i] -= 2.0 * cfl.v[i]; }
       }
     }
-    const double fold = (rfin >= 0) ? ring[(rfin & 7) * PS + me] : 0.0;
+    if (rfin >= 0) fold = lds<NP>(sm, L.ring + slot9(rfin) * RSB + me_r);
     // saturation spectrum of row rb for SDISSIP_ARD (sdissip_ard.F90:142-160): cyclic window of 2*NSDSNTH+1 directions
-    double b_next = 0.0;
     if (ard && rb >= 0 && rb < F) {
-      const double* rr = ring + (rb & 7) * PS + p * A;
-      const double* ws = satw + k;
-      int kk = ksat0;
-      double b = 0.0;
-      for (int x = 0; x < NS; ++x) {
-        b += ws[0] * rr[kk];
-        ws += A;
-        kk = (kk + 1 == A) ? 0 : kk + 1;
+      const unsigned wb = L.ring + slot9(rb) * RSB + me_r - (unsigned)NSD * 64u;
+      V b;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) b.v[i] = 0.0;
+#pragma unroll
+      for (int x = 0; x < ST_NSMAX; ++x) {
+        if (x < NS) {
+          const double w = *reinterpret_cast<const double*>(sm + satw_me + x * 8);
+          const V f = lds<NP>(sm, wb + x * 64);
+#pragma unroll
+          for (int i = 0; i < NP; ++i) b.v[i] += w * f.v[i];
+        }
       }
-      b_next = b * tb[(TQ_FACSAT * F + rb) * NPT + p];
-      bthv[me] = b_next;
+      const V fs = lds<NP>(sm, L.tbs + (unsigned)(((rb & 3) * TQ_N + TQ_FACSAT) * 64) + jo);
+      V mx;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) { b_next.v[i] = b.v[i] * fs.v[i]; mx.v[i] = b_next.v[i]; }
+      // BTH0 = max over direction: over the directions of this warp with shuffles, then one partial per warp
+#pragma unroll
+      for (int o = 16; o >= NG; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < NP; ++i) mx.v[i] = fmax(mx.v[i], __shfl_xor_sync(FULLMASK, mx.v[i], o));
+      if (lane < NG) sts<NP>(sm, L.part + (par * (unsigned)nwarp + ((unsigned)t >> 5)) * 64u + jo, mx);
     }
-    sin_[mt] = xI;
+    if (rin < F) {   // depth-limited (+ floored at NFRE) row rin -> ring
+      const V fac = lds<NP>(sm, L.pc + PC_FAC * 64 + jo);
+      V v;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        v.v[i] = fmax(xF.v[i] * fac.v[i], c_dc.EPSMIN);
+        if (rin == F - 1) v.v[i] = fmax(v.v[i], flm.v[i]);
+      }
+      if (act) {
+        const unsigned rbse = L.ring + slot9(rin) * RSB + me_r;
+        sts<NP>(sm, rbse, v);
+        if (k < H) sts<NP>(sm, rbse + (unsigned)A * 64u, v);
+        if (k >= A - H) sts<NP>(sm, rbse - (unsigned)A * 64u, v);
+      }
+    }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
     __syncthreads();
     // ================= phase B =================
-    // gather the quadruplet contributions of MC into the pending rows (snonlin.F90:253-308, :333-410, :446-490)
-    {
-      double sl_mm = 0, fl_mm = 0, sl_mm1 = 0, fl_mm1 = 0, sl_mp = 0, fl_mp = 0, sl_mp1 = 0, fl_mp1 = 0;
+    if (st >= 0) {
+      // gather the quadruplet contributions of MC into the pending rows (snonlin.F90:253-308, :333-410, :446-490)
+      const int MC0 = st, MC = st + 1;
+      const double* R = c_dc.RNLCOEF[MC0];
+      const int branch = (MC > MFR1STFR && MC < MFRLSTFR) ? 0 : (MC >= MFRLSTFR ? 1 : 2);
+      bool do_mm, do_mm1, do_mp, do_mp1;
+      {
+        const int MP = MC + 2, MP1 = MC + 3, MM1 = MC - 3;
+        if (branch == 0) { do_mm = do_mm1 = do_mp = do_mp1 = true; }
+        else if (branch == 1) { do_mm = true; do_mm1 = MM1 <= F; const bool dc = do_mm1 && MC <= F; do_mp = dc && MP <= F; do_mp1 = do_mp && MP1 <= F; }
+        else { do_mm = false; do_mm1 = MM1 >= 1; do_mp = true; do_mp1 = true; }
+      }
+      const unsigned cb = L.cur + par * 6u * PSB + me_c;
+      V sl_mm, fl_mm, sl_mm1, fl_mm1, sl_mp, fl_mp, sl_mp1, fl_mp1;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) { sl_mm.v[i] = fl_mm.v[i] = sl_mm1.v[i] = fl_mm1.v[i] = sl_mp.v[i] = fl_mp.v[i] = sl_mp1.v[i] = fl_mp1.v[i] = 0.0; }
 #pragma unroll
       for (int kh = 0; kh < 2; ++kh) {
-        const double* cA = cur + (0 + kh) * PS;
-        const double* cP = cur + (2 + kh) * PS;
-        const double* cM = cur + (4 + kh) * PS;
-        const int g1 = g1p[kh] & 0xffff, g11 = g1p[kh] >> 16, g2 = g2p[kh] & 0xffff, g21 = g2p[kh] >> 16;
-        const double a2 = cA[g2], a21 = cA[g21], m2 = cM[g2], m21 = cM[g21];
-        const double a1 = cA[g1], a11 = cA[g11], q1 = cP[g1], q11 = cP[g11];
-        sl_mm += a2 * R[20] + a21 * R[19];   fl_mm += m2 * R[23] + m21 * R[24];     // FKLAMM1, FKLAMM2 | FKLAM12, FKLAM22
-        sl_mm1 += a2 * R[17] + a21 * R[18];  fl_mm1 += m2 * R[21] + m21 * R[22];    // FKLAMMA, FKLAMMB | FKLAMA2, FKLAMB2
-        sl_mp += a1 * R[8] + a11 * R[7];     fl_mp += q1 * R[11] + q11 * R[12];     // FKLAMP1, FKLAMP2 | FKLAP12, FKLAP22
-        sl_mp1 += a1 * R[5] + a11 * R[6];    fl_mp1 += q1 * R[9] + q11 * R[10];     // FKLAMPA, FKLAMPB | FKLAPA2, FKLAPB2
+        const unsigned cA = cb + (0 + kh) * PSB, cP = cb + (2 + kh) * PSB, cM = cb + (4 + kh) * PSB;
+        const V a2 = lds<NP>(sm, cA - so[kh][2]), a21 = lds<NP>(sm, cA - so[kh][3]);
+        const V m2 = lds<NP>(sm, cM - so[kh][2]), m21 = lds<NP>(sm, cM - so[kh][3]);
+        const V a1 = lds<NP>(sm, cA - so[kh][0]), a11 = lds<NP>(sm, cA - so[kh][1]);
+        const V q1 = lds<NP>(sm, cP - so[kh][0]), q11 = lds<NP>(sm, cP - so[kh][1]);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          sl_mm.v[i] += a2.v[i] * R[20] + a21.v[i] * R[19];   fl_mm.v[i] += m2.v[i] * R[23] + m21.v[i] * R[24];     // FKLAMM1, FKLAMM2 | FKLAM12, FKLAM22
+          sl_mm1.v[i] += a2.v[i] * R[17] + a21.v[i] * R[18];  fl_mm1.v[i] += m2.v[i] * R[21] + m21.v[i] * R[22];    // FKLAMMA, FKLAMMB | FKLAMA2, FKLAMB2
+          sl_mp.v[i] += a1.v[i] * R[8] + a11.v[i] * R[7];     fl_mp.v[i] += q1.v[i] * R[11] + q11.v[i] * R[12];     // FKLAMP1, FKLAMP2 | FKLAP12, FKLAP22
+          sl_mp1.v[i] += a1.v[i] * R[5] + a11.v[i] * R[6];    fl_mp1.v[i] += q1.v[i] * R[9] + q11.v[i] * R[10];     // FKLAMPA, FKLAMPB | FKLAPA2, FKLAPB2
+        }
       }
-      if (do_c) { acc_sl[4] -= 2.0 * (ad[0] + ad[1]); acc_fld[4] -= 2.0 * (delad[0] + delad[1]); }
-      if (do_mm) { acc_sl[0] += sl_mm; acc_fld[0] += fl_mm; }
-      if (do_mm1) { acc_sl[1] += sl_mm1; acc_fld[1] += fl_mm1; }
-      if (do_mp) { acc_sl[6] += sl_mp; acc_fld[6] += fl_mp; }
-      if (do_mp1) { acc_sl[7] += sl_mp1; acc_fld[7] += fl_mp1; }
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        if (do_mm) { asl[0][i] += sl_mm.v[i]; afl[0][i] += fl_mm.v[i]; }
+        if (do_mm1) { asl[1][i] += sl_mm1.v[i]; afl[1][i] += fl_mm1.v[i]; }
+        if (do_mp) { asl[6][i] += sl_mp.v[i]; afl[6][i] += fl_mp.v[i]; }
+        if (do_mp1) { asl[7][i] += sl_mp1.v[i]; afl[7][i] += fl_mp1.v[i]; }
+      }
     }
-    // finish row rfin (implsch.F90:276-395 for this bin)
+    // finish row rfin (implsch.F90:276-395 for these bins)
     if (rfin >= 0) {
       const int r = rfin;
-      const double f0 = fold;
-      double fldv = sin_[me];                          // wind input (SINPUT, second SINFLX call)
-      double slv = fldv * f0;
-      double dd;
+      const unsigned tq = L.tbs + (unsigned)((r & 3) * TQ_N * 64) + jo;
+      const V usfm = lds<NP>(sm, L.pc + PC_USFMDELT * 64 + jo), sdsbk = lds<NP>(sm, L.pc + PC_SDSBK * 64 + jo);
+      const V tsbo = lds<NP>(sm, tq + TQ_SBO * 64), tcinv = lds<NP>(sm, tq + TQ_CINV * 64), ttail = lds<NP>(sm, tq + TQ_TAIL * 64);
+      const V tstf = lds<NP>(sm, tq + TQ_STF * 64), rtail = lds<NP>(sm, L.pc + PC_RTAIL * 64 + jo), icefree = lds<NP>(sm, L.pc + PC_ICEFREE * 64 + jo);
+      V dd;
       if (ard) {
-        const double* bp = bth0 + ((r & 3) * NPT + p) * 4;
-        const double b0 = fmax(fmax(bp[0], bp[1]), fmax(bp[2], bp[3]));
+        const V b0 = lds<NP>(sm, L.bth0 + (par ^ 1u) * 64u + jo);
         const double ssdsc2_sig = c_dc.SSDSC2 * c_dc.ZPIFR[r];
-        dd = ssdsc2_sig * c_dc.SSDSC6 * sq(fmax(0., b0 * tmp03 - c_dc.SSDSC4)) +
-             ssdsc2_sig * (1. - c_dc.SSDSC6) * sq(fmax(0., b_prev * tmp03 - c_dc.SSDSC4));
-      } else dd = tb[(TQ_JAN * F + r) * NPT + p];
-      slv = slv + dd * f0; fldv = fldv + dd;           // SDISSIP
-      slv = slv + acc_sl[0]; fldv = fldv + acc_fld[0]; // SNONLIN
-      double ssource = 0.0;
-      if (c_dc.lcflx && c_dc.lwvflx_snl) ssource = slv / fmax(1.0 - delt5 * fldv, 1.0);
-      if (r < c_dc.Fr) {
-        if (brk) { slv = slv - sds_bk * f0; fldv = fldv - sds_bk; }              // SDIWBK
-        const double sbo = tb[(TQ_SBO * F + r) * NPT + p];
-        slv = slv + sbo * f0; fldv = fldv + sbo;                                 // SBOTTOM
+#pragma unroll
+        for (int i = 0; i < NP; ++i)
+          dd.v[i] = ssdsc2_sig * c_dc.SSDSC6 * sq(fmax(0., b0.v[i] * tmp03 - c_dc.SSDSC4)) +
+                    ssdsc2_sig * (1. - c_dc.SSDSC6) * sq(fmax(0., b_prev.v[i] * tmp03 - c_dc.SSDSC4));
+      } else dd = lds<NP>(sm, tq + TQ_JAN * 64);
+      const double cofrm4 = c_dc.COFRM4[r], flmax = c_dc.FLMAX[r], dfim = c_dc.DFIM[r], dfimofr = c_dc.DFIMOFR[r];
+      const double rhowg = c_dc.RHOWG_DFIM[r];
+      V fnv;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const double f0 = fold.v[i];
+        double fldv = xI.v[i];                             // wind input (SINPUT, second SINFLX call)
+        double slv = fldv * f0;
+        slv = slv + dd.v[i] * f0; fldv = fldv + dd.v[i];   // SDISSIP
+        slv = slv + asl[0][i]; fldv = fldv + afl[0][i];    // SNONLIN
+        double ssource = 0.0;
+        if (lssource) ssource = div_ge1(slv, fmax(1.0 - delt5 * fldv, 1.0));
+        if (r < c_dc.Fr) {
+          slv = slv - sdsbk.v[i] * f0; fldv = fldv - sdsbk.v[i];            // SDIWBK (0 where it does not apply)
+          slv = slv + tsbo.v[i] * f0; fldv = fldv + tsbo.v[i];              // SBOTTOM
+        }
+        const double gtemp1 = fmax(1.0 - delt5 * fldv, 1.0);
+        const double gtemp2 = div_ge1(delt * slv, gtemp1);
+        const double flhab = fmin(fabs(gtemp2), usfm.v[i] * cofrm4);
+        double fn = f0 + copysign(flhab, gtemp2);
+        fn = fmax(fn, flm.v[i]);
+        ssource = ssource + deltm * fmin(flmax - fn, 0.0);
+        fn = fmin(fn, flmax);
+        {   // WNFLUXES sums (wnfluxes.F90:200-220); RHOWGDFTH of frcutindex.F90:99-108
+          double rr = (r + 1 > mij[i]) ? 0.0 : rhowg;
+          if (r + 1 == mij[i] && mij[i] != F) rr = 0.5 * rr;
+          a_philf.v[i] += ssource * rr;
+          a_ts.v[i] += ssource * (tcinv.v[i] * rr);
+        }
+        if (LWFLUX) {   // FEMEANWS on the new spectrum (before the tail is imposed)
+          const double xf = (xL.v[i] != 0.0) ? fn : 0.0;
+          a_e1.v[i] += dfim * xf; a_e2.v[i] += dfimofr * xf;
+          if (r == F - 1) a_el.v[i] += xf;
+        }
+        if (r == mij[i] - 1) fmij.v[i] = fn;                                                   // IMPHFTAIL reference row
+        if (r > mij[i] - 1) fn = fmax((ttail.v[i] * rtail.v[i]) * fmij.v[i], flm.v[i]);
+        if (setice) fn = fn * icefree.v[i] + iceadd.v[i];                                      // SETICE
+        a_tu.v[i] += tstf.v[i] * fn;                                                           // STOKESDRIFT
+        if (r == c_dc.NFRE_ODD - 1) {
+          const double cst = 2.0 * c_dc.DELTH * c_dc.ZPI * c_dc.ZPI * c_dc.ZPI / c_dc.G * p4(c_dc.FR[c_dc.NFRE_ODD - 1]);
+          a_tu.v[i] += cst * fn;
+        }
+        fnv.v[i] = fn;
       }
-      const double gtemp1 = fmax(1.0 - delt5 * fldv, 1.0);
-      const double gtemp2 = delt * slv / gtemp1;
-      const double flhab = fmin(fabs(gtemp2), usfm_delt * c_dc.COFRM4[r]);
-      double fn = f0 + copysign(flhab, gtemp2);
-      fn = fmax(fn, flm);
-      ssource = ssource + deltm * fmin(c_dc.FLMAX[r] - fn, 0.0);
-      fn = fmin(fn, c_dc.FLMAX[r]);
-      {   // WNFLUXES sums (wnfluxes.F90:200-220)
-        const double rr = rhowgdfth(r, mij);
-        const double cmr = tb[(TQ_CINV * F + r) * NPT + p] * rr;
-        a_philf += ssource * rr; a_xs += sinth * ssource * cmr; a_ys += costh * ssource * cmr;
-      }
-      if (LWFLUX) {   // FEMEANWS on the new spectrum (before the tail is imposed)
-        const double xf = (d.f.xllws[off_xl + (size_t)r * rstr] != 0.0) ? fn : 0.0;
-        a_e1 += c_dc.DFIM[r] * xf; a_e2 += c_dc.DFIMOFR[r] * xf;
-        if (r == F - 1) a_el += xf;
-      }
-      if (r == mij - 1) fmij = fn;                                               // IMPHFTAIL reference row
-      if (r > mij - 1) fn = fmax((tb[(TQ_TAIL * F + r) * NPT + p] / tail_mij) * fmij, flm);
-      if (setice) fn = fn * icefree + ice_add;                                   // SETICE
-      const double stf = tb[(TQ_STF * F + r) * NPT + p];
-      a_us += stf * fn * sinth; a_vs += stf * fn * costh;                        // STOKESDRIFT
-      if (r == c_dc.NFRE_ODD - 1) {
-        const double cst = 2.0 * c_dc.DELTH * c_dc.ZPI * c_dc.ZPI * c_dc.ZPI / c_dc.G * p4(c_dc.FR[c_dc.NFRE_ODD - 1]);
-        a_us += cst * sinth * fn; a_vs += cst * costh * fn;
-      }
-      sout[me] = fn;
+      if (dost) stg<NP>(dst + (size_t)r * rstr, fnv);
     }
-    if (rin < F) ring[(rin & 7) * PS + mt] = xF;
-    if (ard && t < 4 * NPT && rb >= 0 && rb < F) {   // BTH0 = max over direction, as 4 partial maxima per point (warp 0)
-      const int q = t >> 2, part = t & 3;
+    if (ard && t < ST_NPT && rb >= 0 && rb < F) {   // BTH0 of row rb from the per-warp partial maxima
+      const double* pp = reinterpret_cast<const double*>(sm + L.part + par * (unsigned)nwarp * 64u) + t;
       double mx = 0.0;
-      for (int kk = part; kk < A; kk += 4) mx = fmax(mx, bthv[q * A + kk]);
-      bth0[((rb & 3) * NPT + q) * 4 + part] = mx;
+      for (int w = 0; w < nwarp; ++w) mx = fmax(mx, pp[w * ST_NPT]);
+      reinterpret_cast<double*>(sm + L.bth0 + par * 64u)[t] = mx;
     }
     b_prev = b_next;
 #pragma unroll
-    for (int i = 0; i < 7; ++i) { acc_sl[i] = acc_sl[i + 1]; acc_fld[i] = acc_fld[i + 1]; }
-    acc_sl[7] = 0.0; acc_fld[7] = 0.0;
-    __syncthreads();
+    for (int x = 0; x < 7; ++x)
+#pragma unroll
+      for (int i = 0; i < NP; ++i) { asl[x][i] = asl[x + 1][i]; afl[x][i] = afl[x + 1][i]; }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) { asl[7][i] = 0.0; afl[7][i] = 0.0; }
   }
-  // last finished row -> HBM
-  if (tvalid) d.f.fl1[off_hi + (size_t)(F - 1) * rstr] = sout[mt];
   // ---- per-point sums over direction, then the scalar closures (one thread per point)
-  double* red = ring;          // 8 planes
-  red[0 * PS + me] = a_philf; red[1 * PS + me] = a_xs; red[2 * PS + me] = a_ys; red[3 * PS + me] = a_us;
-  red[4 * PS + me] = a_vs; red[5 * PS + me] = a_e1; red[6 * PS + me] = a_e2; red[7 * PS + me] = a_el;
   __syncthreads();
-  if (k == 0 && pvalid) {
+  {
+    // red[q][k][pt]: 8 planes of A*8 doubles in the (now free) ring area
+    const unsigned RP = (unsigned)A * 64u;
+    const unsigned ro = (unsigned)k * 64u + jo;
+    V a_xs, a_ys, a_us, a_vs;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) { a_xs.v[i] = sinth * a_ts.v[i]; a_ys.v[i] = costh * a_ts.v[i]; a_us.v[i] = a_tu.v[i] * sinth; a_vs.v[i] = a_tu.v[i] * costh; }
+    if (act) {
+      sts<NP>(sm, L.ring + 0 * RP + ro, a_philf); sts<NP>(sm, L.ring + 1 * RP + ro, a_xs); sts<NP>(sm, L.ring + 2 * RP + ro, a_ys);
+      sts<NP>(sm, L.ring + 3 * RP + ro, a_us); sts<NP>(sm, L.ring + 4 * RP + ro, a_vs);
+      if (LWFLUX) { sts<NP>(sm, L.ring + 5 * RP + ro, a_e1); sts<NP>(sm, L.ring + 6 * RP + ro, a_e2); sts<NP>(sm, L.ring + 7 * RP + ro, a_el); }
+    }
+  }
+  __syncthreads();
+  double* red = reinterpret_cast<double*>(sm + L.ring);
+  double* qs = reinterpret_cast<double*>(sm + L.cur);      // [8][8] reduced sums
+  if (t < 8 * ST_NPT) {
+    const int x = t >> 3, pt = t & 7;
+    double v = 0.0;
+    if (x < 5 || LWFLUX) for (int kk = 0; kk < A; ++kk) v += red[(x * A + kk) * ST_NPT + pt];
+    qs[x * ST_NPT + pt] = v;
+  }
+  __syncthreads();
+  if (t < ST_NPT && pbase + t <= plast) {
+    const long long pp = pbase + t;
     double q[8];
 #pragma unroll
-    for (int x = 0; x < 8; ++x) { double v = 0.0; for (int kk = 0; kk < A; ++kk) v += red[x * PS + p * A + kk]; q[x] = v; }
+    for (int x = 0; x < 8; ++x) q[x] = qs[x * ST_NPT + t];
+    const double* pcv = reinterpret_cast<const double*>(sm + L.pc) + t;
+    const double snw = pcv[PC_SNW * ST_NPT], csw = pcv[PC_CSW * ST_NPT];
+    const double cicover = d.f.cicover[pp];
     const double ufric = d.f.ufric[pp], aird = d.f.aird[pp], wsw = d.f.wswave[pp];
     // STOKESDRIFT closure (stokesdrift.F90:118-142)
     double us = q[3], vs = q[4];
@@ -936,10 +1126,25 @@ __global__ void __maxnreg__(112) k_stencil(ImplDev d, long long p0, long long np
   }
 }
 
+template <int NP, bool LW>
+static int launch_stencil(const ImplDev& d, long long p0, long long np, cudaStream_t st) {
+  const int nth = ((d.A * (ST_NPT / NP) + 31) / 32) * 32;
+  const StencilSmem L = stencil_smem(d.A, d.halo_r, d.halo_c, nth / 32);
+  static bool attr_done = false;
+  if (!attr_done) {
+    EW_CUDA_CHECK(cudaFuncSetAttribute(k_stencil<NP, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    EW_CUDA_CHECK(cudaFuncSetAttribute(k_stencil<NP, LW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attr_done = true;
+  }
+  if (L.total > 100 * 1024) { ew_set_error("k_stencil: shared memory %u B", L.total); return ECWAM_B200_EINVAL; }
+  k_stencil<NP, LW><<<(unsigned)((np + ST_NPT - 1) / ST_NPT), nth, L.total, st>>>(d, p0, np);
+  return 0;
+}
+
 int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage, cudaStream_t st) {
   if (np <= 0) return 0;
   const int A = d.A;
-  if (A > 36) { ew_set_error("k_stencil is built for NANG <= 36"); return ECWAM_B200_EINVAL; }
+  if (A > 36 || 2 * d.halo_r > A || 2 * d.halo_c > A) { ew_set_error("k_stencil is built for NANG <= 36 and direction halos <= NANG/2"); return ECWAM_B200_EINVAL; }
   if (stage == 0) {
     const size_t smp = (size_t)2 * A * KP_NTH * sizeof(double);
     static bool attr_p = false;
@@ -950,17 +1155,11 @@ int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage
     }
     k_point<<<(unsigned)((np + KP_NTH - 1) / KP_NTH), KP_NTH, smp, st>>>(d, p0, np);
   } else if (stage == 1) {
-    const size_t sm = ((size_t)17 * ST_NPT * A + (size_t)EW_MAXSAT * A + (size_t)TQ_N * d.F * ST_NPT + 16 * ST_NPT) * sizeof(double);
-    static bool attr_done = false;
-    if (!attr_done) {
-      EW_CUDA_CHECK(cudaFuncSetAttribute(k_stencil<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      EW_CUDA_CHECK(cudaFuncSetAttribute(k_stencil<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      EW_CUDA_CHECK(cudaFuncSetAttribute(k_stencil<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      EW_CUDA_CHECK(cudaFuncSetAttribute(k_stencil<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      attr_done = true;
-    }
-    if (d.lwflux) k_stencil<true><<<(unsigned)((np + ST_NPT - 1) / ST_NPT), ST_NPT * A, sm, st>>>(d, p0, np);
-    else k_stencil<false><<<(unsigned)((np + ST_NPT - 1) / ST_NPT), ST_NPT * A, sm, st>>>(d, p0, np);
+    // two grid points per thread (16-byte shared / global accesses) need an even NPROMA and an even first point
+    const uintptr_t al = (uintptr_t)d.f.fl1 | (uintptr_t)d.f.xllws | (uintptr_t)d.fldin | (uintptr_t)d.fl_lo;
+    const bool pair = (d.P % 2 == 0) && (p0 % 2 == 0) && (np % 2 == 0) && (al & 15) == 0;
+    if (pair) return d.lwflux ? launch_stencil<2, true>(d, p0, np, st) : launch_stencil<2, false>(d, p0, np, st);
+    return d.lwflux ? launch_stencil<1, true>(d, p0, np, st) : launch_stencil<1, false>(d, p0, np, st);
   } else return ECWAM_B200_EINVAL;
   return 0;
 }

@@ -45,7 +45,7 @@ void launch_pack(const PropDev& d, const double* src, int srcF, const double* cg
 void launch_unpack_cg(const PropDev& d, const double* in, const int* recv_pre, const int* recv_peer_of, const int* recv_e,
                       int ntot, int nfull, double* cgext, cudaStream_t st);
 void launch_copyback(const PropDev& d, const double* fl3, double* fl1, int m0, int m1, cudaStream_t st);
-void launch_pad(const PropDev& d, double* fl1, int m0, int m1, cudaStream_t st);
+void launch_pad(const PropDev& d, double* fl, int flF, int m0, int m1, cudaStream_t st);
 
 // ---- IMPLSCH -----------------------------------------------------------------------------------------------
 struct ImplDev {
@@ -60,7 +60,11 @@ struct ImplDev {
   int lwflux;              // YOWCOUP LWFLUX (selects the k_stencil instance that also forms WSEMEAN/WSFMEAN)
   long long nloc;          // own points (slots >= nloc of the last chunk are padding)
   DevTabPtr tab;
+  double* tbg;             // [TQ_N][F][npts] per-(point, frequency) scalars handed from k_point to k_stencil
+  int dsh[2][4];           // signed cyclic shifts of K1W, K11W, K2W, K21W (.,KH): K1W(K,KH) = K + dsh[KH][0] (mod NANG)
+  int halo_r, halo_c;      // direction halo of the shared-memory spectrum rows / interaction planes of k_stencil
 };
+#define EW_TQ_N 6          // number of planes of ImplDev::tbg
 int upload_dev_const(const DevConst& h, cudaStream_t st);
 // launches stage 0..1 of the IMPLSCH kernel sequence (k_point, k_stencil) for points [p0, p0+np)
 #define EW_IMPLSCH_NSTAGE 2

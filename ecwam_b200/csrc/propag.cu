@@ -323,7 +323,7 @@ __global__ void copyback_kernel(PropDev d, const double* __restrict__ fl3, doubl
   fl1[i + d.P * (km + (long long)d.A * d.F * c)] = fl3[is + d.P * (km + (long long)d.A * d.Fr * c)];
 }
 // padded lanes only (used when the last sub-step already wrote FL1 directly)
-__global__ void pad_kernel(PropDev d, double* __restrict__ fl1, int m0, int m1) {
+__global__ void pad_kernel(PropDev d, double* __restrict__ fl1, int flF, int m0, int m1) {
   const int c = d.nchnk - 1;
   const int kijl = d.nloc - c * d.P;
   const int npad = d.P - kijl;
@@ -332,7 +332,7 @@ __global__ void pad_kernel(PropDev d, double* __restrict__ fl1, int m0, int m1) 
   if (idx >= n) return;
   const int i = kijl + (int)(idx % npad);
   const long long km = idx / npad + (long long)m0 * d.A;
-  double* p = fl1 + d.P * (km + (long long)d.A * d.F * c);
+  double* p = fl1 + d.P * (km + (long long)d.A * flF * c);
   p[i] = p[0];
 }
 
@@ -380,12 +380,12 @@ void launch_copyback(const PropDev& d, const double* fl3, double* fl1, int m0, i
   dim3 grid((unsigned)((n + 255) / 256), d.nchnk);
   copyback_kernel<<<grid, 256, 0, st>>>(d, fl3, fl1, m0, m1);
 }
-void launch_pad(const PropDev& d, double* fl1, int m0, int m1, cudaStream_t st) {
+void launch_pad(const PropDev& d, double* fl1, int flF, int m0, int m1, cudaStream_t st) {
   const int kijl = d.nloc - (d.nchnk - 1) * d.P;
   const int npad = d.P - kijl;
   if (npad <= 0 || m1 <= m0) return;
   const long long n = (long long)npad * d.A * (m1 - m0);
-  pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, fl1, m0, m1);
+  pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, fl1, flF, m0, m1);
 }
 
 }  // namespace ew
