@@ -33,7 +33,7 @@ UNIT = "spectra/s"
 def workload_cfg(name):
     from ecwam_b200 import synth
     c = dict(synth.CONFIGS[name])
-    nproma = {"O48": 32, "O320": 64, "O640": 32, "O1280": 32}[name]
+    nproma = {"O48": 32, "O320": 64, "O640": 32, "O1280": 32, "P256": 32}[name]
     return c, nproma
 
 
@@ -307,7 +307,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="O640", choices=["O48", "O320", "O640", "O1280"])
+    ap.add_argument("--workload", default="O640", choices=["O48", "O320", "O640", "O1280", "P256"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)

@@ -71,7 +71,7 @@ struct ecwam_b200_handle_s {
   // implsch
   DBuf<double> scr, satw, swellft, fldin, tbg;
   int dsh[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-  int halo_r = 0, halo_c = 0;
+  int halo_r = 0, halo_c = 0, nsdsnth = 0;
   DBuf<int> kw, isat;
   DevTabPtr tab;
   // fields
@@ -204,9 +204,10 @@ static int fill_dev_const(const ecwam_b200_params& p, const ecwam_b200_tables& t
   for (int mc = 0; mc < t.mlsthg; ++mc) {
     c.IKP[mc] = t.ikp[off + mc]; c.IKP1[mc] = t.ikp1[off + mc]; c.IKM[mc] = t.ikm[off + mc]; c.IKM1[mc] = t.ikm1[off + mc];
     c.AF11[mc] = t.af11[off + mc];
-    for (int j = 0; j < 5; ++j) c.INLCOEF[mc][j] = t.inlcoef[j + 5 * mc];
+    for (int j = 0; j < 5; ++j) { c.INLCOEF[mc][j] = t.inlcoef[j + 5 * mc]; c.NLSLOT[mc][j] = (t.inlcoef[j + 5 * mc] - 1) % 9; }
     for (int j = 0; j < 25; ++j) c.RNLCOEF[mc][j] = t.rnlcoef[j + 25 * mc];
   }
+  for (int r = 0; r < EW_MAXF + 8; ++r) c.SLOT9[r] = r % 9;
   return 0;
 }
 
@@ -387,6 +388,7 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
         maxsh = std::max(maxsh, std::abs(sh));
       }
     h->halo_c = maxsh;
+    h->nsdsnth = tables->nsdsnth;
     h->halo_r = std::max(maxsh, p.iphys == 1 ? tables->nsdsnth : 0);
     if (ok && (2 * h->halo_r > A || (p.iphys == 1 && 2 * tables->nsdsnth + 1 > 17))) { ok = false; ew_set_error("direction halo %d too wide for NANG=%d", h->halo_r, A); }
   }
@@ -578,8 +580,9 @@ static ImplDev make_impl(H* h, bool from_fl3) {
   d.lwflux = h->par.lwflux;
   d.tab = h->tab;
   d.tbg = h->tbg.p;
-  memcpy(d.dsh, h->dsh, sizeof(d.dsh));
+  for (int kh = 0; kh < 2; ++kh) for (int q = 0; q < 4; ++q) d.dsb[kh][q] = h->dsh[kh][q] * 64;
   d.halo_r = h->halo_r; d.halo_c = h->halo_c;
+  d.iphys = h->par.iphys; d.nsdsnth = h->nsdsnth;
   return d;
 }
 

@@ -41,6 +41,9 @@ struct DevConst {
   int INLCOEF[EW_MAXMC][5];
   double RNLCOEF[EW_MAXMC][25];
   double AF11[EW_MAXMC];
+  // k_stencil: slot (row % 9) of the 9-row shared-memory ring for every frequency row and for INLCOEF(1:5,MC)
+  int SLOT9[EW_MAXF + 8];
+  int NLSLOT[EW_MAXMC][5];
 };
 
 // tables too irregular / large for constant memory (per-lane indexed)

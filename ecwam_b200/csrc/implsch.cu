@@ -44,6 +44,9 @@ __device__ __forceinline__ double wmax(double v) {
   return v;
 }
 __device__ __forceinline__ double sq(double x) { return x * x; }
+// max / min without fmax's NaN bookkeeping (DSETP + 2 selects instead of ~8 instructions); no NaNs occur on this path
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
 __device__ __forceinline__ double p4(double x) { double y = x * x; return y * y; }
 
 // (P,C) field element of point p
@@ -667,15 +670,17 @@ __device__ __forceinline__ double div_ge1(double a, double b) {
   const double q = a * r;
   return fma(fma(-b, q, a), r, q);
 }
-__device__ __forceinline__ unsigned slot9(int r) { return (unsigned)(r % ST_RING); }
+__device__ __forceinline__ unsigned slot9(int r) { return (unsigned)c_dc.SLOT9[r]; }   // r % ST_RING, 0 <= r < EW_MAXF
 
 struct StencilSmem {   // byte offsets into dynamic shared memory
-  unsigned ring, cur, satw, tbs, pc, part, bth0, total, RSB, PSB;
+  unsigned ring, cur, satw, tbs, pc, part, bth0, stage, total, RSB, PSB, SSB;
 };
-__host__ __device__ inline StencilSmem stencil_smem(int A, int halo_r, int halo_c, int nwarp) {
-  StencilSmem s;
+__host__ __device__ constexpr StencilSmem stencil_smem(int A, int halo_r, int halo_c, int nth, int np) {
+  StencilSmem s{};
+  const int nwarp = nth / 32;
   s.RSB = (unsigned)(A + 2 * halo_r) * ST_NPT * 8;
   s.PSB = (unsigned)(A + 2 * halo_c) * ST_NPT * 8;
+  s.SSB = (unsigned)nth * np * 8;
   unsigned o = 0;
   s.ring = o; o += ST_RING * s.RSB;
   s.cur = o; o += 2 * 6 * s.PSB;
@@ -684,22 +689,54 @@ __host__ __device__ inline StencilSmem stencil_smem(int A, int halo_r, int halo_
   s.pc = o; o += PC_N * ST_NPT * 8;
   s.part = o; o += 2u * (unsigned)nwarp * ST_NPT * 8;
   s.bth0 = o; o += 2 * ST_NPT * 8;
+  s.stage = o; o += 3 * s.SSB;      // thread-private landing slots of the cp.async row loads (FL1 row, wind-input row, XLLWS row)
   s.total = o;
   return s;
 }
+template <int NB> __device__ __forceinline__ void cp_async(unsigned sa, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(sa), "l"(g), "n"(NB));
+}
+template <int N> struct IC { static constexpr int value = N; };
+// Direction geometry of the standard ecWAM grids (NANG = 12, 24, 36), known at compile time so that every shared-memory
+// offset of k_stencil is an immediate: NSDSNTH = min(nint(80 deg / DELTH), NANG/2-1) (init_sdiss_ardh.F90:72) and the DIA
+// partner shifts K1W, K11W, K2W, K21W(K,KH) - K of nlweigt.F90:108-206 (checked against the run-time tables on the host).
+__host__ __device__ constexpr int geo_nsd(int A) { return A == 36 ? 8 : (A == 24 ? 5 : (A == 12 ? 3 : 0)); }
+__host__ __device__ constexpr int geo_sh(int A, int kh, int q) {
+  const int a = (A == 36) ? 1 : 0, b = (A == 36) ? 3 : (A == 24 ? 2 : 1);
+  const int mag = q == 0 ? a : (q == 1 ? a + 1 : (q == 2 ? b : b + 1));
+  const int sgn = ((q < 2) == (kh == 0)) ? -1 : 1;
+  return (A == 36 || A == 24 || A == 12) ? sgn * mag : 0;
+}
+__host__ __device__ constexpr int geo_hc(int A) { return A == 36 ? 4 : (A == 24 ? 3 : (A == 12 ? 2 : 0)); }
+__host__ __device__ constexpr int stencil_threads(int A, int np) { return ((A * (ST_NPT / np) + 31) / 32) * 32; }
 
-template <int NP, bool LWFLUX>
-__global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? 3 : 2) k_stencil(ImplDev d, long long p0, long long np) {
+#ifndef ST_U
+#define ST_U 1   // steps per trip of the frequency loop (the pending-row window slides ST_U rows per trip)
+#endif
+#ifndef ST_MINB
+#define ST_MINB 2   // resident CTAs per SM the two-point instance is compiled for
+#endif
+
+// TA = NANG when it is one of the standard grids (compile-time geometry), 0 = run-time geometry (any NANG <= 36)
+template <int TA, int NP, bool LWFLUX>
+__global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? ST_MINB : 2) k_stencil(ImplDev d, long long p0, long long np, StencilSmem Lrt) {
   extern __shared__ __align__(16) char sm[];
   typedef Vd<NP> V;
-  const int A = c_dc.A, F = c_dc.F;
+  const int A = TA > 0 ? TA : c_dc.A, F = c_dc.F;
   constexpr int NG = ST_NPT / NP;                    // point groups per CTA
-  const int NSD = c_dc.NSDSNTH, NS = 2 * NSD + 1;
+  const int NSD = TA > 0 ? geo_nsd(TA) : c_dc.NSDSNTH, NS = 2 * NSD + 1;
   const bool ard = c_dc.iphys == 1;
-  const int H = d.halo_r, HC = d.halo_c;
-  const int nwarp = (int)(blockDim.x >> 5);
-  const StencilSmem L = stencil_smem(A, H, HC, nwarp);
+  const int H = TA > 0 ? geo_nsd(TA) : d.halo_r, HC = TA > 0 ? geo_hc(TA) : d.halo_c;
+  const int nwarp = TA > 0 ? stencil_threads(TA, NP) / 32 : (int)(blockDim.x >> 5);
+  constexpr StencilSmem Lct = stencil_smem(TA, geo_nsd(TA), geo_hc(TA), stencil_threads(TA, NP), NP);
+  const StencilSmem L = TA > 0 ? Lct : Lrt;
   const unsigned RSB = L.RSB, PSB = L.PSB;
+  int dsb[2][4];
+#pragma unroll
+  for (int kh = 0; kh < 2; ++kh)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dsb[kh][q] = TA > 0 ? geo_sh(TA, kh, q) * (ST_NPT * 8) : d.dsb[kh][q];
+  const unsigned smb = (unsigned)__cvta_generic_to_shared(sm);
   const int t = threadIdx.x;
   int k = t / NG;
   const int j = t - k * NG;
@@ -708,6 +745,7 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? 3 : 2) k_stenci
   const unsigned jo = (unsigned)(j * NP * 8);
   const unsigned me_r = (unsigned)(k + H) * (ST_NPT * 8) + jo;     // own bin inside a ring row
   const unsigned me_c = (unsigned)(k + HC) * (ST_NPT * 8) + jo;    // own bin inside an interaction plane
+  const unsigned me_s = L.stage + (unsigned)t * (NP * 8);          // own landing slot
   // ---- points
   const long long pbase = p0 + (long long)blockIdx.x * ST_NPT;
   const long long plast = p0 + np - 1;
@@ -722,14 +760,13 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? 3 : 2) k_stenci
   const long long pc_ = pq / d.P;
   const int pi_ = (int)(pq - pc_ * d.P);
   const size_t off_hi = (size_t)pi_ + P * A * F * (size_t)pc_ + P * (size_t)k;    // element (pi, k, 0, pc) of a (P,A,F,C) array
-  const double* src_lo = d.f.fl1 + off_hi;
-  size_t rstr_dummy = 0; (void)rstr_dummy;
+  const double* src_hi = d.f.fl1 + off_hi;
+  const double* src_lo = src_hi;
   int mlo = 0;
   if (d.lo_on) {   // propagated frequencies come from the propagation scratch (P,A,Fr,C); its padded lanes are filled (launch_pad)
     src_lo = d.fl_lo + (size_t)pi_ + P * A * d.lo_F * (size_t)pc_ + P * (size_t)k;
     mlo = d.Fr;
   }
-  const double* src_hi = d.f.fl1 + off_hi;
   double* dst = d.f.fl1 + off_hi;
   const double* src_in = d.fldin + off_hi;
   const double* src_xl = d.f.xllws + off_hi;
@@ -741,7 +778,7 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? 3 : 2) k_stenci
     const double wd = d.f.wdwave[qp], ci = d.f.cicover[qp], dep = d.f.depth[qp];
     double snw, csw;
     sincos(wd, &snw, &csw);
-    double enhfr = fmax(0.75 * dep * s[S_AKMEAN * n + qp], 0.5);
+    double enhfr = dmax(0.75 * dep * s[S_AKMEAN * n + qp], 0.5);
     enhfr = 1.0 + (5.5 / enhfr) * (1.0 - .833 * enhfr) * exp(-1.25 * enhfr);
     const int mijq = (int)s[S_MIJ * n + qp];
     const bool seticeq = c_dc.licerun && c_dc.lmaskice && ci > c_dc.cithrsh;
@@ -750,8 +787,8 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? 3 : 2) k_stenci
     pcv[PC_USFMDELT * ST_NPT] = s[S_USFM * n + qp] * c_dc.delt;
     pcv[PC_SDSBK * ST_NPT] = (c_dc.lbiwbk && dep < 50.0) ? s[S_SDS * n + qp] : 0.0;
     pcv[PC_RTAIL * ST_NPT] = 1.0 / d.tbg[((size_t)TQ_TAIL * F + (mijq - 1)) * n + qp];
-    pcv[PC_FLMC * ST_NPT] = (1. - 0.9 * fmin(ci, 0.99)) * c_dc.flmin;
-    pcv[PC_ICEADD * ST_NPT] = seticeq ? fmax(c_dc.EPSMIN, 1.0 - ci) * c_dc.flmin : 0.0;
+    pcv[PC_FLMC * ST_NPT] = (1. - 0.9 * dmin(ci, 0.99)) * c_dc.flmin;
+    pcv[PC_ICEADD * ST_NPT] = seticeq ? dmax(c_dc.EPSMIN, 1.0 - ci) * c_dc.flmin : 0.0;
     pcv[PC_ICEFREE * ST_NPT] = seticeq ? 0.0 : 1.0;
     pcv[PC_SNW * ST_NPT] = snw;
     pcv[PC_CSW * ST_NPT] = csw;
@@ -762,16 +799,13 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? 3 : 2) k_stenci
   }
   __syncthreads();
   const double sinth = c_dc.SINTH[k], costh = c_dc.COSTH[k];
-  V flm, iceadd;
+  V cw2;      // max(0, cos(TH(k) - WDWAVE))**2: FLM(k) = FLMC*cw2 (implsch.F90:236-247), SETICE's noise floor likewise
   int mij[NP];
   {
     const V snw = lds<NP>(sm, L.pc + PC_SNW * 64 + jo), csw = lds<NP>(sm, L.pc + PC_CSW * 64 + jo);
-    const V flmc = lds<NP>(sm, L.pc + PC_FLMC * 64 + jo), ia = lds<NP>(sm, L.pc + PC_ICEADD * 64 + jo);
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
-      const double cw2 = sq(fmax(0.0, costh * csw.v[i] + sinth * snw.v[i]));
-      flm.v[i] = flmc.v[i] * cw2;
-      iceadd.v[i] = ia.v[i] * cw2;
+      cw2.v[i] = sq(dmax(0.0, costh * csw.v[i] + sinth * snw.v[i]));
       mij[i] = (int)s[S_MIJ * n + pq + i];
     }
   }
@@ -780,16 +814,11 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? 3 : 2) k_stenci
   const double tmp03 = 1.0 / (c_dc.SDSBR * c_dc.MICHE);
   const int MFR1STFR = -c_dc.MFRSTLW + 1, MFRLSTFR = F - c_dc.KFRH + MFR1STFR, MLSTHG = c_dc.MLSTHG;
   const bool lssource = c_dc.lcflx && c_dc.lwvflx_snl;
-  // uniform shared-memory offsets of the interaction partners (bytes)
-  int so[2][4];
-#pragma unroll
-  for (int kh = 0; kh < 2; ++kh)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) so[kh][q] = d.dsh[kh][q] * (ST_NPT * 8);
 
-  double asl[8][NP], afl[8][NP];   // pending SNONLIN sums of rows s-4 .. s+3 (window slides one row per step)
+  constexpr int NACC = 8 + ST_U - 1;
+  double asl[NACC][NP], afl[NACC][NP];   // pending SNONLIN sums of rows st-4 .. st+3+(ST_U-1) (the window slides ST_U rows per trip)
 #pragma unroll
-  for (int x = 0; x < 8; ++x)
+  for (int x = 0; x < NACC; ++x)
 #pragma unroll
     for (int i = 0; i < NP; ++i) { asl[x][i] = 0.0; afl[x][i] = 0.0; }
   V b_prev, fmij, a_philf, a_ts, a_tu, a_e1, a_e2, a_el;
@@ -798,42 +827,40 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? 3 : 2) k_stenci
   const unsigned satw_me = L.satw + (unsigned)k * (EW_MAXSAT * 8);
   const unsigned lane = (unsigned)t & 31u;
 
-#pragma unroll 1
-  for (int st = -4; st < MLSTHG; ++st) {
+  // one step of the sweep; O = compile-time position of row st-4 inside the pending-row window
+  auto step = [&](auto OC, const int st) {
+    constexpr int O = decltype(OC)::value;
     // ================= phase A =================
-    const int rin = st + 4, rfin = st - 4, rb = st - 3, rtb = st - 2;
+    const int rnew = st + 5, rfin = st - 4, rb = st - 3, rtb = st - 2;
     const unsigned par = (unsigned)st & 1u;
-    V xF, xI, xL, fold, b_next;
-#pragma unroll
-    for (int i = 0; i < NP; ++i) { xF.v[i] = 0.0; xI.v[i] = 0.0; xL.v[i] = 0.0; fold.v[i] = 0.0; b_next.v[i] = 0.0; }
-    if (rin < F) xF = ldg<NP>((rin < mlo ? src_lo : src_hi) + (size_t)rin * rstr);
-    if (rfin >= 0) {
-      xI = ldg<NP>(src_in + (size_t)rfin * rstr);
-      if (LWFLUX) xL = ldg<NP>(src_xl + (size_t)rfin * rstr);
+    const bool dia = st >= 0 && st < MLSTHG;
+    const bool fin = rfin >= 0 && rfin < F;
+    const bool sat = ard && rb >= 0 && rb < F;
+    // row loads of this step land in shared memory behind the barrier: FL1 row st+5 (enters the ring in phase B),
+    // wind-input (and XLLWS) row st-4 (consumed by the finish in phase B)
+    if (rnew >= 0 && rnew < F) cp_async<NP * 8>(smb + me_s, (rnew < mlo ? src_lo : src_hi) + (size_t)rnew * rstr);
+    if (fin) {
+      cp_async<NP * 8>(smb + me_s + L.SSB, src_in + (size_t)rfin * rstr);
+      if (LWFLUX) cp_async<NP * 8>(smb + me_s + 2 * L.SSB, src_xl + (size_t)rfin * rstr);
     }
     if (rtb >= 0 && rtb < F && t < TQ_N * ST_NPT) {   // per-(point, frequency) scalars of row rtb (used from the next step on)
       const int q = t >> 3, pt = t & 7;
-      const double* g = d.tbg + ((size_t)q * F + rtb) * n + min(pbase + pt, plast);
-      const unsigned sa = (unsigned)__cvta_generic_to_shared(sm + L.tbs + (unsigned)(((rtb & 3) * TQ_N + q) * 64 + pt * 8));
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(g));
+      cp_async<8>(smb + L.tbs + (unsigned)(((rtb & 3) * TQ_N + q) * 64 + pt * 8), d.tbg + ((size_t)q * F + rtb) * n + min(pbase + pt, plast));
     }
-    if (st >= 0) {
+    V b_next;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) b_next.v[i] = 0.0;
+    if (dia) {
       // DIA interaction values of centre frequency MC = st+1 (snonlin.F90:225-250)
       const int MC0 = st, MC = st + 1;
       const double* R = c_dc.RNLCOEF[MC0];
       const int branch = (MC > MFR1STFR && MC < MFRLSTFR) ? 0 : (MC >= MFRLSTFR ? 1 : 2);
-      bool do_c;
-      {
-        const int MM1 = MC - 3;
-        if (branch == 0) do_c = true;
-        else if (branch == 1) do_c = (MM1 <= F) && MC <= F;
-        else do_c = true;
-      }
-      const unsigned bIC = L.ring + slot9(c_dc.INLCOEF[MC0][0] - 1) * RSB + me_r;
-      const unsigned bIP = L.ring + slot9(c_dc.INLCOEF[MC0][1] - 1) * RSB + me_r;
-      const unsigned bIP1 = L.ring + slot9(c_dc.INLCOEF[MC0][2] - 1) * RSB + me_r;
-      const unsigned bIM = L.ring + slot9(c_dc.INLCOEF[MC0][3] - 1) * RSB + me_r;
-      const unsigned bIM1 = L.ring + slot9(c_dc.INLCOEF[MC0][4] - 1) * RSB + me_r;
+      const bool do_c = (branch == 1) ? ((MC - 3 <= F) && MC <= F) : true;
+      const unsigned bIC = L.ring + (unsigned)c_dc.NLSLOT[MC0][0] * RSB + me_r;
+      const unsigned bIP = L.ring + (unsigned)c_dc.NLSLOT[MC0][1] * RSB + me_r;
+      const unsigned bIP1 = L.ring + (unsigned)c_dc.NLSLOT[MC0][2] * RSB + me_r;
+      const unsigned bIM = L.ring + (unsigned)c_dc.NLSLOT[MC0][3] * RSB + me_r;
+      const unsigned bIM1 = L.ring + (unsigned)c_dc.NLSLOT[MC0][4] * RSB + me_r;
       const unsigned cb = L.cur + par * 6u * PSB + me_c;
       const V fc = lds<NP>(sm, bIC);
       const V enh = lds<NP>(sm, L.pc + PC_ENH * 64 + jo);
@@ -850,10 +877,10 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? 3 : 2) k_stenci
       for (int i = 0; i < NP; ++i) { csl.v[i] = 0.0; cfl.v[i] = 0.0; }
 #pragma unroll
       for (int kh = 0; kh < 2; ++kh) {
-        const V p1 = lds<NP>(sm, bIP + so[kh][0]), p11 = lds<NP>(sm, bIP + so[kh][1]);
-        const V q1 = lds<NP>(sm, bIP1 + so[kh][0]), q11 = lds<NP>(sm, bIP1 + so[kh][1]);
-        const V m2 = lds<NP>(sm, bIM + so[kh][2]), m21 = lds<NP>(sm, bIM + so[kh][3]);
-        const V n2 = lds<NP>(sm, bIM1 + so[kh][2]), n21 = lds<NP>(sm, bIM1 + so[kh][3]);
+        const V p1 = lds<NP>(sm, bIP + dsb[kh][0]), p11 = lds<NP>(sm, bIP + dsb[kh][1]);
+        const V q1 = lds<NP>(sm, bIP1 + dsb[kh][0]), q11 = lds<NP>(sm, bIP1 + dsb[kh][1]);
+        const V m2 = lds<NP>(sm, bIM + dsb[kh][2]), m21 = lds<NP>(sm, bIM + dsb[kh][3]);
+        const V n2 = lds<NP>(sm, bIM1 + dsb[kh][2]), n21 = lds<NP>(sm, bIM1 + dsb[kh][3]);
         V vad, vdp, vdm;
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
@@ -886,12 +913,11 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? 3 : 2) k_stenci
       }
       if (do_c) {
 #pragma unroll
-        for (int i = 0; i < NP; ++i) { asl[4][i] -= 2.0 * csl.v[i]; afl[4][i] -= 2.0 * cfl.v[i]; }
+        for (int i = 0; i < NP; ++i) { asl[O + 4][i] -= 2.0 * csl.v[i]; afl[O + 4][i] -= 2.0 * cfl.v[i]; }
       }
     }
-    if (rfin >= 0) fold = lds<NP>(sm, L.ring + slot9(rfin) * RSB + me_r);
     // saturation spectrum of row rb for SDISSIP_ARD (sdissip_ard.F90:142-160): cyclic window of 2*NSDSNTH+1 directions
-    if (ard && rb >= 0 && rb < F) {
+    if (sat) {
       const unsigned wb = L.ring + slot9(rb) * RSB + me_r - (unsigned)NSD * 64u;
       V b;
 #pragma unroll
@@ -913,28 +939,13 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? 3 : 2) k_stenci
 #pragma unroll
       for (int o = 16; o >= NG; o >>= 1)
 #pragma unroll
-        for (int i = 0; i < NP; ++i) mx.v[i] = fmax(mx.v[i], __shfl_xor_sync(FULLMASK, mx.v[i], o));
+        for (int i = 0; i < NP; ++i) mx.v[i] = dmax(mx.v[i], __shfl_xor_sync(FULLMASK, mx.v[i], o));
       if (lane < NG) sts<NP>(sm, L.part + (par * (unsigned)nwarp + ((unsigned)t >> 5)) * 64u + jo, mx);
-    }
-    if (rin < F) {   // depth-limited (+ floored at NFRE) row rin -> ring
-      const V fac = lds<NP>(sm, L.pc + PC_FAC * 64 + jo);
-      V v;
-#pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        v.v[i] = fmax(xF.v[i] * fac.v[i], c_dc.EPSMIN);
-        if (rin == F - 1) v.v[i] = fmax(v.v[i], flm.v[i]);
-      }
-      if (act) {
-        const unsigned rbse = L.ring + slot9(rin) * RSB + me_r;
-        sts<NP>(sm, rbse, v);
-        if (k < H) sts<NP>(sm, rbse + (unsigned)A * 64u, v);
-        if (k >= A - H) sts<NP>(sm, rbse - (unsigned)A * 64u, v);
-      }
     }
     asm volatile("cp.async.wait_all;\n" ::: "memory");
     __syncthreads();
     // ================= phase B =================
-    if (st >= 0) {
+    if (dia) {
       // gather the quadruplet contributions of MC into the pending rows (snonlin.F90:253-308, :333-410, :446-490)
       const int MC0 = st, MC = st + 1;
       const double* R = c_dc.RNLCOEF[MC0];
@@ -953,10 +964,10 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? 3 : 2) k_stenci
 #pragma unroll
       for (int kh = 0; kh < 2; ++kh) {
         const unsigned cA = cb + (0 + kh) * PSB, cP = cb + (2 + kh) * PSB, cM = cb + (4 + kh) * PSB;
-        const V a2 = lds<NP>(sm, cA - so[kh][2]), a21 = lds<NP>(sm, cA - so[kh][3]);
-        const V m2 = lds<NP>(sm, cM - so[kh][2]), m21 = lds<NP>(sm, cM - so[kh][3]);
-        const V a1 = lds<NP>(sm, cA - so[kh][0]), a11 = lds<NP>(sm, cA - so[kh][1]);
-        const V q1 = lds<NP>(sm, cP - so[kh][0]), q11 = lds<NP>(sm, cP - so[kh][1]);
+        const V a2 = lds<NP>(sm, cA - dsb[kh][2]), a21 = lds<NP>(sm, cA - dsb[kh][3]);
+        const V m2 = lds<NP>(sm, cM - dsb[kh][2]), m21 = lds<NP>(sm, cM - dsb[kh][3]);
+        const V a1 = lds<NP>(sm, cA - dsb[kh][0]), a11 = lds<NP>(sm, cA - dsb[kh][1]);
+        const V q1 = lds<NP>(sm, cP - dsb[kh][0]), q11 = lds<NP>(sm, cP - dsb[kh][1]);
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
           sl_mm.v[i] += a2.v[i] * R[20] + a21.v[i] * R[19];   fl_mm.v[i] += m2.v[i] * R[23] + m21.v[i] * R[24];     // FKLAMM1, FKLAMM2 | FKLAM12, FKLAM22
@@ -967,29 +978,35 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? 3 : 2) k_stenci
       }
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
-        if (do_mm) { asl[0][i] += sl_mm.v[i]; afl[0][i] += fl_mm.v[i]; }
-        if (do_mm1) { asl[1][i] += sl_mm1.v[i]; afl[1][i] += fl_mm1.v[i]; }
-        if (do_mp) { asl[6][i] += sl_mp.v[i]; afl[6][i] += fl_mp.v[i]; }
-        if (do_mp1) { asl[7][i] += sl_mp1.v[i]; afl[7][i] += fl_mp1.v[i]; }
+        if (do_mm) { asl[O + 0][i] += sl_mm.v[i]; afl[O + 0][i] += fl_mm.v[i]; }
+        if (do_mm1) { asl[O + 1][i] += sl_mm1.v[i]; afl[O + 1][i] += fl_mm1.v[i]; }
+        if (do_mp) { asl[O + 6][i] += sl_mp.v[i]; afl[O + 6][i] += fl_mp.v[i]; }
+        if (do_mp1) { asl[O + 7][i] += sl_mp1.v[i]; afl[O + 7][i] += fl_mp1.v[i]; }
       }
     }
+    const V flmc = lds<NP>(sm, L.pc + PC_FLMC * 64 + jo);
+    V flm;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) flm.v[i] = flmc.v[i] * cw2.v[i];
     // finish row rfin (implsch.F90:276-395 for these bins)
-    if (rfin >= 0) {
+    if (fin) {
       const int r = rfin;
       const unsigned tq = L.tbs + (unsigned)((r & 3) * TQ_N * 64) + jo;
+      const V fold = lds<NP>(sm, L.ring + slot9(r) * RSB + me_r);
+      const V xI = lds<NP>(sm, me_s + L.SSB);
       const V usfm = lds<NP>(sm, L.pc + PC_USFMDELT * 64 + jo), sdsbk = lds<NP>(sm, L.pc + PC_SDSBK * 64 + jo);
       const V tsbo = lds<NP>(sm, tq + TQ_SBO * 64), tcinv = lds<NP>(sm, tq + TQ_CINV * 64), ttail = lds<NP>(sm, tq + TQ_TAIL * 64);
-      const V tstf = lds<NP>(sm, tq + TQ_STF * 64), rtail = lds<NP>(sm, L.pc + PC_RTAIL * 64 + jo), icefree = lds<NP>(sm, L.pc + PC_ICEFREE * 64 + jo);
+      const V tstf = lds<NP>(sm, tq + TQ_STF * 64), rtail = lds<NP>(sm, L.pc + PC_RTAIL * 64 + jo);
       V dd;
       if (ard) {
         const V b0 = lds<NP>(sm, L.bth0 + (par ^ 1u) * 64u + jo);
         const double ssdsc2_sig = c_dc.SSDSC2 * c_dc.ZPIFR[r];
 #pragma unroll
         for (int i = 0; i < NP; ++i)
-          dd.v[i] = ssdsc2_sig * c_dc.SSDSC6 * sq(fmax(0., b0.v[i] * tmp03 - c_dc.SSDSC4)) +
-                    ssdsc2_sig * (1. - c_dc.SSDSC6) * sq(fmax(0., b_prev.v[i] * tmp03 - c_dc.SSDSC4));
+          dd.v[i] = ssdsc2_sig * c_dc.SSDSC6 * sq(dmax(0., b0.v[i] * tmp03 - c_dc.SSDSC4)) +
+                    ssdsc2_sig * (1. - c_dc.SSDSC6) * sq(dmax(0., b_prev.v[i] * tmp03 - c_dc.SSDSC4));
       } else dd = lds<NP>(sm, tq + TQ_JAN * 64);
-      const double cofrm4 = c_dc.COFRM4[r], flmax = c_dc.FLMAX[r], dfim = c_dc.DFIM[r], dfimofr = c_dc.DFIMOFR[r];
+      const double cofrm4 = c_dc.COFRM4[r], flmax = c_dc.FLMAX[r];
       const double rhowg = c_dc.RHOWG_DFIM[r];
       V fnv;
 #pragma unroll
@@ -998,20 +1015,20 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? 3 : 2) k_stenci
         double fldv = xI.v[i];                             // wind input (SINPUT, second SINFLX call)
         double slv = fldv * f0;
         slv = slv + dd.v[i] * f0; fldv = fldv + dd.v[i];   // SDISSIP
-        slv = slv + asl[0][i]; fldv = fldv + afl[0][i];    // SNONLIN
+        slv = slv + asl[O][i]; fldv = fldv + afl[O][i];    // SNONLIN
         double ssource = 0.0;
-        if (lssource) ssource = div_ge1(slv, fmax(1.0 - delt5 * fldv, 1.0));
+        if (lssource) ssource = div_ge1(slv, dmax(1.0 - delt5 * fldv, 1.0));
         if (r < c_dc.Fr) {
           slv = slv - sdsbk.v[i] * f0; fldv = fldv - sdsbk.v[i];            // SDIWBK (0 where it does not apply)
           slv = slv + tsbo.v[i] * f0; fldv = fldv + tsbo.v[i];              // SBOTTOM
         }
-        const double gtemp1 = fmax(1.0 - delt5 * fldv, 1.0);
+        const double gtemp1 = dmax(1.0 - delt5 * fldv, 1.0);
         const double gtemp2 = div_ge1(delt * slv, gtemp1);
-        const double flhab = fmin(fabs(gtemp2), usfm.v[i] * cofrm4);
+        const double flhab = dmin(fabs(gtemp2), usfm.v[i] * cofrm4);
         double fn = f0 + copysign(flhab, gtemp2);
-        fn = fmax(fn, flm.v[i]);
-        ssource = ssource + deltm * fmin(flmax - fn, 0.0);
-        fn = fmin(fn, flmax);
+        fn = dmax(fn, flm.v[i]);
+        ssource = ssource + deltm * dmin(flmax - fn, 0.0);
+        fn = dmin(fn, flmax);
         {   // WNFLUXES sums (wnfluxes.F90:200-220); RHOWGDFTH of frcutindex.F90:99-108
           double rr = (r + 1 > mij[i]) ? 0.0 : rhowg;
           if (r + 1 == mij[i] && mij[i] != F) rr = 0.5 * rr;
@@ -1019,35 +1036,69 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? 3 : 2) k_stenci
           a_ts.v[i] += ssource * (tcinv.v[i] * rr);
         }
         if (LWFLUX) {   // FEMEANWS on the new spectrum (before the tail is imposed)
+          const V xL = lds<NP>(sm, me_s + 2 * L.SSB);
           const double xf = (xL.v[i] != 0.0) ? fn : 0.0;
-          a_e1.v[i] += dfim * xf; a_e2.v[i] += dfimofr * xf;
+          a_e1.v[i] += c_dc.DFIM[r] * xf; a_e2.v[i] += c_dc.DFIMOFR[r] * xf;
           if (r == F - 1) a_el.v[i] += xf;
         }
         if (r == mij[i] - 1) fmij.v[i] = fn;                                                   // IMPHFTAIL reference row
-        if (r > mij[i] - 1) fn = fmax((ttail.v[i] * rtail.v[i]) * fmij.v[i], flm.v[i]);
-        if (setice) fn = fn * icefree.v[i] + iceadd.v[i];                                      // SETICE
-        a_tu.v[i] += tstf.v[i] * fn;                                                           // STOKESDRIFT
+        if (r > mij[i] - 1) fn = dmax((ttail.v[i] * rtail.v[i]) * fmij.v[i], flm.v[i]);
+        fnv.v[i] = fn;
+      }
+      if (setice) {                                                                            // SETICE
+        const V icefree = lds<NP>(sm, L.pc + PC_ICEFREE * 64 + jo), ia = lds<NP>(sm, L.pc + PC_ICEADD * 64 + jo);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) fnv.v[i] = fnv.v[i] * icefree.v[i] + ia.v[i] * cw2.v[i];
+      }
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        a_tu.v[i] += tstf.v[i] * fnv.v[i];                                                     // STOKESDRIFT
         if (r == c_dc.NFRE_ODD - 1) {
           const double cst = 2.0 * c_dc.DELTH * c_dc.ZPI * c_dc.ZPI * c_dc.ZPI / c_dc.G * p4(c_dc.FR[c_dc.NFRE_ODD - 1]);
-          a_tu.v[i] += cst * fn;
+          a_tu.v[i] += cst * fnv.v[i];
         }
-        fnv.v[i] = fn;
       }
       if (dost) stg<NP>(dst + (size_t)r * rstr, fnv);
     }
-    if (ard && t < ST_NPT && rb >= 0 && rb < F) {   // BTH0 of row rb from the per-warp partial maxima
+    if (rnew >= 0 && rnew < F) {   // depth-limited (+ floored at NFRE) row st+5 -> ring (slot of row st-4, whose last reader is the line above)
+      const V xF = lds<NP>(sm, me_s);
+      const V fac = lds<NP>(sm, L.pc + PC_FAC * 64 + jo);
+      V v;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        v.v[i] = dmax(xF.v[i] * fac.v[i], c_dc.EPSMIN);
+        if (rnew == F - 1) v.v[i] = dmax(v.v[i], flm.v[i]);
+      }
+      if (act) {
+        const unsigned rbse = L.ring + slot9(rnew) * RSB + me_r;
+        sts<NP>(sm, rbse, v);
+        if (k < H) sts<NP>(sm, rbse + (unsigned)A * 64u, v);
+        if (k >= A - H) sts<NP>(sm, rbse - (unsigned)A * 64u, v);
+      }
+    }
+    if (sat && t < ST_NPT) {   // BTH0 of row rb from the per-warp partial maxima
       const double* pp = reinterpret_cast<const double*>(sm + L.part + par * (unsigned)nwarp * 64u) + t;
       double mx = 0.0;
-      for (int w = 0; w < nwarp; ++w) mx = fmax(mx, pp[w * ST_NPT]);
+      for (int w = 0; w < nwarp; ++w) mx = dmax(mx, pp[w * ST_NPT]);
       reinterpret_cast<double*>(sm + L.bth0 + par * 64u)[t] = mx;
     }
     b_prev = b_next;
+  };
+
+  constexpr int ST0 = -((5 + ST_U - 1) / ST_U) * ST_U;
+#pragma unroll 1
+  for (int st = ST0; st < MLSTHG; st += ST_U) {
+    step(IC<0>(), st);
+    if (ST_U > 1) step(IC<(ST_U > 1 ? 1 : 0)>(), st + 1);
+    if (ST_U > 2) { step(IC<(ST_U > 2 ? 2 : 0)>(), st + 2); step(IC<(ST_U > 2 ? 3 : 0)>(), st + 3); }
 #pragma unroll
-    for (int x = 0; x < 7; ++x)
+    for (int x = 0; x < 8 - 1; ++x)
 #pragma unroll
-      for (int i = 0; i < NP; ++i) { asl[x][i] = asl[x + 1][i]; afl[x][i] = afl[x + 1][i]; }
+      for (int i = 0; i < NP; ++i) { asl[x][i] = asl[x + ST_U][i]; afl[x][i] = afl[x + ST_U][i]; }
 #pragma unroll
-    for (int i = 0; i < NP; ++i) { asl[7][i] = 0.0; afl[7][i] = 0.0; }
+    for (int x = 8 - 1; x < NACC; ++x)
+#pragma unroll
+      for (int i = 0; i < NP; ++i) { asl[x][i] = 0.0; afl[x][i] = 0.0; }
   }
   // ---- per-point sums over direction, then the scalar closures (one thread per point)
   __syncthreads();
@@ -1086,7 +1137,7 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? 3 : 2) k_stenci
     // STOKESDRIFT closure (stokesdrift.F90:118-142)
     double us = q[3], vs = q[4];
     if (c_dc.licerun && c_dc.lwamrsetci && cicover > c_dc.cithrsh) { us = 0.016 * wsw * snw * (1.0 - cicover); vs = 0.016 * wsw * csw * (1.0 - cicover); }
-    d.f.ustokes[pp] = fmin(fmax(us, -1.5), 1.5); d.f.vstokes[pp] = fmin(fmax(vs, -1.5), 1.5);
+    d.f.ustokes[pp] = dmin(dmax(us, -1.5), 1.5); d.f.vstokes[pp] = dmin(dmax(vs, -1.5), 1.5);
     if (LWFLUX) {   // implsch.F90:435-446
       const double DELT25 = c_dc.WETAIL * c_dc.FR[F - 1] * c_dc.DELTH;
       const double em2 = c_dc.EPSMIN + q[5] + DELT25 * q[7];
@@ -1097,48 +1148,54 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? 3 : 2) k_stenci
     if (c_dc.lcflx) {    // WNFLUXES closure (wnfluxes.F90:222-331, LWNEMOCOU=F)
       const double PHIOC_ICE = -3.75, PHIAW_ICE = 3.75, C1 = 1.03e-3, C2 = 0.04e-3, P1 = 1.48, P2 = -0.21, CDMAX_LOC = 0.003;
       const double epsus3 = c_dc.EPSUS * sqrt(c_dc.EPSUS);
-      const double cithrsh_inv = 1.0 / fmax(c_dc.cithrsh, 0.01);
+      const double cithrsh_inv = 1.0 / dmax(c_dc.cithrsh, 0.01);
       const double phiwa = s[S_PHIWA * n + pp];
       double ooval = 1.0, ustar = ufric;
       if (c_dc.licerun && c_dc.lwamrsetci && cicover > c_dc.ciblock) {
-        ooval = exp(-fmin(p4(cicover * cithrsh_inv), 10.0));
-        const double u10p = fmax(wsw, c_dc.EPSU10);
-        const double cd_bulk = fmin((C1 + C2 * pow(u10p, P1)) * pow(u10p, P2), CDMAX_LOC);
+        ooval = exp(-dmin(p4(cicover * cithrsh_inv), 10.0));
+        const double u10p = dmax(wsw, c_dc.EPSU10);
+        const double cd_bulk = dmin((C1 + C2 * pow(u10p, P1)) * pow(u10p, P2), CDMAX_LOC);
         const double cd_wave = sq(ufric / u10p);
-        ustar = fmax(sqrt(ooval * cd_wave + (1.0 - ooval) * cd_bulk) * u10p, c_dc.EPSUS);
+        ustar = dmax(sqrt(ooval * cd_wave + (1.0 - ooval) * cd_bulk) * u10p, c_dc.EPSUS);
       }
-      const double tau = aird * fmax(sq(ustar), c_dc.EPSUS);
+      const double tau = aird * dmax(sq(ustar), c_dc.EPSUS);
       double tauxd = tau * snw, tauyd = tau * csw;
       double tauocxd = tauxd - ooval * q[1], tauocyd = tauyd - ooval * q[2];
-      const double tauoc = fmin(fmax(sqrt(sq(tauocxd) + sq(tauocyd)) / tau, c_dc.TAUOCMIN), c_dc.TAUOCMAX);
+      const double tauoc = dmin(dmax(sqrt(sq(tauocxd) + sq(tauocyd)) / tau, c_dc.TAUOCMIN), c_dc.TAUOCMAX);
       if (c_dc.lwcouast) {
         const double ua = d.f.ustra[pp], va = d.f.vstra[pp];
         if (ua != 0.0 || va != 0.0) { tauxd = ua; tauocxd = ua * tauoc; tauyd = va; tauocyd = va * tauoc; }
       }
       d.f.tauxd[pp] = tauxd; d.f.tauyd[pp] = tauyd; d.f.tauocxd[pp] = tauocxd; d.f.tauocyd[pp] = tauocyd; d.f.tauoc[pp] = tauoc;
       d.f.tauicx[pp] = 0.0; d.f.tauicy[pp] = 0.0;
-      const double xn = aird * fmax(ustar * ustar * ustar, epsus3);
+      const double xn = aird * dmax(ustar * ustar * ustar, epsus3);
       double phiocd = ooval * (q[0] - phiwa) + (1.0 - ooval) * PHIOC_ICE * xn;
-      const double phieps = fmin(fmax(phiocd / xn, c_dc.PHIEPSMIN), c_dc.PHIEPSMAX);
+      const double phieps = dmin(dmax(phiocd / xn, c_dc.PHIEPSMIN), c_dc.PHIEPSMAX);
       phiocd = phieps * xn;
       d.f.phiocd[pp] = phiocd; d.f.phieps[pp] = phieps; d.f.phiaw[pp] = ooval * phiwa / xn + (1.0 - ooval) * PHIAW_ICE;
     }
   }
 }
 
-template <int NP, bool LW>
+template <int TA, int NP, bool LW>
 static int launch_stencil(const ImplDev& d, long long p0, long long np, cudaStream_t st) {
-  const int nth = ((d.A * (ST_NPT / NP) + 31) / 32) * 32;
-  const StencilSmem L = stencil_smem(d.A, d.halo_r, d.halo_c, nth / 32);
+  const int nth = stencil_threads(d.A, NP);
+  const StencilSmem L = stencil_smem(d.A, TA > 0 ? geo_nsd(TA) : d.halo_r, TA > 0 ? geo_hc(TA) : d.halo_c, nth, NP);
   static bool attr_done = false;
   if (!attr_done) {
-    EW_CUDA_CHECK(cudaFuncSetAttribute(k_stencil<NP, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    EW_CUDA_CHECK(cudaFuncSetAttribute(k_stencil<NP, LW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    EW_CUDA_CHECK(cudaFuncSetAttribute(k_stencil<TA, NP, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    EW_CUDA_CHECK(cudaFuncSetAttribute(k_stencil<TA, NP, LW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_done = true;
   }
-  if (L.total > 100 * 1024) { ew_set_error("k_stencil: shared memory %u B", L.total); return ECWAM_B200_EINVAL; }
-  k_stencil<NP, LW><<<(unsigned)((np + ST_NPT - 1) / ST_NPT), nth, L.total, st>>>(d, p0, np);
+  if (L.total > 110 * 1024) { ew_set_error("k_stencil: shared memory %u B", L.total); return ECWAM_B200_EINVAL; }
+  k_stencil<TA, NP, LW><<<(unsigned)((np + ST_NPT - 1) / ST_NPT), nth, L.total, st>>>(d, p0, np, L);
   return 0;
+}
+template <int TA>
+static bool geo_matches(const ImplDev& d, int iphys, int nsdsnth) {
+  if (d.A != TA) return false;
+  for (int kh = 0; kh < 2; ++kh) for (int q = 0; q < 4; ++q) if (d.dsb[kh][q] != geo_sh(TA, kh, q) * ST_NPT * 8) return false;
+  return iphys != 1 || nsdsnth == geo_nsd(TA);
 }
 
 int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage, cudaStream_t st) {
@@ -1158,8 +1215,13 @@ int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage
     // two grid points per thread (16-byte shared / global accesses) need an even NPROMA and an even first point
     const uintptr_t al = (uintptr_t)d.f.fl1 | (uintptr_t)d.f.xllws | (uintptr_t)d.fldin | (uintptr_t)d.fl_lo;
     const bool pair = (d.P % 2 == 0) && (p0 % 2 == 0) && (np % 2 == 0) && (al & 15) == 0;
-    if (pair) return d.lwflux ? launch_stencil<2, true>(d, p0, np, st) : launch_stencil<2, false>(d, p0, np, st);
-    return d.lwflux ? launch_stencil<1, true>(d, p0, np, st) : launch_stencil<1, false>(d, p0, np, st);
+    if (pair) {
+      if (geo_matches<36>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_stencil<36, 2, true>(d, p0, np, st) : launch_stencil<36, 2, false>(d, p0, np, st);
+      if (geo_matches<24>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_stencil<24, 2, true>(d, p0, np, st) : launch_stencil<24, 2, false>(d, p0, np, st);
+      if (geo_matches<12>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_stencil<12, 2, true>(d, p0, np, st) : launch_stencil<12, 2, false>(d, p0, np, st);
+      return d.lwflux ? launch_stencil<0, 2, true>(d, p0, np, st) : launch_stencil<0, 2, false>(d, p0, np, st);
+    }
+    return d.lwflux ? launch_stencil<0, 1, true>(d, p0, np, st) : launch_stencil<0, 1, false>(d, p0, np, st);
   } else return ECWAM_B200_EINVAL;
   return 0;
 }

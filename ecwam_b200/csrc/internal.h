@@ -61,7 +61,9 @@ struct ImplDev {
   long long nloc;          // own points (slots >= nloc of the last chunk are padding)
   DevTabPtr tab;
   double* tbg;             // [TQ_N][F][npts] per-(point, frequency) scalars handed from k_point to k_stencil
-  int dsh[2][4];           // signed cyclic shifts of K1W, K11W, K2W, K21W (.,KH): K1W(K,KH) = K + dsh[KH][0] (mod NANG)
+  int dsb[2][4];           // signed cyclic shifts of K1W, K11W, K2W, K21W (.,KH) (K1W(K,KH) = K + shift mod NANG) in bytes of
+                           // k_stencil's shared-memory planes (shift * 8 points * 8 B)
+  int iphys, nsdsnth;      // copies of the host-side switches the launcher needs
   int halo_r, halo_c;      // direction halo of the shared-memory spectrum rows / interaction planes of k_stencil
 };
 #define EW_TQ_N 6          // number of planes of ImplDev::tbg

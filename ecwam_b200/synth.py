@@ -30,6 +30,8 @@ CONFIGS = {
     "O320": dict(N=320, nang=24, nfre_red=29, idelt=900.0, idelpro=900.0, ifrelfmax=0, delpro_lf=900.0),
     "O640": dict(N=640, nang=36, nfre_red=29, idelt=450.0, idelpro=450.0, ifrelfmax=0, delpro_lf=450.0),
     "O1280": dict(N=1280, nang=36, nfre_red=29, idelt=450.0, idelpro=450.0, ifrelfmax=5, delpro_lf=225.0),
+    # profiling only: the O640 spectrum (36 x 36(29)) on a small grid, so that ncu replays stay short
+    "P256": dict(N=256, nang=36, nfre_red=29, idelt=450.0, idelpro=450.0, ifrelfmax=0, delpro_lf=450.0),
 }
 
 

@@ -1,0 +1,18 @@
+#!/bin/bash
+# Build kernel-variant copies of libecwam_b200.so for A/B timing on the GPU box (developer tool).
+# usage: scripts/build_variants.sh name1 "-DST_U=4 -DST_MINB=2" name2 "..." ...   -> build_variants/lib_<name>.so
+set -e
+cd "$(dirname "$0")/../ecwam_b200/csrc"
+make -s
+mkdir -p ../../build_variants
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+FL="$ARCH -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -I../../include"
+while [ $# -gt 1 ]; do
+  name=$1; flags=$2; shift 2
+  ( $NVCC $FL $flags -Xptxas -v -c implsch.cu -o ../../build_variants/implsch_$name.o 2> ../../build_variants/implsch_$name.log
+    $NVCC $FL $flags -fmad=false -c propag.cu -o ../../build_variants/propag_$name.o
+    $NVCC $ARCH -shared -o ../../build_variants/lib_$name.so api.o ../../build_variants/propag_$name.o ../../build_variants/implsch_$name.o host_tables.o host_grid.o -lnccl -lcudart -lgomp
+    echo "$name: $(grep -A3 'k_stencilILi2ELb0' ../../build_variants/implsch_$name.log | grep -o 'Used [0-9]* registers\|[0-9]* bytes spill stores' | tr '\n' ' ')" ) &
+done
+wait
