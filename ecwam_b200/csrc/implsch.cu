@@ -33,6 +33,20 @@ enum { TQ_FACSAT = 0, TQ_SBO, TQ_CINV, TQ_TAIL, TQ_STF, TQ_JAN, TQ_N };
 static_assert(TQ_N == EW_TQ_N, "tbg planes");
 
 #define FULLMASK 0xffffffffu
+// max / min without fmax's NaN bookkeeping (DSETP + 2 selects instead of ~8 instructions); no NaNs occur on this path
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
+// a / b for b in the normal range (no overflow / denormal / zero paths): reciprocal seed, 2 Newton steps, residual correction
+__device__ __forceinline__ double div_norm(double a, double b) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  double e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  const double q = a * r;
+  return fma(fma(-b, q, a), r, q);
+}
 __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
@@ -40,13 +54,10 @@ __device__ __forceinline__ double wsum(double v) {
 }
 __device__ __forceinline__ double wmax(double v) {
 #pragma unroll
-  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(FULLMASK, v, o));
+  for (int o = 16; o; o >>= 1) v = dmax(v, __shfl_xor_sync(FULLMASK, v, o));
   return v;
 }
 __device__ __forceinline__ double sq(double x) { return x * x; }
-// max / min without fmax's NaN bookkeeping (DSETP + 2 selects instead of ~8 instructions); no NaNs occur on this path
-__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
-__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
 __device__ __forceinline__ double p4(double x) { double y = x * x; return y * y; }
 
 // (P,C) field element of point p
@@ -70,7 +81,7 @@ __device__ void taut_z0(int iusfg, double utop, double udir, double tauw, double
   const double xlogxl = log(c_dc.XNLEV);
   const double us2totauw = 1.0 + c_dc.EPS1;
   const double cosdiff = cos(udir - tauwdir);
-  const double tauwact = fmax(tauw * cosdiff, c_dc.EPSMIN);
+  const double tauwact = dmax(tauw * cosdiff, c_dc.EPSMIN);
   const double tauweff = tauwact * us2totauw;
   double xmin, alphaog;
   if (c_dc.llcapchnk) {
@@ -82,13 +93,13 @@ __device__ void taut_z0(int iusfg, double utop, double udir, double tauw, double
     alphaog = c_dc.ALPHA * c_dc.GM1;
   }
   const double xkutop = c_dc.XKAPPA * utop;
-  const double ustold = (1 - iusfg) * utop * sqrt(fmin(c_dc.ACD + c_dc.BCD * utop, c_dc.CDMAX)) + iusfg * ustar;
-  double tauold = fmax(sq(ustold), tauweff);
+  const double ustold = (1 - iusfg) * utop * sqrt(dmin(c_dc.ACD + c_dc.BCD * utop, c_dc.CDMAX)) + iusfg * ustar;
+  double tauold = dmax(sq(ustold), tauweff);
   ustar = sqrt(tauold);
-  double ustm1 = 1.0 / fmax(ustar, c_dc.EPSUS);
+  double ustm1 = 1.0 / dmax(ustar, c_dc.EPSUS);
   double z0ch = 0.0;
   for (int iter = 1; iter <= NITER; ++iter) {
-    const double x = fmax(tauwact / tauold, xmin);
+    const double x = dmax(tauwact / tauold, xmin);
     z0ch = alphaog * tauold / sqrt(1.0 - x);
     const double z0vis = c_dc.rnum * ustm1;
     const double z0tot = z0ch + z0vis;
@@ -97,15 +108,15 @@ __device__ void taut_z0(int iusfg, double utop, double udir, double tauw, double
     const double zz = ustm1 * (z0ch * (2.0 - TWOXMP1 * x) / (1.0 - x) - z0vis) / z0tot;
     const double delf = 1.0 - xkutop * sq(xologz0) * zz;
     if (delf != 0.0) ustar = ustar - f / delf;
-    const double taunew = fmax(sq(ustar), tauweff);
+    const double taunew = dmax(sq(ustar), tauweff);
     ustar = sqrt(taunew);
     if (taunew == tauold) break;
-    ustm1 = 1.0 / fmax(ustar, c_dc.EPSUS);
+    ustm1 = 1.0 / dmax(ustar, c_dc.EPSUS);
     tauold = taunew;
   }
   z0 = z0ch;
   z0b = alphaog * tauold;
-  chrnck = fmax(c_dc.G * z0 * sq(ustm1), c_dc.ALPHAMIN);
+  chrnck = dmax(c_dc.G * z0 * sq(ustm1), c_dc.ALPHAMIN);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -116,14 +127,14 @@ __device__ void tau_phi_hf(int mij, bool shelter, double z0m, double aird, doubl
   const double x0g = c_dc.X0TAUHF * c_dc.G;
   double ustph = ust;
   const double xloggz0 = log(c_dc.G * z0m);
-  const double omegacc = fmax(c_dc.ZPIFR[mij - 1], x0g / ust);
+  const double omegacc = dmax(c_dc.ZPIFR[mij - 1], x0g / ust);
   const double sqrtz0og = sqrt(z0m * c_dc.GM1);
   const double sqrtgz0 = 1.0 / sqrtz0og;
   const double yc = omegacc * sqrtz0og;
   const double zinf = log(yc);
   const double consttau = c_dc.ZPI4GM2 * c_dc.FR5[mij - 1];
   double taul = sq(ust);
-  double delz = fmax((ZSUPMAX - zinf) / (double)(c_dc.JTOT - 1), 0.0);
+  double delz = dmax((ZSUPMAX - zinf) / (double)(c_dc.JTOT - 1), 0.0);
   tauhf = 0.0;
   if (shelter) {
     for (int j = 1; j <= c_dc.JTOT; ++j) {
@@ -133,10 +144,10 @@ __device__ void tau_phi_hf(int mij, bool shelter, double z0m, double aird, doubl
       const double zx = ust * cm1 + c_dc.ZALP;
       const double zarg = c_dc.XKAPPA / zx;
       double zlog = xloggz0 + 2.0 * log(cm1) + zarg;
-      zlog = fmin(zlog, 0.0);
+      zlog = dmin(zlog, 0.0);
       const double zbeta = p4(zlog) * exp(zlog);
       const double fnc2 = f1dcos3 * consttau * zbeta * taul * c_dc.WTAUHF[j - 1] * delz;
-      taul = fmax(taul - c_dc.TAUWSHELTER * fnc2, 0.0);
+      taul = dmax(taul - c_dc.TAUWSHELTER * fnc2, 0.0);
       ust = sqrt(taul);
       tauhf = tauhf + fnc2;
     }
@@ -148,7 +159,7 @@ __device__ void tau_phi_hf(int mij, bool shelter, double z0m, double aird, doubl
       const double zx = ust * cm1 + c_dc.ZALP;
       const double zarg = c_dc.XKAPPA / zx;
       double zlog = xloggz0 + 2.0 * log(cm1) + zarg;
-      zlog = fmin(zlog, 0.0);
+      zlog = dmin(zlog, 0.0);
       const double zbeta = p4(zlog) * exp(zlog);
       tauhf = tauhf + zbeta * c_dc.WTAUHF[j - 1];
     }
@@ -157,7 +168,7 @@ __device__ void tau_phi_hf(int mij, bool shelter, double z0m, double aird, doubl
   phihf = 0.0;
   if (llphihf) {
     taul = sq(ustph);
-    delz = fmax((ZSUPMAX - zinf) / (double)(c_dc.JTOT - 1), 0.0);
+    delz = dmax((ZSUPMAX - zinf) / (double)(c_dc.JTOT - 1), 0.0);
     const double constphi = aird * c_dc.ZPI4GM1 * c_dc.FR5[mij - 1];
     if (shelter) {
       for (int j = 1; j <= c_dc.JTOT; ++j) {
@@ -167,10 +178,10 @@ __device__ void tau_phi_hf(int mij, bool shelter, double z0m, double aird, doubl
         const double zx = ustph * cm1 + c_dc.ZALP;
         const double zarg = c_dc.XKAPPA / zx;
         double zlog = xloggz0 + 2.0 * log(cm1) + zarg;
-        zlog = fmin(zlog, 0.0);
+        zlog = dmin(zlog, 0.0);
         const double zbeta = p4(zlog) * exp(zlog);
         const double fnc2 = zbeta * taul * c_dc.WTAUHF[j - 1] * delz;
-        taul = fmax(taul - c_dc.TAUWSHELTER * f1dcos3 * consttau * fnc2, 0.0);
+        taul = dmax(taul - c_dc.TAUWSHELTER * f1dcos3 * consttau * fnc2, 0.0);
         ustph = sqrt(taul);
         phihf = phihf + fnc2 / y;
       }
@@ -183,7 +194,7 @@ __device__ void tau_phi_hf(int mij, bool shelter, double z0m, double aird, doubl
         const double zx = ustph * cm1 + c_dc.ZALP;
         const double zarg = c_dc.XKAPPA / zx;
         double zlog = xloggz0 + 2.0 * log(cm1) + zarg;
-        zlog = fmin(zlog, 0.0);
+        zlog = dmin(zlog, 0.0);
         const double zbeta = p4(zlog) * exp(zlog);
         phihf = phihf + zbeta * c_dc.WTAUHF[j - 1] / y;
       }
@@ -197,14 +208,14 @@ __device__ double wsigstar(double ufric, double z0m, double wstar) {
   const double ONETHIRD = 1.0 / 3.0, SIG_NMAX = 0.9, C1 = 1.03e-3, C2 = 0.04e-3, P1 = 1.48, P2 = -0.21;
   const double xkappad = 1.0 / c_dc.XKAPPA;
   double u10 = ufric * xkappad * (log(10.0) - log(z0m));
-  u10 = fmax(u10, c_dc.wspmin);
+  u10 = dmax(u10, c_dc.wspmin);
   const double u10m1 = 1.0 / u10;
   const double c2u10p1 = C2 * pow(u10, P1);
   const double u10p2 = pow(u10, P2);
   const double c_d = (C1 + c2u10p1) * u10p2;
   const double dc_ddu = (P2 * C1 + (P1 + P2) * c2u10p1) * u10p2 * u10m1;
   const double sig_conv = 1.0 + 0.5 * u10 / c_d * dc_ddu;
-  return fmin(SIG_NMAX, sig_conv * u10m1 * pow(0.0 * ufric * ufric * ufric + 0.5 * c_dc.XKAPPA * wstar * wstar * wstar, ONETHIRD));
+  return dmin(SIG_NMAX, sig_conv * u10m1 * pow(0.0 * ufric * ufric * ufric + 0.5 * c_dc.XKAPPA * wstar * wstar * wstar, ONETHIRD));
 }
 
 // RHOWGDFTH(IJ,M) of frcutindex.F90:99-108 (m 0-based)
@@ -249,7 +260,7 @@ template <int N>
 __device__ __forceinline__ void row_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 __device__ __forceinline__ const double* row_ptr(const PointSrc& S, int m, int A) { return S.stage + (size_t)(m & 1) * A * KP_NTH; }
 
-template <int NGST, bool LLSNEG, bool STORE>
+template <bool ARD, int NGST, bool LLSNEG, bool STORE>
 __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d, long long p, double fac, double flmc,
                                              double snw, double csw, double ufric, double z0m, double raorw, double sig_n,
                                              double temp2_sw, double pturb, double aird_pvisc, double* __restrict__ fld_out,
@@ -261,7 +272,7 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
   const double CONST1 = c_dc.BETAMAXOXKAPPA2;
   const size_t kstr = S.kstr;
   ws_em = 0.0; ws_fm = 0.0; ws_last = 0.0; phiwa_acc = 0.0; uorbt_acc = 0.0; aorb_acc = 0.0;
-  const bool ard = c_dc.iphys == 1;
+  constexpr bool ard = ARD;
   const double abs_shelter = fabs(c_dc.TAUWSHELTER);
   const bool ltauwshelter = ard && abs_shelter != 0.0;
   double ustp[NGST], xstress[NGST], ystress[NGST], taux[NGST], tauy[NGST], wsin[NGST];
@@ -299,7 +310,7 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
         const double xk = d.f.xk2cg[o3];
         tg[TQ_FACSAT * qs] = wavnum * (1.0 / c_dc.ZPI) * xk;                                        // sdissip_ard.F90:142-160
         double sbo = 0.0;
-        if (m < c_dc.Fr && depth < c_dc.bathymax) sbo = (-2.0 * 0.038 * c_dc.GM1) * wavnum / sinh(fmin(2.0 * depth * wavnum, 50.0));   // sbottom.F90:76-97
+        if (m < c_dc.Fr && depth < c_dc.bathymax) sbo = (-2.0 * 0.038 * c_dc.GM1) * wavnum / sinh(dmin(2.0 * depth * wavnum, 50.0));   // sbottom.F90:76-97
         tg[TQ_SBO * qs] = sbo;
         tg[TQ_CINV * qs] = cinv;
         tg[TQ_TAIL * qs] = 1.0 / xk / wavnum;                                                       // imphftail.F90:73-81
@@ -359,11 +370,11 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
     for (int g = 0; g < NGST; ++g) { sx[g] = 0.0; sy[g] = 0.0; }
 #pragma unroll 2
     for (int k = 0; k < A; ++k) {
-      double f = fmax(fsrc[k * KP_NTH] * fac, c_dc.EPSMIN);                      // SDEPTHLIM applied on the fly
+      double f = dmax(fsrc[k * KP_NTH] * fac, c_dc.EPSMIN);                      // SDEPTHLIM applied on the fly
       const double snk = c_dc.SINTH[k], csk = c_dc.COSTH[k];
       const double cwd = csk * csw + snk * snw;                                  // COSWDIF(K)
       traw += f;                                                                 // FKMEAN sees the spectrum before the floor
-      if (lastm) f = fmax(f, flmc * sq(fmax(0.0, cwd)));                         // sinflx.F90:126-129
+      if (lastm) f = dmax(f, flmc * sq(dmax(0.0, cwd)));                         // sinflx.F90:126-129
       tsum += f;
       double slp_avg = 0.0, flp_avg = 0.0, ufac2 = 0.0;
       bool xll = false;
@@ -374,7 +385,7 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
           const double coslp = ltauwshelter ? (csk * cosu[g] + snk * sinu[g]) : cwd;
           if (coslp > 0.01) {
             const double x = coslp * ucn[g];
-            const double zlog = zcn + ucnzalpd[g] / coslp;
+            const double zlog = zcn + div_norm(ucnzalpd[g], coslp);
             if (zlog < 0.0) {
               const double zlog2x = zlog * zlog * x;
               gam0 = exp(zlog) * zlog2x * zlog2x * cnsn;
@@ -388,7 +399,7 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
           slp_avg += slp; flp_avg += gam0 + dstab;
         } else {
           if (cwd > 0.01) {
-            const double zlog = zcn + c_dc.XKAPPA / cwd * ucnzalpd[g];
+            const double zlog = zcn + div_norm(c_dc.XKAPPA, cwd) * ucnzalpd[g];
             if (zlog < 0.0) {
               const double x = cwd * ucn[g];
               const double zlog2x = zlog * zlog * x;
@@ -407,9 +418,10 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
       st += spos;
       if (STORE) {
         if (dostore) {
-          fo[(size_t)k * kstr] = fldv;
-          xo[(size_t)k * kstr] = xll ? 1.0 : 0.0;
+          *fo = fldv;
+          *xo = xll ? 1.0 : 0.0;
         }
+        fo += kstr; xo += kstr;
         phiwa_acc += (slv - spos) * rhowg;
       }
       if (xll) { ws_em += dfim * f; ws_fm += dfimofr * f; if (lastm) ws_last += f; }
@@ -435,6 +447,7 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
   }
 }
 
+template <bool ARD>
 __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, long long np) {
   extern __shared__ double smem[];
   long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -456,10 +469,10 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
     S.mlo = d.Fr;
   } else { S.lo = S.hi; S.mlo = 0; }
   const double aird = d.f.aird[p], wdwave = d.f.wdwave[p], cicover = d.f.cicover[p], wswave = d.f.wswave[p];
-  const double raorw = fmax(aird, 1.0) * c_dc.ROWATERM1;
+  const double raorw = dmax(aird, 1.0) * c_dc.ROWATERM1;
   double snw, csw;
   sincos(wdwave, &snw, &csw);
-  const double flmc = (1. - 0.9 * fmin(cicover, 0.99)) * c_dc.flmin;      // FLM(K) = flmc*max(0,COSWDIF)**2
+  const double flmc = (1. - 0.9 * dmin(cicover, 0.99)) * c_dc.flmin;      // FLM(K) = flmc*max(0,COSWDIF)**2
   const double DELT25 = c_dc.WETAIL * c_dc.FR[F - 1] * c_dc.DELTH;
   // ---- SDEPTHLIM (sdepthlim.F90:50-82): EM of the incoming spectrum -> limiting factor
   double fac = 1.0;
@@ -476,7 +489,7 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
       last = t;
     }
     em += DELT25 * last;
-    fac = fmin(d.f.emaxdpt[p] / em, 1.0);
+    fac = dmin(d.f.emaxdpt[p] / em, 1.0);
   }
   // ---- SINFLX call 1: AIRSEA (IUSFG=0), SINPUT (NGST=1), FEMEANWS, FRCUTINDEX, STRESSO
   double ustar = d.f.ufric[p], z0, z0b, ch;
@@ -485,7 +498,7 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
   double sumx[EW_MAXF], sumy[EW_MAXF], sumt[EW_MAXF];
   double ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc;
   double mom[6] = {0, 0, 0, 0, 0, 0};
-  sinput_point<1, false, false>(S, d, p, fac, flmc, snw, csw, ustar, z0, raorw, 0.0, 0.0, 0.0, 0.0, nullptr, nullptr, sumx, sumy,
+  sinput_point<ARD, 1, false, false>(S, d, p, fac, flmc, snw, csw, ustar, z0, raorw, 0.0, 0.0, 0.0, 0.0, nullptr, nullptr, sumx, sumy,
                                 sumt, ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc, mom, false);
   // FKMEAN (fkmean.F90:60-154)
   const double COEFM1 = c_dc.FRTAIL * c_dc.DELTH;
@@ -507,9 +520,9 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
     if (cicover > c_dc.cithrsh_tail) return F;
     const double fpmh = c_dc.TAILFACTOR / c_dc.FR[0];
     const double fppm = c_dc.TAILFACTOR_PM * c_dc.G / (28.0 * c_dc.ZPIFR[0]);
-    const double fm2 = fmax(fmeanws, fmean) * fpmh;
-    const double fpm = fppm / fmax(ust, c_dc.EPSMIN);
-    const double fpm4 = fmax(fm2, fpm);
+    const double fm2 = dmax(fmeanws, fmean) * fpmh;
+    const double fpm = fppm / dmax(ust, c_dc.EPSMIN);
+    const double fpm4 = dmax(fm2, fpm);
     int mij = (int)lround(log10(fpm4) * c_dc.FLOGSPRDM1) + 1;
     return min(max(1, mij), F);
   };
@@ -521,7 +534,7 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
       const double cm = r * d.f.cinv[idx3(d, p, m)];
       xs += cm * sumx[m]; ys += cm * sumy[m]; pw += r * sumt[m];
     }
-    const double am = fmax(aird, 1.0);
+    const double am = dmax(aird, 1.0);
     xs = xs / am; ys = ys / am;
     // directional moments of the spectrum at the cut-off frequency (tau_phi_hf.F90:150-178)
     double f3 = 0.0, f2 = 0.0;
@@ -529,10 +542,10 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
       const int m = mij - 1;
       const double* fsrc = (m < S.mlo ? S.lo : S.hi) + (size_t)m * A * S.kstr;
       for (int k = 0; k < A; ++k) {
-        double f = fmax(__ldg(fsrc + (size_t)k * S.kstr) * fac, c_dc.EPSMIN);
+        double f = dmax(__ldg(fsrc + (size_t)k * S.kstr) * fac, c_dc.EPSMIN);
         const double cwd = c_dc.COSTH[k] * csw + c_dc.SINTH[k] * snw;
-        if (m == F - 1) f = fmax(f, flmc * sq(fmax(0.0, cwd)));
-        const double cw = fmax(cwd, 0.0);
+        if (m == F - 1) f = dmax(f, flmc * sq(dmax(0.0, cwd)));
+        const double cw = dmax(cwd, 0.0);
         const double fc2 = f * cw * cw;
         f3 += fc2 * cw; f2 += fc2;
       }
@@ -540,7 +553,7 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
     }
     bool shelter;
     double usdirp_s, usdirp_c, ust;
-    if (c_dc.iphys == 0 || c_dc.TAUWSHELTER == 0.0) { shelter = false; usdirp_s = snw; usdirp_c = csw; ust = ust_in; }
+    if (!ARD || c_dc.TAUWSHELTER == 0.0) { shelter = false; usdirp_s = snw; usdirp_c = csw; ust = ust_in; }
     else {
       shelter = true;
       const double taupx = sq(ust_in) * snw - c_dc.TAUWSHELTER * xs, taupy = sq(ust_in) * csw - c_dc.TAUWSHELTER * ys;
@@ -552,9 +565,9 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
     tau_phi_hf(mij, shelter, z0m, aird, f3, f2, ust, tauhf, phihf, llphiwa);
     xs = xs + tauhf * usdirp_s;
     ys = ys + tauhf * usdirp_c;
-    tw = fmax(sqrt(sq(xs) + sq(ys)), 0.0);
+    tw = dmax(sqrt(sq(xs) + sq(ys)), 0.0);
     twd = atan2(xs, ys);
-    tw = fmin(tw, sq(ust_in) * (1.0 / (1.0 + c_dc.EPS1)));
+    tw = dmin(tw, sq(ust_in) * (1.0 / (1.0 + c_dc.EPS1)));
     phiwa = llphiwa ? pw + phihf : 0.0;
   };
   {
@@ -569,16 +582,16 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
   if (valid) { d.f.ufric[p] = ustar; d.f.z0m[p] = z0; d.f.z0b[p] = z0b; d.f.chrnck[p] = ch; }
   const double sig_n = wsigstar(ustar, z0, d.f.wstar[p]);
   double temp2_sw = 0.0, pturb = 0.0, aird_pvisc = 0.0;
-  if (c_dc.iphys == 1) {   // sinput_ard.F90:179-271
+  if (ARD) {   // sinput_ard.F90:179-271
     const double uorbt = 2.0 * sqrt(c_dc.EPSMIN + uorbt_acc), aorb = 2.0 * sqrt(c_dc.EPSMIN + aorb_acc);
     const double re = (4.0 / c_dc.rnu) * uorbt * aorb;
-    const double z0vis = c_dc.rnum / fmax(ustar, 0.0001);
-    const double z0tub = c_dc.Z0RAT * fmin(c_dc.Z0TUBMAX, z0);
-    const double zorb = aorb / fmax(z0vis, z0tub);
+    const double z0vis = c_dc.rnum / dmax(ustar, 0.0001);
+    const double z0tub = c_dc.Z0RAT * dmin(c_dc.Z0TUBMAX, z0);
+    const double zorb = aorb / dmax(z0vis, z0tub);
     const double delabm1 = (double)c_dc.IAB / (c_dc.ABMAX - c_dc.ABMIN);
-    const double xi = (log10(fmax(zorb, 3.0)) - c_dc.ABMIN) * delabm1;
+    const double xi = (log10(dmax(zorb, 3.0)) - c_dc.ABMIN) * delabm1;
     const int ind = min(c_dc.IAB - 1, (int)xi);
-    const double deli1 = fmin(1.0, xi - (double)ind), deli2 = 1.0 - deli1;
+    const double deli1 = dmin(1.0, xi - (double)ind), deli2 = 1.0 - deli1;
     const double fww = __ldg(d.tab.swellft + ind - 1) * deli2 + __ldg(d.tab.swellft + ind) * deli1;
     temp2_sw = fww * uorbt;
     const double re_c = (c_dc.SWELLF6 == 1.0) ? c_dc.SWELLF4 : c_dc.SWELLF4 * pow(2.0 / aorb, 1.0 - c_dc.SWELLF6);
@@ -591,7 +604,7 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
   double* fld_out = d.fldin + (size_t)i + (size_t)d.P * A * F * (size_t)c;
   double* xl_out = d.f.xllws + (size_t)i + (size_t)d.P * A * F * (size_t)c;
   double dum[6];
-  sinput_point<2, true, true>(S, d, p, fac, flmc, snw, csw, ustar, z0, raorw, sig_n, temp2_sw, pturb, aird_pvisc, fld_out, xl_out,
+  sinput_point<ARD, 2, true, true>(S, d, p, fac, flmc, snw, csw, ustar, z0, raorw, sig_n, temp2_sw, pturb, aird_pvisc, fld_out, xl_out,
                               sumx, sumy, sumt, ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc, dum, valid, d.f.depth[p],
                               c_dc.CDIS * c_dc.ZPI * f1mean * sq(emean) * p4(xkmean), xkmean);
   const double emeanws = c_dc.EPSMIN + ws_em + DELT25 * ws_last;
@@ -603,13 +616,13 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
     d.f.tauw[p] = tauw; d.f.tauwdir[p] = tauwdir; d.f.mij[p] = mij;
     s[S_PHIWA * n + p] = phiwa;
     s[S_MIJ * n + p] = (double)mij;
-    s[S_USFM * n + p] = ustar * fmax(fmeanws, fmean);
+    s[S_USFM * n + p] = ustar * dmax(fmeanws, fmean);
   }
   // ---- SDIWBK (sdiwbk.F90:69-104)
   double sds = 0.0;
   if (c_dc.lbiwbk && d.f.depth[p] < 50.0) {
     const double alph = 2.0 * d.f.emaxdpt[p] / emean;
-    const double arg = fmin(alph, 50.0);
+    const double arg = dmin(alph, 50.0);
     double q_old = exp(-arg), q = q_old;
     for (int ic = 1; ic <= 15; ++ic) {
       const double expq = exp(-arg * (1.0 - q_old));
@@ -618,7 +631,7 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
       if (rel_err < 0.00001) break;
       q_old = q;
     }
-    q = fmin(q, 1.0);
+    q = dmin(q, 1.0);
     sds = 2.0 * alph * q * f1mean;
   }
   if (valid) s[S_SDS * n + p] = sds;
@@ -659,17 +672,6 @@ template <> __device__ __forceinline__ Vd<2> ldg<2>(const double* p) {
   Vd<2> r; r.v[0] = t.x; r.v[1] = t.y; return r;
 }
 template <int NP> __device__ __forceinline__ void stg(double* p, const Vd<NP>& x) { *reinterpret_cast<Vd<NP>*>(p) = x; }
-// a / b for b >= 1 (no overflow / denormal paths needed): reciprocal seed + 2 Newton steps + residual correction
-__device__ __forceinline__ double div_ge1(double a, double b) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-  double e = fma(-b, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-b, r, 1.0);
-  r = fma(r, e, r);
-  const double q = a * r;
-  return fma(fma(-b, q, a), r, q);
-}
 __device__ __forceinline__ unsigned slot9(int r) { return (unsigned)c_dc.SLOT9[r]; }   // r % ST_RING, 0 <= r < EW_MAXF
 
 struct StencilSmem {   // byte offsets into dynamic shared memory
@@ -1017,13 +1019,13 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? ST_MINB : 2) k_
         slv = slv + dd.v[i] * f0; fldv = fldv + dd.v[i];   // SDISSIP
         slv = slv + asl[O][i]; fldv = fldv + afl[O][i];    // SNONLIN
         double ssource = 0.0;
-        if (lssource) ssource = div_ge1(slv, dmax(1.0 - delt5 * fldv, 1.0));
+        if (lssource) ssource = div_norm(slv, dmax(1.0 - delt5 * fldv, 1.0));
         if (r < c_dc.Fr) {
           slv = slv - sdsbk.v[i] * f0; fldv = fldv - sdsbk.v[i];            // SDIWBK (0 where it does not apply)
           slv = slv + tsbo.v[i] * f0; fldv = fldv + tsbo.v[i];              // SBOTTOM
         }
         const double gtemp1 = dmax(1.0 - delt5 * fldv, 1.0);
-        const double gtemp2 = div_ge1(delt * slv, gtemp1);
+        const double gtemp2 = div_norm(delt * slv, gtemp1);
         const double flhab = dmin(fabs(gtemp2), usfm.v[i] * cofrm4);
         double fn = f0 + copysign(flhab, gtemp2);
         fn = dmax(fn, flm.v[i]);
@@ -1206,11 +1208,14 @@ int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage
     const size_t smp = (size_t)2 * A * KP_NTH * sizeof(double);
     static bool attr_p = false;
     if (!attr_p) {
-      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       attr_p = true;
     }
-    k_point<<<(unsigned)((np + KP_NTH - 1) / KP_NTH), KP_NTH, smp, st>>>(d, p0, np);
+    if (d.iphys == 1) k_point<true><<<(unsigned)((np + KP_NTH - 1) / KP_NTH), KP_NTH, smp, st>>>(d, p0, np);
+    else k_point<false><<<(unsigned)((np + KP_NTH - 1) / KP_NTH), KP_NTH, smp, st>>>(d, p0, np);
   } else if (stage == 1) {
     // two grid points per thread (16-byte shared / global accesses) need an even NPROMA and an even first point
     const uintptr_t al = (uintptr_t)d.f.fl1 | (uintptr_t)d.f.xllws | (uintptr_t)d.fldin | (uintptr_t)d.fl_lo;

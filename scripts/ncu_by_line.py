@@ -17,7 +17,11 @@ for l in lines[start + 1:]:
         per_inst.append(cur)
 rows = list(csv.reader(open(ncsv)))
 hdr = rows[1]; iN = hdr.index('Instructions Executed'); iS = hdr.index('# Samples')
-data = [r for r in rows[2:] if len(r) > iN]
+data = []
+for r in rows[2:]:
+    if len(r) <= iN or r[iN] == 'Instructions Executed' or r[0] == 'Kernel Name':
+        break
+    data.append(r)
 print('sass insts', len(per_inst), 'csv rows', len(data))
 agg = collections.defaultdict(lambda: [0, 0])
 for li, r in zip(per_inst, data):
