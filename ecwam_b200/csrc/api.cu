@@ -206,6 +206,23 @@ static int fill_dev_const(const ecwam_b200_params& p, const ecwam_b200_tables& t
     c.AF11[mc] = t.af11[off + mc];
     for (int j = 0; j < 5; ++j) { c.INLCOEF[mc][j] = t.inlcoef[j + 5 * mc]; c.NLSLOT[mc][j] = (t.inlcoef[j + 5 * mc] - 1) % 9; }
     for (int j = 0; j < 25; ++j) c.RNLCOEF[mc][j] = t.rnlcoef[j + 25 * mc];
+    // The spectrum-edge cases of SNONLIN (snonlin.F90:310-498: rows of the quadruplet outside 1..NFRE receive nothing) are folded
+    // into the coefficients: a skipped update has zero weights, so k_stencil's sweep is branch-free.
+    {
+      const int MC = mc + 1, F = p.nfre;
+      const int MFR1STFR = -t.mfrstlw + 1, MFRLSTFR = F - t.kfrh + MFR1STFR;
+      const int MP = MC + 2, MP1 = MC + 3, MM1 = MC - 3;
+      bool do_c, do_mm, do_mm1, do_mp, do_mp1;
+      if (MC > MFR1STFR && MC < MFRLSTFR) { do_c = do_mm = do_mm1 = do_mp = do_mp1 = true; c.RNLCOEF[mc][0] = 1.0; /* FTAIL = 1 there */ }
+      else if (MC >= MFRLSTFR) { do_mm = true; do_mm1 = MM1 <= F; do_c = do_mm1 && MC <= F; do_mp = do_c && MP <= F; do_mp1 = do_mp && MP1 <= F; }
+      else { do_mm = false; do_mm1 = MM1 >= 1; do_c = true; do_mp = true; do_mp1 = true; }
+      double* R = c.RNLCOEF[mc];
+      if (!do_mm) R[19] = R[20] = R[23] = R[24] = 0.0;     // FKLAMM2, FKLAMM1, FKLAM12, FKLAM22 -> row MC-4
+      if (!do_mm1) R[17] = R[18] = R[21] = R[22] = 0.0;    // FKLAMMA, FKLAMMB, FKLAMA2, FKLAMB2 -> row MC-3
+      if (!do_mp) R[7] = R[8] = R[11] = R[12] = 0.0;       // FKLAMP2, FKLAMP1, FKLAP12, FKLAP22 -> row MC+2
+      if (!do_mp1) R[5] = R[6] = R[9] = R[10] = 0.0;       // FKLAMPA, FKLAMPB, FKLAPA2, FKLAPB2 -> row MC+3
+      c.RNLC2[mc] = do_c ? 2.0 : 0.0;                      // weight of the centre bin (-2 AD, -2 DELAD)
+    }
   }
   for (int r = 0; r < EW_MAXF + 8; ++r) c.SLOT9[r] = r % 9;
   return 0;

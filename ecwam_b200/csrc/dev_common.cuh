@@ -44,6 +44,7 @@ struct DevConst {
   // k_stencil: slot (row % 9) of the 9-row shared-memory ring for every frequency row and for INLCOEF(1:5,MC)
   int SLOT9[EW_MAXF + 8];
   int NLSLOT[EW_MAXMC][5];
+  double RNLC2[EW_MAXMC];   // 2 (or 0 where the centre row is outside the spectrum): weight of -AD, -DELAD at the centre bin
 };
 
 // tables too irregular / large for constant memory (per-lane indexed)

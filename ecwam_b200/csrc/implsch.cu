@@ -712,9 +712,6 @@ __host__ __device__ constexpr int geo_sh(int A, int kh, int q) {
 __host__ __device__ constexpr int geo_hc(int A) { return A == 36 ? 4 : (A == 24 ? 3 : (A == 12 ? 2 : 0)); }
 __host__ __device__ constexpr int stencil_threads(int A, int np) { return ((A * (ST_NPT / np) + 31) / 32) * 32; }
 
-#ifndef ST_U
-#define ST_U 1   // steps per trip of the frequency loop (the pending-row window slides ST_U rows per trip)
-#endif
 #ifndef ST_MINB
 #define ST_MINB 2   // resident CTAs per SM the two-point instance is compiled for
 #endif
@@ -814,13 +811,13 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? ST_MINB : 2) k_
   const bool setice = c_dc.licerun && c_dc.lmaskice;
   const double delt = c_dc.delt, deltm = 1.0 / delt, delt5 = c_dc.ximp * delt;
   const double tmp03 = 1.0 / (c_dc.SDSBR * c_dc.MICHE);
-  const int MFR1STFR = -c_dc.MFRSTLW + 1, MFRLSTFR = F - c_dc.KFRH + MFR1STFR, MLSTHG = c_dc.MLSTHG;
+  const int MLSTHG = c_dc.MLSTHG;
   const bool lssource = c_dc.lcflx && c_dc.lwvflx_snl;
 
-  constexpr int NACC = 8 + ST_U - 1;
-  double asl[NACC][NP], afl[NACC][NP];   // pending SNONLIN sums of rows st-4 .. st+3+(ST_U-1) (the window slides ST_U rows per trip)
+  // pending SNONLIN sums of rows st-4 .. st+2 (row st+3 receives its first contribution, MC -> MC+3, at this step)
+  double asl[7][NP], afl[7][NP];
 #pragma unroll
-  for (int x = 0; x < NACC; ++x)
+  for (int x = 0; x < 7; ++x)
 #pragma unroll
     for (int i = 0; i < NP; ++i) { asl[x][i] = 0.0; afl[x][i] = 0.0; }
   V b_prev, fmij, a_philf, a_ts, a_tu, a_e1, a_e2, a_el;
@@ -829,9 +826,8 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? ST_MINB : 2) k_
   const unsigned satw_me = L.satw + (unsigned)k * (EW_MAXSAT * 8);
   const unsigned lane = (unsigned)t & 31u;
 
-  // one step of the sweep; O = compile-time position of row st-4 inside the pending-row window
-  auto step = [&](auto OC, const int st) {
-    constexpr int O = decltype(OC)::value;
+  // one step of the sweep
+  auto step = [&](const int st) {
     // ================= phase A =================
     const int rnew = st + 5, rfin = st - 4, rb = st - 3, rtb = st - 2;
     const unsigned par = (unsigned)st & 1u;
@@ -855,9 +851,7 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? ST_MINB : 2) k_
     if (dia) {
       // DIA interaction values of centre frequency MC = st+1 (snonlin.F90:225-250)
       const int MC0 = st, MC = st + 1;
-      const double* R = c_dc.RNLCOEF[MC0];
-      const int branch = (MC > MFR1STFR && MC < MFRLSTFR) ? 0 : (MC >= MFRLSTFR ? 1 : 2);
-      const bool do_c = (branch == 1) ? ((MC - 3 <= F) && MC <= F) : true;
+      const double* R = c_dc.RNLCOEF[MC0];   // spectrum-edge cases are folded into the coefficients (fill_dev_const)
       const unsigned bIC = L.ring + (unsigned)c_dc.NLSLOT[MC0][0] * RSB + me_r;
       const unsigned bIP = L.ring + (unsigned)c_dc.NLSLOT[MC0][1] * RSB + me_r;
       const unsigned bIP1 = L.ring + (unsigned)c_dc.NLSLOT[MC0][2] * RSB + me_r;
@@ -867,12 +861,14 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? ST_MINB : 2) k_
       const V fc = lds<NP>(sm, bIC);
       const V enh = lds<NP>(sm, L.pc + PC_ENH * 64 + jo);
       const double af11 = c_dc.AF11[MC0];
-      V fij, fcen, ftemp;
+      V fij, fcen, ftemp, fcd1, fcd2;
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
         ftemp.v[i] = af11 * enh.v[i];
-        fij.v[i] = (branch == 0) ? fc.v[i] : fc.v[i] * R[0];
+        fij.v[i] = fc.v[i] * R[0];
         fcen.v[i] = ftemp.v[i] * fij.v[i];
+        fcd1.v[i] = c_dc.DAL1 * fcen.v[i];
+        fcd2.v[i] = c_dc.DAL2 * fcen.v[i];
       }
       V csl, cfl;
 #pragma unroll
@@ -889,13 +885,14 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? ST_MINB : 2) k_
           const double sap = R[1] * p1.v[i] + R[2] * p11.v[i] + R[3] * q1.v[i] + R[4] * q11.v[i];
           const double sam = R[13] * m2.v[i] + R[14] * m21.v[i] + R[15] * n2.v[i] + R[16] * n21.v[i];
           double fad1 = fij.v[i] * (sap + sam);
-          const double fad2 = fad1 - 2.0 * sap * sam;
+          const double sap2 = 2.0 * sap;
+          const double fad2 = fma(-sap2, sam, fad1);              // FAD1 - 2 SAP SAM
           fad1 = fad1 + fad2;
           vad.v[i] = fad2 * fcen.v[i];
           csl.v[i] += vad.v[i];
-          cfl.v[i] += fad1 * ftemp.v[i];
-          vdp.v[i] = (fij.v[i] - 2.0 * sam) * c_dc.DAL1 * fcen.v[i];   // DELAP
-          vdm.v[i] = (fij.v[i] - 2.0 * sap) * c_dc.DAL2 * fcen.v[i];   // DELAM
+          cfl.v[i] = fma(fad1, ftemp.v[i], cfl.v[i]);
+          vdp.v[i] = fma(-2.0, sam, fij.v[i]) * fcd1.v[i];        // DELAP = (FIJ - 2 SAM) DAL1 FCEN
+          vdm.v[i] = (fij.v[i] - sap2) * fcd2.v[i];               // DELAM = (FIJ - 2 SAP) DAL2 FCEN
         }
         if (act) {
           sts<NP>(sm, cb + (0 + kh) * PSB, vad);
@@ -913,10 +910,9 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? ST_MINB : 2) k_
           }
         }
       }
-      if (do_c) {
+      const double c2 = c_dc.RNLC2[MC0];
 #pragma unroll
-        for (int i = 0; i < NP; ++i) { asl[O + 4][i] -= 2.0 * csl.v[i]; afl[O + 4][i] -= 2.0 * cfl.v[i]; }
-      }
+      for (int i = 0; i < NP; ++i) { asl[4][i] = fma(-c2, csl.v[i], asl[4][i]); afl[4][i] = fma(-c2, cfl.v[i], afl[4][i]); }
     }
     // saturation spectrum of row rb for SDISSIP_ARD (sdissip_ard.F90:142-160): cyclic window of 2*NSDSNTH+1 directions
     if (sat) {
@@ -947,43 +943,42 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? ST_MINB : 2) k_
     asm volatile("cp.async.wait_all;\n" ::: "memory");
     __syncthreads();
     // ================= phase B =================
-    if (dia) {
-      // gather the quadruplet contributions of MC into the pending rows (snonlin.F90:253-308, :333-410, :446-490)
-      const int MC0 = st, MC = st + 1;
-      const double* R = c_dc.RNLCOEF[MC0];
-      const int branch = (MC > MFR1STFR && MC < MFRLSTFR) ? 0 : (MC >= MFRLSTFR ? 1 : 2);
-      bool do_mm, do_mm1, do_mp, do_mp1;
-      {
-        const int MP = MC + 2, MP1 = MC + 3, MM1 = MC - 3;
-        if (branch == 0) { do_mm = do_mm1 = do_mp = do_mp1 = true; }
-        else if (branch == 1) { do_mm = true; do_mm1 = MM1 <= F; const bool dc = do_mm1 && MC <= F; do_mp = dc && MP <= F; do_mp1 = do_mp && MP1 <= F; }
-        else { do_mm = false; do_mm1 = MM1 >= 1; do_mp = true; do_mp1 = true; }
-      }
-      const unsigned cb = L.cur + par * 6u * PSB + me_c;
+    V tot_sl, tot_fl;   // SNONLIN sums of the row that is finished at this step
+    {
+      // gather the quadruplet contributions of MC into the pending rows (snonlin.F90:253-308, :333-410, :446-490) and slide the
+      // window: row st-3 -> slot 0, ..., row st+3 (first contribution) -> slot 6
       V sl_mm, fl_mm, sl_mm1, fl_mm1, sl_mp, fl_mp, sl_mp1, fl_mp1;
 #pragma unroll
       for (int i = 0; i < NP; ++i) { sl_mm.v[i] = fl_mm.v[i] = sl_mm1.v[i] = fl_mm1.v[i] = sl_mp.v[i] = fl_mp.v[i] = sl_mp1.v[i] = fl_mp1.v[i] = 0.0; }
+      if (dia) {
+        const double* R = c_dc.RNLCOEF[st];
+        const unsigned cb = L.cur + par * 6u * PSB + me_c;
 #pragma unroll
-      for (int kh = 0; kh < 2; ++kh) {
-        const unsigned cA = cb + (0 + kh) * PSB, cP = cb + (2 + kh) * PSB, cM = cb + (4 + kh) * PSB;
-        const V a2 = lds<NP>(sm, cA - dsb[kh][2]), a21 = lds<NP>(sm, cA - dsb[kh][3]);
-        const V m2 = lds<NP>(sm, cM - dsb[kh][2]), m21 = lds<NP>(sm, cM - dsb[kh][3]);
-        const V a1 = lds<NP>(sm, cA - dsb[kh][0]), a11 = lds<NP>(sm, cA - dsb[kh][1]);
-        const V q1 = lds<NP>(sm, cP - dsb[kh][0]), q11 = lds<NP>(sm, cP - dsb[kh][1]);
+        for (int kh = 0; kh < 2; ++kh) {
+          const unsigned cA = cb + (0 + kh) * PSB, cP = cb + (2 + kh) * PSB, cM = cb + (4 + kh) * PSB;
+          const V a2 = lds<NP>(sm, cA - dsb[kh][2]), a21 = lds<NP>(sm, cA - dsb[kh][3]);
+          const V m2 = lds<NP>(sm, cM - dsb[kh][2]), m21 = lds<NP>(sm, cM - dsb[kh][3]);
+          const V a1 = lds<NP>(sm, cA - dsb[kh][0]), a11 = lds<NP>(sm, cA - dsb[kh][1]);
+          const V q1 = lds<NP>(sm, cP - dsb[kh][0]), q11 = lds<NP>(sm, cP - dsb[kh][1]);
 #pragma unroll
-        for (int i = 0; i < NP; ++i) {
-          sl_mm.v[i] += a2.v[i] * R[20] + a21.v[i] * R[19];   fl_mm.v[i] += m2.v[i] * R[23] + m21.v[i] * R[24];     // FKLAMM1, FKLAMM2 | FKLAM12, FKLAM22
-          sl_mm1.v[i] += a2.v[i] * R[17] + a21.v[i] * R[18];  fl_mm1.v[i] += m2.v[i] * R[21] + m21.v[i] * R[22];    // FKLAMMA, FKLAMMB | FKLAMA2, FKLAMB2
-          sl_mp.v[i] += a1.v[i] * R[8] + a11.v[i] * R[7];     fl_mp.v[i] += q1.v[i] * R[11] + q11.v[i] * R[12];     // FKLAMP1, FKLAMP2 | FKLAP12, FKLAP22
-          sl_mp1.v[i] += a1.v[i] * R[5] + a11.v[i] * R[6];    fl_mp1.v[i] += q1.v[i] * R[9] + q11.v[i] * R[10];     // FKLAMPA, FKLAMPB | FKLAPA2, FKLAPB2
+          for (int i = 0; i < NP; ++i) {
+            sl_mm.v[i] = fma(a21.v[i], R[19], fma(a2.v[i], R[20], sl_mm.v[i]));   fl_mm.v[i] = fma(m21.v[i], R[24], fma(m2.v[i], R[23], fl_mm.v[i]));     // FKLAMM1, FKLAMM2 | FKLAM12, FKLAM22
+            sl_mm1.v[i] = fma(a21.v[i], R[18], fma(a2.v[i], R[17], sl_mm1.v[i])); fl_mm1.v[i] = fma(m21.v[i], R[22], fma(m2.v[i], R[21], fl_mm1.v[i]));   // FKLAMMA, FKLAMMB | FKLAMA2, FKLAMB2
+            sl_mp.v[i] = fma(a11.v[i], R[7], fma(a1.v[i], R[8], sl_mp.v[i]));     fl_mp.v[i] = fma(q11.v[i], R[12], fma(q1.v[i], R[11], fl_mp.v[i]));     // FKLAMP1, FKLAMP2 | FKLAP12, FKLAP22
+            sl_mp1.v[i] = fma(a11.v[i], R[6], fma(a1.v[i], R[5], sl_mp1.v[i]));   fl_mp1.v[i] = fma(q11.v[i], R[10], fma(q1.v[i], R[9], fl_mp1.v[i]));    // FKLAMPA, FKLAMPB | FKLAPA2, FKLAPB2
+          }
         }
       }
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
-        if (do_mm) { asl[O + 0][i] += sl_mm.v[i]; afl[O + 0][i] += fl_mm.v[i]; }
-        if (do_mm1) { asl[O + 1][i] += sl_mm1.v[i]; afl[O + 1][i] += fl_mm1.v[i]; }
-        if (do_mp) { asl[O + 6][i] += sl_mp.v[i]; afl[O + 6][i] += fl_mp.v[i]; }
-        if (do_mp1) { asl[O + 7][i] += sl_mp1.v[i]; afl[O + 7][i] += fl_mp1.v[i]; }
+        tot_sl.v[i] = asl[0][i] + sl_mm.v[i];   tot_fl.v[i] = afl[0][i] + fl_mm.v[i];
+        asl[0][i] = asl[1][i] + sl_mm1.v[i];    afl[0][i] = afl[1][i] + fl_mm1.v[i];
+        asl[1][i] = asl[2][i];                  afl[1][i] = afl[2][i];
+        asl[2][i] = asl[3][i];                  afl[2][i] = afl[3][i];
+        asl[3][i] = asl[4][i];                  afl[3][i] = afl[4][i];
+        asl[4][i] = asl[5][i];                  afl[4][i] = afl[5][i];
+        asl[5][i] = asl[6][i] + sl_mp.v[i];     afl[5][i] = afl[6][i] + fl_mp.v[i];
+        asl[6][i] = sl_mp1.v[i];                afl[6][i] = fl_mp1.v[i];
       }
     }
     const V flmc = lds<NP>(sm, L.pc + PC_FLMC * 64 + jo);
@@ -1017,7 +1012,7 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? ST_MINB : 2) k_
         double fldv = xI.v[i];                             // wind input (SINPUT, second SINFLX call)
         double slv = fldv * f0;
         slv = slv + dd.v[i] * f0; fldv = fldv + dd.v[i];   // SDISSIP
-        slv = slv + asl[O][i]; fldv = fldv + afl[O][i];    // SNONLIN
+        slv = slv + tot_sl.v[i]; fldv = fldv + tot_fl.v[i];    // SNONLIN
         double ssource = 0.0;
         if (lssource) ssource = div_norm(slv, dmax(1.0 - delt5 * fldv, 1.0));
         if (r < c_dc.Fr) {
@@ -1087,21 +1082,8 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? ST_MINB : 2) k_
     b_prev = b_next;
   };
 
-  constexpr int ST0 = -((5 + ST_U - 1) / ST_U) * ST_U;
 #pragma unroll 1
-  for (int st = ST0; st < MLSTHG; st += ST_U) {
-    step(IC<0>(), st);
-    if (ST_U > 1) step(IC<(ST_U > 1 ? 1 : 0)>(), st + 1);
-    if (ST_U > 2) { step(IC<(ST_U > 2 ? 2 : 0)>(), st + 2); step(IC<(ST_U > 2 ? 3 : 0)>(), st + 3); }
-#pragma unroll
-    for (int x = 0; x < 8 - 1; ++x)
-#pragma unroll
-      for (int i = 0; i < NP; ++i) { asl[x][i] = asl[x + ST_U][i]; afl[x][i] = afl[x + ST_U][i]; }
-#pragma unroll
-    for (int x = 8 - 1; x < NACC; ++x)
-#pragma unroll
-      for (int i = 0; i < NP; ++i) { asl[x][i] = 0.0; afl[x][i] = 0.0; }
-  }
+  for (int st = -5; st < MLSTHG; ++st) step(st);
   // ---- per-point sums over direction, then the scalar closures (one thread per point)
   __syncthreads();
   {
