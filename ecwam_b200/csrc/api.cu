@@ -2,8 +2,10 @@
 // PROPAG_WAM / IMPLSCH / WAMINTGR entry points.
 #include "internal.h"
 #include <nccl.h>
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -81,6 +83,11 @@ struct ecwam_b200_handle_s {
   ecwam_b200_fields mir;
   bool mir_alloc = false, mir_static_done = false;
   std::vector<void*> mir_bufs;
+  // banded copy/compute pipeline of the host-buffer entry point
+  cudaStream_t st_up = nullptr, st_dn = nullptr;
+  std::vector<cudaEvent_t> ev_up, ev_done;
+  cudaEvent_t ev_start = nullptr;
+  int nbr_reach = 0;       // max |l' - l| over the own-point neighbours of every own point l
   // stats
   long long nlaunch = 0;
   bool timing = false;
@@ -357,6 +364,15 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
   halo_off[nbot + ntop] = (int)halo_elems;   // land: one zero element, stride 0
   halo_str[nbot + ntop] = 0;
 
+  {
+    int reach = 0;
+    for (int j = 0; j < 14; ++j)
+      for (int l = 0; l < nloc; ++l) {
+        const int e = nbr[(size_t)j * nloc + l];
+        if (e >= nbot && e < nbot + nloc) reach = std::max(reach, std::abs(e - nbot - l));
+      }
+    h->nbr_reach = reach;
+  }
   cudaStream_t st = h->st;
   bool ok = true;
   ok = ok && !h->nbr.upload(nbr, st) && !h->wl.upload(wl, st) && !h->pt.upload(pt, st) && !h->cosph_m.upload(cpm, st) &&
@@ -453,6 +469,11 @@ int ecwam_b200_destroy(ecwam_b200_handle h) {
   h->cgext.free(); h->halo.free(); h->sendbuf.free(); h->fl3.free(); h->cosph_m.free(); h->cosph_p.free();
   h->land_cg.free(); h->cgrecv.free(); h->scr.free(); h->fldin.free(); h->tbg.free(); h->satw.free(); h->swellft.free(); h->kw.free(); h->isat.free();
   for (void* b : h->mir_bufs) cudaFree(b);
+  for (cudaEvent_t e : h->ev_up) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
+  if (h->ev_start) cudaEventDestroy(h->ev_start);
+  if (h->st_up) cudaStreamDestroy(h->st_up);
+  if (h->st_dn) cudaStreamDestroy(h->st_dn);
   delete h;
   return 0;
 }
@@ -688,48 +709,122 @@ inline void*& fptr(ecwam_b200_fields& f, size_t off) { return *(void**)((char*)&
 inline void* fptr_c(const ecwam_b200_fields& f, size_t off) { return *(void* const*)((const char*)&f + off); }
 }  // namespace
 
+// Host-buffer entry: the caller's arrays live in (pinned) host memory.  Copies and kernels are pipelined over bands of
+// NPROMA chunks on three streams: upload of band b+2 | PROPAGS2 of band b+1 | IMPLSCH of band b | download of band b-1.
+//   * full pipeline (one rank, no fast-wave sub-steps, CTU set-up done): PROPAGS2 of a band only needs the bands next to it
+//     (a band is at least as long as the largest neighbour distance of the grid), and IMPLSCH of band b is issued after
+//     PROPAGS2 of band b+1, which is the last reader of the old spectrum of band b;
+//   * otherwise: upload everything, PROPAG_WAM as a whole (it needs the halo), then IMPLSCH / download band by band.
 int ecwam_b200_wamintgr_host(ecwam_b200_handle h, const ecwam_b200_fields* host, int with_xllws, long long* h2d_bytes,
                              long long* d2h_bytes) {
   if (!h || !host) EW_FAIL(ECWAM_B200_EINVAL, "null argument");
   const ecwam_b200_params& p = h->par;
   const size_t npts = (size_t)p.nproma * p.nchnk;
-  auto bytes_of = [&](int kind) -> size_t {
-    switch (kind) { case 0: return npts * p.nang * p.nfre * 8; case 1: return npts * p.nfre * 8; case 2: return npts * 8; default: return npts * 4; }
+  auto chunk_bytes = [&](int kind) -> size_t {
+    switch (kind) { case 0: return (size_t)p.nproma * p.nang * p.nfre * 8; case 1: return (size_t)p.nproma * p.nfre * 8; case 2: return (size_t)p.nproma * 8; default: return (size_t)p.nproma * 4; }
   };
   if (!h->mir_alloc) {
     for (const FieldDesc& fd : kFields) {
       void* b = nullptr;
-      EW_CUDA_CHECK(cudaMalloc(&b, bytes_of(fd.kind)));
-      EW_CUDA_CHECK(cudaMemsetAsync(b, 0, bytes_of(fd.kind), h->st));
+      EW_CUDA_CHECK(cudaMalloc(&b, chunk_bytes(fd.kind) * p.nchnk));
+      EW_CUDA_CHECK(cudaMemsetAsync(b, 0, chunk_bytes(fd.kind) * p.nchnk, h->st));
       h->mir_bufs.push_back(b);
       fptr(h->mir, fd.off) = b;
     }
+    EW_CUDA_CHECK(cudaStreamCreateWithFlags(&h->st_up, cudaStreamNonBlocking));
+    EW_CUDA_CHECK(cudaStreamCreateWithFlags(&h->st_dn, cudaStreamNonBlocking));
+    EW_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
     h->mir_alloc = true;
     int rc = ecwam_b200_bind_fields(h, &h->mir);
     if (rc) return rc;
   }
+  (void)npts;
+  // ---- bands of chunks
+  const int nchnk = p.nchnk, P = p.nproma;
+  const int reach_chunks = (h->nbr_reach + P - 1) / P + 1;
+  static const int kBands = []() { const char* e = getenv("ECWAM_B200_HOST_BANDS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 24; }();
+  int band = std::max((nchnk + kBands - 1) / kBands, reach_chunks);
+  const int nband = (nchnk + band - 1) / band;
+  const bool substeps = p.ifrelfmax > 0 && p.ifrelfmax < p.nfre_red;
+  const bool full = h->nproc <= 1 && !substeps && !h->weights_dirty && h->mir_static_done && nband >= 3;
+  while ((int)h->ev_up.size() < nband) { cudaEvent_t e; EW_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_up.push_back(e); }
+  while ((int)h->ev_done.size() < nband) { cudaEvent_t e; EW_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_done.push_back(e); }
   long long nin = 0, nout = 0;
-  for (const FieldDesc& fd : kFields) {
-    const void* src = fptr_c(*host, fd.off);
-    const bool is_static = (fd.dir & 1) != 0, per_step = (fd.dir & 2) != 0;
-    if (!src) continue;
-    if ((is_static && !h->mir_static_done) || per_step) {
-      EW_CUDA_CHECK(cudaMemcpyAsync(fptr(h->mir, fd.off), src, bytes_of(fd.kind), cudaMemcpyHostToDevice, h->st));
-      nin += (long long)bytes_of(fd.kind);
+  const bool first = !h->mir_static_done;
+  auto upload = [&](int c0, int c1, cudaStream_t s) -> int {
+    for (const FieldDesc& fd : kFields) {
+      const char* src = (const char*)fptr_c(*host, fd.off);
+      const bool is_static = (fd.dir & 1) != 0, per_step = (fd.dir & 2) != 0;
+      if (!src || !((is_static && first) || per_step)) continue;
+      const size_t cb = chunk_bytes(fd.kind);
+      EW_CUDA_CHECK(cudaMemcpyAsync((char*)fptr(h->mir, fd.off) + cb * c0, src + cb * c0, cb * (c1 - c0), cudaMemcpyHostToDevice, s));
+      nin += (long long)(cb * (c1 - c0));
+    }
+    return 0;
+  };
+  auto download = [&](int c0, int c1, cudaStream_t s) -> int {
+    for (const FieldDesc& fd : kFields) {
+      char* dst = (char*)fptr_c(*host, fd.off);
+      if (!dst || !((fd.dir & 4) || ((fd.dir & 8) && with_xllws))) continue;
+      const size_t cb = chunk_bytes(fd.kind);
+      EW_CUDA_CHECK(cudaMemcpyAsync(dst + cb * c0, (char*)fptr(h->mir, fd.off) + cb * c0, cb * (c1 - c0), cudaMemcpyDeviceToHost, s));
+      nout += (long long)(cb * (c1 - c0));
+    }
+    return 0;
+  };
+  auto c0_of = [&](int b) { return b * band; };
+  auto c1_of = [&](int b) { return std::min(nchnk, (b + 1) * band); };
+  // the side streams start after everything already queued on the compute stream
+  EW_CUDA_CHECK(cudaEventRecord(h->ev_start, h->st));
+  EW_CUDA_CHECK(cudaStreamWaitEvent(h->st_up, h->ev_start, 0));
+  EW_CUDA_CHECK(cudaStreamWaitEvent(h->st_dn, h->ev_start, 0));
+  int rc = 0;
+  if (full) {
+    rc = ensure_const(h);
+    if (rc) return rc;
+    const PropDev& d = h->pd;
+    for (int b = 0; b < nband; ++b) {
+      if ((rc = upload(c0_of(b), c1_of(b), h->st_up))) return rc;
+      EW_CUDA_CHECK(cudaEventRecord(h->ev_up[b], h->st_up));
+    }
+    for (int b = 0; b <= nband; ++b) {
+      if (b < nband) {   // PROPAGS2 of band b reads bands b-1 .. b+1
+        EW_CUDA_CHECK(cudaStreamWaitEvent(h->st, h->ev_up[std::min(b + 1, nband - 1)], 0));
+        ScopedTimer t(h, "propags2");
+        launch_propags2(d, h->dev.fl1, d.F, h->fl3.p, d.Fr, 0, d.Fr, h->msplit, h->st, c0_of(b) * P, c1_of(b) * P);
+        h->nlaunch++;
+        if (b == nband - 1) launch_pad(d, h->fl3.p, d.Fr, 0, d.Fr, h->st);   // padded lanes of the last chunk (propag_wam.F90:388-398)
+      }
+      if (b >= 1) {      // IMPLSCH of band b-1, then its way back to the host
+        const int bb = b - 1;
+        if ((rc = implsch_range(h, c0_of(bb) + 1, c1_of(bb) - c0_of(bb), true))) return rc;
+        EW_CUDA_CHECK(cudaEventRecord(h->ev_done[bb], h->st));
+        EW_CUDA_CHECK(cudaStreamWaitEvent(h->st_dn, h->ev_done[bb], 0));
+        if ((rc = download(c0_of(bb), c1_of(bb), h->st_dn))) return rc;
+      }
+    }
+  } else {
+    if ((rc = upload(0, nchnk, h->st))) return rc;
+    h->mir_static_done = true;
+    bool lf_in_fl3 = true;
+    rc = propag_core(h, &lf_in_fl3);
+    if (rc) return rc;
+    const PropDev& d = h->pd;
+    if (!lf_in_fl3) {   // odd number of fast-wave sub-steps left the low frequencies in FL1: finish PROPAG_WAM the plain way
+      launch_copyback(d, h->fl3.p, h->dev.fl1, p.ifrelfmax, d.Fr, h->st);
+      launch_pad(d, h->dev.fl1, d.F, 0, p.ifrelfmax, h->st);
+      h->nlaunch += 2;
+    } else launch_pad(d, h->fl3.p, d.Fr, 0, d.Fr, h->st);
+    for (int b = 0; b < nband; ++b) {
+      if ((rc = implsch_range(h, c0_of(b) + 1, c1_of(b) - c0_of(b), lf_in_fl3))) return rc;
+      EW_CUDA_CHECK(cudaEventRecord(h->ev_done[b], h->st));
+      EW_CUDA_CHECK(cudaStreamWaitEvent(h->st_dn, h->ev_done[b], 0));
+      if ((rc = download(c0_of(b), c1_of(b), h->st_dn))) return rc;
     }
   }
-  h->mir_static_done = true;
-  int rc = ecwam_b200_wamintgr(h);
-  if (rc) return rc;
-  for (const FieldDesc& fd : kFields) {
-    void* dst = fptr_c(*host, fd.off);
-    if (!dst) continue;
-    if ((fd.dir & 4) || ((fd.dir & 8) && with_xllws)) {
-      EW_CUDA_CHECK(cudaMemcpyAsync(dst, fptr(h->mir, fd.off), bytes_of(fd.kind), cudaMemcpyDeviceToHost, h->st));
-      nout += (long long)bytes_of(fd.kind);
-    }
-  }
+  EW_CUDA_CHECK(cudaStreamSynchronize(h->st_dn));
   EW_CUDA_CHECK(cudaStreamSynchronize(h->st));
+  EW_CUDA_CHECK(cudaStreamSynchronize(h->st_up));
   if (h2d_bytes) *h2d_bytes = nin;
   if (d2h_bytes) *d2h_bytes = nout;
   return 0;

@@ -677,7 +677,7 @@ __device__ __forceinline__ unsigned slot9(int r) { return (unsigned)c_dc.SLOT9[r
 struct StencilSmem {   // byte offsets into dynamic shared memory
   unsigned ring, cur, satw, tbs, pc, part, bth0, stage, total, RSB, PSB, SSB;
 };
-__host__ __device__ constexpr StencilSmem stencil_smem(int A, int halo_r, int halo_c, int nth, int np) {
+__host__ __device__ constexpr StencilSmem stencil_smem(int A, int halo_r, int halo_c, int nth, int np, bool lwflux) {
   StencilSmem s{};
   const int nwarp = nth / 32;
   s.RSB = (unsigned)(A + 2 * halo_r) * ST_NPT * 8;
@@ -686,12 +686,12 @@ __host__ __device__ constexpr StencilSmem stencil_smem(int A, int halo_r, int ha
   unsigned o = 0;
   s.ring = o; o += ST_RING * s.RSB;
   s.cur = o; o += 2 * 6 * s.PSB;
-  s.satw = o; o += (unsigned)A * EW_MAXSAT * 8; o = (o + 15u) & ~15u;
+  s.satw = o; o += (unsigned)A * ST_NSMAX * 8; o = (o + 15u) & ~15u;
   s.tbs = o; o += 4 * TQ_N * ST_NPT * 8;
   s.pc = o; o += PC_N * ST_NPT * 8;
   s.part = o; o += 2u * (unsigned)nwarp * ST_NPT * 8;
   s.bth0 = o; o += 2 * ST_NPT * 8;
-  s.stage = o; o += 3 * s.SSB;      // thread-private landing slots of the cp.async row loads (FL1 row, wind-input row, XLLWS row)
+  s.stage = o; o += (lwflux ? 3 : 2) * s.SSB;      // thread-private landing slots of the cp.async row loads (FL1 row, wind-input row, XLLWS row)
   s.total = o;
   return s;
 }
@@ -712,13 +712,14 @@ __host__ __device__ constexpr int geo_sh(int A, int kh, int q) {
 __host__ __device__ constexpr int geo_hc(int A) { return A == 36 ? 4 : (A == 24 ? 3 : (A == 12 ? 2 : 0)); }
 __host__ __device__ constexpr int stencil_threads(int A, int np) { return ((A * (ST_NPT / np) + 31) / 32) * 32; }
 
-#ifndef ST_MINB
-#define ST_MINB 2   // resident CTAs per SM the two-point instance is compiled for
+#ifndef ST_MAXREG
+#define ST_MAXREG 168   // register cap of the two-point instance (168: 2 CTAs of 160 threads per SM; 136: 3 CTAs)
 #endif
+#define ST_BOUNDS(NP) __maxnreg__(NP == 2 ? ST_MAXREG : 112)
 
 // TA = NANG when it is one of the standard grids (compile-time geometry), 0 = run-time geometry (any NANG <= 36)
 template <int TA, int NP, bool LWFLUX>
-__global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? ST_MINB : 2) k_stencil(ImplDev d, long long p0, long long np, StencilSmem Lrt) {
+__global__ void ST_BOUNDS(NP) k_stencil(ImplDev d, long long p0, long long np, StencilSmem Lrt) {
   extern __shared__ __align__(16) char sm[];
   typedef Vd<NP> V;
   const int A = TA > 0 ? TA : c_dc.A, F = c_dc.F;
@@ -727,7 +728,7 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? ST_MINB : 2) k_
   const bool ard = c_dc.iphys == 1;
   const int H = TA > 0 ? geo_nsd(TA) : d.halo_r, HC = TA > 0 ? geo_hc(TA) : d.halo_c;
   const int nwarp = TA > 0 ? stencil_threads(TA, NP) / 32 : (int)(blockDim.x >> 5);
-  constexpr StencilSmem Lct = stencil_smem(TA, geo_nsd(TA), geo_hc(TA), stencil_threads(TA, NP), NP);
+  constexpr StencilSmem Lct = stencil_smem(TA, geo_nsd(TA), geo_hc(TA), stencil_threads(TA, NP), NP, LWFLUX);
   const StencilSmem L = TA > 0 ? Lct : Lrt;
   const unsigned RSB = L.RSB, PSB = L.PSB;
   int dsb[2][4];
@@ -794,7 +795,7 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? ST_MINB : 2) k_
   }
   if (ard) for (int x = t; x < NS * A; x += blockDim.x) {   // (x, kk) -> [kk][x]
     const int xs = x / A, kk = x - xs * A;
-    reinterpret_cast<double*>(sm + L.satw)[kk * EW_MAXSAT + xs] = __ldg(d.tab.satweights + x);
+    reinterpret_cast<double*>(sm + L.satw)[kk * ST_NSMAX + xs] = __ldg(d.tab.satweights + x);
   }
   __syncthreads();
   const double sinth = c_dc.SINTH[k], costh = c_dc.COSTH[k];
@@ -823,7 +824,7 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? ST_MINB : 2) k_
   V b_prev, fmij, a_philf, a_ts, a_tu, a_e1, a_e2, a_el;
 #pragma unroll
   for (int i = 0; i < NP; ++i) { b_prev.v[i] = 0.0; fmij.v[i] = 0.0; a_philf.v[i] = 0.0; a_ts.v[i] = 0.0; a_tu.v[i] = 0.0; a_e1.v[i] = 0.0; a_e2.v[i] = 0.0; a_el.v[i] = 0.0; }
-  const unsigned satw_me = L.satw + (unsigned)k * (EW_MAXSAT * 8);
+  const unsigned satw_me = L.satw + (unsigned)k * (ST_NSMAX * 8);
   const unsigned lane = (unsigned)t & 31u;
 
   // one step of the sweep
@@ -1164,7 +1165,7 @@ __global__ void __launch_bounds__(NP == 2 ? 160 : 288, NP == 2 ? ST_MINB : 2) k_
 template <int TA, int NP, bool LW>
 static int launch_stencil(const ImplDev& d, long long p0, long long np, cudaStream_t st) {
   const int nth = stencil_threads(d.A, NP);
-  const StencilSmem L = stencil_smem(d.A, TA > 0 ? geo_nsd(TA) : d.halo_r, TA > 0 ? geo_hc(TA) : d.halo_c, nth, NP);
+  const StencilSmem L = stencil_smem(d.A, TA > 0 ? geo_nsd(TA) : d.halo_r, TA > 0 ? geo_hc(TA) : d.halo_c, nth, NP, LW);
   static bool attr_done = false;
   if (!attr_done) {
     EW_CUDA_CHECK(cudaFuncSetAttribute(k_stencil<TA, NP, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
@@ -1201,13 +1202,20 @@ int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage
   } else if (stage == 1) {
     // two grid points per thread (16-byte shared / global accesses) need an even NPROMA and an even first point
     const uintptr_t al = (uintptr_t)d.f.fl1 | (uintptr_t)d.f.xllws | (uintptr_t)d.fldin | (uintptr_t)d.fl_lo;
+#ifdef ST_TRY_NP1
+    const bool pair = false;
+#else
     const bool pair = (d.P % 2 == 0) && (p0 % 2 == 0) && (np % 2 == 0) && (al & 15) == 0;
+#endif
     if (pair) {
       if (geo_matches<36>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_stencil<36, 2, true>(d, p0, np, st) : launch_stencil<36, 2, false>(d, p0, np, st);
       if (geo_matches<24>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_stencil<24, 2, true>(d, p0, np, st) : launch_stencil<24, 2, false>(d, p0, np, st);
       if (geo_matches<12>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_stencil<12, 2, true>(d, p0, np, st) : launch_stencil<12, 2, false>(d, p0, np, st);
       return d.lwflux ? launch_stencil<0, 2, true>(d, p0, np, st) : launch_stencil<0, 2, false>(d, p0, np, st);
     }
+#ifdef ST_TRY_NP1
+    if (geo_matches<36>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_stencil<36, 1, true>(d, p0, np, st) : launch_stencil<36, 1, false>(d, p0, np, st);
+#endif
     return d.lwflux ? launch_stencil<0, 1, true>(d, p0, np, st) : launch_stencil<0, 1, false>(d, p0, np, st);
   } else return ECWAM_B200_EINVAL;
   return 0;

@@ -34,8 +34,9 @@ struct PropConst {
 };
 int upload_prop_const(const PropConst& h, cudaStream_t st);
 
+// own points [l0, l1) (l1 < 0: all)
 void launch_propags2(const PropDev& d, const double* src, int srcF, double* dst, int dstF, int m0, int m1, int msplit,
-                     cudaStream_t st);
+                     cudaStream_t st, int l0 = 0, int l1 = -1);
 void launch_ctu_check(const PropDev& d, int m0, int m1, int msplit, int* flag, int* count, cudaStream_t st);
 void launch_setup_points(const PropDev& d, const double* cosphm1_fld, const double* cosph_m, const double* cosph_p,
                          double* pt, cudaStream_t st);

@@ -138,9 +138,9 @@ __device__ __forceinline__ void ctu_quadrant(const PropDev& d, const SpecSrc& sr
 }
 
 __global__ void __launch_bounds__(128, 4) propags2_kernel(PropDev d, SpecSrc src, double* __restrict__ dst, long long dcstride,
-                                                          int m0, int m1, int MG, int msplit) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= d.nloc) return;
+                                                          int m0, int m1, int MG, int msplit, int l0, int l1) {
+  const int l = l0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= l1) return;
   const int mb = m0 + blockIdx.y * MG;
   const int me = min(mb + MG, m1);
   const int nl = d.nloc;
@@ -338,12 +338,14 @@ __global__ void pad_kernel(PropDev d, double* __restrict__ fl1, int flF, int m0,
 
 // ---- host launchers --------------------------------------------------------------------------------------
 void launch_propags2(const PropDev& d, const double* src, int srcF, double* dst, int dstF, int m0, int m1, int msplit,
-                     cudaStream_t st) {
-  if (m1 <= m0 || d.nloc <= 0) return;
+                     cudaStream_t st, int l0, int l1) {
+  if (l1 < 0) l1 = d.nloc;
+  l1 = l1 < d.nloc ? l1 : d.nloc;
+  if (m1 <= m0 || l1 <= l0) return;
   const int MG = 8;
   SpecSrc s{src, (long long)d.P * d.A * srcF};
-  dim3 grid((d.nloc + 127) / 128, (m1 - m0 + MG - 1) / MG);
-  propags2_kernel<<<grid, 128, 0, st>>>(d, s, dst, (long long)d.P * d.A * dstF, m0, m1, MG, msplit);
+  dim3 grid((l1 - l0 + 127) / 128, (m1 - m0 + MG - 1) / MG);
+  propags2_kernel<<<grid, 128, 0, st>>>(d, s, dst, (long long)d.P * d.A * dstF, m0, m1, MG, msplit, l0, l1);
 }
 void launch_ctu_check(const PropDev& d, int m0, int m1, int msplit, int* flag, int* count, cudaStream_t st) {
   cudaMemsetAsync(flag, 0, sizeof(int) * d.nloc, st);
