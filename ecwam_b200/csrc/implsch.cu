@@ -8,6 +8,8 @@
 //              DIA quadruplets) fused with SDIWBK, SBOTTOM, the implicit update, WNFLUXES, IMPHFTAIL, SETICE, STOKESDRIFT
 // Nothing but FL1, XLLWS, the 1-D outputs and one scratch array (the wind-input linearisation) touches HBM.
 #include "internal.h"
+#include <cstdlib>
+#include <cstring>
 
 namespace ew {
 
@@ -1202,20 +1204,19 @@ int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage
   } else if (stage == 1) {
     // two grid points per thread (16-byte shared / global accesses) need an even NPROMA and an even first point
     const uintptr_t al = (uintptr_t)d.f.fl1 | (uintptr_t)d.f.xllws | (uintptr_t)d.fldin | (uintptr_t)d.fl_lo;
-#ifdef ST_TRY_NP1
-    const bool pair = false;
-#else
-    const bool pair = (d.P % 2 == 0) && (p0 % 2 == 0) && (np % 2 == 0) && (al & 15) == 0;
-#endif
+    bool pair = (d.P % 2 == 0) && (p0 % 2 == 0) && (np % 2 == 0) && (al & 15) == 0;
+    // test hook: ECWAM_B200_STENCIL=generic (run-time geometry instance) | single (one point per thread, run-time geometry)
+    const char* force = getenv("ECWAM_B200_STENCIL");
+    const bool generic = force && (!strcmp(force, "generic") || !strcmp(force, "single"));
+    if (force && !strcmp(force, "single")) pair = false;
     if (pair) {
-      if (geo_matches<36>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_stencil<36, 2, true>(d, p0, np, st) : launch_stencil<36, 2, false>(d, p0, np, st);
-      if (geo_matches<24>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_stencil<24, 2, true>(d, p0, np, st) : launch_stencil<24, 2, false>(d, p0, np, st);
-      if (geo_matches<12>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_stencil<12, 2, true>(d, p0, np, st) : launch_stencil<12, 2, false>(d, p0, np, st);
+      if (!generic) {
+        if (geo_matches<36>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_stencil<36, 2, true>(d, p0, np, st) : launch_stencil<36, 2, false>(d, p0, np, st);
+        if (geo_matches<24>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_stencil<24, 2, true>(d, p0, np, st) : launch_stencil<24, 2, false>(d, p0, np, st);
+        if (geo_matches<12>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_stencil<12, 2, true>(d, p0, np, st) : launch_stencil<12, 2, false>(d, p0, np, st);
+      }
       return d.lwflux ? launch_stencil<0, 2, true>(d, p0, np, st) : launch_stencil<0, 2, false>(d, p0, np, st);
     }
-#ifdef ST_TRY_NP1
-    if (geo_matches<36>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_stencil<36, 1, true>(d, p0, np, st) : launch_stencil<36, 1, false>(d, p0, np, st);
-#endif
     return d.lwflux ? launch_stencil<0, 1, true>(d, p0, np, st) : launch_stencil<0, 1, false>(d, p0, np, st);
   } else return ECWAM_B200_EINVAL;
   return 0;

@@ -78,6 +78,29 @@ def test_wamintgr_steps_match_oracle(built, case):
         assert abs(red(hs_g) - red(hs_o[w.own])) <= 1e-12 * abs(red(hs_o))
 
 
+@pytest.mark.parametrize("mode,case", [("generic", "o640like"), ("generic", "o48_iphys0"), ("single", "o640like"), ("single", "o320like")])
+def test_stencil_kernel_instances_agree(built, monkeypatch, mode, case):
+    """k_stencil has compile-time-geometry instances (NANG 12/24/36, two points per thread), a run-time-geometry instance and a
+    one-point-per-thread instance (odd NPROMA / unaligned arrays).  All of them must match the oracle."""
+    monkeypatch.setenv("ECWAM_B200_STENCIL", mode)
+    g, o, f, fl = make_oracle(case)
+    _, s, w = make_gpu(case)
+    for _ in range(2):
+        assert o.step() == 0 and w.step() == 0
+    w.synchronize()
+    check_state(w, o)
+
+
+def test_odd_nproma(built):
+    """NPROMA is a namelist value: an odd one takes the one-point-per-thread k_stencil instance."""
+    g, o, f, fl = make_oracle("o640like", nproma=25)
+    _, s, w = make_gpu("o640like", nproma=25)
+    for _ in range(2):
+        assert o.step() == 0 and w.step() == 0
+    w.synchronize()
+    check_state(w, o)
+
+
 def test_fused_step_equals_separate_calls(built):
     _, s, w1 = make_gpu("o640like")
     _, _, w2 = make_gpu("o640like")
