@@ -635,7 +635,7 @@ static int implsch_range(H* h, int ichnk0, int nchnk, bool from_fl3) {
     ScopedTimer t(h, kStage[s]);
     rc = launch_implsch_stage(d, (long long)(ichnk0 - 1) * d.P, (long long)nchnk * d.P, s, h->st);
     if (rc) return rc;
-    h->nlaunch++;
+    h->nlaunch += (s == 0) ? 2 : 1;   // stage 0 = the two k_point kernels
   }
   EW_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -27,6 +27,7 @@ enum {
   S_SDS,                                                  // SDIWBK
   S_PHILF, S_XSTROC, S_YSTROC,                            // WNFLUXES sums
   S_MIJ, S_USTOLD, S_FAC, S_USFM,
+  S_USTAR1, S_TAUW1, S_TWDIR1,                            // result of the first SINFLX call (k_point<.,1> -> k_point<.,2>)
   NSCR
 };
 size_t implsch_scratch_doubles(long long npts) { return (size_t)NSCR * (size_t)npts; }
@@ -238,6 +239,9 @@ __device__ __forceinline__ double rhowgdfth(int m, int mij) {
 // linearisation FLD (scratch, same layout as FL1), XLLWS (final), MIJ and the 1-D stress fields.
 // =========================================================================================================
 #define KP_NTH 128    // threads per block of k_point
+#ifndef KP_UNROLL
+#define KP_UNROLL 1   // the direction loop stays rolled: the frequency loop of the second SINFLX call must fit the 32 KB instruction cache
+#endif
 struct PointSrc {
   const double* lo;   // frequencies [0, mlo): propagation scratch or FL1 itself
   const double* hi;   // FL1
@@ -315,7 +319,7 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
         if (m < c_dc.Fr && depth < c_dc.bathymax) sbo = (-2.0 * 0.038 * c_dc.GM1) * wavnum / sinh(dmin(2.0 * depth * wavnum, 50.0));   // sbottom.F90:76-97
         tg[TQ_SBO * qs] = sbo;
         tg[TQ_CINV * qs] = cinv;
-        tg[TQ_TAIL * qs] = 1.0 / xk / wavnum;                                                       // imphftail.F90:73-81
+        tg[TQ_TAIL * qs] = div_norm(div_norm(1.0, xk), wavnum);                                                       // imphftail.F90:73-81
         tg[TQ_STF * qs] = (m < c_dc.NFRE_ODD) ? d.f.stokfac[o3] * c_dc.DFIM_SIM[m] : 0.0;          // stokesdrift.F90:100-116
         double tj = 0.0;
         if (!ard) {   // SDISSIP_JAN (sdissip_jan.F90:96-132)
@@ -349,11 +353,11 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
           const double t2 = taupx * taupx + taupy * taupy;
           const double rt = sqrt(t2);
           ustp[g] = sqrt(rt);
-          if (rt > 0.0) { const double ri = 1.0 / rt; cosu[g] = taupy * ri; sinu[g] = taupx * ri; }
+          if (rt > 1e-300) { const double ri = div_norm(1.0, rt); cosu[g] = taupy * ri; sinu[g] = taupx * ri; }
           else { cosu[g] = 1.0; sinu[g] = 0.0; }
         } else { cosu[g] = csw; sinu[g] = snw; }
         ucn[g] = ustp[g] * cinv;
-        ucnzalpd[g] = c_dc.XKAPPA / (ucn[g] + c_dc.ZALP);
+        ucnzalpd[g] = div_norm(c_dc.XKAPPA, ucn[g] + c_dc.ZALP);
       }
     } else {
       const double ztanhkd = sig2 / (c_dc.G * wavnum);
@@ -370,7 +374,8 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
     double sx[NGST], sy[NGST], st = 0.0, tsum = 0.0, traw = 0.0;
 #pragma unroll
     for (int g = 0; g < NGST; ++g) { sx[g] = 0.0; sy[g] = 0.0; }
-#pragma unroll 2
+    constexpr int kUnroll = KP_UNROLL;
+#pragma unroll kUnroll
     for (int k = 0; k < A; ++k) {
       double f = dmax(fsrc[k * KP_NTH] * fac, c_dc.EPSMIN);                      // SDEPTHLIM applied on the fly
       const double snk = c_dc.SINTH[k], csk = c_dc.COSTH[k];
@@ -449,7 +454,11 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
   }
 }
 
-template <bool ARD>
+// PH = 1: SDEPTHLIM, first SINFLX call (AIRSEA, SINPUT with NGST=1, FKMEAN, FEMEANWS, FRCUTINDEX, STRESSO), SDIWBK's Q
+// PH = 2: second SINFLX call (AIRSEA, WSIGSTAR, SINPUT with NGST=2 and swell damping -> FLD, XLLWS; FRCUTINDEX; STRESSO with PHIWA)
+// Two kernels instead of one: each frequency loop then fits the 32 KB instruction cache (no_instruction stalls of the fused
+// kernel were as frequent as its dependency stalls), and the few scalars in between travel through the scratch slots.
+template <bool ARD, int PH>
 __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, long long np) {
   extern __shared__ double smem[];
   long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -478,7 +487,7 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
   const double DELT25 = c_dc.WETAIL * c_dc.FR[F - 1] * c_dc.DELTH;
   // ---- SDEPTHLIM (sdepthlim.F90:50-82): EM of the incoming spectrum -> limiting factor
   double fac = 1.0;
-  if (c_dc.lbiwbk) {
+  if (PH == 1 && c_dc.lbiwbk) {
     double em = c_dc.EPSMIN, last = 0.0;
     row_issue(S, 0, A);
     for (int m = 0; m < F; ++m) {
@@ -493,29 +502,39 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
     em += DELT25 * last;
     fac = dmin(d.f.emaxdpt[p] / em, 1.0);
   }
-  // ---- SINFLX call 1: AIRSEA (IUSFG=0), SINPUT (NGST=1), FEMEANWS, FRCUTINDEX, STRESSO
-  double ustar = d.f.ufric[p], z0, z0b, ch;
-  double tauw = d.f.tauw[p], tauwdir = d.f.tauwdir[p];
-  taut_z0(0, wswave, wdwave, tauw, tauwdir, ustar, z0, z0b, ch);
+  double ustar = d.f.ufric[p], z0 = 0.0, z0b = 0.0, ch = 0.0;
+  double tauw, tauwdir;
   double sumx[EW_MAXF], sumy[EW_MAXF], sumt[EW_MAXF];
   double ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc;
-  double mom[6] = {0, 0, 0, 0, 0, 0};
-  sinput_point<ARD, 1, false, false>(S, d, p, fac, flmc, snw, csw, ustar, z0, raorw, 0.0, 0.0, 0.0, 0.0, nullptr, nullptr, sumx, sumy,
-                                sumt, ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc, mom, false);
-  // FKMEAN (fkmean.F90:60-154)
-  const double COEFM1 = c_dc.FRTAIL * c_dc.DELTH;
-  const double COEF1 = c_dc.WP1TAIL * c_dc.DELTH * sq(c_dc.FR[F - 1]);
-  const double COEFA = COEFM1 * sqrt(c_dc.G) / c_dc.ZPI;
-  const double COEFX = COEF1 * (c_dc.ZPI / sqrt(c_dc.G));
-  const double emean = c_dc.EPSMIN + mom[0] + DELT25 * mom[5];
-  const double fmean = emean / (c_dc.EPSMIN + mom[1] + COEFM1 * mom[5]);
-  const double f1mean = (c_dc.EPSMIN + mom[2] + COEF1 * mom[5]) / emean;
-  const double akmean = sq(emean / (c_dc.EPSMIN + mom[3] + COEFA * mom[5]));
-  const double xkmean = sq((c_dc.EPSMIN + mom[4] + COEFX * mom[5]) / emean);
-  if (valid) {
-    s[S_EMEAN * n + p] = emean; s[S_FMEAN * n + p] = fmean; s[S_F1MEAN * n + p] = f1mean;
-    s[S_AKMEAN * n + p] = akmean; s[S_XKMEAN * n + p] = xkmean;
-    s[S_FAC * n + p] = fac;
+  double emean, fmean, f1mean, xkmean;
+  if (PH == 1) {
+    // ---- SINFLX call 1: AIRSEA (IUSFG=0), SINPUT (NGST=1), FEMEANWS, FRCUTINDEX, STRESSO
+    tauw = d.f.tauw[p]; tauwdir = d.f.tauwdir[p];
+    taut_z0(0, wswave, wdwave, tauw, tauwdir, ustar, z0, z0b, ch);
+    double mom[6] = {0, 0, 0, 0, 0, 0};
+    sinput_point<ARD, 1, false, false>(S, d, p, fac, flmc, snw, csw, ustar, z0, raorw, 0.0, 0.0, 0.0, 0.0, nullptr, nullptr, sumx, sumy,
+                                       sumt, ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc, mom, false);
+    // FKMEAN (fkmean.F90:60-154)
+    const double COEFM1 = c_dc.FRTAIL * c_dc.DELTH;
+    const double COEF1 = c_dc.WP1TAIL * c_dc.DELTH * sq(c_dc.FR[F - 1]);
+    const double COEFA = COEFM1 * sqrt(c_dc.G) / c_dc.ZPI;
+    const double COEFX = COEF1 * (c_dc.ZPI / sqrt(c_dc.G));
+    emean = c_dc.EPSMIN + mom[0] + DELT25 * mom[5];
+    fmean = emean / (c_dc.EPSMIN + mom[1] + COEFM1 * mom[5]);
+    f1mean = (c_dc.EPSMIN + mom[2] + COEF1 * mom[5]) / emean;
+    const double akmean = sq(emean / (c_dc.EPSMIN + mom[3] + COEFA * mom[5]));
+    xkmean = sq((c_dc.EPSMIN + mom[4] + COEFX * mom[5]) / emean);
+    if (valid) {
+      s[S_EMEAN * n + p] = emean; s[S_FMEAN * n + p] = fmean; s[S_F1MEAN * n + p] = f1mean;
+      s[S_AKMEAN * n + p] = akmean; s[S_XKMEAN * n + p] = xkmean;
+      s[S_FAC * n + p] = fac;
+      s[S_UORBT * n + p] = uorbt_acc; s[S_AORB * n + p] = aorb_acc;
+    }
+  } else {
+    fac = s[S_FAC * n + p];
+    emean = s[S_EMEAN * n + p]; fmean = s[S_FMEAN * n + p]; f1mean = s[S_F1MEAN * n + p]; xkmean = s[S_XKMEAN * n + p];
+    ustar = s[S_USTAR1 * n + p]; tauw = s[S_TAUW1 * n + p]; tauwdir = s[S_TWDIR1 * n + p];
+    uorbt_acc = s[S_UORBT * n + p]; aorb_acc = s[S_AORB * n + p];
   }
 
   auto frcut = [&](double fmeanws, double ust) -> int {   // frcutindex.F90:84-97
@@ -572,12 +591,30 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
     tw = dmin(tw, sq(ust_in) * (1.0 / (1.0 + c_dc.EPS1)));
     phiwa = llphiwa ? pw + phihf : 0.0;
   };
-  {
+  if (PH == 1) {
     const double emeanws = c_dc.EPSMIN + ws_em + DELT25 * ws_last;
     const double fmeanws = emeanws / (c_dc.EPSMIN + ws_fm + c_dc.FRTAIL * c_dc.DELTH * ws_last);
     const int mij1 = frcut(fmeanws, ustar);
     double ph;
     stresso(mij1, ustar, z0, false, 0.0, tauw, tauwdir, ph);
+    // ---- SDIWBK (sdiwbk.F90:69-104)
+    double sds = 0.0;
+    if (c_dc.lbiwbk && d.f.depth[p] < 50.0) {
+      const double alph = 2.0 * d.f.emaxdpt[p] / emean;
+      const double arg = dmin(alph, 50.0);
+      double q_old = exp(-arg), q = q_old;
+      for (int ic = 1; ic <= 15; ++ic) {
+        const double expq = exp(-arg * (1.0 - q_old));
+        q = q_old - (expq - q_old) / (arg * expq - 1.0);
+        const double rel_err = fabs(q - q_old) / q_old;
+        if (rel_err < 0.00001) break;
+        q_old = q;
+      }
+      q = dmin(q, 1.0);
+      sds = 2.0 * alph * q * f1mean;
+    }
+    if (valid) { s[S_USTAR1 * n + p] = ustar; s[S_TAUW1 * n + p] = tauw; s[S_TWDIR1 * n + p] = tauwdir; s[S_SDS * n + p] = sds; }
+    return;
   }
   // ---- SINFLX call 2: AIRSEA (IUSFG=1), SINPUT (NGST=2, LLSNEG), FEMEANWS, FRCUTINDEX, STRESSO (LLPHIWA)
   taut_z0(1, wswave, wdwave, tauw, tauwdir, ustar, z0, z0b, ch);
@@ -620,23 +657,6 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
     s[S_MIJ * n + p] = (double)mij;
     s[S_USFM * n + p] = ustar * dmax(fmeanws, fmean);
   }
-  // ---- SDIWBK (sdiwbk.F90:69-104)
-  double sds = 0.0;
-  if (c_dc.lbiwbk && d.f.depth[p] < 50.0) {
-    const double alph = 2.0 * d.f.emaxdpt[p] / emean;
-    const double arg = dmin(alph, 50.0);
-    double q_old = exp(-arg), q = q_old;
-    for (int ic = 1; ic <= 15; ++ic) {
-      const double expq = exp(-arg * (1.0 - q_old));
-      q = q_old - (expq - q_old) / (arg * expq - 1.0);
-      const double rel_err = fabs(q - q_old) / q_old;
-      if (rel_err < 0.00001) break;
-      q_old = q;
-    }
-    q = dmin(q, 1.0);
-    sds = 2.0 * alph * q * f1mean;
-  }
-  if (valid) s[S_SDS * n + p] = sds;
 }
 
 
@@ -1193,14 +1213,19 @@ int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage
     const size_t smp = (size_t)2 * A * KP_NTH * sizeof(double);
     static bool attr_p = false;
     if (!attr_p) {
-      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<true, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<true, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<false, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       attr_p = true;
     }
-    if (d.iphys == 1) k_point<true><<<(unsigned)((np + KP_NTH - 1) / KP_NTH), KP_NTH, smp, st>>>(d, p0, np);
-    else k_point<false><<<(unsigned)((np + KP_NTH - 1) / KP_NTH), KP_NTH, smp, st>>>(d, p0, np);
+    const unsigned nb = (unsigned)((np + KP_NTH - 1) / KP_NTH);
+    if (d.iphys == 1) { k_point<true, 1><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<true, 2><<<nb, KP_NTH, smp, st>>>(d, p0, np); }
+    else { k_point<false, 1><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<false, 2><<<nb, KP_NTH, smp, st>>>(d, p0, np); }
   } else if (stage == 1) {
     // two grid points per thread (16-byte shared / global accesses) need an even NPROMA and an even first point
     const uintptr_t al = (uintptr_t)d.f.fl1 | (uintptr_t)d.f.xllws | (uintptr_t)d.fldin | (uintptr_t)d.fl_lo;
