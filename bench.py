@@ -174,6 +174,31 @@ def make_case(workload, world, rank, device, mask="continents"):
     return g, s, w, f
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs next to its GPU (sysfs local_cpulist of the PCI device) so that the pinned host buffers of
+    the end-to-end leg are allocated on the GPU's NUMA node.  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dev = "/sys/bus/pci/devices/" + bus.lower()[-12:]
+        with open(dev + "/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            with open(dev + "/numa_node") as f:
+                return "numa node %s (%d cpus)" % (f.read().strip(), len(cpus))
+    except Exception as e:  # no sysfs / NVML in this container: leave the affinity alone
+        return "unbound (%s)" % type(e).__name__
+    return "unbound"
+
+
 def run_gpu(args):
     import torch
     from ecwam_b200 import lib as L
@@ -184,6 +209,7 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device — the WAMINTGR hot path has no CPU fallback (use --impl reference for the CPU arm)")
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
+    numa = bind_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -261,7 +287,7 @@ def run_gpu(args):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             dist.all_reduce(bts, op=dist.ReduceOp.SUM)
         e2e = {"value": npts_total * Ke / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(bts[0].item()),
-               "d2h_bytes_per_step": int(bts[1].item()), "steps": Ke,
+               "d2h_bytes_per_step": int(bts[1].item()), "steps": Ke, "host_affinity": numa,
                "what": "ecwam_b200_wamintgr_host: FL1 + forcing + stress state host->device from pinned buffers, step, "
                        "FL1 + all 1-D outputs + MIJ device->host, every step"}
 

@@ -137,7 +137,10 @@ __device__ __forceinline__ void ctu_quadrant(const PropDev& d, const SpecSrc& sr
   }
 }
 
-__global__ void __launch_bounds__(128, 4) propags2_kernel(PropDev d, SpecSrc src, double* __restrict__ dst, long long dcstride,
+#ifndef PG_MINB
+#define PG_MINB 4
+#endif
+__global__ void __launch_bounds__(128, PG_MINB) propags2_kernel(PropDev d, SpecSrc src, double* __restrict__ dst, long long dcstride,
                                                           int m0, int m1, int MG, int msplit, int l0, int l1) {
   const int l = l0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= l1) return;
