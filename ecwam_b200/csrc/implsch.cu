@@ -371,13 +371,15 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
         cosu[g] = csw; sinu[g] = snw;
       }
     }
-    double sx[NGST], sy[NGST], st = 0.0, tsum = 0.0, traw = 0.0;
+    double sx[NGST], sy[NGST], st = 0.0, tsum = 0.0, traw = 0.0, rawt = 0.0;
 #pragma unroll
     for (int g = 0; g < NGST; ++g) { sx[g] = 0.0; sy[g] = 0.0; }
     constexpr int kUnroll = KP_UNROLL;
 #pragma unroll kUnroll
     for (int k = 0; k < A; ++k) {
-      double f = dmax(fsrc[k * KP_NTH] * fac, c_dc.EPSMIN);                      // SDEPTHLIM applied on the fly
+      const double fraw = fsrc[k * KP_NTH];
+      if (!STORE) rawt += fraw;                                                  // SEMEAN of the incoming spectrum (sdepthlim.F90:60-70)
+      double f = dmax(fraw * fac, c_dc.EPSMIN);                                  // SDEPTHLIM applied on the fly
       const double snk = c_dc.SINTH[k], csk = c_dc.COSTH[k];
       const double cwd = csk * csw + snk * snw;                                  // COSWDIF(K)
       traw += f;                                                                 // FKMEAN sees the spectrum before the floor
@@ -438,6 +440,7 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
       const double sqk = sqrt(wavnum);
       mom[0] += dfim * traw; mom[1] += dfimofr * traw; mom[2] += c_dc.DFIMFR[m] * traw;
       mom[3] += (dfim / sqk) * traw; mom[4] += (sqk * dfim) * traw; mom[5] = traw;
+      mom[6] += dfim * rawt; mom[7] = rawt;
       uorbt_acc += dfim * sig2 * tsum; aorb_acc += dfim * tsum;
     }
     double sxa = 0.0, sya = 0.0;
@@ -485,23 +488,7 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
   sincos(wdwave, &snw, &csw);
   const double flmc = (1. - 0.9 * dmin(cicover, 0.99)) * c_dc.flmin;      // FLM(K) = flmc*max(0,COSWDIF)**2
   const double DELT25 = c_dc.WETAIL * c_dc.FR[F - 1] * c_dc.DELTH;
-  // ---- SDEPTHLIM (sdepthlim.F90:50-82): EM of the incoming spectrum -> limiting factor
   double fac = 1.0;
-  if (PH == 1 && c_dc.lbiwbk) {
-    double em = c_dc.EPSMIN, last = 0.0;
-    row_issue(S, 0, A);
-    for (int m = 0; m < F; ++m) {
-      if (m + 1 < F) { row_issue(S, m + 1, A); row_wait<1>(); } else row_wait<0>();
-      const double* fsrc = row_ptr(S, m, A);
-      double t = 0.0;
-#pragma unroll 4
-      for (int k = 0; k < A; ++k) t += fsrc[k * KP_NTH];
-      em += c_dc.DFIM[m] * t;
-      last = t;
-    }
-    em += DELT25 * last;
-    fac = dmin(d.f.emaxdpt[p] / em, 1.0);
-  }
   double ustar = d.f.ufric[p], z0 = 0.0, z0b = 0.0, ch = 0.0;
   double tauw, tauwdir;
   double sumx[EW_MAXF], sumy[EW_MAXF], sumt[EW_MAXF];
@@ -511,9 +498,21 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
     // ---- SINFLX call 1: AIRSEA (IUSFG=0), SINPUT (NGST=1), FEMEANWS, FRCUTINDEX, STRESSO
     tauw = d.f.tauw[p]; tauwdir = d.f.tauwdir[p];
     taut_z0(0, wswave, wdwave, tauw, tauwdir, ustar, z0, z0b, ch);
-    double mom[6] = {0, 0, 0, 0, 0, 0};
-    sinput_point<ARD, 1, false, false>(S, d, p, fac, flmc, snw, csw, ustar, z0, raorw, 0.0, 0.0, 0.0, 0.0, nullptr, nullptr, sumx, sumy,
-                                       sumt, ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc, mom, false);
+    // SDEPTHLIM (sdepthlim.F90:50-82) needs the total energy of the incoming spectrum before anything else can be formed.
+    // Instead of a separate pass over FL1, the first SINPUT pass is run with the limiting factor 1 (exact wherever the
+    // spectrum is not depth-limited, i.e. almost everywhere) and sums that energy on the side; only the lanes that turn
+    // out to be depth-limited repeat the pass with their factor.
+    double mom[8];
+    for (int attempt = 0; attempt < 2; ++attempt) {
+#pragma unroll
+      for (int x = 0; x < 8; ++x) mom[x] = 0.0;
+      sinput_point<ARD, 1, false, false>(S, d, p, fac, flmc, snw, csw, ustar, z0, raorw, 0.0, 0.0, 0.0, 0.0, nullptr, nullptr, sumx, sumy,
+                                         sumt, ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc, mom, false);
+      if (attempt == 1 || !c_dc.lbiwbk) break;
+      const double em = (c_dc.EPSMIN + mom[6]) + DELT25 * mom[7];
+      fac = dmin(d.f.emaxdpt[p] / em, 1.0);
+      if (fac == 1.0) break;
+    }
     // FKMEAN (fkmean.F90:60-154)
     const double COEFM1 = c_dc.FRTAIL * c_dc.DELTH;
     const double COEF1 = c_dc.WP1TAIL * c_dc.DELTH * sq(c_dc.FR[F - 1]);
@@ -642,7 +641,7 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
   }
   double* fld_out = d.fldin + (size_t)i + (size_t)d.P * A * F * (size_t)c;
   double* xl_out = d.f.xllws + (size_t)i + (size_t)d.P * A * F * (size_t)c;
-  double dum[6];
+  double dum[8];
   sinput_point<ARD, 2, true, true>(S, d, p, fac, flmc, snw, csw, ustar, z0, raorw, sig_n, temp2_sw, pturb, aird_pvisc, fld_out, xl_out,
                               sumx, sumy, sumt, ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc, dum, valid, d.f.depth[p],
                               c_dc.CDIS * c_dc.ZPI * f1mean * sq(emean) * p4(xkmean), xkmean);
