@@ -14,9 +14,17 @@ CASES = {
 }
 
 
-def make_oracle(case, npr=1, **extra):
+def make_grid(case, grid_hook=None):
     c = CASES[case]
     g = synth.make_grid(c["N"], c["mask"])
+    if grid_hook is not None:
+        grid_hook(g)
+    return g
+
+
+def make_oracle(case, npr=1, grid_hook=None, **extra):
+    c = CASES[case]
+    g = make_grid(case, grid_hook)
     kw = dict(nang=c["A"], nfre_red=c["Fr"], nproma=c["nproma"], npr=npr, iphys=c["iphys"], idelt=c["dt"], idelpro=c["dt"],
               delpro_lf=c["dt"])
     kw.update(extra)
@@ -30,9 +38,9 @@ def make_oracle(case, npr=1, **extra):
     return g, o, f, fl
 
 
-def make_setup(case, nproc=1, **extra):
+def make_setup(case, nproc=1, grid_hook=None, **extra):
     c = CASES[case]
-    g = synth.make_grid(c["N"], c["mask"])
+    g = make_grid(case, grid_hook)
     kw = dict(nang=c["A"], nfre_red=c["Fr"], iphys=c["iphys"], nproma=c["nproma"], idelt=c["dt"], idelpro=c["dt"], delpro_lf=c["dt"])
     kw.update(extra)
     return g, M.WamSetup(g, nproc=nproc, **kw)

@@ -91,6 +91,25 @@ def test_stencil_kernel_instances_agree(built, monkeypatch, mode, case):
     check_state(w, o)
 
 
+def test_depth_limited_points(built):
+    """SDEPTHLIM (sdepthlim.F90:50-82): where the total energy exceeds EMAXDPT = 0.0625 (0.8 d)^2 the spectrum is scaled down.
+    The CUDA path finds those points during the first SINPUT pass and repeats it for them: very shallow water everywhere in
+    the northern half makes many lanes (and whole warps, and mixed warps) take that route."""
+    def shallow(g):
+        n = g.depth.size
+        g.depth[n // 2:] = np.minimum(g.depth[n // 2:], 2.0 + 3.0 * (np.arange(n - n // 2) % 7 == 0))
+    g, o, f, fl = make_oracle("o640like", grid_hook=shallow)
+    _, s, w = make_gpu("o640like", grid_hook=shallow)
+    emax = 0.0625 * (0.8 * g.depth) ** 2
+    hs_o, _ = o.hs_fm()
+    frac = np.mean(hs_o ** 2 / 16.0 > emax)
+    assert 0.02 < frac < 0.5, "the case must mix depth-limited and unlimited points (%g)" % frac
+    for _ in range(2):
+        assert o.step() == 0 and w.step() == 0
+    w.synchronize()
+    check_state(w, o)
+
+
 def test_odd_nproma(built):
     """NPROMA is a namelist value: an odd one takes the one-point-per-thread k_stencil instance."""
     g, o, f, fl = make_oracle("o640like", nproma=25)
