@@ -232,6 +232,18 @@ static int fill_dev_const(const ecwam_b200_params& p, const ecwam_b200_tables& t
     }
   }
   for (int r = 0; r < EW_MAXF + 8; ++r) c.SLOT9[r] = r % 9;
+  if (p.iphys == 1) {
+    // cos(TH(K)-TH(J))**ISB only depends on K-J (init_sdiss_ardh.F90:69-96): the table rows agree to rounding (checked), so
+    // k_stencil takes the weights of the middle direction as warp-uniform constants
+    const int ns = 2 * t.nsdsnth + 1, kmid = p.nang / 2;
+    for (int x = 0; x < ns; ++x) {
+      const double w = t.satweights[kmid + p.nang * x];
+      for (int k = 0; k < p.nang; ++k)
+        if (std::fabs(t.satweights[k + p.nang * x] - w) > 1e-12 * std::fabs(t.satweights[kmid + p.nang * (ns / 2)]))
+          EW_FAIL(ECWAM_B200_EINVAL, "SATWEIGHTS depends on the direction (x=%d, k=%d): unsupported", x, k);
+      c.SATW1[x] = w;
+    }
+  }
   return 0;
 }
 

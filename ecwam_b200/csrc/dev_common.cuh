@@ -44,6 +44,7 @@ struct DevConst {
   // k_stencil: slot (row % 9) of the 9-row shared-memory ring for every frequency row and for INLCOEF(1:5,MC)
   int SLOT9[EW_MAXF + 8];
   int NLSLOT[EW_MAXMC][5];
+  double SATW1[EW_MAXSAT];  // SATWEIGHTS(NANG/2, 1:2*NSDSNTH+1): the saturation window weights (they do not depend on the direction)
   double RNLC2[EW_MAXMC];   // 2 (or 0 where the centre row is outside the spectrum): weight of -AD, -DELAD at the centre bin
 };
 

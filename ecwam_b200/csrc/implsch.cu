@@ -707,7 +707,7 @@ __host__ __device__ constexpr StencilSmem stencil_smem(int A, int halo_r, int ha
   unsigned o = 0;
   s.ring = o; o += ST_RING * s.RSB;
   s.cur = o; o += 2 * 6 * s.PSB;
-  s.satw = o; o += (unsigned)A * ST_NSMAX * 8; o = (o + 15u) & ~15u;
+  s.satw = o;
   s.tbs = o; o += 4 * TQ_N * ST_NPT * 8;
   s.pc = o; o += PC_N * ST_NPT * 8;
   s.part = o; o += 2u * (unsigned)nwarp * ST_NPT * 8;
@@ -734,7 +734,8 @@ __host__ __device__ constexpr int geo_hc(int A) { return A == 36 ? 4 : (A == 24 
 __host__ __device__ constexpr int stencil_threads(int A, int np) { return ((A * (ST_NPT / np) + 31) / 32) * 32; }
 
 #ifndef ST_MAXREG
-#define ST_MAXREG 168   // register cap of the two-point instance (168: 2 CTAs of 160 threads per SM; 136: 3 CTAs)
+#define ST_MAXREG 168   // register cap of the two-point instance: 2 CTAs of 5 warps per SM put 3 warps on two of the four
+                        // sub-partitions (16384 registers each), so 3 x 32 x 168 is the most that still fits (176 halves the occupancy)
 #endif
 #define ST_BOUNDS(NP) __maxnreg__(NP == 2 ? ST_MAXREG : 112)
 
@@ -814,10 +815,6 @@ __global__ void ST_BOUNDS(NP) k_stencil(ImplDev d, long long p0, long long np, S
     pcv[PC_SNW * ST_NPT] = snw;
     pcv[PC_CSW * ST_NPT] = csw;
   }
-  if (ard) for (int x = t; x < NS * A; x += blockDim.x) {   // (x, kk) -> [kk][x]
-    const int xs = x / A, kk = x - xs * A;
-    reinterpret_cast<double*>(sm + L.satw)[kk * ST_NSMAX + xs] = __ldg(d.tab.satweights + x);
-  }
   __syncthreads();
   const double sinth = c_dc.SINTH[k], costh = c_dc.COSTH[k];
   V cw2;      // max(0, cos(TH(k) - WDWAVE))**2: FLM(k) = FLMC*cw2 (implsch.F90:236-247), SETICE's noise floor likewise
@@ -845,7 +842,6 @@ __global__ void ST_BOUNDS(NP) k_stencil(ImplDev d, long long p0, long long np, S
   V b_prev, fmij, a_philf, a_ts, a_tu, a_e1, a_e2, a_el;
 #pragma unroll
   for (int i = 0; i < NP; ++i) { b_prev.v[i] = 0.0; fmij.v[i] = 0.0; a_philf.v[i] = 0.0; a_ts.v[i] = 0.0; a_tu.v[i] = 0.0; a_e1.v[i] = 0.0; a_e2.v[i] = 0.0; a_el.v[i] = 0.0; }
-  const unsigned satw_me = L.satw + (unsigned)k * (ST_NSMAX * 8);
   const unsigned lane = (unsigned)t & 31u;
 
   // one step of the sweep
@@ -945,7 +941,7 @@ __global__ void ST_BOUNDS(NP) k_stencil(ImplDev d, long long p0, long long np, S
 #pragma unroll
       for (int x = 0; x < ST_NSMAX; ++x) {
         if (x < NS) {
-          const double w = *reinterpret_cast<const double*>(sm + satw_me + x * 8);
+          const double w = c_dc.SATW1[x];   // SATWEIGHTS(K, x) of the middle direction: cos(TH(K)-TH(K+x-NSD))**2 does not depend on K
           const V f = lds<NP>(sm, wb + x * 64);
 #pragma unroll
           for (int i = 0; i < NP; ++i) b.v[i] += w * f.v[i];
