@@ -696,7 +696,7 @@ template <int NP> __device__ __forceinline__ void stg(double* p, const Vd<NP>& x
 __device__ __forceinline__ unsigned slot9(int r) { return (unsigned)c_dc.SLOT9[r]; }   // r % ST_RING, 0 <= r < EW_MAXF
 
 struct StencilSmem {   // byte offsets into dynamic shared memory
-  unsigned ring, cur, satw, tbs, pc, part, bth0, stage, total, RSB, PSB, SSB;
+  unsigned ring, cur, tbs, pc, part, bth0, stage, bsl, mbar, total, RSB, PSB, SSB;
 };
 __host__ __device__ constexpr StencilSmem stencil_smem(int A, int halo_r, int halo_c, int nth, int np, bool lwflux) {
   StencilSmem s{};
@@ -707,12 +707,13 @@ __host__ __device__ constexpr StencilSmem stencil_smem(int A, int halo_r, int ha
   unsigned o = 0;
   s.ring = o; o += ST_RING * s.RSB;
   s.cur = o; o += 2 * 6 * s.PSB;
-  s.satw = o;
-  s.tbs = o; o += 4 * TQ_N * ST_NPT * 8;
+  s.tbs = o; o += 8 * TQ_N * ST_NPT * 8;
   s.pc = o; o += PC_N * ST_NPT * 8;
-  s.part = o; o += 2u * (unsigned)nwarp * ST_NPT * 8;
+  s.part = o; o += 3u * (unsigned)nwarp * ST_NPT * 8;
   s.bth0 = o; o += 2 * ST_NPT * 8;
   s.stage = o; o += (lwflux ? 3 : 2) * s.SSB;      // thread-private landing slots of the cp.async row loads (FL1 row, wind-input row, XLLWS row)
+  s.bsl = o; o += 3 * s.SSB;        // thread-private saturation values of the three rows between their window sum and their finish
+  s.mbar = o; o += 16;
   s.total = o;
   return s;
 }
@@ -720,6 +721,13 @@ template <int NB> __device__ __forceinline__ void cp_async(unsigned sa, const vo
   asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(sa), "l"(g), "n"(NB));
 }
 template <int N> struct IC { static constexpr int value = N; };
+// split CTA barrier (arrive early, wait late) on a shared-memory mbarrier; cp.async completion is part of the phase
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(unsigned bar) { asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_cp_async(unsigned bar) { asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile("{\n .reg .pred p;\n WAIT_LOOP:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra WAIT_DONE;\n bra WAIT_LOOP;\n WAIT_DONE:\n}\n" ::"r"(bar), "r"(parity) : "memory");
+}
 // Direction geometry of the standard ecWAM grids (NANG = 12, 24, 36), known at compile time so that every shared-memory
 // offset of k_stencil is an immediate: NSDSNTH = min(nint(80 deg / DELTH), NANG/2-1) (init_sdiss_ardh.F90:72) and the DIA
 // partner shifts K1W, K11W, K2W, K21W(K,KH) - K of nlweigt.F90:108-206 (checked against the run-time tables on the host).
@@ -793,7 +801,8 @@ __global__ void ST_BOUNDS(NP) k_stencil(ImplDev d, long long p0, long long np, S
   const double* src_in = d.fldin + off_hi;
   const double* src_xl = d.f.xllws + off_hi;
 
-  // ---- prologue: per-point constants, saturation weights
+  // ---- prologue: per-point constants, barrier
+  if (t == 0) mbar_init(smb + L.mbar, 2u * blockDim.x);   // per phase and thread: one arrive + one arrive on completion of its cp.async
   if (t < ST_NPT) {
     const long long qp = min(pbase + t, plast);
     double* pcv = reinterpret_cast<double*>(sm + L.pc) + t;
@@ -839,19 +848,20 @@ __global__ void ST_BOUNDS(NP) k_stencil(ImplDev d, long long p0, long long np, S
   for (int x = 0; x < 7; ++x)
 #pragma unroll
     for (int i = 0; i < NP; ++i) { asl[x][i] = 0.0; afl[x][i] = 0.0; }
-  V b_prev, fmij, a_philf, a_ts, a_tu, a_e1, a_e2, a_el;
+  V fmij, a_philf, a_ts, a_tu, a_e1, a_e2, a_el;
 #pragma unroll
-  for (int i = 0; i < NP; ++i) { b_prev.v[i] = 0.0; fmij.v[i] = 0.0; a_philf.v[i] = 0.0; a_ts.v[i] = 0.0; a_tu.v[i] = 0.0; a_e1.v[i] = 0.0; a_e2.v[i] = 0.0; a_el.v[i] = 0.0; }
+  for (int i = 0; i < NP; ++i) { fmij.v[i] = 0.0; a_philf.v[i] = 0.0; a_ts.v[i] = 0.0; a_tu.v[i] = 0.0; a_e1.v[i] = 0.0; a_e2.v[i] = 0.0; a_el.v[i] = 0.0; }
   const unsigned lane = (unsigned)t & 31u;
 
   // one step of the sweep
   auto step = [&](const int st) {
     // ================= phase A =================
-    const int rnew = st + 5, rfin = st - 4, rb = st - 3, rtb = st - 2;
+    const int rnew = st + 5, rfin = st - 4, rb = st - 2, rtb = st - 1;
     const unsigned par = (unsigned)st & 1u;
     const bool dia = st >= 0 && st < MLSTHG;
     const bool fin = rfin >= 0 && rfin < F;
     const bool sat = ard && rb >= 0 && rb < F;
+    const unsigned p3 = (unsigned)(st + 6) % 3u;   // triple buffers: per-warp maxima, thread-private saturation values
     // row loads of this step land in shared memory behind the barrier: FL1 row st+5 (enters the ring in phase B),
     // wind-input (and XLLWS) row st-4 (consumed by the finish in phase B)
     if (rnew >= 0 && rnew < F) cp_async<NP * 8>(smb + me_s, (rnew < mlo ? src_lo : src_hi) + (size_t)rnew * rstr);
@@ -861,11 +871,9 @@ __global__ void ST_BOUNDS(NP) k_stencil(ImplDev d, long long p0, long long np, S
     }
     if (rtb >= 0 && rtb < F && t < TQ_N * ST_NPT) {   // per-(point, frequency) scalars of row rtb (used from the next step on)
       const int q = t >> 3, pt = t & 7;
-      cp_async<8>(smb + L.tbs + (unsigned)(((rtb & 3) * TQ_N + q) * 64 + pt * 8), d.tbg + ((size_t)q * F + rtb) * n + min(pbase + pt, plast));
+      cp_async<8>(smb + L.tbs + (unsigned)(((rtb & 7) * TQ_N + q) * 64 + pt * 8), d.tbg + ((size_t)q * F + rtb) * n + min(pbase + pt, plast));
     }
-    V b_next;
-#pragma unroll
-    for (int i = 0; i < NP; ++i) b_next.v[i] = 0.0;
+    mbar_arrive_cp_async(smb + L.mbar);
     if (dia) {
       // DIA interaction values of centre frequency MC = st+1 (snonlin.F90:225-250)
       const int MC0 = st, MC = st + 1;
@@ -932,6 +940,7 @@ __global__ void ST_BOUNDS(NP) k_stencil(ImplDev d, long long p0, long long np, S
 #pragma unroll
       for (int i = 0; i < NP; ++i) { asl[4][i] = fma(-c2, csl.v[i], asl[4][i]); afl[4][i] = fma(-c2, cfl.v[i], afl[4][i]); }
     }
+    mbar_arrive(smb + L.mbar);   // the interaction planes of this step are written; what follows does not touch them
     // saturation spectrum of row rb for SDISSIP_ARD (sdissip_ard.F90:142-160): cyclic window of 2*NSDSNTH+1 directions
     if (sat) {
       const unsigned wb = L.ring + slot9(rb) * RSB + me_r - (unsigned)NSD * 64u;
@@ -947,19 +956,19 @@ __global__ void ST_BOUNDS(NP) k_stencil(ImplDev d, long long p0, long long np, S
           for (int i = 0; i < NP; ++i) b.v[i] += w * f.v[i];
         }
       }
-      const V fs = lds<NP>(sm, L.tbs + (unsigned)(((rb & 3) * TQ_N + TQ_FACSAT) * 64) + jo);
+      const V fs = lds<NP>(sm, L.tbs + (unsigned)(((rb & 7) * TQ_N + TQ_FACSAT) * 64) + jo);
       V mx;
 #pragma unroll
-      for (int i = 0; i < NP; ++i) { b_next.v[i] = b.v[i] * fs.v[i]; mx.v[i] = b_next.v[i]; }
+      for (int i = 0; i < NP; ++i) mx.v[i] = b.v[i] * fs.v[i];
+      sts<NP>(sm, L.bsl + p3 * L.SSB + (unsigned)t * (NP * 8), mx);
       // BTH0 = max over direction: over the directions of this warp with shuffles, then one partial per warp
 #pragma unroll
       for (int o = 16; o >= NG; o >>= 1)
 #pragma unroll
         for (int i = 0; i < NP; ++i) mx.v[i] = dmax(mx.v[i], __shfl_xor_sync(FULLMASK, mx.v[i], o));
-      if (lane < NG) sts<NP>(sm, L.part + (par * (unsigned)nwarp + ((unsigned)t >> 5)) * 64u + jo, mx);
+      if (lane < NG) sts<NP>(sm, L.part + (p3 * (unsigned)nwarp + ((unsigned)t >> 5)) * 64u + jo, mx);
     }
-    asm volatile("cp.async.wait_all;\n" ::: "memory");
-    __syncthreads();
+    mbar_wait(smb + L.mbar, (unsigned)(st + 5) & 1u);
     // ================= phase B =================
     V tot_sl, tot_fl;   // SNONLIN sums of the row that is finished at this step
     {
@@ -1006,7 +1015,7 @@ __global__ void ST_BOUNDS(NP) k_stencil(ImplDev d, long long p0, long long np, S
     // finish row rfin (implsch.F90:276-395 for these bins)
     if (fin) {
       const int r = rfin;
-      const unsigned tq = L.tbs + (unsigned)((r & 3) * TQ_N * 64) + jo;
+      const unsigned tq = L.tbs + (unsigned)((r & 7) * TQ_N * 64) + jo;
       const V fold = lds<NP>(sm, L.ring + slot9(r) * RSB + me_r);
       const V xI = lds<NP>(sm, me_s + L.SSB);
       const V usfm = lds<NP>(sm, L.pc + PC_USFMDELT * 64 + jo), sdsbk = lds<NP>(sm, L.pc + PC_SDSBK * 64 + jo);
@@ -1015,6 +1024,7 @@ __global__ void ST_BOUNDS(NP) k_stencil(ImplDev d, long long p0, long long np, S
       V dd;
       if (ard) {
         const V b0 = lds<NP>(sm, L.bth0 + (par ^ 1u) * 64u + jo);
+        const V b_prev = lds<NP>(sm, L.bsl + ((unsigned)(r + 8) % 3u) * L.SSB + (unsigned)t * (NP * 8));
         const double ssdsc2_sig = c_dc.SSDSC2 * c_dc.ZPIFR[r];
 #pragma unroll
         for (int i = 0; i < NP; ++i)
@@ -1091,13 +1101,12 @@ __global__ void ST_BOUNDS(NP) k_stencil(ImplDev d, long long p0, long long np, S
         if (k >= A - H) sts<NP>(sm, rbse - (unsigned)A * 64u, v);
       }
     }
-    if (sat && t < ST_NPT) {   // BTH0 of row rb from the per-warp partial maxima
-      const double* pp = reinterpret_cast<const double*>(sm + L.part + par * (unsigned)nwarp * 64u) + t;
+    if (ard && t < ST_NPT && rb - 1 >= 0 && rb - 1 < F) {   // BTH0 of row st-3 from the per-warp partial maxima of the previous step
+      const double* pp = reinterpret_cast<const double*>(sm + L.part + ((unsigned)(st + 5) % 3u) * (unsigned)nwarp * 64u) + t;
       double mx = 0.0;
       for (int w = 0; w < nwarp; ++w) mx = dmax(mx, pp[w * ST_NPT]);
       reinterpret_cast<double*>(sm + L.bth0 + par * 64u)[t] = mx;
     }
-    b_prev = b_next;
   };
 
 #pragma unroll 1
