@@ -258,6 +258,27 @@ def run_gpu(args):
         tot, cnt = w.timing(nm)
         if cnt:
             kern[nm] = tot / cnt
+    # ---- the output step next to the path (not part of `value`): NEWWIND, OUTBS over all built parameters, WAMNORM ----
+    aux = {}
+    if not args.no_aux:
+        from ecwam_b200 import model as M
+        itg = sorted(M.OUTBLOCK_PARAMS)
+        ice, sea = [M.OUTBLOCK_PARAMS[i][0] for i in itg], [M.OUTBLOCK_PARAMS[i][1] for i in itg]
+        nxt = {k.lower(): v for k, v in forcing.items()}
+        nxt.update(ustra=np.zeros(npts_total), vstra=np.zeros(npts_total))
+        for it in range(3):
+            if it == 1:
+                L.check(lib.ecwam_b200_timing_reset(w.h), "timing_reset")
+            w.newwind(nxt)
+            w.outbs(itg, ice, sea)
+            wn = w.outwnorm(True)
+            w.outwnorm(False)
+        for nm in ("newwind", "outblock", "outwnorm"):
+            tot, cnt = w.timing(nm)
+            if cnt:
+                aux[nm + "_ms"] = tot / cnt
+        aux["columns"] = len(itg)
+        aux["swh_norm_avg_min_max_count"] = [float(x) for x in wn[0]]
     lib.ecwam_b200_timing_enable(w.h, 0)
     value = npts_total * K / (ms_total * 1e-3)
 
@@ -329,7 +350,7 @@ def run_gpu(args):
             "config": {"workload": "%s octahedral grid, synthetic continents (%d sea points), %dx%d spectrum (%d propagated), "
                                    "IPHYS=1, NPROMA=%d, dt=%gs" % (args.workload, npts_total, A, F, Fr, w.par.nproma, w.par.idelt),
                        "parallelism": "mpdecomp%d" % world, "l2": "inputs larger than L2 (FL1 %.1f GB per GPU)" % (w.t["fl1"].numel() * 8 / 1e9)},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "kernel_ms": kern, "roofline": roof, "cpu_baseline": cpu}
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "kernel_ms": kern, "output_step": aux or None, "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -344,6 +365,7 @@ def main():
     ap.add_argument("--workload", default="O640", choices=["O48", "O320", "O640", "O1280", "P256"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="skip the NEWWIND / OUTBS / WAMNORM timing next to the path")
     ap.add_argument("--e2e-steps", type=int, default=5)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -88,6 +88,10 @@ struct ecwam_b200_handle_s {
   std::vector<cudaEvent_t> ev_up, ev_done;
   cudaEvent_t ev_start = nullptr;
   int nbr_reach = 0;       // max |l' - l| over the own-point neighbours of every own point l
+  // NEWWIND / OUTBLOCK / WAMNORM
+  DBuf<double> normbuf, zglobal;
+  DBuf<int> ij2new_d;
+  long long ij2new_n = 0;
   // stats
   long long nlaunch = 0;
   bool timing = false;
@@ -677,6 +681,142 @@ int ecwam_b200_wamintgr(ecwam_b200_handle h) {
   }
   launch_pad(h->pd, h->fl3.p, h->pd.Fr, 0, h->pd.Fr, h->st);   // padded lanes of the last chunk (propag_wam.F90:388-398)
   return implsch_range(h, 1, h->par.nchnk, true);
+}
+
+// ---- the steps either side of the hot path: NEWWIND, OUTBS/OUTBLOCK core, OUTWNORM -------------------------------
+int ecwam_b200_newwind(ecwam_b200_handle h, const ecwam_b200_forcing_next* next) {
+  if (!h || !next) EW_FAIL(ECWAM_B200_EINVAL, "null argument");
+  if (!h->bound) EW_FAIL(ECWAM_B200_ESTATE, "fields not bound");
+  if (h->par.icode_wnd != 3) EW_FAIL(ECWAM_B200_EINVAL, "NEWWIND: only ICODE_WND = 3 (10 m wind speed) is built");
+  const void* const* pp = (const void* const*)next;
+  for (size_t i = 0; i < sizeof(*next) / sizeof(void*); ++i) if (!pp[i]) EW_FAIL(ECWAM_B200_EINVAL, "NEWWIND: FF_NEXT member %zu is null", i);
+  ScopedTimer t(h, "newwind");
+  launch_newwind((long long)h->par.nproma * h->par.nchnk, h->dev, *next, h->dc.ACD, h->dc.BCD, h->dc.EPSMIN, h->st);
+  h->nlaunch++;
+  EW_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int ecwam_b200_outparam_supported(int itg) {
+  static const int ok[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 12, 13, 14, 15, 16, 20, 21, 22, 23, 24, 25, 26, 27, 28, 32, 35, 36, 37, 38,
+                           39, 40, 41, 53, 54, 55, 56, 62, 63, 73, 74, 75, 76, 77};
+  for (int v : ok) if (v == itg) return 1;
+  return 0;
+}
+
+static int check_outsel(const ecwam_b200_outsel* sel) {
+  if (!sel || !sel->itg || !sel->icemask || !sel->seamask) EW_FAIL(ECWAM_B200_EINVAL, "null output selection");
+  if (sel->niprmout < 1 || sel->niprmout > EW_OUT_MAXCOL) EW_FAIL(ECWAM_B200_EINVAL, "NIPRMOUT must be 1..%d", EW_OUT_MAXCOL);
+  for (int i = 0; i < sel->niprmout; ++i)
+    if (!ecwam_b200_outparam_supported(sel->itg[i])) EW_FAIL(ECWAM_B200_EINVAL, "OUTBLOCK parameter %d is not built (see ecwam_b200.h)", sel->itg[i]);
+  return 0;
+}
+
+int ecwam_b200_outbs(ecwam_b200_handle h, const ecwam_b200_outsel* sel, const int* iodp, double* bout) {
+  if (!h || !bout) EW_FAIL(ECWAM_B200_EINVAL, "null argument");
+  if (!h->bound) EW_FAIL(ECWAM_B200_ESTATE, "fields not bound");
+  int rc = check_outsel(sel);
+  if (rc) return rc;
+  const DevConst& c = h->dc;
+  OutConst oc;
+  memset(&oc, 0, sizeof(oc));
+  oc.A = c.A; oc.F = c.F; oc.NFRE_ODD = c.NFRE_ODD; oc.licerun = c.licerun; oc.lmaskice = c.lmaskice; oc.llsource = sel->llsource;
+  oc.ncol = sel->niprmout;
+  for (int i = 0; i < oc.ncol; ++i) { oc.itg[i] = sel->itg[i]; oc.icemask[i] = sel->icemask[i]; oc.seamask[i] = sel->seamask[i]; }
+  oc.EPSMIN = c.EPSMIN; oc.EPSUS = c.EPSUS; oc.DELTH = c.DELTH; oc.WETAIL = c.WETAIL; oc.FRTAIL = c.FRTAIL; oc.WP1TAIL = c.WP1TAIL;
+  oc.WP2TAIL = 0.5;          // yowfred.F90:54
+  oc.ZPI = c.ZPI; oc.G = c.G; oc.GM1 = c.GM1;
+  oc.DEG = 360.0 / c.ZPI;    // = 180/PI bit for bit (iniwcst.F90:63)
+  oc.XKAPPA = c.XKAPPA; oc.XNLEV = c.XNLEV; oc.ALPHAMIN = c.ALPHAMIN;
+  oc.ALPHAMAX = 0.11;        // yowphys.F90:55
+  oc.ROWATER = 1000.0;       // yowpcons.F90
+  oc.rnum = c.rnum; oc.flmin = c.flmin; oc.cithrsh = c.cithrsh; oc.zmiss = sel->zmiss;
+  for (int m = 0; m < c.F; ++m) { oc.FR[m] = c.FR[m]; oc.DFIM[m] = c.DFIM[m]; oc.DFIMOFR[m] = c.DFIMOFR[m]; oc.DFIMFR[m] = c.DFIMFR[m]; oc.DFIM_SIM[m] = c.DFIM_SIM[m]; }
+  for (int k = 0; k < c.A; ++k) { oc.TH[k] = c.TH[k]; oc.COSTH[k] = c.COSTH[k]; oc.SINTH[k] = c.SINTH[k]; }
+  rc = upload_out_const(oc, h->st);
+  if (rc) return rc;
+  OutDev d;
+  d.P = h->par.nproma; d.A = c.A; d.F = c.F; d.nchnk = h->par.nchnk;
+  d.npts = (long long)d.P * d.nchnk;
+  d.f = h->dev; d.iodp = iodp; d.bout = bout;
+  ScopedTimer t(h, "outblock");
+  rc = launch_outblock(d, h->st);
+  if (rc) return rc;
+  h->nlaunch++;
+  EW_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int ecwam_b200_outwnorm(ecwam_b200_handle h, const ecwam_b200_outsel* sel, const double* bout, int llglobal, int niblo,
+                        const int* ij2newij, const int* nstart, const int* nend, double* wnorm) {
+  if (!h || !bout || !wnorm) EW_FAIL(ECWAM_B200_EINVAL, "null argument");
+  int rc = check_outsel(sel);
+  if (rc) return rc;
+  const int ncol = sel->niprmout, P = h->par.nproma, np = h->nproc;
+  const long long nloc = h->pd.nloc;
+  const double HUGE_ = 1.7976931348623157e308;
+  ScopedTimer t(h, "outwnorm");
+  if (!llglobal) {   // mpminmaxavg.F90:160-191
+    const size_t ns = norm_scratch_doubles(ncol);
+    if (h->normbuf.n < ns + (size_t)4 * ncol * np) { rc = h->normbuf.alloc(ns + (size_t)4 * ncol * np); if (rc) return rc; }
+    double* out4 = h->normbuf.p + ns - (size_t)4 * ncol;
+    double* gath = h->normbuf.p + ns;
+    launch_norm_local(bout, P, ncol, nloc, sel->zmiss, h->normbuf.p, out4, h->st);
+    h->nlaunch += 2;
+    if (np > 1) EW_NCCL_CHECK(ncclAllGather(out4, gath, (size_t)4 * ncol, ncclDouble, h->comm, h->st));
+    else EW_CUDA_CHECK(cudaMemcpyAsync(gath, out4, sizeof(double) * 4 * ncol, cudaMemcpyDeviceToDevice, h->st));
+    std::vector<double> hg((size_t)4 * ncol * np);
+    EW_CUDA_CHECK(cudaMemcpyAsync(hg.data(), gath, hg.size() * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    EW_CUDA_CHECK(cudaStreamSynchronize(h->st));
+    for (int i = 0; i < ncol; ++i) {
+      double s = 0.0, c = 0.0, mn = HUGE_, mx = -HUGE_;
+      for (int q = 0; q < np; ++q) {   // fixed rank order (the reference's MPL_ALLREDUCE with LDREPROD)
+        const double* v = &hg[((size_t)q * ncol + i) * 4];
+        s += v[0]; c += v[1]; mn = std::min(mn, v[2]); mx = std::max(mx, v[3]);
+      }
+      wnorm[4 * i + 1] = mn; wnorm[4 * i + 2] = mx; wnorm[4 * i + 3] = c;
+      wnorm[4 * i + 0] = c < 1.0 ? -HUGE_ : s / c;
+    }
+    return 0;
+  }
+  // LLNORMWAMOUT_GLOBAL (mpminmaxavg.F90:121-153)
+  if (niblo < nloc) EW_FAIL(ECWAM_B200_EINVAL, "outwnorm: niblo < own points");
+  if (np > 1 && (!nstart || !nend)) EW_FAIL(ECWAM_B200_EINVAL, "outwnorm: the global norm over %d ranks needs nstart/nend", np);
+  if (np == 1 && niblo != nloc) EW_FAIL(ECWAM_B200_EINVAL, "outwnorm: niblo must equal the own points on one rank");
+  const size_t nz = (size_t)ncol * niblo + (size_t)4 * ncol;
+  if (h->zglobal.n < nz) { rc = h->zglobal.alloc(nz); if (rc) return rc; }
+  double* zg = h->zglobal.p;
+  double* out4 = zg + (size_t)ncol * niblo;
+  const long long off = np > 1 ? nstart[h->irank0] - 1 : 0;
+  launch_pack_cols(bout, P, ncol, nloc, zg + off, niblo, h->st);
+  h->nlaunch++;
+  const int* ijd = nullptr;
+  if (np > 1) {
+    EW_NCCL_CHECK(ncclGroupStart());
+    for (int q = 0; q < np; ++q) {
+      const size_t cnt = (size_t)(nend[q] - nstart[q] + 1);
+      for (int i = 0; i < ncol; ++i) {
+        double* seg = zg + (size_t)i * niblo + (nstart[q] - 1);
+        EW_NCCL_CHECK(ncclBroadcast(seg, seg, cnt, ncclDouble, q, h->comm, h->st));
+      }
+    }
+    EW_NCCL_CHECK(ncclGroupEnd());
+    if (ij2newij) {   // IJ = IJ2NEWIJ(IJOLD) unless LL1D (mpminmaxavg.F90:134-138)
+      if (h->ij2new_n != niblo + 1) {
+        std::vector<int> v(ij2newij, ij2newij + niblo + 1);
+        rc = h->ij2new_d.upload(v, h->st);
+        if (rc) return rc;
+        h->ij2new_n = niblo + 1;
+      }
+      ijd = h->ij2new_d.p;
+    }
+  }
+  launch_norm_seq(zg, ijd, niblo, ncol, sel->zmiss, out4, h->st);
+  h->nlaunch++;
+  EW_CUDA_CHECK(cudaMemcpyAsync(wnorm, out4, sizeof(double) * 4 * ncol, cudaMemcpyDeviceToHost, h->st));
+  EW_CUDA_CHECK(cudaStreamSynchronize(h->st));
+  EW_CUDA_CHECK(cudaGetLastError());
+  return 0;
 }
 
 int ecwam_b200_synchronize(ecwam_b200_handle h) {

@@ -74,4 +74,30 @@ int upload_dev_const(const DevConst& h, cudaStream_t st);
 int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage, cudaStream_t st);
 size_t implsch_scratch_doubles(long long npts);
 
+// ---- NEWWIND / OUTBLOCK core / WAMNORM (outparam.cu) ------------------------------------------------------------
+#define EW_OUT_MAXCOL 64
+struct OutConst {   // constant memory of outparam.cu
+  int A, F, NFRE_ODD, licerun, lmaskice, llsource, ncol;
+  int itg[EW_OUT_MAXCOL], icemask[EW_OUT_MAXCOL], seamask[EW_OUT_MAXCOL];
+  double EPSMIN, EPSUS, DELTH, WETAIL, FRTAIL, WP1TAIL, WP2TAIL, ZPI, G, GM1, DEG, XKAPPA, XNLEV, ALPHAMIN, ALPHAMAX, ROWATER,
+      rnum, flmin, cithrsh, zmiss;
+  double FR[EW_MAXF], DFIM[EW_MAXF], DFIMOFR[EW_MAXF], DFIMFR[EW_MAXF], DFIM_SIM[EW_MAXF];
+  double TH[EW_MAXA], COSTH[EW_MAXA], SINTH[EW_MAXA];
+};
+struct OutDev {
+  int P, A, F, nchnk;
+  long long npts;          // P*nchnk: OUTBLOCK runs over all lanes of every chunk (outbs.F90:100-101)
+  ecwam_b200_fields f;
+  const int* iodp;         // (P,C) or null (= 1 everywhere)
+  double* bout;            // (P, NIPRMOUT, C)
+};
+int upload_out_const(const OutConst& h, cudaStream_t st);
+void launch_newwind(long long npts, const ecwam_b200_fields& f, const ecwam_b200_forcing_next& nx, double acd, double bcd, double epsmin,
+                    cudaStream_t st);
+int launch_outblock(const OutDev& d, cudaStream_t st);
+size_t norm_scratch_doubles(int ncol);
+void launch_norm_local(const double* bout, int P, int ncol, long long nloc, double zmiss, double* scratch, double* out4, cudaStream_t st);
+void launch_pack_cols(const double* bout, int P, int ncol, long long nloc, double* out, long long ostride, cudaStream_t st);
+void launch_norm_seq(const double* zg, const int* ij2new, long long niblo, int ncol, double zmiss, double* out4, cudaStream_t st);
+
 }  // namespace ew

@@ -21,6 +21,14 @@ F2 = ("depth", "emaxdpt", "dellam1", "cosphm1", "ucur", "vcur", "aird", "wdwave"
       "strnms", "tauxd", "tauyd", "tauocxd", "tauocyd", "tauoc", "tauicx", "tauicy", "phiocd", "phieps", "phiaw")
 FI = ("mij",)
 
+# OUTBLOCK parameters built by ecwam_b200_outbs -> (sea-ice mask, shallow-to-missing) flags of MPCRTBL's DEFINE_PARAMETER
+# calls (mpcrtbl.F90:93-431, numbering with NTRAIN = 3)
+OUTBLOCK_PARAMS = {1: (1, 1), 2: (1, 1), 3: (1, 1), 4: (0, 1), 5: (0, 0), 6: (1, 1), 7: (0, 0), 8: (1, 1), 10: (0, 0), 11: (1, 1),
+                   12: (1, 1), 13: (1, 1), 14: (1, 1), 15: (1, 1), 16: (1, 1), 20: (1, 1), 21: (1, 1), 22: (1, 1), 23: (1, 1),
+                   24: (1, 1), 25: (1, 1), 26: (1, 1), 27: (1, 1), 28: (1, 1), 32: (0, 1), 35: (1, 1), 36: (1, 1), 37: (0, 1),
+                   38: (0, 1), 39: (0, 1), 40: (0, 1), 41: (0, 1), 53: (0, 0), 54: (0, 0), 55: (0, 1), 56: (0, 1), 62: (1, 1),
+                   63: (1, 1), 73: (0, 1), 74: (0, 1), 75: (0, 1), 76: (0, 1), 77: (0, 1)}
+
 
 def default_params(**kw) -> L.Params:
     """Namelist values of the reference's test configurations."""
@@ -231,6 +239,61 @@ class WamIntgr:
         """One WAMINTGR sub-step with IDELPRO == IDELT."""
         return L.check(self.lib.ecwam_b200_wamintgr(self.h), "wamintgr")
 
+    # ---- the steps either side of the hot path: NEWWIND, OUTBS, OUTWNORM
+    NEXT_FIELDS = ("wswave", "wdwave", "aird", "wstar", "cicover", "cithick", "ustra", "vstra")
+
+    def newwind(self, nxt: dict):
+        """NEWWIND (newwind.F90:105-167): FF_NOW <- FF_NEXT on the device; nxt maps field names to global arrays."""
+        torch = self.torch
+        keep, fn = [], L.ForcingNext()
+        for n in self.NEXT_FIELDS:
+            v = nxt[n] if n in nxt else nxt[n.upper()]
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(v, dtype=np.float64)[self.src])).to(self.device)
+            keep.append(t)
+            setattr(fn, n, C.cast(t.data_ptr(), C.POINTER(C.c_double)))
+        L.check(self.lib.ecwam_b200_newwind(self.h, C.byref(fn)), "newwind")
+        self.synchronize()      # `keep` may be released once the kernel has read it
+
+    def _outsel(self, itg, icemask, seamask, zmiss, llsource):
+        n = len(itg)
+        arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in (itg, icemask, seamask)]
+        sel = L.OutSel(niprmout=n, llsource=int(llsource), zmiss=float(zmiss))
+        for nm, a in zip(("itg", "icemask", "seamask"), arrs):
+            setattr(sel, nm, a.ctypes.data_as(C.POINTER(C.c_int)))
+        return sel, arrs
+
+    def outbs(self, itg, icemask, seamask, zmiss=-999.0, llsource=1, iodp=None):
+        """OUTBS/OUTBLOCK (outbs.F90:97-122) on the device: returns BOUT[column, own point] (slot order, see .own)."""
+        torch = self.torch
+        sel, keep = self._outsel(itg, icemask, seamask, zmiss, llsource)
+        n = len(itg)
+        self.bout = torch.empty((self.C, n, self.P), dtype=torch.float64, device=self.device)
+        self._sel = (list(itg), list(icemask), list(seamask), zmiss, llsource)
+        io = None
+        if iodp is not None:
+            io = torch.from_numpy(np.ascontiguousarray(np.asarray(iodp, dtype=np.int32)[self.src])).to(self.device)
+        L.check(self.lib.ecwam_b200_outbs(self.h, C.byref(sel), C.c_void_p(io.data_ptr()) if io is not None else None,
+                                          C.c_void_p(self.bout.data_ptr())), "outbs")
+        self.synchronize()
+        return self.bout.permute(1, 0, 2).reshape(n, -1)[:, : self.nloc].cpu().numpy()
+
+    def outwnorm(self, global_norm=True):
+        """OUTWNORM/MPMINMAXAVG on the last outbs(): rows = columns, (average, minimum, maximum, count)."""
+        sel, keep = self._outsel(*self._sel)
+        n = len(self._sel[0])
+        w = np.empty((n, 4))
+        s = self.s
+        ip = C.POINTER(C.c_int)
+        multi = s.nproc > 1
+        ij2 = np.ascontiguousarray(s.ij2new, dtype=np.int32)
+        ns = np.ascontiguousarray(s.nstart, dtype=np.int32)
+        ne = np.ascontiguousarray(s.nend, dtype=np.int32)
+        L.check(self.lib.ecwam_b200_outwnorm(self.h, C.byref(sel), C.c_void_p(self.bout.data_ptr()), int(global_norm), int(s.niblo),
+                                             ij2.ctypes.data_as(ip) if multi else None, ns.ctypes.data_as(ip) if multi else None,
+                                             ne.ctypes.data_as(ip) if multi else None, w.ctypes.data_as(C.POINTER(C.c_double))),
+                "outwnorm")
+        return w
+
     def synchronize(self):
         L.check(self.lib.ecwam_b200_synchronize(self.h), "synchronize")
 
@@ -272,7 +335,7 @@ def hs_fm(setup: WamSetup, fl: np.ndarray):
     delth = setup.tables.delth
     eps = setup.tables.epsmin
     t2 = np.maximum(fl, eps).sum(axis=1)                       # (F, n)
-    em = eps + (t2 * dfim[:, None]).sum(axis=0) + setup.tables.wetail * fr[-1] * delth * t2[-1]
-    fm = eps + (t2 * dfimofr[:, None]).sum(axis=0) + setup.tables.frtail * delth * t2[-1]
+    em = (t2 * dfim[:, None]).sum(axis=0) + setup.tables.wetail * fr[-1] * delth * t2[-1]
+    fm = (t2 * dfimofr[:, None]).sum(axis=0) + setup.tables.frtail * delth * t2[-1]
     fm = np.maximum(em / fm, fr[0])
     return 4.0 * np.sqrt(em), fm

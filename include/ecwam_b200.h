@@ -315,6 +315,53 @@ int ecwam_b200_wamintgr(ecwam_b200_handle h);
 int ecwam_b200_wamintgr_host(ecwam_b200_handle h, const ecwam_b200_fields* host, int with_xllws,
                              long long* h2d_bytes, long long* d2h_bytes);
 
+/* ---------------------------------------------------------------------------------------------------
+ * The steps either side of the hot path each time step / output step, kept on the device.   */
+
+/* FF_NEXT members NEWWIND copies (device pointers, (P,C)); src/ecwam/newwind.F90:127-162.                  */
+typedef struct ecwam_b200_forcing_next {
+  const double* wswave;
+  const double* wdwave;
+  const double* aird;
+  const double* wstar;
+  const double* cicover;
+  const double* cithick;
+  const double* ustra;
+  const double* vstra;
+} ecwam_b200_forcing_next;
+/* NEWWIND's update of FF_NOW from FF_NEXT (src/ecwam/newwind.F90:105-167, ICODE_WND = 3: 10 m wind speed with the
+ * low-wind cap on the first-guess wave stress TAUW).  The date bookkeeping (CDATEWH, INCDATE) stays with the caller:
+ * call this when NEWWIND's `CDATE >= CDATEWH` test holds.                                                   */
+int ecwam_b200_newwind(ecwam_b200_handle h, const ecwam_b200_forcing_next* next);
+
+/* Selection of OUTBLOCK's output columns = YOWCOUT after MPCRTBL (src/ecwam/mpcrtbl.F90:89-460).  Host pointers.  */
+typedef struct ecwam_b200_outsel {
+  int niprmout;              /* YOWCOUT NIPRMOUT: number of BOUT columns                                     */
+  const int* itg;            /* (NIPRMOUT) reference parameter number of each column (the inverse of ITOBOUT) */
+  const int* icemask;        /* (NIPRMOUT) IPRMINFO(itg,6): sea-ice mask imposed                              */
+  const int* seamask;        /* (NIPRMOUT) IPRMINFO(itg,7): too shallow points set to missing                 */
+  int llsource;              /* YOWSTAT LLSOURCE                                                              */
+  double zmiss;              /* YOWPCONS ZMISS                                                                */
+} ecwam_b200_outsel;
+/* 1 if OUTBLOCK parameter `itg` is built: 1-8, 10-16, 20-28, 32, 35-41, 53-56, 62, 63, 73-77 (numbering of
+ * mpcrtbl.F90 with NTRAIN = 3).  Not built: MEANSQS (9), altimeter (17-19), KURTOSIS family (29-31, 33, 34, 57,
+ * 70-72), swell partitions (42-50, LLPARTITION), CIMSSTRN (51), SEBTMEAN bands (52, 64-69), NEMO fields (58-61),
+ * W_MAXH (78-81), 82+.                                                                                       */
+int ecwam_b200_outparam_supported(int itg);
+/* OUTBS (src/ecwam/outbs.F90:97-122): OUTBLOCK over all chunks (src/ecwam/outblock.F90:150-610, IREFRA = 0,
+ * LSECONDORDER = F) with FEMEAN, STHQ, DOMINANT_PERIOD, SEPWISW, MWP1, MWP2, WDIRSPREAD, OUTBETA, WEFLUX and
+ * OUTSETWMASK.  bout: DEVICE (NPROMA, NIPRMOUT, NCHNK); iodp: DEVICE (NPROMA, NCHNK) WVENVI%IODP or NULL (= 1).
+ * Reads the bound fields (FL1, XLLWS, CINV, CGROUP, forcing, IMPLSCH outputs).                                */
+int ecwam_b200_outbs(ecwam_b200_handle h, const ecwam_b200_outsel* sel, const int* iodp, double* bout);
+/* OUTWNORM -> MPMINMAXAVG (src/ecwam/mpminmaxavg.F90:68-195) on a BOUT made by ecwam_b200_outbs.
+ * wnorm: HOST (4, NIPRMOUT) = average, minimum, maximum, number of non-missing points (every rank gets it).
+ * llglobal = 0: per-rank sums combined over ranks (MPL_ALLREDUCE branch, :160-191);
+ * llglobal = 1: LLNORMWAMOUT_GLOBAL, one sequential sum over the ORIGINAL global point order (:121-153), bit-
+ *   reproducible for any number of ranks; needs niblo and, when nproc > 1, ij2newij (HOST, (0:NIBLO), mpdecomp.F90:667-686)
+ *   and nstart/nend (HOST, (NPROC)).                                                                          */
+int ecwam_b200_outwnorm(ecwam_b200_handle h, const ecwam_b200_outsel* sel, const double* bout, int llglobal, int niblo,
+                        const int* ij2newij, const int* nstart, const int* nend, double* wnorm);
+
 int ecwam_b200_synchronize(ecwam_b200_handle h);
 /* Kernel launch counter (all kernels launched through this handle since creation). */
 long long ecwam_b200_launch_count(ecwam_b200_handle h);

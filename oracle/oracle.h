@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <stdexcept>
 #include <string>
+#include <limits>
 
 namespace orc {
 
@@ -186,6 +187,14 @@ struct Fields {
   ArrD LAND_WAVNUM, LAND_CGROUP, LAND_OMOSNH2KD;
 };
 
+// selection of OUTBLOCK output columns (orc_output.cpp)
+struct OutSel {
+  int n = 0;                            // NIPRMOUT
+  std::vector<int> itg, icemask, seamask;  // per BOUT column: reference parameter number, IPRMINFO(:,6), IPRMINFO(:,7)
+  double zmiss = -999.0;                // YOWPCONS ZMISS
+  int llsource = 1;                     // YOWSTAT LLSOURCE
+};
+
 struct Model {
   Config cfg;
   Tables tab;
@@ -193,6 +202,8 @@ struct Model {
   std::vector<RankDecomp> ranks;
   std::vector<Fields> fld;
   std::vector<double> depth0;  // depth per sea point, original order (1..NIBLO)
+  OutSel sel;                              // last orc_outbs selection
+  std::vector<std::vector<double>> bout;   // [rank] BOUT (P, NIPRMOUT, C) of the last orc_outbs
 };
 
 void alloc_fields(Model& m);
@@ -202,5 +213,13 @@ void propag_wam(Model& m);  // all ranks, with in-process MPEXCHNG
 void implsch_all(Model& m); // all ranks, all chunks (wamintgr.F90:117-146)
 void implsch_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int ichnk);
 void femean(const Tables& t, const Config& c, int KIJL, const double* F /*(KIJL,A,F)*/, double* EM, double* FM);
+
+// ---------------------------------------------------------------------------
+// The steps either side of the hot path (orc_output.cpp): NEWWIND, OUTBLOCK core parameters, WAMNORM statistics.
+bool outparam_supported(int itg);
+void newwind(Model& m, int ir, const Fields& next);
+void outblock(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK, const OutSel& sel, double* BOUT /*(KIJL,NIPRMOUT)*/);
+void mpminmaxavg(Model& m, const OutSel& sel, const std::vector<std::vector<double>>& bout /*[rank](P,NIPRMOUT,C)*/, bool global,
+                 double* WNORM /*(4,NIPRMOUT)*/);
 
 }  // namespace orc

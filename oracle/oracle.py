@@ -77,6 +77,9 @@ def _lib(fast=False):
             getattr(lib, f).argtypes = [C.c_void_p, C.c_void_p]
         lib.orc_get_hs_fm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_propag.argtypes = [C.c_void_p]
+        lib.orc_newwind.argtypes = [C.c_void_p, C.c_void_p]
+        lib.orc_outbs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p]
+        lib.orc_outwnorm.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.orc_implsch.argtypes = [C.c_void_p]
         assert lib.orc_config_size() == C.sizeof(Config), "oracle Config layout mismatch"
         _libs[fast] = lib
@@ -189,6 +192,35 @@ class Oracle:
     def implsch(self):
         if self.lib.orc_implsch(self.h) != 0:
             raise RuntimeError("orc_implsch failed")
+
+    # ---- the steps either side of the hot path (oracle/orc_output.cpp)
+    NEXT_FIELDS = ("WSWAVE", "WDWAVE", "AIRD", "WSTAR", "CICOVER", "CITHICK", "USTRA", "VSTRA")
+
+    def newwind(self, nxt: dict):
+        """NEWWIND (newwind.F90:105-167, ICODE_WND=3): FF_NOW <- FF_NEXT; nxt maps the 8 field names to global arrays."""
+        arrs = [np.ascontiguousarray(nxt[k], dtype=np.float64) for k in self.NEXT_FIELDS]
+        ptrs = (C.c_void_p * 8)(*[a.ctypes.data for a in arrs])
+        if self.lib.orc_newwind(self.h, ptrs) != 0:
+            raise RuntimeError("orc_newwind failed")
+
+    def outbs(self, itg, icemask, seamask, zmiss=-999.0, llsource=1):
+        """OUTBS/OUTBLOCK (outbs.F90:97-122): returns BOUT[column, ij] in original global order."""
+        itg = np.ascontiguousarray(itg, dtype=np.int32)
+        im = np.ascontiguousarray(icemask, dtype=np.int32)
+        sm = np.ascontiguousarray(seamask, dtype=np.int32)
+        out = np.empty((len(itg), self.niblo))
+        if self.lib.orc_outbs(self.h, len(itg), itg.ctypes.data, im.ctypes.data, sm.ctypes.data, float(zmiss), int(llsource),
+                              out.ctypes.data) != 0:
+            raise RuntimeError("orc_outbs failed (unsupported parameter?)")
+        self._nout = len(itg)
+        return out
+
+    def outwnorm(self, global_norm=True):
+        """OUTWNORM/MPMINMAXAVG on the last outbs(): rows = columns, (average, minimum, maximum, count)."""
+        w = np.empty((self._nout, 4))
+        if self.lib.orc_outwnorm(self.h, int(global_norm), w.ctypes.data) != 0:
+            raise RuntimeError("orc_outwnorm failed")
+        return w
 
     def step(self):
         """One WAMINTGR sub-step with IDELPRO == IDELT (wamintgr.F90:94-146)."""

@@ -242,4 +242,53 @@ int orc_get_hs_fm(void* h, double* hs, double* fm) {
   return 0;
 }
 
+// NEWWIND (newwind.F90) with FF_NEXT given in original global order: wswave, wdwave, aird, wstar, cicover, cithick, ustra, vstra
+int orc_newwind(void* h, const double* const* next8) {
+  Model* m = (Model*)h;
+  std::vector<Fields> nx(m->cfg.npr);
+  ArrD Fields::*mem[8] = {&Fields::WSWAVE, &Fields::WDWAVE, &Fields::AIRD, &Fields::WSTAR, &Fields::CICOVER, &Fields::CITHICK,
+                          &Fields::USTRA, &Fields::VSTRA};
+  for (int ir = 0; ir < m->cfg.npr; ++ir) for (auto mp : mem) (nx[ir].*mp).alloc(1, m->ranks[ir].NPROMA, 1, m->ranks[ir].NCHNK);
+  for (int q = 0; q < 8; ++q) {
+    for (int ij = 1; ij <= m->grid.NIBLO; ++ij) { int ir, ip, ic; locate(m, ij, ir, ip, ic); (nx[ir].*mem[q])(ip, ic) = next8[q][ij - 1]; }
+    for (int ir = 0; ir < m->cfg.npr; ++ir) {
+      RankDecomp& r = m->ranks[ir];
+      ArrD& a = nx[ir].*mem[q];
+      for (int j = r.KIJL4CHNK(r.NCHNK) + 1; j <= r.NPROMA; ++j) a(j, r.NCHNK) = a(1, r.NCHNK);
+    }
+  }
+  for (int ir = 0; ir < m->cfg.npr; ++ir) newwind(*m, ir, nx[ir]);
+  return 0;
+}
+// OUTBS: OUTBLOCK for every chunk of every rank (outbs.F90:97-122); out[(column) * NIBLO + ij] in original global order
+int orc_outbs(void* h, int n, const int* itg, const int* icemask, const int* seamask, double zmiss, int llsource, double* out) {
+  Model* m = (Model*)h;
+  for (int i = 0; i < n; ++i) if (!outparam_supported(itg[i])) return -1;
+  OutSel& s = m->sel;
+  s.n = n; s.itg.assign(itg, itg + n); s.icemask.assign(icemask, icemask + n); s.seamask.assign(seamask, seamask + n);
+  s.zmiss = zmiss; s.llsource = llsource;
+  m->bout.assign(m->cfg.npr, {});
+  for (int ir = 0; ir < m->cfg.npr; ++ir) {
+    RankDecomp& r = m->ranks[ir];
+    m->bout[ir].assign((size_t)r.NPROMA * n * r.NCHNK, 0.0);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int ic = 1; ic <= r.NCHNK; ++ic)
+      outblock(m->cfg, m->tab, m->fld[ir], r.NPROMA, ic, s, m->bout[ir].data() + (size_t)r.NPROMA * n * (ic - 1));
+  }
+  const long N = m->grid.NIBLO;
+  for (int ij = 1; ij <= N; ++ij) {
+    int ir, ip, ic; locate(m, ij, ir, ip, ic);
+    const RankDecomp& r = m->ranks[ir];
+    for (int i = 0; i < n; ++i) out[(size_t)i * N + ij - 1] = m->bout[ir][(ip - 1) + (size_t)r.NPROMA * (i + (size_t)n * (ic - 1))];
+  }
+  return 0;
+}
+// OUTWNORM -> MPMINMAXAVG on the BOUT of the last orc_outbs; wnorm (4, NIPRMOUT): average, minimum, maximum, count
+int orc_outwnorm(void* h, int global, double* wnorm) {
+  Model* m = (Model*)h;
+  if (m->bout.empty()) return -1;
+  mpminmaxavg(*m, m->sel, m->bout, global != 0, wnorm);
+  return 0;
+}
+
 }  // extern "C"

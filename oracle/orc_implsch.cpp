@@ -933,7 +933,7 @@ void STOKESDRIFT(const Ctx& x, V3 FL1, V2 STOKFAC, V1 WSWAVE, V1 WDWAVE, V1 CICO
 void femean(const Tables& t, const Config& c, int KIJL, const double* Fp, double* EM, double* FM) {
   V3 F{const_cast<double*>(Fp), KIJL, c.nang};
   std::vector<double> TEMP2(KIJL + 1);
-  for (int IJ = 1; IJ <= KIJL; ++IJ) { EM[IJ - 1] = t.EPSMIN; FM[IJ - 1] = t.EPSMIN; }
+  for (int IJ = 1; IJ <= KIJL; ++IJ) { EM[IJ - 1] = 0.0; FM[IJ - 1] = 0.0; }   // femean.F90:84-87
   double DELT25 = t.WETAIL * t.FR(c.nfre) * t.DELTH;
   double DELT2 = t.FRTAIL * t.DELTH;
   for (int M = 1; M <= c.nfre; ++M) {

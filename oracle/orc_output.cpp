@@ -1,0 +1,402 @@
+// ORACLE (test infrastructure) — the steps either side of the hot path each time step / output step:
+// NEWWIND (newwind.F90:105-167), OUTBS/OUTBLOCK's core integrated parameters (outbs.F90:97-126, outblock.F90:150-610 with
+// FEMEAN, STHQ, DOMINANT_PERIOD, SEPWISW (LLPARTITION=F), MWP1, MWP2, WDIRSPREAD/PEAKFRI/SCOSFL, OUTBETA, WEFLUX,
+// OUTSETWMASK) and the WAMNORM statistics (outwnorm.F90:83, mpminmaxavg.F90:68-195).  Loop by loop, in the reference's
+// operation order.  Paths relative to /root/reference/src/ecwam.
+#include "oracle.h"
+
+namespace orc {
+
+namespace {
+struct S3 {   // (KIJL, NANG, NFRE) view, 1-based
+  const double* p; long P, A;
+  inline double operator()(int ij, int k, int m) const { return p[(ij - 1) + P * ((k - 1) + A * (long)(m - 1))]; }
+};
+struct W3 {
+  std::vector<double> d; long P, A;
+  W3(long P_, long A_, long F_) : d((size_t)P_ * A_ * F_, 0.0), P(P_), A(A_) {}
+  inline double& operator()(int ij, int k, int m) { return d[(ij - 1) + P * ((k - 1) + A * (long)(m - 1))]; }
+  S3 view() const { return S3{d.data(), P, A}; }
+};
+typedef std::vector<double> V;
+
+// femean.F90:84-121
+void femean_out(const Tables& t, int KIJL, int NANG, int NFRE, const S3& F, V& EM, V& FM) {
+  V TEMP2(KIJL + 1);
+  for (int IJ = 1; IJ <= KIJL; ++IJ) { EM[IJ] = 0.0; FM[IJ] = 0.0; }
+  const double DELT25 = t.WETAIL * t.FR(NFRE) * t.DELTH;
+  const double DELT2 = t.FRTAIL * t.DELTH;
+  for (int M = 1; M <= NFRE; ++M) {
+    for (int IJ = 1; IJ <= KIJL; ++IJ) TEMP2[IJ] = std::max(F(IJ, 1, M), t.EPSMIN);
+    for (int K = 2; K <= NANG; ++K)
+      for (int IJ = 1; IJ <= KIJL; ++IJ) TEMP2[IJ] = TEMP2[IJ] + std::max(F(IJ, K, M), t.EPSMIN);
+    for (int IJ = 1; IJ <= KIJL; ++IJ) { EM[IJ] = EM[IJ] + TEMP2[IJ] * t.DFIM(M); FM[IJ] = FM[IJ] + t.DFIMOFR(M) * TEMP2[IJ]; }
+  }
+  for (int IJ = 1; IJ <= KIJL; ++IJ) {
+    EM[IJ] = EM[IJ] + DELT25 * TEMP2[IJ];
+    FM[IJ] = FM[IJ] + DELT2 * TEMP2[IJ];
+    FM[IJ] = EM[IJ] / FM[IJ];
+    FM[IJ] = std::max(FM[IJ], t.FR(1));
+  }
+}
+
+// sthq.F90:69-115
+void sthq(const Tables& t, int KIJL, int NANG, int NFRE, const S3& F, V& THQ) {
+  V TEMP(KIJL + 1), SI(KIJL + 1, 0.0), CI(KIJL + 1, 0.0);
+  for (int K = 1; K <= NANG; ++K) {
+    for (int IJ = 1; IJ <= KIJL; ++IJ) TEMP[IJ] = 0.0;
+    for (int M = 1; M <= NFRE; ++M)
+      for (int IJ = 1; IJ <= KIJL; ++IJ) TEMP[IJ] = TEMP[IJ] + F(IJ, K, M) * t.DFIM(M);
+    for (int IJ = 1; IJ <= KIJL; ++IJ) { SI[IJ] = SI[IJ] + t.SINTH(K) * TEMP[IJ]; CI[IJ] = CI[IJ] + t.COSTH(K) * TEMP[IJ]; }
+  }
+  for (int IJ = 1; IJ <= KIJL; ++IJ) if (CI[IJ] == 0.0) CI[IJ] = t.EPSMIN;
+  for (int IJ = 1; IJ <= KIJL; ++IJ) THQ[IJ] = std::atan2(SI[IJ], CI[IJ]);
+  for (int IJ = 1; IJ <= KIJL; ++IJ) if (THQ[IJ] < 0.0) THQ[IJ] = THQ[IJ] + t.ZPI;
+}
+
+// mwp1.F90:75-112 (IP=1) and mwp2.F90 (IP=2): same loops with DFIMFR_SIM / DFIMFR2_SIM (initmdl.F90:497-502)
+void mwp12(const Tables& t, int KIJL, int NANG, int IP, const S3& F, V& MEANWP) {
+  V TEMP(KIJL + 1), EM(KIJL + 1, 0.0);
+  const int NO = t.NFRE_ODD;
+  for (int IJ = 1; IJ <= KIJL; ++IJ) MEANWP[IJ] = 0.0;
+  for (int M = 1; M <= NO; ++M) {
+    for (int IJ = 1; IJ <= KIJL; ++IJ) TEMP[IJ] = 0.0;
+    for (int K = 1; K <= NANG; ++K)
+      for (int IJ = 1; IJ <= KIJL; ++IJ) TEMP[IJ] = TEMP[IJ] + F(IJ, K, M);
+    const double w = IP == 1 ? t.DFIM_SIM(M) * t.FR(M) : t.DFIM_SIM(M) * (t.FR(M) * t.FR(M));
+    for (int IJ = 1; IJ <= KIJL; ++IJ) { EM[IJ] = EM[IJ] + t.DFIM_SIM(M) * TEMP[IJ]; MEANWP[IJ] = MEANWP[IJ] + w * TEMP[IJ]; }
+  }
+  const double FR1M1 = 1.0 / t.FR(1);
+  const double DELT25 = t.WETAIL * t.FR(NO) * t.DELTH;
+  const double COEF_FR = IP == 1 ? t.WP1TAIL * t.DELTH * (t.FR(NO) * t.FR(NO)) : t.WP2TAIL * t.DELTH * (t.FR(NO) * t.FR(NO) * t.FR(NO));
+  for (int IJ = 1; IJ <= KIJL; ++IJ) {
+    EM[IJ] = EM[IJ] + DELT25 * TEMP[IJ];
+    MEANWP[IJ] = MEANWP[IJ] + COEF_FR * TEMP[IJ];
+    if (EM[IJ] > 0.0 && MEANWP[IJ] > t.EPSMIN) {
+      MEANWP[IJ] = IP == 1 ? EM[IJ] / MEANWP[IJ] : std::sqrt(EM[IJ] / MEANWP[IJ]);
+      MEANWP[IJ] = std::min(MEANWP[IJ], FR1M1);
+    } else MEANWP[IJ] = 0.0;
+  }
+}
+
+// scosfl.F90:74-104
+void scosfl(const Tables& t, int KIJL, int NANG, const S3& F, const std::vector<int>& MM, V& MEANCOSFL) {
+  V SI(KIJL + 1, 0.0), CI(KIJL + 1, 0.0), MEANDIR(KIJL + 1);
+  for (int IJ = 1; IJ <= KIJL; ++IJ) MEANCOSFL[IJ] = 0.0;
+  for (int K = 1; K <= NANG; ++K)
+    for (int IJ = 1; IJ <= KIJL; ++IJ) { SI[IJ] = SI[IJ] + t.SINTH(K) * F(IJ, K, MM[IJ]); CI[IJ] = CI[IJ] + t.COSTH(K) * F(IJ, K, MM[IJ]); }
+  for (int IJ = 1; IJ <= KIJL; ++IJ) MEANDIR[IJ] = (CI[IJ] == 0.0 && SI[IJ] == 0.0) ? 0.0 : std::atan2(SI[IJ], CI[IJ]);
+  for (int K = 1; K <= NANG; ++K)
+    for (int IJ = 1; IJ <= KIJL; ++IJ) MEANCOSFL[IJ] = MEANCOSFL[IJ] + std::cos(t.TH(K) - MEANDIR[IJ]) * F(IJ, K, MM[IJ]);
+  for (int IJ = 1; IJ <= KIJL; ++IJ) MEANCOSFL[IJ] = t.DELTH * MEANCOSFL[IJ];
+}
+
+// wdirspread.F90:92-140 with peakfri.F90:66-88
+void wdirspread(const Tables& t, int KIJL, int NANG, int NFRE, const S3& F, const V& EMEAN, bool LLPEAKF, V& WDIRSPRD) {
+  const double ONE = 1.0, COEF_FR = t.WETAIL * t.FR(NFRE);
+  V TEMP(KIJL + 1, 0.0);
+  std::vector<int> IFRINDEX(KIJL + 1, NFRE);
+  for (int IJ = 1; IJ <= KIJL; ++IJ) WDIRSPRD[IJ] = 0.0;
+  if (LLPEAKF) {
+    V F1D(KIJL + 1);
+    for (int IJ = 1; IJ <= KIJL; ++IJ) { TEMP[IJ] = 0.0; IFRINDEX[IJ] = NFRE; }
+    for (int M = 1; M <= NFRE; ++M) {
+      for (int IJ = 1; IJ <= KIJL; ++IJ) F1D[IJ] = 0.0;
+      for (int K = 1; K <= NANG; ++K)
+        for (int IJ = 1; IJ <= KIJL; ++IJ) F1D[IJ] = F1D[IJ] + F(IJ, K, M) * t.DELTH;
+      for (int IJ = 1; IJ <= KIJL; ++IJ) if (TEMP[IJ] < F1D[IJ]) { TEMP[IJ] = F1D[IJ]; IFRINDEX[IJ] = M; }
+    }
+    scosfl(t, KIJL, NANG, F, IFRINDEX, WDIRSPRD);
+    for (int IJ = 1; IJ <= KIJL; ++IJ) WDIRSPRD[IJ] = TEMP[IJ] > 0.0 ? std::min(WDIRSPRD[IJ] / TEMP[IJ], ONE) : ONE;
+  } else {
+    for (int M = 1; M <= NFRE; ++M) {
+      for (int IJ = 1; IJ <= KIJL; ++IJ) IFRINDEX[IJ] = M;
+      scosfl(t, KIJL, NANG, F, IFRINDEX, TEMP);
+      for (int IJ = 1; IJ <= KIJL; ++IJ) WDIRSPRD[IJ] = WDIRSPRD[IJ] + TEMP[IJ] * t.DFIM(M);
+    }
+    for (int IJ = 1; IJ <= KIJL; ++IJ) WDIRSPRD[IJ] = WDIRSPRD[IJ] / t.DELTH + TEMP[IJ] * COEF_FR;
+    for (int IJ = 1; IJ <= KIJL; ++IJ) WDIRSPRD[IJ] = EMEAN[IJ] > t.EPSMIN ? std::min(WDIRSPRD[IJ] / EMEAN[IJ], ONE) : ONE;
+  }
+  for (int IJ = 1; IJ <= KIJL; ++IJ) WDIRSPRD[IJ] = std::sqrt(2.0 * (ONE - WDIRSPRD[IJ]));
+}
+
+// dominant_period.F90:63-123
+void dominant_period(const Tables& t, int KIJL, int NANG, int NFRE, const S3& F, V& DP) {
+  const double FLTHRS = 0.1;
+  V EM(KIJL + 1, 0.0), FCROP(KIJL + 1, 0.0), F1D4((size_t)(KIJL + 1) * (NFRE + 1), 0.0);
+  for (int IJ = 1; IJ <= KIJL; ++IJ) DP[IJ] = 0.0;
+  for (int M = 1; M <= NFRE; ++M)
+    for (int K = 1; K <= NANG; ++K)
+      for (int IJ = 1; IJ <= KIJL; ++IJ) if (F(IJ, K, M) > FCROP[IJ]) FCROP[IJ] = F(IJ, K, M);
+  for (int IJ = 1; IJ <= KIJL; ++IJ) FCROP[IJ] = FLTHRS * FCROP[IJ];
+  auto f1 = [&](int IJ, int M) -> double& { return F1D4[(size_t)M * (KIJL + 1) + IJ]; };
+  for (int M = 1; M <= NFRE; ++M)
+    for (int K = 1; K <= NANG; ++K)
+      for (int IJ = 1; IJ <= KIJL; ++IJ) if (F(IJ, K, M) > FCROP[IJ]) f1(IJ, M) = f1(IJ, M) + F(IJ, K, M) * t.DELTH;
+  for (int M = 1; M <= NFRE; ++M)
+    for (int IJ = 1; IJ <= KIJL; ++IJ) {
+      const double x = f1(IJ, M);
+      f1(IJ, M) = (x * x) * (x * x);   // F1D4**4
+      EM[IJ] = EM[IJ] + t.DFIM(M) * f1(IJ, M);
+      DP[IJ] = DP[IJ] + t.DFIMFR(M) * f1(IJ, M);
+    }
+  for (int IJ = 1; IJ <= KIJL; ++IJ) DP[IJ] = (EM[IJ] > 0.0 && DP[IJ] > t.EPSMIN) ? EM[IJ] / DP[IJ] : 0.0;
+}
+
+struct SepOut { V ESWELL, FSWELL, THSWELL, P1SWELL, P2SWELL, SPRDSWELL, ESEA, FSEA, THWISEA, P1SEA, P2SEA, SPRDSEA; };
+
+// sepwisw.F90:128-300, LLPARTITION = .FALSE. (mpcrtbl.F90:535), CLDOMAIN /= 's'
+void sepwisw(const Tables& t, int KIJL, int NANG, int NFRE, const S3& FL1, const S3& XLLWS, const double* CINV /*(KIJL,NFRE)*/,
+             const double* UFRIC, const double* WDWAVE, const V& COSWDIF /*(KIJL,NANG) 1-based*/, SepOut& o) {
+  const double FRIC = 28.0, OLDWSFC = 1.2;   // yowfred.F90:81-82
+  const double COEF = OLDWSFC * FRIC;
+  auto cwd = [&](int IJ, int K) { return COSWDIF[(size_t)(K - 1) * KIJL + IJ]; };
+  V R(KIJL + 1), XINVWVAGE((size_t)KIJL * NFRE + 1), DIRCOEF((size_t)KIJL * NANG + 1);
+  auto xin = [&](int IJ, int M) -> double& { return XINVWVAGE[(size_t)(M - 1) * KIJL + IJ]; };
+  auto dco = [&](int IJ, int K) -> double& { return DIRCOEF[(size_t)(K - 1) * KIJL + IJ]; };
+  W3 SWM(KIJL, NANG, NFRE), F1(KIJL, NANG, NFRE);
+  for (V* v : {&o.ESWELL, &o.FSWELL, &o.THSWELL, &o.P1SWELL, &o.P2SWELL, &o.SPRDSWELL, &o.ESEA, &o.FSEA, &o.THWISEA, &o.P1SEA,
+               &o.P2SEA, &o.SPRDSEA}) v->assign(KIJL + 1, 0.0);
+  for (int M = 1; M <= NFRE; ++M) for (int IJ = 1; IJ <= KIJL; ++IJ) xin(IJ, M) = UFRIC[IJ - 1] * CINV[(size_t)(M - 1) * KIJL + IJ - 1];
+  for (int K = 1; K <= NANG; ++K) for (int IJ = 1; IJ <= KIJL; ++IJ) dco(IJ, K) = COEF * cwd(IJ, K);
+  for (int M = 1; M <= NFRE; ++M)
+    for (int K = 1; K <= NANG; ++K)
+      for (int IJ = 1; IJ <= KIJL; ++IJ) {
+        if (XLLWS(IJ, K, M) != 0.0) SWM(IJ, K, M) = 0.0;
+        else {
+          const double CHECKTA = xin(IJ, M) * dco(IJ, K);
+          SWM(IJ, K, M) = CHECKTA >= 1.0 ? 0.0 : 1.0;
+        }
+      }
+  // swell / windsea mean frequencies -> reset of the wind sector (sepwisw.F90:166-212)
+  for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = 1; IJ <= KIJL; ++IJ) F1(IJ, K, M) = FL1(IJ, K, M) * SWM(IJ, K, M);
+  femean_out(t, KIJL, NANG, NFRE, F1.view(), o.ESWELL, o.FSWELL);
+  for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = 1; IJ <= KIJL; ++IJ) F1(IJ, K, M) = std::max(FL1(IJ, K, M) - F1(IJ, K, M), 0.0);
+  femean_out(t, KIJL, NANG, NFRE, F1.view(), o.ESEA, o.FSEA);
+  for (int IJ = 1; IJ <= KIJL; ++IJ) R[IJ] = o.FSWELL[IJ] > 0.96 * o.FSEA[IJ] ? 1.0 : 0.0;
+  for (int K = 1; K <= NANG; ++K) for (int IJ = 1; IJ <= KIJL; ++IJ) dco(IJ, K) = R[IJ] * COEF * sign(1.0, 0.4 + cwd(IJ, K));
+  for (int M = 1; M <= NFRE; ++M)
+    for (int K = 1; K <= NANG; ++K)
+      for (int IJ = 1; IJ <= KIJL; ++IJ) { const double CHECKTA = xin(IJ, M) * dco(IJ, K); if (CHECKTA >= 1.0) SWM(IJ, K, M) = 0.0; }
+  // connect the low-frequency boundary of the windsea area (sepwisw.F90:216-226)
+  for (int IJ = 1; IJ <= KIJL; ++IJ)
+    for (int K = 1; K <= NANG; ++K)
+      for (int M = NFRE; M >= 2; --M) {
+        if (SWM(IJ, K, M) == 1.0 && SWM(IJ, K, M - 1) == 1.0) break;
+        else if (SWM(IJ, K, M) == 0.0 && SWM(IJ, K, M - 1) == 1.0) { if (FL1(IJ, K, M) >= FL1(IJ, K, M - 1)) SWM(IJ, K, M - 1) = 0.0; }
+      }
+  for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = 1; IJ <= KIJL; ++IJ) F1(IJ, K, M) = std::max(FL1(IJ, K, M), t.EPSMIN) * SWM(IJ, K, M);
+  // total swell (sepwisw.F90:254-265)
+  femean_out(t, KIJL, NANG, NFRE, F1.view(), o.ESWELL, o.FSWELL);
+  sthq(t, KIJL, NANG, NFRE, F1.view(), o.THSWELL);
+  mwp12(t, KIJL, NANG, 1, F1.view(), o.P1SWELL);
+  mwp12(t, KIJL, NANG, 2, F1.view(), o.P2SWELL);
+  wdirspread(t, KIJL, NANG, NFRE, F1.view(), o.ESWELL, true, o.SPRDSWELL);
+  // wind sea (sepwisw.F90:271-298)
+  for (int M = 1; M <= NFRE; ++M)
+    for (int K = 1; K <= NANG; ++K)
+      for (int IJ = 1; IJ <= KIJL; ++IJ) {
+        if (cwd(IJ, K) > 0.8 && M >= NFRE / 2) {
+          const double c2 = cwd(IJ, K) * cwd(IJ, K);
+          F1(IJ, K, M) = std::max(FL1(IJ, K, M) - F1(IJ, K, M) + t.EPSMIN * (c2 * c2), 0.0);
+        } else F1(IJ, K, M) = std::max(FL1(IJ, K, M) - F1(IJ, K, M), 0.0);
+      }
+  femean_out(t, KIJL, NANG, NFRE, F1.view(), o.ESEA, o.FSEA);
+  sthq(t, KIJL, NANG, NFRE, F1.view(), o.THWISEA);
+  for (int IJ = 1; IJ <= KIJL; ++IJ) if (o.ESEA[IJ] <= 1.0e-9) o.THWISEA[IJ] = WDWAVE[IJ - 1];
+  mwp12(t, KIJL, NANG, 1, F1.view(), o.P1SEA);
+  mwp12(t, KIJL, NANG, 2, F1.view(), o.P2SEA);
+  wdirspread(t, KIJL, NANG, NFRE, F1.view(), o.ESEA, true, o.SPRDSEA);
+}
+
+// weflux.F90:70-140
+void weflux(const Tables& t, int KIJL, int NANG, int NFRE, const S3& FL1, const double* CGROUP, V& WEFMAG, V& WEFDIR) {
+  V TEMP(KIJL + 1), TEMPX(KIJL + 1), TEMPY(KIJL + 1), WEFX(KIJL + 1, 0.0), WEFY(KIJL + 1, 0.0);
+  for (int IJ = 1; IJ <= KIJL; ++IJ) WEFMAG[IJ] = 0.0;
+  const double ROG = t.ROWATER * t.G;
+  const double DELT = t.FRTAIL * t.DELTH * t.G / (2.0 * t.ZPI);
+  for (int M = 1; M <= NFRE + 1; ++M) {   // M = NFRE+1: the tail block (weflux.F90:108-130) without CGROUP
+    const bool tail = M == NFRE + 1;
+    const int MM = tail ? NFRE : M;
+    for (int IJ = 1; IJ <= KIJL; ++IJ) {
+      const double FCG = tail ? FL1(IJ, 1, MM) : FL1(IJ, 1, MM) * CGROUP[(size_t)(MM - 1) * KIJL + IJ - 1];
+      TEMP[IJ] = FCG; TEMPX[IJ] = FCG * t.SINTH(1); TEMPY[IJ] = FCG * t.COSTH(1);
+    }
+    for (int K = 2; K <= NANG; ++K)
+      for (int IJ = 1; IJ <= KIJL; ++IJ) {
+        const double FCG = tail ? FL1(IJ, K, MM) : FL1(IJ, K, MM) * CGROUP[(size_t)(MM - 1) * KIJL + IJ - 1];
+        TEMP[IJ] = TEMP[IJ] + FCG; TEMPX[IJ] = TEMPX[IJ] + FCG * t.SINTH(K); TEMPY[IJ] = TEMPY[IJ] + FCG * t.COSTH(K);
+      }
+    const double w = tail ? DELT : t.DFIM(MM);
+    for (int IJ = 1; IJ <= KIJL; ++IJ) { WEFMAG[IJ] = WEFMAG[IJ] + w * TEMP[IJ]; WEFX[IJ] = WEFX[IJ] + w * TEMPX[IJ]; WEFY[IJ] = WEFY[IJ] + w * TEMPY[IJ]; }
+  }
+  for (int IJ = 1; IJ <= KIJL; ++IJ) WEFMAG[IJ] = ROG * WEFMAG[IJ];
+  for (int IJ = 1; IJ <= KIJL; ++IJ) if (WEFY[IJ] == 0.0) WEFY[IJ] = t.EPSMIN;
+  for (int IJ = 1; IJ <= KIJL; ++IJ) WEFDIR[IJ] = std::atan2(WEFX[IJ], WEFY[IJ]);
+  for (int IJ = 1; IJ <= KIJL; ++IJ) if (WEFDIR[IJ] < 0.0) WEFDIR[IJ] = WEFDIR[IJ] + t.ZPI;
+}
+}  // namespace
+
+// newwind.F90:105-167 for ICODE_WND = 3: FF_NOW <- FF_NEXT with the low-wind cap on the first-guess wave stress
+void newwind(Model& m, int ir, const Fields& nx) {
+  const Tables& t = m.tab;
+  Fields& f = m.fld[ir];
+  const double WSPMIN_RESET_TAUW = 4.0;   // yowwind.F90:19
+  const double WGHT = 1.0 / std::max(WSPMIN_RESET_TAUW, t.EPSMIN);
+  const RankDecomp& r = m.ranks[ir];
+  for (int ICHNK = 1; ICHNK <= r.NCHNK; ++ICHNK) {
+    for (int IJ = 1; IJ <= r.NPROMA; ++IJ) {
+      f.WSWAVE(IJ, ICHNK) = nx.WSWAVE.d[(IJ - 1) + (size_t)r.NPROMA * (ICHNK - 1)];
+      if (f.WSWAVE(IJ, ICHNK) < WSPMIN_RESET_TAUW) {
+        const double w = f.WSWAVE(IJ, ICHNK);
+        const double TLWMAX = WGHT * (t.ACD + t.BCD * w) * (w * w * w);
+        f.TAUW(IJ, ICHNK) = std::min(f.TAUW(IJ, ICHNK), TLWMAX);
+      }
+    }
+    for (int IJ = 1; IJ <= r.NPROMA; ++IJ) {
+      const size_t o = (IJ - 1) + (size_t)r.NPROMA * (ICHNK - 1);
+      f.WDWAVE(IJ, ICHNK) = nx.WDWAVE.d[o]; f.AIRD(IJ, ICHNK) = nx.AIRD.d[o]; f.WSTAR(IJ, ICHNK) = nx.WSTAR.d[o];
+      f.CICOVER(IJ, ICHNK) = nx.CICOVER.d[o]; f.CITHICK(IJ, ICHNK) = nx.CITHICK.d[o];
+      f.USTRA(IJ, ICHNK) = nx.USTRA.d[o]; f.VSTRA(IJ, ICHNK) = nx.VSTRA.d[o];
+    }
+  }
+}
+
+bool outparam_supported(int itg) {
+  static const int ok[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 12, 13, 14, 15, 16, 20, 21, 22, 23, 24, 25, 26, 27, 28, 32, 35, 36, 37, 38,
+                           39, 40, 41, 53, 54, 55, 56, 62, 63, 73, 74, 75, 76, 77};
+  for (int v : ok) if (v == itg) return true;
+  return false;
+}
+
+// outblock.F90:150-610 for one chunk; BOUT (KIJL, NIPRMOUT).  sel.itg[c] = reference parameter number of column c+1.
+void outblock(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK, const OutSel& sel, double* BOUT) {
+  const int NANG = c.nang, NFRE = c.nfre, NTRAIN = 3, NTEWH = 6;   // yowcout.F90:19, mpcrtbl.F90:373-399
+  const S3 FL1{&f.FL1(1, 1, 1, ICHNK), KIJL, NANG}, XLLWS{&f.XLLWS(1, 1, 1, ICHNK), KIJL, NANG};
+  auto p1 = [&](ArrD& a) { return &a(1, ICHNK); };
+  const double *CINV = &f.CINV(1, 1, ICHNK), *CGROUP = &f.CGROUP(1, 1, ICHNK);
+  const double *UFRIC = p1(f.UFRIC), *WSWAVE = p1(f.WSWAVE), *WDWAVE = p1(f.WDWAVE), *CICOVER = p1(f.CICOVER);
+  auto col = [&](int itg) -> double* {   // ITOBOUT
+    for (int i = 0; i < sel.n; ++i) if (sel.itg[i] == itg) return BOUT + (size_t)i * KIJL - 1;   // 1-based IJ
+    return nullptr;
+  };
+  for (size_t i = 0; i < (size_t)KIJL * sel.n; ++i) BOUT[i] = 0.0;
+  // output spectrum (outblock.F90:168-194): IREFRA = 0, LSECONDORDER = F; noise-level restructuring under sea ice
+  W3 FL2ND(KIJL, NANG, NFRE);
+  for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = 1; IJ <= KIJL; ++IJ) FL2ND(IJ, K, M) = FL1(IJ, K, M);
+  if (c.licerun && !c.lmaskice) {
+    V ZTHRS(KIJL + 1), ZRDUC(KIJL + 1);
+    for (int IJ = 1; IJ <= KIJL; ++IJ) ZTHRS[IJ] = (1.0 - 0.9 * std::min(CICOVER[IJ - 1], 0.99)) * c.flmin;
+    for (int M = 1; M <= NFRE; ++M) {
+      for (int IJ = 1; IJ <= KIJL; ++IJ) ZRDUC[IJ] = std::exp(-10.0 * (t.FR(M) * t.FR(M)) / std::sqrt(std::max(WSWAVE[IJ - 1], 1.0)));
+      for (int K = 1; K <= NANG; ++K)
+        for (int IJ = 1; IJ <= KIJL; ++IJ)
+          if (FL2ND(IJ, K, M) <= ZTHRS[IJ]) FL2ND(IJ, K, M) = std::max(ZRDUC[IJ] * FL2ND(IJ, K, M), ZTHRS[IJ] * (ZRDUC[IJ] * ZRDUC[IJ]));
+    }
+  }
+  V COSWDIF((size_t)KIJL * NANG + 1);
+  for (int K = 1; K <= NANG; ++K) for (int IJ = 1; IJ <= KIJL; ++IJ) COSWDIF[(size_t)(K - 1) * KIJL + IJ] = std::cos(t.TH(K) - WDWAVE[IJ - 1]);
+  V EM(KIJL + 1), FM(KIJL + 1), DP(KIJL + 1), TMP(KIJL + 1), TMP2(KIJL + 1);
+  femean_out(t, KIJL, NANG, NFRE, FL2ND.view(), EM, FM);
+  dominant_period(t, KIJL, NANG, NFRE, FL2ND.view(), DP);
+  SepOut so;
+  sepwisw(t, KIJL, NANG, NFRE, FL1, XLLWS, CINV, UFRIC, WDWAVE, COSWDIF, so);
+  auto todeg = [&](double th) { return std::fmod(t.DEG * th + 180.0, 360.0); };
+  auto invf = [&](double fq) { return fq > 0.0 ? 1.0 / fq : sel.zmiss; };
+  double* b;
+  if ((b = col(1))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = 4.0 * std::sqrt(std::max(EM[IJ], 0.0));
+  if ((b = col(2))) { sthq(t, KIJL, NANG, NFRE, FL2ND.view(), TMP); for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = todeg(TMP[IJ]); }
+  if ((b = col(3))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = invf(FM[IJ]);
+  if ((b = col(4))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = UFRIC[IJ - 1];
+  if ((b = col(5))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = todeg(WDWAVE[IJ - 1]);
+  if ((b = col(6))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = DP[IJ] > 0.0 ? DP[IJ] : sel.zmiss;
+  if ((b = col(7))) {   // outbeta.F90:66-91 (LLGCBZ0 = F)
+    const double AMAX = 0.02, BMAX = 0.01;
+    const double *Z0M = p1(f.Z0M), *Z0B = p1(f.Z0B), *CHRNCK = p1(f.CHRNCK);
+    (void)Z0M; (void)Z0B;
+    for (int IJ = 1; IJ <= KIJL; ++IJ) {
+      const double ALPHAMAXU10 = std::min(t.ALPHAMAX, AMAX + BMAX * WSWAVE[IJ - 1]);
+      const double USM = 1.0 / std::max(UFRIC[IJ - 1], t.EPSUS);
+      const double BETAM = std::max(std::min(CHRNCK[IJ - 1], ALPHAMAXU10), t.ALPHAMIN);
+      const double Z0ATM = c.rnum * USM + t.GM1 * BETAM * (UFRIC[IJ - 1] * UFRIC[IJ - 1]);
+      const double q = t.XKAPPA / std::log(1.0 + t.XNLEV / Z0ATM);
+      b[IJ] = std::min(q * q, 0.01);
+    }
+  }
+  if ((b = col(8))) { const double* TAUW = p1(f.TAUW); for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = TAUW[IJ - 1] / std::max(UFRIC[IJ - 1] * UFRIC[IJ - 1], t.EPSUS); }
+  if ((b = col(10))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = WSWAVE[IJ - 1];
+  if ((b = col(11))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = 4.0 * std::sqrt(std::max(so.ESEA[IJ], 0.0));
+  if ((b = col(12))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = 4.0 * std::sqrt(std::max(so.ESWELL[IJ], 0.0));
+  if ((b = col(13))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = todeg(so.THWISEA[IJ]);
+  if ((b = col(14))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = todeg(so.THSWELL[IJ]);
+  if ((b = col(15))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = invf(so.FSEA[IJ]);
+  if ((b = col(16))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = invf(so.FSWELL[IJ]);
+  if ((b = col(20))) { mwp12(t, KIJL, NANG, 1, FL2ND.view(), TMP); for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = TMP[IJ]; }
+  if ((b = col(21))) { mwp12(t, KIJL, NANG, 2, FL2ND.view(), TMP); for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = TMP[IJ]; }
+  if ((b = col(22))) { wdirspread(t, KIJL, NANG, NFRE, FL2ND.view(), EM, false, TMP); for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = TMP[IJ]; }
+  struct { int itg; V* v; } sw[] = {{23, &so.P1SEA}, {24, &so.P1SWELL}, {25, &so.P2SEA}, {26, &so.P2SWELL}, {27, &so.SPRDSEA}, {28, &so.SPRDSWELL}};
+  for (auto& e : sw) if ((b = col(e.itg))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = (*e.v)[IJ];
+  struct { int itg; ArrD* a; } cp[] = {{32, &f.DEPTH}, {35, &f.USTOKES}, {36, &f.VSTOKES}, {37, &f.UCUR}, {38, &f.VCUR}, {39, &f.PHIEPS},
+                                       {40, &f.PHIAW}, {41, &f.TAUOC}, {44 + 3 * NTRAIN, &f.AIRD}, {45 + 3 * NTRAIN, &f.WSTAR},
+                                       {46 + 3 * NTRAIN, &f.CICOVER}, {47 + 3 * NTRAIN, &f.CITHICK},
+                                       {58 + 3 * NTRAIN + NTEWH, &f.TAUXD}, {59 + 3 * NTRAIN + NTEWH, &f.TAUYD},
+                                       {60 + 3 * NTRAIN + NTEWH, &f.TAUOCXD}, {61 + 3 * NTRAIN + NTEWH, &f.TAUOCYD}};
+  for (auto& e : cp) if ((b = col(e.itg))) { const double* s = p1(*e.a); for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = s[IJ - 1]; }
+  if (col(53 + 3 * NTRAIN) || col(54 + 3 * NTRAIN)) {
+    weflux(t, KIJL, NANG, NFRE, FL1, CGROUP, TMP, TMP2);
+    if ((b = col(53 + 3 * NTRAIN))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = TMP[IJ];
+    if ((b = col(54 + 3 * NTRAIN))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = todeg(TMP2[IJ]);
+  }
+  if ((b = col(62 + 3 * NTRAIN + NTEWH))) { const double* s = p1(f.PHIOCD); for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = std::max(-s[IJ - 1], 0.0); }
+  // outsetwmask.F90:62-78
+  for (int i = 0; i < sel.n; ++i) {
+    double* bc = BOUT + (size_t)i * KIJL - 1;
+    if (c.licerun && sel.llsource && sel.icemask[i] == 1)
+      for (int IJ = 1; IJ <= KIJL; ++IJ) if (CICOVER[IJ - 1] > c.cithrsh) bc[IJ] = sel.zmiss;
+    if (sel.seamask[i] == 1)
+      for (int IJ = 1; IJ <= KIJL; ++IJ) { const int io = f.IODP(IJ, ICHNK); bc[IJ] = bc[IJ] * io + (1 - io) * sel.zmiss; }
+  }
+}
+
+// mpminmaxavg.F90:68-195 over all emulated ranks.  global = LLNORMWAMOUT_GLOBAL: sums in the ORIGINAL global point order
+// on one rank (reproducible for any NPROC); otherwise per-rank partial sums combined in rank order (MPL_ALLREDUCE).
+void mpminmaxavg(Model& m, const OutSel& sel, const std::vector<std::vector<double>>& bout, bool global, double* WNORM /*(4,NIPRMOUT)*/) {
+  const int NI = sel.n;
+  const double HUGE_ = std::numeric_limits<double>::max();
+  if (global) {
+    std::vector<double> ZGLOBAL(m.grid.NIBLO + 1);
+    for (int it = 0; it < NI; ++it) {
+      for (int ir = 0; ir < m.cfg.npr; ++ir) {
+        const RankDecomp& r = m.ranks[ir];
+        for (int ICHNK = 1; ICHNK <= r.NCHNK; ++ICHNK)
+          for (int IJ = 1; IJ <= r.KIJL4CHNK(ICHNK); ++IJ)
+            ZGLOBAL[r.IJFROMCHNK(IJ, ICHNK)] = bout[ir][(IJ - 1) + (size_t)r.NPROMA * (it + (size_t)NI * (ICHNK - 1))];
+      }
+      double ZSUM = 0.0, ZMIN = HUGE_, ZMAX = -HUGE_;
+      int ICOUNT = 0;
+      for (int IJOLD = 1; IJOLD <= m.grid.NIBLO; ++IJOLD) {
+        const int IJ = (m.cfg.ll1d || m.cfg.npr == 1) ? IJOLD : m.grid.IJ2NEWIJ(IJOLD);
+        if (ZGLOBAL[IJ] != sel.zmiss) { ICOUNT = ICOUNT + 1; ZSUM = ZSUM + ZGLOBAL[IJ]; ZMIN = std::min(ZMIN, ZGLOBAL[IJ]); ZMAX = std::max(ZMAX, ZGLOBAL[IJ]); }
+      }
+      WNORM[4 * it + 0] = ZSUM / std::max(ICOUNT, 1); WNORM[4 * it + 1] = ZMIN; WNORM[4 * it + 2] = ZMAX; WNORM[4 * it + 3] = ICOUNT;
+    }
+    return;
+  }
+  for (int it = 0; it < NI; ++it) {
+    double ZSUMT = 0.0, ZCNT = 0.0, ZMIN = HUGE_, ZMAX = -HUGE_;
+    for (int ir = 0; ir < m.cfg.npr; ++ir) {
+      const RankDecomp& r = m.ranks[ir];
+      double ZSUM = 0.0, ZC = 0.0;
+      for (int ICHNK = 1; ICHNK <= r.NCHNK; ++ICHNK)
+        for (int IPRM = 1; IPRM <= r.KIJL4CHNK(ICHNK); ++IPRM) {
+          const double v = bout[ir][(IPRM - 1) + (size_t)r.NPROMA * (it + (size_t)NI * (ICHNK - 1))];
+          if (v != sel.zmiss) { ZSUM = ZSUM + v; ZC = ZC + 1.0; ZMIN = std::min(ZMIN, v); ZMAX = std::max(ZMAX, v); }
+        }
+      ZSUMT += ZSUM; ZCNT += ZC;
+    }
+    WNORM[4 * it + 1] = ZMIN; WNORM[4 * it + 2] = ZMAX; WNORM[4 * it + 3] = ZCNT;
+    WNORM[4 * it + 0] = ZCNT < 1.0 ? -HUGE_ : ZSUMT / ZCNT;
+  }
+}
+
+}  // namespace orc

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from common import CASES, make_oracle, relerr
+from common import CASES, OUT_ICE, OUT_ITG, OUT_SEA, compare_bout, make_oracle, relerr
 from ecwam_b200 import lib as L, model as M, synth
 
 
@@ -49,6 +49,18 @@ def main():
         mij_ok = bool((w.get_field("mij") == o.get_field("MIJ")[w.own]).all())
         print("rank %d %s: propag bit-exact %s, FL1 rel err after 3 steps %.2e, MIJ exact %s" % (rank, case, same, e, mij_ok), flush=True)
         ok = ok and same and e < 1e-12 and mij_ok
+        # OUTBS + WAMNORM over the ranks: the global-order norm is the reference's reproducible one (mpminmaxavg.F90:121-153)
+        b = o.outbs(OUT_ITG, OUT_ICE, OUT_SEA)
+        a = w.outbs(OUT_ITG, OUT_ICE, OUT_SEA)
+        compare_bout(a, b[:, w.own])
+        for glob in (True, False):
+            wa, wb = w.outwnorm(glob), o.outwnorm(glob)
+            circ = np.array([itg in (2, 5, 13, 14, 63, 22, 27, 28) for itg in OUT_ITG])
+            scale = np.maximum(np.maximum(np.abs(wb[:, 1]), np.abs(wb[:, 2])), 1e-6)[:, None]
+            nerr = float((np.abs(wa[:, :3] - wb[:, :3]) / scale)[~circ].max())
+            cnt_ok = bool((wa[:, 3] == wb[:, 3]).all())
+            print("rank %d %s: WAMNORM global=%s max rel err %.2e, counts equal %s" % (rank, case, glob, nerr, cnt_ok), flush=True)
+            ok = ok and nerr < 1e-10 and cnt_ok
         w.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

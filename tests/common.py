@@ -66,3 +66,58 @@ def relerr(a, b):
 
 OUT_FIELDS = ("UFRIC", "TAUW", "TAUWDIR", "Z0M", "Z0B", "CHRNCK", "USTOKES", "VSTOKES", "TAUXD", "TAUYD", "TAUOCXD", "TAUOCYD",
               "TAUOC", "PHIOCD", "PHIEPS", "PHIAW")
+
+# ---- the steps either side of the hot path: NEWWIND, OUTBS/OUTBLOCK, OUTWNORM ------------------------------------------
+# OUTBLOCK parameters built here (numbering of mpcrtbl.F90, NTRAIN = 3) with MPCRTBL's mask flags
+# (IPRMINFO(:,6) sea-ice mask, IPRMINFO(:,7) shallow points to missing; mpcrtbl.F90:93-431)
+OUT_PARAMS = {1: (1, 1), 2: (1, 1), 3: (1, 1), 4: (0, 1), 5: (0, 0), 6: (1, 1), 7: (0, 0), 8: (1, 1), 10: (0, 0), 11: (1, 1),
+              12: (1, 1), 13: (1, 1), 14: (1, 1), 15: (1, 1), 16: (1, 1), 20: (1, 1), 21: (1, 1), 22: (1, 1), 23: (1, 1),
+              24: (1, 1), 25: (1, 1), 26: (1, 1), 27: (1, 1), 28: (1, 1), 32: (0, 1), 35: (1, 1), 36: (1, 1), 37: (0, 1),
+              38: (0, 1), 39: (0, 1), 40: (0, 1), 41: (0, 1), 53: (0, 0), 54: (0, 0), 55: (0, 1), 56: (0, 1), 62: (1, 1),
+              63: (1, 1), 73: (0, 1), 74: (0, 1), 75: (0, 1), 76: (0, 1), 77: (0, 1)}
+OUT_ITG = sorted(OUT_PARAMS)
+OUT_ICE = [OUT_PARAMS[i][0] for i in OUT_ITG]
+OUT_SEA = [OUT_PARAMS[i][1] for i in OUT_ITG]
+OUT_DIRECTIONS = {2: 1, 13: 11, 14: 12, 63: 62, 5: None}    # direction column -> column of the matching height / magnitude
+OUT_COPIES = (4, 10, 32, 35, 36, 37, 38, 39, 40, 41, 53, 54, 55, 56, 73, 74, 75, 76, 77)
+ZMISS = -999.0
+
+
+def next_forcing(f, k=1):
+    """A second, different forcing set (what GETWND would deliver for the next wind step): rotated and rescaled winds."""
+    n = f["WSWAVE"].size
+    ramp = 0.5 + 1.2 * ((np.arange(n) * 7919 * k) % 101) / 100.0
+    return dict(WSWAVE=np.maximum(f["WSWAVE"] * ramp, 0.3), WDWAVE=np.mod(f["WDWAVE"] + 0.9 * k, 2 * np.pi), AIRD=f["AIRD"] * 1.02,
+                WSTAR=f["WSTAR"] * 0.5, CICOVER=np.clip(f["CICOVER"] * 1.1, 0, 1), CITHICK=f["CITHICK"] + 0.1,
+                USTRA=0.01 * np.cos(np.arange(n)), VSTRA=0.01 * np.sin(np.arange(n)))
+
+
+def compare_bout(a, b, itgs=OUT_ITG):
+    """a (CUDA) vs b (oracle) BOUT[column, point]; the tolerances are the ones stated in tests/test_gpu_output.py."""
+    worst = {}
+    for i, itg in enumerate(itgs):
+        x, y = a[i], b[i]
+        assert np.array_equal(x == ZMISS, y == ZMISS), "parameter %d: missing-value pattern differs" % itg
+        ok = y != ZMISS
+        x, y = x[ok], y[ok]
+        if itg in OUT_COPIES:            # copies of model fields: as close as the fields themselves (exactness vs the own
+            scale = np.maximum(np.abs(y), 1e-8 * max(float(np.abs(y).max()), 1e-300))   # fields is checked by the caller)
+            worst[itg] = float((np.abs(x - y) / scale).max())
+            assert worst[itg] <= 1e-10, "parameter %d (copy of a field): relative difference %g" % (itg, worst[itg])
+            continue
+        if itg in OUT_DIRECTIONS:
+            d = np.abs(x - y)
+            d = np.minimum(d, 360.0 - d)
+            ref = OUT_DIRECTIONS[itg]
+            if ref is not None:          # a mean direction is only defined where there is energy
+                h = b[itgs.index(ref)][ok]
+                d = d[h > 1e-3 * max(h.max(), 1e-300)]
+            worst[itg] = float(d.max()) if d.size else 0.0
+            assert worst[itg] <= 1e-7, "parameter %d: direction differs by %g deg" % (itg, worst[itg])
+        elif itg in (22, 27, 28):        # sqrt(2 (1 - x)) amplifies rounding where the spectrum is narrow
+            worst[itg] = float(np.abs(x - y).max())
+            assert worst[itg] <= 1e-7, "parameter %d: spread differs by %g" % (itg, worst[itg])
+        else:
+            worst[itg] = float((np.abs(x - y) / np.maximum(np.abs(y), 1e-30)).max())
+            assert worst[itg] <= 1e-10, "parameter %d: relative difference %g" % (itg, worst[itg])
+    return worst

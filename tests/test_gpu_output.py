@@ -1,0 +1,94 @@
+"""GPU parity of the steps either side of the hot path (pytest -m gpu): NEWWIND, OUTBS/OUTBLOCK core parameters and the
+WAMNORM statistics, through the C ABI, against the CPU oracle on the same seeded inputs.
+
+Tolerances (written in tests/common.py compare_bout):
+  * missing-value pattern, norm counts, copies of model fields vs the rank's own fields .. exact
+  * heights, periods, drag, fluxes .................................................. relative 1e-10
+  * mean directions (where the matching height is above 1e-3 of its maximum) ....... 1e-7 degrees
+  * directional spreads sqrt(2(1-x)) ................................................ absolute 1e-7
+  * WAMNORM average / minimum / maximum ............................................. relative 1e-10
+(the CUDA kernel sums the frequencies from NFRE down to 1 in one sweep; the reference sums upwards, routine by routine.)
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from common import OUT_ICE, OUT_ITG, OUT_SEA, ZMISS, compare_bout, make_gpu, make_oracle, next_forcing
+from ecwam_b200 import lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+def both(case, steps=3, **extra):
+    g, o, f, fl = make_oracle(case, **extra)
+    _, s, w = make_gpu(case, **extra)
+    for _ in range(steps):
+        assert o.step() == 0 and w.step() == 0
+    w.synchronize()
+    return g, o, f, s, w
+
+
+def check_norms(w, o):
+    for glob in (True, False):
+        a, b = w.outwnorm(glob), o.outwnorm(glob)
+        np.testing.assert_array_equal(a[:, 3], b[:, 3])                                  # non-missing points
+        scale = np.maximum(np.maximum(np.abs(b[:, 1]), np.abs(b[:, 2])), 1e-6)           # an average of signed values cancels
+        circ = np.array([itg in (2, 5, 13, 14, 63) for itg in OUT_ITG])                  # directions, spreads: looser, as in
+        sprd = np.array([itg in (22, 27, 28) for itg in OUT_ITG])                        # compare_bout
+        tight = ~circ & ~sprd
+        for c in range(3):
+            d = np.abs(a[:, c] - b[:, c])
+            assert (d[tight] <= 1e-10 * scale[tight]).all(), (glob, c, [OUT_ITG[i] for i in np.nonzero(tight & (d > 1e-10 * scale))[0]])
+            assert (d[circ] <= 1e-5).all() and (d[sprd] <= 1e-7).all(), (glob, c)
+
+
+@pytest.mark.parametrize("case,extra", [("o48like", {}), ("o48_iphys0", {}), ("o640like", {}), ("o320like", dict(lmaskice=0))])
+def test_outblock_and_norms_match_oracle(built, case, extra):
+    g, o, f, s, w = both(case, **extra)
+    b = o.outbs(OUT_ITG, OUT_ICE, OUT_SEA)
+    a = w.outbs(OUT_ITG, OUT_ICE, OUT_SEA)
+    worst = compare_bout(a, b[:, w.own])
+    assert (b[0] != ZMISS).sum() > 100 and max(worst.values()) < 1e-7
+    # pass-through columns are bit copies of the rank's own fields (outblock.F90:236-238, 290, 404-470)
+    for itg, nm in ((4, "ufric"), (10, "wswave"), (32, "depth"), (35, "ustokes"), (41, "tauoc"), (53, "aird"), (73, "tauxd")):
+        col, fld = a[OUT_ITG.index(itg)], w.get_field(nm)
+        keep = col != ZMISS
+        np.testing.assert_array_equal(col[keep], fld[keep], err_msg=nm)
+    check_norms(w, o)
+
+
+def test_newwind_then_steps(built):
+    g, o, f, s, w = both("o640like", steps=2)
+    nx = next_forcing(f)
+    tauw0 = w.get_field("tauw")
+    o.newwind(nx)
+    w.newwind(nx)
+    for k in ("WSWAVE", "WDWAVE", "AIRD", "WSTAR", "CICOVER", "CITHICK", "USTRA", "VSTRA"):
+        np.testing.assert_array_equal(w.get_field(k), o.get_field(k)[w.own], err_msg=k)   # NEWWIND copies: bit-exact
+    ws = nx["WSWAVE"][w.own]
+    cap = (1.0 / 4.0) * (8.0e-4 + 8.0e-5 * ws) * (ws * ws * ws)                           # newwind.F90:133-139
+    np.testing.assert_allclose(w.get_field("tauw"), np.where(ws < 4.0, np.minimum(tauw0, cap), tauw0), rtol=1e-15)
+    np.testing.assert_allclose(w.get_field("tauw"), o.get_field("TAUW")[w.own], rtol=1e-10)
+    for _ in range(2):
+        assert o.step() == 0 and w.step() == 0
+    w.synchronize()
+    iodp = (np.arange(g.niblo) % 11 != 0).astype(np.int32)                                # some "too shallow" points
+    b = o.outbs(OUT_ITG, OUT_ICE, [0] * len(OUT_ITG))
+    a = w.outbs(OUT_ITG, OUT_ICE, [0] * len(OUT_ITG), iodp=None)
+    compare_bout(a, b[:, w.own])
+    # OUTSETWMASK's sea mask (outsetwmask.F90:72-76) with a caller-supplied IODP
+    a2 = w.outbs(OUT_ITG, OUT_ICE, OUT_SEA, iodp=iodp)
+    for i, itg in enumerate(OUT_ITG):
+        exp = np.where((iodp[w.own] == 0) & bool(OUT_SEA[i]), ZMISS, a[i])
+        np.testing.assert_array_equal(a2[i], exp, err_msg=str(itg))
+
+
+def test_unsupported_parameter_is_rejected(built):
+    g, o, f, s, w = both("o48like", steps=1)
+    for bad in (9, 29, 42, 52, 64, 78):
+        assert w.lib.ecwam_b200_outparam_supported(bad) == 0
+        with pytest.raises(L.EcwamError):
+            w.outbs([1, bad], [1, 1], [1, 1])
+    nx = L.ForcingNext()
+    assert w.lib.ecwam_b200_newwind(w.h, C.byref(nx)) == -1                               # null FF_NEXT members

@@ -1,0 +1,77 @@
+"""CPU tests of the oracle's NEWWIND / OUTBLOCK / WAMNORM restatement (oracle/orc_output.cpp): decomposition independence,
+reproducible global norms (LLNORMWAMOUT_GLOBAL), and an independent numpy restatement of the simple parameters."""
+import numpy as np
+import pytest
+
+from common import OUT_ICE, OUT_ITG, OUT_SEA, ZMISS, make_oracle, next_forcing
+
+
+def run(case, npr, steps=3, **extra):
+    g, o, f, fl = make_oracle(case, npr=npr, **extra)
+    for _ in range(steps):
+        assert o.step() == 0
+    return g, o, f
+
+
+def test_outblock_is_decomposition_independent_and_norms_reproducible(built):
+    res = []
+    for npr in (1, 3):
+        g, o, f = run("o48like", npr)
+        b = o.outbs(OUT_ITG, OUT_ICE, OUT_SEA)
+        res.append((b, o.outwnorm(True), o.outwnorm(False)))
+    np.testing.assert_array_equal(res[0][0], res[1][0])
+    np.testing.assert_array_equal(res[0][1], res[1][1])          # global-order sum: bit-reproducible for any NPROC
+    np.testing.assert_allclose(res[0][2], res[1][2], rtol=1e-12, atol=1e-13)
+    b, wg, wl = res[0]
+    ok = b[0] != ZMISS
+    assert wg[0, 3] == ok.sum() and wl[0, 3] == ok.sum()
+    assert wg[0, 1] == b[0][ok].min() and wg[0, 2] == b[0][ok].max()
+    np.testing.assert_allclose(wg[:, 0], [c[c != ZMISS].mean() for c in b], rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("case", ["o48like", "o640like"])
+def test_outblock_against_numpy(built, case):
+    g, o, f = run(case, 1)
+    b = dict(zip(OUT_ITG, o.outbs(OUT_ITG, [0] * len(OUT_ITG), [0] * len(OUT_ITG))))
+    fl = o.get_fl1()                                             # [m, k, ij]
+    F, A, n = fl.shape
+    fr, dfim, th = o.table("FR"), o.table("DFIM"), o.table("TH")
+    delth = o.table("DELTH")[0]
+    dfimofr = o.table("DFIMOFR")
+    eps = 1e-33
+    t2 = np.maximum(fl, eps).sum(axis=1)
+    em = (t2 * dfim[:, None]).sum(0) + 0.25 * fr[-1] * delth * t2[-1]
+    fm = np.maximum(em / ((t2 * dfimofr[:, None]).sum(0) + 0.2 * delth * t2[-1]), fr[0])
+    np.testing.assert_allclose(b[1], 4 * np.sqrt(em), rtol=1e-12)
+    np.testing.assert_allclose(b[3], 1 / fm, rtol=1e-12)
+    tk = (fl * dfim[:, None, None]).sum(0)                        # [k, ij]
+    thq = np.arctan2((np.sin(th)[:, None] * tk).sum(0), (np.cos(th)[:, None] * tk).sum(0)) % (2 * np.pi)
+    d = np.abs(np.mod(np.degrees(thq) + 180.0, 360.0) - b[2])
+    assert np.minimum(d, 360 - d).max() < 1e-8
+    # wind sea + swell = total (sepwisw.F90: the two spectra partition FL1), heights 11 / 12 vs 1
+    e1, es, ew = (b[1] / 4) ** 2, (b[12] / 4) ** 2, (b[11] / 4) ** 2
+    assert np.abs(es + ew - e1).max() <= 1e-12 * e1.max()
+    # simple copies
+    np.testing.assert_array_equal(b[4], o.get_field("UFRIC"))
+    np.testing.assert_array_equal(b[10], o.get_field("WSWAVE"))
+    np.testing.assert_array_equal(b[77], np.maximum(-o.get_field("PHIOCD"), 0.0))
+    sea = b[1] > 0.01                                           # ice-covered points hold the noise floor only (SETICE)
+    assert (b[22] >= 0).all() and (b[22] <= np.sqrt(2.0)).all() and (b[6][sea] > 0).all() and (b[7] <= 0.01).all()
+
+
+def test_masks_and_newwind(built):
+    g, o, f = run("o48like", 2, steps=1)
+    nx = next_forcing(f)
+    tauw0, ws = o.get_field("TAUW"), nx["WSWAVE"]
+    o.newwind(nx)
+    for k in ("WSWAVE", "WDWAVE", "AIRD", "WSTAR", "CICOVER", "CITHICK"):
+        np.testing.assert_array_equal(o.get_field(k), nx[k])
+    cap = (1.0 / 4.0) * (8.0e-4 + 8.0e-5 * ws) * ws ** 3           # newwind.F90:133-139
+    np.testing.assert_allclose(o.get_field("TAUW"), np.where(ws < 4.0, np.minimum(tauw0, cap), tauw0), rtol=1e-15)
+    assert (ws < 4.0).any() and (o.get_field("TAUW") < tauw0).any()
+    assert o.step() == 0
+    b = o.outbs(OUT_ITG, OUT_ICE, OUT_SEA)
+    ice = o.get_field("CICOVER") > 0.3
+    assert ice.any() and not ice.all()
+    for i, itg in enumerate(OUT_ITG):
+        assert ((b[i] == ZMISS) == (ice & bool(OUT_ICE[i]))).all(), itg      # outsetwmask.F90:62-78 (IODP = 1 everywhere)
