@@ -747,6 +747,61 @@ __host__ __device__ constexpr int stencil_threads(int A, int np) { return ((A * 
 #endif
 #define ST_BOUNDS(NP) __maxnreg__(NP == 2 ? ST_MAXREG : 112)
 
+// scalar closures of one grid point after the sweep: STOKESDRIFT, the new wind-sea mean parameters, WNFLUXES
+// qs: the eight direction sums of the point (stride ST_NPT), pcv: its PC_* constants (stride ST_NPT)
+template <bool LWFLUX>
+__device__ __forceinline__ void stencil_closure(const ImplDev& d, const long long pp, const double* qs, const double* pcv) {
+    const int F = c_dc.F;
+    const long long n = d.npts;
+    const double* s = d.scr;
+    double q[8];
+#pragma unroll
+    for (int x = 0; x < 8; ++x) q[x] = qs[x * ST_NPT];
+    const double snw = pcv[PC_SNW * ST_NPT], csw = pcv[PC_CSW * ST_NPT];
+    const double cicover = d.f.cicover[pp];
+    const double ufric = d.f.ufric[pp], aird = d.f.aird[pp], wsw = d.f.wswave[pp];
+    // STOKESDRIFT closure (stokesdrift.F90:118-142)
+    double us = q[3], vs = q[4];
+    if (c_dc.licerun && c_dc.lwamrsetci && cicover > c_dc.cithrsh) { us = 0.016 * wsw * snw * (1.0 - cicover); vs = 0.016 * wsw * csw * (1.0 - cicover); }
+    d.f.ustokes[pp] = dmin(dmax(us, -1.5), 1.5); d.f.vstokes[pp] = dmin(dmax(vs, -1.5), 1.5);
+    if (LWFLUX) {   // implsch.F90:435-446
+      const double DELT25 = c_dc.WETAIL * c_dc.FR[F - 1] * c_dc.DELTH;
+      const double em2 = c_dc.EPSMIN + q[5] + DELT25 * q[7];
+      const double fm2 = em2 / (c_dc.EPSMIN + q[6] + c_dc.FRTAIL * c_dc.DELTH * q[7]);
+      if (em2 < c_dc.WSEMEAN_MIN) { d.f.wsemean[pp] = c_dc.WSEMEAN_MIN; d.f.wsfmean[pp] = 2. * c_dc.FR[F - 1]; }
+      else { d.f.wsemean[pp] = em2; d.f.wsfmean[pp] = fm2; }
+    }
+    if (c_dc.lcflx) {    // WNFLUXES closure (wnfluxes.F90:222-331, LWNEMOCOU=F)
+      const double PHIOC_ICE = -3.75, PHIAW_ICE = 3.75, C1 = 1.03e-3, C2 = 0.04e-3, P1 = 1.48, P2 = -0.21, CDMAX_LOC = 0.003;
+      const double epsus3 = c_dc.EPSUS * sqrt(c_dc.EPSUS);
+      const double cithrsh_inv = 1.0 / dmax(c_dc.cithrsh, 0.01);
+      const double phiwa = s[S_PHIWA * n + pp];
+      double ooval = 1.0, ustar = ufric;
+      if (c_dc.licerun && c_dc.lwamrsetci && cicover > c_dc.ciblock) {
+        ooval = exp(-dmin(p4(cicover * cithrsh_inv), 10.0));
+        const double u10p = dmax(wsw, c_dc.EPSU10);
+        const double cd_bulk = dmin((C1 + C2 * pow(u10p, P1)) * pow(u10p, P2), CDMAX_LOC);
+        const double cd_wave = sq(ufric / u10p);
+        ustar = dmax(sqrt(ooval * cd_wave + (1.0 - ooval) * cd_bulk) * u10p, c_dc.EPSUS);
+      }
+      const double tau = aird * dmax(sq(ustar), c_dc.EPSUS);
+      double tauxd = tau * snw, tauyd = tau * csw;
+      double tauocxd = tauxd - ooval * q[1], tauocyd = tauyd - ooval * q[2];
+      const double tauoc = dmin(dmax(sqrt(sq(tauocxd) + sq(tauocyd)) / tau, c_dc.TAUOCMIN), c_dc.TAUOCMAX);
+      if (c_dc.lwcouast) {
+        const double ua = d.f.ustra[pp], va = d.f.vstra[pp];
+        if (ua != 0.0 || va != 0.0) { tauxd = ua; tauocxd = ua * tauoc; tauyd = va; tauocyd = va * tauoc; }
+      }
+      d.f.tauxd[pp] = tauxd; d.f.tauyd[pp] = tauyd; d.f.tauocxd[pp] = tauocxd; d.f.tauocyd[pp] = tauocyd; d.f.tauoc[pp] = tauoc;
+      d.f.tauicx[pp] = 0.0; d.f.tauicy[pp] = 0.0;
+      const double xn = aird * dmax(ustar * ustar * ustar, epsus3);
+      double phiocd = ooval * (q[0] - phiwa) + (1.0 - ooval) * PHIOC_ICE * xn;
+      const double phieps = dmin(dmax(phiocd / xn, c_dc.PHIEPSMIN), c_dc.PHIEPSMAX);
+      phiocd = phieps * xn;
+      d.f.phiocd[pp] = phiocd; d.f.phieps[pp] = phieps; d.f.phiaw[pp] = ooval * phiwa / xn + (1.0 - ooval) * PHIAW_ICE;
+    }
+}
+
 // TA = NANG when it is one of the standard grids (compile-time geometry), 0 = run-time geometry (any NANG <= 36)
 template <int TA, int NP, bool LWFLUX>
 __global__ void ST_BOUNDS(NP) k_stencil(ImplDev d, long long p0, long long np, StencilSmem Lrt) {
@@ -1136,56 +1191,457 @@ __global__ void ST_BOUNDS(NP) k_stencil(ImplDev d, long long p0, long long np, S
     qs[x * ST_NPT + pt] = v;
   }
   __syncthreads();
-  if (t < ST_NPT && pbase + t <= plast) {
-    const long long pp = pbase + t;
-    double q[8];
+  if (t < ST_NPT && pbase + t <= plast)
+    stencil_closure<LWFLUX>(d, pbase + t, qs + t, reinterpret_cast<const double*>(sm + L.pc) + t);
+}
+
+
+// =========================================================================================================
+// k_stencil_dp: the same sweep with thread = (TWO ADJACENT DIRECTIONS, one grid point) for the standard grids (compile-time
+// geometry, even NANG).  The shared-memory rows are laid out [row][point][direction + cyclic halo] (direction fastest), so
+//   * the 2*NSDSNTH+1 window of SDISSIP_ARD for both bins of a thread is NSDSNTH+1 aligned 16-byte loads (18 values for
+//     two 17-point windows) instead of 17 per bin pair,
+//   * the two bilinear partners of a DIA quadruplet family (shifts s and s+-1) of both bins are three consecutive values:
+//     one 16-byte + one 8-byte load instead of two 16-byte loads,
+//   * everything that is per grid point (the PC_* constants, the per-(point, frequency) scalars) is an 8-byte load that
+//     eight lanes of a quarter-warp share, instead of a 16-byte load per lane.
+// About 30 % fewer shared-memory wavefronts per bin than the two-points-per-thread mapping, which is what bounds that kernel;
+// any NPROMA (no 16-byte alignment of the global rows is needed: 8-byte cp.async / stores, 8 points x 8 B = 64-byte segments).
+// The point stride of a row is padded to 8 (mod 16) doubles so that the two points of a quarter-warp use disjoint banks.
+// =========================================================================================================
+__host__ __device__ constexpr int dp_hr(int A) { return geo_nsd(A) + (geo_nsd(A) & 1); }            // ring halo (even, >= NSDSNTH)
+__host__ __device__ constexpr int dp_hc(int A) { return geo_hc(A) + (geo_hc(A) & 1); }              // interaction-plane halo (even)
+__host__ __device__ constexpr int dp_pad(int n) { return n + ((8 - (n % 16)) + 16) % 16; }          // -> 8 (mod 16)
+__host__ __device__ constexpr int dp_pst(int A) { return dp_pad(A + 2 * dp_hr(A)); }                // point stride of a ring row [doubles]
+__host__ __device__ constexpr int dp_pstc(int A) { return dp_pad(A + 2 * dp_hc(A)); }               // point stride of an interaction plane
+__host__ __device__ constexpr int dp_threads(int A) { return (((A / 2) * ST_NPT + 31) / 32) * 32; }
+struct DpSmem { unsigned ring, cur, tbs, pc, part, bth0, stage, bsl, mbar, total, RSB, PSB, SSB; };
+__host__ __device__ constexpr DpSmem dp_smem(int A, bool lwflux) {
+  DpSmem s{};
+  const int nth = dp_threads(A), nwarp = nth / 32;
+  s.RSB = (unsigned)dp_pst(A) * ST_NPT * 8;
+  s.PSB = (unsigned)dp_pstc(A) * ST_NPT * 8;
+  s.SSB = (unsigned)nth * 16;
+  unsigned o = 0;
+  s.ring = o; o += ST_RING * s.RSB;
+  s.cur = o; o += 2 * 6 * s.PSB;
+  s.tbs = o; o += 8 * TQ_N * ST_NPT * 8;
+  s.pc = o; o += PC_N * ST_NPT * 8;
+  s.part = o; o += 3u * (unsigned)nwarp * ST_NPT * 8;
+  s.bth0 = o; o += 2 * ST_NPT * 8;
+  s.stage = o; o += (lwflux ? 3 : 2) * s.SSB;
+  s.bsl = o; o += 3 * s.SSB;
+  s.mbar = o; o += 16;
+  s.total = o;
+  return s;
+}
+__device__ __forceinline__ double lds1(const char* sm, unsigned off) { return *reinterpret_cast<const double*>(sm + off); }
+// three consecutive directions starting LO elements from the thread's (even) first direction: one aligned pair + one single
+template <int LO>
+__device__ __forceinline__ void load3(const char* sm, unsigned base, double (&d)[3]) {
+  constexpr bool even = ((LO % 2) + 2) % 2 == 0;
+  if (even) {
+    const Vd<2> a = lds<2>(sm, base + LO * 8);
+    d[0] = a.v[0]; d[1] = a.v[1]; d[2] = lds1(sm, base + (LO + 2) * 8);
+  } else {
+    d[0] = lds1(sm, base + LO * 8);
+    const Vd<2> a = lds<2>(sm, base + (LO + 1) * 8);
+    d[1] = a.v[0]; d[2] = a.v[1];
+  }
+}
+__host__ __device__ constexpr int cmin(int a, int b) { return a < b ? a : b; }
+
+template <int TA, bool LWFLUX>
+__global__ void __maxnreg__(ST_MAXREG) k_stencil_dp(ImplDev d, long long p0, long long np) {
+  extern __shared__ __align__(16) char sm[];
+  typedef Vd<2> V;
+  constexpr int A = TA, NSD = geo_nsd(TA), NS = 2 * NSD + 1, HR = dp_hr(TA), HC = dp_hc(TA);
+  constexpr unsigned PSTB = dp_pst(TA) * 8, PSTCB = dp_pstc(TA) * 8;
+  constexpr DpSmem L = dp_smem(TA, LWFLUX);
+  constexpr unsigned RSB = L.RSB, PSB = L.PSB;
+  constexpr int nwarp = dp_threads(TA) / 32;
+  const int F = c_dc.F;
+  const bool ard = c_dc.iphys == 1;
+  const unsigned smb = (unsigned)__cvta_generic_to_shared(sm);
+  const int t = threadIdx.x;
+  const int lane = t & 31, wq = t >> 5;
+  const int pt = lane >> 2;                          // grid point of the CTA's eight
+  int pr = 4 * wq + (lane & 3);                      // direction pair
+  const bool act = pr < A / 2;                       // lanes beyond NANG/2 pairs shadow the last pair and never store
+  if (!act) pr = A / 2 - 1;
+  const int k0 = 2 * pr;
+  const unsigned po = (unsigned)pt * 8u;
+  const unsigned me_r = (unsigned)pt * PSTB + (unsigned)(k0 + HR) * 8u;     // own pair inside a ring row
+  const unsigned me_c = (unsigned)pt * PSTCB + (unsigned)(k0 + HC) * 8u;    // own pair inside an interaction plane
+  const unsigned me_s = L.stage + (unsigned)t * 16u;                         // own landing slot
+  // ---- points
+  const long long pbase = p0 + (long long)blockIdx.x * ST_NPT;
+  const long long plast = p0 + np - 1;
+  long long pq = pbase + pt;
+  const bool pvalid = pq <= plast;
+  if (!pvalid) pq = plast;
+  const bool dost = act && pvalid;
+  const long long n = d.npts;
+  const double* s = d.scr;
+  const size_t P = (size_t)d.P;
+  const size_t rstr = P * A;
+  const long long pc_ = pq / d.P;
+  const int pi_ = (int)(pq - pc_ * d.P);
+  const size_t off_hi = (size_t)pi_ + P * A * F * (size_t)pc_ + P * (size_t)k0;
+  const double* src_hi = d.f.fl1 + off_hi;
+  const double* src_lo = src_hi;
+  int mlo = 0;
+  if (d.lo_on) {
+    src_lo = d.fl_lo + (size_t)pi_ + P * A * d.lo_F * (size_t)pc_ + P * (size_t)k0;
+    mlo = d.Fr;
+  }
+  double* dst = d.f.fl1 + off_hi;
+  const double* src_in = d.fldin + off_hi;
+  const double* src_xl = d.f.xllws + off_hi;
+
+  // ---- prologue: per-point constants, barrier
+  if (t == 0) mbar_init(smb + L.mbar, 2u * blockDim.x);   // per phase and thread: one arrive + one arrive on completion of its cp.async
+  if (t < ST_NPT) {
+    const long long qp = min(pbase + t, plast);
+    double* pcv = reinterpret_cast<double*>(sm + L.pc) + t;
+    const double wd = d.f.wdwave[qp], ci = d.f.cicover[qp], dep = d.f.depth[qp];
+    double snw, csw;
+    sincos(wd, &snw, &csw);
+    double enhfr = dmax(0.75 * dep * s[S_AKMEAN * n + qp], 0.5);
+    enhfr = 1.0 + (5.5 / enhfr) * (1.0 - .833 * enhfr) * exp(-1.25 * enhfr);
+    const int mijq = (int)s[S_MIJ * n + qp];
+    const bool seticeq = c_dc.licerun && c_dc.lmaskice && ci > c_dc.cithrsh;
+    pcv[PC_FAC * ST_NPT] = s[S_FAC * n + qp];
+    pcv[PC_ENH * ST_NPT] = enhfr;
+    pcv[PC_USFMDELT * ST_NPT] = s[S_USFM * n + qp] * c_dc.delt;
+    pcv[PC_SDSBK * ST_NPT] = (c_dc.lbiwbk && dep < 50.0) ? s[S_SDS * n + qp] : 0.0;
+    pcv[PC_RTAIL * ST_NPT] = 1.0 / d.tbg[((size_t)TQ_TAIL * F + (mijq - 1)) * n + qp];
+    pcv[PC_FLMC * ST_NPT] = (1. - 0.9 * dmin(ci, 0.99)) * c_dc.flmin;
+    pcv[PC_ICEADD * ST_NPT] = seticeq ? dmax(c_dc.EPSMIN, 1.0 - ci) * c_dc.flmin : 0.0;
+    pcv[PC_ICEFREE * ST_NPT] = seticeq ? 0.0 : 1.0;
+    pcv[PC_SNW * ST_NPT] = snw;
+    pcv[PC_CSW * ST_NPT] = csw;
+  }
+  __syncthreads();
+  double sinth[2], costh[2];
+  V flm, iaw;    // FLM(k) = FLMC*max(0,cos(TH(k)-WDWAVE))**2 (implsch.F90:236-247); SETICE's noise floor likewise
+  {
+    const double snw = lds1(sm, L.pc + PC_SNW * 64 + po), csw = lds1(sm, L.pc + PC_CSW * 64 + po);
+    const double flmc = lds1(sm, L.pc + PC_FLMC * 64 + po), ia = lds1(sm, L.pc + PC_ICEADD * 64 + po);
 #pragma unroll
-    for (int x = 0; x < 8; ++x) q[x] = qs[x * ST_NPT + t];
-    const double* pcv = reinterpret_cast<const double*>(sm + L.pc) + t;
-    const double snw = pcv[PC_SNW * ST_NPT], csw = pcv[PC_CSW * ST_NPT];
-    const double cicover = d.f.cicover[pp];
-    const double ufric = d.f.ufric[pp], aird = d.f.aird[pp], wsw = d.f.wswave[pp];
-    // STOKESDRIFT closure (stokesdrift.F90:118-142)
-    double us = q[3], vs = q[4];
-    if (c_dc.licerun && c_dc.lwamrsetci && cicover > c_dc.cithrsh) { us = 0.016 * wsw * snw * (1.0 - cicover); vs = 0.016 * wsw * csw * (1.0 - cicover); }
-    d.f.ustokes[pp] = dmin(dmax(us, -1.5), 1.5); d.f.vstokes[pp] = dmin(dmax(vs, -1.5), 1.5);
-    if (LWFLUX) {   // implsch.F90:435-446
-      const double DELT25 = c_dc.WETAIL * c_dc.FR[F - 1] * c_dc.DELTH;
-      const double em2 = c_dc.EPSMIN + q[5] + DELT25 * q[7];
-      const double fm2 = em2 / (c_dc.EPSMIN + q[6] + c_dc.FRTAIL * c_dc.DELTH * q[7]);
-      if (em2 < c_dc.WSEMEAN_MIN) { d.f.wsemean[pp] = c_dc.WSEMEAN_MIN; d.f.wsfmean[pp] = 2. * c_dc.FR[F - 1]; }
-      else { d.f.wsemean[pp] = em2; d.f.wsfmean[pp] = fm2; }
-    }
-    if (c_dc.lcflx) {    // WNFLUXES closure (wnfluxes.F90:222-331, LWNEMOCOU=F)
-      const double PHIOC_ICE = -3.75, PHIAW_ICE = 3.75, C1 = 1.03e-3, C2 = 0.04e-3, P1 = 1.48, P2 = -0.21, CDMAX_LOC = 0.003;
-      const double epsus3 = c_dc.EPSUS * sqrt(c_dc.EPSUS);
-      const double cithrsh_inv = 1.0 / dmax(c_dc.cithrsh, 0.01);
-      const double phiwa = s[S_PHIWA * n + pp];
-      double ooval = 1.0, ustar = ufric;
-      if (c_dc.licerun && c_dc.lwamrsetci && cicover > c_dc.ciblock) {
-        ooval = exp(-dmin(p4(cicover * cithrsh_inv), 10.0));
-        const double u10p = dmax(wsw, c_dc.EPSU10);
-        const double cd_bulk = dmin((C1 + C2 * pow(u10p, P1)) * pow(u10p, P2), CDMAX_LOC);
-        const double cd_wave = sq(ufric / u10p);
-        ustar = dmax(sqrt(ooval * cd_wave + (1.0 - ooval) * cd_bulk) * u10p, c_dc.EPSUS);
-      }
-      const double tau = aird * dmax(sq(ustar), c_dc.EPSUS);
-      double tauxd = tau * snw, tauyd = tau * csw;
-      double tauocxd = tauxd - ooval * q[1], tauocyd = tauyd - ooval * q[2];
-      const double tauoc = dmin(dmax(sqrt(sq(tauocxd) + sq(tauocyd)) / tau, c_dc.TAUOCMIN), c_dc.TAUOCMAX);
-      if (c_dc.lwcouast) {
-        const double ua = d.f.ustra[pp], va = d.f.vstra[pp];
-        if (ua != 0.0 || va != 0.0) { tauxd = ua; tauocxd = ua * tauoc; tauyd = va; tauocyd = va * tauoc; }
-      }
-      d.f.tauxd[pp] = tauxd; d.f.tauyd[pp] = tauyd; d.f.tauocxd[pp] = tauocxd; d.f.tauocyd[pp] = tauocyd; d.f.tauoc[pp] = tauoc;
-      d.f.tauicx[pp] = 0.0; d.f.tauicy[pp] = 0.0;
-      const double xn = aird * dmax(ustar * ustar * ustar, epsus3);
-      double phiocd = ooval * (q[0] - phiwa) + (1.0 - ooval) * PHIOC_ICE * xn;
-      const double phieps = dmin(dmax(phiocd / xn, c_dc.PHIEPSMIN), c_dc.PHIEPSMAX);
-      phiocd = phieps * xn;
-      d.f.phiocd[pp] = phiocd; d.f.phieps[pp] = phieps; d.f.phiaw[pp] = ooval * phiwa / xn + (1.0 - ooval) * PHIAW_ICE;
+    for (int i = 0; i < 2; ++i) {
+      sinth[i] = c_dc.SINTH[k0 + i]; costh[i] = c_dc.COSTH[k0 + i];
+      const double cw2 = sq(dmax(0.0, costh[i] * csw + sinth[i] * snw));
+      flm.v[i] = flmc * cw2; iaw.v[i] = ia * cw2;
     }
   }
+  const int mij = (int)s[S_MIJ * n + pq];
+  const bool setice = c_dc.licerun && c_dc.lmaskice;
+  const double delt = c_dc.delt, deltm = 1.0 / delt, delt5 = c_dc.ximp * delt;
+  const double tmp03 = 1.0 / (c_dc.SDSBR * c_dc.MICHE);
+  const int MLSTHG = c_dc.MLSTHG;
+  const bool lssource = c_dc.lcflx && c_dc.lwvflx_snl;
+
+  double asl[7][2], afl[7][2];
+#pragma unroll
+  for (int x = 0; x < 7; ++x)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { asl[x][i] = 0.0; afl[x][i] = 0.0; }
+  V fmij, a_philf, a_ts, a_tu, a_e1, a_e2, a_el;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) { fmij.v[i] = 0.0; a_philf.v[i] = 0.0; a_ts.v[i] = 0.0; a_tu.v[i] = 0.0; a_e1.v[i] = 0.0; a_e2.v[i] = 0.0; a_el.v[i] = 0.0; }
+
+  auto step = [&](const int st) {
+    // ================= phase A =================
+    const int rnew = st + 5, rfin = st - 4, rb = st - 2, rtb = st - 1;
+    const unsigned par = (unsigned)st & 1u;
+    const bool dia = st >= 0 && st < MLSTHG;
+    const bool fin = rfin >= 0 && rfin < F;
+    const bool sat = ard && rb >= 0 && rb < F;
+    const unsigned p3 = (unsigned)(st + 6) % 3u;
+    if (rnew >= 0 && rnew < F) {
+      const double* g = (rnew < mlo ? src_lo : src_hi) + (size_t)rnew * rstr;
+      cp_async<8>(smb + me_s, g); cp_async<8>(smb + me_s + 8, g + P);
+    }
+    if (fin) {
+      const double* g = src_in + (size_t)rfin * rstr;
+      cp_async<8>(smb + me_s + L.SSB, g); cp_async<8>(smb + me_s + L.SSB + 8, g + P);
+      if (LWFLUX) { const double* gx = src_xl + (size_t)rfin * rstr; cp_async<8>(smb + me_s + 2 * L.SSB, gx); cp_async<8>(smb + me_s + 2 * L.SSB + 8, gx + P); }
+    }
+    if (rtb >= 0 && rtb < F && t < TQ_N * ST_NPT) {
+      const int q = t >> 3, p8 = t & 7;
+      cp_async<8>(smb + L.tbs + (unsigned)(((rtb & 7) * TQ_N + q) * 64 + p8 * 8), d.tbg + ((size_t)q * F + rtb) * n + min(pbase + p8, plast));
+    }
+    mbar_arrive_cp_async(smb + L.mbar);
+    if (dia) {
+      const int MC0 = st;
+      const double* R = c_dc.RNLCOEF[MC0];
+      const unsigned bIC = L.ring + (unsigned)c_dc.NLSLOT[MC0][0] * RSB + me_r;
+      const unsigned bIP = L.ring + (unsigned)c_dc.NLSLOT[MC0][1] * RSB + me_r;
+      const unsigned bIP1 = L.ring + (unsigned)c_dc.NLSLOT[MC0][2] * RSB + me_r;
+      const unsigned bIM = L.ring + (unsigned)c_dc.NLSLOT[MC0][3] * RSB + me_r;
+      const unsigned bIM1 = L.ring + (unsigned)c_dc.NLSLOT[MC0][4] * RSB + me_r;
+      const unsigned cb = L.cur + par * 6u * PSB + me_c;
+      const V fc = lds<2>(sm, bIC);
+      const double enh = lds1(sm, L.pc + PC_ENH * 64 + po);
+      const double ftemp = c_dc.AF11[MC0] * enh;
+      V fij, fcen, fcd1, fcd2;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        fij.v[i] = fc.v[i] * R[0];
+        fcen.v[i] = ftemp * fij.v[i];
+        fcd1.v[i] = c_dc.DAL1 * fcen.v[i];
+        fcd2.v[i] = c_dc.DAL2 * fcen.v[i];
+      }
+      V csl, cfl;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) { csl.v[i] = 0.0; cfl.v[i] = 0.0; }
+      auto half = [&](auto KH) {
+        constexpr int kh = decltype(KH)::value;
+        constexpr int s0 = geo_sh(TA, kh, 0), s1 = geo_sh(TA, kh, 1), s2 = geo_sh(TA, kh, 2), s3 = geo_sh(TA, kh, 3);
+        constexpr int lp = cmin(s0, s1), lm = cmin(s2, s3);
+        double p[3], q[3], m[3], nn[3];
+        load3<lp>(sm, bIP, p); load3<lp>(sm, bIP1, q); load3<lm>(sm, bIM, m); load3<lm>(sm, bIM1, nn);
+        V vad, vdp, vdm;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const double sap = R[1] * p[s0 - lp + i] + R[2] * p[s1 - lp + i] + R[3] * q[s0 - lp + i] + R[4] * q[s1 - lp + i];
+          const double sam = R[13] * m[s2 - lm + i] + R[14] * m[s3 - lm + i] + R[15] * nn[s2 - lm + i] + R[16] * nn[s3 - lm + i];
+          double fad1 = fij.v[i] * (sap + sam);
+          const double sap2 = 2.0 * sap;
+          const double fad2 = fma(-sap2, sam, fad1);
+          fad1 = fad1 + fad2;
+          vad.v[i] = fad2 * fcen.v[i];
+          csl.v[i] += vad.v[i];
+          cfl.v[i] = fma(fad1, ftemp, cfl.v[i]);
+          vdp.v[i] = fma(-2.0, sam, fij.v[i]) * fcd1.v[i];
+          vdm.v[i] = (fij.v[i] - sap2) * fcd2.v[i];
+        }
+        if (act) {
+          sts<2>(sm, cb + (0 + kh) * PSB, vad);
+          sts<2>(sm, cb + (2 + kh) * PSB, vdp);
+          sts<2>(sm, cb + (4 + kh) * PSB, vdm);
+          if (k0 < HC) {
+            sts<2>(sm, cb + (0 + kh) * PSB + (unsigned)A * 8u, vad);
+            sts<2>(sm, cb + (2 + kh) * PSB + (unsigned)A * 8u, vdp);
+            sts<2>(sm, cb + (4 + kh) * PSB + (unsigned)A * 8u, vdm);
+          }
+          if (k0 >= A - HC) {
+            sts<2>(sm, cb + (0 + kh) * PSB - (unsigned)A * 8u, vad);
+            sts<2>(sm, cb + (2 + kh) * PSB - (unsigned)A * 8u, vdp);
+            sts<2>(sm, cb + (4 + kh) * PSB - (unsigned)A * 8u, vdm);
+          }
+        }
+      };
+      half(IC<0>{}); half(IC<1>{});
+      const double c2 = c_dc.RNLC2[MC0];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) { asl[4][i] = fma(-c2, csl.v[i], asl[4][i]); afl[4][i] = fma(-c2, cfl.v[i], afl[4][i]); }
+    }
+    mbar_arrive(smb + L.mbar);
+    // saturation spectrum of row rb (sdissip_ard.F90:142-160): both windows of the pair from HR+1 aligned 16-byte loads
+    if (sat) {
+      const unsigned wb = L.ring + slot9(rb) * RSB + me_r - (unsigned)HR * 8u;
+      V b;
+      b.v[0] = 0.0; b.v[1] = 0.0;
+#pragma unroll
+      for (int jp = 0; jp <= HR; ++jp) {
+        const V f = lds<2>(sm, wb + jp * 16);
+        // f.v[e] is direction k0 - HR + 2 jp + e; window index of bin i: x = (2 jp + e) - (HR - NSD) - i
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int x = 2 * jp + e - (HR - NSD) - i;
+            if (x >= 0 && x < NS) b.v[i] += c_dc.SATW1[x] * f.v[e];
+          }
+      }
+      const double fs = lds1(sm, L.tbs + (unsigned)(((rb & 7) * TQ_N + TQ_FACSAT) * 64) + po);
+      V mx;
+      mx.v[0] = b.v[0] * fs; mx.v[1] = b.v[1] * fs;
+      sts<2>(sm, L.bsl + p3 * L.SSB + (unsigned)t * 16u, mx);
+      double m1 = dmax(mx.v[0], mx.v[1]);     // BTH0 = max over direction: the four pairs of this warp, then one partial per warp
+      m1 = dmax(m1, __shfl_xor_sync(FULLMASK, m1, 1));
+      m1 = dmax(m1, __shfl_xor_sync(FULLMASK, m1, 2));
+      if ((lane & 3) == 0) *reinterpret_cast<double*>(sm + L.part + (p3 * (unsigned)nwarp + (unsigned)wq) * 64u + po) = m1;
+    }
+    mbar_wait(smb + L.mbar, (unsigned)(st + 5) & 1u);
+    // ================= phase B =================
+    V tot_sl, tot_fl;
+    {
+      V sl_mm, fl_mm, sl_mm1, fl_mm1, sl_mp, fl_mp, sl_mp1, fl_mp1;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) { sl_mm.v[i] = fl_mm.v[i] = sl_mm1.v[i] = fl_mm1.v[i] = sl_mp.v[i] = fl_mp.v[i] = sl_mp1.v[i] = fl_mp1.v[i] = 0.0; }
+      if (dia) {
+        const double* R = c_dc.RNLCOEF[st];
+        const unsigned cb = L.cur + par * 6u * PSB + me_c;
+        auto half = [&](auto KH) {
+          constexpr int kh = decltype(KH)::value;
+          constexpr int s0 = -geo_sh(TA, kh, 0), s1 = -geo_sh(TA, kh, 1), s2 = -geo_sh(TA, kh, 2), s3 = -geo_sh(TA, kh, 3);
+          constexpr int lp = cmin(s0, s1), lm = cmin(s2, s3);
+          const unsigned cA = cb + (0 + kh) * PSB, cP = cb + (2 + kh) * PSB, cM = cb + (4 + kh) * PSB;
+          double am[3], mm[3], ap[3], pp[3];
+          load3<lm>(sm, cA, am); load3<lm>(sm, cM, mm); load3<lp>(sm, cA, ap); load3<lp>(sm, cP, pp);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const double a2 = am[s2 - lm + i], a21 = am[s3 - lm + i], m2 = mm[s2 - lm + i], m21 = mm[s3 - lm + i];
+            const double a1 = ap[s0 - lp + i], a11 = ap[s1 - lp + i], q1 = pp[s0 - lp + i], q11 = pp[s1 - lp + i];
+            sl_mm.v[i] = fma(a21, R[19], fma(a2, R[20], sl_mm.v[i]));   fl_mm.v[i] = fma(m21, R[24], fma(m2, R[23], fl_mm.v[i]));
+            sl_mm1.v[i] = fma(a21, R[18], fma(a2, R[17], sl_mm1.v[i])); fl_mm1.v[i] = fma(m21, R[22], fma(m2, R[21], fl_mm1.v[i]));
+            sl_mp.v[i] = fma(a11, R[7], fma(a1, R[8], sl_mp.v[i]));     fl_mp.v[i] = fma(q11, R[12], fma(q1, R[11], fl_mp.v[i]));
+            sl_mp1.v[i] = fma(a11, R[6], fma(a1, R[5], sl_mp1.v[i]));   fl_mp1.v[i] = fma(q11, R[10], fma(q1, R[9], fl_mp1.v[i]));
+          }
+        };
+        half(IC<0>{}); half(IC<1>{});
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        tot_sl.v[i] = asl[0][i] + sl_mm.v[i];   tot_fl.v[i] = afl[0][i] + fl_mm.v[i];
+        asl[0][i] = asl[1][i] + sl_mm1.v[i];    afl[0][i] = afl[1][i] + fl_mm1.v[i];
+        asl[1][i] = asl[2][i];                  afl[1][i] = afl[2][i];
+        asl[2][i] = asl[3][i];                  afl[2][i] = afl[3][i];
+        asl[3][i] = asl[4][i];                  afl[3][i] = afl[4][i];
+        asl[4][i] = asl[5][i];                  afl[4][i] = afl[5][i];
+        asl[5][i] = asl[6][i] + sl_mp.v[i];     afl[5][i] = afl[6][i] + fl_mp.v[i];
+        asl[6][i] = sl_mp1.v[i];                afl[6][i] = fl_mp1.v[i];
+      }
+    }
+    // finish row rfin (implsch.F90:276-395 for these bins)
+    if (fin) {
+      const int r = rfin;
+      const unsigned tq = L.tbs + (unsigned)((r & 7) * TQ_N * 64) + po;
+      const V fold = lds<2>(sm, L.ring + slot9(r) * RSB + me_r);
+      const V xI = lds<2>(sm, me_s + L.SSB);
+      const double usfm = lds1(sm, L.pc + PC_USFMDELT * 64 + po), sdsbk = lds1(sm, L.pc + PC_SDSBK * 64 + po);
+      const double tsbo = lds1(sm, tq + TQ_SBO * 64), tcinv = lds1(sm, tq + TQ_CINV * 64), ttail = lds1(sm, tq + TQ_TAIL * 64);
+      const double tstf = lds1(sm, tq + TQ_STF * 64), rtail = lds1(sm, L.pc + PC_RTAIL * 64 + po);
+      V dd;
+      if (ard) {
+        const double b0 = lds1(sm, L.bth0 + (par ^ 1u) * 64u + po);
+        const V b_prev = lds<2>(sm, L.bsl + ((unsigned)(r + 8) % 3u) * L.SSB + (unsigned)t * 16u);
+        const double ssdsc2_sig = c_dc.SSDSC2 * c_dc.ZPIFR[r];
+        const double d0 = ssdsc2_sig * c_dc.SSDSC6 * sq(dmax(0., b0 * tmp03 - c_dc.SSDSC4));
+#pragma unroll
+        for (int i = 0; i < 2; ++i) dd.v[i] = d0 + ssdsc2_sig * (1. - c_dc.SSDSC6) * sq(dmax(0., b_prev.v[i] * tmp03 - c_dc.SSDSC4));
+      } else { const double dj = lds1(sm, tq + TQ_JAN * 64); dd.v[0] = dj; dd.v[1] = dj; }
+      const double cofrm4 = c_dc.COFRM4[r], flmax = c_dc.FLMAX[r];
+      double rr = (r + 1 > mij) ? 0.0 : c_dc.RHOWG_DFIM[r];      // RHOWGDFTH of frcutindex.F90:99-108
+      if (r + 1 == mij && mij != F) rr = 0.5 * rr;
+      V xL;
+      if (LWFLUX) xL = lds<2>(sm, me_s + 2 * L.SSB);
+      V fnv;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double f0 = fold.v[i];
+        double fldv = xI.v[i];
+        double slv = fldv * f0;
+        slv = slv + dd.v[i] * f0; fldv = fldv + dd.v[i];
+        slv = slv + tot_sl.v[i]; fldv = fldv + tot_fl.v[i];
+        double ssource = 0.0;
+        if (lssource) ssource = div_norm(slv, dmax(1.0 - delt5 * fldv, 1.0));
+        if (r < c_dc.Fr) {
+          slv = slv - sdsbk * f0; fldv = fldv - sdsbk;
+          slv = slv + tsbo * f0; fldv = fldv + tsbo;
+        }
+        const double gtemp1 = dmax(1.0 - delt5 * fldv, 1.0);
+        const double gtemp2 = div_norm(delt * slv, gtemp1);
+        const double flhab = dmin(fabs(gtemp2), usfm * cofrm4);
+        double fn = f0 + copysign(flhab, gtemp2);
+        fn = dmax(fn, flm.v[i]);
+        ssource = ssource + deltm * dmin(flmax - fn, 0.0);
+        fn = dmin(fn, flmax);
+        a_philf.v[i] += ssource * rr;
+        a_ts.v[i] += ssource * (tcinv * rr);
+        if (LWFLUX) {
+          const double xf = (xL.v[i] != 0.0) ? fn : 0.0;
+          a_e1.v[i] += c_dc.DFIM[r] * xf; a_e2.v[i] += c_dc.DFIMOFR[r] * xf;
+          if (r == F - 1) a_el.v[i] += xf;
+        }
+        if (r == mij - 1) fmij.v[i] = fn;
+        if (r > mij - 1) fn = dmax((ttail * rtail) * fmij.v[i], flm.v[i]);
+        fnv.v[i] = fn;
+      }
+      if (setice) {
+        const double icefree = lds1(sm, L.pc + PC_ICEFREE * 64 + po);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) fnv.v[i] = fnv.v[i] * icefree + iaw.v[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        a_tu.v[i] += tstf * fnv.v[i];
+        if (r == c_dc.NFRE_ODD - 1) {
+          const double cst = 2.0 * c_dc.DELTH * c_dc.ZPI * c_dc.ZPI * c_dc.ZPI / c_dc.G * p4(c_dc.FR[c_dc.NFRE_ODD - 1]);
+          a_tu.v[i] += cst * fnv.v[i];
+        }
+      }
+      if (dost) { double* o = dst + (size_t)r * rstr; o[0] = fnv.v[0]; o[P] = fnv.v[1]; }
+    }
+    if (rnew >= 0 && rnew < F) {
+      const V xF = lds<2>(sm, me_s);
+      const double fac = lds1(sm, L.pc + PC_FAC * 64 + po);
+      V v;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        v.v[i] = dmax(xF.v[i] * fac, c_dc.EPSMIN);
+        if (rnew == F - 1) v.v[i] = dmax(v.v[i], flm.v[i]);
+      }
+      if (act) {
+        const unsigned rbse = L.ring + slot9(rnew) * RSB + me_r;
+        sts<2>(sm, rbse, v);
+        if (k0 < HR) sts<2>(sm, rbse + (unsigned)A * 8u, v);
+        if (k0 >= A - HR) sts<2>(sm, rbse - (unsigned)A * 8u, v);
+      }
+    }
+    if (ard && t < ST_NPT && rb - 1 >= 0 && rb - 1 < F) {
+      const double* pp = reinterpret_cast<const double*>(sm + L.part + ((unsigned)(st + 5) % 3u) * (unsigned)nwarp * 64u) + t;
+      double mx = 0.0;
+      for (int w = 0; w < nwarp; ++w) mx = dmax(mx, pp[w * ST_NPT]);
+      reinterpret_cast<double*>(sm + L.bth0 + par * 64u)[t] = mx;
+    }
+  };
+
+#pragma unroll 1
+  for (int st = -5; st < MLSTHG; ++st) step(st);
+  // ---- per-point sums over direction, then the scalar closures (one thread per point)
+  __syncthreads();
+  double* red = reinterpret_cast<double*>(sm + L.ring);     // red[q][k][pt]: 8 planes of A*8 doubles in the (now free) ring area
+  if (act) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int k = k0 + i;
+      red[(0 * A + k) * ST_NPT + pt] = a_philf.v[i];
+      red[(1 * A + k) * ST_NPT + pt] = sinth[i] * a_ts.v[i];
+      red[(2 * A + k) * ST_NPT + pt] = costh[i] * a_ts.v[i];
+      red[(3 * A + k) * ST_NPT + pt] = a_tu.v[i] * sinth[i];
+      red[(4 * A + k) * ST_NPT + pt] = a_tu.v[i] * costh[i];
+      if (LWFLUX) { red[(5 * A + k) * ST_NPT + pt] = a_e1.v[i]; red[(6 * A + k) * ST_NPT + pt] = a_e2.v[i]; red[(7 * A + k) * ST_NPT + pt] = a_el.v[i]; }
+    }
+  }
+  __syncthreads();
+  double* qs = reinterpret_cast<double*>(sm + L.cur);
+  if (t < 8 * ST_NPT) {
+    const int x = t >> 3, p8 = t & 7;
+    double v = 0.0;
+    if (x < 5 || LWFLUX) for (int kk = 0; kk < A; ++kk) v += red[(x * A + kk) * ST_NPT + p8];
+    qs[x * ST_NPT + p8] = v;
+  }
+  __syncthreads();
+  if (t < ST_NPT && pbase + t <= plast)
+    stencil_closure<LWFLUX>(d, pbase + t, qs + t, reinterpret_cast<const double*>(sm + L.pc) + t);
+}
+
+template <int TA, bool LW>
+static int launch_stencil_dp(const ImplDev& d, long long p0, long long np, cudaStream_t st) {
+  constexpr DpSmem L = dp_smem(TA, LW);
+  static_assert(L.total <= 110 * 1024, "k_stencil_dp shared memory");
+  static bool attr_done = false;
+  if (!attr_done) {
+    EW_CUDA_CHECK(cudaFuncSetAttribute(k_stencil_dp<TA, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    EW_CUDA_CHECK(cudaFuncSetAttribute(k_stencil_dp<TA, LW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attr_done = true;
+  }
+  k_stencil_dp<TA, LW><<<(unsigned)((np + ST_NPT - 1) / ST_NPT), dp_threads(TA), L.total, st>>>(d, p0, np);
+  return 0;
 }
 
 template <int TA, int NP, bool LW>
@@ -1238,6 +1694,13 @@ int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage
     const char* force = getenv("ECWAM_B200_STENCIL");
     const bool generic = force && (!strcmp(force, "generic") || !strcmp(force, "single"));
     if (force && !strcmp(force, "single")) pair = false;
+    // default for the standard grids: thread = (two adjacent directions, one point); ECWAM_B200_STENCIL=pp keeps the
+    // two-points-per-thread instance (A/B timing, tests)
+    if (!force) {
+      if (geo_matches<36>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_stencil_dp<36, true>(d, p0, np, st) : launch_stencil_dp<36, false>(d, p0, np, st);
+      if (geo_matches<24>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_stencil_dp<24, true>(d, p0, np, st) : launch_stencil_dp<24, false>(d, p0, np, st);
+      if (geo_matches<12>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_stencil_dp<12, true>(d, p0, np, st) : launch_stencil_dp<12, false>(d, p0, np, st);
+    }
     if (pair) {
       if (!generic) {
         if (geo_matches<36>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_stencil<36, 2, true>(d, p0, np, st) : launch_stencil<36, 2, false>(d, p0, np, st);

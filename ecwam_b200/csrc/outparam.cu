@@ -90,8 +90,17 @@ struct SpecAcc {
 };
 
 #define OB_NTH 128
+#ifndef OB_MINB
+#define OB_MINB 4   // CTAs per SM (register cap): the kernel is bound by the latency of its row loads
+#endif
+#ifndef OB_UNR
+#define OB_UNR 4    // directions in flight per thread
+#endif
+#define OB_STR2(x) #x
+#define OB_STR(x) OB_STR2(x)
+#define OB_UNROLL _Pragma(OB_STR(unroll OB_UNR))
 
-__global__ void __launch_bounds__(OB_NTH) k_outblock(OutDev d) {
+__global__ void __launch_bounds__(OB_NTH, OB_MINB) k_outblock(OutDev d) {
   extern __shared__ double cwd_s[];   // [A][OB_NTH]: COSWDIF(IJ,K) = cos(TH(K) - WDWAVE(IJ)) (outblock.F90:198-202)
   const int A = c_oc.A, F = c_oc.F, P = d.P;
   const int tid = threadIdx.x;
@@ -123,6 +132,7 @@ __global__ void __launch_bounds__(OB_NTH) k_outblock(OutDev d) {
       const double xinv = ufric * __ldg(cinv + (size_t)m * P);
       const double zr = icen ? exp(-10.0 * (c_oc.FR[m] * c_oc.FR[m]) / wsq) : 1.0;
       t2s = 0.0; t2w = 0.0;
+      OB_UNROLL
       for (int k = 0; k < A; ++k) {
         const size_t o = (size_t)m * rs + (size_t)k * P;
         const double f = __ldg(fl + o), x = __ldg(xl + o), c = cw[k * OB_NTH];
@@ -169,6 +179,7 @@ __global__ void __launch_bounds__(OB_NTH) k_outblock(OutDev d) {
     double w_t2 = 0, w_t0 = 0, w_s = 0, w_c = 0, w_f1 = 0;
     double t_t2 = 0, t_t0 = 0, t_s = 0, t_c = 0, t_dp = 0;
     double r_t0 = 0, r_s = 0, r_c = 0;
+    OB_UNROLL
     for (int k = 0; k < A; ++k) {
       const size_t o = (size_t)m * rs + (size_t)k * P;
       const double f = __ldg(fl + o), c = cw[k * OB_NTH];

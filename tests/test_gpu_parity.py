@@ -78,7 +78,8 @@ def test_wamintgr_steps_match_oracle(built, case):
         assert abs(red(hs_g) - red(hs_o[w.own])) <= 1e-12 * abs(red(hs_o))
 
 
-@pytest.mark.parametrize("mode,case", [("generic", "o640like"), ("generic", "o48_iphys0"), ("single", "o640like"), ("single", "o320like")])
+@pytest.mark.parametrize("mode,case", [("generic", "o640like"), ("generic", "o48_iphys0"), ("single", "o640like"), ("single", "o320like"),
+                                       ("pp", "o640like"), ("pp", "o320like"), ("pp", "o48like")])
 def test_stencil_kernel_instances_agree(built, monkeypatch, mode, case):
     """k_stencil has compile-time-geometry instances (NANG 12/24/36, two points per thread), a run-time-geometry instance and a
     one-point-per-thread instance (odd NPROMA / unaligned arrays).  All of them must match the oracle."""
