@@ -28,8 +28,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "grid-point spectra/s per timestep (IMPLSCH+PROPAGS2)"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of the bench workload
-NCU_DRAM_SOURCE = "profiles/r01h_ncu_summary_O640.txt"
-NCU_DRAM_BYTES = {("O640", 1): {"implsch_stencil": 36.195e9, "implsch_point": 53.64e9, "propags2": 19.692e9}}
+NCU_DRAM_SOURCE = "profiles/r01j_ncu_summary_O640.txt"
+NCU_DRAM_BYTES = {("O640", 1): {"implsch_stencil": 36.197e9, "implsch_point": 53.643e9, "propags2": 19.688e9}}
 UNIT = "spectra/s"
 
 
@@ -338,9 +338,10 @@ def run_gpu(args):
                 "traffic_source": NCU_DRAM_SOURCE if traffic else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_point": alg[dom], "points_per_launch": pts_rank,
                 "ms_per_launch": kern[dom],
-                "note": "the dominant kernel (k_stencil: DIA quadruplets + implicit update) is bound by the shared-memory pipe "
-                        "(68 % busy), issue slots (48 %) and the FP64 pipe (32 %), not by HBM: the HBM fraction is reported "
-                        "as the contract asks; per-kernel DRAM GB/s and pipe utilisation are in profiles/"}
+                "note": "the dominant kernel (k_stencil_dp: DIA quadruplets + saturation window + implicit update) is bound by "
+                        "instruction issue / dependency latency at 10 warps per SM (issue 50 %, FP64 pipe 33 %, shared-memory "
+                        "pipe ~60 %), not by HBM: the HBM fraction is reported as the contract asks; per-kernel DRAM GB/s and "
+                        "pipe utilisation are in profiles/"}
     cpu = None
     if not args.no_cpu:
         v, msc, cores, sample = cpu_reference_run(args.workload, 2, 1)
