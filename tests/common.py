@@ -109,7 +109,7 @@ def compare_bout(a, b, itgs=OUT_ITG):
             d = np.abs(x - y)
             d = np.minimum(d, 360.0 - d)
             ref = OUT_DIRECTIONS[itg]
-            if ref is not None:          # a mean direction is only defined where there is energy
+            if ref is not None and ref in itgs:   # a mean direction is only defined where there is energy
                 h = b[itgs.index(ref)][ok]
                 d = d[h > 1e-3 * max(h.max(), 1e-300)]
             worst[itg] = float(d.max()) if d.size else 0.0

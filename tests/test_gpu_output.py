@@ -92,3 +92,24 @@ def test_unsupported_parameter_is_rejected(built):
             w.outbs([1, bad], [1, 1], [1, 1])
     nx = L.ForcingNext()
     assert w.lib.ecwam_b200_newwind(w.h, C.byref(nx)) == -1                               # null FF_NEXT members
+
+
+@pytest.mark.parametrize("case,nproma", [("o48like", 32), ("o48_iphys0", 24)])
+def test_o48_full_size_hourly_norms(built, case, nproma):
+    """BASELINE configs[0] / [1] at their real size (O48, 12 directions x 36(25) frequencies, dt = 900 s, NPROMA 32 / 24): four
+    steps = the first hourly output step of tests/etopo1_oper_an_fc_O48*.yml, then the seven fields those configs request
+    (swh mwd mwp pp1d dwi cdww wind) and their WAMNORM lines - the quantity the reference's `validation:` blocks record."""
+    from common import CASES
+    CASES["_o48"] = dict(CASES[case], N=48, nproma=nproma)
+    g, o, f, s, w = both("_o48", steps=4)
+    assert g.niblo > 7000
+    itg = [1, 2, 3, 6, 5, 7, 10]
+    ice = [1, 1, 1, 1, 0, 0, 0]
+    sea = [1, 1, 1, 1, 0, 0, 0]
+    b = o.outbs(itg, ice, sea)
+    a = w.outbs(itg, ice, sea)
+    compare_bout(a, b[:, w.own], itgs=itg)
+    wa, wb = w.outwnorm(True), o.outwnorm(True)
+    np.testing.assert_array_equal(wa[:, 3], wb[:, 3])
+    for row, name in ((0, "swh"), (2, "mwp"), (3, "pp1d"), (5, "cdww"), (6, "wind")):
+        np.testing.assert_allclose(wa[row, :3], wb[row, :3], rtol=1e-11, err_msg=name)      # average, minimum, maximum
