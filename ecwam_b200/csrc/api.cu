@@ -697,6 +697,16 @@ int ecwam_b200_newwind(ecwam_b200_handle h, const ecwam_b200_forcing_next* next)
   return 0;
 }
 
+int ecwam_b200_no_source(ecwam_b200_handle h, int llsource_off) {
+  if (!h) EW_FAIL(ECWAM_B200_EINVAL, "null handle");
+  if (!h->bound) EW_FAIL(ECWAM_B200_ESTATE, "fields not bound");
+  const long long n2 = (long long)h->par.nproma * h->par.nchnk;
+  launch_no_source(n2 * h->par.nang * h->par.nfre, n2, h->dev.fl1, h->dev.xllws, h->dev.mij, h->par.nfre, llsource_off != 0, h->dc.EPSMIN, h->st);
+  h->nlaunch++;
+  EW_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int ecwam_b200_outparam_supported(int itg) {
   static const int ok[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 12, 13, 14, 15, 16, 20, 21, 22, 23, 24, 25, 26, 27, 28, 32, 35, 36, 37, 38,
                            39, 40, 41, 53, 54, 55, 56, 62, 63, 73, 74, 75, 76, 77};

@@ -94,6 +94,7 @@ struct OutDev {
 int upload_out_const(const OutConst& h, cudaStream_t st);
 void launch_newwind(long long npts, const ecwam_b200_fields& f, const ecwam_b200_forcing_next& nx, double acd, double bcd, double epsmin,
                     cudaStream_t st);
+void launch_no_source(long long n4, long long n2, double* fl1, double* xllws, int* mij, int nfre, int clip, double epsmin, cudaStream_t st);
 int launch_outblock(const OutDev& d, cudaStream_t st);
 size_t norm_scratch_doubles(int ncol);
 void launch_norm_local(const double* bout, int P, int ncol, long long nloc, double zmiss, double* scratch, double* out4, cudaStream_t st);

@@ -38,6 +38,17 @@ __global__ void k_newwind(long long n, ecwam_b200_fields f, ecwam_b200_forcing_n
   f.cithick[p] = nx.cithick[p]; f.ustra[p] = nx.ustra[p]; f.vstra[p] = nx.vstra[p];
 }
 
+// WAMINTGR without a source-term update (wamintgr.F90:163-171 when LLSOURCE = F, :188-195 when it is not yet time to
+// integrate): MIJ = NFRE, XLLWS = 0 and, for LLSOURCE = F, FL1 = MAX(FL1, EPSMIN)
+__global__ void k_no_source(long long n4, long long n2, double* __restrict__ fl1, double* __restrict__ xllws, int* __restrict__ mij,
+                            int nfre, int clip, double epsmin) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n2) mij[i] = nfre;
+  if (i >= n4) return;
+  xllws[i] = 0.0;
+  if (clip) fl1[i] = omax(fl1[i], epsmin);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // per-spectrum accumulators of the frequency sweep (FEMEAN, STHQ, MWP1/MWP2, PEAKFRI + SCOSFL)
 struct SpecAcc {
@@ -377,6 +388,10 @@ void launch_newwind(long long npts, const ecwam_b200_fields& f, const ecwam_b200
                     cudaStream_t st) {
   if (npts <= 0) return;
   k_newwind<<<(unsigned)((npts + 255) / 256), 256, 0, st>>>(npts, f, nx, acd, bcd, epsmin);
+}
+void launch_no_source(long long n4, long long n2, double* fl1, double* xllws, int* mij, int nfre, int clip, double epsmin, cudaStream_t st) {
+  if (n4 <= 0) return;
+  k_no_source<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(n4, n2, fl1, xllws, mij, nfre, clip, epsmin);
 }
 int launch_outblock(const OutDev& d, cudaStream_t st) {
   if (d.npts <= 0) return 0;

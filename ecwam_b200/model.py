@@ -122,6 +122,20 @@ class WamSetup:
             pass
 
 
+class WamClock:
+    """The dates WAMODEL / WAMINTGR step through (wamodel.F90:181-185, 228-233, 283-300; wamintgr.F90:92-186), in seconds since
+    the start of the run instead of CHARACTER(14) dates: CDATE, CDTPRA / CDTPRO (start / end of the running propagation step),
+    CDTIMP / CDTIMPNEXT (source-term integration), CDATEWH (date of the next forcing fields)."""
+
+    def __init__(self, idelpro, idelt, idelwo):
+        self.idelpro, self.idelt, self.idelwo = int(idelpro), int(idelt), int(idelwo)
+        self.cdtpro = 0
+        self.cdtpra = self.cdate = 0
+        self.cdtimp = 0                       # wamodel.F90:185
+        self.cdtimpnext = self.idelt          # wamodel.F90:182-183
+        self.cdatewh = self.idelwo
+
+
 class WamIntgr:
     """One rank of the WAMINTGR hot path on one GPU."""
 
@@ -293,6 +307,44 @@ class WamIntgr:
                                              ne.ctypes.data_as(ip) if multi else None, w.ctypes.data_as(C.POINTER(C.c_double))),
                 "outwnorm")
         return w
+
+    def no_source(self, llsource_off: bool):
+        L.check(self.lib.ecwam_b200_no_source(self.h, int(llsource_off)), "no_source")
+
+    def wamintgr(self, clk: "WamClock", ff_next=None, llsource=True) -> int:
+        """One call of WAMINTGR (wamintgr.F90:92-197) with its time bookkeeping; times are seconds since the start of the
+        run instead of the reference's CHARACTER(14) dates.  Returns the CFL count of PROPAG_WAM (0 = ok).
+        ff_next: callable(time) -> dict of the FF_NEXT fields, asked when NEWWIND's `CDATE >= CDATEWH` test holds."""
+        cfl = 0
+        if clk.cdate == clk.cdtpra:                       # :92-98  PROPAGATION TIME
+            cfl = self.propag()
+            clk.cdate = clk.cdtpro
+        if clk.cdtimp >= clk.cdatewh:                     # :103-104 NEWWIND (newwind.F90:107-169)
+            if ff_next is not None:
+                self.newwind(ff_next(clk.cdatewh))
+            clk.cdatewh += clk.idelwo
+        if clk.cdate >= clk.cdtimpnext:                   # :108-186 IT IS TIME TO INTEGRATE THE SOURCE TERMS
+            if llsource:
+                self.implsch()
+            else:
+                self.no_source(True)
+            clk.cdtimp = clk.cdtimpnext
+            clk.cdtimpnext += clk.idelt
+        else:                                             # :187-195 NO SOURCE TERM CONTRIBUTION
+            self.no_source(False)
+        return cfl
+
+    def advection_step(self, clk: "WamClock", ff_next=None, llsource=True) -> int:
+        """One iteration of WAMODEL's ADVECTION loop (wamodel.F90:228-233, 283-300): fix the end date of the propagation
+        step, then call WAMINTGR until the source terms have caught up with it."""
+        clk.cdtpra = clk.cdtpro
+        clk.cdtpro += clk.idelpro
+        clk.cdate = clk.cdtpra
+        cfl, iloop = 0, 1
+        while iloop == 1 or clk.cdtimpnext <= clk.cdtpro:
+            cfl += self.wamintgr(clk, ff_next, llsource)
+            iloop += 1
+        return cfl
 
     def synchronize(self):
         L.check(self.lib.ecwam_b200_synchronize(self.h), "synchronize")

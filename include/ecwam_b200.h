@@ -308,6 +308,11 @@ int ecwam_b200_implsch(ecwam_b200_handle h, int ichnk0, int nchnk);
  * block->chunk copy of PROPAG_WAM fused into IMPLSCH's load.  Same results as _propag + _implsch_all.  */
 int ecwam_b200_wamintgr(ecwam_b200_handle h);
 
+/* WAMINTGR's branches without a source-term update: llsource_off != 0 = the LLSOURCE = F branch (wamintgr.F90:163-171:
+ * MIJ = NFRE, FL1 = MAX(FL1, EPSMIN), XLLWS = 0); llsource_off == 0 = "not yet time to integrate" (:188-195: MIJ = NFRE,
+ * XLLWS = 0).                                                                                           */
+int ecwam_b200_no_source(ecwam_b200_handle h, int llsource_off);
+
 /* Same step for callers whose fields live in HOST memory (pinned or pageable): copies the IMPLSCH /
  * PROPAG_WAM inputs host->device, runs the step, copies FL1, XLLWS(optional) and the 1-D outputs back.
  * `host` uses the same struct with host pointers; with_xllws != 0 also returns XLLWS.

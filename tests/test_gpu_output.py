@@ -113,3 +113,50 @@ def test_o48_full_size_hourly_norms(built, case, nproma):
     np.testing.assert_array_equal(wa[:, 3], wb[:, 3])
     for row, name in ((0, "swh"), (2, "mwp"), (3, "pp1d"), (5, "cdww"), (6, "wind")):
         np.testing.assert_allclose(wa[row, :3], wb[row, :3], rtol=1e-11, err_msg=name)      # average, minimum, maximum
+
+
+def test_wamintgr_sequencing_idelpro_twice_idelt(built):
+    """WAMINTGR / WAMODEL time bookkeeping (wamintgr.F90:92-197, wamodel.F90:228-300) with IDELPRO = 2 IDELT and a new wind
+    every IDELWO = IDELPRO: per advection step PROPAG_WAM once, NEWWIND when due, IMPLSCH twice.  The oracle is driven through
+    the same sequence call by call."""
+    from ecwam_b200 import model as M
+    extra = dict(idelpro=1800.0, delpro_lf=1800.0)
+    g, o, f, fl = make_oracle("o48like", **extra)
+    _, s, w = make_gpu("o48like", **extra)
+    clk = M.WamClock(idelpro=1800, idelt=900, idelwo=1800)
+    calls = []
+
+    def ff_next(t):
+        calls.append(t)
+        return next_forcing(f, k=1 + t // 1800)
+
+    for kadv in range(3):
+        assert w.advection_step(clk, ff_next) == 0
+        # the same sequence on the oracle: propagation, then (NEWWIND if CDTIMP >= CDATEWH, IMPLSCH) x 2
+        assert o.propag() == 0
+        for sub in range(2):
+            t_imp = kadv * 1800 + sub * 900
+            if t_imp >= 1800 and t_imp % 1800 == 0:
+                o.newwind(next_forcing(f, k=1 + t_imp // 1800))
+            o.implsch()
+    w.synchronize()
+    assert calls == [1800, 3600] and clk.cdtpro == 5400 and clk.cdtimp == 5400 and clk.cdatewh == 5400
+    assert np.abs(w.get_spec("fl1") - o.get_fl1()[:, :, w.own]).max() <= 1e-12 * o.get_fl1().max()
+    assert (w.get_field("mij") == o.get_field("MIJ")[w.own]).all()
+
+
+def test_wamintgr_without_source_terms(built):
+    """LLSOURCE = F (wamintgr.F90:163-171) and the "not yet time" branch (:188-195): MIJ = NFRE, XLLWS = 0, FL1 floored."""
+    from ecwam_b200 import model as M
+    g, o, f, fl = make_oracle("o48like")
+    _, s, w = make_gpu("o48like")
+    clk = M.WamClock(idelpro=900, idelt=900, idelwo=10 ** 9)
+    assert w.advection_step(clk, llsource=False) == 0
+    assert o.propag() == 0
+    w.synchronize()
+    np.testing.assert_array_equal(w.get_spec("fl1"), np.maximum(o.get_fl1()[:, :, w.own], 1e-33))     # PROPAGS2 is bit-exact
+    assert (w.get_field("mij") == w.F).all() and (w.get_spec("xllws") == 0).all()
+    w.implsch()
+    w.no_source(False)
+    w.synchronize()
+    assert (w.get_field("mij") == w.F).all() and (w.get_spec("xllws") == 0).all()
