@@ -66,6 +66,8 @@ struct ecwam_b200_handle_s {
   PropDev pd;
   DBuf<int> nbr, halo_off, halo_str, send_l, send_pre, send_peer_of, recv_pre, recv_peer_of, recv_e, flag, count;
   DBuf<double> wl, pt, cgext, halo, sendbuf, fl3, cosph_m, cosph_p, land_cg, cgrecv;
+  DBuf<double> wlat_raw, dellam, grad;   // IREFRA = 1: WLAT as PROPCONNECT left it, DELLAM(KXLT), depth gradients
+  double oneo2delphi = 0.0;
   std::vector<int> h_spre, h_rpre;   // per peer prefix sums (size nproc+1)
   int nsend = 0, nrecv = 0;
   int msplit = 0;
@@ -169,7 +171,8 @@ static int fill_dev_const(const ecwam_b200_params& p, const ecwam_b200_tables& t
   memset(&c, 0, sizeof(c));
   if (p.nang < 4 || p.nang > EW_MAXA || p.nfre < 2 || p.nfre > EW_MAXF || p.nfre_red < 1 || p.nfre_red > p.nfre)
     EW_FAIL(ECWAM_B200_EINVAL, "unsupported spectral dimensions NANG=%d NFRE=%d NFRE_RED=%d", p.nang, p.nfre, p.nfre_red);
-  if (p.irefra != 0 || p.icase != 1) EW_FAIL(ECWAM_B200_EINVAL, "only IREFRA=0, ICASE=1 is implemented (SURVEY 8f rank 3)");
+  if ((p.irefra != 0 && p.irefra != 1) || p.icase != 1)
+    EW_FAIL(ECWAM_B200_EINVAL, "only IREFRA = 0 | 1 (depth refraction), ICASE = 1 are implemented (current refraction: SURVEY 8f rank 3)");
   if (p.isnonlin != 0) EW_FAIL(ECWAM_B200_EINVAL, "only ISNONLIN=0 is implemented");
   if (p.llgcbz0 || p.llnormagam) EW_FAIL(ECWAM_B200_EINVAL, "LLGCBZ0 / LLNORMAGAM branches are not implemented (SURVEY 8f rank 2)");
   if (p.lciwa) EW_FAIL(ECWAM_B200_EINVAL, "LCIWA* / LCISCAL sea-ice attenuation is not implemented (SURVEY 8f rank 2)");
@@ -293,6 +296,7 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
   pc.delpro[0] = p.delpro_lf; pc.delpro[1] = p.idelpro;
   for (int v = 0; v < 2; ++v) {
     const double delth0 = 0.25 * pc.delpro[v] / tables->delth;
+    pc.delth0[v] = delth0;
     for (int k = 0; k < A; ++k) {
       pc.sp[v][k] = delth0 * (tables->sinth[k] + tables->sinth[pc.kpm_p[k]]) / tables->r_earth;
       pc.sm[v][k] = delth0 * (tables->sinth[k] + tables->sinth[pc.kpm_m[k]]) / tables->r_earth;
@@ -395,11 +399,22 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
        !h->cosph_p.upload(cpp, st) && !h->halo_off.upload(halo_off, st) && !h->halo_str.upload(halo_str, st) &&
        !h->send_l.upload(send_l, st) && !h->send_peer_of.upload(send_peer, st) && !h->send_pre.upload(h->h_spre, st) &&
        !h->recv_pre.upload(h->h_rpre, st) && !h->recv_peer_of.upload(recv_peer, st) && !h->recv_e.upload(recv_e, st);
-  std::vector<double> landcg(Fr, 0.0);
+  const int nenv = Fr + (p.irefra == 1 ? 1 : 0);
+  std::vector<double> landcg(nenv, 0.0);
   if (dec->land_cgroup) for (int m = 0; m < Fr; ++m) landcg[m] = dec->land_cgroup[m];
+  if (p.irefra == 1) {
+    landcg[Fr] = p.bathymax;                                   // DEPTH_EXT(NSUP+1) (proenvhalo.F90:104)
+    std::vector<double> wr((size_t)2 * nloc), dl(nloc);
+    for (int l = 0; l < nloc; ++l) {
+      wr[l] = dec->wlat[l]; wr[(size_t)nloc + l] = dec->wlat[l + (size_t)nloc];
+      dl[l] = dec->zdello[dec->kxlt[l] - 1] * tables->circ / 360.0;   // DELLAM(KX) (readmdlconf.F90:153)
+    }
+    h->oneo2delphi = 0.5 / (dec->xdella * tables->circ / 360.0);      // gradi.F90:113, readmdlconf.F90:136
+    ok = ok && !h->wlat_raw.upload(wr, st) && !h->dellam.upload(dl, st) && !h->grad.alloc((size_t)2 * nloc);
+  }
   ok = ok && !h->land_cg.upload(landcg, st);
-  ok = ok && !h->cgext.alloc((size_t)Fr * next) && !h->halo.alloc(halo_elems + 1) &&
-       !h->sendbuf.alloc((size_t)h->nsend * A * Fr) && !h->cgrecv.alloc((size_t)h->nrecv * Fr) &&
+  ok = ok && !h->cgext.alloc((size_t)nenv * next) && !h->halo.alloc(halo_elems + 1) &&
+       !h->sendbuf.alloc((size_t)h->nsend * A * Fr) && !h->cgrecv.alloc((size_t)h->nrecv * nenv) &&
        !h->fl3.alloc((size_t)P * A * Fr * p.nchnk) && !h->flag.alloc(nloc) && !h->count.alloc(1);
   // IMPLSCH tables
   std::vector<int> kw((size_t)16 * A, -1);
@@ -464,6 +479,7 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
   PropDev& d = h->pd;
   d.nloc = nloc; d.nbot = nbot; d.ntop = ntop; d.next = next; d.P = P; d.A = A; d.F = F; d.Fr = Fr; d.nchnk = p.nchnk;
   d.nbr = h->nbr.p; d.wl = h->wl.p; d.pt = h->pt.p; d.cgext = h->cgext.p; d.halo_off = h->halo_off.p;
+  d.irefra = p.irefra; d.nenv = nenv; d.omos = nullptr; d.grad = h->grad.p;
   d.halo_str = h->halo_str.p; d.halo = h->halo.p;
   h->tab.k1w = h->kw.p; h->tab.k2w = h->kw.p + 2 * A; h->tab.k11w = h->kw.p + 4 * A; h->tab.k21w = h->kw.p + 6 * A;
   h->tab.ik1w = h->kw.p + 8 * A; h->tab.ik2w = h->kw.p + 10 * A; h->tab.ik11w = h->kw.p + 12 * A; h->tab.ik21w = h->kw.p + 14 * A;
@@ -502,7 +518,9 @@ int ecwam_b200_bind_fields(ecwam_b200_handle h, const ecwam_b200_fields* dev) {
       !dev->tauxd || !dev->tauyd || !dev->tauocxd || !dev->tauocyd || !dev->tauoc || !dev->tauicx || !dev->tauicy ||
       !dev->phiocd || !dev->phieps || !dev->phiaw || !dev->mij || !dev->wsemean || !dev->wsfmean || !dev->ustra || !dev->vstra)
     EW_FAIL(ECWAM_B200_EINVAL, "bind_fields: a required field pointer is NULL");
+  if (h->par.irefra == 1 && !dev->omosnh2kd) EW_FAIL(ECWAM_B200_EINVAL, "bind_fields: IREFRA = 1 needs OMOSNH2KD");
   h->dev = *dev;
+  h->pd.omos = dev->omosnh2kd;
   h->bound = true;
   h->weights_dirty = true;
   return 0;
@@ -541,15 +559,19 @@ static int halo_spectrum(H* h, const double* src, int srcF, int nm) {
 static int update_weights(H* h, int* cfl) {
   const PropDev& d = h->pd;
   launch_setup_points(d, h->dev.cosphm1, h->cosph_m.p, h->cosph_p.p, h->pt.p, h->st);
-  launch_fill_cgext(d, h->dev.cgroup, h->cgext.p, h->land_cg.p, h->st);
+  launch_fill_cgext(d, h->dev.cgroup, h->dev.depth, h->cgext.p, h->land_cg.p, h->st);
   h->nlaunch += 3;
-  if (h->nproc > 1) {
-    launch_pack(d, nullptr, 0, h->cgext.p, 1, 1, d.Fr, d.Fr, h->send_l.p, h->send_pre.p, h->send_peer_of.p, h->nsend,
+  if (h->nproc > 1) {   // PROENVHALO: group velocity (+ depth when IREFRA = 1) of the halo points
+    launch_pack(d, nullptr, 0, h->cgext.p, 1, 1, d.nenv, d.nenv, h->send_l.p, h->send_pre.p, h->send_peer_of.p, h->nsend,
                 h->sendbuf.p, h->st);
-    int rc = exchange(h, h->sendbuf.p, h->cgrecv.p, (size_t)d.Fr, (size_t)d.Fr);
+    int rc = exchange(h, h->sendbuf.p, h->cgrecv.p, (size_t)d.nenv, (size_t)d.nenv);
     if (rc) return rc;
-    launch_unpack_cg(d, h->cgrecv.p, h->recv_pre.p, h->recv_peer_of.p, h->recv_e.p, h->nrecv, d.Fr, h->cgext.p, h->st);
+    launch_unpack_cg(d, h->cgrecv.p, h->recv_pre.p, h->recv_peer_of.p, h->recv_e.p, h->nrecv, d.nenv, h->cgext.p, h->st);
     h->nlaunch += 2;
+  }
+  if (d.irefra == 1) {   // PROPDOT/GRADI (propag_wam.F90:171-216)
+    launch_depth_gradients(d, h->wlat_raw.p, h->dellam.p, h->oneo2delphi, h->grad.p, h->st);
+    h->nlaunch++;
   }
   launch_ctu_check(d, 0, d.Fr, h->msplit, h->flag.p, h->count.p, h->st);
   h->nlaunch += 2;

@@ -1241,11 +1241,11 @@ template <int LO>
 __device__ __forceinline__ void load3(const char* sm, unsigned base, double (&d)[3]) {
   constexpr bool even = ((LO % 2) + 2) % 2 == 0;
   if (even) {
-    const Vd<2> a = lds<2>(sm, base + LO * 8);
-    d[0] = a.v[0]; d[1] = a.v[1]; d[2] = lds1(sm, base + (LO + 2) * 8);
+    const Vd<2> a = lds<2>(sm, base + (unsigned)(LO * 8));
+    d[0] = a.v[0]; d[1] = a.v[1]; d[2] = lds1(sm, base + (unsigned)((LO + 2) * 8));
   } else {
-    d[0] = lds1(sm, base + LO * 8);
-    const Vd<2> a = lds<2>(sm, base + (LO + 1) * 8);
+    d[0] = lds1(sm, base + (unsigned)(LO * 8));
+    const Vd<2> a = lds<2>(sm, base + (unsigned)((LO + 1) * 8));
     d[1] = a.v[0]; d[2] = a.v[1];
   }
 }

@@ -13,7 +13,10 @@ struct PropDev {
   const int* nbr;        // [14][nloc]: KLON(1..2), KLAT(ic,icl) at 2+(ic-1)+2(icl-1), KCOR(icr,icl) at 6+(icr-1)+4(icl-1)
   const double* wl;      // [6][nloc]: WLAT(1..2), WCOR(1..4) after CTUWINI's land edit (ctuwini.F90:61-99)
   const double* pt;      // [5][nloc]: COSPHM1, DP(1), DP(2), ZDELLO(ky), TANPH(ky)
-  const double* cgext;   // [Fr][next] group velocity incl. halo and land slot (proenvhalo.F90)
+  const double* cgext;   // [nenv][next] group velocity incl. halo and land slot (proenvhalo.F90); row Fr = DEPTH_EXT when IREFRA = 1
+  int irefra, nenv;      // YOWSTAT IREFRA (0 | 1 depth refraction); rows of cgext (Fr or Fr+1)
+  const double* omos;    // WVPRPT%OMOSNH2KD (P,F,C) (IREFRA = 1)
+  const double* grad;    // [2][nloc]: DDPHI, DDLAM of GRADI (gradi.F90:120-153), IREFRA = 1
   const int* halo_off;   // [nbot+ntop+1] offset of (k=0,m=0) of a halo point in `halo`; land -> a zero element
   const int* halo_str;   // [nbot+ntop+1] direction stride (= points received from that peer); land -> 0
   const double* halo;    // received spectra, per peer block [m][k][ih]
@@ -29,6 +32,7 @@ struct PropConst {
   double sp[2][EW_MAXA];    // DELTH0*(SINTH(K)+SINTH(KP1))/R for the two DELPRO values (ctuw.F90:423-431)
   double sm[2][EW_MAXA];
   double delpro[2];
+  double delth0[2];         // 0.25*DELPRO/DELTH (ctuw.F90:407)
   double cmtodeg;           // 360/CIRC
   double xdella;
 };
@@ -40,7 +44,8 @@ void launch_propags2(const PropDev& d, const double* src, int srcF, double* dst,
 void launch_ctu_check(const PropDev& d, int m0, int m1, int msplit, int* flag, int* count, cudaStream_t st);
 void launch_setup_points(const PropDev& d, const double* cosphm1_fld, const double* cosph_m, const double* cosph_p,
                          double* pt, cudaStream_t st);
-void launch_fill_cgext(const PropDev& d, const double* cgroup, double* cgext, const double* land_cg, cudaStream_t st);
+void launch_fill_cgext(const PropDev& d, const double* cgroup, const double* depth, double* cgext, const double* land_cg, cudaStream_t st);
+void launch_depth_gradients(const PropDev& d, const double* wlat_raw, const double* dellam, double oneo2delphi, double* grad, cudaStream_t st);
 void launch_pack(const PropDev& d, const double* src, int srcF, const double* cgext, int mode, int nk, int nm, int nfull,
                  const int* send_l, const int* send_pre, const int* send_peer_of, int ntot, double* out, cudaStream_t st);
 void launch_unpack_cg(const PropDev& d, const double* in, const int* recv_pre, const int* recv_peer_of, const int* recv_e,

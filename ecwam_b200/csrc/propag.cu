@@ -12,6 +12,13 @@
 // operation order, so the result is bit-identical to the reference's stored-weight formulation.
 #include "internal.h"
 
+#ifndef PG_UNR
+#define PG_UNR 1   // direction pairs of ctu_quadrant's loop unrolled together (12 gathers in flight per pair)
+#endif
+#define PG_STR2(x) #x
+#define PG_STR(x) PG_STR2(x)
+#define PG_UNROLL _Pragma(PG_STR(unroll PG_UNR))
+
 namespace ew {
 
 // per-direction tables of the CTU scheme (ctuwupdt.F90:111-161): struct PropConst in internal.h
@@ -48,9 +55,13 @@ __device__ __forceinline__ void nbr_base(const PropDev& d, const SpecSrc& s, int
 struct PointM {            // k-independent quantities of one (point, frequency)
   double hx[2], hy[2];     // 0.5*(CG+CG_lon(ic)), 0.5*(CG+DP(ic)*CGYP(ic))      (ctuw.F90:160-171,199-210)
   double cg, tanph, cosphm1, zdello, gam1, wlat[2], wlatm1[2], wcor[4], wcorm1[4];
+  double omos, ddphi, ddlam;   // IREFRA = 1: OMOSNH2KD(ij,m), depth gradients of GRADI
 };
 
-template <int JX1, int JY1, int KC>
+// depth-refraction part of THETA DOT (propdot.F90:156: THDD = SD*DDPHI - CD*DDLAM*DCO, ICASE = 1: DCO = COSPHM1)
+__device__ __forceinline__ double thdd(const PointM& q, int k) { return c_prop.sinth[k] * q.ddphi - c_prop.costh[k] * q.ddlam * q.cosphm1; }
+
+template <int JX1, int JY1, int KC, bool REFRA>
 __device__ __forceinline__ double ctu_update(const PointM& q, int k, int idp, double f0, double flon, double flat1,
                                              double flat2, double fc1, double fc2, double fkm, double fkp) {
   constexpr int JX2 = 3 - JX1, JY2 = 3 - JY1;
@@ -72,8 +83,15 @@ __device__ __forceinline__ double ctu_update(const PointM& q, int k, int idp, do
   const double wcorn2 = q.wcorm1[KC - 1] * wc;
   double sumwn = (q.zdello * dyu2 + c_prop.xdella * dxu2 - dxu2 * dyu2) * q.gam1;   // (ctuw.F90:268-274)
   // great-circle turning (ctuw.F90:404-501, IREFRA=0: DRCP=DRCM=0)
-  const double dthp = q.tanph * c_prop.sp[idp][k] * q.cg;
-  const double dthm = q.tanph * c_prop.sm[idp][k] * q.cg;
+  double dthp = q.tanph * c_prop.sp[idp][k] * q.cg;
+  double dthm = q.tanph * c_prop.sm[idp][k] * q.cg;
+  if (REFRA) {   // depth refraction (ctuw.F90:434-439, 487-501): DTHP = DRGP*CG + OMOSNH2KD*DRDP + DRCP(=0)
+    const double th = thdd(q, k);
+    const double drdp = (th + thdd(q, c_prop.kpm_p[k])) * c_prop.delth0[idp];
+    const double drdm = (th + thdd(q, c_prop.kpm_m[k])) * c_prop.delth0[idp];
+    dthp = dthp + q.omos * drdp + 0.0;
+    dthm = dthm + q.omos * drdm + 0.0;
+  }
   const double w0 = (dthp + fabs(dthp)) + (fabs(dthm) - dthm);
   const double wp = -dthp + fabs(dthp);
   const double wm = dthm + fabs(dthm);
@@ -89,7 +107,7 @@ __device__ __forceinline__ double ctu_update(const PointM& q, int k, int idp, do
 // in flight per iteration (12 independent gathers).
 // grid = (ceil(nloc/blockDim), ngroups): blockIdx.x (points) varies fastest so that the rows north and south
 // of the running row stay L2-resident for one frequency group at a time.
-template <int JX1, int JY1, int KC>
+template <int JX1, int JY1, int KC, bool REFRA>
 __device__ __forceinline__ void ctu_quadrant(const PropDev& d, const SpecSrc& src, PointM& q, int l, int m, int idp, int k0, int k1,
                                              const double* __restrict__ ps, double* __restrict__ pd) {
   if (k0 >= k1) return;
@@ -113,6 +131,7 @@ __device__ __forceinline__ void ctu_quadrant(const PropDev& d, const SpecSrc& sr
   q.wcorm1[KC - 1] = 1.0 - q.wcor[KC - 1];
   const int P = d.P;
   int k = k0;
+  PG_UNROLL
   for (; k + 1 < k1; k += 2) {
     const int ka = k, kb = k + 1;
     const double a0 = ps[(size_t)ka * P], b0 = ps[(size_t)kb * P];
@@ -123,15 +142,15 @@ __device__ __forceinline__ void ctu_quadrant(const PropDev& d, const SpecSrc& sr
     const double a4 = __ldg(p_c1 + (size_t)ka * s_c1), b4 = __ldg(p_c1 + (size_t)kb * s_c1);
     const double a5 = __ldg(p_c2 + (size_t)ka * s_c2), b5 = __ldg(p_c2 + (size_t)kb * s_c2);
     // KPM(ka,+1) = kb and KPM(kb,-1) = ka inside a quadrant
-    const double ra = ctu_update<JX1, JY1, KC>(q, ka, idp, a0, a1, a2, a3, a4, a5, am, b0);
-    const double rb = ctu_update<JX1, JY1, KC>(q, kb, idp, b0, b1, b2, b3, b4, b5, a0, bp);
+    const double ra = ctu_update<JX1, JY1, KC, REFRA>(q, ka, idp, a0, a1, a2, a3, a4, a5, am, b0);
+    const double rb = ctu_update<JX1, JY1, KC, REFRA>(q, kb, idp, b0, b1, b2, b3, b4, b5, a0, bp);
     pd[(size_t)ka * P] = ra;
     pd[(size_t)kb * P] = rb;
   }
   for (; k < k1; ++k) {
     const double f0 = ps[(size_t)k * P];
     const double fkm = ps[(size_t)c_prop.kpm_m[k] * P], fkp = ps[(size_t)c_prop.kpm_p[k] * P];
-    pd[(size_t)k * P] = ctu_update<JX1, JY1, KC>(q, k, idp, f0, __ldg(p_lon + (size_t)k * s_lon), __ldg(p_la1 + (size_t)k * s_la1),
+    pd[(size_t)k * P] = ctu_update<JX1, JY1, KC, REFRA>(q, k, idp, f0, __ldg(p_lon + (size_t)k * s_lon), __ldg(p_la1 + (size_t)k * s_la1),
                                                  __ldg(p_la2 + (size_t)k * s_la2), __ldg(p_c1 + (size_t)k * s_c1),
                                                  __ldg(p_c2 + (size_t)k * s_c2), fkm, fkp);
   }
@@ -140,6 +159,7 @@ __device__ __forceinline__ void ctu_quadrant(const PropDev& d, const SpecSrc& sr
 #ifndef PG_MINB
 #define PG_MINB 4
 #endif
+template <bool REFRA>
 __global__ void __launch_bounds__(128, PG_MINB) propags2_kernel(PropDev d, SpecSrc src, double* __restrict__ dst, long long dcstride,
                                                           int m0, int m1, int MG, int msplit, int l0, int l1) {
   const int l = l0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -160,10 +180,13 @@ __global__ void __launch_bounds__(128, PG_MINB) propags2_kernel(PropDev d, SpecS
   const int e0 = d.nbot + l;
   const int c = l / d.P, i = l - c * d.P;
   const int A = d.A;
+  q.omos = 0.0; q.ddphi = 0.0; q.ddlam = 0.0;
+  if (REFRA) { q.ddphi = __ldg(d.grad + l); q.ddlam = __ldg(d.grad + nl + l); }
   for (int m = mb; m < me; ++m) {
     const int idp = (m < msplit) ? 0 : 1;
     const double* cgm = d.cgext + (size_t)m * d.next;
     q.cg = __ldg(cgm + e0);
+    if (REFRA) q.omos = __ldg(d.omos + i + (size_t)d.P * (m + (size_t)d.F * c));
     q.hx[0] = 0.5 * (q.cg + __ldg(cgm + nb[0]));
     q.hx[1] = 0.5 * (q.cg + __ldg(cgm + nb[1]));
     {
@@ -175,10 +198,10 @@ __global__ void __launch_bounds__(128, PG_MINB) propags2_kernel(PropDev d, SpecS
     const double* ps = src.base + i + (long long)c * src.cstride + (long long)m * d.P * A;
     double* pd = dst + i + (long long)c * dcstride + (long long)m * d.P * A;
     // quadrant k-ranges [kq[j], kq[j+1]) in the order: (sin>=0,cos>=0) (sin>=0,cos<0) (sin<0,cos<0) (sin<0,cos>=0)
-    ctu_quadrant<1, 1, 3>(d, src, q, l, m, idp, c_prop.kq[0], c_prop.kq[1], ps, pd);   // west, south, SW
-    ctu_quadrant<1, 2, 4>(d, src, q, l, m, idp, c_prop.kq[1], c_prop.kq[2], ps, pd);   // west, north, NW
-    ctu_quadrant<2, 2, 1>(d, src, q, l, m, idp, c_prop.kq[2], c_prop.kq[3], ps, pd);   // east, north, NE
-    ctu_quadrant<2, 1, 2>(d, src, q, l, m, idp, c_prop.kq[3], c_prop.kq[4], ps, pd);   // east, south, SE
+    ctu_quadrant<1, 1, 3, REFRA>(d, src, q, l, m, idp, c_prop.kq[0], c_prop.kq[1], ps, pd);   // west, south, SW
+    ctu_quadrant<1, 2, 4, REFRA>(d, src, q, l, m, idp, c_prop.kq[1], c_prop.kq[2], ps, pd);   // west, north, NW
+    ctu_quadrant<2, 2, 1, REFRA>(d, src, q, l, m, idp, c_prop.kq[2], c_prop.kq[3], ps, pd);   // east, north, NE
+    ctu_quadrant<2, 1, 2, REFRA>(d, src, q, l, m, idp, c_prop.kq[3], c_prop.kq[4], ps, pd);   // east, south, SE
   }
 }
 
@@ -197,6 +220,7 @@ __global__ void __launch_bounds__(128) ctu_check_kernel(PropDev d, int m0, int m
                tanph = d.pt[4 * (size_t)nl + l];
   const double xdella = c_prop.xdella, gam1 = 1.0 / (zdello * xdella);
   const int e0 = d.nbot + l;
+  const double ddphi = d.irefra == 1 ? d.grad[l] : 0.0, ddlam = d.irefra == 1 ? d.grad[nl + l] : 0.0;
   bool bad = false;
   auto chk = [&](double w) { if (w > 1.0 || w < 0.0) bad = true; };
   for (int m = m0 + blockIdx.y; m < m1; m += gridDim.y) {
@@ -234,7 +258,14 @@ __global__ void __launch_bounds__(128) ctu_check_kernel(PropDev d, int m0, int m
       double w4[4] = {dxu[jx1] * dyu[jy1] * gam1, 0.0 * dyu[jy1] * gam1, dxu[jx1] * 0.0 * gam1, 0.0};
       for (int icr = 0; icr < 4; ++icr) { chk(wcor[kcr[icr]] * w4[icr]); chk((1.0 - wcor[kcr[icr]]) * w4[icr]); }
       double sumwn = (zdello * dyu[jy2] + xdella * dxu[jx2] - dxu[jx2] * dyu[jy2]) * gam1;
-      const double dthp = tanph * c_prop.sp[idp][k] * cg, dthm = tanph * c_prop.sm[idp][k] * cg;
+      double dthp = tanph * c_prop.sp[idp][k] * cg, dthm = tanph * c_prop.sm[idp][k] * cg;
+      if (d.irefra == 1) {
+        auto th = [&](int kk) { return c_prop.sinth[kk] * ddphi - c_prop.costh[kk] * ddlam * cosphm1; };
+        const double t0 = th(k);
+        const double omos = d.omos[(l - (l / d.P) * d.P) + (size_t)d.P * (m + (size_t)d.F * (l / d.P))];
+        dthp = dthp + omos * ((t0 + th(c_prop.kpm_p[k])) * c_prop.delth0[idp]) + 0.0;
+        dthm = dthm + omos * ((t0 + th(c_prop.kpm_m[k])) * c_prop.delth0[idp]) + 0.0;
+      }
       const double w0 = (dthp + fabs(dthp)) + (fabs(dthm) - dthm), wp = -dthp + fabs(dthp), wm = dthm + fabs(dthm);
       chk(w0); chk(wp); chk(wm);
       sumwn = sumwn + w0;
@@ -265,12 +296,37 @@ __global__ void setup_points_kernel(PropDev d, const double* __restrict__ cosphm
 }
 
 // CGROUP(P,F,C) -> CG_EXT[m][nbot + l]   (proenvhalo.F90:67-83, group velocity only)
-__global__ void fill_cgext_kernel(PropDev d, const double* __restrict__ cgroup, double* __restrict__ cgext) {
+__global__ void fill_cgext_kernel(PropDev d, const double* __restrict__ cgroup, const double* __restrict__ depth, double* __restrict__ cgext) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = blockIdx.y;
   if (l >= d.nloc) return;
   const int c = l / d.P, i = l - c * d.P;
-  cgext[(size_t)m * d.next + d.nbot + l] = cgroup[i + (size_t)d.P * (m + (size_t)d.F * c)];
+  // row Fr (IREFRA = 1 only) = DEPTH_EXT (proenvhalo.F90:81)
+  cgext[(size_t)m * d.next + d.nbot + l] = m < d.Fr ? cgroup[i + (size_t)d.P * (m + (size_t)d.F * c)] : depth[i + (size_t)d.P * c];
+}
+// GRADI's depth gradients (gradi.F90:120-153) with WLAT as PROPCONNECT left it (PROPDOT runs before CTUWINI, propag_wam.F90:171-216)
+__global__ void depth_grad_kernel(PropDev d, const double* __restrict__ wlat_raw, const double* __restrict__ dellam, double oneo2delphi,
+                                  double* __restrict__ grad) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= d.nloc) return;
+  const int nl = d.nloc, land = d.next - 1;
+  const double* dep = d.cgext + (size_t)d.Fr * d.next;
+  const int ilm = d.nbr[l], ilp = d.nbr[(size_t)nl + l];                                              // KLON(IJ,1), KLON(IJ,2)
+  const int ipm = d.nbr[2 * (size_t)nl + l], ipp = d.nbr[3 * (size_t)nl + l];                         // KLAT(IJ,1,1), KLAT(IJ,2,1)
+  const int ipm2 = d.nbr[4 * (size_t)nl + l], ipp2 = d.nbr[5 * (size_t)nl + l];                       // KLAT(IJ,1,2), KLAT(IJ,2,2)
+  const double w1 = wlat_raw[l], w2 = wlat_raw[(size_t)nl + l];
+  double ddphi, ddlam;
+  if (ipp != land && ipm != land && ipp2 != land && ipm2 != land) {
+    const double dptp = w2 * dep[ipp] + (1.0 - w2) * dep[ipp2];
+    const double dptm = w1 * dep[ipm] + (1.0 - w1) * dep[ipm2];
+    ddphi = (dptp - dptm) * oneo2delphi;
+  } else if (ipp != land && ipm != land) ddphi = (dep[ipp] - dep[ipm]) * oneo2delphi;
+  else if (ipp2 != land && ipm2 != land) ddphi = (dep[ipp2] - dep[ipm2]) * oneo2delphi;
+  else ddphi = 0.0;
+  if (ilp != land && ilm != land) ddlam = (dep[ilp] - dep[ilm]) / (2. * dellam[l]);
+  else ddlam = 0.0;
+  grad[l] = ddphi;
+  grad[(size_t)nl + l] = ddlam;
 }
 
 // gather a (points, nk, nm) message block for every peer: out[peerblock + ih + ns*(k + nk*m)]
@@ -309,7 +365,7 @@ __global__ void unpack_cg_kernel(PropDev d, const double* __restrict__ in, const
 }
 __global__ void land_cg_kernel(PropDev d, const double* __restrict__ land_cg, double* __restrict__ cgext) {
   const int m = threadIdx.x;
-  if (m < d.Fr) cgext[(size_t)m * d.next + d.next - 1] = land_cg[m];
+  if (m < d.nenv) cgext[(size_t)m * d.next + d.next - 1] = land_cg[m];   // land_cg[Fr] = BATHYMAX (proenvhalo.F90:104)
 }
 
 // FL3 (P,A,Fr,C) -> FL1 (P,A,F,C) for m in [m0,m1) + refresh of the padded lanes of the last chunk
@@ -348,7 +404,8 @@ void launch_propags2(const PropDev& d, const double* src, int srcF, double* dst,
   const int MG = 8;
   SpecSrc s{src, (long long)d.P * d.A * srcF};
   dim3 grid((l1 - l0 + 127) / 128, (m1 - m0 + MG - 1) / MG);
-  propags2_kernel<<<grid, 128, 0, st>>>(d, s, dst, (long long)d.P * d.A * dstF, m0, m1, MG, msplit, l0, l1);
+  if (d.irefra == 1) propags2_kernel<true><<<grid, 128, 0, st>>>(d, s, dst, (long long)d.P * d.A * dstF, m0, m1, MG, msplit, l0, l1);
+  else propags2_kernel<false><<<grid, 128, 0, st>>>(d, s, dst, (long long)d.P * d.A * dstF, m0, m1, MG, msplit, l0, l1);
 }
 void launch_ctu_check(const PropDev& d, int m0, int m1, int msplit, int* flag, int* count, cudaStream_t st) {
   cudaMemsetAsync(flag, 0, sizeof(int) * d.nloc, st);
@@ -361,10 +418,13 @@ void launch_setup_points(const PropDev& d, const double* cosphm1_fld, const doub
                          double* pt, cudaStream_t st) {
   setup_points_kernel<<<(d.nloc + 255) / 256, 256, 0, st>>>(d, cosphm1_fld, cosph_m, cosph_p, pt);
 }
-void launch_fill_cgext(const PropDev& d, const double* cgroup, double* cgext, const double* land_cg, cudaStream_t st) {
-  dim3 grid((d.nloc + 255) / 256, d.Fr);
-  fill_cgext_kernel<<<grid, 256, 0, st>>>(d, cgroup, cgext);
+void launch_fill_cgext(const PropDev& d, const double* cgroup, const double* depth, double* cgext, const double* land_cg, cudaStream_t st) {
+  dim3 grid((d.nloc + 255) / 256, d.nenv);
+  fill_cgext_kernel<<<grid, 256, 0, st>>>(d, cgroup, depth, cgext);
   land_cg_kernel<<<1, 64, 0, st>>>(d, land_cg, cgext);
+}
+void launch_depth_gradients(const PropDev& d, const double* wlat_raw, const double* dellam, double oneo2delphi, double* grad, cudaStream_t st) {
+  depth_grad_kernel<<<(d.nloc + 255) / 256, 256, 0, st>>>(d, wlat_raw, dellam, oneo2delphi, grad);
 }
 void launch_pack(const PropDev& d, const double* src, int srcF, const double* cgext, int mode, int nk, int nm, int nfull,
                  const int* send_l, const int* send_pre, const int* send_peer_of, int ntot, double* out, cudaStream_t st) {
@@ -376,7 +436,7 @@ void launch_pack(const PropDev& d, const double* src, int srcF, const double* cg
 void launch_unpack_cg(const PropDev& d, const double* in, const int* recv_pre, const int* recv_peer_of, const int* recv_e,
                       int ntot, int nfull, double* cgext, cudaStream_t st) {
   if (ntot <= 0) return;
-  dim3 grid((ntot + 127) / 128, d.Fr);
+  dim3 grid((ntot + 127) / 128, nfull);
   unpack_cg_kernel<<<grid, 128, 0, st>>>(d, in, recv_pre, recv_peer_of, recv_e, ntot, nfull, cgext);
 }
 void launch_copyback(const PropDev& d, const double* fl3, double* fl1, int m0, int m1, cudaStream_t st) {

@@ -43,7 +43,7 @@ typedef struct ecwam_b200_params {
   int iphys;       /* YOWSTAT IPHYS: 0 = Janssen/WAM4, 1 = Ardhuin et al. 2010          */
   int isnonlin;    /* YOWSTAT ISNONLIN (0 only)                                         */
   int idamping;    /* YOWSTAT IDAMPING (SINPUT_JAN)                                     */
-  int irefra;      /* YOWSTAT IREFRA (0 only)                                           */
+  int irefra;      /* YOWSTAT IREFRA (0 = none, 1 = depth refraction; 2, 3 = currents: not built) */
   int icase;       /* YOWSTAT ICASE (1 = spherical, only)                               */
   int llgcbz0;     /* YOWCOUP LLGCBZ0 (0 only)                                          */
   int llnormagam;  /* YOWCOUP LLNORMAGAM (0 only)                                       */
@@ -228,7 +228,7 @@ typedef struct ecwam_b200_fields {
   const double* cinv;
   const double* cgroup;
   const double* xk2cg;
-  const double* omosnh2kd;   /* PROPAG_WAM only (IREFRA/=0; unused) */
+  const double* omosnh2kd;   /* PROPAG_WAM only (read when IREFRA = 1) */
   const double* stokfac;
   const double* ciwa;        /* unused (LCIWA*=F) */
   const double* depth;       /* (P,C) */

@@ -198,6 +198,33 @@ static void ctuwupdt(Model& m, int ir, ArrD& BUF) {
     r.WCORN.alloc(IJS, IJL, 1, NANG, 1, FR, 1, 4, 1, 2);
     r.WKPMN.alloc(IJS, IJL, 1, NANG, 1, FR, -1, 1);
   }
+  // depth refraction (IREFRA = 1): THDD(IJ,K) of PROPDOT with GRADI's depth gradients (propag_wam.F90:171-216 runs it BEFORE
+  // CTUWUPDT, i.e. with WLAT as PROPCONNECT left it; gradi.F90:120-153, propdot.F90:117-156, ICASE = 1)
+  ArrD THDD;
+  if (c.irefra == 1) {
+    THDD.alloc(IJS, IJL, 1, NANG);
+    const double DELPHI = g.XDELLA * t.CIRC / 360.0;   // readmdlconf.F90:136
+    const double ONEO2DELPHI = 0.5 / DELPHI;
+    auto DPTHEXT = [&](int ij) { return BUF(ij, 3 * FR + 3, 1); };
+    for (int IJ = IJS; IJ <= IJL; ++IJ) {
+      const int IPP = r.KLAT(IJ, 2, 1), IPM = r.KLAT(IJ, 1, 1), IPP2 = r.KLAT(IJ, 2, 2), IPM2 = r.KLAT(IJ, 1, 2);
+      double DDPHI, DDLAM;
+      if (IPP != NLAND && IPM != NLAND && IPP2 != NLAND && IPM2 != NLAND) {
+        const double DPTP = r.WLAT(IJ, 2) * DPTHEXT(IPP) + (1.0 - r.WLAT(IJ, 2)) * DPTHEXT(IPP2);
+        const double DPTM = r.WLAT(IJ, 1) * DPTHEXT(IPM) + (1.0 - r.WLAT(IJ, 1)) * DPTHEXT(IPM2);
+        DDPHI = (DPTP - DPTM) * ONEO2DELPHI;
+      } else if (IPP != NLAND && IPM != NLAND) {
+        DDPHI = (DPTHEXT(IPP) - DPTHEXT(IPM)) * ONEO2DELPHI;
+      } else if (IPP2 != NLAND && IPM2 != NLAND) {
+        DDPHI = (DPTHEXT(IPP2) - DPTHEXT(IPM2)) * ONEO2DELPHI;
+      } else DDPHI = 0.0;
+      const int ILP = r.KLON(IJ, 2), ILM = r.KLON(IJ, 1), KX = g.KXLT(IJ);
+      if (ILP != NLAND && ILM != NLAND) DDLAM = (DPTHEXT(ILP) - DPTHEXT(ILM)) / (2. * g.DELLAM(KX));
+      else DDLAM = 0.0;
+      const double DCO = BUF(IJ, 3 * FR + 2, 1);       // COSPHM1_EXT
+      for (int K = 1; K <= NANG; ++K) THDD(IJ, K) = t.SINTH(K) * DDPHI - t.COSTH(K) * DDLAM * DCO;
+    }
+  } else if (c.irefra != 0) throw std::runtime_error("CTUW: only IREFRA = 0 and 1 are restated");
   ArrD WLATM1, WCORM1, DP;
   WLATM1.alloc(IJS, IJL, 1, 2); WCORM1.alloc(IJS, IJL, 1, 4); DP.alloc(IJS, IJL, 1, 2);
   // CTUWINI
@@ -317,8 +344,16 @@ static void ctuwupdt(Model& m, int ir, ArrD& BUF) {
           double TANPH = g.SINPH(JH) / g.COSPH(JH);
           double DRGP = TANPH * SP, DRGM = TANPH * SM;
           double DRCP = 0.0, DRCM = 0.0;
-          double DTHP = DRGP * CG(IJ, M) + DRCP;
-          double DTHM = DRGM * CG(IJ, M) + DRCM;
+          double DTHP, DTHM;
+          if (c.irefra == 0) {                     // ctuw.F90:471-486
+            DTHP = DRGP * CG(IJ, M) + DRCP;
+            DTHM = DRGM * CG(IJ, M) + DRCM;
+          } else {                                 // ctuw.F90:434-439, 487-501 (IREFRA = 1)
+            const double DRDP = (THDD(IJ, K) + THDD(IJ, KP1)) * DELTH0;
+            const double DRDM = (THDD(IJ, K) + THDD(IJ, KM1)) * DELTH0;
+            DTHP = DRGP * CG(IJ, M) + BUF(IJ, 2 * FR + M, 1) * DRDP + DRCP;
+            DTHM = DRGM * CG(IJ, M) + BUF(IJ, 2 * FR + M, 1) * DRDM + DRCM;
+          }
           double w0 = (DTHP + std::fabs(DTHP)) + (std::fabs(DTHM) - DTHM);
           double wp = -DTHP + std::fabs(DTHP);
           double wm = DTHM + std::fabs(DTHM);

@@ -174,6 +174,25 @@ def test_against_golden(built, name):
         assert relerr(w.get_field(nm)[inv], z[nm]) <= RTOL_FIELD, nm
 
 
+@pytest.mark.parametrize("case", ["o48like", "o640like"])
+def test_depth_refraction_bit_exact(built, case):
+    """IREFRA = 1: GRADI's depth gradients, PROPDOT's THDD and the depth-refraction term of the direction weights
+    (ctuw.F90:434-439, 487-501) are recomputed in the kernel in the reference's operation order -> PROPAGS2 stays bit-exact."""
+    g, o0, f, fl = make_oracle(case)
+    g, o, f, fl = make_oracle(case, irefra=1)
+    _, s, w = make_gpu(case, irefra=1)
+    assert o.propag() == 0 and o0.propag() == 0 and w.propag() == 0
+    w.synchronize()
+    np.testing.assert_array_equal(w.get_spec("fl1"), o.get_fl1()[:, :, w.own])
+    changed = (o.get_fl1() != o0.get_fl1()).any(axis=(0, 1)).mean()
+    assert changed > 0.1, "the case must have points where depth refraction acts (%g)" % changed
+    o.implsch(); w.implsch()
+    for _ in range(2):
+        assert o.step() == 0 and w.step() == 0
+    w.synchronize()
+    check_state(w, o)
+
+
 def test_cfl_violation_is_reported(built):
     """a 10x too long advection step must come back as a positive count (the reference aborts, ctuwdrv.F90:127-146)."""
     g, o, f, fl = make_oracle("o48like", idelpro=20000.0, delpro_lf=20000.0)

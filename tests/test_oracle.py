@@ -102,3 +102,20 @@ def test_wave_growth_is_physical(built):
     assert 0.0 < u.min() and u.max() < 2.0
     windy = f["WSWAVE"] > 12.0
     assert hs[windy].mean() > hs0[windy].mean()      # growing wind sea under strong wind
+
+
+def test_depth_refraction_oracle_properties(built):
+    """IREFRA = 1 (gradi.F90:120-153, propdot.F90:156, ctuw.F90:434-439, 487-501): the turning weights only move energy between
+    directions, the result does not depend on the decomposition, and only points with a depth gradient in finite depth change."""
+    out = {}
+    for key, kw in (("r0", dict(irefra=0)), ("r1", dict(irefra=1)), ("r1n3", dict(irefra=1, npr=3))):
+        g, o, f, fl = make_oracle("o48like", **kw)
+        assert o.propag() == 0
+        out[key] = o.get_fl1()
+    np.testing.assert_array_equal(out["r1"], out["r1n3"])
+    changed = (out["r1"] != out["r0"]).any(axis=(0, 1))
+    assert 0.1 < changed.mean() < 0.9
+    deep_flat = g.depth > 990.0
+    # a point whose whole neighbourhood is at BATHYMAX has no depth gradient: rows of constant depth stay untouched
+    assert (~changed[deep_flat]).sum() > 0
+    np.testing.assert_allclose(out["r1"].sum(), out["r0"].sum(), rtol=1e-9)
