@@ -731,9 +731,57 @@ int ecwam_b200_no_source(ecwam_b200_handle h, int llsource_off) {
 
 int ecwam_b200_outparam_supported(int itg) {
   static const int ok[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 12, 13, 14, 15, 16, 20, 21, 22, 23, 24, 25, 26, 27, 28, 32, 35, 36, 37, 38,
-                           39, 40, 41, 53, 54, 55, 56, 62, 63, 73, 74, 75, 76, 77};
+                           39, 40, 41, 52, 53, 54, 55, 56, 62, 63, 64, 65, 66, 67, 68, 69, 73, 74, 75, 76, 77};
   for (int v : ok) if (v == itg) return 1;
   return 0;
+}
+
+// SEBTMEAN (sebtmean.F90:66-198) as weights on the 1-D spectrum rows: EBT = EPSMIN + sum_m w[m] * sum_k F(k,m).  The routine is
+// linear in F (trapezoid between the cut-offs, linear interpolation at the two ends, f**-5 tail), so the weights depend on
+// (TB, TT) and the frequency grid only.
+static void sebtmean_weights(const DevConst& c, double TB, double TT, double* w) {
+  const int NFRE = c.F;
+  auto FR = [&](int m) { return c.FR[m - 1]; };
+  for (int m = 0; m < NFRE; ++m) w[m] = 0.0;
+  std::vector<double> FRLOC(NFRE + 2, 0.0);
+  std::vector<std::vector<double>> node(NFRE + 2, std::vector<double>(NFRE + 1, 0.0));   // node[M][row]: F1D(:,M) as a combination of rows
+  double FBOT = 1.0 / std::max(TT, c.EPSMIN);
+  const double FCUTB_FT = std::min(FBOT, FR(NFRE));
+  const double FCUTB = std::max(FR(1), FCUTB_FT);
+  FBOT = std::max(FBOT, FR(NFRE));
+  int MCUTB = 1;
+  while (FR(MCUTB) < FCUTB && MCUTB < NFRE) ++MCUTB;
+  double FTOP = 1.0 / std::max(TB, c.EPSMIN);
+  const double FCUTT = std::max(FR(1), std::min(FTOP, FR(NFRE)));
+  FTOP = std::max(FTOP, FR(NFRE));
+  int MCUTT = NFRE;
+  while (FR(MCUTT) > FCUTT && MCUTT > 1) --MCUTT;
+  if (FCUTB == FCUTT) MCUTT = MCUTB - 1;
+  if (MCUTB > 1) {
+    FRLOC[MCUTB - 1] = FCUTB;
+    const double WL = (FR(MCUTB) - FCUTB) / (FR(MCUTB) - FR(MCUTB - 1));
+    node[MCUTB - 1][MCUTB - 1] = WL; node[MCUTB - 1][MCUTB] = 1.0 - WL;
+  }
+  for (int M = MCUTB; M <= MCUTT; ++M) { FRLOC[M] = FR(M); std::fill(node[M].begin(), node[M].end(), 0.0); node[M][M] = 1.0; }
+  if (MCUTT < NFRE) {
+    FRLOC[MCUTT + 1] = FCUTT;
+    // MCUTT = 0 (band entirely below FR(1)): the reference's WL = 0/(FR(1)-FR(0)) reads FR(0) out of bounds; take WL = 0
+    const double WL = MCUTT >= 1 ? (FR(MCUTT + 1) - FCUTT) / (FR(MCUTT + 1) - FR(MCUTT)) : 0.0;
+    std::fill(node[MCUTT + 1].begin(), node[MCUTT + 1].end(), 0.0);
+    if (MCUTT >= 1) node[MCUTT + 1][MCUTT] = WL;
+    node[MCUTT + 1][MCUTT + 1] = 1.0 - WL;
+  }
+  for (int M = std::max(MCUTB - 1, 1); M <= std::min(MCUTT, NFRE - 1); ++M) {
+    const double DF = 0.5 * (FRLOC[M + 1] - FRLOC[M]);
+    for (int r = 1; r <= NFRE; ++r) w[r - 1] += DF * (node[M + 1][r] + node[M][r]);
+  }
+  if (FCUTB_FT < FCUTB && FCUTB == FR(1)) {
+    const double WL = (FR(1) - FCUTB_FT) / FR(1), WR = 1.0 - WL;
+    const double DF = 0.5 * (FR(1) - FCUTB_FT) * (1.0 + WR);
+    for (int r = 1; r <= NFRE; ++r) w[r - 1] += DF * node[1][r];
+  }
+  if (FBOT < FTOP) w[NFRE - 1] += 0.25 * c.FR5[NFRE - 1] * (1.0 / (FBOT * FBOT * FBOT * FBOT) - 1.0 / (FTOP * FTOP * FTOP * FTOP));
+  for (int m = 0; m < NFRE; ++m) w[m] *= c.DELTH;
 }
 
 static int check_outsel(const ecwam_b200_outsel* sel) {
@@ -765,6 +813,10 @@ int ecwam_b200_outbs(ecwam_b200_handle h, const ecwam_b200_outsel* sel, const in
   oc.rnum = c.rnum; oc.flmin = c.flmin; oc.cithrsh = c.cithrsh; oc.zmiss = sel->zmiss;
   for (int m = 0; m < c.F; ++m) { oc.FR[m] = c.FR[m]; oc.DFIM[m] = c.DFIM[m]; oc.DFIMOFR[m] = c.DFIMOFR[m]; oc.DFIMFR[m] = c.DFIMFR[m]; oc.DFIM_SIM[m] = c.DFIM_SIM[m]; }
   for (int k = 0; k < c.A; ++k) { oc.TH[k] = c.TH[k]; oc.COSTH[k] = c.COSTH[k]; oc.SINTH[k] = c.SINTH[k]; }
+  {   // SE10MEAN (se10mean.F90:60-66: 10 s .. 1/FR(1)) and the six bands of mpcrtbl.F90:373-399
+    static const double BANDS[7][2] = {{10, 0}, {10, 12}, {12, 14}, {14, 17}, {17, 21}, {21, 25}, {25, 30}};
+    for (int b = 0; b < 7; ++b) sebtmean_weights(c, BANDS[b][0], b == 0 ? 1.0 / c.FR[0] : BANDS[b][1], oc.SEBT[b]);
+  }
   rc = upload_out_const(oc, h->st);
   if (rc) return rc;
   OutDev d;

@@ -88,6 +88,9 @@ struct OutConst {   // constant memory of outparam.cu
       rnum, flmin, cithrsh, zmiss;
   double FR[EW_MAXF], DFIM[EW_MAXF], DFIMOFR[EW_MAXF], DFIMFR[EW_MAXF], DFIM_SIM[EW_MAXF];
   double TH[EW_MAXA], COSTH[EW_MAXA], SINTH[EW_MAXA];
+  // SEBTMEAN (sebtmean.F90) is linear in the 1-D spectrum: EBT = EPSMIN + sum_m SEBT[band][m] * sum_k F(k,m); band 0 = SE10MEAN
+  // (T > 10 s), bands 1..6 = the period intervals of mpcrtbl.F90:373-399
+  double SEBT[7][EW_MAXF];
 };
 struct OutDev {
   int P, A, F, nchnk;

@@ -181,6 +181,9 @@ __global__ void __launch_bounds__(OB_NTH, OB_MINB) k_outblock(OutDev d) {
   S.zero(); W.zero(); T.zero();
   double wds = 0.0, rlast = 0.0, em4 = 0.0, dp4 = 0.0;          // WDIRSPREAD (LLPEAKF=F), DOMINANT_PERIOD
   double wfm = 0.0, wfx = 0.0, wfy = 0.0, wt0 = 0.0, wts = 0.0, wtc = 0.0;   // WEFLUX
+  double ebt[7];                                                               // SE10MEAN + the six SEBTMEAN period bands
+#pragma unroll
+  for (int b = 0; b < 7; ++b) ebt[b] = EPSMIN;
   for (int m = F - 1; m >= 0; --m) {
     const double xinv1 = m > 0 ? ufric * __ldg(cinv + (size_t)(m - 1) * P) : 0.0;
     const double zr = icen ? exp(-10.0 * (c_oc.FR[m] * c_oc.FR[m]) / wsq) : 1.0;
@@ -225,6 +228,8 @@ __global__ void __launch_bounds__(OB_NTH, OB_MINB) k_outblock(OutDev d) {
     if (m == F - 1) { rlast = rr; wt0 = r_t0; wts = r_s; wtc = r_c; }
     const double q2 = t_dp * t_dp, q4 = q2 * q2;
     em4 += c_oc.DFIM[m] * q4; dp4 += c_oc.DFIMFR[m] * q4;
+#pragma unroll
+    for (int b = 0; b < 7; ++b) ebt[b] += c_oc.SEBT[b][m] * t_t0;
     const double cg = __ldg(cgr + (size_t)m * P);
     wfm += c_oc.DFIM[m] * (cg * r_t0); wfx += c_oc.DFIM[m] * (cg * r_s); wfy += c_oc.DFIM[m] * (cg * r_c);
     cur = nxt;
@@ -297,6 +302,9 @@ __global__ void __launch_bounds__(OB_NTH, OB_MINB) k_outblock(OutDev d) {
       case 45 + 3 * NT: v = d.f.wstar[p]; break;
       case 46 + 3 * NT: v = cic; break;
       case 47 + 3 * NT: v = d.f.cithick[p]; break;
+      case 43 + 3 * NT: v = 4.0 * sqrt(omax(ebt[0], 0.0)); break;
+      case 55 + 3 * NT: case 56 + 3 * NT: case 57 + 3 * NT: case 58 + 3 * NT: case 59 + 3 * NT: case 60 + 3 * NT:
+        v = 4.0 * sqrt(omax(ebt[itg - (54 + 3 * NT)], 0.0)); break;
       case 53 + 3 * NT: v = wefmag; break;
       case 54 + 3 * NT: v = fmod(DEG * wefdir + 180.0, 360.0); break;
       case 58 + 3 * NT + NW: v = d.f.tauxd[p]; break;

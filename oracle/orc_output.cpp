@@ -235,6 +235,62 @@ void weflux(const Tables& t, int KIJL, int NANG, int NFRE, const S3& FL1, const 
   for (int IJ = 1; IJ <= KIJL; ++IJ) WEFDIR[IJ] = std::atan2(WEFX[IJ], WEFY[IJ]);
   for (int IJ = 1; IJ <= KIJL; ++IJ) if (WEFDIR[IJ] < 0.0) WEFDIR[IJ] = WEFDIR[IJ] + t.ZPI;
 }
+// sebtmean.F90:66-198: energy between the periods TB and TT (trapezoid over the frequencies inside the band, linear
+// interpolation at its two ends, f**-5 tail above FR(NFRE))
+void sebtmean(const Tables& t, int KIJL, int NANG, int NFRE, const S3& FL1, double TB, double TT, V& EBT) {
+  std::vector<double> FRLOC(NFRE + 2, 0.0), F1D((size_t)(KIJL + 1) * (NFRE + 2), 0.0);
+  auto f1 = [&](int IJ, int M) -> double& { return F1D[(size_t)M * (KIJL + 1) + IJ]; };
+  double FBOT = 1.0 / std::max(TT, t.EPSMIN);
+  const double FCUTB_FT = std::min(FBOT, t.FR(NFRE));
+  const double FCUTB = std::max(t.FR(1), FCUTB_FT);
+  FBOT = std::max(FBOT, t.FR(NFRE));
+  int MCUTB = 1;
+  while (t.FR(MCUTB) < FCUTB && MCUTB < NFRE) MCUTB = MCUTB + 1;
+  double FTOP = 1.0 / std::max(TB, t.EPSMIN);
+  const double FCUTT = std::max(t.FR(1), std::min(FTOP, t.FR(NFRE)));
+  FTOP = std::max(FTOP, t.FR(NFRE));
+  int MCUTT = NFRE;
+  while (t.FR(MCUTT) > FCUTT && MCUTT > 1) MCUTT = MCUTT - 1;
+  if (FCUTB == FCUTT) MCUTT = MCUTB - 1;
+  for (int IJ = 1; IJ <= KIJL; ++IJ) EBT[IJ] = t.EPSMIN;
+  if (MCUTB > 1) {
+    FRLOC[MCUTB - 1] = FCUTB;
+    const double WL = (t.FR(MCUTB) - FCUTB) / (t.FR(MCUTB) - t.FR(MCUTB - 1)), WR = 1.0 - WL;
+    for (int IJ = 1; IJ <= KIJL; ++IJ) f1(IJ, MCUTB - 1) = (WL * FL1(IJ, 1, MCUTB - 1) + WR * FL1(IJ, 1, MCUTB)) * t.DELTH;
+    for (int K = 2; K <= NANG; ++K)
+      for (int IJ = 1; IJ <= KIJL; ++IJ) f1(IJ, MCUTB - 1) = f1(IJ, MCUTB - 1) + (WL * FL1(IJ, K, MCUTB - 1) + WR * FL1(IJ, K, MCUTB)) * t.DELTH;
+  }
+  for (int M = MCUTB; M <= MCUTT; ++M) {
+    FRLOC[M] = t.FR(M);
+    for (int IJ = 1; IJ <= KIJL; ++IJ) f1(IJ, M) = FL1(IJ, 1, M) * t.DELTH;
+    for (int K = 2; K <= NANG; ++K) for (int IJ = 1; IJ <= KIJL; ++IJ) f1(IJ, M) = f1(IJ, M) + FL1(IJ, K, M) * t.DELTH;
+  }
+  if (MCUTT < NFRE) {
+    FRLOC[MCUTT + 1] = FCUTT;
+    // MCUTT = 0 (band entirely below FR(1), e.g. 25-30 s on the 25-frequency grid): the reference reads FR(0) and FL1(:,:,0)
+    // out of bounds with WL = (FR(1)-FCUTT)/(FR(1)-FR(0)) = 0/x; the restatement takes that limit (WL = 0, F1D(:,1) = row 1)
+    const double WL = MCUTT >= 1 ? (t.FR(MCUTT + 1) - FCUTT) / (t.FR(MCUTT + 1) - t.FR(MCUTT)) : 0.0, WR = 1.0 - WL;
+    auto lo = [&](int IJ, int K) { return MCUTT >= 1 ? WL * FL1(IJ, K, MCUTT) : 0.0; };
+    for (int IJ = 1; IJ <= KIJL; ++IJ) f1(IJ, MCUTT + 1) = (lo(IJ, 1) + WR * FL1(IJ, 1, MCUTT + 1)) * t.DELTH;
+    for (int K = 2; K <= NANG; ++K)
+      for (int IJ = 1; IJ <= KIJL; ++IJ) f1(IJ, MCUTT + 1) = f1(IJ, MCUTT + 1) + (lo(IJ, K) + WR * FL1(IJ, K, MCUTT + 1)) * t.DELTH;
+  }
+  for (int M = std::max(MCUTB - 1, 1); M <= std::min(MCUTT, NFRE - 1); ++M) {
+    const double DF = 0.5 * (FRLOC[M + 1] - FRLOC[M]);
+    for (int IJ = 1; IJ <= KIJL; ++IJ) EBT[IJ] = EBT[IJ] + DF * (f1(IJ, M + 1) + f1(IJ, M));
+  }
+  if (FCUTB_FT < FCUTB && FCUTB == t.FR(1)) {
+    const double WL = (t.FR(1) - FCUTB_FT) / t.FR(1), WR = 1.0 - WL;
+    const double DF = 0.5 * (t.FR(1) - FCUTB_FT) * (1.0 + WR);
+    for (int IJ = 1; IJ <= KIJL; ++IJ) EBT[IJ] = EBT[IJ] + DF * f1(IJ, 1);
+  }
+  if (FBOT < FTOP) {
+    const double ZW = 0.25 * t.FR5(NFRE) * (1.0 / (FBOT * FBOT * FBOT * FBOT) - 1.0 / (FTOP * FTOP * FTOP * FTOP));
+    for (int IJ = 1; IJ <= KIJL; ++IJ) f1(IJ, NFRE) = FL1(IJ, 1, NFRE) * t.DELTH;
+    for (int K = 2; K <= NANG; ++K) for (int IJ = 1; IJ <= KIJL; ++IJ) f1(IJ, NFRE) = f1(IJ, NFRE) + FL1(IJ, K, NFRE) * t.DELTH;
+    for (int IJ = 1; IJ <= KIJL; ++IJ) EBT[IJ] = EBT[IJ] + ZW * f1(IJ, NFRE);
+  }
+}
 }  // namespace
 
 // newwind.F90:105-167 for ICODE_WND = 3: FF_NOW <- FF_NEXT with the low-wind cap on the first-guess wave stress
@@ -264,7 +320,7 @@ void newwind(Model& m, int ir, const Fields& nx) {
 
 bool outparam_supported(int itg) {
   static const int ok[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 12, 13, 14, 15, 16, 20, 21, 22, 23, 24, 25, 26, 27, 28, 32, 35, 36, 37, 38,
-                           39, 40, 41, 53, 54, 55, 56, 62, 63, 73, 74, 75, 76, 77};
+                           39, 40, 41, 52, 53, 54, 55, 56, 62, 63, 64, 65, 66, 67, 68, 69, 73, 74, 75, 76, 77};
   for (int v : ok) if (v == itg) return true;
   return false;
 }
@@ -347,6 +403,17 @@ void outblock(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK, 
     if ((b = col(53 + 3 * NTRAIN))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = TMP[IJ];
     if ((b = col(54 + 3 * NTRAIN))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = todeg(TMP2[IJ]);
   }
+  // SE10MEAN (se10mean.F90:60-66) and the period bands of mpcrtbl.F90:373-399 (IPRMINFO(:,4:5)), outblock.F90:443-446, 525-533
+  static const double BANDS[6][2] = {{10, 12}, {12, 14}, {14, 17}, {17, 21}, {21, 25}, {25, 30}};
+  if ((b = col(43 + 3 * NTRAIN))) {
+    sebtmean(t, KIJL, NANG, NFRE, FL2ND.view(), 10.0, 1.0 / t.FR(1), TMP);
+    for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = 4.0 * std::sqrt(std::max(TMP[IJ], 0.0));
+  }
+  for (int IH = 1; IH <= NTEWH; ++IH)
+    if ((b = col(54 + 3 * NTRAIN + IH))) {
+      sebtmean(t, KIJL, NANG, NFRE, FL2ND.view(), BANDS[IH - 1][0], BANDS[IH - 1][1], TMP);
+      for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = 4.0 * std::sqrt(std::max(TMP[IJ], 0.0));
+    }
   if ((b = col(62 + 3 * NTRAIN + NTEWH))) { const double* s = p1(f.PHIOCD); for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = std::max(-s[IJ - 1], 0.0); }
   // outsetwmask.F90:62-78
   for (int i = 0; i < sel.n; ++i) {

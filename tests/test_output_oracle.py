@@ -51,6 +51,16 @@ def test_outblock_against_numpy(built, case):
     # wind sea + swell = total (sepwisw.F90: the two spectra partition FL1), heights 11 / 12 vs 1
     e1, es, ew = (b[1] / 4) ** 2, (b[12] / 4) ** 2, (b[11] / 4) ** 2
     assert np.abs(es + ew - e1).max() <= 1e-12 * e1.max()
+    # period bands (sebtmean.F90): an independent trapezoid of the 1-D spectrum between the two cut-off frequencies
+    f1d = fl.sum(axis=1) * delth                                 # [m, ij]
+    def band(tb, tt):
+        lo, hi = max(1.0 / tt, fr[0]), min(1.0 / tb, fr[-1])
+        nodes = np.concatenate(([lo], fr[(fr > lo) & (fr < hi)], [hi]))
+        vals = np.stack([np.interp(nodes, fr, f1d[:, j]) for j in range(0, n, max(1, n // 50))], axis=1)
+        return np.trapezoid(vals, nodes, axis=0), slice(0, n, max(1, n // 50))
+    for itg, (tb, tt) in ((64, (10., 12.)), (66, (14., 17.)), (52, (10., 1.0 / fr[0]))):
+        e, sl = band(tb, tt)
+        np.testing.assert_allclose((b[itg][sl] / 4.0) ** 2, e + 1e-33, rtol=1e-9, atol=1e-30, err_msg=str(itg))
     # simple copies
     np.testing.assert_array_equal(b[4], o.get_field("UFRIC"))
     np.testing.assert_array_equal(b[10], o.get_field("WSWAVE"))
