@@ -213,6 +213,8 @@ void propag_wam(Model& m);  // all ranks, with in-process MPEXCHNG
 void implsch_all(Model& m); // all ranks, all chunks (wamintgr.F90:117-146)
 void implsch_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int ichnk);
 void femean(const Tables& t, const Config& c, int KIJL, const double* F /*(KIJL,A,F)*/, double* EM, double* FM);
+// SNONLIN alone on one chunk (tests: conservation properties of the DIA); SL, FLD (KIJL,A,F) are overwritten
+void snonlin_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK, double* SL, double* FLD);
 
 // ---------------------------------------------------------------------------
 // The steps either side of the hot path (orc_output.cpp): NEWWIND, OUTBLOCK core parameters, WAMNORM statistics.

@@ -78,6 +78,7 @@ def _lib(fast=False):
         lib.orc_get_hs_fm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_propag.argtypes = [C.c_void_p]
         lib.orc_newwind.argtypes = [C.c_void_p, C.c_void_p]
+        lib.orc_snonlin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_outbs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p]
         lib.orc_outwnorm.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.orc_implsch.argtypes = [C.c_void_p]
@@ -214,6 +215,14 @@ class Oracle:
             raise RuntimeError("orc_outbs failed (unsupported parameter?)")
         self._nout = len(itg)
         return out
+
+    def snonlin(self):
+        """SNONLIN alone (snonlin.F90): (SL, FLD)[m, k, ij] of the current spectra."""
+        sl = np.empty((self.cfg.nfre, self.cfg.nang, self.niblo))
+        fld = np.empty_like(sl)
+        if self.lib.orc_snonlin(self.h, sl.ctypes.data, fld.ctypes.data) != 0:
+            raise RuntimeError("orc_snonlin failed")
+        return sl, fld
 
     def outwnorm(self, global_norm=True):
         """OUTWNORM/MPMINMAXAVG on the last outbs(): rows = columns, (average, minimum, maximum, count)."""

@@ -242,6 +242,30 @@ int orc_get_hs_fm(void* h, double* hs, double* fm) {
   return 0;
 }
 
+// SNONLIN source term SL and its functional derivative FLD of the current spectra, [m][k][ij] in original global order
+int orc_snonlin(void* h, double* sl, double* fld) {
+  Model* m = (Model*)h;
+  const long N = m->grid.NIBLO;
+  const int A = m->cfg.nang, F = m->cfg.nfre;
+  for (int ir = 0; ir < m->cfg.npr; ++ir) {
+    RankDecomp& r = m->ranks[ir];
+    const int P = r.NPROMA;
+    std::vector<double> S((size_t)P * A * F), D((size_t)P * A * F);
+    for (int ic = 1; ic <= r.NCHNK; ++ic) {
+      snonlin_chunk(m->cfg, m->tab, m->fld[ir], P, ic, S.data(), D.data());
+      for (int ip = 1; ip <= r.KIJL4CHNK(ic); ++ip) {
+        const int ij0 = m->grid.NEWIJ2IJ(r.IJFROMCHNK(ip, ic));
+        for (int M = 1; M <= F; ++M)
+          for (int K = 1; K <= A; ++K) {
+            const size_t o = ((size_t)(M - 1) * A + (K - 1)) * N + ij0 - 1, q = (ip - 1) + (size_t)P * ((K - 1) + (size_t)A * (M - 1));
+            sl[o] = S[q]; fld[o] = D[q];
+          }
+      }
+    }
+  }
+  return 0;
+}
+
 // NEWWIND (newwind.F90) with FF_NEXT given in original global order: wswave, wdwave, aird, wstar, cicover, cithick, ustra, vstra
 int orc_newwind(void* h, const double* const* next8) {
   Model* m = (Model*)h;

@@ -1053,6 +1053,21 @@ void implsch_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int IC
   STOKESDRIFT(x, FL1, STOKFAC, WSWAVE, WDWAVE, CICOVER, USTOKES, VSTOKES);  // stokestrn.F90:76 (no NEMO coupling)
 }
 
+// SNONLIN (snonlin.F90) on its own with AKMEAN from FKMEAN, as IMPLSCH calls it (implsch.F90:288)
+void snonlin_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK, double* SLp, double* FLDp) {
+  const int NANG = c.nang, NFRE = c.nfre, KIJS = 1;
+  Ctx x{c, t, KIJS, KIJL, NANG, NFRE};
+  const int P = KIJL;
+  V3 FL1{&f.FL1(1, 1, 1, ICHNK), P, NANG};
+  V2 WAVNUM{&f.WAVNUM(1, 1, ICHNK), P};
+  V1 DEPTH{&f.DEPTH(1, ICHNK)};
+  L1 lEM(P), lFM(P), lF1(P), lAK(P), lXK(P);
+  FKMEAN(x, FL1, WAVNUM, lEM.view(), lFM.view(), lF1.view(), lAK.view(), lXK.view());
+  const size_t n3 = (size_t)P * NANG * NFRE;
+  for (size_t i = 0; i < n3; ++i) { SLp[i] = 0.0; FLDp[i] = 0.0; }
+  SNONLIN(x, FL1, V3{FLDp, P, NANG}, V3{SLp, P, NANG}, WAVNUM, DEPTH, lAK.view());
+}
+
 // wamintgr.F90:117-146
 void implsch_all(Model& m) {
   for (int ir = 0; ir < m.cfg.npr; ++ir) {

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
 
-from common import CASES, make_oracle, OUT_FIELDS  # noqa: E402
+from common import CASES, make_oracle, OUT_FIELDS, OUT_ITG, OUT_ICE, OUT_SEA  # noqa: E402
 
 GOLDEN = {"g_iphys1": ("o48like", 8), "g_iphys0": ("o48_iphys0", 8), "g_a36": ("o640like", 6)}
 
@@ -33,6 +33,9 @@ def main():
             out[nm] = o.get_field(nm)
         hs, fm = o.hs_fm()
         out["hs"], out["fm"] = hs, fm
+        out["bout"] = o.outbs(OUT_ITG, OUT_ICE, OUT_SEA)             # OUTBS columns in the order of common.OUT_ITG
+        out["bout_itg"] = np.array(OUT_ITG, dtype=np.int32)
+        out["wnorm"] = o.outwnorm(True)
         out["nsteps"] = nsteps
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(name, case, "niblo", g.niblo, "Hs mean", hs.mean())

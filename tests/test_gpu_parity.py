@@ -172,6 +172,14 @@ def test_against_golden(built, name):
     np.testing.assert_array_equal(np.packbits(w.get_spec("xllws")[:, :, inv].astype(np.uint8).ravel()), z["xllws"])
     for nm in OUT_FIELDS:
         assert relerr(w.get_field(nm)[inv], z[nm]) <= RTOL_FIELD, nm
+    # OUTBS columns and the WAMNORM lines of the fixture (tests/golden/make_golden.py)
+    from common import OUT_ICE, OUT_SEA, compare_bout
+    itg = [int(i) for i in z["bout_itg"]]
+    b = w.outbs(itg, OUT_ICE, OUT_SEA)[:, inv]
+    compare_bout(b, z["bout"], itgs=itg)
+    wn = w.outwnorm(True)
+    np.testing.assert_array_equal(wn[:, 3], z["wnorm"][:, 3])
+    np.testing.assert_allclose(wn[0, :3], z["wnorm"][0, :3], rtol=1e-11)      # swh: average, minimum, maximum
 
 
 @pytest.mark.parametrize("case", ["o48like", "o640like"])

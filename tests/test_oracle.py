@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from common import CASES, OUT_FIELDS, make_oracle
+from common import CASES, OUT_FIELDS, OUT_ICE, OUT_SEA, ZMISS, make_oracle
 from ecwam_b200 import synth
 from oracle import oracle as O
 
@@ -29,6 +29,11 @@ def test_oracle_reproduces_golden(built, name):
     np.testing.assert_array_equal(np.packbits(o.get_xllws().astype(np.uint8).ravel()), z["xllws"])
     for nm in OUT_FIELDS:
         np.testing.assert_allclose(o.get_field(nm), z[nm], rtol=1e-11, atol=1e-14, err_msg=nm)
+    itg = [int(i) for i in z["bout_itg"]]
+    b = o.outbs(itg, OUT_ICE, OUT_SEA)
+    assert np.array_equal(b == ZMISS, z["bout"] == ZMISS)
+    np.testing.assert_allclose(b, z["bout"], rtol=1e-9, atol=1e-9)           # directions / spreads amplify rounding
+    np.testing.assert_allclose(o.outwnorm(True)[:, 3], z["wnorm"][:, 3])
 
 
 def test_ctu_weights_in_range_and_sum(built):
@@ -119,3 +124,29 @@ def test_depth_refraction_oracle_properties(built):
     # a point whose whole neighbourhood is at BATHYMAX has no depth gradient: rows of constant depth stay untouched
     assert (~changed[deep_flat]).sum() > 0
     np.testing.assert_allclose(out["r1"].sum(), out["r0"].sum(), rtol=1e-9)
+
+
+def test_dia_conserves_energy_and_action(built):
+    """SNONLIN (snonlin.F90) with the NLWEIGT/INISNONLIN tables: for a deep-water spectrum that vanishes near both ends of the
+    frequency grid every quadruplet is resolved, and the discrete interaction approximation conserves energy and action to
+    rounding (the bilinear weights are built for that); momentum only to the accuracy of the direction grid.  This pins the
+    restated DIA loops, the edge-case branches and the coefficient tables independently of any reference run."""
+    g, o, f, fl = make_oracle("aqua")
+    F, A, n = fl.shape
+    fr, th, dfim = o.table("FR"), o.table("TH"), o.table("DFIM")
+    m0 = 12
+    spec = np.exp(-0.5 * ((np.arange(F) - m0) / 1.5) ** 2)[:, None] * np.maximum(np.cos(th - 1.0), 0)[None, :] ** 4
+    spec[np.abs(np.arange(F) - m0) > 6] = 0.0
+    o.set_fl1(np.repeat(spec[:, :, None], n, axis=2) * (0.5 + np.arange(n) % 5)[None, None, :])
+    sl, fld = o.snonlin()
+    assert np.abs(sl).max() > 0
+    for w in (dfim, dfim / fr):                                   # energy, action
+        tot = (sl * w[:, None, None]).sum(axis=(0, 1))
+        ref = (np.abs(sl) * w[:, None, None]).sum(axis=(0, 1))
+        assert (np.abs(tot) <= 5e-15 * ref).all()
+    k = (2 * np.pi * fr) ** 2 / 9.806
+    wk = (dfim * k / fr)[:, None, None] * np.sin(th)[None, :, None]
+    assert (np.abs((sl * wk).sum(axis=(0, 1))) <= 0.05 * np.abs(sl * wk).sum(axis=(0, 1))).all()      # momentum: ~2 %
+    # the source term is cubic in the spectrum (points 0 and 1 carry 0.5 and 1.5 times the same shape)
+    r = sl[:, :, 1][np.abs(sl[:, :, 0]) > 0] / sl[:, :, 0][np.abs(sl[:, :, 0]) > 0]
+    np.testing.assert_allclose(r, (1.5 / 0.5) ** 3, rtol=1e-12)
