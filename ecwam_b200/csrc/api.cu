@@ -66,7 +66,7 @@ struct ecwam_b200_handle_s {
   PropDev pd;
   DBuf<int> nbr, halo_off, halo_str, send_l, send_pre, send_peer_of, recv_pre, recv_peer_of, recv_e, flag, count;
   DBuf<double> wl, pt, cgext, halo, sendbuf, fl3, cosph_m, cosph_p, land_cg, cgrecv;
-  DBuf<double> wlat_raw, dellam, grad;   // IREFRA = 1: WLAT as PROPCONNECT left it, DELLAM(KXLT), depth gradients
+  DBuf<double> wlat_raw, dellam, grad, curmask;   // IREFRA /= 0: WLAT as PROPCONNECT left it, DELLAM/COSPH(KXLT), gradients, CURMASK
   double oneo2delphi = 0.0;
   std::vector<int> h_spre, h_rpre;   // per peer prefix sums (size nproc+1)
   int nsend = 0, nrecv = 0;
@@ -171,8 +171,9 @@ static int fill_dev_const(const ecwam_b200_params& p, const ecwam_b200_tables& t
   memset(&c, 0, sizeof(c));
   if (p.nang < 4 || p.nang > EW_MAXA || p.nfre < 2 || p.nfre > EW_MAXF || p.nfre_red < 1 || p.nfre_red > p.nfre)
     EW_FAIL(ECWAM_B200_EINVAL, "unsupported spectral dimensions NANG=%d NFRE=%d NFRE_RED=%d", p.nang, p.nfre, p.nfre_red);
-  if ((p.irefra != 0 && p.irefra != 1) || p.icase != 1)
-    EW_FAIL(ECWAM_B200_EINVAL, "only IREFRA = 0 | 1 (depth refraction), ICASE = 1 are implemented (current refraction: SURVEY 8f rank 3)");
+  if (p.irefra < 0 || p.irefra > 3 || p.icase != 1) EW_FAIL(ECWAM_B200_EINVAL, "IREFRA must be 0..3 and ICASE = 1 (spherical)");
+  if (p.irefra >= 2 && p.ifrelfmax > 0 && p.ifrelfmax < p.nfre_red)
+    EW_FAIL(ECWAM_B200_EINVAL, "fast-wave sub-stepping (IFRELFMAX) together with current refraction (IREFRA = 2, 3) is not built");
   if (p.isnonlin != 0) EW_FAIL(ECWAM_B200_EINVAL, "only ISNONLIN=0 is implemented");
   if (p.llgcbz0 || p.llnormagam) EW_FAIL(ECWAM_B200_EINVAL, "LLGCBZ0 / LLNORMAGAM branches are not implemented (SURVEY 8f rank 2)");
   if (p.lciwa) EW_FAIL(ECWAM_B200_EINVAL, "LCIWA* / LCISCAL sea-ice attenuation is not implemented (SURVEY 8f rank 2)");
@@ -297,12 +298,15 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
   for (int v = 0; v < 2; ++v) {
     const double delth0 = 0.25 * pc.delpro[v] / tables->delth;
     pc.delth0[v] = delth0;
+    pc.delfr0[v] = 0.25 * pc.delpro[v] / ((tables->fratio - 1) * tables->zpi);
     for (int k = 0; k < A; ++k) {
       pc.sp[v][k] = delth0 * (tables->sinth[k] + tables->sinth[pc.kpm_p[k]]) / tables->r_earth;
       pc.sm[v][k] = delth0 * (tables->sinth[k] + tables->sinth[pc.kpm_m[k]]) / tables->r_earth;
     }
   }
   pc.cmtodeg = 360.0 / tables->circ;
+  pc.fratio = tables->fratio;
+  for (int m = 0; m < p.nfre && m < EW_MAXF; ++m) pc.fr[m] = tables->fr[m];
   pc.xdella = dec->xdella;
   h->msplit = (p.ifrelfmax > 0) ? std::min(p.ifrelfmax, Fr) : 0;   // ctuwupdt.F90:193-235
 
@@ -399,18 +403,20 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
        !h->cosph_p.upload(cpp, st) && !h->halo_off.upload(halo_off, st) && !h->halo_str.upload(halo_str, st) &&
        !h->send_l.upload(send_l, st) && !h->send_peer_of.upload(send_peer, st) && !h->send_pre.upload(h->h_spre, st) &&
        !h->recv_pre.upload(h->h_rpre, st) && !h->recv_peer_of.upload(recv_peer, st) && !h->recv_e.upload(recv_e, st);
-  const int nenv = Fr + (p.irefra == 1 ? 1 : 0);
+  const int nenv = Fr + (p.irefra == 0 ? 0 : (p.irefra == 1 ? 1 : 3));   // + DEPTH_EXT (+ U_EXT, V_EXT) rows
   std::vector<double> landcg(nenv, 0.0);
   if (dec->land_cgroup) for (int m = 0; m < Fr; ++m) landcg[m] = dec->land_cgroup[m];
-  if (p.irefra == 1) {
-    landcg[Fr] = p.bathymax;                                   // DEPTH_EXT(NSUP+1) (proenvhalo.F90:104)
-    std::vector<double> wr((size_t)2 * nloc), dl(nloc);
+  if (p.irefra != 0) {
+    landcg[Fr] = p.bathymax;                                   // DEPTH_EXT(NSUP+1); U_EXT, V_EXT = 0 there (proenvhalo.F90:104-106)
+    std::vector<double> wr((size_t)2 * nloc), dl((size_t)2 * nloc);
     for (int l = 0; l < nloc; ++l) {
       wr[l] = dec->wlat[l]; wr[(size_t)nloc + l] = dec->wlat[l + (size_t)nloc];
       dl[l] = dec->zdello[dec->kxlt[l] - 1] * tables->circ / 360.0;   // DELLAM(KX) (readmdlconf.F90:153)
+      dl[(size_t)nloc + l] = dec->cosph[dec->kxlt[l] - 1];           // COSPH(KX) (gradi.F90:221)
     }
     h->oneo2delphi = 0.5 / (dec->xdella * tables->circ / 360.0);      // gradi.F90:113, readmdlconf.F90:136
-    ok = ok && !h->wlat_raw.upload(wr, st) && !h->dellam.upload(dl, st) && !h->grad.alloc((size_t)2 * nloc);
+    std::vector<double> ones(nloc, 1.0);
+    ok = ok && !h->wlat_raw.upload(wr, st) && !h->dellam.upload(dl, st) && !h->grad.alloc((size_t)7 * nloc) && !h->curmask.upload(ones, st);
   }
   ok = ok && !h->land_cg.upload(landcg, st);
   ok = ok && !h->cgext.alloc((size_t)nenv * next) && !h->halo.alloc(halo_elems + 1) &&
@@ -479,7 +485,7 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
   PropDev& d = h->pd;
   d.nloc = nloc; d.nbot = nbot; d.ntop = ntop; d.next = next; d.P = P; d.A = A; d.F = F; d.Fr = Fr; d.nchnk = p.nchnk;
   d.nbr = h->nbr.p; d.wl = h->wl.p; d.pt = h->pt.p; d.cgext = h->cgext.p; d.halo_off = h->halo_off.p;
-  d.irefra = p.irefra; d.nenv = nenv; d.omos = nullptr; d.grad = h->grad.p;
+  d.irefra = p.irefra; d.nenv = nenv; d.omos = nullptr; d.grad = h->grad.p; d.wavn = nullptr; d.curmask = h->curmask.p;
   d.halo_str = h->halo_str.p; d.halo = h->halo.p;
   h->tab.k1w = h->kw.p; h->tab.k2w = h->kw.p + 2 * A; h->tab.k11w = h->kw.p + 4 * A; h->tab.k21w = h->kw.p + 6 * A;
   h->tab.ik1w = h->kw.p + 8 * A; h->tab.ik2w = h->kw.p + 10 * A; h->tab.ik11w = h->kw.p + 12 * A; h->tab.ik21w = h->kw.p + 14 * A;
@@ -518,9 +524,11 @@ int ecwam_b200_bind_fields(ecwam_b200_handle h, const ecwam_b200_fields* dev) {
       !dev->tauxd || !dev->tauyd || !dev->tauocxd || !dev->tauocyd || !dev->tauoc || !dev->tauicx || !dev->tauicy ||
       !dev->phiocd || !dev->phieps || !dev->phiaw || !dev->mij || !dev->wsemean || !dev->wsfmean || !dev->ustra || !dev->vstra)
     EW_FAIL(ECWAM_B200_EINVAL, "bind_fields: a required field pointer is NULL");
-  if (h->par.irefra == 1 && !dev->omosnh2kd) EW_FAIL(ECWAM_B200_EINVAL, "bind_fields: IREFRA = 1 needs OMOSNH2KD");
+  if (h->par.irefra != 0 && !dev->omosnh2kd) EW_FAIL(ECWAM_B200_EINVAL, "bind_fields: IREFRA /= 0 needs OMOSNH2KD");
+  if (h->par.irefra >= 2 && (!dev->ucur || !dev->vcur)) EW_FAIL(ECWAM_B200_EINVAL, "bind_fields: IREFRA = 2, 3 needs UCUR and VCUR");
   h->dev = *dev;
   h->pd.omos = dev->omosnh2kd;
+  h->pd.wavn = dev->wavnum;
   h->bound = true;
   h->weights_dirty = true;
   return 0;
@@ -559,7 +567,7 @@ static int halo_spectrum(H* h, const double* src, int srcF, int nm) {
 static int update_weights(H* h, int* cfl) {
   const PropDev& d = h->pd;
   launch_setup_points(d, h->dev.cosphm1, h->cosph_m.p, h->cosph_p.p, h->pt.p, h->st);
-  launch_fill_cgext(d, h->dev.cgroup, h->dev.depth, h->cgext.p, h->land_cg.p, h->st);
+  launch_fill_cgext(d, h->dev.cgroup, h->dev.depth, h->dev.ucur, h->dev.vcur, h->cgext.p, h->land_cg.p, h->st);
   h->nlaunch += 3;
   if (h->nproc > 1) {   // PROENVHALO: group velocity (+ depth when IREFRA = 1) of the halo points
     launch_pack(d, nullptr, 0, h->cgext.p, 1, 1, d.nenv, d.nenv, h->send_l.p, h->send_pre.p, h->send_peer_of.p, h->nsend,
@@ -569,13 +577,26 @@ static int update_weights(H* h, int* cfl) {
     launch_unpack_cg(d, h->cgrecv.p, h->recv_pre.p, h->recv_peer_of.p, h->recv_e.p, h->nrecv, d.nenv, h->cgext.p, h->st);
     h->nlaunch += 2;
   }
-  if (d.irefra == 1) {   // PROPDOT/GRADI (propag_wam.F90:171-216)
+  if (d.irefra != 0) {   // PROPDOT/GRADI (propag_wam.F90:171-216)
     launch_depth_gradients(d, h->wlat_raw.p, h->dellam.p, h->oneo2delphi, h->grad.p, h->st);
     h->nlaunch++;
   }
-  launch_ctu_check(d, 0, d.Fr, h->msplit, h->flag.p, h->count.p, h->st);
-  h->nlaunch += 2;
   int cnt = 0;
+  if (d.irefra >= 2) {   // CTUWDRV with currents (ctuwdrv.F90:83-123): ICALL = 1, then ICALL = 2 with CURMASK where it failed
+    launch_curmask(d, h->flag.p, h->curmask.p, 1, h->st);
+    launch_ctu_check_cur(d, 0, d.Fr, h->msplit, h->flag.p, h->count.p, h->st);
+    h->nlaunch += 3;
+    EW_CUDA_CHECK(cudaMemcpyAsync(&cnt, h->count.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    EW_CUDA_CHECK(cudaStreamSynchronize(h->st));
+    if (cnt > 0 && h->par.llcflcuroff) {
+      launch_curmask(d, h->flag.p, h->curmask.p, 0, h->st);
+      launch_ctu_check_cur(d, 0, d.Fr, h->msplit, h->flag.p, h->count.p, h->st);
+      h->nlaunch += 3;
+    }
+  } else {
+    launch_ctu_check(d, 0, d.Fr, h->msplit, h->flag.p, h->count.p, h->st);
+    h->nlaunch += 2;
+  }
   EW_CUDA_CHECK(cudaMemcpyAsync(&cnt, h->count.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
   EW_CUDA_CHECK(cudaStreamSynchronize(h->st));
   *cfl = cnt;
@@ -797,6 +818,7 @@ int ecwam_b200_outbs(ecwam_b200_handle h, const ecwam_b200_outsel* sel, const in
   if (!h->bound) EW_FAIL(ECWAM_B200_ESTATE, "fields not bound");
   int rc = check_outsel(sel);
   if (rc) return rc;
+  if (h->par.irefra >= 2) EW_FAIL(ECWAM_B200_EINVAL, "OUTBLOCK with currents needs INTPOL (outblock.F90:168-169): not built");
   const DevConst& c = h->dc;
   OutConst oc;
   memset(&oc, 0, sizeof(oc));
@@ -982,7 +1004,7 @@ int ecwam_b200_wamintgr_host(ecwam_b200_handle h, const ecwam_b200_fields* host,
   int band = std::max((nchnk + kBands - 1) / kBands, reach_chunks);
   const int nband = (nchnk + band - 1) / band;
   const bool substeps = p.ifrelfmax > 0 && p.ifrelfmax < p.nfre_red;
-  const bool full = h->nproc <= 1 && !substeps && !h->weights_dirty && h->mir_static_done && nband >= 3;
+  const bool full = h->nproc <= 1 && !substeps && !h->weights_dirty && h->mir_static_done && nband >= 3 && h->par.irefra < 2;
   while ((int)h->ev_up.size() < nband) { cudaEvent_t e; EW_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_up.push_back(e); }
   while ((int)h->ev_done.size() < nband) { cudaEvent_t e; EW_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_done.push_back(e); }
   long long nin = 0, nout = 0;

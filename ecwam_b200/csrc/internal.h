@@ -16,7 +16,10 @@ struct PropDev {
   const double* cgext;   // [nenv][next] group velocity incl. halo and land slot (proenvhalo.F90); row Fr = DEPTH_EXT when IREFRA = 1
   int irefra, nenv;      // YOWSTAT IREFRA (0 | 1 depth refraction); rows of cgext (Fr or Fr+1)
   const double* omos;    // WVPRPT%OMOSNH2KD (P,F,C) (IREFRA = 1)
-  const double* grad;    // [2][nloc]: DDPHI, DDLAM of GRADI (gradi.F90:120-153), IREFRA = 1
+  const double* grad;    // [7][nloc]: DDPHI, DDLAM (gradi.F90:120-153, IREFRA = 1, 3), DUPHI, DULAM, DVPHI, DVLAM (clamped, :167-229),
+                         // OMDD (propdot.F90:134-143)  (IREFRA = 2, 3)
+  const double* wavn;    // WVPRPT%WAVNUM (P,F,C) (IREFRA = 2, 3: SDOT)
+  const double* curmask; // [nloc] CURMASK of CTUW (ctuw.F90:113-127), IREFRA = 2, 3
   const int* halo_off;   // [nbot+ntop+1] offset of (k=0,m=0) of a halo point in `halo`; land -> a zero element
   const int* halo_str;   // [nbot+ntop+1] direction stride (= points received from that peer); land -> 0
   const double* halo;    // received spectra, per peer block [m][k][ih]
@@ -33,6 +36,9 @@ struct PropConst {
   double sm[2][EW_MAXA];
   double delpro[2];
   double delth0[2];         // 0.25*DELPRO/DELTH (ctuw.F90:407)
+  double delfr0[2];         // 0.25*DELPRO/((FRATIO-1)*ZPI) (ctuw.F90:508)
+  double fratio;
+  double fr[EW_MAXF];       // FR(M)
   double cmtodeg;           // 360/CIRC
   double xdella;
 };
@@ -44,8 +50,12 @@ void launch_propags2(const PropDev& d, const double* src, int srcF, double* dst,
 void launch_ctu_check(const PropDev& d, int m0, int m1, int msplit, int* flag, int* count, cudaStream_t st);
 void launch_setup_points(const PropDev& d, const double* cosphm1_fld, const double* cosph_m, const double* cosph_p,
                          double* pt, cudaStream_t st);
-void launch_fill_cgext(const PropDev& d, const double* cgroup, const double* depth, double* cgext, const double* land_cg, cudaStream_t st);
+void launch_fill_cgext(const PropDev& d, const double* cgroup, const double* depth, const double* ucur, const double* vcur, double* cgext,
+                       const double* land_cg, cudaStream_t st);
 void launch_depth_gradients(const PropDev& d, const double* wlat_raw, const double* dellam, double oneo2delphi, double* grad, cudaStream_t st);
+// CTUW's CFL / weight-range scan with currents (ICALL = 1: curmask = 1; ICALL = 2: curmask = 0 where the first scan failed)
+void launch_ctu_check_cur(const PropDev& d, int m0, int m1, int msplit, int* flag, int* count, cudaStream_t st);
+void launch_curmask(const PropDev& d, const int* flag, double* curmask, int reset, cudaStream_t st);
 void launch_pack(const PropDev& d, const double* src, int srcF, const double* cgext, int mode, int nk, int nm, int nfull,
                  const int* send_l, const int* send_pre, const int* send_peer_of, int ntot, double* out, cudaStream_t st);
 void launch_unpack_cg(const PropDev& d, const double* in, const int* recv_pre, const int* recv_peer_of, const int* recv_e,

@@ -296,16 +296,23 @@ __global__ void setup_points_kernel(PropDev d, const double* __restrict__ cosphm
 }
 
 // CGROUP(P,F,C) -> CG_EXT[m][nbot + l]   (proenvhalo.F90:67-83, group velocity only)
-__global__ void fill_cgext_kernel(PropDev d, const double* __restrict__ cgroup, const double* __restrict__ depth, double* __restrict__ cgext) {
+__global__ void fill_cgext_kernel(PropDev d, const double* __restrict__ cgroup, const double* __restrict__ depth, const double* __restrict__ ucur,
+                                  const double* __restrict__ vcur, double* __restrict__ cgext) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = blockIdx.y;
   if (l >= d.nloc) return;
   const int c = l / d.P, i = l - c * d.P;
-  // row Fr (IREFRA = 1 only) = DEPTH_EXT (proenvhalo.F90:81)
-  cgext[(size_t)m * d.next + d.nbot + l] = m < d.Fr ? cgroup[i + (size_t)d.P * (m + (size_t)d.F * c)] : depth[i + (size_t)d.P * c];
+  // rows Fr, Fr+1, Fr+2 (IREFRA /= 0) = DEPTH_EXT, U_EXT, V_EXT (proenvhalo.F90:81-83)
+  double v;
+  if (m < d.Fr) v = cgroup[i + (size_t)d.P * (m + (size_t)d.F * c)];
+  else if (m == d.Fr) v = depth[i + (size_t)d.P * c];
+  else if (m == d.Fr + 1) v = ucur[i + (size_t)d.P * c];
+  else v = vcur[i + (size_t)d.P * c];
+  cgext[(size_t)m * d.next + d.nbot + l] = v;
 }
-// GRADI's depth gradients (gradi.F90:120-153) with WLAT as PROPCONNECT left it (PROPDOT runs before CTUWINI, propag_wam.F90:171-216)
-__global__ void depth_grad_kernel(PropDev d, const double* __restrict__ wlat_raw, const double* __restrict__ dellam, double oneo2delphi,
+// GRADI (gradi.F90:120-229) + the per-point part of PROPDOT (propdot.F90:134-143), with WLAT as PROPCONNECT left it (PROPDOT runs
+// before CTUWINI, propag_wam.F90:171-216).  tab[0] = DELLAM(KX), tab[1] = COSPH(KX).
+__global__ void depth_grad_kernel(PropDev d, const double* __restrict__ wlat_raw, const double* __restrict__ tab, double oneo2delphi,
                                   double* __restrict__ grad) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= d.nloc) return;
@@ -315,20 +322,230 @@ __global__ void depth_grad_kernel(PropDev d, const double* __restrict__ wlat_raw
   const int ipm = d.nbr[2 * (size_t)nl + l], ipp = d.nbr[3 * (size_t)nl + l];                         // KLAT(IJ,1,1), KLAT(IJ,2,1)
   const int ipm2 = d.nbr[4 * (size_t)nl + l], ipp2 = d.nbr[5 * (size_t)nl + l];                       // KLAT(IJ,1,2), KLAT(IJ,2,2)
   const double w1 = wlat_raw[l], w2 = wlat_raw[(size_t)nl + l];
-  double ddphi, ddlam;
-  if (ipp != land && ipm != land && ipp2 != land && ipm2 != land) {
-    const double dptp = w2 * dep[ipp] + (1.0 - w2) * dep[ipp2];
-    const double dptm = w1 * dep[ipm] + (1.0 - w1) * dep[ipm2];
-    ddphi = (dptp - dptm) * oneo2delphi;
-  } else if (ipp != land && ipm != land) ddphi = (dep[ipp] - dep[ipm]) * oneo2delphi;
-  else if (ipp2 != land && ipm2 != land) ddphi = (dep[ipp2] - dep[ipm2]) * oneo2delphi;
-  else ddphi = 0.0;
-  if (ilp != land && ilm != land) ddlam = (dep[ilp] - dep[ilm]) / (2. * dellam[l]);
-  else ddlam = 0.0;
+  const double dellam = tab[l];
+  double ddphi = 0.0, ddlam = 0.0;
+  if (d.irefra == 1 || d.irefra == 3) {
+    if (ipp != land && ipm != land && ipp2 != land && ipm2 != land) {
+      const double dptp = w2 * dep[ipp] + (1.0 - w2) * dep[ipp2];
+      const double dptm = w1 * dep[ipm] + (1.0 - w1) * dep[ipm2];
+      ddphi = (dptp - dptm) * oneo2delphi;
+    } else if (ipp != land && ipm != land) ddphi = (dep[ipp] - dep[ipm]) * oneo2delphi;
+    else if (ipp2 != land && ipm2 != land) ddphi = (dep[ipp2] - dep[ipm2]) * oneo2delphi;
+    else ddphi = 0.0;
+    if (ilp != land && ilm != land) ddlam = (dep[ilp] - dep[ilm]) / (2. * dellam);
+    else ddlam = 0.0;
+  }
   grad[l] = ddphi;
   grad[(size_t)nl + l] = ddlam;
+  if (d.irefra < 2) return;
+  const double* U = d.cgext + (size_t)(d.Fr + 1) * d.next;
+  const double* V = d.cgext + (size_t)(d.Fr + 2) * d.next;
+  // exact 0 means that the current field was not defined: no gradient is extrapolated (gradi.F90:171-181, 205-210)
+  auto mk = [&](int e) { return (U[e] == 0.0 && V[e] == 0.0) ? land : e; };
+  const int jpp = mk(ipp), jpm = mk(ipm), jpp2 = mk(ipp2), jpm2 = mk(ipm2), jlp = mk(ilp), jlm = mk(ilm);
+  double duphi, dvphi, dulam, dvlam;
+  if (jpp != land && jpm != land && jpp2 != land && jpm2 != land) {
+    const double up = w2 * U[jpp] + (1.0 - w2) * U[jpp2], vp = w2 * V[jpp] + (1.0 - w2) * V[jpp2];
+    const double um = w1 * U[jpm] + (1.0 - w1) * U[jpm2], vm = w1 * V[jpm] + (1.0 - w1) * V[jpm2];
+    duphi = (up - um) * oneo2delphi; dvphi = (vp - vm) * oneo2delphi;
+  } else if (jpp != land && jpm != land) {
+    duphi = (U[jpp] - U[jpm]) * oneo2delphi; dvphi = (V[jpp] - V[jpm]) * oneo2delphi;
+  } else { duphi = 0.0; dvphi = 0.0; }
+  if (jlp != land && jlm != land) { dulam = (U[jlp] - U[jlm]) / (2.0 * dellam); dvlam = (V[jlp] - V[jlm]) / (2.0 * dellam); }
+  else { dulam = 0.0; dvlam = 0.0; }
+  const double cgmax = 0.00001 * tab[(size_t)nl + l];      // CURRENT_GRADIENT_MAX*COSPH(KX) (yowcurr.F90:19, gradi.F90:221)
+  duphi = copysign(fmin(fabs(duphi), cgmax), duphi); dvphi = copysign(fmin(fabs(dvphi), cgmax), dvphi);
+  dulam = copysign(fmin(fabs(dulam), cgmax), dulam); dvlam = copysign(fmin(fabs(dvlam), cgmax), dvlam);
+  grad[2 * (size_t)nl + l] = duphi; grad[3 * (size_t)nl + l] = dulam; grad[4 * (size_t)nl + l] = dvphi; grad[5 * (size_t)nl + l] = dvlam;
+  const int e0 = d.nbot + l;
+  grad[6 * (size_t)nl + l] = d.irefra == 3 ? V[e0] * ddphi + U[e0] * ddlam * d.pt[l] : 0.0;   // OMDD (propdot.F90:134-143), DCO = COSPHM1
 }
 
+// ---- IREFRA = 2, 3: currents (ctuw.F90:156-275 with ISSU/ISSV, :451-456, :503-525; propags2.F90:123-194) -----------------
+// All weights of one bin in the reference's operation order; shared by the CFL scan and the propagation kernel.
+struct CurPoint {
+  int nb[14];
+  double wlat[2], wlatm1[2], wcor[4], wcorm1[4];
+  double cosphm1, dp[2], zdello, tanph, gam1, u, v, curmask, duphi, dulam, dvphi, dvlam, omdd;
+};
+struct CurW {
+  double sumwn, wlonn[2], wlatn[2][2], wcorn[4][2], wkpm[3], wmpm[3];   // wkpm/wmpm: [0] = IC -1, [1] = IC 0, [2] = IC +1
+  int kcr[4];
+  bool bad;
+};
+__device__ __forceinline__ void cur_load_point(const PropDev& d, int l, CurPoint& q) {
+  const int nl = d.nloc;
+  for (int j = 0; j < 14; ++j) q.nb[j] = __ldg(d.nbr + (size_t)j * nl + l);
+  for (int j = 0; j < 2; ++j) { q.wlat[j] = __ldg(d.wl + (size_t)j * nl + l); q.wlatm1[j] = 1.0 - q.wlat[j]; }
+  for (int j = 0; j < 4; ++j) { q.wcor[j] = __ldg(d.wl + (size_t)(2 + j) * nl + l); q.wcorm1[j] = 1.0 - q.wcor[j]; }
+  q.cosphm1 = d.pt[l]; q.dp[0] = d.pt[nl + l]; q.dp[1] = d.pt[2 * (size_t)nl + l]; q.zdello = d.pt[3 * (size_t)nl + l];
+  q.tanph = d.pt[4 * (size_t)nl + l];
+  q.gam1 = 1.0 / (q.zdello * c_prop.xdella);
+  const int e0 = d.nbot + l;
+  q.u = d.cgext[(size_t)(d.Fr + 1) * d.next + e0]; q.v = d.cgext[(size_t)(d.Fr + 2) * d.next + e0];
+  q.curmask = d.curmask[l];
+  q.duphi = d.grad[2 * (size_t)nl + l]; q.dulam = d.grad[3 * (size_t)nl + l]; q.dvphi = d.grad[4 * (size_t)nl + l];
+  q.dvlam = d.grad[5 * (size_t)nl + l]; q.omdd = d.grad[6 * (size_t)nl + l];
+}
+__device__ __forceinline__ double cur_thdc(const CurPoint& q, int k) {     // propdot.F90:180-181
+  const double sd = c_prop.sinth[k], cd = c_prop.costh[k], ss = sd * sd, sc = sd * cd, cc = cd * cd;
+  return ss * q.duphi + sc * q.dvphi - (sc * q.dulam + cc * q.dvlam) * q.cosphm1;
+}
+__device__ __forceinline__ double cur_s0(const CurPoint& q, int k) {       // propdot.F90:178-179 (SDOT(IJ,K,NFRE_RED) as temporary)
+  const double sd = c_prop.sinth[k], cd = c_prop.costh[k], ss = sd * sd, sc = sd * cd, cc = cd * cd;
+  return -sc * q.duphi - cc * q.dvphi - (ss * q.dulam + sc * q.dvlam) * q.cosphm1;
+}
+// cg3/om3/wn3: CGROUP_EXT, OMOSNH2KD_EXT, WAVNUM_EXT of the own point at M-1 (clamped), M, M+1 (clamped); frm/frmm1: FR(M), FR(MM1)
+__device__ __forceinline__ void cur_weights(const CurPoint& q, int k, int idp, const double hx[2], const double hy[2], const double cg3[3],
+                                            const double om3[3], const double wn3[3], double frm, double frmm1, CurW& w) {
+  const double snk = c_prop.sinth[k], csk = c_prop.costh[k];
+  const double mdel = -c_prop.delpro[idp];
+  const int qd = c_prop.quad[k];
+  const int jx1 = (qd & 1) ? 1 : 0, jx2 = 1 - jx1, jy1 = (qd & 2) ? 1 : 0, jy2 = 1 - jy1;   // JXO(K,1..2), JYO(K,1..2), 0-based
+  if (qd == 0) { w.kcr[0] = 2; w.kcr[1] = 1; w.kcr[2] = 3; w.kcr[3] = 0; }
+  else if (qd == 1) { w.kcr[0] = 1; w.kcr[1] = 2; w.kcr[2] = 0; w.kcr[3] = 3; }
+  else if (qd == 2) { w.kcr[0] = 3; w.kcr[1] = 0; w.kcr[2] = 2; w.kcr[3] = 1; }
+  else { w.kcr[0] = 0; w.kcr[1] = 3; w.kcr[2] = 1; w.kcr[3] = 2; }
+  w.bad = false;
+  double dxup[2], dxdw[2], dyup[2], dydw[2];
+  for (int ic = 0; ic < 2; ++ic) {
+    const double cgx = hx[ic] * snk * q.cosphm1, cgy = hy[ic] * csk;
+    const double uu = q.u * q.cosphm1, urel = cgx + uu;
+    const double vv = q.v * 0.5 * (1.0 + q.dp[ic]), vrel = cgy + vv;
+    const double issu = (copysign(1.0, urel) == copysign(1.0, cgx)) ? 1.0 : 0.0, issv = (copysign(1.0, vrel) == copysign(1.0, cgy)) ? 1.0 : 0.0;
+    const double adxp = fabs(mdel * urel * c_prop.cmtodeg), adyp = fabs(mdel * vrel * c_prop.cmtodeg);
+    dxup[ic] = adxp * issu; dxdw[ic] = adxp * (1.0 - issu);
+    dyup[ic] = adyp * issv; dydw[ic] = adyp * (1.0 - issv);
+    if (adxp > q.zdello || adyp > c_prop.xdella) w.bad = true;
+  }
+  const double dxx = q.zdello - dxup[jx2] - dxdw[jx1];
+  const double dyy = c_prop.xdella - dyup[jy2] - dydw[jy1];
+  double wgt[2];
+  wgt[jy1] = dxx * dyup[jy1] * q.gam1;
+  wgt[jy2] = dxx * dydw[jy2] * q.gam1;
+  for (int ic = 0; ic < 2; ++ic) { w.wlatn[ic][0] = q.wlat[ic] * wgt[ic]; w.wlatn[ic][1] = q.wlatm1[ic] * wgt[ic]; }
+  w.wlonn[jx1] = dyy * dxup[jx1] * q.gam1;
+  w.wlonn[jx2] = dyy * dxdw[jx2] * q.gam1;
+  const double w4[4] = {dxup[jx1] * dyup[jy1] * q.gam1, dxdw[jx2] * dyup[jy1] * q.gam1, dxup[jx1] * dydw[jy2] * q.gam1,
+                        dxdw[jx2] * dydw[jy2] * q.gam1};
+  for (int icr = 0; icr < 4; ++icr) { w.wcorn[icr][0] = q.wcor[w.kcr[icr]] * w4[icr]; w.wcorn[icr][1] = q.wcorm1[w.kcr[icr]] * w4[icr]; }
+  double sumwn = (q.zdello * (dydw[jy1] + dyup[jy2]) + c_prop.xdella * (dxup[jx2] + dxdw[jx1]) -
+                  (dxdw[jx1] + dxup[jx2]) * (dydw[jy1] + dyup[jy2])) * q.gam1;
+  // direction space (ctuw.F90:423-431, 451-456, 487-501; DRDP = 0 because IREFRA /= 1)
+  const int kp1 = c_prop.kpm_p[k], km1 = c_prop.kpm_m[k];
+  const double thk = cur_thdc(q, k);
+  const double drcp = q.curmask * (thk + cur_thdc(q, kp1)) * c_prop.delth0[idp];
+  const double drcm = q.curmask * (thk + cur_thdc(q, km1)) * c_prop.delth0[idp];
+  const double dthp = q.tanph * c_prop.sp[idp][k] * cg3[1] + om3[1] * 0.0 + drcp;
+  const double dthm = q.tanph * c_prop.sm[idp][k] * cg3[1] + om3[1] * 0.0 + drcm;
+  w.wkpm[1] = (dthp + fabs(dthp)) + (fabs(dthm) - dthm);
+  w.wkpm[2] = -dthp + fabs(dthp);
+  w.wkpm[0] = dthm + fabs(dthm);
+  // frequency space (ctuw.F90:503-525): SDOT(IJ,K,M) = (S0*CGROUP + OMDD*OMOSNH2KD)*WAVNUM (propdot.F90:190-191)
+  const double s0 = cur_s0(q, k);
+  const double sdm = (s0 * cg3[0] + q.omdd * om3[0]) * wn3[0], sd0 = (s0 * cg3[1] + q.omdd * om3[1]) * wn3[1],
+               sdp = (s0 * cg3[2] + q.omdd * om3[2]) * wn3[2];
+  const double dfp = c_prop.delfr0[idp] / frm, dfm = c_prop.delfr0[idp] / frmm1;
+  const double dtp = q.curmask * (sd0 + sdp) * dfp, dtm = q.curmask * (sd0 + sdm) * dfm;
+  w.wmpm[1] = (dtp + fabs(dtp)) + (fabs(dtm) - dtm);
+  w.wmpm[2] = (-dtp + fabs(dtp)) / c_prop.fratio;
+  w.wmpm[0] = (dtm + fabs(dtm)) * c_prop.fratio;
+  sumwn = sumwn + w.wkpm[1];
+  sumwn = sumwn + w.wmpm[1];
+  w.sumwn = sumwn;
+  auto chk = [&](double x) { if (x > 1.0 || x < 0.0) w.bad = true; };
+  for (int ic = 0; ic < 2; ++ic) { chk(w.wlonn[ic]); chk(w.wlatn[ic][0]); chk(w.wlatn[ic][1]); }
+  for (int icr = 0; icr < 4; ++icr) { chk(w.wcorn[icr][0]); chk(w.wcorn[icr][1]); }
+  for (int j = 0; j < 3; ++j) { chk(w.wkpm[j]); chk(w.wmpm[j]); }
+  chk(sumwn);
+}
+// k-independent part of one (point, frequency): interface group velocities and the own-point dispersion values at M-1, M, M+1
+__device__ __forceinline__ void cur_point_m(const PropDev& d, const CurPoint& q, int l, int m, double hx[2], double hy[2], double cg3[3],
+                                            double om3[3], double wn3[3]) {
+  const int e0 = d.nbot + l;
+  const int c = l / d.P, i = l - c * d.P;
+  const int mm[3] = {m > 0 ? m - 1 : 0, m, m + 1 < d.Fr ? m + 1 : d.Fr - 1};      // MPM(M,-1), M, MPM(M,+1) (ctuwupdt.F90:98-102)
+  for (int j = 0; j < 3; ++j) {
+    cg3[j] = __ldg(d.cgext + (size_t)mm[j] * d.next + e0);
+    om3[j] = __ldg(d.omos + i + (size_t)d.P * (mm[j] + (size_t)d.F * c));
+    wn3[j] = __ldg(d.wavn + i + (size_t)d.P * (mm[j] + (size_t)d.F * c));
+  }
+  const double* cgm = d.cgext + (size_t)m * d.next;
+  const double cg = cg3[1];
+  hx[0] = 0.5 * (cg + __ldg(cgm + q.nb[0]));
+  hx[1] = 0.5 * (cg + __ldg(cgm + q.nb[1]));
+  hy[0] = 0.5 * (cg + q.dp[0] * (q.wlat[0] * __ldg(cgm + q.nb[2]) + (1.0 - q.wlat[0]) * __ldg(cgm + q.nb[4])));
+  hy[1] = 0.5 * (cg + q.dp[1] * (q.wlat[1] * __ldg(cgm + q.nb[3]) + (1.0 - q.wlat[1]) * __ldg(cgm + q.nb[5])));
+}
+
+// CFL / weight-range scan with currents (ctuw.F90:282-358, 536-690) -> flag per own point
+__global__ void __launch_bounds__(128) ctu_check_cur_kernel(PropDev d, int m0, int m1, int msplit, int* __restrict__ flag) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= d.nloc) return;
+  CurPoint q;
+  cur_load_point(d, l, q);
+  bool bad = false;
+  for (int m = m0 + blockIdx.y; m < m1; m += gridDim.y) {
+    const int idp = (m < msplit) ? 0 : 1;
+    double hx[2], hy[2], cg3[3], om3[3], wn3[3];
+    cur_point_m(d, q, l, m, hx, hy, cg3, om3, wn3);
+    const double frm = c_prop.fr[m], frmm1 = c_prop.fr[m > 0 ? m - 1 : 0];
+    for (int k = 0; k < d.A; ++k) {
+      CurW w;
+      cur_weights(q, k, idp, hx, hy, cg3, om3, wn3, frm, frmm1, w);
+      bad = bad || w.bad;
+    }
+  }
+  if (bad) flag[l] = 1;
+}
+// CURMASK of the second CTUW call (ctuw.F90:113-127): 0 where the first scan failed; reset != 0: all ones
+__global__ void curmask_kernel(int n, const int* __restrict__ flag, double* __restrict__ curmask, int reset) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < n) curmask[l] = (reset || !flag[l]) ? 1.0 : 0.0;
+}
+
+// PROPAGS2 with depth and current refraction (propags2.F90:123-194): every neighbour, the two neighbouring directions and the
+// two neighbouring frequencies, in the reference's order of additions.  Thread = one own point x a group of frequencies.
+__global__ void __launch_bounds__(128, 2) propags2_cur_kernel(PropDev d, SpecSrc src, double* __restrict__ dst, long long dcstride,
+                                                              int m0, int m1, int MG, int msplit, int l0, int l1) {
+  const int l = l0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= l1) return;
+  const int mb = m0 + blockIdx.y * MG;
+  const int me = min(mb + MG, m1);
+  CurPoint q;
+  cur_load_point(d, l, q);
+  const int c = l / d.P, i = l - c * d.P;
+  const int A = d.A, P = d.P;
+  for (int m = mb; m < me; ++m) {
+    const int idp = (m < msplit) ? 0 : 1;
+    double hx[2], hy[2], cg3[3], om3[3], wn3[3];
+    cur_point_m(d, q, l, m, hx, hy, cg3, om3, wn3);
+    const int mm1 = m > 0 ? m - 1 : 0, mp1 = m + 1 < d.Fr ? m + 1 : d.Fr - 1;
+    const double frm = c_prop.fr[m], frmm1 = c_prop.fr[mm1];
+    const double* ps = src.base + i + (long long)c * src.cstride + (long long)m * P * A;
+    const double* psm = src.base + i + (long long)c * src.cstride + (long long)mm1 * P * A;
+    const double* psp = src.base + i + (long long)c * src.cstride + (long long)mp1 * P * A;
+    double* pd = dst + i + (long long)c * dcstride + (long long)m * P * A;
+    const double* pn[14];
+    int sn[14];
+    for (int j = 0; j < 14; ++j) nbr_base(d, src, q.nb[j], m, pn[j], sn[j]);
+    for (int k = 0; k < A; ++k) {
+      CurW w;
+      cur_weights(q, k, idp, hx, hy, cg3, om3, wn3, frm, frmm1, w);
+      double v = (1.0 - w.sumwn) * ps[(size_t)k * P];
+      for (int ic = 0; ic < 2; ++ic) v = v + w.wlonn[ic] * __ldg(pn[ic] + (size_t)k * sn[ic]);                  // KLON(IJ,IC)
+      for (int icl = 0; icl < 2; ++icl) {
+        for (int ic = 0; ic < 2; ++ic) { const int j = 2 + ic + 2 * icl; v = v + w.wlatn[ic][icl] * __ldg(pn[j] + (size_t)k * sn[j]); }        // KLAT(IJ,IC,ICL)
+        for (int icr = 0; icr < 4; ++icr) { const int j = 6 + w.kcr[icr] + 4 * icl; v = v + w.wcorn[icr][icl] * __ldg(pn[j] + (size_t)k * sn[j]); }   // KCOR(IJ,KCR(K,ICR),ICL)
+      }
+      v = v + w.wkpm[0] * ps[(size_t)c_prop.kpm_m[k] * P];
+      v = v + w.wmpm[0] * psm[(size_t)k * P];
+      v = v + w.wkpm[2] * ps[(size_t)c_prop.kpm_p[k] * P];
+      v = v + w.wmpm[2] * psp[(size_t)k * P];
+      pd[(size_t)k * P] = v;
+    }
+  }
+}
 // gather a (points, nk, nm) message block for every peer: out[peerblock + ih + ns*(k + nk*m)]
 // mode 0: spectrum from the chunked layout; mode 1: CG_EXT (nk = 1)
 __global__ void pack_kernel(PropDev d, SpecSrc src, const double* __restrict__ cgext, int mode, int nk, int nm, int nfull,
@@ -404,7 +621,8 @@ void launch_propags2(const PropDev& d, const double* src, int srcF, double* dst,
   const int MG = 8;
   SpecSrc s{src, (long long)d.P * d.A * srcF};
   dim3 grid((l1 - l0 + 127) / 128, (m1 - m0 + MG - 1) / MG);
-  if (d.irefra == 1) propags2_kernel<true><<<grid, 128, 0, st>>>(d, s, dst, (long long)d.P * d.A * dstF, m0, m1, MG, msplit, l0, l1);
+  if (d.irefra >= 2) propags2_cur_kernel<<<grid, 128, 0, st>>>(d, s, dst, (long long)d.P * d.A * dstF, m0, m1, MG, msplit, l0, l1);
+  else if (d.irefra == 1) propags2_kernel<true><<<grid, 128, 0, st>>>(d, s, dst, (long long)d.P * d.A * dstF, m0, m1, MG, msplit, l0, l1);
   else propags2_kernel<false><<<grid, 128, 0, st>>>(d, s, dst, (long long)d.P * d.A * dstF, m0, m1, MG, msplit, l0, l1);
 }
 void launch_ctu_check(const PropDev& d, int m0, int m1, int msplit, int* flag, int* count, cudaStream_t st) {
@@ -418,13 +636,24 @@ void launch_setup_points(const PropDev& d, const double* cosphm1_fld, const doub
                          double* pt, cudaStream_t st) {
   setup_points_kernel<<<(d.nloc + 255) / 256, 256, 0, st>>>(d, cosphm1_fld, cosph_m, cosph_p, pt);
 }
-void launch_fill_cgext(const PropDev& d, const double* cgroup, const double* depth, double* cgext, const double* land_cg, cudaStream_t st) {
+void launch_fill_cgext(const PropDev& d, const double* cgroup, const double* depth, const double* ucur, const double* vcur, double* cgext,
+                       const double* land_cg, cudaStream_t st) {
   dim3 grid((d.nloc + 255) / 256, d.nenv);
-  fill_cgext_kernel<<<grid, 256, 0, st>>>(d, cgroup, depth, cgext);
+  fill_cgext_kernel<<<grid, 256, 0, st>>>(d, cgroup, depth, ucur, vcur, cgext);
   land_cg_kernel<<<1, 64, 0, st>>>(d, land_cg, cgext);
 }
-void launch_depth_gradients(const PropDev& d, const double* wlat_raw, const double* dellam, double oneo2delphi, double* grad, cudaStream_t st) {
-  depth_grad_kernel<<<(d.nloc + 255) / 256, 256, 0, st>>>(d, wlat_raw, dellam, oneo2delphi, grad);
+void launch_depth_gradients(const PropDev& d, const double* wlat_raw, const double* tab, double oneo2delphi, double* grad, cudaStream_t st) {
+  depth_grad_kernel<<<(d.nloc + 255) / 256, 256, 0, st>>>(d, wlat_raw, tab, oneo2delphi, grad);
+}
+void launch_ctu_check_cur(const PropDev& d, int m0, int m1, int msplit, int* flag, int* count, cudaStream_t st) {
+  cudaMemsetAsync(flag, 0, sizeof(int) * d.nloc, st);
+  cudaMemsetAsync(count, 0, sizeof(int), st);
+  dim3 grid((d.nloc + 127) / 128, min(m1 - m0, 8));
+  ctu_check_cur_kernel<<<grid, 128, 0, st>>>(d, m0, m1, msplit, flag);
+  count_flags_kernel<<<148, 256, 0, st>>>(flag, d.nloc, count);
+}
+void launch_curmask(const PropDev& d, const int* flag, double* curmask, int reset, cudaStream_t st) {
+  curmask_kernel<<<(d.nloc + 255) / 256, 256, 0, st>>>(d.nloc, flag, curmask, reset);
 }
 void launch_pack(const PropDev& d, const double* src, int srcF, const double* cgext, int mode, int nk, int nm, int nfull,
                  const int* send_l, const int* send_pre, const int* send_peer_of, int ntot, double* out, cudaStream_t st) {

@@ -43,7 +43,7 @@ typedef struct ecwam_b200_params {
   int iphys;       /* YOWSTAT IPHYS: 0 = Janssen/WAM4, 1 = Ardhuin et al. 2010          */
   int isnonlin;    /* YOWSTAT ISNONLIN (0 only)                                         */
   int idamping;    /* YOWSTAT IDAMPING (SINPUT_JAN)                                     */
-  int irefra;      /* YOWSTAT IREFRA (0 = none, 1 = depth refraction; 2, 3 = currents: not built) */
+  int irefra;      /* YOWSTAT IREFRA (0 none, 1 depth, 2 current, 3 depth + current refraction)   */
   int icase;       /* YOWSTAT ICASE (1 = spherical, only)                               */
   int llgcbz0;     /* YOWCOUP LLGCBZ0 (0 only)                                          */
   int llnormagam;  /* YOWCOUP LLNORMAGAM (0 only)                                       */
@@ -74,6 +74,7 @@ typedef struct ecwam_b200_params {
   double ciblock;  /* YOWICE CIBLOCK                                                    */
   double flmin;    /* YOWICE FLMIN                                                      */
   double bathymax; /* YOWSHAL BATHYMAX                                                  */
+  int llcflcuroff; /* YOWSTAT LLCFLCUROFF (IREFRA = 2, 3): retry the CFL check without current refraction */
 } ecwam_b200_params;
 
 /* ---------------------------------------------------------------------------------------------------
@@ -235,7 +236,7 @@ typedef struct ecwam_b200_fields {
   const double* emaxdpt;
   const double* dellam1;
   const double* cosphm1;
-  const double* ucur;        /* unused (IREFRA=0) */
+  const double* ucur;        /* surface current (read when IREFRA = 2, 3) */
   const double* vcur;
   double* aird;
   double* wdwave;
@@ -293,7 +294,9 @@ int ecwam_b200_bind_fields(ecwam_b200_handle h, const ecwam_b200_fields* dev);
 
 /* PROPAG_WAM over the whole local block (src/ecwam/propag_wam.F90:10-419, IPROPAGS=2, IREFRA=0):
  * halo exchange of FL1 (MPEXCHNG -> NCCL), first-call CTU weight set-up + CFL check (CTUWUPDT),
- * PROPAGS2 (+ fast-wave sub-steps), result back in FL1 with padded lanes refreshed.
+ * PROPAGS2 (+ fast-wave sub-steps), result back in FL1 with padded lanes refreshed.  IREFRA = 1: depth refraction;
+ * IREFRA = 2, 3: advection by / refraction and frequency shift due to the surface current (UCUR, VCUR), with CTUWDRV's
+ * LLCFLCUROFF retry.
  * Returns the number of own grid points that violate the CFL / weight-range checks (0 = ok).           */
 int ecwam_b200_propag(ecwam_b200_handle h);
 /* Force the CTU set-up to be redone at the next ecwam_b200_propag (LUPDTWGHT, getcurr.F90:289).        */

@@ -87,6 +87,7 @@ struct Config {
   int ll1d = 0;
   int store_all_weights = 0;  // keep the reference's 18 weight arrays (tests only; 150 KB/point at 36x29)
   int nthreads = 1;  // OpenMP threads for the CPU-baseline leg (WAM_NPROMA is NOT applied: LLNO_WAM_NPROMA)
+  int llcflcuroff = 1;  // YOWSTAT LLCFLCUROFF (mpuserin.F90:575): retry without current refraction where the CFL check failed
 };
 
 // ---------------------------------------------------------------------------
@@ -162,7 +163,8 @@ struct RankDecomp {
   // CTUWUPDT index helpers
   ArrI MPM, KPM, JXO, JYO, KCR;
   // CTU weights (stored, as the reference does)
-  ArrD SUMWN, WLATN, WLONN, WCORN, WKPMN;  // all 18 arrays: only when cfg.store_all_weights (ctuwupdt.F90:171-178)
+  ArrD SUMWN, WLATN, WLONN, WCORN, WKPMN;  // all 18 arrays: only when cfg.store_all_weights (ctuwupdt.F90:171-178) or IREFRA >= 2
+  ArrD WMPMN;                              // frequency-shift weights (IREFRA = 2, 3; ctuw.F90:503-525)
   ArrD W8;  // (IJ,K,M,8): the 8 weights PROPAGS2 reads when IREFRA=0 (propags2.F90:107-116)
   bool LUPDTWGHT = true;
   int cfl_fail = 0;

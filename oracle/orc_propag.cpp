@@ -189,8 +189,10 @@ static void ctuwupdt(Model& m, int ir, ArrD& BUF) {
   RankDecomp& r = m.ranks[ir];
   const int NANG = c.nang, FR = c.nfre_red, IJS = r.IJS, IJL = r.IJL, NSUP = r.NSUP, NLAND = NSUP + 1;
   ctu_index_tables(c, t, r);
-  const bool FULL = c.store_all_weights != 0;
+  const bool CUR = c.irefra == 2 || c.irefra == 3;
+  const bool FULL = c.store_all_weights != 0 || CUR;
   r.W8.alloc(IJS, IJL, 1, NANG, 1, FR, 1, 8);
+  if (CUR) r.WMPMN.alloc(IJS, IJL, 1, NANG, 1, FR, -1, 1);
   if (FULL) {
     r.SUMWN.alloc(IJS, IJL, 1, NANG, 1, FR);
     r.WLATN.alloc(IJS, IJL, 1, NANG, 1, FR, 1, 2, 1, 2);
@@ -198,33 +200,78 @@ static void ctuwupdt(Model& m, int ir, ArrD& BUF) {
     r.WCORN.alloc(IJS, IJL, 1, NANG, 1, FR, 1, 4, 1, 2);
     r.WKPMN.alloc(IJS, IJL, 1, NANG, 1, FR, -1, 1);
   }
-  // depth refraction (IREFRA = 1): THDD(IJ,K) of PROPDOT with GRADI's depth gradients (propag_wam.F90:171-216 runs it BEFORE
-  // CTUWUPDT, i.e. with WLAT as PROPCONNECT left it; gradi.F90:120-153, propdot.F90:117-156, ICASE = 1)
-  ArrD THDD;
-  if (c.irefra == 1) {
+  // PROPDOT / GRADI (propag_wam.F90:171-216 runs them BEFORE CTUWUPDT, i.e. with WLAT as PROPCONNECT left it): depth part
+  // THDD (IREFRA = 1; gradi.F90:120-153, propdot.F90:117-164), current part THDC, SDOT (IREFRA = 2, 3; gradi.F90:167-229,
+  // propdot.F90:166-200), ICASE = 1
+  ArrD THDD, THDC, SDOT;
+  if (c.irefra < 0 || c.irefra > 3) throw std::runtime_error("CTUW: IREFRA must be 0..3");
+  if (c.irefra != 0) {
     THDD.alloc(IJS, IJL, 1, NANG);
+    if (CUR) { THDC.alloc(IJS, IJL, 1, NANG); SDOT.alloc(IJS, IJL, 1, NANG, 1, FR); }
     const double DELPHI = g.XDELLA * t.CIRC / 360.0;   // readmdlconf.F90:136
     const double ONEO2DELPHI = 0.5 / DELPHI;
+    const double CURRENT_GRADIENT_MAX = 0.00001;       // yowcurr.F90:19
     auto DPTHEXT = [&](int ij) { return BUF(ij, 3 * FR + 3, 1); };
+    auto UEXT = [&](int ij) { return BUF(ij, 3 * FR + 4, 1); };
+    auto VEXT = [&](int ij) { return BUF(ij, 3 * FR + 5, 1); };
     for (int IJ = IJS; IJ <= IJL; ++IJ) {
-      const int IPP = r.KLAT(IJ, 2, 1), IPM = r.KLAT(IJ, 1, 1), IPP2 = r.KLAT(IJ, 2, 2), IPM2 = r.KLAT(IJ, 1, 2);
-      double DDPHI, DDLAM;
-      if (IPP != NLAND && IPM != NLAND && IPP2 != NLAND && IPM2 != NLAND) {
-        const double DPTP = r.WLAT(IJ, 2) * DPTHEXT(IPP) + (1.0 - r.WLAT(IJ, 2)) * DPTHEXT(IPP2);
-        const double DPTM = r.WLAT(IJ, 1) * DPTHEXT(IPM) + (1.0 - r.WLAT(IJ, 1)) * DPTHEXT(IPM2);
-        DDPHI = (DPTP - DPTM) * ONEO2DELPHI;
-      } else if (IPP != NLAND && IPM != NLAND) {
-        DDPHI = (DPTHEXT(IPP) - DPTHEXT(IPM)) * ONEO2DELPHI;
-      } else if (IPP2 != NLAND && IPM2 != NLAND) {
-        DDPHI = (DPTHEXT(IPP2) - DPTHEXT(IPM2)) * ONEO2DELPHI;
-      } else DDPHI = 0.0;
-      const int ILP = r.KLON(IJ, 2), ILM = r.KLON(IJ, 1), KX = g.KXLT(IJ);
-      if (ILP != NLAND && ILM != NLAND) DDLAM = (DPTHEXT(ILP) - DPTHEXT(ILM)) / (2. * g.DELLAM(KX));
-      else DDLAM = 0.0;
+      double DDPHI = 0.0, DDLAM = 0.0, DUPHI = 0.0, DVPHI = 0.0, DULAM = 0.0, DVLAM = 0.0;
+      const int KX = g.KXLT(IJ);
+      if (c.irefra == 1 || c.irefra == 3) {
+        const int IPP = r.KLAT(IJ, 2, 1), IPM = r.KLAT(IJ, 1, 1), IPP2 = r.KLAT(IJ, 2, 2), IPM2 = r.KLAT(IJ, 1, 2);
+        if (IPP != NLAND && IPM != NLAND && IPP2 != NLAND && IPM2 != NLAND) {
+          const double DPTP = r.WLAT(IJ, 2) * DPTHEXT(IPP) + (1.0 - r.WLAT(IJ, 2)) * DPTHEXT(IPP2);
+          const double DPTM = r.WLAT(IJ, 1) * DPTHEXT(IPM) + (1.0 - r.WLAT(IJ, 1)) * DPTHEXT(IPM2);
+          DDPHI = (DPTP - DPTM) * ONEO2DELPHI;
+        } else if (IPP != NLAND && IPM != NLAND) {
+          DDPHI = (DPTHEXT(IPP) - DPTHEXT(IPM)) * ONEO2DELPHI;
+        } else if (IPP2 != NLAND && IPM2 != NLAND) {
+          DDPHI = (DPTHEXT(IPP2) - DPTHEXT(IPM2)) * ONEO2DELPHI;
+        } else DDPHI = 0.0;
+        const int ILP = r.KLON(IJ, 2), ILM = r.KLON(IJ, 1);
+        if (ILP != NLAND && ILM != NLAND) DDLAM = (DPTHEXT(ILP) - DPTHEXT(ILM)) / (2. * g.DELLAM(KX));
+        else DDLAM = 0.0;
+      }
+      if (CUR) {
+        // exact 0 means that the current field was not defined: no gradient is extrapolated (gradi.F90:171-181, 205-210)
+        auto undef = [&](int ij) { return UEXT(ij) == 0.0 && VEXT(ij) == 0.0; };
+        int IPP = r.KLAT(IJ, 2, 1); if (undef(IPP)) IPP = NLAND;
+        int IPM = r.KLAT(IJ, 1, 1); if (undef(IPM)) IPM = NLAND;
+        int IPP2 = r.KLAT(IJ, 2, 2); if (undef(IPP2)) IPP2 = NLAND;
+        int IPM2 = r.KLAT(IJ, 1, 2); if (undef(IPM2)) IPM2 = NLAND;
+        if (IPP != NLAND && IPM != NLAND && IPP2 != NLAND && IPM2 != NLAND) {
+          const double UP = r.WLAT(IJ, 2) * UEXT(IPP) + (1.0 - r.WLAT(IJ, 2)) * UEXT(IPP2);
+          const double VP = r.WLAT(IJ, 2) * VEXT(IPP) + (1.0 - r.WLAT(IJ, 2)) * VEXT(IPP2);
+          const double UM = r.WLAT(IJ, 1) * UEXT(IPM) + (1.0 - r.WLAT(IJ, 1)) * UEXT(IPM2);
+          const double VM = r.WLAT(IJ, 1) * VEXT(IPM) + (1.0 - r.WLAT(IJ, 1)) * VEXT(IPM2);
+          DUPHI = (UP - UM) * ONEO2DELPHI; DVPHI = (VP - VM) * ONEO2DELPHI;
+        } else if (IPP != NLAND && IPM != NLAND) {
+          DUPHI = (UEXT(IPP) - UEXT(IPM)) * ONEO2DELPHI; DVPHI = (VEXT(IPP) - VEXT(IPM)) * ONEO2DELPHI;
+        } else { DUPHI = 0.0; DVPHI = 0.0; }
+        int ILP = r.KLON(IJ, 2); if (undef(ILP)) ILP = NLAND;
+        int ILM = r.KLON(IJ, 1); if (undef(ILM)) ILM = NLAND;
+        if (ILP != NLAND && ILM != NLAND) {
+          DULAM = (UEXT(ILP) - UEXT(ILM)) / (2.0 * g.DELLAM(KX)); DVLAM = (VEXT(ILP) - VEXT(ILM)) / (2.0 * g.DELLAM(KX));
+        } else { DULAM = 0.0; DVLAM = 0.0; }
+        const double CGMAX = CURRENT_GRADIENT_MAX * g.COSPH(KX);
+        DUPHI = sign(std::min(std::fabs(DUPHI), CGMAX), DUPHI); DVPHI = sign(std::min(std::fabs(DVPHI), CGMAX), DVPHI);
+        DULAM = sign(std::min(std::fabs(DULAM), CGMAX), DULAM); DVLAM = sign(std::min(std::fabs(DVLAM), CGMAX), DVLAM);
+      }
       const double DCO = BUF(IJ, 3 * FR + 2, 1);       // COSPHM1_EXT
-      for (int K = 1; K <= NANG; ++K) THDD(IJ, K) = t.SINTH(K) * DDPHI - t.COSTH(K) * DDLAM * DCO;
+      double OMDD = 0.0;
+      if (c.irefra == 3) OMDD = VEXT(IJ) * DDPHI + UEXT(IJ) * DDLAM * DCO;
+      for (int K = 1; K <= NANG; ++K) {
+        const double SD = t.SINTH(K), CD = t.COSTH(K);
+        THDD(IJ, K) = (c.irefra == 1 || c.irefra == 3) ? SD * DDPHI - CD * DDLAM * DCO : 0.0;
+        if (CUR) {
+          const double SS = SD * SD, SC = SD * CD, CC = CD * CD;
+          const double S0 = -SC * DUPHI - CC * DVPHI - (SS * DULAM + SC * DVLAM) * DCO;
+          THDC(IJ, K) = SS * DUPHI + SC * DVPHI - (SC * DULAM + CC * DVLAM) * DCO;
+          for (int M = 1; M <= FR; ++M) SDOT(IJ, K, M) = (S0 * BUF(IJ, FR + M, 1) + OMDD * BUF(IJ, 2 * FR + M, 1)) * BUF(IJ, M, 1);
+        }
+      }
     }
-  } else if (c.irefra != 0) throw std::runtime_error("CTUW: only IREFRA = 0 and 1 are restated");
+  }
   ArrD WLATM1, WCORM1, DP;
   WLATM1.alloc(IJS, IJL, 1, 2); WCORM1.alloc(IJS, IJL, 1, 4); DP.alloc(IJS, IJL, 1, 2);
   // CTUWINI
@@ -262,6 +309,7 @@ static void ctuwupdt(Model& m, int ir, ArrD& BUF) {
   // CTUWDRV: one or two calls of CTUW depending on the fast-wave split (ctuwupdt.F90:193-235)
   auto CG = [&](int ij, int M) -> double { return BUF(ij, FR + M, 1); };
   std::vector<char> LCFLFAIL(IJL - IJS + 1, 0);
+  std::vector<double> CURMASK(IJL - IJS + 1, 1.0);
   auto ctuw = [&](double DELPRO, int MSTART, int MEND) {
     const double CMTODEG = 360.0 / t.CIRC;
     const double XDELLA = g.XDELLA;
@@ -279,6 +327,13 @@ static void ctuwupdt(Model& m, int ir, ArrD& BUF) {
             CGY[IC] = 0.5 * (CG(IJ, M) + DP(IJ, IC) * CGYP) * t.COSTH(K);
             double UREL = CGX[IC], VREL = CGY[IC];
             int ISSU = 1, ISSV = 1;
+            if (CUR) {   // ctuw.F90:175-181, 211-217
+              auto isamesign = [](double a, double b) { return sign(1.0, a) == sign(1.0, b) ? 1 : 0; };
+              const double UU = BUF(IJ, 3 * FR + 4, 1) * COSPHM1;
+              UREL = CGX[IC] + UU; ISSU = isamesign(UREL, CGX[IC]);
+              const double VV = BUF(IJ, 3 * FR + 5, 1) * 0.5 * (1.0 + DP(IJ, IC));
+              VREL = CGY[IC] + VV; ISSV = isamesign(VREL, CGY[IC]);
+            }
             double DXP = -DELPRO * UREL * CMTODEG, DYP = -DELPRO * VREL * CMTODEG;
             ADXP[IC] = std::fabs(DXP); ADYP[IC] = std::fabs(DYP);
             DXUP[IC] = ADXP[IC] * ISSU; DXDW[IC] = ADXP[IC] * (1 - ISSU);
@@ -344,13 +399,17 @@ static void ctuwupdt(Model& m, int ir, ArrD& BUF) {
           double TANPH = g.SINPH(JH) / g.COSPH(JH);
           double DRGP = TANPH * SP, DRGM = TANPH * SM;
           double DRCP = 0.0, DRCM = 0.0;
+          if (CUR) {                               // ctuw.F90:451-456
+            DRCP = CURMASK[IJ - IJS] * (THDC(IJ, K) + THDC(IJ, KP1)) * DELTH0;
+            DRCM = CURMASK[IJ - IJS] * (THDC(IJ, K) + THDC(IJ, KM1)) * DELTH0;
+          }
           double DTHP, DTHM;
           if (c.irefra == 0) {                     // ctuw.F90:471-486
             DTHP = DRGP * CG(IJ, M) + DRCP;
             DTHM = DRGM * CG(IJ, M) + DRCM;
-          } else {                                 // ctuw.F90:434-439, 487-501 (IREFRA = 1)
-            const double DRDP = (THDD(IJ, K) + THDD(IJ, KP1)) * DELTH0;
-            const double DRDM = (THDD(IJ, K) + THDD(IJ, KM1)) * DELTH0;
+          } else {                                 // ctuw.F90:434-439, 487-501 (depth refraction only for IREFRA = 1)
+            const double DRDP = c.irefra == 1 ? (THDD(IJ, K) + THDD(IJ, KP1)) * DELTH0 : 0.0;
+            const double DRDM = c.irefra == 1 ? (THDD(IJ, K) + THDD(IJ, KM1)) * DELTH0 : 0.0;
             DTHP = DRGP * CG(IJ, M) + BUF(IJ, 2 * FR + M, 1) * DRDP + DRCP;
             DTHM = DRGM * CG(IJ, M) + BUF(IJ, 2 * FR + M, 1) * DRDM + DRCM;
           }
@@ -363,20 +422,51 @@ static void ctuwupdt(Model& m, int ir, ArrD& BUF) {
           r.W8(IJ, K, M, 1) = s;
           r.W8(IJ, K, M, 7) = wm;
           r.W8(IJ, K, M, 8) = wp;
+          if (CUR) {   // frequency shifting due to currents (ctuw.F90:503-525) + its checks and share of SUMWN (:611-633)
+            const double DELFR0 = 0.25 * DELPRO / ((t.FRATIO - 1) * t.ZPI);
+            const int MP1 = std::min(FR, M + 1), MM1 = std::max(1, M - 1);
+            const double DFP = DELFR0 / t.FR(M), DFM = DELFR0 / t.FR(MM1);
+            const double DTP = CURMASK[IJ - IJS] * (SDOT(IJ, K, M) + SDOT(IJ, K, MP1)) * DFP;
+            const double DTM = CURMASK[IJ - IJS] * (SDOT(IJ, K, M) + SDOT(IJ, K, MM1)) * DFM;
+            const double f0 = (DTP + std::fabs(DTP)) + (std::fabs(DTM) - DTM);
+            const double fp = (-DTP + std::fabs(DTP)) / t.FRATIO;
+            const double fm = (DTM + std::fabs(DTM)) * t.FRATIO;
+            if (f0 > 1.0 || f0 < 0.0 || fp > 1.0 || fp < 0.0 || fm > 1.0 || fm < 0.0) LCFLFAIL[IJ - IJS] = 1;
+            r.WMPMN(IJ, K, M, 0) = f0; r.WMPMN(IJ, K, M, 1) = fp; r.WMPMN(IJ, K, M, -1) = fm;
+            s = s + f0;
+          }
           if (s > 1.0 || s < 0.0) LCFLFAIL[IJ - IJS] = 1;
           if (FULL) { r.WKPMN(IJ, K, M, 0) = w0; r.WKPMN(IJ, K, M, 1) = wp; r.WKPMN(IJ, K, M, -1) = wm; r.SUMWN(IJ, K, M) = s; }
         }
     }
     // obstruction coefficients OBSLAT/OBSLON/OBSCOR are all 1.0 (LSUBGRID=F): :700-733 is a no-op.
   };
+  // CTUWDRV (ctuwdrv.F90:83-123): ICALL = 1 with the currents everywhere; with LLCFLCUROFF a second call switches the current
+  // REFRACTION (not the advection by the current) off at the points that failed (CURMASK, ctuw.F90:113-127)
+  std::vector<char> FAILALL(IJL - IJS + 1, 0);
+  auto ctuwdrv = [&](double DELPRO, int MSTART, int MEND) {
+    std::fill(LCFLFAIL.begin(), LCFLFAIL.end(), 0);
+    std::fill(CURMASK.begin(), CURMASK.end(), 1.0);
+    ctuw(DELPRO, MSTART, MEND);
+    if (c.llcflcuroff && CUR) {
+      bool any = false;
+      for (char f : LCFLFAIL) any = any || f;
+      if (any) {
+        for (size_t i = 0; i < LCFLFAIL.size(); ++i) CURMASK[i] = LCFLFAIL[i] ? 0.0 : 1.0;
+        std::fill(LCFLFAIL.begin(), LCFLFAIL.end(), 0);
+        ctuw(DELPRO, MSTART, MEND);
+      }
+    }
+    for (size_t i = 0; i < LCFLFAIL.size(); ++i) FAILALL[i] = FAILALL[i] || LCFLFAIL[i];
+  };
   if (c.ifrelfmax <= 0) {
-    ctuw(c.idelpro, 1, FR);
+    ctuwdrv(c.idelpro, 1, FR);
   } else {
-    ctuw(c.delpro_lf, 1, c.ifrelfmax);
-    if (c.ifrelfmax < FR) ctuw(c.idelpro, c.ifrelfmax + 1, FR);
+    ctuwdrv(c.delpro_lf, 1, c.ifrelfmax);
+    if (c.ifrelfmax < FR) ctuwdrv(c.idelpro, c.ifrelfmax + 1, FR);
   }
   r.cfl_fail = 0;
-  for (char f : LCFLFAIL) r.cfl_fail += f;
+  for (char f : FAILALL) r.cfl_fail += f;
 }
 
 // propags2.F90:99-121
@@ -385,6 +475,27 @@ static void propags2(const Config& c, const RankDecomp& r, const ArrD& F1c, ArrD
   ArrD& F1 = const_cast<ArrD&>(F1c);
   RankDecomp& rr = const_cast<RankDecomp&>(r);
   const int NANG = c.nang;
+  if (c.irefra == 2 || c.irefra == 3) {   // propags2.F90:123-194 (depth and current refraction: all neighbours, frequency shift)
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int M = ND3S; M <= ND3E; ++M) {
+      for (int K = 1; K <= NANG; ++K) {
+        for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+          double v = (1.0 - rr.SUMWN(IJ, K, M)) * F1(IJ, K, M);
+          for (int IC = 1; IC <= 2; ++IC) v = v + rr.WLONN(IJ, K, M, IC) * F1(rr.KLON(IJ, IC), K, M);
+          for (int ICL = 1; ICL <= 2; ++ICL) {
+            for (int IC = 1; IC <= 2; ++IC) v = v + rr.WLATN(IJ, K, M, IC, ICL) * F1(rr.KLAT(IJ, IC, ICL), K, M);
+            for (int ICR = 1; ICR <= 4; ++ICR) v = v + rr.WCORN(IJ, K, M, ICR, ICL) * F1(rr.KCOR(IJ, rr.KCR(K, ICR), ICL), K, M);
+          }
+          for (int IC = -1; IC <= 1; IC += 2) {
+            v = v + rr.WKPMN(IJ, K, M, IC) * F1(IJ, rr.KPM(K, IC), M);
+            v = v + rr.WMPMN(IJ, K, M, IC) * F1(IJ, K, rr.MPM(M, IC));
+          }
+          F3(IJ, K, M) = v;
+        }
+      }
+    }
+    return;
+  }
 #pragma omp parallel for collapse(2) schedule(static)
   for (int M = ND3S; M <= ND3E; ++M) {
     for (int K = 1; K <= NANG; ++K) {

@@ -121,3 +121,15 @@ def compare_bout(a, b, itgs=OUT_ITG):
             worst[itg] = float((np.abs(x - y) / np.maximum(np.abs(y), 1e-30)).max())
             assert worst[itg] <= 1e-10, "parameter %d: relative difference %g" % (itg, worst[itg])
     return worst
+
+
+def synthetic_currents(g, amp=0.8):
+    """Smooth surface currents with an area of exact zeros (= "no current data": gradi.F90:171-181 extrapolates no gradient
+    there)."""
+    lam, phi = np.deg2rad(g.lon), np.deg2rad(g.lat)
+    u = amp * np.cos(phi) * np.sin(3 * lam) * (1 + 0.3 * np.cos(5 * phi))
+    v = 0.5 * amp * np.sin(2 * phi) * np.cos(2 * lam)
+    m = np.abs(g.lat) > 60
+    u[m] = 0.0
+    v[m] = 0.0
+    return u, v

@@ -201,6 +201,76 @@ def test_depth_refraction_bit_exact(built, case):
     check_state(w, o)
 
 
+@pytest.mark.parametrize("irefra", [2, 3])
+def test_current_refraction_bit_exact(built, irefra):
+    """IREFRA = 2, 3: advection by the surface current (ISSU/ISSV up- and down-wind splitting), current refraction THDC,
+    frequency shift WMPMN (ctuw.F90:156-275, 451-456, 503-525), GRADI's current gradients incl. the "exact zero = undefined"
+    rule, and the all-neighbour branch of PROPAGS2 (propags2.F90:123-194): weights recomputed in the kernel in the reference's
+    operation order -> bit-exact."""
+    from common import synthetic_currents
+    g, o0, f, fl = make_oracle("o48like")
+    g, o, f, fl = make_oracle("o48like", irefra=irefra)
+    _, s, w = make_gpu("o48like", irefra=irefra)
+    u, v = synthetic_currents(g)
+    o.set_field("UCUR", u); o.set_field("VCUR", v)
+    w.set_field("ucur", u); w.set_field("vcur", v)
+    assert o.propag() == 0 and o0.propag() == 0 and w.propag() == 0
+    w.synchronize()
+    np.testing.assert_array_equal(w.get_spec("fl1"), o.get_fl1()[:, :, w.own])
+    assert (o.get_fl1() != o0.get_fl1()).any(axis=(0, 1)).mean() > 0.5
+    o.implsch(); w.implsch()
+    for _ in range(2):
+        assert o.step() == 0 and w.step() == 0
+    w.synchronize()
+    check_state(w, o)
+    with pytest.raises(L.EcwamError):                   # OUTBLOCK with currents needs INTPOL: rejected, not silently wrong
+        w.outbs([1], [1], [1])
+
+
+def test_current_cfl_fallback(built):
+    """LLCFLCUROFF (ctuwdrv.F90:101-121): with a long propagation step and strong current shear the direction / frequency
+    weights of the current refraction leave [0,1] at a few points; the second CTUW call switches the current refraction off at
+    those points only (CURMASK, ctuw.F90:113-127) and the run goes on.  Without the fallback the same points are reported."""
+    from common import synthetic_currents
+    extra = dict(irefra=3, idelpro=4200.0, delpro_lf=4200.0, idelt=4200.0)
+    g, o, f, fl = make_oracle("o640like", **extra)
+    _, s, w = make_gpu("o640like", **extra)
+    u, v = synthetic_currents(g, amp=24.0)
+    o.set_field("UCUR", u); o.set_field("VCUR", v)
+    w.set_field("ucur", u); w.set_field("vcur", v)
+    g2, o_off, f2, fl2 = make_oracle("o640like", llcflcuroff=0, **extra)
+    o_off.set_field("UCUR", u); o_off.set_field("VCUR", v)
+    nfail = o_off.propag()
+    assert nfail > 0, "the case must violate the CFL check with the current refraction on"
+    assert o.propag() == 0 and w.propag() == 0
+    w.synchronize()
+    np.testing.assert_array_equal(w.get_spec("fl1"), o.get_fl1()[:, :, w.own])
+    _, s3, w3 = make_gpu("o640like", llcflcuroff=0, **extra)
+    w3.set_field("ucur", u); w3.set_field("vcur", v)
+    assert w3.lib.ecwam_b200_propag(w3.h) == nfail
+
+
+def test_gpu_outputs_satisfy_oracle_independent_invariants(built):
+    """Properties the CUDA path must have whatever the oracle says: the stress solution satisfies the neutral log profile
+    (taut_z0.F90:303-341), TAUW <= u*^2, MIJ inside 1..NFRE, spectra finite and >= the noise floor, and the swell + wind-sea
+    energies of OUTBS add up to the total (sepwisw.F90 partitions FL1)."""
+    _, s, w = make_gpu("o640like")
+    for _ in range(4):
+        assert w.step() == 0
+    w.synchronize()
+    u, z0, u10 = w.get_field("ufric"), w.get_field("z0m"), w.get_field("wswave")
+    rhs = 0.4 * u10 / (np.log(10.0) - np.log(z0 + 0.11 * 1.5e-5 / np.maximum(u, 1e-6)))
+    assert (np.abs(u - rhs) <= 1e-12 * u).all()
+    assert (w.get_field("tauw") <= u * u * (1 + 1e-12)).all()
+    mij = w.get_field("mij")
+    assert mij.min() >= 1 and mij.max() <= w.F
+    fl = w.get_spec("fl1")
+    assert np.isfinite(fl).all() and fl.min() >= 0.0
+    b = w.outbs([1, 11, 12], [0, 0, 0], [0, 0, 0])
+    e, ew, es = (b[0] / 4) ** 2, (b[1] / 4) ** 2, (b[2] / 4) ** 2
+    assert np.abs(ew + es - e).max() <= 1e-12 * e.max()
+
+
 def test_cfl_violation_is_reported(built):
     """a 10x too long advection step must come back as a positive count (the reference aborts, ctuwdrv.F90:127-146)."""
     g, o, f, fl = make_oracle("o48like", idelpro=20000.0, delpro_lf=20000.0)
@@ -213,7 +283,7 @@ def test_cfl_violation_is_reported(built):
 def test_unsupported_switches_are_rejected(built):
     from ecwam_b200 import synth
     g = synth.make_grid(8, "aqua")
-    for kw in (dict(irefra=2), dict(llgcbz0=1), dict(isnonlin=1), dict(lciwa=1)):
+    for kw in (dict(irefra=4), dict(irefra=2, ifrelfmax=5), dict(llgcbz0=1), dict(isnonlin=1), dict(lciwa=1)):
         s = M.WamSetup(g, nproc=1, **kw)
         with pytest.raises(L.EcwamError):
             M.WamIntgr(s, 0)

@@ -150,3 +150,43 @@ def test_dia_conserves_energy_and_action(built):
     # the source term is cubic in the spectrum (points 0 and 1 carry 0.5 and 1.5 times the same shape)
     r = sl[:, :, 1][np.abs(sl[:, :, 0]) > 0] / sl[:, :, 0][np.abs(sl[:, :, 0]) > 0]
     np.testing.assert_allclose(r, (1.5 / 0.5) ** 3, rtol=1e-12)
+
+
+def test_stress_solution_satisfies_the_log_profile(built):
+    """TAUT_Z0's Newton iteration (taut_z0.F90:303-341) stops when TAUNEW == TAUOLD: the returned UFRIC and Z0M then satisfy
+    the neutral profile U10 = (u*/kappa) ln(z / (z0 + 0.11 nu/u*)) to rounding, the wave stress never exceeds u*^2, and the
+    Charnock parameter stays inside [ALPHAMIN, ~0.1].  Independent of any reference run."""
+    g, o, f, fl = make_oracle("o48like")
+    for _ in range(3):
+        assert o.step() == 0
+    u, z0, u10 = o.get_field("UFRIC"), o.get_field("Z0M"), o.get_field("WSWAVE")
+    rhs = 0.4 * u10 / (np.log(10.0) - np.log(z0 + 0.11 * 1.5e-5 / np.maximum(u, 1e-6)))
+    assert (np.abs(u - rhs) <= 1e-13 * u).all()
+    assert (o.get_field("TAUW") <= u * u * (1 + 1e-12)).all()
+    ch = o.get_field("CHRNCK")
+    assert ch.min() >= 1e-4 and ch.max() < 0.2
+
+
+def test_current_refraction_oracle_properties(built):
+    """IREFRA = 2, 3 (ctuw.F90:156-275, 451-456, 503-525; gradi.F90:167-229; propdot.F90:166-200; propags2.F90:123-194):
+    decomposition independence, IREFRA = 3 differs from 2 only through the depth term of SIGMA DOT, and LLCFLCUROFF's second
+    CTUW call removes the failures caused by the current refraction but not the others."""
+    from common import synthetic_currents
+    out = {}
+    for key, kw in (("r0", dict(irefra=0)), ("r2", dict(irefra=2)), ("r3", dict(irefra=3)), ("r3n3", dict(irefra=3, npr=3))):
+        g, o, f, fl = make_oracle("o48like", **kw)
+        u, v = synthetic_currents(g)
+        o.set_field("UCUR", u); o.set_field("VCUR", v)
+        assert o.propag() == 0
+        out[key] = o.get_fl1()
+    np.testing.assert_array_equal(out["r3"], out["r3n3"])
+    assert (out["r2"] != out["r0"]).any(axis=(0, 1)).mean() > 0.5 and np.isfinite(out["r3"]).all() and out["r3"].min() >= 0.0
+    assert 0 < np.abs(out["r3"] - out["r2"]).max() < 1e-3 * out["r0"].max()
+    extra = dict(irefra=3, idelpro=4200.0, delpro_lf=4200.0, idelt=4200.0)
+    n = []
+    for off in (0, 1):
+        g, o, f, fl = make_oracle("o640like", llcflcuroff=off, **extra)
+        u, v = synthetic_currents(g, amp=24.0)
+        o.set_field("UCUR", u); o.set_field("VCUR", v)
+        n.append(o.propag())
+    assert n[0] > 0 and n[1] == 0
