@@ -292,7 +292,7 @@ int ecwam_b200_nccl_comm_destroy(void* comm);
  * src/ecwam/wamintgr_loki_gpu.F90:141-157).                                                            */
 int ecwam_b200_bind_fields(ecwam_b200_handle h, const ecwam_b200_fields* dev);
 
-/* PROPAG_WAM over the whole local block (src/ecwam/propag_wam.F90:10-419, IPROPAGS=2, IREFRA=0):
+/* PROPAG_WAM over the whole local block (src/ecwam/propag_wam.F90:10-419, IPROPAGS=2, IREFRA=0..3):
  * halo exchange of FL1 (MPEXCHNG -> NCCL), first-call CTU weight set-up + CFL check (CTUWUPDT),
  * PROPAGS2 (+ fast-wave sub-steps), result back in FL1 with padded lanes refreshed.  IREFRA = 1: depth refraction;
  * IREFRA = 2, 3: advection by / refraction and frequency shift due to the surface current (UCUR, VCUR), with CTUWDRV's
