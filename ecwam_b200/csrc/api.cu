@@ -176,7 +176,8 @@ static int fill_dev_const(const ecwam_b200_params& p, const ecwam_b200_tables& t
     EW_FAIL(ECWAM_B200_EINVAL, "fast-wave sub-stepping (IFRELFMAX) together with current refraction (IREFRA = 2, 3) is not built");
   if (p.isnonlin != 0) EW_FAIL(ECWAM_B200_EINVAL, "only ISNONLIN=0 is implemented");
   if (p.llgcbz0 || p.llnormagam) EW_FAIL(ECWAM_B200_EINVAL, "LLGCBZ0 / LLNORMAGAM branches are not implemented (SURVEY 8f rank 2)");
-  if (p.lciwa) EW_FAIL(ECWAM_B200_EINVAL, "LCIWA* / LCISCAL sea-ice attenuation is not implemented (SURVEY 8f rank 2)");
+  if (p.lciwa & 3) EW_FAIL(ECWAM_B200_EINVAL, "LCIWA1 / LCIWA2 sea-ice attenuation (SDICE1, SDICE2) is not implemented (SURVEY 8f rank 2)");
+  if (p.lciwa & ~15) EW_FAIL(ECWAM_B200_EINVAL, "lciwa: unknown bits");
   if (p.lwnemocou) EW_FAIL(ECWAM_B200_EINVAL, "NEMO coupling accumulators are not implemented");
   if (p.icode_wnd != 3) EW_FAIL(ECWAM_B200_EINVAL, "only ICODE_WND=3 (10 m wind forcing) is implemented");
   if ((p.lwflux || p.lwfluxout) && !p.lwvflx_snl) EW_FAIL(ECWAM_B200_EINVAL, "LWVFLX_SNL=F is not implemented");
@@ -189,6 +190,11 @@ static int fill_dev_const(const ecwam_b200_params& p, const ecwam_b200_tables& t
   c.A = p.nang; c.F = p.nfre; c.Fr = p.nfre_red; c.iphys = p.iphys; c.idamping = p.idamping; c.llcapchnk = p.llcapchnk;
   c.lbiwbk = p.lbiwbk; c.licerun = p.licerun; c.lmaskice = p.lmaskice; c.lwamrsetci = p.lwamrsetci; c.lwflux = p.lwflux;
   c.lcflx = (p.lwflux || p.lwfluxout || p.lwnemocou) ? 1 : 0;   // implsch.F90:187
+  c.lciwa3 = (p.lciwa & 4) ? 1 : 0; c.lciscal = (p.lciwa & 8) ? 1 : 0; c.zalpfacx = p.zalpfacx;
+  {   // SDICE3, IMODEL = 2: ALP = (2*CDICE*CITH**1.25*FR(M)**4.5)*ALPFAC with CDICE = 0.1274*(ZPI/SQRT(G))**4.5 (sdice3.F90:123-129)
+    const double cdice = 0.1274 * std::pow(t.zpi / std::sqrt(t.g), 4.5);
+    for (int m = 0; m < p.nfre && m < EW_MAXF; ++m) c.fr45[m] = 2. * cdice * std::pow(t.fr[m], 4.5);
+  }
   c.lwvflx_snl = p.lwvflx_snl; c.lwcouast = p.lwcouast;
   c.delt = p.idelt; c.ximp = p.ximp; c.rnu = p.rnu; c.rnum = p.rnum; c.wspmin = p.wspmin; c.cithrsh = p.cithrsh;
   c.cithrsh_tail = p.cithrsh_tail; c.ciblock = p.ciblock; c.flmin = p.flmin; c.bathymax = p.bathymax;

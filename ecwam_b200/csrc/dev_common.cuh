@@ -17,6 +17,8 @@ struct DevConst {
   int A, F, Fr, iphys, idamping, llcapchnk, lbiwbk, licerun, lmaskice, lwamrsetci, lwflux, lcflx, lwvflx_snl,
       lwcouast;
   double delt, ximp, rnu, rnum, wspmin, cithrsh, cithrsh_tail, ciblock, flmin, bathymax;
+  int lciwa3, lciscal;          // YOWICE LCIWA3 (SDICE3), LCISCAL
+  double zalpfacx, fr45[EW_MAXF];   // YOWICE ZALPFACX; 2*CDICE*FR(M)**4.5 of SDICE3 (sdice3.F90:123-129)
   // YOWPCONS
   double G, GM1, ZPI, ZPI4GM1, ZPI4GM2, ROWATERM1, EPSMIN, EPSUS, EPSU10, ACD, BCD, CDMAX, TAUOCMIN, TAUOCMAX,
       PHIEPSMIN, PHIEPSMAX, WSEMEAN_MIN;

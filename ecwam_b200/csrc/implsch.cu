@@ -279,6 +279,8 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
   const size_t kstr = S.kstr;
   ws_em = 0.0; ws_fm = 0.0; ws_last = 0.0; phiwa_acc = 0.0; uorbt_acc = 0.0; aorb_acc = 0.0;
   constexpr bool ard = ARD;
+  double cicover_pt = 0.0, cith125 = 0.0;   // SDICE3: CICV and CITH**1.25 of the point (only when LCIWA3)
+  if (STORE && c_dc.licerun && c_dc.lciwa3) { cicover_pt = d.f.cicover[p]; cith125 = pow(d.f.cithick[p], 1.25); }
   const double abs_shelter = fabs(c_dc.TAUWSHELTER);
   const bool ltauwshelter = ard && abs_shelter != 0.0;
   double ustp[NGST], xstress[NGST], ystress[NGST], taux[NGST], tauy[NGST], wsin[NGST];
@@ -317,6 +319,8 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
         tg[TQ_FACSAT * qs] = wavnum * (1.0 / c_dc.ZPI) * xk;                                        // sdissip_ard.F90:142-160
         double sbo = 0.0;
         if (m < c_dc.Fr && depth < c_dc.bathymax) sbo = (-2.0 * 0.038 * c_dc.GM1) * wavnum / sinh(dmin(2.0 * depth * wavnum, 50.0));   // sbottom.F90:76-97
+        if (c_dc.licerun && c_dc.lciwa3)   // SDICE3 (sdice3.F90:131-141): TEMP = -CICV*ALP*CGROUP, added to SL/FLD like SBOTTOM's coefficient
+          sbo += -cicover_pt * ((c_dc.fr45[m] * cith125) * c_dc.zalpfacx) * d.f.cgroup[o3];
         tg[TQ_SBO * qs] = sbo;
         tg[TQ_CINV * qs] = cinv;
         tg[TQ_TAIL * qs] = div_norm(div_norm(1.0, xk), wavnum);                                                       // imphftail.F90:73-81
@@ -679,7 +683,7 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
 #define ST_NPT 8
 #define ST_RING 9
 #define ST_NSMAX 17   // 2*NSDSNTH+1 <= 17 (NANG <= 36, init_sdiss_ardh.F90:72)
-enum { PC_FAC = 0, PC_ENH, PC_USFMDELT, PC_SDSBK, PC_RTAIL, PC_FLMC, PC_ICEADD, PC_ICEFREE, PC_SNW, PC_CSW, PC_N };
+enum { PC_FAC = 0, PC_ENH, PC_USFMDELT, PC_SDSBK, PC_RTAIL, PC_FLMC, PC_ICEADD, PC_ICEFREE, PC_SNW, PC_CSW, PC_BETA, PC_N };
 
 template <int NP> struct Vd;
 template <> struct Vd<1> { double v[1]; };
@@ -774,11 +778,13 @@ __device__ __forceinline__ void stencil_closure(const ImplDev& d, const long lon
     if (c_dc.lcflx) {    // WNFLUXES closure (wnfluxes.F90:222-331, LWNEMOCOU=F)
       const double PHIOC_ICE = -3.75, PHIAW_ICE = 3.75, C1 = 1.03e-3, C2 = 0.04e-3, P1 = 1.48, P2 = -0.21, CDMAX_LOC = 0.003;
       const double epsus3 = c_dc.EPSUS * sqrt(c_dc.EPSUS);
-      const double cithrsh_inv = 1.0 / dmax(c_dc.cithrsh, 0.01);
+      // wnfluxes.F90:150-158: with a sea-ice attenuation scheme the open-water weight decays over CICOVER 0..0.02
+      const double cithrsh_inv = c_dc.lciwa3 ? 50.0 : 1.0 / dmax(c_dc.cithrsh, 0.01);
+      const double zcithrs = c_dc.lciwa3 ? 0.0 : c_dc.ciblock, zmaxexp = c_dc.lciwa3 ? 20.0 : 10.0;
       const double phiwa = s[S_PHIWA * n + pp];
       double ooval = 1.0, ustar = ufric;
-      if (c_dc.licerun && c_dc.lwamrsetci && cicover > c_dc.ciblock) {
-        ooval = exp(-dmin(p4(cicover * cithrsh_inv), 10.0));
+      if (c_dc.licerun && c_dc.lwamrsetci && cicover > zcithrs) {
+        ooval = exp(-dmin(p4(cicover * cithrsh_inv), zmaxexp));
         const double u10p = dmax(wsw, c_dc.EPSU10);
         const double cd_bulk = dmin((C1 + C2 * pow(u10p, P1)) * pow(u10p, P2), CDMAX_LOC);
         const double cd_wave = sq(ufric / u10p);
@@ -878,6 +884,7 @@ __global__ void ST_BOUNDS(NP) k_stencil(ImplDev d, long long p0, long long np, S
     pcv[PC_ICEFREE * ST_NPT] = seticeq ? 0.0 : 1.0;
     pcv[PC_SNW * ST_NPT] = snw;
     pcv[PC_CSW * ST_NPT] = csw;
+    pcv[PC_BETA * ST_NPT] = (c_dc.licerun && c_dc.lciscal) ? 1.0 - ci : 1.0;
   }
   __syncthreads();
   const double sinth = c_dc.SINTH[k], costh = c_dc.COSTH[k];
@@ -1076,6 +1083,8 @@ __global__ void ST_BOUNDS(NP) k_stencil(ImplDev d, long long p0, long long np, S
       const V usfm = lds<NP>(sm, L.pc + PC_USFMDELT * 64 + jo), sdsbk = lds<NP>(sm, L.pc + PC_SDSBK * 64 + jo);
       const V tsbo = lds<NP>(sm, tq + TQ_SBO * 64), tcinv = lds<NP>(sm, tq + TQ_CINV * 64), ttail = lds<NP>(sm, tq + TQ_TAIL * 64);
       const V tstf = lds<NP>(sm, tq + TQ_STF * 64), rtail = lds<NP>(sm, L.pc + PC_RTAIL * 64 + jo);
+      V beta;
+      if (c_dc.lciscal) beta = lds<NP>(sm, L.pc + PC_BETA * 64 + jo);
       V dd;
       if (ard) {
         const V b0 = lds<NP>(sm, L.bth0 + (par ^ 1u) * 64u + jo);
@@ -1098,10 +1107,9 @@ __global__ void ST_BOUNDS(NP) k_stencil(ImplDev d, long long p0, long long np, S
         slv = slv + tot_sl.v[i]; fldv = fldv + tot_fl.v[i];    // SNONLIN
         double ssource = 0.0;
         if (lssource) ssource = div_norm(slv, dmax(1.0 - delt5 * fldv, 1.0));
-        if (r < c_dc.Fr) {
-          slv = slv - sdsbk.v[i] * f0; fldv = fldv - sdsbk.v[i];            // SDIWBK (0 where it does not apply)
-          slv = slv + tsbo.v[i] * f0; fldv = fldv + tsbo.v[i];              // SBOTTOM
-        }
+        if (r < c_dc.Fr) { slv = slv - sdsbk.v[i] * f0; fldv = fldv - sdsbk.v[i]; }   // SDIWBK (0 where it does not apply)
+        if (c_dc.lciscal) { slv = slv * beta.v[i]; fldv = fldv * beta.v[i]; }        // LCISCAL (implsch.F90:315-325)
+        slv = slv + tsbo.v[i] * f0; fldv = fldv + tsbo.v[i];                         // SDICE3 + SBOTTOM (plane is 0 where neither applies)
         const double gtemp1 = dmax(1.0 - delt5 * fldv, 1.0);
         const double gtemp2 = div_norm(delt * slv, gtemp1);
         const double flhab = dmin(fabs(gtemp2), usfm.v[i] * cofrm4);
@@ -1324,6 +1332,7 @@ __global__ void __maxnreg__(ST_MAXREG) k_stencil_dp(ImplDev d, long long p0, lon
     pcv[PC_ICEFREE * ST_NPT] = seticeq ? 0.0 : 1.0;
     pcv[PC_SNW * ST_NPT] = snw;
     pcv[PC_CSW * ST_NPT] = csw;
+    pcv[PC_BETA * ST_NPT] = (c_dc.licerun && c_dc.lciscal) ? 1.0 - ci : 1.0;
   }
   __syncthreads();
   double sinth[2], costh[2];
@@ -1518,6 +1527,7 @@ __global__ void __maxnreg__(ST_MAXREG) k_stencil_dp(ImplDev d, long long p0, lon
       const double usfm = lds1(sm, L.pc + PC_USFMDELT * 64 + po), sdsbk = lds1(sm, L.pc + PC_SDSBK * 64 + po);
       const double tsbo = lds1(sm, tq + TQ_SBO * 64), tcinv = lds1(sm, tq + TQ_CINV * 64), ttail = lds1(sm, tq + TQ_TAIL * 64);
       const double tstf = lds1(sm, tq + TQ_STF * 64), rtail = lds1(sm, L.pc + PC_RTAIL * 64 + po);
+      const double beta = c_dc.lciscal ? lds1(sm, L.pc + PC_BETA * 64 + po) : 1.0;
       V dd;
       if (ard) {
         const double b0 = lds1(sm, L.bth0 + (par ^ 1u) * 64u + po);
@@ -1542,10 +1552,9 @@ __global__ void __maxnreg__(ST_MAXREG) k_stencil_dp(ImplDev d, long long p0, lon
         slv = slv + tot_sl.v[i]; fldv = fldv + tot_fl.v[i];
         double ssource = 0.0;
         if (lssource) ssource = div_norm(slv, dmax(1.0 - delt5 * fldv, 1.0));
-        if (r < c_dc.Fr) {
-          slv = slv - sdsbk * f0; fldv = fldv - sdsbk;
-          slv = slv + tsbo * f0; fldv = fldv + tsbo;
-        }
+        if (r < c_dc.Fr) { slv = slv - sdsbk * f0; fldv = fldv - sdsbk; }            // SDIWBK (0 where it does not apply)
+        if (c_dc.lciscal) { slv = slv * beta; fldv = fldv * beta; }                  // LCISCAL (implsch.F90:315-325)
+        slv = slv + tsbo * f0; fldv = fldv + tsbo;                                   // SDICE3 + SBOTTOM (plane is 0 where neither applies)
         const double gtemp1 = dmax(1.0 - delt5 * fldv, 1.0);
         const double gtemp2 = div_norm(delt * slv, gtemp1);
         const double flhab = dmin(fabs(gtemp2), usfm * cofrm4);

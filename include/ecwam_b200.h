@@ -52,7 +52,7 @@ typedef struct ecwam_b200_params {
   int licerun;     /* YOWICE LICERUN                                                    */
   int lmaskice;    /* YOWICE LMASKICE                                                   */
   int lwamrsetci;  /* YOWICE LWAMRSETCI                                                 */
-  int lciwa;       /* LCIWA1|LCIWA2|LCIWA3|LCISCAL (must be 0)                          */
+  int lciwa;       /* YOWICE bit mask: 1 LCIWA1, 2 LCIWA2 (both not built), 4 LCIWA3 (SDICE3), 8 LCISCAL */
   int lwflux;      /* YOWCOUP LWFLUX                                                    */
   int lwfluxout;   /* YOWCOUP LWFLUXOUT (userin.F90:470 sets it .TRUE.)                 */
   int lwnemocou;   /* YOWCOUP LWNEMOCOU (0 only)                                        */
@@ -75,6 +75,7 @@ typedef struct ecwam_b200_params {
   double flmin;    /* YOWICE FLMIN                                                      */
   double bathymax; /* YOWSHAL BATHYMAX                                                  */
   int llcflcuroff; /* YOWSTAT LLCFLCUROFF (IREFRA = 2, 3): retry the CFL check without current refraction */
+  double zalpfacx; /* YOWICE ZALPFACX (attenuation factor of SDICE3, 1 = no reduction)    */
 } ecwam_b200_params;
 
 /* ---------------------------------------------------------------------------------------------------

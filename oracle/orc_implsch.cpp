@@ -809,6 +809,7 @@ void WNFLUXES(const Ctx& x, I1 MIJ, V2 RHOWGDFTH, V2 CINV, V3 SSURF, V1 CICOVER,
   std::vector<double> XSTRESS(n, 0.0), YSTRESS(n, 0.0), USTAR(n), PHILF(n, 0.0), OOVAL(n), EM_OC(n), F1_OC(n), SUMT(n), SUMX(n), SUMY(n);
   double EPSUS3 = t.EPSUS * std::sqrt(t.EPSUS);
   double ZCITHRS = c.ciblock, CITHRSH_INV = 1. / std::max(c.cithrsh, 0.01), ZMAXEXP = 10.;
+  if (c.lciwa1 || c.lciwa2 || c.lciwa3) { ZCITHRS = 0.; CITHRSH_INV = 50.; ZMAXEXP = 20.; }   // wnfluxes.F90:150-158
   double EFD_FAC = 4.0 * t.EGRCRV / (t.G * t.G);
   double FFD_FAC = std::pow(t.EGRCRV / t.AFCRV, 1.0 / t.BFCRV) * t.G;
   for (int M = 1; M <= NFRE; ++M) {
@@ -1019,8 +1020,24 @@ void implsch_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int IC
       SSOURCE(IJ, K, M) = SL(IJ, K, M) / GTEMP1;
     }
   SDIWBK(x, FL1, FLD, SL, DEPTH, EMAXDPT, EMEAN, F1MEAN);
-  if (c.licerun) {
-    if (c.lciscal || c.lciwa1 || c.lciwa2 || c.lciwa3) throw std::runtime_error("sea-ice attenuation branches not restated (SURVEY 8f)");
+  if (c.licerun) {   // implsch.F90:312-339
+    if (c.lciwa1 || c.lciwa2) throw std::runtime_error("SDICE1 / SDICE2 not restated (SURVEY 8f)");
+    if (c.lciscal)
+      for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+        const double BETA = 1. - CICOVER(IJ);
+        SL(IJ, K, M) = BETA * SL(IJ, K, M);
+        FLD(IJ, K, M) = BETA * FLD(IJ, K, M);
+      }
+    if (c.lciwa3) {    // SDICE3 (sdice3.F90:107-147), IMODEL = 2 (Jie Yu 2022), ALPFAC = ZALPFACX (no ice-breakup coupling)
+      V1 CITHICK = s1(f.CITHICK);
+      const double CDICE = 0.1274 * std::pow(t.ZPI / std::sqrt(t.G), 4.5);
+      for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+        const double ALP = (2. * CDICE * std::pow(CITHICK(IJ), 1.25) * std::pow(t.FR(M), 4.5)) * c.zalpfacx;
+        const double TEMP = -CICOVER(IJ) * ALP * CGROUP(IJ, M);
+        SL(IJ, K, M) = SL(IJ, K, M) + FL1(IJ, K, M) * TEMP;
+        FLD(IJ, K, M) = FLD(IJ, K, M) + TEMP;
+      }
+    }
   }
   SBOTTOM(x, FL1, FLD, SL, WAVNUM, DEPTH);
   // ---- 2.4 new spectra (implsch.F90:352-395)

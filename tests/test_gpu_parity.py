@@ -250,6 +250,28 @@ def test_current_cfl_fallback(built):
     assert w3.lib.ecwam_b200_propag(w3.h) == nfail
 
 
+@pytest.mark.parametrize("case,mask", [("o48like", 12), ("o640like", 4), ("o48_iphys0", 8)])
+def test_sea_ice_attenuation(built, case, mask):
+    """LCIWA3 (SDICE3, sdice3.F90:107-147) and LCISCAL (implsch.F90:315-325) with waves allowed under the ice (LMASKICE = F):
+    the attenuation coefficient rides on SBOTTOM's per-(point, frequency) plane, the (1 - CICOVER) scaling is applied between
+    SDIWBK and SDICE as in the reference, WNFLUXES switches to its sea-ice constants (wnfluxes.F90:150-158)."""
+    okw = dict(lmaskice=0, lciwa3=1 if mask & 4 else 0, lciscal=1 if mask & 8 else 0)
+    g, o, f, fl = make_oracle(case, **okw)
+    g, o0, f, fl = make_oracle(case, lmaskice=0)
+    _, s, w = make_gpu(case, lmaskice=0, lciwa=mask)
+    cith = np.where(f["CICOVER"] > 0, 0.3 + 1.5 * f["CICOVER"], 0.0)
+    for m in (o, o0):
+        m.set_field("CITHICK", cith)
+    w.set_field("cithick", cith)
+    for _ in range(3):
+        assert o.step() == 0 and o0.step() == 0 and w.step() == 0
+    w.synchronize()
+    check_state(w, o)
+    ice = f["CICOVER"] > 0.2
+    a, b = o.get_fl1()[:, :, ice], o0.get_fl1()[:, :, ice]
+    assert a.sum() < 0.98 * b.sum(), "the attenuation must act under the ice (%g)" % (a.sum() / b.sum())
+
+
 def test_gpu_outputs_satisfy_oracle_independent_invariants(built):
     """Properties the CUDA path must have whatever the oracle says: the stress solution satisfies the neutral log profile
     (taut_z0.F90:303-341), TAUW <= u*^2, MIJ inside 1..NFRE, spectra finite and >= the noise floor, and the swell + wind-sea
@@ -283,7 +305,7 @@ def test_cfl_violation_is_reported(built):
 def test_unsupported_switches_are_rejected(built):
     from ecwam_b200 import synth
     g = synth.make_grid(8, "aqua")
-    for kw in (dict(irefra=4), dict(irefra=2, ifrelfmax=5), dict(llgcbz0=1), dict(isnonlin=1), dict(lciwa=1)):
+    for kw in (dict(irefra=4), dict(irefra=2, ifrelfmax=5), dict(llgcbz0=1), dict(isnonlin=1), dict(lciwa=1), dict(lciwa=2)):
         s = M.WamSetup(g, nproc=1, **kw)
         with pytest.raises(L.EcwamError):
             M.WamIntgr(s, 0)
