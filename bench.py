@@ -28,8 +28,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "grid-point spectra/s per timestep (IMPLSCH+PROPAGS2)"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of the bench workload
-NCU_DRAM_SOURCE = "profiles/r01j_ncu_summary_O640.txt"
-NCU_DRAM_BYTES = {("O640", 1): {"implsch_stencil": 36.197e9, "implsch_point": 53.643e9, "propags2": 19.688e9}}
+NCU_DRAM_SOURCE = "profiles/r01l_ncu_summary_O640.txt"
+NCU_DRAM_BYTES = {("O640", 1): {"implsch_stencil": 36.193e9, "implsch_point": 53.645e9, "propags2": 19.585e9}}
 UNIT = "spectra/s"
 
 

@@ -272,6 +272,26 @@ def test_sea_ice_attenuation(built, case, mask):
     assert a.sum() < 0.98 * b.sum(), "the attenuation must act under the ice (%g)" % (a.sum() / b.sum())
 
 
+def test_runs_are_bitwise_reproducible(built):
+    """No atomics, fixed summation orders (the DIA scatter is a gather, WNFLUXES / BTH0 reductions are ordered): two runs from
+    the same state give the same bits, also with the current-refraction kernel."""
+    from common import synthetic_currents
+    for extra in (dict(), dict(irefra=3)):
+        outs = []
+        for rep in range(2):
+            g, s, w = make_gpu("o640like", **extra)
+            if extra:
+                u, v = synthetic_currents(g)
+                w.set_field("ucur", u); w.set_field("vcur", v)
+            for _ in range(3):
+                assert w.step() == 0
+            w.synchronize()
+            outs.append((w.get_spec("fl1"), w.get_field("ufric"), w.get_field("phiocd"), w.get_field("mij")))
+            w.close()
+        for a, b in zip(*outs):
+            np.testing.assert_array_equal(a, b)
+
+
 def test_gpu_outputs_satisfy_oracle_independent_invariants(built):
     """Properties the CUDA path must have whatever the oracle says: the stress solution satisfies the neutral log profile
     (taut_z0.F90:303-341), TAUW <= u*^2, MIJ inside 1..NFRE, spectra finite and >= the noise floor, and the swell + wind-sea
