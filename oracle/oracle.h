@@ -118,6 +118,11 @@ struct Tables {
   ArrI INDICESSAT;
   ArrD SATWEIGHTS;
   double EGRCRV, AFCRV, BFCRV;
+  // gravity-capillary model (yowfred.F90:61-65, yowpcons.F90:47-48, initgc.F90, setwavphys.F90: ANG_GC_*)
+  double SURFT = 0.0000717, SQRTGOSURFT = 0.0, ANG_GC_A = 0.0, ANG_GC_B = 0.0, ANG_GC_C = 0.0;
+  int NWAV_GC = 0;
+  ArrD XK_GC, XKM_GC, OMEGA_GC, OMXKM3_GC, VG_GC, C_GC, CM_GC, C2OSQRTVG_GC, XKMSQRTVGOC2_GC, OM3GMKM_GC, DELKCC_GC, DELKCC_GC_NS,
+      DELKCC_OMXKM3_GC;
   // YOWTABL
   int IAB = 200;
   double EPS1 = 0.00001;

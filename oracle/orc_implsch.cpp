@@ -131,11 +131,144 @@ void FRCUTINDEX(const Ctx& x, V1 FM, V1 FMWS, V1 UFRIC, V1 CICOVER, I1 MIJ, V2 R
 // chnkmin.F90
 double CHNKMIN(const Tables& t, double U10) { return t.ALPHAMIN + (t.ALPHA - t.ALPHAMIN) * 0.5 * (1.0 - std::tanh(U10 - t.CHNKMIN_U)); }
 
-// taut_z0.F90:281-341 (LLGCBZ0 = .FALSE. branch) via airsea.F90 ICODE_WND == 3
-void TAUT_Z0(const Ctx& x, int IUSFG, V1 UTOP, V1 UDIR, V1 TAUW, V1 TAUWDIR, V1 USTAR, V1 Z0, V1 Z0B, V1 CHRNCK) {
+// ns_gc.F90:44-48
+static int NS_GC(const Tables& t, double USTAR) {
+  const double XLOGKRATIOM1_GC = 1.0 / std::log(1.2);   // yowfred.F90:62-63
+  const double XKS = t.SQRTGOSURFT / (1.48 + 2.05 * USTAR);
+  return std::min((int)(std::log(std::max(XKS * t.XKM_GC(1), 1.0)) * XLOGKRATIOM1_GC) + 1, t.NWAV_GC - 1);
+}
+// stress_gc.F90:70-130: wave-induced stress of the gravity-capillary waves (part of the unresolved spectrum)
+static double STRESS_GC(const Ctx& x, double ANG_GC, double USTAR, double Z0, double Z0MIN, double HALP, double RNFAC) {
+  const Tables& t = x.t;
+  const double XLAMA = 0.25, XLAMB = 4.0;
+  const int NS = NS_GC(t, USTAR);
+  const double TAUWCG_MIN = sq(USTAR * (Z0MIN / Z0));
+  const double XLAMBDA = 1.0 + XLAMA * std::tanh(XLAMB * p4(USTAR));
+  const double ZABHRC = ANG_GC * t.BETAMAXOXKAPPA2 * HALP * t.C2OSQRTVG_GC(NS);
+  const double CONST = x.c.llnormagam ? RNFAC * t.BMAXOKAP * HALP * t.C2OSQRTVG_GC(NS) / std::max(USTAR, t.EPSUS) : 0.0;
+  double TAUWCG = 0.0;
+  for (int I = NS; I <= t.NWAV_GC; ++I) {
+    const double X = USTAR * t.CM_GC(I);
+    const double XLOG = std::log(t.XK_GC(I) * Z0) + t.XKAPPA / (X + t.ZALP);
+    double ZLOG = XLOG - std::log(XLAMBDA);
+    ZLOG = std::min(ZLOG, 0.0);
+    const double ZLOG2X = ZLOG * ZLOG * X;
+    const double GAM_W = ZLOG2X * ZLOG2X * std::exp(XLOG) * t.OM3GMKM_GC(I);
+    const double ZN = CONST * t.XKMSQRTVGOC2_GC(I) * GAM_W;
+    const double GAMNORMA = (1.0 + t.RN1_RN * ZN) / (1.0 + ZN);
+    if (I == NS) TAUWCG = GAM_W * t.DELKCC_GC_NS(NS) * t.OMXKM3_GC(NS) * GAMNORMA;
+    else TAUWCG = TAUWCG + GAM_W * t.DELKCC_OMXKM3_GC(I) * GAMNORMA;
+  }
+  return std::max(ZABHRC * TAUWCG, TAUWCG_MIN);
+}
+// cdm.func.h
+static double CDM(double U) { return std::max(std::min(0.0006 + 0.00008 * U, 0.001 + 0.0018 * std::exp(-0.05 * (U - 33.))), 0.001); }
+
+// taut_z0.F90:120-341 via airsea.F90 ICODE_WND == 3: the gravity-capillary model (LLGCBZ0, :148-279) or the Charnock/Janssen
+// relation (:281-341)
+void TAUT_Z0(const Ctx& x, int IUSFG, V1 HALP, V1 UTOP, V1 UDIR, V1 TAUW, V1 TAUWDIR, V1 RNFAC, V1 USTAR, V1 Z0, V1 Z0B, V1 CHRNCK) {
+  if (x.c.llgcbz0) {
+    const Tables& t = x.t;
+    const Config& c = x.c;
+    const int NITER = 18;
+    const double PMAX = 0.99, Z0MIN = 0.000001;   // taut_z0.F90:93-99
+    const double US2TOTAUW = 1.0 + t.EPS1;
+    const double RNUEFF = 0.04 * c.rnu, RNUKAPPAM1 = RNUEFF / t.XKAPPA;
+    const double PCE_GC = 0.001 * IUSFG + (1 - IUSFG) * 0.005;
+    const double ACDLIN = t.ACDLIN, BCDLIN = t.BCDLIN;
+    for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) {
+      const double COSDIFF = std::cos(UDIR(IJ) - TAUWDIR(IJ));
+      const double TAUWACT = std::max(TAUW(IJ) * COSDIFF, t.EPSMIN);
+      const bool LLCOSDIFF = COSDIFF > 0.9;
+      const double ALPHAOG = c.llcapchnk ? CHNKMIN(t, UTOP(IJ)) * t.GM1 : 0.0;
+      const double u = UTOP(IJ);
+      const double USMAX = std::max(-0.21339 + 0.093698 * u - 0.0020944 * (u * u) + 5.5091E-5 * (u * u * u), 0.03);
+      const double TAUWEFF = std::min(TAUWACT * US2TOTAUW, USMAX * USMAX);
+      if (IUSFG == 0) {
+        const double ALPHAGM1 = t.ALPHA * t.GM1;
+        double CDFG;
+        if (u < 1.0) CDFG = 0.002;
+        else if (LLCOSDIFF) {
+          const double X = std::min(TAUWACT / sq(std::max(USTAR(IJ), t.EPSUS)), PMAX);
+          double ZCHAR = std::min(ALPHAGM1 * sq(USTAR(IJ)) / std::sqrt(1.0 - X), 0.05 * std::exp(-0.05 * (u - 35.)));
+          ZCHAR = std::min(ZCHAR, t.ALPHAMAX);
+          CDFG = ACDLIN + BCDLIN * std::sqrt(ZCHAR) * u;
+        } else CDFG = CDM(u);
+        USTAR(IJ) = u * std::sqrt(CDFG);
+      }
+      const double W1 = 0.85 - 0.05 * (std::tanh(10.0 * (u - 5.0)) + 1.0);
+      const double XKUTOP = t.XKAPPA * u;
+      double USTOLD = USTAR(IJ), TAUOLD = USTOLD * USTOLD, TAUUNR = 0.0, X;
+      int ITER;
+      for (ITER = 1; ITER <= NITER; ++ITER) {
+        Z0(IJ) = std::max(t.XNLEV / (std::exp(std::min(XKUTOP / USTOLD, 50.0)) - 1.0), Z0MIN);
+        const double TAUV = RNUKAPPAM1 * USTOLD / Z0(IJ);
+        const double ANG_GC = t.ANG_GC_A + t.ANG_GC_B * std::tanh(t.ANG_GC_C * TAUOLD);
+        TAUUNR = STRESS_GC(x, ANG_GC, USTAR(IJ), Z0(IJ), Z0MIN, HALP(IJ), RNFAC(IJ));
+        const double TAUNEW = TAUWEFF + TAUV + TAUUNR;
+        const double USTNEW = std::sqrt(TAUNEW);
+        USTAR(IJ) = W1 * USTOLD + (1.0 - W1) * USTNEW;
+        const double DEL = USTAR(IJ) - USTOLD;
+        if (std::fabs(DEL) < PCE_GC * USTAR(IJ)) break;
+        TAUOLD = sq(USTAR(IJ));
+        USTOLD = USTAR(IJ);
+      }
+      X = TAUWEFF / TAUOLD;
+      if (ITER > NITER && X >= PMAX) {   // protection just in case there is no convergence
+        const double CDFG = CDM(u);
+        USTAR(IJ) = u * std::sqrt(CDFG);
+        const double Z0MINRST = sq(USTAR(IJ)) * t.ALPHA * t.GM1;
+        Z0(IJ) = std::max(t.XNLEV / (std::exp(XKUTOP / USTAR(IJ)) - 1.0), Z0MINRST);
+        Z0B(IJ) = Z0MINRST;
+      } else {
+        Z0(IJ) = std::max(t.XNLEV / (std::exp(XKUTOP / USTAR(IJ)) - 1.0), Z0MIN);
+        Z0B(IJ) = Z0(IJ) * std::sqrt(TAUUNR / TAUOLD);
+      }
+      if (X < PMAX) {                    // refine the solution (taut_z0.F90:230-276)
+        const double USNRF = USTAR(IJ), Z0NRF = Z0(IJ), Z0BNRF = Z0B(IJ);
+        USTOLD = USTAR(IJ);
+        TAUOLD = std::max(USTOLD * USTOLD, TAUWEFF);
+        const double ALPOG = std::max(std::min(Z0B(IJ) / TAUOLD, t.ALPHAMAX), ALPHAOG);
+        double USTM1 = 0.0, Z0VIS = 0.0;
+        for (ITER = 1; ITER <= NITER; ++ITER) {
+          X = std::min(TAUWEFF / TAUOLD, PMAX);
+          USTM1 = 1.0 / std::max(USTOLD, t.EPSUS);
+          Z0VIS = c.rnum * USTM1;
+          const double HZ0VISO1MX = 0.5 * Z0VIS / (1.0 - X);
+          Z0B(IJ) = ALPOG * TAUOLD;
+          Z0(IJ) = HZ0VISO1MX + std::sqrt(sq(HZ0VISO1MX) + sq(Z0B(IJ)) / (1.0 - X));
+          const double XOLOGZ0 = 1.0 / std::log(t.XNLEV / Z0(IJ) + 1.0);
+          const double F = USTOLD - XKUTOP * XOLOGZ0;
+          const double ZZ = 2.0 * USTM1 * (3.0 * sq(Z0B(IJ)) + 0.5 * Z0VIS * Z0(IJ) - sq(Z0(IJ))) /
+                            (2.0 * sq(Z0(IJ)) * (1.0 - X) - Z0VIS * Z0(IJ));
+          const double DELF = 1.0 - XKUTOP * sq(XOLOGZ0) * ZZ;
+          if (DELF != 0.0) USTAR(IJ) = USTOLD - F / DELF;
+          const double TAUNEW = std::max(sq(USTAR(IJ)), TAUWEFF);
+          USTAR(IJ) = std::sqrt(TAUNEW);
+          const double DEL = TAUNEW - TAUOLD;
+          if (std::fabs(DEL) < PCE_GC * TAUOLD) break;
+          TAUOLD = TAUNEW;
+          USTOLD = USTAR(IJ);
+        }
+        if (ITER > NITER) {
+          USTAR(IJ) = USNRF; Z0(IJ) = Z0NRF; Z0B(IJ) = Z0BNRF;
+          USTM1 = 1.0 / std::max(USTAR(IJ), t.EPSUS);
+          Z0VIS = c.rnum * USTM1;
+          CHRNCK(IJ) = std::max(t.G * (Z0(IJ) - Z0VIS) * sq(USTM1), t.ALPHAMIN);
+        } else {
+          CHRNCK(IJ) = std::max(t.G * (Z0B(IJ) / std::sqrt(1.0 - X)) / sq(std::max(USTAR(IJ), t.EPSUS)), t.ALPHAMIN);
+        }
+      } else {
+        const double USTM1 = 1.0 / std::max(USTAR(IJ), t.EPSUS);
+        const double Z0VIS = c.rnum * USTM1;
+        CHRNCK(IJ) = std::max(t.G * (Z0(IJ) - Z0VIS) * sq(USTM1), t.ALPHAMIN);
+      }
+    }
+    return;
+  }
+
   const Tables& t = x.t;
   const Config& c = x.c;
-  if (c.llgcbz0) throw std::runtime_error("TAUT_Z0: LLGCBZ0 branch not restated (SURVEY 8f)");
   const int NITER = 18;
   const double TWOXMP1 = 3.0;
   double XLOGXL = std::log(t.XNLEV);
@@ -187,8 +320,22 @@ void TAUT_Z0(const Ctx& x, int IUSFG, V1 UTOP, V1 UDIR, V1 TAUW, V1 TAUWDIR, V1 
 // wsigstar.F90:105-129 (LLGCBZ0=LLNORMAGAM=F branch)
 void WSIGSTAR(const Ctx& x, V1 WSWAVE, V1 UFRIC, V1 Z0M, V1 WSTAR, V1 SIG_N) {
   const Tables& t = x.t;
-  if (x.c.llgcbz0 || x.c.llnormagam) throw std::runtime_error("WSIGSTAR: GC branch not restated");
   const double BG_GUST = 0.0, ONETHIRD = 1.0 / 3.0, SIG_NMAX = 0.9, C1 = 1.03e-3, C2 = 0.04e-3, P1 = 1.48, P2 = -0.21;
+  if (x.c.llgcbz0 || x.c.llnormagam) {   // wsigstar.F90:87-103
+    const double ZN = x.c.rnum;
+    for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) {
+      const double U10M1 = 1.0 / std::max(WSWAVE(IJ), x.c.wspmin);
+      const double Z0VIS = ZN / std::max(UFRIC(IJ), t.EPSUS);
+      double ZCHAR = t.G * (Z0M(IJ) - Z0VIS) / std::max(sq(UFRIC(IJ)), t.EPSUS);
+      ZCHAR = std::max(std::min(ZCHAR, t.ALPHAMAX), t.ALPHAMIN);
+      const double BCD_LOC = t.BCDLIN * std::sqrt(ZCHAR);
+      const double C_D = t.ACDLIN + BCD_LOC * WSWAVE(IJ);
+      const double DC_DDU = BCD_LOC;
+      const double SIG_CONV = 1.0 + 0.5 * WSWAVE(IJ) / C_D * DC_DDU;
+      SIG_N(IJ) = std::min(SIG_NMAX, SIG_CONV * U10M1 * std::pow(BG_GUST * UFRIC(IJ) * UFRIC(IJ) * UFRIC(IJ) + 0.5 * t.XKAPPA * WSTAR(IJ) * WSTAR(IJ) * WSTAR(IJ), ONETHIRD));
+    }
+    return;
+  }
   double XKAPPAD = 1.0 / t.XKAPPA;
   for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) {
     double U10 = UFRIC(IJ) * XKAPPAD * (std::log(10.0) - std::log(Z0M(IJ)));
@@ -205,12 +352,10 @@ void WSIGSTAR(const Ctx& x, V1 WSWAVE, V1 UFRIC, V1 Z0M, V1 WSTAR, V1 SIG_N) {
 
 // sinput_ard.F90:149-524
 void SINPUT_ARD(const Ctx& x, int NGST, bool LLSNEG, V3 FL1, V2 WAVNUM, V2 CINV, V2 XK2CG, V1 WDWAVE, V1 WSWAVE,
-                V1 UFRIC, V1 Z0M, V2 COSWDIF, V2 SINWDIF2, V1 RAORW, V1 WSTAR, V3 FLD, V3 SL, V3 SPOS, V3 XLLWS) {
-  (void)XK2CG; (void)SINWDIF2;
+                V1 UFRIC, V1 Z0M, V2 COSWDIF, V2 SINWDIF2, V1 RAORW, V1 WSTAR, V1 RNFAC, V3 FLD, V3 SL, V3 SPOS, V3 XLLWS) {
   const Tables& t = x.t;
   const Config& c = x.c;
   const int KIJS = x.KIJS, KIJL = x.KIJL, NANG = x.NANG, NFRE = x.NFRE;
-  if (c.llnormagam) throw std::runtime_error("SINPUT_ARD: LLNORMAGAM branch not restated");
   const int n = KIJL + 1;
   std::vector<double> CONSTF(n), Z0VIS(n), Z0NOZ(n), FWW(n), PVISC(n), PTURB(n), ZCN(n), SIG_Ns(n), UORBT(n), AORB(n),
       TEMP(n), RE(n), RE_C(n), ZORB(n), CNSN(n), FLP_AVG(n), SLP_AVG(n), ROGOROAIR(n), AIRD_PVISC(n), USG2(n), FLP(n),
@@ -224,6 +369,9 @@ void SINPUT_ARD(const Ctx& x, int NGST, bool LLSNEG, V3 FL1, V2 WAVNUM, V2 CINV,
 
   double AVG_GST = 1.0 / NGST;
   double CONST1 = t.BETAMAXOXKAPPA2;
+  const double CONSTN = t.DELTH / (t.XKAPPA * t.ZPI);
+  std::vector<double> CSTRNFAC(n, 0.0), XNGAMCONST(n, 0.0);
+  if (c.llnormagam) for (int IJ = KIJS; IJ <= KIJL; ++IJ) CSTRNFAC[IJ] = CONSTN * RNFAC(IJ) / RAORW(IJ);   // sinput_ard.F90:172-176
   double ABS_TAUWSHELTER = std::fabs(t.TAUWSHELTER);
   bool LTAUWSHELTER = ABS_TAUWSHELTER != 0.0;
   if (NGST > 1) WSIGSTAR(x, WSWAVE, UFRIC, Z0M, WSTAR, V1{SIG_Ns.data() + 1});
@@ -310,6 +458,7 @@ void SINPUT_ARD(const Ctx& x, int NGST, bool LLSNEG, V3 FL1, V2 WAVNUM, V2 CINV,
       }
     for (int IJ = KIJS; IJ <= KIJL; ++IJ) { ZCN[IJ] = std::log(WAVNUM(IJ, M) * Z0M(IJ)); CNSN[IJ] = CONST * RAORW(IJ); }
     for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) XLLWS(IJ, K, M) = 0.0;
+    if (c.llnormagam) for (int IJ = KIJS; IJ <= KIJL; ++IJ) XNGAMCONST[IJ] = CSTRNFAC[IJ] * XK2CG(IJ, M);
     if (LLSNEG) for (int IJ = KIJS; IJ <= KIJL; ++IJ) { DSTAB1[IJ] = COEF5 * AIRD_PVISC[IJ] * WAVNUM(IJ, M); TEMP1[IJ] = COEF * RAORW(IJ); }
     for (int IGST = 1; IGST <= NGST; ++IGST) {
       for (int K = 1; K <= NANG; ++K) {
@@ -325,6 +474,17 @@ void SINPUT_ARD(const Ctx& x, int NGST, bool LLSNEG, V3 FL1, V2 WAVNUM, V2 CINV,
               XLLWS(IJ, K, M) = 1.0;
             }
           }
+        }
+      }
+      if (c.llnormagam) {   // sinput_ard.F90:436-452
+        for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+          double SUMF = 0.0, SUMFSIN2 = 0.0;
+          for (int K = 1; K <= NANG; ++K) {
+            SUMF = SUMF + GAM0[i3(IJ, K, IGST)] * FL1(IJ, K, M);
+            SUMFSIN2 = SUMFSIN2 + GAM0[i3(IJ, K, IGST)] * FL1(IJ, K, M) * SINWDIF2(IJ, K);
+          }
+          const double ZNZ = XNGAMCONST[IJ] * USTPM1[i2(IJ, IGST)];
+          GAMNORMA[i2(IJ, IGST)] = (1.0 + ZNZ * SUMFSIN2) / (1.0 + ZNZ * SUMF);
         }
       }
       if (LLSNEG)
@@ -355,12 +515,10 @@ void SINPUT_ARD(const Ctx& x, int NGST, bool LLSNEG, V3 FL1, V2 WAVNUM, V2 CINV,
 
 // sinput_jan.F90:150-400
 void SINPUT_JAN(const Ctx& x, int NGST, bool LLSNEG, V3 FL1, V2 WAVNUM, V2 CINV, V2 XK2CG, V1 WSWAVE, V1 UFRIC, V1 Z0M,
-                V2 COSWDIF, V2 SINWDIF2, V1 RAORW, V1 WSTAR, V3 FLD, V3 SL, V3 SPOS, V3 XLLWS) {
-  (void)XK2CG; (void)SINWDIF2;
+                V2 COSWDIF, V2 SINWDIF2, V1 RAORW, V1 WSTAR, V1 RNFAC, V3 FLD, V3 SL, V3 SPOS, V3 XLLWS) {
   const Tables& t = x.t;
   const Config& c = x.c;
   const int KIJS = x.KIJS, KIJL = x.KIJL, NANG = x.NANG, NFRE = x.NFRE;
-  if (c.llnormagam) throw std::runtime_error("SINPUT_JAN: LLNORMAGAM branch not restated");
   const int n = KIJL + 1;
   auto i2 = [n](int ij, int ig) { return ij + n * (ig - 1); };
   auto i3 = [n, NANG](int ij, int k, int ig) { return ij + (size_t)n * ((k - 1) + (size_t)NANG * (ig - 1)); };
@@ -412,6 +570,20 @@ void SINPUT_JAN(const Ctx& x, int NGST, bool LLSNEG, V3 FL1, V2 WAVNUM, V2 CINV,
           } else GAM0[i3(IJ, K, IGST)] = 0.0;
         }
     }
+    if (c.llnormagam) {   // sinput_jan.F90:329-348
+      const double CONSTN = t.DELTH / (t.XKAPPA * t.ZPI);
+      for (int IGST = 1; IGST <= NGST; ++IGST)
+        for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+          const double XNGAMCONST = (CONSTN * RNFAC(IJ) / RAORW(IJ)) * XK2CG(IJ, M);
+          double SUMF = 0.0, SUMFSIN2 = 0.0;
+          for (int K = 1; K <= NANG; ++K) {
+            SUMF = SUMF + GAM0[i3(IJ, K, IGST)] * FL1(IJ, K, M);
+            SUMFSIN2 = SUMFSIN2 + GAM0[i3(IJ, K, IGST)] * FL1(IJ, K, M) * SINWDIF2(IJ, K);
+          }
+          const double ZNZ = XNGAMCONST * USTPM1[i2(IJ, IGST)];
+          GAMNORMA[i2(IJ, IGST)] = (1.0 + ZNZ * SUMFSIN2) / (1.0 + ZNZ * SUMF);
+        }
+    }
     for (int K = 1; K <= NANG; ++K) {
       for (int IJ = KIJS; IJ <= KIJL; ++IJ) UFAC1[IJ] = WSIN[1] * GAM0[i3(IJ, K, 1)] * GAMNORMA[i2(IJ, 1)];
       if (NGST == 2) for (int IJ = KIJS; IJ <= KIJL; ++IJ) UFAC1[IJ] = UFAC1[IJ] + WSIN[2] * GAM0[i3(IJ, K, 2)] * GAMNORMA[i2(IJ, 2)];
@@ -428,10 +600,9 @@ void SINPUT_JAN(const Ctx& x, int NGST, bool LLSNEG, V3 FL1, V2 WAVNUM, V2 CINV,
   }
 }
 
-// tau_phi_hf.F90:111-305 (LLGCBZ0=F, LLNORMAGAM=F)
-void TAU_PHI_HF(const Ctx& x, I1 MIJ, bool LTAUWSHELTER, V1 UFRIC, V1 Z0M, V3 FL1, V1 AIRD, V2 COSWDIF, V2 SINWDIF2,
+// tau_phi_hf.F90:111-305
+void TAU_PHI_HF(const Ctx& x, I1 MIJ, bool LTAUWSHELTER, V1 UFRIC, V1 Z0M, V3 FL1, V1 AIRD, V1 RNFAC, V2 COSWDIF, V2 SINWDIF2,
                 V1 UST, V1 TAUHF, V1 PHIHF, bool LLPHIHF) {
-  (void)UFRIC;
   const Tables& t = x.t;
   const int KIJS = x.KIJS, KIJL = x.KIJL, NANG = x.NANG;
   const int n = KIJL + 1;
@@ -466,7 +637,16 @@ void TAU_PHI_HF(const Ctx& x, I1 MIJ, bool LTAUWSHELTER, V1 UFRIC, V1 Z0M, V3 FL
       F1D[IJ] = F1D[IJ] + FL1(IJ, K, MIJ(IJ));
     }
   for (int IJ = KIJS; IJ <= KIJL; ++IJ) { F1DCOS3[IJ] = t.DELTH * F1DCOS3[IJ]; F1DCOS2[IJ] = t.DELTH * F1DCOS2[IJ]; F1DSIN2[IJ] = t.DELTH * F1DSIN2[IJ]; F1D[IJ] = t.DELTH * F1D[IJ]; }
-  for (int IJ = KIJS; IJ <= KIJL; ++IJ) ZSUP[IJ] = ZSUPMAX;
+  if (x.c.llnormagam)   // tau_phi_hf.F90:177-182
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      const double CONFG = t.GAMNCONST * t.FR5(MIJ(IJ)) * RNFAC(IJ) * SQRTGZ0[IJ];
+      CONST1[IJ] = CONFG * F1DSIN2[IJ];
+      CONST2[IJ] = CONFG * F1D[IJ];
+    }
+  if (x.c.llgcbz0)      // omegagc.F90:51-55, tau_phi_hf.F90:190-193
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) ZSUP[IJ] = std::min(std::log(t.OMEGA_GC(NS_GC(t, UFRIC(IJ))) * SQRTZ0OG[IJ]), ZSUPMAX);
+  else
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) ZSUP[IJ] = ZSUPMAX;
   for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
     TAUL[IJ] = sq(UST(IJ));
     DELZ[IJ] = std::max((ZSUP[IJ] - ZINF[IJ]) / (double)(t.JTOT_TAUHF - 1), 0.0);
@@ -560,7 +740,7 @@ void TAU_PHI_HF(const Ctx& x, I1 MIJ, bool LTAUWSHELTER, V1 UFRIC, V1 Z0M, V3 FL
 }
 
 // stresso.F90:120-233
-void STRESSO(const Ctx& x, I1 MIJ, V2 RHOWGDFTH, V3 FL1, V3 SL, V3 SPOS, V2 CINV, V1 WDWAVE, V1 UFRIC, V1 Z0M, V1 AIRD,
+void STRESSO(const Ctx& x, I1 MIJ, V2 RHOWGDFTH, V3 FL1, V3 SL, V3 SPOS, V2 CINV, V1 WDWAVE, V1 UFRIC, V1 Z0M, V1 AIRD, V1 RNFAC,
              V2 COSWDIF, V2 SINWDIF2, V1 TAUW, V1 TAUWDIR, V1 PHIWA, bool LLPHIWA) {
   const Tables& t = x.t;
   const int KIJS = x.KIJS, KIJL = x.KIJL, NANG = x.NANG, NFRE = x.NFRE;
@@ -600,7 +780,7 @@ void STRESSO(const Ctx& x, I1 MIJ, V2 RHOWGDFTH, V3 FL1, V3 SL, V3 SPOS, V2 CINV
       UST[IJ] = std::pow(TAUPX * TAUPX + TAUPY * TAUPY, 0.25);
     }
   }
-  TAU_PHI_HF(x, MIJ, LTAUWSHELTER, UFRIC, Z0M, FL1, AIRD, COSWDIF, SINWDIF2, V1{UST.data() + 1}, V1{TAUHF.data() + 1},
+  TAU_PHI_HF(x, MIJ, LTAUWSHELTER, UFRIC, Z0M, FL1, AIRD, RNFAC, COSWDIF, SINWDIF2, V1{UST.data() + 1}, V1{TAUHF.data() + 1},
              V1{PHIHF.data() + 1}, LLPHIWA);
   for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
     XSTRESS[IJ] = XSTRESS[IJ] + TAUHF[IJ] * std::sin(USDIRP[IJ]);
@@ -950,6 +1130,41 @@ void femean(const Tables& t, const Config& c, int KIJL, const double* Fp, double
   }
 }
 
+// halphap.F90:68-115 with meansqs_lf.F90:80-100 (NFRE_EFF = NFRE) and FEMEAN on the spectrum in the wind direction
+void HALPHAP(const Ctx& x, V2 WAVNUM, V2 COSWDIF, V3 FL1, V1 HALP) {
+  const Tables& t = x.t;
+  const int KIJS = x.KIJS, KIJL = x.KIJL, NANG = x.NANG, NFRE = x.NFRE;
+  const double ZLNFRNFRE = std::log(t.FR(NFRE));
+  std::vector<double> sFLWD((size_t)KIJL * NANG * NFRE), XMSS(KIJL + 1, 0.0), EM(KIJL), FM(KIJL);
+  V3 FLWD{sFLWD.data(), KIJL, NANG};
+  for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+    const double WD = 0.5 + 0.5 * std::copysign(1.0, COSWDIF(IJ, K));
+    FLWD(IJ, K, M) = FL1(IJ, K, M) * WD;
+  }
+  for (int M = 1; M <= NFRE; ++M)
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      const double TEMP1 = t.DFIM(M) * sq(WAVNUM(IJ, M));
+      double TEMP2 = 0.0;
+      for (int K = 1; K <= NANG; ++K) TEMP2 = TEMP2 + FLWD(IJ, K, M);
+      XMSS[IJ] = XMSS[IJ] + TEMP1 * TEMP2;
+    }
+  femean(t, x.c, KIJL, sFLWD.data(), EM.data(), FM.data());
+  for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+    double ALPHAP;
+    bool tail = true;
+    if (EM[IJ - 1] > 0.0 && FM[IJ - 1] < t.FR(NFRE - 2)) {
+      ALPHAP = XMSS[IJ] / (ZLNFRNFRE - std::log(FM[IJ - 1]));
+      tail = ALPHAP > t.ALPHAPMAX;
+    }
+    if (tail) {
+      double F1D = 0.0;
+      for (int K = 1; K <= NANG; ++K) F1D = F1D + FLWD(IJ, K, NFRE) * t.DELTH;
+      ALPHAP = t.ZPI4GM2 * t.FR5(NFRE) * F1D;
+    }
+    HALP(IJ) = 0.5 * std::min(ALPHAP, t.ALPHAPMAX);
+  }
+}
+
 // implsch.F90:177-465 for one NPROMA chunk, with sinflx.F90:101-185 inlined as a lambda
 void implsch_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK) {
   const int NANG = c.nang, NFRE = c.nfre, KIJS = 1;
@@ -973,9 +1188,9 @@ void implsch_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int IC
   V3 FLD{sFLD.data(), P, NANG}, SL{sSL.data(), P, NANG}, SPOS{sSPOS.data(), P, NANG}, SSOURCE{sSSOURCE.data(), P, NANG};
   std::vector<double> sFLM((size_t)P * NANG), sCOSWDIF((size_t)P * NANG), sSINWDIF2((size_t)P * NANG), sTEMP((size_t)P * NFRE), sRHOWGDFTH((size_t)P * NFRE);
   V2 FLM{sFLM.data(), P}, COSWDIF{sCOSWDIF.data(), P}, SINWDIF2{sSINWDIF2.data(), P}, TEMP{sTEMP.data(), P}, RHOWGDFTH{sRHOWGDFTH.data(), P};
-  L1 lRAORW(P), lEMEAN(P), lFMEAN(P), lHALP(P), lEMEANWS(P), lFMEANWS(P), lUSFM(P), lF1MEAN(P), lAKMEAN(P), lXKMEAN(P), lPHIWA(P);
+  L1 lRAORW(P), lEMEAN(P), lFMEAN(P), lHALP(P), lEMEANWS(P), lFMEANWS(P), lUSFM(P), lF1MEAN(P), lAKMEAN(P), lXKMEAN(P), lPHIWA(P), lRNFAC(P);
   V1 RAORW = lRAORW.view(), EMEAN = lEMEAN.view(), FMEAN = lFMEAN.view(), HALP = lHALP.view(), FMEANWS = lFMEANWS.view(),
-     USFM = lUSFM.view(), F1MEAN = lF1MEAN.view(), AKMEAN = lAKMEAN.view(), XKMEAN = lXKMEAN.view(), PHIWA = lPHIWA.view();
+     USFM = lUSFM.view(), F1MEAN = lF1MEAN.view(), AKMEAN = lAKMEAN.view(), XKMEAN = lXKMEAN.view(), PHIWA = lPHIWA.view(), RNFAC = lRNFAC.view();
   std::vector<double> DELFL(NFRE + 1);
 
   double DELT = c.idelt, DELTM = 1.0 / DELT, DELT5 = c.ximp * DELT;
@@ -998,17 +1213,19 @@ void implsch_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int IC
     if (ICODE_WND != 3) throw std::runtime_error("AIRSEA: only ICODE_WND=3 restated");
     if (ICALL == 1) {
       for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) FL1(IJ, K, NFRE) = std::max(FL1(IJ, K, NFRE), FLM(IJ, K));
-      if (c.llgcbz0) throw std::runtime_error("HALPHAP not restated");
-      for (int IJ = KIJS; IJ <= KIJL; ++IJ) HALP(IJ) = 0.0;
+      if (c.llgcbz0) HALPHAP(x, WAVNUM, COSWDIF, FL1, HALP);
+      else for (int IJ = KIJS; IJ <= KIJL; ++IJ) HALP(IJ) = 0.0;
     }
-    TAUT_Z0(x, IUSFG, WSWAVE, WDWAVE, TAUW, TAUWDIR, UFRIC, Z0M, Z0B, CHRNCK);
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ)   // sinflx.F90:117-121
+      RNFAC(IJ) = (c.llnormagam && c.llcapchnk) ? 1.0 + t.DTHRN_A * (1.0 + std::tanh(WSWAVE(IJ) - t.DTHRN_U)) : 1.0;
+    TAUT_Z0(x, IUSFG, HALP, WSWAVE, WDWAVE, TAUW, TAUWDIR, RNFAC, UFRIC, Z0M, Z0B, CHRNCK);
     int NGST; bool LLPHIWA, LLSNEG;
     if (ICALL < NCALL) { NGST = 1; LLPHIWA = false; LLSNEG = false; } else { NGST = 2; LLPHIWA = true; LLSNEG = true; }
-    if (c.iphys == 0) SINPUT_JAN(x, NGST, LLSNEG, FL1, WAVNUM, CINV, XK2CG, WSWAVE, UFRIC, Z0M, COSWDIF, SINWDIF2, RAORW, WSTAR, FLD, SL, SPOS, XLLWS);
-    else SINPUT_ARD(x, NGST, LLSNEG, FL1, WAVNUM, CINV, XK2CG, WDWAVE, WSWAVE, UFRIC, Z0M, COSWDIF, SINWDIF2, RAORW, WSTAR, FLD, SL, SPOS, XLLWS);
+    if (c.iphys == 0) SINPUT_JAN(x, NGST, LLSNEG, FL1, WAVNUM, CINV, XK2CG, WSWAVE, UFRIC, Z0M, COSWDIF, SINWDIF2, RAORW, WSTAR, RNFAC, FLD, SL, SPOS, XLLWS);
+    else SINPUT_ARD(x, NGST, LLSNEG, FL1, WAVNUM, CINV, XK2CG, WDWAVE, WSWAVE, UFRIC, Z0M, COSWDIF, SINWDIF2, RAORW, WSTAR, RNFAC, FLD, SL, SPOS, XLLWS);
     FEMEANWS(x, FL1, XLLWS, FMEANWS, nullptr);
     FRCUTINDEX(x, FMEAN, FMEANWS, UFRIC, CICOVER, MIJ, RHOWGDFTH);
-    STRESSO(x, MIJ, RHOWGDFTH, FL1, SL, SPOS, CINV, WDWAVE, UFRIC, Z0M, AIRD, COSWDIF, SINWDIF2, TAUW, TAUWDIR, PHIWA, LLPHIWA);
+    STRESSO(x, MIJ, RHOWGDFTH, FL1, SL, SPOS, CINV, WDWAVE, UFRIC, Z0M, AIRD, RNFAC, COSWDIF, SINWDIF2, TAUW, TAUWDIR, PHIWA, LLPHIWA);
   }
   if (c.iphys == 0) SDISSIP_JAN(x, FL1, FLD, SL, WAVNUM, EMEAN, F1MEAN, XKMEAN);
   else SDISSIP_ARD(x, FL1, FLD, SL, WAVNUM, CGROUP, XK2CG, UFRIC, COSWDIF, RAORW);

@@ -366,12 +366,12 @@ void outblock(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK, 
   if ((b = col(4))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = UFRIC[IJ - 1];
   if ((b = col(5))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = todeg(WDWAVE[IJ - 1]);
   if ((b = col(6))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = DP[IJ] > 0.0 ? DP[IJ] : sel.zmiss;
-  if ((b = col(7))) {   // outbeta.F90:66-91 (LLGCBZ0 = F)
+  if ((b = col(7))) {   // outbeta.F90:66-91, 113-117
     const double AMAX = 0.02, BMAX = 0.01;
     const double *Z0M = p1(f.Z0M), *Z0B = p1(f.Z0B), *CHRNCK = p1(f.CHRNCK);
     (void)Z0M; (void)Z0B;
     for (int IJ = 1; IJ <= KIJL; ++IJ) {
-      const double ALPHAMAXU10 = std::min(t.ALPHAMAX, AMAX + BMAX * WSWAVE[IJ - 1]);
+      const double ALPHAMAXU10 = c.llgcbz0 ? t.ALPHAMAX : std::min(t.ALPHAMAX, AMAX + BMAX * WSWAVE[IJ - 1]);
       const double USM = 1.0 / std::max(UFRIC[IJ - 1], t.EPSUS);
       const double BETAM = std::max(std::min(CHRNCK[IJ - 1], ALPHAMAXU10), t.ALPHAMIN);
       const double Z0ATM = c.rnum * USM + t.GM1 * BETAM * (UFRIC[IJ - 1] * UFRIC[IJ - 1]);

@@ -50,6 +50,50 @@ static void setwavphys(const Config& c, Tables& t) {
   } else {
     throw std::runtime_error("SETWAVPHYS: unknown IPHYS");
   }
+  if (c.nang <= 24) { t.ANG_GC_A = 0.40; t.ANG_GC_B = 0.60; t.ANG_GC_C = 3.0; }   // setwavphys.F90:52-60, 107-115
+  else { t.ANG_GC_A = 0.35; t.ANG_GC_B = 0.65; t.ANG_GC_C = 3.0; }
+}
+
+// real ** integer as compilers expand it (repeated squaring), not pow()
+static double powi(double x, int m) {
+  unsigned n = (unsigned)(m < 0 ? -m : m);
+  double y = (n & 1) ? x : 1.0;
+  while (n >>= 1) { x = x * x; if (n & 1) y = y * x; }
+  return m < 0 ? 1.0 / y : y;
+}
+// initgc.F90:63-110 with gc_dispersion.h
+static void initgc(Tables& t) {
+  const double KRATIO_GC = 1.2, XKS_GC = 0.006, XKL_GC = 20000.0;   // yowfred.F90:62-65
+  t.SURFT = 0.0717 / t.ROWATER;                                     // iniwcst.F90:69 (GAM_SURF, mpuserin.F90:828)
+  t.SQRTGOSURFT = std::sqrt(t.G / t.SURFT);
+  t.NWAV_GC = (int)nint(std::log(XKL_GC / XKS_GC) / std::log(KRATIO_GC));
+  const int N = t.NWAV_GC;
+  for (ArrD* a : {&t.XK_GC, &t.XKM_GC, &t.OMEGA_GC, &t.OMXKM3_GC, &t.VG_GC, &t.C_GC, &t.CM_GC, &t.C2OSQRTVG_GC, &t.XKMSQRTVGOC2_GC,
+                  &t.OM3GMKM_GC, &t.DELKCC_GC, &t.DELKCC_GC_NS, &t.DELKCC_OMXKM3_GC}) a->alloc(1, N);
+  auto FOMEG = [&](double k) { return std::sqrt(t.G * k + t.SURFT * (k * k * k)); };
+  auto FVG = [&](double k) { return 0.5 / FOMEG(k) * (t.G + 3.0 * t.SURFT * (k * k)); };
+  auto FC = [&](double k) { return FOMEG(k) / k; };
+  for (int I = 1; I <= N; ++I) {
+    t.XK_GC(I) = XKS_GC * powi(KRATIO_GC, I - 1);
+    t.XKM_GC(I) = 1.0 / t.XK_GC(I);
+    t.OMEGA_GC(I) = FOMEG(t.XK_GC(I));
+    t.OMXKM3_GC(I) = t.OMEGA_GC(I) * (t.XKM_GC(I) * t.XKM_GC(I) * t.XKM_GC(I));
+    t.VG_GC(I) = FVG(t.XK_GC(I));
+    t.C_GC(I) = FC(t.XK_GC(I));
+    t.CM_GC(I) = 1.0 / t.C_GC(I);
+    t.C2OSQRTVG_GC(I) = (t.C_GC(I) * t.C_GC(I)) / std::sqrt(t.VG_GC(I));
+    t.XKMSQRTVGOC2_GC(I) = t.XKM_GC(I) / t.C2OSQRTVG_GC(I);
+    t.OM3GMKM_GC(I) = (t.OMEGA_GC(I) * t.OMEGA_GC(I) * t.OMEGA_GC(I)) / (t.G * t.XK_GC(I));
+  }
+  t.DELKCC_GC(1) = 0.5 * (t.XK_GC(2) - t.XK_GC(1)) / t.C2OSQRTVG_GC(1);
+  t.DELKCC_GC_NS(1) = t.DELKCC_GC(1);
+  for (int I = 2; I <= N - 1; ++I) {
+    t.DELKCC_GC(I) = 0.5 * (t.XK_GC(I + 1) - t.XK_GC(I - 1)) / t.C2OSQRTVG_GC(I);
+    t.DELKCC_GC_NS(I) = 0.5 * (t.XK_GC(I + 1) - t.XK_GC(I)) / t.C2OSQRTVG_GC(I);
+  }
+  t.DELKCC_GC(N) = 0.5 * (t.XK_GC(N) - t.XK_GC(N - 1)) / t.C2OSQRTVG_GC(N);
+  t.DELKCC_GC_NS(N) = t.DELKCC_GC(N);
+  for (int I = 1; I <= N; ++I) t.DELKCC_OMXKM3_GC(I) = t.DELKCC_GC(I) * t.OMXKM3_GC(I);
 }
 
 // mfr.F90 + mfredir.F90:90-129
@@ -472,6 +516,7 @@ void init_tables(const Config& c, Tables& t) {
   initmdl_freq(c, t);
   tabu_swellft(t);
   init_x0tauhf(c, t);
+  initgc(t);
   if (c.iphys == 1) init_sdiss_ardh(c, t);
   inisnonlin(c, t);
 }

@@ -11,6 +11,11 @@ CASES = {
     "o320like": dict(N=16, A=24, Fr=29, mask="continents", iphys=1, nproma=64, dt=900.0),     # ..._O320.yml
     "o640like": dict(N=16, A=36, Fr=29, mask="continents", iphys=1, nproma=24, dt=450.0),     # ..._O640.yml
     "aqua": dict(N=16, A=12, Fr=25, mask="aqua", iphys=1, nproma=32, dt=900.0),
+    # ..._O48_cy49r1.yml: gravity-capillary roughness + renormalised growth (WSPMIN = 0.3 with LLGCBZ0, userin.F90:913-918)
+    "o48_cy49r1": dict(N=20, A=12, Fr=25, mask="continents", iphys=1, nproma=32, dt=900.0,
+                       cfg=dict(llgcbz0=1, llnormagam=1, wspmin=0.3)),
+    "o48_iphys0_gc": dict(N=20, A=12, Fr=25, mask="continents", iphys=0, nproma=24, dt=900.0,
+                          cfg=dict(llgcbz0=1, llnormagam=1, wspmin=0.3)),
 }
 
 
@@ -27,6 +32,7 @@ def make_oracle(case, npr=1, grid_hook=None, **extra):
     g = make_grid(case, grid_hook)
     kw = dict(nang=c["A"], nfre_red=c["Fr"], nproma=c["nproma"], npr=npr, iphys=c["iphys"], idelt=c["dt"], idelpro=c["dt"],
               delpro_lf=c["dt"])
+    kw.update(c.get("cfg", {}))
     kw.update(extra)
     cfg = O.default_config(**kw)
     o = O.Oracle(cfg, g)

@@ -15,11 +15,14 @@ sys.path.insert(0, os.path.dirname(HERE))
 
 from common import CASES, make_oracle, OUT_FIELDS, OUT_ITG, OUT_ICE, OUT_SEA  # noqa: E402
 
-GOLDEN = {"g_iphys1": ("o48like", 8), "g_iphys0": ("o48_iphys0", 8), "g_a36": ("o640like", 6)}
+GOLDEN = {"g_iphys1": ("o48like", 8), "g_iphys0": ("o48_iphys0", 8), "g_a36": ("o640like", 6), "g_cy49r1": ("o48_cy49r1", 8)}
 
 
 def main():
+    only = sys.argv[1:]               # optional: the fixtures to (re)generate
     for name, (case, N) in GOLDEN.items():
+        if only and name not in only:
+            continue
         CASES["_tmp"] = dict(CASES[case], N=N)
         g, o, f, fl0 = make_oracle("_tmp")
         out = dict(case=case, N=N)      # the inputs are regenerated from ecwam_b200.synth (deterministic)

@@ -17,7 +17,7 @@ from oracle import oracle as O
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("name", ["g_iphys1", "g_iphys0", "g_a36"])
+@pytest.mark.parametrize("name", ["g_iphys1", "g_iphys0", "g_a36", "g_cy49r1"])
 def test_oracle_reproduces_golden(built, name):
     z = np.load(os.path.join(GOLD, name + ".npz"))
     CASES["_gold"] = dict(CASES[str(z["case"])], N=int(z["N"]))
@@ -190,3 +190,43 @@ def test_current_refraction_oracle_properties(built):
         o.set_field("UCUR", u); o.set_field("VCUR", v)
         n.append(o.propag())
     assert n[0] > 0 and n[1] == 0
+
+
+def test_gravity_capillary_roughness_oracle_properties(built):
+    """LLGCBZ0 + LLNORMAGAM, the cy49r1 physics (taut_z0.F90:148-279, stress_gc.F90:70-130, halphap.F90:68-115,
+    sinput_ard.F90:436-452, tau_phi_hf.F90:177-193).  Independent of any reference run: (i) the returned u*, z0 satisfy the
+    neutral profile U10 = (u*/kappa) ln(1 + z/z0) to the iteration's own stopping tolerance (0.1-0.5 %), and to ~1e-7 at most
+    points; (ii) the background roughness is part of the total; (iii) the result does not depend on the decomposition or
+    NPROMA; (iv) the mean wave height stays within a per cent of the Charnock-relation run (the reference's own O48 norms of
+    the two configurations differ by 0.65 %, tests/etopo1_oper_an_fc_O48{,_cy49r1}.yml)."""
+    g, o, f, fl = make_oracle("o48_cy49r1")
+    g, o0, f, fl = make_oracle("o48like")
+    g, o3, f, fl = make_oracle("o48_cy49r1", npr=3, nproma=17)
+    for _ in range(6):
+        assert o.step() == 0 and o0.step() == 0 and o3.step() == 0
+    u, z0, z0b, u10 = (o.get_field(k) for k in ("UFRIC", "Z0M", "Z0B", "WSWAVE"))
+    r = np.abs(u - 0.4 * u10 / np.log1p(10.0 / z0)) / u
+    assert r.max() < 5e-3 and np.median(r) < 1e-6
+    assert (z0b <= z0).all() and (z0 >= 1e-6).all()
+    ch = o.get_field("CHRNCK")
+    assert ch.min() >= 1e-4 and ch.max() < 0.11 + 1e-12          # ALPHAMAX
+    assert np.isfinite(o.get_fl1()).all()
+    np.testing.assert_array_equal(o3.get_fl1(), o.get_fl1())
+    for nm in OUT_FIELDS:
+        np.testing.assert_array_equal(o3.get_field(nm), o.get_field(nm), err_msg=nm)
+    hs, hs0 = o.hs_fm()[0], o0.hs_fm()[0]
+    assert abs(hs.mean() / hs0.mean() - 1.0) < 0.01
+    assert np.abs(o.get_field("UFRIC") - o0.get_field("UFRIC")).max() > 1e-3     # but it is a different stress model
+
+
+def test_growth_renormalisation_reduces_the_wind_input(built):
+    """LLNORMAGAM alone (same BETAMAX: IPHYS=0 keeps 1.20 without LLGCBZ0, setwavphys.F90:46-100): GAMNORMA =
+    (1 + c sum(gam F sin^2)) / (1 + c sum(gam F)) <= 1 (sinput_jan.F90:329-348), so one source step from the same state gives
+    a smaller wave-induced stress wherever there is wind input."""
+    g, o, f, fl = make_oracle("o48_iphys0", llnormagam=1)
+    g, o0, f, fl = make_oracle("o48_iphys0")
+    o.implsch(); o0.implsch()
+    tw, tw0 = o.get_field("TAUW"), o0.get_field("TAUW")
+    sea = f["CICOVER"] <= 0.3
+    assert (tw[sea] <= tw0[sea] * (1 + 1e-12)).all()
+    assert tw[sea].sum() < 0.97 * tw0[sea].sum()
