@@ -16,6 +16,8 @@ struct HostTables {
   std::vector<double> fr, dfim, dfimofr, dfimfr, zpifr, fr5, cofrm4, flmax, rhowg_dfim, dfim_sim, th, costh, sinth;
   std::vector<double> satweights, swellft, wtauhf, rnlcoef, af11;
   std::vector<int> indicessat, ikp, ikp1, ikm, ikm1, k1w, k2w, k11w, k21w, inlcoef;
+  std::vector<double> xk_gc, omega_gc, cm_gc, c2osqrtvg_gc, xkmsqrtvgoc2_gc, om3gmkm_gc, omxkm3_gc, delkcc_gc_ns, delkcc_omxkm3_gc;
+  double delta_theta_rn = 0.75;
 };
 
 inline long fnint(double x) { return std::lround(x); }   // Fortran NINT
@@ -39,11 +41,14 @@ void constants(ecwam_b200_tables& t) {
   t.iab = 200; t.eps1 = 0.00001; t.jtot_tauhf = 19;
 }
 
-// ---- src/ecwam/setwavphys.F90:46-205 (LLGCBZ0 = LLNORMAGAM = F values; the other combinations are rejected
-//      by ecwam_b200_create anyway but are filled for completeness)
+// ---- src/ecwam/setwavphys.F90:46-205
 int wave_physics(const ecwam_b200_params& p, ecwam_b200_tables& t, double& alphapmax) {
   const bool gc = p.llgcbz0 != 0, ng = p.llnormagam != 0;
   t.zalp = 0.008; t.tailfactor = 2.5;
+  t.alphamax = 0.11; t.acdlin = 0.0008; t.bcdlin = 0.00047;        // yowphys.F90:55, yowpcons.F90:58-59
+  t.rn1_rn = 0.25; t.dthrn_a = (p.iphys == 0) ? 0.80 : 0.60; t.dthrn_u = (p.iphys == 0 || gc) ? 33.0 : 200.0;
+  if (p.nang <= 24) { t.ang_gc_a = 0.40; t.ang_gc_b = 0.60; } else { t.ang_gc_a = 0.35; t.ang_gc_b = 0.65; }
+  t.ang_gc_c = 3.0;
   if (p.iphys == 0) {
     t.alphamin = 0.0001; alphapmax = 0.03; t.tauwshelter = 0.0; t.tailfactor_pm = 0.0;
     if (gc) { t.alpha = 0.0055; t.chnkmin_u = 28.; t.betamaxoxkappa2 = ng ? 1.32 : 1.25; t.cdis = -1.3; t.delta_sdis = 0.6; t.cdisvis = -4.0; }
@@ -65,8 +70,50 @@ int wave_physics(const ecwam_b200_params& p, ecwam_b200_tables& t, double& alpha
     t.cdis = -1.33; t.delta_sdis = 0.5; t.cdisvis = 0.0;
   } else return ECWAM_B200_EINVAL;
   t.swellf7m1 = 1.0 / t.swellf7;
+  t.alphapmax = alphapmax;
   // betamaxoxkappa2 holds BETAMAX until INIT_X0TAUHF divides it by XKAPPA**2
   return 0;
+}
+
+// ---- src/ecwam/initgc.F90:63-110 with gc_dispersion.h: the gravity-capillary wavenumber grid of STRESS_GC / OMEGAGC
+double ipow(double x, int m) {   // real ** integer by repeated squaring
+  unsigned n = (unsigned)(m < 0 ? -m : m);
+  double y = (n & 1) ? x : 1.0;
+  while (n >>= 1) { x = x * x; if (n & 1) y = y * x; }
+  return m < 0 ? 1.0 / y : y;
+}
+void gravity_capillary_tables(HostTables& h) {
+  ecwam_b200_tables& t = h.t;
+  const double KRATIO = 1.2, XKS = 0.006, XKL = 20000.0, SURFT = 0.0717 / 1000.0;   // yowfred.F90:62-65, iniwcst.F90:69
+  t.sqrtgosurft = std::sqrt(t.g / SURFT);
+  const int N = (int)fnint(std::log(XKL / XKS) / std::log(KRATIO));
+  t.nwav_gc = N;
+  std::vector<double> xkm(N), vg(N), c(N), delkcc(N);
+  for (auto* v : {&h.xk_gc, &h.omega_gc, &h.cm_gc, &h.c2osqrtvg_gc, &h.xkmsqrtvgoc2_gc, &h.om3gmkm_gc, &h.omxkm3_gc, &h.delkcc_gc_ns,
+                  &h.delkcc_omxkm3_gc}) v->assign(N, 0.0);
+  for (int i = 0; i < N; ++i) {
+    const double k = XKS * ipow(KRATIO, i);
+    h.xk_gc[i] = k;
+    xkm[i] = 1.0 / k;
+    const double om = std::sqrt(t.g * k + SURFT * (k * k * k));
+    h.omega_gc[i] = om;
+    h.omxkm3_gc[i] = om * (xkm[i] * xkm[i] * xkm[i]);
+    vg[i] = 0.5 / om * (t.g + 3.0 * SURFT * (k * k));
+    c[i] = om / k;
+    h.cm_gc[i] = 1.0 / c[i];
+    h.c2osqrtvg_gc[i] = (c[i] * c[i]) / std::sqrt(vg[i]);
+    h.xkmsqrtvgoc2_gc[i] = xkm[i] / h.c2osqrtvg_gc[i];
+    h.om3gmkm_gc[i] = (om * om * om) / (t.g * k);
+  }
+  delkcc[0] = 0.5 * (h.xk_gc[1] - h.xk_gc[0]) / h.c2osqrtvg_gc[0];
+  h.delkcc_gc_ns[0] = delkcc[0];
+  for (int i = 1; i < N - 1; ++i) {
+    delkcc[i] = 0.5 * (h.xk_gc[i + 1] - h.xk_gc[i - 1]) / h.c2osqrtvg_gc[i];
+    h.delkcc_gc_ns[i] = 0.5 * (h.xk_gc[i + 1] - h.xk_gc[i]) / h.c2osqrtvg_gc[i];
+  }
+  delkcc[N - 1] = 0.5 * (h.xk_gc[N - 1] - h.xk_gc[N - 2]) / h.c2osqrtvg_gc[N - 1];
+  h.delkcc_gc_ns[N - 1] = delkcc[N - 1];
+  for (int i = 0; i < N; ++i) h.delkcc_omxkm3_gc[i] = delkcc[i] * h.omxkm3_gc[i];
 }
 
 // ---- Kelvin functions through the modified Bessel functions of complex argument
@@ -241,6 +288,8 @@ void hf_stress_tables(const ecwam_b200_params& p, HostTables& h) {
   ecwam_b200_tables& t = h.t;
   const double betamax = t.betamaxoxkappa2;
   t.betamaxoxkappa2 = betamax / (t.xkappa * t.xkappa);
+  t.bmaxokap = h.delta_theta_rn * t.betamaxoxkappa2 / t.xkappa;
+  t.gamnconst = t.bmaxokap * 0.5 * std::pow(t.zpi, 4) * std::pow(t.gm1, 3);
   const double alph = (p.llgcbz0 || p.llcapchnk || p.llnormagam) ? t.alphamin : t.alpha;
   double x0 = 0.005;
   for (int j = 0; j < 30; ++j) {
@@ -462,7 +511,11 @@ int ecwam_b200_host_tables_create(const ecwam_b200_params* params, int ifre1, do
   hf_stress_tables(*params, h);
   saturation_tables(*params, h);
   dia_tables(*params, h);
+  gravity_capillary_tables(h);
   ecwam_b200_tables& t = h.t;
+  t.xk_gc = h.xk_gc.data(); t.omega_gc = h.omega_gc.data(); t.cm_gc = h.cm_gc.data(); t.c2osqrtvg_gc = h.c2osqrtvg_gc.data();
+  t.xkmsqrtvgoc2_gc = h.xkmsqrtvgoc2_gc.data(); t.om3gmkm_gc = h.om3gmkm_gc.data(); t.omxkm3_gc = h.omxkm3_gc.data();
+  t.delkcc_gc_ns = h.delkcc_gc_ns.data(); t.delkcc_omxkm3_gc = h.delkcc_omxkm3_gc.data();
   t.fr = h.fr.data(); t.dfim = h.dfim.data(); t.dfimofr = h.dfimofr.data(); t.dfimfr = h.dfimfr.data();
   t.zpifr = h.zpifr.data(); t.fr5 = h.fr5.data(); t.cofrm4 = h.cofrm4.data(); t.flmax = h.flmax.data();
   t.rhowg_dfim = h.rhowg_dfim.data(); t.dfim_sim = h.dfim_sim.data(); t.th = h.th.data(); t.costh = h.costh.data();

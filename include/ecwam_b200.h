@@ -187,6 +187,32 @@ typedef struct ecwam_b200_tables {
   const int* inlcoef;        /* (5, MLSTHG) */
   const double* rnlcoef;     /* (25, MLSTHG) */
   const double* af11;        /* (MFRSTLW:MLSTHG) */
+  /* Gravity-capillary roughness model and growth renormalisation (LLGCBZ0 / LLNORMAGAM, the cy49r1 physics):
+   * YOWPHYS (yowphys.F90:45-75, setwavphys.F90:46-205, init_x0tauhf.F90:65-72), YOWPCONS ACDLIN/BCDLIN
+   * (yowpcons.F90:58-59), YOWFRED *_GC (yowfred.F90:62-150, initgc.F90:63-110).  Read only when the switches are on. */
+  double alphamax;
+  double alphapmax;
+  double acdlin;
+  double bcdlin;
+  double bmaxokap;
+  double gamnconst;
+  double rn1_rn;
+  double dthrn_a;
+  double dthrn_u;
+  double ang_gc_a;
+  double ang_gc_b;
+  double ang_gc_c;
+  double sqrtgosurft;
+  int nwav_gc;
+  const double* xk_gc;            /* (NWAV_GC) */
+  const double* omega_gc;         /* (NWAV_GC) */
+  const double* cm_gc;            /* (NWAV_GC) */
+  const double* c2osqrtvg_gc;     /* (NWAV_GC) */
+  const double* xkmsqrtvgoc2_gc;  /* (NWAV_GC) */
+  const double* om3gmkm_gc;       /* (NWAV_GC) */
+  const double* omxkm3_gc;        /* (NWAV_GC) */
+  const double* delkcc_gc_ns;     /* (NWAV_GC) */
+  const double* delkcc_omxkm3_gc; /* (NWAV_GC) */
 } ecwam_b200_tables;
 
 /* ---------------------------------------------------------------------------------------------------

@@ -77,13 +77,21 @@ long orc_get_table(void* h, const char* name, double* out, long cap) {
       {"FLMAX", &t.FLMAX}, {"RHOWG_DFIM", &t.RHOWG_DFIM}, {"DFIM_SIM", &t.DFIM_SIM}, {"SATWEIGHTS", &t.SATWEIGHTS},
       {"SWELLFT", &t.SWELLFT}, {"WTAUHF", &t.WTAUHF}, {"AF11", &t.AF11}, {"FKLAP", &t.FKLAP}, {"FKLAP1", &t.FKLAP1},
       {"FKLAM", &t.FKLAM}, {"FKLAM1", &t.FKLAM1}, {"FRH", &t.FRH}, {"RNLCOEF", &t.RNLCOEF}, {"FTRF", &t.FTRF},
+      {"XK_GC", &t.XK_GC}, {"OMEGA_GC", &t.OMEGA_GC}, {"CM_GC", &t.CM_GC}, {"C2OSQRTVG_GC", &t.C2OSQRTVG_GC},
+      {"XKMSQRTVGOC2_GC", &t.XKMSQRTVGOC2_GC}, {"OM3GMKM_GC", &t.OM3GMKM_GC}, {"OMXKM3_GC", &t.OMXKM3_GC},
+      {"DELKCC_GC_NS", &t.DELKCC_GC_NS}, {"DELKCC_OMXKM3_GC", &t.DELKCC_OMXKM3_GC},
       {"ZDELLO", &m->grid.ZDELLO}, {"COSPH", &m->grid.COSPH}, {"SINPH", &m->grid.SINPH}, {"DELLAM", &m->grid.DELLAM}};
   auto it = mp.find(n);
   if (it != mp.end()) return copy_out(it->second->d, out, cap);
   std::map<std::string, double> sc = {
       {"X0TAUHF", t.X0TAUHF}, {"DELTH", t.DELTH}, {"FLOGSPRDM1", t.FLOGSPRDM1}, {"BETAMAXOXKAPPA2", t.BETAMAXOXKAPPA2},
       {"DAL1", t.DAL1}, {"DAL2", t.DAL2}, {"ACL1", t.ACL1}, {"ACL2", t.ACL2}, {"CL11", t.CL11}, {"CL21", t.CL21},
-      {"XDELLA", m->grid.XDELLA}, {"R", t.R}, {"ZPI", t.ZPI}, {"TAUWSHELTER", t.TAUWSHELTER}, {"BETAMAX", t.BETAMAX}};
+      {"XDELLA", m->grid.XDELLA}, {"R", t.R}, {"ZPI", t.ZPI}, {"TAUWSHELTER", t.TAUWSHELTER}, {"BETAMAX", t.BETAMAX},
+      {"ALPHA", t.ALPHA}, {"ALPHAMIN", t.ALPHAMIN}, {"ALPHAMAX", t.ALPHAMAX}, {"ALPHAPMAX", t.ALPHAPMAX}, {"CHNKMIN_U", t.CHNKMIN_U},
+      {"ACDLIN", t.ACDLIN}, {"BCDLIN", t.BCDLIN}, {"BMAXOKAP", t.BMAXOKAP}, {"GAMNCONST", t.GAMNCONST}, {"RN1_RN", t.RN1_RN},
+      {"DTHRN_A", t.DTHRN_A}, {"DTHRN_U", t.DTHRN_U}, {"ANG_GC_A", t.ANG_GC_A}, {"ANG_GC_B", t.ANG_GC_B}, {"ANG_GC_C", t.ANG_GC_C},
+      {"SQRTGOSURFT", t.SQRTGOSURFT}, {"NWAV_GC", (double)t.NWAV_GC}, {"Z0RAT", t.Z0RAT}, {"Z0TUBMAX", t.Z0TUBMAX},
+      {"SWELLF4", t.SWELLF4}, {"SWELLF7", t.SWELLF7}, {"CDIS", t.CDIS}, {"DELTA_SDIS", t.DELTA_SDIS}, {"CDISVIS", t.CDISVIS}};
   auto is = sc.find(n);
   if (is != sc.end()) { if (cap < 1) return -1; out[0] = is->second; return 1; }
   return 0;

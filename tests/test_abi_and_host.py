@@ -85,6 +85,30 @@ def test_host_tables_and_decomposition_match_oracle(built, N, A, Fr, mask, npr, 
             np.testing.assert_array_equal(d["ijtope"], o.itable("IJTOPE", r))
 
 
+@pytest.mark.parametrize("A,iphys,gc,ng", [(12, 1, 1, 1), (36, 1, 1, 1), (12, 0, 1, 1), (24, 1, 0, 1), (12, 1, 1, 0), (12, 1, 0, 0)])
+def test_gravity_capillary_tables_match_oracle(built, A, iphys, gc, ng):
+    """SETWAVPHYS for every LLGCBZ0 / LLNORMAGAM combination (setwavphys.F90:46-205), INIT_X0TAUHF's BMAXOKAP / GAMNCONST
+    (init_x0tauhf.F90:65-72) and INITGC's wavenumber grid (initgc.F90:63-110): host tables of the product == oracle, bit for bit."""
+    g = synth.make_grid(8, "aqua")
+    kw = dict(nang=A, nfre_red=25, iphys=iphys, llgcbz0=gc, llnormagam=ng, wspmin=0.3 if gc else 1.0)
+    o = O.Oracle(O.default_config(nproma=32, npr=1, **kw), g)
+    s = M.WamSetup(g, nproc=1, **kw)
+    for nm in ("alpha", "alphamin", "alphamax", "alphapmax", "chnkmin_u", "acdlin", "bcdlin", "bmaxokap", "gamnconst", "rn1_rn",
+               "dthrn_a", "dthrn_u", "ang_gc_a", "ang_gc_b", "ang_gc_c", "sqrtgosurft", "betamaxoxkappa2", "tauwshelter", "x0tauhf",
+               "z0rat", "z0tubmax", "swellf4", "swellf7", "cdis", "delta_sdis", "cdisvis"):
+        assert getattr(s.tables, nm) == o.table(nm.upper())[0], nm
+    n = s.tables.nwav_gc
+    assert n == int(o.table("NWAV_GC")[0]) == 82
+    for nm in ("xk_gc", "omega_gc", "cm_gc", "c2osqrtvg_gc", "xkmsqrtvgoc2_gc", "om3gmkm_gc", "omxkm3_gc", "delkcc_gc_ns",
+               "delkcc_omxkm3_gc"):
+        np.testing.assert_array_equal(s.table(nm, n), o.table(nm.upper()), err_msg=nm)
+    for nm, k in (("wtauhf", 19), ("flmax", 36)):
+        np.testing.assert_array_equal(s.table(nm, k), o.table(nm.upper()), err_msg=nm)
+    # the dispersion relation the tables are built on: omega^2 = g k + T k^3 (gc_dispersion.h)
+    k, om = s.table("xk_gc", n), s.table("omega_gc", n)
+    np.testing.assert_allclose(om ** 2, 9.806 * k + 7.17e-5 * k ** 3, rtol=1e-14)
+
+
 def test_depthprpt_matches_oracle(built):
     g = synth.make_grid(16, "continents")
     o = O.Oracle(O.default_config(nang=12, nfre_red=25), g)
