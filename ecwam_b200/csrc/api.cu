@@ -73,7 +73,7 @@ struct ecwam_b200_handle_s {
   int msplit = 0;
   bool weights_dirty = true;
   // implsch
-  DBuf<double> scr, satw, swellft, fldin, tbg;
+  DBuf<double> scr, satw, swellft, fldin, tbg, gctab;
   int dsh[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
   int halo_r = 0, halo_c = 0, nsdsnth = 0;
   DBuf<int> kw, isat;
@@ -175,7 +175,9 @@ static int fill_dev_const(const ecwam_b200_params& p, const ecwam_b200_tables& t
   if (p.irefra >= 2 && p.ifrelfmax > 0 && p.ifrelfmax < p.nfre_red)
     EW_FAIL(ECWAM_B200_EINVAL, "fast-wave sub-stepping (IFRELFMAX) together with current refraction (IREFRA = 2, 3) is not built");
   if (p.isnonlin != 0) EW_FAIL(ECWAM_B200_EINVAL, "only ISNONLIN=0 is implemented");
-  if (p.llgcbz0 || p.llnormagam) EW_FAIL(ECWAM_B200_EINVAL, "LLGCBZ0 / LLNORMAGAM branches are not implemented (SURVEY 8f rank 2)");
+  if ((p.llgcbz0 || p.llnormagam) && (t.nwav_gc < 2 || !t.xk_gc || !t.omega_gc || !t.cm_gc || !t.c2osqrtvg_gc || !t.xkmsqrtvgoc2_gc ||
+                                      !t.om3gmkm_gc || !t.omxkm3_gc || !t.delkcc_gc_ns || !t.delkcc_omxkm3_gc))
+    EW_FAIL(ECWAM_B200_EINVAL, "LLGCBZ0 / LLNORMAGAM need the gravity-capillary tables (ecwam_b200_tables: nwav_gc, *_gc)");
   if (p.lciwa & 3) EW_FAIL(ECWAM_B200_EINVAL, "LCIWA1 / LCIWA2 sea-ice attenuation (SDICE1, SDICE2) is not implemented (SURVEY 8f rank 2)");
   if (p.lciwa & ~15) EW_FAIL(ECWAM_B200_EINVAL, "lciwa: unknown bits");
   if (p.lwnemocou) EW_FAIL(ECWAM_B200_EINVAL, "NEMO coupling accumulators are not implemented");
@@ -219,6 +221,14 @@ static int fill_dev_const(const ecwam_b200_params& p, const ecwam_b200_tables& t
   c.SSDSC4 = t.ssdsc4; c.SSDSC5 = t.ssdsc5; c.SSDSC6 = t.ssdsc6; c.MICHE = t.miche; c.EGRCRV = t.egrcrv;
   c.AFCRV = t.afcrv; c.BFCRV = t.bfcrv; c.NSDSNTH = t.nsdsnth;
   c.IAB = t.iab; c.JTOT = t.jtot_tauhf; c.EPS1 = t.eps1; c.X0TAUHF = t.x0tauhf;
+  c.llgcbz0 = p.llgcbz0 ? 1 : 0; c.llnormagam = p.llnormagam ? 1 : 0;
+  if (c.llgcbz0 || c.llnormagam) {
+    c.NWAV_GC = t.nwav_gc; c.ALPHAMAX = t.alphamax; c.ALPHAPMAX = t.alphapmax; c.ACDLIN = t.acdlin; c.BCDLIN = t.bcdlin;
+    c.BMAXOKAP = t.bmaxokap; c.GAMNCONST = t.gamnconst; c.RN1_RN = t.rn1_rn; c.DTHRN_A = t.dthrn_a; c.DTHRN_U = t.dthrn_u;
+    c.ANG_GC_A = t.ang_gc_a; c.ANG_GC_B = t.ang_gc_b; c.ANG_GC_C = t.ang_gc_c; c.SQRTGOSURFT = t.sqrtgosurft;
+    c.XKM1_GC = 1.0 / t.xk_gc[0];                 // XKM_GC(1) (initgc.F90:87)
+    c.XLOGKRATIOM1_GC = 1.0 / std::log(1.2);      // yowfred.F90:62-63
+  }
   for (int j = 0; j < t.jtot_tauhf; ++j) c.WTAUHF[j] = t.wtauhf[j];
   c.MLSTHG = t.mlsthg; c.MFRSTLW = t.mfrstlw; c.KFRH = t.kfrh; c.DAL1 = t.dal1; c.DAL2 = t.dal2;
   const int off = 1 - t.mfrstlw;   // index of MC=1 inside the (MFRSTLW:MLSTHG) arrays
@@ -479,6 +489,14 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
   }
   std::vector<double> sw(tables->swellft, tables->swellft + tables->iab);
   ok = ok && !h->swellft.upload(sw, st);
+  if (p.llgcbz0 || p.llnormagam) {   // [GC_NT][NWAV_GC]
+    const int ng = tables->nwav_gc;
+    const double* src[GC_NT] = {tables->xk_gc, tables->omega_gc, tables->cm_gc, tables->c2osqrtvg_gc, tables->xkmsqrtvgoc2_gc,
+                                tables->om3gmkm_gc, tables->omxkm3_gc, tables->delkcc_gc_ns, tables->delkcc_omxkm3_gc};
+    std::vector<double> gc((size_t)GC_NT * ng);
+    for (int r = 0; r < GC_NT; ++r) for (int i = 0; i < ng; ++i) gc[(size_t)r * ng + i] = src[r][i];
+    ok = ok && !h->gctab.upload(gc, st);
+  }
   const long long npts = (long long)P * p.nchnk;
   ok = ok && !h->scr.alloc(implsch_scratch_doubles(npts)) && !h->fldin.alloc((size_t)npts * A * F) &&
        !h->tbg.alloc((size_t)EW_TQ_N * F * npts);
@@ -511,7 +529,7 @@ int ecwam_b200_destroy(ecwam_b200_handle h) {
   h->nbr.free(); h->halo_off.free(); h->halo_str.free(); h->send_l.free(); h->send_pre.free(); h->send_peer_of.free();
   h->recv_pre.free(); h->recv_peer_of.free(); h->recv_e.free(); h->flag.free(); h->count.free(); h->wl.free(); h->pt.free();
   h->cgext.free(); h->halo.free(); h->sendbuf.free(); h->fl3.free(); h->cosph_m.free(); h->cosph_p.free();
-  h->land_cg.free(); h->cgrecv.free(); h->scr.free(); h->fldin.free(); h->tbg.free(); h->satw.free(); h->swellft.free(); h->kw.free(); h->isat.free();
+  h->land_cg.free(); h->cgrecv.free(); h->scr.free(); h->fldin.free(); h->tbg.free(); h->satw.free(); h->swellft.free(); h->gctab.free(); h->kw.free(); h->isat.free();
   for (void* b : h->mir_bufs) cudaFree(b);
   for (cudaEvent_t e : h->ev_up) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
@@ -686,6 +704,8 @@ static ImplDev make_impl(H* h, bool from_fl3) {
   for (int kh = 0; kh < 2; ++kh) for (int q = 0; q < 4; ++q) d.dsb[kh][q] = h->dsh[kh][q] * 64;
   d.halo_r = h->halo_r; d.halo_c = h->halo_c;
   d.iphys = h->par.iphys; d.nsdsnth = h->nsdsnth;
+  d.cy49 = (h->par.llgcbz0 || h->par.llnormagam) ? 1 : 0;
+  d.gc = h->gctab.p;
   return d;
 }
 
@@ -837,6 +857,7 @@ int ecwam_b200_outbs(ecwam_b200_handle h, const ecwam_b200_outsel* sel, const in
   oc.DEG = 360.0 / c.ZPI;    // = 180/PI bit for bit (iniwcst.F90:63)
   oc.XKAPPA = c.XKAPPA; oc.XNLEV = c.XNLEV; oc.ALPHAMIN = c.ALPHAMIN;
   oc.ALPHAMAX = 0.11;        // yowphys.F90:55
+  oc.llgcbz0 = c.llgcbz0;
   oc.ROWATER = 1000.0;       // yowpcons.F90
   oc.rnum = c.rnum; oc.flmin = c.flmin; oc.cithrsh = c.cithrsh; oc.zmiss = sel->zmiss;
   for (int m = 0; m < c.F; ++m) { oc.FR[m] = c.FR[m]; oc.DFIM[m] = c.DFIM[m]; oc.DFIMOFR[m] = c.DFIMOFR[m]; oc.DFIMFR[m] = c.DFIMFR[m]; oc.DFIM_SIM[m] = c.DFIM_SIM[m]; }

@@ -48,7 +48,13 @@ struct DevConst {
   int NLSLOT[EW_MAXMC][5];
   double SATW1[EW_MAXSAT];  // SATWEIGHTS(NANG/2, 1:2*NSDSNTH+1): the saturation window weights (they do not depend on the direction)
   double RNLC2[EW_MAXMC];   // 2 (or 0 where the centre row is outside the spectrum): weight of -AD, -DELAD at the centre bin
+  // LLGCBZ0 / LLNORMAGAM (gravity-capillary roughness, growth renormalisation; appended so that the other offsets stay put)
+  int llgcbz0, llnormagam, NWAV_GC, pad_gc;
+  double ALPHAMAX, ALPHAPMAX, ACDLIN, BCDLIN, BMAXOKAP, GAMNCONST, RN1_RN, DTHRN_A, DTHRN_U, ANG_GC_A, ANG_GC_B, ANG_GC_C,
+      SQRTGOSURFT, XKM1_GC, XLOGKRATIOM1_GC;
 };
+// rows of the gravity-capillary table ImplDev::gc [GC_NT][NWAV_GC] (YOWFRED *_GC, initgc.F90)
+enum { GC_XK = 0, GC_OMEGA, GC_CM, GC_C2OSQRTVG, GC_XKMSQRTVGOC2, GC_OM3GMKM, GC_OMXKM3, GC_DELKCC_NS, GC_DELKCC_OMXKM3, GC_NT };
 
 // tables too irregular / large for constant memory (per-lane indexed)
 struct DevTabPtr {

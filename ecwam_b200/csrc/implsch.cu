@@ -28,6 +28,7 @@ enum {
   S_PHILF, S_XSTROC, S_YSTROC,                            // WNFLUXES sums
   S_MIJ, S_USTOLD, S_FAC, S_USFM,
   S_USTAR1, S_TAUW1, S_TWDIR1,                            // result of the first SINFLX call (k_point<.,1> -> k_point<.,2>)
+  S_HALP,                                                 // HALPHAP of the first SINFLX call (LLGCBZ0)
   NSCR
 };
 size_t implsch_scratch_doubles(long long npts) { return (size_t)NSCR * (size_t)npts; }
@@ -123,9 +124,131 @@ __device__ void taut_z0(int iusfg, double utop, double udir, double tauw, double
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// tau_phi_hf.F90:111-305 (LLGCBZ0=F, LLNORMAGAM=F: CONST1=CONST2=0 so GAMNORMA=1)
+// LLGCBZ0, the gravity-capillary model of the background roughness: ns_gc.F90:44-48, stress_gc.F90:70-130, cdm.func.h and
+// the first branch of taut_z0.F90 (:148-279).  gc = ImplDev::gc, [GC_NT][NWAV_GC].
+__device__ __forceinline__ int ns_gc(double ustar) {   // 1-based index of the first gravity-capillary wavenumber
+  const double xks = c_dc.SQRTGOSURFT / (1.48 + 2.05 * ustar);
+  return min((int)(log(dmax(xks * c_dc.XKM1_GC, 1.0)) * c_dc.XLOGKRATIOM1_GC) + 1, c_dc.NWAV_GC - 1);
+}
+__device__ double stress_gc(const double* __restrict__ gc, double ang_gc, double ustar, double z0, double z0min, double halp,
+                            double rnfac) {
+  const int N = c_dc.NWAV_GC;
+  const int ns = ns_gc(ustar);
+  const double tauwcg_min = sq(ustar * (z0min / z0));
+  const double xlambda = 1.0 + 0.25 * tanh(4.0 * p4(ustar));
+  const double c2 = __ldg(gc + GC_C2OSQRTVG * N + ns - 1);
+  const double zabhrc = ang_gc * c_dc.BETAMAXOXKAPPA2 * halp * c2;
+  const double cst = c_dc.llnormagam ? rnfac * c_dc.BMAXOKAP * halp * c2 / dmax(ustar, c_dc.EPSUS) : 0.0;
+  const double logl = log(xlambda);
+  double tauwcg = 0.0;
+  for (int i = ns; i <= N; ++i) {
+    const double x = ustar * __ldg(gc + GC_CM * N + i - 1);
+    const double xlog = log(__ldg(gc + GC_XK * N + i - 1) * z0) + c_dc.XKAPPA / (x + c_dc.ZALP);
+    const double zlog = dmin(xlog - logl, 0.0);
+    const double zlog2x = zlog * zlog * x;
+    const double gam_w = zlog2x * zlog2x * exp(xlog) * __ldg(gc + GC_OM3GMKM * N + i - 1);
+    const double zn = cst * __ldg(gc + GC_XKMSQRTVGOC2 * N + i - 1) * gam_w;
+    const double gamnorma = (1.0 + c_dc.RN1_RN * zn) / (1.0 + zn);
+    if (i == ns) tauwcg = gam_w * __ldg(gc + GC_DELKCC_NS * N + ns - 1) * __ldg(gc + GC_OMXKM3 * N + ns - 1) * gamnorma;
+    else tauwcg = tauwcg + gam_w * __ldg(gc + GC_DELKCC_OMXKM3 * N + i - 1) * gamnorma;
+  }
+  return dmax(zabhrc * tauwcg, tauwcg_min);
+}
+__device__ __forceinline__ double cdm(double u) { return dmax(dmin(0.0006 + 0.00008 * u, 0.001 + 0.0018 * exp(-0.05 * (u - 33.))), 0.001); }
+__device__ void taut_z0_gc(const double* __restrict__ gc, int iusfg, double halp, double utop, double udir, double tauw,
+                           double tauwdir, double rnfac, double& ustar, double& z0, double& z0b, double& chrnck) {
+  const int NITER = 18;
+  const double PMAX = 0.99, Z0MIN = 0.000001;
+  const double us2totauw = 1.0 + c_dc.EPS1;
+  const double rnukappam1 = (0.04 * c_dc.rnu) / c_dc.XKAPPA;
+  const double pce_gc = 0.001 * iusfg + (1 - iusfg) * 0.005;
+  const double cosdiff = cos(udir - tauwdir);
+  const double tauwact = dmax(tauw * cosdiff, c_dc.EPSMIN);
+  const double alphaog = c_dc.llcapchnk ? chnkmin(utop) * c_dc.GM1 : 0.0;
+  const double usmax = dmax(-0.21339 + 0.093698 * utop - 0.0020944 * (utop * utop) + 5.5091E-5 * (utop * utop * utop), 0.03);
+  const double tauweff = dmin(tauwact * us2totauw, usmax * usmax);
+  if (iusfg == 0) {
+    double cdfg;
+    if (utop < 1.0) cdfg = 0.002;
+    else if (cosdiff > 0.9) {
+      const double x = dmin(tauwact / sq(dmax(ustar, c_dc.EPSUS)), PMAX);
+      double zchar = dmin((c_dc.ALPHA * c_dc.GM1) * sq(ustar) / sqrt(1.0 - x), 0.05 * exp(-0.05 * (utop - 35.)));
+      zchar = dmin(zchar, c_dc.ALPHAMAX);
+      cdfg = c_dc.ACDLIN + c_dc.BCDLIN * sqrt(zchar) * utop;
+    } else cdfg = cdm(utop);
+    ustar = utop * sqrt(cdfg);
+  }
+  const double w1 = 0.85 - 0.05 * (tanh(10.0 * (utop - 5.0)) + 1.0);
+  const double xkutop = c_dc.XKAPPA * utop;
+  double ustold = ustar, tauold = ustold * ustold, tauunr = 0.0, x;
+  int iter;
+  for (iter = 1; iter <= NITER; ++iter) {
+    z0 = dmax(c_dc.XNLEV / (exp(dmin(xkutop / ustold, 50.0)) - 1.0), Z0MIN);
+    const double tauv = rnukappam1 * ustold / z0;
+    const double ang_gc = c_dc.ANG_GC_A + c_dc.ANG_GC_B * tanh(c_dc.ANG_GC_C * tauold);
+    tauunr = stress_gc(gc, ang_gc, ustar, z0, Z0MIN, halp, rnfac);
+    const double taunew = tauweff + tauv + tauunr;
+    const double ustnew = sqrt(taunew);
+    ustar = w1 * ustold + (1.0 - w1) * ustnew;
+    const double del = ustar - ustold;
+    if (fabs(del) < pce_gc * ustar) break;
+    tauold = sq(ustar);
+    ustold = ustar;
+  }
+  x = tauweff / tauold;
+  if (iter > NITER && x >= PMAX) {   // protection just in case there is no convergence
+    ustar = utop * sqrt(cdm(utop));
+    const double z0minrst = sq(ustar) * c_dc.ALPHA * c_dc.GM1;
+    z0 = dmax(c_dc.XNLEV / (exp(xkutop / ustar) - 1.0), z0minrst);
+    z0b = z0minrst;
+  } else {
+    z0 = dmax(c_dc.XNLEV / (exp(xkutop / ustar) - 1.0), Z0MIN);
+    z0b = z0 * sqrt(tauunr / tauold);
+  }
+  if (x < PMAX) {                    // refine the solution (taut_z0.F90:230-276)
+    const double usnrf = ustar, z0nrf = z0, z0bnrf = z0b;
+    ustold = ustar;
+    tauold = dmax(ustold * ustold, tauweff);
+    const double alpog = dmax(dmin(z0b / tauold, c_dc.ALPHAMAX), alphaog);
+    for (iter = 1; iter <= NITER; ++iter) {
+      x = dmin(tauweff / tauold, PMAX);
+      const double ustm1 = 1.0 / dmax(ustold, c_dc.EPSUS);
+      const double z0vis = c_dc.rnum * ustm1;
+      const double hz0viso1mx = 0.5 * z0vis / (1.0 - x);
+      z0b = alpog * tauold;
+      z0 = hz0viso1mx + sqrt(sq(hz0viso1mx) + sq(z0b) / (1.0 - x));
+      const double xologz0 = 1.0 / log(c_dc.XNLEV / z0 + 1.0);
+      const double f = ustold - xkutop * xologz0;
+      const double zz = 2.0 * ustm1 * (3.0 * sq(z0b) + 0.5 * z0vis * z0 - sq(z0)) / (2.0 * sq(z0) * (1.0 - x) - z0vis * z0);
+      const double delf = 1.0 - xkutop * sq(xologz0) * zz;
+      if (delf != 0.0) ustar = ustold - f / delf;
+      const double taunew = dmax(sq(ustar), tauweff);
+      ustar = sqrt(taunew);
+      const double del = taunew - tauold;
+      if (fabs(del) < pce_gc * tauold) break;
+      tauold = taunew;
+      ustold = ustar;
+    }
+    if (iter > NITER) {
+      ustar = usnrf; z0 = z0nrf; z0b = z0bnrf;
+      const double ustm1 = 1.0 / dmax(ustar, c_dc.EPSUS);
+      chrnck = dmax(c_dc.G * (z0 - c_dc.rnum * ustm1) * sq(ustm1), c_dc.ALPHAMIN);
+    } else {
+      chrnck = dmax(c_dc.G * (z0b / sqrt(1.0 - x)) / sq(dmax(ustar, c_dc.EPSUS)), c_dc.ALPHAMIN);
+    }
+  } else {
+    const double ustm1 = 1.0 / dmax(ustar, c_dc.EPSUS);
+    chrnck = dmax(c_dc.G * (z0 - c_dc.rnum * ustm1) * sq(ustm1), c_dc.ALPHAMIN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tau_phi_hf.F90:111-305.  CY: the LLNORMAGAM renormalisation (CONST1, CONST2 of :177-182; both 0 otherwise, so GAMNORMA = 1)
+// and LLGCBZ0's upper limit ZSUP of the TAUHF integral (:190-193); PHIHF always integrates to ZSUPMAX (:246-250).
+template <bool CY>
 __device__ void tau_phi_hf(int mij, bool shelter, double z0m, double aird, double f1dcos3, double f1dcos2, double& ust,
-                           double& tauhf, double& phihf, bool llphihf) {
+                           double& tauhf, double& phihf, bool llphihf, double confg0 = 0.0, double f1dsin2 = 0.0, double f1d = 0.0,
+                           double oms = 0.0) {   // confg0 = GAMNCONST*FR5(MIJ)*RNFAC (0 without LLNORMAGAM), oms = OMEGA_GC(NS_GC(UFRIC))
   const double ZSUPMAX = 0.0;
   const double x0g = c_dc.X0TAUHF * c_dc.G;
   double ustph = ust;
@@ -137,7 +260,14 @@ __device__ void tau_phi_hf(int mij, bool shelter, double z0m, double aird, doubl
   const double zinf = log(yc);
   const double consttau = c_dc.ZPI4GM2 * c_dc.FR5[mij - 1];
   double taul = sq(ust);
-  double delz = dmax((ZSUPMAX - zinf) / (double)(c_dc.JTOT - 1), 0.0);
+  double zsup = ZSUPMAX;
+  double const1 = 0.0, const2 = 0.0;
+  if (CY) {
+    const double confg = confg0 * sqrtgz0;
+    const1 = confg * f1dsin2; const2 = confg * f1d;
+    if (c_dc.llgcbz0) zsup = dmin(log(oms * sqrtz0og), ZSUPMAX);
+  }
+  double delz = dmax((zsup - zinf) / (double)(c_dc.JTOT - 1), 0.0);
   tauhf = 0.0;
   if (shelter) {
     for (int j = 1; j <= c_dc.JTOT; ++j) {
@@ -149,7 +279,8 @@ __device__ void tau_phi_hf(int mij, bool shelter, double z0m, double aird, doubl
       double zlog = xloggz0 + 2.0 * log(cm1) + zarg;
       zlog = dmin(zlog, 0.0);
       const double zbeta = p4(zlog) * exp(zlog);
-      const double fnc2 = f1dcos3 * consttau * zbeta * taul * c_dc.WTAUHF[j - 1] * delz;
+      double fnc2 = f1dcos3 * consttau * zbeta * taul * c_dc.WTAUHF[j - 1] * delz;
+      if (CY) { const double znz = zbeta * ust * y; fnc2 = fnc2 * ((1.0 + const1 * znz) / (1.0 + const2 * znz)); }
       taul = dmax(taul - c_dc.TAUWSHELTER * fnc2, 0.0);
       ust = sqrt(taul);
       tauhf = tauhf + fnc2;
@@ -164,7 +295,8 @@ __device__ void tau_phi_hf(int mij, bool shelter, double z0m, double aird, doubl
       double zlog = xloggz0 + 2.0 * log(cm1) + zarg;
       zlog = dmin(zlog, 0.0);
       const double zbeta = p4(zlog) * exp(zlog);
-      tauhf = tauhf + zbeta * c_dc.WTAUHF[j - 1];
+      if (CY) { const double znz = zbeta * ust * y; tauhf = tauhf + (zbeta * c_dc.WTAUHF[j - 1]) * ((1.0 + const1 * znz) / (1.0 + const2 * znz)); }
+      else tauhf = tauhf + zbeta * c_dc.WTAUHF[j - 1];
     }
     tauhf = f1dcos3 * consttau * taul * tauhf * delz;
   }
@@ -183,7 +315,8 @@ __device__ void tau_phi_hf(int mij, bool shelter, double z0m, double aird, doubl
         double zlog = xloggz0 + 2.0 * log(cm1) + zarg;
         zlog = dmin(zlog, 0.0);
         const double zbeta = p4(zlog) * exp(zlog);
-        const double fnc2 = zbeta * taul * c_dc.WTAUHF[j - 1] * delz;
+        double fnc2 = zbeta * taul * c_dc.WTAUHF[j - 1] * delz;
+        if (CY) { const double znz = zbeta * ust * y; fnc2 = fnc2 * ((1.0 + const1 * znz) / (1.0 + const2 * znz)); }
         taul = dmax(taul - c_dc.TAUWSHELTER * f1dcos3 * consttau * fnc2, 0.0);
         ustph = sqrt(taul);
         phihf = phihf + fnc2 / y;
@@ -199,7 +332,8 @@ __device__ void tau_phi_hf(int mij, bool shelter, double z0m, double aird, doubl
         double zlog = xloggz0 + 2.0 * log(cm1) + zarg;
         zlog = dmin(zlog, 0.0);
         const double zbeta = p4(zlog) * exp(zlog);
-        phihf = phihf + zbeta * c_dc.WTAUHF[j - 1] / y;
+        if (CY) { const double znz = zbeta * ust * y; phihf = phihf + ((zbeta * c_dc.WTAUHF[j - 1]) * ((1.0 + const1 * znz) / (1.0 + const2 * znz))) / y; }
+        else phihf = phihf + zbeta * c_dc.WTAUHF[j - 1] / y;
       }
       phihf = f1dcos2 * constphi * sqrtz0og * taul * phihf * delz;
     }
@@ -218,6 +352,19 @@ __device__ double wsigstar(double ufric, double z0m, double wstar) {
   const double c_d = (C1 + c2u10p1) * u10p2;
   const double dc_ddu = (P2 * C1 + (P1 + P2) * c2u10p1) * u10p2 * u10m1;
   const double sig_conv = 1.0 + 0.5 * u10 / c_d * dc_ddu;
+  return dmin(SIG_NMAX, sig_conv * u10m1 * pow(0.0 * ufric * ufric * ufric + 0.5 * c_dc.XKAPPA * wstar * wstar * wstar, ONETHIRD));
+}
+
+// wsigstar.F90:87-103 (LLGCBZ0 or LLNORMAGAM): the drag law is linearised around the model's own Charnock parameter
+__device__ double wsigstar_gc(double wswave, double ufric, double z0m, double wstar) {
+  const double ONETHIRD = 1.0 / 3.0, SIG_NMAX = 0.9;
+  const double u10m1 = 1.0 / dmax(wswave, c_dc.wspmin);
+  const double z0vis = c_dc.rnum / dmax(ufric, c_dc.EPSUS);
+  double zchar = c_dc.G * (z0m - z0vis) / dmax(sq(ufric), c_dc.EPSUS);
+  zchar = dmax(dmin(zchar, c_dc.ALPHAMAX), c_dc.ALPHAMIN);
+  const double bcd_loc = c_dc.BCDLIN * sqrt(zchar);
+  const double c_d = c_dc.ACDLIN + bcd_loc * wswave;
+  const double sig_conv = 1.0 + 0.5 * wswave / c_d * bcd_loc;
   return dmin(SIG_NMAX, sig_conv * u10m1 * pow(0.0 * ufric * ufric * ufric + 0.5 * c_dc.XKAPPA * wstar * wstar * wstar, ONETHIRD));
 }
 
@@ -266,8 +413,8 @@ template <int N>
 __device__ __forceinline__ void row_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 __device__ __forceinline__ const double* row_ptr(const PointSrc& S, int m, int A) { return S.stage + (size_t)(m & 1) * A * KP_NTH; }
 
-template <bool ARD, int NGST, bool LLSNEG, bool STORE>
-__device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d, long long p, double fac, double flmc,
+template <bool ARD, int NGST, bool LLSNEG, bool STORE, bool CY>
+__device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d, long long p, double rnfac, double fac, double flmc,
                                              double snw, double csw, double ufric, double z0m, double raorw, double sig_n,
                                              double temp2_sw, double pturb, double aird_pvisc, double* __restrict__ fld_out,
                                              double* __restrict__ xl_out, double* sumx, double* sumy, double* sumt,
@@ -303,6 +450,12 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
   const double CONST3 = c_dc.idamping * (2.0 * c_dc.XKAPPA / CONST1);
   const double xkappad = 1.0 / c_dc.XKAPPA;
   const double avg = 1.0 / NGST;
+  // LLNORMAGAM (sinput_ard.F90:172-176, 400-404, 436-452; sinput_jan.F90:203-207, 329-348)
+  const bool normagam = CY && c_dc.llnormagam;
+  const double cstrnfac = normagam ? (c_dc.DELTH / (c_dc.XKAPPA * c_dc.ZPI)) * rnfac / raorw : 0.0;
+  double gamnorma[NGST];
+#pragma unroll
+  for (int g = 0; g < NGST; ++g) gamnorma[g] = 1.0;
   row_issue(S, 0, A);
   for (int m = 0; m < F; ++m) {
     if (m + 1 < F) { row_issue(S, m + 1, A); row_wait<1>(); } else row_wait<0>();
@@ -375,6 +528,43 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
         cosu[g] = csw; sinu[g] = snw;
       }
     }
+    if (CY) {
+      if (normagam) {   // GAMNORMA(IGST) of this frequency: the growth rates once more, summed over direction
+        const double xngamconst = cstrnfac * d.f.xk2cg[o3];
+        double sumf[NGST], sumfsin2[NGST];
+#pragma unroll
+        for (int g = 0; g < NGST; ++g) { sumf[g] = 0.0; sumfsin2[g] = 0.0; }
+        for (int k = 0; k < A; ++k) {
+          double f = dmax(fsrc[k * KP_NTH] * fac, c_dc.EPSMIN);
+          const double snk = c_dc.SINTH[k], csk = c_dc.COSTH[k];
+          const double cwd = csk * csw + snk * snw;
+          if (lastm) f = dmax(f, flmc * sq(dmax(0.0, cwd)));
+          const double sinwdif2 = sq(snk * csw - csk * snw);
+#pragma unroll
+          for (int g = 0; g < NGST; ++g) {
+            double gam0 = 0.0;
+            if (ard) {
+              const double coslp = ltauwshelter ? (csk * cosu[g] + snk * sinu[g]) : cwd;
+              if (coslp > 0.01) {
+                const double x = coslp * ucn[g];
+                const double zlog = zcn + div_norm(ucnzalpd[g], coslp);
+                if (zlog < 0.0) { const double zlog2x = zlog * zlog * x; gam0 = exp(zlog) * zlog2x * zlog2x * cnsn; }
+              }
+            } else if (cwd > 0.01) {
+              const double zlog = zcn + div_norm(c_dc.XKAPPA, cwd) * ucnzalpd[g];
+              if (zlog < 0.0) { const double x = cwd * ucn[g]; const double zlog2x = zlog * zlog * x; gam0 = zlog2x * zlog2x * exp(zlog) * cnsn; }
+            }
+            sumf[g] = sumf[g] + gam0 * f;
+            sumfsin2[g] = sumfsin2[g] + gam0 * f * sinwdif2;
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < NGST; ++g) {
+          const double znz = xngamconst * (1.0 / dmax(ustp[g], c_dc.EPSUS));
+          gamnorma[g] = (1.0 + znz * sumfsin2[g]) / (1.0 + znz * sumf[g]);
+        }
+      }
+    }
     double sx[NGST], sy[NGST], st = 0.0, tsum = 0.0, traw = 0.0, rawt = 0.0;
 #pragma unroll
     for (int g = 0; g < NGST; ++g) { sx[g] = 0.0; sy[g] = 0.0; }
@@ -407,6 +597,7 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
           }
           double dstab = 0.0;
           if (LLSNEG) dstab = dstab1 + pturb * (temp1 * (temp2_sw + (FU + FUD * coslp) * ustp[g]));
+          if (CY) gam0 = gam0 * gamnorma[g];
           const double slp = gam0 * f;
           sx[g] += slp * snk; sy[g] += slp * csk;
           slp_avg += slp; flp_avg += gam0 + dstab;
@@ -420,7 +611,8 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
               xll = true;
             }
           }
-          slp_avg += wsin[g] * gam0;                   // UFAC1
+          if (CY) slp_avg += wsin[g] * gam0 * gamnorma[g];
+          else slp_avg += wsin[g] * gam0;              // UFAC1
           if (LLSNEG) ufac2 += wsin[g] * (const3_ucn2[g] * (cwd - xvd[g]));
         }
       }
@@ -465,7 +657,9 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
 // PH = 2: second SINFLX call (AIRSEA, WSIGSTAR, SINPUT with NGST=2 and swell damping -> FLD, XLLWS; FRCUTINDEX; STRESSO with PHIWA)
 // Two kernels instead of one: each frequency loop then fits the 32 KB instruction cache (no_instruction stalls of the fused
 // kernel were as frequent as its dependency stalls), and the few scalars in between travel through the scratch slots.
-template <bool ARD, int PH>
+// CY: the cy49r1 physics instance (LLGCBZ0 and/or LLNORMAGAM, read at run time inside it); the CY = false instances do not
+// contain any of it.
+template <bool ARD, int PH, bool CY>
 __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, long long np) {
   extern __shared__ double smem[];
   long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -498,10 +692,65 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
   double sumx[EW_MAXF], sumy[EW_MAXF], sumt[EW_MAXF];
   double ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc;
   double emean, fmean, f1mean, xkmean;
+  // RNFAC (sinflx.F90:117-121) and 1/2 ALPHAP of the Phillips tail (HALPHAP)
+  double rnfac = 1.0, halp = 0.0;
+  if (CY) { if (c_dc.llnormagam && c_dc.llcapchnk) rnfac = 1.0 + c_dc.DTHRN_A * (1.0 + tanh(wswave - c_dc.DTHRN_U)); }
+  bool fac_known = false;
   if (PH == 1) {
     // ---- SINFLX call 1: AIRSEA (IUSFG=0), SINPUT (NGST=1), FEMEANWS, FRCUTINDEX, STRESSO
     tauw = d.f.tauw[p]; tauwdir = d.f.tauwdir[p];
-    taut_z0(0, wswave, wdwave, tauw, tauwdir, ustar, z0, z0b, ch);
+    if (CY) {
+      if (c_dc.llgcbz0) {
+        // HALPHAP (halphap.F90:68-115 with MEANSQS_LF and FEMEAN on the spectrum in the wind direction) needs the depth-limited,
+        // floored spectrum before AIRSEA: its own pass over FL1, which also settles SDEPTHLIM's factor (same optimistic scheme
+        // as below: factor 1 first, depth-limited lanes repeat the pass).
+        const double zlnfrnfre = log(c_dc.FR[F - 1]);
+        for (int attempt = 0; attempt < 2; ++attempt) {
+          double xmss = 0.0, em = 0.0, fm = 0.0, temp2 = 0.0, f1d = 0.0, m6 = 0.0, rawt = 0.0;
+          row_issue(S, 0, A);
+          for (int m = 0; m < F; ++m) {
+            if (m + 1 < F) { row_issue(S, m + 1, A); row_wait<1>(); } else row_wait<0>();
+            const double* fsrc = row_ptr(S, m, A);
+            const double wavnum = d.f.wavnum[idx3(d, p, m)];
+            double sflwd = 0.0;
+            temp2 = 0.0; rawt = 0.0;
+            for (int k = 0; k < A; ++k) {
+              const double fraw = fsrc[k * KP_NTH];
+              rawt += fraw;
+              double f = dmax(fraw * fac, c_dc.EPSMIN);
+              const double cwd = c_dc.COSTH[k] * csw + c_dc.SINTH[k] * snw;
+              if (m == F - 1) f = dmax(f, flmc * sq(dmax(0.0, cwd)));
+              const double flwd = signbit(cwd) ? f * 0.0 : f;          // FL1 * (0.5 + 0.5*SIGN(1,COSWDIF))
+              sflwd = sflwd + flwd;
+              temp2 = temp2 + dmax(flwd, c_dc.EPSMIN);
+              if (m == F - 1) f1d = f1d + flwd * c_dc.DELTH;
+            }
+            xmss = xmss + (c_dc.DFIM[m] * sq(wavnum)) * sflwd;
+            em = em + temp2 * c_dc.DFIM[m];
+            fm = fm + c_dc.DFIMOFR[m] * temp2;
+            m6 += c_dc.DFIM[m] * rawt;
+          }
+          em = em + DELT25 * temp2;
+          fm = fm + (c_dc.FRTAIL * c_dc.DELTH) * temp2;
+          fm = dmax(em / fm, c_dc.FR[0]);
+          double alphap;
+          bool tail = true;
+          if (em > 0.0 && fm < c_dc.FR[F - 3]) {
+            alphap = xmss / (zlnfrnfre - log(fm));
+            tail = alphap > c_dc.ALPHAPMAX;
+          }
+          if (tail) alphap = c_dc.ZPI4GM2 * c_dc.FR5[F - 1] * f1d;
+          halp = 0.5 * dmin(alphap, c_dc.ALPHAPMAX);
+          if (attempt == 1 || !c_dc.lbiwbk) break;
+          const double emr = (c_dc.EPSMIN + m6) + DELT25 * rawt;
+          fac = dmin(d.f.emaxdpt[p] / emr, 1.0);
+          if (fac == 1.0) break;
+        }
+        fac_known = true;
+        if (valid) s[S_HALP * n + p] = halp;
+        taut_z0_gc(d.gc, 0, halp, wswave, wdwave, tauw, tauwdir, rnfac, ustar, z0, z0b, ch);
+      } else taut_z0(0, wswave, wdwave, tauw, tauwdir, ustar, z0, z0b, ch);
+    } else taut_z0(0, wswave, wdwave, tauw, tauwdir, ustar, z0, z0b, ch);
     // SDEPTHLIM (sdepthlim.F90:50-82) needs the total energy of the incoming spectrum before anything else can be formed.
     // Instead of a separate pass over FL1, the first SINPUT pass is run with the limiting factor 1 (exact wherever the
     // spectrum is not depth-limited, i.e. almost everywhere) and sums that energy on the side; only the lanes that turn
@@ -510,8 +759,9 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
     for (int attempt = 0; attempt < 2; ++attempt) {
 #pragma unroll
       for (int x = 0; x < 8; ++x) mom[x] = 0.0;
-      sinput_point<ARD, 1, false, false>(S, d, p, fac, flmc, snw, csw, ustar, z0, raorw, 0.0, 0.0, 0.0, 0.0, nullptr, nullptr, sumx, sumy,
-                                         sumt, ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc, mom, false);
+      sinput_point<ARD, 1, false, false, CY>(S, d, p, rnfac, fac, flmc, snw, csw, ustar, z0, raorw, 0.0, 0.0, 0.0, 0.0, nullptr, nullptr,
+                                             sumx, sumy, sumt, ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc, mom, false);
+      if (CY) { if (fac_known) break; }
       if (attempt == 1 || !c_dc.lbiwbk) break;
       const double em = (c_dc.EPSMIN + mom[6]) + DELT25 * mom[7];
       fac = dmin(d.f.emaxdpt[p] / em, 1.0);
@@ -538,6 +788,7 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
     emean = s[S_EMEAN * n + p]; fmean = s[S_FMEAN * n + p]; f1mean = s[S_F1MEAN * n + p]; xkmean = s[S_XKMEAN * n + p];
     ustar = s[S_USTAR1 * n + p]; tauw = s[S_TAUW1 * n + p]; tauwdir = s[S_TWDIR1 * n + p];
     uorbt_acc = s[S_UORBT * n + p]; aorb_acc = s[S_AORB * n + p];
+    if (CY) halp = s[S_HALP * n + p];
   }
 
   auto frcut = [&](double fmeanws, double ust) -> int {   // frcutindex.F90:84-97
@@ -561,7 +812,7 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
     const double am = dmax(aird, 1.0);
     xs = xs / am; ys = ys / am;
     // directional moments of the spectrum at the cut-off frequency (tau_phi_hf.F90:150-178)
-    double f3 = 0.0, f2 = 0.0;
+    double f3 = 0.0, f2 = 0.0, f1d = 0.0, f1dsin2 = 0.0;
     {
       const int m = mij - 1;
       const double* fsrc = (m < S.mlo ? S.lo : S.hi) + (size_t)m * A * S.kstr;
@@ -572,8 +823,10 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
         const double cw = dmax(cwd, 0.0);
         const double fc2 = f * cw * cw;
         f3 += fc2 * cw; f2 += fc2;
+        if (CY) { f1d += f; f1dsin2 += f * sq(c_dc.SINTH[k] * csw - c_dc.COSTH[k] * snw); }
       }
       f3 *= c_dc.DELTH; f2 *= c_dc.DELTH;
+      if (CY) { f1d *= c_dc.DELTH; f1dsin2 *= c_dc.DELTH; }
     }
     bool shelter;
     double usdirp_s, usdirp_c, ust;
@@ -586,12 +839,17 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
       if (rt > 0.0) { usdirp_s = taupx / rt; usdirp_c = taupy / rt; } else { usdirp_s = 0.0; usdirp_c = 1.0; }
     }
     double tauhf, phihf;
-    tau_phi_hf(mij, shelter, z0m, aird, f3, f2, ust, tauhf, phihf, llphiwa);
+    if (CY) {
+      const double confg0 = c_dc.llnormagam ? c_dc.GAMNCONST * c_dc.FR5[mij - 1] * rnfac : 0.0;
+      const double oms = c_dc.llgcbz0 ? __ldg(d.gc + GC_OMEGA * c_dc.NWAV_GC + ns_gc(ust_in) - 1) : 0.0;   // omegagc.F90:51-55
+      tau_phi_hf<true>(mij, shelter, z0m, aird, f3, f2, ust, tauhf, phihf, llphiwa, confg0, f1dsin2, f1d, oms);
+    } else tau_phi_hf<false>(mij, shelter, z0m, aird, f3, f2, ust, tauhf, phihf, llphiwa);
     xs = xs + tauhf * usdirp_s;
     ys = ys + tauhf * usdirp_c;
     tw = dmax(sqrt(sq(xs) + sq(ys)), 0.0);
     twd = atan2(xs, ys);
-    tw = dmin(tw, sq(ust_in) * (1.0 / (1.0 + c_dc.EPS1)));
+    if (CY) { if (!c_dc.llgcbz0) tw = dmin(tw, sq(ust_in) * (1.0 / (1.0 + c_dc.EPS1))); }   // stresso.F90:218-223
+    else tw = dmin(tw, sq(ust_in) * (1.0 / (1.0 + c_dc.EPS1)));
     phiwa = llphiwa ? pw + phihf : 0.0;
   };
   if (PH == 1) {
@@ -620,9 +878,12 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
     return;
   }
   // ---- SINFLX call 2: AIRSEA (IUSFG=1), SINPUT (NGST=2, LLSNEG), FEMEANWS, FRCUTINDEX, STRESSO (LLPHIWA)
-  taut_z0(1, wswave, wdwave, tauw, tauwdir, ustar, z0, z0b, ch);
+  if (CY) {
+    if (c_dc.llgcbz0) taut_z0_gc(d.gc, 1, halp, wswave, wdwave, tauw, tauwdir, rnfac, ustar, z0, z0b, ch);
+    else taut_z0(1, wswave, wdwave, tauw, tauwdir, ustar, z0, z0b, ch);
+  } else taut_z0(1, wswave, wdwave, tauw, tauwdir, ustar, z0, z0b, ch);
   if (valid) { d.f.ufric[p] = ustar; d.f.z0m[p] = z0; d.f.z0b[p] = z0b; d.f.chrnck[p] = ch; }
-  const double sig_n = wsigstar(ustar, z0, d.f.wstar[p]);
+  const double sig_n = CY ? wsigstar_gc(wswave, ustar, z0, d.f.wstar[p]) : wsigstar(ustar, z0, d.f.wstar[p]);
   double temp2_sw = 0.0, pturb = 0.0, aird_pvisc = 0.0;
   if (ARD) {   // sinput_ard.F90:179-271
     const double uorbt = 2.0 * sqrt(c_dc.EPSMIN + uorbt_acc), aorb = 2.0 * sqrt(c_dc.EPSMIN + aorb_acc);
@@ -646,7 +907,7 @@ __global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, lo
   double* fld_out = d.fldin + (size_t)i + (size_t)d.P * A * F * (size_t)c;
   double* xl_out = d.f.xllws + (size_t)i + (size_t)d.P * A * F * (size_t)c;
   double dum[8];
-  sinput_point<ARD, 2, true, true>(S, d, p, fac, flmc, snw, csw, ustar, z0, raorw, sig_n, temp2_sw, pturb, aird_pvisc, fld_out, xl_out,
+  sinput_point<ARD, 2, true, true, CY>(S, d, p, rnfac, fac, flmc, snw, csw, ustar, z0, raorw, sig_n, temp2_sw, pturb, aird_pvisc, fld_out, xl_out,
                               sumx, sumy, sumt, ws_em, ws_fm, ws_last, phiwa_acc, uorbt_acc, aorb_acc, dum, valid, d.f.depth[p],
                               c_dc.CDIS * c_dc.ZPI * f1mean * sq(emean) * p4(xkmean), xkmean);
   const double emeanws = c_dc.EPSMIN + ws_em + DELT25 * ws_last;
@@ -1685,19 +1946,21 @@ int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage
     const size_t smp = (size_t)2 * A * KP_NTH * sizeof(double);
     static bool attr_p = false;
     if (!attr_p) {
-      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<true, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<true, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      EW_CUDA_CHECK(cudaFuncSetAttribute(k_point<false, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      const void* kp[8] = {(const void*)k_point<true, 1, false>, (const void*)k_point<true, 2, false>, (const void*)k_point<false, 1, false>,
+                           (const void*)k_point<false, 2, false>, (const void*)k_point<true, 1, true>, (const void*)k_point<true, 2, true>,
+                           (const void*)k_point<false, 1, true>, (const void*)k_point<false, 2, true>};
+      for (int i = 0; i < 8; ++i) {
+        EW_CUDA_CHECK(cudaFuncSetAttribute(kp[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        EW_CUDA_CHECK(cudaFuncSetAttribute(kp[i], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      }
       attr_p = true;
     }
     const unsigned nb = (unsigned)((np + KP_NTH - 1) / KP_NTH);
-    if (d.iphys == 1) { k_point<true, 1><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<true, 2><<<nb, KP_NTH, smp, st>>>(d, p0, np); }
-    else { k_point<false, 1><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<false, 2><<<nb, KP_NTH, smp, st>>>(d, p0, np); }
+    if (d.cy49) {
+      if (d.iphys == 1) { k_point<true, 1, true><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<true, 2, true><<<nb, KP_NTH, smp, st>>>(d, p0, np); }
+      else { k_point<false, 1, true><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<false, 2, true><<<nb, KP_NTH, smp, st>>>(d, p0, np); }
+    } else if (d.iphys == 1) { k_point<true, 1, false><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<true, 2, false><<<nb, KP_NTH, smp, st>>>(d, p0, np); }
+    else { k_point<false, 1, false><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<false, 2, false><<<nb, KP_NTH, smp, st>>>(d, p0, np); }
   } else if (stage == 1) {
     // two grid points per thread (16-byte shared / global accesses) need an even NPROMA and an even first point
     const uintptr_t al = (uintptr_t)d.f.fl1 | (uintptr_t)d.f.xllws | (uintptr_t)d.fldin | (uintptr_t)d.fl_lo;

@@ -81,6 +81,8 @@ struct ImplDev {
                            // k_stencil's shared-memory planes (shift * 8 points * 8 B)
   int iphys, nsdsnth;      // copies of the host-side switches the launcher needs
   int halo_r, halo_c;      // direction halo of the shared-memory spectrum rows / interaction planes of k_stencil
+  int cy49;                // LLGCBZ0 or LLNORMAGAM is on: k_point runs its gravity-capillary / renormalised-growth instance
+  const double* gc;        // [GC_NT][NWAV_GC] gravity-capillary tables (device), read by that instance only
 };
 #define EW_TQ_N 6          // number of planes of ImplDev::tbg
 int upload_dev_const(const DevConst& h, cudaStream_t st);
@@ -101,6 +103,7 @@ struct OutConst {   // constant memory of outparam.cu
   // SEBTMEAN (sebtmean.F90) is linear in the 1-D spectrum: EBT = EPSMIN + sum_m SEBT[band][m] * sum_k F(k,m); band 0 = SE10MEAN
   // (T > 10 s), bands 1..6 = the period intervals of mpcrtbl.F90:373-399
   double SEBT[7][EW_MAXF];
+  int llgcbz0;             // OUTBETA: no wind-speed cap of the Charnock parameter (outbeta.F90:113-117)
 };
 struct OutDev {
   int P, A, F, nchnk;

@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(OB_NTH, OB_MINB) k_outblock(OutDev d) {
       case 5: v = fmod(DEG * wd + 180.0, 360.0); break;
       case 6: { const double dp = (em4 > 0.0 && dp4 > EPSMIN) ? em4 / dp4 : 0.0; v = dp > 0.0 ? dp : ZMISS; } break;
       case 7: {   // outbeta.F90:66-91, LLGCBZ0 = F
-        const double amx = omin(c_oc.ALPHAMAX, 0.02 + 0.01 * wsw);
+        const double amx = c_oc.llgcbz0 ? c_oc.ALPHAMAX : omin(c_oc.ALPHAMAX, 0.02 + 0.01 * wsw);   // outbeta.F90:113-117
         const double usm = 1.0 / omax(ufric, c_oc.EPSUS);
         const double betam = omax(omin(d.f.chrnck[p], amx), c_oc.ALPHAMIN);
         const double z0atm = c_oc.rnum * usm + c_oc.GM1 * betam * (ufric * ufric);

@@ -48,6 +48,7 @@ def make_setup(case, nproc=1, grid_hook=None, **extra):
     c = CASES[case]
     g = make_grid(case, grid_hook)
     kw = dict(nang=c["A"], nfre_red=c["Fr"], iphys=c["iphys"], nproma=c["nproma"], idelt=c["dt"], idelpro=c["dt"], delpro_lf=c["dt"])
+    kw.update(c.get("cfg", {}))
     kw.update(extra)
     return g, M.WamSetup(g, nproc=nproc, **kw)
 
