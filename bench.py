@@ -99,7 +99,10 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------------------
-def cpu_reference_run(workload, steps, warmup, sample_N=None, quiet=True):
+PHYSICS = {"default": {}, "cy49r1": dict(llgcbz0=1, llnormagam=1, wspmin=0.3)}   # tests/etopo1_oper_an_fc_O48{,_cy49r1}.yml
+
+
+def cpu_reference_run(workload, steps, warmup, sample_N=None, quiet=True, physics="default"):
     """Times the CPU restatement of the reference (oracle/, -O3 build, OpenMP over NPROMA chunks as
     wamintgr.F90:117) on a bounded sample of the workload: same spectral resolution, physics and time step, on a
     smaller octahedral grid with the same synthetic-continent recipe.  Returns (spectra/s, ms/step, cores, sample)."""
@@ -114,7 +117,8 @@ def cpu_reference_run(workload, steps, warmup, sample_N=None, quiet=True):
             sample_N = cfgw["N"]
     g = synth.make_grid(sample_N, "continents")
     cfg = O.default_config(nang=cfgw["nang"], nfre_red=cfgw["nfre_red"], nproma=24, npr=1, iphys=1, idelt=cfgw["idelt"],
-                           idelpro=cfgw["idelpro"], delpro_lf=cfgw["delpro_lf"], ifrelfmax=cfgw["ifrelfmax"], nthreads=cores)
+                           idelpro=cfgw["idelpro"], delpro_lf=cfgw["delpro_lf"], ifrelfmax=cfgw["ifrelfmax"], nthreads=cores,
+                           **PHYSICS[physics])
     o = O.Oracle(cfg, g, fast=True)
     f = synth.make_forcing(g)
     for k, v in f.items():
@@ -137,7 +141,7 @@ def run_reference(args):
         return
     steps = max(1, args.steps)
     warm = max(0, min(args.warmup, 1))
-    val, ms, cores, sample = cpu_reference_run(args.workload, min(steps, 3), warm)
+    val, ms, cores, sample = cpu_reference_run(args.workload, min(steps, 3), warm, physics=args.physics)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": min(steps, 3),
             "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": {"workload": args.workload + " (bounded CPU sample: " + sample + ")"},
@@ -147,14 +151,14 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------------------
-def make_case(workload, world, rank, device, mask="continents"):
+def make_case(workload, world, rank, device, mask="continents", physics="default"):
     """Set-up (not timed): grid, MPDECOMP for `world` ranks, tables, this rank's fields on its GPU."""
     from ecwam_b200 import synth, model as M, lib as L
     import torch
     cfgw, nproma = workload_cfg(workload)
     g = synth.make_grid(cfgw["N"], mask)
     s = M.WamSetup(g, nproc=world, nang=cfgw["nang"], nfre_red=cfgw["nfre_red"], iphys=1, nproma=nproma, idelt=cfgw["idelt"],
-                   idelpro=cfgw["idelpro"], delpro_lf=cfgw["delpro_lf"], ifrelfmax=cfgw["ifrelfmax"])
+                   idelpro=cfgw["idelpro"], delpro_lf=cfgw["delpro_lf"], ifrelfmax=cfgw["ifrelfmax"], **PHYSICS[physics])
     comm = None
     if world > 1:
         import torch.distributed as dist
@@ -218,7 +222,7 @@ def run_gpu(args):
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
-    g, s, w, forcing = make_case(args.workload, world, rank, device)
+    g, s, w, forcing = make_case(args.workload, world, rank, device, physics=args.physics)
     lib = w.lib
     npts_total = g.niblo
     K, W = args.steps, max(args.warmup, 3)
@@ -344,12 +348,14 @@ def run_gpu(args):
                         "pipe utilisation are in profiles/"}
     cpu = None
     if not args.no_cpu:
-        v, msc, cores, sample = cpu_reference_run(args.workload, 2, 1)
+        v, msc, cores, sample = cpu_reference_run(args.workload, 2, 1, physics=args.physics)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_step_sample": msc}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s octahedral grid, synthetic continents (%d sea points), %dx%d spectrum (%d propagated), "
-                                   "IPHYS=1, NPROMA=%d, dt=%gs" % (args.workload, npts_total, A, F, Fr, w.par.nproma, w.par.idelt),
+                                   "IPHYS=1%s, NPROMA=%d, dt=%gs" % (args.workload, npts_total, A, F, Fr,
+                                                                      "" if args.physics == "default" else " + LLGCBZ0 + LLNORMAGAM (cy49r1)",
+                                                                      w.par.nproma, w.par.idelt),
                        "parallelism": "mpdecomp%d" % world, "l2": "inputs larger than L2 (FL1 %.1f GB per GPU)" % (w.t["fl1"].numel() * 8 / 1e9)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "kernel_ms": kern, "output_step": aux or None, "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line))
@@ -368,6 +374,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the NEWWIND / OUTBS / WAMNORM timing next to the path")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--physics", default="default", choices=sorted(PHYSICS),
+                    help="default = BASELINE.json's configuration; cy49r1 = gravity-capillary roughness + renormalised growth")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -45,8 +45,8 @@ typedef struct ecwam_b200_params {
   int idamping;    /* YOWSTAT IDAMPING (SINPUT_JAN)                                     */
   int irefra;      /* YOWSTAT IREFRA (0 none, 1 depth, 2 current, 3 depth + current refraction)   */
   int icase;       /* YOWSTAT ICASE (1 = spherical, only)                               */
-  int llgcbz0;     /* YOWCOUP LLGCBZ0 (0 only)                                          */
-  int llnormagam;  /* YOWCOUP LLNORMAGAM (0 only)                                       */
+  int llgcbz0;     /* YOWCOUP LLGCBZ0 (needs the *_gc members of ecwam_b200_tables)      */
+  int llnormagam;  /* YOWCOUP LLNORMAGAM (needs the *_gc members of ecwam_b200_tables)   */
   int llcapchnk;   /* YOWCOUP LLCAPCHNK                                                 */
   int lbiwbk;      /* YOWSTAT LBIWBK                                                    */
   int licerun;     /* YOWICE LICERUN                                                    */

@@ -27,13 +27,15 @@ def main():
     cm = C.c_void_p()
     L.check(lib.ecwam_b200_nccl_comm_init(bytes(t.cpu().numpy().tobytes()), world, rank, C.byref(cm)), "comm_init")
     ok = True
-    for case, extra in (("o48like", {}), ("o640like", dict(ifrelfmax=5, delpro_lf=225.0)), ("o48like", dict(irefra=1)), ("o48like", dict(irefra=3))):
+    for case, extra in (("o48like", {}), ("o640like", dict(ifrelfmax=5, delpro_lf=225.0)), ("o48like", dict(irefra=1)), ("o48like", dict(irefra=3)),
+                        ("o48like", dict(llgcbz0=1, llnormagam=1, wspmin=0.3))):
         CASES["_mr"] = dict(CASES[case], N=28)
         g, o, f, fl = make_oracle("_mr", **extra)
         c = CASES["_mr"]
         s = M.WamSetup(g, nproc=world, nang=c["A"], nfre_red=c["Fr"], iphys=c["iphys"], nproma=c["nproma"], idelt=c["dt"],
                        idelpro=c["dt"], delpro_lf=extra.get("delpro_lf", c["dt"]), ifrelfmax=extra.get("ifrelfmax", 0),
-                       irefra=extra.get("irefra", 0))
+                       irefra=extra.get("irefra", 0), llgcbz0=extra.get("llgcbz0", 0), llnormagam=extra.get("llnormagam", 0),
+                       wspmin=extra.get("wspmin", 1.0))
         w = M.WamIntgr(s, rank, device="cuda:%d" % local, nccl_comm=cm.value)
         w.set_static(g.depth)
         for k, v in f.items():

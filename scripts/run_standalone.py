@@ -37,6 +37,8 @@ def main():
     ap.add_argument("--wind-every", type=float, default=1.0, help="hours between forcing updates (IDELWO)")
     ap.add_argument("--iphys", type=int, default=1)
     ap.add_argument("--mask", default="continents", choices=["continents", "aqua"])
+    ap.add_argument("--cycle", default="default", choices=["default", "cy49r1"],
+                    help="cy49r1: LLGCBZ0 + LLNORMAGAM, WSPMIN = 0.3 (tests/etopo1_oper_an_fc_O48_cy49r1.yml)")
     ap.add_argument("--check", action="store_true", help="run the CPU oracle alongside and compare the norms (test infrastructure)")
     args = ap.parse_args()
 
@@ -65,6 +67,8 @@ def main():
     g = synth.make_grid(cfg["N"], args.mask)
     kw = dict(nang=cfg["nang"], nfre_red=cfg["nfre_red"], iphys=args.iphys, nproma=nproma, idelt=cfg["idelt"], idelpro=cfg["idelpro"],
               delpro_lf=cfg["delpro_lf"], ifrelfmax=cfg["ifrelfmax"])
+    if args.cycle == "cy49r1":
+        kw.update(llgcbz0=1, llnormagam=1, wspmin=0.3)
     s = M.WamSetup(g, nproc=world, **kw)
     w = M.WamIntgr(s, rank, device=dev, nccl_comm=comm)
     w.set_static(g.depth)

@@ -157,7 +157,7 @@ def test_fast_wave_substeps_bit_exact(built):
     check_state(w, o)
 
 
-@pytest.mark.parametrize("name", ["g_iphys1", "g_iphys0", "g_a36"])
+@pytest.mark.parametrize("name", ["g_iphys1", "g_iphys0", "g_a36", "g_cy49r1"])
 def test_against_golden(built, name):
     z = np.load(os.path.join(GOLD, name + ".npz"))
     CASES["_gold"] = dict(CASES[str(z["case"])], N=int(z["N"]))
@@ -180,6 +180,33 @@ def test_against_golden(built, name):
     wn = w.outwnorm(True)
     np.testing.assert_array_equal(wn[:, 3], z["wnorm"][:, 3])
     np.testing.assert_allclose(wn[0, :3], z["wnorm"][0, :3], rtol=1e-11)      # swh: average, minimum, maximum
+
+
+@pytest.mark.parametrize("case,extra", [("o48_cy49r1", {}), ("o48_iphys0_gc", {}), ("o640like", dict(llgcbz0=1, llnormagam=1, wspmin=0.3)),
+                                        ("o48like", dict(llnormagam=1)), ("o48like", dict(llgcbz0=1, wspmin=0.3)),
+                                        ("o48_iphys0", dict(llnormagam=1)), ("o320like", dict(llgcbz0=1, llnormagam=1, wspmin=0.3, llcapchnk=0))])
+def test_gravity_capillary_physics_matches_oracle(built, case, extra):
+    """LLGCBZ0 / LLNORMAGAM (the reference's cy49r1 / cy50r1 test configurations): k_point's CY instance = HALPHAP pass over FL1
+    (halphap.F90:68-115), gravity-capillary TAUT_Z0 with STRESS_GC (taut_z0.F90:148-279, stress_gc.F90:70-130), GAMNORMA in SINPUT
+    (sinput_ard.F90:436-452, sinput_jan.F90:329-348) and TAU_PHI_HF (:177-193), WSIGSTAR's linearised drag law (wsigstar.F90:87-103),
+    no TAUW cap in STRESSO (:218-223), OUTBETA without the wind-speed cap (outbeta.F90:113-117).  Every switch combination, both
+    physics packages, NANG = 12 / 24 / 36, same tolerances as the default physics."""
+    from common import OUT_ICE, OUT_ITG, OUT_SEA, compare_bout
+    g, o, f, fl = make_oracle(case, **extra)
+    _, s, w = make_gpu(case, **extra)
+    o.implsch(); w.implsch()
+    w.synchronize()
+    check_state(w, o)
+    for _ in range(3):
+        assert o.step() == 0 and w.step() == 0
+    w.synchronize()
+    check_state(w, o)
+    compare_bout(w.outbs(OUT_ITG, OUT_ICE, OUT_SEA), o.outbs(OUT_ITG, OUT_ICE, OUT_SEA)[:, w.own])
+    if extra.get("llgcbz0") or "cfg" in CASES[case]:
+        g, o0, f, fl = make_oracle(case.replace("_cy49r1", "like").replace("_gc", ""))
+        for _ in range(3):
+            o0.step()
+        assert np.abs(o.get_field("UFRIC") - o0.get_field("UFRIC")).max() > 1e-3, "the switch must change the stress"
 
 
 @pytest.mark.parametrize("case", ["o48like", "o640like"])
@@ -325,7 +352,7 @@ def test_cfl_violation_is_reported(built):
 def test_unsupported_switches_are_rejected(built):
     from ecwam_b200 import synth
     g = synth.make_grid(8, "aqua")
-    for kw in (dict(irefra=4), dict(irefra=2, ifrelfmax=5), dict(llgcbz0=1), dict(isnonlin=1), dict(lciwa=1), dict(lciwa=2)):
+    for kw in (dict(irefra=4), dict(irefra=2, ifrelfmax=5), dict(isnonlin=1), dict(lciwa=1), dict(lciwa=2)):
         s = M.WamSetup(g, nproc=1, **kw)
         with pytest.raises(L.EcwamError):
             M.WamIntgr(s, 0)
