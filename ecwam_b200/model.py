@@ -242,6 +242,75 @@ class WamIntgr:
         x = self.t[name].permute(1, 2, 0, 3).reshape(self.F, self.A, -1)[:, :, : self.nloc]
         return x.cpu().numpy()
 
+    # ---- restart files in the reference's formats (SAVSPEC / SAVSTRESS, GETSPEC / GETSTRESS; host_io.cpp)
+    LAW_FIELDS = ("wswave", "wdwave", "ufric", "tauw", "tauwdir", "z0m", "z0b", "chrnck", "aird", "wstar", "cicover", "cithick",
+                  "ustra", "vstra", "ucur", "vcur")                       # savstress.F90:110-125 (NREAL = 16)
+
+    def _ijorig(self):
+        return np.ascontiguousarray(self.own + 1, dtype=np.int32)
+
+    def _set_own(self, name, v_own):
+        """v_own[..., own point] (slot order) -> the (.., C, P) device array; padded lanes repeat the chunk's first point."""
+        slot = np.arange(self.P * self.C)
+        slot = np.where(slot < self.nloc, slot, (slot // self.P) * self.P)
+        x = self.torch.from_numpy(np.ascontiguousarray(v_own[..., slot]))
+        if x.dim() == 3:
+            self.t[name].copy_(x.view(self.F, self.A, self.C, self.P).permute(2, 0, 1, 3))
+        else:
+            self.t[name].copy_(x.view(self.C, self.P))
+
+    def savspec(self, filename: str, create: bool = True, parallel: bool = False):
+        """SAVSPEC (savspec.F90:86-166): this rank's spectra into the BLS file.  Global file: every rank writes its own points in
+        place; the rank called with create=True must finish first (the caller places the barrier).  parallel=True is LRSTPARALW:
+        one file per rank, FILENAME.<irank>_<nproc>."""
+        self.synchronize()
+        fl = np.ascontiguousarray(self.get_spec("fl1"))           # [m][k][own point] = Fortran (IJ, K, M)
+        dp = C.POINTER(C.c_double)
+        if parallel:
+            buf = C.create_string_buffer(512)
+            L.check(self.lib.ecwam_b200_restart_par_name(filename.encode(), self.rank + 1, self.s.nproc, buf, 512), "restart_par_name")
+            L.check(self.lib.ecwam_b200_savspec_par(buf.value, self.nloc, self.A, self.F, fl.ctypes.data_as(dp)), "savspec_par")
+            return buf.value.decode()
+        ij = self._ijorig()
+        L.check(self.lib.ecwam_b200_savspec(filename.encode(), self.s.niblo, self.A, self.F, self.nloc, ij.ctypes.data_as(C.POINTER(C.c_int)),
+                                            fl.ctypes.data_as(dp), int(create)), "savspec")
+        return filename
+
+    def getspec(self, filename: str, parallel: bool = False):
+        """GETSPEC's binary-restart branch (getspec.F90 -> READFL, readfl.F90:118-145): this rank's spectra out of the BLS file."""
+        fl = np.empty((self.F, self.A, self.nloc))
+        dp = C.POINTER(C.c_double)
+        if parallel:
+            buf = C.create_string_buffer(512)
+            L.check(self.lib.ecwam_b200_restart_par_name(filename.encode(), self.rank + 1, self.s.nproc, buf, 512), "restart_par_name")
+            L.check(self.lib.ecwam_b200_getspec_par(buf.value, self.nloc, self.A, self.F, fl.ctypes.data_as(dp)), "getspec_par")
+        else:
+            ij = self._ijorig()
+            L.check(self.lib.ecwam_b200_getspec(filename.encode(), self.s.niblo, self.A, self.F, self.nloc, ij.ctypes.data_as(C.POINTER(C.c_int)),
+                                                fl.ctypes.data_as(dp)), "getspec")
+        self._set_own("fl1", fl)
+
+    def savstress(self, filename: str, cdtpro: str, cdatewo: str = "", cdawifl: str = "", cdatefl: str = "", create: bool = True):
+        """SAVSTRESS (savstress.F90:80-152): the 16 forcing / stress fields of the LAW file (global file, rank-wise as savspec)."""
+        self.synchronize()
+        r = np.ascontiguousarray(np.stack([self.get_field(n) for n in self.LAW_FIELDS]))      # [field][own point]
+        ij = self._ijorig()
+        L.check(self.lib.ecwam_b200_savstress(filename.encode(), cdtpro.encode(), (cdatewo or cdtpro).encode(), (cdawifl or cdtpro).encode(),
+                                              (cdatefl or cdtpro).encode(), self.s.niblo, len(self.LAW_FIELDS), self.nloc,
+                                              ij.ctypes.data_as(C.POINTER(C.c_int)), r.ctypes.data_as(C.POINTER(C.c_double)), int(create)),
+                "savstress")
+
+    def getstress(self, filename: str):
+        """GETSTRESS -> READSTRESS (readstress.F90:97-124); returns (CDTPRO, CDATEWO, CDAWIFL, CDATEFL)."""
+        r = np.empty((len(self.LAW_FIELDS), self.nloc))
+        ij = self._ijorig()
+        dates = C.create_string_buffer(60)
+        L.check(self.lib.ecwam_b200_getstress(filename.encode(), dates, self.s.niblo, len(self.LAW_FIELDS), self.nloc,
+                                              ij.ctypes.data_as(C.POINTER(C.c_int)), r.ctypes.data_as(C.POINTER(C.c_double))), "getstress")
+        for i, n in enumerate(self.LAW_FIELDS):
+            self._set_own(n, r[i])
+        return tuple(dates.raw[15 * i: 15 * i + 14].decode() for i in range(4))
+
     # ---- the hot path
     def propag(self) -> int:
         return L.check(self.lib.ecwam_b200_propag(self.h), "propag")

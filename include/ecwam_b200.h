@@ -32,6 +32,7 @@ extern "C" {
 #define ECWAM_B200_ECUDA (-2)    /* CUDA runtime error                                  */
 #define ECWAM_B200_ENCCL (-3)    /* NCCL error                                          */
 #define ECWAM_B200_ESTATE (-4)   /* call out of order (e.g. fields not bound)           */
+#define ECWAM_B200_EIO (-5)      /* restart / grid-table file: open, size or record error */
 
 /* ---------------------------------------------------------------------------------------------------
  * Run parameters = the NALINE namelist values the hot path reads (src/ecwam/mpuserin.F90:180-260,
@@ -435,6 +436,47 @@ int ecwam_b200_host_grid_free(ecwam_b200_host_grid_t g);
 /* DEPTHPRPT/AKI (depthprpt.F90:60-81, aki.F90:71-91): dispersion fields for n points, arrays (n,NFRE). */
 int ecwam_b200_host_depthprpt(const ecwam_b200_tables* t, int nfre, long long n, const double* depth, double* wavnum,
                               double* cinv, double* cgroup, double* xk2cg, double* omosnh2kd, double* stokfac);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Restart files and the grid-table file in the reference's own on-disk formats (host only, no GPU):
+ * Fortran unformatted sequential records, [int32 n][n bytes][int32 n] little endian, gfortran sub-records
+ * above 2147483639 bytes; reals are REAL*8 (the double-precision build).
+ *   BLS  SAVSPEC/WRITEFL/READFL (savspec.F90:86-166, writefl.F90:86-120, readfl.F90:118-145):
+ *        NFRE*NANG records (frequency outside, direction inside; KDEL = MDEL = 1, yowcout.F90:70-71), each
+ *        FL(1:NIBLO) of one (K,M) in the ORIGINAL sea-point order (the file position IJ holds the model's
+ *        point IJ2NEWIJ(IJ)).  LRSTPARALW: one file per task, FILENAME.%p_%n, one record (IJSG:IJLG,NANG,NFRE).
+ *   LAW  SAVSTRESS/WRITESTRESS/READSTRESS (savstress.F90:80-152, writestress.F90:76-109): one record
+ *        CDTPRO,CDATEWO,CDAWIFL,CDATEFL (4 x CHARACTER*14), then NREAL records of NIBLO reals in the order
+ *        WSWAVE WDWAVE UFRIC TAUW TAUWDIR Z0M Z0B CHRNCK AIRD WSTAR CICOVER CITHICK USTRA VSTRA UCUR VCUR.
+ *   wam_grid_tables  OUTCOM/READPRE (outcom.F90:139-144, readpre.F90:262-345): NKIND,IMDLGRBID_G | NGX,NGY |
+ *        NLONRGG(NGY) | IPER,IRGG,AMOWEP,AMOSOP,AMOEAP,AMONOP,XDELLA,XDELLO | BATHY(NGX,NGY).
+ * Writers are rank-wise: every rank passes its own points (nown of them, ijorig = their 1-based ORIGINAL
+ * indices, NULL = 1..NIBLO) and writes them into their places of the shared file; the rank called with
+ * create = 1 sizes the file and writes the record markers and must return before the others start.
+ * fl is (nown, NANG, NFRE), rfield (nown, NREAL), point index fastest.                                  */
+int ecwam_b200_grstname(const char* cdated, const char* cdatef, int ifcst, const char* fileid, const char* cpad,
+                        char* filename, int cap);                                 /* grstname.F90:88-142 */
+int ecwam_b200_restart_par_name(const char* filename, int irank, int nproc, char* out, int cap);
+int ecwam_b200_savspec(const char* filename, long long niblo, int nang, int nfre, long long nown, const int* ijorig,
+                       const double* fl, int create);
+int ecwam_b200_getspec(const char* filename, long long niblo, int nang, int nfre, long long nown, const int* ijorig,
+                       double* fl);
+int ecwam_b200_savspec_par(const char* filename, long long nown, int nang, int nfre, const double* fl);
+int ecwam_b200_getspec_par(const char* filename, long long nown, int nang, int nfre, double* fl);
+int ecwam_b200_savstress(const char* filename, const char* cdtpro, const char* cdatewo, const char* cdawifl,
+                         const char* cdatefl, long long niblo, int nreal, long long nown, const int* ijorig,
+                         const double* rfield, int create);
+/* dates: 4 x 15 bytes, NUL-terminated CDTPRO, CDATEWO, CDAWIFL, CDATEFL (may be NULL) */
+int ecwam_b200_getstress(const char* filename, char* dates, long long niblo, int nreal, long long nown,
+                         const int* ijorig, double* rfield);
+/* amo = AMOWEP, AMOSOP, AMOEAP, AMONOP, XDELLA, XDELLO; bathy (NGX,NGY), land = -999 */
+int ecwam_b200_grid_tables_write(const char* filename, int imdlgrbid_g, int ngx, int ngy, const int* nlonrgg, int iper,
+                                 int irgg, const double* amo, const double* bathy);
+/* nlonrgg = bathy = NULL: dimensions only */
+int ecwam_b200_grid_tables_read(const char* filename, int* nkind, int* kmdlgrdid, int* ngx, int* ngy, int* nlonrgg,
+                                int nlon_cap, int* iper, int* irgg, double* amo, double* bathy, long long bathy_cap);
+/* test hook: the sub-record limit (default and maximum 2147483639) */
+int ecwam_b200_io_set_max_subrecord(long long nbytes);
 
 #ifdef __cplusplus
 }

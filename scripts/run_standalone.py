@@ -39,6 +39,9 @@ def main():
     ap.add_argument("--mask", default="continents", choices=["continents", "aqua"])
     ap.add_argument("--cycle", default="default", choices=["default", "cy49r1"],
                     help="cy49r1: LLGCBZ0 + LLNORMAGAM, WSPMIN = 0.3 (tests/etopo1_oper_an_fc_O48_cy49r1.yml)")
+    ap.add_argument("--restart-in", default="", help="directory with BLS/LAW restart files (reference format) to start from")
+    ap.add_argument("--restart-out", default="", help="directory to write the BLS/LAW restart files of the final state to")
+    ap.add_argument("--start", default="20220101000000", help="CDATEF, YYYYMMDDHHmmss")
     ap.add_argument("--check", action="store_true", help="run the CPU oracle alongside and compare the norms (test infrastructure)")
     args = ap.parse_args()
 
@@ -78,8 +81,36 @@ def main():
     fl = synth.jonswap_cold_start(f0["WSWAVE"], f0["WDWAVE"], cfg["nang"], 36, cfg["nfre_red"])
     w.set_fl1(fl)
 
+    def restart_names(directory, t_sec):       # GRSTNAME: <ID><CDATEF>_<forecast range> (grstname.F90:88-142)
+        import datetime
+        cdt = (datetime.datetime.strptime(args.start, "%Y%m%d%H%M%S") + datetime.timedelta(seconds=t_sec)).strftime("%Y%m%d%H%M%S")
+        out = []
+        for fid in (b"BLS", b"LAW"):
+            buf = C.create_string_buffer(400)
+            L.check(w.lib.ecwam_b200_grstname(cdt.encode(), args.start.encode(), 0, fid, directory.encode(), buf, 400), "grstname")
+            out.append(buf.value.decode())
+        return cdt, out[0], out[1]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+
+    t_start = 0
+    if args.restart_in:
+        found = sorted(n for n in os.listdir(args.restart_in) if n.startswith("BLS") and "." not in n)
+        if not found:
+            raise SystemExit("no BLS restart file in " + args.restart_in)
+        bls = os.path.join(args.restart_in, found[-1])
+        law = os.path.join(args.restart_in, "LAW" + found[-1][3:])
+        w.getspec(bls)
+        cdt = w.getstress(law)[0]
+        rng = found[-1].split("_")[1]
+        t_start = int(rng[:6]) * 86400 + int(rng[6:8]) * 3600 + int(rng[8:10]) * 60 + int(rng[10:12])
+        if rank == 0:
+            print("restart from %s (CDTPRO %s, +%d s)" % (bls, cdt, t_start))
+
     def ff_next(t_sec):          # what GETWND would deliver for the wind step starting at t_sec
-        f = synth.make_forcing(g, t_hours=t_sec / 3600.0)
+        f = synth.make_forcing(g, t_hours=(t_start + t_sec) / 3600.0)
         f.update(USTRA=np.zeros(g.niblo), VSTRA=np.zeros(g.niblo))
         return f
 
@@ -120,7 +151,7 @@ def main():
             w.outbs(itg, ice, sea)
             wn = w.outwnorm(True)
             if rank == 0:
-                print("  WAMNORM ON +%05.1f h" % (clk.cdtpro / 3600.0))
+                print("  WAMNORM ON +%05.1f h" % ((t_start + clk.cdtpro) / 3600.0))
                 for (name, _), row in zip(FIELDS, wn):
                     print("    %-5s avg %.14e  min %.14e  max %.14e  n %d" % (name, row[0], row[1], row[2], int(row[3])))
             if o is not None:
@@ -136,6 +167,17 @@ def main():
         if o is not None:
             print("max relative difference of the swh/mwp/pp1d/cdww/wind norms vs the CPU oracle: %.2e" % worst)
             assert worst < 1e-10
+    if args.restart_out:
+        os.makedirs(args.restart_out, exist_ok=True)
+        cdt, bls, law = restart_names(args.restart_out, t_start + clk.cdtpro)
+        if rank == 0:                        # rank 0 lays the files out, then every rank writes its own points in place
+            w.savspec(bls, create=True); w.savstress(law, cdt, create=True)
+        barrier()
+        if rank != 0:
+            w.savspec(bls, create=False); w.savstress(law, cdt, create=False)
+        barrier()
+        if rank == 0:
+            print("restart files: %s (%d bytes), %s" % (bls, os.path.getsize(bls), law))
     w.close()
     if world > 1:
         L.check(L.load().ecwam_b200_nccl_comm_destroy(C.c_void_p(comm)), "comm_destroy")

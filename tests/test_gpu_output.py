@@ -160,3 +160,33 @@ def test_wamintgr_without_source_terms(built):
     w.no_source(False)
     w.synchronize()
     assert (w.get_field("mij") == w.F).all() and (w.get_spec("xllws") == 0).all()
+
+
+@pytest.mark.parametrize("parallel", [False, True])
+def test_restart_round_trip_is_bit_exact(built, tmp_path, parallel):
+    """SAVSPEC + SAVSTRESS after two steps, GETSPEC + GETSTRESS into a fresh handle, two more steps: the same bits as the
+    uninterrupted run (the BLS / LAW files carry the whole prognostic state: spectrum, forcing, u*, tau_w, z0, Charnock)."""
+    from common import make_gpu
+    from oracle import restart_io as R
+    g, s, w = make_gpu("o48like")
+    for _ in range(2):
+        assert w.step() == 0
+    saved = w.get_spec("fl1")
+    bls, law = str(tmp_path / "BLS20220101000000_000000003000"), str(tmp_path / "LAW20220101000000_000000003000")
+    w.savspec(bls, parallel=parallel)
+    w.savstress(law, "20220101003000")
+    for _ in range(2):
+        assert w.step() == 0
+    w.synchronize()
+    _, _, v = make_gpu("o48like", setup=s, grid=g)
+    v.t["fl1"].zero_()
+    assert v.getstress(law)[0] == "20220101003000"
+    v.getspec(bls, parallel=parallel)
+    for _ in range(2):
+        assert v.step() == 0
+    v.synchronize()
+    np.testing.assert_array_equal(v.get_spec("fl1"), w.get_spec("fl1"))
+    for nm in ("ufric", "tauw", "z0m", "chrnck", "phiocd", "mij"):
+        np.testing.assert_array_equal(v.get_field(nm), w.get_field(nm), err_msg=nm)
+    if not parallel:   # the file is the reference's global layout: original point order, one record per (direction, frequency)
+        np.testing.assert_array_equal(R.readfl(bls, s.niblo, w.A, w.F)[:, :, w.own], saved)
