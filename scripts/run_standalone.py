@@ -103,7 +103,7 @@ def main():
         bls = os.path.join(args.restart_in, found[-1])
         law = os.path.join(args.restart_in, "LAW" + found[-1][3:])
         w.getspec(bls)
-        cdt = w.getstress(law)[0]
+        cdt, cdatewo = w.getstress(law)[:2]
         rng = found[-1].split("_")[1]
         t_start = int(rng[:6]) * 86400 + int(rng[6:8]) * 3600 + int(rng[8:10]) * 60 + int(rng[10:12])
         if rank == 0:
@@ -126,6 +126,10 @@ def main():
     ice = [M.OUTBLOCK_PARAMS[i][0] for i in itg]
     sea = [M.OUTBLOCK_PARAMS[i][1] for i in itg]
     clk = M.WamClock(idelpro=cfg["idelpro"], idelt=cfg["idelt"], idelwo=int(args.wind_every * 3600))
+    if args.restart_in:          # CDATEWO of the LAW file: when the next forcing fields are due (savstress.F90:157-159)
+        import datetime
+        fmt = "%Y%m%d%H%M%S"
+        clk.cdatewh = int((datetime.datetime.strptime(cdatewo, fmt) - datetime.datetime.strptime(cdt, fmt)).total_seconds())
     nadv = int(round(args.hours * 3600 / cfg["idelpro"]))
     out_every = int(round(args.output_every * 3600))
     if rank == 0:
@@ -170,11 +174,12 @@ def main():
     if args.restart_out:
         os.makedirs(args.restart_out, exist_ok=True)
         cdt, bls, law = restart_names(args.restart_out, t_start + clk.cdtpro)
+        cdatewo = restart_names(args.restart_out, t_start + clk.cdatewh)[0]
         if rank == 0:                        # rank 0 lays the files out, then every rank writes its own points in place
-            w.savspec(bls, create=True); w.savstress(law, cdt, create=True)
+            w.savspec(bls, create=True); w.savstress(law, cdt, cdatewo, create=True)
         barrier()
         if rank != 0:
-            w.savspec(bls, create=False); w.savstress(law, cdt, create=False)
+            w.savspec(bls, create=False); w.savstress(law, cdt, cdatewo, create=False)
         barrier()
         if rank == 0:
             print("restart files: %s (%d bytes), %s" % (bls, os.path.getsize(bls), law))
