@@ -74,6 +74,9 @@ struct ecwam_b200_handle_s {
   bool weights_dirty = true;
   // implsch
   DBuf<double> scr, satw, swellft, fldin, tbg, gctab;
+  bool have_gc = false, mss_ok = false;     // gravity-capillary tables supplied; DELKCC_GC too (MEANSQS)
+  int gc_n = 0;
+  double gc_sqrtgosurft = 0, gc_xk1 = 0, gc_xkn = 0, alphapmax = 0, fratio = 1.1;
   int dsh[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
   int halo_r = 0, halo_c = 0, nsdsnth = 0;
   DBuf<int> kw, isat;
@@ -489,13 +492,18 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
   }
   std::vector<double> sw(tables->swellft, tables->swellft + tables->iab);
   ok = ok && !h->swellft.upload(sw, st);
-  if (p.llgcbz0 || p.llnormagam) {   // [GC_NT][NWAV_GC]
+  h->have_gc = tables->nwav_gc >= 2 && tables->xk_gc && tables->omega_gc && tables->cm_gc && tables->c2osqrtvg_gc &&
+               tables->xkmsqrtvgoc2_gc && tables->om3gmkm_gc && tables->omxkm3_gc && tables->delkcc_gc_ns && tables->delkcc_omxkm3_gc;
+  if (h->have_gc) {   // [GC_NT][NWAV_GC]; the last row (DELKCC_GC) is only read by MEANSQS_GC
     const int ng = tables->nwav_gc;
     const double* src[GC_NT] = {tables->xk_gc, tables->omega_gc, tables->cm_gc, tables->c2osqrtvg_gc, tables->xkmsqrtvgoc2_gc,
-                                tables->om3gmkm_gc, tables->omxkm3_gc, tables->delkcc_gc_ns, tables->delkcc_omxkm3_gc};
-    std::vector<double> gc((size_t)GC_NT * ng);
-    for (int r = 0; r < GC_NT; ++r) for (int i = 0; i < ng; ++i) gc[(size_t)r * ng + i] = src[r][i];
+                                tables->om3gmkm_gc, tables->omxkm3_gc, tables->delkcc_gc_ns, tables->delkcc_omxkm3_gc, tables->delkcc_gc};
+    std::vector<double> gc((size_t)GC_NT * ng, 0.0);
+    for (int r = 0; r < GC_NT; ++r) if (src[r]) for (int i = 0; i < ng; ++i) gc[(size_t)r * ng + i] = src[r][i];
     ok = ok && !h->gctab.upload(gc, st);
+    h->mss_ok = tables->delkcc_gc != nullptr;
+    h->gc_n = ng; h->gc_sqrtgosurft = tables->sqrtgosurft; h->gc_xk1 = tables->xk_gc[0]; h->gc_xkn = tables->xk_gc[ng - 1];
+    h->alphapmax = tables->alphapmax; h->fratio = tables->fratio;
   }
   const long long npts = (long long)P * p.nchnk;
   ok = ok && !h->scr.alloc(implsch_scratch_doubles(npts)) && !h->fldin.alloc((size_t)npts * A * F) &&
@@ -777,7 +785,7 @@ int ecwam_b200_no_source(ecwam_b200_handle h, int llsource_off) {
 }
 
 int ecwam_b200_outparam_supported(int itg) {
-  static const int ok[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 12, 13, 14, 15, 16, 20, 21, 22, 23, 24, 25, 26, 27, 28, 32, 35, 36, 37, 38,
+  static const int ok[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 20, 21, 22, 23, 24, 25, 26, 27, 28, 32, 35, 36, 37, 38,
                            39, 40, 41, 52, 53, 54, 55, 56, 62, 63, 64, 65, 66, 67, 68, 69, 73, 74, 75, 76, 77};
   for (int v : ok) if (v == itg) return 1;
   return 0;
@@ -838,6 +846,10 @@ static int check_outsel(const ecwam_b200_outsel* sel) {
     if (!ecwam_b200_outparam_supported(sel->itg[i])) EW_FAIL(ECWAM_B200_EINVAL, "OUTBLOCK parameter %d is not built (see ecwam_b200.h)", sel->itg[i]);
   return 0;
 }
+static bool wants(const ecwam_b200_outsel* sel, int itg) {
+  for (int i = 0; i < sel->niprmout; ++i) if (sel->itg[i] == itg) return true;
+  return false;
+}
 
 int ecwam_b200_outbs(ecwam_b200_handle h, const ecwam_b200_outsel* sel, const int* iodp, double* bout) {
   if (!h || !bout) EW_FAIL(ECWAM_B200_EINVAL, "null argument");
@@ -858,6 +870,17 @@ int ecwam_b200_outbs(ecwam_b200_handle h, const ecwam_b200_outsel* sel, const in
   oc.XKAPPA = c.XKAPPA; oc.XNLEV = c.XNLEV; oc.ALPHAMIN = c.ALPHAMIN;
   oc.ALPHAMAX = 0.11;        // yowphys.F90:55
   oc.llgcbz0 = c.llgcbz0;
+  if (wants(sel, 9)) {   // MEANSQS (meansqs.F90:80-100) with XKMSS_CUTOFF = XK_GC(NWAV_GC) (userin.F90:1213-1215)
+    if (!h->mss_ok) EW_FAIL(ECWAM_B200_EINVAL, "OUTBLOCK parameter 9 (MEANSQS) needs the gravity-capillary tables incl. delkcc_gc");
+    oc.want_mss = 1; oc.NWAV_GC = h->gc_n; oc.SQRTGOSURFT = h->gc_sqrtgosurft; oc.XKM1_GC = 1.0 / h->gc_xk1;
+    oc.XLOGKRATIOM1_GC = 1.0 / std::log(1.2);
+    oc.XKMSS = h->gc_xkn;
+    oc.NE_MSS = std::min(std::max((int)std::lround(std::log(oc.XKMSS * oc.XKM1_GC) * oc.XLOGKRATIOM1_GC), 1), oc.NWAV_GC);   // meansqs_gc.F90:60
+    oc.FCUT_MSS = std::sqrt(c.G * oc.XKMSS) / c.ZPI;
+    const int nfre_mss = (int)(std::log(oc.FCUT_MSS / c.FR[0]) / std::log(h->fratio)) + 1;
+    oc.NFRE_EFF = std::min(c.F, nfre_mss);
+    oc.ALPHAPMAX = h->alphapmax; oc.ZPI4GM2_FR5N = c.ZPI4GM2 * c.FR5[c.F - 1];
+  }
   oc.ROWATER = 1000.0;       // yowpcons.F90
   oc.rnum = c.rnum; oc.flmin = c.flmin; oc.cithrsh = c.cithrsh; oc.zmiss = sel->zmiss;
   for (int m = 0; m < c.F; ++m) { oc.FR[m] = c.FR[m]; oc.DFIM[m] = c.DFIM[m]; oc.DFIMOFR[m] = c.DFIMOFR[m]; oc.DFIMFR[m] = c.DFIMFR[m]; oc.DFIM_SIM[m] = c.DFIM_SIM[m]; }
@@ -871,7 +894,7 @@ int ecwam_b200_outbs(ecwam_b200_handle h, const ecwam_b200_outsel* sel, const in
   OutDev d;
   d.P = h->par.nproma; d.A = c.A; d.F = c.F; d.nchnk = h->par.nchnk;
   d.npts = (long long)d.P * d.nchnk;
-  d.f = h->dev; d.iodp = iodp; d.bout = bout;
+  d.f = h->dev; d.iodp = iodp; d.bout = bout; d.gc = h->gctab.p;
   ScopedTimer t(h, "outblock");
   rc = launch_outblock(d, h->st);
   if (rc) return rc;

@@ -54,7 +54,7 @@ struct DevConst {
       SQRTGOSURFT, XKM1_GC, XLOGKRATIOM1_GC;
 };
 // rows of the gravity-capillary table ImplDev::gc [GC_NT][NWAV_GC] (YOWFRED *_GC, initgc.F90)
-enum { GC_XK = 0, GC_OMEGA, GC_CM, GC_C2OSQRTVG, GC_XKMSQRTVGOC2, GC_OM3GMKM, GC_OMXKM3, GC_DELKCC_NS, GC_DELKCC_OMXKM3, GC_NT };
+enum { GC_XK = 0, GC_OMEGA, GC_CM, GC_C2OSQRTVG, GC_XKMSQRTVGOC2, GC_OM3GMKM, GC_OMXKM3, GC_DELKCC_NS, GC_DELKCC_OMXKM3, GC_DELKCC, GC_NT };
 
 // tables too irregular / large for constant memory (per-lane indexed)
 struct DevTabPtr {

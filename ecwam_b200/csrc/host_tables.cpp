@@ -16,7 +16,7 @@ struct HostTables {
   std::vector<double> fr, dfim, dfimofr, dfimfr, zpifr, fr5, cofrm4, flmax, rhowg_dfim, dfim_sim, th, costh, sinth;
   std::vector<double> satweights, swellft, wtauhf, rnlcoef, af11;
   std::vector<int> indicessat, ikp, ikp1, ikm, ikm1, k1w, k2w, k11w, k21w, inlcoef;
-  std::vector<double> xk_gc, omega_gc, cm_gc, c2osqrtvg_gc, xkmsqrtvgoc2_gc, om3gmkm_gc, omxkm3_gc, delkcc_gc_ns, delkcc_omxkm3_gc;
+  std::vector<double> xk_gc, omega_gc, cm_gc, c2osqrtvg_gc, xkmsqrtvgoc2_gc, om3gmkm_gc, omxkm3_gc, delkcc_gc_ns, delkcc_omxkm3_gc, delkcc_gc;
   double delta_theta_rn = 0.75;
 };
 
@@ -114,6 +114,7 @@ void gravity_capillary_tables(HostTables& h) {
   delkcc[N - 1] = 0.5 * (h.xk_gc[N - 1] - h.xk_gc[N - 2]) / h.c2osqrtvg_gc[N - 1];
   h.delkcc_gc_ns[N - 1] = delkcc[N - 1];
   for (int i = 0; i < N; ++i) h.delkcc_omxkm3_gc[i] = delkcc[i] * h.omxkm3_gc[i];
+  h.delkcc_gc = delkcc;
 }
 
 // ---- Kelvin functions through the modified Bessel functions of complex argument
@@ -515,7 +516,7 @@ int ecwam_b200_host_tables_create(const ecwam_b200_params* params, int ifre1, do
   ecwam_b200_tables& t = h.t;
   t.xk_gc = h.xk_gc.data(); t.omega_gc = h.omega_gc.data(); t.cm_gc = h.cm_gc.data(); t.c2osqrtvg_gc = h.c2osqrtvg_gc.data();
   t.xkmsqrtvgoc2_gc = h.xkmsqrtvgoc2_gc.data(); t.om3gmkm_gc = h.om3gmkm_gc.data(); t.omxkm3_gc = h.omxkm3_gc.data();
-  t.delkcc_gc_ns = h.delkcc_gc_ns.data(); t.delkcc_omxkm3_gc = h.delkcc_omxkm3_gc.data();
+  t.delkcc_gc_ns = h.delkcc_gc_ns.data(); t.delkcc_omxkm3_gc = h.delkcc_omxkm3_gc.data(); t.delkcc_gc = h.delkcc_gc.data();
   t.fr = h.fr.data(); t.dfim = h.dfim.data(); t.dfimofr = h.dfimofr.data(); t.dfimfr = h.dfimfr.data();
   t.zpifr = h.zpifr.data(); t.fr5 = h.fr5.data(); t.cofrm4 = h.cofrm4.data(); t.flmax = h.flmax.data();
   t.rhowg_dfim = h.rhowg_dfim.data(); t.dfim_sim = h.dfim_sim.data(); t.th = h.th.data(); t.costh = h.costh.data();

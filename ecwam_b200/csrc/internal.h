@@ -104,6 +104,9 @@ struct OutConst {   // constant memory of outparam.cu
   // (T > 10 s), bands 1..6 = the period intervals of mpcrtbl.F90:373-399
   double SEBT[7][EW_MAXF];
   int llgcbz0;             // OUTBETA: no wind-speed cap of the Charnock parameter (outbeta.F90:113-117)
+  // MEANSQS (parameter 9): HALPHAP + MEANSQS_GC + MEANSQS_LF (meansqs.F90:80-100)
+  int want_mss, NWAV_GC, NE_MSS, NFRE_EFF;
+  double ALPHAPMAX, ZPI4GM2_FR5N, SQRTGOSURFT, XKM1_GC, XLOGKRATIOM1_GC, XKMSS, FCUT_MSS;
 };
 struct OutDev {
   int P, A, F, nchnk;
@@ -111,6 +114,7 @@ struct OutDev {
   ecwam_b200_fields f;
   const int* iodp;         // (P,C) or null (= 1 everywhere)
   double* bout;            // (P, NIPRMOUT, C)
+  const double* gc;        // [GC_NT][NWAV_GC] gravity-capillary tables (MEANSQS_GC), null when not supplied
 };
 int upload_out_const(const OutConst& h, cudaStream_t st);
 void launch_newwind(long long npts, const ecwam_b200_fields& f, const ecwam_b200_forcing_next& nx, double acd, double bcd, double epsmin,

@@ -135,14 +135,19 @@ __global__ void __launch_bounds__(OB_NTH, OB_MINB) k_outblock(OutDev d) {
   const double zthrs = (1.0 - 0.9 * omin(cic, 0.99)) * c_oc.flmin;
   const double wsq = sqrt(omax(wsw, 1.0));
 
-  // ---------------- pass 1: first-guess swell mask -> FSWELL, FSEA -> R (sepwisw.F90:138-196); maximum for FCROP
-  double fmax = 0.0, Rf;
+  // ---------------- pass 1: first-guess swell mask -> FSWELL, FSEA -> R (sepwisw.F90:138-196); maximum for FCROP;
+  //                  with parameter 9 also the moments of the spectrum in the wind direction (HALPHAP, MEANSQS_LF)
+  double fmax = 0.0, Rf, xmss9 = 0.0;
   {
     double es = 0, fs = 0, ew = 0, fw = 0, t2s = 0, t2w = 0;
+    double h_xm = 0, h_em = 0, h_fm = 0, h_t2 = 0, h_f1d = 0, lf = 0;    // HALPHAP's XMSS / EM / FM / F1D, MEANSQS_LF of FL1
+    const bool mss = c_oc.want_mss != 0;
     for (int m = 0; m < F; ++m) {
       const double xinv = ufric * __ldg(cinv + (size_t)m * P);
       const double zr = icen ? exp(-10.0 * (c_oc.FR[m] * c_oc.FR[m]) / wsq) : 1.0;
       t2s = 0.0; t2w = 0.0;
+      double h_s = 0.0, r_s = 0.0;
+      h_t2 = 0.0;
       OB_UNROLL
       for (int k = 0; k < A; ++k) {
         const size_t o = (size_t)m * rs + (size_t)k * P;
@@ -153,9 +158,45 @@ __global__ void __launch_bounds__(OB_NTH, OB_MINB) k_outblock(OutDev d) {
         t2w += omax(omax(f - f1, 0.0), EPSMIN);
         const double f2 = (icen && f <= zthrs) ? omax(zr * f, zthrs * (zr * zr)) : f;
         fmax = omax(fmax, f2);
+        if (mss) {
+          const double flwd = signbit(c) ? f * 0.0 : f;      // FL1 * (0.5 + 0.5*SIGN(1,COSWDIF)) (halphap.F90:72-84)
+          h_s += flwd; h_t2 += omax(flwd, EPSMIN); r_s += f;
+          if (m == F - 1) h_f1d += flwd * DELTH;
+        }
       }
       es += t2s * c_oc.DFIM[m]; fs += c_oc.DFIMOFR[m] * t2s;
       ew += t2w * c_oc.DFIM[m]; fw += c_oc.DFIMOFR[m] * t2w;
+      if (mss) {
+        const double wn = __ldg(d.f.wavnum + b3 + (size_t)m * P);
+        const double t1 = c_oc.DFIM[m] * (wn * wn);           // meansqs_lf.F90:87-100
+        h_xm += t1 * h_s;
+        if (m < c_oc.NFRE_EFF) lf += t1 * r_s;
+        h_em += h_t2 * c_oc.DFIM[m]; h_fm += c_oc.DFIMOFR[m] * h_t2;
+      }
+    }
+    if (mss) {
+      // HALPHAP (halphap.F90:92-115)
+      const double em = h_em + (c_oc.WETAIL * c_oc.FR[F - 1] * DELTH) * h_t2;
+      const double fm = omax(em / (h_fm + (c_oc.FRTAIL * DELTH) * h_t2), c_oc.FR[0]);
+      double alphap = 0.0;
+      bool tail = true;
+      if (em > 0.0 && fm < c_oc.FR[F - 3]) { alphap = h_xm / (log(c_oc.FR[F - 1]) - log(fm)); tail = alphap > c_oc.ALPHAPMAX; }
+      if (tail) alphap = c_oc.ZPI4GM2_FR5N * h_f1d;
+      const double halp = 0.5 * omin(alphap, c_oc.ALPHAPMAX);
+      // MEANSQS_GC (meansqs_gc.F90:60-82) with OMEGAGC / NS_GC
+      const int N = c_oc.NWAV_GC;
+      const double xks0 = c_oc.SQRTGOSURFT / (1.48 + 2.05 * ufric);
+      int ns = min((int)(log(omax(xks0 * c_oc.XKM1_GC, 1.0)) * c_oc.XLOGKRATIOM1_GC) + 1, N - 1);
+      const double xks = __ldg(d.gc + GC_XK * N + ns - 1), oms = __ldg(d.gc + GC_OMEGA * N + ns - 1);
+      const double frgc = oms / c_oc.ZPI;
+      double cg;
+      if (xks > c_oc.XKMSS) { ns = c_oc.NE_MSS; cg = 0.0; }
+      else cg = __ldg(d.gc + GC_DELKCC_NS * N + ns - 1) * (1.0 / __ldg(d.gc + GC_XK * N + ns - 1));
+      for (int i = ns + 1; i <= c_oc.NE_MSS; ++i) cg = cg + __ldg(d.gc + GC_DELKCC * N + i - 1) * (1.0 / __ldg(d.gc + GC_XK * N + i - 1));
+      cg = cg * (__ldg(d.gc + GC_C2OSQRTVG * N + ns - 1) * halp);
+      // meansqs.F90:90-99
+      const double tl = 2.0 * halp * omax(log(omin(frgc, c_oc.FCUT_MSS)) - log(c_oc.FR[c_oc.NFRE_EFF - 1]), 0.0);
+      xmss9 = (cg + lf) + tl;
     }
     const double d25 = c_oc.WETAIL * c_oc.FR[F - 1] * DELTH, d2 = c_oc.FRTAIL * DELTH;
     const double fswell = omax((es + d25 * t2s) / (fs + d2 * t2s), c_oc.FR[0]);
@@ -270,6 +311,7 @@ __global__ void __launch_bounds__(OB_NTH, OB_MINB) k_outblock(OutDev d) {
         v = omin(q * q, 0.01);
       } break;
       case 8: v = d.f.tauw[p] / omax(ufric * ufric, c_oc.EPSUS); break;
+      case 9: v = xmss9; break;
       case 10: v = wsw; break;
       case 11: v = 4.0 * sqrt(omax(ESE, 0.0)); break;
       case 12: v = 4.0 * sqrt(omax(ESW, 0.0)); break;

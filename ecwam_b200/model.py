@@ -23,7 +23,7 @@ FI = ("mij",)
 
 # OUTBLOCK parameters built by ecwam_b200_outbs -> (sea-ice mask, shallow-to-missing) flags of MPCRTBL's DEFINE_PARAMETER
 # calls (mpcrtbl.F90:93-431, numbering with NTRAIN = 3)
-OUTBLOCK_PARAMS = {1: (1, 1), 2: (1, 1), 3: (1, 1), 4: (0, 1), 5: (0, 0), 6: (1, 1), 7: (0, 0), 8: (1, 1), 10: (0, 0), 11: (1, 1),
+OUTBLOCK_PARAMS = {1: (1, 1), 2: (1, 1), 3: (1, 1), 4: (0, 1), 5: (0, 0), 6: (1, 1), 7: (0, 0), 8: (1, 1), 9: (1, 1), 10: (0, 0), 11: (1, 1),
                    12: (1, 1), 13: (1, 1), 14: (1, 1), 15: (1, 1), 16: (1, 1), 20: (1, 1), 21: (1, 1), 22: (1, 1), 23: (1, 1),
                    24: (1, 1), 25: (1, 1), 26: (1, 1), 27: (1, 1), 28: (1, 1), 32: (0, 1), 35: (1, 1), 36: (1, 1), 37: (0, 1),
                    38: (0, 1), 39: (0, 1), 40: (0, 1), 41: (0, 1), 52: (1, 1), 53: (0, 0), 54: (0, 0), 55: (0, 1), 56: (0, 1), 62: (1, 1),

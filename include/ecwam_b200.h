@@ -214,6 +214,7 @@ typedef struct ecwam_b200_tables {
   const double* omxkm3_gc;        /* (NWAV_GC) */
   const double* delkcc_gc_ns;     /* (NWAV_GC) */
   const double* delkcc_omxkm3_gc; /* (NWAV_GC) */
+  const double* delkcc_gc;        /* (NWAV_GC) read by MEANSQS_GC (OUTBLOCK parameter 9) */
 } ecwam_b200_tables;
 
 /* ---------------------------------------------------------------------------------------------------
@@ -379,8 +380,9 @@ typedef struct ecwam_b200_outsel {
   int llsource;              /* YOWSTAT LLSOURCE                                                              */
   double zmiss;              /* YOWPCONS ZMISS                                                                */
 } ecwam_b200_outsel;
-/* 1 if OUTBLOCK parameter `itg` is built: 1-8, 10-16, 20-28, 32, 35-41, 52-56, 62-69, 73-77 (numbering of
- * mpcrtbl.F90 with NTRAIN = 3).  Not built: MEANSQS (9), altimeter (17-19), KURTOSIS family (29-31, 33, 34, 57,
+/* 1 if OUTBLOCK parameter `itg` is built: 1-16, 20-28, 32, 35-41, 52-56, 62-69, 73-77 (numbering of
+ * mpcrtbl.F90 with NTRAIN = 3; 9 = MEANSQS with XKMSS_CUTOFF = XK_GC(NWAV_GC), userin.F90:1213-1215, needs the *_gc
+ * tables).  Not built: altimeter (17-19), KURTOSIS family (29-31, 33, 34, 57,
  * 70-72), swell partitions (42-50, LLPARTITION), CIMSSTRN (51), NEMO fields (58-61), W_MAXH (78-81), 82+.     */
 int ecwam_b200_outparam_supported(int itg);
 /* OUTBS (src/ecwam/outbs.F90:97-122): OUTBLOCK over all chunks (src/ecwam/outblock.F90:150-610, IREFRA = 0,

@@ -318,8 +318,73 @@ void newwind(Model& m, int ir, const Fields& nx) {
   }
 }
 
+// meansqs.F90:80-100 with halphap.F90:68-115, meansqs_gc.F90:60-82 (OMEGAGC / NS_GC) and meansqs_lf.F90:80-100
+void meansqs(const Config& c, const Tables& t, double XKMSS, int KIJL, int NANG, int NFRE, const S3& F, const double* WAVNUM /*(KIJL,NFRE)*/,
+             const double* USTAR, const V& COSWDIF /*(K-1)*KIJL+IJ*/, double* XMSS /*1-based*/) {
+  auto WN = [&](int IJ, int M) { return WAVNUM[(IJ - 1) + (size_t)KIJL * (M - 1)]; };
+  // HALPHAP
+  V HALP(KIJL + 1), XM(KIJL + 1, 0.0), EM(KIJL + 1), FM(KIJL + 1);
+  W3 FLWD(KIJL, NANG, NFRE);
+  for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = 1; IJ <= KIJL; ++IJ) {
+    const double WD = 0.5 + 0.5 * std::copysign(1.0, COSWDIF[(size_t)(K - 1) * KIJL + IJ]);
+    FLWD(IJ, K, M) = F(IJ, K, M) * WD;
+  }
+  auto lf = [&](int NFRE_EFF, const S3& G, V& OUT) {       // MEANSQS_LF
+    const int KFRE = std::min(NFRE_EFF, NFRE);
+    for (int IJ = 1; IJ <= KIJL; ++IJ) OUT[IJ] = 0.0;
+    for (int M = 1; M <= KFRE; ++M)
+      for (int IJ = 1; IJ <= KIJL; ++IJ) {
+        const double TEMP1 = t.DFIM(M) * (WN(IJ, M) * WN(IJ, M));
+        double TEMP2 = 0.0;
+        for (int K = 1; K <= NANG; ++K) TEMP2 = TEMP2 + G(IJ, K, M);
+        OUT[IJ] = OUT[IJ] + TEMP1 * TEMP2;
+      }
+  };
+  lf(NFRE, FLWD.view(), XM);
+  femean_out(t, KIJL, NANG, NFRE, FLWD.view(), EM, FM);
+  const double ZLNFRNFRE = std::log(t.FR(NFRE));
+  for (int IJ = 1; IJ <= KIJL; ++IJ) {
+    double ALPHAP = 0.0;
+    bool tail = true;
+    if (EM[IJ] > 0.0 && FM[IJ] < t.FR(NFRE - 2)) { ALPHAP = XM[IJ] / (ZLNFRNFRE - std::log(FM[IJ])); tail = ALPHAP > t.ALPHAPMAX; }
+    if (tail) {
+      double F1D = 0.0;
+      for (int K = 1; K <= NANG; ++K) F1D = F1D + FLWD(IJ, K, NFRE) * t.DELTH;
+      ALPHAP = t.ZPI4GM2 * t.FR5(NFRE) * F1D;
+    }
+    HALP[IJ] = 0.5 * std::min(ALPHAP, t.ALPHAPMAX);
+  }
+  // MEANSQS_GC
+  const double XLOGKRATIOM1_GC = 1.0 / std::log(1.2);
+  const int NE = std::min(std::max((int)nint(std::log(XKMSS * t.XKM_GC(1)) * XLOGKRATIOM1_GC), 1), t.NWAV_GC);
+  V FRGC(KIJL + 1);
+  for (int IJ = 1; IJ <= KIJL; ++IJ) {
+    const double XKS0 = t.SQRTGOSURFT / (1.48 + 2.05 * USTAR[IJ - 1]);                                  // ns_gc.F90:44-48
+    int NS = std::min((int)(std::log(std::max(XKS0 * t.XKM_GC(1), 1.0)) * XLOGKRATIOM1_GC) + 1, t.NWAV_GC - 1);
+    const double XKS = t.XK_GC(NS), OMS = t.OMEGA_GC(NS);                                                // omegagc.F90:51-55
+    FRGC[IJ] = OMS / t.ZPI;
+    double XMSSCG;
+    if (XKS > XKMSS) { NS = NE; XMSSCG = 0.0; }
+    else XMSSCG = t.DELKCC_GC_NS(NS) * t.XKM_GC(NS);
+    for (int I = NS + 1; I <= NE; ++I) XMSSCG = XMSSCG + t.DELKCC_GC(I) * t.XKM_GC(I);
+    const double COEF = t.C2OSQRTVG_GC(NS) * HALP[IJ];
+    XMSS[IJ] = XMSSCG * COEF;
+  }
+  const double FCUT = std::sqrt(t.G * XKMSS) / t.ZPI;
+  const int NFRE_MSS = (int)(std::log(FCUT / t.FR(1)) / std::log(t.FRATIO)) + 1;
+  const int NFRE_EFF = std::min(NFRE, NFRE_MSS);
+  V XMSSLF(KIJL + 1);
+  lf(NFRE_EFF, F, XMSSLF);
+  const double XLOGFS = std::log(t.FR(NFRE_EFF));
+  for (int IJ = 1; IJ <= KIJL; ++IJ) {
+    XMSS[IJ] = XMSS[IJ] + XMSSLF[IJ];
+    const double XMSS_TAIL = 2.0 * HALP[IJ] * std::max(std::log(std::min(FRGC[IJ], FCUT)) - XLOGFS, 0.0);
+    XMSS[IJ] = XMSS[IJ] + XMSS_TAIL;
+  }
+}
+
 bool outparam_supported(int itg) {
-  static const int ok[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 12, 13, 14, 15, 16, 20, 21, 22, 23, 24, 25, 26, 27, 28, 32, 35, 36, 37, 38,
+  static const int ok[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 20, 21, 22, 23, 24, 25, 26, 27, 28, 32, 35, 36, 37, 38,
                            39, 40, 41, 52, 53, 54, 55, 56, 62, 63, 64, 65, 66, 67, 68, 69, 73, 74, 75, 76, 77};
   for (int v : ok) if (v == itg) return true;
   return false;
@@ -380,6 +445,7 @@ void outblock(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK, 
     }
   }
   if ((b = col(8))) { const double* TAUW = p1(f.TAUW); for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = TAUW[IJ - 1] / std::max(UFRIC[IJ - 1] * UFRIC[IJ - 1], t.EPSUS); }
+  if ((b = col(9))) meansqs(c, t, t.XK_GC(t.NWAV_GC), KIJL, NANG, NFRE, FL1, &f.WAVNUM(1, 1, ICHNK), UFRIC, COSWDIF, b);   // outblock.F90:285-287, userin.F90:1213-1215
   if ((b = col(10))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = WSWAVE[IJ - 1];
   if ((b = col(11))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = 4.0 * std::sqrt(std::max(so.ESEA[IJ], 0.0));
   if ((b = col(12))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = 4.0 * std::sqrt(std::max(so.ESWELL[IJ], 0.0));

@@ -86,7 +86,7 @@ def test_newwind_then_steps(built):
 
 def test_unsupported_parameter_is_rejected(built):
     g, o, f, s, w = both("o48like", steps=1)
-    for bad in (9, 29, 42, 51, 70, 78):
+    for bad in (17, 29, 42, 51, 70, 78):
         assert w.lib.ecwam_b200_outparam_supported(bad) == 0
         with pytest.raises(L.EcwamError):
             w.outbs([1, bad], [1, 1], [1, 1])

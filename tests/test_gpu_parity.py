@@ -173,9 +173,9 @@ def test_against_golden(built, name):
     for nm in OUT_FIELDS:
         assert relerr(w.get_field(nm)[inv], z[nm]) <= RTOL_FIELD, nm
     # OUTBS columns and the WAMNORM lines of the fixture (tests/golden/make_golden.py)
-    from common import OUT_ICE, OUT_SEA, compare_bout
+    from common import OUT_PARAMS, compare_bout
     itg = [int(i) for i in z["bout_itg"]]
-    b = w.outbs(itg, OUT_ICE, OUT_SEA)[:, inv]
+    b = w.outbs(itg, [OUT_PARAMS[i][0] for i in itg], [OUT_PARAMS[i][1] for i in itg])[:, inv]
     compare_bout(b, z["bout"], itgs=itg)
     wn = w.outwnorm(True)
     np.testing.assert_array_equal(wn[:, 3], z["wnorm"][:, 3])

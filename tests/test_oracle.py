@@ -30,7 +30,8 @@ def test_oracle_reproduces_golden(built, name):
     for nm in OUT_FIELDS:
         np.testing.assert_allclose(o.get_field(nm), z[nm], rtol=1e-11, atol=1e-14, err_msg=nm)
     itg = [int(i) for i in z["bout_itg"]]
-    b = o.outbs(itg, OUT_ICE, OUT_SEA)
+    from common import OUT_PARAMS
+    b = o.outbs(itg, [OUT_PARAMS[i][0] for i in itg], [OUT_PARAMS[i][1] for i in itg])
     assert np.array_equal(b == ZMISS, z["bout"] == ZMISS)
     np.testing.assert_allclose(b, z["bout"], rtol=1e-9, atol=1e-9)           # directions / spreads amplify rounding
     np.testing.assert_allclose(o.outwnorm(True)[:, 3], z["wnorm"][:, 3])

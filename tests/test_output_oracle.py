@@ -85,3 +85,29 @@ def test_masks_and_newwind(built):
     assert ice.any() and not ice.all()
     for i, itg in enumerate(OUT_ITG):
         assert ((b[i] == ZMISS) == (ice & bool(OUT_ICE[i]))).all(), itg      # outsetwmask.F90:62-78 (IODP = 1 everywhere)
+
+
+def test_mean_square_slope_parts(built):
+    """Parameter 9, MEANSQS (meansqs.F90:80-100): resolved part (MEANSQS_LF, restated in numpy) + Phillips tail up to the
+    gravity-capillary transition + MEANSQS_GC.  The total exceeds the resolved part, the excess is at most ALPHAPMAX times the
+    logarithmic width of the unresolved range (2 HALP ln(f_gc/f_N) + the k^-4 gravity-capillary integral), and the slope grows
+    with the wind speed."""
+    from oracle import oracle as O
+    g, o, f, fl = make_oracle("o48like")
+    for _ in range(3):
+        assert o.step() == 0
+    b = o.outbs([9, 1, 10], [0, 0, 0], [0, 0, 0])
+    mss = b[0]
+    F = o.get_fl1()                                   # [m, k, ij]
+    wn = o.get_field3("WAVNUM")                       # [m, ij]
+    dfim = o.table("DFIM")
+    lf = np.einsum("m,mi,mi->i", dfim, wn ** 2, F.sum(axis=1))
+    assert (mss >= lf * (1 - 1e-12)).all()
+    n = int(o.table("NWAV_GC")[0])
+    xk = o.table("XK_GC")
+    width = np.log(np.sqrt(9.806 * xk[-1] + 7.17e-5 * xk[-1] ** 3) / (2 * np.pi) / o.table("FR")[-1])
+    assert ((mss - lf) <= 0.031 * (width + 2.0)).all() and n == xk.size
+    sea = (b[1] > 0.2) & (f["CICOVER"] < 0.01)
+    r = np.corrcoef(mss[sea], b[2][sea])[0, 1]
+    assert r > 0.6, r
+    assert 1e-4 < np.median(mss[sea]) < 0.08
