@@ -80,3 +80,69 @@ def test_halo_exchange_plan_over_gloo(built, world):
         p.join(timeout=60)
     assert sorted(r for r, _ in res) == list(range(world))
     assert all(ok for _, ok in res), res
+
+
+def _restart_worker(rank, world, port, q, tmpdir):
+    """Every rank writes its own points of the shared BLS / LAW files at the same time (rank 0 lays the files out first,
+    then a barrier, as scripts/run_standalone.py does), reads its points back, and rank 0 compares the files with the oracle's."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ctypes as C
+    import torch.distributed as dist
+    from ecwam_b200 import lib as L, synth, model as M
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lib = L.load()
+        g = synth.make_grid(20, "continents")
+        s = M.WamSetup(g, nproc=world, nang=12, nfre_red=25)
+        n, A, F, NREAL = s.niblo, 12, 36, 16
+        rng = np.random.default_rng(11)                     # same numbers on every rank
+        fl_new, r_new = rng.random((F, A, n)), rng.normal(size=(NREAL, n))
+        a, b = int(s.nstart[rank]), int(s.nend[rank])
+        ij = np.ascontiguousarray(s.new2ij[a: b + 1], dtype=np.int32)
+        mine, rmine = np.ascontiguousarray(fl_new[:, :, a - 1: b]), np.ascontiguousarray(r_new[:, a - 1: b])
+        bls, law = os.path.join(tmpdir, "BLS").encode(), os.path.join(tmpdir, "LAW").encode()
+        dates = [b"20220101060000"] * 4
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+
+        def write(create):
+            L.check(lib.ecwam_b200_savspec(bls, n, A, F, ij.size, ij.ctypes.data_as(ip), mine.ctypes.data_as(dp), create), "savspec")
+            L.check(lib.ecwam_b200_savstress(law, *dates, n, NREAL, ij.size, ij.ctypes.data_as(ip), rmine.ctypes.data_as(dp), create), "savstress")
+        if rank == 0:
+            write(1)
+        dist.barrier()
+        if rank != 0:
+            write(0)
+        dist.barrier()
+        got, rgot = np.empty_like(mine), np.empty_like(rmine)
+        L.check(lib.ecwam_b200_getspec(bls, n, A, F, ij.size, ij.ctypes.data_as(ip), got.ctypes.data_as(dp)), "getspec")
+        L.check(lib.ecwam_b200_getstress(law, None, n, NREAL, ij.size, ij.ctypes.data_as(ip), rgot.ctypes.data_as(dp)), "getstress")
+        ok = np.array_equal(got, mine) and np.array_equal(rgot, rmine)
+        if rank == 0:
+            from oracle import restart_io as R
+            ij2new = np.asarray(s.ij2new[1:], dtype=np.int64)
+            R.writefl(os.path.join(tmpdir, "BLS_ref"), fl_new, ij2new)
+            R.writestress(os.path.join(tmpdir, "LAW_ref"), [d.decode() for d in dates], r_new, ij2new)
+            for nm in ("BLS", "LAW"):
+                ok = ok and open(os.path.join(tmpdir, nm), "rb").read() == open(os.path.join(tmpdir, nm + "_ref"), "rb").read()
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_concurrent_restart_writes_over_gloo(built, tmp_path, world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_restart_worker, args=(r, world, port, q, str(tmp_path))) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r for r, _ in res) == list(range(world))
+    assert all(ok for _, ok in res), res
