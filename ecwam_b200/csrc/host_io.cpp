@@ -17,6 +17,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cerrno>
 #include <cstdint>
 #include <cstdio>
@@ -93,25 +94,39 @@ long long read_record(int fd, long long off, void* data, long long n) {
   return got == n ? off : -2;
 }
 
-// runs of consecutive original indices in ijorig (1-based); NULL = identity
-struct Run { long long src, dst, len; };   // src: first local point, dst: first original index (0-based)
-std::vector<Run> runs_of(long long nown, const int* ijorig) {
-  std::vector<Run> r;
-  if (!ijorig) { r.push_back({0, 0, nown}); return r; }
+// The points of a rank sorted by original index fall into a few runs of consecutive file positions (an MPDECOMP rank is one
+// run per latitude row), although the rank's own order walks through them differently: `perm` lists the local points in
+// file order, a run is a stretch of it that is contiguous in the file.
+struct Run { long long src, dst, len; };   // src: first position in perm, dst: first original index (0-based)
+struct Plan {
+  std::vector<long long> perm;             // empty = identity
+  std::vector<Run> runs;
+};
+Plan plan_of(long long nown, const int* ijorig) {
+  Plan pl;
+  if (!ijorig) { pl.runs.push_back({0, 0, nown}); return pl; }
+  bool sorted = true;
+  for (long long i = 1; i < nown && sorted; ++i) sorted = ijorig[i] > ijorig[i - 1];
+  if (!sorted) {
+    pl.perm.resize((size_t)nown);
+    for (long long i = 0; i < nown; ++i) pl.perm[(size_t)i] = i;
+    std::sort(pl.perm.begin(), pl.perm.end(), [&](long long a, long long b) { return ijorig[a] < ijorig[b]; });
+  }
+  auto at = [&](long long j) { return (long long)ijorig[pl.perm.empty() ? j : pl.perm[(size_t)j]]; };
   long long i = 0;
   while (i < nown) {
     long long j = i + 1;
-    while (j < nown && ijorig[j] == ijorig[j - 1] + 1) ++j;
-    r.push_back({i, (long long)ijorig[i] - 1, j - i});
+    while (j < nown && at(j) == at(j - 1) + 1) ++j;
+    pl.runs.push_back({i, at(i) - 1, j - i});
     i = j;
   }
-  return r;
+  return pl;
 }
 int check_points(long long niblo, long long nown, const int* ijorig) {
   if (niblo < 1 || nown < 0 || nown > niblo) return 1;
   if (!ijorig) return nown == niblo ? 0 : 1;
   for (long long i = 0; i < nown; ++i) if (ijorig[i] < 1 || ijorig[i] > niblo) return 1;
-  return 0;
+  return 0;   // (a repeated index would only make the last writer win; MPDECOMP's maps are permutations)
 }
 // `nrec` records of niblo doubles starting at byte `base`: size the file and write every marker
 int lay_out_records(int fd, long long base, long long nrec, long long niblo) {
@@ -124,19 +139,24 @@ int lay_out_records(int fd, long long base, long long nrec, long long niblo) {
   return 0;
 }
 // scatter / gather the points of this rank into / out of record r (data of point i at data[i + nown*r])
-int rw_points(int fd, bool wr, long long base, long long nrec, long long niblo, long long nown, const std::vector<Run>& runs, double* data) {
+int rw_points(int fd, bool wr, long long base, long long nrec, long long niblo, long long nown, const Plan& pl, double* data) {
   const long long span = record_span(niblo * 8);
+  std::vector<double> tmp(pl.perm.empty() ? 0 : (size_t)nown);
   for (long long r = 0; r < nrec; ++r) {
     const long long rb = base + r * span + 4;
+    double* row = data + nown * r;
     if (!wr) {   // the record markers must be what a record of NIBLO reals carries
       int32_t m[1];
       if (pread_all(fd, m, 4, rb - 4) || m[0] != (int32_t)(niblo * 8)) return -2;
+    } else if (!pl.perm.empty()) {
+      for (long long j = 0; j < nown; ++j) tmp[(size_t)j] = row[pl.perm[(size_t)j]];
     }
-    for (const Run& q : runs) {
-      double* p = data + q.src + nown * r;
-      const int rc = wr ? pwrite_all(fd, p, (size_t)q.len * 8, rb + q.dst * 8) : pread_all(fd, p, (size_t)q.len * 8, rb + q.dst * 8);
+    double* buf = pl.perm.empty() ? row : tmp.data();
+    for (const Run& q : pl.runs) {
+      const int rc = wr ? pwrite_all(fd, buf + q.src, (size_t)q.len * 8, rb + q.dst * 8) : pread_all(fd, buf + q.src, (size_t)q.len * 8, rb + q.dst * 8);
       if (rc) return rc;
     }
+    if (!wr && !pl.perm.empty()) for (long long j = 0; j < nown; ++j) row[pl.perm[(size_t)j]] = tmp[(size_t)j];
   }
   return 0;
 }
@@ -215,7 +235,7 @@ int ecwam_b200_savspec(const char* filename, long long niblo, int nang, int nfre
     struct stat st;
     if (fstat(f.fd, &st) || st.st_size != nrec * record_span(niblo * 8)) IO_FAIL("savspec: %s was not laid out for NIBLO=%lld, %dx%d", filename, niblo, nang, nfre);
   }
-  if (rw_points(f.fd, true, 0, nrec, niblo, nown, runs_of(nown, ijorig), const_cast<double*>(fl))) IO_FAIL("savspec: write to %s failed: %s", filename, strerror(errno));
+  if (rw_points(f.fd, true, 0, nrec, niblo, nown, plan_of(nown, ijorig), const_cast<double*>(fl))) IO_FAIL("savspec: write to %s failed: %s", filename, strerror(errno));
   return 0;
 }
 
@@ -231,7 +251,7 @@ int ecwam_b200_getspec(const char* filename, long long niblo, int nang, int nfre
   struct stat st;
   if (fstat(f.fd, &st) || st.st_size != nrec * record_span(niblo * 8))
     IO_FAIL("getspec: %s does not hold %lld records of %lld reals (size %lld)", filename, nrec, niblo, (long long)st.st_size);
-  if (rw_points(f.fd, false, 0, nrec, niblo, nown, runs_of(nown, ijorig), fl)) IO_FAIL("getspec: %s: record markers do not match NIBLO=%lld", filename, niblo);
+  if (rw_points(f.fd, false, 0, nrec, niblo, nown, plan_of(nown, ijorig), fl)) IO_FAIL("getspec: %s: record markers do not match NIBLO=%lld", filename, niblo);
   return 0;
 }
 
@@ -269,7 +289,7 @@ int ecwam_b200_savstress(const char* filename, const char* cdtpro, const char* c
     const int rc = lay_out_records(f.fd, base, nreal, niblo);
     if (rc) IO_FAIL("savstress: cannot lay out %s", filename);
   }
-  if (rw_points(f.fd, true, base, nreal, niblo, nown, runs_of(nown, ijorig), const_cast<double*>(rfield))) IO_FAIL("savstress: write to %s failed: %s", filename, strerror(errno));
+  if (rw_points(f.fd, true, base, nreal, niblo, nown, plan_of(nown, ijorig), const_cast<double*>(rfield))) IO_FAIL("savstress: write to %s failed: %s", filename, strerror(errno));
   return 0;
 }
 
@@ -284,7 +304,7 @@ int ecwam_b200_getstress(const char* filename, char* dates, long long niblo, int
   if (dates) for (int i = 0; i < 4; ++i) { memcpy(dates + 15 * i, hdr + 14 * i, 14); dates[15 * i + 14] = 0; }
   struct stat st;
   if (fstat(f.fd, &st) || st.st_size != base + nreal * record_span(niblo * 8)) IO_FAIL("getstress: %s does not hold %d records of %lld reals", filename, nreal, niblo);
-  if (rw_points(f.fd, false, base, nreal, niblo, nown, runs_of(nown, ijorig), rfield)) IO_FAIL("getstress: %s: record markers do not match NIBLO=%lld", filename, niblo);
+  if (rw_points(f.fd, false, base, nreal, niblo, nown, plan_of(nown, ijorig), rfield)) IO_FAIL("getstress: %s: record markers do not match NIBLO=%lld", filename, niblo);
   return 0;
 }
 
