@@ -98,6 +98,52 @@ def make_grid(N: int, mask_kind: str = "aqua", seed: int = 20230101) -> SynthGri
                      lon=lon[sea].copy(), lat=lat[sea].copy(), depth=depth[sea].copy(), niblo=int(sea.sum()))
 
 
+def write_grid_tables(g: SynthGrid, path: str, imdlgrbid_g: int = 108) -> None:
+    """The grid as a `wam_grid_tables` file in the reference's binary format (OUTCOM, outcom.F90:139-144): BATHY(NGX,NGY)
+    with the sea-point depths and ZMISS = -999 on land."""
+    import ctypes as C
+    from . import lib as L
+    ngy, ngx = int(g.ngy), int(max(g.nlonrgg))
+    bathy = np.full((ngy, ngx), -999.0)
+    start = np.concatenate([[0], np.cumsum(g.nlonrgg)[:-1]])
+    cell = np.flatnonzero(np.asarray(g.mask).astype(bool))
+    bathy[g.row_of[cell], cell - start[g.row_of[cell]]] = g.depth
+    nl = np.ascontiguousarray(g.nlonrgg, dtype=np.int32)
+    amo = np.array([0.0, g.amosop, 360.0 - 360.0 / ngx, g.amonop, (g.amonop - g.amosop) / (ngy - 1), 360.0 / ngx])
+    L.check(L.load().ecwam_b200_grid_tables_write(path.encode(), imdlgrbid_g, ngx, ngy, nl.ctypes.data_as(C.POINTER(C.c_int)), 1, 1,
+                                                  amo.ctypes.data_as(C.POINTER(C.c_double)), bathy.ctypes.data_as(C.POINTER(C.c_double))),
+            "grid_tables_write")
+
+
+def grid_from_tables(path: str) -> SynthGrid:
+    """A grid read from a `wam_grid_tables` file (READPRE's binary branch, readpre.F90:262-345): rows south -> north with
+    NLONRGG points each, sea where BATHY > ZMISS (mgrid.F90:72), longitudes AMOWEP + i * 360/NLONRGG (IPER = 1)."""
+    import ctypes as C
+    from . import lib as L
+    lib = L.load()
+    v = [C.c_int() for _ in range(6)]
+    L.check(lib.ecwam_b200_grid_tables_read(path.encode(), C.byref(v[0]), C.byref(v[1]), C.byref(v[2]), C.byref(v[3]), None, 0, None, None,
+                                            None, None, 0), "grid_tables_read")
+    ngx, ngy = v[2].value, v[3].value
+    nl, amo, bathy = np.empty(ngy, np.int32), np.empty(6), np.empty((ngy, ngx))
+    L.check(lib.ecwam_b200_grid_tables_read(path.encode(), C.byref(v[0]), C.byref(v[1]), C.byref(v[2]), C.byref(v[3]),
+                                            nl.ctypes.data_as(C.POINTER(C.c_int)), ngy, C.byref(v[4]), C.byref(v[5]),
+                                            amo.ctypes.data_as(C.POINTER(C.c_double)), bathy.ctypes.data_as(C.POINTER(C.c_double)), bathy.size),
+            "grid_tables_read")
+    if v[4].value != 1:
+        raise ValueError("only periodic (IPER = 1) grids are handled")
+    amowep, amosop, amonop, xdella = amo[0], amo[1], amo[3], amo[4]
+    row = np.repeat(np.arange(ngy, dtype=np.int32), nl)
+    start = np.concatenate([[0], np.cumsum(nl)[:-1]])
+    icol = np.arange(int(nl.sum())) - np.repeat(start, nl)
+    b = bathy[row, icol]
+    sea = b > -990.0
+    lon = amowep + icol * (360.0 / np.repeat(nl, nl))
+    lat = amosop + row * xdella
+    return SynthGrid(N=ngy // 2, ngy=ngy, nlonrgg=nl.astype(np.int64), amosop=float(amosop), amonop=float(amonop), mask=sea.astype(np.uint8),
+                     row_of=row, lon=lon[sea].copy(), lat=lat[sea].copy(), depth=b[sea].copy(), niblo=int(sea.sum()))
+
+
 def make_forcing(g: SynthGrid, t_hours: float = 0.0, wstar_max: float = 1.5):
     """Analytic forcing fields per sea point (FORCING_FIELDS members used by IMPLSCH)."""
     lam = np.deg2rad(g.lon)

@@ -39,6 +39,8 @@ def main():
     ap.add_argument("--mask", default="continents", choices=["continents", "aqua"])
     ap.add_argument("--cycle", default="default", choices=["default", "cy49r1"],
                     help="cy49r1: LLGCBZ0 + LLNORMAGAM, WSPMIN = 0.3 (tests/etopo1_oper_an_fc_O48_cy49r1.yml)")
+    ap.add_argument("--grid-tables", default="", help="a wam_grid_tables file (reference binary format) to take the grid and the "
+                    "bathymetry from; --grid then only selects the spectral resolution and the time steps")
     ap.add_argument("--restart-in", default="", help="directory with BLS/LAW restart files (reference format) to start from")
     ap.add_argument("--restart-out", default="", help="directory to write the BLS/LAW restart files of the final state to")
     ap.add_argument("--start", default="20220101000000", help="CDATEF, YYYYMMDDHHmmss")
@@ -67,7 +69,7 @@ def main():
 
     cfg = synth.CONFIGS[args.grid]
     nproma = {"O48": 32, "O320": 64}.get(args.grid, 32)
-    g = synth.make_grid(cfg["N"], args.mask)
+    g = synth.grid_from_tables(args.grid_tables) if args.grid_tables else synth.make_grid(cfg["N"], args.mask)
     kw = dict(nang=cfg["nang"], nfre_red=cfg["nfre_red"], iphys=args.iphys, nproma=nproma, idelt=cfg["idelt"], idelpro=cfg["idelpro"],
               delpro_lf=cfg["delpro_lf"], ifrelfmax=cfg["ifrelfmax"])
     if args.cycle == "cy49r1":

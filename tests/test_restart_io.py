@@ -194,3 +194,21 @@ def test_restart_errors_are_loud(built, tmp_path):
     assert lib.ecwam_b200_savspec(p.encode(), 10, 12, 36, 3, _ptr(ij, ip), _ptr(x), 1) == -1
     # a rank that is not the creating one must find the file laid out for the same dimensions
     assert lib.ecwam_b200_savspec(p.encode(), 10, 12, 36, 10, None, _ptr(x), 0) == -5
+
+
+def test_grid_from_grid_tables_file_rebuilds_the_decomposition(built, tmp_path):
+    """synth.write_grid_tables -> synth.grid_from_tables: a grid that only exists as a `wam_grid_tables` file gives the same sea
+    points, depths and MPDECOMP tables as the grid it was written from."""
+    g = synth.make_grid(16, "continents")
+    p = str(tmp_path / "wam_grid_tables")
+    synth.write_grid_tables(g, p)
+    h = synth.grid_from_tables(p)
+    assert (h.ngy, h.niblo, h.amosop, h.amonop) == (g.ngy, g.niblo, g.amosop, g.amonop)
+    for k in ("nlonrgg", "mask", "row_of", "lon", "lat", "depth"):
+        np.testing.assert_array_equal(np.asarray(getattr(h, k)), np.asarray(getattr(g, k)), err_msg=k)
+    a, b = M.WamSetup(g, nproc=3, nang=12, nfre_red=25), M.WamSetup(h, nproc=3, nang=12, nfre_red=25)
+    np.testing.assert_array_equal(a.ij2new, b.ij2new)
+    for r in range(3):
+        da, db = a.decomp_arrays(r), b.decomp_arrays(r)
+        for nm in ("klat", "klon", "kcor", "wlat", "wcor", "ntope", "nfrompe"):
+            np.testing.assert_array_equal(da[nm], db[nm], err_msg=nm)
