@@ -774,6 +774,33 @@ int ecwam_b200_newwind(ecwam_b200_handle h, const ecwam_b200_forcing_next* next)
   return 0;
 }
 
+int ecwam_b200_getwnd(ecwam_b200_handle h, const ecwam_b200_fieldg* g, const ecwam_b200_getwnd_opts* o, const int* ifromij,
+                      const int* jfromij, const ecwam_b200_forcing_next* next) {
+  if (!h || !g || !o || !ifromij || !jfromij || !next) EW_FAIL(ECWAM_B200_EINVAL, "null argument");
+  if (!h->bound) EW_FAIL(ECWAM_B200_ESTATE, "fields not bound");
+  if (h->par.icode_wnd != 3) EW_FAIL(ECWAM_B200_EINVAL, "GETWND: only ICODE_WND = 3 (10 m wind components) is built");
+  if (o->nxe < o->nxs || o->nye < o->nys) EW_FAIL(ECWAM_B200_EINVAL, "GETWND: empty forcing grid");
+  if (o->iparamci != 31 && o->iparamci != 139) EW_FAIL(ECWAM_B200_EINVAL, "GETWND: IPARAMCI must be 31 (sea-ice fraction) or 139 (SST)");
+  if (!g->uwnd || !g->vwnd || !g->aird || !g->wstar || !g->cicover || !g->cithick || !g->ustra || !g->vstra)
+    EW_FAIL(ECWAM_B200_EINVAL, "GETWND: a FIELDG member is null");
+  if ((o->llwswave && !g->wswave) || (o->llwdwave && !g->wdwave)) EW_FAIL(ECWAM_B200_EINVAL, "GETWND: LLWSWAVE / LLWDWAVE need FIELDG%%WSWAVE / WDWAVE");
+  const void* const* pp = (const void* const*)next;
+  for (size_t i = 0; i < sizeof(*next) / sizeof(void*); ++i) if (!pp[i]) EW_FAIL(ECWAM_B200_EINVAL, "GETWND: FF_NEXT member %zu is null", i);
+  GetwndArgs a;
+  a.npts = (long long)h->par.nproma * h->par.nchnk;
+  a.nx = o->nxe - o->nxs + 1;
+  a.lcorrel = (o->lrelwind && (h->par.irefra == 2 || h->par.irefra == 3)) ? 1 : 0;      // wamwnd.F90:122-127 (LWCOU = F)
+  a.licerun = h->par.licerun; a.lmaskice = h->par.lmaskice;
+  a.wspmin = h->par.wspmin; a.zpi = h->dc.ZPI;
+  a.ucur = h->dev.ucur; a.vcur = h->dev.vcur;
+  if (a.lcorrel && (!a.ucur || !a.vcur)) EW_FAIL(ECWAM_B200_ESTATE, "GETWND: the relative-wind correction needs UCUR / VCUR bound");
+  ScopedTimer t(h, "getwnd");
+  launch_getwnd(a, *g, *o, ifromij, jfromij, *next, h->st);
+  h->nlaunch++;
+  EW_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int ecwam_b200_no_source(ecwam_b200_handle h, int llsource_off) {
   if (!h) EW_FAIL(ECWAM_B200_EINVAL, "null handle");
   if (!h->bound) EW_FAIL(ECWAM_B200_ESTATE, "fields not bound");

@@ -119,6 +119,14 @@ struct OutDev {
 int upload_out_const(const OutConst& h, cudaStream_t st);
 void launch_newwind(long long npts, const ecwam_b200_fields& f, const ecwam_b200_forcing_next& nx, double acd, double bcd, double epsmin,
                     cudaStream_t st);
+struct GetwndArgs {
+  long long npts;
+  int nx, lcorrel, licerun, lmaskice;
+  double wspmin, zpi;
+  const double *ucur, *vcur;
+};
+void launch_getwnd(const GetwndArgs& a, const ecwam_b200_fieldg& g, const ecwam_b200_getwnd_opts& o, const int* ifromij, const int* jfromij,
+                   const ecwam_b200_forcing_next& nx, cudaStream_t st);
 void launch_no_source(long long n4, long long n2, double* fl1, double* xllws, int* mij, int nfre, int clip, double epsmin, cudaStream_t st);
 int launch_outblock(const OutDev& d, cudaStream_t st);
 size_t norm_scratch_doubles(int ncol);

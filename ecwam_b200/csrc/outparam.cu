@@ -38,6 +38,62 @@ __global__ void k_newwind(long long n, ecwam_b200_fields f, ecwam_b200_forcing_n
   f.cithick[p] = nx.cithick[p]; f.ustra[p] = nx.ustra[p]; f.vstra[p] = nx.vstra[p];
 }
 
+// GETWND's blocking step: WAMWND (wamwnd.F90:120-300, ICODE_WND = 3) + MICEP (micep.F90:84-240, uncoupled) per grid point
+__global__ void k_getwnd(GetwndArgs a, ecwam_b200_fieldg g, ecwam_b200_getwnd_opts o, const int* __restrict__ ifromij,
+                         const int* __restrict__ jfromij, ecwam_b200_forcing_next nx) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.npts) return;
+  const size_t q = (size_t)(ifromij[p] - o.nxs) + (size_t)a.nx * (size_t)(jfromij[p] - o.nys);
+  double uu = g.uwnd[q], vv = g.vwnd[q];
+  double u10, thw;
+  auto polar = [&](bool strict) {           // speed and direction of (UU, VV); :163-171 tests > 0, :214-219 tests /= 0
+    u10 = sqrt(uu * uu + vv * vv);
+    if (strict ? (u10 > 0.0) : (u10 != 0.0)) thw = atan2(uu, vv);
+    else { u10 = strict ? 0.0 : u10; thw = 0.0; }
+  };
+  const double RWFAC = 0.5;                 // yowwind.F90:21
+  if (o.llwswave && o.llwdwave) {           // wamwnd.F90:152-190
+    u10 = g.wswave[q]; thw = g.wdwave[q];
+    if (u10 <= 0.0) polar(true);
+    if (a.lcorrel) {
+      uu = u10 * sin(thw); vv = u10 * cos(thw);
+      uu = uu - RWFAC * a.ucur[p]; vv = vv - RWFAC * a.vcur[p];
+      polar(true);
+    }
+  } else {
+    if (o.llwswave) {                       // :192-205 rescale the components to the wave model's wind speed
+      const double ws = g.wswave[q];
+      if (ws != o.zmiss && ws > 0.0) {
+        const double wspeed = sqrt(uu * uu + vv * vv);
+        if (wspeed > 0.0) { const double rescale = ws / wspeed; uu = uu * rescale; vv = vv * rescale; }
+      }
+    }
+    if (a.lcorrel) { uu = uu + RWFAC * a.ucur[p]; vv = vv + RWFAC * a.vcur[p]; }   // :206-211, :223-228
+    polar(false);
+  }
+  u10 = omax(u10, a.wspmin);                // :240-242
+  if (thw < 0.0) thw = thw + a.zpi;         // :290-292
+  // MICEP
+  const double ci = g.cicover[q];
+  double cicvr = 0.0;
+  if (o.iparamci == 31) {                   // micep.F90:113-125
+    if (ci == o.zmiss || ci < 0.01 || ci > 1.01) cicvr = 0.0;
+    else if (ci > 0.95) cicvr = 1.0;
+    else cicvr = ci;
+  } else cicvr = ci < 271.5 ? 1.0 : 0.0;    // 139: sea-surface temperature (:126-135)
+  double cith = g.cithick[q];               // WAMWND's CITH (:136)
+  if (!a.licerun || a.lmaskice) cith = 0.0;                                             // micep.F90:139-142
+  else if (!o.liceth) cith = cicvr > 0.0 ? omax(0.2 + 0.4 * cicvr, 0.0) : 0.0;         // :181-188 (C1 = 0.2, C2 = 0.4)
+  else {
+    cith = cicvr * cith;                                                               // :231-233
+    if (cicvr > 0.0 && cith < 0.5 * 0.2) { cicvr = 0.0; cith = 0.0; }                  // HICMIN = 0.2 (:234-239)
+  }
+  const_cast<double*>(nx.wswave)[p] = u10; const_cast<double*>(nx.wdwave)[p] = thw;
+  const_cast<double*>(nx.aird)[p] = g.aird[q]; const_cast<double*>(nx.wstar)[p] = g.wstar[q];
+  const_cast<double*>(nx.cicover)[p] = cicvr; const_cast<double*>(nx.cithick)[p] = cith;
+  const_cast<double*>(nx.ustra)[p] = g.ustra[q]; const_cast<double*>(nx.vstra)[p] = g.vstra[q];
+}
+
 // WAMINTGR without a source-term update (wamintgr.F90:163-171 when LLSOURCE = F, :188-195 when it is not yet time to
 // integrate): MIJ = NFRE, XLLWS = 0 and, for LLSOURCE = F, FL1 = MAX(FL1, EPSMIN)
 __global__ void k_no_source(long long n4, long long n2, double* __restrict__ fl1, double* __restrict__ xllws, int* __restrict__ mij,
@@ -438,6 +494,11 @@ void launch_newwind(long long npts, const ecwam_b200_fields& f, const ecwam_b200
                     cudaStream_t st) {
   if (npts <= 0) return;
   k_newwind<<<(unsigned)((npts + 255) / 256), 256, 0, st>>>(npts, f, nx, acd, bcd, epsmin);
+}
+void launch_getwnd(const GetwndArgs& a, const ecwam_b200_fieldg& g, const ecwam_b200_getwnd_opts& o, const int* ifromij, const int* jfromij,
+                   const ecwam_b200_forcing_next& nx, cudaStream_t st) {
+  if (a.npts <= 0) return;
+  k_getwnd<<<(unsigned)((a.npts + 255) / 256), 256, 0, st>>>(a, g, o, ifromij, jfromij, nx);
 }
 void launch_no_source(long long n4, long long n2, double* fl1, double* xllws, int* mij, int nfre, int clip, double epsmin, cudaStream_t st) {
   if (n4 <= 0) return;

@@ -242,6 +242,36 @@ class WamIntgr:
         x = self.t[name].permute(1, 2, 0, 3).reshape(self.F, self.A, -1)[:, :, : self.nloc]
         return x.cpu().numpy()
 
+    # ---- GETWND's blocking step (WAMWND + MICEP): forcing grid -> FF_NEXT on the device
+    def getwnd(self, fieldg: dict, ifromij, jfromij, nxs=1, nys=1, llwswave=0, llwdwave=0, lrelwind=1, iparamci=31, liceth=0, zmiss=-999.0):
+        """fieldg: dict of (NY, NX) host arrays (FIELDG members); ifromij / jfromij: per sea point in the original global order.
+        Returns the FF_NEXT device tensors, ready for newwind_device()."""
+        torch = self.torch
+        ny, nx = np.asarray(fieldg["uwnd"]).shape
+        keep, g = [], L.FieldG()
+        for n_, _ in L.FieldG._fields_:
+            if n_ in fieldg:
+                t = torch.from_numpy(np.ascontiguousarray(fieldg[n_], dtype=np.float64)).to(self.device)
+                keep.append(t)
+                setattr(g, n_, C.cast(t.data_ptr(), C.POINTER(C.c_double)))
+        ii = torch.from_numpy(np.ascontiguousarray(np.asarray(ifromij, dtype=np.int32)[self.src])).to(self.device)
+        jj = torch.from_numpy(np.ascontiguousarray(np.asarray(jfromij, dtype=np.int32)[self.src])).to(self.device)
+        o = L.GetwndOpts(nxs=nxs, nxe=nxs + nx - 1, nys=nys, nye=nys + ny - 1, llwswave=llwswave, llwdwave=llwdwave, lrelwind=lrelwind,
+                         iparamci=iparamci, liceth=liceth, zmiss=zmiss)
+        nxt, out = L.ForcingNext(), {}
+        for n_, _ in L.ForcingNext._fields_:
+            out[n_] = torch.empty((self.C, self.P), dtype=torch.float64, device=self.device)
+            setattr(nxt, n_, C.cast(out[n_].data_ptr(), C.POINTER(C.c_double)))
+        L.check(self.lib.ecwam_b200_getwnd(self.h, C.byref(g), C.byref(o), C.c_void_p(ii.data_ptr()), C.c_void_p(jj.data_ptr()), C.byref(nxt)),
+                "getwnd")
+        self.synchronize()
+        self._next = (nxt, out)
+        return out
+
+    def newwind_device(self):
+        """NEWWIND on the FF_NEXT tensors the last getwnd() produced."""
+        L.check(self.lib.ecwam_b200_newwind(self.h, C.byref(self._next[0])), "newwind")
+
     # ---- restart files in the reference's formats (SAVSPEC / SAVSTRESS, GETSPEC / GETSTRESS; host_io.cpp)
     LAW_FIELDS = ("wswave", "wdwave", "ufric", "tauw", "tauwdir", "z0m", "z0b", "chrnck", "aird", "wstar", "cicover", "cithick",
                   "ustra", "vstra", "ucur", "vcur")                       # savstress.F90:110-125 (NREAL = 16)

@@ -371,6 +371,40 @@ typedef struct ecwam_b200_forcing_next {
  * call this when NEWWIND's `CDATE >= CDATEWH` test holds.                                                   */
 int ecwam_b200_newwind(ecwam_b200_handle h, const ecwam_b200_forcing_next* next);
 
+/* GETWND's blocking step (src/ecwam/getwnd.F90:196-212): WAMWND (wamwnd.F90:120-300, ICODE_WND = 3) + MICEP
+ * (micep.F90:84-240, uncoupled) turn the forcing fields on the forcing grid into the FF_NEXT members that NEWWIND
+ * copies.  FIELDG arrays: DEVICE, (NXS:NXE, NYS:NYE) first index fastest; wswave / wdwave are read only with
+ * LLWSWAVE / LLWDWAVE.  ifromij / jfromij: DEVICE (NPROMA,NCHNK) = BLK2LOC%IFROMIJ / JFROMIJ.  The relative-wind
+ * correction (LRELWIND with IREFRA = 2, 3) reads the bound UCUR / VCUR.  Not built: ICODE_WND = 1, 2; the coupled
+ * (LWCOU, NEMO) branches; the swamp domain.                                                                   */
+typedef struct ecwam_b200_fieldg {
+  const double* uwnd;
+  const double* vwnd;
+  const double* aird;
+  const double* wstar;
+  const double* cicover;
+  const double* cithick;
+  const double* ustra;
+  const double* vstra;
+  const double* wswave;
+  const double* wdwave;
+} ecwam_b200_fieldg;
+typedef struct ecwam_b200_getwnd_opts {
+  int nxs;
+  int nxe;
+  int nys;
+  int nye;
+  int llwswave;    /* YOWWIND LLWSWAVE */
+  int llwdwave;    /* YOWWIND LLWDWAVE */
+  int lrelwind;    /* YOWCURR LRELWIND */
+  int iparamci;    /* YOWICE IPARAMCI: 31 sea-ice fraction, 139 sea-surface temperature */
+  int liceth;      /* YOWICE LICETH: FIELDG%CITHICK holds a thickness */
+  double zmiss;    /* YOWPCONS ZMISS */
+} ecwam_b200_getwnd_opts;
+/* next: DEVICE (NPROMA,NCHNK) arrays that are WRITTEN (the same struct ecwam_b200_newwind reads afterwards) */
+int ecwam_b200_getwnd(ecwam_b200_handle h, const ecwam_b200_fieldg* fieldg, const ecwam_b200_getwnd_opts* opts,
+                      const int* ifromij, const int* jfromij, const ecwam_b200_forcing_next* next);
+
 /* Selection of OUTBLOCK's output columns = YOWCOUT after MPCRTBL (src/ecwam/mpcrtbl.F90:89-460).  Host pointers.  */
 typedef struct ecwam_b200_outsel {
   int niprmout;              /* YOWCOUT NIPRMOUT: number of BOUT columns                                     */

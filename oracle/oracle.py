@@ -82,9 +82,36 @@ def _lib(fast=False):
         lib.orc_outbs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p]
         lib.orc_outwnorm.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.orc_implsch.argtypes = [C.c_void_p]
+        lib.orc_getwnd_points.argtypes = [C.c_long, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]
         assert lib.orc_config_size() == C.sizeof(Config), "oracle Config layout mismatch"
         _libs[fast] = lib
     return _libs[fast]
+
+
+FIELDG_NAMES = ("uwnd", "vwnd", "aird", "wstar", "cicover", "cithick", "ustra", "vstra", "wswave", "wdwave")
+NEXT_NAMES = ("wswave", "wdwave", "aird", "wstar", "cicover", "cithick", "ustra", "vstra")
+
+
+def getwnd_points(ifromij, jfromij, fieldg, nxs=1, nys=1, ucur=None, vcur=None, llwswave=0, llwdwave=0, lcorrel=0, iparamci=31, liceth=0,
+                  licerun=1, lmaskice=1, wspmin=1.0, zmiss=-999.0):
+    """WAMWND + MICEP (getwnd.F90:196-212) for the points (ifromij, jfromij) of the forcing grid; fieldg: dict of (NY, NX) arrays.
+    Returns the FF_NEXT members as a dict."""
+    lib = _lib()
+    n = len(ifromij)
+    ii, jj = np.ascontiguousarray(ifromij, dtype=np.int32), np.ascontiguousarray(jfromij, dtype=np.int32)
+    ny, nx = np.asarray(fieldg["uwnd"]).shape
+    zero = np.zeros((ny, nx))
+    g = [np.ascontiguousarray(fieldg.get(k, zero), dtype=np.float64) for k in FIELDG_NAMES]
+    gp = (C.c_void_p * 10)(*[a.ctypes.data for a in g])
+    uc = np.ascontiguousarray(ucur if ucur is not None else np.zeros(n))
+    vc = np.ascontiguousarray(vcur if vcur is not None else np.zeros(n))
+    out = [np.empty(n) for _ in range(8)]
+    op = (C.c_void_p * 8)(*[a.ctypes.data for a in out])
+    opt = np.array([llwswave, llwdwave, lcorrel, iparamci, liceth, licerun, lmaskice], dtype=np.int32)
+    ropt = np.array([wspmin, zmiss, 2.0 * np.pi])
+    lib.orc_getwnd_points(n, ii.ctypes.data, jj.ctypes.data, nxs, nys, nx, gp, uc.ctypes.data, vc.ctypes.data, opt.ctypes.data, ropt.ctypes.data, op)
+    return dict(zip(NEXT_NAMES, out))
 
 
 class Oracle:

@@ -532,4 +532,77 @@ void mpminmaxavg(Model& m, const OutSel& sel, const std::vector<std::vector<doub
   }
 }
 
+// getwnd.F90:196-212: WAMWND (wamwnd.F90:120-300, ICODE_WND = 3) followed by MICEP (micep.F90:84-240, LWCOU = F, no NEMO
+// fields, CLDOMAIN /= 's') for N points.  FIELDG arrays (NX, NY) first index fastest, IFROMIJ / JFROMIJ relative to NXS / NYS.
+void getwnd_points(long N, const int* IFROMIJ, const int* JFROMIJ, int NXS, int NYS, int NX, const double* UWND, const double* VWND,
+                   const double* AIRD, const double* WSTARG, const double* CICOVERG, const double* CITHICKG, const double* USTRAG,
+                   const double* VSTRAG, const double* WSWAVEG, const double* WDWAVEG, const double* UCUR, const double* VCUR,
+                   int LLWSWAVE, int LLWDWAVE, int LCORREL, int IPARAM, int LICETH, int LICERUN, int LMASKICE, double WSPMIN, double ZMISS,
+                   double ZPI, double* U10, double* THW, double* ADS, double* WSTAR, double* CICVR, double* CITH, double* USTRA, double* VSTRA) {
+  const double RWFAC = 0.5, C1 = 0.2, C2 = 0.4, HICMIN = 0.2;   // yowwind.F90:21, micep.F90:81-82, yowice.F90:23
+  auto G = [&](const double* a, long IJ) { return a[(size_t)(IFROMIJ[IJ] - NXS) + (size_t)NX * (size_t)(JFROMIJ[IJ] - NYS)]; };
+  std::vector<double> UU(N), VV(N), WSPEED(N);
+  for (long IJ = 0; IJ < N; ++IJ) {
+    UU[IJ] = G(UWND, IJ); VV[IJ] = G(VWND, IJ); ADS[IJ] = G(AIRD, IJ); WSTAR[IJ] = G(WSTARG, IJ); CITH[IJ] = G(CITHICKG, IJ);
+    USTRA[IJ] = G(USTRAG, IJ); VSTRA[IJ] = G(VSTRAG, IJ);
+  }
+  if (LLWSWAVE && LLWDWAVE) {
+    for (long IJ = 0; IJ < N; ++IJ) { U10[IJ] = G(WSWAVEG, IJ); THW[IJ] = G(WDWAVEG, IJ); }
+    for (long IJ = 0; IJ < N; ++IJ)
+      if (U10[IJ] <= 0.0) {
+        WSPEED[IJ] = std::sqrt(UU[IJ] * UU[IJ] + VV[IJ] * VV[IJ]);
+        if (WSPEED[IJ] > 0.0) { U10[IJ] = WSPEED[IJ]; THW[IJ] = std::atan2(UU[IJ], VV[IJ]); } else { U10[IJ] = 0.0; THW[IJ] = 0.0; }
+      }
+    if (LCORREL)
+      for (long IJ = 0; IJ < N; ++IJ) {
+        UU[IJ] = U10[IJ] * std::sin(THW[IJ]); VV[IJ] = U10[IJ] * std::cos(THW[IJ]);
+        UU[IJ] = UU[IJ] - RWFAC * UCUR[IJ]; VV[IJ] = VV[IJ] - RWFAC * VCUR[IJ];
+        WSPEED[IJ] = std::sqrt(UU[IJ] * UU[IJ] + VV[IJ] * VV[IJ]);
+        if (WSPEED[IJ] > 0.0) { U10[IJ] = WSPEED[IJ]; THW[IJ] = std::atan2(UU[IJ], VV[IJ]); } else { U10[IJ] = 0.0; THW[IJ] = 0.0; }
+      }
+  } else {
+    if (LLWSWAVE)
+      for (long IJ = 0; IJ < N; ++IJ) {
+        const double WS = G(WSWAVEG, IJ);
+        if (WS != ZMISS && WS > 0.0) {
+          WSPEED[IJ] = std::sqrt(UU[IJ] * UU[IJ] + VV[IJ] * VV[IJ]);
+          if (WSPEED[IJ] > 0.0) { const double RESCALE = WS / WSPEED[IJ]; UU[IJ] = UU[IJ] * RESCALE; VV[IJ] = VV[IJ] * RESCALE; }
+        }
+      }
+    if (LCORREL) for (long IJ = 0; IJ < N; ++IJ) { UU[IJ] = UU[IJ] + RWFAC * UCUR[IJ]; VV[IJ] = VV[IJ] + RWFAC * VCUR[IJ]; }
+    for (long IJ = 0; IJ < N; ++IJ) {
+      U10[IJ] = std::sqrt(UU[IJ] * UU[IJ] + VV[IJ] * VV[IJ]);
+      THW[IJ] = U10[IJ] != 0.0 ? std::atan2(UU[IJ], VV[IJ]) : 0.0;
+    }
+  }
+  for (long IJ = 0; IJ < N; ++IJ) U10[IJ] = std::max(U10[IJ], WSPMIN);
+  for (long IJ = 0; IJ < N; ++IJ) if (THW[IJ] < 0.0) THW[IJ] = THW[IJ] + ZPI;
+  // MICEP
+  if (IPARAM == 31) {
+    for (long IJ = 0; IJ < N; ++IJ) {
+      const double CI = G(CICOVERG, IJ);
+      if (CI == ZMISS || CI < 0.01 || CI > 1.01) CICVR[IJ] = 0.0;
+      else if (CI > 0.95) CICVR[IJ] = 1.0;
+      else CICVR[IJ] = CI;
+    }
+  } else if (IPARAM == 139) {
+    for (long IJ = 0; IJ < N; ++IJ) CICVR[IJ] = G(CICOVERG, IJ) < 271.5 ? 1.0 : 0.0;
+  }
+  if (!LICERUN || LMASKICE) {
+    for (long IJ = 0; IJ < N; ++IJ) CITH[IJ] = 0.0;
+  } else if (!LICETH) {
+    for (long IJ = 0; IJ < N; ++IJ) CITH[IJ] = CICVR[IJ] > 0.0 ? std::max(C1 + C2 * CICVR[IJ], 0.0) : 0.0;
+  } else {
+    for (long IJ = 0; IJ < N; ++IJ) CITH[IJ] = CICVR[IJ] * CITH[IJ];
+    for (long IJ = 0; IJ < N; ++IJ) if (CICVR[IJ] > 0.0 && CITH[IJ] < 0.5 * HICMIN) { CICVR[IJ] = 0.0; CITH[IJ] = 0.0; }
+  }
+}
+
 }  // namespace orc
+
+extern "C" void orc_getwnd_points(long N, const int* IFROMIJ, const int* JFROMIJ, int NXS, int NYS, int NX, const double* const* FIELDG /*[10]*/,
+                                  const double* UCUR, const double* VCUR, const int* OPT /*[7]*/, const double* ROPT /*[3]*/, double* const* OUT /*[8]*/) {
+  orc::getwnd_points(N, IFROMIJ, JFROMIJ, NXS, NYS, NX, FIELDG[0], FIELDG[1], FIELDG[2], FIELDG[3], FIELDG[4], FIELDG[5], FIELDG[6], FIELDG[7],
+                     FIELDG[8], FIELDG[9], UCUR, VCUR, OPT[0], OPT[1], OPT[2], OPT[3], OPT[4], OPT[5], OPT[6], ROPT[0], ROPT[1], ROPT[2],
+                     OUT[0], OUT[1], OUT[2], OUT[3], OUT[4], OUT[5], OUT[6], OUT[7]);
+}

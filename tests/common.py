@@ -140,3 +140,26 @@ def synthetic_currents(g, amp=0.8):
     u[m] = 0.0
     v[m] = 0.0
     return u, v
+
+
+def synthetic_fieldg(g, seed=7, with_ws=True):
+    """Forcing fields on the (NGY, NGX) wave grid itself plus IFROMIJ / JFROMIJ of every sea point (original order): what
+    GETWND's blocking step (WAMWND + MICEP) reads.  Includes calm cells, cells with missing / out-of-range ice values, both
+    signs of every component."""
+    ngy, ngx = int(g.ngy), int(max(g.nlonrgg))
+    rng = np.random.default_rng(seed)
+    start = np.concatenate([[0], np.cumsum(g.nlonrgg)[:-1]])
+    cell = np.flatnonzero(np.asarray(g.mask).astype(bool))
+    jj = g.row_of[cell].astype(np.int32) + 1
+    ii = (cell - start[g.row_of[cell]]).astype(np.int32) + 1
+    f = dict(uwnd=rng.normal(0, 7, (ngy, ngx)), vwnd=rng.normal(0, 7, (ngy, ngx)), aird=1.1 + 0.2 * rng.random((ngy, ngx)),
+             wstar=rng.random((ngy, ngx)), cicover=np.clip(rng.normal(0.3, 0.5, (ngy, ngx)), -0.2, 1.3), cithick=2.0 * rng.random((ngy, ngx)),
+             ustra=rng.normal(0, 0.1, (ngy, ngx)), vstra=rng.normal(0, 0.1, (ngy, ngx)))
+    calm = rng.random((ngy, ngx)) < 0.05
+    f["uwnd"][calm] = 0.0; f["vwnd"][calm] = 0.0
+    f["cicover"][rng.random((ngy, ngx)) < 0.05] = ZMISS
+    if with_ws:
+        f["wswave"] = np.where(rng.random((ngy, ngx)) < 0.2, 0.0, np.abs(rng.normal(8, 4, (ngy, ngx))))
+        f["wswave"][rng.random((ngy, ngx)) < 0.05] = ZMISS
+        f["wdwave"] = 2 * np.pi * rng.random((ngy, ngx))
+    return f, ii, jj

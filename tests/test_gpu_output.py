@@ -190,3 +190,40 @@ def test_restart_round_trip_is_bit_exact(built, tmp_path, parallel):
         np.testing.assert_array_equal(v.get_field(nm), w.get_field(nm), err_msg=nm)
     if not parallel:   # the file is the reference's global layout: original point order, one record per (direction, frequency)
         np.testing.assert_array_equal(R.readfl(bls, s.niblo, w.A, w.F)[:, :, w.own], saved)
+
+
+@pytest.mark.parametrize("opts,extra", [(dict(), {}), (dict(llwswave=1), {}), (dict(llwswave=1, llwdwave=1), {}), (dict(liceth=1), dict(lmaskice=0)),
+                                        (dict(iparamci=139), {}), (dict(), dict(irefra=3)), (dict(llwswave=1, llwdwave=1), dict(irefra=2))])
+def test_getwnd_on_device_matches_oracle(built, opts, extra):
+    """ecwam_b200_getwnd = WAMWND + MICEP (getwnd.F90:196-212) from the forcing grid to FF_NEXT on the device, then NEWWIND from those
+    tensors: every option branch, with the relative-wind correction when currents are on (LRELWIND, IREFRA = 2, 3)."""
+    from common import make_gpu, make_oracle, synthetic_currents, synthetic_fieldg
+    from oracle import oracle as O
+    g, o, f0, fl = make_oracle("o48like", wspmin=0.3, **extra)
+    _, s, w = make_gpu("o48like", wspmin=0.3, **extra)
+    uc = vc = None
+    if extra.get("irefra", 0) >= 2:
+        uc, vc = synthetic_currents(g)
+        w.set_field("ucur", uc); w.set_field("vcur", vc)
+        o.set_field("UCUR", uc); o.set_field("VCUR", vc)
+    f, ii, jj = synthetic_fieldg(g)
+    if opts.get("iparamci") == 139:
+        f["cicover"] = 268.0 + 8.0 * np.random.default_rng(2).random(f["uwnd"].shape)
+    out = w.getwnd(f, ii, jj, **opts)
+    ref = O.getwnd_points(ii, jj, f, ucur=uc, vcur=vc, lcorrel=int(extra.get("irefra", 0) >= 2), wspmin=0.3,
+                          lmaskice=extra.get("lmaskice", 1), **opts)
+    for k, t in out.items():
+        a = t.reshape(-1)[: w.nloc].cpu().numpy()
+        if k in ("wswave", "wdwave", "cithick"):
+            np.testing.assert_allclose(a, ref[k][w.own], rtol=1e-13, atol=1e-14, err_msg=k)
+        else:
+            np.testing.assert_array_equal(a, ref[k][w.own], err_msg=k)
+    # NEWWIND straight from the device tensors == the oracle's NEWWIND fed with the oracle's GETWND
+    w.newwind_device()
+    w.synchronize()
+    o.newwind({k.upper(): v for k, v in ref.items()})
+    for k in ("wswave", "wdwave", "cicover", "cithick", "tauw", "ustra"):
+        np.testing.assert_allclose(w.get_field(k), o.get_field(k.upper())[w.own], rtol=1e-13, atol=1e-14, err_msg=k)
+    assert w.step() == 0 and o.step() == 0            # and the step that follows runs on that forcing
+    w.synchronize()
+    assert np.abs(w.get_spec("fl1") - o.get_fl1()[:, :, w.own]).max() <= 1e-10 * np.abs(o.get_fl1()).max()

@@ -111,3 +111,59 @@ def test_mean_square_slope_parts(built):
     r = np.corrcoef(mss[sea], b[2][sea])[0, 1]
     assert r > 0.6, r
     assert 1e-4 < np.median(mss[sea]) < 0.08
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(llwswave=1), dict(llwswave=1, llwdwave=1), dict(lcorrel=1), dict(llwswave=1, llwdwave=1, lcorrel=1),
+                                  dict(lmaskice=0), dict(lmaskice=0, liceth=1), dict(iparamci=139)])
+def test_getwnd_blocking_step(built, opts):
+    """WAMWND + MICEP (getwnd.F90:196-212, wamwnd.F90:120-300, micep.F90:84-240) against an independent numpy statement of the
+    same rules: wind speed / direction of the components (optionally rescaled to the wave model's speed, optionally relative to
+    half the surface current), WSPMIN floor, directions in [0, 2 pi); ice cover clipped to {0} U [0.01, 0.95] U {1} or taken from
+    the SST; thickness 0.2 + 0.4 c when none is supplied, c * h with the 0.1 m cut-off when it is."""
+    from common import make_grid, synthetic_fieldg
+    from oracle import oracle as O
+    g = make_grid("o48like")
+    f, ii, jj = synthetic_fieldg(g)
+    if opts.get("iparamci") == 139:
+        f["cicover"] = 268.0 + 8.0 * np.random.default_rng(2).random(f["uwnd"].shape)
+    rng = np.random.default_rng(4)
+    uc, vc = rng.normal(0, 1, g.niblo), rng.normal(0, 1, g.niblo)
+    r = O.getwnd_points(ii, jj, f, ucur=uc, vcur=vc, wspmin=0.3, **opts)
+    pick = lambda a: a[jj - 1, ii - 1]
+    u, v = pick(f["uwnd"]).copy(), pick(f["vwnd"]).copy()
+    if opts.get("llwswave") and opts.get("llwdwave"):
+        ws, wd = pick(f["wswave"]).copy(), pick(f["wdwave"]).copy()
+        bad = ws <= 0
+        ws[bad], wd[bad] = np.hypot(u, v)[bad], np.arctan2(u, v)[bad]
+        wd[bad & (np.hypot(u, v) == 0)] = 0.0
+        if opts.get("lcorrel"):
+            u, v = ws * np.sin(wd) - 0.5 * uc, ws * np.cos(wd) - 0.5 * vc
+            ws, wd = np.hypot(u, v), np.arctan2(u, v)
+    else:
+        if opts.get("llwswave"):
+            w0, sp = pick(f["wswave"]), np.hypot(u, v)
+            ok = (w0 != ZMISS) & (w0 > 0) & (sp > 0)
+            u[ok], v[ok] = (u * w0 / np.where(sp > 0, sp, 1))[ok], (v * w0 / np.where(sp > 0, sp, 1))[ok]
+        if opts.get("lcorrel"):
+            u, v = u + 0.5 * uc, v + 0.5 * vc
+        ws, wd = np.hypot(u, v), np.where(np.hypot(u, v) != 0, np.arctan2(u, v), 0.0)
+    np.testing.assert_allclose(r["wswave"], np.maximum(ws, 0.3), rtol=1e-14)
+    np.testing.assert_allclose(r["wdwave"], np.where(wd < 0, wd + 2 * np.pi, wd), rtol=1e-13, atol=1e-15)
+    assert r["wswave"].min() >= 0.3 and r["wdwave"].min() >= 0.0 and r["wdwave"].max() < 2 * np.pi + 1e-12
+    ci = pick(f["cicover"])
+    if opts.get("iparamci") == 139:
+        c = np.where(ci < 271.5, 1.0, 0.0)
+    else:
+        c = np.where((ci == ZMISS) | (ci < 0.01) | (ci > 1.01), 0.0, np.where(ci > 0.95, 1.0, ci))
+    if opts.get("lmaskice", 1):
+        h = np.zeros_like(c)
+    elif not opts.get("liceth"):
+        h = np.where(c > 0, 0.2 + 0.4 * c, 0.0)
+    else:
+        h = c * pick(f["cithick"])
+        thin = (c > 0) & (h < 0.1)
+        c, h = np.where(thin, 0.0, c), np.where(thin, 0.0, h)
+    np.testing.assert_array_equal(r["cicover"], c)
+    np.testing.assert_allclose(r["cithick"], h, rtol=1e-15)
+    for k in ("aird", "wstar", "ustra", "vstra"):
+        np.testing.assert_array_equal(r[k], pick(f[k]))
