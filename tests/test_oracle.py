@@ -231,3 +231,26 @@ def test_growth_renormalisation_reduces_the_wind_input(built):
     sea = f["CICOVER"] <= 0.3
     assert (tw[sea] <= tw0[sea] * (1 + 1e-12)).all()
     assert tw[sea].sum() < 0.97 * tw0[sea].sum()
+
+
+def test_cy50r1_configuration_in_the_oracle(built):
+    """tests/etopo1_oper_an_fc_O48_cy50r1.yml = cy49r1 + LCIWA3 + LCISCAL.  With waves allowed under the ice (LMASKICE = F) the two
+    switches only act where there is ice: identical spectra on ice-free points that no ice-covered point can have reached in the
+    steps taken, less energy under the ice; and the result does not depend on the decomposition."""
+    cy50 = dict(llgcbz0=1, llnormagam=1, wspmin=0.3, lciwa3=1, lciscal=1, lmaskice=0)
+    g, o, f, fl = make_oracle("o48like", **cy50)
+    g, o49, f, fl = make_oracle("o48like", llgcbz0=1, llnormagam=1, wspmin=0.3, lmaskice=0)
+    g, o3, f, fl = make_oracle("o48like", npr=3, nproma=17, **cy50)
+    cith = np.where(f["CICOVER"] > 0, 0.3 + 1.5 * f["CICOVER"], 0.0)
+    for m in (o, o49, o3):
+        m.set_field("CITHICK", cith)
+    o.implsch(); o49.implsch(); o3.implsch()
+    a, b = o.get_fl1(), o49.get_fl1()
+    free = f["CICOVER"] == 0.0
+    np.testing.assert_array_equal(a[:, :, free], b[:, :, free])          # one source step: no propagation yet
+    ice = f["CICOVER"] > 0.2
+    assert ice.any() and a[:, :, ice].sum() < 0.99 * b[:, :, ice].sum()
+    for _ in range(3):
+        assert o.step() == 0 and o3.step() == 0
+    np.testing.assert_array_equal(o3.get_fl1(), o.get_fl1())
+    assert np.isfinite(o.get_fl1()).all()
