@@ -222,6 +222,7 @@ void implsch_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int ic
 void femean(const Tables& t, const Config& c, int KIJL, const double* F /*(KIJL,A,F)*/, double* EM, double* FM);
 // SNONLIN alone on one chunk (tests: conservation properties of the DIA); SL, FLD (KIJL,A,F) are overwritten
 void snonlin_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK, double* SL, double* FLD);
+void term_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK, int which, double* SL, double* FLD);
 
 // ---------------------------------------------------------------------------
 // The steps either side of the hot path (orc_output.cpp): NEWWIND, OUTBLOCK core parameters, WAMNORM statistics.

@@ -79,6 +79,7 @@ def _lib(fast=False):
         lib.orc_propag.argtypes = [C.c_void_p]
         lib.orc_newwind.argtypes = [C.c_void_p, C.c_void_p]
         lib.orc_snonlin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.orc_term.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.orc_outbs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p]
         lib.orc_outwnorm.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.orc_implsch.argtypes = [C.c_void_p]
@@ -249,6 +250,14 @@ class Oracle:
         fld = np.empty_like(sl)
         if self.lib.orc_snonlin(self.h, sl.ctypes.data, fld.ctypes.data) != 0:
             raise RuntimeError("orc_snonlin failed")
+        return sl, fld
+
+    def term(self, which):
+        """One source term alone: "sinput" (NGST = 1, LLSNEG = F, stored UFRIC / Z0M) or "sdissip": (SL, FLD)[m, k, ij]."""
+        sl = np.empty((self.cfg.nfre, self.cfg.nang, self.niblo))
+        fld = np.empty_like(sl)
+        if self.lib.orc_term(self.h, {"sinput": 1, "sdissip": 2}[which], sl.ctypes.data, fld.ctypes.data) != 0:
+            raise RuntimeError("orc_term failed")
         return sl, fld
 
     def outwnorm(self, global_norm=True):

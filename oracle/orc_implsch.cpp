@@ -1302,6 +1302,42 @@ void snonlin_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int IC
   SNONLIN(x, FL1, V3{FLDp, P, NANG}, V3{SLp, P, NANG}, WAVNUM, DEPTH, lAK.view());
 }
 
+// One source term alone for a chunk, from the fields as they are stored (test infrastructure for the per-term cross-checks):
+// which = 1: SINPUT with NGST = 1, LLSNEG = F (the first SINFLX call, sinflx.F90:156-167) using the stored UFRIC, Z0M;
+// which = 2: SDISSIP (sdissip.F90).  SL, FLD: (KIJL, NANG, NFRE).
+void term_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK, int which, double* SLp, double* FLDp) {
+  const int NANG = c.nang, NFRE = c.nfre, KIJS = 1;
+  Ctx x{c, t, KIJS, KIJL, NANG, NFRE};
+  const int P = KIJL;
+  auto s1 = [&](ArrD& a) { return V1{&a(1, ICHNK)}; };
+  V3 FL1{&f.FL1(1, 1, 1, ICHNK), P, NANG};
+  V2 WAVNUM{&f.WAVNUM(1, 1, ICHNK), P}, CINV{&f.CINV(1, 1, ICHNK), P}, XK2CG{&f.XK2CG(1, 1, ICHNK), P}, CGROUP{&f.CGROUP(1, 1, ICHNK), P};
+  V1 WSWAVE = s1(f.WSWAVE), WDWAVE = s1(f.WDWAVE), UFRIC = s1(f.UFRIC), Z0M = s1(f.Z0M), AIRD = s1(f.AIRD), WSTAR = s1(f.WSTAR);
+  const size_t n3 = (size_t)P * NANG * NFRE;
+  for (size_t i = 0; i < n3; ++i) { SLp[i] = 0.0; FLDp[i] = 0.0; }
+  V3 SL{SLp, P, NANG}, FLD{FLDp, P, NANG};
+  std::vector<double> sCOS((size_t)P * NANG), sSIN2((size_t)P * NANG);
+  V2 COSWDIF{sCOS.data(), P}, SINWDIF2{sSIN2.data(), P};
+  L1 lRAORW(P), lRNFAC(P);
+  V1 RAORW = lRAORW.view(), RNFAC = lRNFAC.view();
+  for (int IJ = KIJS; IJ <= KIJL; ++IJ) { RAORW(IJ) = std::max(AIRD(IJ), 1.0) * t.ROWATERM1; RNFAC(IJ) = 1.0; }
+  for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+    COSWDIF(IJ, K) = std::cos(t.TH(K) - WDWAVE(IJ));
+    SINWDIF2(IJ, K) = sq(std::sin(t.TH(K) - WDWAVE(IJ)));
+  }
+  if (which == 1) {
+    std::vector<double> sSPOS(n3), sX(n3);
+    V3 SPOS{sSPOS.data(), P, NANG}, XLLWS{sX.data(), P, NANG};
+    if (c.iphys == 0) SINPUT_JAN(x, 1, false, FL1, WAVNUM, CINV, XK2CG, WSWAVE, UFRIC, Z0M, COSWDIF, SINWDIF2, RAORW, WSTAR, RNFAC, FLD, SL, SPOS, XLLWS);
+    else SINPUT_ARD(x, 1, false, FL1, WAVNUM, CINV, XK2CG, WDWAVE, WSWAVE, UFRIC, Z0M, COSWDIF, SINWDIF2, RAORW, WSTAR, RNFAC, FLD, SL, SPOS, XLLWS);
+  } else if (which == 2) {
+    L1 lEM(P), lFM(P), lF1(P), lAK(P), lXK(P);
+    FKMEAN(x, FL1, WAVNUM, lEM.view(), lFM.view(), lF1.view(), lAK.view(), lXK.view());
+    if (c.iphys == 0) SDISSIP_JAN(x, FL1, FLD, SL, WAVNUM, lEM.view(), lF1.view(), lXK.view());
+    else SDISSIP_ARD(x, FL1, FLD, SL, WAVNUM, CGROUP, XK2CG, UFRIC, COSWDIF, RAORW);
+  } else throw std::runtime_error("term_chunk: unknown term");
+}
+
 // wamintgr.F90:117-146
 void implsch_all(Model& m) {
   for (int ir = 0; ir < m.cfg.npr; ++ir) {

@@ -254,3 +254,91 @@ def test_cy50r1_configuration_in_the_oracle(built):
         assert o.step() == 0 and o3.step() == 0
     np.testing.assert_array_equal(o3.get_fl1(), o.get_fl1())
     assert np.isfinite(o.get_fl1()).all()
+
+
+def _consts(o):
+    return {k: o.table(k)[0] for k in ("BETAMAXOXKAPPA2", "TAUWSHELTER", "ZPI", "DELTH")}
+
+
+@pytest.mark.parametrize("case", ["o48like", "o640like", "o48_iphys0"])
+def test_wind_input_term_against_numpy(built, case):
+    """SINPUT of the first SINFLX call (NGST = 1, no swell damping) restated in vectorised numpy from the formulas
+    (sinput_ard.F90:273-500: Janssen's growth rate gamma = eps beta_max/kappa^2 mu ln^4(mu) x^2 omega with the sheltering
+    recurrence tau' = tau - s_u int gamma F c^-1 ... over frequency; sinput_jan.F90:215-420 for IPHYS = 0).  Guards the
+    oracle's loop structure and index arithmetic; the constants are the table values."""
+    g, o, f, fl = make_oracle(case)
+    for _ in range(2):
+        assert o.step() == 0
+    sl, fld = o.term("sinput")
+    F1 = o.get_fl1()                                           # [m, k, ij]
+    wn, cinv = o.get_field3("WAVNUM"), o.get_field3("CINV")    # [m, ij]
+    us, z0, aird, wd = (o.get_field(k) for k in ("UFRIC", "Z0M", "AIRD", "WDWAVE"))
+    th, zpifr, dfim = o.table("TH"), o.table("ZPIFR"), o.table("DFIM")
+    c = _consts(o)
+    G, XKAPPA, ZALP = 9.806, 0.40, 0.008
+    raorw = np.maximum(aird, 1.0) / 1000.0
+    gam = np.zeros_like(F1)
+    if CASES[case]["iphys"] == 1:
+        sh = abs(c["TAUWSHELTER"])
+        taux, tauy = us ** 2 * np.sin(wd), us ** 2 * np.cos(wd)
+        xs, ys = np.zeros_like(us), np.zeros_like(us)
+        for m in range(F1.shape[0]):
+            tpx, tpy = taux - sh * xs, tauy - sh * ys
+            ustp, usd = (tpx ** 2 + tpy ** 2) ** 0.25, np.arctan2(tpx, tpy)
+            coslp = np.cos(th[:, None] - usd[None, :]) if sh != 0 else np.cos(th[:, None] - wd[None, :])
+            ucn = ustp * cinv[m]
+            zcn = np.log(wn[m] * z0)
+            with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+                zlog = zcn[None, :] + (XKAPPA / (ucn + ZALP))[None, :] / coslp
+                x = coslp * ucn[None, :]
+                gm = np.exp(zlog) * (zlog * zlog * x) ** 2 * (zpifr[m] * c["BETAMAXOXKAPPA2"] * raorw)[None, :]
+            gm = np.where((coslp > 0.01) & (zlog < 0.0), gm, 0.0)
+            gam[m] = gm
+            slp = gm * F1[m]
+            constf = (G / raorw) * cinv[m] * dfim[m]
+            xs = xs + (slp * np.sin(th)[:, None]).sum(axis=0) * constf
+            ys = ys + (slp * np.cos(th)[:, None]).sum(axis=0) * constf
+    else:
+        cosw = np.cos(th[:, None] - wd[None, :])
+        for m in range(F1.shape[0]):
+            ucn = us * cinv[m] + ZALP
+            zcn = np.log(wn[m] * z0)
+            cnsn = zpifr[m] * c["BETAMAXOXKAPPA2"] * (zpifr[m] ** 2 / (G * wn[m])) * raorw
+            with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+                zlog = zcn[None, :] + XKAPPA / cosw / ucn[None, :]
+                x = cosw * ucn[None, :]
+                gm = (zlog * zlog * x) ** 2 * np.exp(zlog) * cnsn[None, :]
+            gam[m] = np.where((cosw > 0.01) & (zlog < 0.0), gm, 0.0)
+    scale = np.abs(fld).max()
+    assert scale > 0 and (gam > 0).mean() > 0.05
+    np.testing.assert_allclose(fld, gam, rtol=1e-9, atol=1e-12 * scale)
+    np.testing.assert_allclose(sl, gam * F1, rtol=1e-9, atol=1e-12 * np.abs(sl).max())
+
+
+def test_saturation_dissipation_term_against_numpy(built):
+    """SDISSIP_ARD (sdissip_ard.F90:131-318 with SSDSC3 = SSDSC5 = 0) from the formulas: saturation B(k, theta) = k^3 c_g/(2 pi)
+    int cos^2(theta - theta') F dtheta' over exactly +-80 degrees (end bins truncated), B0 its maximum over direction, D = SSDSC2 sigma [SSDSC6 max(B0/B_r - 1,
+    0)^2 + (1 - SSDSC6) max(B/B_r - 1, 0)^2]; the direction window is rebuilt here with cyclic shifts instead of the
+    INDICESSAT / SATWEIGHTS tables (init_sdiss_ardh.F90:69-96)."""
+    g, o, f, fl = make_oracle("o640like")
+    for _ in range(2):
+        assert o.step() == 0
+    sl, fld = o.term("sdissip")
+    F1 = o.get_fl1()
+    wn, xk2cg = o.get_field3("WAVNUM"), o.get_field3("XK2CG")
+    th, zpifr = o.table("TH"), o.table("ZPIFR")
+    A = th.size
+    delth = 2 * np.pi / A
+    nsd = min(int(round(80.0 * np.pi / 180.0 / delth)), A // 2 - 1)
+    assert nsd == o.iscalar("NSDSNTH")
+    B = np.zeros_like(F1)
+    trunc = min(max(np.deg2rad(80.0) - nsd * delth + 0.5 * delth, 0.0), delth)      # the end bins only count up to +-80 degrees
+    for s in range(-nsd, nsd + 1):
+        B += (trunc if abs(s) == nsd else delth) * np.cos(s * delth) ** 2 * np.roll(F1, -s, axis=1)
+    B *= (wn / (2 * np.pi) * xk2cg)[:, None, :]
+    B0 = B.max(axis=1, keepdims=True)
+    SDSBR, SSDSC2, SSDSC4, SSDSC6 = 9.0e-4, -2.2e-5, 1.0, 0.3
+    D = (SSDSC2 * zpifr)[:, None, None] * (SSDSC6 * np.maximum(0.0, B0 / SDSBR - SSDSC4) ** 2 + (1 - SSDSC6) * np.maximum(0.0, B / SDSBR - SSDSC4) ** 2)
+    assert (D < 0).mean() > 0.01                                # there is breaking in the case
+    np.testing.assert_allclose(fld, D, rtol=1e-9, atol=1e-13 * np.abs(D).max())
+    np.testing.assert_allclose(sl, D * F1, rtol=1e-9, atol=1e-13 * np.abs(sl).max())
