@@ -342,3 +342,33 @@ def test_saturation_dissipation_term_against_numpy(built):
     assert (D < 0).mean() > 0.01                                # there is breaking in the case
     np.testing.assert_allclose(fld, D, rtol=1e-9, atol=1e-13 * np.abs(D).max())
     np.testing.assert_allclose(sl, D * F1, rtol=1e-9, atol=1e-13 * np.abs(sl).max())
+
+
+@pytest.mark.parametrize("k", [1, 4, 8, 11])
+def test_advection_moves_energy_with_the_group_velocity(built, k):
+    """A smooth blob in one spectral bin on the aqua planet, 24 PROPAGS2 steps: its centre of mass moves by c_g t towards the
+    bin's direction (clockwise from north: d(lat)/dt = c_g cos(theta)/R, d(lon)/dt = c_g sin(theta)/(R cos(lat))) within the
+    few per cent a first-order upwind scheme on the reduced grid allows.  Pins the direction and sign conventions of CTUW's
+    weights and of the neighbour tables independently of any reference run."""
+    CASES["_adv"] = dict(N=48, A=12, Fr=25, mask="aqua", iphys=1, nproma=32, dt=900.0)
+    g, o, f, fl = make_oracle("_adv")
+    th, fr = o.table("TH"), o.table("FR")
+    m, n, lon0, lat0, R = 4, 24, 180.0, 10.0, 6371229.0
+    cg = 9.806 / (4 * np.pi * fr[m])
+    blob = np.exp(-(((g.lon - lon0) * np.cos(np.deg2rad(g.lat))) ** 2 + (g.lat - lat0) ** 2) / (2 * 6.0 ** 2))
+    F = np.zeros_like(fl)
+    F[m, k] = blob
+    o.set_fl1(F)
+    for _ in range(n):
+        assert o.propag() == 0
+    G = o.get_fl1()
+    other = G.sum() - G[m].sum()
+    assert other <= 1e-12 * G.sum()                       # no exchange between frequencies without refraction
+    w0, w1 = blob / blob.sum(), G[m].sum(axis=0) / G[m].sum()
+    dlat, dlon = (w1 * g.lat).sum() - (w0 * g.lat).sum(), (w1 * g.lon).sum() - (w0 * g.lon).sum()
+    t = n * 900.0
+    elat = np.rad2deg(cg * np.cos(th[k]) * t / R)
+    elon = np.rad2deg(cg * np.sin(th[k]) * t / (R * np.cos(np.deg2rad(lat0))))
+    dist = np.hypot(elat, elon * np.cos(np.deg2rad(lat0)))
+    assert abs(dlat - elat) < 0.08 * dist and abs((dlon - elon) * np.cos(np.deg2rad(lat0))) < 0.08 * dist, (dlat, elat, dlon, elon)
+    assert abs(G.sum() / F.sum() - 1.0) < 0.05
