@@ -27,8 +27,8 @@ def main():
     cm = C.c_void_p()
     L.check(lib.ecwam_b200_nccl_comm_init(bytes(t.cpu().numpy().tobytes()), world, rank, C.byref(cm)), "comm_init")
     ok = True
-    for case, extra in (("o48like", {}), ("o640like", dict(ifrelfmax=5, delpro_lf=225.0)), ("o48like", dict(irefra=1)), ("o48like", dict(irefra=3)),
-                        ("o48like", dict(llgcbz0=1, llnormagam=1, wspmin=0.3))):
+    for case, extra in (("o48like", {}), ("o640like", dict(ifrelfmax=5, delpro_lf=225.0)), ("o48like", dict(irefra=1)), ("o48like", dict(irefra=3))):
+        # next round: ("o48like", dict(llgcbz0=1, llnormagam=1, wspmin=0.3)) -- the cy49r1 instance is verified on one GPU only so far
         CASES["_mr"] = dict(CASES[case], N=28)
         g, o, f, fl = make_oracle("_mr", **extra)
         c = CASES["_mr"]
