@@ -1484,7 +1484,10 @@ __host__ __device__ constexpr int dp_pad(int n) { return n + ((8 - (n % 16)) + 1
 __host__ __device__ constexpr int dp_pst(int A) { return dp_pad(A + 2 * dp_hr(A)); }                // point stride of a ring row [doubles]
 __host__ __device__ constexpr int dp_pstc(int A) { return dp_pad(A + 2 * dp_hc(A)); }               // point stride of an interaction plane
 __host__ __device__ constexpr int dp_threads(int A) { return (((A / 2) * ST_NPT + 31) / 32) * 32; }
-struct DpSmem { unsigned ring, cur, tbs, pc, part, bth0, stage, bsl, mbar, total, RSB, PSB, SSB; };
+#ifndef ST_DP_FIFO
+#define ST_DP_FIFO 0   // experiment for the next round: the three pending SNONLIN rows that receive nothing live in a per-thread
+#endif                 // shared-memory FIFO instead of sliding through 24 registers every step
+struct DpSmem { unsigned ring, cur, tbs, pc, part, bth0, stage, bsl, fifo, mbar, total, RSB, PSB, SSB; };
 __host__ __device__ constexpr DpSmem dp_smem(int A, bool lwflux) {
   DpSmem s{};
   const int nth = dp_threads(A), nwarp = nth / 32;
@@ -1500,6 +1503,9 @@ __host__ __device__ constexpr DpSmem dp_smem(int A, bool lwflux) {
   s.bth0 = o; o += 2 * ST_NPT * 8;
   s.stage = o; o += (lwflux ? 3 : 2) * s.SSB;
   s.bsl = o; o += 3 * s.SSB;
+#if ST_DP_FIFO
+  s.fifo = o; o += 6 * s.SSB;    // 3 quiet pending rows x (SL, FLD), one 16-byte pair per thread and slot
+#endif
   s.mbar = o; o += 16;
   s.total = o;
   return s;
@@ -1620,6 +1626,14 @@ __global__ void __maxnreg__(ST_MAXREG) k_stencil_dp(ImplDev d, long long p0, lon
   for (int x = 0; x < 7; ++x)
 #pragma unroll
     for (int i = 0; i < 2; ++i) { asl[x][i] = 0.0; afl[x][i] = 0.0; }
+#if ST_DP_FIFO
+  unsigned fifo_at = L.fifo + (unsigned)t * 16u;   // slot of the oldest quiet row (the rows at positions 1..3 of the slide)
+  {
+    V z; z.v[0] = 0.0; z.v[1] = 0.0;
+#pragma unroll
+    for (int x = 0; x < 6; ++x) sts<2>(sm, L.fifo + (unsigned)x * L.SSB + (unsigned)t * 16u, z);
+  }
+#endif
   V fmij, a_philf, a_ts, a_tu, a_e1, a_e2, a_el;
 #pragma unroll
   for (int i = 0; i < 2; ++i) { fmij.v[i] = 0.0; a_philf.v[i] = 0.0; a_ts.v[i] = 0.0; a_tu.v[i] = 0.0; a_e1.v[i] = 0.0; a_e2.v[i] = 0.0; a_el.v[i] = 0.0; }
@@ -1767,6 +1781,24 @@ __global__ void __maxnreg__(ST_MAXREG) k_stencil_dp(ImplDev d, long long p0, lon
         };
         half(IC<0>{}); half(IC<1>{});
       }
+#if ST_DP_FIFO
+      {   // pop the oldest quiet row (position 1), push the row leaving position 4 into the slot it frees
+        const V q_sl = lds<2>(sm, fifo_at), q_fl = lds<2>(sm, fifo_at + 3u * L.SSB);
+        V p_sl, p_fl;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { p_sl.v[i] = asl[4][i]; p_fl.v[i] = afl[4][i]; }
+        sts<2>(sm, fifo_at, p_sl); sts<2>(sm, fifo_at + 3u * L.SSB, p_fl);
+        fifo_at = (fifo_at == L.fifo + 2u * L.SSB + (unsigned)t * 16u) ? L.fifo + (unsigned)t * 16u : fifo_at + L.SSB;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          tot_sl.v[i] = asl[0][i] + sl_mm.v[i];   tot_fl.v[i] = afl[0][i] + fl_mm.v[i];
+          asl[0][i] = q_sl.v[i] + sl_mm1.v[i];    afl[0][i] = q_fl.v[i] + fl_mm1.v[i];
+          asl[4][i] = asl[5][i];                  afl[4][i] = afl[5][i];
+          asl[5][i] = asl[6][i] + sl_mp.v[i];     afl[5][i] = afl[6][i] + fl_mp.v[i];
+          asl[6][i] = sl_mp1.v[i];                afl[6][i] = fl_mp1.v[i];
+        }
+      }
+#else
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         tot_sl.v[i] = asl[0][i] + sl_mm.v[i];   tot_fl.v[i] = afl[0][i] + fl_mm.v[i];
@@ -1778,6 +1810,7 @@ __global__ void __maxnreg__(ST_MAXREG) k_stencil_dp(ImplDev d, long long p0, lon
         asl[5][i] = asl[6][i] + sl_mp.v[i];     afl[5][i] = afl[6][i] + fl_mp.v[i];
         asl[6][i] = sl_mp1.v[i];                afl[6][i] = fl_mp1.v[i];
       }
+#endif
     }
     // finish row rfin (implsch.F90:276-395 for these bins)
     if (fin) {
