@@ -13,7 +13,7 @@ while [ $# -gt 1 ]; do
   ( $NVCC $FL $flags -Xptxas -v -c implsch.cu -o ../../build_variants/implsch_$name.o 2> ../../build_variants/implsch_$name.log
     $NVCC $FL $flags -fmad=false -c propag.cu -o ../../build_variants/propag_$name.o
     $NVCC $FL $flags -c outparam.cu -o ../../build_variants/outparam_$name.o
-    $NVCC $ARCH -shared -o ../../build_variants/lib_$name.so api.o ../../build_variants/propag_$name.o ../../build_variants/implsch_$name.o ../../build_variants/outparam_$name.o host_tables.o host_grid.o -lnccl -lcudart -lgomp
-    echo "$name: $(grep -A3 'k_stencilILi2ELb0' ../../build_variants/implsch_$name.log | grep -o 'Used [0-9]* registers\|[0-9]* bytes spill stores' | tr '\n' ' ')" ) &
+    $NVCC $ARCH -shared -o ../../build_variants/lib_$name.so api.o ../../build_variants/propag_$name.o ../../build_variants/implsch_$name.o ../../build_variants/outparam_$name.o host_tables.o host_grid.o host_io.o -lnccl -lcudart -lgomp
+    echo "$name: $(grep -A3 'k_stencil_dpILi36ELb0' ../../build_variants/implsch_$name.log | grep -o 'Used [0-9]* registers\|[0-9]* bytes spill stores' | tr '\n' ' ')" ) &
 done
 wait
