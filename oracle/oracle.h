@@ -227,6 +227,7 @@ void term_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK
 // ---------------------------------------------------------------------------
 // The steps either side of the hot path (orc_output.cpp): NEWWIND, OUTBLOCK core parameters, WAMNORM statistics.
 bool outparam_supported(int itg);
+double aki(const Tables& t, double OM, double BETA);   // aki.F90:71-91
 void newwind(Model& m, int ir, const Fields& next);
 void outblock(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK, const OutSel& sel, double* BOUT /*(KIJL,NIPRMOUT)*/);
 void mpminmaxavg(Model& m, const OutSel& sel, const std::vector<std::vector<double>>& bout /*[rank](P,NIPRMOUT,C)*/, bool global,

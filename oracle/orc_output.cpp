@@ -383,9 +383,190 @@ void meansqs(const Config& c, const Tables& t, double XKMSS, int KIJL, int NANG,
   }
 }
 
+// ---- the KURTOSIS family of OUTBLOCK (outblock.F90:208-211): skewness, kurtosis, Benjamin-Feir index, Goda's peakedness,
+//      expected maximum wave height and its period.  Oracle only so far: the product rejects these parameters.
+// transf_r.F90:57-82
+static double transf_r(const Tables& t, const Config& c, double XK0, double D) {
+  const double EPS = 0.0001, XKDMIN = 0.75;   // yowshal.F90:23
+  if (D < c.bathymax && D > 0.0 && XK0 > 0.0) {
+    double X = XK0 * D;
+    if (X > t.DKMAX) return 0.5;
+    const double XK = std::max(XK0, XKDMIN / D);
+    X = XK * D;
+    const double T_0 = std::tanh(X), T_0_SQ = T_0 * T_0;
+    const double OM = std::sqrt(t.G * XK * T_0), C_0 = OM / XK;
+    const double V_G = X < EPS ? C_0 : 0.5 * C_0 * (1.0 + 2.0 * X / std::sinh(2.0 * X));
+    const double a = T_0 - X * (1.0 - T_0_SQ);
+    const double D2OM = a * a + 4.0 * (X * X) * T_0_SQ * (1.0 - T_0_SQ);
+    const double q = V_G / C_0;
+    return 4.0 * (q * q * q) * T_0_SQ / D2OM;
+  }
+  return 0.5;
+}
+// transf_bfi.F90:62-105
+static double transf_bfi(const Tables& t, const Config& c, double XK0, double D, double XNU, double SIG_TH) {
+  const double EPS = 0.0001, XKDMIN = 0.75, TMIN = -4.0, TMAX = 4.0;
+  if (D < c.bathymax && D > 0.0) {
+    double X = XK0 * D;
+    if (X > t.DKMAX) return 1.0;
+    const double XK = std::max(XK0, XKDMIN / D);
+    X = XK * D;
+    const double T_0 = std::tanh(X), T_0_SQ = T_0 * T_0;
+    const double OM = std::sqrt(t.G * XK * T_0), C_0 = OM / XK, C_S_SQ = t.G * D;
+    const double V_G = X < EPS ? C_0 : 0.5 * C_0 * (1.0 + 2.0 * X / std::sinh(2.0 * X));
+    const double V_G_SQ = V_G * V_G;
+    const double a = T_0 - X * (1.0 - T_0_SQ);
+    const double D2OM = a * a + 4.0 * (X * X) * T_0_SQ * (1.0 - T_0_SQ);
+    const double XNL_1 = (9.0 * (T_0_SQ * T_0_SQ) - 10.0 * T_0_SQ + 9.0) / (8.0 * T_0_SQ * T_0);
+    const double b = 2.0 * V_G - 0.5 * C_0;
+    const double XNL_2 = (b * b / (t.G * D - V_G_SQ) + 1.0) / X;
+    const double e = 2.0 * C_0 + V_G * (1.0 - T_0_SQ);
+    const double XNL_4 = 1. / (4.0 * T_0) * (e * e) / (C_S_SQ - V_G_SQ);
+    const double ALP = (1.0 - V_G_SQ / C_S_SQ) * (C_0 * C_0) / V_G_SQ;
+    const double ZFAC = (SIG_TH * SIG_TH) / (SIG_TH * SIG_TH + ALP * (XNU * XNU));
+    const double XNL_3 = ZFAC * XNL_4;
+    const double T_NL = XNL_1 - XNL_2 + XNL_3;
+    const double q = V_G / C_0;
+    return std::max(std::min(TMAX, 4.0 * (q * q) * T_NL * T_0 / D2OM), TMIN);
+  }
+  return 1.0;
+}
+struct KurtOut { V C3, C4, BF2, QP, HMAX, TMAX, ETA_M, R, XNSLC, SIG_TH, EPS, XNU; };
+void kurtosis(const Config& c, const Tables& t, int KIJL, int NANG, int NFRE, const S3& FL1, const double* DEPTH, KurtOut& o) {
+  for (V* v : {&o.C3, &o.C4, &o.BF2, &o.QP, &o.HMAX, &o.TMAX, &o.ETA_M, &o.R, &o.XNSLC, &o.SIG_TH, &o.EPS, &o.XNU}) v->assign(KIJL + 1, 0.0);
+  const double ZEPSILON = 10.0 * 2.220446049250313e-16, ZSQREPSILON = std::sqrt(ZEPSILON);
+  const double DELT25 = t.WETAIL * t.FR(NFRE) * t.DELTH, COEF_FR1 = t.WP1TAIL * t.DELTH * (t.FR(NFRE) * t.FR(NFRE));
+  const double COEF_FR2 = t.WP2TAIL * t.DELTH * (t.FR(NFRE) * t.FR(NFRE) * t.FR(NFRE)), DELT2 = t.FRTAIL * t.DELTH;
+  auto DFIMFR2 = [&](int M) { return t.DFIM(M) * (t.FR(M) * t.FR(M)); };   // initmdl.F90:447
+  // ---- PEAK_ANG (peak_ang.F90:72-175): spectral width XNU and the angular width SIG_TH around the peak
+  {
+    const int NSH = 1 + (int)(std::log(1.5) / std::log(t.FRATIO));
+    for (int IJ = 1; IJ <= KIJL; ++IJ) {
+      double SUM0 = ZEPSILON, SUM1 = 0.0, SUM2 = 0.0, TEMP = 0.0;
+      for (int M = 1; M <= NFRE; ++M) {
+        TEMP = FL1(IJ, 1, M);
+        for (int K = 2; K <= NANG; ++K) TEMP = TEMP + FL1(IJ, K, M);
+        SUM0 = SUM0 + TEMP * t.DFIM(M); SUM1 = SUM1 + TEMP * t.DFIMFR(M); SUM2 = SUM2 + TEMP * DFIMFR2(M);
+      }
+      SUM0 = SUM0 + DELT25 * TEMP; SUM1 = SUM1 + COEF_FR1 * TEMP; SUM2 = SUM2 + COEF_FR2 * TEMP;
+      o.XNU[IJ] = SUM0 > ZEPSILON ? std::sqrt(std::max(ZEPSILON, SUM2 * SUM0 / (SUM1 * SUM1) - 1.0)) : ZEPSILON;
+      double XMAX = 0.0;
+      int MMAX = 2;
+      for (int M = 2; M <= NFRE - 1; ++M) for (int K = 1; K <= NANG; ++K) if (FL1(IJ, K, M) > XMAX) { MMAX = M; XMAX = FL1(IJ, K, M); }
+      double S1 = ZEPSILON, S2 = 0.0, SUM_S = 0.0, SUM_C = ZEPSILON, THMEAN = 0.0;
+      for (int M = std::max(1, MMAX - NSH); M <= std::min(NFRE, MMAX + NSH); ++M) {
+        for (int K = 1; K <= NANG; ++K) { SUM_S = SUM_S + t.SINTH(K) * FL1(IJ, K, M); SUM_C = SUM_C + t.COSTH(K) * FL1(IJ, K, M); }
+        THMEAN = std::atan2(SUM_S, SUM_C);
+        for (int K = 1; K <= NANG; ++K) {
+          S1 = S1 + FL1(IJ, K, M) * t.DFIM(M);
+          S2 = S2 + std::cos(t.TH(K) - THMEAN) * FL1(IJ, K, M) * t.DFIM(M);
+        }
+      }
+      o.SIG_TH[IJ] = S1 > ZEPSILON ? std::sqrt(2.0 * (1.0 - S2 / S1)) : 0.0;
+    }
+  }
+  // ---- KURTOSIS (kurtosis.F90:239-350)
+  const double CONST_SIG_SQRTPIM1 = 1.0 / std::sqrt(t.PI), CONST_OM_ZPI = 0.89 * t.ZPI, FRMAX = t.FR(NFRE), FRMIN = t.FR(1);
+  const double QPMIN = 0.5, QPMAX = 15.0, BF2MIN = -5.0, BF2MAX = 5.0, FLTHRS = 0.4;
+  V SUM0(KIJL + 1), SUM1(KIJL + 1), F_M(KIJL + 1), XKP(KIJL + 1);
+  std::vector<double> FF(NFRE + 1);
+  for (int IJ = 1; IJ <= KIJL; ++IJ) {
+    for (int M = 1; M <= NFRE; ++M) { FF[M] = FL1(IJ, 1, M); for (int K = 2; K <= NANG; ++K) FF[M] = FF[M] + FL1(IJ, K, M); }
+    double FFMAX = FF[1];
+    for (int M = 2; M <= NFRE; ++M) FFMAX = std::max(FFMAX, FF[M]);
+    double S0 = ZEPSILON, S1 = 0.0, S2 = 0.0, S6 = 0.0;
+    for (int M = 1; M <= NFRE; ++M) { S0 = S0 + FF[M] * t.DFIM(M); S1 = S1 + FF[M] * t.DFIMFR(M); S2 = S2 + FF[M] * DFIMFR2(M); S6 = S6 + FF[M] * t.DFIMOFR(M); }
+    S0 = S0 + DELT25 * FF[NFRE]; S1 = S1 + COEF_FR1 * FF[NFRE]; S2 = S2 + COEF_FR2 * FF[NFRE]; S6 = S6 + DELT2 * FF[NFRE];
+    (void)S2;
+    double S40 = ZSQREPSILON, S4 = 0.0;
+    FFMAX = FLTHRS * FFMAX;
+    for (int M = 1; M <= NFRE; ++M) if (FF[M] > FFMAX) { S40 = S40 + FF[M] * t.DFIM(M); S4 = S4 + (FF[M] * FF[M]) * (2.0 * t.DELTH * t.DFIMFR(M)); }
+    SUM0[IJ] = S0; SUM1[IJ] = S1;
+    if (S1 > ZSQREPSILON && S0 > ZEPSILON) {
+      F_M[IJ] = std::max(std::min(S1 / S0, FRMAX), FRMIN);
+      o.QP[IJ] = std::max(std::min(S4 / (S40 * S40), QPMAX), QPMIN);
+      const double SIG_OM = CONST_SIG_SQRTPIM1 / o.QP[IJ];
+      const double OM_MEAN = CONST_OM_ZPI * std::max(std::min(S0 / S6, FRMAX), FRMIN);
+      XKP[IJ] = aki(t, OM_MEAN, DEPTH[IJ - 1]);
+      o.EPS[IJ] = XKP[IJ] * std::sqrt(S0);
+      const double TRANS = transf_bfi(t, c, XKP[IJ], DEPTH[IJ - 1], o.XNU[IJ], o.SIG_TH[IJ]);
+      const double r = o.EPS[IJ] / std::max(SIG_OM, ZEPSILON);
+      o.BF2[IJ] = std::max(std::min(2.0 * TRANS * (r * r), BF2MAX), BF2MIN);
+    } else {
+      F_M[IJ] = 0.0; o.QP[IJ] = 0.0;
+      const double OM_MEAN = CONST_OM_ZPI * FRMAX;
+      XKP[IJ] = OM_MEAN * OM_MEAN / t.G; o.EPS[IJ] = 0.0; o.BF2[IJ] = 0.0;
+    }
+  }
+  // ---- STAT_NL (stat_nl.F90:74-170)
+  {
+    const double EPS = 0.0001, XKDMIN = 0.75, RMIN = 0.0, RMAX = 16.0, C3MIN = 0.0, C3MAX = 0.25, C4MIN = -0.25, C4MAX = 0.25;
+    const double CONST_C3 = 1.12 * 2.0, CONST_C4 = 0.93 * 8.0, C3DELTA_ADJ = 0.9, SQRT3 = std::sqrt(3.0);
+    const double C4_CONST = 0.9 * t.PI / (3.0 * SQRT3), ZC1 = 4.0 * SQRT3 / t.PI, ZC2 = (1.0 / 3.0 + 2.0 * SQRT3 / t.PI), ZC3 = 2.0 * SQRT3 / t.PI - 4.0 / 3.0;
+    for (int IJ = 1; IJ <= KIJL; ++IJ) {
+      const double TRANSF = transf_r(t, c, XKP[IJ], DEPTH[IJ - 1]);
+      const double D = DEPTH[IJ - 1], XM0 = SUM0[IJ];
+      if (XM0 > ZEPSILON && D > 0.0 && XKP[IJ] > 0.0) {
+        const double XK = std::max(XKP[IJ], XKDMIN / D), X = XK * D, T0 = std::tanh(X), OM = std::sqrt(t.G * XK * T0), T0_SQ = T0 * T0;
+        const double ALPH = XK / (4.0 * T0_SQ * T0) * (3.0 - T0_SQ), GAM = -0.5 * (ALPH * ALPH);
+        const double C_0 = OM / XK, C_S_SQ = t.G * D;
+        double V_G;
+        if (X > t.DKMAX) V_G = 0.5 * C_0; else if (X < EPS) V_G = C_0; else V_G = 0.5 * C_0 * (1.0 + 2.0 * X / std::sinh(2.0 * X));
+        const double V_G_SQ = V_G * V_G;
+        const double ZFAC = -0.25 * XK * C_S_SQ / (C_S_SQ - V_G_SQ);
+        const double DELTA_1D = ZFAC * (2.0 * (1.0 - T0_SQ) / T0 + 1.0 / X);
+        const double ZFAC1 = 0.5 * C_0 * C_S_SQ * V_G / T0;
+        const double XKAPPA1 = ZFAC1 * (2.0 * C_0 + V_G * (1.0 - T0_SQ)) / (C_S_SQ - V_G_SQ);
+        const double ALPHA = (1.0 - V_G_SQ / C_S_SQ) * (C_0 * C_0) / V_G_SQ;
+        const double st2 = o.SIG_TH[IJ] * o.SIG_TH[IJ];
+        const double ZFAC2 = st2 / (st2 + ALPHA * (o.XNU[IJ] * o.XNU[IJ]));
+        const double DELTA_2D = 0.5 * (XK * XK) * XKAPPA1 / (OM * C_S_SQ) * ZFAC2;
+        const double DELTA = DELTA_1D + DELTA_2D;
+        o.ETA_M[IJ] = 2.0 * XM0 * DELTA;
+        o.C3[IJ] = std::max(std::min(C3MAX, CONST_C3 * std::sqrt(XM0) * (ALPH + C3DELTA_ADJ * DELTA)), C3MIN);
+        const double C4_B = CONST_C4 * XM0 * (GAM + ALPH * ALPH + (ALPH + DELTA) * (ALPH + DELTA));
+        const double q = o.SIG_TH[IJ] / o.XNU[IJ];
+        o.R[IJ] = std::max(std::min(TRANSF * (q * q), RMAX), RMIN);
+        const double ZR = o.R[IJ];
+        const double XJ = ZR > 1.0 ? -C4_CONST / ZR * (1.0 - ZC1 / std::sqrt(ZR) + ZC2 / ZR + ZC3 / (ZR * ZR))
+                                   : C4_CONST * (1.0 - ZC1 * std::sqrt(ZR) + ZC2 * ZR + ZC3 * (ZR * ZR));
+        o.C4[IJ] = std::max(std::min(C4MAX, XJ * o.BF2[IJ] + C4_B), C4MIN);
+      }
+    }
+  }
+  // ---- number of waves, H_MAX (h_max.F90:60-110), TMAX, HMAX (kurtosis.F90:360-403)
+  const double ZFACN = 2.0 * t.ZPI / std::sqrt(t.ZPI), DUR = 1200.0;
+  const double GAMC = 0.5772, EB = 10.0, FLOGMIN = 0.1, AA_MAX = 1000.0, H_C = 2.0, H_C_MIN = 1.0, H_C_MAX = 4.0;
+  const double TWOG1 = -2.0 * GAMC, G2 = GAMC * GAMC + t.PI * t.PI / 6.0, AE = 0.5 * EB * (EB - 2.0), BE = 0.5 * EB * (EB * EB - 6.0 * EB + 6.0);
+  const double EMIN = 2.0 * H_C_MIN * H_C_MIN, EMAX = 2.0 * H_C_MAX * H_C_MAX, EVAL = 2.0 * H_C * H_C;
+  for (int IJ = 1; IJ <= KIJL; ++IJ) {
+    o.XNSLC[IJ] = F_M[IJ] > 0.0 ? (double)nint(DUR * (ZFACN * o.XNU[IJ] * F_M[IJ])) : 0.0;
+    double HMAXN, E = EVAL;
+    const double DFNORMA = o.C4[IJ] * AE + (o.C3[IJ] * o.C3[IJ]) * BE;
+    if (o.XNSLC[IJ] > 0.0 && std::fabs(DFNORMA) > ZEPSILON) {
+      const double F = std::log(std::max(1.0 + DFNORMA, FLOGMIN));
+      const double AA = std::min(((EB - F) * (EB - F) - 2.0 * EB) / (2.0 * F), AA_MAX), BB = 2.0 * (1.0 + AA);
+      const double BBM1 = 1.0 / (BB + ZEPSILON * std::copysign(1.0, BB));
+      for (int I = 1; I <= 5; ++I) {
+        const double Z0 = std::log(o.XNSLC[IJ] * std::sqrt(0.5 * E));
+        E = (G2 - TWOG1 * (AA + Z0) + (2.0 * AA + Z0) * Z0) * BBM1;
+        E = std::min(std::max(E, EMIN), EMAX);
+      }
+      HMAXN = std::sqrt(0.5 * E);
+    } else HMAXN = H_C_MIN;
+    if (SUM1[IJ] > ZEPSILON && HMAXN > ZEPSILON) {
+      const double ZEPS = o.XNU[IJ] / (std::sqrt(2.0) * HMAXN), z2 = ZEPS * ZEPS;
+      o.TMAX[IJ] = (SUM0[IJ] / SUM1[IJ]) * (1.0 + 0.5 * z2 + 0.75 * (z2 * z2));
+    } else o.TMAX[IJ] = 0.0;
+    o.HMAX[IJ] = SUM0[IJ] > 0.0 ? HMAXN * (4.0 * std::sqrt(SUM0[IJ])) : 0.0;
+    if (SUM0[IJ] <= 0.0) o.XNU[IJ] = 0.0;
+  }
+}
+
 bool outparam_supported(int itg) {
   static const int ok[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 20, 21, 22, 23, 24, 25, 26, 27, 28, 32, 35, 36, 37, 38,
-                           39, 40, 41, 52, 53, 54, 55, 56, 62, 63, 64, 65, 66, 67, 68, 69, 73, 74, 75, 76, 77};
+                           39, 40, 41, 52, 53, 54, 55, 56, 62, 63, 64, 65, 66, 67, 68, 69, 73, 74, 75, 76, 77,
+                           29, 30, 31, 33, 34, 57, 70, 71, 72};   // the KURTOSIS family: oracle only so far
   for (int v : ok) if (v == itg) return true;
   return false;
 }
@@ -446,6 +627,13 @@ void outblock(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK, 
   }
   if ((b = col(8))) { const double* TAUW = p1(f.TAUW); for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = TAUW[IJ - 1] / std::max(UFRIC[IJ - 1] * UFRIC[IJ - 1], t.EPSUS); }
   if ((b = col(9))) meansqs(c, t, t.XK_GC(t.NWAV_GC), KIJL, NANG, NFRE, FL1, &f.WAVNUM(1, 1, ICHNK), UFRIC, COSWDIF, b);   // outblock.F90:285-287, userin.F90:1213-1215
+  if (col(29) || col(30) || col(31) || col(33) || col(34) || col(57) || col(70) || col(71) || col(72)) {   // outblock.F90:208-211, 385-404, 481, 526-535
+    KurtOut ko;
+    kurtosis(c, t, KIJL, NANG, NFRE, FL1, p1(f.DEPTH), ko);
+    const std::pair<int, V*> cols[] = {{29, &ko.C4}, {30, &ko.BF2}, {31, &ko.QP}, {33, &ko.HMAX}, {34, &ko.TMAX}, {57, &ko.C3}, {70, &ko.ETA_M},
+                                       {71, &ko.R}, {72, &ko.XNSLC}};
+    for (auto& pr : cols) if ((b = col(pr.first))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = (*pr.second)[IJ];
+  }
   if ((b = col(10))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = WSWAVE[IJ - 1];
   if ((b = col(11))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = 4.0 * std::sqrt(std::max(so.ESEA[IJ], 0.0));
   if ((b = col(12))) for (int IJ = 1; IJ <= KIJL; ++IJ) b[IJ] = 4.0 * std::sqrt(std::max(so.ESWELL[IJ], 0.0));

@@ -8,7 +8,7 @@
 namespace orc {
 
 // aki.F90:71-91
-static double aki(const Tables& t, double OM, double BETA) {
+double aki(const Tables& t, double OM, double BETA) {
   const double EBS = 0.0001;
   double AKM1 = OM * OM / (4.0 * t.G);
   double AKM2 = OM / (2.0 * std::sqrt(t.G * BETA));

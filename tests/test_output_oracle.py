@@ -167,3 +167,44 @@ def test_getwnd_blocking_step(built, opts):
     np.testing.assert_allclose(r["cithick"], h, rtol=1e-15)
     for k in ("aird", "wstar", "ustra", "vstra"):
         np.testing.assert_array_equal(r[k], pick(f[k]))
+
+
+def test_kurtosis_family_in_the_oracle(built):
+    """OUTBLOCK parameters 29-31, 33, 34, 57, 70-72 (KURTOSIS with PEAK_ANG, TRANSF_BFI, STAT_NL, H_MAX; kurtosis.F90:239-403) —
+    oracle only so far (the product rejects them).  The spectral sums are restated in numpy (width nu = sqrt(m0 m2/m1^2 - 1),
+    Goda's peakedness Qp = 2 int f E^2 df / (int E df)^2 over the bins above 40 % of the peak, angular width around the peak);
+    the derived statistics must stay inside the clips of stat_nl.F90 / h_max.F90 and behave as extreme-value statistics do."""
+    g, o, f, fl = make_oracle("o48like")
+    for _ in range(4):
+        assert o.step() == 0
+    itg = [29, 30, 31, 33, 34, 57, 70, 71, 72, 1, 3]
+    b = dict(zip(itg, o.outbs(itg, [0] * len(itg), [0] * len(itg))))
+    F = o.get_fl1()
+    fr, dfim, th = o.table("FR"), o.table("DFIM"), o.table("TH")
+    delth = 2 * np.pi / th.size
+    FF = F.sum(axis=1)                                           # [m, ij]
+    eps = 10 * np.finfo(float).eps
+    tail = FF[-1]
+    m0 = eps + (FF * dfim[:, None]).sum(0) + 0.25 * fr[-1] * delth * tail
+    m1 = (FF * (dfim * fr)[:, None]).sum(0) + (1.0 / 3.0) * delth * fr[-1] ** 2 * tail
+    m2 = (FF * (dfim * fr ** 2)[:, None]).sum(0) + 0.5 * delth * fr[-1] ** 3 * tail
+    xnu = np.sqrt(np.maximum(eps, m2 * m0 / m1 ** 2 - 1.0))
+    sel = FF > 0.4 * FF.max(axis=0)[None, :]
+    s40 = np.sqrt(eps) + np.where(sel, FF * dfim[:, None], 0.0).sum(0)
+    s4 = np.where(sel, FF ** 2 * (2 * delth * dfim * fr)[:, None], 0.0).sum(0)
+    qp = np.clip(s4 / s40 ** 2, 0.5, 15.0)
+    hs = b[1]
+    sea = hs > 0.05                                              # (the routine returns zeros where there is no energy)
+    np.testing.assert_allclose(b[31][sea], qp[sea], rtol=1e-12)
+    # number of waves in 20 minutes: N = nint(1200 * sqrt(2 pi) nu f_mean)  (kurtosis.F90:360-369)
+    fmean = np.clip(m1 / m0, fr[0], fr[-1])
+    np.testing.assert_array_equal(b[72][sea], np.rint(1200.0 * (2 * (2 * np.pi) / np.sqrt(2 * np.pi)) * xnu * fmean)[sea])
+    assert (np.abs(b[29]) <= 0.25).all() and (b[57] >= 0).all() and (b[57] <= 0.25).all() and (np.abs(b[30]) <= 5).all()
+    assert (b[71] >= 0).all() and (b[71] <= 16).all()
+    r = b[33][sea] / hs[sea]
+    assert r.min() >= 1.0 and r.max() <= 4.0 and 1.5 < np.median(r) < 2.3          # Hmax ~ 1.6 - 2.1 Hs for 100 - 300 waves
+    assert (b[34][sea] >= (m0 / m1)[sea] * (1 - 1e-12)).all()                        # the period of the highest wave exceeds T_m01
+    # deep-water narrow-band limit of the skewness: C3 -> 1.12 k_p sqrt(m0) (stat_nl.F90:128-130 with tanh = 1, Delta -> 0)
+    deep = sea & (o.get_field("DEPTH") > 900.0) & (b[57] < 0.249)
+    kp = (0.89 * 2 * np.pi * np.clip(m0 / ((FF * (dfim / fr)[:, None]).sum(0) + 0.2 * delth * tail), fr[0], fr[-1])) ** 2 / 9.806
+    np.testing.assert_allclose(b[57][deep], 1.12 * kp[deep] * np.sqrt(m0[deep]), rtol=0.03)
