@@ -854,21 +854,116 @@ void SDISSIP_JAN(const Ctx& x, V3 FL1, V3 FLD, V3 SL, V2 WAVNUM, V1 EMEAN, V1 F1
   }
 }
 
-// snonlin.F90:116-498 (ISNONLIN = 0)
+// transf.F90: ratio of the shallow- to the deep-water narrow-band interaction coefficient (Janssen & Onorato 2007)
+static double TRANSF(const Ctx& x, double XK, double D) {
+  const Tables& t = x.t;
+  const double EPS = 0.0001;
+  if (D < x.c.bathymax && D > 0.0) {
+    const double X = XK * D;
+    if (X > t.DKMAX) return 1.0;
+    const double T_0 = std::tanh(X), OM = std::sqrt(t.G * XK * T_0), C_0 = OM / XK;
+    const double V_G = X < EPS ? C_0 : 0.5 * C_0 * (1.0 + 2.0 * X / std::sinh(2.0 * X));
+    const double T2 = T_0 * T_0;
+    const double a = T_0 - X * (1.0 - T2);
+    const double DV_G = a * a + 4.0 * (X * X) * T2 * (1.0 - T2);
+    const double XNL_1 = (9.0 * (T2 * T2) - 10.0 * T2 + 9.0) / (8.0 * (T2 * T_0));
+    const double b = 2.0 * V_G - 0.5 * C_0;
+    const double XNL_2 = (b * b / (t.G * D - V_G * V_G) + 1.0) / X;
+    const double XNL = XNL_1 - XNL_2;
+    return XNL * XNL / (DV_G * ((T2 * T2) * (T2 * T2)));
+  }
+  return 1.0;
+}
+// transf_snl.F90:57-100: the same with the directional-width correction of the mean-flow term
+static double TRANSF_SNL(const Ctx& x, double XK0, double D, double XNU, double SIG_TH) {
+  const Tables& t = x.t;
+  const double EPS = 0.0001, XKDMIN = 0.75, TMIN = 0.1, TMAX = 10.0;
+  if (D < x.c.bathymax && D > 0.0) {
+    double X = XK0 * D;
+    if (X > t.DKMAX) return 1.0;
+    const double XK = std::max(XK0, XKDMIN / D);
+    X = XK * D;
+    const double T_0 = std::tanh(X), T_0_SQ = T_0 * T_0, OM = std::sqrt(t.G * XK * T_0), C_0 = OM / XK, C_S_SQ = t.G * D;
+    const double V_G = X < EPS ? C_0 : 0.5 * C_0 * (1.0 + 2.0 * X / std::sinh(2.0 * X));
+    const double V_G_SQ = V_G * V_G;
+    const double a = T_0 - X * (1. - T_0_SQ);
+    const double DV_G = a * a + 4.0 * (X * X) * T_0_SQ * (1.0 - T_0_SQ);
+    const double XNL_1 = (9.0 * (T_0_SQ * T_0_SQ) - 10.0 * T_0_SQ + 9.0) / (8.0 * T_0_SQ * T_0);
+    const double b = 2.0 * V_G - 0.5 * C_0;
+    const double XNL_2 = (b * b / (t.G * D - V_G_SQ) + 1.0) / X;
+    const double e = 2.0 * C_0 + V_G * (1.0 - T_0_SQ);
+    const double XNL_4 = 1. / (4.0 * T_0) * (e * e) / (C_S_SQ - V_G_SQ);
+    const double ALP = (1. - V_G_SQ / C_S_SQ) * (C_0 * C_0) / V_G_SQ;
+    const double ZFAC = (SIG_TH * SIG_TH) / (SIG_TH * SIG_TH + ALP * (XNU * XNU));
+    const double XNL = XNL_1 - XNL_2 + ZFAC * XNL_4;
+    const double T4 = (T_0_SQ * T_0_SQ) * (T_0_SQ * T_0_SQ);
+    return std::max(std::min(TMAX, XNL * XNL / (DV_G * T4)), TMIN);
+  }
+  return 1.0;
+}
+// peak_ang.F90:72-175 (same statements as in orc_output.cpp's kurtosis, on the chunk views of this file)
+static void PEAK_ANG(const Ctx& x, V3 FL1, std::vector<double>& XNU, std::vector<double>& SIG_TH) {
+  const Tables& t = x.t;
+  const int NANG = x.NANG, NFRE = x.NFRE;
+  const double ZEPSILON = 10.0 * 2.220446049250313e-16;
+  const int NSH = 1 + (int)(std::log(1.5) / std::log(t.FRATIO));
+  const double DELT25 = t.WETAIL * t.FR(NFRE) * t.DELTH, COEF_FR = t.WP1TAIL * t.DELTH * (t.FR(NFRE) * t.FR(NFRE));
+  const double COEF_FR2 = t.WP2TAIL * t.DELTH * (t.FR(NFRE) * t.FR(NFRE) * t.FR(NFRE));
+  for (int IJ = x.KIJS; IJ <= x.KIJL; ++IJ) {
+    double SUM0 = ZEPSILON, SUM1 = 0.0, SUM2 = 0.0, TEMP = 0.0;
+    for (int M = 1; M <= NFRE; ++M) {
+      TEMP = FL1(IJ, 1, M);
+      for (int K = 2; K <= NANG; ++K) TEMP = TEMP + FL1(IJ, K, M);
+      SUM0 = SUM0 + TEMP * t.DFIM(M); SUM1 = SUM1 + TEMP * t.DFIMFR(M); SUM2 = SUM2 + TEMP * (t.DFIM(M) * (t.FR(M) * t.FR(M)));
+    }
+    SUM0 = SUM0 + DELT25 * TEMP; SUM1 = SUM1 + COEF_FR * TEMP; SUM2 = SUM2 + COEF_FR2 * TEMP;
+    XNU[IJ] = SUM0 > ZEPSILON ? std::sqrt(std::max(ZEPSILON, SUM2 * SUM0 / (SUM1 * SUM1) - 1.0)) : ZEPSILON;
+    double XMAX = 0.0;
+    int MMAX = 2;
+    for (int M = 2; M <= NFRE - 1; ++M) for (int K = 1; K <= NANG; ++K) if (FL1(IJ, K, M) > XMAX) { MMAX = M; XMAX = FL1(IJ, K, M); }
+    double S1 = ZEPSILON, S2 = 0.0, SUM_S = 0.0, SUM_C = ZEPSILON, THMEAN = 0.0;
+    for (int M = std::max(1, MMAX - NSH); M <= std::min(NFRE, MMAX + NSH); ++M) {
+      for (int K = 1; K <= NANG; ++K) { SUM_S = SUM_S + t.SINTH(K) * FL1(IJ, K, M); SUM_C = SUM_C + t.COSTH(K) * FL1(IJ, K, M); }
+      THMEAN = std::atan2(SUM_S, SUM_C);
+      for (int K = 1; K <= NANG; ++K) { S1 = S1 + FL1(IJ, K, M) * t.DFIM(M); S2 = S2 + std::cos(t.TH(K) - THMEAN) * FL1(IJ, K, M) * t.DFIM(M); }
+    }
+    SIG_TH[IJ] = S1 > ZEPSILON ? std::sqrt(2.0 * (1.0 - S2 / S1)) : 0.0;
+  }
+}
+
+// snonlin.F90:116-498
 void SNONLIN(const Ctx& x, V3 FL1, V3 FLD, V3 SL, V2 WAVNUM, V1 DEPTH, V1 AKMEAN) {
-  (void)WAVNUM;
   const Tables& t = x.t;
   const int KIJS = x.KIJS, KIJL = x.KIJL, NANG = x.NANG, NFRE = x.NFRE;
-  if (x.c.isnonlin != 0) throw std::runtime_error("SNONLIN: ISNONLIN != 0 not restated");
   const int n = KIJL + 1;
   std::vector<double> FTEMP(n), AD(n), DELAD(n), DELAP(n), DELAM(n), ENHFR(n);
   std::vector<double> ENH((size_t)n * t.MLSTHG);
   auto enh = [&](int ij, int mc) -> double& { return ENH[ij + (size_t)n * (mc - 1)]; };
-  for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
-    ENHFR[IJ] = std::max(0.75 * DEPTH(IJ) * AKMEAN(IJ), 0.5);
-    ENHFR[IJ] = 1.0 + (5.5 / ENHFR[IJ]) * (1.0 - .833 * ENHFR[IJ]) * std::exp(-1.25 * ENHFR[IJ]);
-  }
-  for (int MC = 1; MC <= t.MLSTHG; ++MC) for (int IJ = KIJS; IJ <= KIJL; ++IJ) enh(IJ, MC) = ENHFR[IJ];
+  const double ENH_MAX = 10.0, ENH_MIN = 0.1;   // snonlin.F90:101-102
+  auto xk_above = [&](int MC) {   // XK = GM1*(ZPIFR(NFRE)*FRATIO**(MC-NFRE))**2 (:145, :157), integer power by repeated multiplication
+    double pw = 1.0;
+    for (int i = 0; i < MC - NFRE; ++i) pw = pw * t.FRATIO;
+    const double w = t.ZPIFR(NFRE) * pw;
+    return t.GM1 * (w * w);
+  };
+  if (x.c.isnonlin == 0) {
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      ENHFR[IJ] = std::max(0.75 * DEPTH(IJ) * AKMEAN(IJ), 0.5);
+      ENHFR[IJ] = 1.0 + (5.5 / ENHFR[IJ]) * (1.0 - .833 * ENHFR[IJ]) * std::exp(-1.25 * ENHFR[IJ]);
+    }
+    for (int MC = 1; MC <= t.MLSTHG; ++MC) for (int IJ = KIJS; IJ <= KIJL; ++IJ) enh(IJ, MC) = ENHFR[IJ];
+  } else if (x.c.isnonlin == 1) {   // snonlin.F90:138-150 (oracle only so far: the product rejects ISNONLIN /= 0)
+    for (int MC = 1; MC <= NFRE; ++MC) for (int IJ = KIJS; IJ <= KIJL; ++IJ)
+      enh(IJ, MC) = std::max(std::min(ENH_MAX, TRANSF(x, WAVNUM(IJ, MC), DEPTH(IJ))), ENH_MIN);
+    for (int MC = NFRE + 1; MC <= t.MLSTHG; ++MC) for (int IJ = KIJS; IJ <= KIJL; ++IJ)
+      enh(IJ, MC) = std::max(std::min(ENH_MAX, TRANSF(x, xk_above(MC), DEPTH(IJ))), ENH_MIN);
+  } else if (x.c.isnonlin == 2) {   // snonlin.F90:151-163
+    std::vector<double> XNU(n), SIG_TH(n);
+    PEAK_ANG(x, FL1, XNU, SIG_TH);
+    for (int MC = 1; MC <= NFRE; ++MC) for (int IJ = KIJS; IJ <= KIJL; ++IJ) enh(IJ, MC) = TRANSF_SNL(x, WAVNUM(IJ, MC), DEPTH(IJ), XNU[IJ], SIG_TH[IJ]);
+    for (int MC = NFRE + 1; MC <= t.MLSTHG; ++MC) for (int IJ = KIJS; IJ <= KIJL; ++IJ)
+      enh(IJ, MC) = TRANSF_SNL(x, xk_above(MC), DEPTH(IJ), XNU[IJ], SIG_TH[IJ]);
+  } else throw std::runtime_error("SNONLIN: ISNONLIN must be 0, 1 or 2");
   int MFR1STFR = -t.MFRSTLW + 1;
   int MFRLSTFR = NFRE - t.KFRH + MFR1STFR;
   for (int MC = 1; MC <= t.MLSTHG; ++MC) {

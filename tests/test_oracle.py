@@ -372,3 +372,33 @@ def test_advection_moves_energy_with_the_group_velocity(built, k):
     dist = np.hypot(elat, elon * np.cos(np.deg2rad(lat0)))
     assert abs(dlat - elat) < 0.08 * dist and abs((dlon - elon) * np.cos(np.deg2rad(lat0))) < 0.08 * dist, (dlat, elat, dlon, elon)
     assert abs(G.sum() / F.sum() - 1.0) < 0.05
+
+
+@pytest.mark.parametrize("isnonlin", [1, 2])
+def test_shallow_water_scalings_of_the_dia(built, isnonlin):
+    """ISNONLIN = 1, 2 (snonlin.F90:138-163 with TRANSF / TRANSF_SNL + PEAK_ANG; oracle only so far, the product rejects them):
+    the Janssen-Onorato factor multiplies every quadruplet family (one factor per point and centre frequency), so (i) in deep
+    water, where the factor is 1, SNONLIN equals the ISNONLIN = 0 term whose own depth scaling has gone to 1 as well; (ii) in
+    shallow water the term differs, but each family still conserves energy, hence the total does; (iii) the factor stays
+    inside its clips [0.1, 10]."""
+    def run(depth, mode):
+        def hook(g):
+            g.depth[:] = depth
+        g, o, f, fl = make_oracle("aqua", grid_hook=hook, isnonlin=mode)
+        F, A, n = fl.shape
+        th = o.table("TH")
+        spec = np.exp(-0.5 * ((np.arange(F) - 12) / 1.5) ** 2)[:, None] * np.maximum(np.cos(th - 1.0), 0)[None, :] ** 4
+        spec[np.abs(np.arange(F) - 12) > 6] = 0.0
+        o.set_fl1(np.repeat(spec[:, :, None], n, axis=2) * 0.05)
+        return o, o.snonlin()[0]
+    o, deep = run(999.0, isnonlin)          # D >= BATHYMAX: the factor is 1 by definition (transf.F90: D < BATHYMAX)
+    _, deep0 = run(999.0, 0)
+    np.testing.assert_allclose(deep, deep0, rtol=1e-6, atol=1e-12 * np.abs(deep0).max())
+    o, sh = run(12.0, isnonlin)
+    _, sh0 = run(12.0, 0)
+    ratio = np.abs(sh).max() / np.abs(deep).max()
+    assert 0.1 <= ratio <= 10.0 and abs(ratio - 1.0) > 0.05                      # kd ~ 1 at the peak: a different interaction strength
+    assert np.abs(sh - sh0).max() > 0.02 * np.abs(sh0).max()                     # and not the ISNONLIN = 0 scaling
+    dfim = o.table("DFIM")
+    tot = (sh * dfim[:, None, None]).sum(axis=(0, 1))
+    assert (np.abs(tot) <= 5e-15 * (np.abs(sh) * dfim[:, None, None]).sum(axis=(0, 1))).all()
