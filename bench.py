@@ -102,50 +102,106 @@ class ClockSampler:
 PHYSICS = {"default": {}, "cy49r1": dict(llgcbz0=1, llnormagam=1, wspmin=0.3)}   # tests/etopo1_oper_an_fc_O48{,_cy49r1}.yml
 
 
-def cpu_reference_run(workload, steps, warmup, sample_N=None, quiet=True, physics="default"):
-    """Times the CPU restatement of the reference (oracle/, -O3 build, OpenMP over NPROMA chunks as
-    wamintgr.F90:117) on a bounded sample of the workload: same spectral resolution, physics and time step, on a
-    smaller octahedral grid with the same synthetic-continent recipe.  Returns (spectra/s, ms/step, cores, sample)."""
+def host_info():
+    """CPU model / cores / memory of the box (BASELINE.md 4.3 asks for the CPU next to every CPU number)."""
+    model, mem_gb = "unknown", None
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name"):
+                    model = ln.split(":", 1)[1].strip()
+                    break
+        with open("/proc/meminfo") as f:
+            for ln in f:
+                if ln.startswith("MemAvailable"):
+                    mem_gb = int(ln.split()[1]) / 1e6
+                    break
+    except OSError:
+        pass
+    return {"cpu_model": model, "cores": os.cpu_count() or 1, "mem_available_gb": mem_gb}
+
+
+def oracle_bytes_per_point(cfgw):
+    """Resident set of the CPU restatement per sea point: FL1, the propagation block + its result, XLLWS, the 8 live CTU weight
+    arrays of PROPAGS2's IREFRA = 0 branch (propags2.F90:107-116; the reference keeps all 18, ctuwupdt.F90:171-178)."""
+    A, F, Fr = cfgw["nang"], 36, cfgw["nfre_red"]
+    return 8 * (2 * A * F + 2 * A * Fr + 8 * A * Fr) + 4096
+
+
+def cpu_reference_run(workload, steps, warmup, sample_N=None, quiet=True, physics="default", full=False, budget_s=None):
+    """Times the CPU restatement of the reference (oracle/, -O3 build, OpenMP over NPROMA chunks as wamintgr.F90:117, stored CTU
+    weights as the reference).  full: the workload's own grid (same configuration as the GPU arm, NPROMA of the yml); otherwise a
+    bounded sample: same spectral resolution, physics and time step on a smaller octahedral grid with the same synthetic-continent
+    recipe.  budget_s: the timed steps are cut short when the projection from the first step exceeds it.
+    Returns (spectra/s, ms/step, cores, sample, steps done, warm-up done)."""
     from ecwam_b200 import synth
     from oracle import oracle as O
     cfgw, _ = workload_cfg(workload)
     cores = os.cpu_count() or 1
-    if sample_N is None:
+    if full:
+        sample_N = cfgw["N"]
+    elif sample_N is None:
         # ~0.3 ms per point per step per core at 36x36: keep one step near 3 s
         sample_N = 96 if cores >= 16 else 64
         if cfgw["N"] < sample_N:
             sample_N = cfgw["N"]
     g = synth.make_grid(sample_N, "continents")
-    cfg = O.default_config(nang=cfgw["nang"], nfre_red=cfgw["nfre_red"], nproma=24, npr=1, iphys=1, idelt=cfgw["idelt"],
-                           idelpro=cfgw["idelpro"], delpro_lf=cfgw["delpro_lf"], ifrelfmax=cfgw["ifrelfmax"], nthreads=cores,
-                           **PHYSICS[physics])
+    nproma_yml = {"O48": 32, "O320": 64, "O640": 24, "O1280": 24}.get(workload, 24)    # tests/etopo1_oper_an_fc_*.yml
+    cfg = O.default_config(nang=cfgw["nang"], nfre_red=cfgw["nfre_red"], nproma=nproma_yml if full else 24, npr=1, iphys=1,
+                           idelt=cfgw["idelt"], idelpro=cfgw["idelpro"], delpro_lf=cfgw["delpro_lf"], ifrelfmax=cfgw["ifrelfmax"],
+                           nthreads=cores, **PHYSICS[physics])
     o = O.Oracle(cfg, g, fast=True)
     f = synth.make_forcing(g)
     for k, v in f.items():
         o.set_field(k, v)
     o.set_fl1(synth.jonswap_cold_start(f["WSWAVE"], f["WDWAVE"], cfgw["nang"], 36, cfgw["nfre_red"]))
+    t_first = time.perf_counter()
+    wdone = 0
     for _ in range(warmup):
         o.step()
+        wdone += 1
+        if budget_s and wdone == 1:
+            one = time.perf_counter() - t_first          # includes the one-off CTU set-up: an upper bound of a step
+            if one * (warmup + steps) > budget_s:
+                steps = max(1, min(steps, int(budget_s / one) - 1))
+                break
     t0 = time.perf_counter()
+    sdone = 0
     for _ in range(steps):
         o.step()
+        sdone += 1
+        if budget_s and time.perf_counter() - t_first > budget_s:
+            break
     dt = time.perf_counter() - t0
-    sample = "O%d synthetic-continent grid, %d sea points, %dx%d(%d) spectrum, %d timed steps, OpenMP %d threads" % (
-        sample_N, g.niblo, cfgw["nang"], 36, cfgw["nfre_red"], steps, cores)
-    return g.niblo * steps / dt, dt / steps * 1e3, cores, sample
+    sample = "%sO%d synthetic-continent grid, %d sea points, %dx%d(%d) spectrum, NPROMA=%d, %d timed steps, OpenMP %d threads" % (
+        "the workload itself: " if full else "", sample_N, g.niblo, cfgw["nang"], 36, cfgw["nfre_red"], cfg.nproma, sdone, cores)
+    return g.niblo * sdone / dt, dt / sdone * 1e3, cores, sample, sdone, wdone
 
 
 def run_reference(args):
+    """The reference arm: the CPU restatement of the reference (the Fortran cannot be built here: no compiler, fiat, field_api,
+    eccodes) on ALL host cores, on the GPU arm's own workload when the host memory holds the stored CTU weights (73 GB at O640),
+    else on the bounded sample; the requested steps / warm-up are honoured unless the projected run exceeds ~10 minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, args.steps)
-    warm = max(0, min(args.warmup, 1))
-    val, ms, cores, sample = cpu_reference_run(args.workload, min(steps, 3), warm, physics=args.physics)
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": min(steps, 3),
-            "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": args.workload + " (bounded CPU sample: " + sample + ")"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+    hi = host_info()
+    cfgw, _ = workload_cfg(args.workload)
+    from ecwam_b200 import synth
+    npts_est = synth.sea_points_estimate(cfgw["N"]) if hasattr(synth, "sea_points_estimate") else int(0.66 * 4 * cfgw["N"] * (cfgw["N"] + 9))
+    need_gb = oracle_bytes_per_point(cfgw) * npts_est / 1e9 * 1.15 + 4
+    full = (not args.ref_sample) and hi["mem_available_gb"] is not None and hi["mem_available_gb"] > need_gb
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    if not full:
+        steps, warm = min(steps, 3), min(warm, 1)
+    val, ms, cores, sample, sdone, wdone = cpu_reference_run(args.workload, steps, warm, physics=args.physics, full=full,
+                                                             budget_s=args.ref_budget if full else None)
+    what = args.workload + (" octahedral grid, synthetic continents: the GPU arm's workload" if full else
+                            " (bounded CPU sample, %.0f GB needed for the workload itself, %.0f GB available)" % (need_gb, hi["mem_available_gb"] or -1))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": sdone,
+            "warmup": wdone, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": what + ": " + sample, "host": hi},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "cpu_model": hi["cpu_model"]},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -348,8 +404,9 @@ def run_gpu(args):
                         "pipe utilisation are in profiles/"}
     cpu = None
     if not args.no_cpu:
-        v, msc, cores, sample = cpu_reference_run(args.workload, 2, 1, physics=args.physics)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_step_sample": msc}
+        v, msc, cores, sample, _, _ = cpu_reference_run(args.workload, 2, 1, physics=args.physics)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_step_sample": msc,
+               "cpu_model": host_info()["cpu_model"]}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s octahedral grid, synthetic continents (%d sea points), %dx%d spectrum (%d propagated), "
@@ -374,6 +431,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the NEWWIND / OUTBS / WAMNORM timing next to the path")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--ref-sample", action="store_true", help="--impl reference: time the bounded O96/O64 sample instead of the workload itself")
+    ap.add_argument("--ref-budget", type=float, default=600.0, help="--impl reference: wall-clock budget [s] of the warm-up + timed steps")
     ap.add_argument("--physics", default="default", choices=sorted(PHYSICS),
                     help="default = BASELINE.json's configuration; cy49r1 = gravity-capillary roughness + renormalised growth")
     args = ap.parse_args()

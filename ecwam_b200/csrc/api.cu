@@ -33,6 +33,10 @@ template <class T>
 struct DBuf {
   T* p = nullptr;
   size_t n = 0;
+  DBuf() = default;
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  ~DBuf() { free(); }
   int alloc(size_t cnt) {
     free();
     n = cnt;
@@ -87,6 +91,9 @@ struct ecwam_b200_handle_s {
   // host-call mirrors
   ecwam_b200_fields mir;
   bool mir_alloc = false, mir_static_done = false;
+  // h->dev is the caller's device binding except inside ecwam_b200_wamintgr_host, which swaps the mirrors in for the call.
+  // The CTU set-up is built from the static fields of one side: cur_side / weights_side = 1 caller's tensors, 2 mirrors.
+  int cur_side = 0, weights_side = 0;
   std::vector<void*> mir_bufs;
   // banded copy/compute pipeline of the host-buffer entry point
   cudaStream_t st_up = nullptr, st_dn = nullptr;
@@ -110,6 +117,8 @@ static int ensure_const(H* h) {
   int rc = upload_dev_const(h->dc, h->st);
   if (rc) return rc;
   rc = upload_prop_const(h->pc, h->st);
+  if (rc) return rc;
+  rc = upload_prop_const_fast(h->pc, h->st);
   if (rc) return rc;
   g_const_owner = h;
   return 0;
@@ -259,6 +268,40 @@ static int fill_dev_const(const ecwam_b200_params& p, const ecwam_b200_tables& t
     }
   }
   for (int r = 0; r < EW_MAXF + 8; ++r) c.SLOT9[r] = r % 9;
+  // separable form of the DIA weights for k_sweep (see DevConst::NLW); every identity it relies on is checked here
+  {
+    c.sweep_ok = 0;
+    const int NM = t.mlsthg;
+    int mi = -1;   // an interior centre frequency (all five rows inside the spectrum)
+    for (int mc = 0; mc < NM; ++mc) { const double* R = c.RNLCOEF[mc]; if (R[5] > 0 && R[6] >= 0 && R[17] > 0 && R[18] >= 0 && R[8] > 0 && R[20] > 0) { mi = mc; break; } }
+    if (mi >= 0 && NM + 1 <= EW_MAXMC + 1) {
+      const double* Ri = c.RNLCOEF[mi];
+      const double cl11 = Ri[5] / (Ri[5] + Ri[6]), acl1 = Ri[6] / (Ri[5] + Ri[6]);
+      const double cl21 = Ri[17] / (Ri[17] + Ri[18]), acl2 = Ri[18] / (Ri[17] + Ri[18]);
+      c.NLD[0] = cl11; c.NLD[1] = acl1; c.NLD[2] = cl21; c.NLD[3] = acl2;
+      c.NLD[4] = cl11 * cl11; c.NLD[5] = acl1 * acl1; c.NLD[6] = cl21 * cl21; c.NLD[7] = acl2 * acl2;
+      bool ok = true;
+      auto same = [&](double a, double b, double scale) { return std::fabs(a - b) <= 1e-13 * std::fabs(scale) + 1e-300; };
+      for (int mc = 0; mc < NM; ++mc) {
+        const double* R = c.RNLCOEF[mc];
+        double* Wt = c.NLW[mc];
+        Wt[0] = R[1] + R[2]; Wt[1] = R[3] + R[4]; Wt[2] = R[13] + R[14]; Wt[3] = R[15] + R[16];
+        Wt[4] = R[7] + R[8]; Wt[5] = R[5] + R[6]; Wt[6] = R[19] + R[20]; Wt[7] = R[17] + R[18];
+        for (int j = 0; j < 4; ++j) Wt[8 + j] = Wt[4 + j] * Wt[4 + j];
+        ok = ok && same(Wt[0] * cl11, R[1], Wt[0]) && same(Wt[0] * acl1, R[2], Wt[0]) && same(Wt[1] * cl11, R[3], Wt[1]) && same(Wt[1] * acl1, R[4], Wt[1]);
+        ok = ok && same(Wt[2] * cl21, R[13], Wt[2]) && same(Wt[2] * acl2, R[14], Wt[2]) && same(Wt[3] * cl21, R[15], Wt[3]) && same(Wt[3] * acl2, R[16], Wt[3]);
+        ok = ok && same(Wt[4] * cl11, R[8], Wt[4]) && same(Wt[4] * acl1, R[7], Wt[4]) && same(Wt[5] * cl11, R[5], Wt[5]) && same(Wt[5] * acl1, R[6], Wt[5]);
+        ok = ok && same(Wt[6] * cl21, R[20], Wt[6]) && same(Wt[6] * acl2, R[19], Wt[6]) && same(Wt[7] * cl21, R[17], Wt[7]) && same(Wt[7] * acl2, R[18], Wt[7]);
+        ok = ok && same(Wt[8] * c.NLD[4], R[11], Wt[8]) && same(Wt[8] * c.NLD[5], R[12], Wt[8]) && same(Wt[9] * c.NLD[4], R[9], Wt[9]) && same(Wt[9] * c.NLD[5], R[10], Wt[9]);
+        ok = ok && same(Wt[10] * c.NLD[6], R[23], Wt[10]) && same(Wt[10] * c.NLD[7], R[24], Wt[10]) && same(Wt[11] * c.NLD[6], R[21], Wt[11]) && same(Wt[11] * c.NLD[7], R[22], Wt[11]);
+        // the row that is IP1 (IM1) of one centre frequency is IP (IM) of the next: k_sweep carries its direction interpolation over
+        if (mc + 1 < NM) ok = ok && c.INLCOEF[mc + 1][1] == c.INLCOEF[mc][2] && c.INLCOEF[mc + 1][3] == c.INLCOEF[mc][4];
+        c.NLS2[mc + 1][0] = c.NLSLOT[mc][2]; c.NLS2[mc + 1][1] = c.NLSLOT[mc][4];
+      }
+      c.NLS2[0][0] = c.NLSLOT[0][1]; c.NLS2[0][1] = c.NLSLOT[0][3];
+      c.sweep_ok = ok ? 1 : 0;
+    }
+  }
   if (p.iphys == 1) {
     // cos(TH(K)-TH(J))**ISB only depends on K-J (init_sdiss_ardh.F90:69-96): the table rows agree to rounding (checked), so
     // k_stencil takes the weights of the middle direction as warp-uniform constants
@@ -563,12 +606,14 @@ int ecwam_b200_bind_fields(ecwam_b200_handle h, const ecwam_b200_fields* dev) {
   h->pd.wavn = dev->wavnum;
   h->bound = true;
   h->weights_dirty = true;
+  h->cur_side = 1;
   return 0;
 }
 
 int ecwam_b200_invalidate_weights(ecwam_b200_handle h) {
   if (!h) EW_FAIL(ECWAM_B200_EINVAL, "null handle");
   h->weights_dirty = true;
+  h->mir_static_done = false;   // the host-buffer path uploads its static fields (currents, depth, dispersion) again
   return 0;
 }
 
@@ -633,6 +678,7 @@ static int update_weights(H* h, int* cfl) {
   EW_CUDA_CHECK(cudaStreamSynchronize(h->st));
   *cfl = cnt;
   h->weights_dirty = false;
+  h->weights_side = h->cur_side;
   return 0;
 }
 
@@ -645,7 +691,7 @@ static int propag_core(H* h, bool* lf_in_fl3) {
   const PropDev& d = h->pd;
   const ecwam_b200_params& p = h->par;
   int cfl = 0;
-  if (h->weights_dirty) {
+  if (h->weights_dirty || h->weights_side != h->cur_side) {
     rc = update_weights(h, &cfl);
     if (rc) return rc;
     if (cfl > 0) { ew_set_error("CTUW: CFL / weight-range check failed at %d grid points (ctuwdrv.F90:127-146)", cfl); h->weights_dirty = true; return cfl; }
@@ -714,6 +760,7 @@ static ImplDev make_impl(H* h, bool from_fl3) {
   d.iphys = h->par.iphys; d.nsdsnth = h->nsdsnth;
   d.cy49 = (h->par.llgcbz0 || h->par.llnormagam) ? 1 : 0;
   d.gc = h->gctab.p;
+  d.sweep_ok = h->dc.sweep_ok;
   return d;
 }
 
@@ -740,6 +787,73 @@ int ecwam_b200_implsch(ecwam_b200_handle h, int ichnk0, int nchnk) {
 int ecwam_b200_implsch_all(ecwam_b200_handle h) {
   if (!h) EW_FAIL(ECWAM_B200_EINVAL, "null handle");
   return implsch_range(h, 1, h->par.nchnk, false);
+}
+
+// ---- the reference argument lists (fortran/implsch_b200.F90, fortran/propag_wam_b200.F90) --------------------------------
+// The Fortran bodies pass what the reference callers pass: the chunk's slices of the FIELD_API arrays.  The library works on
+// the arrays bound with ecwam_b200_bind_fields, so every argument is checked against the bound array (a re-allocated FIELD_API
+// buffer that was not re-bound is an error, not a silent use of stale memory) and the chunk is derived from FL1's address.
+namespace {
+struct ArgCheck {
+  H* h; long long ichnk0; const char* who; int bad = 0; char first[48] = "";
+  void chk(const void* passed, const void* bound, size_t chunk_bytes, const char* name) {
+    if (!passed || !bound) return;   // optional argument / field that is not bound
+    if ((const char*)passed != (const char*)bound + chunk_bytes * (size_t)ichnk0) { if (!bad) snprintf(first, sizeof(first), "%s", name); ++bad; }
+  }
+};
+}  // namespace
+
+int ecwam_b200_implsch_f(ecwam_b200_handle h, int kijs, int kijl, double* fl1, const double* wavnum, const double* cgroup,
+                         const double* ciwa, const double* cinv, const double* xk2cg, const double* stokfac, const double* emaxdpt,
+                         const double* depth, const int* iobnd, const int* iodp, const double* ibrmem, double* aird, double* wdwave,
+                         double* cicover, double* wswave, double* wstar, double* ustra, double* vstra, double* ufric, double* tauw,
+                         double* tauwdir, double* z0m, double* z0b, double* chrnck, double* cithick, double* nemoustokes,
+                         double* nemovstokes, double* nemostrn, double* nphieps, double* ntauoc, double* nswh, double* nmwp,
+                         double* nemotaux, double* nemotauy, double* nemotauicx, double* nemotauicy, double* nemowswave,
+                         double* nemophif, double* wsemean, double* wsfmean, double* ustokes, double* vstokes, double* strnms,
+                         double* tauxd, double* tauyd, double* tauocxd, double* tauocyd, double* tauoc, double* tauicx,
+                         double* tauicy, double* phiocd, double* phieps, double* phiaw, int* mij, double* xllws) {
+  if (!h || !fl1) EW_FAIL(ECWAM_B200_EINVAL, "IMPLSCH: null handle or FL1");
+  if (!h->bound) EW_FAIL(ECWAM_B200_ESTATE, "IMPLSCH: fields not bound");
+  const ecwam_b200_params& p = h->par;
+  if (kijs != 1 || kijl != p.nproma) EW_FAIL(ECWAM_B200_EINVAL, "IMPLSCH: KIJS:KIJL must be 1:NPROMA_WAM = 1:%d (got %d:%d)", p.nproma, kijs, kijl);
+  const size_t b4 = (size_t)p.nproma * p.nang * p.nfre * 8, b3 = (size_t)p.nproma * p.nfre * 8, b2 = (size_t)p.nproma * 8, bi = (size_t)p.nproma * 4;
+  const ptrdiff_t off = (const char*)fl1 - (const char*)h->dev.fl1;
+  if (off < 0 || off % (ptrdiff_t)b4 != 0 || off / (ptrdiff_t)b4 >= p.nchnk)
+    EW_FAIL(ECWAM_B200_ESTATE, "IMPLSCH: FL1 is not a chunk of the bound FL1 array (re-bind the fields after FIELD_API re-allocates)");
+  ArgCheck a{h, (long long)(off / (ptrdiff_t)b4), "IMPLSCH"};
+  const ecwam_b200_fields& f = h->dev;
+  a.chk(xllws, f.xllws, b4, "XLLWS");
+  a.chk(wavnum, f.wavnum, b3, "WAVNUM"); a.chk(cgroup, f.cgroup, b3, "CGROUP"); a.chk(ciwa, f.ciwa, b3, "CIWA"); a.chk(cinv, f.cinv, b3, "CINV");
+  a.chk(xk2cg, f.xk2cg, b3, "XK2CG"); a.chk(stokfac, f.stokfac, b3, "STOKFAC");
+  a.chk(emaxdpt, f.emaxdpt, b2, "EMAXDPT"); a.chk(depth, f.depth, b2, "DEPTH");
+  a.chk(aird, f.aird, b2, "AIRD"); a.chk(wdwave, f.wdwave, b2, "WDWAVE"); a.chk(cicover, f.cicover, b2, "CICOVER"); a.chk(wswave, f.wswave, b2, "WSWAVE");
+  a.chk(wstar, f.wstar, b2, "WSTAR"); a.chk(ustra, f.ustra, b2, "USTRA"); a.chk(vstra, f.vstra, b2, "VSTRA"); a.chk(ufric, f.ufric, b2, "UFRIC");
+  a.chk(tauw, f.tauw, b2, "TAUW"); a.chk(tauwdir, f.tauwdir, b2, "TAUWDIR"); a.chk(z0m, f.z0m, b2, "Z0M"); a.chk(z0b, f.z0b, b2, "Z0B");
+  a.chk(chrnck, f.chrnck, b2, "CHRNCK"); a.chk(cithick, f.cithick, b2, "CITHICK");
+  a.chk(wsemean, f.wsemean, b2, "WSEMEAN"); a.chk(wsfmean, f.wsfmean, b2, "WSFMEAN"); a.chk(ustokes, f.ustokes, b2, "USTOKES"); a.chk(vstokes, f.vstokes, b2, "VSTOKES");
+  a.chk(strnms, f.strnms, b2, "STRNMS"); a.chk(tauxd, f.tauxd, b2, "TAUXD"); a.chk(tauyd, f.tauyd, b2, "TAUYD"); a.chk(tauocxd, f.tauocxd, b2, "TAUOCXD");
+  a.chk(tauocyd, f.tauocyd, b2, "TAUOCYD"); a.chk(tauoc, f.tauoc, b2, "TAUOC"); a.chk(tauicx, f.tauicx, b2, "TAUICX"); a.chk(tauicy, f.tauicy, b2, "TAUICY");
+  a.chk(phiocd, f.phiocd, b2, "PHIOCD"); a.chk(phieps, f.phieps, b2, "PHIEPS"); a.chk(phiaw, f.phiaw, b2, "PHIAW");
+  a.chk(mij, f.mij, bi, "MIJ");
+  if (a.bad) EW_FAIL(ECWAM_B200_ESTATE, "IMPLSCH: %d argument(s) are not chunk %lld of the bound arrays (first: %s): re-bind the fields", a.bad, a.ichnk0 + 1, a.first);
+  // IOBND, IODP, IBRMEM and the NEMO accumulators (LWNEMOCOU = F, rejected at create otherwise) are not read on this path
+  (void)iobnd; (void)iodp; (void)ibrmem; (void)nemoustokes; (void)nemovstokes; (void)nemostrn; (void)nphieps; (void)ntauoc; (void)nswh; (void)nmwp;
+  (void)nemotaux; (void)nemotauy; (void)nemotauicx; (void)nemotauicy; (void)nemowswave; (void)nemophif;
+  return implsch_range(h, (int)a.ichnk0 + 1, 1, false);
+}
+
+int ecwam_b200_propag_wam_f(ecwam_b200_handle h, const double* wavnum, const double* cgroup, const double* omosnh2kd, double* fl1,
+                            const double* depth, const double* dellam1, const double* cosphm1, const double* ucur, const double* vcur) {
+  if (!h || !fl1) EW_FAIL(ECWAM_B200_EINVAL, "PROPAG_WAM: null handle or FL1");
+  if (!h->bound) EW_FAIL(ECWAM_B200_ESTATE, "PROPAG_WAM: fields not bound");
+  ArgCheck a{h, 0, "PROPAG_WAM"};
+  const ecwam_b200_fields& f = h->dev;
+  a.chk(fl1, f.fl1, 0, "FL1"); a.chk(wavnum, f.wavnum, 0, "WAVNUM"); a.chk(cgroup, f.cgroup, 0, "CGROUP"); a.chk(omosnh2kd, f.omosnh2kd, 0, "OMOSNH2KD");
+  a.chk(depth, f.depth, 0, "DEPTH"); a.chk(dellam1, f.dellam1, 0, "DELLAM1"); a.chk(cosphm1, f.cosphm1, 0, "COSPHM1");
+  a.chk(ucur, f.ucur, 0, "UCUR"); a.chk(vcur, f.vcur, 0, "VCUR");
+  if (a.bad) EW_FAIL(ECWAM_B200_ESTATE, "PROPAG_WAM: %d argument(s) are not the bound arrays (first: %s): re-bind the fields", a.bad, a.first);
+  return ecwam_b200_propag(h);
 }
 
 // PROPAG_WAM + IMPLSCH with the block->chunk copy of PROPAG_WAM (propag_wam.F90:368-405) folded into IMPLSCH's loads:
@@ -1070,10 +1184,16 @@ int ecwam_b200_wamintgr_host(ecwam_b200_handle h, const ecwam_b200_fields* host,
     EW_CUDA_CHECK(cudaStreamCreateWithFlags(&h->st_dn, cudaStreamNonBlocking));
     EW_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
     h->mir_alloc = true;
-    int rc = ecwam_b200_bind_fields(h, &h->mir);
-    if (rc) return rc;
   }
   (void)npts;
+  // The host path works on the library's mirrors, the device entry points on the caller's bound tensors: the binding is swapped
+  // for the duration of this call only.  The CTU set-up depends on the bound static fields, so a handle that uses both paths
+  // rebuilds it whenever it changes sides.
+  struct BindGuard {
+    H* h; ecwam_b200_fields saved; bool saved_bound;
+    ~BindGuard() { h->dev = saved; h->bound = saved_bound; h->pd.omos = saved.omosnh2kd; h->pd.wavn = saved.wavnum; h->cur_side = saved_bound ? 1 : 0; }
+  } guard{h, h->dev, h->bound};
+  h->dev = h->mir; h->pd.omos = h->mir.omosnh2kd; h->pd.wavn = h->mir.wavnum; h->bound = true; h->cur_side = 2;
   // ---- bands of chunks
   const int nchnk = p.nchnk, P = p.nproma;
   const int reach_chunks = (h->nbr_reach + P - 1) / P + 1;
@@ -1081,7 +1201,7 @@ int ecwam_b200_wamintgr_host(ecwam_b200_handle h, const ecwam_b200_fields* host,
   int band = std::max((nchnk + kBands - 1) / kBands, reach_chunks);
   const int nband = (nchnk + band - 1) / band;
   const bool substeps = p.ifrelfmax > 0 && p.ifrelfmax < p.nfre_red;
-  const bool full = h->nproc <= 1 && !substeps && !h->weights_dirty && h->mir_static_done && nband >= 3 && h->par.irefra < 2;
+  const bool full = h->nproc <= 1 && !substeps && !h->weights_dirty && h->weights_side == h->cur_side && h->mir_static_done && nband >= 3 && h->par.irefra < 2;
   while ((int)h->ev_up.size() < nband) { cudaEvent_t e; EW_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_up.push_back(e); }
   while ((int)h->ev_done.size() < nband) { cudaEvent_t e; EW_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_done.push_back(e); }
   long long nin = 0, nout = 0;

@@ -52,6 +52,16 @@ struct DevConst {
   int llgcbz0, llnormagam, NWAV_GC, pad_gc;
   double ALPHAMAX, ALPHAPMAX, ACDLIN, BCDLIN, BMAXOKAP, GAMNCONST, RN1_RN, DTHRN_A, DTHRN_U, ANG_GC_A, ANG_GC_B, ANG_GC_C,
       SQRTGOSURFT, XKM1_GC, XLOGKRATIOM1_GC;
+  // k_sweep: the DIA weights in separable form (nlweigt.F90: every RNLCOEF entry is a per-MC frequency weight times one of the
+  // two direction-interpolation weights).  NLW[mc] = {WP, WP1, WM, WM1, CMP, CMP1, CMM, CMM1, CMP^2, CMP1^2, CMM^2, CMM1^2}:
+  // SAP = WP*D+(IP) + WP1*D+(IP1), SAM = WM*D-(IM) + WM1*D-(IM1) with D+ = CL11*F(K1W) + ACL1*F(K11W), D- = CL21*F(K2W) + ACL2*F(K21W);
+  // rows MC+2, MC+3, MC-4, MC-3 receive CMP, CMP1, CMM, CMM1 (squared for FLD) times the direction-interpolated gather.
+  // NLD = {CL11, ACL1, CL21, ACL2, CL11^2, ACL1^2, CL21^2, ACL2^2}.  NLS2[st+1] = ring slots of rows IP1(MC0=st), IM1(MC0=st)
+  // (entry 0: IP, IM of the first centre frequency).  sweep_ok: the tables have that structure (checked at create).
+  double NLW[EW_MAXMC][12];
+  double NLD[8];
+  int NLS2[EW_MAXMC + 1][2];
+  int sweep_ok, pad_sw;
 };
 // rows of the gravity-capillary table ImplDev::gc [GC_NT][NWAV_GC] (YOWFRED *_GC, initgc.F90)
 enum { GC_XK = 0, GC_OMEGA, GC_CM, GC_C2OSQRTVG, GC_XKMSQRTVGOC2, GC_OM3GMKM, GC_OMXKM3, GC_DELKCC_NS, GC_DELKCC_OMXKM3, GC_DELKCC, GC_NT };

@@ -288,6 +288,12 @@ int ecwam_b200_savstress(const char* filename, const char* cdtpro, const char* c
     if (write_record(f.fd, 0, hdr, 56) < 0) IO_FAIL("savstress: write to %s failed: %s", filename, strerror(errno));
     const int rc = lay_out_records(f.fd, base, nreal, niblo);
     if (rc) IO_FAIL("savstress: cannot lay out %s", filename);
+  } else {   // the laying-out rank must have finished (the caller's barrier): header record and size as laid out for this NIBLO/NREAL
+    struct stat st;
+    int32_t mk[2] = {0, 0};
+    if (fstat(f.fd, &st) || st.st_size != base + nreal * record_span(niblo * 8) || pread(f.fd, &mk[0], 4, 0) != 4 ||
+        pread(f.fd, &mk[1], 4, 4 + 56) != 4 || mk[0] != 56 || mk[1] != 56)
+      IO_FAIL("savstress: %s was not laid out for NIBLO=%lld, NREAL=%d", filename, niblo, nreal);
   }
   if (rw_points(f.fd, true, base, nreal, niblo, nown, plan_of(nown, ijorig), const_cast<double*>(rfield))) IO_FAIL("savstress: write to %s failed: %s", filename, strerror(errno));
   return 0;

@@ -1014,15 +1014,15 @@ __host__ __device__ constexpr int stencil_threads(int A, int np) { return ((A * 
 
 // scalar closures of one grid point after the sweep: STOKESDRIFT, the new wind-sea mean parameters, WNFLUXES
 // qs: the eight direction sums of the point (stride ST_NPT), pcv: its PC_* constants (stride ST_NPT)
-template <bool LWFLUX>
+template <bool LWFLUX, int PST = ST_NPT>
 __device__ __forceinline__ void stencil_closure(const ImplDev& d, const long long pp, const double* qs, const double* pcv) {
     const int F = c_dc.F;
     const long long n = d.npts;
     const double* s = d.scr;
     double q[8];
 #pragma unroll
-    for (int x = 0; x < 8; ++x) q[x] = qs[x * ST_NPT];
-    const double snw = pcv[PC_SNW * ST_NPT], csw = pcv[PC_CSW * ST_NPT];
+    for (int x = 0; x < 8; ++x) q[x] = qs[x * PST];
+    const double snw = pcv[PC_SNW * PST], csw = pcv[PC_CSW * PST];
     const double cicover = d.f.cicover[pp];
     const double ufric = d.f.ufric[pp], aird = d.f.aird[pp], wsw = d.f.wswave[pp];
     // STOKESDRIFT closure (stokesdrift.F90:118-142)
@@ -1964,6 +1964,542 @@ static int launch_stencil(const ImplDev& d, long long p0, long long np, cudaStre
   k_stencil<TA, NP, LW><<<(unsigned)((np + ST_NPT - 1) / ST_NPT), nth, L.total, st>>>(d, p0, np, L);
   return 0;
 }
+
+// =========================================================================================================
+// k_sweep: the default instance of the frequency sweep for the standard grids.  Same algorithm and hazard structure as
+// k_stencil_dp (thread = two adjacent directions of one grid point, rows [row][point][direction + cyclic halo], one split
+// barrier per step), re-cut for the machine:
+//   * CTA = NPT grid points x NANG/2 direction pairs with consecutive threads = consecutive pairs of one point.  For NANG = 36,
+//     NPT = 7 gives 126 threads = 4 warps (2 idle lanes instead of 16 of 160) and one warp per SM sub-partition and CTA, so
+//     3 CTAs per SM load the four schedulers evenly (5-warp CTAs put 3 + 3 + 2 + 2 warps on them: the slow pair sets the pace).
+//     Thread order and point stride are chosen so that every 16-byte shared-memory access of a warp is conflict-free AND the
+//     global row loads / stores of a warp are a few 56-byte runs (see sw_step below).
+//   * the DIA weights in separable form (DevConst::NLW): the direction interpolation D+(row) = CL11 F(K1W) + ACL1 F(K11W) of a
+//     row is formed ONCE, when the row is IP1 of the running centre frequency, and carried in registers to the next step where
+//     the same row is IP (likewise D- for IM1 -> IM): half the partner loads of the product phase; the gather phase forms the
+//     direction-interpolated sums first and scales them per target row: 24 instead of 32 FMAs per bin.
+//   * both KH partners of the P rows are one run of six consecutive directions (three aligned 16-byte loads).
+//   * the saturation values of the rows between their window sum and their finish live in registers, not in shared memory.
+// Shared memory per CTA (NANG = 36): 9-row ring 30.2 KB + 2 x 6 interaction planes 29.6 KB + scalars = 70.3 KB -> 3 CTAs per SM.
+// =========================================================================================================
+// Thread order inside the CTA: t = (g * NPT + pt) * 2 + j with direction pair 2 g + j: a quarter-warp is four grid points x two
+// adjacent pairs, i.e. four 32-byte pieces of shared memory, and the same pair of seven or eight consecutive grid points is
+// 56 / 64 consecutive bytes of global memory (one or two sectors per direction instead of one per lane).  The four pieces use
+// distinct bank groups when the point stride is 32 a (mod 128) bytes with a odd, and, where quarter-warps straddle two pair
+// groups (2 NPT not a multiple of 8), a = 1 / NPT (mod 4): the pieces then step through the bank groups uniformly.
+__host__ __device__ constexpr int sw_step(int npt) { return (2 * npt) % 8 == 0 ? 1 : ((npt % 4 == 1) ? 1 : 3); }
+__host__ __device__ constexpr int sw_pad(int need, int npt) {   // >= need, = 4 a (mod 16) doubles (a = 1: also 12 (mod 16) when the groups are aligned)
+  int s = need;
+  while (!(s % 16 == 4 * sw_step(npt) || ((2 * npt) % 8 == 0 && s % 16 == 12))) ++s;
+  return s;
+}
+__host__ __device__ constexpr int sw_pst(int A, int npt) { return sw_pad(A + 2 * dp_hr(A), npt); }
+__host__ __device__ constexpr int sw_pstc(int A, int npt) { return sw_pad(A + 2 * dp_hc(A), npt); }
+__host__ __device__ constexpr int sw_threads(int A, int npt) { return (((A / 2) * npt + 31) / 32) * 32; }
+__host__ __device__ constexpr int sw_nptp(int npt) { return (npt + 7) / 8 * 8; }
+struct SwSmem { unsigned ring, cur, tbs, pc, part, bth0, stage, mbar, total, RSB, PSB, SSB, PRB; };
+__host__ __device__ constexpr SwSmem sw_smem(int A, int npt, bool lwflux) {
+  SwSmem s{};
+  const int nth = sw_threads(A, npt);
+  s.RSB = (unsigned)sw_pst(A, npt) * npt * 8;
+  s.PSB = (unsigned)sw_pstc(A, npt) * npt * 8;
+  s.SSB = (unsigned)nth * 16;
+  s.PRB = (unsigned)sw_nptp(npt) * 8;
+  unsigned o = 0;
+  s.ring = o; o += ST_RING * s.RSB;
+  s.cur = o; o += 2 * 6 * s.PSB;
+  s.tbs = o; o += 8 * TQ_N * s.PRB;
+  s.pc = o; o += PC_N * s.PRB;
+  s.part = o; o += 3u * (unsigned)nth * 8;
+  s.bth0 = o; o += 2 * s.PRB;
+  s.stage = o; o += (lwflux ? 3 : 2) * s.SSB;
+  s.mbar = o; o += 16;
+  s.total = o;
+  return s;
+}
+__host__ __device__ constexpr int floordiv2(int x) { return x >= 0 ? x / 2 : -((-x + 1) / 2); }
+// the directions k0+LO .. k0+HI of a shared-memory row (k0 even): the aligned pairs that cover them, one 16-byte load each
+template <int LO, int HI>
+struct Run {
+  static constexpr int P0 = floordiv2(LO), P1 = floordiv2(HI), N = P1 - P0 + 1;
+  double v[2 * N];
+  __device__ __forceinline__ void load(const char* sm, unsigned base) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const Vd<2> a = lds<2>(sm, base + (unsigned)((P0 + j) * 16));
+      v[2 * j] = a.v[0]; v[2 * j + 1] = a.v[1];
+    }
+  }
+  __device__ __forceinline__ double at(int off) const { return v[off - 2 * P0]; }
+};
+// a / b as div_norm with one Newton step less: the seed has >= 20 bits, so r is good to 2^-40 and the residual step to 2^-80
+__device__ __forceinline__ double div_fast(double a, double b) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  const double e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  const double q = a * r;
+  return fma(fma(-b, q, a), r, q);
+}
+#ifndef SW_MINB
+#define SW_MINB 3
+#endif
+#ifndef SW_CARRY
+#define SW_CARRY 1   // carry the direction interpolation of the IP1 / IM1 rows to the step where they are IP / IM
+#endif
+
+template <int TA, int NPT, bool LWFLUX>
+__global__ void __launch_bounds__(sw_threads(TA, NPT), SW_MINB) k_sweep(ImplDev d, long long p0, long long np) {
+  extern __shared__ __align__(16) char sm[];
+  typedef Vd<2> V;
+  constexpr int A = TA, NPR = TA / 2, NSD = geo_nsd(TA), NS = 2 * NSD + 1, HR = dp_hr(TA), HC = dp_hc(TA);
+  constexpr int NACT = NPT * NPR;
+  constexpr unsigned PSTB = sw_pst(TA, NPT) * 8, PSTCB = sw_pstc(TA, NPT) * 8;
+  constexpr SwSmem L = sw_smem(TA, NPT, LWFLUX);
+  constexpr unsigned RSB = L.RSB, PSB = L.PSB, PRB = L.PRB;
+  constexpr int GA = -geo_sh(TA, 0, 0), GB = geo_sh(TA, 0, 2);   // |K1W - K| and |K2W - K|; K11W, K21W are one further out
+  const int F = c_dc.F;
+  const bool ard = c_dc.iphys == 1;
+  const unsigned smb = (unsigned)__cvta_generic_to_shared(sm);
+  const int t = threadIdx.x;
+  const bool act = t < NACT;                       // lanes beyond NPT*NANG/2 shadow the last thread and never store
+  const int ta = act ? t : NACT - 1;
+  const int pt = (ta % (2 * NPT)) >> 1;            // grid point of the CTA
+  const int k0 = 2 * (2 * (ta / (2 * NPT)) + (ta & 1));   // first direction of the pair
+  unsigned po = (unsigned)pt * 8u;
+  unsigned me_r = (unsigned)pt * PSTB + (unsigned)(k0 + HR) * 8u;     // own pair inside a ring row
+  unsigned me_c = (unsigned)pt * PSTCB + (unsigned)(k0 + HC) * 8u;    // own pair inside an interaction plane
+  unsigned me_s = L.stage + (unsigned)t * 16u;                         // own landing slot
+  asm volatile("" : "+r"(po), "+r"(me_r), "+r"(me_c), "+r"(me_s));
+  // ---- points
+  const long long pbase = p0 + (long long)blockIdx.x * NPT;
+  const long long plast = p0 + np - 1;
+  long long pq = pbase + pt;
+  const bool pvalid = pq <= plast;
+  if (!pvalid) pq = plast;
+  const bool dost = act && pvalid;
+  const long long n = d.npts;
+  const double* s = d.scr;
+  const size_t P = (size_t)d.P;
+  const size_t rstr = P * A;
+  const long long pc_ = pq / d.P;
+  const int pi_ = (int)(pq - pc_ * d.P);
+  const size_t off_hi = (size_t)pi_ + P * A * F * (size_t)pc_ + P * (size_t)k0;
+  const double* src_hi = d.f.fl1 + off_hi;
+  const double* src_lo = src_hi;
+  int mlo = 0;
+  if (d.lo_on) {
+    src_lo = d.fl_lo + (size_t)pi_ + P * A * d.lo_F * (size_t)pc_ + P * (size_t)k0;
+    mlo = d.Fr;
+  }
+  double* dst = d.f.fl1 + off_hi;
+  const double* src_in = d.fldin + off_hi;
+  const double* src_xl = d.f.xllws + off_hi;
+  // loader of the per-(point, frequency) scalars: thread (q, p8) of the first TQ_N*NPT
+  const int tq_q = t / NPT, tq_p = t - tq_q * NPT;
+  const bool tq_on = t < TQ_N * NPT;
+  const double* tq_g = d.tbg + (size_t)(tq_on ? tq_q : 0) * F * n + min(pbase + tq_p, plast);
+  const unsigned tq_s = L.tbs + (unsigned)(tq_on ? tq_q : 0) * PRB + (unsigned)tq_p * 8u;
+
+  // ---- prologue: per-point constants, barrier
+  if (t == 0) mbar_init(smb + L.mbar, 2u * blockDim.x);
+  if (t < NPT) {
+    const long long qp = min(pbase + t, plast);
+    double* pcv = reinterpret_cast<double*>(sm + L.pc) + t;
+    constexpr int PS = sw_nptp(NPT);
+    const double wd = d.f.wdwave[qp], ci = d.f.cicover[qp], dep = d.f.depth[qp];
+    double snw, csw;
+    sincos(wd, &snw, &csw);
+    double enhfr = dmax(0.75 * dep * s[S_AKMEAN * n + qp], 0.5);
+    enhfr = 1.0 + (5.5 / enhfr) * (1.0 - .833 * enhfr) * exp(-1.25 * enhfr);
+    const int mijq = (int)s[S_MIJ * n + qp];
+    const bool seticeq = c_dc.licerun && c_dc.lmaskice && ci > c_dc.cithrsh;
+    pcv[PC_FAC * PS] = s[S_FAC * n + qp];
+    pcv[PC_ENH * PS] = enhfr;
+    pcv[PC_USFMDELT * PS] = s[S_USFM * n + qp] * c_dc.delt;
+    pcv[PC_SDSBK * PS] = (c_dc.lbiwbk && dep < 50.0) ? s[S_SDS * n + qp] : 0.0;
+    pcv[PC_RTAIL * PS] = 1.0 / d.tbg[((size_t)TQ_TAIL * F + (mijq - 1)) * n + qp];
+    pcv[PC_FLMC * PS] = (1. - 0.9 * dmin(ci, 0.99)) * c_dc.flmin;
+    pcv[PC_ICEADD * PS] = seticeq ? dmax(c_dc.EPSMIN, 1.0 - ci) * c_dc.flmin : 0.0;
+    pcv[PC_ICEFREE * PS] = seticeq ? 0.0 : 1.0;
+    pcv[PC_SNW * PS] = snw;
+    pcv[PC_CSW * PS] = csw;
+    pcv[PC_BETA * PS] = (c_dc.licerun && c_dc.lciscal) ? 1.0 - ci : 1.0;
+  }
+  __syncthreads();
+  V flm, iaw;    // FLM(k) = FLMC*max(0,cos(TH(k)-WDWAVE))**2 (implsch.F90:236-247); SETICE's noise floor likewise
+  {
+    const double snw = lds1(sm, L.pc + PC_SNW * PRB + po), csw = lds1(sm, L.pc + PC_CSW * PRB + po);
+    const double flmc = lds1(sm, L.pc + PC_FLMC * PRB + po), ia = lds1(sm, L.pc + PC_ICEADD * PRB + po);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const double cw2 = sq(dmax(0.0, c_dc.COSTH[k0 + i] * csw + c_dc.SINTH[k0 + i] * snw));
+      flm.v[i] = flmc * cw2; iaw.v[i] = ia * cw2;
+    }
+  }
+  const int mij = (int)s[S_MIJ * n + pq];
+  const bool setice = c_dc.licerun && c_dc.lmaskice;
+  const double delt = c_dc.delt, deltm = 1.0 / delt, delt5 = c_dc.ximp * delt;
+  const double tmp03 = 1.0 / (c_dc.SDSBR * c_dc.MICHE);
+  const int MLSTHG = c_dc.MLSTHG;
+  const bool lssource = c_dc.lcflx && c_dc.lwvflx_snl;
+
+  double asl[7][2], afl[7][2];
+#pragma unroll
+  for (int x = 0; x < 7; ++x)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { asl[x][i] = 0.0; afl[x][i] = 0.0; }
+  // direction interpolations D+ / D- [kh][bin] of the rows that are IP / IM of the next centre frequency
+  double dpc[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, dmc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  V bs1, bs2;    // saturation values of the own bins of rows st-3, st-4
+  bs1.v[0] = bs1.v[1] = bs2.v[0] = bs2.v[1] = 0.0;
+  V fmij, a_philf, a_ts, a_tu, a_e1, a_e2, a_el;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) { fmij.v[i] = 0.0; a_philf.v[i] = 0.0; a_ts.v[i] = 0.0; a_tu.v[i] = 0.0; a_e1.v[i] = 0.0; a_e2.v[i] = 0.0; a_el.v[i] = 0.0; }
+
+  auto step = [&](const int st) {
+    // ================= phase A =================
+    const int rnew = st + 5, rfin = st - 4, rb = st - 2, rtb = st - 1;
+    const unsigned par = (unsigned)st & 1u;
+    const bool dia = st >= 0 && st < MLSTHG;
+    const bool fin = rfin >= 0 && rfin < F;
+    const bool sat = ard && rb >= 0 && rb < F;
+    const unsigned p3 = (unsigned)(st + 6) % 3u;
+    if (rnew >= 0 && rnew < F) {
+      const double* g = (rnew < mlo ? src_lo : src_hi) + (size_t)rnew * rstr;
+      cp_async<8>(smb + me_s, g); cp_async<8>(smb + me_s + 8, g + P);
+    }
+    if (fin) {
+      const double* g = src_in + (size_t)rfin * rstr;
+      cp_async<8>(smb + me_s + L.SSB, g); cp_async<8>(smb + me_s + L.SSB + 8, g + P);
+      if (LWFLUX) { const double* gx = src_xl + (size_t)rfin * rstr; cp_async<8>(smb + me_s + 2 * L.SSB, gx); cp_async<8>(smb + me_s + 2 * L.SSB + 8, gx + P); }
+    }
+    if (rtb >= 0 && rtb < F && tq_on) cp_async<8>(smb + tq_s + (unsigned)((rtb & 7) * TQ_N) * PRB, tq_g + (size_t)rtb * n);
+    mbar_arrive_cp_async(smb + L.mbar);
+    V bnew;
+    bnew.v[0] = 0.0; bnew.v[1] = 0.0;
+    if (st >= -1 && st < MLSTHG) {
+      // direction interpolation of the rows that join the quadruplets at this centre frequency (IP1, IM1; at st = -1: IP, IM of
+      // the first one), both KH families: D+[kh] = CL11 F(k + s0) + ACL1 F(k + s1), D-[kh] = CL21 F(k + s2) + ACL2 F(k + s3)
+      double dpn[2][2], dmn[2][2];
+      {
+        const unsigned bP = L.ring + (unsigned)c_dc.NLS2[st + 1][0] * RSB + me_r;
+        const unsigned bM = L.ring + (unsigned)c_dc.NLS2[st + 1][1] * RSB + me_r;
+        Run<-GA - 1, GA + 2> rp;
+        Run<GB, GB + 2> rm0;
+        Run<-GB - 1, -GB + 1> rm1;
+        rp.load(sm, bP); rm0.load(sm, bM); rm1.load(sm, bM);
+        const double cl11 = c_dc.NLD[0], acl1 = c_dc.NLD[1], cl21 = c_dc.NLD[2], acl2 = c_dc.NLD[3];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          dpn[0][i] = fma(acl1, rp.at(i - GA - 1), cl11 * rp.at(i - GA));
+          dpn[1][i] = fma(acl1, rp.at(i + GA + 1), cl11 * rp.at(i + GA));
+          dmn[0][i] = fma(acl2, rm0.at(i + GB + 1), cl21 * rm0.at(i + GB));
+          dmn[1][i] = fma(acl2, rm1.at(i - GB - 1), cl21 * rm1.at(i - GB));
+        }
+      }
+      if (dia) {
+        const int MC0 = st;
+        const double* Wc = c_dc.NLW[MC0];
+#if !SW_CARRY
+        {   // no carry: the IP / IM rows are interpolated again
+          const unsigned bP = L.ring + (unsigned)c_dc.NLSLOT[MC0][1] * RSB + me_r;
+          const unsigned bM = L.ring + (unsigned)c_dc.NLSLOT[MC0][3] * RSB + me_r;
+          Run<-GA - 1, GA + 2> rp;
+          Run<GB, GB + 2> rm0;
+          Run<-GB - 1, -GB + 1> rm1;
+          rp.load(sm, bP); rm0.load(sm, bM); rm1.load(sm, bM);
+          const double cl11 = c_dc.NLD[0], acl1 = c_dc.NLD[1], cl21 = c_dc.NLD[2], acl2 = c_dc.NLD[3];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            dpc[0][i] = fma(acl1, rp.at(i - GA - 1), cl11 * rp.at(i - GA));
+            dpc[1][i] = fma(acl1, rp.at(i + GA + 1), cl11 * rp.at(i + GA));
+            dmc[0][i] = fma(acl2, rm0.at(i + GB + 1), cl21 * rm0.at(i + GB));
+            dmc[1][i] = fma(acl2, rm1.at(i - GB - 1), cl21 * rm1.at(i - GB));
+          }
+        }
+#endif
+        const unsigned cb = L.cur + par * 6u * PSB + me_c;
+        const V fc = lds<2>(sm, L.ring + (unsigned)c_dc.NLSLOT[MC0][0] * RSB + me_r);
+        const double enh = lds1(sm, L.pc + PC_ENH * PRB + po);
+        const double ftemp = c_dc.AF11[MC0] * enh;
+        const double r0 = c_dc.RNLCOEF[MC0][0];
+        V fij, fcen, fcd1, fcd2;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          fij.v[i] = fc.v[i] * r0;
+          fcen.v[i] = ftemp * fij.v[i];
+          fcd1.v[i] = c_dc.DAL1 * fcen.v[i];
+          fcd2.v[i] = c_dc.DAL2 * fcen.v[i];
+        }
+        V csl, cfl;
+        csl.v[0] = csl.v[1] = cfl.v[0] = cfl.v[1] = 0.0;
+#pragma unroll
+        for (int kh = 0; kh < 2; ++kh) {
+          V vad, vdp, vdm;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const double sap = fma(Wc[1], dpn[kh][i], Wc[0] * dpc[kh][i]);
+            const double sam = fma(Wc[3], dmn[kh][i], Wc[2] * dmc[kh][i]);
+            double fad1 = fij.v[i] * (sap + sam);
+            const double sap2 = 2.0 * sap;
+            const double fad2 = fma(-sap2, sam, fad1);
+            fad1 = fad1 + fad2;
+            vad.v[i] = fad2 * fcen.v[i];
+            csl.v[i] += vad.v[i];
+            cfl.v[i] = fma(fad1, ftemp, cfl.v[i]);
+            vdp.v[i] = fma(-2.0, sam, fij.v[i]) * fcd1.v[i];
+            vdm.v[i] = (fij.v[i] - sap2) * fcd2.v[i];
+          }
+          if (act) {
+            sts<2>(sm, cb + (0 + kh) * PSB, vad);
+            sts<2>(sm, cb + (2 + kh) * PSB, vdp);
+            sts<2>(sm, cb + (4 + kh) * PSB, vdm);
+            if (k0 < HC) {
+              sts<2>(sm, cb + (0 + kh) * PSB + (unsigned)A * 8u, vad);
+              sts<2>(sm, cb + (2 + kh) * PSB + (unsigned)A * 8u, vdp);
+              sts<2>(sm, cb + (4 + kh) * PSB + (unsigned)A * 8u, vdm);
+            }
+            if (k0 >= A - HC) {
+              sts<2>(sm, cb + (0 + kh) * PSB - (unsigned)A * 8u, vad);
+              sts<2>(sm, cb + (2 + kh) * PSB - (unsigned)A * 8u, vdp);
+              sts<2>(sm, cb + (4 + kh) * PSB - (unsigned)A * 8u, vdm);
+            }
+          }
+        }
+        const double c2 = c_dc.RNLC2[MC0];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { asl[4][i] = fma(-c2, csl.v[i], asl[4][i]); afl[4][i] = fma(-c2, cfl.v[i], afl[4][i]); }
+      }
+#if SW_CARRY
+#pragma unroll
+      for (int kh = 0; kh < 2; ++kh)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { dpc[kh][i] = dpn[kh][i]; dmc[kh][i] = dmn[kh][i]; }
+#endif
+    }
+    mbar_arrive(smb + L.mbar);
+    // saturation spectrum of row rb (sdissip_ard.F90:142-160): both windows of the pair from HR+1 aligned 16-byte loads
+    if (sat) {
+      const unsigned wb = L.ring + slot9(rb) * RSB + me_r - (unsigned)HR * 8u;
+      V b;
+      b.v[0] = 0.0; b.v[1] = 0.0;
+#pragma unroll
+      for (int jp = 0; jp <= HR; ++jp) {
+        const V f = lds<2>(sm, wb + jp * 16);
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int x = 2 * jp + e - (HR - NSD) - i;
+            if (x >= 0 && x < NS) b.v[i] += c_dc.SATW1[x] * f.v[e];
+          }
+      }
+      const double fs = lds1(sm, L.tbs + (unsigned)(((rb & 7) * TQ_N + TQ_FACSAT)) * PRB + po);
+      bnew.v[0] = b.v[0] * fs; bnew.v[1] = b.v[1] * fs;
+      // BTH0 = max over direction: one partial per thread, reduced by four lanes per point in phase B of the next step
+      *reinterpret_cast<double*>(sm + L.part + p3 * (unsigned)(blockDim.x * 8u) + (unsigned)t * 8u) = dmax(bnew.v[0], bnew.v[1]);
+    }
+    mbar_wait(smb + L.mbar, (unsigned)(st + 5) & 1u);
+    // ================= phase B =================
+    V tot_sl, tot_fl;
+    {
+      double tap[2] = {0.0, 0.0}, tpp[2] = {0.0, 0.0}, tam[2] = {0.0, 0.0}, tmm[2] = {0.0, 0.0};
+      if (dia) {
+        // gather of the quadruplet contributions of MC (snonlin.F90:253-308) through the inverse shifts, direction interpolation first
+        const unsigned cb = L.cur + par * 6u * PSB + me_c;
+        const double cl11 = c_dc.NLD[0], acl1 = c_dc.NLD[1], cl21 = c_dc.NLD[2], acl2 = c_dc.NLD[3];
+        const double cl11s = c_dc.NLD[4], acl1s = c_dc.NLD[5], cl21s = c_dc.NLD[6], acl2s = c_dc.NLD[7];
+        {   // KH = 1: products at k - s: K1W, K11W families at +GA, +GA+1; K2W, K21W families at -GB, -GB-1
+          Run<GA, GA + 2> ap, pp;
+          Run<-GB - 1, -GB + 1> am, mm;
+          ap.load(sm, cb + 0 * PSB); pp.load(sm, cb + 2 * PSB); am.load(sm, cb + 0 * PSB); mm.load(sm, cb + 4 * PSB);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            tap[i] = fma(acl1, ap.at(i + GA + 1), cl11 * ap.at(i + GA));
+            tpp[i] = fma(acl1s, pp.at(i + GA + 1), cl11s * pp.at(i + GA));
+            tam[i] = fma(acl2, am.at(i - GB - 1), cl21 * am.at(i - GB));
+            tmm[i] = fma(acl2s, mm.at(i - GB - 1), cl21s * mm.at(i - GB));
+          }
+        }
+        {   // KH = 2: mirrored
+          Run<-GA - 1, -GA + 1> ap, pp;
+          Run<GB, GB + 2> am, mm;
+          ap.load(sm, cb + 1 * PSB); pp.load(sm, cb + 3 * PSB); am.load(sm, cb + 1 * PSB); mm.load(sm, cb + 5 * PSB);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            tap[i] = fma(acl1, ap.at(i - GA - 1), fma(cl11, ap.at(i - GA), tap[i]));
+            tpp[i] = fma(acl1s, pp.at(i - GA - 1), fma(cl11s, pp.at(i - GA), tpp[i]));
+            tam[i] = fma(acl2, am.at(i + GB + 1), fma(cl21, am.at(i + GB), tam[i]));
+            tmm[i] = fma(acl2s, mm.at(i + GB + 1), fma(cl21s, mm.at(i + GB), tmm[i]));
+          }
+        }
+      }
+      const double* Wc = c_dc.NLW[dia ? st : 0];
+      // slide the window of pending rows: row st-3 -> slot 0, ..., row st+3 (first contribution) -> slot 6
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        tot_sl.v[i] = fma(Wc[6], tam[i], asl[0][i]);    tot_fl.v[i] = fma(Wc[10], tmm[i], afl[0][i]);
+        asl[0][i] = fma(Wc[7], tam[i], asl[1][i]);      afl[0][i] = fma(Wc[11], tmm[i], afl[1][i]);
+        asl[1][i] = asl[2][i];                          afl[1][i] = afl[2][i];
+        asl[2][i] = asl[3][i];                          afl[2][i] = afl[3][i];
+        asl[3][i] = asl[4][i];                          afl[3][i] = afl[4][i];
+        asl[4][i] = asl[5][i];                          afl[4][i] = afl[5][i];
+        asl[5][i] = fma(Wc[4], tap[i], asl[6][i]);      afl[5][i] = fma(Wc[8], tpp[i], afl[6][i]);
+        asl[6][i] = Wc[5] * tap[i];                     afl[6][i] = Wc[9] * tpp[i];
+      }
+    }
+    // finish row rfin (implsch.F90:276-395 for these bins)
+    if (fin) {
+      const int r = rfin;
+      const unsigned tq = L.tbs + (unsigned)((r & 7) * TQ_N) * PRB + po;
+      const V fold = lds<2>(sm, L.ring + slot9(r) * RSB + me_r);
+      const V xI = lds<2>(sm, me_s + L.SSB);
+      const double usfm = lds1(sm, L.pc + PC_USFMDELT * PRB + po), sdsbk = lds1(sm, L.pc + PC_SDSBK * PRB + po);
+      const double tsbo = lds1(sm, tq + TQ_SBO * PRB), tcinv = lds1(sm, tq + TQ_CINV * PRB), ttail = lds1(sm, tq + TQ_TAIL * PRB);
+      const double tstf = lds1(sm, tq + TQ_STF * PRB), rtail = lds1(sm, L.pc + PC_RTAIL * PRB + po);
+      const double beta = c_dc.lciscal ? lds1(sm, L.pc + PC_BETA * PRB + po) : 1.0;
+      V dd;
+      if (ard) {
+        const double b0 = lds1(sm, L.bth0 + (par ^ 1u) * PRB + po);
+        const double ssdsc2_sig = c_dc.SSDSC2 * c_dc.ZPIFR[r];
+        const double d0 = ssdsc2_sig * c_dc.SSDSC6 * sq(dmax(0., b0 * tmp03 - c_dc.SSDSC4));
+#pragma unroll
+        for (int i = 0; i < 2; ++i) dd.v[i] = d0 + ssdsc2_sig * (1. - c_dc.SSDSC6) * sq(dmax(0., bs2.v[i] * tmp03 - c_dc.SSDSC4));
+      } else { const double dj = lds1(sm, tq + TQ_JAN * PRB); dd.v[0] = dj; dd.v[1] = dj; }
+      const double cofrm4 = c_dc.COFRM4[r], flmax = c_dc.FLMAX[r];
+      double rr = (r + 1 > mij) ? 0.0 : c_dc.RHOWG_DFIM[r];      // RHOWGDFTH of frcutindex.F90:99-108
+      if (r + 1 == mij && mij != F) rr = 0.5 * rr;
+      V xL;
+      if (LWFLUX) xL = lds<2>(sm, me_s + 2 * L.SSB);
+      V fnv;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double f0 = fold.v[i];
+        double fldv = xI.v[i];
+        double slv = fldv * f0;
+        slv = slv + dd.v[i] * f0; fldv = fldv + dd.v[i];
+        slv = slv + tot_sl.v[i]; fldv = fldv + tot_fl.v[i];
+        double ssource = 0.0;
+        if (lssource) ssource = div_fast(slv, dmax(1.0 - delt5 * fldv, 1.0));
+        if (r < c_dc.Fr) { slv = slv - sdsbk * f0; fldv = fldv - sdsbk; }            // SDIWBK (0 where it does not apply)
+        if (c_dc.lciscal) { slv = slv * beta; fldv = fldv * beta; }                  // LCISCAL (implsch.F90:315-325)
+        slv = slv + tsbo * f0; fldv = fldv + tsbo;                                   // SDICE3 + SBOTTOM (plane is 0 where neither applies)
+        const double gtemp1 = dmax(1.0 - delt5 * fldv, 1.0);
+        const double gtemp2 = div_fast(delt * slv, gtemp1);
+        const double flhab = dmin(fabs(gtemp2), usfm * cofrm4);
+        double fn = f0 + copysign(flhab, gtemp2);
+        fn = dmax(fn, flm.v[i]);
+        ssource = ssource + deltm * dmin(flmax - fn, 0.0);
+        fn = dmin(fn, flmax);
+        a_philf.v[i] += ssource * rr;
+        a_ts.v[i] += ssource * (tcinv * rr);
+        if (LWFLUX) {
+          const double xf = (xL.v[i] != 0.0) ? fn : 0.0;
+          a_e1.v[i] += c_dc.DFIM[r] * xf; a_e2.v[i] += c_dc.DFIMOFR[r] * xf;
+          if (r == F - 1) a_el.v[i] += xf;
+        }
+        if (r == mij - 1) fmij.v[i] = fn;
+        if (r > mij - 1) fn = dmax((ttail * rtail) * fmij.v[i], flm.v[i]);
+        fnv.v[i] = fn;
+      }
+      if (setice) {
+        const double icefree = lds1(sm, L.pc + PC_ICEFREE * PRB + po);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) fnv.v[i] = fnv.v[i] * icefree + iaw.v[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        a_tu.v[i] += tstf * fnv.v[i];
+        if (r == c_dc.NFRE_ODD - 1) {
+          const double cst = 2.0 * c_dc.DELTH * c_dc.ZPI * c_dc.ZPI * c_dc.ZPI / c_dc.G * p4(c_dc.FR[c_dc.NFRE_ODD - 1]);
+          a_tu.v[i] += cst * fnv.v[i];
+        }
+      }
+      if (dost) { double* o = dst + (size_t)r * rstr; o[0] = fnv.v[0]; o[P] = fnv.v[1]; }
+    }
+    bs2 = bs1; bs1 = bnew;
+    if (rnew >= 0 && rnew < F) {   // depth-limited (+ floored at NFRE) row st+5 -> ring slot of row st-4 (last read just above)
+      const V xF = lds<2>(sm, me_s);
+      const double fac = lds1(sm, L.pc + PC_FAC * PRB + po);
+      V v;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        v.v[i] = dmax(xF.v[i] * fac, c_dc.EPSMIN);
+        if (rnew == F - 1) v.v[i] = dmax(v.v[i], flm.v[i]);
+      }
+      if (act) {
+        const unsigned rbse = L.ring + slot9(rnew) * RSB + me_r;
+        sts<2>(sm, rbse, v);
+        if (k0 < HR) sts<2>(sm, rbse + (unsigned)A * 8u, v);
+        if (k0 >= A - HR) sts<2>(sm, rbse - (unsigned)A * 8u, v);
+      }
+    }
+    if (ard && t < 4 * NPT && rb - 1 >= 0 && rb - 1 < F) {   // BTH0 of row st-3 from the partial maxima of the previous step
+      const int qp = t >> 2, j = t & 3;
+      const double* pp = reinterpret_cast<const double*>(sm + L.part + ((unsigned)(st + 5) % 3u) * (unsigned)(blockDim.x * 8u)) + 2 * qp;
+      double mx = 0.0;
+#pragma unroll
+      for (int x = 0; x < (NPR + 3) / 4; ++x) {   // pair e = j + 4 x of the point sits at thread ((e / 2) * NPT + qp) * 2 + (e & 1)
+        const int e = j + 4 * x;
+        if (e < NPR) mx = dmax(mx, pp[(e >> 1) * (2 * NPT) + (e & 1)]);
+      }
+      // only the first 4*NPT lanes are here: the member mask must name exactly them
+      constexpr unsigned RM = (4 * NPT >= 32) ? 0xffffffffu : ((1u << ((4 * NPT) & 31)) - 1u);
+      mx = dmax(mx, __shfl_xor_sync(RM, mx, 1));
+      mx = dmax(mx, __shfl_xor_sync(RM, mx, 2));
+      if (j == 0) reinterpret_cast<double*>(sm + L.bth0 + par * PRB)[qp] = mx;
+    }
+  };
+
+#pragma unroll 1
+  for (int st = -5; st < MLSTHG; ++st) step(st);
+  // ---- per-point sums over direction, then the scalar closures (one thread per point)
+  __syncthreads();
+  constexpr int PS = sw_nptp(NPT);
+  double* red = reinterpret_cast<double*>(sm + L.ring);     // red[q][k][pt]: 8 planes of A*PS doubles in the (now free) ring area
+  static_assert(8u * A * PS * 8u <= ST_RING * L.RSB, "reduction planes must fit the ring");
+  if (act) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int k = k0 + i;
+      const double sinth = c_dc.SINTH[k], costh = c_dc.COSTH[k];
+      red[(0 * A + k) * PS + pt] = a_philf.v[i];
+      red[(1 * A + k) * PS + pt] = sinth * a_ts.v[i];
+      red[(2 * A + k) * PS + pt] = costh * a_ts.v[i];
+      red[(3 * A + k) * PS + pt] = a_tu.v[i] * sinth;
+      red[(4 * A + k) * PS + pt] = a_tu.v[i] * costh;
+      if (LWFLUX) { red[(5 * A + k) * PS + pt] = a_e1.v[i]; red[(6 * A + k) * PS + pt] = a_e2.v[i]; red[(7 * A + k) * PS + pt] = a_el.v[i]; }
+    }
+  }
+  __syncthreads();
+  double* qs = reinterpret_cast<double*>(sm + L.cur);        // [8][PS] reduced sums
+  if (t < 8 * NPT) {
+    const int x = t / NPT, p8 = t - x * NPT;
+    double v = 0.0;
+    if (x < 5 || LWFLUX) for (int kk = 0; kk < A; ++kk) v += red[(x * A + kk) * PS + p8];
+    qs[x * PS + p8] = v;
+  }
+  __syncthreads();
+  if (t < NPT && pbase + t <= plast)
+    stencil_closure<LWFLUX, sw_nptp(NPT)>(d, pbase + t, qs + t, reinterpret_cast<const double*>(sm + L.pc) + t);
+}
+
+template <int TA, int NPT, bool LW>
+static int launch_sweep(const ImplDev& d, long long p0, long long np, cudaStream_t st) {
+  constexpr SwSmem L = sw_smem(TA, NPT, LW);
+  static_assert(L.total <= 110 * 1024, "k_sweep shared memory");
+  static_assert(8 * NPT <= sw_threads(TA, NPT) && TQ_N * NPT <= sw_threads(TA, NPT) && 4 * NPT <= 32, "k_sweep: too few threads for the per-point loops");
+  static bool attr_done = false;
+  if (!attr_done) {
+    EW_CUDA_CHECK(cudaFuncSetAttribute(k_sweep<TA, NPT, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    EW_CUDA_CHECK(cudaFuncSetAttribute(k_sweep<TA, NPT, LW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attr_done = true;
+  }
+  k_sweep<TA, NPT, LW><<<(unsigned)((np + NPT - 1) / NPT), sw_threads(TA, NPT), L.total, st>>>(d, p0, np);
+  return 0;
+}
+
 template <int TA>
 static bool geo_matches(const ImplDev& d, int iphys, int nsdsnth) {
   if (d.A != TA) return false;
@@ -2004,7 +2540,14 @@ int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage
     if (force && !strcmp(force, "single")) pair = false;
     // default for the standard grids: thread = (two adjacent directions, one point); ECWAM_B200_STENCIL=pp keeps the
     // two-points-per-thread instance (A/B timing, tests)
-    if (!force) {
+    // default for the standard grids: k_sweep (NPT points x NANG/2 direction pairs = four full warps where NANG allows)
+    if (!force && d.sweep_ok) {
+      if (geo_matches<36>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_sweep<36, 7, true>(d, p0, np, st) : launch_sweep<36, 7, false>(d, p0, np, st);
+      if (geo_matches<24>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_sweep<24, 8, true>(d, p0, np, st) : launch_sweep<24, 8, false>(d, p0, np, st);
+      if (geo_matches<12>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_sweep<12, 8, true>(d, p0, np, st) : launch_sweep<12, 8, false>(d, p0, np, st);
+    }
+    // ECWAM_B200_STENCIL=dp: thread = (two adjacent directions, one point), 8 points x 160 threads (the previous default; tests, A/B)
+    if (!force || !strcmp(force, "dp")) {
       if (geo_matches<36>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_stencil_dp<36, true>(d, p0, np, st) : launch_stencil_dp<36, false>(d, p0, np, st);
       if (geo_matches<24>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_stencil_dp<24, true>(d, p0, np, st) : launch_stencil_dp<24, false>(d, p0, np, st);
       if (geo_matches<12>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_stencil_dp<12, true>(d, p0, np, st) : launch_stencil_dp<12, false>(d, p0, np, st);

@@ -43,6 +43,11 @@ struct PropConst {
   double xdella;
 };
 int upload_prop_const(const PropConst& h, cudaStream_t st);
+int upload_prop_const_fast(const PropConst& h, cudaStream_t st);   // the copy read by propag_fast.cu
+// 1: ECWAM_B200_PROPAG=exact, the bit-exact PROPAGS2 kernel of propag.cu is used for IREFRA = 0, 1 as well (verifier)
+bool propag_exact_mode();
+void launch_propags2_fast(const PropDev& d, const double* src, int srcF, double* dst, int dstF, int m0, int m1, int msplit,
+                          cudaStream_t st, int l0, int l1);
 
 // own points [l0, l1) (l1 < 0: all)
 void launch_propags2(const PropDev& d, const double* src, int srcF, double* dst, int dstF, int m0, int m1, int msplit,
@@ -83,6 +88,7 @@ struct ImplDev {
   int halo_r, halo_c;      // direction halo of the shared-memory spectrum rows / interaction planes of k_stencil
   int cy49;                // LLGCBZ0 or LLNORMAGAM is on: k_point runs its gravity-capillary / renormalised-growth instance
   const double* gc;        // [GC_NT][NWAV_GC] gravity-capillary tables (device), read by that instance only
+  int sweep_ok;            // the DIA tables have the separable structure k_sweep relies on (DevConst::NLW)
 };
 #define EW_TQ_N 6          // number of planes of ImplDev::tbg
 int upload_dev_const(const DevConst& h, cudaStream_t st);

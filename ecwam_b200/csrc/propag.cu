@@ -11,6 +11,8 @@
 // This translation unit is compiled with -fmad=false and the weight arithmetic keeps the reference's
 // operation order, so the result is bit-identical to the reference's stored-weight formulation.
 #include "internal.h"
+#include <cstdlib>
+#include <cstring>
 
 #ifndef PG_UNR
 #define PG_UNR 1   // direction pairs of ctu_quadrant's loop unrolled together (12 gathers in flight per pair)
@@ -589,8 +591,10 @@ __global__ void land_cg_kernel(PropDev d, const double* __restrict__ land_cg, do
 // (propag_wam.F90:368-405).  One thread per (lane, k, m, chunk) element; lane fastest.
 __global__ void copyback_kernel(PropDev d, const double* __restrict__ fl3, double* __restrict__ fl1, int m0, int m1) {
   const long long n = (long long)d.P * d.A * (m1 - m0);
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int c = blockIdx.y;
+  // chunk = block index / blocks per chunk (the chunk count of O1280 on one GPU exceeds the 65535 limit of gridDim.y)
+  const unsigned bpc = (unsigned)((n + blockDim.x - 1) / blockDim.x);
+  const int c = (int)(blockIdx.x / bpc);
+  const long long idx = (long long)(blockIdx.x - (unsigned)c * bpc) * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   const int i = (int)(idx % d.P);
   const long long km = idx / d.P + (long long)m0 * d.A;
@@ -613,11 +617,16 @@ __global__ void pad_kernel(PropDev d, double* __restrict__ fl1, int flF, int m0,
 }
 
 // ---- host launchers --------------------------------------------------------------------------------------
+bool propag_exact_mode() {   // read at every launch: the tests switch it per case
+  const char* e = getenv("ECWAM_B200_PROPAG");
+  return e && !strcmp(e, "exact");
+}
 void launch_propags2(const PropDev& d, const double* src, int srcF, double* dst, int dstF, int m0, int m1, int msplit,
                      cudaStream_t st, int l0, int l1) {
   if (l1 < 0) l1 = d.nloc;
   l1 = l1 < d.nloc ? l1 : d.nloc;
   if (m1 <= m0 || l1 <= l0) return;
+  if (d.irefra < 2 && !propag_exact_mode()) { launch_propags2_fast(d, src, srcF, dst, dstF, m0, m1, msplit, st, l0, l1); return; }
   const int MG = 8;
   SpecSrc s{src, (long long)d.P * d.A * srcF};
   dim3 grid((l1 - l0 + 127) / 128, (m1 - m0 + MG - 1) / MG);
@@ -671,8 +680,8 @@ void launch_unpack_cg(const PropDev& d, const double* in, const int* recv_pre, c
 void launch_copyback(const PropDev& d, const double* fl3, double* fl1, int m0, int m1, cudaStream_t st) {
   if (m1 <= m0) return;
   const long long n = (long long)d.P * d.A * (m1 - m0);
-  dim3 grid((unsigned)((n + 255) / 256), d.nchnk);
-  copyback_kernel<<<grid, 256, 0, st>>>(d, fl3, fl1, m0, m1);
+  const long long nb = ((n + 255) / 256) * (long long)d.nchnk;   // < 2^31 for any grid that fits one GPU
+  copyback_kernel<<<(unsigned)nb, 256, 0, st>>>(d, fl3, fl1, m0, m1);
 }
 void launch_pad(const PropDev& d, double* fl1, int flF, int m0, int m1, cudaStream_t st) {
   const int kijl = d.nloc - (d.nchnk - 1) * d.P;

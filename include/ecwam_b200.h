@@ -328,13 +328,37 @@ int ecwam_b200_bind_fields(ecwam_b200_handle h, const ecwam_b200_fields* dev);
  * LLCFLCUROFF retry.
  * Returns the number of own grid points that violate the CFL / weight-range checks (0 = ok).           */
 int ecwam_b200_propag(ecwam_b200_handle h);
-/* Force the CTU set-up to be redone at the next ecwam_b200_propag (LUPDTWGHT, getcurr.F90:289).        */
+/* Force the CTU set-up to be redone at the next ecwam_b200_propag (LUPDTWGHT, getcurr.F90:289).  Also makes the next
+ * ecwam_b200_wamintgr_host call upload its static fields again (see there).                             */
 int ecwam_b200_invalidate_weights(ecwam_b200_handle h);
 
 /* IMPLSCH for all NCHNK chunks in one go = the chunk loop of WAMINTGR (src/ecwam/wamintgr.F90:117-146). */
 int ecwam_b200_implsch_all(ecwam_b200_handle h);
 /* IMPLSCH for chunks ichnk0 .. ichnk0+nchnk-1 (1-based): the single-chunk reference call is nchnk=1.   */
 int ecwam_b200_implsch(ecwam_b200_handle h, int ichnk0, int nchnk);
+
+/* The reference argument lists, for Fortran bodies that keep the reference's call signatures (fortran/implsch_b200.F90,
+ * fortran/propag_wam_b200.F90):
+ *   SUBROUTINE IMPLSCH(KIJS, KIJL, FL1, WAVNUM, ..., MIJ, XLLWS)                       src/ecwam/implsch.F90:10-23, 117-143
+ *   SUBROUTINE PROPAG_WAM(BLK2GLO, WAVNUM, CGROUP, OMOSNH2KD, FL1, DEPTH, DELLAM1, COSPHM1, UCUR, VCUR)   propag_wam.F90:10-11, 74-77
+ * (BLK2GLO is consumed at ecwam_b200_create).  The arguments are the DEVICE addresses of what the reference caller passes —
+ * for IMPLSCH the slices of chunk ICHNK, `FL1(:,:,:,ICHNK)` etc. (wamintgr.F90:119-146).  The kernels work on the arrays bound
+ * with ecwam_b200_bind_fields: every argument is checked to be chunk ICHNK (derived from FL1's address) of its bound array, so
+ * that a FIELD_API re-allocation that was not followed by a re-bind fails with ECWAM_B200_ESTATE instead of using stale
+ * memory.  KIJS:KIJL must be 1:NPROMA_WAM as in the reference call.  IOBND, IODP, IBRMEM and the NEMO accumulators
+ * (LWNEMOCOU = F) are accepted and not read.                                                             */
+int ecwam_b200_implsch_f(ecwam_b200_handle h, int kijs, int kijl, double* fl1, const double* wavnum, const double* cgroup,
+                         const double* ciwa, const double* cinv, const double* xk2cg, const double* stokfac, const double* emaxdpt,
+                         const double* depth, const int* iobnd, const int* iodp, const double* ibrmem, double* aird, double* wdwave,
+                         double* cicover, double* wswave, double* wstar, double* ustra, double* vstra, double* ufric, double* tauw,
+                         double* tauwdir, double* z0m, double* z0b, double* chrnck, double* cithick, double* nemoustokes,
+                         double* nemovstokes, double* nemostrn, double* nphieps, double* ntauoc, double* nswh, double* nmwp,
+                         double* nemotaux, double* nemotauy, double* nemotauicx, double* nemotauicy, double* nemowswave,
+                         double* nemophif, double* wsemean, double* wsfmean, double* ustokes, double* vstokes, double* strnms,
+                         double* tauxd, double* tauyd, double* tauocxd, double* tauocyd, double* tauoc, double* tauicx,
+                         double* tauicy, double* phiocd, double* phieps, double* phiaw, int* mij, double* xllws);
+int ecwam_b200_propag_wam_f(ecwam_b200_handle h, const double* wavnum, const double* cgroup, const double* omosnh2kd, double* fl1,
+                            const double* depth, const double* dellam1, const double* cosphm1, const double* ucur, const double* vcur);
 
 /* One WAMINTGR sub-step with IDELPRO == IDELT: PROPAG_WAM then IMPLSCH (wamintgr.F90:94-146) with the
  * block->chunk copy of PROPAG_WAM fused into IMPLSCH's load.  Same results as _propag + _implsch_all.  */
@@ -348,7 +372,13 @@ int ecwam_b200_no_source(ecwam_b200_handle h, int llsource_off);
 /* Same step for callers whose fields live in HOST memory (pinned or pageable): copies the IMPLSCH /
  * PROPAG_WAM inputs host->device, runs the step, copies FL1, XLLWS(optional) and the 1-D outputs back.
  * `host` uses the same struct with host pointers; with_xllws != 0 also returns XLLWS.
- * h2d_bytes / d2h_bytes (optional) receive the bytes moved.                                            */
+ * h2d_bytes / d2h_bytes (optional) receive the bytes moved.
+ * Caching: the static fields (WAVNUM, CINV, CGROUP, XK2CG, OMOSNH2KD, STOKFAC, CIWA, DEPTH, EMAXDPT, DELLAM1, COSPHM1,
+ * UCUR, VCUR) are uploaded by the first call only; after changing any of them (new currents with IREFRA = 2, 3,
+ * getcurr.F90 LUPDTWGHT) call ecwam_b200_invalidate_weights: the next call uploads them again and redoes the CTU set-up.
+ * The call works on device mirrors owned by the handle and leaves the binding made with ecwam_b200_bind_fields as it
+ * was: the device entry points keep operating on the caller's own tensors.  (The CTU set-up is built from the static
+ * fields of one side; a handle that alternates between the two paths rebuilds it at every change of side.)      */
 int ecwam_b200_wamintgr_host(ecwam_b200_handle h, const ecwam_b200_fields* host, int with_xllws,
                              long long* h2d_bytes, long long* d2h_bytes);
 
@@ -443,6 +473,10 @@ int ecwam_b200_timing_get(ecwam_b200_handle h, const char* name, double* total_m
 int ecwam_b200_timing_reset(ecwam_b200_handle h);
 const char* ecwam_b200_last_error(void);
 int ecwam_b200_version(void);
+/* Roofline denominators measured on the current device (bench.py): FP64 FMA rate [TFLOP/s] (16 independent DFMA chains
+ * per thread, 8 CTAs of 256 threads per SM) — the bound of the IMPLSCH kernels — and a streaming-copy
+ * bandwidth [GB/s, read + write].  Either pointer may be NULL.  Not part of the hot path.                */
+int ecwam_b200_measure_peaks(double* fp64_tflops, double* copy_gbs);
 
 /* ---------------------------------------------------------------------------------------------------
  * Host-side builders (C++; one-off, init only) for callers that do not bring ecWAM's module state:

@@ -11,9 +11,9 @@ FL="$ARCH -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -I../../include"
 while [ $# -gt 1 ]; do
   name=$1; flags=$2; shift 2
   ( $NVCC $FL $flags -Xptxas -v -c implsch.cu -o ../../build_variants/implsch_$name.o 2> ../../build_variants/implsch_$name.log
-    $NVCC $FL $flags -fmad=false -c propag.cu -o ../../build_variants/propag_$name.o
-    $NVCC $FL $flags -c outparam.cu -o ../../build_variants/outparam_$name.o
-    $NVCC $ARCH -shared -o ../../build_variants/lib_$name.so api.o ../../build_variants/propag_$name.o ../../build_variants/implsch_$name.o ../../build_variants/outparam_$name.o host_tables.o host_grid.o host_io.o -lnccl -lcudart -lgomp
-    echo "$name: $(grep -A3 'k_stencil_dpILi36ELb0' ../../build_variants/implsch_$name.log | grep -o 'Used [0-9]* registers\|[0-9]* bytes spill stores' | tr '\n' ' ')" ) &
+    $NVCC $FL $flags -Xptxas -v -c propag_fast.cu -o ../../build_variants/propag_fast_$name.o 2> ../../build_variants/propag_fast_$name.log
+    $NVCC $ARCH -shared -o ../../build_variants/lib_$name.so api.o peaks.o propag.o outparam.o ../../build_variants/propag_fast_$name.o ../../build_variants/implsch_$name.o host_tables.o host_grid.o host_io.o -lnccl -lcudart -lgomp
+    echo "$name: propags2_fast $(grep -A2 'propags2_fast_kernelILb0' ../../build_variants/propag_fast_$name.log | grep -o 'Used [0-9]* registers\|[0-9]* bytes spill stores' | tr '\n' ' ')"
+    echo "$name: $(grep -A3 'k_sweepILi36ELi7ELb0' ../../build_variants/implsch_$name.log | grep -o 'Used [0-9]* registers\|[0-9]* bytes spill stores' | tr '\n' ' ')" ) &
 done
 wait

@@ -1,5 +1,7 @@
 """Run under torchrun: N ranks (one GPU each) propagate + integrate with the NCCL halo and every rank compares its own points
 with the 1-rank CPU oracle.  PROPAGS2 must be bit-identical to the 1-rank result (it is order-independent per point)."""
+import os
+os.environ.setdefault("ECWAM_B200_PROPAG", "exact")   # the N-rank = 1-rank bit-for-bit check needs the exact PROPAGS2 kernel
 import ctypes as C
 import os
 import sys

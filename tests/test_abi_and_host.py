@@ -139,3 +139,50 @@ def test_halo_plan_is_symmetric(built):
     for p in range(npr):
         for nm in ("klat", "klon", "kcor"):
             assert ds[p][nm].min() >= ds[p]["ninf"] and ds[p][nm].max() <= ds[p]["nsup"] + 1
+
+
+# ---- the Fortran side of the boundary (fortran/*.F90; no Fortran compiler in the image: checked mechanically) ------------------
+def _fortran_dummies(path, name):
+    """Dummy-argument names of SUBROUTINE `name` in a free-form Fortran file."""
+    import re
+    with open(path) as f:
+        src = f.read()
+    m = re.search(r"SUBROUTINE\s+%s\s*\((.*?)\)\s*\n" % name, src, re.S | re.I)
+    assert m, "%s not found in %s" % (name, path)
+    return [a.strip().upper() for a in m.group(1).replace("&", " ").split(",")]
+
+
+IMPLSCH_REF = ("KIJS KIJL FL1 WAVNUM CGROUP CIWA CINV XK2CG STOKFAC EMAXDPT DEPTH IOBND IODP IBRMEM AIRD WDWAVE CICOVER WSWAVE WSTAR USTRA "
+               "VSTRA UFRIC TAUW TAUWDIR Z0M Z0B CHRNCK CITHICK NEMOUSTOKES NEMOVSTOKES NEMOSTRN NPHIEPS NTAUOC NSWH NMWP NEMOTAUX NEMOTAUY "
+               "NEMOTAUICX NEMOTAUICY NEMOWSWAVE NEMOPHIF WSEMEAN WSFMEAN USTOKES VSTOKES STRNMS TAUXD TAUYD TAUOCXD TAUOCYD TAUOC TAUICX "
+               "TAUICY PHIOCD PHIEPS PHIAW MIJ XLLWS").split()          # src/ecwam/implsch.F90:10-23 (ecWAM 1.5.13)
+PROPAG_REF = "BLK2GLO WAVNUM CGROUP OMOSNH2KD FL1 DEPTH DELLAM1 COSPHM1 UCUR VCUR".split()   # src/ecwam/propag_wam.F90:10-11
+
+
+def test_fortran_module_is_generated_from_the_header():
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert subprocess.call([sys.executable, os.path.join(root, "scripts", "gen_fortran_mod.py"), "--check"]) == 0, \
+        "fortran/ecwam_b200_mod.F90 is stale: run scripts/gen_fortran_mod.py"
+    with open(os.path.join(root, "fortran", "ecwam_b200_mod.F90")) as f:
+        mod = f.read().upper()
+    for name in L.EXPORTS:      # one interface per exported function
+        assert "FUNCTION %s(" % name.upper() in mod, name
+
+
+def test_fortran_bodies_keep_the_reference_signatures():
+    import os, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert _fortran_dummies(os.path.join(root, "fortran", "implsch_b200.F90"), "IMPLSCH") == IMPLSCH_REF
+    assert _fortran_dummies(os.path.join(root, "fortran", "propag_wam_b200.F90"), "PROPAG_WAM") == PROPAG_REF
+    ref = "/root/reference/src/ecwam"       # present in the build container only
+    if os.path.isdir(ref):
+        assert _fortran_dummies(os.path.join(ref, "implsch.F90"), "IMPLSCH") == IMPLSCH_REF
+        assert _fortran_dummies(os.path.join(ref, "propag_wam.F90"), "PROPAG_WAM") == PROPAG_REF
+    # the C entry points take the same lists (handle first; BLK2GLO is consumed at create)
+    src = re.sub(r"/\*.*?\*/", "", L._SRC, flags=re.S)
+    def cargs(fn):
+        m = re.search(r"int %s\((.*?)\);" % fn, src, re.S)
+        return [re.split(r"[ *]", a.strip())[-1].upper() for a in m.group(1).split(",")]
+    assert cargs("ecwam_b200_implsch_f") == ["H"] + IMPLSCH_REF
+    assert cargs("ecwam_b200_propag_wam_f") == ["H"] + PROPAG_REF[1:]

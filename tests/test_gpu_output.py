@@ -145,8 +145,9 @@ def test_wamintgr_sequencing_idelpro_twice_idelt(built):
     assert (w.get_field("mij") == o.get_field("MIJ")[w.own]).all()
 
 
-def test_wamintgr_without_source_terms(built):
+def test_wamintgr_without_source_terms(built, monkeypatch):
     """LLSOURCE = F (wamintgr.F90:163-171) and the "not yet time" branch (:188-195): MIJ = NFRE, XLLWS = 0, FL1 floored."""
+    monkeypatch.setenv("ECWAM_B200_PROPAG", "exact")
     from ecwam_b200 import model as M
     g, o, f, fl = make_oracle("o48like")
     _, s, w = make_gpu("o48like")

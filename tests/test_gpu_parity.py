@@ -3,7 +3,9 @@ inputs, against the committed golden outputs, and through size-independent prope
 
 Tolerances (BASELINE.json north_star: "integer tables and cut-off indices bit-exact; spectra and integrated parameters
 within a stated relative tolerance"):
-  * PROPAGS2 from identical inputs ............ bit-exact (propag.cu keeps the reference's operation order, -fmad=false)
+  * PROPAGS2 from identical inputs ............ default kernel (factored weights, FMA): |a-b| <= 1e-13 max|b| and 1e-12 per
+                                                 significant bin; ECWAM_B200_PROPAG=exact (propag.cu keeps the reference's
+                                                 operation order, -fmad=false): bit-exact
   * MIJ, XLLWS ................................ exact
   * FL1 after IMPLSCH / WAMINTGR steps ........ max |a-b| / max|b| <= 1e-12  and, per bin above 1e-8*max, relative 1e-10
   * UFRIC, TAUW, Z0M, stresses, fluxes, Hs .... relative 1e-10
@@ -37,8 +39,51 @@ def check_state(w, o, fields=True):
             assert relerr(w.get_field(nm), o.get_field(nm)[w.own]) <= RTOL_FIELD, nm
 
 
+RTOL_PROPAG, RTOL_PROPAG_BIN = 1e-13, 1e-12
+
+
+def check_propag(w, o):
+    a, b = w.get_spec("fl1"), o.get_fl1()[:, :, w.own]
+    assert np.isfinite(a).all()
+    assert relerr(a, b) <= RTOL_PROPAG
+    big = b > 1e-8 * b.max()
+    assert (np.abs(a - b)[big] / b[big]).max() <= RTOL_PROPAG_BIN
+
+
 @pytest.mark.parametrize("case", ["o48like", "o320like", "o640like", "aqua"])
-def test_propags2_bit_exact(built, case):
+def test_propags2_default_kernel_within_tolerance(built, case):
+    """The default PROPAGS2 kernel (propag_fast.cu: CTU weights factored into per-(point, frequency) and per-direction terms,
+    FMA contraction) against the stored-weight oracle; 3 advection steps so that rounding differences could accumulate."""
+    g, o, f, fl = make_oracle(case)
+    _, s, w = make_gpu(case)
+    for _ in range(3):
+        assert o.propag() == 0 and w.propag() == 0
+    w.synchronize()
+    check_propag(w, o)
+    assert not np.array_equal(w.get_spec("fl1"), o.get_fl1()[:, :, w.own]) or case == "never", "expected the tolerance-mode kernel"
+
+
+@pytest.mark.parametrize("case", ["o48like", "o640like"])
+def test_depth_refraction_default_kernel(built, case):
+    g, o, f, fl = make_oracle(case, irefra=1)
+    _, s, w = make_gpu(case, irefra=1)
+    for _ in range(2):
+        assert o.propag() == 0 and w.propag() == 0
+    w.synchronize()
+    check_propag(w, o)
+
+
+def test_fast_wave_substeps_default_kernel(built):
+    g, o, f, fl = make_oracle("o640like", ifrelfmax=5, delpro_lf=225.0)
+    _, s, w = make_gpu("o640like", ifrelfmax=5, delpro_lf=225.0)
+    assert o.propag() == 0 and w.propag() == 0
+    w.synchronize()
+    check_propag(w, o)
+
+
+@pytest.mark.parametrize("case", ["o48like", "o320like", "o640like", "aqua"])
+def test_propags2_bit_exact(built, case, monkeypatch):
+    monkeypatch.setenv("ECWAM_B200_PROPAG", "exact")
     g, o, f, fl = make_oracle(case)
     _, s, w = make_gpu(case)
     assert o.propag() == 0 and w.propag() == 0
@@ -79,10 +124,12 @@ def test_wamintgr_steps_match_oracle(built, case):
 
 
 @pytest.mark.parametrize("mode,case", [("generic", "o640like"), ("generic", "o48_iphys0"), ("single", "o640like"), ("single", "o320like"),
-                                       ("pp", "o640like"), ("pp", "o320like"), ("pp", "o48like")])
+                                       ("pp", "o640like"), ("pp", "o320like"), ("pp", "o48like"),
+                                       ("dp", "o640like"), ("dp", "o320like"), ("dp", "o48like")])
 def test_stencil_kernel_instances_agree(built, monkeypatch, mode, case):
-    """k_stencil has compile-time-geometry instances (NANG 12/24/36, two points per thread), a run-time-geometry instance and a
-    one-point-per-thread instance (odd NPROMA / unaligned arrays).  All of them must match the oracle."""
+    """Besides the default k_sweep, the frequency sweep has the previous default (dp: 8 points x 160 threads), compile-time-geometry
+    instances with two points per thread (pp), a run-time-geometry instance and a one-point-per-thread instance (odd NPROMA /
+    unaligned arrays).  All of them must match the oracle."""
     monkeypatch.setenv("ECWAM_B200_STENCIL", mode)
     g, o, f, fl = make_oracle(case)
     _, s, w = make_gpu(case)
@@ -145,7 +192,8 @@ def test_single_chunk_implsch_equals_all_chunks(built):
     np.testing.assert_array_equal(w1.get_field("ufric"), w2.get_field("ufric"))
 
 
-def test_fast_wave_substeps_bit_exact(built):
+def test_fast_wave_substeps_bit_exact(built, monkeypatch):
+    monkeypatch.setenv("ECWAM_B200_PROPAG", "exact")
     g, o, f, fl = make_oracle("o640like", ifrelfmax=5, delpro_lf=225.0)
     _, s, w = make_gpu("o640like", ifrelfmax=5, delpro_lf=225.0)
     assert o.propag() == 0 and w.propag() == 0
@@ -210,9 +258,10 @@ def test_gravity_capillary_physics_matches_oracle(built, case, extra):
 
 
 @pytest.mark.parametrize("case", ["o48like", "o640like"])
-def test_depth_refraction_bit_exact(built, case):
+def test_depth_refraction_bit_exact(built, case, monkeypatch):
     """IREFRA = 1: GRADI's depth gradients, PROPDOT's THDD and the depth-refraction term of the direction weights
     (ctuw.F90:434-439, 487-501) are recomputed in the kernel in the reference's operation order -> PROPAGS2 stays bit-exact."""
+    monkeypatch.setenv("ECWAM_B200_PROPAG", "exact")
     g, o0, f, fl = make_oracle(case)
     g, o, f, fl = make_oracle(case, irefra=1)
     _, s, w = make_gpu(case, irefra=1)
@@ -377,6 +426,48 @@ def test_host_buffer_entry_point(built):
     np.testing.assert_array_equal(host["xllws"].numpy(), w1.t["xllws"].cpu().numpy())
     np.testing.assert_array_equal(host["ufric"].numpy(), w1.t["ufric"].cpu().numpy())
     np.testing.assert_array_equal(host["mij"].numpy(), w1.t["mij"].cpu().numpy())
+
+
+def test_reference_signature_entry_points(built):
+    """ecwam_b200_implsch_f / _propag_wam_f take the reference argument lists (implsch.F90:10-23, propag_wam.F90:10-11) as the
+    Fortran bodies in fortran/ pass them: the chunk's slices of the bound arrays.  Chunk by chunk they must reproduce the
+    all-chunk calls bit for bit; a pointer that is not the matching slice of the bound array is an ESTATE error."""
+    import torch
+    _, s, w1 = make_gpu("o48like")
+    _, _, w2 = make_gpu("o48like")
+    lib = w2.lib
+    P, A, F, nch = w2.P, w2.A, w2.F, w2.C
+    t = w2.t
+    order = ("fl1 wavnum cgroup ciwa cinv xk2cg stokfac emaxdpt depth IOBND IODP IBRMEM aird wdwave cicover wswave wstar ustra vstra ufric "
+             "tauw tauwdir z0m z0b chrnck cithick N N N N N N N N N N N N N wsemean wsfmean ustokes vstokes strnms tauxd tauyd tauocxd "
+             "tauocyd tauoc tauicx tauicy phiocd phieps phiaw mij xllws").split()
+    assert len(order) == 56
+    dummy = torch.zeros(P, dtype=torch.float64, device=t["fl1"].device)      # IOBND, IODP, IBRMEM, NEMO accumulators: not read
+
+    def args(ichnk, wrong=None):
+        out = []
+        for nm in order:
+            if nm.isupper():
+                out.append(dummy.data_ptr())
+                continue
+            x = t[nm]
+            per = x.numel() // nch * x.element_size()
+            out.append(x.data_ptr() + per * (ichnk if nm != wrong else (ichnk + 1) % nch))
+        return out
+
+    w1.propag(); w1.implsch()
+    assert lib.ecwam_b200_propag_wam_f(w2.h, *[t[n].data_ptr() for n in ("wavnum", "cgroup", "omosnh2kd", "fl1", "depth", "dellam1", "cosphm1", "ucur", "vcur")]) == 0
+    for ic in range(nch):
+        L.check(lib.ecwam_b200_implsch_f(w2.h, 1, P, *args(ic)), "implsch_f")
+    w1.synchronize(); w2.synchronize()
+    for nm in ("fl1", "xllws", "ufric", "tauw", "mij", "phiaw", "ustokes"):
+        assert torch.equal(w1.t[nm], w2.t[nm]), nm
+    # wrong slices / wrong chunk bounds are refused
+    assert lib.ecwam_b200_implsch_f(w2.h, 1, P, *args(0, wrong="ufric")) == -4 and b"UFRIC" in lib.ecwam_b200_last_error()
+    assert lib.ecwam_b200_implsch_f(w2.h, 1, P - 1, *args(0)) == -1
+    bad = args(0); bad[0] += 8
+    assert lib.ecwam_b200_implsch_f(w2.h, 1, P, *bad) == -4
+    assert lib.ecwam_b200_propag_wam_f(w2.h, *[t[n].data_ptr() for n in ("cgroup", "cgroup", "omosnh2kd", "fl1", "depth", "dellam1", "cosphm1", "ucur", "vcur")]) == -4
 
 
 def test_full_size_properties_o320(built):
