@@ -27,9 +27,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "grid-point spectra/s per timestep (IMPLSCH+PROPAGS2)"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of the bench workload
-NCU_DRAM_SOURCE = "profiles/r01l_ncu_summary_O640.txt"
-NCU_DRAM_BYTES = {("O640", 1): {"implsch_stencil": 36.193e9, "implsch_point": 53.645e9, "propags2": 19.585e9}}
+# From the committed ncu --set full capture of the bench workload (profiles/, O640, 1 GPU): DRAM bytes per launch
+# (dram__bytes_read.sum + dram__bytes_write.sum) and executed FP64 flops per grid point and launch
+# (2 x smsp__sass_thread_inst_executed_op_dfma_pred_on + ..._dmul_pred_on + ..._dadd_pred_on, divided by the points of the launch).
+NCU_SOURCE = "profiles/r02_ncu_summary_O640.txt"
+NCU_DRAM_BYTES = {("O640", 1): {"implsch_stencil": 36.196e9, "implsch_point": 53.654e9, "propags2": 19.83e9}}
+NCU_FP64_FLOP_PER_POINT = {36: {"implsch_stencil": 289.2e3, "implsch_point": 157.0e3, "propags2": 46.5e3}}
 UNIT = "spectra/s"
 
 
@@ -46,6 +49,15 @@ def peaks():
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def fp64_peak(lib):
+    """FP64 FMA rate of this GPU, measured live with the library's own micro-benchmark (csrc/peaks.cu: 16 independent DFMA
+    chains per thread, 8 CTAs of 256 threads per SM): MEASURED_PEAKS.json has no FP64 figure."""
+    a, b = C.c_double(), C.c_double()
+    if lib.ecwam_b200_measure_peaks(C.byref(a), C.byref(b)) != 0:
+        return None, None
+    return a.value, b.value
 
 
 class ClockSampler:
@@ -207,11 +219,12 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------------------
-def make_case(workload, world, rank, device, mask="continents", physics="default"):
+def make_case(workload, world, rank, device, mask="continents", physics="default", nproma=None):
     """Set-up (not timed): grid, MPDECOMP for `world` ranks, tables, this rank's fields on its GPU."""
     from ecwam_b200 import synth, model as M, lib as L
     import torch
-    cfgw, nproma = workload_cfg(workload)
+    cfgw, nproma_default = workload_cfg(workload)
+    nproma = nproma or nproma_default
     g = synth.make_grid(cfgw["N"], mask)
     s = M.WamSetup(g, nproc=world, nang=cfgw["nang"], nfre_red=cfgw["nfre_red"], iphys=1, nproma=nproma, idelt=cfgw["idelt"],
                    idelpro=cfgw["idelpro"], delpro_lf=cfgw["delpro_lf"], ifrelfmax=cfgw["ifrelfmax"], **PHYSICS[physics])
@@ -260,6 +273,45 @@ def bind_to_gpu_numa_node(index):
     except Exception as e:  # no sysfs / NVML in this container: leave the affinity alone
         return "unbound (%s)" % type(e).__name__
     return "unbound"
+
+
+def resident_run(workload, world, rank, device, dist, nproma, steps, warmup):
+    """Device-resident timing of another BASELINE.json configuration (same recipe as the headline: warm-up, CUDA events, max over ranks)."""
+    import torch
+    from ecwam_b200 import lib as L
+    g, s, w, forcing = make_case(workload, world, rank, device, nproma=nproma)
+    for _ in range(warmup):
+        if w.step():
+            raise RuntimeError("CFL violated in the synthetic case")
+    L.check(w.lib.ecwam_b200_timing_reset(w.h), "timing_reset")
+    w.lib.ecwam_b200_timing_enable(w.h, 1)
+    torch.cuda.synchronize(device)
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        w.step()
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    kern = {}
+    for nm in ("propags2", "halo", "copyback", "implsch_point", "implsch_stencil"):
+        tot, cnt = w.timing(nm)
+        if cnt:
+            kern[nm] = tot / cnt
+    w.lib.ecwam_b200_timing_enable(w.h, 0)
+    out = {"workload": "%s, %d sea points, %dx%d(%d), NPROMA=%d, dt=%gs" % (workload, g.niblo, w.A, w.F, w.Fr, w.par.nproma, w.par.idelt),
+           "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": float(ms.item()) / steps,
+           "value": g.niblo * steps / (float(ms.item()) * 1e-3), "unit": UNIT, "kernel_ms": kern}
+    w.close()
+    del w
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_gpu(args):
@@ -375,33 +427,75 @@ def run_gpu(args):
                "what": "ecwam_b200_wamintgr_host: FL1 + forcing + stress state host->device from pinned buffers, step, "
                        "FL1 + all 1-D outputs + MIJ device->host, every step"}
 
+    # what the report below needs of the headline case (it is released before the extra configurations run)
+    class _W:
+        pass
+    wi = _W()
+    wi.A, wi.F, wi.Fr, wi.P, wi.C, wi.nloc = w.A, w.F, w.Fr, w.P, w.C, w.nloc
+    wi.nproma, wi.idelt, wi.fl1_gb = w.par.nproma, w.par.idelt, w.t["fl1"].numel() * 8 / 1e9
+    # ---- the other BASELINE.json configurations next to the headline one (every rank takes part) --------------------------
+    extra = None
+    if not args.no_extra and args.workload == "O640" and args.physics == "default":
+        import gc
+        w.close()
+        del w
+        gc.collect()
+        torch.cuda.empty_cache()
+        todo = []
+        if world == 1:
+            todo += [("O640", 24, "o640_nproma24"), ("O320", None, "o320")]     # tests/etopo1_oper_an_fc_O640.yml:19 nproma: 24
+        elif world == 2:
+            todo += [("O320", None, "o320")]
+        elif world == 8:
+            todo += [("O1280", None, "o1280")]
+        extra = {}
+        for wl, npro, key in todo:
+            try:
+                extra[key] = resident_run(wl, world, rank, device, dist, npro, 5, 3)
+            except Exception as e:          # an extra line must never take the headline down
+                extra[key] = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel ------------------------------------------------------------------------
-    A, F, Fr = w.A, w.F, w.Fr
-    # algorithmic bytes per grid point and launch (DESIGN.md "Kernels"): k_point reads FL1 once and writes XLLWS and the
-    # wind-input scratch; k_stencil reads FL1 + scratch and writes FL1; PROPAGS2 reads and writes the propagated part
-    # (DESIGN.md 2): k_point (two kernels) reads FL1 twice and writes the wind-input scratch, XLLWS and the per-(point,
-    # frequency) scalars; k_stencil reads FL1 + scratch + those scalars and writes FL1; PROPAGS2 reads and writes the propagated part
+    # ---- rooflines ---------------------------------------------------------------------------------------------------
+    A, F, Fr = wi.A, wi.F, wi.Fr
+    # algorithmic bytes per grid point and launch: k_point (two kernels) reads FL1 twice and writes the wind-input
+    # scratch, XLLWS and the per-(point, frequency) scalars; the sweep reads FL1 + scratch + those scalars and writes FL1;
+    # PROPAGS2 reads and writes the propagated part + its per-point tables
     alg = {"implsch_point": (4 * A * F * 8 + 12 * F * 8 + 40 * 8), "implsch_stencil": (3 * A * F * 8 + 6 * F * 8 + 30 * 8),
            "propags2": (2 * A * Fr * 8 + 14 * 4 + 11 * 8 + Fr * 8), "copyback": 2 * A * Fr * 8}
+    flop = NCU_FP64_FLOP_PER_POINT.get(A, {})
     dom = max((k for k in kern if k in alg), key=lambda k: kern[k]) if kern else None
     peak, peak_src = peaks()
+    f64_peak, copy_gbs = fp64_peak(lib)
+    roofs = []
+    for k in ("propags2", "implsch_point", "implsch_stencil"):
+        if k not in kern:
+            continue
+        pts_rank = wi.P * wi.C if k.startswith("implsch") else wi.nloc
+        gbs = alg[k] * pts_rank / (kern[k] * 1e-3) / 1e9
+        e = {"kernel": k, "ms_per_launch": kern[k], "points_per_launch": pts_rank,
+             "hbm": {"achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "algorithmic_bytes_per_point": alg[k]}}
+        if k in flop and f64_peak:
+            tf = flop[k] * pts_rank / (kern[k] * 1e-3) / 1e12
+            e["fp64"] = {"achieved": tf, "peak": f64_peak, "unit": "TFLOP/s", "frac": tf / f64_peak, "executed_flop_per_point": flop[k]}
+        e["bound"] = "hbm" if k == "propags2" else "fp64"
+        roofs.append(e)
     roof = None
     if dom:
-        pts_rank = w.P * w.C if dom.startswith("implsch") else w.nloc
-        ach = alg[dom] * pts_rank / (kern[dom] * 1e-3) / 1e9
+        rd = next(r for r in roofs if r["kernel"] == dom)
         traffic = NCU_DRAM_BYTES.get((args.workload, world), {}).get(dom)
-        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                "traffic_source": NCU_DRAM_SOURCE if traffic else None,
-                "peak_source": peak_src, "algorithmic_bytes_per_point": alg[dom], "points_per_launch": pts_rank,
-                "ms_per_launch": kern[dom],
-                "note": "the dominant kernel (k_stencil_dp: DIA quadruplets + saturation window + implicit update) is bound by "
-                        "instruction issue / dependency latency at 10 warps per SM (issue 50 %, FP64 pipe 33 %, shared-memory "
-                        "pipe ~60 %), not by HBM: the HBM fraction is reported as the contract asks; per-kernel DRAM GB/s and "
-                        "pipe utilisation are in profiles/"}
+        roof = {"kernel": dom, "bound": "hbm", "achieved": rd["hbm"]["achieved"], "peak": peak, "unit": "GB/s", "frac": rd["hbm"]["frac"],
+                "traffic": traffic, "traffic_source": NCU_SOURCE if traffic else None, "peak_source": peak_src,
+                "algorithmic_bytes_per_point": alg[dom], "points_per_launch": rd["points_per_launch"], "ms_per_launch": kern[dom],
+                "fp64": rd.get("fp64"), "fp64_peak_source": "ecwam_b200_measure_peaks, live on this GPU (DFMA chains); streaming copy %.0f GB/s" % (copy_gbs or 0),
+                "per_kernel": roofs,
+                "note": "the dominant kernel (k_sweep_ws: DIA quadruplets + saturation window + implicit update, producer / consumer "
+                        "warp groups) is bound by FP64 issue and dependency latency at 16 warps per SM, not by HBM (its DRAM traffic equals "
+                        "the algorithmic bytes): the HBM fraction is reported as the contract asks, `fp64` is the roofline that governs it "
+                        "(executed FP64 flops of the committed ncu capture / live kernel time / live DFMA peak); PROPAGS2 is the "
+                        "HBM-bound kernel (per_kernel[0])"}
     cpu = None
     if not args.no_cpu:
         v, msc, cores, sample, _, _ = cpu_reference_run(args.workload, 2, 1, physics=args.physics)
@@ -412,9 +506,10 @@ def run_gpu(args):
             "config": {"workload": "%s octahedral grid, synthetic continents (%d sea points), %dx%d spectrum (%d propagated), "
                                    "IPHYS=1%s, NPROMA=%d, dt=%gs" % (args.workload, npts_total, A, F, Fr,
                                                                       "" if args.physics == "default" else " + LLGCBZ0 + LLNORMAGAM (cy49r1)",
-                                                                      w.par.nproma, w.par.idelt),
-                       "parallelism": "mpdecomp%d" % world, "l2": "inputs larger than L2 (FL1 %.1f GB per GPU)" % (w.t["fl1"].numel() * 8 / 1e9)},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "kernel_ms": kern, "output_step": aux or None, "roofline": roof, "cpu_baseline": cpu}
+                                                                      wi.nproma, wi.idelt),
+                       "parallelism": "mpdecomp%d" % world, "l2": "inputs larger than L2 (FL1 %.1f GB per GPU)" % wi.fl1_gb},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "kernel_ms": kern, "output_step": aux or None, "roofline": roof, "cpu_baseline": cpu,
+            "extra": extra}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -429,6 +524,7 @@ def main():
     ap.add_argument("--workload", default="O640", choices=["O48", "O320", "O640", "O1280", "P256"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the O320 / O1280 / NPROMA=24 lines next to the headline workload")
     ap.add_argument("--no-aux", action="store_true", help="skip the NEWWIND / OUTBS / WAMNORM timing next to the path")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--ref-sample", action="store_true", help="--impl reference: time the bounded O96/O64 sample instead of the workload itself")

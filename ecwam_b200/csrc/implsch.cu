@@ -993,6 +993,20 @@ __device__ __forceinline__ void mbar_arrive_cp_async(unsigned bar) { asm volatil
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
   asm volatile("{\n .reg .pred p;\n WAIT_LOOP:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra WAIT_DONE;\n bra WAIT_LOOP;\n WAIT_DONE:\n}\n" ::"r"(bar), "r"(parity) : "memory");
 }
+#ifndef SW_SLEEP
+#define SW_SLEEP 64   // ns between polls of a role that waits for its partner
+#endif
+// the same with a back-off: a role that runs ahead of the other one must not spend the issue slots its partner needs
+__device__ __forceinline__ void mbar_wait_backoff(unsigned bar, unsigned parity) {
+  unsigned done;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  while (!done) {
+#if SW_SLEEP > 0
+    __nanosleep(SW_SLEEP);
+#endif
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  }
+}
 // Direction geometry of the standard ecWAM grids (NANG = 12, 24, 36), known at compile time so that every shared-memory
 // offset of k_stencil is an immediate: NSDSNTH = min(nint(80 deg / DELTH), NANG/2-1) (init_sdiss_ardh.F90:72) and the DIA
 // partner shifts K1W, K11W, K2W, K21W(K,KH) - K of nlweigt.F90:108-206 (checked against the run-time tables on the host).
@@ -2485,6 +2499,518 @@ __global__ void __launch_bounds__(sw_threads(TA, NPT), SW_MINB) k_sweep(ImplDev 
     stencil_closure<LWFLUX, sw_nptp(NPT)>(d, pbase + t, qs + t, reinterpret_cast<const double*>(sm + L.pc) + t);
 }
 
+// =========================================================================================================
+// k_sweep_ws: k_sweep with the step split over two warp roles (producer / consumer warp groups of one CTA).
+// What bounds the one-role kernels is neither a pipe nor a memory level but latency at low occupancy: the sweep needs ~220
+// registers per thread to be scheduled well (56 of them the pending SNONLIN rows), i.e. 8 warps per SM; capped at 168 registers
+// for 12 warps it spills and rematerialises, and either way it runs at the pace of the 10-warp k_stencil_dp (45 ms at O640), with
+// 13 % of the warp time in the per-step CTA barrier.  Here
+//   * the PRODUCER warp group forms what only reads the spectrum: the direction interpolation of the rows entering the
+//     quadruplets, the DIA products of the centre frequency -> interaction planes, the centre bin's own share, and the saturation
+//     window of SDISSIP_ARD with its maximum over direction.  Its persistent state is the carried interpolation (16 registers);
+//   * the CONSUMER warp group gathers the products into the pending rows (56 registers), finishes one row per step (implicit
+//     update, WNFLUXES sums, tail, ice, Stokes), stores it, and feeds the next row of the spectrum into the ring.
+//     (Moving the gather to the producers balances the instruction counts but costs a producer barrier in mid-step: 38.1 vs 35.6 ms.)
+//   setmaxnreg moves registers from the producers (SW_RP) to the consumers (SW_RC): 2 CTAs = 16 warps per SM, each role with the
+//   registers it needs.  The roles run up to two steps apart: the hand-over slots are double-buffered and passed with two mbarriers
+//   per buffer (full: producers -> consumers; empty: consumers -> producers — the consumers' "empty" of step s also publishes ring
+//   row s+5, the newest row the producers read at step s+2) and so are the interaction planes; the four producer warps meet once
+//   per step at a named barrier for the direction maximum.  No CTA-wide barrier inside the sweep; a role that waits for the other
+//   one polls with a back-off (a spinning producer group took 16 % of the issue slots).
+// =========================================================================================================
+#ifndef SW_RP
+#define SW_RP 96     // registers per producer thread
+#endif
+#ifndef SW_RC
+#define SW_RC 160    // registers per consumer thread   (SW_RP + SW_RC <= 256: 2 CTAs of 2 x 128 threads per SM)
+#endif
+struct WsSmem { unsigned ring, cur, tbs, pc, part, bth0, hand, stage, mbar, total, RSB, PSB, SSB, PRB; };
+__host__ __device__ constexpr WsSmem ws_smem(int A, int npt, bool lwflux) {
+  WsSmem s{};
+  const int nth = sw_threads(A, npt);     // threads per role
+  s.RSB = (unsigned)sw_pst(A, npt) * npt * 8;
+  s.PSB = (unsigned)sw_pstc(A, npt) * npt * 8;
+  s.SSB = (unsigned)nth * 16;
+  s.PRB = (unsigned)sw_nptp(npt) * 8;
+  unsigned o = 0;
+  s.ring = o; o += ST_RING * s.RSB;
+  s.cur = o; o += 2 * 6 * s.PSB;
+  s.tbs = o; o += 8 * TQ_N * s.PRB;
+  s.pc = o; o += PC_N * s.PRB;
+  s.part = o; o += 2u * (unsigned)nth * 8;
+  s.bth0 = o; o += 2 * s.PRB;
+  s.hand = o; o += 2 * 3 * s.SSB;         // per buffer, one pair per thread: saturation values, centre share of SL, centre share of FLD
+  s.stage = o; o += (lwflux ? 3 : 2) * s.SSB;
+  s.mbar = o; o += 32;                    // full[0], full[1], empty[0], empty[1]
+  s.total = o;
+  return s;
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+template <int ID, int NT> __device__ __forceinline__ void named_bar_sync() { asm volatile("bar.sync %0, %1;\n" ::"n"(ID), "n"(NT) : "memory"); }
+
+template <int TA, int NPT, bool LWFLUX>
+__global__ void __launch_bounds__(2 * sw_threads(TA, NPT), 2) k_sweep_ws(ImplDev d, long long p0, long long np) {
+  extern __shared__ __align__(16) char sm[];
+  typedef Vd<2> V;
+  constexpr int A = TA, NPR = TA / 2, NSD = geo_nsd(TA), NS = 2 * NSD + 1, HR = dp_hr(TA), HC = dp_hc(TA);
+  constexpr int NACT = NPT * NPR, NTHR = sw_threads(TA, NPT);
+  constexpr unsigned PSTB = sw_pst(TA, NPT) * 8, PSTCB = sw_pstc(TA, NPT) * 8;
+  constexpr WsSmem L = ws_smem(TA, NPT, LWFLUX);
+  constexpr unsigned RSB = L.RSB, PSB = L.PSB, PRB = L.PRB;
+  constexpr int GA = -geo_sh(TA, 0, 0), GB = geo_sh(TA, 0, 2);
+  static_assert(NTHR == 128, "k_sweep_ws: one warp group (4 warps) per role");
+  const int F = c_dc.F;
+  const bool ard = c_dc.iphys == 1;
+  const unsigned smb = (unsigned)__cvta_generic_to_shared(sm);
+  const int t = threadIdx.x;
+  const bool consumer = t >= NTHR;
+  const int tr = consumer ? t - NTHR : t;          // thread of the role
+  const bool act = tr < NACT;                      // lanes beyond NPT*NANG/2 shadow the last thread and never store
+  const int ta = act ? tr : NACT - 1;
+  const int pt = (ta % (2 * NPT)) >> 1;            // grid point of the CTA
+  const int k0 = 2 * (2 * (ta / (2 * NPT)) + (ta & 1));   // first direction of the pair
+  unsigned po = (unsigned)pt * 8u;
+  unsigned me_r = (unsigned)pt * PSTB + (unsigned)(k0 + HR) * 8u;
+  unsigned me_c = (unsigned)pt * PSTCB + (unsigned)(k0 + HC) * 8u;
+  unsigned me_h = L.hand + (unsigned)tr * 16u;     // own hand-over slot
+  asm volatile("" : "+r"(po), "+r"(me_r), "+r"(me_c), "+r"(me_h));
+  const long long pbase = p0 + (long long)blockIdx.x * NPT;
+  const long long plast = p0 + np - 1;
+  const long long n = d.npts;
+  const double* s = d.scr;
+  const int MLSTHG = c_dc.MLSTHG;
+  const unsigned bar_full = smb + L.mbar, bar_empty = smb + L.mbar + 16;
+
+  // ---- prologue: barriers, per-point constants
+  if (t == 0) { mbar_init(bar_full, NTHR); mbar_init(bar_full + 8, NTHR); mbar_init(bar_empty, NTHR); mbar_init(bar_empty + 8, NTHR); }
+  if (t < NPT) {
+    const long long qp = min(pbase + t, plast);
+    double* pcv = reinterpret_cast<double*>(sm + L.pc) + t;
+    constexpr int PS = sw_nptp(NPT);
+    const double wd = d.f.wdwave[qp], ci = d.f.cicover[qp], dep = d.f.depth[qp];
+    double snw, csw;
+    sincos(wd, &snw, &csw);
+    double enhfr = dmax(0.75 * dep * s[S_AKMEAN * n + qp], 0.5);
+    enhfr = 1.0 + (5.5 / enhfr) * (1.0 - .833 * enhfr) * exp(-1.25 * enhfr);
+    const int mijq = (int)s[S_MIJ * n + qp];
+    const bool seticeq = c_dc.licerun && c_dc.lmaskice && ci > c_dc.cithrsh;
+    pcv[PC_FAC * PS] = s[S_FAC * n + qp];
+    pcv[PC_ENH * PS] = enhfr;
+    pcv[PC_USFMDELT * PS] = s[S_USFM * n + qp] * c_dc.delt;
+    pcv[PC_SDSBK * PS] = (c_dc.lbiwbk && dep < 50.0) ? s[S_SDS * n + qp] : 0.0;
+    pcv[PC_RTAIL * PS] = 1.0 / d.tbg[((size_t)TQ_TAIL * F + (mijq - 1)) * n + qp];
+    pcv[PC_FLMC * PS] = (1. - 0.9 * dmin(ci, 0.99)) * c_dc.flmin;
+    pcv[PC_ICEADD * PS] = seticeq ? dmax(c_dc.EPSMIN, 1.0 - ci) * c_dc.flmin : 0.0;
+    pcv[PC_ICEFREE * PS] = seticeq ? 0.0 : 1.0;
+    pcv[PC_SNW * PS] = snw;
+    pcv[PC_CSW * PS] = csw;
+    pcv[PC_BETA * PS] = (c_dc.licerun && c_dc.lciscal) ? 1.0 - ci : 1.0;
+  }
+  __syncthreads();
+  V a_philf, a_ts, a_tu, a_e1, a_e2, a_el;     // consumer accumulators (reduced over direction after the sweep)
+#pragma unroll
+  for (int i = 0; i < 2; ++i) { a_philf.v[i] = 0.0; a_ts.v[i] = 0.0; a_tu.v[i] = 0.0; a_e1.v[i] = 0.0; a_e2.v[i] = 0.0; a_el.v[i] = 0.0; }
+
+  if (!consumer) {
+    // ================================================= PRODUCER =================================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(SW_RP));
+    double dpc[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, dmc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll 1
+    for (int st = -5; st < MLSTHG; ++st) {
+      const unsigned sidx = (unsigned)(st + 5), b = sidx & 1u, u = sidx >> 1;
+      // buffer b is free and ring rows up to st+3 are in place once the consumers have finished step st-2
+      if (sidx >= 2u) mbar_wait_backoff(bar_empty + 8u * b, (u - 1u) & 1u);
+      const unsigned hb = me_h + b * 3u * L.SSB;
+      if (st >= -1) {
+        // direction interpolation of the rows that join the quadruplets at this centre frequency (IP1, IM1; at st = -1: IP, IM of
+        // the first one), both KH families
+        double dpn[2][2], dmn[2][2];
+        {
+          const unsigned bP = L.ring + (unsigned)c_dc.NLS2[st + 1][0] * RSB + me_r;
+          const unsigned bM = L.ring + (unsigned)c_dc.NLS2[st + 1][1] * RSB + me_r;
+          Run<-GA - 1, GA + 2> rp;
+          Run<GB, GB + 2> rm0;
+          Run<-GB - 1, -GB + 1> rm1;
+          rp.load(sm, bP); rm0.load(sm, bM); rm1.load(sm, bM);
+          const double cl11 = c_dc.NLD[0], acl1 = c_dc.NLD[1], cl21 = c_dc.NLD[2], acl2 = c_dc.NLD[3];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            dpn[0][i] = fma(acl1, rp.at(i - GA - 1), cl11 * rp.at(i - GA));
+            dpn[1][i] = fma(acl1, rp.at(i + GA + 1), cl11 * rp.at(i + GA));
+            dmn[0][i] = fma(acl2, rm0.at(i + GB + 1), cl21 * rm0.at(i + GB));
+            dmn[1][i] = fma(acl2, rm1.at(i - GB - 1), cl21 * rm1.at(i - GB));
+          }
+        }
+        if (st >= 0) {
+          const int MC0 = st;
+          const double* Wc = c_dc.NLW[MC0];
+          const unsigned cb = L.cur + b * 6u * PSB + me_c;
+          const V fc = lds<2>(sm, L.ring + (unsigned)c_dc.NLSLOT[MC0][0] * RSB + me_r);
+          const double enh = lds1(sm, L.pc + PC_ENH * PRB + po);
+          const double ftemp = c_dc.AF11[MC0] * enh;
+          const double r0 = c_dc.RNLCOEF[MC0][0];
+          V fij, fcen, fcd1, fcd2;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            fij.v[i] = fc.v[i] * r0;
+            fcen.v[i] = ftemp * fij.v[i];
+            fcd1.v[i] = c_dc.DAL1 * fcen.v[i];
+            fcd2.v[i] = c_dc.DAL2 * fcen.v[i];
+          }
+          V csl, cfl;
+          csl.v[0] = csl.v[1] = cfl.v[0] = cfl.v[1] = 0.0;
+#pragma unroll
+          for (int kh = 0; kh < 2; ++kh) {
+            V vad, vdp, vdm;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const double sap = fma(Wc[1], dpn[kh][i], Wc[0] * dpc[kh][i]);
+              const double sam = fma(Wc[3], dmn[kh][i], Wc[2] * dmc[kh][i]);
+              double fad1 = fij.v[i] * (sap + sam);
+              const double sap2 = 2.0 * sap;
+              const double fad2 = fma(-sap2, sam, fad1);
+              fad1 = fad1 + fad2;
+              vad.v[i] = fad2 * fcen.v[i];
+              csl.v[i] += vad.v[i];
+              cfl.v[i] = fma(fad1, ftemp, cfl.v[i]);
+              vdp.v[i] = fma(-2.0, sam, fij.v[i]) * fcd1.v[i];
+              vdm.v[i] = (fij.v[i] - sap2) * fcd2.v[i];
+            }
+            if (act) {
+              sts<2>(sm, cb + (0 + kh) * PSB, vad);
+              sts<2>(sm, cb + (2 + kh) * PSB, vdp);
+              sts<2>(sm, cb + (4 + kh) * PSB, vdm);
+              if (k0 < HC) {
+                sts<2>(sm, cb + (0 + kh) * PSB + (unsigned)A * 8u, vad);
+                sts<2>(sm, cb + (2 + kh) * PSB + (unsigned)A * 8u, vdp);
+                sts<2>(sm, cb + (4 + kh) * PSB + (unsigned)A * 8u, vdm);
+              }
+              if (k0 >= A - HC) {
+                sts<2>(sm, cb + (0 + kh) * PSB - (unsigned)A * 8u, vad);
+                sts<2>(sm, cb + (2 + kh) * PSB - (unsigned)A * 8u, vdp);
+                sts<2>(sm, cb + (4 + kh) * PSB - (unsigned)A * 8u, vdm);
+              }
+            }
+          }
+          // the centre bin's own share (-2 AD, -2 DELAD; snonlin.F90:253-262) is handed to the consumer thread of the same bins
+          const double c2 = c_dc.RNLC2[MC0];
+          V ccs, ccf;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) { ccs.v[i] = -c2 * csl.v[i]; ccf.v[i] = -c2 * cfl.v[i]; }
+          sts<2>(sm, hb + 1u * L.SSB, ccs);
+          sts<2>(sm, hb + 2u * L.SSB, ccf);
+        }
+#pragma unroll
+        for (int kh = 0; kh < 2; ++kh)
+#pragma unroll
+          for (int i = 0; i < 2; ++i) { dpc[kh][i] = dpn[kh][i]; dmc[kh][i] = dmn[kh][i]; }
+      }
+      // saturation spectrum of the row the consumers finish at this step (sdissip_ard.F90:142-160); two partial sums per bin
+      // halve the dependent FMA chain
+      const int rs = st - 4;
+      const bool sat = ard && rs >= 0 && rs < F;
+      if (sat) {
+        const unsigned wb = L.ring + slot9(rs) * RSB + me_r - (unsigned)HR * 8u;
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int jp = 0; jp <= HR; ++jp) {
+          const V f = lds<2>(sm, wb + jp * 16);
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int x = 2 * jp + e - (HR - NSD) - i;
+              if (x >= 0 && x < NS) acc[jp & 1][i] = fma(c_dc.SATW1[x], f.v[e], acc[jp & 1][i]);
+            }
+        }
+        V bsat;
+        bsat.v[0] = acc[0][0] + acc[1][0]; bsat.v[1] = acc[0][1] + acc[1][1];
+        const double fs = lds1(sm, L.tbs + (unsigned)(((rs & 7) * TQ_N + TQ_FACSAT)) * PRB + po);
+        bsat.v[0] *= fs; bsat.v[1] *= fs;
+        sts<2>(sm, hb, bsat);
+        *reinterpret_cast<double*>(sm + L.part + b * (unsigned)(NTHR * 8) + (unsigned)tr * 8u) = dmax(bsat.v[0], bsat.v[1]);
+      }
+      named_bar_sync<1, NTHR>();          // the partial maxima of all four producer warps are written
+      if (sat && tr < 4 * NPT) {          // BTH0 = max over direction: four lanes per grid point
+        const int qp = tr >> 2, j = tr & 3;
+        const double* pp = reinterpret_cast<const double*>(sm + L.part + b * (unsigned)(NTHR * 8)) + 2 * qp;
+        double mx = 0.0;
+#pragma unroll
+        for (int x = 0; x < (NPR + 3) / 4; ++x) {   // pair e = j + 4 x of the point sits at thread ((e / 2) * NPT + qp) * 2 + (e & 1)
+          const int e = j + 4 * x;
+          if (e < NPR) mx = dmax(mx, pp[(e >> 1) * (2 * NPT) + (e & 1)]);
+        }
+        constexpr unsigned RM = (4 * NPT >= 32) ? 0xffffffffu : ((1u << ((4 * NPT) & 31)) - 1u);
+        mx = dmax(mx, __shfl_xor_sync(RM, mx, 1));
+        mx = dmax(mx, __shfl_xor_sync(RM, mx, 2));
+        if (j == 0) reinterpret_cast<double*>(sm + L.bth0 + b * PRB)[qp] = mx;
+      }
+      mbar_arrive(bar_full + 8u * b);
+    }
+  } else {
+    // ================================================= CONSUMER =================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(SW_RC));
+    unsigned me_s = L.stage + (unsigned)tr * 16u;      // own landing slot
+    asm volatile("" : "+r"(me_s));
+    long long pq = pbase + pt;
+    const bool pvalid = pq <= plast;
+    if (!pvalid) pq = plast;
+    const bool dost = act && pvalid;
+    const size_t P = (size_t)d.P;
+    const size_t rstr = P * A;
+    const long long pc_ = pq / d.P;
+    const int pi_ = (int)(pq - pc_ * d.P);
+    const size_t off_hi = (size_t)pi_ + P * A * F * (size_t)pc_ + P * (size_t)k0;
+    const double* src_hi = d.f.fl1 + off_hi;
+    const double* src_lo = src_hi;
+    int mlo = 0;
+    if (d.lo_on) {
+      src_lo = d.fl_lo + (size_t)pi_ + P * A * d.lo_F * (size_t)pc_ + P * (size_t)k0;
+      mlo = d.Fr;
+    }
+    double* dst = d.f.fl1 + off_hi;
+    const double* src_in = d.fldin + off_hi;
+    const double* src_xl = d.f.xllws + off_hi;
+    // loader of the per-(point, frequency) scalars: thread (q, p8) of the first TQ_N*NPT consumer threads
+    const int tq_q = tr / NPT, tq_p = tr - tq_q * NPT;
+    const bool tq_on = tr < TQ_N * NPT;
+    const double* tq_g = d.tbg + (size_t)(tq_on ? tq_q : 0) * F * n + min(pbase + tq_p, plast);
+    const unsigned tq_s = L.tbs + (unsigned)(tq_on ? tq_q : 0) * PRB + (unsigned)tq_p * 8u;
+    V flm, iaw;    // FLM(k) = FLMC*max(0,cos(TH(k)-WDWAVE))**2 (implsch.F90:236-247); SETICE's noise floor likewise
+    {
+      const double snw = lds1(sm, L.pc + PC_SNW * PRB + po), csw = lds1(sm, L.pc + PC_CSW * PRB + po);
+      const double flmc = lds1(sm, L.pc + PC_FLMC * PRB + po), ia = lds1(sm, L.pc + PC_ICEADD * PRB + po);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double cw2 = sq(dmax(0.0, c_dc.COSTH[k0 + i] * csw + c_dc.SINTH[k0 + i] * snw));
+        flm.v[i] = flmc * cw2; iaw.v[i] = ia * cw2;
+      }
+    }
+    const int mij = (int)s[S_MIJ * n + pq];
+    const bool setice = c_dc.licerun && c_dc.lmaskice;
+    const double delt = c_dc.delt, deltm = 1.0 / delt, delt5 = c_dc.ximp * delt;
+    const double tmp03 = 1.0 / (c_dc.SDSBR * c_dc.MICHE);
+    const bool lssource = c_dc.lcflx && c_dc.lwvflx_snl;
+    // pending SNONLIN sums of rows st-4 .. st+2 (row st+3 receives its first contribution, MC -> MC+3, at this step)
+    double asl[7][2], afl[7][2];
+#pragma unroll
+    for (int x = 0; x < 7; ++x)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) { asl[x][i] = 0.0; afl[x][i] = 0.0; }
+    V fmij;
+    fmij.v[0] = fmij.v[1] = 0.0;
+
+#pragma unroll 1
+    for (int st = -5; st < MLSTHG; ++st) {
+      const unsigned sidx = (unsigned)(st + 5), b = sidx & 1u, u = sidx >> 1;
+      const int rnew = st + 5, rfin = st - 4, rtb = st - 1;
+      const bool dia = st >= 0;
+      const bool fin = rfin >= 0 && rfin < F;
+      // row loads of this step: group 1 = wind-input (and XLLWS) row of the row that is finished, group 2 = FL1 row st+5 for the
+      // ring and the per-(point, frequency) scalars of row st-1
+      if (fin) {
+        const double* g = src_in + (size_t)rfin * rstr;
+        cp_async<8>(smb + me_s + L.SSB, g); cp_async<8>(smb + me_s + L.SSB + 8, g + P);
+        if (LWFLUX) { const double* gx = src_xl + (size_t)rfin * rstr; cp_async<8>(smb + me_s + 2 * L.SSB, gx); cp_async<8>(smb + me_s + 2 * L.SSB + 8, gx + P); }
+      }
+      cp_async_commit();
+      if (rnew < F) {
+        const double* g = (rnew < mlo ? src_lo : src_hi) + (size_t)rnew * rstr;
+        cp_async<8>(smb + me_s, g); cp_async<8>(smb + me_s + 8, g + P);
+      }
+      if (rtb >= 0 && rtb < F && tq_on) cp_async<8>(smb + tq_s + (unsigned)((rtb & 7) * TQ_N) * PRB, tq_g + (size_t)rtb * n);
+      cp_async_commit();
+      mbar_wait_backoff(bar_full + 8u * b, u & 1u);
+      const unsigned hb = me_h + b * 3u * L.SSB;
+      V tot_sl, tot_fl;
+      {
+        double tap[2] = {0.0, 0.0}, tpp[2] = {0.0, 0.0}, tam[2] = {0.0, 0.0}, tmm[2] = {0.0, 0.0};
+        if (dia) {
+          // gather of the quadruplet contributions of MC (snonlin.F90:253-308) through the inverse shifts, direction interpolation first
+          const unsigned cb = L.cur + b * 6u * PSB + me_c;
+          const double cl11 = c_dc.NLD[0], acl1 = c_dc.NLD[1], cl21 = c_dc.NLD[2], acl2 = c_dc.NLD[3];
+          const double cl11s = c_dc.NLD[4], acl1s = c_dc.NLD[5], cl21s = c_dc.NLD[6], acl2s = c_dc.NLD[7];
+          {   // KH = 1
+            Run<GA, GA + 2> ap, pp;
+            Run<-GB - 1, -GB + 1> am, mm;
+            ap.load(sm, cb + 0 * PSB); pp.load(sm, cb + 2 * PSB); am.load(sm, cb + 0 * PSB); mm.load(sm, cb + 4 * PSB);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              tap[i] = fma(acl1, ap.at(i + GA + 1), cl11 * ap.at(i + GA));
+              tpp[i] = fma(acl1s, pp.at(i + GA + 1), cl11s * pp.at(i + GA));
+              tam[i] = fma(acl2, am.at(i - GB - 1), cl21 * am.at(i - GB));
+              tmm[i] = fma(acl2s, mm.at(i - GB - 1), cl21s * mm.at(i - GB));
+            }
+          }
+          {   // KH = 2: mirrored
+            Run<-GA - 1, -GA + 1> ap, pp;
+            Run<GB, GB + 2> am, mm;
+            ap.load(sm, cb + 1 * PSB); pp.load(sm, cb + 3 * PSB); am.load(sm, cb + 1 * PSB); mm.load(sm, cb + 5 * PSB);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              tap[i] = fma(acl1, ap.at(i - GA - 1), fma(cl11, ap.at(i - GA), tap[i]));
+              tpp[i] = fma(acl1s, pp.at(i - GA - 1), fma(cl11s, pp.at(i - GA), tpp[i]));
+              tam[i] = fma(acl2, am.at(i + GB + 1), fma(cl21, am.at(i + GB), tam[i]));
+              tmm[i] = fma(acl2s, mm.at(i + GB + 1), fma(cl21s, mm.at(i + GB), tmm[i]));
+            }
+          }
+          const V ccs = lds<2>(sm, hb + 1u * L.SSB), ccf = lds<2>(sm, hb + 2u * L.SSB);    // the centre bin's own share
+#pragma unroll
+          for (int i = 0; i < 2; ++i) { asl[4][i] += ccs.v[i]; afl[4][i] += ccf.v[i]; }
+        }
+        const double* Wc = c_dc.NLW[dia ? st : 0];
+        // slide the window of pending rows: row st-3 -> slot 0, ..., row st+3 (first contribution) -> slot 6
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          tot_sl.v[i] = fma(Wc[6], tam[i], asl[0][i]);    tot_fl.v[i] = fma(Wc[10], tmm[i], afl[0][i]);
+          asl[0][i] = fma(Wc[7], tam[i], asl[1][i]);      afl[0][i] = fma(Wc[11], tmm[i], afl[1][i]);
+          asl[1][i] = asl[2][i];                          afl[1][i] = afl[2][i];
+          asl[2][i] = asl[3][i];                          afl[2][i] = afl[3][i];
+          asl[3][i] = asl[4][i];                          afl[3][i] = afl[4][i];
+          asl[4][i] = asl[5][i];                          afl[4][i] = afl[5][i];
+          asl[5][i] = fma(Wc[4], tap[i], asl[6][i]);      afl[5][i] = fma(Wc[8], tpp[i], afl[6][i]);
+          asl[6][i] = Wc[5] * tap[i];                     afl[6][i] = Wc[9] * tpp[i];
+        }
+      }
+      // finish row rfin (implsch.F90:276-395 for these bins)
+      if (fin) {
+        const int r = rfin;
+        const unsigned tq = L.tbs + (unsigned)((r & 7) * TQ_N) * PRB + po;
+        const V fold = lds<2>(sm, L.ring + slot9(r) * RSB + me_r);
+        cp_async_wait<1>();                              // the wind-input row of this step has landed (own slot)
+        const V xI = lds<2>(sm, me_s + L.SSB);
+        const double usfm = lds1(sm, L.pc + PC_USFMDELT * PRB + po), sdsbk = lds1(sm, L.pc + PC_SDSBK * PRB + po);
+        const double tsbo = lds1(sm, tq + TQ_SBO * PRB), tcinv = lds1(sm, tq + TQ_CINV * PRB), ttail = lds1(sm, tq + TQ_TAIL * PRB);
+        const double tstf = lds1(sm, tq + TQ_STF * PRB), rtail = lds1(sm, L.pc + PC_RTAIL * PRB + po);
+        const double beta = c_dc.lciscal ? lds1(sm, L.pc + PC_BETA * PRB + po) : 1.0;
+        V dd;
+        if (ard) {
+          const double b0 = lds1(sm, L.bth0 + b * PRB + po);
+          const V bs = lds<2>(sm, hb);
+          const double ssdsc2_sig = c_dc.SSDSC2 * c_dc.ZPIFR[r];
+          const double d0 = ssdsc2_sig * c_dc.SSDSC6 * sq(dmax(0., b0 * tmp03 - c_dc.SSDSC4));
+#pragma unroll
+          for (int i = 0; i < 2; ++i) dd.v[i] = d0 + ssdsc2_sig * (1. - c_dc.SSDSC6) * sq(dmax(0., bs.v[i] * tmp03 - c_dc.SSDSC4));
+        } else { const double dj = lds1(sm, tq + TQ_JAN * PRB); dd.v[0] = dj; dd.v[1] = dj; }
+        const double cofrm4 = c_dc.COFRM4[r], flmax = c_dc.FLMAX[r];
+        double rr = (r + 1 > mij) ? 0.0 : c_dc.RHOWG_DFIM[r];      // RHOWGDFTH of frcutindex.F90:99-108
+        if (r + 1 == mij && mij != F) rr = 0.5 * rr;
+        V xL;
+        if (LWFLUX) xL = lds<2>(sm, me_s + 2 * L.SSB);
+        V fnv;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const double f0 = fold.v[i];
+          double fldv = xI.v[i];
+          double slv = fldv * f0;
+          slv = slv + dd.v[i] * f0; fldv = fldv + dd.v[i];
+          slv = slv + tot_sl.v[i]; fldv = fldv + tot_fl.v[i];
+          double ssource = 0.0;
+          if (lssource) ssource = div_fast(slv, dmax(1.0 - delt5 * fldv, 1.0));
+          if (r < c_dc.Fr) { slv = slv - sdsbk * f0; fldv = fldv - sdsbk; }            // SDIWBK (0 where it does not apply)
+          if (c_dc.lciscal) { slv = slv * beta; fldv = fldv * beta; }                  // LCISCAL (implsch.F90:315-325)
+          slv = slv + tsbo * f0; fldv = fldv + tsbo;                                   // SDICE3 + SBOTTOM (plane is 0 where neither applies)
+          const double gtemp1 = dmax(1.0 - delt5 * fldv, 1.0);
+          const double gtemp2 = div_fast(delt * slv, gtemp1);
+          const double flhab = dmin(fabs(gtemp2), usfm * cofrm4);
+          double fn = f0 + copysign(flhab, gtemp2);
+          fn = dmax(fn, flm.v[i]);
+          ssource = ssource + deltm * dmin(flmax - fn, 0.0);
+          fn = dmin(fn, flmax);
+          a_philf.v[i] += ssource * rr;
+          a_ts.v[i] += ssource * (tcinv * rr);
+          if (LWFLUX) {
+            const double xf = (xL.v[i] != 0.0) ? fn : 0.0;
+            a_e1.v[i] += c_dc.DFIM[r] * xf; a_e2.v[i] += c_dc.DFIMOFR[r] * xf;
+            if (r == F - 1) a_el.v[i] += xf;
+          }
+          if (r == mij - 1) fmij.v[i] = fn;
+          if (r > mij - 1) fn = dmax((ttail * rtail) * fmij.v[i], flm.v[i]);
+          fnv.v[i] = fn;
+        }
+        if (setice) {
+          const double icefree = lds1(sm, L.pc + PC_ICEFREE * PRB + po);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) fnv.v[i] = fnv.v[i] * icefree + iaw.v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          a_tu.v[i] += tstf * fnv.v[i];
+          if (r == c_dc.NFRE_ODD - 1) {
+            const double cst = 2.0 * c_dc.DELTH * c_dc.ZPI * c_dc.ZPI * c_dc.ZPI / c_dc.G * p4(c_dc.FR[c_dc.NFRE_ODD - 1]);
+            a_tu.v[i] += cst * fnv.v[i];
+          }
+        }
+        if (dost) { double* o = dst + (size_t)r * rstr; o[0] = fnv.v[0]; o[P] = fnv.v[1]; }
+      }
+      cp_async_wait<0>();          // FL1 row st+5 (own slot) and, for the loader lanes, the scalars of row st-1
+      if (rnew < F) {              // depth-limited (+ floored at NFRE) row st+5 -> ring slot of row st-4 (last read just above)
+        const V xF = lds<2>(sm, me_s);
+        const double fac = lds1(sm, L.pc + PC_FAC * PRB + po);
+        V v;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          v.v[i] = dmax(xF.v[i] * fac, c_dc.EPSMIN);
+          if (rnew == F - 1) v.v[i] = dmax(v.v[i], flm.v[i]);
+        }
+        if (act) {
+          const unsigned rbse = L.ring + slot9(rnew) * RSB + me_r;
+          sts<2>(sm, rbse, v);
+          if (k0 < HR) sts<2>(sm, rbse + (unsigned)A * 8u, v);
+          if (k0 >= A - HR) sts<2>(sm, rbse - (unsigned)A * 8u, v);
+        }
+      }
+      mbar_arrive(bar_empty + 8u * b);
+    }
+  }
+  // ---- per-point sums over direction, then the scalar closures (one thread per point)
+  __syncthreads();
+  constexpr int PS = sw_nptp(NPT);
+  double* red = reinterpret_cast<double*>(sm + L.ring);     // red[q][k][pt]: 8 planes of A*PS doubles in the (now free) ring area
+  static_assert(8u * A * PS * 8u <= ST_RING * L.RSB, "reduction planes must fit the ring");
+  if (consumer && act) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int k = k0 + i;
+      const double sinth = c_dc.SINTH[k], costh = c_dc.COSTH[k];
+      red[(0 * A + k) * PS + pt] = a_philf.v[i];
+      red[(1 * A + k) * PS + pt] = sinth * a_ts.v[i];
+      red[(2 * A + k) * PS + pt] = costh * a_ts.v[i];
+      red[(3 * A + k) * PS + pt] = a_tu.v[i] * sinth;
+      red[(4 * A + k) * PS + pt] = a_tu.v[i] * costh;
+      if (LWFLUX) { red[(5 * A + k) * PS + pt] = a_e1.v[i]; red[(6 * A + k) * PS + pt] = a_e2.v[i]; red[(7 * A + k) * PS + pt] = a_el.v[i]; }
+    }
+  }
+  __syncthreads();
+  double* qs = reinterpret_cast<double*>(sm + L.cur);        // [8][PS] reduced sums
+  if (t < 8 * NPT) {
+    const int x = t / NPT, p8 = t - x * NPT;
+    double v = 0.0;
+    if (x < 5 || LWFLUX) for (int kk = 0; kk < A; ++kk) v += red[(x * A + kk) * PS + p8];
+    qs[x * PS + p8] = v;
+  }
+  __syncthreads();
+  if (t < NPT && pbase + t <= plast)
+    stencil_closure<LWFLUX, sw_nptp(NPT)>(d, pbase + t, qs + t, reinterpret_cast<const double*>(sm + L.pc) + t);
+}
+
+template <int TA, int NPT, bool LW>
+static int launch_sweep_ws(const ImplDev& d, long long p0, long long np, cudaStream_t st) {
+  constexpr WsSmem L = ws_smem(TA, NPT, LW);
+  static_assert(L.total <= 113 * 1024, "k_sweep_ws shared memory");
+  static_assert(8 * NPT <= 2 * sw_threads(TA, NPT) && TQ_N * NPT <= sw_threads(TA, NPT) && 4 * NPT <= 32, "k_sweep_ws: too few threads for the per-point loops");
+  static bool attr_done = false;
+  if (!attr_done) {
+    EW_CUDA_CHECK(cudaFuncSetAttribute(k_sweep_ws<TA, NPT, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    EW_CUDA_CHECK(cudaFuncSetAttribute(k_sweep_ws<TA, NPT, LW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attr_done = true;
+  }
+  k_sweep_ws<TA, NPT, LW><<<(unsigned)((np + NPT - 1) / NPT), 2 * sw_threads(TA, NPT), L.total, st>>>(d, p0, np);
+  return 0;
+}
+
+
 template <int TA, int NPT, bool LW>
 static int launch_sweep(const ImplDev& d, long long p0, long long np, cudaStream_t st) {
   constexpr SwSmem L = sw_smem(TA, NPT, LW);
@@ -2540,8 +3066,11 @@ int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage
     if (force && !strcmp(force, "single")) pair = false;
     // default for the standard grids: thread = (two adjacent directions, one point); ECWAM_B200_STENCIL=pp keeps the
     // two-points-per-thread instance (A/B timing, tests)
-    // default for the standard grids: k_sweep (NPT points x NANG/2 direction pairs = four full warps where NANG allows)
-    if (!force && d.sweep_ok) {
+    // default for NANG = 36: k_sweep_ws (producer / consumer warp groups); ECWAM_B200_STENCIL=sweep: the one-role k_sweep
+    if (!force && d.sweep_ok && geo_matches<36>(d, d.iphys, d.nsdsnth))
+      return d.lwflux ? launch_sweep_ws<36, 7, true>(d, p0, np, st) : launch_sweep_ws<36, 7, false>(d, p0, np, st);
+    // default for the other standard grids: k_sweep (NPT points x NANG/2 direction pairs)
+    if ((!force || !strcmp(force, "sweep")) && d.sweep_ok) {
       if (geo_matches<36>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_sweep<36, 7, true>(d, p0, np, st) : launch_sweep<36, 7, false>(d, p0, np, st);
       if (geo_matches<24>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_sweep<24, 8, true>(d, p0, np, st) : launch_sweep<24, 8, false>(d, p0, np, st);
       if (geo_matches<12>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_sweep<12, 8, true>(d, p0, np, st) : launch_sweep<12, 8, false>(d, p0, np, st);

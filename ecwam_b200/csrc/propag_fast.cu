@@ -13,6 +13,8 @@
 // Differences from the exact kernel are rounding only (<= 1e-15 relative per step; tests/test_gpu_parity.py bounds them at 1e-13).
 // ECWAM_B200_PROPAG=exact selects the bit-exact kernel (the verifier); IREFRA = 2, 3 always uses the exact current kernel.
 #include "internal.h"
+#include <cstdlib>
+#include <cstring>
 
 namespace ew {
 
@@ -203,15 +205,192 @@ __global__ void __launch_bounds__(128, PF_MINB) propags2_fast_kernel(PropDev d, 
     }
   }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// propags2_q_kernel: the same arithmetic with the loads decoupled from the arithmetic.
+// The kernels above are latency-bound (ncu: 10 long-scoreboard stall cycles per issued instruction at 16 warps per SM, DRAM at
+// 17 % of peak): a thread issues the 14 gathers of a direction pair, waits for them, computes, and only then issues the next
+// ones.  Here thread = (own grid point, compass quadrant, group of MG frequencies): the neighbour pointers of the quadrant are
+// set up once for all its frequencies, the per-thread state is small enough for 4-5 CTAs per SM, and the 14 values of direction
+// pair i+1 travel HBM/L2 -> shared memory with cp.async (thread-private slots, [stage][value][thread]) while pair i is computed.
+// ---------------------------------------------------------------------------------------------------------------------------
+#ifndef PQ_MINB
+#define PQ_MINB 4
+#endif
+#define PQ_NTH 128
+#ifndef PQ_ST
+#define PQ_ST 3      // stages of the cp.async pipeline: PQ_ST - 1 direction pairs in flight ahead of the one being computed
+#endif
+#define PQ_NV 14     // a0 b0 am bp | lon a,b | lat1 a,b | lat2 a,b | cor1 a,b | cor2 a,b
+__device__ __forceinline__ void nbr_base_m(const PropDev& d, const Src& s, int e, int m, const double*& p, int& kstr, int& mstr) {
+  const int l = e - d.nbot;
+  if ((unsigned)l < (unsigned)d.nloc) {
+    const int c = l / d.P;
+    const int i = l - c * d.P;
+    p = s.base + i + (long long)c * s.cstride + (long long)m * d.P * d.A;
+    kstr = d.P; mstr = d.P * d.A;
+  } else {
+    const int h = (e < d.nbot) ? e : e - d.nloc;
+    const int st = __ldg(d.halo_str + h);
+    p = d.halo + __ldg(d.halo_off + h) + (long long)m * d.A * st;
+    kstr = st; mstr = d.A * st;
+  }
+}
+__device__ __forceinline__ void cpa8(unsigned sa, const double* g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(g)); }
+
+template <bool REFRA>
+__global__ void __launch_bounds__(PQ_NTH, PQ_MINB) propags2_q_kernel(PropDev d, Src src, double* __restrict__ dst, long long dcstride, int m0,
+                                                                     int m1, int MG, int msplit, int l0, int l1) {
+  extern __shared__ double stage[];     // [PQ_ST][PQ_NV][PQ_NTH]
+  const int l = l0 + blockIdx.x * PQ_NTH + threadIdx.x;
+  if (l >= l1) return;                  // no CTA-wide synchronisation below: a thread without a point just leaves
+  const int qd = blockIdx.y & 3;
+  const int mb = m0 + (blockIdx.y >> 2) * MG;
+  const int me = min(mb + MG, m1);
+  const int k0 = c_pf.kq[qd], k1 = c_pf.kq[qd + 1];
+  if (k0 >= k1 || mb >= me) return;
+  // quadrants in the order of increasing TH: (west, south, SW) (west, north, NW) (east, north, NE) (east, south, SE)
+  const int jx1 = qd < 2 ? 1 : 2, jy1 = (qd == 1 || qd == 2) ? 2 : 1, kc = qd == 0 ? 3 : (qd == 1 ? 4 : (qd == 2 ? 1 : 2));
+  const int nl = d.nloc, P = d.P, A = d.A;
+  const int npair = (k1 - k0 + 1) >> 1;
+  const int c = l / P, i = l - c * P;
+  // ---- neighbour pointers of the quadrant at frequency mb
+  const double *p_lon, *p_la1, *p_la2, *p_c1, *p_c2;
+  int s_lon, s_la1, s_la2, s_c1, s_c2, t_lon, t_la1, t_la2, t_c1, t_c2;
+  nbr_base_m(d, src, __ldg(d.nbr + (size_t)(jx1 - 1) * nl + l), mb, p_lon, s_lon, t_lon);
+  nbr_base_m(d, src, __ldg(d.nbr + (size_t)(2 + (jy1 - 1)) * nl + l), mb, p_la1, s_la1, t_la1);
+  nbr_base_m(d, src, __ldg(d.nbr + (size_t)(4 + (jy1 - 1)) * nl + l), mb, p_la2, s_la2, t_la2);
+  nbr_base_m(d, src, __ldg(d.nbr + (size_t)(6 + (kc - 1)) * nl + l), mb, p_c1, s_c1, t_c1);
+  nbr_base_m(d, src, __ldg(d.nbr + (size_t)(10 + (kc - 1)) * nl + l), mb, p_c2, s_c2, t_c2);
+  const double* ps = src.base + i + (long long)c * src.cstride + (long long)mb * P * A;
+  double* pd = dst + i + (long long)c * dcstride + (long long)mb * P * A;
+  const int PA = P * A;
+  // ---- per-point constants
+  int nb[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) nb[j] = __ldg(d.nbr + (size_t)j * nl + l);
+  const double wlat0 = __ldg(d.wl + l), wlat1 = __ldg(d.wl + nl + l);
+  const double cosphm1 = __ldg(d.pt + l);
+  const double dp1 = __ldg(d.pt + nl + l), dp2 = __ldg(d.pt + 2 * (size_t)nl + l);
+  const double zdello = __ldg(d.pt + 3 * (size_t)nl + l);
+  const double tanph = __ldg(d.pt + 4 * (size_t)nl + l);
+  const double gam1 = 1.0 / (zdello * c_pf.xdella);
+  const int e0 = d.nbot + l;
+  QuadW q;
+  q.zdello = zdello;
+  q.wlat = __ldg(d.wl + (size_t)(jy1 - 1) * nl + l);
+  q.wcor = __ldg(d.wl + (size_t)(2 + kc - 1) * nl + l);
+  q.omos = 0.0; q.ddphi = 0.0; q.ddlam_c = 0.0;
+  if (REFRA) { q.ddphi = __ldg(d.grad + l); q.ddlam_c = __ldg(d.grad + nl + l) * cosphm1; }
+  // group velocity of the 7-point neighbourhood at frequency m (ctuw.F90:160-171, 199-210), loaded one frequency ahead
+  double g0, g1, g2, g3, g4, g5, g6;
+  auto load_cg = [&](int m) {
+    const double* cgm = d.cgext + (size_t)m * d.next;
+    g0 = __ldg(cgm + e0); g1 = __ldg(cgm + nb[0]); g2 = __ldg(cgm + nb[1]); g3 = __ldg(cgm + nb[2]); g4 = __ldg(cgm + nb[4]);
+    g5 = __ldg(cgm + nb[3]); g6 = __ldg(cgm + nb[5]);
+  };
+  auto make_quad = [&](int m, int idp) {
+    const double hx0 = 0.5 * (g0 + g1), hx1 = 0.5 * (g0 + g2);
+    const double hy0 = 0.5 * fma(dp1, fma(wlat0, g3 - g4, g4), g0), hy1 = 0.5 * fma(dp2, fma(wlat1, g5 - g6, g6), g0);
+    const double cy = c_pf.delpro[idp] * c_pf.cmtodeg, cx = cy * cosphm1;
+    const double x1 = (jx1 == 1 ? hx0 : hx1) * cx, x2 = (jx1 == 1 ? hx1 : hx0) * cx;
+    const double y1 = (jy1 == 1 ? hy0 : hy1) * cy, y2 = (jy1 == 1 ? hy1 : hy0) * cy;
+    q.a1 = x1 * gam1; q.b1 = y1 * gam1; q.c1 = x1 * q.b1;
+    q.x2 = x2; q.y2 = y2;
+    q.e1 = zdello * y2 * gam1; q.e2 = c_pf.xdella * x2 * gam1; q.e3 = x2 * y2 * gam1;
+    q.t = tanph * g0;
+    if (REFRA) q.omos = __ldg(d.omos + i + (size_t)P * (m + (size_t)d.F * c));
+  };
+  // ---- the pipeline: iteration = (frequency, direction pair), flattened
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(stage) + threadIdx.x * 8u;
+  auto issue = [&](int im, int ip, int st) {     // im: frequency - mb, ip: pair of the quadrant
+    const int ka = k0 + 2 * ip, kb = min(ka + 1, k1 - 1);
+    const unsigned sa = sbase + (unsigned)st * (PQ_NV * PQ_NTH * 8);
+    const double* o = ps + (size_t)im * PA;
+    cpa8(sa + 0 * PQ_NTH * 8, o + (size_t)ka * P);
+    cpa8(sa + 1 * PQ_NTH * 8, o + (size_t)kb * P);
+    cpa8(sa + 2 * PQ_NTH * 8, o + (size_t)c_pf.kpm_m[ka] * P);
+    cpa8(sa + 3 * PQ_NTH * 8, o + (size_t)c_pf.kpm_p[kb] * P);
+    const double* n1 = p_lon + (size_t)im * t_lon;
+    cpa8(sa + 4 * PQ_NTH * 8, n1 + (size_t)ka * s_lon); cpa8(sa + 5 * PQ_NTH * 8, n1 + (size_t)kb * s_lon);
+    const double* n2 = p_la1 + (size_t)im * t_la1;
+    cpa8(sa + 6 * PQ_NTH * 8, n2 + (size_t)ka * s_la1); cpa8(sa + 7 * PQ_NTH * 8, n2 + (size_t)kb * s_la1);
+    const double* n3 = p_la2 + (size_t)im * t_la2;
+    cpa8(sa + 8 * PQ_NTH * 8, n3 + (size_t)ka * s_la2); cpa8(sa + 9 * PQ_NTH * 8, n3 + (size_t)kb * s_la2);
+    const double* n4 = p_c1 + (size_t)im * t_c1;
+    cpa8(sa + 10 * PQ_NTH * 8, n4 + (size_t)ka * s_c1); cpa8(sa + 11 * PQ_NTH * 8, n4 + (size_t)kb * s_c1);
+    const double* n5 = p_c2 + (size_t)im * t_c2;
+    cpa8(sa + 12 * PQ_NTH * 8, n5 + (size_t)ka * s_c2); cpa8(sa + 13 * PQ_NTH * 8, n5 + (size_t)kb * s_c2);
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  const int nm = me - mb;
+  const int NI = nm * npair;
+  load_cg(mb);
+  int im_i = 0, ip_i = 0, st_i = 0;  // issue side: position and stage of the next iteration to issue
+  auto issue_next = [&](int itn) {
+    if (itn < NI) {
+      issue(im_i, ip_i, st_i);
+      if (++ip_i == npair) { ip_i = 0; ++im_i; }
+    } else asm volatile("cp.async.commit_group;\n" ::);     // keep one group per iteration so that wait_group counts stay fixed
+    if (++st_i == PQ_ST) st_i = 0;
+  };
+#pragma unroll
+  for (int pre = 0; pre < PQ_ST - 1; ++pre) issue_next(pre);
+  int im = 0, ip = 0, st_c = 0;      // compute side
+  for (int it = 0; it < NI; ++it) {
+    issue_next(it + PQ_ST - 1);
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(PQ_ST - 1) : "memory");
+    const int m = mb + im;
+    const int idp = (m < msplit) ? 0 : 1;
+    if (ip == 0) {
+      make_quad(m, idp);
+      if (im + 1 < nm) load_cg(m + 1);     // used when the next frequency starts: npair iterations from now
+    }
+    const int ka = k0 + 2 * ip;
+    const bool pair = ka + 1 < k1;
+    const int kb = pair ? ka + 1 : ka;
+    const double* sv = stage + (size_t)st_c * (PQ_NV * PQ_NTH) + threadIdx.x;
+    const double a0 = sv[0 * PQ_NTH], b0 = sv[1 * PQ_NTH], am = sv[2 * PQ_NTH], bp = sv[3 * PQ_NTH];
+    const double a1 = sv[4 * PQ_NTH], b1 = sv[5 * PQ_NTH], a2 = sv[6 * PQ_NTH], b2 = sv[7 * PQ_NTH];
+    const double a3 = sv[8 * PQ_NTH], b3 = sv[9 * PQ_NTH], a4 = sv[10 * PQ_NTH], b4 = sv[11 * PQ_NTH];
+    const double a5 = sv[12 * PQ_NTH], b5 = sv[13 * PQ_NTH];
+    double* o = pd + (size_t)im * PA;
+    // KPM(ka,+1) = kb and KPM(kb,-1) = ka inside a quadrant; a single last direction takes its own KPM(+1) value (slot bp)
+    const double ra = ctu_bin<REFRA>(q, ka, idp, a0, a1, a2, a3, a4, a5, am, pair ? b0 : bp);
+    o[(size_t)ka * P] = ra;
+    if (pair) {
+      const double rb = ctu_bin<REFRA>(q, kb, idp, b0, b1, b2, b3, b4, b5, a0, bp);
+      o[(size_t)kb * P] = rb;
+    }
+    if (++ip == npair) { ip = 0; ++im; }
+    if (++st_c == PQ_ST) st_c = 0;
+  }
+}
 }  // namespace
 
 void launch_propags2_fast(const PropDev& d, const double* src, int srcF, double* dst, int dstF, int m0, int m1, int msplit, cudaStream_t st,
                           int l0, int l1) {
   const int MG = 8;
   Src s{src, (long long)d.P * d.A * srcF};
-  dim3 grid((l1 - l0 + 127) / 128, (m1 - m0 + MG - 1) / MG);
-  if (d.irefra == 1) propags2_fast_kernel<true><<<grid, 128, 0, st>>>(d, s, dst, (long long)d.P * d.A * dstF, m0, m1, MG, msplit, l0, l1);
-  else propags2_fast_kernel<false><<<grid, 128, 0, st>>>(d, s, dst, (long long)d.P * d.A * dstF, m0, m1, MG, msplit, l0, l1);
+  static const int mode = []() { const char* e = getenv("ECWAM_B200_PROPAG"); return (e && !strcmp(e, "fast1")) ? 1 : 0; }();
+  if (mode == 1) {   // the one-thread-per-(point, frequency group) kernel (A/B)
+    dim3 grid((l1 - l0 + 127) / 128, (m1 - m0 + MG - 1) / MG);
+    if (d.irefra == 1) propags2_fast_kernel<true><<<grid, 128, 0, st>>>(d, s, dst, (long long)d.P * d.A * dstF, m0, m1, MG, msplit, l0, l1);
+    else propags2_fast_kernel<false><<<grid, 128, 0, st>>>(d, s, dst, (long long)d.P * d.A * dstF, m0, m1, MG, msplit, l0, l1);
+    return;
+  }
+  const size_t smem = (size_t)PQ_ST * PQ_NV * PQ_NTH * sizeof(double);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(propags2_q_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(propags2_q_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(propags2_q_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(propags2_q_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    attr_done = true;
+  }
+  dim3 grid((l1 - l0 + PQ_NTH - 1) / PQ_NTH, 4 * ((m1 - m0 + MG - 1) / MG));
+  if (d.irefra == 1) propags2_q_kernel<true><<<grid, PQ_NTH, smem, st>>>(d, s, dst, (long long)d.P * d.A * dstF, m0, m1, MG, msplit, l0, l1);
+  else propags2_q_kernel<false><<<grid, PQ_NTH, smem, st>>>(d, s, dst, (long long)d.P * d.A * dstF, m0, m1, MG, msplit, l0, l1);
 }
 
 }  // namespace ew
