@@ -2056,7 +2056,7 @@ __device__ __forceinline__ double div_fast(double a, double b) {
   return fma(fma(-b, q, a), r, q);
 }
 #ifndef SW_MINB
-#define SW_MINB 3
+#define SW_MINB 2   // k_sweep wants ~224 registers: capped at 168 for 3 CTAs per SM it spills and runs 30 % slower
 #endif
 #ifndef SW_CARRY
 #define SW_CARRY 1   // carry the direction interpolation of the IP1 / IM1 rows to the step where they are IP / IM
@@ -2083,7 +2083,7 @@ __global__ void __launch_bounds__(sw_threads(TA, NPT), SW_MINB) k_sweep(ImplDev 
   unsigned po = (unsigned)pt * 8u;
   unsigned me_r = (unsigned)pt * PSTB + (unsigned)(k0 + HR) * 8u;     // own pair inside a ring row
   unsigned me_c = (unsigned)pt * PSTCB + (unsigned)(k0 + HC) * 8u;    // own pair inside an interaction plane
-  unsigned me_s = L.stage + (unsigned)t * 16u;                         // own landing slot
+  unsigned me_s = L.stage + (unsigned)t * 8u;                          // own landing slots: [array][element of the pair][thread]
   asm volatile("" : "+r"(po), "+r"(me_r), "+r"(me_c), "+r"(me_s));
   // ---- points
   const long long pbase = p0 + (long long)blockIdx.x * NPT;
@@ -2181,12 +2181,12 @@ __global__ void __launch_bounds__(sw_threads(TA, NPT), SW_MINB) k_sweep(ImplDev 
     const unsigned p3 = (unsigned)(st + 6) % 3u;
     if (rnew >= 0 && rnew < F) {
       const double* g = (rnew < mlo ? src_lo : src_hi) + (size_t)rnew * rstr;
-      cp_async<8>(smb + me_s, g); cp_async<8>(smb + me_s + 8, g + P);
+      cp_async<8>(smb + me_s, g); cp_async<8>(smb + me_s + L.SSB / 2, g + P);
     }
     if (fin) {
       const double* g = src_in + (size_t)rfin * rstr;
-      cp_async<8>(smb + me_s + L.SSB, g); cp_async<8>(smb + me_s + L.SSB + 8, g + P);
-      if (LWFLUX) { const double* gx = src_xl + (size_t)rfin * rstr; cp_async<8>(smb + me_s + 2 * L.SSB, gx); cp_async<8>(smb + me_s + 2 * L.SSB + 8, gx + P); }
+      cp_async<8>(smb + me_s + L.SSB, g); cp_async<8>(smb + me_s + L.SSB + L.SSB / 2, g + P);
+      if (LWFLUX) { const double* gx = src_xl + (size_t)rfin * rstr; cp_async<8>(smb + me_s + 2 * L.SSB, gx); cp_async<8>(smb + me_s + 2 * L.SSB + L.SSB / 2, gx + P); }
     }
     if (rtb >= 0 && rtb < F && tq_on) cp_async<8>(smb + tq_s + (unsigned)((rtb & 7) * TQ_N) * PRB, tq_g + (size_t)rtb * n);
     mbar_arrive_cp_async(smb + L.mbar);
@@ -2368,7 +2368,8 @@ __global__ void __launch_bounds__(sw_threads(TA, NPT), SW_MINB) k_sweep(ImplDev 
       const int r = rfin;
       const unsigned tq = L.tbs + (unsigned)((r & 7) * TQ_N) * PRB + po;
       const V fold = lds<2>(sm, L.ring + slot9(r) * RSB + me_r);
-      const V xI = lds<2>(sm, me_s + L.SSB);
+      V xI;
+      xI.v[0] = lds1(sm, me_s + L.SSB); xI.v[1] = lds1(sm, me_s + L.SSB + L.SSB / 2);
       const double usfm = lds1(sm, L.pc + PC_USFMDELT * PRB + po), sdsbk = lds1(sm, L.pc + PC_SDSBK * PRB + po);
       const double tsbo = lds1(sm, tq + TQ_SBO * PRB), tcinv = lds1(sm, tq + TQ_CINV * PRB), ttail = lds1(sm, tq + TQ_TAIL * PRB);
       const double tstf = lds1(sm, tq + TQ_STF * PRB), rtail = lds1(sm, L.pc + PC_RTAIL * PRB + po);
@@ -2385,7 +2386,7 @@ __global__ void __launch_bounds__(sw_threads(TA, NPT), SW_MINB) k_sweep(ImplDev 
       double rr = (r + 1 > mij) ? 0.0 : c_dc.RHOWG_DFIM[r];      // RHOWGDFTH of frcutindex.F90:99-108
       if (r + 1 == mij && mij != F) rr = 0.5 * rr;
       V xL;
-      if (LWFLUX) xL = lds<2>(sm, me_s + 2 * L.SSB);
+      if (LWFLUX) { xL.v[0] = lds1(sm, me_s + 2 * L.SSB); xL.v[1] = lds1(sm, me_s + 2 * L.SSB + L.SSB / 2); }
       V fnv;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
@@ -2434,7 +2435,8 @@ __global__ void __launch_bounds__(sw_threads(TA, NPT), SW_MINB) k_sweep(ImplDev 
     }
     bs2 = bs1; bs1 = bnew;
     if (rnew >= 0 && rnew < F) {   // depth-limited (+ floored at NFRE) row st+5 -> ring slot of row st-4 (last read just above)
-      const V xF = lds<2>(sm, me_s);
+      V xF;
+      xF.v[0] = lds1(sm, me_s); xF.v[1] = lds1(sm, me_s + L.SSB / 2);
       const double fac = lds1(sm, L.pc + PC_FAC * PRB + po);
       V v;
 #pragma unroll
@@ -2751,7 +2753,8 @@ __global__ void __launch_bounds__(2 * sw_threads(TA, NPT), 2) k_sweep_ws(ImplDev
   } else {
     // ================================================= CONSUMER =================================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(SW_RC));
-    unsigned me_s = L.stage + (unsigned)tr * 16u;      // own landing slot
+    unsigned me_s = L.stage + (unsigned)tr * 8u;       // own landing slots: [array][element of the pair][thread], 8 bytes each, so that
+                                                       // a warp's cp.async writes are 256 contiguous bytes (16-byte slots cost 4x the wavefronts)
     asm volatile("" : "+r"(me_s));
     long long pq = pbase + pt;
     const bool pvalid = pq <= plast;
@@ -2811,13 +2814,13 @@ __global__ void __launch_bounds__(2 * sw_threads(TA, NPT), 2) k_sweep_ws(ImplDev
       // ring and the per-(point, frequency) scalars of row st-1
       if (fin) {
         const double* g = src_in + (size_t)rfin * rstr;
-        cp_async<8>(smb + me_s + L.SSB, g); cp_async<8>(smb + me_s + L.SSB + 8, g + P);
-        if (LWFLUX) { const double* gx = src_xl + (size_t)rfin * rstr; cp_async<8>(smb + me_s + 2 * L.SSB, gx); cp_async<8>(smb + me_s + 2 * L.SSB + 8, gx + P); }
+        cp_async<8>(smb + me_s + L.SSB, g); cp_async<8>(smb + me_s + L.SSB + L.SSB / 2, g + P);
+        if (LWFLUX) { const double* gx = src_xl + (size_t)rfin * rstr; cp_async<8>(smb + me_s + 2 * L.SSB, gx); cp_async<8>(smb + me_s + 2 * L.SSB + L.SSB / 2, gx + P); }
       }
       cp_async_commit();
       if (rnew < F) {
         const double* g = (rnew < mlo ? src_lo : src_hi) + (size_t)rnew * rstr;
-        cp_async<8>(smb + me_s, g); cp_async<8>(smb + me_s + 8, g + P);
+        cp_async<8>(smb + me_s, g); cp_async<8>(smb + me_s + L.SSB / 2, g + P);
       }
       if (rtb >= 0 && rtb < F && tq_on) cp_async<8>(smb + tq_s + (unsigned)((rtb & 7) * TQ_N) * PRB, tq_g + (size_t)rtb * n);
       cp_async_commit();
@@ -2879,7 +2882,8 @@ __global__ void __launch_bounds__(2 * sw_threads(TA, NPT), 2) k_sweep_ws(ImplDev
         const unsigned tq = L.tbs + (unsigned)((r & 7) * TQ_N) * PRB + po;
         const V fold = lds<2>(sm, L.ring + slot9(r) * RSB + me_r);
         cp_async_wait<1>();                              // the wind-input row of this step has landed (own slot)
-        const V xI = lds<2>(sm, me_s + L.SSB);
+        V xI;
+        xI.v[0] = lds1(sm, me_s + L.SSB); xI.v[1] = lds1(sm, me_s + L.SSB + L.SSB / 2);
         const double usfm = lds1(sm, L.pc + PC_USFMDELT * PRB + po), sdsbk = lds1(sm, L.pc + PC_SDSBK * PRB + po);
         const double tsbo = lds1(sm, tq + TQ_SBO * PRB), tcinv = lds1(sm, tq + TQ_CINV * PRB), ttail = lds1(sm, tq + TQ_TAIL * PRB);
         const double tstf = lds1(sm, tq + TQ_STF * PRB), rtail = lds1(sm, L.pc + PC_RTAIL * PRB + po);
@@ -2897,7 +2901,7 @@ __global__ void __launch_bounds__(2 * sw_threads(TA, NPT), 2) k_sweep_ws(ImplDev
         double rr = (r + 1 > mij) ? 0.0 : c_dc.RHOWG_DFIM[r];      // RHOWGDFTH of frcutindex.F90:99-108
         if (r + 1 == mij && mij != F) rr = 0.5 * rr;
         V xL;
-        if (LWFLUX) xL = lds<2>(sm, me_s + 2 * L.SSB);
+        if (LWFLUX) { xL.v[0] = lds1(sm, me_s + 2 * L.SSB); xL.v[1] = lds1(sm, me_s + 2 * L.SSB + L.SSB / 2); }
         V fnv;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -2946,7 +2950,8 @@ __global__ void __launch_bounds__(2 * sw_threads(TA, NPT), 2) k_sweep_ws(ImplDev
       }
       cp_async_wait<0>();          // FL1 row st+5 (own slot) and, for the loader lanes, the scalars of row st-1
       if (rnew < F) {              // depth-limited (+ floored at NFRE) row st+5 -> ring slot of row st-4 (last read just above)
-        const V xF = lds<2>(sm, me_s);
+        V xF;
+        xF.v[0] = lds1(sm, me_s); xF.v[1] = lds1(sm, me_s + L.SSB / 2);
         const double fac = lds1(sm, L.pc + PC_FAC * PRB + po);
         V v;
 #pragma unroll
