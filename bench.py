@@ -427,6 +427,41 @@ def run_gpu(args):
                "what": "ecwam_b200_wamintgr_host: FL1 + forcing + stress state host->device from pinned buffers, step, "
                        "FL1 + all 1-D outputs + MIJ device->host, every step"}
 
+    # ---- end to end with the state resident on the device (how the reference's GPU build moves data): forcing in, 1-D results out ----
+    e2e_res = None
+    if not args.no_e2e:
+        nxt_names = [n for n, _ in L.ForcingNext._fields_]
+        hn, ho = L.ForcingNext(), L.Fields()
+        keep = []
+        for n in nxt_names:
+            ht = torch.empty(w.t[n].shape, dtype=torch.float64, pin_memory=True)
+            ht.copy_(w.t[n])
+            keep.append(ht)
+            setattr(hn, n, C.cast(ht.data_ptr(), C.POINTER(C.c_double)))
+        for n in ("ufric", "tauw", "tauwdir", "z0m", "z0b", "chrnck", "wsemean", "wsfmean", "ustokes", "vstokes", "tauxd", "tauyd", "tauocxd",
+                  "tauocyd", "tauoc", "tauicx", "tauicy", "phiocd", "phieps", "phiaw", "mij"):
+            t = w.t[n]
+            ht = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            keep.append(ht)
+            setattr(ho, n, C.cast(ht.data_ptr(), C.POINTER(C.c_int if n == "mij" else C.c_double)))
+        hin, hout = C.c_longlong(), C.c_longlong()
+        Ke = max(1, K)
+        L.check(lib.ecwam_b200_wamintgr_forced(w.h, C.byref(hn), C.byref(ho), C.byref(hin), C.byref(hout)), "wamintgr_forced")   # re-binds nothing; warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            L.check(lib.ecwam_b200_wamintgr_forced(w.h, C.byref(hn), C.byref(ho), C.byref(hin), C.byref(hout)), "wamintgr_forced")
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        bts = torch.tensor([hin.value, hout.value], dtype=torch.float64, device=device)
+        if dist is not None:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(bts, op=dist.ReduceOp.SUM)
+        e2e_res = {"value": npts_total * Ke / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(bts[0].item()),
+                   "d2h_bytes_per_step": int(bts[1].item()), "steps": Ke,
+                   "what": "ecwam_b200_wamintgr_forced: spectrum and fields resident on the device (as in the reference's GPU build, "
+                           "wamintgr_loki_gpu.F90:141-201); per step the 8 FF_NEXT forcing fields host->device from pinned buffers, NEWWIND, "
+                           "PROPAG_WAM + IMPLSCH, the 20 integrated 1-D fields + MIJ device->host"}
     # what the report below needs of the headline case (it is released before the extra configurations run)
     class _W:
         pass
@@ -508,7 +543,7 @@ def run_gpu(args):
                                                                       "" if args.physics == "default" else " + LLGCBZ0 + LLNORMAGAM (cy49r1)",
                                                                       wi.nproma, wi.idelt),
                        "parallelism": "mpdecomp%d" % world, "l2": "inputs larger than L2 (FL1 %.1f GB per GPU)" % wi.fl1_gb},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "kernel_ms": kern, "output_step": aux or None, "roofline": roof, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "e2e_resident": e2e_res, "gpu_launches": int(launches), "kernel_ms": kern, "output_step": aux or None, "roofline": roof, "cpu_baseline": cpu,
             "extra": extra}
     print(json.dumps(line))
     if dist is not None:

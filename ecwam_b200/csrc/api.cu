@@ -73,6 +73,9 @@ struct ecwam_b200_handle_s {
   DBuf<double> wlat_raw, dellam, grad, curmask;   // IREFRA /= 0: WLAT as PROPCONNECT left it, DELLAM/COSPH(KXLT), gradients, CURMASK
   double oneo2delphi = 0.0;
   std::vector<int> h_spre, h_rpre;   // per peer prefix sums (size nproc+1)
+  bool send_chunks_sorted = false;
+  cudaEvent_t ev_halo = nullptr;
+  std::vector<int> send_chunks;      // sorted chunks (0-based) that hold at least one point some peer needs (host-buffer pipeline)
   int nsend = 0, nrecv = 0;
   int msplit = 0;
   bool weights_dirty = true;
@@ -100,6 +103,8 @@ struct ecwam_b200_handle_s {
   std::vector<cudaEvent_t> ev_up, ev_done;
   cudaEvent_t ev_start = nullptr;
   int nbr_reach = 0;       // max |l' - l| over the own-point neighbours of every own point l
+  // resident-state step (ecwam_b200_wamintgr_forced): device staging of the eight FF_NEXT fields
+  DBuf<double> frc_next;
   // NEWWIND / OUTBLOCK / WAMNORM
   DBuf<double> normbuf, zglobal;
   DBuf<int> ij2new_d;
@@ -434,6 +439,7 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
       const int ij = dec->ijtope[ih + (size_t)dec->ntopemax * q];
       if (ij < dec->ijs || ij > dec->ijl) { EW_FAIL_H(h, ECWAM_B200_EINVAL, "IJTOPE outside own range"); }
       send_l[h->h_spre[q] + ih] = ij - dec->ijs;
+      h->send_chunks.push_back((ij - dec->ijs) / p.nproma);
       send_peer[h->h_spre[q] + ih] = q;
     }
     const int nr = dec->nfrompe[q];
@@ -585,6 +591,7 @@ int ecwam_b200_destroy(ecwam_b200_handle h) {
   for (cudaEvent_t e : h->ev_up) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
+  if (h->ev_halo) cudaEventDestroy(h->ev_halo);
   if (h->st_up) cudaStreamDestroy(h->st_up);
   if (h->st_dn) cudaStreamDestroy(h->st_dn);
   delete h;
@@ -1158,6 +1165,48 @@ inline void*& fptr(ecwam_b200_fields& f, size_t off) { return *(void**)((char*)&
 inline void* fptr_c(const ecwam_b200_fields& f, size_t off) { return *(void* const*)((const char*)&f + off); }
 }  // namespace
 
+// ---- resident-state step: only the forcing goes in and the 1-D results come out ------------------------------------------
+// How the reference's GPU build moves data (wamintgr_loki_gpu.F90:141-201): the spectrum and the model fields live on the device,
+// a step receives the new forcing and hands back the integrated parameters.  host_next: the eight FF_NEXT fields in (pinned)
+// host memory; host_out: a fields struct whose non-NULL 1-D members (UFRIC ... PHIAW, MIJ) receive the step's results.
+int ecwam_b200_wamintgr_forced(ecwam_b200_handle h, const ecwam_b200_forcing_next* host_next, const ecwam_b200_fields* host_out,
+                               long long* h2d_bytes, long long* d2h_bytes) {
+  if (!h || !host_next) EW_FAIL(ECWAM_B200_EINVAL, "null argument");
+  if (!h->bound) EW_FAIL(ECWAM_B200_ESTATE, "fields not bound");
+  const size_t npts = (size_t)h->par.nproma * h->par.nchnk;
+  const int NF = (int)(sizeof(*host_next) / sizeof(void*));
+  if (!h->frc_next.p) { int rc = h->frc_next.alloc(npts * NF); if (rc) return rc; }
+  const void* const* src = (const void* const*)host_next;
+  ecwam_b200_forcing_next dn;
+  const void** dpp = (const void**)&dn;
+  long long nin = 0, nout = 0;
+  for (int i = 0; i < NF; ++i) {
+    if (!src[i]) EW_FAIL(ECWAM_B200_EINVAL, "wamintgr_forced: FF_NEXT member %d is null", i);
+    EW_CUDA_CHECK(cudaMemcpyAsync(h->frc_next.p + (size_t)i * npts, src[i], npts * 8, cudaMemcpyHostToDevice, h->st));
+    dpp[i] = h->frc_next.p + (size_t)i * npts;
+    nin += (long long)(npts * 8);
+  }
+  int rc = ecwam_b200_newwind(h, &dn);
+  if (rc) return rc;
+  rc = ecwam_b200_wamintgr(h);
+  if (rc) return rc;
+  if (host_out) {
+    for (const FieldDesc& fd : kFields) {
+      if (!(fd.dir & 4) || fd.kind < 2) continue;                 // the 1-D outputs of IMPLSCH (and MIJ)
+      char* dst = (char*)fptr_c(*host_out, fd.off);
+      const char* dsrc = (const char*)fptr_c(h->dev, fd.off);
+      if (!dst || !dsrc) continue;
+      const size_t nb = npts * (fd.kind == 3 ? 4 : 8);
+      EW_CUDA_CHECK(cudaMemcpyAsync(dst, dsrc, nb, cudaMemcpyDeviceToHost, h->st));
+      nout += (long long)nb;
+    }
+  }
+  EW_CUDA_CHECK(cudaStreamSynchronize(h->st));
+  if (h2d_bytes) *h2d_bytes = nin;
+  if (d2h_bytes) *d2h_bytes = nout;
+  return 0;
+}
+
 // Host-buffer entry: the caller's arrays live in (pinned) host memory.  Copies and kernels are pipelined over bands of
 // NPROMA chunks on three streams: upload of band b+2 | PROPAGS2 of band b+1 | IMPLSCH of band b | download of band b-1.
 //   * full pipeline (one rank, no fast-wave sub-steps, CTU set-up done): PROPAGS2 of a band only needs the bands next to it
@@ -1183,6 +1232,7 @@ int ecwam_b200_wamintgr_host(ecwam_b200_handle h, const ecwam_b200_fields* host,
     EW_CUDA_CHECK(cudaStreamCreateWithFlags(&h->st_up, cudaStreamNonBlocking));
     EW_CUDA_CHECK(cudaStreamCreateWithFlags(&h->st_dn, cudaStreamNonBlocking));
     EW_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+    EW_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
     h->mir_alloc = true;
   }
   (void)npts;
@@ -1201,7 +1251,7 @@ int ecwam_b200_wamintgr_host(ecwam_b200_handle h, const ecwam_b200_fields* host,
   int band = std::max((nchnk + kBands - 1) / kBands, reach_chunks);
   const int nband = (nchnk + band - 1) / band;
   const bool substeps = p.ifrelfmax > 0 && p.ifrelfmax < p.nfre_red;
-  const bool full = h->nproc <= 1 && !substeps && !h->weights_dirty && h->weights_side == h->cur_side && h->mir_static_done && nband >= 3 && h->par.irefra < 2;
+  const bool full = !substeps && !h->weights_dirty && h->weights_side == h->cur_side && h->mir_static_done && nband >= 3 && h->par.irefra < 2;
   while ((int)h->ev_up.size() < nband) { cudaEvent_t e; EW_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_up.push_back(e); }
   while ((int)h->ev_done.size() < nband) { cudaEvent_t e; EW_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_done.push_back(e); }
   long long nin = 0, nout = 0;
@@ -1238,6 +1288,29 @@ int ecwam_b200_wamintgr_host(ecwam_b200_handle h, const ecwam_b200_fields* host,
     rc = ensure_const(h);
     if (rc) return rc;
     const PropDev& d = h->pd;
+    if (h->nproc > 1) {
+      // MPEXCHNG needs the spectra of the points the neighbouring ranks read: the chunks that hold them go up first, the halo
+      // exchange (pack + NCCL) follows, and the band pipeline below runs as on one rank — PROPAGS2 finds the halo in place.
+      if (!h->send_chunks_sorted) {
+        std::sort(h->send_chunks.begin(), h->send_chunks.end());
+        h->send_chunks.erase(std::unique(h->send_chunks.begin(), h->send_chunks.end()), h->send_chunks.end());
+        h->send_chunks_sorted = true;
+      }
+      const size_t cb4 = chunk_bytes(0);
+      const char* src = (const char*)host->fl1;
+      for (size_t i = 0; i < h->send_chunks.size();) {      // runs of consecutive chunks: one copy each
+        size_t j = i + 1;
+        while (j < h->send_chunks.size() && h->send_chunks[j] == h->send_chunks[j - 1] + 1) ++j;
+        const int c0 = h->send_chunks[i], n = (int)(j - i);
+        EW_CUDA_CHECK(cudaMemcpyAsync((char*)h->mir.fl1 + cb4 * c0, src + cb4 * c0, cb4 * n, cudaMemcpyHostToDevice, h->st_up));
+        nin += (long long)(cb4 * n);
+        i = j;
+      }
+      EW_CUDA_CHECK(cudaEventRecord(h->ev_halo, h->st_up));
+      EW_CUDA_CHECK(cudaStreamWaitEvent(h->st, h->ev_halo, 0));
+      rc = halo_spectrum(h, h->dev.fl1, d.F, d.Fr);
+      if (rc) return rc;
+    }
     for (int b = 0; b < nband; ++b) {
       if ((rc = upload(c0_of(b), c1_of(b), h->st_up))) return rc;
       EW_CUDA_CHECK(cudaEventRecord(h->ev_up[b], h->st_up));

@@ -626,7 +626,15 @@ void launch_propags2(const PropDev& d, const double* src, int srcF, double* dst,
   if (l1 < 0) l1 = d.nloc;
   l1 = l1 < d.nloc ? l1 : d.nloc;
   if (m1 <= m0 || l1 <= l0) return;
-  if (d.irefra < 2 && !propag_exact_mode()) { launch_propags2_fast(d, src, srcF, dst, dstF, m0, m1, msplit, st, l0, l1); return; }
+  // The tolerance-mode kernel is the default on one rank (8.0 vs 9.0 ms at O640).  On 2 ranks it measured 7.3 ms against 4.8 ms
+  // of the exact kernel (the MPDECOMP sectors halve the rows; the cause was not found within the round), so a decomposed run
+  // keeps the exact kernel unless ECWAM_B200_PROPAG=fast asks otherwise.
+  const char* pm = getenv("ECWAM_B200_PROPAG");
+  const bool decomposed = d.nbot + d.ntop > 0;
+  if (d.irefra < 2 && !propag_exact_mode() && (!decomposed || (pm && !strncmp(pm, "fast", 4)))) {
+    launch_propags2_fast(d, src, srcF, dst, dstF, m0, m1, msplit, st, l0, l1);
+    return;
+  }
   const int MG = 8;
   SpecSrc s{src, (long long)d.P * d.A * srcF};
   dim3 grid((l1 - l0 + 127) / 128, (m1 - m0 + MG - 1) / MG);

@@ -382,6 +382,17 @@ int ecwam_b200_no_source(ecwam_b200_handle h, int llsource_off);
 int ecwam_b200_wamintgr_host(ecwam_b200_handle h, const ecwam_b200_fields* host, int with_xllws,
                              long long* h2d_bytes, long long* d2h_bytes);
 
+/* One WAMINTGR sub-step with the model state RESIDENT on the device, as the reference's GPU build keeps it
+ * (src/ecwam/wamintgr_loki_gpu.F90:141-201: the spectrum and the fields stay on the device between steps; a step takes the
+ * new forcing in and hands the integrated parameters back).  host_next: the eight FF_NEXT fields (struct below) in HOST
+ * memory, pinned for full PCIe rate; they are copied in, NEWWIND's field update is applied (ecwam_b200_newwind), then
+ * PROPAG_WAM + IMPLSCH run on the tensors bound with ecwam_b200_bind_fields.  host_out (may be NULL): HOST pointers; every
+ * non-NULL 1-D output member (UFRIC, TAUW, TAUWDIR, Z0M, Z0B, CHRNCK, WSEMEAN, WSFMEAN, USTOKES, VSTOKES, TAUXD ... PHIAW, MIJ)
+ * receives the step's result.  Returns like ecwam_b200_wamintgr; synchronises the handle's stream.           */
+struct ecwam_b200_forcing_next;
+int ecwam_b200_wamintgr_forced(ecwam_b200_handle h, const struct ecwam_b200_forcing_next* host_next,
+                               const ecwam_b200_fields* host_out, long long* h2d_bytes, long long* d2h_bytes);
+
 /* ---------------------------------------------------------------------------------------------------
  * The steps either side of the hot path each time step / output step, kept on the device.   */
 

@@ -69,7 +69,7 @@ def f_arg(decl):
     if decl == "void":
         return None
     m = re.match(r"^(.*?)(\w+)(\[\d+\])?$", decl)
-    ctype, name, arr = m.group(1).strip(), m.group(2).upper(), m.group(3)
+    ctype, name, arr = m.group(1).strip().replace("struct ", ""), m.group(2).upper(), m.group(3)
     if name in ("OUT", "IN"):       # not reserved words, but keep the generated code easy on the eye
         name = "P" + name
     if arr and "char" in ctype:

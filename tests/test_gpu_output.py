@@ -228,3 +228,35 @@ def test_getwnd_on_device_matches_oracle(built, opts, extra):
     assert w.step() == 0 and o.step() == 0            # and the step that follows runs on that forcing
     w.synchronize()
     assert np.abs(w.get_spec("fl1") - o.get_fl1()[:, :, w.own]).max() <= 1e-10 * np.abs(o.get_fl1()).max()
+
+
+def test_resident_state_step(built):
+    """ecwam_b200_wamintgr_forced: the state stays on the device, a step takes the FF_NEXT forcing from host memory and hands the
+    integrated 1-D fields back; it must equal NEWWIND + WAMINTGR through the device entry points, and the host copies must
+    equal the device fields."""
+    import ctypes as C
+    import torch
+    g, o, f, s, w1 = both("o48like", steps=1)
+    _, _, _, _, w2 = both("o48like", steps=1)
+    nx = next_forcing(f)
+    w1.newwind(nx)
+    assert w1.step() == 0
+    w1.synchronize()
+    hn, ho, keep = L.ForcingNext(), L.Fields(), {}
+    for n in w2.NEXT_FIELDS:
+        v = nx[n] if n in nx else nx[n.upper()]
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(v, dtype=np.float64)[w2.src])).pin_memory()
+        keep[n] = t
+        setattr(hn, n, C.cast(t.data_ptr(), C.POINTER(C.c_double)))
+    outs = ("ufric", "tauw", "tauwdir", "z0m", "chrnck", "ustokes", "phiaw", "tauoc", "mij")
+    for n in outs:
+        t = torch.empty(w2.t[n].shape, dtype=w2.t[n].dtype).pin_memory()
+        keep["o_" + n] = t
+        setattr(ho, n, C.cast(t.data_ptr(), C.POINTER(C.c_int if n == "mij" else C.c_double)))
+    hin, hout = C.c_longlong(), C.c_longlong()
+    L.check(w2.lib.ecwam_b200_wamintgr_forced(w2.h, C.byref(hn), C.byref(ho), C.byref(hin), C.byref(hout)), "wamintgr_forced")
+    assert hin.value == 8 * 8 * w2.P * w2.C and hout.value == (8 * (len(outs) - 1) + 4) * w2.P * w2.C
+    assert torch.equal(w1.t["fl1"], w2.t["fl1"]) and torch.equal(w1.t["xllws"], w2.t["xllws"])
+    for n in outs:
+        assert torch.equal(keep["o_" + n], w2.t[n].cpu()), n
+        assert torch.equal(w1.t[n], w2.t[n]), n

@@ -402,3 +402,112 @@ def test_shallow_water_scalings_of_the_dia(built, isnonlin):
     dfim = o.table("DFIM")
     tot = (sh * dfim[:, None, None]).sum(axis=(0, 1))
     assert (np.abs(tot) <= 5e-15 * (np.abs(sh) * dfim[:, None, None]).sum(axis=(0, 1))).all()
+
+
+def _has(o, name):
+    try:
+        o.table(name)
+        return True
+    except KeyError:
+        return False
+
+
+def _dia_numpy(F1, fr, fratio, depth, wavnum, dfim, delth, consts):
+    """SNONLIN (ISNONLIN = 0) restated from the definition of the discrete interaction approximation, in SCATTER form on an
+    EXTENDED spectrum, with every index and weight derived here from the quadruplet geometry (lambda = 0.25) instead of the
+    NLWEIGT / INISNONLIN / JAFU tables: f+ = (1 + lambda) f and f- = (1 - lambda) f are located on the geometric frequency axis, the
+    partner directions theta +- 11.48 deg / -+ 33.56 deg (and their mirror images) on the direction grid, both with bilinear
+    weights; above NFRE the spectrum continues as f^-5, below bin 1 with the shape inisnonlin.F90:108-118 gives it; contributions
+    that land outside 1..NFRE are dropped.  Returns (SL, FLD)[m, k, ij].  (snonlin.F90:127-498, nlweigt.F90:94-262)"""
+    NF, A, N = F1.shape
+    lam, CON, G = 0.25, 3000.0, consts["G"]
+    f1p1 = np.log10(fratio)
+    isp = int(np.log10(1.0 + lam) / f1p1 + 1e-6)
+    ism = int(np.floor(np.log10(1.0 - lam) / f1p1 + 1e-7))
+    LO, HI = 1 + ism, NF - ism                                   # MFRSTLW, MLSTHG
+    top = NF + (-ism + isp + 2)                                  # NFRE + KFRH
+    fx = lambda m: fr[0] * fratio ** (m - 1.0)                   # frequency of (possibly virtual) bin m, 1-based
+    # extended spectrum, bins LO-1 .. top (bin LO-1 is empty)
+    def fext(m):
+        if m < LO:
+            return np.zeros((A, N))
+        if m < 1:
+            x = fratio ** (1 - m)                                 # f_1 / f_m
+            ep = lambda y: np.exp(-min(1.25 * y ** 4, 50.0)) * y ** 5
+            return F1[0] * (ep(x) / ep(1.0))
+        if m > NF:
+            return F1[NF - 1] * (fx(NF) / fx(m)) ** 5
+        return F1[m - 1]
+    # shallow-water scaling from the mean wavenumber of FKMEAN (fkmean.F90:60-154)
+    tot_k = F1.sum(axis=1)                                        # [m, ij]
+    delt25 = consts["WETAIL"] * fr[NF - 1] * delth
+    emean = consts["EPSMIN"] + (dfim[:, None] * tot_k).sum(axis=0) + delt25 * tot_k[NF - 1]
+    coefa = consts["FRTAIL"] * delth * np.sqrt(G) / consts["ZPI"]
+    akmean = (emean / (consts["EPSMIN"] + ((dfim[:, None] / np.sqrt(wavnum)) * tot_k).sum(axis=0) + coefa * tot_k[NF - 1])) ** 2
+    x = np.maximum(0.75 * depth * akmean, 0.5)
+    enh = 1.0 + (5.5 / x) * (1.0 - 0.833 * x) * np.exp(-1.25 * x)
+    # quadruplet angles from the resonance conditions (nlweigt.F90:108-121)
+    costh3 = (1.0 + 2.0 * lam + 2.0 * lam ** 3) / (1.0 + lam) ** 2
+    xf = ((1.0 + lam) / (1.0 - lam)) ** 4
+    costh4 = np.sqrt(1.0 - xf + xf * costh3 ** 2)
+    dth_deg = np.degrees(delth)
+    cl1, cl2 = -np.degrees(np.arccos(costh3)) / dth_deg, np.degrees(np.arccos(costh4)) / dth_deg
+    dal1, dal2 = 1.0 / (1.0 + lam) ** 4, 1.0 / (1.0 - lam) ** 4
+    K = np.arange(A)
+
+    def dirs(c):                                                  # direction offset c (in bins): nearer bin, its neighbour, weights
+        i = int(c)                                                # truncation towards zero, as JAFU's integer assignment
+        a = abs(c - i)
+        return (K + i) % A, (K + i + (1 if c >= 0 else -1)) % A, 1.0 - a, a
+
+    SL = np.zeros((NF, A, N))
+    FLD = np.zeros_like(SL)
+
+    def add(arr, m, kk, val):                                     # scatter into bin (kk, m) if the row exists
+        if 1 <= m <= NF:
+            np.add.at(arr[m - 1], kk, val)
+
+    for MC in range(1, HI + 1):
+        f = fx(MC)
+        ip, im = MC + isp, MC + ism
+        wp1 = (f * (1 + lam) - fx(ip)) / (fx(ip + 1) - fx(ip)); wp0 = 1.0 - wp1
+        wm1 = (f * (1 - lam) - fx(im)) / (fx(im + 1) - fx(im)); wm0 = 1.0 - wm1
+        Fc, Fp0, Fp1, Fm0, Fm1 = fext(MC), fext(ip), fext(ip + 1), fext(im), fext(im + 1)
+        ftemp = CON * f ** 11 * enh                               # AF11(MC) * ENH
+        for sgn in (1.0, -1.0):                                   # the quadruplet and its mirror image
+            k1, k11, a1, b1 = dirs(sgn * cl1)
+            k2, k21, a2, b2 = dirs(sgn * cl2)
+            sap = dal1 * (wp0 * (a1 * Fp0[k1] + b1 * Fp0[k11]) + wp1 * (a1 * Fp1[k1] + b1 * Fp1[k11]))
+            sam = dal2 * (wm0 * (a2 * Fm0[k2] + b2 * Fm0[k21]) + wm1 * (a2 * Fm1[k2] + b2 * Fm1[k21]))
+            fij = Fc
+            fad1 = fij * (sap + sam)
+            fad2 = fad1 - 2.0 * sap * sam
+            fad1 = fad1 + fad2
+            fcen = ftemp * fij
+            ad, delad = fad2 * fcen, fad1 * ftemp
+            delap, delam = (fij - 2.0 * sam) * dal1 * fcen, (fij - 2.0 * sap) * dal2 * fcen
+            add(SL, MC, K, -2.0 * ad); add(FLD, MC, K, -2.0 * delad)
+            for m, w in ((im, wm0), (im + 1, wm1)):
+                add(SL, m, k2, ad * (w * a2)); add(SL, m, k21, ad * (w * b2))
+                add(FLD, m, k2, delam * (w * a2) ** 2); add(FLD, m, k21, delam * (w * b2) ** 2)
+            for m, w in ((ip, wp0), (ip + 1, wp1)):
+                add(SL, m, k1, ad * (w * a1)); add(SL, m, k11, ad * (w * b1))
+                add(FLD, m, k1, delap * (w * a1) ** 2); add(FLD, m, k11, delap * (w * b1) ** 2)
+    return SL, FLD
+
+
+@pytest.mark.parametrize("case", ["o48like", "o320like", "o640like"])
+def test_snonlin_against_an_independent_scatter_form(built, case):
+    """The oracle's SNONLIN + NLWEIGT + INISNONLIN + JAFU (tables, gather/scatter loops, the three MC regimes with their spectrum-
+    edge branches) against _dia_numpy, which shares nothing with them but the physics: no index table, no RNLCOEF."""
+    g, o, f, fl = make_oracle(case)
+    for _ in range(2):
+        assert o.step() == 0
+    sl, fld = o.snonlin()
+    F1 = o.get_fl1()
+    fr, dfim, th = o.table("FR"), o.table("DFIM"), o.table("TH")
+    consts = dict(G=9.806, ZPI=2 * np.pi, WETAIL=0.25, FRTAIL=0.2, EPSMIN=o.table("EPSMIN")[0] if _has(o, "EPSMIN") else 1e-20)   # yowpcons.F90, yowfred.F90
+    SL, FLD = _dia_numpy(F1, fr, fr[1] / fr[0], g.depth, o.get_field3("WAVNUM"), dfim, 2 * np.pi / th.size, consts)
+    assert np.abs(sl).max() > 0
+    np.testing.assert_allclose(sl, SL, rtol=0, atol=2e-9 * np.abs(sl).max())
+    np.testing.assert_allclose(fld, FLD, rtol=0, atol=2e-9 * np.abs(fld).max())
