@@ -223,6 +223,7 @@ void femean(const Tables& t, const Config& c, int KIJL, const double* F /*(KIJL,
 // SNONLIN alone on one chunk (tests: conservation properties of the DIA); SL, FLD (KIJL,A,F) are overwritten
 void snonlin_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK, double* SL, double* FLD);
 void term_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK, int which, double* SL, double* FLD);
+void stresso_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK, double* SL, double* SPOS, double* OUT);
 
 // ---------------------------------------------------------------------------
 // The steps either side of the hot path (orc_output.cpp): NEWWIND, OUTBLOCK core parameters, WAMNORM statistics.

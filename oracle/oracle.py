@@ -80,6 +80,7 @@ def _lib(fast=False):
         lib.orc_newwind.argtypes = [C.c_void_p, C.c_void_p]
         lib.orc_snonlin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_term.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        lib.orc_stresso.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_outbs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p]
         lib.orc_outwnorm.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.orc_implsch.argtypes = [C.c_void_p]
@@ -259,6 +260,16 @@ class Oracle:
         if self.lib.orc_term(self.h, {"sinput": 1, "sdissip": 2}[which], sl.ctypes.data, fld.ctypes.data) != 0:
             raise RuntimeError("orc_term failed")
         return sl, fld
+
+    def stresso(self):
+        """The wind input of the second SINFLX call (NGST = 2, LLSNEG = T) and STRESSO + TAU_PHI_HF on it, with the stored UFRIC, Z0M, MIJ:
+        (SL, SPOS)[m, k, ij] and (TAUW, TAUWDIR, PHIWA)[ij]."""
+        sl = np.empty((self.cfg.nfre, self.cfg.nang, self.niblo))
+        spos = np.empty_like(sl)
+        out = np.empty((3, self.niblo))
+        if self.lib.orc_stresso(self.h, sl.ctypes.data, spos.ctypes.data, out.ctypes.data) != 0:
+            raise RuntimeError("orc_stresso failed")
+        return sl, spos, out
 
     def outwnorm(self, global_norm=True):
         """OUTWNORM/MPMINMAXAVG on the last outbs(): rows = columns, (average, minimum, maximum, count)."""

@@ -274,6 +274,33 @@ int orc_snonlin(void* h, double* sl, double* fld) {
   return 0;
 }
 
+// second-call wind input + STRESSO alone: sl, spos [m][k][ij]; out [3][ij] = TAUW, TAUWDIR, PHIWA
+int orc_stresso(void* h, double* sl, double* spos, double* out) {
+  Model* m = (Model*)h;
+  const long N = m->grid.NIBLO;
+  const int A = m->cfg.nang, F = m->cfg.nfre;
+  try {
+    for (int ir = 0; ir < m->cfg.npr; ++ir) {
+      RankDecomp& r = m->ranks[ir];
+      const int P = r.NPROMA;
+      std::vector<double> S((size_t)P * A * F), D((size_t)P * A * F), O((size_t)3 * P);
+      for (int ic = 1; ic <= r.NCHNK; ++ic) {
+        stresso_chunk(m->cfg, m->tab, m->fld[ir], P, ic, S.data(), D.data(), O.data());
+        for (int ip = 1; ip <= r.KIJL4CHNK(ic); ++ip) {
+          const int ij0 = m->grid.NEWIJ2IJ(r.IJFROMCHNK(ip, ic));
+          for (int q = 0; q < 3; ++q) out[(size_t)q * N + ij0 - 1] = O[(size_t)q * P + ip - 1];
+          for (int M = 1; M <= F; ++M)
+            for (int K = 1; K <= A; ++K) {
+              const size_t o = ((size_t)(M - 1) * A + (K - 1)) * N + ij0 - 1, q = (ip - 1) + (size_t)P * ((K - 1) + (size_t)A * (M - 1));
+              sl[o] = S[q]; spos[o] = D[q];
+            }
+        }
+      }
+    }
+  } catch (const std::exception& e) { fprintf(stderr, "orc_stresso: %s\n", e.what()); return 1; }
+  return 0;
+}
+
 // SINPUT (which = 1) or SDISSIP (which = 2) alone, same layout as orc_snonlin
 int orc_term(void* h, int which, double* sl, double* fld) {
   Model* m = (Model*)h;

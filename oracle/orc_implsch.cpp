@@ -1433,6 +1433,41 @@ void term_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK
   } else throw std::runtime_error("term_chunk: unknown term");
 }
 
+// STRESSO + TAU_PHI_HF alone for a chunk (test infrastructure for the per-term cross-checks): the wind input of the second SINFLX
+// call (NGST = 2, LLSNEG = T; sinflx.F90:156-167) from the stored UFRIC / Z0M, then STRESSO with LLPHIWA = T on the stored MIJ
+// (stresso.F90:120-233).  SL, SPOS: (KIJL, NANG, NFRE); OUT: (KIJL, 3) = TAUW, TAUWDIR, PHIWA.
+void stresso_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK, double* SLp, double* SPOSp, double* OUTp) {
+  const int NANG = c.nang, NFRE = c.nfre, KIJS = 1;
+  Ctx x{c, t, KIJS, KIJL, NANG, NFRE};
+  const int P = KIJL;
+  auto s1 = [&](ArrD& a) { return V1{&a(1, ICHNK)}; };
+  V3 FL1{&f.FL1(1, 1, 1, ICHNK), P, NANG};
+  V2 WAVNUM{&f.WAVNUM(1, 1, ICHNK), P}, CINV{&f.CINV(1, 1, ICHNK), P}, XK2CG{&f.XK2CG(1, 1, ICHNK), P};
+  V1 WSWAVE = s1(f.WSWAVE), WDWAVE = s1(f.WDWAVE), UFRIC = s1(f.UFRIC), Z0M = s1(f.Z0M), AIRD = s1(f.AIRD), WSTAR = s1(f.WSTAR);
+  const size_t n3 = (size_t)P * NANG * NFRE;
+  std::vector<double> sFLD(n3, 0.0), sX(n3), sCOS((size_t)P * NANG), sSIN2((size_t)P * NANG), sRH((size_t)P * NFRE);
+  for (size_t i = 0; i < n3; ++i) { SLp[i] = 0.0; SPOSp[i] = 0.0; }
+  V3 SL{SLp, P, NANG}, SPOS{SPOSp, P, NANG}, FLD{sFLD.data(), P, NANG}, XLLWS{sX.data(), P, NANG};
+  V2 COSWDIF{sCOS.data(), P}, SINWDIF2{sSIN2.data(), P}, RHOWGDFTH{sRH.data(), P};
+  L1 lRAORW(P), lRNFAC(P);
+  V1 RAORW = lRAORW.view(), RNFAC = lRNFAC.view();
+  std::vector<int> sMIJ(P);
+  I1 MIJ{sMIJ.data()};
+  for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+    RAORW(IJ) = std::max(AIRD(IJ), 1.0) * t.ROWATERM1; RNFAC(IJ) = 1.0;
+    MIJ(IJ) = f.MIJ(IJ, ICHNK);
+    for (int M = 1; M <= NFRE; ++M) RHOWGDFTH(IJ, M) = M <= MIJ(IJ) ? t.RHOWG_DFIM(M) : 0.0;     // frcutindex.F90:99-108
+    if (MIJ(IJ) != NFRE) RHOWGDFTH(IJ, MIJ(IJ)) = 0.5 * RHOWGDFTH(IJ, MIJ(IJ));
+  }
+  for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+    COSWDIF(IJ, K) = std::cos(t.TH(K) - WDWAVE(IJ));
+    SINWDIF2(IJ, K) = sq(std::sin(t.TH(K) - WDWAVE(IJ)));
+  }
+  if (c.iphys == 0) SINPUT_JAN(x, 2, true, FL1, WAVNUM, CINV, XK2CG, WSWAVE, UFRIC, Z0M, COSWDIF, SINWDIF2, RAORW, WSTAR, RNFAC, FLD, SL, SPOS, XLLWS);
+  else SINPUT_ARD(x, 2, true, FL1, WAVNUM, CINV, XK2CG, WDWAVE, WSWAVE, UFRIC, Z0M, COSWDIF, SINWDIF2, RAORW, WSTAR, RNFAC, FLD, SL, SPOS, XLLWS);
+  STRESSO(x, MIJ, RHOWGDFTH, FL1, SL, SPOS, CINV, WDWAVE, UFRIC, Z0M, AIRD, RNFAC, COSWDIF, SINWDIF2, V1{OUTp}, V1{OUTp + P}, V1{OUTp + 2 * P}, true);
+}
+
 // wamintgr.F90:117-146
 void implsch_all(Model& m) {
   for (int ir = 0; ir < m.cfg.npr; ++ir) {
