@@ -73,6 +73,18 @@ struct ecwam_b200_handle_s {
   DBuf<double> wlat_raw, dellam, grad, curmask;   // IREFRA /= 0: WLAT as PROPCONNECT left it, DELLAM/COSPH(KXLT), gradients, CURMASK
   double oneo2delphi = 0.0;
   std::vector<int> h_spre, h_rpre;   // per peer prefix sums (size nproc+1)
+  // MPEXCHNG through the host's own message passing instead of NCCL (ecwam_b200_set_exchange)
+  ecwam_b200_exchange_fn xchg_fn = nullptr;
+  void* xchg_user = nullptr;
+  bool xchg_staged = false;
+  double *xchg_hs = nullptr, *xchg_hr = nullptr;   // pinned staging of the send / receive buffers (staged mode)
+  size_t xchg_ns = 0, xchg_nr = 0;
+  // halo / compute overlap of PROPAG_WAM: own points [int_lo, int_hi) have no halo neighbour and are propagated while the
+  // exchange is in flight on st_x; the strips below and above follow it
+  int int_lo = 0, int_hi = 0;
+  bool overlap = false;
+  cudaStream_t st_x = nullptr;
+  cudaEvent_t ev_pack = nullptr, ev_x = nullptr;
   bool send_chunks_sorted = false;
   cudaEvent_t ev_halo = nullptr;
   std::vector<int> send_chunks;      // sorted chunks (0-based) that hold at least one point some peer needs (host-buffer pipeline)
@@ -131,16 +143,17 @@ static int ensure_const(H* h) {
 
 namespace {
 struct ScopedTimer {
-  H* h; TimingClass* tc = nullptr; cudaEvent_t a = nullptr, b = nullptr;
-  ScopedTimer(H* h_, const char* name) : h(h_) {
+  H* h; TimingClass* tc = nullptr; cudaEvent_t a = nullptr, b = nullptr; cudaStream_t s = nullptr;
+  ScopedTimer(H* h_, const char* name, cudaStream_t on = nullptr) : h(h_) {
     if (!h->timing) return;
+    s = on ? on : h->st;
     tc = &h->tm[name];
     cudaEventCreate(&a); cudaEventCreate(&b);
-    cudaEventRecord(a, h->st);
+    cudaEventRecord(a, s);
   }
   ~ScopedTimer() {
     if (!tc) return;
-    cudaEventRecord(b, h->st);
+    cudaEventRecord(b, s);
     tc->pending.push_back({a, b});
   }
 };
@@ -333,7 +346,7 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
   h->st = (cudaStream_t)cuda_stream;
   h->comm = (ncclComm_t)nccl_comm;
   h->nproc = dec->nproc; h->irank0 = dec->irank - 1;
-  if (h->nproc > 1 && !h->comm) { EW_FAIL_H(h, ECWAM_B200_EINVAL, "nproc > 1 needs an NCCL communicator"); }
+  // nproc > 1 without a communicator: the halo exchange must be supplied with ecwam_b200_set_exchange before the first step
   int rc = fill_dev_const(*params, *tables, h->dc);
   if (rc) { delete h; return rc; }
   const ecwam_b200_params& p = h->par;
@@ -457,13 +470,24 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
   halo_str[nbot + ntop] = 0;
 
   {
-    int reach = 0;
+    int reach = 0, lo = 0, hi = nloc;
     for (int j = 0; j < 14; ++j)
       for (int l = 0; l < nloc; ++l) {
         const int e = nbr[(size_t)j * nloc + l];
         if (e >= nbot && e < nbot + nloc) reach = std::max(reach, std::abs(e - nbot - l));
+        else if (e < nbot) lo = std::max(lo, l + 1);            // reads the halo below the own block
+        else if (e < next - 1) hi = std::min(hi, l);            // ... above it (next-1 is the land slot)
       }
     h->nbr_reach = reach;
+    h->int_lo = lo; h->int_hi = std::max(lo, hi);
+    const char* ov = getenv("ECWAM_B200_OVERLAP");
+    // worth it when most of the block is interior (MPDECOMP's latitude bands: one or two rows at either end are not)
+    h->overlap = np > 1 && !(ov && ov[0] == '0') && (long long)(h->int_hi - h->int_lo) * 4 >= (long long)nloc * 3;
+    if (h->overlap) {
+      EW_CUDA_CHECK(cudaStreamCreateWithFlags(&h->st_x, cudaStreamNonBlocking));
+      EW_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming));
+      EW_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_x, cudaEventDisableTiming));
+    }
   }
   cudaStream_t st = h->st;
   bool ok = true;
@@ -592,6 +616,11 @@ int ecwam_b200_destroy(ecwam_b200_handle h) {
   for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
   if (h->ev_halo) cudaEventDestroy(h->ev_halo);
+  if (h->ev_pack) cudaEventDestroy(h->ev_pack);
+  if (h->ev_x) cudaEventDestroy(h->ev_x);
+  if (h->st_x) cudaStreamDestroy(h->st_x);
+  if (h->xchg_hs) cudaFreeHost(h->xchg_hs);
+  if (h->xchg_hr) cudaFreeHost(h->xchg_hr);
   if (h->st_up) cudaStreamDestroy(h->st_up);
   if (h->st_dn) cudaStreamDestroy(h->st_dn);
   delete h;
@@ -617,6 +646,12 @@ int ecwam_b200_bind_fields(ecwam_b200_handle h, const ecwam_b200_fields* dev) {
   return 0;
 }
 
+int ecwam_b200_set_exchange(ecwam_b200_handle h, ecwam_b200_exchange_fn fn, void* user, int staged) {
+  if (!h) EW_FAIL(ECWAM_B200_EINVAL, "null handle");
+  h->xchg_fn = fn; h->xchg_user = user; h->xchg_staged = staged != 0;
+  return 0;
+}
+
 int ecwam_b200_invalidate_weights(ecwam_b200_handle h) {
   if (!h) EW_FAIL(ECWAM_B200_EINVAL, "null handle");
   h->weights_dirty = true;
@@ -625,13 +660,41 @@ int ecwam_b200_invalidate_weights(ecwam_b200_handle h) {
 }
 
 // MPEXCHNG (mpexchng.F90:164-206) over NCCL: one grouped send/recv per neighbouring rank.
-static int exchange(H* h, const double* sendbuf, double* recvbuf, size_t per_point_full, size_t per_point_now) {
+static int exchange(H* h, const double* sendbuf, double* recvbuf, size_t per_point_full, size_t per_point_now, cudaStream_t xs = nullptr) {
   if (h->nproc <= 1) return 0;
+  if (!xs) xs = h->st;
+  if (h->xchg_fn) {
+    const int np = h->nproc;
+    std::vector<long long> so(np), sc(np), ro(np), rcn(np);
+    for (int q = 0; q < np; ++q) {
+      so[q] = (long long)h->h_spre[q] * (long long)per_point_full; sc[q] = (long long)(h->h_spre[q + 1] - h->h_spre[q]) * (long long)per_point_now;
+      ro[q] = (long long)h->h_rpre[q] * (long long)per_point_full; rcn[q] = (long long)(h->h_rpre[q + 1] - h->h_rpre[q]) * (long long)per_point_now;
+    }
+    if (!h->xchg_staged) {   // device pointers: a CUDA-aware message-passing library moves them
+      EW_CUDA_CHECK(cudaStreamSynchronize(xs));
+      const int rc = h->xchg_fn(h->xchg_user, np, sendbuf, so.data(), sc.data(), recvbuf, ro.data(), rcn.data());
+      if (rc) EW_FAIL(ECWAM_B200_ESTATE, "the exchange callback returned %d", rc);
+      return 0;
+    }
+    const size_t ns = (size_t)h->h_spre[np] * per_point_full, nr = (size_t)h->h_rpre[np] * per_point_full;
+    if (ns > h->xchg_ns) { if (h->xchg_hs) cudaFreeHost(h->xchg_hs); h->xchg_hs = nullptr; EW_CUDA_CHECK(cudaMallocHost((void**)&h->xchg_hs, ns * 8)); h->xchg_ns = ns; }
+    if (nr > h->xchg_nr) { if (h->xchg_hr) cudaFreeHost(h->xchg_hr); h->xchg_hr = nullptr; EW_CUDA_CHECK(cudaMallocHost((void**)&h->xchg_hr, nr * 8)); h->xchg_nr = nr; }
+    for (int q = 0; q < np; ++q)
+      if (sc[q] > 0) EW_CUDA_CHECK(cudaMemcpyAsync(h->xchg_hs + so[q], sendbuf + so[q], (size_t)sc[q] * 8, cudaMemcpyDeviceToHost, xs));
+    EW_CUDA_CHECK(cudaStreamSynchronize(xs));
+    const int rc = h->xchg_fn(h->xchg_user, np, h->xchg_hs, so.data(), sc.data(), h->xchg_hr, ro.data(), rcn.data());
+    if (rc) EW_FAIL(ECWAM_B200_ESTATE, "the exchange callback returned %d", rc);
+    for (int q = 0; q < np; ++q)
+      if (rcn[q] > 0) EW_CUDA_CHECK(cudaMemcpyAsync(recvbuf + ro[q], h->xchg_hr + ro[q], (size_t)rcn[q] * 8, cudaMemcpyHostToDevice, xs));
+    EW_CUDA_CHECK(cudaStreamSynchronize(xs));   // the staging buffer is reused by the next exchange
+    return 0;
+  }
+  if (!h->comm) EW_FAIL(ECWAM_B200_ESTATE, "nproc > 1: neither an NCCL communicator (ecwam_b200_create) nor an exchange callback (ecwam_b200_set_exchange)");
   EW_NCCL_CHECK(ncclGroupStart());
   for (int q = 0; q < h->nproc; ++q) {
     const int ns = h->h_spre[q + 1] - h->h_spre[q], nr = h->h_rpre[q + 1] - h->h_rpre[q];
-    if (ns > 0) EW_NCCL_CHECK(ncclSend(sendbuf + (size_t)h->h_spre[q] * per_point_full, (size_t)ns * per_point_now, ncclDouble, q, h->comm, h->st));
-    if (nr > 0) EW_NCCL_CHECK(ncclRecv(recvbuf + (size_t)h->h_rpre[q] * per_point_full, (size_t)nr * per_point_now, ncclDouble, q, h->comm, h->st));
+    if (ns > 0) EW_NCCL_CHECK(ncclSend(sendbuf + (size_t)h->h_spre[q] * per_point_full, (size_t)ns * per_point_now, ncclDouble, q, h->comm, xs));
+    if (nr > 0) EW_NCCL_CHECK(ncclRecv(recvbuf + (size_t)h->h_rpre[q] * per_point_full, (size_t)nr * per_point_now, ncclDouble, q, h->comm, xs));
   }
   EW_NCCL_CHECK(ncclGroupEnd());
   return 0;
@@ -645,6 +708,38 @@ static int halo_spectrum(H* h, const double* src, int srcF, int nm) {
   launch_pack(d, src, srcF, nullptr, 0, d.A, nm, d.Fr, h->send_l.p, h->send_pre.p, h->send_peer_of.p, h->nsend, h->sendbuf.p, h->st);
   h->nlaunch += (h->nsend > 0);
   return exchange(h, h->sendbuf.p, h->halo.p, (size_t)d.A * d.Fr, (size_t)d.A * nm);
+}
+
+// MPEXCHNG + PROPAGS2 of frequencies [0, m1) (propag_wam.F90:166, 245-251).  With several ranks the exchange runs on its own
+// stream while the own points without a halo neighbour are propagated; the two strips that read the halo follow it
+// (the reference posts non-blocking receives the same way, mpexchng.F90:164-206).
+static int halo_propags2(H* h, const double* src, int srcF, double* dst, int dstF, int m1) {
+  const PropDev& d = h->pd;
+  if (!h->overlap) {
+    int rc = halo_spectrum(h, src, srcF, m1);
+    if (rc) return rc;
+    ScopedTimer t(h, "propags2");
+    launch_propags2(d, src, srcF, dst, dstF, 0, m1, h->msplit, h->st);
+    h->nlaunch++;
+    return 0;
+  }
+  ScopedTimer t(h, "propags2");      // the whole overlapped region on the main stream: pack, interior, wait, strips
+  launch_pack(d, src, srcF, nullptr, 0, d.A, m1, d.Fr, h->send_l.p, h->send_pre.p, h->send_peer_of.p, h->nsend, h->sendbuf.p, h->st);
+  h->nlaunch += (h->nsend > 0);
+  EW_CUDA_CHECK(cudaEventRecord(h->ev_pack, h->st));
+  EW_CUDA_CHECK(cudaStreamWaitEvent(h->st_x, h->ev_pack, 0));
+  launch_propags2(d, src, srcF, dst, dstF, 0, m1, h->msplit, h->st, h->int_lo, h->int_hi);
+  h->nlaunch++;
+  {
+    ScopedTimer tx(h, "halo", h->st_x);
+    int rc = exchange(h, h->sendbuf.p, h->halo.p, (size_t)d.A * d.Fr, (size_t)d.A * m1, h->st_x);
+    if (rc) return rc;
+  }
+  EW_CUDA_CHECK(cudaEventRecord(h->ev_x, h->st_x));
+  EW_CUDA_CHECK(cudaStreamWaitEvent(h->st, h->ev_x, 0));
+  if (h->int_lo > 0) { launch_propags2(d, src, srcF, dst, dstF, 0, m1, h->msplit, h->st, 0, h->int_lo); h->nlaunch++; }
+  if (h->int_hi < d.nloc) { launch_propags2(d, src, srcF, dst, dstF, 0, m1, h->msplit, h->st, h->int_hi, d.nloc); h->nlaunch++; }
+  return 0;
 }
 
 // CTUWUPDT equivalent: PROENVHALO of the group velocity + per-point set-up + CFL scan (propag_wam.F90:221-236)
@@ -703,13 +798,8 @@ static int propag_core(H* h, bool* lf_in_fl3) {
     if (rc) return rc;
     if (cfl > 0) { ew_set_error("CTUW: CFL / weight-range check failed at %d grid points (ctuwdrv.F90:127-146)", cfl); h->weights_dirty = true; return cfl; }
   }
-  rc = halo_spectrum(h, h->dev.fl1, d.F, d.Fr);   // propag_wam.F90:166
+  rc = halo_propags2(h, h->dev.fl1, d.F, h->fl3.p, d.Fr, d.Fr);   // propag_wam.F90:166, 245-251
   if (rc) return rc;
-  {
-    ScopedTimer t(h, "propags2");
-    launch_propags2(d, h->dev.fl1, d.F, h->fl3.p, d.Fr, 0, d.Fr, h->msplit, h->st);   // propag_wam.F90:245-251
-    h->nlaunch++;
-  }
   *lf_in_fl3 = true;
   if (p.ifrelfmax > 0 && p.ifrelfmax < d.Fr) {   // propag_wam.F90:257-313
     const int nstep = (int)nint_l(p.idelpro / p.delpro_lf);
@@ -717,11 +807,8 @@ static int propag_core(H* h, bool* lf_in_fl3) {
       const double* src = *lf_in_fl3 ? h->fl3.p : h->dev.fl1;
       double* dst = *lf_in_fl3 ? h->dev.fl1 : h->fl3.p;
       const int sF = *lf_in_fl3 ? d.Fr : d.F, dF = *lf_in_fl3 ? d.F : d.Fr;
-      rc = halo_spectrum(h, src, sF, p.ifrelfmax);
+      rc = halo_propags2(h, src, sF, dst, dF, p.ifrelfmax);
       if (rc) return rc;
-      ScopedTimer t(h, "propags2");
-      launch_propags2(d, src, sF, dst, dF, 0, p.ifrelfmax, h->msplit, h->st);
-      h->nlaunch++;
       *lf_in_fl3 = !*lf_in_fl3;
     }
   }
@@ -1059,6 +1146,7 @@ int ecwam_b200_outwnorm(ecwam_b200_handle h, const ecwam_b200_outsel* sel, const
   const int ncol = sel->niprmout, P = h->par.nproma, np = h->nproc;
   const long long nloc = h->pd.nloc;
   const double HUGE_ = 1.7976931348623157e308;
+  if (np > 1 && !h->comm) EW_FAIL(ECWAM_B200_ESTATE, "outwnorm over %d ranks needs the NCCL communicator (its gather is not part of the exchange callback)", np);
   ScopedTimer t(h, "outwnorm");
   if (!llglobal) {   // mpminmaxavg.F90:160-191
     const size_t ns = norm_scratch_doubles(ncol);

@@ -302,7 +302,8 @@ typedef struct ecwam_b200_fields {
 typedef struct ecwam_b200_handle_s* ecwam_b200_handle;
 
 /* Create the per-rank state: uploads tables, builds the device neighbour tables and halo plan.
- * nccl_comm: an ncclComm_t (or NULL when nproc==1); cuda_stream: a cudaStream_t (NULL = default stream).
+ * nccl_comm: an ncclComm_t (NULL when nproc==1, or when ecwam_b200_set_exchange supplies the halo exchange);
+ * cuda_stream: a cudaStream_t (NULL = default stream).
  * Replaces the one-off set-up the reference does in INITMDL/MPDECOMP/CTUWUPDT index helpers
  * (src/ecwam/ctuwupdt.F90:93-166).                                                                     */
 int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* tables,
@@ -316,6 +317,20 @@ int ecwam_b200_destroy(ecwam_b200_handle h);
 int ecwam_b200_nccl_unique_id(char id_out[128]);
 int ecwam_b200_nccl_comm_init(const char id[128], int nranks, int rank, void** comm_out);
 int ecwam_b200_nccl_comm_destroy(void* comm);
+
+/* MPEXCHNG through the host's own message passing instead of NCCL (src/ecwam/mpexchng.F90:164-206 posts MPL_SEND / MPL_RECV per
+ * neighbouring rank; a host that keeps that code passes nccl_comm = NULL to ecwam_b200_create and registers this callback).
+ * Whenever the library needs a halo exchange (the spectrum in PROPAG_WAM, the group velocity / depth / currents in PROENVHALO) it
+ * packs the send buffer on the device, synchronises its stream and calls fn: for every rank q, send_count[q] doubles starting at
+ * sendbuf + send_offset[q] go to q, and recv_count[q] doubles from q land at recvbuf + recv_offset[q] (counts may be 0; the
+ * message order between a pair of ranks is the call order).  fn returns 0 when recvbuf is complete.
+ * staged = 0: sendbuf / recvbuf are DEVICE pointers (CUDA-aware MPI); staged = 1: the library stages both through pinned HOST
+ * buffers and fn sees host pointers (plain MPI, or the gloo-staged two-processes-on-one-GPU test).  fn = NULL restores NCCL.
+ * OUTWNORM over several ranks still needs the NCCL communicator.                                                              */
+typedef int (*ecwam_b200_exchange_fn)(void* user, int nproc, const double* sendbuf, const long long* send_offset,
+                                      const long long* send_count, double* recvbuf, const long long* recv_offset,
+                                      const long long* recv_count);
+int ecwam_b200_set_exchange(ecwam_b200_handle h, ecwam_b200_exchange_fn fn, void* user, int staged);
 
 /* Bind DEVICE pointers of the model fields (FIELD_API GET_DEVICE_DATA_* + C_LOC on the Fortran side,
  * src/ecwam/wamintgr_loki_gpu.F90:141-157).                                                            */

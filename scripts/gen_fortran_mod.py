@@ -86,6 +86,8 @@ def f_arg(decl):
         return "INTEGER(C_INT) :: %s(*)" % name, name
     if ctype == "long long*":
         return "INTEGER(C_LONG_LONG) :: %s" % name, name
+    if ctype == "ecwam_b200_exchange_fn":     # a BIND(C) procedure of the host: pass C_FUNLOC(...)
+        return "TYPE(C_FUNPTR), VALUE :: %s" % name, name
     if ctype == "ecwam_b200_handle" or ctype in ("void*", "const void*", "ecwam_b200_host_tables_t", "ecwam_b200_host_grid_t"):
         return "TYPE(C_PTR), VALUE :: %s" % name, name
     if ctype in ("ecwam_b200_handle*", "void**", "ecwam_b200_host_tables_t*", "ecwam_b200_host_grid_t*"):

@@ -511,3 +511,115 @@ def test_snonlin_against_an_independent_scatter_form(built, case):
     assert np.abs(sl).max() > 0
     np.testing.assert_allclose(sl, SL, rtol=0, atol=2e-9 * np.abs(sl).max())
     np.testing.assert_allclose(fld, FLD, rtol=0, atol=2e-9 * np.abs(fld).max())
+
+
+def _simpson_weights(n, scale):
+    w = np.full(n, 2.0 * scale)
+    w[1::2] = 4.0 * scale
+    w[0] = w[-1] = scale
+    return w
+
+
+@pytest.mark.parametrize("case", ["o48like", "o640like", "o48_iphys0"])
+def test_stresso_and_tau_phi_hf_against_numpy(built, case):
+    """STRESSO + TAU_PHI_HF restated in vectorised numpy straight from the formulas (stresso.F90:120-233: resolved-range momentum and
+    energy fluxes of the positive wind input, weighted with RHOWGDFTH up to the cut-off MIJ; tau_phi_hf.F90:131-303: the
+    unresolved tail as a Simpson integral over Z = ln(omega sqrt(z0/g)) from the cut-off to Y = 1 of beta_max/kappa^2 mu ln^4 mu,
+    with the friction velocity reduced along the integral when sheltering is on).  Simpson weights, the lower integration limit
+    X0 (Newton iteration of init_x0tauhf.F90:79-90) and RHOWG_DFIM (initmdl.F90:479-484) are rebuilt here; the inputs are the
+    oracle's own second-call wind input (SL, SPOS) and its stored UFRIC, Z0M, MIJ."""
+    g, o, f, fl = make_oracle(case)
+    for _ in range(2):
+        assert o.step() == 0
+    sl, spos, out = o.stresso()
+    F1 = o.get_fl1()
+    NF, A, N = F1.shape
+    cinv = o.get_field3("CINV")
+    us, z0, aird, wd = (o.get_field(k) for k in ("UFRIC", "Z0M", "AIRD", "WDWAVE"))
+    mij = o.get_field("MIJ").astype(int)
+    th, fr = o.table("TH"), o.table("FR")
+    G, ZPI, XKAPPA, ZALP, ROWATER, EPS1 = 9.806, 2 * np.pi, 0.40, 0.008, 1000.0, 1e-5
+    GM1 = 0.101978381                    # yowpcons.F90:19 (a rounded 1/G that INIWCST does not reset; 4e-9 away from 1/9.806)
+    delth = ZPI / A
+    fratio = fr[1] / fr[0]
+    # frequency weights of the flux integrals up to the cut-off (frcutindex.F90:99-108)
+    rdf = ROWATER * G * delth * np.log(fratio) * fr
+    rdf[0] *= 0.5; rdf[-1] *= 0.5
+    m1 = np.arange(1, NF + 1)[:, None]
+    w = np.where(m1 <= mij[None, :], rdf[:, None], 0.0)
+    w = np.where((m1 == mij[None, :]) & (mij[None, :] != NF), 0.5 * w, w)
+    sx = (spos * np.sin(th)[None, :, None]).sum(axis=1)
+    sy = (spos * np.cos(th)[None, :, None]).sum(axis=1)
+    am = np.maximum(aird, 1.0)
+    xs = (w * cinv * sx).sum(axis=0) / am
+    ys = (w * cinv * sy).sum(axis=0) / am
+    phiwa = ((sl - spos).sum(axis=1) * rdf[:, None]).sum(axis=0) + (w * spos.sum(axis=1)).sum(axis=0)
+    # direction of the reduced stress and the friction velocity the tail starts from
+    shelter_on = CASES[case]["iphys"] == 1 and o.table("TAUWSHELTER")[0] != 0.0
+    tsh = o.table("TAUWSHELTER")[0]
+    if shelter_on:
+        tpx, tpy = us ** 2 * np.sin(wd) - tsh * xs, us ** 2 * np.cos(wd) - tsh * ys
+        usdirp, ust = np.arctan2(tpx, tpy), (tpx ** 2 + tpy ** 2) ** 0.25
+    else:
+        usdirp, ust = wd, us.copy()
+    # X0: ALPHA X0^2 exp(kappa / (X0 + ZALP)) = 1
+    alph = o.table("ALPHAMIN")[0] if (o.cfg.llcapchnk or o.cfg.llgcbz0 or o.cfg.llnormagam) else o.table("ALPHA")[0]   # init_x0tauhf.F90:74-78
+    x0 = 0.005
+    for _ in range(30):
+        ff = np.exp(XKAPPA / (x0 + ZALP))
+        fv = alph * x0 ** 2 * ff - 1.0
+        if fv == 0.0:
+            break
+        x0 -= fv / (alph * ff * (2.0 * x0 - XKAPPA * (x0 / (x0 + ZALP)) ** 2))
+    assert abs(x0 - o.table("X0TAUHF")[0]) <= 1e-14
+    jtot = o.table("WTAUHF").size
+    wt = _simpson_weights(jtot, o.table("BETAMAXOXKAPPA2")[0] / 3.0)
+    np.testing.assert_allclose(wt, o.table("WTAUHF"), rtol=1e-15)
+    # moments of the spectrum at the cut-off frequency
+    fm = F1[mij - 1, :, np.arange(N)].T                                   # [k, ij]
+    cw = np.maximum(np.cos(th[:, None] - wd[None, :]), 0.0)
+    f3, f2 = delth * (fm * cw ** 3).sum(axis=0), delth * (fm * cw ** 2).sum(axis=0)
+    fr5 = fr[mij - 1] ** 5
+    consttau, constphi = ZPI ** 4 / G ** 2 * fr5, aird * (ZPI ** 4 / G) * fr5
+    sq_z0og = np.sqrt(z0 * GM1)
+    xloggz0 = np.log(G * z0)
+    zinf = np.log(np.maximum(ZPI * fr[mij - 1], x0 * G / ust) * sq_z0og)
+    delz = np.maximum((0.0 - zinf) / (jtot - 1), 0.0)
+
+    def beta(y, u):
+        cm1 = y / sq_z0og * GM1
+        zlog = np.minimum(xloggz0 + 2.0 * np.log(cm1) + XKAPPA / (u * cm1 + ZALP), 0.0)
+        return zlog ** 4 * np.exp(zlog)
+
+    taul, u = ust ** 2, ust.copy()
+    tauhf = np.zeros(N)
+    for j in range(jtot):
+        y = np.exp(zinf + j * delz)
+        if shelter_on:
+            fnc2 = f3 * consttau * beta(y, u) * taul * wt[j] * delz
+            taul = np.maximum(taul - tsh * fnc2, 0.0)
+            u = np.sqrt(taul)
+            tauhf += fnc2
+        else:
+            tauhf += beta(y, u) * wt[j]
+    if not shelter_on:
+        tauhf = f3 * consttau * taul * tauhf * delz
+    taul, u = ust ** 2, ust.copy()
+    phihf = np.zeros(N)
+    for j in range(jtot):
+        y = np.exp(zinf + j * delz)
+        if shelter_on:
+            fnc2 = beta(y, u) * taul * wt[j] * delz
+            taul = np.maximum(taul - tsh * f3 * consttau * fnc2, 0.0)
+            u = np.sqrt(taul)
+            phihf += fnc2 / y
+        else:
+            phihf += beta(y, u) * wt[j] / y
+    phihf = f2 * constphi * sq_z0og * phihf * (1.0 if shelter_on else taul * delz)
+    xs2, ys2 = xs + tauhf * np.sin(usdirp), ys + tauhf * np.cos(usdirp)
+    tauw = np.minimum(np.hypot(xs2, ys2), us ** 2 / (1.0 + EPS1))
+    assert (tauhf > 0).mean() > 0.5 and np.abs(out[0]).max() > 0
+    np.testing.assert_allclose(out[0], tauw, rtol=1e-9, atol=1e-13 * tauw.max())
+    dd = np.angle(np.exp(1j * (out[1] - np.arctan2(xs2, ys2))))
+    assert np.abs(dd[tauw > 1e-10 * tauw.max()]).max() <= 1e-9
+    np.testing.assert_allclose(out[2], phiwa + phihf, rtol=1e-9, atol=1e-12 * np.abs(out[2]).max())
