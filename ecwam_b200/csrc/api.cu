@@ -117,6 +117,7 @@ struct ecwam_b200_handle_s {
   int nbr_reach = 0;       // max |l' - l| over the own-point neighbours of every own point l
   // resident-state step (ecwam_b200_wamintgr_forced): device staging of the eight FF_NEXT fields
   DBuf<double> frc_next;
+  DBuf<double> enhp;       // ENH(IJ,MC) plane of ISNONLIN = 1, 2
   // NEWWIND / OUTBLOCK / WAMNORM
   DBuf<double> normbuf, zglobal;
   DBuf<int> ij2new_d;
@@ -204,7 +205,7 @@ static int fill_dev_const(const ecwam_b200_params& p, const ecwam_b200_tables& t
   if (p.irefra < 0 || p.irefra > 3 || p.icase != 1) EW_FAIL(ECWAM_B200_EINVAL, "IREFRA must be 0..3 and ICASE = 1 (spherical)");
   if (p.irefra >= 2 && p.ifrelfmax > 0 && p.ifrelfmax < p.nfre_red)
     EW_FAIL(ECWAM_B200_EINVAL, "fast-wave sub-stepping (IFRELFMAX) together with current refraction (IREFRA = 2, 3) is not built");
-  if (p.isnonlin != 0) EW_FAIL(ECWAM_B200_EINVAL, "only ISNONLIN=0 is implemented");
+  if (p.isnonlin < 0 || p.isnonlin > 2) EW_FAIL(ECWAM_B200_EINVAL, "ISNONLIN must be 0, 1 or 2");
   if ((p.llgcbz0 || p.llnormagam) && (t.nwav_gc < 2 || !t.xk_gc || !t.omega_gc || !t.cm_gc || !t.c2osqrtvg_gc || !t.xkmsqrtvgoc2_gc ||
                                       !t.om3gmkm_gc || !t.omxkm3_gc || !t.delkcc_gc_ns || !t.delkcc_omxkm3_gc))
     EW_FAIL(ECWAM_B200_EINVAL, "LLGCBZ0 / LLNORMAGAM need the gravity-capillary tables (ecwam_b200_tables: nwav_gc, *_gc)");
@@ -581,6 +582,7 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
   const long long npts = (long long)P * p.nchnk;
   ok = ok && !h->scr.alloc(implsch_scratch_doubles(npts)) && !h->fldin.alloc((size_t)npts * A * F) &&
        !h->tbg.alloc((size_t)EW_TQ_N * F * npts);
+  if (p.isnonlin != 0) ok = ok && !h->enhp.alloc((size_t)tables->mlsthg * npts);
   if (!ok) { ecwam_b200_destroy(h); return ECWAM_B200_ECUDA; }
   cudaMemsetAsync(h->halo.p, 0, (halo_elems + 1) * sizeof(double), st);
   cudaMemsetAsync(h->fl3.p, 0, h->fl3.n * sizeof(double), st);
@@ -855,6 +857,8 @@ static ImplDev make_impl(H* h, bool from_fl3) {
   d.cy49 = (h->par.llgcbz0 || h->par.llnormagam) ? 1 : 0;
   d.gc = h->gctab.p;
   d.sweep_ok = h->dc.sweep_ok;
+  d.isnonlin = h->par.isnonlin;
+  d.enh = h->enhp.p;
   return d;
 }
 

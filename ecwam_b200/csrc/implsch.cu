@@ -1222,7 +1222,11 @@ __global__ void ST_BOUNDS(NP) k_stencil(ImplDev d, long long p0, long long np, S
       const unsigned bIM1 = L.ring + (unsigned)c_dc.NLSLOT[MC0][4] * RSB + me_r;
       const unsigned cb = L.cur + par * 6u * PSB + me_c;
       const V fc = lds<NP>(sm, bIC);
-      const V enh = lds<NP>(sm, L.pc + PC_ENH * 64 + jo);
+      V enh = lds<NP>(sm, L.pc + PC_ENH * 64 + jo);
+      if (d.enh) {   // ISNONLIN = 1, 2: ENH(IJ,MC) from k_enh's plane
+#pragma unroll
+        for (int i = 0; i < NP; ++i) enh.v[i] = __ldg(d.enh + (size_t)MC0 * n + pq + i);
+      }
       const double af11 = c_dc.AF11[MC0];
       V fij, fcen, ftemp, fcd1, fcd2;
 #pragma unroll
@@ -1684,7 +1688,7 @@ __global__ void __maxnreg__(ST_MAXREG) k_stencil_dp(ImplDev d, long long p0, lon
       const unsigned bIM1 = L.ring + (unsigned)c_dc.NLSLOT[MC0][4] * RSB + me_r;
       const unsigned cb = L.cur + par * 6u * PSB + me_c;
       const V fc = lds<2>(sm, bIC);
-      const double enh = lds1(sm, L.pc + PC_ENH * 64 + po);
+      const double enh = d.enh ? __ldg(d.enh + (size_t)MC0 * n + pq) : lds1(sm, L.pc + PC_ENH * 64 + po);   // ISNONLIN = 1, 2: k_enh's plane
       const double ftemp = c_dc.AF11[MC0] * enh;
       V fij, fcen, fcd1, fcd2;
 #pragma unroll
@@ -2235,7 +2239,7 @@ __global__ void __launch_bounds__(sw_threads(TA, NPT), SW_MINB) k_sweep(ImplDev 
 #endif
         const unsigned cb = L.cur + par * 6u * PSB + me_c;
         const V fc = lds<2>(sm, L.ring + (unsigned)c_dc.NLSLOT[MC0][0] * RSB + me_r);
-        const double enh = lds1(sm, L.pc + PC_ENH * PRB + po);
+        const double enh = d.enh ? __ldg(d.enh + (size_t)MC0 * n + pq) : lds1(sm, L.pc + PC_ENH * PRB + po);   // ISNONLIN = 1, 2: k_enh's plane
         const double ftemp = c_dc.AF11[MC0] * enh;
         const double r0 = c_dc.RNLCOEF[MC0][0];
         V fij, fcen, fcd1, fcd2;
@@ -2649,7 +2653,7 @@ __global__ void __launch_bounds__(2 * sw_threads(TA, NPT), 2) k_sweep_ws(ImplDev
           const double* Wc = c_dc.NLW[MC0];
           const unsigned cb = L.cur + b * 6u * PSB + me_c;
           const V fc = lds<2>(sm, L.ring + (unsigned)c_dc.NLSLOT[MC0][0] * RSB + me_r);
-          const double enh = lds1(sm, L.pc + PC_ENH * PRB + po);
+          const double enh = d.enh ? __ldg(d.enh + (size_t)MC0 * n + min(pbase + pt, plast)) : lds1(sm, L.pc + PC_ENH * PRB + po);   // ISNONLIN = 1, 2
           const double ftemp = c_dc.AF11[MC0] * enh;
           const double r0 = c_dc.RNLCOEF[MC0][0];
           V fij, fcen, fcd1, fcd2;
@@ -3038,6 +3042,123 @@ static bool geo_matches(const ImplDev& d, int iphys, int nsdsnth) {
   return iphys != 1 || nsdsnth == geo_nsd(TA);
 }
 
+// =========================================================================================================
+// k_enh: ENH(IJ,MC) of ISNONLIN = 1, 2 (snonlin.F90:138-163), one thread per grid point, written to ImplDev::enh [MLSTHG][npts]
+// between k_point (SDEPTHLIM's factor) and the frequency sweep, which reads it instead of its per-point constant.
+//   ISNONLIN = 1: Janssen & Onorato's shallow-water transfer function of the centre wavenumber (transf.F90:62-110), clipped to
+//                 [0.1, 10]; above NFRE the wavenumber continues as deep water on the geometric frequency axis.
+//   ISNONLIN = 2: the same with the directional-width correction of the mean-flow term (transf_snl.F90:57-100); the relative
+//                 spectral width XNU and the angular width SIG_TH come from PEAK_ANG (peak_ang.F90:72-175) on the depth-limited,
+//                 floored spectrum SNONLIN sees (two more reads of FL1 per point: an optional mode).
+// =========================================================================================================
+__device__ double transf_enh(double xk, double dep) {
+  const double EPS = 0.0001, DKMAX = 40.0;
+  if (!(dep < c_dc.bathymax && dep > 0.0)) return 1.0;
+  const double x = xk * dep;
+  if (x > DKMAX) return 1.0;
+  const double t0 = tanh(x), om = sqrt(c_dc.G * xk * t0), c0 = om / xk;
+  const double vg = x < EPS ? c0 : 0.5 * c0 * (1.0 + 2.0 * x / sinh(2.0 * x));
+  const double t2 = t0 * t0;
+  const double a = t0 - x * (1.0 - t2);
+  const double dvg = a * a + 4.0 * (x * x) * t2 * (1.0 - t2);
+  const double xnl1 = (9.0 * (t2 * t2) - 10.0 * t2 + 9.0) / (8.0 * (t2 * t0));
+  const double b = 2.0 * vg - 0.5 * c0;
+  const double xnl2 = (b * b / (c_dc.G * dep - vg * vg) + 1.0) / x;
+  const double xnl = xnl1 - xnl2;
+  return xnl * xnl / (dvg * ((t2 * t2) * (t2 * t2)));
+}
+__device__ double transf_snl_enh(double xk0, double dep, double xnu, double sig_th) {
+  const double EPS = 0.0001, DKMAX = 40.0, XKDMIN = 0.75, TMIN = 0.1, TMAX = 10.0;
+  if (!(dep < c_dc.bathymax && dep > 0.0)) return 1.0;
+  double x = xk0 * dep;
+  if (x > DKMAX) return 1.0;
+  const double xk = dmax(xk0, XKDMIN / dep);
+  x = xk * dep;
+  const double t0 = tanh(x), t2 = t0 * t0, om = sqrt(c_dc.G * xk * t0), c0 = om / xk, cs2 = c_dc.G * dep;
+  const double vg = x < EPS ? c0 : 0.5 * c0 * (1.0 + 2.0 * x / sinh(2.0 * x));
+  const double vg2 = vg * vg;
+  const double a = t0 - x * (1. - t2);
+  const double dvg = a * a + 4.0 * (x * x) * t2 * (1.0 - t2);
+  const double xnl1 = (9.0 * (t2 * t2) - 10.0 * t2 + 9.0) / (8.0 * t2 * t0);
+  const double b = 2.0 * vg - 0.5 * c0;
+  const double xnl2 = (b * b / (c_dc.G * dep - vg2) + 1.0) / x;
+  const double e = 2.0 * c0 + vg * (1.0 - t2);
+  const double xnl4 = 1. / (4.0 * t0) * (e * e) / (cs2 - vg2);
+  const double alp = (1. - vg2 / cs2) * (c0 * c0) / vg2;
+  const double zfac = (sig_th * sig_th) / (sig_th * sig_th + alp * (xnu * xnu));
+  const double xnl = xnl1 - xnl2 + zfac * xnl4;
+  const double t4 = (t2 * t2) * (t2 * t2);
+  return dmax(dmin(TMAX, xnl * xnl / (dvg * t4)), TMIN);
+}
+
+__global__ void __launch_bounds__(128) k_enh(ImplDev d, long long p0, long long np) {
+  const long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= p0 + np) return;
+  const int A = c_dc.A, F = c_dc.F;
+  const long long n = d.npts;
+  const double dep = d.f.depth[p];
+  double xnu = 0.0, sig_th = 0.0;
+  if (d.isnonlin == 2) {
+    const long long c = p / d.P;
+    const int i = (int)(p - c * d.P);
+    const size_t kstr = (size_t)d.P;
+    const double* hi = d.f.fl1 + (size_t)i + (size_t)d.P * A * F * (size_t)c;
+    const double* lo = hi;
+    int mlo = 0;
+    if (d.lo_on) { const int il = (p < d.nloc) ? i : 0; lo = d.fl_lo + (size_t)il + (size_t)d.P * A * d.lo_F * (size_t)c; mlo = d.Fr; }
+    const double fac = d.scr[S_FAC * n + p];
+    double snw, csw;
+    sincos(d.f.wdwave[p], &snw, &csw);
+    const double flmc = (1. - 0.9 * dmin(d.f.cicover[p], 0.99)) * c_dc.flmin;
+    auto spec = [&](int m, int k) {      // FL1 as SNONLIN sees it: SDEPTHLIM applied, last frequency floored at FLM (sinflx.F90:126-129)
+      double f = dmax(__ldg((m < mlo ? lo : hi) + ((size_t)m * A + k) * kstr) * fac, c_dc.EPSMIN);
+      if (m == F - 1) f = dmax(f, flmc * sq(dmax(0.0, c_dc.COSTH[k] * csw + c_dc.SINTH[k] * snw)));
+      return f;
+    };
+    const double ZEPS = 10.0 * 2.220446049250313e-16;
+    const double frl = c_dc.FR[F - 1];
+    const double DELT25 = c_dc.WETAIL * frl * c_dc.DELTH, COEF_FR = c_dc.WP1TAIL * c_dc.DELTH * (frl * frl);
+    const double COEF_FR2 = 0.5 * c_dc.DELTH * (frl * frl * frl);     // WP2TAIL = 0.5 (yowfred.F90:54)
+    const int NSH = 1 + (int)(log(1.5) / log(c_dc.FRATIO));
+    double sum0 = ZEPS, sum1 = 0.0, sum2 = 0.0, temp = 0.0, xmax = 0.0;
+    int mmax = 2;
+    for (int m = 0; m < F; ++m) {
+      temp = spec(m, 0);
+      if (m >= 1 && m <= F - 2 && temp > xmax) { mmax = m + 1; xmax = temp; }
+      for (int k = 1; k < A; ++k) {
+        const double f = spec(m, k);
+        temp = temp + f;
+        if (m >= 1 && m <= F - 2 && f > xmax) { mmax = m + 1; xmax = f; }
+      }
+      sum0 = sum0 + temp * c_dc.DFIM[m]; sum1 = sum1 + temp * c_dc.DFIMFR[m]; sum2 = sum2 + temp * (c_dc.DFIM[m] * (c_dc.FR[m] * c_dc.FR[m]));
+    }
+    sum0 = sum0 + DELT25 * temp; sum1 = sum1 + COEF_FR * temp; sum2 = sum2 + COEF_FR2 * temp;
+    xnu = sum0 > ZEPS ? sqrt(dmax(ZEPS, sum2 * sum0 / (sum1 * sum1) - 1.0)) : ZEPS;
+    double s1 = ZEPS, s2 = 0.0, sum_s = 0.0, sum_c = ZEPS;
+    for (int M = max(1, mmax - NSH); M <= min(F, mmax + NSH); ++M) {
+      for (int k = 0; k < A; ++k) { const double f = spec(M - 1, k); sum_s = sum_s + c_dc.SINTH[k] * f; sum_c = sum_c + c_dc.COSTH[k] * f; }
+      const double thmean = atan2(sum_s, sum_c);
+      for (int k = 0; k < A; ++k) {
+        const double f = spec(M - 1, k);
+        s1 = s1 + f * c_dc.DFIM[M - 1];
+        s2 = s2 + cos(c_dc.TH[k] - thmean) * f * c_dc.DFIM[M - 1];
+      }
+    }
+    sig_th = s1 > ZEPS ? sqrt(2.0 * (1.0 - s2 / s1)) : 0.0;
+  }
+  for (int mc = 0; mc < c_dc.MLSTHG; ++mc) {
+    double xk;
+    if (mc < F) xk = d.f.wavnum[idx3(d, p, mc)];
+    else {      // XK = GM1*(ZPIFR(NFRE)*FRATIO**(MC-NFRE))**2 (snonlin.F90:145, 157)
+      double pw = 1.0;
+      for (int j = 0; j < mc + 1 - F; ++j) pw = pw * c_dc.FRATIO;
+      const double w = c_dc.ZPIFR[F - 1] * pw;
+      xk = c_dc.GM1 * (w * w);
+    }
+    d.enh[(size_t)mc * n + p] = d.isnonlin == 1 ? dmax(dmin(10.0, transf_enh(xk, dep)), 0.1) : transf_snl_enh(xk, dep, xnu, sig_th);
+  }
+}
+
 int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage, cudaStream_t st) {
   if (np <= 0) return 0;
   const int A = d.A;
@@ -3061,6 +3182,7 @@ int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage
       else { k_point<false, 1, true><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<false, 2, true><<<nb, KP_NTH, smp, st>>>(d, p0, np); }
     } else if (d.iphys == 1) { k_point<true, 1, false><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<true, 2, false><<<nb, KP_NTH, smp, st>>>(d, p0, np); }
     else { k_point<false, 1, false><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<false, 2, false><<<nb, KP_NTH, smp, st>>>(d, p0, np); }
+    if (d.isnonlin != 0) k_enh<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(d, p0, np);
   } else if (stage == 1) {
     // two grid points per thread (16-byte shared / global accesses) need an even NPROMA and an even first point
     const uintptr_t al = (uintptr_t)d.f.fl1 | (uintptr_t)d.f.xllws | (uintptr_t)d.fldin | (uintptr_t)d.fl_lo;

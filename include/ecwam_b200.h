@@ -42,7 +42,7 @@ typedef struct ecwam_b200_params {
   int nfre;        /* YOWPARAM NFRE   (physics frequencies, 36)                         */
   int nfre_red;    /* YOWPARAM NFRE_RED (propagated frequencies)                        */
   int iphys;       /* YOWSTAT IPHYS: 0 = Janssen/WAM4, 1 = Ardhuin et al. 2010          */
-  int isnonlin;    /* YOWSTAT ISNONLIN (0 only)                                         */
+  int isnonlin;    /* YOWSTAT ISNONLIN 0, 1, 2 (snonlin.F90:127-163; 1, 2: k_enh)          */
   int idamping;    /* YOWSTAT IDAMPING (SINPUT_JAN)                                     */
   int irefra;      /* YOWSTAT IREFRA (0 none, 1 depth, 2 current, 3 depth + current refraction)   */
   int icase;       /* YOWSTAT ICASE (1 = spherical, only)                               */

@@ -401,7 +401,7 @@ def test_cfl_violation_is_reported(built):
 def test_unsupported_switches_are_rejected(built):
     from ecwam_b200 import synth
     g = synth.make_grid(8, "aqua")
-    for kw in (dict(irefra=4), dict(irefra=2, ifrelfmax=5), dict(isnonlin=1), dict(lciwa=1), dict(lciwa=2)):
+    for kw in (dict(irefra=4), dict(irefra=2, ifrelfmax=5), dict(isnonlin=3), dict(lciwa=1), dict(lciwa=2)):
         s = M.WamSetup(g, nproc=1, **kw)
         with pytest.raises(L.EcwamError):
             M.WamIntgr(s, 0)
@@ -564,3 +564,25 @@ def test_full_size_o320_against_oracle(built):
     hs_o, fm_o = o.hs_fm()
     hs_g, fm_g = M.hs_fm(s, a)
     assert relerr(hs_g, hs_o[w.own]) <= RTOL_FIELD
+
+
+@pytest.mark.parametrize("isnonlin", [1, 2])
+@pytest.mark.parametrize("case,mode", [("o48like", None), ("o640like", None), ("o320like", "dp"), ("o48_iphys0", "generic"), ("o640like", "sweep")])
+def test_shallow_water_dia_scaling_matches_oracle(built, monkeypatch, case, mode, isnonlin):
+    """ISNONLIN = 1, 2 (snonlin.F90:138-163): ENH(IJ,MC) per centre frequency from TRANSF / TRANSF_SNL + PEAK_ANG (k_enh) instead of
+    the per-point factor, read by every instance of the frequency sweep.  Intermediate depths (10 - 80 m, kd ~ 1 around the peak) in
+    half of the domain make the factor differ from 1 and from ISNONLIN = 0."""
+    if mode:
+        monkeypatch.setenv("ECWAM_B200_STENCIL", mode)
+
+    def shelf(g):
+        n = g.depth.size
+        g.depth[n // 2:] = 10.0 + 70.0 * ((np.arange(n - n // 2) * 37) % 101) / 100.0
+    g, o, f, fl = make_oracle(case, grid_hook=shelf, isnonlin=isnonlin)
+    _, o0, _, _ = make_oracle(case, grid_hook=shelf, isnonlin=0)
+    _, s, w = make_gpu(case, grid_hook=shelf, isnonlin=isnonlin)
+    for _ in range(3):
+        assert o.step() == 0 and w.step() == 0 and o0.step() == 0
+    w.synchronize()
+    check_state(w, o)
+    assert relerr(o.get_fl1(), o0.get_fl1()) > 1e-6          # the mode matters in this case
