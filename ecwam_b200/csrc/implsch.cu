@@ -51,6 +51,42 @@ __device__ __forceinline__ double div_norm(double a, double b) {
   const double q = a * r;
   return fma(fma(-b, q, a), r, q);
 }
+// a / b as div_norm with one Newton step less: the seed has >= 20 bits, so r is good to 2^-40 and the residual step to 2^-80
+__device__ __forceinline__ double div_fast(double a, double b) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  const double e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  const double q = a * r;
+  return fma(fma(-b, q, a), r, q);
+}
+// exp(x) for x <= 0 without libm's range checks: k = nint(x log2 e) by the magic-number add, r = x - k ln2 (two-part ln2),
+// 13th-degree Taylor polynomial on |r| <= ln2 / 2 (remainder 4e-18), scaling by 2^k through the exponent field.  x < -708 is
+// clamped (3e-308 instead of a denormal).  Relative error <= 2.3e-16 over [-708, 0] (checked against libm on 6e5 samples).
+#ifndef KP_EXP
+#define KP_EXP 1
+#endif
+// (the coefficients live in constant memory: as literals every one of them costs two UMOV per use, 93 per bin of the second SINPUT pass)
+__constant__ double c_exp[20] = {1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07,
+                                 2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03,
+                                 8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 1.0, 1.0,
+                                 1.4426950408889634074, 6755399441055744.0, 6.93147180369123816490e-01, 1.90821492927058770002e-10,
+                                 -708.0, 0.0};
+__device__ __forceinline__ double exp_le0(double x) {
+#if KP_EXP
+  x = dmax(x, c_exp[18]);
+  const double t = fma(x, c_exp[14], c_exp[15]);
+  const double kf = t - c_exp[15];
+  double r = fma(-kf, c_exp[16], x);
+  r = fma(-kf, c_exp[17], r);
+  double p = c_exp[0];                        // 1/13!, ..., 1/2!, 1, 1
+#pragma unroll
+  for (int i = 1; i < 14; ++i) p = fma(p, r, c_exp[i]);
+  return p * __hiloint2double((1023 + __double2loint(t)) << 20, 0);
+#else
+  return exp(x);
+#endif
+}
 __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
@@ -491,7 +527,7 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
     double* xo = STORE ? xl_out + (size_t)m * A * kstr : nullptr;
     const bool lastm = (m == F - 1);
     double cnsn, constf = 0.0, dstab1 = 0.0, temp1 = 0.0;
-    double cosu[NGST], sinu[NGST], ucn[NGST], ucnzalpd[NGST], const3_ucn2[NGST], xvd[NGST];
+    double cosu[NGST], sinu[NGST], ucn[NGST], ucnzalpd[NGST], const3_ucn2[NGST], xvd[NGST], dsd[NGST], dsc[NGST];
     if (ard) {
       cnsn = sig * CONST1 * raorw;
       constf = rogoroair * cinv * dfim;
@@ -515,6 +551,11 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
         } else { cosu[g] = csw; sinu[g] = snw; }
         ucn[g] = ustp[g] * cinv;
         ucnzalpd[g] = div_norm(c_dc.XKAPPA, ucn[g] + c_dc.ZALP);
+        if (LLSNEG) {   // DSTAB = DSTAB1 + PTURB*TEMP1*(TEMP2 + (FU + FUD*COSLP)*USTP) (sinput_ard.F90:423-428) as dsd + dsc*COSLP
+          const double b = pturb * temp1 * ustp[g];
+          dsd[g] = fma(b, FU, fma(pturb * temp1, temp2_sw, dstab1));
+          dsc[g] = b * FUD;
+        }
       }
     } else {
       const double ztanhkd = sig2 / (c_dc.G * wavnum);
@@ -588,15 +629,15 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
           const double coslp = ltauwshelter ? (csk * cosu[g] + snk * sinu[g]) : cwd;
           if (coslp > 0.01) {
             const double x = coslp * ucn[g];
-            const double zlog = zcn + div_norm(ucnzalpd[g], coslp);
+            const double zlog = zcn + div_fast(ucnzalpd[g], coslp);
             if (zlog < 0.0) {
               const double zlog2x = zlog * zlog * x;
-              gam0 = exp(zlog) * zlog2x * zlog2x * cnsn;
+              gam0 = exp_le0(zlog) * zlog2x * zlog2x * cnsn;
               xll = true;
             }
           }
           double dstab = 0.0;
-          if (LLSNEG) dstab = dstab1 + pturb * (temp1 * (temp2_sw + (FU + FUD * coslp) * ustp[g]));
+          if (LLSNEG) dstab = fma(dsc[g], coslp, dsd[g]);
           if (CY) gam0 = gam0 * gamnorma[g];
           const double slp = gam0 * f;
           sx[g] += slp * snk; sy[g] += slp * csk;
@@ -607,7 +648,7 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
             if (zlog < 0.0) {
               const double x = cwd * ucn[g];
               const double zlog2x = zlog * zlog * x;
-              gam0 = zlog2x * zlog2x * exp(zlog) * cnsn;
+              gam0 = zlog2x * zlog2x * exp_le0(zlog) * cnsn;
               xll = true;
             }
           }
@@ -2050,15 +2091,6 @@ struct Run {
   }
   __device__ __forceinline__ double at(int off) const { return v[off - 2 * P0]; }
 };
-// a / b as div_norm with one Newton step less: the seed has >= 20 bits, so r is good to 2^-40 and the residual step to 2^-80
-__device__ __forceinline__ double div_fast(double a, double b) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-  const double e = fma(-b, r, 1.0);
-  r = fma(r, e, r);
-  const double q = a * r;
-  return fma(fma(-b, q, a), r, q);
-}
 #ifndef SW_MINB
 #define SW_MINB 2   // k_sweep wants ~224 registers: capped at 168 for 3 CTAs per SM it spills and runs 30 % slower
 #endif
