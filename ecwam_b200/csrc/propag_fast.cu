@@ -301,42 +301,52 @@ __global__ void __launch_bounds__(PQ_NTH, PQ_MINB) propags2_q_kernel(PropDev d, 
     q.t = tanph * g0;
     if (REFRA) q.omos = __ldg(d.omos + i + (size_t)P * (m + (size_t)d.F * c));
   };
-  // ---- the pipeline: iteration = (frequency, direction pair), flattened
+  // ---- the pipeline: iteration = (frequency, direction pair), flattened.  The seven source pointers (own + five neighbours) and
+  // the destination pointer RUN with the iteration (one IMAD.WIDE each: + two directions, or + the rest of the row at the last
+  // pair of a frequency) instead of being rebuilt from (frequency, direction) every time: ~130 of the 351 instructions of an
+  // iteration were 64-bit address arithmetic, in a kernel that issues at 59 % with the FP64 pipe at 26 %.
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(stage) + threadIdx.x * 8u;
-  auto issue = [&](int im, int ip, int st) {     // im: frequency - mb, ip: pair of the quadrant
-    const int ka = k0 + 2 * ip, kb = min(ka + 1, k1 - 1);
-    const unsigned sa = sbase + (unsigned)st * (PQ_NV * PQ_NTH * 8);
-    const double* o = ps + (size_t)im * PA;
-    cpa8(sa + 0 * PQ_NTH * 8, o + (size_t)ka * P);
-    cpa8(sa + 1 * PQ_NTH * 8, o + (size_t)kb * P);
-    cpa8(sa + 2 * PQ_NTH * 8, o + (size_t)c_pf.kpm_m[ka] * P);
-    cpa8(sa + 3 * PQ_NTH * 8, o + (size_t)c_pf.kpm_p[kb] * P);
-    const double* n1 = p_lon + (size_t)im * t_lon;
-    cpa8(sa + 4 * PQ_NTH * 8, n1 + (size_t)ka * s_lon); cpa8(sa + 5 * PQ_NTH * 8, n1 + (size_t)kb * s_lon);
-    const double* n2 = p_la1 + (size_t)im * t_la1;
-    cpa8(sa + 6 * PQ_NTH * 8, n2 + (size_t)ka * s_la1); cpa8(sa + 7 * PQ_NTH * 8, n2 + (size_t)kb * s_la1);
-    const double* n3 = p_la2 + (size_t)im * t_la2;
-    cpa8(sa + 8 * PQ_NTH * 8, n3 + (size_t)ka * s_la2); cpa8(sa + 9 * PQ_NTH * 8, n3 + (size_t)kb * s_la2);
-    const double* n4 = p_c1 + (size_t)im * t_c1;
-    cpa8(sa + 10 * PQ_NTH * 8, n4 + (size_t)ka * s_c1); cpa8(sa + 11 * PQ_NTH * 8, n4 + (size_t)kb * s_c1);
-    const double* n5 = p_c2 + (size_t)im * t_c2;
-    cpa8(sa + 12 * PQ_NTH * 8, n5 + (size_t)ka * s_c2); cpa8(sa + 13 * PQ_NTH * 8, n5 + (size_t)kb * s_c2);
-    asm volatile("cp.async.commit_group;\n" ::);
-  };
   const int nm = me - mb;
   const int NI = nm * npair;
-  load_cg(mb);
-  int im_i = 0, ip_i = 0, st_i = 0;  // issue side: position and stage of the next iteration to issue
+  const int last = npair - 1;
+  const double* io = ps + (size_t)k0 * P;
+  const double* i1 = p_lon + (size_t)k0 * s_lon;
+  const double* i2 = p_la1 + (size_t)k0 * s_la1;
+  const double* i3 = p_la2 + (size_t)k0 * s_la2;
+  const double* i4 = p_c1 + (size_t)k0 * s_c1;
+  const double* i5 = p_c2 + (size_t)k0 * s_c2;
+  const int eo = PA - last * 2 * P, e1 = t_lon - last * 2 * s_lon, e2 = t_la1 - last * 2 * s_la1, e3 = t_la2 - last * 2 * s_la2,
+            e4 = t_c1 - last * 2 * s_c1, e5 = t_c2 - last * 2 * s_c2;
+  int ip_i = 0, st_i = 0;            // issue side: pair and stage of the next iteration to issue
   auto issue_next = [&](int itn) {
     if (itn < NI) {
-      issue(im_i, ip_i, st_i);
-      if (++ip_i == npair) { ip_i = 0; ++im_i; }
-    } else asm volatile("cp.async.commit_group;\n" ::);     // keep one group per iteration so that wait_group counts stay fixed
+      const int ka = k0 + 2 * ip_i;
+      const bool pr = ka + 1 < k1;
+      const int kb = pr ? ka + 1 : ka;
+      const unsigned sa = sbase + (unsigned)st_i * (PQ_NV * PQ_NTH * 8);
+      cpa8(sa + 0 * PQ_NTH * 8, io);
+      cpa8(sa + 1 * PQ_NTH * 8, io + (pr ? P : 0));
+      cpa8(sa + 2 * PQ_NTH * 8, io + (c_pf.kpm_m[ka] - ka) * P);
+      cpa8(sa + 3 * PQ_NTH * 8, io + (c_pf.kpm_p[kb] - ka) * P);
+      cpa8(sa + 4 * PQ_NTH * 8, i1); cpa8(sa + 5 * PQ_NTH * 8, i1 + (pr ? s_lon : 0));
+      cpa8(sa + 6 * PQ_NTH * 8, i2); cpa8(sa + 7 * PQ_NTH * 8, i2 + (pr ? s_la1 : 0));
+      cpa8(sa + 8 * PQ_NTH * 8, i3); cpa8(sa + 9 * PQ_NTH * 8, i3 + (pr ? s_la2 : 0));
+      cpa8(sa + 10 * PQ_NTH * 8, i4); cpa8(sa + 11 * PQ_NTH * 8, i4 + (pr ? s_c1 : 0));
+      cpa8(sa + 12 * PQ_NTH * 8, i5); cpa8(sa + 13 * PQ_NTH * 8, i5 + (pr ? s_c2 : 0));
+      const bool rowend = ip_i == last;
+      io += rowend ? eo : 2 * P;
+      i1 += rowend ? e1 : 2 * s_lon; i2 += rowend ? e2 : 2 * s_la1; i3 += rowend ? e3 : 2 * s_la2;
+      i4 += rowend ? e4 : 2 * s_c1; i5 += rowend ? e5 : 2 * s_c2;
+      ip_i = rowend ? 0 : ip_i + 1;
+    }
+    asm volatile("cp.async.commit_group;\n" ::);     // one group per iteration so that the wait_group counts stay fixed
     if (++st_i == PQ_ST) st_i = 0;
   };
+  load_cg(mb);
 #pragma unroll
   for (int pre = 0; pre < PQ_ST - 1; ++pre) issue_next(pre);
   int im = 0, ip = 0, st_c = 0;      // compute side
+  double* o = pd + (size_t)k0 * P;   // destination of direction ka of the iteration being computed
   for (int it = 0; it < NI; ++it) {
     issue_next(it + PQ_ST - 1);
     asm volatile("cp.async.wait_group %0;\n" ::"n"(PQ_ST - 1) : "memory");
@@ -354,15 +364,17 @@ __global__ void __launch_bounds__(PQ_NTH, PQ_MINB) propags2_q_kernel(PropDev d, 
     const double a1 = sv[4 * PQ_NTH], b1 = sv[5 * PQ_NTH], a2 = sv[6 * PQ_NTH], b2 = sv[7 * PQ_NTH];
     const double a3 = sv[8 * PQ_NTH], b3 = sv[9 * PQ_NTH], a4 = sv[10 * PQ_NTH], b4 = sv[11 * PQ_NTH];
     const double a5 = sv[12 * PQ_NTH], b5 = sv[13 * PQ_NTH];
-    double* o = pd + (size_t)im * PA;
     // KPM(ka,+1) = kb and KPM(kb,-1) = ka inside a quadrant; a single last direction takes its own KPM(+1) value (slot bp)
     const double ra = ctu_bin<REFRA>(q, ka, idp, a0, a1, a2, a3, a4, a5, am, pair ? b0 : bp);
-    o[(size_t)ka * P] = ra;
+    o[0] = ra;
     if (pair) {
       const double rb = ctu_bin<REFRA>(q, kb, idp, b0, b1, b2, b3, b4, b5, a0, bp);
-      o[(size_t)kb * P] = rb;
+      o[P] = rb;
     }
-    if (++ip == npair) { ip = 0; ++im; }
+    const bool rowend = ip == last;
+    o += rowend ? eo : 2 * P;
+    ip = rowend ? 0 : ip + 1;
+    im += rowend ? 1 : 0;
     if (++st_c == PQ_ST) st_c = 0;
   }
 }
