@@ -2559,6 +2559,9 @@ __global__ void __launch_bounds__(sw_threads(TA, NPT), SW_MINB) k_sweep(ImplDev 
 #ifndef SW_RP
 #define SW_RP 96     // registers per producer thread
 #endif
+#ifndef SW_RUNPTR
+#define SW_RUNPTR 1  // global row addresses of the consumers: 0 rebuilt from the row index (36.1 ms), 1 one running offset (35.6), 2 running pointers (spills: 44.2)
+#endif
 #ifndef SW_RC
 #define SW_RC 160    // registers per consumer thread   (SW_RP + SW_RC <= 256: 2 CTAs of 2 x 128 threads per SM)
 #endif
@@ -2839,6 +2842,22 @@ __global__ void __launch_bounds__(2 * sw_threads(TA, NPT), 2) k_sweep_ws(ImplDev
       for (int i = 0; i < 2; ++i) { asl[x][i] = 0.0; afl[x][i] = 0.0; }
     V fmij;
     fmij.v[0] = fmij.v[1] = 0.0;
+    // the global rows of a step through ONE running offset (+ one row per step) and a running pointer for the scalar planes:
+    // rebuilt from the row index they cost ~100 of the consumers' 596 instructions per step in 64-bit multiplies.
+    // roff: element offset of row st-4 (negative until row 0: not dereferenced before); row st+5 = roff + 9 rows.
+#if SW_RUNPTR == 1
+    ptrdiff_t roff = -9 * (ptrdiff_t)rstr;
+    const double* src_lo9 = src_lo + 9 * rstr;
+    const double* src_hi9 = src_hi + 9 * rstr;
+    const double* g_tq = tq_g - 6 * (ptrdiff_t)n;
+#elif SW_RUNPTR == 2
+    const double* g_in = src_in - 9 * (ptrdiff_t)rstr;
+    const double* g_xl = src_xl - 9 * (ptrdiff_t)rstr;
+    double* g_dst = dst - 9 * (ptrdiff_t)rstr;
+    const double* g_lo = src_lo;
+    const double* g_hi = src_hi;
+    const double* g_tq = tq_g - 6 * (ptrdiff_t)n;
+#endif
 
 #pragma unroll 1
     for (int st = -5; st < MLSTHG; ++st) {
@@ -2848,6 +2867,36 @@ __global__ void __launch_bounds__(2 * sw_threads(TA, NPT), 2) k_sweep_ws(ImplDev
       const bool fin = rfin >= 0 && rfin < F;
       // row loads of this step: group 1 = wind-input (and XLLWS) row of the row that is finished, group 2 = FL1 row st+5 for the
       // ring and the per-(point, frequency) scalars of row st-1
+#if SW_RUNPTR == 1
+      if (fin) {
+        const double* g = src_in + roff;
+        cp_async<8>(smb + me_s + L.SSB, g); cp_async<8>(smb + me_s + L.SSB + L.SSB / 2, g + P);
+        if (LWFLUX) { const double* gx = src_xl + roff; cp_async<8>(smb + me_s + 2 * L.SSB, gx); cp_async<8>(smb + me_s + 2 * L.SSB + L.SSB / 2, gx + P); }
+      }
+      cp_async_commit();
+      if (rnew < F) {
+        const double* g = (rnew < mlo ? src_lo9 : src_hi9) + roff;
+        cp_async<8>(smb + me_s, g); cp_async<8>(smb + me_s + L.SSB / 2, g + P);
+      }
+      if (rtb >= 0 && rtb < F && tq_on) cp_async<8>(smb + tq_s + (unsigned)((rtb & 7) * TQ_N) * PRB, g_tq);
+      cp_async_commit();
+      double* const o_row = dst + roff;
+      roff += (ptrdiff_t)rstr; g_tq += n;
+#elif SW_RUNPTR == 2
+      if (fin) {
+        cp_async<8>(smb + me_s + L.SSB, g_in); cp_async<8>(smb + me_s + L.SSB + L.SSB / 2, g_in + P);
+        if (LWFLUX) { cp_async<8>(smb + me_s + 2 * L.SSB, g_xl); cp_async<8>(smb + me_s + 2 * L.SSB + L.SSB / 2, g_xl + P); }
+      }
+      cp_async_commit();
+      if (rnew < F) {
+        const double* g = rnew < mlo ? g_lo : g_hi;
+        cp_async<8>(smb + me_s, g); cp_async<8>(smb + me_s + L.SSB / 2, g + P);
+      }
+      if (rtb >= 0 && rtb < F && tq_on) cp_async<8>(smb + tq_s + (unsigned)((rtb & 7) * TQ_N) * PRB, g_tq);
+      cp_async_commit();
+      double* const o_row = g_dst;
+      g_in += rstr; g_xl += rstr; g_dst += rstr; g_lo += rstr; g_hi += rstr; g_tq += n;
+#else
       if (fin) {
         const double* g = src_in + (size_t)rfin * rstr;
         cp_async<8>(smb + me_s + L.SSB, g); cp_async<8>(smb + me_s + L.SSB + L.SSB / 2, g + P);
@@ -2860,6 +2909,8 @@ __global__ void __launch_bounds__(2 * sw_threads(TA, NPT), 2) k_sweep_ws(ImplDev
       }
       if (rtb >= 0 && rtb < F && tq_on) cp_async<8>(smb + tq_s + (unsigned)((rtb & 7) * TQ_N) * PRB, tq_g + (size_t)rtb * n);
       cp_async_commit();
+      double* const o_row = dst + (size_t)rfin * rstr;
+#endif
       mbar_wait_backoff(bar_full + 8u * b, u & 1u);
       const unsigned hb = me_h + b * 3u * L.SSB;
       V tot_sl, tot_fl;
@@ -2982,7 +3033,7 @@ __global__ void __launch_bounds__(2 * sw_threads(TA, NPT), 2) k_sweep_ws(ImplDev
             a_tu.v[i] += cst * fnv.v[i];
           }
         }
-        if (dost) { double* o = dst + (size_t)r * rstr; o[0] = fnv.v[0]; o[P] = fnv.v[1]; }
+        if (dost) { o_row[0] = fnv.v[0]; o_row[P] = fnv.v[1]; }
       }
       cp_async_wait<0>();          // FL1 row st+5 (own slot) and, for the loader lanes, the scalars of row st-1
       if (rnew < F) {              // depth-limited (+ floored at NFRE) row st+5 -> ring slot of row st-4 (last read just above)
