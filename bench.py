@@ -30,9 +30,14 @@ METRIC = "grid-point spectra/s per timestep (IMPLSCH+PROPAGS2)"
 # From the committed ncu --set full capture of the bench workload (profiles/, O640, 1 GPU): DRAM bytes per launch
 # (dram__bytes_read.sum + dram__bytes_write.sum) and executed FP64 flops per grid point and launch
 # (2 x smsp__sass_thread_inst_executed_op_dfma_pred_on + ..._dmul_pred_on + ..._dadd_pred_on, divided by the points of the launch).
-NCU_SOURCE = "profiles/r02_ncu_summary_O640.txt"
-NCU_DRAM_BYTES = {("O640", 1): {"implsch_stencil": 36.196e9, "implsch_point": 53.654e9, "propags2": 19.83e9}}
-NCU_FP64_FLOP_PER_POINT = {36: {"implsch_stencil": 289.2e3, "implsch_point": 157.0e3, "propags2": 46.5e3}}
+NCU_SOURCE = "profiles/r02y_ncu_summary_O640.txt"
+NCU_DRAM_BYTES = {("O640", 1): {"implsch_stencil": 36.189e9, "implsch_point": 53.663e9, "propags2": 23.030e9}}
+NCU_FP64_FLOP_PER_POINT = {36: {"implsch_stencil": 290.8e3, "implsch_point": 139.7e3, "propags2": 46.9e3}}
+# pipe utilisation of the same capture (sm__inst_executed_pipe_fp64 / sm__issue_active, % of peak; the FP64 pipe takes a warp
+# instruction every 2 cycles, so issue-cycle occupancy of a scheduler = issue% + fp64% / 2 ... of the cycles it could issue in)
+NCU_PIPES = {36: {"implsch_stencil": {"fp64_pipe_pct": 35.5, "issue_active_pct": 56.6, "warps_active_pct": 24.4, "ms_under_ncu": 35.65},
+                  "implsch_point": {"fp64_pipe_pct": 39.5, "issue_active_pct": 47.7, "warps_active_pct": 17.9, "ms_under_ncu": 17.35},
+                  "propags2": {"fp64_pipe_pct": 25.7, "issue_active_pct": 56.9, "warps_active_pct": 24.6, "ms_under_ncu": 7.98}}}
 UNIT = "spectra/s"
 
 
@@ -459,9 +464,11 @@ def run_gpu(args):
             dist.all_reduce(bts, op=dist.ReduceOp.SUM)
         e2e_res = {"value": npts_total * Ke / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(bts[0].item()),
                    "d2h_bytes_per_step": int(bts[1].item()), "steps": Ke,
-                   "what": "ecwam_b200_wamintgr_forced: spectrum and fields resident on the device (as in the reference's GPU build, "
-                           "wamintgr_loki_gpu.F90:141-201); per step the 8 FF_NEXT forcing fields host->device from pinned buffers, NEWWIND, "
-                           "PROPAG_WAM + IMPLSCH, the 20 integrated 1-D fields + MIJ device->host"}
+                   "what": "ecwam_b200_wamintgr_forced: spectrum and fields stay on the device between steps (FIELD_API keeps the device "
+                           "copy current, wamintgr_loki_gpu.F90:123-129,146-157); per step the 8 FF_NEXT forcing fields host->device from "
+                           "pinned buffers, NEWWIND, PROPAG_WAM + IMPLSCH, the 20 integrated 1-D fields + MIJ device->host. NOT included: "
+                           "the asynchronous FL1 device->host sync the reference's GPU build queues after IMPLSCH (:193) -- the `e2e` "
+                           "flavour above moves FL1 both ways every step"}
     # what the report below needs of the headline case (it is released before the extra configurations run)
     class _W:
         pass
@@ -516,6 +523,8 @@ def run_gpu(args):
             tf = flop[k] * pts_rank / (kern[k] * 1e-3) / 1e12
             e["fp64"] = {"achieved": tf, "peak": f64_peak, "unit": "TFLOP/s", "frac": tf / f64_peak, "executed_flop_per_point": flop[k]}
         e["bound"] = "hbm" if k == "propags2" else "fp64"
+        if k in NCU_PIPES.get(A, {}) and args.workload == "O640" and world == 1:
+            e["ncu"] = dict(NCU_PIPES[A][k], source=NCU_SOURCE)
         roofs.append(e)
     roof = None
     if dom:
