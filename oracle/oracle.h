@@ -190,6 +190,10 @@ struct Fields {
   ArrD WSEMEAN, WSFMEAN, USTOKES, VSTOKES, STRNMS, TAUXD, TAUYD, TAUOCXD, TAUOCYD, TAUOC, TAUICX, TAUICY, PHIOCD,
       PHIEPS, PHIAW;
   ArrI MIJ;
+  // test hook (orc_capture): the inputs of WNFLUXES that are internal to IMPLSCH, kept from the last implsch_chunk call
+  bool capture = false;
+  ArrD DBG_SSOURCE;            // (P,A,F,C)
+  ArrD DBG_EM, DBG_F1, DBG_PHIWA;   // (P,C): EMEAN, F1MEAN of the first FKMEAN, PHIWA of the second STRESSO
   // land-point dispersion (WVPRPT_LAND, initdpthflds.F90:80-88)
   ArrD LAND_WAVNUM, LAND_CGROUP, LAND_OMOSNH2KD;
 };

@@ -81,6 +81,8 @@ def _lib(fast=False):
         lib.orc_snonlin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_term.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.orc_stresso.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.orc_capture.argtypes = [C.c_void_p, C.c_int]
+        lib.orc_get_capture.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_outbs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p]
         lib.orc_outwnorm.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.orc_implsch.argtypes = [C.c_void_p]
@@ -270,6 +272,17 @@ class Oracle:
         if self.lib.orc_stresso(self.h, sl.ctypes.data, spos.ctypes.data, out.ctypes.data) != 0:
             raise RuntimeError("orc_stresso failed")
         return sl, spos, out
+
+    def capture(self, on=True):
+        """Keep the IMPLSCH-internal inputs of WNFLUXES (SSOURCE, EMEAN, F1MEAN, PHIWA) of the next implsch() / step()."""
+        self.lib.orc_capture(self.h, int(on))
+
+    def captured(self):
+        ss = np.empty((self.cfg.nfre, self.cfg.nang, self.niblo))
+        em, f1, ph = np.empty(self.niblo), np.empty(self.niblo), np.empty(self.niblo)
+        if self.lib.orc_get_capture(self.h, ss.ctypes.data, em.ctypes.data, f1.ctypes.data, ph.ctypes.data) != 0:
+            raise RuntimeError("orc_get_capture: capture() was not switched on")
+        return ss, em, f1, ph
 
     def outwnorm(self, global_norm=True):
         """OUTWNORM/MPMINMAXAVG on the last outbs(): rows = columns, (average, minimum, maximum, count)."""

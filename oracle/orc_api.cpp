@@ -222,6 +222,35 @@ int orc_set_fl1(void* h, const double* v) { return spec_io((Model*)h, false, con
 int orc_get_fl1(void* h, double* v) { return spec_io((Model*)h, false, v, false); }
 int orc_get_xllws(void* h, double* v) { return spec_io((Model*)h, true, v, false); }
 
+// test hook: keep WNFLUXES' IMPLSCH-internal inputs of the next orc_implsch; read them back in original point order
+int orc_capture(void* h, int on) {
+  Model* m = (Model*)h;
+  for (int ir = 0; ir < m->cfg.npr; ++ir) {
+    Fields& f = m->fld[ir];
+    RankDecomp& r = m->ranks[ir];
+    f.capture = on != 0;
+    if (on) {
+      f.DBG_SSOURCE.alloc(1, r.NPROMA, 1, m->cfg.nang, 1, m->cfg.nfre, 1, r.NCHNK);
+      for (ArrD* a : {&f.DBG_EM, &f.DBG_F1, &f.DBG_PHIWA}) a->alloc(1, r.NPROMA, 1, r.NCHNK);
+    }
+  }
+  return 0;
+}
+int orc_get_capture(void* h, double* ssource, double* em, double* f1, double* phiwa) {
+  Model* m = (Model*)h;
+  const long N = m->grid.NIBLO;
+  const int A = m->cfg.nang, F = m->cfg.nfre;
+  if (!m->fld[0].capture) return -1;
+  for (int ij = 1; ij <= N; ++ij) {
+    int ir, ip, ic; locate(m, ij, ir, ip, ic);
+    Fields& f = m->fld[ir];
+    em[ij - 1] = f.DBG_EM(ip, ic); f1[ij - 1] = f.DBG_F1(ip, ic); phiwa[ij - 1] = f.DBG_PHIWA(ip, ic);
+    for (int M = 1; M <= F; ++M)
+      for (int K = 1; K <= A; ++K) ssource[((size_t)(M - 1) * A + (K - 1)) * N + ij - 1] = f.DBG_SSOURCE(ip, K, M, ic);
+  }
+  return 0;
+}
+
 // the hot path ---------------------------------------------------------------------------------------
 int orc_propag(void* h) {
   try { propag_wam(*(Model*)h); } catch (std::exception& e) { fprintf(stderr, "orc_propag: %s\n", e.what()); return -1; }

@@ -1366,6 +1366,10 @@ void implsch_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int IC
     SSOURCE(IJ, K, M) = SSOURCE(IJ, K, M) + DELTM * std::min(t.FLMAX(M) - FL1(IJ, K, M), 0.0);
     FL1(IJ, K, M) = std::min(FL1(IJ, K, M), t.FLMAX(M));
   }
+  if (f.capture) {
+    for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) f.DBG_SSOURCE(IJ, K, M, ICHNK) = SSOURCE(IJ, K, M);
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) { f.DBG_EM(IJ, ICHNK) = EMEAN(IJ); f.DBG_F1(IJ, ICHNK) = F1MEAN(IJ); f.DBG_PHIWA(IJ, ICHNK) = PHIWA(IJ); }
+  }
   if (LCFLX)
     WNFLUXES(x, MIJ, RHOWGDFTH, CINV, SSOURCE, CICOVER, PHIWA, EMEAN, F1MEAN, WSWAVE, WDWAVE, USTRA, VSTRA, UFRIC, AIRD,
              TAUXD, TAUYD, TAUOCXD, TAUOCYD, TAUOC, TAUICX, TAUICY, PHIOCD, PHIEPS, PHIAW);

@@ -623,3 +623,143 @@ def test_stresso_and_tau_phi_hf_against_numpy(built, case):
     dd = np.angle(np.exp(1j * (out[1] - np.arctan2(xs2, ys2))))
     assert np.abs(dd[tauw > 1e-10 * tauw.max()]).max() <= 1e-9
     np.testing.assert_allclose(out[2], phiwa + phihf, rtol=1e-9, atol=1e-12 * np.abs(out[2]).max())
+
+
+@pytest.mark.parametrize("case", ["o48like", "o640like", "o48_iphys0"])
+def test_wnfluxes_against_numpy(built, case):
+    """WNFLUXES restated in vectorised numpy from the formulas (wnfluxes.F90:146-300, uncoupled: no NEMO accumulators, LWCOUAST
+    off): momentum and energy fluxes of the implicit-scheme source SSOURCE integrated up to the cut-off MIJ, the drag blend under sea
+    ice (Hersbach's CD(U10) where the ice cover exceeds CIBLOCK), atmosphere-side stress TAUXD/TAUYD, ocean-side stress
+    TAUOCXD/TAUOCYD, their ratio TAUOC with its clips, and the normalised energy fluxes PHIOCD / PHIEPS / PHIAW with theirs.
+    SSOURCE, EMEAN, F1MEAN and PHIWA are internal to IMPLSCH: the oracle's capture hook hands them out."""
+    g, o, f, fl = make_oracle(case)
+    assert o.step() == 0
+    o.capture(True)
+    assert o.step() == 0
+    ss, em, f1, phiwa = o.captured()
+    NF, A, N = ss.shape
+    cinv = o.get_field3("CINV")
+    us, aird, wd, ws, ci = (o.get_field(k) for k in ("UFRIC", "AIRD", "WDWAVE", "WSWAVE", "CICOVER"))
+    mij = o.get_field("MIJ").astype(int)
+    th, fr = o.table("TH"), o.table("FR")
+    G, ZPI, ROWATER = 9.806, 2 * np.pi, 1000.0
+    EPSUS, EPSU10 = 1.0e-6, np.sqrt(1.0e-3)              # yowpcons.F90:52-53
+    TAUOCMIN, TAUOCMAX, PHIEPSMIN, PHIEPSMAX = 0.01, 50.0, -3276.80, -0.05
+    PHIOC_ICE, PHIAW_ICE = -3.75, 3.75
+    # (EM_OC / F1_OC of wnfluxes.F90:237-244 only feed the NEMO fields NSWH / NMWP: not part of the uncoupled outputs)
+    delth = ZPI / A
+    rdf = ROWATER * G * delth * np.log(fr[1] / fr[0]) * fr
+    rdf[0] *= 0.5; rdf[-1] *= 0.5
+    m1 = np.arange(1, NF + 1)[:, None]
+    w = np.where(m1 <= mij[None, :], rdf[:, None], 0.0)
+    w = np.where((m1 == mij[None, :]) & (mij[None, :] != NF), 0.5 * w, w)
+    philf = (w * ss.sum(axis=1)).sum(axis=0)
+    xs = (w * cinv * (ss * np.sin(th)[None, :, None]).sum(axis=1)).sum(axis=0)
+    ys = (w * cinv * (ss * np.cos(th)[None, :, None]).sum(axis=1)).sum(axis=0)
+    # sea ice: blend towards the bulk drag / fully developed sea (LICERUN and LWAMRSETCI, no LCIWA*: ZCITHRS = CIBLOCK, exponent cap 10)
+    ciblock, cithrsh = o.cfg.ciblock, o.cfg.cithrsh
+    iced = (ci > ciblock) & bool(o.cfg.licerun and o.cfg.lwamrsetci)
+    ooval = np.where(iced, np.exp(-np.minimum((ci / max(cithrsh, 0.01)) ** 4, 10.0)), 1.0)
+    u10p = np.maximum(ws, EPSU10)
+    cd_bulk = np.minimum((1.03e-3 + 0.04e-3 * u10p ** 1.48) * u10p ** -0.21, 0.003)
+    cd_ice = ooval * (us / u10p) ** 2 + (1.0 - ooval) * cd_bulk
+    ustar = np.where(iced, np.maximum(np.sqrt(cd_ice) * u10p, EPSUS), us)
+    tau = aird * np.maximum(ustar ** 2, EPSUS)
+    tauxd, tauyd = tau * np.sin(wd), tau * np.cos(wd)
+    tocx, tocy = tauxd - ooval * xs, tauyd - ooval * ys
+    tauoc = np.clip(np.hypot(tocx, tocy) / tau, TAUOCMIN, TAUOCMAX)
+    xn = aird * np.maximum(ustar ** 3, EPSUS * np.sqrt(EPSUS))
+    phieps = np.clip((ooval * (philf - phiwa) + (1.0 - ooval) * PHIOC_ICE * xn) / xn, PHIEPSMIN, PHIEPSMAX)
+    phiocd = phieps * xn
+    phiaw = ooval * phiwa / xn + (1.0 - ooval) * PHIAW_ICE
+    assert iced.any() and (~iced).any() and np.abs(xs).max() > 0
+    for nm, ref in (("TAUXD", tauxd), ("TAUYD", tauyd), ("TAUOCXD", tocx), ("TAUOCYD", tocy), ("TAUOC", tauoc), ("PHIEPS", phieps),
+                    ("PHIOCD", phiocd), ("PHIAW", phiaw)):
+        got = o.get_field(nm)
+        np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-12 * np.abs(ref).max(), err_msg=nm)
+
+
+def test_ctu_weights_against_numpy(built):
+    """The corner-transport-upstream weights of CTUW (ctuw.F90:156-275 advection, :404-501 grid refraction; IREFRA = 0) restated in
+    vectorised numpy: interface group speeds (mean of the two cells, the meridional one interpolated between the two closest points
+    of the neighbouring row and scaled with cos(phi) of that row), displacements in degrees, up-wind selection by the sign of
+    sin / cos of the direction (JXO / JYO / KCR of ctuwupdt.F90:111-161 rebuilt from those signs), area fractions of the displaced
+    cell, and the great-circle turning rate.  Compared at the points whose 14 neighbours are all sea points (the land value of the
+    group speed is not part of the cross-check)."""
+    g, o, f, fl = make_oracle("o48like", store_all_weights=1)
+    assert o.propag() == 0
+    N, A, Fr = g.niblo, CASES["o48like"]["A"], CASES["o48like"]["Fr"]
+    F_ = lambda a, *shape: np.asarray(a)[: int(np.prod(shape))].reshape(shape, order="F")
+    klon = F_(o.itable("KLON"), N, 2)
+    klat = F_(o.itable("KLAT"), N, 2, 2)
+    kcor = F_(o.itable("KCOR"), N, 4, 2)
+    wlat, wcor = F_(o.rank_double("WLAT", 0), N, 2), F_(o.rank_double("WCOR", 0), N, 4)
+    cap = 1 << 26
+    WLATN = F_(o.rank_double("WLATN", 0, cap=cap), N, A, Fr, 2, 2)
+    WLONN = F_(o.rank_double("WLONN", 0, cap=cap), N, A, Fr, 2)
+    WCORN = F_(o.rank_double("WCORN", 0, cap=cap), N, A, Fr, 4, 2)
+    WKPMN = F_(o.rank_double("WKPMN", 0, cap=cap), N, A, Fr, 3)
+    SUMWN = F_(o.rank_double("SUMWN", 0, cap=cap), N, A, Fr)
+    kxlt = o.itable("KXLT")[:N]
+    cosph, sinph, zdello_row = o.table("COSPH"), o.table("SINPH"), o.table("ZDELLO")
+    xdella, R = o.table("XDELLA")[0], o.table("R")[0]
+    th = o.table("TH")
+    cg = o.get_field3("CGROUP")[:Fr]                      # [m, ij]
+    delpro = CASES["o48like"]["dt"]
+    CIRC = 40007993.95                                     # yowpcons.F90:22
+    cmtodeg = 360.0 / CIRC
+    land = N + 1
+    nbrs = np.concatenate([klon, klat.reshape(N, 4), kcor.reshape(N, 8)], axis=1)
+    inner = (nbrs != land).all(axis=1)
+    assert inner.sum() > N // 3
+    ij = np.nonzero(inner)[0]
+    ky = kxlt[ij] - 1
+    cosphm1 = 1.0 / cosph[ky]
+    zdello = zdello_row[ky]
+    ngy = cosph.size
+    dp = np.stack([cosph[np.clip(ky - 1, 0, ngy - 1)], cosph[np.clip(ky + 1, 0, ngy - 1)]], axis=1) * cosphm1[:, None]
+    wl = wlat[ij]
+    cgi = cg[:, ij]                                        # [m, n]
+    gam1 = 1.0 / (zdello * xdella)
+    for k in range(A):
+        s_, c_ = np.sin(th[k]), np.cos(th[k])
+        # interface speeds towards IC = 1, 2 in x (west / east) and y (south / north), as displacements in degrees
+        adx, ady = [], []
+        for ic in range(2):
+            cgx = 0.5 * (cgi + cg[:, klon[ij, ic] - 1]) * s_ * cosphm1[None, :]
+            cgyp = wl[None, :, ic] * cg[:, klat[ij, ic, 0] - 1] + (1.0 - wl[None, :, ic]) * cg[:, klat[ij, ic, 1] - 1]
+            cgy = 0.5 * (cgi + dp[None, :, ic] * cgyp) * c_
+            adx.append(np.abs(delpro * cgx * cmtodeg)); ady.append(np.abs(delpro * cgy * cmtodeg))
+        # up-wind side: energy travelling towards +x (sin >= 0) comes from the western neighbour (IC = 1), etc.
+        jx_up, jx_dw = (0, 1) if s_ >= 0 else (1, 0)
+        jy_up, jy_dw = (0, 1) if c_ >= 0 else (1, 0)
+        # without currents ISSU = ISSV = 1: DXUP(ic) = ADXP(ic), DXDW(ic) = 0 (ctuw.F90:186-199), so the cell keeps
+        # ZDELLO - (what leaves through the down-wind face) of its width and XDELLA - (...) of its height
+        dxx, dyy = zdello[None, :] - adx[jx_dw], xdella - ady[jy_dw]
+        w_lat_up = dxx * ady[jy_up] * gam1[None, :]
+        w_lon_up = dyy * adx[jx_up] * gam1[None, :]
+        w_cor = adx[jx_up] * ady[jy_up] * gam1[None, :]
+        sumw = (zdello[None, :] * ady[jy_dw] + xdella * adx[jx_dw] - adx[jx_dw] * ady[jy_dw]) * gam1[None, :]
+        tol = dict(rtol=1e-10, atol=1e-15)
+        np.testing.assert_allclose(WLONN[ij, k, :, jx_up].T, w_lon_up, **tol)
+        np.testing.assert_allclose(WLONN[ij, k, :, jx_dw], 0.0, atol=1e-300)
+        for icl, frac in ((0, wl[:, jy_up]), (1, 1.0 - wl[:, jy_up])):
+            np.testing.assert_allclose(WLATN[ij, k, :, jy_up, icl].T, w_lat_up * frac[None, :], **tol)
+        np.testing.assert_allclose(WLATN[ij, k, :, jy_dw, :], 0.0, atol=1e-300)
+        # the one corner that is up-wind in both directions: KCR(K,1) (ctuwupdt.F90:121-157)
+        kcr1 = {(True, True): 3, (True, False): 2, (False, True): 4, (False, False): 1}[(c_ >= 0, s_ >= 0)] - 1
+        wc = wcor[ij, kcr1]
+        np.testing.assert_allclose(WCORN[ij, k, :, 0, 0].T, w_cor * wc[None, :], **tol)
+        np.testing.assert_allclose(WCORN[ij, k, :, 0, 1].T, w_cor * (1.0 - wc)[None, :], **tol)
+        np.testing.assert_allclose(WCORN[ij, k, :, 1:, :], 0.0, atol=1e-300)
+        # great-circle turning (ctuw.F90:404-431, 471-486)
+        kp1, km1 = (k + 1) % A, (k - 1) % A
+        delth0 = 0.25 * delpro / (2 * np.pi / A)
+        tanph = sinph[ky] / cosph[ky]
+        dthp = (tanph * delth0 * (np.sin(th[k]) + np.sin(th[kp1])) / R)[None, :] * cgi
+        dthm = (tanph * delth0 * (np.sin(th[k]) + np.sin(th[km1])) / R)[None, :] * cgi
+        w0 = (dthp + np.abs(dthp)) + (np.abs(dthm) - dthm)
+        np.testing.assert_allclose(WKPMN[ij, k, :, 1].T, w0, rtol=1e-10, atol=1e-16)
+        np.testing.assert_allclose(WKPMN[ij, k, :, 2].T, np.abs(dthp) - dthp, rtol=1e-10, atol=1e-16)
+        np.testing.assert_allclose(WKPMN[ij, k, :, 0].T, dthm + np.abs(dthm), rtol=1e-10, atol=1e-16)
+        np.testing.assert_allclose(SUMWN[ij, k, :].T, sumw + w0, rtol=1e-10, atol=1e-15)
