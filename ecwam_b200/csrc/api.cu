@@ -213,7 +213,7 @@ static int fill_dev_const(const ecwam_b200_params& p, const ecwam_b200_tables& t
   if (p.lciwa & ~15) EW_FAIL(ECWAM_B200_EINVAL, "lciwa: unknown bits");
   if (p.lwnemocou) EW_FAIL(ECWAM_B200_EINVAL, "NEMO coupling accumulators are not implemented");
   if (p.icode_wnd != 3) EW_FAIL(ECWAM_B200_EINVAL, "only ICODE_WND=3 (10 m wind forcing) is implemented");
-  if ((p.lwflux || p.lwfluxout) && !p.lwvflx_snl) EW_FAIL(ECWAM_B200_EINVAL, "LWVFLX_SNL=F is not implemented");
+
   if (p.iphys != 0 && p.iphys != 1) EW_FAIL(ECWAM_B200_EINVAL, "IPHYS must be 0 or 1");
   if (t.mlsthg > EW_MAXMC || t.mlsthg < 1 || t.mfrstlw > 1) EW_FAIL(ECWAM_B200_EINVAL, "bad MLSTHG/MFRSTLW");
   if (t.jtot_tauhf > EW_MAXJT) EW_FAIL(ECWAM_B200_EINVAL, "JTOT_TAUHF too large");
@@ -857,6 +857,7 @@ static ImplDev make_impl(H* h, bool from_fl3) {
   d.cy49 = (h->par.llgcbz0 || h->par.llnormagam) ? 1 : 0;
   d.gc = h->gctab.p;
   d.sweep_ok = h->dc.sweep_ok;
+  d.ssource_pre = (h->dc.lcflx && !h->par.lwvflx_snl) ? 1 : 0;
   d.isnonlin = h->par.isnonlin;
   d.enh = h->enhp.p;
   return d;

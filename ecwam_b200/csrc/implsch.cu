@@ -1218,7 +1218,7 @@ __global__ void ST_BOUNDS(NP) k_stencil(ImplDev d, long long p0, long long np, S
   const double delt = c_dc.delt, deltm = 1.0 / delt, delt5 = c_dc.ximp * delt;
   const double tmp03 = 1.0 / (c_dc.SDSBR * c_dc.MICHE);
   const int MLSTHG = c_dc.MLSTHG;
-  const bool lssource = c_dc.lcflx && c_dc.lwvflx_snl;
+  const bool lssource = c_dc.lcflx && c_dc.lwvflx_snl, lsspre = c_dc.lcflx && !c_dc.lwvflx_snl;
 
   // pending SNONLIN sums of rows st-4 .. st+2 (row st+3 receives its first contribution, MC -> MC+3, at this step)
   double asl[7][NP], afl[7][NP];
@@ -1427,6 +1427,7 @@ __global__ void ST_BOUNDS(NP) k_stencil(ImplDev d, long long p0, long long np, S
         slv = slv + tot_sl.v[i]; fldv = fldv + tot_fl.v[i];    // SNONLIN
         double ssource = 0.0;
         if (lssource) ssource = div_norm(slv, dmax(1.0 - delt5 * fldv, 1.0));
+        else if (lsspre) ssource = slv - tot_sl.v[i];    // LWVFLX_SNL = F: SL before SNONLIN, not modulated (implsch.F90:279-288)
         if (r < c_dc.Fr) { slv = slv - sdsbk.v[i] * f0; fldv = fldv - sdsbk.v[i]; }   // SDIWBK (0 where it does not apply)
         if (c_dc.lciscal) { slv = slv * beta.v[i]; fldv = fldv * beta.v[i]; }        // LCISCAL (implsch.F90:315-325)
         slv = slv + tsbo.v[i] * f0; fldv = fldv + tsbo.v[i];                         // SDICE3 + SBOTTOM (plane is 0 where neither applies)
@@ -1678,7 +1679,7 @@ __global__ void __maxnreg__(ST_MAXREG) k_stencil_dp(ImplDev d, long long p0, lon
   const double delt = c_dc.delt, deltm = 1.0 / delt, delt5 = c_dc.ximp * delt;
   const double tmp03 = 1.0 / (c_dc.SDSBR * c_dc.MICHE);
   const int MLSTHG = c_dc.MLSTHG;
-  const bool lssource = c_dc.lcflx && c_dc.lwvflx_snl;
+  const bool lssource = c_dc.lcflx && c_dc.lwvflx_snl, lsspre = c_dc.lcflx && !c_dc.lwvflx_snl;
 
   double asl[7][2], afl[7][2];
 #pragma unroll
@@ -1905,6 +1906,7 @@ __global__ void __maxnreg__(ST_MAXREG) k_stencil_dp(ImplDev d, long long p0, lon
         slv = slv + tot_sl.v[i]; fldv = fldv + tot_fl.v[i];
         double ssource = 0.0;
         if (lssource) ssource = div_norm(slv, dmax(1.0 - delt5 * fldv, 1.0));
+        else if (lsspre) ssource = slv - tot_sl.v[i];    // LWVFLX_SNL = F: SL before SNONLIN, not modulated (implsch.F90:279-288)
         if (r < c_dc.Fr) { slv = slv - sdsbk * f0; fldv = fldv - sdsbk; }            // SDIWBK (0 where it does not apply)
         if (c_dc.lciscal) { slv = slv * beta; fldv = fldv * beta; }                  // LCISCAL (implsch.F90:315-325)
         slv = slv + tsbo * f0; fldv = fldv + tsbo;                                   // SDICE3 + SBOTTOM (plane is 0 where neither applies)
@@ -2192,7 +2194,7 @@ __global__ void __launch_bounds__(sw_threads(TA, NPT), SW_MINB) k_sweep(ImplDev 
   const double delt = c_dc.delt, deltm = 1.0 / delt, delt5 = c_dc.ximp * delt;
   const double tmp03 = 1.0 / (c_dc.SDSBR * c_dc.MICHE);
   const int MLSTHG = c_dc.MLSTHG;
-  const bool lssource = c_dc.lcflx && c_dc.lwvflx_snl;
+  const bool lssource = c_dc.lcflx && c_dc.lwvflx_snl, lsspre = c_dc.lcflx && !c_dc.lwvflx_snl;
 
   double asl[7][2], afl[7][2];
 #pragma unroll
@@ -2833,7 +2835,7 @@ __global__ void __launch_bounds__(2 * sw_threads(TA, NPT), 2) k_sweep_ws(ImplDev
     const bool setice = c_dc.licerun && c_dc.lmaskice;
     const double delt = c_dc.delt, deltm = 1.0 / delt, delt5 = c_dc.ximp * delt;
     const double tmp03 = 1.0 / (c_dc.SDSBR * c_dc.MICHE);
-    const bool lssource = c_dc.lcflx && c_dc.lwvflx_snl;
+    const bool lssource = c_dc.lcflx && c_dc.lwvflx_snl, lsspre = c_dc.lcflx && !c_dc.lwvflx_snl;
     // pending SNONLIN sums of rows st-4 .. st+2 (row st+3 receives its first contribution, MC -> MC+3, at this step)
     double asl[7][2], afl[7][2];
 #pragma unroll
@@ -3276,11 +3278,13 @@ int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage
     if (force && !strcmp(force, "single")) pair = false;
     // default for the standard grids: thread = (two adjacent directions, one point); ECWAM_B200_STENCIL=pp keeps the
     // two-points-per-thread instance (A/B timing, tests)
+    // LWVFLX_SNL = F (SSOURCE = SL before SNONLIN, implsch.F90:279-288) is built into k_stencil / k_stencil_dp only
+    const bool sweep_ok = d.sweep_ok && !d.ssource_pre;
     // default for NANG = 36: k_sweep_ws (producer / consumer warp groups); ECWAM_B200_STENCIL=sweep: the one-role k_sweep
-    if (!force && d.sweep_ok && geo_matches<36>(d, d.iphys, d.nsdsnth))
+    if (!force && sweep_ok && geo_matches<36>(d, d.iphys, d.nsdsnth))
       return d.lwflux ? launch_sweep_ws<36, 7, true>(d, p0, np, st) : launch_sweep_ws<36, 7, false>(d, p0, np, st);
     // default for the other standard grids: k_sweep (NPT points x NANG/2 direction pairs)
-    if ((!force || !strcmp(force, "sweep")) && d.sweep_ok) {
+    if ((!force || !strcmp(force, "sweep")) && sweep_ok) {
       if (geo_matches<36>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_sweep<36, 7, true>(d, p0, np, st) : launch_sweep<36, 7, false>(d, p0, np, st);
       if (geo_matches<24>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_sweep<24, 8, true>(d, p0, np, st) : launch_sweep<24, 8, false>(d, p0, np, st);
       if (geo_matches<12>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_sweep<12, 8, true>(d, p0, np, st) : launch_sweep<12, 8, false>(d, p0, np, st);

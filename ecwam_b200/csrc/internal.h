@@ -89,6 +89,7 @@ struct ImplDev {
   int cy49;                // LLGCBZ0 or LLNORMAGAM is on: k_point runs its gravity-capillary / renormalised-growth instance
   const double* gc;        // [GC_NT][NWAV_GC] gravity-capillary tables (device), read by that instance only
   int sweep_ok;            // the DIA tables have the separable structure k_sweep relies on (DevConst::NLW)
+  int ssource_pre;         // LCFLX and not LWVFLX_SNL: WNFLUXES takes SL before SNONLIN (only k_stencil / k_stencil_dp carry that branch)
   int isnonlin;            // YOWSTAT ISNONLIN (0: ENH from the mean wavenumber; 1, 2: per centre frequency, snonlin.F90:138-163)
   double* enh;             // [MLSTHG][npts] ENH(IJ,MC) of ISNONLIN = 1, 2 (k_enh writes it between k_point and the sweep); null otherwise
 };

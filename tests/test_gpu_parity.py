@@ -586,3 +586,20 @@ def test_shallow_water_dia_scaling_matches_oracle(built, monkeypatch, case, mode
     w.synchronize()
     check_state(w, o)
     assert relerr(o.get_fl1(), o0.get_fl1()) > 1e-6          # the mode matters in this case
+
+
+@pytest.mark.parametrize("case,mode", [("o48like", None), ("o640like", None), ("o320like", "generic"), ("o48_iphys0", None)])
+def test_fluxes_without_the_nonlinear_transfer(built, monkeypatch, case, mode):
+    """LWVFLX_SNL = F (implsch.F90:279-288): WNFLUXES integrates SL as it stands after SDISSIP -- before SNONLIN and without the
+    implicit factor.  The switch routes the sweep to the k_stencil_dp / k_stencil instances, which carry that branch."""
+    if mode:
+        monkeypatch.setenv("ECWAM_B200_STENCIL", mode)
+    g, o, f, fl = make_oracle(case, lwvflx_snl=0)
+    _, o1, _, _ = make_oracle(case)
+    _, s, w = make_gpu(case, lwvflx_snl=0)
+    for _ in range(3):
+        assert o.step() == 0 and w.step() == 0 and o1.step() == 0
+    w.synchronize()
+    check_state(w, o)
+    assert relerr(o.get_field("PHIOCD"), o1.get_field("PHIOCD")) > 1e-4          # the switch matters for the fluxes ...
+    np.testing.assert_array_equal(o.get_fl1(), o1.get_fl1())                      # ... and not for the spectrum
