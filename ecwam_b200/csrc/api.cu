@@ -84,6 +84,9 @@ struct ecwam_b200_handle_s {
   int int_lo = 0, int_hi = 0;
   bool overlap = false;
   cudaStream_t st_x = nullptr;
+  std::vector<cudaStream_t> st_part;   // IMPLSCH in parts on streams of their own (implsch_range)
+  std::vector<cudaEvent_t> ev_part;
+  cudaEvent_t ev_fork = nullptr;
   cudaEvent_t ev_pack = nullptr, ev_x = nullptr;
   bool send_chunks_sorted = false;
   cudaEvent_t ev_halo = nullptr;
@@ -618,6 +621,9 @@ int ecwam_b200_destroy(ecwam_b200_handle h) {
   for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
   if (h->ev_halo) cudaEventDestroy(h->ev_halo);
+  for (cudaStream_t x : h->st_part) cudaStreamDestroy(x);
+  for (cudaEvent_t e : h->ev_part) cudaEventDestroy(e);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_pack) cudaEventDestroy(h->ev_pack);
   if (h->ev_x) cudaEventDestroy(h->ev_x);
   if (h->st_x) cudaStreamDestroy(h->st_x);
@@ -870,6 +876,39 @@ static int implsch_range(H* h, int ichnk0, int nchnk, bool from_fl3) {
   if (rc) return rc;
   ImplDev d = make_impl(h, from_fl3);
   static const char* kStage[EW_IMPLSCH_NSTAGE] = {"implsch_point", "implsch_stencil"};
+  // Small blocks (several ranks, or O320 and below): the chunk range is cut into parts that run the kernel sequence on streams of
+  // their own.  IMPLSCH is point-wise, so the parts are independent, and a kernel boundary stops being a device-wide barrier: the
+  // partial last wave of a k_point phase (2.41 waves at 8 GPUs: the third one is 41 % full but takes as long as a full one) shares
+  // the SMs with the next kernel of the other part.  ECWAM_B200_IMPLSCH_SPLIT = 0 | n overrides the automatic choice.
+  static const int split_env = []() { const char* e = getenv("ECWAM_B200_IMPLSCH_SPLIT"); return e ? atoi(e) : -1; }();
+  const long long np_all = (long long)nchnk * d.P;
+  int ns = split_env >= 0 ? split_env : ((np_all >= 60000 && np_all <= 700000) ? 2 : 1);
+  ns = std::max(1, std::min(std::min(ns, 4), nchnk));
+  if (ns > 1) {
+    while ((int)h->st_part.size() < ns - 1) {
+      cudaStream_t x; cudaEvent_t e;
+      EW_CUDA_CHECK(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+      EW_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->st_part.push_back(x); h->ev_part.push_back(e);
+    }
+    if (!h->ev_fork) EW_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    ScopedTimer t(h, "implsch");
+    EW_CUDA_CHECK(cudaEventRecord(h->ev_fork, h->st));
+    for (int k = 1; k < ns; ++k) EW_CUDA_CHECK(cudaStreamWaitEvent(h->st_part[k - 1], h->ev_fork, 0));
+    for (int s = 0; s < EW_IMPLSCH_NSTAGE; ++s)
+      for (int k = 0; k < ns; ++k) {
+        const long long c0 = (long long)nchnk * k / ns, c1 = (long long)nchnk * (k + 1) / ns;
+        rc = launch_implsch_stage(d, ((long long)(ichnk0 - 1) + c0) * d.P, (c1 - c0) * d.P, s, k == 0 ? h->st : h->st_part[k - 1]);
+        if (rc) return rc;
+        h->nlaunch += (s == 0) ? 2 : 1;
+      }
+    for (int k = 1; k < ns; ++k) {
+      EW_CUDA_CHECK(cudaEventRecord(h->ev_part[k - 1], h->st_part[k - 1]));
+      EW_CUDA_CHECK(cudaStreamWaitEvent(h->st, h->ev_part[k - 1], 0));
+    }
+    EW_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   for (int s = 0; s < EW_IMPLSCH_NSTAGE; ++s) {
     ScopedTimer t(h, kStage[s]);
     rc = launch_implsch_stage(d, (long long)(ichnk0 - 1) * d.P, (long long)nchnk * d.P, s, h->st);
