@@ -466,23 +466,35 @@ __global__ void k_pack_cols(const double* bout, int P, int ncol, long long nloc,
   out[(size_t)i * ostride + l] = bout[(size_t)(l - ic * P) + (size_t)P * ((size_t)i + (size_t)ncol * (size_t)ic)];
 }
 // MPMINMAXAVG, LLGLOBAL = T (mpminmaxavg.F90:121-153): one strictly sequential sum per column over the ORIGINAL global
-// point order (IJ = IJ2NEWIJ(IJOLD)), reproducible for any number of ranks.  One warp per column: the 32 lanes fetch 32
-// consecutive elements (so the gathers overlap), then every lane replays the same 32 additions in order.
+// point order (IJ = IJ2NEWIJ(IJOLD)), reproducible for any number of ranks.  One warp per column.  The sum is the reference's
+// left-to-right chain, so its cost is one dependent DADD per element and nothing else may sit on that chain: the 32 lanes fetch 32
+// consecutive elements one block AHEAD (the gathers overlap the chain of the block before), missing values enter the chain as
+// +0.0, every lane replays the same 32 unrolled additions (the shuffles pipeline in front of them), and count / minimum / maximum
+// are order-independent: per-lane partials, reduced once at the end.  (First version: shuffle, test and four updates per element
+// inside a rolled loop, ~55 cycles per element = 31 ms per call at O640; now ~18 = the latency of the dependent FP64 add, 11 ms;
+// feeding the chain from shared memory instead of shuffles changes nothing.)
 __global__ void __launch_bounds__(32) k_norm_seq(const double* zg /*[ncol][niblo] relabelled order*/, const int* ij2new /*(0:NIBLO) or null*/,
                                                  long long niblo, double zmiss, double* out /*[ncol][4]: avg, min, max, count*/) {
   const int i = blockIdx.x, lane = threadIdx.x;
   const double* z = zg + (size_t)i * niblo;
   double s = 0.0, mn = 1.7976931348623157e308, mx = -1.7976931348623157e308;
   long long cnt = 0;
+  auto fetch = [&](long long j) { return j < niblo ? z[ij2new ? (long long)ij2new[j + 1] - 1 : j] : zmiss; };
+  double v = fetch(lane);
   for (long long j0 = 0; j0 < niblo; j0 += 32) {
-    const long long j = j0 + lane;
-    double v = zmiss;
-    if (j < niblo) v = z[ij2new ? (long long)ij2new[j + 1] - 1 : j];
-    const int nn = niblo - j0 < 32 ? (int)(niblo - j0) : 32;
-    for (int q = 0; q < nn; ++q) {
-      const double x = __shfl_sync(0xffffffffu, v, q);
-      if (x != zmiss) { cnt += 1; s = s + x; mn = omin(mn, x); mx = omax(mx, x); }
-    }
+    const double vnext = fetch(j0 + 32 + lane);
+    const bool ok = v != zmiss;
+    if (ok) { cnt += 1; mn = omin(mn, v); mx = omax(mx, v); }
+    const double vv = ok ? v : 0.0;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) s = s + __shfl_sync(0xffffffffu, vv, q);
+    v = vnext;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    mn = omin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = omax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   }
   if (lane == 0) {
     out[i * 4 + 0] = s / (double)(cnt > 1 ? cnt : 1); out[i * 4 + 1] = mn; out[i * 4 + 2] = mx; out[i * 4 + 3] = (double)cnt;
