@@ -438,7 +438,12 @@ __device__ __forceinline__ double rhowgdfth(int m, int mij) {
 // and the direction tables come out of constant memory with a warp-uniform index.  Writes: the wind-input
 // linearisation FLD (scratch, same layout as FL1), XLLWS (final), MIJ and the 1-D stress fields.
 // =========================================================================================================
+#ifndef KP_NTH
 #define KP_NTH 128    // threads per block of k_point
+#endif
+#ifndef KP_MINB
+#define KP_MINB 3     // resident CTAs per SM the register allocation aims at (the double-buffered row stage allows 3 at 128 threads)
+#endif
 #ifndef KP_UNROLL
 #define KP_UNROLL 1   // the direction loop stays rolled: the frequency loop of the second SINFLX call must fit the 32 KB instruction cache
 #endif
@@ -718,7 +723,7 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
 // CY: the cy49r1 physics instance (LLGCBZ0 and/or LLNORMAGAM, read at run time inside it); the CY = false instances do not
 // contain any of it.
 template <bool ARD, int PH, bool CY>
-__global__ void __launch_bounds__(KP_NTH, 3) k_point(ImplDev d, long long p0, long long np) {
+__global__ void __launch_bounds__(KP_NTH, KP_MINB) k_point(ImplDev d, long long p0, long long np) {
   extern __shared__ double smem[];
   long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = p < p0 + np;
