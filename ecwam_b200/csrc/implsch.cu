@@ -2806,7 +2806,9 @@ __global__ void __launch_bounds__(2 * sw_threads(TA, NPT), 2) k_sweep_ws(ImplDev
           const int e = j + 4 * x;
           if (e < NPR) mx = dmax(mx, pp[(e >> 1) * (2 * NPT) + (e & 1)]);
         }
-        constexpr unsigned RM = (4 * NPT >= 32) ? 0xffffffffu : ((1u << ((4 * NPT) & 31)) - 1u);
+        // lanes of this warp that take part: 4 NPT consecutive role threads, possibly over two warps (NPT > 8)
+        const int lane0 = tr & ~31, nin = min(32, 4 * NPT - lane0);
+        const unsigned RM = nin >= 32 ? 0xffffffffu : ((1u << nin) - 1u);
         mx = dmax(mx, __shfl_xor_sync(RM, mx, 1));
         mx = dmax(mx, __shfl_xor_sync(RM, mx, 2));
         if (j == 0) reinterpret_cast<double*>(sm + L.bth0 + b * PRB)[qp] = mx;
@@ -3115,7 +3117,7 @@ template <int TA, int NPT, bool LW>
 static int launch_sweep_ws(const ImplDev& d, long long p0, long long np, cudaStream_t st) {
   constexpr WsSmem L = ws_smem(TA, NPT, LW);
   static_assert(L.total <= 113 * 1024, "k_sweep_ws shared memory");
-  static_assert(8 * NPT <= 2 * sw_threads(TA, NPT) && TQ_N * NPT <= sw_threads(TA, NPT) && 4 * NPT <= 32, "k_sweep_ws: too few threads for the per-point loops");
+  static_assert(8 * NPT <= 2 * sw_threads(TA, NPT) && TQ_N * NPT <= sw_threads(TA, NPT) && 4 * NPT <= sw_threads(TA, NPT), "k_sweep_ws: too few threads for the per-point loops");
   static bool attr_done = false;
   if (!attr_done) {
     EW_CUDA_CHECK(cudaFuncSetAttribute(k_sweep_ws<TA, NPT, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
@@ -3305,6 +3307,9 @@ int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage
     // default for NANG = 36: k_sweep_ws (producer / consumer warp groups); ECWAM_B200_STENCIL=sweep: the one-role k_sweep
     if (!force && sweep_ok && geo_matches<36>(d, d.iphys, d.nsdsnth))
       return d.lwflux ? launch_sweep_ws<36, 7, true>(d, p0, np, st) : launch_sweep_ws<36, 7, false>(d, p0, np, st);
+    // NANG = 24: k_sweep_ws with 10 points per CTA (120 of 128 lanes per role); ECWAM_B200_STENCIL=sweep keeps the one-role k_sweep
+    if ((!force || !strcmp(force, "ws")) && sweep_ok && geo_matches<24>(d, d.iphys, d.nsdsnth))
+      return d.lwflux ? launch_sweep_ws<24, 10, true>(d, p0, np, st) : launch_sweep_ws<24, 10, false>(d, p0, np, st);
     // default for the other standard grids: k_sweep (NPT points x NANG/2 direction pairs)
     if ((!force || !strcmp(force, "sweep")) && sweep_ok) {
       if (geo_matches<36>(d, d.iphys, d.nsdsnth)) return d.lwflux ? launch_sweep<36, 7, true>(d, p0, np, st) : launch_sweep<36, 7, false>(d, p0, np, st);

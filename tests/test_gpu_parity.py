@@ -125,9 +125,11 @@ def test_wamintgr_steps_match_oracle(built, case):
 
 @pytest.mark.parametrize("mode,case", [("generic", "o640like"), ("generic", "o48_iphys0"), ("single", "o640like"), ("single", "o320like"),
                                        ("pp", "o640like"), ("pp", "o320like"), ("pp", "o48like"),
-                                       ("dp", "o640like"), ("dp", "o320like"), ("dp", "o48like")])
+                                       ("dp", "o640like"), ("dp", "o320like"), ("dp", "o48like"),
+                                       ("sweep", "o640like"), ("sweep", "o320like")])
 def test_stencil_kernel_instances_agree(built, monkeypatch, mode, case):
-    """Besides the default k_sweep, the frequency sweep has the previous default (dp: 8 points x 160 threads), compile-time-geometry
+    """Besides the defaults (k_sweep_ws for NANG = 36 and 24, k_sweep for NANG = 12), the frequency sweep has the one-role k_sweep
+    (sweep), the round-1 default (dp: 8 points x 160 threads), compile-time-geometry
     instances with two points per thread (pp), a run-time-geometry instance and a one-point-per-thread instance (odd NPROMA /
     unaligned arrays).  All of them must match the oracle."""
     monkeypatch.setenv("ECWAM_B200_STENCIL", mode)
