@@ -574,9 +574,11 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
   if (h->have_gc) {   // [GC_NT][NWAV_GC]; the last row (DELKCC_GC) is only read by MEANSQS_GC
     const int ng = tables->nwav_gc;
     const double* src[GC_NT] = {tables->xk_gc, tables->omega_gc, tables->cm_gc, tables->c2osqrtvg_gc, tables->xkmsqrtvgoc2_gc,
-                                tables->om3gmkm_gc, tables->omxkm3_gc, tables->delkcc_gc_ns, tables->delkcc_omxkm3_gc, tables->delkcc_gc};
+                                tables->om3gmkm_gc, tables->omxkm3_gc, tables->delkcc_gc_ns, tables->delkcc_omxkm3_gc, tables->delkcc_gc,
+                                nullptr};
     std::vector<double> gc((size_t)GC_NT * ng, 0.0);
     for (int r = 0; r < GC_NT; ++r) if (src[r]) for (int i = 0; i < ng; ++i) gc[(size_t)r * ng + i] = src[r][i];
+    for (int i = 0; i < ng; ++i) gc[(size_t)GC_LXK * ng + i] = std::log(tables->xk_gc[i]);
     ok = ok && !h->gctab.upload(gc, st);
     h->mss_ok = tables->delkcc_gc != nullptr;
     h->gc_n = ng; h->gc_sqrtgosurft = tables->sqrtgosurft; h->gc_xk1 = tables->xk_gc[0]; h->gc_xkn = tables->xk_gc[ng - 1];

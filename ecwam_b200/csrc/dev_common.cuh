@@ -64,7 +64,8 @@ struct DevConst {
   int sweep_ok, pad_sw;
 };
 // rows of the gravity-capillary table ImplDev::gc [GC_NT][NWAV_GC] (YOWFRED *_GC, initgc.F90)
-enum { GC_XK = 0, GC_OMEGA, GC_CM, GC_C2OSQRTVG, GC_XKMSQRTVGOC2, GC_OM3GMKM, GC_OMXKM3, GC_DELKCC_NS, GC_DELKCC_OMXKM3, GC_DELKCC, GC_NT };
+enum { GC_XK = 0, GC_OMEGA, GC_CM, GC_C2OSQRTVG, GC_XKMSQRTVGOC2, GC_OM3GMKM, GC_OMXKM3, GC_DELKCC_NS, GC_DELKCC_OMXKM3, GC_DELKCC,
+       GC_LXK /* log(XK_GC), derived at create: STRESS_GC's LOG(XK_GC*Z0) = GC_LXK + log(Z0) */, GC_NT };
 
 // tables too irregular / large for constant memory (per-lane indexed)
 struct DevTabPtr {

@@ -176,15 +176,18 @@ __device__ double stress_gc(const double* __restrict__ gc, double ang_gc, double
   const double zabhrc = ang_gc * c_dc.BETAMAXOXKAPPA2 * halp * c2;
   const double cst = c_dc.llnormagam ? rnfac * c_dc.BMAXOKAP * halp * c2 / dmax(ustar, c_dc.EPSUS) : 0.0;
   const double logl = log(xlambda);
+  // LOG(XK_GC(I)*Z0) = log XK_GC(I) (a table row) + log Z0 (once per call), and exp_le0 (valid up to +709) for EXP(XLOG): the loop runs
+  // ~26 wavenumbers x 18 iterations x 2 calls per point and grid point, libm's log + exp were most of the cy49r1 instance's extra cost
+  const double lz0 = log(z0);
   double tauwcg = 0.0;
   for (int i = ns; i <= N; ++i) {
     const double x = ustar * __ldg(gc + GC_CM * N + i - 1);
-    const double xlog = log(__ldg(gc + GC_XK * N + i - 1) * z0) + c_dc.XKAPPA / (x + c_dc.ZALP);
+    const double xlog = (__ldg(gc + GC_LXK * N + i - 1) + lz0) + div_fast(c_dc.XKAPPA, x + c_dc.ZALP);
     const double zlog = dmin(xlog - logl, 0.0);
     const double zlog2x = zlog * zlog * x;
-    const double gam_w = zlog2x * zlog2x * exp(xlog) * __ldg(gc + GC_OM3GMKM * N + i - 1);
+    const double gam_w = zlog2x * zlog2x * exp_le0(xlog) * __ldg(gc + GC_OM3GMKM * N + i - 1);
     const double zn = cst * __ldg(gc + GC_XKMSQRTVGOC2 * N + i - 1) * gam_w;
-    const double gamnorma = (1.0 + c_dc.RN1_RN * zn) / (1.0 + zn);
+    const double gamnorma = div_fast(1.0 + c_dc.RN1_RN * zn, 1.0 + zn);
     if (i == ns) tauwcg = gam_w * __ldg(gc + GC_DELKCC_NS * N + ns - 1) * __ldg(gc + GC_OMXKM3 * N + ns - 1) * gamnorma;
     else tauwcg = tauwcg + gam_w * __ldg(gc + GC_DELKCC_OMXKM3 * N + i - 1) * gamnorma;
   }
@@ -611,11 +614,11 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
               if (coslp > 0.01) {
                 const double x = coslp * ucn[g];
                 const double zlog = zcn + div_norm(ucnzalpd[g], coslp);
-                if (zlog < 0.0) { const double zlog2x = zlog * zlog * x; gam0 = exp(zlog) * zlog2x * zlog2x * cnsn; }
+                if (zlog < 0.0) { const double zlog2x = zlog * zlog * x; gam0 = exp_le0(zlog) * zlog2x * zlog2x * cnsn; }
               }
             } else if (cwd > 0.01) {
               const double zlog = zcn + div_norm(c_dc.XKAPPA, cwd) * ucnzalpd[g];
-              if (zlog < 0.0) { const double x = cwd * ucn[g]; const double zlog2x = zlog * zlog * x; gam0 = zlog2x * zlog2x * exp(zlog) * cnsn; }
+              if (zlog < 0.0) { const double x = cwd * ucn[g]; const double zlog2x = zlog * zlog * x; gam0 = zlog2x * zlog2x * exp_le0(zlog) * cnsn; }
             }
             sumf[g] = sumf[g] + gam0 * f;
             sumfsin2[g] = sumfsin2[g] + gam0 * f * sinwdif2;
