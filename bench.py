@@ -33,8 +33,7 @@ METRIC = "grid-point spectra/s per timestep (IMPLSCH+PROPAGS2)"
 NCU_SOURCE = "profiles/r02y_ncu_summary_O640.txt"
 NCU_DRAM_BYTES = {("O640", 1): {"implsch_stencil": 36.189e9, "implsch_point": 53.663e9, "propags2": 23.030e9}}
 NCU_FP64_FLOP_PER_POINT = {36: {"implsch_stencil": 290.8e3, "implsch_point": 139.7e3, "propags2": 46.9e3}}
-# pipe utilisation of the same capture (sm__inst_executed_pipe_fp64 / sm__issue_active, % of peak; the FP64 pipe takes a warp
-# instruction every 2 cycles, so issue-cycle occupancy of a scheduler = issue% + fp64% / 2 ... of the cycles it could issue in)
+# pipe utilisation of the same capture (sm__inst_executed_pipe_fp64 / sm__issue_active / sm__warps_active, % of peak)
 NCU_PIPES = {36: {"implsch_stencil": {"fp64_pipe_pct": 35.5, "issue_active_pct": 56.6, "warps_active_pct": 24.4, "ms_under_ncu": 35.65},
                   "implsch_point": {"fp64_pipe_pct": 39.5, "issue_active_pct": 47.7, "warps_active_pct": 17.9, "ms_under_ncu": 17.35},
                   "propags2": {"fp64_pipe_pct": 25.7, "issue_active_pct": 56.9, "warps_active_pct": 24.6, "ms_under_ncu": 7.98}}}
