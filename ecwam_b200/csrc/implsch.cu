@@ -740,8 +740,13 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
 // kernel were as frequent as its dependency stalls), and the few scalars in between travel through the scratch slots.
 // CY: the cy49r1 physics instance (LLGCBZ0 and/or LLNORMAGAM, read at run time inside it); the CY = false instances do not
 // contain any of it.
+#ifdef KP_MAXREG2   // experiment: register cap of the second-call instance
+#define KP_BOUNDS(PH) __maxnreg__((PH) == 2 ? KP_MAXREG2 : 168)
+#else
+#define KP_BOUNDS(PH) __launch_bounds__(KP_NTH, KP_MINB)
+#endif
 template <bool ARD, int PH, bool CY>
-__global__ void __launch_bounds__(KP_NTH, KP_MINB) k_point(ImplDev d, long long p0, long long np) {
+__global__ void KP_BOUNDS(PH) k_point(ImplDev d, long long p0, long long np) {
   extern __shared__ double smem[];
   long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = p < p0 + np;
