@@ -201,6 +201,8 @@ int ecwam_b200_grstname(const char* cdated, const char* cdatef, int ifcst, const
   }
   const bool before = strncmp(cdated, cdatef, 14) < 0;          // grstname.F90:99-122
   const char* cdateh = before ? cdated : cdatef;
+  // 64-bit seconds: the reference's ISHIFTDAY / IMAXYEAR chunking (grstname.F90:108-120) only keeps its default-kind DIFDATE from
+  // overflowing beyond ~67 years; day count + remainder are the same numbers
   const long long ishift = before ? ifcst : sd - sf;
   const long long dd = ishift / 86400, hh = (ishift - dd * 86400) / 3600, mi = (ishift - dd * 86400 - hh * 3600) / 60;
   const long long ss = ishift - dd * 86400 - hh * 3600 - mi * 60;
