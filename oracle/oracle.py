@@ -256,10 +256,10 @@ class Oracle:
         return sl, fld
 
     def term(self, which):
-        """One source term alone: "sinput" (NGST = 1, LLSNEG = F, stored UFRIC / Z0M) or "sdissip": (SL, FLD)[m, k, ij]."""
+        """One source term alone: "sinput" (NGST = 1, LLSNEG = F, stored UFRIC / Z0M), "sdissip", "sbottom" or "sdiwbk": (SL, FLD)[m, k, ij]."""
         sl = np.empty((self.cfg.nfre, self.cfg.nang, self.niblo))
         fld = np.empty_like(sl)
-        if self.lib.orc_term(self.h, {"sinput": 1, "sdissip": 2}[which], sl.ctypes.data, fld.ctypes.data) != 0:
+        if self.lib.orc_term(self.h, {"sinput": 1, "sdissip": 2, "sbottom": 3, "sdiwbk": 4}[which], sl.ctypes.data, fld.ctypes.data) != 0:
             raise RuntimeError("orc_term failed")
         return sl, fld
 

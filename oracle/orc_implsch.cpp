@@ -1403,7 +1403,7 @@ void snonlin_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int IC
 
 // One source term alone for a chunk, from the fields as they are stored (test infrastructure for the per-term cross-checks):
 // which = 1: SINPUT with NGST = 1, LLSNEG = F (the first SINFLX call, sinflx.F90:156-167) using the stored UFRIC, Z0M;
-// which = 2: SDISSIP (sdissip.F90).  SL, FLD: (KIJL, NANG, NFRE).
+// which = 2: SDISSIP (sdissip.F90); which = 3: SBOTTOM; which = 4: SDIWBK (with FKMEAN's EMEAN, F1MEAN).  SL, FLD: (KIJL, NANG, NFRE).
 void term_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK, int which, double* SLp, double* FLDp) {
   const int NANG = c.nang, NFRE = c.nfre, KIJS = 1;
   Ctx x{c, t, KIJS, KIJL, NANG, NFRE};
@@ -1434,6 +1434,14 @@ void term_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK
     FKMEAN(x, FL1, WAVNUM, lEM.view(), lFM.view(), lF1.view(), lAK.view(), lXK.view());
     if (c.iphys == 0) SDISSIP_JAN(x, FL1, FLD, SL, WAVNUM, lEM.view(), lF1.view(), lXK.view());
     else SDISSIP_ARD(x, FL1, FLD, SL, WAVNUM, CGROUP, XK2CG, UFRIC, COSWDIF, RAORW);
+  } else if (which == 3) {
+    V1 DEPTH = s1(f.DEPTH);
+    SBOTTOM(x, FL1, FLD, SL, WAVNUM, DEPTH);
+  } else if (which == 4) {
+    V1 DEPTH = s1(f.DEPTH), EMAXDPT = s1(f.EMAXDPT);
+    L1 lEM(P), lFM(P), lF1(P), lAK(P), lXK(P);
+    FKMEAN(x, FL1, WAVNUM, lEM.view(), lFM.view(), lF1.view(), lAK.view(), lXK.view());
+    SDIWBK(x, FL1, FLD, SL, DEPTH, EMAXDPT, lEM.view(), lF1.view());
   } else throw std::runtime_error("term_chunk: unknown term");
 }
 

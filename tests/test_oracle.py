@@ -763,3 +763,125 @@ def test_ctu_weights_against_numpy(built):
         np.testing.assert_allclose(WKPMN[ij, k, :, 2].T, np.abs(dthp) - dthp, rtol=1e-10, atol=1e-16)
         np.testing.assert_allclose(WKPMN[ij, k, :, 0].T, dthm + np.abs(dthm), rtol=1e-10, atol=1e-16)
         np.testing.assert_allclose(SUMWN[ij, k, :].T, sumw + w0, rtol=1e-10, atol=1e-15)
+
+
+@pytest.mark.parametrize("case", ["o48like", "o640like"])
+def test_stokes_drift_against_numpy(built, case):
+    """STOKESDRIFT (stokesdrift.F90:95-145) from the final spectrum: surface Stokes drift = int 2 g k^2 / (omega tanh 2kd) F dk-ish,
+    integrated with Simpson weights over the odd number of frequencies (DFIM_SIM rebuilt from initmdl.F90:486-493), plus the f^-5 tail
+    beyond FR(NFRE_ODD); under sea ice (LWAMRSETCI, CICOVER > CITHRSH) the 1.6 % of the wind rule; clipped at 1.5 m/s.  The Stokes
+    factor is rebuilt from the dispersion relation with the oracle's own wavenumber (depthprpt.F90:66-76)."""
+    g, o, f, fl = make_oracle(case)
+    for _ in range(2):
+        assert o.step() == 0
+    F1 = o.get_fl1()
+    NF, A, N = F1.shape
+    th, fr = o.table("TH"), o.table("FR")
+    wn = o.get_field3("WAVNUM")
+    G, ZPI = 9.806, 2 * np.pi
+    delth, xlf = ZPI / A, np.log(fr[1] / fr[0])
+    nodd = NF - 1 + NF % 2
+    w = np.zeros(NF)
+    w[0] = delth * xlf * fr[0] / 3.0
+    for m in range(1, nodd - 1, 2):                       # Fortran M = 2, NFRE_ODD-1, 2
+        w[m] = 4.0 * delth * xlf * fr[m] / 3.0
+        w[m + 1] = 2.0 * delth * xlf * fr[m + 1] / 3.0
+    w[nodd - 1] = delth * xlf * fr[nodd - 1] / 3.0
+    np.testing.assert_allclose(w, o.table("DFIM_SIM"), rtol=1e-14, atol=0)
+    om = ZPI * fr[:, None]
+    akd = wn * g.depth[None, :]
+    stokfac = np.where(akd <= 10.0, 2.0 * G * wn ** 2 / (om * np.tanh(2.0 * akd)), 2.0 / G * om ** 3)     # deep-water form beyond kd = 10
+    np.testing.assert_allclose(stokfac, o.get_field3("STOKFAC"), rtol=1e-12)
+    sx = (F1 * np.sin(th)[None, :, None]).sum(axis=1)
+    sy = (F1 * np.cos(th)[None, :, None]).sum(axis=1)
+    const = 2.0 * delth * ZPI ** 3 / G * fr[nodd - 1] ** 4
+    us = ((stokfac * w[:, None])[:nodd] * sx[:nodd]).sum(axis=0) + const * sx[nodd - 1]
+    vs = ((stokfac * w[:, None])[:nodd] * sy[:nodd]).sum(axis=0) + const * sy[nodd - 1]
+    ci, ws, wd = (o.get_field(k) for k in ("CICOVER", "WSWAVE", "WDWAVE"))
+    ice = (ci > o.cfg.cithrsh) & bool(o.cfg.licerun and o.cfg.lwamrsetci)
+    us = np.where(ice, 0.016 * ws * np.sin(wd) * (1.0 - ci), us)
+    vs = np.where(ice, 0.016 * ws * np.cos(wd) * (1.0 - ci), vs)
+    us, vs = np.clip(us, -1.5, 1.5), np.clip(vs, -1.5, 1.5)
+    assert ice.any() and (~ice).any()
+    np.testing.assert_allclose(o.get_field("USTOKES"), us, rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(o.get_field("VSTOKES"), vs, rtol=1e-10, atol=1e-14)
+
+
+def _mean_parameters(F1, wn, fr, dfim, delth):
+    """FKMEAN (fkmean.F90:60-154): total energy, mean frequency from F/f, and the two mean wavenumbers, each with its f^-5 tail."""
+    G, ZPI, EPSMIN, WETAIL, FRTAIL, WP1TAIL = 9.806, 2 * np.pi, 1e-33, 0.25, 0.2, 1.0 / 3.0
+    NF = F1.shape[0]
+    tot = F1.sum(axis=1)                                   # [m, ij]
+    last = tot[NF - 1]
+    delt25 = WETAIL * fr[NF - 1] * delth
+    coef1 = WP1TAIL * delth * fr[NF - 1] ** 2
+    em = EPSMIN + (dfim[:, None] * tot).sum(axis=0) + delt25 * last
+    f1 = (EPSMIN + ((dfim * fr)[:, None] * tot).sum(axis=0) + coef1 * last) / em
+    xk = ((EPSMIN + (np.sqrt(wn) * dfim[:, None] * tot).sum(axis=0) + coef1 * (ZPI / np.sqrt(G)) * last) / em) ** 2
+    return em, f1, xk
+
+
+def test_depth_induced_terms_against_numpy(built):
+    """SBOTTOM (sbottom.F90:76-97: JONSWAP bottom friction -2 * 0.038/g * k / sinh(2kd), propagated frequencies only) and SDIWBK
+    (sdiwbk.F90:84-117: Battjes-Janssen depth-induced breaking, the fraction of breaking waves Q from exp(-alpha (1 - Q)) = Q by
+    Newton's iteration, below 50 m) on a grid whose northern half is a 3 - 30 m shelf."""
+    def shelf(g):
+        n = g.depth.size
+        g.depth[n // 2:] = 3.0 + 27.0 * ((np.arange(n - n // 2) * 29) % 97) / 96.0
+    g, o, f, fl = make_oracle("o640like", grid_hook=shelf)
+    for _ in range(2):
+        assert o.step() == 0
+    F1 = o.get_fl1()
+    NF, A, N = F1.shape
+    Fr = CASES["o640like"]["Fr"]
+    wn = o.get_field3("WAVNUM")
+    fr, dfim = o.table("FR"), o.table("DFIM")
+    GM1 = 0.101978381
+    # SBOTTOM
+    sl, fld = o.term("sbottom")
+    sbo = np.where(g.depth[None, :] < o.cfg.bathymax, -2.0 * 0.038 * GM1 * wn / np.sinh(np.minimum(2.0 * g.depth[None, :] * wn, 50.0)), 0.0)
+    sbo[Fr:] = 0.0
+    np.testing.assert_allclose(fld, np.repeat(sbo[:, None, :], A, axis=1), rtol=1e-12, atol=0)
+    np.testing.assert_allclose(sl, sbo[:, None, :] * F1, rtol=1e-12, atol=0)
+    assert (sbo < 0).mean() > 0.3
+    # SDIWBK
+    sl, fld = o.term("sdiwbk")
+    em, f1, _ = _mean_parameters(F1, wn, fr, dfim, 2 * np.pi / A)
+    emax = o.get_field("EMAXDPT")
+    alph = 2.0 * emax / em
+    arg = np.minimum(alph, 50.0)
+    q_old = np.exp(-arg)
+    q = q_old.copy()
+    done = np.zeros(N, bool)
+    for _ in range(15):
+        expq = np.exp(-arg * (1.0 - q_old))
+        qn = q_old - (expq - q_old) / (arg * expq - 1.0)
+        q = np.where(done, q, qn)
+        conv = np.abs(qn - q_old) / q_old < 1e-5
+        q_old = np.where(done | conv, q_old, qn)
+        done |= conv
+    sds = np.where(g.depth < 50.0, 2.0 * alph * np.minimum(q, 1.0) * f1, 0.0)
+    ref = np.zeros((NF, N)); ref[:Fr] = -sds[None, :]
+    assert (sds > 1e-6).sum() > 10                            # waves break on the shelf
+    np.testing.assert_allclose(fld, np.repeat(ref[:, None, :], A, axis=1), rtol=1e-9, atol=1e-14 * np.abs(ref).max())
+    np.testing.assert_allclose(sl, ref[:, None, :] * F1, rtol=1e-9, atol=1e-14 * np.abs(sl).max())
+
+
+def test_whitecapping_of_the_wam4_package_against_numpy(built):
+    """SDISSIP_JAN (sdissip_jan.F90:96-132, IPHYS = 0): CDIS 2 pi <f> E^2 <k>^4 * x ((1 - delta) + delta x), x = k / <k>, plus the viscous
+    term; the mean parameters are FKMEAN's, rebuilt here."""
+    g, o, f, fl = make_oracle("o48_iphys0")
+    for _ in range(2):
+        assert o.step() == 0
+    sl, fld = o.term("sdissip")
+    F1 = o.get_fl1()
+    NF, A, N = F1.shape
+    wn = o.get_field3("WAVNUM")
+    em, f1, xk = _mean_parameters(F1, wn, o.table("FR"), o.table("DFIM"), 2 * np.pi / A)
+    cdis, delta, cdisvis = o.table("CDIS")[0], o.table("DELTA_SDIS")[0], o.table("CDISVIS")[0]
+    sds = cdis * 2 * np.pi * f1 * em ** 2 * xk ** 4
+    x = wn / xk[None, :]
+    d = sds[None, :] * x * ((1.0 - delta) + delta * x) + o.cfg.rnu * cdisvis * wn ** 2
+    assert (d < 0).all()
+    np.testing.assert_allclose(fld, np.repeat(d[:, None, :], A, axis=1), rtol=1e-9)
+    np.testing.assert_allclose(sl, d[:, None, :] * F1, rtol=1e-9, atol=1e-14 * np.abs(sl).max())
