@@ -885,3 +885,50 @@ def test_whitecapping_of_the_wam4_package_against_numpy(built):
     assert (d < 0).all()
     np.testing.assert_allclose(fld, np.repeat(d[:, None, :], A, axis=1), rtol=1e-9)
     np.testing.assert_allclose(sl, d[:, None, :] * F1, rtol=1e-9, atol=1e-14 * np.abs(sl).max())
+
+
+@pytest.mark.parametrize("case", ["o48like", "o640like"])
+def test_cutoff_index_against_numpy(built, case):
+    """MIJ, the last prognostic frequency (frcutindex.F90:79-97) -- the quantity that must be BIT-EXACT on the GPU -- rebuilt from its
+    definition: 2.5 x max(mean frequency of the wind sea, mean frequency) or the Pierson-Moskowitz frequency 3 g / (28 u* 2 pi),
+    whichever is larger, located on the geometric frequency axis; NFRE under sea ice.  The spectrum IMPLSCH sees is rebuilt from
+    the propagated one (SDEPTHLIM's factor, the EPSMIN floor, FLM at the last frequency), the wind-sea part is XLLWS of the second
+    SINPUT call (femeanws.F90:60-110), the mean frequency FKMEAN's."""
+    g, o, f, fl = make_oracle(case)
+    assert o.step() == 0
+    assert o.propag() == 0
+    raw = o.get_fl1()
+    NF, A, N = raw.shape
+    th, fr, dfim, dfimofr = o.table("TH"), o.table("FR"), o.table("DFIM"), o.table("DFIMOFR")
+    delth = 2 * np.pi / A
+    G, ZPI, EPSMIN, WETAIL, FRTAIL = 9.806, 2 * np.pi, 1e-33, 0.25, 0.2
+    delt25 = WETAIL * fr[NF - 1] * delth
+    ci, wd = o.get_field("CICOVER"), o.get_field("WDWAVE")
+    emax = o.get_field("EMAXDPT")
+    o.implsch()
+    # the spectrum inside IMPLSCH: SEMEAN -> SDEPTHLIM -> floor at NFRE (sdepthlim.F90:60-75, semean.F90, sinflx.F90:126-129)
+    tot = raw.sum(axis=1)
+    em0 = EPSMIN + (dfim[:, None] * tot).sum(axis=0) + delt25 * tot[NF - 1]
+    fac = np.minimum(emax / em0, 1.0) if o.cfg.lbiwbk else np.ones(N)
+    F1 = np.maximum(raw * fac[None, None, :], EPSMIN)
+    flm = (1.0 - 0.9 * np.minimum(ci, 0.99)) * o.cfg.flmin * np.maximum(0.0, np.cos(th[:, None] - wd[None, :])) ** 2
+    F1[NF - 1] = np.maximum(F1[NF - 1], flm)
+    # FKMEAN's mean frequency and FEMEANWS's wind-sea mean frequency
+    t = F1.sum(axis=1)
+    em = EPSMIN + (dfim[:, None] * t).sum(axis=0) + delt25 * t[NF - 1]
+    fm = em / (EPSMIN + (dfimofr[:, None] * t).sum(axis=0) + FRTAIL * delth * t[NF - 1])
+    x = o.get_xllws()
+    tw = (x * F1).sum(axis=1)
+    emw = EPSMIN + (dfim[:, None] * tw).sum(axis=0) + delt25 * tw[NF - 1]
+    fmw = emw / (EPSMIN + (dfimofr[:, None] * tw).sum(axis=0) + FRTAIL * delth * tw[NF - 1])
+    us = o.get_field("UFRIC")
+    fpmh = 2.5 / fr[0]
+    fppm = 3.0 * G / (28.0 * ZPI * fr[0])
+    fpm4 = np.maximum(np.maximum(fmw, fm) * fpmh, fppm / np.maximum(us, EPSMIN))
+    arg = np.log10(fpm4) / np.log10(fr[1] / fr[0])
+    mij = np.clip(np.floor(arg + 0.5).astype(int) + 1, 1, NF)
+    mij = np.where(ci > o.cfg.cithrsh_tail, NF, mij)
+    got = o.get_field("MIJ").astype(int)
+    near_half = np.abs(arg - np.floor(arg) - 0.5) < 1e-9          # NINT on a rounding boundary: not decidable from here
+    assert (got == mij)[~near_half].all() and near_half.mean() < 0.01
+    assert mij.min() < NF and (ci > o.cfg.cithrsh_tail).any()
