@@ -121,6 +121,9 @@ struct ecwam_b200_handle_s {
   // resident-state step (ecwam_b200_wamintgr_forced): device staging of the eight FF_NEXT fields
   DBuf<double> frc_next;
   DBuf<double> enhp;       // ENH(IJ,MC) plane of ISNONLIN = 1, 2
+  DBuf<double> ice1, ice2; // SDICE1's table (+ per-frequency period interpolation), SDICE2's per-(point, frequency) factor (k_ice)
+  int ice_nt = 0, ice_nh = 0;
+  double ice_hmin = 0.0, ice_dh = 1.0;
   // NEWWIND / OUTBLOCK / WAMNORM
   DBuf<double> normbuf, zglobal;
   DBuf<int> ij2new_d;
@@ -212,7 +215,8 @@ static int fill_dev_const(const ecwam_b200_params& p, const ecwam_b200_tables& t
   if ((p.llgcbz0 || p.llnormagam) && (t.nwav_gc < 2 || !t.xk_gc || !t.omega_gc || !t.cm_gc || !t.c2osqrtvg_gc || !t.xkmsqrtvgoc2_gc ||
                                       !t.om3gmkm_gc || !t.omxkm3_gc || !t.delkcc_gc_ns || !t.delkcc_omxkm3_gc))
     EW_FAIL(ECWAM_B200_EINVAL, "LLGCBZ0 / LLNORMAGAM need the gravity-capillary tables (ecwam_b200_tables: nwav_gc, *_gc)");
-  if (p.lciwa & 3) EW_FAIL(ECWAM_B200_EINVAL, "LCIWA1 / LCIWA2 sea-ice attenuation (SDICE1, SDICE2) is not implemented (SURVEY 8f rank 2)");
+  if ((p.lciwa & 1) && (t.nict < 2 || t.nich < 2 || !t.cideac || !(t.dtic > 0.0) || !(t.dhic > 0.0)))
+    EW_FAIL(ECWAM_B200_EINVAL, "LCIWA1 (SDICE1) needs the CIDEAC table (ecwam_b200_tables: nict, nich, ticmin, hicmin, dtic, dhic, cideac)");
   if (p.lciwa & ~15) EW_FAIL(ECWAM_B200_EINVAL, "lciwa: unknown bits");
   if (p.lwnemocou) EW_FAIL(ECWAM_B200_EINVAL, "NEMO coupling accumulators are not implemented");
   if (p.icode_wnd != 3) EW_FAIL(ECWAM_B200_EINVAL, "only ICODE_WND=3 (10 m wind forcing) is implemented");
@@ -227,6 +231,8 @@ static int fill_dev_const(const ecwam_b200_params& p, const ecwam_b200_tables& t
   c.lbiwbk = p.lbiwbk; c.licerun = p.licerun; c.lmaskice = p.lmaskice; c.lwamrsetci = p.lwamrsetci; c.lwflux = p.lwflux;
   c.lcflx = (p.lwflux || p.lwfluxout || p.lwnemocou) ? 1 : 0;   // implsch.F90:187
   c.lciwa3 = (p.lciwa & 4) ? 1 : 0; c.lciscal = (p.lciwa & 8) ? 1 : 0; c.zalpfacx = p.zalpfacx;
+  c.lciwa1 = (p.lciwa & 1) ? 1 : 0; c.lciwa2 = (p.lciwa & 2) ? 1 : 0; c.lciwa_any = (p.lciwa & 7) ? 1 : 0;
+  c.zalpfacb = p.zalpfacb; c.cdicwa = p.cdicwa;
   {   // SDICE3, IMODEL = 2: ALP = (2*CDICE*CITH**1.25*FR(M)**4.5)*ALPFAC with CDICE = 0.1274*(ZPI/SQRT(G))**4.5 (sdice3.F90:123-129)
     const double cdice = 0.1274 * std::pow(t.zpi / std::sqrt(t.g), 4.5);
     for (int m = 0; m < p.nfre && m < EW_MAXF; ++m) c.fr45[m] = 2. * cdice * std::pow(t.fr[m], 4.5);
@@ -588,6 +594,22 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
   ok = ok && !h->scr.alloc(implsch_scratch_doubles(npts)) && !h->fldin.alloc((size_t)npts * A * F) &&
        !h->tbg.alloc((size_t)EW_TQ_N * F * npts);
   if (p.isnonlin != 0) ok = ok && !h->enhp.alloc((size_t)tables->mlsthg * npts);
+  if (p.licerun && (p.lciwa & 1)) {   // SDICE1: the table and, per frequency, the wave-period interpolation (sdice1.F90:144-151)
+    const int NT = tables->nict, NH = tables->nich;
+    std::vector<double> ice((size_t)NT * NH + 3 * (size_t)F);
+    for (size_t i = 0; i < (size_t)NT * NH; ++i) ice[i] = tables->cideac[i];
+    for (int m = 0; m < F; ++m) {
+      const double tw = 1.0 / tables->fr[m];
+      int it = (int)std::floor((tw - tables->ticmin) / tables->dtic + 1);
+      it = std::max(1, std::min(it, NT));
+      const int it1 = std::max(1, std::min(it + 1, NT));
+      const double wt1 = std::max(std::min(1.0, (tw - (tables->ticmin + (it - 1) * tables->dtic)) / tables->dtic), 0.0);
+      ice[(size_t)NT * NH + m] = wt1; ice[(size_t)NT * NH + F + m] = it - 1; ice[(size_t)NT * NH + 2 * F + m] = it1 - 1;
+    }
+    ok = ok && !h->ice1.upload(ice, st);
+    h->ice_nt = NT; h->ice_nh = NH; h->ice_hmin = tables->hicmin; h->ice_dh = tables->dhic;
+  }
+  if (p.licerun && (p.lciwa & 2)) ok = ok && !h->ice2.alloc((size_t)F * npts);
   if (!ok) { ecwam_b200_destroy(h); return ECWAM_B200_ECUDA; }
   cudaMemsetAsync(h->halo.p, 0, (halo_elems + 1) * sizeof(double), st);
   cudaMemsetAsync(h->fl3.p, 0, h->fl3.n * sizeof(double), st);
@@ -868,6 +890,8 @@ static ImplDev make_impl(H* h, bool from_fl3) {
   d.ssource_pre = (h->dc.lcflx && !h->par.lwvflx_snl) ? 1 : 0;
   d.isnonlin = h->par.isnonlin;
   d.enh = h->enhp.p;
+  d.ice1 = h->ice1.p; d.ice_nt = h->ice_nt; d.ice_nh = h->ice_nh; d.ice_hmin = h->ice_hmin; d.ice_dh = h->ice_dh;
+  d.ice2 = h->ice2.p;
   return d;
 }
 

@@ -62,6 +62,9 @@ struct DevConst {
   double NLD[8];
   int NLS2[EW_MAXMC + 1][2];
   int sweep_ok, pad_sw;
+  // SDICE1 / SDICE2 (appended: the offsets above stay put)
+  int lciwa1, lciwa2, lciwa_any, pad_ice;   // lciwa_any: LCIWA1 or LCIWA2 or LCIWA3 (WNFLUXES' sea-ice constants, wnfluxes.F90:150-158)
+  double zalpfacb, cdicwa;                  // YOWICE ZALPFACB, CDICWA
 };
 // rows of the gravity-capillary table ImplDev::gc [GC_NT][NWAV_GC] (YOWFRED *_GC, initgc.F90)
 enum { GC_XK = 0, GC_OMEGA, GC_CM, GC_C2OSQRTVG, GC_XKMSQRTVGOC2, GC_OM3GMKM, GC_OMXKM3, GC_DELKCC_NS, GC_DELKCC_OMXKM3, GC_DELKCC,

@@ -17,6 +17,7 @@ struct HostTables {
   std::vector<double> satweights, swellft, wtauhf, rnlcoef, af11;
   std::vector<int> indicessat, ikp, ikp1, ikm, ikm1, k1w, k2w, k11w, k21w, inlcoef;
   std::vector<double> xk_gc, omega_gc, cm_gc, c2osqrtvg_gc, xkmsqrtvgoc2_gc, om3gmkm_gc, omxkm3_gc, delkcc_gc_ns, delkcc_omxkm3_gc, delkcc_gc;
+  std::vector<double> cideac;
   double delta_theta_rn = 0.75;
 };
 
@@ -493,6 +494,25 @@ void dia_tables(const ecwam_b200_params& p, HostTables& h) {
   }
 }
 
+// ---- src/ecwam/cigetdeac.F90:60-75: ln of the attenuation per floe as a function of wave period (1..16 s) and ice thickness
+// (0.2..3.7 m).  Periods 6..16 s are Kohout & Meylan's data; the 1 s column is assumed (-2 at 0.2 m to -1 at 3.7 m, linear in the
+// thickness) and the periods in between are a straight line from the 1 s to the 6 s value.
+void ice_attenuation_table(HostTables& h) {
+  static const double data[36][11] = {
+#include "kohout_meylan_fig6.inc"
+  };
+  ecwam_b200_tables& t = h.t;
+  t.nict = 16; t.nich = 36; t.ticmin = 1.0; t.hicmin = 0.2; t.dtic = 1.0; t.dhic = 0.1;
+  h.cideac.assign((size_t)t.nict * t.nich, 0.0);
+  for (int ih = 0; ih < t.nich; ++ih) {
+    double* col = &h.cideac[(size_t)t.nict * ih];      // CIDEAC(:, ih+1)
+    col[0] = (ih == 0) ? -2.0 : (ih == t.nich - 1) ? -1.0 : -2.0 + ih * (-1.0 - -2.0) / (t.nich - 1);
+    for (int it = 5; it < t.nict; ++it) col[it] = data[ih][it - 5];
+    const double dci = col[5] - col[0];
+    for (int it = 1; it < 5; ++it) col[it] = col[0] + dci * it * t.dtic / (5 * t.dtic);
+  }
+}
+
 }  // namespace
 
 struct ecwam_b200_host_tables_s { HostTables h; };
@@ -513,7 +533,9 @@ int ecwam_b200_host_tables_create(const ecwam_b200_params* params, int ifre1, do
   saturation_tables(*params, h);
   dia_tables(*params, h);
   gravity_capillary_tables(h);
+  ice_attenuation_table(h);
   ecwam_b200_tables& t = h.t;
+  t.cideac = h.cideac.data();
   t.xk_gc = h.xk_gc.data(); t.omega_gc = h.omega_gc.data(); t.cm_gc = h.cm_gc.data(); t.c2osqrtvg_gc = h.c2osqrtvg_gc.data();
   t.xkmsqrtvgoc2_gc = h.xkmsqrtvgoc2_gc.data(); t.om3gmkm_gc = h.om3gmkm_gc.data(); t.omxkm3_gc = h.omxkm3_gc.data();
   t.delkcc_gc_ns = h.delkcc_gc_ns.data(); t.delkcc_omxkm3_gc = h.delkcc_omxkm3_gc.data(); t.delkcc_gc = h.delkcc_gc.data();

@@ -1140,8 +1140,8 @@ __device__ __forceinline__ void stencil_closure(const ImplDev& d, const long lon
       const double PHIOC_ICE = -3.75, PHIAW_ICE = 3.75, C1 = 1.03e-3, C2 = 0.04e-3, P1 = 1.48, P2 = -0.21, CDMAX_LOC = 0.003;
       const double epsus3 = c_dc.EPSUS * sqrt(c_dc.EPSUS);
       // wnfluxes.F90:150-158: with a sea-ice attenuation scheme the open-water weight decays over CICOVER 0..0.02
-      const double cithrsh_inv = c_dc.lciwa3 ? 50.0 : 1.0 / dmax(c_dc.cithrsh, 0.01);
-      const double zcithrs = c_dc.lciwa3 ? 0.0 : c_dc.ciblock, zmaxexp = c_dc.lciwa3 ? 20.0 : 10.0;
+      const double cithrsh_inv = c_dc.lciwa_any ? 50.0 : 1.0 / dmax(c_dc.cithrsh, 0.01);
+      const double zcithrs = c_dc.lciwa_any ? 0.0 : c_dc.ciblock, zmaxexp = c_dc.lciwa_any ? 20.0 : 10.0;
       const double phiwa = s[S_PHIWA * n + pp];
       double ooval = 1.0, ustar = ufric;
       if (c_dc.licerun && c_dc.lwamrsetci && cicover > zcithrs) {
@@ -1475,7 +1475,11 @@ __global__ void ST_BOUNDS(NP) k_stencil(ImplDev d, long long p0, long long np, S
         else if (lsspre) ssource = slv - tot_sl.v[i];    // LWVFLX_SNL = F: SL before SNONLIN, not modulated (implsch.F90:279-288)
         if (r < c_dc.Fr) { slv = slv - sdsbk.v[i] * f0; fldv = fldv - sdsbk.v[i]; }   // SDIWBK (0 where it does not apply)
         if (c_dc.lciscal) { slv = slv * beta.v[i]; fldv = fldv * beta.v[i]; }        // LCISCAL (implsch.F90:315-325)
-        slv = slv + tsbo.v[i] * f0; fldv = fldv + tsbo.v[i];                         // SDICE3 + SBOTTOM (plane is 0 where neither applies)
+        if (d.ice2) {   // SDICE2 (sdice2.F90:97-113): ALP = CDICWA*k^2*4*sqrt(max(EPSMIN, F*DFIM))*ZALPFACB, the per-(point, frequency) part from k_ice
+          const double e = __ldg(d.ice2 + (size_t)r * n + pq + i) * sqrt(dmax(c_dc.EPSMIN, f0 * c_dc.DFIM[r]));
+          slv = slv - e * f0; fldv = fldv - e;
+        }
+        slv = slv + tsbo.v[i] * f0; fldv = fldv + tsbo.v[i];                         // SDICE1 + SDICE3 + SBOTTOM (plane is 0 where none applies)
         const double gtemp1 = dmax(1.0 - delt5 * fldv, 1.0);
         const double gtemp2 = div_norm(delt * slv, gtemp1);
         const double flhab = dmin(fabs(gtemp2), usfm.v[i] * cofrm4);
@@ -1954,6 +1958,10 @@ __global__ void __maxnreg__(ST_MAXREG) k_stencil_dp(ImplDev d, long long p0, lon
         else if (lsspre) ssource = slv - tot_sl.v[i];    // LWVFLX_SNL = F: SL before SNONLIN, not modulated (implsch.F90:279-288)
         if (r < c_dc.Fr) { slv = slv - sdsbk * f0; fldv = fldv - sdsbk; }            // SDIWBK (0 where it does not apply)
         if (c_dc.lciscal) { slv = slv * beta; fldv = fldv * beta; }                  // LCISCAL (implsch.F90:315-325)
+        if (d.ice2) {   // SDICE2 (sdice2.F90:97-113), see k_stencil
+          const double e = __ldg(d.ice2 + (size_t)r * n + pq) * sqrt(dmax(c_dc.EPSMIN, f0 * c_dc.DFIM[r]));
+          slv = slv - e * f0; fldv = fldv - e;
+        }
         slv = slv + tsbo * f0; fldv = fldv + tsbo;                                   // SDICE3 + SBOTTOM (plane is 0 where neither applies)
         const double gtemp1 = dmax(1.0 - delt5 * fldv, 1.0);
         const double gtemp2 = div_norm(delt * slv, gtemp1);
@@ -3291,6 +3299,68 @@ __global__ void __launch_bounds__(128) k_enh(ImplDev d, long long p0, long long 
   }
 }
 
+// =========================================================================================================
+// k_ice: the per-(point, frequency) parts of SDICE1 and SDICE2 (sdice.F90:99-107), one thread per grid point, between k_point and the
+// frequency sweep.
+//   LCIWA1 (sdice1.F90:102-187): scattering by ice floes.  ALP = exp(CIDEAC(T, h)) / <D> * ZALPFACB with Kohout & Meylan's table
+//     interpolated bilinearly in wave period and ice thickness and the mean floe size <D> of Dumont et al.'s fragmentation cascade
+//     (a function of the ice cover).  The term is linear in the spectrum (SL += CICV*FLDICE*F, FLD += CICV*FLDICE) like SBOTTOM and
+//     SDICE3, so it is added to their plane tbg[TQ_SBO].
+//   LCIWA2 (sdice2.F90:97-113): friction under the ice, ALP = CDICWA*k^2*4*sqrt(max(EPSMIN, F*DFIM))*ZALPFACB depends on the bin:
+//     ice2[m][p] = CICV*CDICWA*ZALPFACB*4*k^2*CGROUP, the sqrt is taken in the finish stage of k_stencil / k_stencil_dp.
+// ice1 = [NICT*NICH] CIDEAC, then per frequency WT1 (F), IT (F, 0-based, as double), IT1 (F).
+// =========================================================================================================
+__global__ void __launch_bounds__(128) k_ice(ImplDev d, long long p0, long long np) {
+  const long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= p0 + np) return;
+  const int F = c_dc.F;
+  const size_t n = (size_t)d.npts;
+  const double ci = d.f.cicover[p], cith = d.f.cithick[p];
+  if (d.ice1) {
+    const int NT = d.ice_nt, NH = d.ice_nh;
+    const double* tabw = d.ice1 + (size_t)NT * NH;
+    double dinv = 20.0;       // CIDMIN (sdice1.F90:127: only reached with CITH <= 0, where ALP = 0 anyway)
+    int ih = 0, ih1 = 0;
+    double wh = 1.0, wh1 = 0.0;
+    if (cith > 0.0) {
+      const double CIFRGL = 0.955, CIDMIN = 20.0, CIFRGMT = 2.0, A0 = 200.0, C0 = 300.0;
+      const int maxicm = (int)(log(A0 / CIDMIN) / log(CIFRGMT));
+      const double cidmax = A0 + C0 * ci;
+      const int icm = min((int)(log(cidmax / CIDMIN) / log(CIFRGMT)), maxicm);
+      double sn = 0.0, sd = 0.0, x = 1.0, fi = 1.0;      // x = (CIFRGMT**2*CIFRGL)**I, fi = CIFRGMT**I
+      for (int i = 0; i <= icm; ++i) {
+        sn = sn + x * cidmax / fi;
+        sd = sd + x;
+        x = x * (CIFRGMT * CIFRGMT * CIFRGL); fi = fi * CIFRGMT;
+      }
+      dinv = 1.0 / (sn / sd);
+      ih = (int)floor((cith - d.ice_hmin) / d.ice_dh + 1) ;
+      ih = max(1, min(ih, NH));
+      ih1 = max(1, min(ih + 1, NH));
+      wh1 = dmax(dmin(1.0, (cith - (d.ice_hmin + (ih - 1) * d.ice_dh)) / d.ice_dh), 0.0);
+      wh = 1.0 - wh1;
+      ih -= 1; ih1 -= 1;
+    }
+    for (int m = 0; m < F; ++m) {
+      double alp = 0.0;
+      if (cith > 0.0) {
+        const double wt1 = tabw[m], wt = 1.0 - wt1;
+        const int it = (int)tabw[F + m], it1 = (int)tabw[2 * F + m];
+        const double c = wt * (wh * d.ice1[it + NT * ih] + wh1 * d.ice1[it + NT * ih1]) + wt1 * (wh * d.ice1[it1 + NT * ih] + wh1 * d.ice1[it1 + NT * ih1]);
+        alp = exp(c) * dinv * c_dc.zalpfacb;
+      }
+      d.tbg[((size_t)TQ_SBO * F + m) * n + p] += ci * (-alp * d.f.cgroup[idx3(d, p, m)]);
+    }
+  }
+  if (d.ice2) {
+    for (int m = 0; m < F; ++m) {
+      const size_t o3 = idx3(d, p, m);
+      const double wk = d.f.wavnum[o3];
+      d.ice2[(size_t)m * n + p] = ci * ((c_dc.cdicwa * (wk * wk) * 4.0 * c_dc.zalpfacb) * d.f.cgroup[o3]);
+    }
+  }
+}
+
 int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage, cudaStream_t st) {
   if (np <= 0) return 0;
   const int A = d.A;
@@ -3315,6 +3385,7 @@ int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage
     } else if (d.iphys == 1) { k_point<true, 1, false><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<true, 2, false><<<nb, KP_NTH, smp, st>>>(d, p0, np); }
     else { k_point<false, 1, false><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<false, 2, false><<<nb, KP_NTH, smp, st>>>(d, p0, np); }
     if (d.isnonlin != 0) k_enh<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(d, p0, np);
+    if (d.ice1 || d.ice2) k_ice<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(d, p0, np);
   } else if (stage == 1) {
     // two grid points per thread (16-byte shared / global accesses) need an even NPROMA and an even first point
     const uintptr_t al = (uintptr_t)d.f.fl1 | (uintptr_t)d.f.xllws | (uintptr_t)d.fldin | (uintptr_t)d.fl_lo;
@@ -3326,7 +3397,8 @@ int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage
     // default for the standard grids: thread = (two adjacent directions, one point); ECWAM_B200_STENCIL=pp keeps the
     // two-points-per-thread instance (A/B timing, tests)
     // LWVFLX_SNL = F (SSOURCE = SL before SNONLIN, implsch.F90:279-288) is built into k_stencil / k_stencil_dp only
-    const bool sweep_ok = d.sweep_ok && !d.ssource_pre;
+    // LCIWA2 (SDICE2's per-bin attenuation) likewise
+    const bool sweep_ok = d.sweep_ok && !d.ssource_pre && !d.ice2;
     // default for NANG = 36: k_sweep_ws (producer / consumer warp groups); ECWAM_B200_STENCIL=sweep: the one-role k_sweep
     if (!force && sweep_ok && geo_matches<36>(d, d.iphys, d.nsdsnth))
       return d.lwflux ? launch_sweep_ws<36, 7, true>(d, p0, np, st) : launch_sweep_ws<36, 7, false>(d, p0, np, st);

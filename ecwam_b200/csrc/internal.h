@@ -92,6 +92,11 @@ struct ImplDev {
   int ssource_pre;         // LCFLX and not LWVFLX_SNL: WNFLUXES takes SL before SNONLIN (only k_stencil / k_stencil_dp carry that branch)
   int isnonlin;            // YOWSTAT ISNONLIN (0: ENH from the mean wavenumber; 1, 2: per centre frequency, snonlin.F90:138-163)
   double* enh;             // [MLSTHG][npts] ENH(IJ,MC) of ISNONLIN = 1, 2 (k_enh writes it between k_point and the sweep); null otherwise
+  const double* ice1;      // LCIWA1: [NICT*NICH] CIDEAC, [F] WT1, [F] IT, [F] IT1 (0-based, as doubles) of SDICE1 (k_ice); null otherwise
+  int ice_nt, ice_nh;      // NICT, NICH
+  double ice_hmin, ice_dh; // HICMIN, DHIC
+  long long pad_ice;       // keeps sizeof(ImplDev) a multiple of 16: the kernels' (p0, np) arguments stay 16-byte aligned (one LDCU.128)
+  double* ice2;            // LCIWA2: [F][npts] per-(point, frequency) factor of SDICE2 (k_ice writes it, k_stencil / k_stencil_dp read it); null otherwise
 };
 #define EW_TQ_N 6          // number of planes of ImplDev::tbg
 int upload_dev_const(const DevConst& h, cudaStream_t st);

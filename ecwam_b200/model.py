@@ -36,7 +36,7 @@ def default_params(**kw) -> L.Params:
                  llcapchnk=1, lbiwbk=1, licerun=1, lmaskice=1, lwamrsetci=1, lciwa=0, lwflux=0, lwfluxout=1, lwnemocou=0,
                  lwvflx_snl=1, lwcouast=0, icode_wnd=3, ifrelfmax=0, nproma=32, nchnk=0, idelt=900.0, idelpro=900.0,
                  delpro_lf=900.0, ximp=1.0, rnu=1.5e-5, rnum=0.11 * 1.5e-5, wspmin=1.0, cithrsh=0.3, cithrsh_tail=0.3,
-                 ciblock=0.0, flmin=1e-5, bathymax=998.999, llcflcuroff=1, zalpfacx=1.0)
+                 ciblock=0.0, flmin=1e-5, bathymax=998.999, llcflcuroff=1, zalpfacx=1.0, zalpfacb=1.0, cdicwa=0.01)
     for k, v in kw.items():
         if not hasattr(p, k):
             raise KeyError(k)

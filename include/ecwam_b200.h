@@ -53,7 +53,7 @@ typedef struct ecwam_b200_params {
   int licerun;     /* YOWICE LICERUN                                                    */
   int lmaskice;    /* YOWICE LMASKICE                                                   */
   int lwamrsetci;  /* YOWICE LWAMRSETCI                                                 */
-  int lciwa;       /* YOWICE bit mask: 1 LCIWA1, 2 LCIWA2 (both not built), 4 LCIWA3 (SDICE3), 8 LCISCAL */
+  int lciwa;       /* YOWICE bit mask: 1 LCIWA1 (SDICE1, needs ecwam_b200_tables cideac), 2 LCIWA2 (SDICE2), 4 LCIWA3 (SDICE3), 8 LCISCAL */
   int lwflux;      /* YOWCOUP LWFLUX                                                    */
   int lwfluxout;   /* YOWCOUP LWFLUXOUT (userin.F90:470 sets it .TRUE.)                 */
   int lwnemocou;   /* YOWCOUP LWNEMOCOU (0 only)                                        */
@@ -77,6 +77,8 @@ typedef struct ecwam_b200_params {
   double bathymax; /* YOWSHAL BATHYMAX                                                  */
   int llcflcuroff; /* YOWSTAT LLCFLCUROFF (IREFRA = 2, 3): retry the CFL check without current refraction */
   double zalpfacx; /* YOWICE ZALPFACX (attenuation factor of SDICE3, 1 = no reduction)    */
+  double zalpfacb; /* YOWICE ZALPFACB (scales SDICE1 / SDICE2; mpuserin.F90:780: 1)             */
+  double cdicwa;   /* YOWICE CDICWA (ice-water drag coefficient of SDICE2; userin.F90:974: 0.01) */
 } ecwam_b200_params;
 
 /* ---------------------------------------------------------------------------------------------------
@@ -215,6 +217,14 @@ typedef struct ecwam_b200_tables {
   const double* delkcc_gc_ns;     /* (NWAV_GC) */
   const double* delkcc_omxkm3_gc; /* (NWAV_GC) */
   const double* delkcc_gc;        /* (NWAV_GC) read by MEANSQS_GC (OUTBLOCK parameter 9) */
+  /* YOWICE (yowice.F90:20-31, cigetdeac.F90:60-75): Kohout & Meylan's attenuation table of SDICE1.  Read only with LCIWA1. */
+  int nict;                       /* wave-period dimension of CIDEAC (16)      */
+  int nich;                       /* ice-thickness dimension of CIDEAC (36)    */
+  double ticmin;                  /* first wave period of the table [s] (1)    */
+  double hicmin;                  /* first ice thickness of the table [m] (0.2) */
+  double dtic;                    /* wave-period increment [s] (1)             */
+  double dhic;                    /* ice-thickness increment [m] (0.1)         */
+  const double* cideac;           /* (NICT, NICH) column-major                 */
 } ecwam_b200_tables;
 
 /* ---------------------------------------------------------------------------------------------------

@@ -81,6 +81,7 @@ struct Config {
   double wspmin = 1.0;                         // userin.F90:913-918 (LLGCBZ0=F)
   double cithrsh = 0.3, cithrsh_tail = 0.3, ciblock = 0.0;
   double flmin = 1e-5, zalpfacx = 1.0;
+  double zalpfacb = 1.0, cdicwa = 0.01;   // YOWICE ZALPFACB (mpuserin.F90:780), CDICWA (userin.F90:962-976: 0.01 with LCIWA2)
   double bathymax = 998.999, deptha = 2.0;
   int nproma = 32;
   int npr = 1;  // emulated MPI ranks (in-process)
@@ -136,6 +137,10 @@ struct Tables {
   ArrI IKP, IKP1, IKM, IKM1, K1W, K2W, K11W, K21W, INLCOEF;
   ArrD AF11, FKLAP, FKLAP1, FKLAM, FKLAM1, FRH, RNLCOEF, FTRF;
   double ACL1, ACL2, CL11, CL21, DAL1, DAL2;
+  // YOWICE (cigetdeac.F90:60-75): Kohout & Meylan's attenuation table of SDICE1
+  int NICT = 0, NICH = 0;
+  double TICMIN = 1.0, HICMIN = 0.2, DTIC = 1.0, DHIC = 0.1;
+  ArrD CIDEAC;   // (NICT,NICH)
 };
 
 void init_tables(const Config& c, Tables& t);

@@ -24,7 +24,8 @@ class Config(C.Structure):
         ("lwcou", C.c_int), ("icode", C.c_int), ("idelt", C.c_double), ("idelpro", C.c_double),
         ("delpro_lf", C.c_double), ("ifrelfmax", C.c_int), ("ximp", C.c_double), ("rnu", C.c_double),
         ("rnum", C.c_double), ("wspmin", C.c_double), ("cithrsh", C.c_double), ("cithrsh_tail", C.c_double),
-        ("ciblock", C.c_double), ("flmin", C.c_double), ("zalpfacx", C.c_double), ("bathymax", C.c_double),
+        ("ciblock", C.c_double), ("flmin", C.c_double), ("zalpfacx", C.c_double), ("zalpfacb", C.c_double), ("cdicwa", C.c_double),
+        ("bathymax", C.c_double),
         ("deptha", C.c_double), ("nproma", C.c_int), ("npr", C.c_int), ("ll1d", C.c_int),
         ("store_all_weights", C.c_int), ("nthreads", C.c_int), ("llcflcuroff", C.c_int),
     ]
@@ -36,7 +37,7 @@ def default_config(**kw) -> Config:
                lwamrsetci=1, lciwa1=0, lciwa2=0, lciwa3=0, lciscal=0, lwflux=0, lwfluxout=1, lwnemocou=0,
                lwvflx_snl=1, lwcouast=0, lwcou=0, icode=3, idelt=900.0, idelpro=900.0, delpro_lf=900.0, ifrelfmax=0,
                ximp=1.0, rnu=1.5e-5, rnum=0.11 * 1.5e-5, wspmin=1.0, cithrsh=0.3, cithrsh_tail=0.3, ciblock=0.0,
-               flmin=1e-5, zalpfacx=1.0, bathymax=998.999, deptha=2.0, nproma=32, npr=1, ll1d=0,
+               flmin=1e-5, zalpfacx=1.0, zalpfacb=1.0, cdicwa=0.01, bathymax=998.999, deptha=2.0, nproma=32, npr=1, ll1d=0,
                store_all_weights=0, nthreads=1, llcflcuroff=1)
     for k, v in kw.items():
         if not hasattr(c, k):
@@ -256,10 +257,10 @@ class Oracle:
         return sl, fld
 
     def term(self, which):
-        """One source term alone: "sinput" (NGST = 1, LLSNEG = F, stored UFRIC / Z0M), "sdissip", "sbottom" or "sdiwbk": (SL, FLD)[m, k, ij]."""
+        """One source term alone: "sinput" (NGST = 1, LLSNEG = F, stored UFRIC / Z0M), "sdissip", "sbottom", "sdiwbk" or "sdice" (the LCIWA1-3 terms that are on): (SL, FLD)[m, k, ij]."""
         sl = np.empty((self.cfg.nfre, self.cfg.nang, self.niblo))
         fld = np.empty_like(sl)
-        if self.lib.orc_term(self.h, {"sinput": 1, "sdissip": 2, "sbottom": 3, "sdiwbk": 4}[which], sl.ctypes.data, fld.ctypes.data) != 0:
+        if self.lib.orc_term(self.h, {"sinput": 1, "sdissip": 2, "sbottom": 3, "sdiwbk": 4, "sdice": 5}[which], sl.ctypes.data, fld.ctypes.data) != 0:
             raise RuntimeError("orc_term failed")
         return sl, fld
 

@@ -79,7 +79,7 @@ long orc_get_table(void* h, const char* name, double* out, long cap) {
       {"FKLAM", &t.FKLAM}, {"FKLAM1", &t.FKLAM1}, {"FRH", &t.FRH}, {"RNLCOEF", &t.RNLCOEF}, {"FTRF", &t.FTRF},
       {"XK_GC", &t.XK_GC}, {"OMEGA_GC", &t.OMEGA_GC}, {"CM_GC", &t.CM_GC}, {"C2OSQRTVG_GC", &t.C2OSQRTVG_GC},
       {"XKMSQRTVGOC2_GC", &t.XKMSQRTVGOC2_GC}, {"OM3GMKM_GC", &t.OM3GMKM_GC}, {"OMXKM3_GC", &t.OMXKM3_GC},
-      {"DELKCC_GC_NS", &t.DELKCC_GC_NS}, {"DELKCC_OMXKM3_GC", &t.DELKCC_OMXKM3_GC},
+      {"DELKCC_GC_NS", &t.DELKCC_GC_NS}, {"DELKCC_OMXKM3_GC", &t.DELKCC_OMXKM3_GC}, {"CIDEAC", &t.CIDEAC},
       {"ZDELLO", &m->grid.ZDELLO}, {"COSPH", &m->grid.COSPH}, {"SINPH", &m->grid.SINPH}, {"DELLAM", &m->grid.DELLAM}};
   auto it = mp.find(n);
   if (it != mp.end()) return copy_out(it->second->d, out, cap);

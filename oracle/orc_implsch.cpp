@@ -1,6 +1,6 @@
 // ORACLE (test infrastructure) — IMPLSCH and its call tree, restated loop by loop from the reference.
 // Branches exercised by the BASELINE configs only: LLGCBZ0=F, LLNORMAGAM=F, ISNONLIN=0,
-// LCIWA*=F, LWNEMOCOU*=F, ICODE_WND=3; IPHYS=0 and 1.  Off-by-default branches throw.
+// LWNEMOCOU*=F, ICODE_WND=3; IPHYS=0 and 1; LCIWA1-3 (SDICE).  Other off-by-default branches throw.
 #include "oracle.h"
 #ifdef _OPENMP
 #include <omp.h>
@@ -1260,6 +1260,82 @@ void HALPHAP(const Ctx& x, V2 WAVNUM, V2 COSWDIF, V3 FL1, V1 HALP) {
   }
 }
 
+// sdice.F90:99-112 with sdice1.F90:102-187, sdice2.F90:97-121, sdice3.F90:107-147
+void SDICE(const Ctx& x, V3 FL1, V3 FLD, V3 SL, V2 WAVNUM, V2 CGROUP, V1 CICOVER, V1 CITHICK) {
+  const Tables& t = x.t;
+  const Config& c = x.c;
+  const int KIJS = x.KIJS, KIJL = x.KIJL, NANG = x.NANG, NFRE = x.NFRE;
+  // SDICE (sdice.F90:99-112): type 1 scattering, type 2 under-ice friction, type 3 viscous friction, in this order.  SLICE (the
+  // attenuation's own source function) only feeds the LWNEMOCOUWRS radiative stress of WNFLUXES (wnfluxes.F90:178-196): not kept.
+  if (c.lciwa1) {    // SDICE1 (sdice1.F90:102-187)
+    const double CIFRGL = 0.955, CIDMIN = 20.0, CIFRGMT = 2.0, A = 200.0, Cc = 300.0;
+    const int MAXICM = (int)(std::log(A / CIDMIN) / std::log(CIFRGMT));
+    std::vector<double> DINV(KIJL + 1), ALP((size_t)(KIJL + 1) * (NFRE + 1));
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      if (CITHICK(IJ) > 0.0) {
+        const double CIDMAX = A + Cc * CICOVER(IJ);
+        const int ICM = std::min((int)(std::log(CIDMAX / CIDMIN) / std::log(CIFRGMT)), MAXICM);
+        double SN = 0.0, SD = 0.0;
+        for (int I = 0; I <= ICM; ++I) {
+          const double X = std::pow(CIFRGMT * CIFRGMT * CIFRGL, I);
+          SN = SN + X * CIDMAX / std::pow(CIFRGMT, I);
+          SD = SD + X;
+        }
+        const double CIDMEAN = SN / SD;
+        DINV[IJ] = 1.0 / CIDMEAN;
+      } else DINV[IJ] = CIDMIN;
+    }
+    for (int M = 1; M <= NFRE; ++M) {
+      const double TW = 1.0 / t.FR(M);
+      int IT = (int)std::floor((TW - t.TICMIN) / t.DTIC + 1);
+      IT = std::max(1, std::min(IT, t.NICT));
+      int IT1 = IT + 1;
+      IT1 = std::max(1, std::min(IT1, t.NICT));
+      const double WT1 = std::max(std::min(1.0, (TW - (t.TICMIN + (IT - 1) * t.DTIC)) / t.DTIC), 0.0);
+      const double WT = 1.0 - WT1;
+      for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+        if (CITHICK(IJ) > 0.0) {
+          int IH = (int)std::floor((CITHICK(IJ) - t.HICMIN) / t.DHIC + 1);
+          IH = std::max(1, std::min(IH, t.NICH));
+          int IH1 = IH + 1;
+          IH1 = std::max(1, std::min(IH1, t.NICH));
+          const double WH1 = std::max(std::min(1., (CITHICK(IJ) - (t.HICMIN + (IH - 1) * t.DHIC)) / t.DHIC), 0.0);
+          const double WH = 1.0 - WH1;
+          const double CIDEAC_INT = WT * (WH * t.CIDEAC(IT, IH) + WH1 * t.CIDEAC(IT, IH1)) +
+                                    WT1 * (WH * t.CIDEAC(IT1, IH) + WH1 * t.CIDEAC(IT1, IH1));
+          ALP[(size_t)M * (KIJL + 1) + IJ] = std::exp(CIDEAC_INT) * DINV[IJ] * c.zalpfacb;
+        } else ALP[(size_t)M * (KIJL + 1) + IJ] = 0.0;
+      }
+    }
+    for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      const double FLDICE = -ALP[(size_t)M * (KIJL + 1) + IJ] * CGROUP(IJ, M);
+      const double SLICE = FL1(IJ, K, M) * FLDICE;
+      SL(IJ, K, M) = SL(IJ, K, M) + CICOVER(IJ) * SLICE;
+      FLD(IJ, K, M) = FLD(IJ, K, M) + CICOVER(IJ) * FLDICE;
+    }
+  }
+  if (c.lciwa2) {    // SDICE2 (sdice2.F90:97-121)
+    for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      const double EWH = 4.0 * std::sqrt(std::max(t.EPSMIN, FL1(IJ, K, M) * t.DFIM(M)));
+      const double XK2 = WAVNUM(IJ, M) * WAVNUM(IJ, M);
+      const double ALP = c.cdicwa * XK2 * EWH * c.zalpfacb;
+      const double FLDICE = -ALP * CGROUP(IJ, M);
+      const double SLICE = FL1(IJ, K, M) * FLDICE;
+      SL(IJ, K, M) = SL(IJ, K, M) + CICOVER(IJ) * SLICE;
+      FLD(IJ, K, M) = FLD(IJ, K, M) + CICOVER(IJ) * FLDICE;
+    }
+  }
+  if (c.lciwa3) {    // SDICE3 (sdice3.F90:107-147), IMODEL = 2 (Jie Yu 2022), ALPFAC = ZALPFACX (no ice-breakup coupling)
+        const double CDICE = 0.1274 * std::pow(t.ZPI / std::sqrt(t.G), 4.5);
+    for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      const double ALP = (2. * CDICE * std::pow(CITHICK(IJ), 1.25) * std::pow(t.FR(M), 4.5)) * c.zalpfacx;
+      const double TEMP = -CICOVER(IJ) * ALP * CGROUP(IJ, M);
+      SL(IJ, K, M) = SL(IJ, K, M) + FL1(IJ, K, M) * TEMP;
+      FLD(IJ, K, M) = FLD(IJ, K, M) + TEMP;
+    }
+  }
+}
+
 // implsch.F90:177-465 for one NPROMA chunk, with sinflx.F90:101-185 inlined as a lambda
 void implsch_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK) {
   const int NANG = c.nang, NFRE = c.nfre, KIJS = 1;
@@ -1333,23 +1409,13 @@ void implsch_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int IC
     }
   SDIWBK(x, FL1, FLD, SL, DEPTH, EMAXDPT, EMEAN, F1MEAN);
   if (c.licerun) {   // implsch.F90:312-339
-    if (c.lciwa1 || c.lciwa2) throw std::runtime_error("SDICE1 / SDICE2 not restated (SURVEY 8f)");
     if (c.lciscal)
       for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
         const double BETA = 1. - CICOVER(IJ);
         SL(IJ, K, M) = BETA * SL(IJ, K, M);
         FLD(IJ, K, M) = BETA * FLD(IJ, K, M);
       }
-    if (c.lciwa3) {    // SDICE3 (sdice3.F90:107-147), IMODEL = 2 (Jie Yu 2022), ALPFAC = ZALPFACX (no ice-breakup coupling)
-      V1 CITHICK = s1(f.CITHICK);
-      const double CDICE = 0.1274 * std::pow(t.ZPI / std::sqrt(t.G), 4.5);
-      for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
-        const double ALP = (2. * CDICE * std::pow(CITHICK(IJ), 1.25) * std::pow(t.FR(M), 4.5)) * c.zalpfacx;
-        const double TEMP = -CICOVER(IJ) * ALP * CGROUP(IJ, M);
-        SL(IJ, K, M) = SL(IJ, K, M) + FL1(IJ, K, M) * TEMP;
-        FLD(IJ, K, M) = FLD(IJ, K, M) + TEMP;
-      }
-    }
+    if (c.lciwa1 || c.lciwa2 || c.lciwa3) SDICE(x, FL1, FLD, SL, WAVNUM, CGROUP, CICOVER, s1(f.CITHICK));
   }
   SBOTTOM(x, FL1, FLD, SL, WAVNUM, DEPTH);
   // ---- 2.4 new spectra (implsch.F90:352-395)
@@ -1403,7 +1469,7 @@ void snonlin_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int IC
 
 // One source term alone for a chunk, from the fields as they are stored (test infrastructure for the per-term cross-checks):
 // which = 1: SINPUT with NGST = 1, LLSNEG = F (the first SINFLX call, sinflx.F90:156-167) using the stored UFRIC, Z0M;
-// which = 2: SDISSIP (sdissip.F90); which = 3: SBOTTOM; which = 4: SDIWBK (with FKMEAN's EMEAN, F1MEAN).  SL, FLD: (KIJL, NANG, NFRE).
+// which = 2: SDISSIP (sdissip.F90); which = 3: SBOTTOM; which = 4: SDIWBK (with FKMEAN's EMEAN, F1MEAN); which = 5: SDICE (the LCIWA1-3 terms that are switched on).  SL, FLD: (KIJL, NANG, NFRE).
 void term_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK, int which, double* SLp, double* FLDp) {
   const int NANG = c.nang, NFRE = c.nfre, KIJS = 1;
   Ctx x{c, t, KIJS, KIJL, NANG, NFRE};
@@ -1442,6 +1508,8 @@ void term_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK
     L1 lEM(P), lFM(P), lF1(P), lAK(P), lXK(P);
     FKMEAN(x, FL1, WAVNUM, lEM.view(), lFM.view(), lF1.view(), lAK.view(), lXK.view());
     SDIWBK(x, FL1, FLD, SL, DEPTH, EMAXDPT, lEM.view(), lF1.view());
+  } else if (which == 5) {
+    SDICE(x, FL1, FLD, SL, WAVNUM, CGROUP, s1(f.CICOVER), s1(f.CITHICK));
   } else throw std::runtime_error("term_chunk: unknown term");
 }
 

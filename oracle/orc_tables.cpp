@@ -509,8 +509,29 @@ static void inisnonlin(const Config& c, Tables& t) {
   }
 }
 
+// cigetdeac.F90:60-75, :77-82 (assumed 1 s column), :end-10 (linear extrapolation of the 2..5 s columns)
+static void cigetdeac(Tables& t) {
+  static const double KM[36][11] = {
+#include "../ecwam_b200/csrc/kohout_meylan_fig6.inc"
+  };
+  t.NICH = 36; t.DHIC = 0.1;
+  t.NICT = 16; t.TICMIN = 1.0; t.DTIC = 1.0;
+  t.CIDEAC.alloc(1, t.NICT, 1, t.NICH);
+  t.CIDEAC(1, 1) = -2.00;
+  t.CIDEAC(1, t.NICH) = -1.00;
+  const double DHI = t.CIDEAC(1, t.NICH) - t.CIDEAC(1, 1);
+  for (int IH = 2; IH <= t.NICH - 1; ++IH) t.CIDEAC(1, IH) = t.CIDEAC(1, 1) + (IH - 1) * DHI / (t.NICH - 1);
+  for (int IH = 1; IH <= t.NICH; ++IH)
+    for (int IT = 6; IT <= 16; ++IT) t.CIDEAC(IT, IH) = KM[IH - 1][IT - 6];
+  for (int IH = 1; IH <= t.NICH; ++IH) {
+    const double DCI = t.CIDEAC(6, IH) - t.CIDEAC(1, IH);
+    for (int IT = 2; IT <= 5; ++IT) t.CIDEAC(IT, IH) = t.CIDEAC(1, IH) + DCI * (IT - 1) * t.DTIC / (5 * t.DTIC);
+  }
+}
+
 void init_tables(const Config& c, Tables& t) {
   iniwcst(t);
+  cigetdeac(t);
   setwavphys(c, t);
   mfredir(c, t);
   initmdl_freq(c, t);

@@ -109,6 +109,17 @@ def test_gravity_capillary_tables_match_oracle(built, A, iphys, gc, ng):
     np.testing.assert_allclose(om ** 2, 9.806 * k + 7.17e-5 * k ** 3, rtol=1e-14)
 
 
+def test_ice_attenuation_table_matches_oracle(built):
+    """CIGETDEAC (cigetdeac.F90:60-end): the product's host table (data include + its own statement of the two extrapolation rules)
+    == the oracle's, bit for bit; dimensions and axes as in YOWICE."""
+    g = synth.make_grid(8, "aqua")
+    o = O.Oracle(O.default_config(nproma=32, npr=1), g)
+    s = M.WamSetup(g, nproc=1)
+    t = s.tables
+    assert (t.nict, t.nich, t.ticmin, t.hicmin, t.dtic, t.dhic) == (16, 36, 1.0, 0.2, 1.0, 0.1)
+    np.testing.assert_array_equal(s.table("cideac", 16 * 36), o.table("CIDEAC"))
+
+
 def test_depthprpt_matches_oracle(built):
     g = synth.make_grid(16, "continents")
     o = O.Oracle(O.default_config(nang=12, nfre_red=25), g)

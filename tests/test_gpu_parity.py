@@ -328,12 +328,14 @@ def test_current_cfl_fallback(built):
     assert w3.lib.ecwam_b200_propag(w3.h) == nfail
 
 
-@pytest.mark.parametrize("case,mask", [("o48like", 12), ("o640like", 4), ("o48_iphys0", 8)])
+@pytest.mark.parametrize("case,mask", [("o48like", 12), ("o640like", 4), ("o48_iphys0", 8), ("o640like", 1), ("o48like", 2), ("o320like", 3),
+                                       ("o48_iphys0", 15), ("o640like", 7)])
 def test_sea_ice_attenuation(built, case, mask):
-    """LCIWA3 (SDICE3, sdice3.F90:107-147) and LCISCAL (implsch.F90:315-325) with waves allowed under the ice (LMASKICE = F):
-    the attenuation coefficient rides on SBOTTOM's per-(point, frequency) plane, the (1 - CICOVER) scaling is applied between
-    SDIWBK and SDICE as in the reference, WNFLUXES switches to its sea-ice constants (wnfluxes.F90:150-158)."""
-    okw = dict(lmaskice=0, lciwa3=1 if mask & 4 else 0, lciscal=1 if mask & 8 else 0)
+    """LCIWA1 (SDICE1, sdice1.F90:102-187: k_ice adds its per-(point, frequency) coefficient to SBOTTOM's plane), LCIWA2 (SDICE2,
+    sdice2.F90:97-113: per-bin, in the finish stage of k_stencil / k_stencil_dp), LCIWA3 (SDICE3, sdice3.F90:107-147) and LCISCAL
+    (implsch.F90:315-325) with waves allowed under the ice (LMASKICE = F): the (1 - CICOVER) scaling is applied between SDIWBK and
+    SDICE as in the reference, WNFLUXES switches to its sea-ice constants (wnfluxes.F90:150-158)."""
+    okw = dict(lmaskice=0, lciwa1=1 if mask & 1 else 0, lciwa2=1 if mask & 2 else 0, lciwa3=1 if mask & 4 else 0, lciscal=1 if mask & 8 else 0)
     g, o, f, fl = make_oracle(case, **okw)
     g, o0, f, fl = make_oracle(case, lmaskice=0)
     _, s, w = make_gpu(case, lmaskice=0, lciwa=mask)
@@ -348,6 +350,22 @@ def test_sea_ice_attenuation(built, case, mask):
     ice = f["CICOVER"] > 0.2
     a, b = o.get_fl1()[:, :, ice], o0.get_fl1()[:, :, ice]
     assert a.sum() < 0.98 * b.sum(), "the attenuation must act under the ice (%g)" % (a.sum() / b.sum())
+
+
+@pytest.mark.parametrize("case,mode", [("o640like", "pp"), ("o48like", "generic"), ("o320like", "single")])
+def test_under_ice_friction_in_every_stencil_instance(built, monkeypatch, case, mode):
+    """LCIWA2 routes the sweep to k_stencil_dp (default) or k_stencil (two points per thread, run-time geometry, one point per
+    thread): the per-bin SDICE2 term is in each of them; here together with SDICE1 on the same plane as SBOTTOM."""
+    monkeypatch.setenv("ECWAM_B200_STENCIL", mode)
+    g, o, f, fl = make_oracle(case, lmaskice=0, lciwa1=1, lciwa2=1)
+    _, s, w = make_gpu(case, lmaskice=0, lciwa=3)
+    cith = np.where(f["CICOVER"] > 0, 0.1 + 3.9 * f["CICOVER"], 0.0)
+    o.set_field("CITHICK", cith)
+    w.set_field("cithick", cith)
+    for _ in range(3):
+        assert o.step() == 0 and w.step() == 0
+    w.synchronize()
+    check_state(w, o)
 
 
 def test_runs_are_bitwise_reproducible(built):
@@ -403,7 +421,7 @@ def test_cfl_violation_is_reported(built):
 def test_unsupported_switches_are_rejected(built):
     from ecwam_b200 import synth
     g = synth.make_grid(8, "aqua")
-    for kw in (dict(irefra=4), dict(irefra=2, ifrelfmax=5), dict(isnonlin=3), dict(lciwa=1), dict(lciwa=2)):
+    for kw in (dict(irefra=4), dict(irefra=2, ifrelfmax=5), dict(isnonlin=3), dict(lciwa=16), dict(icode_wnd=1)):
         s = M.WamSetup(g, nproc=1, **kw)
         with pytest.raises(L.EcwamError):
             M.WamIntgr(s, 0)

@@ -932,3 +932,73 @@ def test_cutoff_index_against_numpy(built, case):
     near_half = np.abs(arg - np.floor(arg) - 0.5) < 1e-9          # NINT on a rounding boundary: not decidable from here
     assert (got == mij)[~near_half].all() and near_half.mean() < 0.01
     assert mij.min() < NF and (ci > o.cfg.cithrsh_tail).any()
+
+
+def _kohout_meylan_table():
+    """CIDEAC(period 1..16 s, thickness 0.2..3.7 m) rebuilt from the data include and CIGETDEAC's two rules (cigetdeac.F90:77-82 and its
+    last loop): the 1 s column runs linearly from -2 to -1 with the thickness, periods 2..5 s lie on the line from 1 s to 6 s."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rows = []
+    with open(os.path.join(root, "ecwam_b200", "csrc", "kohout_meylan_fig6.inc")) as fh:
+        for line in fh:
+            line = line.strip()
+            if line.startswith("{"):
+                rows.append([float(x) for x in line.strip("{},").split(",")])
+    data = np.array(rows)                       # [thickness, period 6..16]
+    assert data.shape == (36, 11)
+    tab = np.empty((16, 36))
+    tab[5:] = data.T
+    tab[0] = np.linspace(-2.0, -1.0, 36)
+    for it in range(1, 5):
+        tab[it] = tab[0] + (tab[5] - tab[0]) * it / 5.0
+    return tab
+
+
+def test_sea_ice_attenuation_terms_against_numpy(built):
+    """SDICE1 (sdice1.F90:102-187: scattering, Kohout & Meylan's table interpolated in wave period and ice thickness, divided by the mean
+    floe size of the fragmentation cascade of Dumont et al. 2011), SDICE2 (sdice2.F90:97-113: friction under the ice, quadratic in the
+    orbital amplitude of the bin) and SDICE3 (sdice3.F90:123-141: Yu et al. 2022, h^1.25 f^4.5), each alone, from the formulas."""
+    from scipy.interpolate import RegularGridInterpolator
+    tab = _kohout_meylan_table()
+    assert (np.diff(tab, axis=0) < 0).mean() > 0.97          # longer waves are scattered less (ln of the attenuation decreases)
+    assert (np.diff(tab[5:], axis=1) > 0).mean() > 0.9       # thicker ice scatters more
+    for key, kw in (("1", dict(lciwa1=1)), ("2", dict(lciwa2=1, cdicwa=0.01, zalpfacb=0.8)), ("3", dict(lciwa3=1, zalpfacx=0.7))):
+        g, o, f, fl = make_oracle("o640like", lmaskice=0, **kw)
+        ci = f["CICOVER"]
+        n = ci.size
+        cith = np.where(ci > 0, 0.05 + 4.2 * ((np.arange(n) * 37) % 101) / 100.0, 0.0)     # 0.05 .. 4.25 m: both ends of the table are clamped
+        o.set_field("CITHICK", cith)
+        for _ in range(2):
+            assert o.step() == 0
+        F1 = o.get_fl1()
+        NF, A, N = F1.shape
+        wn, cg = o.get_field3("WAVNUM"), o.get_field3("CGROUP")
+        fr, dfim = o.table("FR"), o.table("DFIM")
+        np.testing.assert_allclose(o.table("CIDEAC").reshape(36, 16).T, tab, rtol=1e-15, atol=0)
+        sl, fld = o.term("sdice")
+        if key == "1":
+            per = np.clip(1.0 / fr, 1.0, 16.0)
+            interp = RegularGridInterpolator((np.arange(1.0, 17.0), 0.2 + 0.1 * np.arange(36)), tab)
+            hh = np.clip(cith, 0.2, 3.7)
+            lnatt = interp(np.stack(np.broadcast_arrays(per[:, None], hh[None, :]), axis=-1))
+            dmax_ = 200.0 + 300.0 * ci
+            ncas = np.minimum(np.floor(np.log(dmax_ / 20.0) / np.log(2.0)), np.floor(np.log(200.0 / 20.0) / np.log(2.0))).astype(int)
+            dmean = np.empty(n)
+            for i in range(n):          # <D> = sum (xi^2 f)^j D / xi^j / sum (xi^2 f)^j, xi = 2, fragility f = 0.955
+                j = np.arange(ncas[i] + 1)
+                w = (4.0 * 0.955) ** j
+                dmean[i] = (w * dmax_[i] / 2.0 ** j).sum() / w.sum()
+            alp = np.where(cith[None, :] > 0, np.exp(lnatt) / dmean[None, :], 0.0)
+            coef = -ci[None, :] * alp * cg
+            ref_fld = np.repeat(coef[:, None, :], A, axis=1)
+        elif key == "2":
+            ewh = 4.0 * np.sqrt(np.maximum(1e-33, F1 * dfim[:, None, None]))
+            ref_fld = -ci[None, None, :] * (0.01 * 0.8) * (wn ** 2 * cg)[:, None, :] * ewh
+        else:
+            cdice = 0.1274 * (2 * np.pi / np.sqrt(9.806)) ** 4.5
+            coef = -ci[None, :] * (2.0 * cdice * cith[None, :] ** 1.25 * fr[:, None] ** 4.5) * 0.7 * cg
+            ref_fld = np.repeat(coef[:, None, :], A, axis=1)
+        assert (ref_fld < 0).mean() > 0.02, key                      # there is ice in the case
+        np.testing.assert_allclose(fld, ref_fld, rtol=1e-11, atol=0, err_msg="SDICE%s FLD" % key)
+        np.testing.assert_allclose(sl, ref_fld * F1, rtol=1e-11, atol=0, err_msg="SDICE%s SL" % key)
+        assert (fld[:, :, ci == 0] == 0).all()
