@@ -69,7 +69,7 @@ struct ecwam_b200_handle_s {
   // propagation
   PropDev pd;
   DBuf<int> nbr, halo_off, halo_str, send_l, send_pre, send_peer_of, recv_pre, recv_peer_of, recv_e, flag, count;
-  DBuf<double> wl, pt, cgext, halo, sendbuf, fl3, cosph_m, cosph_p, land_cg, cgrecv;
+  DBuf<double> wl, pt, cgext, halo, sendbuf, fl3, cosph_m, cosph_p, land_cg, cgrecv, obs;
   DBuf<double> wlat_raw, dellam, grad, curmask;   // IREFRA /= 0: WLAT as PROPCONNECT left it, DELLAM/COSPH(KXLT), gradients, CURMASK
   double oneo2delphi = 0.0;
   std::vector<int> h_spre, h_rpre;   // per peer prefix sums (size nproc+1)
@@ -209,8 +209,6 @@ static int fill_dev_const(const ecwam_b200_params& p, const ecwam_b200_tables& t
   if (p.nang < 4 || p.nang > EW_MAXA || p.nfre < 2 || p.nfre > EW_MAXF || p.nfre_red < 1 || p.nfre_red > p.nfre)
     EW_FAIL(ECWAM_B200_EINVAL, "unsupported spectral dimensions NANG=%d NFRE=%d NFRE_RED=%d", p.nang, p.nfre, p.nfre_red);
   if (p.irefra < 0 || p.irefra > 3 || p.icase != 1) EW_FAIL(ECWAM_B200_EINVAL, "IREFRA must be 0..3 and ICASE = 1 (spherical)");
-  if (p.irefra >= 2 && p.ifrelfmax > 0 && p.ifrelfmax < p.nfre_red)
-    EW_FAIL(ECWAM_B200_EINVAL, "fast-wave sub-stepping (IFRELFMAX) together with current refraction (IREFRA = 2, 3) is not built");
   if (p.isnonlin < 0 || p.isnonlin > 2) EW_FAIL(ECWAM_B200_EINVAL, "ISNONLIN must be 0, 1 or 2");
   if ((p.llgcbz0 || p.llnormagam) && (t.nwav_gc < 2 || !t.xk_gc || !t.omega_gc || !t.cm_gc || !t.c2osqrtvg_gc || !t.xkmsqrtvgoc2_gc ||
                                       !t.om3gmkm_gc || !t.omxkm3_gc || !t.delkcc_gc_ns || !t.delkcc_omxkm3_gc))
@@ -521,6 +519,16 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
     ok = ok && !h->wlat_raw.upload(wr, st) && !h->dellam.upload(dl, st) && !h->grad.alloc((size_t)7 * nloc) && !h->curmask.upload(ones, st);
   }
   ok = ok && !h->land_cg.upload(landcg, st);
+  if (dec->obslon || dec->obslat || dec->obscor) {   // LSUBGRID: [8][Fr][nloc] = OBSLON(:,:,1:2), OBSLAT(:,:,1:2), OBSCOR(:,:,1:4)
+    if (!dec->obslon || !dec->obslat || !dec->obscor) { EW_FAIL_H(h, ECWAM_B200_EINVAL, "LSUBGRID: OBSLON, OBSLAT and OBSCOR must be given together"); }
+    const size_t pl = (size_t)Fr * nloc;
+    std::vector<double> ob(8 * pl);
+    for (size_t i = 0; i < 2 * pl; ++i) { ob[i] = dec->obslon[i]; ob[2 * pl + i] = dec->obslat[i]; }
+    for (size_t i = 0; i < 4 * pl; ++i) ob[4 * pl + i] = dec->obscor[i];
+    for (size_t i = 0; i < 8 * pl; ++i)
+      if (!(ob[i] >= 0.0 && ob[i] <= 1.0)) { EW_FAIL_H(h, ECWAM_B200_EINVAL, "LSUBGRID: obstruction coefficient outside [0, 1]"); }
+    ok = ok && !h->obs.upload(ob, st);
+  }
   ok = ok && !h->cgext.alloc((size_t)nenv * next) && !h->halo.alloc(halo_elems + 1) &&
        !h->sendbuf.alloc((size_t)h->nsend * A * Fr) && !h->cgrecv.alloc((size_t)h->nrecv * nenv) &&
        !h->fl3.alloc((size_t)P * A * Fr * p.nchnk) && !h->flag.alloc(nloc) && !h->count.alloc(1);
@@ -620,7 +628,7 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
   d.nloc = nloc; d.nbot = nbot; d.ntop = ntop; d.next = next; d.P = P; d.A = A; d.F = F; d.Fr = Fr; d.nchnk = p.nchnk;
   d.nbr = h->nbr.p; d.wl = h->wl.p; d.pt = h->pt.p; d.cgext = h->cgext.p; d.halo_off = h->halo_off.p;
   d.irefra = p.irefra; d.nenv = nenv; d.omos = nullptr; d.grad = h->grad.p; d.wavn = nullptr; d.curmask = h->curmask.p;
-  d.halo_str = h->halo_str.p; d.halo = h->halo.p;
+  d.halo_str = h->halo_str.p; d.halo = h->halo.p; d.obs = h->obs.p; d.pad_obs = nullptr;
   h->tab.k1w = h->kw.p; h->tab.k2w = h->kw.p + 2 * A; h->tab.k11w = h->kw.p + 4 * A; h->tab.k21w = h->kw.p + 6 * A;
   h->tab.ik1w = h->kw.p + 8 * A; h->tab.ik2w = h->kw.p + 10 * A; h->tab.ik11w = h->kw.p + 12 * A; h->tab.ik21w = h->kw.p + 14 * A;
   h->tab.indicessat = h->isat.p; h->tab.satweights = h->satw.p; h->tab.swellft = h->swellft.p;
@@ -745,13 +753,13 @@ static int halo_spectrum(H* h, const double* src, int srcF, int nm) {
 // MPEXCHNG + PROPAGS2 of frequencies [0, m1) (propag_wam.F90:166, 245-251).  With several ranks the exchange runs on its own
 // stream while the own points without a halo neighbour are propagated; the two strips that read the halo follow it
 // (the reference posts non-blocking receives the same way, mpexchng.F90:164-206).
-static int halo_propags2(H* h, const double* src, int srcF, double* dst, int dstF, int m1) {
+static int halo_propags2(H* h, const double* src, int srcF, double* dst, int dstF, int m1, const double* top = nullptr, int topF = 0) {
   const PropDev& d = h->pd;
   if (!h->overlap) {
     int rc = halo_spectrum(h, src, srcF, m1);
     if (rc) return rc;
     ScopedTimer t(h, "propags2");
-    launch_propags2(d, src, srcF, dst, dstF, 0, m1, h->msplit, h->st);
+    launch_propags2(d, src, srcF, dst, dstF, 0, m1, h->msplit, h->st, 0, -1, top, topF);
     h->nlaunch++;
     return 0;
   }
@@ -760,7 +768,7 @@ static int halo_propags2(H* h, const double* src, int srcF, double* dst, int dst
   h->nlaunch += (h->nsend > 0);
   EW_CUDA_CHECK(cudaEventRecord(h->ev_pack, h->st));
   EW_CUDA_CHECK(cudaStreamWaitEvent(h->st_x, h->ev_pack, 0));
-  launch_propags2(d, src, srcF, dst, dstF, 0, m1, h->msplit, h->st, h->int_lo, h->int_hi);
+  launch_propags2(d, src, srcF, dst, dstF, 0, m1, h->msplit, h->st, h->int_lo, h->int_hi, top, topF);
   h->nlaunch++;
   {
     ScopedTimer tx(h, "halo", h->st_x);
@@ -769,8 +777,8 @@ static int halo_propags2(H* h, const double* src, int srcF, double* dst, int dst
   }
   EW_CUDA_CHECK(cudaEventRecord(h->ev_x, h->st_x));
   EW_CUDA_CHECK(cudaStreamWaitEvent(h->st, h->ev_x, 0));
-  if (h->int_lo > 0) { launch_propags2(d, src, srcF, dst, dstF, 0, m1, h->msplit, h->st, 0, h->int_lo); h->nlaunch++; }
-  if (h->int_hi < d.nloc) { launch_propags2(d, src, srcF, dst, dstF, 0, m1, h->msplit, h->st, h->int_hi, d.nloc); h->nlaunch++; }
+  if (h->int_lo > 0) { launch_propags2(d, src, srcF, dst, dstF, 0, m1, h->msplit, h->st, 0, h->int_lo, top, topF); h->nlaunch++; }
+  if (h->int_hi < d.nloc) { launch_propags2(d, src, srcF, dst, dstF, 0, m1, h->msplit, h->st, h->int_hi, d.nloc, top, topF); h->nlaunch++; }
   return 0;
 }
 
@@ -839,7 +847,9 @@ static int propag_core(H* h, bool* lf_in_fl3) {
       const double* src = *lf_in_fl3 ? h->fl3.p : h->dev.fl1;
       double* dst = *lf_in_fl3 ? h->dev.fl1 : h->fl3.p;
       const int sF = *lf_in_fl3 ? d.Fr : d.F, dF = *lf_in_fl3 ? d.F : d.Fr;
-      rc = halo_propags2(h, src, sF, dst, dF, p.ifrelfmax);
+      // with currents the frequency shift of row IFRELFMAX reads row IFRELFMAX + 1 of the spectrum of the start of the step: the bound
+      // FL1, whose rows >= IFRELFMAX no sub-step writes
+      rc = halo_propags2(h, src, sF, dst, dF, p.ifrelfmax, p.irefra >= 2 ? h->dev.fl1 : nullptr, d.F);
       if (rc) return rc;
       *lf_in_fl3 = !*lf_in_fl3;
     }

@@ -23,6 +23,8 @@ struct PropDev {
   const int* halo_off;   // [nbot+ntop+1] offset of (k=0,m=0) of a halo point in `halo`; land -> a zero element
   const int* halo_str;   // [nbot+ntop+1] direction stride (= points received from that peer); land -> 0
   const double* halo;    // received spectra, per peer block [m][k][ih]
+  const double* obs;     // LSUBGRID: [8][Fr][nloc] OBSLON(.,.,1:2), OBSLAT(.,.,1:2), OBSCOR(.,.,1:4) (ctuw.F90:700-733); null = all 1
+  const double* pad_obs; // keeps sizeof(PropDev) a multiple of 16 (the kernel arguments after it stay 16-byte aligned)
 };
 
 // per-direction tables of the CTU scheme (ctuwupdt.F90:111-161), constant memory
@@ -50,8 +52,9 @@ void launch_propags2_fast(const PropDev& d, const double* src, int srcF, double*
                           cudaStream_t st, int l0, int l1);
 
 // own points [l0, l1) (l1 < 0: all)
+// top / topF: IREFRA = 2, 3 in a fast-wave sub-step: the array (layout (P,A,topF,C)) whose row m1 is the frequency neighbour of row m1-1
 void launch_propags2(const PropDev& d, const double* src, int srcF, double* dst, int dstF, int m0, int m1, int msplit,
-                     cudaStream_t st, int l0 = 0, int l1 = -1);
+                     cudaStream_t st, int l0 = 0, int l1 = -1, const double* top = nullptr, int topF = 0);
 void launch_ctu_check(const PropDev& d, int m0, int m1, int msplit, int* flag, int* count, cudaStream_t st);
 void launch_setup_points(const PropDev& d, const double* cosphm1_fld, const double* cosph_m, const double* cosph_p,
                          double* pt, cudaStream_t st);

@@ -58,12 +58,13 @@ struct PointM {            // k-independent quantities of one (point, frequency)
   double hx[2], hy[2];     // 0.5*(CG+CG_lon(ic)), 0.5*(CG+DP(ic)*CGYP(ic))      (ctuw.F90:160-171,199-210)
   double cg, tanph, cosphm1, zdello, gam1, wlat[2], wlatm1[2], wcor[4], wcorm1[4];
   double omos, ddphi, ddlam;   // IREFRA = 1: OMOSNH2KD(ij,m), depth gradients of GRADI
+  double olon, olat, ocor;     // LSUBGRID: OBSLON(ij,m,JX1), OBSLAT(ij,m,JY1), OBSCOR(ij,m,KC) of the running quadrant
 };
 
 // depth-refraction part of THETA DOT (propdot.F90:156: THDD = SD*DDPHI - CD*DDLAM*DCO, ICASE = 1: DCO = COSPHM1)
 __device__ __forceinline__ double thdd(const PointM& q, int k) { return c_prop.sinth[k] * q.ddphi - c_prop.costh[k] * q.ddlam * q.cosphm1; }
 
-template <int JX1, int JY1, int KC, bool REFRA>
+template <int JX1, int JY1, int KC, bool REFRA, bool OBS>
 __device__ __forceinline__ double ctu_update(const PointM& q, int k, int idp, double f0, double flon, double flat1,
                                              double flat2, double fc1, double fc2, double fkm, double fkp) {
   constexpr int JX2 = 3 - JX1, JY2 = 3 - JY1;
@@ -77,12 +78,15 @@ __device__ __forceinline__ double ctu_update(const PointM& q, int k, int idp, do
   const double dxx = q.zdello - dxu2;           // - DXDW(JXO(K,1)) = 0
   const double dyy = c_prop.xdella - dyu2;
   const double wl = dxx * dyu1 * q.gam1;        // WEIGHT(JYO(K,1))      (ctuw.F90:243)
-  const double wlatn1 = q.wlat[JY1 - 1] * wl;
-  const double wlatn2 = q.wlatm1[JY1 - 1] * wl;
-  const double wlonn = dyy * dxu1 * q.gam1;     // WLONN(..,JXO(K,1))     (ctuw.F90:253)
+  double wlatn1 = q.wlat[JY1 - 1] * wl;
+  double wlatn2 = q.wlatm1[JY1 - 1] * wl;
+  double wlonn = dyy * dxu1 * q.gam1;           // WLONN(..,JXO(K,1))     (ctuw.F90:253)
   const double wc = dxu1 * dyu1 * q.gam1;       // WEIGHT(1)              (ctuw.F90:258)
-  const double wcorn1 = q.wcor[KC - 1] * wc;
-  const double wcorn2 = q.wcorm1[KC - 1] * wc;
+  double wcorn1 = q.wcor[KC - 1] * wc;
+  double wcorn2 = q.wcorm1[KC - 1] * wc;
+  if (OBS) {   // the blocking coefficients scale the weights of the surrounding points, not SUMWN (ctuw.F90:700-733)
+    wlatn1 = wlatn1 * q.olat; wlatn2 = wlatn2 * q.olat; wlonn = wlonn * q.olon; wcorn1 = wcorn1 * q.ocor; wcorn2 = wcorn2 * q.ocor;
+  }
   double sumwn = (q.zdello * dyu2 + c_prop.xdella * dxu2 - dxu2 * dyu2) * q.gam1;   // (ctuw.F90:268-274)
   // great-circle turning (ctuw.F90:404-501, IREFRA=0: DRCP=DRCM=0)
   double dthp = q.tanph * c_prop.sp[idp][k] * q.cg;
@@ -109,7 +113,7 @@ __device__ __forceinline__ double ctu_update(const PointM& q, int k, int idp, do
 // in flight per iteration (12 independent gathers).
 // grid = (ceil(nloc/blockDim), ngroups): blockIdx.x (points) varies fastest so that the rows north and south
 // of the running row stay L2-resident for one frequency group at a time.
-template <int JX1, int JY1, int KC, bool REFRA>
+template <int JX1, int JY1, int KC, bool REFRA, bool OBS>
 __device__ __forceinline__ void ctu_quadrant(const PropDev& d, const SpecSrc& src, PointM& q, int l, int m, int idp, int k0, int k1,
                                              const double* __restrict__ ps, double* __restrict__ pd) {
   if (k0 >= k1) return;
@@ -131,6 +135,11 @@ __device__ __forceinline__ void ctu_quadrant(const PropDev& d, const SpecSrc& sr
   q.wlatm1[JY1 - 1] = 1.0 - q.wlat[JY1 - 1];
   q.wcor[KC - 1] = __ldg(d.wl + (size_t)(2 + KC - 1) * nl + l);
   q.wcorm1[KC - 1] = 1.0 - q.wcor[KC - 1];
+  if (OBS) {
+    const double* ob = d.obs + (size_t)m * nl + l;
+    const size_t pl = (size_t)d.Fr * nl;
+    q.olon = __ldg(ob + (size_t)(JX1 - 1) * pl); q.olat = __ldg(ob + (size_t)(2 + JY1 - 1) * pl); q.ocor = __ldg(ob + (size_t)(4 + KC - 1) * pl);
+  }
   const int P = d.P;
   int k = k0;
   PG_UNROLL
@@ -144,15 +153,15 @@ __device__ __forceinline__ void ctu_quadrant(const PropDev& d, const SpecSrc& sr
     const double a4 = __ldg(p_c1 + (size_t)ka * s_c1), b4 = __ldg(p_c1 + (size_t)kb * s_c1);
     const double a5 = __ldg(p_c2 + (size_t)ka * s_c2), b5 = __ldg(p_c2 + (size_t)kb * s_c2);
     // KPM(ka,+1) = kb and KPM(kb,-1) = ka inside a quadrant
-    const double ra = ctu_update<JX1, JY1, KC, REFRA>(q, ka, idp, a0, a1, a2, a3, a4, a5, am, b0);
-    const double rb = ctu_update<JX1, JY1, KC, REFRA>(q, kb, idp, b0, b1, b2, b3, b4, b5, a0, bp);
+    const double ra = ctu_update<JX1, JY1, KC, REFRA, OBS>(q, ka, idp, a0, a1, a2, a3, a4, a5, am, b0);
+    const double rb = ctu_update<JX1, JY1, KC, REFRA, OBS>(q, kb, idp, b0, b1, b2, b3, b4, b5, a0, bp);
     pd[(size_t)ka * P] = ra;
     pd[(size_t)kb * P] = rb;
   }
   for (; k < k1; ++k) {
     const double f0 = ps[(size_t)k * P];
     const double fkm = ps[(size_t)c_prop.kpm_m[k] * P], fkp = ps[(size_t)c_prop.kpm_p[k] * P];
-    pd[(size_t)k * P] = ctu_update<JX1, JY1, KC, REFRA>(q, k, idp, f0, __ldg(p_lon + (size_t)k * s_lon), __ldg(p_la1 + (size_t)k * s_la1),
+    pd[(size_t)k * P] = ctu_update<JX1, JY1, KC, REFRA, OBS>(q, k, idp, f0, __ldg(p_lon + (size_t)k * s_lon), __ldg(p_la1 + (size_t)k * s_la1),
                                                  __ldg(p_la2 + (size_t)k * s_la2), __ldg(p_c1 + (size_t)k * s_c1),
                                                  __ldg(p_c2 + (size_t)k * s_c2), fkm, fkp);
   }
@@ -161,7 +170,7 @@ __device__ __forceinline__ void ctu_quadrant(const PropDev& d, const SpecSrc& sr
 #ifndef PG_MINB
 #define PG_MINB 4
 #endif
-template <bool REFRA>
+template <bool REFRA, bool OBS = false>
 __global__ void __launch_bounds__(128, PG_MINB) propags2_kernel(PropDev d, SpecSrc src, double* __restrict__ dst, long long dcstride,
                                                           int m0, int m1, int MG, int msplit, int l0, int l1) {
   const int l = l0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -200,10 +209,10 @@ __global__ void __launch_bounds__(128, PG_MINB) propags2_kernel(PropDev d, SpecS
     const double* ps = src.base + i + (long long)c * src.cstride + (long long)m * d.P * A;
     double* pd = dst + i + (long long)c * dcstride + (long long)m * d.P * A;
     // quadrant k-ranges [kq[j], kq[j+1]) in the order: (sin>=0,cos>=0) (sin>=0,cos<0) (sin<0,cos<0) (sin<0,cos>=0)
-    ctu_quadrant<1, 1, 3, REFRA>(d, src, q, l, m, idp, c_prop.kq[0], c_prop.kq[1], ps, pd);   // west, south, SW
-    ctu_quadrant<1, 2, 4, REFRA>(d, src, q, l, m, idp, c_prop.kq[1], c_prop.kq[2], ps, pd);   // west, north, NW
-    ctu_quadrant<2, 2, 1, REFRA>(d, src, q, l, m, idp, c_prop.kq[2], c_prop.kq[3], ps, pd);   // east, north, NE
-    ctu_quadrant<2, 1, 2, REFRA>(d, src, q, l, m, idp, c_prop.kq[3], c_prop.kq[4], ps, pd);   // east, south, SE
+    ctu_quadrant<1, 1, 3, REFRA, OBS>(d, src, q, l, m, idp, c_prop.kq[0], c_prop.kq[1], ps, pd);   // west, south, SW
+    ctu_quadrant<1, 2, 4, REFRA, OBS>(d, src, q, l, m, idp, c_prop.kq[1], c_prop.kq[2], ps, pd);   // west, north, NW
+    ctu_quadrant<2, 2, 1, REFRA, OBS>(d, src, q, l, m, idp, c_prop.kq[2], c_prop.kq[3], ps, pd);   // east, north, NE
+    ctu_quadrant<2, 1, 2, REFRA, OBS>(d, src, q, l, m, idp, c_prop.kq[3], c_prop.kq[4], ps, pd);   // east, south, SE
   }
 }
 
@@ -508,8 +517,11 @@ __global__ void curmask_kernel(int n, const int* __restrict__ flag, double* __re
 
 // PROPAGS2 with depth and current refraction (propags2.F90:123-194): every neighbour, the two neighbouring directions and the
 // two neighbouring frequencies, in the reference's order of additions.  Thread = one own point x a group of frequencies.
+// `top` (fast-wave sub-steps, propag_wam.F90:257-313): the sub-step advects frequencies [m0, m1) only, and the frequency-shift term of
+// the last one reads row m1 of FL1_EXT, which still holds the spectrum of the start of the step (only rows < m1 are refreshed from
+// FL3_EXT between sub-steps): that row comes from `top` (the bound FL1) instead of the ping-pong source.
 __global__ void __launch_bounds__(128, 2) propags2_cur_kernel(PropDev d, SpecSrc src, double* __restrict__ dst, long long dcstride,
-                                                              int m0, int m1, int MG, int msplit, int l0, int l1) {
+                                                              int m0, int m1, int MG, int msplit, int l0, int l1, SpecSrc top) {
   const int l = l0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= l1) return;
   const int mb = m0 + blockIdx.y * MG;
@@ -526,7 +538,8 @@ __global__ void __launch_bounds__(128, 2) propags2_cur_kernel(PropDev d, SpecSrc
     const double frm = c_prop.fr[m], frmm1 = c_prop.fr[mm1];
     const double* ps = src.base + i + (long long)c * src.cstride + (long long)m * P * A;
     const double* psm = src.base + i + (long long)c * src.cstride + (long long)mm1 * P * A;
-    const double* psp = src.base + i + (long long)c * src.cstride + (long long)mp1 * P * A;
+    const double* psp = (top.base && mp1 >= m1) ? top.base + i + (long long)c * top.cstride + (long long)mp1 * P * A
+                                                : src.base + i + (long long)c * src.cstride + (long long)mp1 * P * A;
     double* pd = dst + i + (long long)c * dcstride + (long long)m * P * A;
     const double* pn[14];
     int sn[14];
@@ -534,6 +547,15 @@ __global__ void __launch_bounds__(128, 2) propags2_cur_kernel(PropDev d, SpecSrc
     for (int k = 0; k < A; ++k) {
       CurW w;
       cur_weights(q, k, idp, hx, hy, cg3, om3, wn3, frm, frmm1, w);
+      if (d.obs) {   // LSUBGRID (ctuw.F90:700-733)
+        const double* ob = d.obs + (size_t)m * d.nloc + l;
+        const size_t pl = (size_t)d.Fr * d.nloc;
+        for (int ic = 0; ic < 2; ++ic) {
+          w.wlonn[ic] = w.wlonn[ic] * __ldg(ob + (size_t)ic * pl);
+          for (int icl = 0; icl < 2; ++icl) w.wlatn[ic][icl] = w.wlatn[ic][icl] * __ldg(ob + (size_t)(2 + ic) * pl);
+        }
+        for (int icr = 0; icr < 4; ++icr) for (int icl = 0; icl < 2; ++icl) w.wcorn[icr][icl] = w.wcorn[icr][icl] * __ldg(ob + (size_t)(4 + w.kcr[icr]) * pl);
+      }
       double v = (1.0 - w.sumwn) * ps[(size_t)k * P];
       for (int ic = 0; ic < 2; ++ic) v = v + w.wlonn[ic] * __ldg(pn[ic] + (size_t)k * sn[ic]);                  // KLON(IJ,IC)
       for (int icl = 0; icl < 2; ++icl) {
@@ -622,7 +644,7 @@ bool propag_exact_mode() {   // read at every launch: the tests switch it per ca
   return e && !strcmp(e, "exact");
 }
 void launch_propags2(const PropDev& d, const double* src, int srcF, double* dst, int dstF, int m0, int m1, int msplit,
-                     cudaStream_t st, int l0, int l1) {
+                     cudaStream_t st, int l0, int l1, const double* top, int topF) {
   if (l1 < 0) l1 = d.nloc;
   l1 = l1 < d.nloc ? l1 : d.nloc;
   if (m1 <= m0 || l1 <= l0) return;
@@ -631,14 +653,22 @@ void launch_propags2(const PropDev& d, const double* src, int srcF, double* dst,
   // keeps the exact kernel unless ECWAM_B200_PROPAG=fast asks otherwise.
   const char* pm = getenv("ECWAM_B200_PROPAG");
   const bool decomposed = d.nbot + d.ntop > 0;
-  if (d.irefra < 2 && !propag_exact_mode() && (!decomposed || (pm && !strncmp(pm, "fast", 4)))) {
+  // LSUBGRID (obstruction coefficients) is built into the exact kernels only
+  if (d.irefra < 2 && !d.obs && !propag_exact_mode() && (!decomposed || (pm && !strncmp(pm, "fast", 4)))) {
     launch_propags2_fast(d, src, srcF, dst, dstF, m0, m1, msplit, st, l0, l1);
     return;
   }
   const int MG = 8;
   SpecSrc s{src, (long long)d.P * d.A * srcF};
   dim3 grid((l1 - l0 + 127) / 128, (m1 - m0 + MG - 1) / MG);
-  if (d.irefra >= 2) propags2_cur_kernel<<<grid, 128, 0, st>>>(d, s, dst, (long long)d.P * d.A * dstF, m0, m1, MG, msplit, l0, l1);
+  if (d.irefra >= 2) {
+    SpecSrc tp{top, (long long)d.P * d.A * topF};
+    propags2_cur_kernel<<<grid, 128, 0, st>>>(d, s, dst, (long long)d.P * d.A * dstF, m0, m1, MG, msplit, l0, l1, tp);
+  }
+  else if (d.obs) {
+    if (d.irefra == 1) propags2_kernel<true, true><<<grid, 128, 0, st>>>(d, s, dst, (long long)d.P * d.A * dstF, m0, m1, MG, msplit, l0, l1);
+    else propags2_kernel<false, true><<<grid, 128, 0, st>>>(d, s, dst, (long long)d.P * d.A * dstF, m0, m1, MG, msplit, l0, l1);
+  }
   else if (d.irefra == 1) propags2_kernel<true><<<grid, 128, 0, st>>>(d, s, dst, (long long)d.P * d.A * dstF, m0, m1, MG, msplit, l0, l1);
   else propags2_kernel<false><<<grid, 128, 0, st>>>(d, s, dst, (long long)d.P * d.A * dstF, m0, m1, MG, msplit, l0, l1);
 }

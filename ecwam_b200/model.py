@@ -96,7 +96,21 @@ class WamSetup:
         out = L.Decomp()
         C.memmove(C.byref(out), C.byref(d), C.sizeof(L.Decomp))
         out.land_cgroup = self.land_cgroup.ctypes.data_as(C.POINTER(C.c_double))
+        if getattr(self, "obstructions", None) is not None:      # LSUBGRID: own-point slices in the layout (IJS:IJL, NFRE_RED, n)
+            own = self.new2ij[int(self.nstart[rank]): int(self.nend[rank]) + 1] - 1
+            keep = [np.ascontiguousarray(x[:, :, own], dtype=np.float64) for x in self.obstructions]
+            self._obs_keep = getattr(self, "_obs_keep", {})
+            self._obs_keep[rank] = keep
+            dpp = C.POINTER(C.c_double)
+            out.obslon, out.obslat, out.obscor = (k.ctypes.data_as(dpp) for k in keep)
         return out
+
+    def set_obstructions(self, lon, lat, cor):
+        """Sub-grid obstruction coefficients (LSUBGRID = T) in the original point order: OBSLON / OBSLAT [ic, m, ij] (2, NFRE_RED, NIBLO),
+        OBSCOR (4, NFRE_RED, NIBLO).  Call before the WamIntgr objects are created."""
+        fr, n = self.par.nfre_red, self.niblo
+        assert lon.shape == (2, fr, n) and lat.shape == (2, fr, n) and cor.shape == (4, fr, n)
+        self.obstructions = (lon, lat, cor)
 
     def decomp_arrays(self, rank: int):
         d = self.decomp(rank)

@@ -256,6 +256,11 @@ typedef struct ecwam_b200_decomp {
   int ntopemax;
   const int* ijtope;         /* (NTOPEMAX, NPROC) */
   const double* land_cgroup; /* (NFRE_RED) WVPRPT_LAND%CGROUP (initdpthflds.F90:80-88) */
+  /* YOWUBUF sub-grid obstruction coefficients (LSUBGRID = T; getbobstrct.F90:395-500, applied by ctuw.F90:700-733).
+   * All three NULL = LSUBGRID F (every coefficient 1, the setting of ecwam_run_model.sh:238).                */
+  const double* obslon;      /* (IJS:IJL, NFRE_RED, 2) */
+  const double* obslat;      /* (IJS:IJL, NFRE_RED, 2) */
+  const double* obscor;      /* (IJS:IJL, NFRE_RED, 4) */
 } ecwam_b200_decomp;
 
 /* ---------------------------------------------------------------------------------------------------

@@ -176,6 +176,9 @@ struct RankDecomp {
   ArrD SUMWN, WLATN, WLONN, WCORN, WKPMN;  // all 18 arrays: only when cfg.store_all_weights (ctuwupdt.F90:171-178) or IREFRA >= 2
   ArrD WMPMN;                              // frequency-shift weights (IREFRA = 2, 3; ctuw.F90:503-525)
   ArrD W8;  // (IJ,K,M,8): the 8 weights PROPAGS2 reads when IREFRA=0 (propags2.F90:107-116)
+  // YOWUBUF OBSLON(IJS:IJL,NFRE_RED,2), OBSLAT(IJS:IJL,NFRE_RED,2), OBSCOR(IJS:IJL,NFRE_RED,4): sub-grid obstruction coefficients
+  // (getbobstrct.F90:395-500); empty = LSUBGRID F (all 1)
+  ArrD OBSLON, OBSLAT, OBSCOR;
   bool LUPDTWGHT = true;
   int cfl_fail = 0;
 };

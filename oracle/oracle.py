@@ -194,6 +194,15 @@ class Oracle:
             raise KeyError(name)
         return v
 
+    def set_obstructions(self, lon, lat, cor):
+        """OBSLON / OBSLAT [ic, m, ij] (2, NFRE_RED, NIBLO) and OBSCOR (4, NFRE_RED, NIBLO) in the original point order (LSUBGRID = T)."""
+        n, fr = self.niblo, self.cfg.nfre_red
+        a = [np.ascontiguousarray(x, dtype=np.float64) for x in (lon, lat, cor)]
+        assert a[0].shape == (2, fr, n) and a[1].shape == (2, fr, n) and a[2].shape == (4, fr, n)
+        self.lib.orc_set_obstructions.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        if self.lib.orc_set_obstructions(self.h, a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data) != 0:
+            raise RuntimeError("orc_set_obstructions failed")
+
     def set_fl1(self, fl):
         fl = np.ascontiguousarray(fl, dtype=np.float64)
         assert fl.shape == (self.cfg.nfre, self.cfg.nang, self.niblo)

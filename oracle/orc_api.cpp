@@ -168,6 +168,30 @@ int orc_set_field(void* h, const char* name, const double* v) {
   (void)pad2d;
   return 0;
 }
+// sub-grid obstruction coefficients in the ORIGINAL point order: lon[ic][m][ij] (2, NFRE_RED, NIBLO), lat likewise, cor (4, NFRE_RED, NIBLO)
+int orc_set_obstructions(void* h, const double* lon, const double* lat, const double* cor) {
+  Model* m = (Model*)h;
+  const int FR = m->cfg.nfre_red;
+  const long N = m->grid.NIBLO;
+  for (int ir = 0; ir < m->cfg.npr; ++ir) {
+    RankDecomp& r = m->ranks[ir];
+    r.OBSLON.alloc(r.IJS, r.IJL, 1, FR, 1, 2); r.OBSLAT.alloc(r.IJS, r.IJL, 1, FR, 1, 2); r.OBSCOR.alloc(r.IJS, r.IJL, 1, FR, 1, 4);
+    r.LUPDTWGHT = true;
+  }
+  for (int ij = 1; ij <= N; ++ij) {
+    int ir, ip, ic; locate(m, ij, ir, ip, ic);
+    RankDecomp& r = m->ranks[ir];
+    const int IJ = r.IJFROMCHNK(1, ic) + ip - 1;
+    for (int M = 1; M <= FR; ++M) {
+      for (int a = 1; a <= 2; ++a) {
+        r.OBSLON(IJ, M, a) = lon[((a - 1) * (long)FR + (M - 1)) * N + ij - 1];
+        r.OBSLAT(IJ, M, a) = lat[((a - 1) * (long)FR + (M - 1)) * N + ij - 1];
+      }
+      for (int a = 1; a <= 4; ++a) r.OBSCOR(IJ, M, a) = cor[((a - 1) * (long)FR + (M - 1)) * N + ij - 1];
+    }
+  }
+  return 0;
+}
 int orc_get_field(void* h, const char* name, double* v) {
   Model* m = (Model*)h;
   std::string n(name);

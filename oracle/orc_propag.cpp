@@ -181,7 +181,7 @@ static void ctu_index_tables(const Config& c, const Tables& t, RankDecomp& r) {
 }
 
 // ctuwini.F90:60-165 (modifies WLAT/WCOR near land) + ctuw.F90:110-275, :404-501, :531-690, :700-733
-// (IREFRA=0, ICASE=1, obstruction coefficients 1 because LSUBGRID=F) + ctuwdrv.F90 CFL flagging.
+// (ICASE=1; obstruction coefficients from RankDecomp::OBS*, 1 when LSUBGRID=F) + ctuwdrv.F90 CFL flagging.
 static void ctuwupdt(Model& m, int ir, ArrD& BUF) {
   const Config& c = m.cfg;
   const Tables& t = m.tab;
@@ -439,7 +439,22 @@ static void ctuwupdt(Model& m, int ir, ArrD& BUF) {
           if (FULL) { r.WKPMN(IJ, K, M, 0) = w0; r.WKPMN(IJ, K, M, 1) = wp; r.WKPMN(IJ, K, M, -1) = wm; r.SUMWN(IJ, K, M) = s; }
         }
     }
-    // obstruction coefficients OBSLAT/OBSLON/OBSCOR are all 1.0 (LSUBGRID=F): :700-733 is a no-op.
+    // the blocking coefficients go into the weights of the surrounding points, not into SUMWN (ctuw.F90:700-733); LSUBGRID = F: all 1
+    if (r.OBSLON.size() > 0) {
+      for (int K = 1; K <= NANG; ++K) for (int M = MSTART; M <= MEND; ++M) for (int IJ = IJS; IJ <= IJL; ++IJ) {
+        const int JX1 = r.JXO(K, 1), JY1 = r.JYO(K, 1);
+        r.W8(IJ, K, M, 2) = r.W8(IJ, K, M, 2) * r.OBSLON(IJ, M, JX1);
+        r.W8(IJ, K, M, 3) = r.W8(IJ, K, M, 3) * r.OBSLAT(IJ, M, JY1);
+        r.W8(IJ, K, M, 4) = r.W8(IJ, K, M, 4) * r.OBSLAT(IJ, M, JY1);
+        r.W8(IJ, K, M, 5) = r.W8(IJ, K, M, 5) * r.OBSCOR(IJ, M, r.KCR(K, 1));
+        r.W8(IJ, K, M, 6) = r.W8(IJ, K, M, 6) * r.OBSCOR(IJ, M, r.KCR(K, 1));
+        if (FULL) {
+          for (int IC = 1; IC <= 2; ++IC) for (int ICL = 1; ICL <= 2; ++ICL) r.WLATN(IJ, K, M, IC, ICL) = r.WLATN(IJ, K, M, IC, ICL) * r.OBSLAT(IJ, M, IC);
+          for (int IC = 1; IC <= 2; ++IC) r.WLONN(IJ, K, M, IC) = r.WLONN(IJ, K, M, IC) * r.OBSLON(IJ, M, IC);
+          for (int ICR = 1; ICR <= 4; ++ICR) for (int ICL = 1; ICL <= 2; ++ICL) r.WCORN(IJ, K, M, ICR, ICL) = r.WCORN(IJ, K, M, ICR, ICL) * r.OBSCOR(IJ, M, r.KCR(K, ICR));
+        }
+      }
+    }
   };
   // CTUWDRV (ctuwdrv.F90:83-123): ICALL = 1 with the currents everywhere; with LLCFLCUROFF a second call switches the current
   // REFRACTION (not the advection by the current) off at the points that failed (CURMASK, ctuw.F90:113-127)

@@ -18,7 +18,7 @@ import os
 import numpy as np
 import pytest
 
-from common import CASES, OUT_FIELDS, make_gpu, make_oracle, relerr
+from common import CASES, OUT_FIELDS, make_gpu, make_oracle, make_setup, relerr
 from ecwam_b200 import lib as L, model as M
 
 pytestmark = pytest.mark.gpu
@@ -305,6 +305,60 @@ def test_current_refraction_bit_exact(built, irefra):
         w.outbs([1], [1], [1])
 
 
+@pytest.mark.parametrize("irefra,dlf", [(2, 225.0), (3, 150.0), (3, 112.5)])
+def test_fast_wave_substeps_with_currents_bit_exact(built, irefra, dlf):
+    """IFRELFMAX > 0 together with IREFRA = 2, 3 (propag_wam.F90:257-313 + propags2.F90:123-194): a sub-step advects frequencies
+    1..IFRELFMAX only, and the frequency-shift term of row IFRELFMAX reads row IFRELFMAX + 1 of FL1_EXT, which keeps the spectrum
+    of the start of the step.  2, 3 and 4 sub-steps: both sides of the FL1 / FL3 ping-pong."""
+    from common import synthetic_currents
+    kw = dict(irefra=irefra, ifrelfmax=5, delpro_lf=dlf)
+    g, o, f, fl = make_oracle("o640like", **kw)
+    _, s, w = make_gpu("o640like", **kw)
+    u, v = synthetic_currents(g)
+    o.set_field("UCUR", u); o.set_field("VCUR", v)
+    w.set_field("ucur", u); w.set_field("vcur", v)
+    fl = fl.copy()
+    fl[:7] *= 1e-3 / fl[:7].max()        # a swell-like load in the sub-stepped frequencies (the cold start leaves ~1e-18 there)
+    o.set_fl1(fl); w.set_fl1(fl)
+    assert o.propag() == 0 and w.propag() == 0
+    w.synchronize()
+    np.testing.assert_array_equal(w.get_spec("fl1"), o.get_fl1()[:, :, w.own])
+    o.implsch(); o.step()
+    w.implsch(); w.step()
+    w.synchronize()
+    check_state(w, o)
+
+
+@pytest.mark.parametrize("case,extra", [("o640like", dict()), ("o48like", dict(irefra=1)), ("o320like", dict(irefra=3)),
+                                        ("o640like", dict(ifrelfmax=5, delpro_lf=225.0))])
+def test_subgrid_obstructions_bit_exact(built, case, extra):
+    """LSUBGRID = T (ctuw.F90:700-733): OBSLON / OBSLAT / OBSCOR of ecwam_b200_decomp scale the weights of the surrounding points in
+    the exact PROPAGS2 kernels (all three refraction flavours, fast-wave sub-steps): bit-identical to the oracle, and different
+    from the unobstructed run."""
+    from common import synthetic_currents
+    from test_oracle import _obstructions
+    g, o, f, fl = make_oracle(case, **extra)
+    _, o1, _, _ = make_oracle(case, **extra)
+    g, s = make_setup(case, **extra)
+    obs = _obstructions(g.niblo, CASES[case]["Fr"])
+    o.set_obstructions(*obs)
+    s.set_obstructions(*obs)
+    _, _, w = make_gpu(case, setup=s, grid=g)
+    if extra.get("irefra", 0) >= 2:
+        u, v = synthetic_currents(g)
+        for m in (o, o1):
+            m.set_field("UCUR", u); m.set_field("VCUR", v)
+        w.set_field("ucur", u); w.set_field("vcur", v)
+    assert o.propag() == 0 and o1.propag() == 0 and w.propag() == 0
+    w.synchronize()
+    np.testing.assert_array_equal(w.get_spec("fl1"), o.get_fl1()[:, :, w.own])
+    assert (o.get_fl1() != o1.get_fl1()).any(axis=(0, 1)).mean() > 0.3
+    o.implsch(); o.step()
+    w.implsch(); w.step()
+    w.synchronize()
+    check_state(w, o)
+
+
 def test_current_cfl_fallback(built):
     """LLCFLCUROFF (ctuwdrv.F90:101-121): with a long propagation step and strong current shear the direction / frequency
     weights of the current refraction leave [0,1] at a few points; the second CTUW call switches the current refraction off at
@@ -421,7 +475,7 @@ def test_cfl_violation_is_reported(built):
 def test_unsupported_switches_are_rejected(built):
     from ecwam_b200 import synth
     g = synth.make_grid(8, "aqua")
-    for kw in (dict(irefra=4), dict(irefra=2, ifrelfmax=5), dict(isnonlin=3), dict(lciwa=16), dict(icode_wnd=1)):
+    for kw in (dict(irefra=4), dict(isnonlin=3), dict(lciwa=16), dict(icode_wnd=1)):
         s = M.WamSetup(g, nproc=1, **kw)
         with pytest.raises(L.EcwamError):
             M.WamIntgr(s, 0)

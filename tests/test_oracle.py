@@ -1002,3 +1002,39 @@ def test_sea_ice_attenuation_terms_against_numpy(built):
         np.testing.assert_allclose(fld, ref_fld, rtol=1e-11, atol=0, err_msg="SDICE%s FLD" % key)
         np.testing.assert_allclose(sl, ref_fld * F1, rtol=1e-11, atol=0, err_msg="SDICE%s SL" % key)
         assert (fld[:, :, ci == 0] == 0).all()
+
+
+def _obstructions(n, fr, seed=5):
+    """Synthetic LSUBGRID coefficients: mostly 1, a fifth of the interfaces partly blocked, a few closed; frequency dependent as in
+    the reference (long waves are blocked less, getbobstrct.F90)."""
+    rng = np.random.default_rng(seed)
+    def one(k):
+        x = np.ones((k, fr, n))
+        part = rng.random((k, 1, n)) < 0.2
+        val = np.round(rng.random((k, 1, n)) * 1000.0) * 0.001          # KOBS* are integers in thousandths
+        x = np.where(part, np.minimum(1.0, val + 0.3 * (1.0 - np.arange(fr)[None, :, None] / fr) * (1.0 - val)), x)
+        x[rng.random((k, 1, n)).repeat(fr, axis=1) < 0.02] = 0.0
+        return x
+    return one(2), one(2), one(4)
+
+
+def test_subgrid_obstructions_in_the_oracle(built):
+    """LSUBGRID (ctuw.F90:700-733): the blocking coefficients multiply the weights of the surrounding points and leave SUMWN alone, so
+    (i) coefficients of 1 change nothing (bit for bit), (ii) the advected spectrum is LINEAR in a uniform coefficient c:
+    F3(c) = F3(0) + c (F3(1) - F3(0)), (iii) blocked interfaces remove energy, never add it."""
+    fr = CASES["o640like"]["Fr"]
+    def run(obs):
+        g, o, f, fl = make_oracle("o640like")
+        if obs is not None:
+            o.set_obstructions(*obs)
+        assert o.propag() == 0
+        return o.get_fl1(), g.niblo
+    ref, n = run(None)
+    ones = (np.ones((2, fr, n)), np.ones((2, fr, n)), np.ones((4, fr, n)))
+    np.testing.assert_array_equal(run(ones)[0], ref)
+    f0 = run(tuple(0.0 * x for x in ones))[0]
+    fh = run(tuple(0.375 * x for x in ones))[0]
+    np.testing.assert_allclose(fh[:fr], f0[:fr] + 0.375 * (ref[:fr] - f0[:fr]), rtol=1e-13, atol=1e-30)
+    assert (f0 <= ref).all() and f0[:fr].sum() < 0.999 * ref[:fr].sum()      # what a step moves between cells is lost
+    fo = run(_obstructions(n, fr))[0]
+    assert (fo <= ref).all() and (fo >= f0).all() and f0[:fr].sum() < fo[:fr].sum() < ref[:fr].sum() * (1 - 1e-5)
