@@ -121,6 +121,9 @@ struct ecwam_b200_handle_s {
   // resident-state step (ecwam_b200_wamintgr_forced): device staging of the eight FF_NEXT fields
   DBuf<double> frc_next;
   DBuf<double> enhp;       // ENH(IJ,MC) plane of ISNONLIN = 1, 2
+  ecwam_b200_nemo_fields nemo{};   // LWNEMOCOU: bound with ecwam_b200_bind_nemo
+  bool nemo_bound = false;
+  DBuf<NemoDev> nemo_dev;          // k_nemo's argument block (allocated when LWNEMOCOU or LWNEMOCOUSTRN)
   DBuf<double> ice1, ice2; // SDICE1's table (+ per-frequency period interpolation), SDICE2's per-(point, frequency) factor (k_ice)
   int ice_nt = 0, ice_nh = 0;
   double ice_hmin = 0.0, ice_dh = 1.0;
@@ -216,7 +219,6 @@ static int fill_dev_const(const ecwam_b200_params& p, const ecwam_b200_tables& t
   if ((p.lciwa & 1) && (t.nict < 2 || t.nich < 2 || !t.cideac || !(t.dtic > 0.0) || !(t.dhic > 0.0)))
     EW_FAIL(ECWAM_B200_EINVAL, "LCIWA1 (SDICE1) needs the CIDEAC table (ecwam_b200_tables: nict, nich, ticmin, hicmin, dtic, dhic, cideac)");
   if (p.lciwa & ~15) EW_FAIL(ECWAM_B200_EINVAL, "lciwa: unknown bits");
-  if (p.lwnemocou) EW_FAIL(ECWAM_B200_EINVAL, "NEMO coupling accumulators are not implemented");
   if (p.icode_wnd != 3) EW_FAIL(ECWAM_B200_EINVAL, "only ICODE_WND=3 (10 m wind forcing) is implemented");
 
   if (p.iphys != 0 && p.iphys != 1) EW_FAIL(ECWAM_B200_EINVAL, "IPHYS must be 0 or 1");
@@ -231,6 +233,9 @@ static int fill_dev_const(const ecwam_b200_params& p, const ecwam_b200_tables& t
   c.lciwa3 = (p.lciwa & 4) ? 1 : 0; c.lciscal = (p.lciwa & 8) ? 1 : 0; c.zalpfacx = p.zalpfacx;
   c.lciwa1 = (p.lciwa & 1) ? 1 : 0; c.lciwa2 = (p.lciwa & 2) ? 1 : 0; c.lciwa_any = (p.lciwa & 7) ? 1 : 0;
   c.zalpfacb = p.zalpfacb; c.cdicwa = p.cdicwa;
+  c.lwnemotauoc = p.lwnemotauoc ? 1 : 0; c.lwnemocoustk = p.lwnemocoustk ? 1 : 0;
+  c.nemo_send = ((p.lwnemocousend && p.lwcou) || !p.lwcou) ? 1 : 0;     // stokestrn.F90:76-78
+  c.ROWATER = 1.0 / t.rowaterm1;
   {   // SDICE3, IMODEL = 2: ALP = (2*CDICE*CITH**1.25*FR(M)**4.5)*ALPFAC with CDICE = 0.1274*(ZPI/SQRT(G))**4.5 (sdice3.F90:123-129)
     const double cdice = 0.1274 * std::pow(t.zpi / std::sqrt(t.g), 4.5);
     for (int m = 0; m < p.nfre && m < EW_MAXF; ++m) c.fr45[m] = 2. * cdice * std::pow(t.fr[m], 4.5);
@@ -342,6 +347,8 @@ static int fill_dev_const(const ecwam_b200_params& p, const ecwam_b200_tables& t
   }
   return 0;
 }
+
+static int upload_nemo_dev(struct ecwam_b200_handle_s* h);
 
 int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* tables, const ecwam_b200_decomp* dec,
                       void* nccl_comm, void* cuda_stream, ecwam_b200_handle* out) {
@@ -618,6 +625,7 @@ int ecwam_b200_create(const ecwam_b200_params* params, const ecwam_b200_tables* 
     h->ice_nt = NT; h->ice_nh = NH; h->ice_hmin = tables->hicmin; h->ice_dh = tables->dhic;
   }
   if (p.licerun && (p.lciwa & 2)) ok = ok && !h->ice2.alloc((size_t)F * npts);
+  ok = ok && !upload_nemo_dev(h);   // LWNEMOCOUSTRN without LWNEMOCOU: CIMSSTRN alone
   if (!ok) { ecwam_b200_destroy(h); return ECWAM_B200_ECUDA; }
   cudaMemsetAsync(h->halo.p, 0, (halo_elems + 1) * sizeof(double), st);
   cudaMemsetAsync(h->fl3.p, 0, h->fl3.n * sizeof(double), st);
@@ -684,6 +692,22 @@ int ecwam_b200_bind_fields(ecwam_b200_handle h, const ecwam_b200_fields* dev) {
   h->weights_dirty = true;
   h->cur_side = 1;
   return 0;
+}
+
+static int upload_nemo_dev(H* h) {
+  if (!h->par.lwnemocou && !h->par.lwnemocoustrn) return 0;
+  NemoDev nd;
+  nd.f = h->nemo; nd.nemo_on = (h->par.lwnemocou && h->nemo_bound) ? 1 : 0; nd.strn_on = h->par.lwnemocoustrn ? 1 : 0;
+  return h->nemo_dev.upload(std::vector<NemoDev>(1, nd), h->st);
+}
+
+int ecwam_b200_bind_nemo(ecwam_b200_handle h, const ecwam_b200_nemo_fields* dev) {
+  if (!h || !dev) EW_FAIL(ECWAM_B200_EINVAL, "null argument");
+  const void* const* pp = (const void* const*)dev;
+  for (size_t i = 0; i < sizeof(*dev) / sizeof(void*); ++i) if (!pp[i]) EW_FAIL(ECWAM_B200_EINVAL, "bind_nemo: member %zu is null", i);
+  h->nemo = *dev;
+  h->nemo_bound = true;
+  return upload_nemo_dev(h);
 }
 
 int ecwam_b200_set_exchange(ecwam_b200_handle h, ecwam_b200_exchange_fn fn, void* user, int staged) {
@@ -902,6 +926,7 @@ static ImplDev make_impl(H* h, bool from_fl3) {
   d.enh = h->enhp.p;
   d.ice1 = h->ice1.p; d.ice_nt = h->ice_nt; d.ice_nh = h->ice_nh; d.ice_hmin = h->ice_hmin; d.ice_dh = h->ice_dh;
   d.ice2 = h->ice2.p;
+  d.nemo = h->nemo_dev.p;
   return d;
 }
 
@@ -910,6 +935,9 @@ static int implsch_range(H* h, int ichnk0, int nchnk, bool from_fl3) {
   if (ichnk0 < 1 || nchnk < 1 || ichnk0 + nchnk - 1 > h->par.nchnk) EW_FAIL(ECWAM_B200_EINVAL, "chunk range out of bounds");
   int rc = ensure_const(h);
   if (rc) return rc;
+  if (h->par.lwnemocou && !h->nemo_bound) EW_FAIL(ECWAM_B200_ESTATE, "IMPLSCH: LWNEMOCOU needs the WAVE2OCEAN fields (ecwam_b200_bind_nemo)");
+  if (h->par.lwnemocoustrn && (!h->dev.strnms || !h->dev.cithick)) EW_FAIL(ECWAM_B200_ESTATE, "IMPLSCH: LWNEMOCOUSTRN needs STRNMS and CITHICK bound");
+  if (h->par.licerun && (h->par.lciwa & 5) && !h->dev.cithick) EW_FAIL(ECWAM_B200_ESTATE, "IMPLSCH: LCIWA1 / LCIWA3 need CITHICK bound");
   ImplDev d = make_impl(h, from_fl3);
   static const char* kStage[EW_IMPLSCH_NSTAGE] = {"implsch_point", "implsch_stencil"};
   // Small blocks (several ranks, or O320 and below): the chunk range is cut into parts that run the kernel sequence on streams of
@@ -1011,9 +1039,20 @@ int ecwam_b200_implsch_f(ecwam_b200_handle h, int kijs, int kijl, double* fl1, c
   a.chk(phiocd, f.phiocd, b2, "PHIOCD"); a.chk(phieps, f.phieps, b2, "PHIEPS"); a.chk(phiaw, f.phiaw, b2, "PHIAW");
   a.chk(mij, f.mij, bi, "MIJ");
   if (a.bad) EW_FAIL(ECWAM_B200_ESTATE, "IMPLSCH: %d argument(s) are not chunk %lld of the bound arrays (first: %s): re-bind the fields", a.bad, a.ichnk0 + 1, a.first);
-  // IOBND, IODP, IBRMEM and the NEMO accumulators (LWNEMOCOU = F, rejected at create otherwise) are not read on this path
-  (void)iobnd; (void)iodp; (void)ibrmem; (void)nemoustokes; (void)nemovstokes; (void)nemostrn; (void)nphieps; (void)ntauoc; (void)nswh; (void)nmwp;
-  (void)nemotaux; (void)nemotauy; (void)nemotauicx; (void)nemotauicy; (void)nemowswave; (void)nemophif;
+  // IOBND, IODP, IBRMEM are not read on this path; the NEMO accumulators must be chunk ICHNK of the arrays bound with bind_nemo
+  (void)iobnd; (void)iodp; (void)ibrmem;
+  if (h->par.lwnemocou) {
+    if (!h->nemo_bound) EW_FAIL(ECWAM_B200_ESTATE, "IMPLSCH: LWNEMOCOU needs ecwam_b200_bind_nemo");
+    const ecwam_b200_nemo_fields& o = h->nemo;
+    a.chk(nemoustokes, o.nemoustokes, b2, "NEMOUSTOKES"); a.chk(nemovstokes, o.nemovstokes, b2, "NEMOVSTOKES"); a.chk(nemostrn, o.nemostrn, b2, "NEMOSTRN");
+    a.chk(nphieps, o.nphieps, b2, "NPHIEPS"); a.chk(ntauoc, o.ntauoc, b2, "NTAUOC"); a.chk(nswh, o.nswh, b2, "NSWH"); a.chk(nmwp, o.nmwp, b2, "NMWP");
+    a.chk(nemotaux, o.nemotaux, b2, "NEMOTAUX"); a.chk(nemotauy, o.nemotauy, b2, "NEMOTAUY"); a.chk(nemotauicx, o.nemotauicx, b2, "NEMOTAUICX");
+    a.chk(nemotauicy, o.nemotauicy, b2, "NEMOTAUICY"); a.chk(nemowswave, o.nemowswave, b2, "NEMOWSWAVE"); a.chk(nemophif, o.nemophif, b2, "NEMOPHIF");
+    if (a.bad) EW_FAIL(ECWAM_B200_ESTATE, "IMPLSCH: %d NEMO argument(s) are not chunk %lld of the arrays bound with bind_nemo (first: %s)", a.bad, a.ichnk0 + 1, a.first);
+  } else {
+    (void)nemoustokes; (void)nemovstokes; (void)nemostrn; (void)nphieps; (void)ntauoc; (void)nswh; (void)nmwp;
+    (void)nemotaux; (void)nemotauy; (void)nemotauicx; (void)nemotauicy; (void)nemowswave; (void)nemophif;
+  }
   return implsch_range(h, (int)a.ichnk0 + 1, 1, false);
 }
 

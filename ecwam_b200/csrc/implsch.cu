@@ -13,6 +13,7 @@
 
 namespace ew {
 
+static_assert(sizeof(DevConst) % 16 == 0, "keep sizeof(DevConst) a multiple of 16 (alignment of the constants behind it)");
 __constant__ DevConst c_dc;
 int upload_dev_const(const DevConst& h, cudaStream_t st) {
   EW_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_dc, &h, sizeof(DevConst), 0, cudaMemcpyHostToDevice, st));
@@ -3361,8 +3362,106 @@ __global__ void __launch_bounds__(128) k_ice(ImplDev d, long long p0, long long 
   }
 }
 
+// =========================================================================================================
+// k_nemo: what IMPLSCH hands to the ocean model, one thread per grid point after the frequency sweep.
+//   LWNEMOCOUSTRN: CIMSSTRN (cimsstrn.F90:83-119), the mean square wave strain in the sea ice from the NEW spectrum, with AKI_ICE's
+//     flexural-gravity wavenumber (aki_ice.F90:66-112) -> STRNMS.
+//   LWNEMOCOU: the NEMO part of WNFLUXES (wnfluxes.F90:304-330, LNUPD = T): NPHIEPS, NTAUOC, NSWH = 4 sqrt(EM_OC), NMWP = 1 / F1_OC
+//     overwritten; NEMOTAUX/Y, NEMOWSWAVE, NEMOPHIF, NEMOTAUICX/Y accumulated; and of STOKESTRN (stokestrn.F90:76-88).  EM_OC, F1_OC
+//     (wnfluxes.F90:222-250) are rebuilt from FKMEAN's EMEAN / F1MEAN of the incoming spectrum (scratch of k_point) exactly as the
+//     sweep's WNFLUXES closure forms OOVAL and USTAR.
+// =========================================================================================================
+__device__ double aki_ice(double xk, double depth, double cith) {
+  const double YMICE = 5.5e9, RMUICE = 0.3, RHOI = 922.5, EBS = 0.000001, AKI_MAX = 20.0;
+  if (cith <= 0.0) return xk;
+  const double ficstf = (YMICE * (cith * cith * cith) / (12.0 * (1.0 - RMUICE * RMUICE))) / c_dc.ROWATER;
+  const double rdh = (RHOI / c_dc.ROWATER) * cith;
+  const double om2 = c_dc.G * xk * tanh(xk * depth);
+  double akiold = 0.0;
+  double aki = dmin(xk, pow(om2 / dmax(ficstf, 1.0), 0.2));
+  while (fabs(aki - akiold) > EBS * akiold && aki < AKI_MAX) {
+    akiold = aki;
+    const double akid = dmin(depth * aki, 50.0);
+    const double a2 = aki * aki, a4 = a2 * a2;
+    const double f = ficstf * (a4 * aki) + c_dc.G * aki - om2 * (rdh * aki + 1.0 / tanh(akid));
+    const double sh = sinh(akid);
+    const double fprime = 5.0 * ficstf * a4 + c_dc.G - om2 * (rdh - depth / (sh * sh));
+    aki = aki - f / fprime;
+    if (aki <= 0.0) aki = AKI_MAX;
+  }
+  return aki;
+}
+
+__global__ void __launch_bounds__(128) k_nemo(ImplDev d, long long p0, long long np) {
+  const long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= p0 + np) return;
+  const int A = c_dc.A, F = c_dc.F;
+  const size_t n = (size_t)d.npts;
+  const NemoDev nd = *d.nemo;
+  if (nd.strn_on) {
+    const long long c = p / d.P;
+    const int i = (int)(p - c * d.P);
+    const double* fl = d.f.fl1 + (size_t)i + (size_t)d.P * A * F * (size_t)c;
+    const double dep = d.f.depth[p], cith = d.f.cithick[p];
+    const double f1lim = c_dc.flmin / c_dc.DELTH;
+    double strn = 0.0;
+    for (int m = 0; m < F; ++m) {
+      const double wk = d.f.wavnum[idx3(d, p, m)];
+      const double xki = aki_ice(wk, dep, cith);
+      const double e = 0.5 * cith * (xki * xki * xki) / wk;
+      double sume = 0.0;
+      for (int k = 0; k < A; ++k) sume = sume + fl[((size_t)m * A + k) * d.P];
+      if (sume > f1lim) strn = strn + e * e * sume * c_dc.DFIM[m];
+    }
+    d.f.strnms[p] = strn;
+  }
+  if (!nd.nemo_on) return;
+  const ecwam_b200_nemo_fields& o = nd.f;
+  {   // WNFLUXES
+    const double C1 = 1.03e-3, C2 = 0.04e-3, P1 = 1.48, P2 = -0.21, CDMAX_LOC = 0.003, EFD_MIN = 0.0625, EFD_MAX = 6.25;
+    const double cicover = d.f.cicover[p], wsw = d.f.wswave[p], ufric = d.f.ufric[p];
+    const double em = d.scr[S_EMEAN * n + p], f1 = d.scr[S_F1MEAN * n + p];
+    const double cithrsh_inv = c_dc.lciwa_any ? 50.0 : 1.0 / dmax(c_dc.cithrsh, 0.01);
+    const double zcithrs = c_dc.lciwa_any ? 0.0 : c_dc.ciblock, zmaxexp = c_dc.lciwa_any ? 20.0 : 10.0;
+    double em_oc = em, f1_oc = f1;
+    if (c_dc.licerun && c_dc.lwamrsetci && cicover > zcithrs) {
+      const double ooval = exp(-dmin(p4(cicover * cithrsh_inv), zmaxexp));
+      const double u10p = dmax(wsw, c_dc.EPSU10);
+      const double cd_bulk = dmin((C1 + C2 * pow(u10p, P1)) * pow(u10p, P2), CDMAX_LOC);
+      const double cd_wave = sq(ufric / u10p);
+      const double ustar = dmax(sqrt(ooval * cd_wave + (1.0 - ooval) * cd_bulk) * u10p, c_dc.EPSUS);
+      const double efd = dmin((4.0 * c_dc.EGRCRV / (c_dc.G * c_dc.G)) * p4(ustar), EFD_MAX);
+      em_oc = dmax(ooval * em + (1.0 - ooval) * efd, EFD_MIN);
+      const double ffd = (pow(c_dc.EGRCRV / c_dc.AFCRV, 1.0 / c_dc.BFCRV) * c_dc.G) / ustar;
+      f1_oc = dmin(dmax(ooval * f1 + (1.0 - ooval) * ffd, c_dc.FR[1]), c_dc.FR[F - 1]);
+    }
+    o.nphieps[p] = d.f.phieps[p];
+    o.ntauoc[p] = d.f.tauoc[p];
+    o.nswh[p] = em_oc != 0.0 ? 4.0 * sqrt(em_oc) : 0.0;
+    o.nmwp[p] = f1_oc != 0.0 ? 1.0 / f1_oc : 0.0;
+    if (c_dc.lwnemotauoc) { o.nemotaux[p] = o.nemotaux[p] + d.f.tauocxd[p]; o.nemotauy[p] = o.nemotauy[p] + d.f.tauocyd[p]; }
+    else { o.nemotaux[p] = o.nemotaux[p] + d.f.tauxd[p]; o.nemotauy[p] = o.nemotauy[p] + d.f.tauyd[p]; }
+    o.nemowswave[p] = o.nemowswave[p] + wsw;
+    o.nemophif[p] = o.nemophif[p] + d.f.phiocd[p];
+    o.nemotauicx[p] = o.nemotauicx[p] + d.f.tauicx[p];
+    o.nemotauicy[p] = o.nemotauicy[p] + d.f.tauicy[p];
+  }
+  if (c_dc.nemo_send) {   // STOKESTRN
+    o.nemoustokes[p] = c_dc.lwnemocoustk ? d.f.ustokes[p] : 0.0;
+    o.nemovstokes[p] = c_dc.lwnemocoustk ? d.f.vstokes[p] : 0.0;
+    if (nd.strn_on) o.nemostrn[p] = d.f.strnms[p];
+  }
+}
+
+static int launch_sweep_stage(const ImplDev& d, long long p0, long long np, cudaStream_t st);
+
 int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage, cudaStream_t st) {
   if (np <= 0) return 0;
+  if (stage == 1) {
+    const int rc = launch_sweep_stage(d, p0, np, st);
+    if (rc == 0 && d.nemo) k_nemo<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(d, p0, np);
+    return rc;
+  }
   const int A = d.A;
   if (A > 36 || 2 * d.halo_r > A || 2 * d.halo_c > A) { ew_set_error("k_stencil is built for NANG <= 36 and direction halos <= NANG/2"); return ECWAM_B200_EINVAL; }
   if (stage == 0) {
@@ -3386,7 +3485,12 @@ int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage
     else { k_point<false, 1, false><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<false, 2, false><<<nb, KP_NTH, smp, st>>>(d, p0, np); }
     if (d.isnonlin != 0) k_enh<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(d, p0, np);
     if (d.ice1 || d.ice2) k_ice<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(d, p0, np);
-  } else if (stage == 1) {
+  } else return ECWAM_B200_EINVAL;
+  return 0;
+}
+
+static int launch_sweep_stage(const ImplDev& d, long long p0, long long np, cudaStream_t st) {
+  {
     // two grid points per thread (16-byte shared / global accesses) need an even NPROMA and an even first point
     const uintptr_t al = (uintptr_t)d.f.fl1 | (uintptr_t)d.f.xllws | (uintptr_t)d.fldin | (uintptr_t)d.fl_lo;
     bool pair = (d.P % 2 == 0) && (p0 % 2 == 0) && (np % 2 == 0) && (al & 15) == 0;
@@ -3426,8 +3530,7 @@ int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage
       return d.lwflux ? launch_stencil<0, 2, true>(d, p0, np, st) : launch_stencil<0, 2, false>(d, p0, np, st);
     }
     return d.lwflux ? launch_stencil<0, 1, true>(d, p0, np, st) : launch_stencil<0, 1, false>(d, p0, np, st);
-  } else return ECWAM_B200_EINVAL;
-  return 0;
+  }
 }
 
 }  // namespace ew

@@ -72,6 +72,10 @@ void launch_copyback(const PropDev& d, const double* fl3, double* fl1, int m0, i
 void launch_pad(const PropDev& d, double* fl, int flF, int m0, int m1, cudaStream_t st);
 
 // ---- IMPLSCH -----------------------------------------------------------------------------------------------
+struct NemoDev {
+  ecwam_b200_nemo_fields f;   // the WAVE2OCEAN fields (valid when nemo_on)
+  int nemo_on, strn_on;       // LWNEMOCOU (fields bound); LWNEMOCOUSTRN (CIMSSTRN fills STRNMS)
+};
 struct ImplDev {
   int P, A, F, Fr, nchnk;
   long long npts;          // P*nchnk (padded lanes included, as the reference: KIJL = NPROMA_WAM, wamintgr.F90:120)
@@ -98,7 +102,9 @@ struct ImplDev {
   const double* ice1;      // LCIWA1: [NICT*NICH] CIDEAC, [F] WT1, [F] IT, [F] IT1 (0-based, as doubles) of SDICE1 (k_ice); null otherwise
   int ice_nt, ice_nh;      // NICT, NICH
   double ice_hmin, ice_dh; // HICMIN, DHIC
-  long long pad_ice;       // keeps sizeof(ImplDev) a multiple of 16: the kernels' (p0, np) arguments stay 16-byte aligned (one LDCU.128)
+  const struct NemoDev* nemo;   // LWNEMOCOU / LWNEMOCOUSTRN: device-resident argument block of k_nemo (after the sweep); null otherwise.
+                           // (A pointer, not the 13 fields: sizeof(ImplDev) stays a multiple of 16 -- the kernels' (p0, np) arguments keep
+                           // their alignment -- and k_point's register allocation, which moved with the larger struct, stays as measured.)
   double* ice2;            // LCIWA2: [F][npts] per-(point, frequency) factor of SDICE2 (k_ice writes it, k_stencil / k_stencil_dp read it); null otherwise
 };
 #define EW_TQ_N 6          // number of planes of ImplDev::tbg

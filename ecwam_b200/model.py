@@ -36,7 +36,8 @@ def default_params(**kw) -> L.Params:
                  llcapchnk=1, lbiwbk=1, licerun=1, lmaskice=1, lwamrsetci=1, lciwa=0, lwflux=0, lwfluxout=1, lwnemocou=0,
                  lwvflx_snl=1, lwcouast=0, icode_wnd=3, ifrelfmax=0, nproma=32, nchnk=0, idelt=900.0, idelpro=900.0,
                  delpro_lf=900.0, ximp=1.0, rnu=1.5e-5, rnum=0.11 * 1.5e-5, wspmin=1.0, cithrsh=0.3, cithrsh_tail=0.3,
-                 ciblock=0.0, flmin=1e-5, bathymax=998.999, llcflcuroff=1, zalpfacx=1.0, zalpfacb=1.0, cdicwa=0.01)
+                 ciblock=0.0, flmin=1e-5, bathymax=998.999, llcflcuroff=1, zalpfacx=1.0, zalpfacb=1.0, cdicwa=0.01, lwnemotauoc=0, lwnemocoustk=0,
+                 lwnemocoustrn=0, lwnemocousend=1, lwcou=0)
     for k, v in kw.items():
         if not hasattr(p, k):
             raise KeyError(k)
@@ -202,6 +203,13 @@ class WamIntgr:
         self.t["mij"] = torch.full((Cn, P), F, dtype=torch.int32, device=dev)
         self.t["ciwa"].fill_(1.0)
         self.bind()
+        if self.par.lwnemocou:      # WAVE2OCEAN fields of the NEMO coupling (accumulators start at 0)
+            nf = L.NemoFields()
+            for n, _ in L.NemoFields._fields_:
+                self.t[n] = torch.zeros((Cn, P), dtype=torch.float64, device=dev)
+                setattr(nf, n, C.cast(self.t[n].data_ptr(), C.POINTER(C.c_double)))
+            self.nemo_fields = nf
+            L.check(self.lib.ecwam_b200_bind_nemo(self.h, C.byref(nf)), "bind_nemo")
 
     def bind(self):
         f = L.Fields()

@@ -56,7 +56,7 @@ typedef struct ecwam_b200_params {
   int lciwa;       /* YOWICE bit mask: 1 LCIWA1 (SDICE1, needs ecwam_b200_tables cideac), 2 LCIWA2 (SDICE2), 4 LCIWA3 (SDICE3), 8 LCISCAL */
   int lwflux;      /* YOWCOUP LWFLUX                                                    */
   int lwfluxout;   /* YOWCOUP LWFLUXOUT (userin.F90:470 sets it .TRUE.)                 */
-  int lwnemocou;   /* YOWCOUP LWNEMOCOU (0 only)                                        */
+  int lwnemocou;   /* YOWCOUP LWNEMOCOU (needs ecwam_b200_bind_nemo; LWNEMOCOUWRS / LWNEMOCOUIBR are not built) */
   int lwvflx_snl;  /* YOWCOUP LWVFLX_SNL                                                */
   int lwcouast;    /* YOWCOUP LWCOUAST                                                  */
   int icode_wnd;   /* YOWWNDG ICODE (3 = 10 m wind, only)                               */
@@ -79,6 +79,11 @@ typedef struct ecwam_b200_params {
   double zalpfacx; /* YOWICE ZALPFACX (attenuation factor of SDICE3, 1 = no reduction)    */
   double zalpfacb; /* YOWICE ZALPFACB (scales SDICE1 / SDICE2; mpuserin.F90:780: 1)             */
   double cdicwa;   /* YOWICE CDICWA (ice-water drag coefficient of SDICE2; userin.F90:974: 0.01) */
+  int lwnemotauoc;   /* YOWCOUP LWNEMOTAUOC: NEMOTAUX/Y accumulate TAUOCXD/YD instead of TAUXD/YD (wnfluxes.F90:317-323) */
+  int lwnemocoustk;  /* YOWCOUP LWNEMOCOUSTK: NEMOUSTOKES/NEMOVSTOKES = USTOKES/VSTOKES, else 0 (stokestrn.F90:79-85)   */
+  int lwnemocoustrn; /* YOWCOUP LWNEMOCOUSTRN: CIMSSTRN fills STRNMS (and NEMOSTRN with LWNEMOCOU) (stokestrn.F90:70-74, 87) */
+  int lwnemocousend; /* YOWCOUP LWNEMOCOUSEND (read with LWCOU only, stokestrn.F90:76-78)                             */
+  int lwcou;         /* YOWCOUP LWCOU (only used in that condition)                                                 */
 } ecwam_b200_params;
 
 /* ---------------------------------------------------------------------------------------------------
@@ -351,6 +356,27 @@ int ecwam_b200_set_exchange(ecwam_b200_handle h, ecwam_b200_exchange_fn fn, void
  * src/ecwam/wamintgr_loki_gpu.F90:141-157).                                                            */
 int ecwam_b200_bind_fields(ecwam_b200_handle h, const ecwam_b200_fields* dev);
 
+/* NEMO coupling fields = the WAVE2OCEAN arguments of IMPLSCH in the reference order (implsch.F90:17-19), DEVICE pointers over all
+ * chunks, (P,C) doubles (JWRO = JWRB in the double-precision build).  Required with LWNEMOCOU.  WNFLUXES (wnfluxes.F90:304-330)
+ * overwrites NPHIEPS, NTAUOC, NSWH, NMWP and ADDS to NEMOTAUX/Y, NEMOWSWAVE, NEMOPHIF, NEMOTAUICX/Y (the caller zeroes them after a
+ * coupling exchange); STOKESTRN (stokestrn.F90:76-88) overwrites NEMOUSTOKES, NEMOVSTOKES and, with LWNEMOCOUSTRN, NEMOSTRN.       */
+typedef struct ecwam_b200_nemo_fields {
+  double* nemoustokes;
+  double* nemovstokes;
+  double* nemostrn;
+  double* nphieps;
+  double* ntauoc;
+  double* nswh;
+  double* nmwp;
+  double* nemotaux;
+  double* nemotauy;
+  double* nemotauicx;
+  double* nemotauicy;
+  double* nemowswave;
+  double* nemophif;
+} ecwam_b200_nemo_fields;
+int ecwam_b200_bind_nemo(ecwam_b200_handle h, const ecwam_b200_nemo_fields* dev);
+
 /* PROPAG_WAM over the whole local block (src/ecwam/propag_wam.F90:10-419, IPROPAGS=2, IREFRA=0..3):
  * halo exchange of FL1 (MPEXCHNG -> NCCL), first-call CTU weight set-up + CFL check (CTUWUPDT),
  * PROPAGS2 (+ fast-wave sub-steps), result back in FL1 with padded lanes refreshed.  IREFRA = 1: depth refraction;
@@ -375,8 +401,8 @@ int ecwam_b200_implsch(ecwam_b200_handle h, int ichnk0, int nchnk);
  * for IMPLSCH the slices of chunk ICHNK, `FL1(:,:,:,ICHNK)` etc. (wamintgr.F90:119-146).  The kernels work on the arrays bound
  * with ecwam_b200_bind_fields: every argument is checked to be chunk ICHNK (derived from FL1's address) of its bound array, so
  * that a FIELD_API re-allocation that was not followed by a re-bind fails with ECWAM_B200_ESTATE instead of using stale
- * memory.  KIJS:KIJL must be 1:NPROMA_WAM as in the reference call.  IOBND, IODP, IBRMEM and the NEMO accumulators
- * (LWNEMOCOU = F) are accepted and not read.                                                             */
+ * memory.  KIJS:KIJL must be 1:NPROMA_WAM as in the reference call.  IOBND, IODP, IBRMEM are accepted and not read; the NEMO
+ * accumulators are checked against ecwam_b200_bind_nemo's arrays when LWNEMOCOU is on and ignored otherwise.                                                            */
 int ecwam_b200_implsch_f(ecwam_b200_handle h, int kijs, int kijl, double* fl1, const double* wavnum, const double* cgroup,
                          const double* ciwa, const double* cinv, const double* xk2cg, const double* stokfac, const double* emaxdpt,
                          const double* depth, const int* iobnd, const int* iodp, const double* ibrmem, double* aird, double* wdwave,

@@ -89,6 +89,8 @@ struct Config {
   int store_all_weights = 0;  // keep the reference's 18 weight arrays (tests only; 150 KB/point at 36x29)
   int nthreads = 1;  // OpenMP threads for the CPU-baseline leg (WAM_NPROMA is NOT applied: LLNO_WAM_NPROMA)
   int llcflcuroff = 1;  // YOWSTAT LLCFLCUROFF (mpuserin.F90:575): retry without current refraction where the CFL check failed
+  // YOWCOUP NEMO coupling (with lwnemocou): LWNEMOTAUOC, LWNEMOCOUSTK, LWNEMOCOUSTRN, LWNEMOCOUSEND (yowcoup.F90:24-33)
+  int lwnemotauoc = 0, lwnemocoustk = 0, lwnemocoustrn = 0, lwnemocousend = 1;
 };
 
 // ---------------------------------------------------------------------------
@@ -198,6 +200,8 @@ struct Fields {
   ArrD WSEMEAN, WSFMEAN, USTOKES, VSTOKES, STRNMS, TAUXD, TAUYD, TAUOCXD, TAUOCYD, TAUOC, TAUICX, TAUICY, PHIOCD,
       PHIEPS, PHIAW;
   ArrI MIJ;
+  // NEMO coupling fields (P,C) (yowdrvtype_config.yml WAVE2OCEAN; JWRO = double here): accumulated / overwritten by WNFLUXES and STOKESTRN
+  ArrD NSWH, NMWP, NPHIEPS, NTAUOC, NEMOTAUX, NEMOTAUY, NEMOTAUICX, NEMOTAUICY, NEMOWSWAVE, NEMOPHIF, NEMOUSTOKES, NEMOVSTOKES, NEMOSTRN;
   // test hook (orc_capture): the inputs of WNFLUXES that are internal to IMPLSCH, kept from the last implsch_chunk call
   bool capture = false;
   ArrD DBG_SSOURCE;            // (P,A,F,C)

@@ -22,7 +22,11 @@ static ArrD* field2d(Fields& f, const std::string& n) {
       {"STRNMS", &Fields::STRNMS}, {"TAUXD", &Fields::TAUXD}, {"TAUYD", &Fields::TAUYD},
       {"TAUOCXD", &Fields::TAUOCXD}, {"TAUOCYD", &Fields::TAUOCYD}, {"TAUOC", &Fields::TAUOC},
       {"TAUICX", &Fields::TAUICX}, {"TAUICY", &Fields::TAUICY}, {"PHIOCD", &Fields::PHIOCD},
-      {"PHIEPS", &Fields::PHIEPS}, {"PHIAW", &Fields::PHIAW}};
+      {"PHIEPS", &Fields::PHIEPS}, {"PHIAW", &Fields::PHIAW},
+      {"NSWH", &Fields::NSWH}, {"NMWP", &Fields::NMWP}, {"NPHIEPS", &Fields::NPHIEPS}, {"NTAUOC", &Fields::NTAUOC},
+      {"NEMOTAUX", &Fields::NEMOTAUX}, {"NEMOTAUY", &Fields::NEMOTAUY}, {"NEMOTAUICX", &Fields::NEMOTAUICX},
+      {"NEMOTAUICY", &Fields::NEMOTAUICY}, {"NEMOWSWAVE", &Fields::NEMOWSWAVE}, {"NEMOPHIF", &Fields::NEMOPHIF},
+      {"NEMOUSTOKES", &Fields::NEMOUSTOKES}, {"NEMOVSTOKES", &Fields::NEMOVSTOKES}, {"NEMOSTRN", &Fields::NEMOSTRN}};
   auto it = mp.find(n);
   return it == mp.end() ? nullptr : &(f.*(it->second));
 }

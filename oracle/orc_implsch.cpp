@@ -1071,9 +1071,11 @@ void SBOTTOM(const Ctx& x, V3 FL1, V3 FLD, V3 SL, V2 WAVNUM, V1 DEPTH) {
 }
 
 // wnfluxes.F90:163-331 (LWNEMOCOU=F, LWNEMOCOUWRS=F, LCIWA*=F)
+// the NEMO fields WNFLUXES updates (wnfluxes.F90:304-330)
+struct NemoFlux { V1 NPHIEPS, NTAUOC, NSWH, NMWP, NEMOTAUX, NEMOTAUY, NEMOTAUICX, NEMOTAUICY, NEMOWSWAVE, NEMOPHIF; };
 void WNFLUXES(const Ctx& x, I1 MIJ, V2 RHOWGDFTH, V2 CINV, V3 SSURF, V1 CICOVER, V1 PHIWA, V1 EM, V1 F1, V1 WSWAVE,
               V1 WDWAVE, V1 USTRA, V1 VSTRA, V1 UFRIC, V1 AIRD, V1 TAUXD, V1 TAUYD, V1 TAUOCXD, V1 TAUOCYD, V1 TAUOC,
-              V1 TAUICX, V1 TAUICY, V1 PHIOCD, V1 PHIEPS, V1 PHIAW) {
+              V1 TAUICX, V1 TAUICY, V1 PHIOCD, V1 PHIEPS, V1 PHIAW, const NemoFlux* NE = nullptr) {
   (void)MIJ;
   const Tables& t = x.t;
   const Config& c = x.c;
@@ -1144,7 +1146,59 @@ void WNFLUXES(const Ctx& x, I1 MIJ, V2 RHOWGDFTH, V2 CINV, V3 SSURF, V1 CICOVER,
     PHIAW(IJ) = PHIWA(IJ) / XN;
     PHIAW(IJ) = OOVAL[IJ] * PHIWA(IJ) / XN + (1.0 - OOVAL[IJ]) * PHIAW_ICE;
   }
-  (void)EM_OC; (void)F1_OC;
+  if (c.lwnemocou && NE) {   // LNUPD = T (implsch.F90:413); wnfluxes.F90:304-330
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      NE->NPHIEPS(IJ) = PHIEPS(IJ);
+      NE->NTAUOC(IJ) = TAUOC(IJ);
+      NE->NSWH(IJ) = EM_OC[IJ] != 0.0 ? 4.0 * std::sqrt(EM_OC[IJ]) : 0.0;
+      NE->NMWP(IJ) = F1_OC[IJ] != 0.0 ? 1.0 / F1_OC[IJ] : 0.0;
+      if (c.lwnemotauoc) { NE->NEMOTAUX(IJ) = NE->NEMOTAUX(IJ) + TAUOCXD(IJ); NE->NEMOTAUY(IJ) = NE->NEMOTAUY(IJ) + TAUOCYD(IJ); }
+      else { NE->NEMOTAUX(IJ) = NE->NEMOTAUX(IJ) + TAUXD(IJ); NE->NEMOTAUY(IJ) = NE->NEMOTAUY(IJ) + TAUYD(IJ); }
+      NE->NEMOWSWAVE(IJ) = NE->NEMOWSWAVE(IJ) + WSWAVE(IJ);
+      NE->NEMOPHIF(IJ) = NE->NEMOPHIF(IJ) + PHIOCD(IJ);
+      NE->NEMOTAUICX(IJ) = NE->NEMOTAUICX(IJ) + TAUICX(IJ);
+      NE->NEMOTAUICY(IJ) = NE->NEMOTAUICY(IJ) + TAUICY(IJ);
+    }
+  }
+}
+
+// aki_ice.F90:66-112: wavenumber of a flexural-gravity wave under an elastic ice sheet (Fox & Squire 1991), Newton's method
+static double AKI_ICE(double G, double XK, double DEPTH, double RHOW, double CITH) {
+  const double YMICE = 5.5E+9, RMUICE = 0.3, RHOI = 922.5, EBS = 0.000001, AKI_MAX = 20.0;
+  double AKI;
+  if (CITH <= 0.0) AKI = XK;
+  else {
+    const double FICSTF = (YMICE * CITH * CITH * CITH / (12 * (1 - RMUICE * RMUICE))) / RHOW;
+    const double RDH = (RHOI / RHOW) * CITH;
+    const double OM2 = G * XK * std::tanh(XK * DEPTH);
+    double AKIOLD = 0.0;
+    AKI = std::min(XK, std::pow(OM2 / std::max(FICSTF, 1.0), 0.2));
+    while (std::fabs(AKI - AKIOLD) > EBS * AKIOLD && AKI < AKI_MAX) {
+      AKIOLD = AKI;
+      const double AKID = std::min(DEPTH * AKI, 50.0);
+      const double F = FICSTF * std::pow(AKI, 5) + G * AKI - OM2 * (RDH * AKI + 1. / std::tanh(AKID));
+      const double FPRIME = 5. * FICSTF * p4(AKI) + G - OM2 * (RDH - DEPTH / sq(std::sinh(AKID)));
+      AKI = AKI - F / FPRIME;
+      if (AKI <= 0.0) AKI = AKI_MAX;
+    }
+  }
+  return AKI;
+}
+
+// cimsstrn.F90:83-119: mean square wave strain in the sea ice
+void CIMSSTRN(const Ctx& x, V3 FL1, V2 WAVNUM, V1 DEPTH, V1 CITHICK, V1 STRN) {
+  const Tables& t = x.t;
+  const int KIJS = x.KIJS, KIJL = x.KIJL, NANG = x.NANG, NFRE = x.NFRE;
+  const double F1LIM = x.c.flmin / t.DELTH;
+  for (int IJ = KIJS; IJ <= KIJL; ++IJ) STRN(IJ) = 0.0;
+  for (int M = 1; M <= NFRE; ++M)
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      const double XKI = AKI_ICE(t.G, WAVNUM(IJ, M), DEPTH(IJ), t.ROWATER, CITHICK(IJ));
+      const double E = 0.5 * CITHICK(IJ) * XKI * XKI * XKI / WAVNUM(IJ, M);
+      double SUME = 0.0;
+      for (int K = 1; K <= NANG; ++K) SUME = SUME + FL1(IJ, K, M);
+      if (SUME > F1LIM) STRN(IJ) = STRN(IJ) + E * E * SUME * t.DFIM(M);
+    }
 }
 
 // imphftail.F90:71-87
@@ -1436,9 +1490,11 @@ void implsch_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int IC
     for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) f.DBG_SSOURCE(IJ, K, M, ICHNK) = SSOURCE(IJ, K, M);
     for (int IJ = KIJS; IJ <= KIJL; ++IJ) { f.DBG_EM(IJ, ICHNK) = EMEAN(IJ); f.DBG_F1(IJ, ICHNK) = F1MEAN(IJ); f.DBG_PHIWA(IJ, ICHNK) = PHIWA(IJ); }
   }
+  NemoFlux NE{s1(f.NPHIEPS), s1(f.NTAUOC), s1(f.NSWH), s1(f.NMWP), s1(f.NEMOTAUX), s1(f.NEMOTAUY), s1(f.NEMOTAUICX), s1(f.NEMOTAUICY),
+              s1(f.NEMOWSWAVE), s1(f.NEMOPHIF)};
   if (LCFLX)
     WNFLUXES(x, MIJ, RHOWGDFTH, CINV, SSOURCE, CICOVER, PHIWA, EMEAN, F1MEAN, WSWAVE, WDWAVE, USTRA, VSTRA, UFRIC, AIRD,
-             TAUXD, TAUYD, TAUOCXD, TAUOCYD, TAUOC, TAUICX, TAUICY, PHIOCD, PHIEPS, PHIAW);
+             TAUXD, TAUYD, TAUOCXD, TAUOCYD, TAUOC, TAUICX, TAUICY, PHIOCD, PHIEPS, PHIAW, &NE);
   // ---- 2.5 tail
   FKMEAN(x, FL1, WAVNUM, EMEAN, FMEAN, F1MEAN, AKMEAN, XKMEAN);
   FEMEANWS(x, FL1, XLLWS, FMEANWS, lEMEANWS.v.data());
@@ -1449,7 +1505,18 @@ void implsch_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int IC
       else { WSEMEAN(IJ) = lEMEANWS.v[IJ - 1]; WSFMEAN(IJ) = FMEANWS(IJ); }
     }
   if (c.licerun && c.lmaskice) SETICE(x, FL1, CICOVER, COSWDIF);
-  STOKESDRIFT(x, FL1, STOKFAC, WSWAVE, WDWAVE, CICOVER, USTOKES, VSTOKES);  // stokestrn.F90:76 (no NEMO coupling)
+  // STOKESTRN (stokestrn.F90:64-88)
+  STOKESDRIFT(x, FL1, STOKFAC, WSWAVE, WDWAVE, CICOVER, USTOKES, VSTOKES);
+  V1 STRNMS = s1(f.STRNMS);
+  if (c.lwnemocoustrn) CIMSSTRN(x, FL1, WAVNUM, DEPTH, s1(f.CITHICK), STRNMS);
+  if (c.lwnemocou && ((c.lwnemocousend && c.lwcou) || !c.lwcou)) {
+    V1 NUS = s1(f.NEMOUSTOKES), NVS = s1(f.NEMOVSTOKES), NST = s1(f.NEMOSTRN);
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+      if (c.lwnemocoustk) { NUS(IJ) = USTOKES(IJ); NVS(IJ) = VSTOKES(IJ); }
+      else { NUS(IJ) = 0.0; NVS(IJ) = 0.0; }
+      if (c.lwnemocoustrn) NST(IJ) = STRNMS(IJ);
+    }
+  }
 }
 
 // SNONLIN (snonlin.F90) on its own with AKMEAN from FKMEAN, as IMPLSCH calls it (implsch.F90:288)

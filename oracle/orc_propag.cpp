@@ -65,7 +65,9 @@ void alloc_fields(Model& m) {
     for (ArrD* a : {&f.DEPTH, &f.EMAXDPT, &f.DELLAM1, &f.COSPHM1, &f.UCUR, &f.VCUR, &f.IBRMEM, &f.AIRD, &f.WDWAVE,
                     &f.CICOVER, &f.WSWAVE, &f.WSTAR, &f.USTRA, &f.VSTRA, &f.UFRIC, &f.TAUW, &f.TAUWDIR, &f.Z0M, &f.Z0B,
                     &f.CHRNCK, &f.CITHICK, &f.WSEMEAN, &f.WSFMEAN, &f.USTOKES, &f.VSTOKES, &f.STRNMS, &f.TAUXD,
-                    &f.TAUYD, &f.TAUOCXD, &f.TAUOCYD, &f.TAUOC, &f.TAUICX, &f.TAUICY, &f.PHIOCD, &f.PHIEPS, &f.PHIAW})
+                    &f.TAUYD, &f.TAUOCXD, &f.TAUOCYD, &f.TAUOC, &f.TAUICX, &f.TAUICY, &f.PHIOCD, &f.PHIEPS, &f.PHIAW,
+                    &f.NSWH, &f.NMWP, &f.NPHIEPS, &f.NTAUOC, &f.NEMOTAUX, &f.NEMOTAUY, &f.NEMOTAUICX, &f.NEMOTAUICY, &f.NEMOWSWAVE,
+                    &f.NEMOPHIF, &f.NEMOUSTOKES, &f.NEMOVSTOKES, &f.NEMOSTRN})
       a->alloc(1, P, 1, C);
     f.MIJ.alloc(1, P, 1, C); f.INDEP.alloc(1, P, 1, C); f.IODP.alloc(1, P, 1, C); f.IOBND.alloc(1, P, 1, C);
     for (size_t i = 0; i < f.CIWA.d.size(); ++i) f.CIWA.d[i] = 1.0;

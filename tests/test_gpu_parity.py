@@ -359,6 +359,39 @@ def test_subgrid_obstructions_bit_exact(built, case, extra):
     check_state(w, o)
 
 
+NEMO_FIELDS = ("NSWH", "NMWP", "NPHIEPS", "NTAUOC", "NEMOTAUX", "NEMOTAUY", "NEMOTAUICX", "NEMOTAUICY", "NEMOWSWAVE", "NEMOPHIF",
+               "NEMOUSTOKES", "NEMOVSTOKES", "NEMOSTRN", "STRNMS")
+
+
+@pytest.mark.parametrize("case,kw", [("o48like", dict(lwnemotauoc=0, lwnemocoustk=1, lwnemocoustrn=1)),
+                                     ("o640like", dict(lwnemotauoc=1, lwnemocoustk=0, lwnemocoustrn=1, lciwa3=1)),
+                                     ("o48_iphys0", dict(lwnemotauoc=1, lwnemocoustk=1, lwnemocoustrn=0))])
+def test_nemo_coupling_fields(built, case, kw):
+    """LWNEMOCOU: the WAVE2OCEAN arguments of IMPLSCH (k_nemo after the sweep): WNFLUXES' NEMO block incl. the accumulators over three
+    steps, STOKESTRN's copies and CIMSSTRN / AKI_ICE (LWNEMOCOUSTRN) against the oracle."""
+    okw = dict(kw)
+    gkw = dict(kw)
+    if gkw.pop("lciwa3", 0):
+        gkw["lciwa"] = 4
+    g, o, f, fl = make_oracle(case, lwnemocou=1, lmaskice=0, **okw)
+    _, s, w = make_gpu(case, lwnemocou=1, lmaskice=0, **gkw)
+    cith = np.where(f["CICOVER"] > 0, 0.3 + 1.5 * f["CICOVER"], 0.0)
+    o.set_field("CITHICK", cith)
+    w.set_field("cithick", cith)
+    for _ in range(3):
+        assert o.step() == 0 and w.step() == 0
+    w.synchronize()
+    check_state(w, o)
+    for nm in NEMO_FIELDS:
+        if nm in ("NEMOSTRN", "STRNMS") and not kw["lwnemocoustrn"]:
+            continue
+        a, b = w.get_field(nm), o.get_field(nm)[w.own]
+        assert np.abs(a - b).max() <= RTOL_FIELD * max(np.abs(b).max(), 1e-300), nm
+    assert np.abs(o.get_field("NEMOTAUX")).max() > 0 and o.get_field("NSWH").min() > 0
+    if kw["lwnemocoustrn"]:
+        assert o.get_field("STRNMS").max() > 0
+
+
 def test_current_cfl_fallback(built):
     """LLCFLCUROFF (ctuwdrv.F90:101-121): with a long propagation step and strong current shear the direction / frequency
     weights of the current refraction leave [0,1] at a few points; the second CTUW call switches the current refraction off at

@@ -1038,3 +1038,66 @@ def test_subgrid_obstructions_in_the_oracle(built):
     assert (f0 <= ref).all() and f0[:fr].sum() < 0.999 * ref[:fr].sum()      # what a step moves between cells is lost
     fo = run(_obstructions(n, fr))[0]
     assert (fo <= ref).all() and (fo >= f0).all() and f0[:fr].sum() < fo[:fr].sum() < ref[:fr].sum() * (1 - 1e-5)
+
+
+@pytest.mark.parametrize("case,tauoc", [("o48like", 0), ("o48_iphys0", 1)])
+def test_nemo_coupling_fields_against_numpy(built, case, tauoc):
+    """The WAVE2OCEAN side of IMPLSCH (LWNEMOCOU): WNFLUXES' NEMO block (wnfluxes.F90:222-250, 304-330: NSWH / NMWP from the wave energy
+    and mean frequency blended towards a fully developed sea under the ice, accumulators of the stresses, wind speed and energy flux),
+    STOKESTRN (stokestrn.F90:76-88) and CIMSSTRN with AKI_ICE's flexural-gravity wavenumber (cimsstrn.F90:83-119, aki_ice.F90:66-112),
+    from the formulas; EMEAN / F1MEAN through the capture hook."""
+    g, o, f, fl = make_oracle(case, lwnemocou=1, lwnemotauoc=tauoc, lwnemocoustk=1, lwnemocoustrn=1, lmaskice=0)
+    ci = f["CICOVER"]
+    cith = np.where(ci > 0, 0.3 + 1.5 * ci, 0.0)
+    o.set_field("CITHICK", cith)
+    acc = {k: 0.0 for k in ("TX", "TY", "WS", "PHI")}
+    o.capture(True)
+    for _ in range(3):
+        assert o.step() == 0
+        acc["TX"] = acc["TX"] + o.get_field("TAUOCXD" if tauoc else "TAUXD")
+        acc["TY"] = acc["TY"] + o.get_field("TAUOCYD" if tauoc else "TAUYD")
+        acc["WS"] = acc["WS"] + o.get_field("WSWAVE")
+        acc["PHI"] = acc["PHI"] + o.get_field("PHIOCD")
+    for nm, k in (("NEMOTAUX", "TX"), ("NEMOTAUY", "TY"), ("NEMOWSWAVE", "WS"), ("NEMOPHIF", "PHI")):
+        np.testing.assert_allclose(o.get_field(nm), acc[k], rtol=1e-14, atol=0, err_msg=nm)
+    assert (o.get_field("NEMOTAUICX") == 0).all() and (o.get_field("NEMOTAUICY") == 0).all()          # no LWNEMOCOUWRS
+    for a, b in (("NPHIEPS", "PHIEPS"), ("NTAUOC", "TAUOC"), ("NEMOUSTOKES", "USTOKES"), ("NEMOVSTOKES", "VSTOKES"), ("NEMOSTRN", "STRNMS")):
+        np.testing.assert_array_equal(o.get_field(a), o.get_field(b), err_msg=a)
+    # NSWH, NMWP
+    _, em, f1, _ = o.captured()
+    us, ws = o.get_field("UFRIC"), o.get_field("WSWAVE")
+    fr = o.table("FR")
+    G = 9.806
+    iced = ci > o.cfg.ciblock
+    ooval = np.where(iced, np.exp(-np.minimum((ci / max(o.cfg.cithrsh, 0.01)) ** 4, 10.0)), 1.0)
+    u10p = np.maximum(ws, np.sqrt(1.0e-3))
+    cd_bulk = np.minimum((1.03e-3 + 0.04e-3 * u10p ** 1.48) * u10p ** -0.21, 0.003)
+    ustar = np.where(iced, np.maximum(np.sqrt(ooval * (us / u10p) ** 2 + (1.0 - ooval) * cd_bulk) * u10p, 1.0e-6), us)
+    # fully developed sea (yowphys.F90: E* = EGRCRV, f* from AFCRV nu**BFCRV): E = 4 E* u*^4 / g^2 capped, f = (E*/A)^(1/B) g / u*
+    EGRCRV, AFCRV, BFCRV = (1065.0, 2.453e-4, -3.1236) if CASES[case]["iphys"] == 1 else (1108.0, 4.0e-4, -3.0)    # setwavphys.F90:103-107, 193-197
+    efd = np.minimum(4.0 * EGRCRV / G ** 2 * ustar ** 4, 6.25)
+    em_oc = np.where(iced, np.maximum(ooval * em + (1.0 - ooval) * efd, 0.0625), em)
+    ffd = (EGRCRV / AFCRV) ** (1.0 / BFCRV) * G / ustar
+    f1_oc = np.where(iced, np.clip(ooval * f1 + (1.0 - ooval) * ffd, fr[1], fr[-1]), f1)
+    assert iced.any() and (~iced).any()
+    np.testing.assert_allclose(o.get_field("NSWH"), 4.0 * np.sqrt(em_oc), rtol=1e-12, err_msg="NSWH")
+    np.testing.assert_allclose(o.get_field("NMWP"), 1.0 / f1_oc, rtol=1e-12, err_msg="NMWP")
+    # CIMSSTRN: the wavenumber under the ice solves D k^5 + g k = w^2 (rho_i/rho_w h k + coth(k d)) with D = Y h^3 / (12 (1 - nu^2) rho_w)
+    F1 = o.get_fl1()
+    wn, dfim = o.get_field3("WAVNUM"), o.table("DFIM")
+    dep = g.depth
+    D = 5.5e9 * cith ** 3 / (12.0 * (1.0 - 0.3 ** 2)) / 1000.0
+    rdh = 922.5 / 1000.0 * cith
+    om2 = G * wn * np.tanh(wn * dep[None, :])
+    k = np.minimum(wn, (om2 / np.maximum(D, 1.0)[None, :]) ** 0.2)
+    for _ in range(60):       # Newton to convergence (the reference stops at 1e-6 relative)
+        kd = np.minimum(dep[None, :] * k, 50.0)
+        fk = D[None, :] * k ** 5 + G * k - om2 * (rdh[None, :] * k + 1.0 / np.tanh(kd))
+        dfk = 5.0 * D[None, :] * k ** 4 + G - om2 * (rdh[None, :] - dep[None, :] / np.sinh(kd) ** 2)
+        k = np.where(cith[None, :] > 0, k - fk / dfk, wn)
+    e = 0.5 * cith[None, :] * k ** 3 / wn
+    sume = F1.sum(axis=1)
+    strn = np.where(sume > o.cfg.flmin / (2 * np.pi / F1.shape[1]), e ** 2 * sume * dfim[:, None], 0.0).sum(axis=0)
+    got = o.get_field("STRNMS")
+    assert (got[cith > 0] > 0).any() and (got[cith == 0] == 0).all()
+    np.testing.assert_allclose(got, strn, rtol=2e-5, atol=1e-30, err_msg="STRNMS")      # 6 x the solver's own 1e-6 (k enters as k^6)
