@@ -1210,7 +1210,6 @@ int ecwam_b200_outbs(ecwam_b200_handle h, const ecwam_b200_outsel* sel, const in
   if (!h->bound) EW_FAIL(ECWAM_B200_ESTATE, "fields not bound");
   int rc = check_outsel(sel);
   if (rc) return rc;
-  if (h->par.irefra >= 2) EW_FAIL(ECWAM_B200_EINVAL, "OUTBLOCK with currents needs INTPOL (outblock.F90:168-169): not built");
   const DevConst& c = h->dc;
   OutConst oc;
   memset(&oc, 0, sizeof(oc));
@@ -1248,8 +1247,13 @@ int ecwam_b200_outbs(ecwam_b200_handle h, const ecwam_b200_outsel* sel, const in
   OutDev d;
   d.P = h->par.nproma; d.A = c.A; d.F = c.F; d.nchnk = h->par.nchnk;
   d.npts = (long long)d.P * d.nchnk;
-  d.f = h->dev; d.iodp = iodp; d.bout = bout; d.gc = h->gctab.p;
+  d.f = h->dev; d.iodp = iodp; d.bout = bout; d.gc = h->gctab.p; d.fl2 = nullptr;
   ScopedTimer t(h, "outblock");
+  if (h->par.irefra >= 2) {   // INTPOL into the wind-input scratch of IMPLSCH (free between steps), outblock.F90:168-169
+    launch_intpol(d, h->fldin.p, h->dc.FRATIO, h->dc.FLOGSPRDM1, h->dc.FR5[c.F - 1], h->st);
+    d.fl2 = h->fldin.p;
+    h->nlaunch++;
+  }
   rc = launch_outblock(d, h->st);
   if (rc) return rc;
   h->nlaunch++;

@@ -138,6 +138,7 @@ struct OutDev {
   const int* iodp;         // (P,C) or null (= 1 everywhere)
   double* bout;            // (P, NIPRMOUT, C)
   const double* gc;        // [GC_NT][NWAV_GC] gravity-capillary tables (MEANSQS_GC), null when not supplied
+  const double* fl2;       // IREFRA = 2, 3: INTPOL's spectrum on the absolute frequency axis (P,A,F,C), written by k_intpol; null otherwise
 };
 int upload_out_const(const OutConst& h, cudaStream_t st);
 void launch_newwind(long long npts, const ecwam_b200_fields& f, const ecwam_b200_forcing_next& nx, double acd, double bcd, double epsmin,
@@ -152,6 +153,7 @@ void launch_getwnd(const GetwndArgs& a, const ecwam_b200_fieldg& g, const ecwam_
                    const ecwam_b200_forcing_next& nx, cudaStream_t st);
 void launch_no_source(long long n4, long long n2, double* fl1, double* xllws, int* mij, int nfre, int clip, double epsmin, cudaStream_t st);
 int launch_outblock(const OutDev& d, cudaStream_t st);
+void launch_intpol(const OutDev& d, double* fla, double fratio, double flogsprdm1, double fr5n, cudaStream_t st);
 size_t norm_scratch_doubles(int ncol);
 void launch_norm_local(const double* bout, int P, int ncol, long long nloc, double zmiss, double* scratch, double* out4, cudaStream_t st);
 void launch_pack_cols(const double* bout, int P, int ncol, long long nloc, double* out, long long ostride, cudaStream_t st);

@@ -167,6 +167,8 @@ struct SpecAcc {
 #define OB_STR(x) OB_STR2(x)
 #define OB_UNROLL _Pragma(OB_STR(unroll OB_UNR))
 
+// CUR: IREFRA = 2, 3 -- the output spectrum FL2ND is INTPOL's (k_intpol, d.fl2) instead of FL1 itself (outblock.F90:168-172)
+template <bool CUR>
 __global__ void __launch_bounds__(OB_NTH, OB_MINB) k_outblock(OutDev d) {
   extern __shared__ double cwd_s[];   // [A][OB_NTH]: COSWDIF(IJ,K) = cos(TH(K) - WDWAVE(IJ)) (outblock.F90:198-202)
   const int A = c_oc.A, F = c_oc.F, P = d.P;
@@ -178,6 +180,7 @@ __global__ void __launch_bounds__(OB_NTH, OB_MINB) k_outblock(OutDev d) {
   const size_t rs = (size_t)P * A;    // frequency stride of a (P,A,F,C) array
   const double* fl = d.f.fl1 + (size_t)pi + rs * F * (size_t)pc;
   const double* xl = d.f.xllws + (size_t)pi + rs * F * (size_t)pc;
+  const double* fl2 = CUR ? d.fl2 + (size_t)pi + rs * F * (size_t)pc : fl;
   const size_t b3 = (size_t)pi + (size_t)P * F * (size_t)pc;
   const double* cinv = d.f.cinv + b3;
   const double* cgr = d.f.cgroup + b3;
@@ -212,7 +215,8 @@ __global__ void __launch_bounds__(OB_NTH, OB_MINB) k_outblock(OutDev d) {
         const double f1 = f * swm;
         t2s += omax(f1, EPSMIN);
         t2w += omax(omax(f - f1, 0.0), EPSMIN);
-        const double f2 = (icen && f <= zthrs) ? omax(zr * f, zthrs * (zr * zr)) : f;
+        const double g = CUR ? __ldg(fl2 + o) : f;
+        const double f2 = (icen && g <= zthrs) ? omax(zr * g, zthrs * (zr * zr)) : g;
         fmax = omax(fmax, f2);
         if (mss) {
           const double flwd = signbit(c) ? f * 0.0 : f;      // FL1 * (0.5 + 0.5*SIGN(1,COSWDIF)) (halphap.F90:72-84)
@@ -310,7 +314,8 @@ __global__ void __launch_bounds__(OB_NTH, OB_MINB) k_outblock(OutDev d) {
       double fw_ = f - fs_;                                                              // wind sea (sepwisw.F90:271-282)
       if (c > 0.8 && noise_rows) { const double c2 = c * c; fw_ = fw_ + EPSMIN * (c2 * c2); }
       fw_ = omax(fw_, 0.0);
-      const double f2 = (icen && f <= zthrs) ? omax(zr * f, zthrs * (zr * zr)) : f;     // output spectrum
+      const double g = CUR ? __ldg(fl2 + o) : f;
+      const double f2 = (icen && g <= zthrs) ? omax(zr * g, zthrs * (zr * zr)) : g;     // output spectrum
       s_t2 += omax(fs_, EPSMIN); s_t0 += fs_; s_s += sth * fs_; s_c += cth * fs_; s_f1 = __dadd_rn(s_f1, __dmul_rn(fs_, DELTH));
       w_t2 += omax(fw_, EPSMIN); w_t0 += fw_; w_s += sth * fw_; w_c += cth * fw_; w_f1 = __dadd_rn(w_f1, __dmul_rn(fw_, DELTH));
       t_t2 += omax(f2, EPSMIN); t_t0 += f2; t_s += sth * f2; t_c += cth * f2;
@@ -520,10 +525,78 @@ int launch_outblock(const OutDev& d, cudaStream_t st) {
   if (d.npts <= 0) return 0;
   const size_t sm = (size_t)d.A * OB_NTH * sizeof(double);
   static bool attr = false;
-  if (!attr) { EW_CUDA_CHECK(cudaFuncSetAttribute(k_outblock, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
+  if (!attr) {
+    EW_CUDA_CHECK(cudaFuncSetAttribute(k_outblock<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    EW_CUDA_CHECK(cudaFuncSetAttribute(k_outblock<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr = true;
+  }
   if (d.A > 64 || sm > 64 * 1024) { ew_set_error("k_outblock: NANG %d too large", d.A); return ECWAM_B200_EINVAL; }
-  k_outblock<<<(unsigned)((d.npts + OB_NTH - 1) / OB_NTH), OB_NTH, sm, st>>>(d);
+  if (d.fl2) k_outblock<true><<<(unsigned)((d.npts + OB_NTH - 1) / OB_NTH), OB_NTH, sm, st>>>(d);
+  else k_outblock<false><<<(unsigned)((d.npts + OB_NTH - 1) / OB_NTH), OB_NTH, sm, st>>>(d);
   return 0;
+}
+
+// INTPOL (intpol.F90:96-271, IRA = 1): the spectrum on the absolute frequency axis from the one relative to the current.  One thread
+// per grid point walks the (frequency, direction) bins in the reference's order and adds each bin's two shares to its own column of
+// `fla` (same (P,A,F,C) layout as FL1; the column is private to the thread: no atomics, the reference's summation order).
+__global__ void __launch_bounds__(128) k_intpol(OutDev d, double* __restrict__ fla, double fratio, double flogsprdm1, double fr5n) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= d.npts) return;
+  const int A = c_oc.A, F = c_oc.F, P = d.P;
+  const long long pc = p / P;
+  const int pi = (int)(p - pc * P);
+  const size_t rs = (size_t)P * A;
+  const double* fl = d.f.fl1 + (size_t)pi + rs * F * (size_t)pc;
+  double* fa = fla + (size_t)pi + rs * F * (size_t)pc;
+  const double* wnp = d.f.wavnum + (size_t)pi + (size_t)P * F * (size_t)pc;
+  const double u = d.f.ucur[p], v = d.f.vcur[p];
+  const double CURRENT_MAX = 1.5;      // yowcurr.F90:18
+  const double fre0 = fratio - 1.0, zpi2gm = c_oc.ZPI * c_oc.ZPI / c_oc.G, coef = 1.0 / c_oc.ZPI;
+  const double fr1 = c_oc.FR[0], frn = c_oc.FR[F - 1];
+  const double fmax = frn + (c_oc.ZPI / c_oc.G) * (frn * frn) * CURRENT_MAX;
+  const int nfre_max = (int)floor(log10(fmax / fr1) * flogsprdm1) + 1;
+  const double cdf = 0.5 * (fratio - 1.0 / fratio) * c_oc.DELTH;
+  bool ice2sea = true;
+  for (int m = 0; m < F; ++m)
+    for (int k = 0; k < A; ++k) {
+      const size_t o = (size_t)m * rs + (size_t)k * P;
+      if (__ldg(fl + o) > c_oc.EPSMIN) ice2sea = false;
+      fa[o] = 0.0;
+    }
+  double freq = frn;
+  for (int m = 0; m < nfre_max; ++m) {
+    double dfreqth, wavn;
+    if (m < F) { freq = c_oc.FR[m]; dfreqth = freq * cdf; wavn = __ldg(wnp + (size_t)m * P); }
+    else { freq = frn * pow(fratio, (double)(m + 1 - F)); dfreqth = freq * cdf; wavn = zpi2gm * (freq * freq); }
+    const double f5 = fr5n / pow(freq, 5.0);
+    for (int k = 0; k < A; ++k) {
+      double fnew = freq + coef * wavn * (c_oc.COSTH[k] * v + c_oc.SINTH[k] * u);
+      int kh = k;
+      if (!(fnew > 0.0)) { kh = (k + A / 2) % A; fnew = -fnew; }
+      int newm = -1;                                   // 1-based bin below FNEW, 0: between FR(1)/FRATIO and FR(1)
+      if (!(fnew <= fr1 / fratio)) newm = (int)floor(log10(fnew / fr1) * flogsprdm1) + 1;
+      double old = 0.0;
+      if (!ice2sea) old = m < F ? __ldg(fl + (size_t)m * rs + (size_t)k * P) : __ldg(fl + (size_t)(F - 1) * rs + (size_t)k * P) * f5;
+      if (newm < F && newm >= 1) {
+        const double fa0 = c_oc.FR[newm - 1], fa1 = c_oc.FR[newm];
+        const double gwh = dfreqth / (fa1 - fa0) * old;
+        fa[(size_t)(newm - 1) * rs + (size_t)kh * P] += gwh * (fa1 - fnew) / (fa0 * cdf);
+        fa[(size_t)newm * rs + (size_t)kh * P] += gwh * (fnew - fa0) / (fa1 * cdf);
+      } else if (newm == 0) {
+        const double gwh = fratio * dfreqth / (fre0 * fr1) * old;
+        fa[(size_t)kh * P] += gwh * (fnew - fr1 / fratio) / (fr1 * cdf);
+      } else if (newm == F) {
+        const double gwh = dfreqth / (fre0 * frn) * old;
+        fa[(size_t)(F - 1) * rs + (size_t)kh * P] += gwh * (fratio * frn - fnew) / (frn * cdf);
+      }
+    }
+  }
+  for (int m = 0; m < F; ++m)
+    for (int k = 0; k < A; ++k) { const size_t o = (size_t)m * rs + (size_t)k * P; fa[o] = omax(fa[o], c_oc.EPSMIN); }
+}
+void launch_intpol(const OutDev& d, double* fla, double fratio, double flogsprdm1, double fr5n, cudaStream_t st) {
+  if (d.npts <= 0) return;
+  k_intpol<<<(unsigned)((d.npts + 127) / 128), 128, 0, st>>>(d, fla, fratio, flogsprdm1, fr5n);
 }
 size_t norm_scratch_doubles(int ncol) { return (size_t)ncol * NM_NB * 4 + (size_t)ncol * 4; }
 void launch_norm_local(const double* bout, int P, int ncol, long long nloc, double zmiss, double* scratch, double* out4, cudaStream_t st) {

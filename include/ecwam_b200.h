@@ -516,8 +516,8 @@ typedef struct ecwam_b200_outsel {
  * tables).  Not built: altimeter (17-19), KURTOSIS family (29-31, 33, 34, 57,
  * 70-72), swell partitions (42-50, LLPARTITION), CIMSSTRN (51), NEMO fields (58-61), W_MAXH (78-81), 82+.     */
 int ecwam_b200_outparam_supported(int itg);
-/* OUTBS (src/ecwam/outbs.F90:97-122): OUTBLOCK over all chunks (src/ecwam/outblock.F90:150-610, IREFRA = 0,
- * LSECONDORDER = F) with FEMEAN, STHQ, DOMINANT_PERIOD, SEPWISW, MWP1, MWP2, WDIRSPREAD, OUTBETA, WEFLUX and
+/* OUTBS (src/ecwam/outbs.F90:97-122): OUTBLOCK over all chunks (src/ecwam/outblock.F90:150-610, LSECONDORDER = F; with
+ * IREFRA = 2, 3 the output spectrum is INTPOL's, intpol.F90:96-271, built in the handle's scratch) with FEMEAN, STHQ, DOMINANT_PERIOD, SEPWISW, MWP1, MWP2, WDIRSPREAD, OUTBETA, WEFLUX and
  * OUTSETWMASK.  bout: DEVICE (NPROMA, NIPRMOUT, NCHNK); iodp: DEVICE (NPROMA, NCHNK) WVENVI%IODP or NULL (= 1).
  * Reads the bound fields (FL1, XLLWS, CINV, CGROUP, forcing, IMPLSCH outputs).                                */
 int ecwam_b200_outbs(ecwam_b200_handle h, const ecwam_b200_outsel* sel, const int* iodp, double* bout);

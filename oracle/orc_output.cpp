@@ -571,6 +571,76 @@ bool outparam_supported(int itg) {
   return false;
 }
 
+// intpol.F90:96-271: the spectrum on the absolute (ground-based) frequency axis from the one relative to the current (IRA = 1):
+// every bin moves to F + k.U / 2 pi and is shared between the two neighbouring frequency bins, energy-conserving on the
+// FR(M)*CDF intervals, with an f**-5 extension above FR(NFRE) up to what CURRENT_MAX can shift back into the grid.
+static void intpol(const Tables& t, int KIJL, int NANG, int NFRE, const S3& FLR, W3& FLA, const double* WAVNUM /*(KIJL,NFRE)*/,
+                   const double* UCUR, const double* VCUR, int IRA) {
+  const double CURRENT_MAX = 1.5;     // yowcurr.F90:18
+  const double FRE0 = t.FRATIO - 1.0, ZPI2GM = t.ZPI * t.ZPI / t.G, COEF = IRA / t.ZPI;
+  const double FMAX = t.FR(NFRE) + (t.ZPI / t.G) * (t.FR(NFRE) * t.FR(NFRE)) * CURRENT_MAX;
+  const int NFRE_MAX = (int)std::floor(std::log10(FMAX / t.FR(1)) * t.FLOGSPRDM1) + 1;
+  const double CDF = 0.5 * (t.FRATIO - 1.0 / t.FRATIO) * t.DELTH;
+  V DFTH(NFRE + 1);
+  for (int M = 1; M <= NFRE; ++M) DFTH[M] = t.FR(M) * CDF;
+  std::vector<char> LICE2SEA(KIJL + 1, 1);
+  for (int K = 1; K <= NANG; ++K) for (int M = 1; M <= NFRE; ++M) for (int IJ = 1; IJ <= KIJL; ++IJ) if (FLR(IJ, K, M) > t.EPSMIN) LICE2SEA[IJ] = 0;
+  for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = 1; IJ <= KIJL; ++IJ) FLA(IJ, K, M) = 0.0;
+  std::vector<int> NEWF(KIJL + 1), NEWFLA(KIJL + 1), KNEW(KIJL + 1);
+  V WAVN(KIJL + 1), FNEF(KIJL + 1), OLDFL(KIJL + 1), GWP(KIJL + 1), GWM(KIJL + 1);
+  for (int M = 1; M <= NFRE_MAX; ++M) {
+    double FREQ, DFREQTH;
+    if (M <= NFRE) {
+      FREQ = t.FR(M); DFREQTH = DFTH[M];
+      for (int IJ = 1; IJ <= KIJL; ++IJ) WAVN[IJ] = WAVNUM[(IJ - 1) + (size_t)KIJL * (M - 1)];
+    } else {
+      FREQ = t.FR(NFRE) * std::pow(t.FRATIO, M - NFRE); DFREQTH = FREQ * CDF;
+      for (int IJ = 1; IJ <= KIJL; ++IJ) WAVN[IJ] = ZPI2GM * (FREQ * FREQ);
+    }
+    const double FR5OFREQ5 = t.FR5(NFRE) / std::pow(FREQ, 5);
+    for (int K = 1; K <= NANG; ++K) {
+      for (int IJ = 1; IJ <= KIJL; ++IJ) {
+        FNEF[IJ] = FREQ + COEF * WAVN[IJ] * (t.COSTH(K) * VCUR[IJ - 1] + t.SINTH(K) * UCUR[IJ - 1]);
+        if (FNEF[IJ] > 0.0) KNEW[IJ] = K;
+        else { KNEW[IJ] = (K + NANG / 2 - 1) % NANG + 1; FNEF[IJ] = -FNEF[IJ]; }
+      }
+      for (int IJ = 1; IJ <= KIJL; ++IJ) {
+        if (FNEF[IJ] <= t.FR(1) / t.FRATIO) NEWF[IJ] = -1;
+        else NEWF[IJ] = (int)std::floor(std::log10(FNEF[IJ] / t.FR(1)) * t.FLOGSPRDM1) + 1;
+      }
+      for (int IJ = 1; IJ <= KIJL; ++IJ) {
+        if (LICE2SEA[IJ]) OLDFL[IJ] = 0.0;
+        else OLDFL[IJ] = M <= NFRE ? FLR(IJ, K, M) : FLR(IJ, K, NFRE) * FR5OFREQ5;
+      }
+      for (int IJ = 1; IJ <= KIJL; ++IJ) {
+        const double FNEW = FNEF[IJ];
+        const int NEWM = NEWF[IJ];
+        if (NEWM < NFRE && NEWM >= 1) {
+          const int NEWM1 = NEWM + 1;
+          const double GWH = DFREQTH / (t.FR(NEWM1) - t.FR(NEWM)) * OLDFL[IJ];
+          GWM[IJ] = GWH * (t.FR(NEWM1) - FNEW) / DFTH[NEWM];
+          GWP[IJ] = GWH * (FNEW - t.FR(NEWM)) / DFTH[NEWM1];
+          NEWFLA[IJ] = NEWM1;
+        } else if (NEWM == 0) {
+          const double GWH = t.FRATIO * DFREQTH / (FRE0 * t.FR(1)) * OLDFL[IJ];
+          GWP[IJ] = GWH * (FNEW - t.FR(1) / t.FRATIO) / DFTH[1];
+          NEWF[IJ] = -1; NEWFLA[IJ] = 1;
+        } else if (NEWM == NFRE) {
+          const double GWH = DFREQTH / (FRE0 * t.FR(NFRE)) * OLDFL[IJ];
+          GWM[IJ] = GWH * (t.FRATIO * t.FR(NFRE) - FNEW) / DFTH[NFRE];
+          NEWFLA[IJ] = -1;
+        } else { NEWF[IJ] = -1; NEWFLA[IJ] = -1; }
+      }
+      for (int IJ = 1; IJ <= KIJL; ++IJ) {
+        const int NEWM = NEWF[IJ], NEWM1 = NEWFLA[IJ], KH = KNEW[IJ];
+        if (NEWM != -1) FLA(IJ, KH, NEWM) = FLA(IJ, KH, NEWM) + GWM[IJ];
+        if (NEWM1 != -1) FLA(IJ, KH, NEWM1) = FLA(IJ, KH, NEWM1) + GWP[IJ];
+      }
+    }
+  }
+  for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = 1; IJ <= KIJL; ++IJ) FLA(IJ, K, M) = std::max(FLA(IJ, K, M), t.EPSMIN);
+}
+
 // outblock.F90:150-610 for one chunk; BOUT (KIJL, NIPRMOUT).  sel.itg[c] = reference parameter number of column c+1.
 void outblock(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK, const OutSel& sel, double* BOUT) {
   const int NANG = c.nang, NFRE = c.nfre, NTRAIN = 3, NTEWH = 6;   // yowcout.F90:19, mpcrtbl.F90:373-399
@@ -583,9 +653,10 @@ void outblock(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK, 
     return nullptr;
   };
   for (size_t i = 0; i < (size_t)KIJL * sel.n; ++i) BOUT[i] = 0.0;
-  // output spectrum (outblock.F90:168-194): IREFRA = 0, LSECONDORDER = F; noise-level restructuring under sea ice
+  // output spectrum (outblock.F90:168-194): INTPOL with currents, LSECONDORDER = F; noise-level restructuring under sea ice
   W3 FL2ND(KIJL, NANG, NFRE);
-  for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = 1; IJ <= KIJL; ++IJ) FL2ND(IJ, K, M) = FL1(IJ, K, M);
+  if (c.irefra == 2 || c.irefra == 3) intpol(t, KIJL, NANG, NFRE, FL1, FL2ND, &f.WAVNUM(1, 1, ICHNK), p1(f.UCUR), p1(f.VCUR), 1);   // outblock.F90:168-169
+  else for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = 1; IJ <= KIJL; ++IJ) FL2ND(IJ, K, M) = FL1(IJ, K, M);
   if (c.licerun && !c.lmaskice) {
     V ZTHRS(KIJL + 1), ZRDUC(KIJL + 1);
     for (int IJ = 1; IJ <= KIJL; ++IJ) ZTHRS[IJ] = (1.0 - 0.9 * std::min(CICOVER[IJ - 1], 0.99)) * c.flmin;

@@ -43,6 +43,31 @@ def check_norms(w, o):
             assert (d[circ] <= 1e-5).all() and (d[sprd] <= 1e-7).all(), (glob, c)
 
 
+@pytest.mark.parametrize("case,irefra,amp", [("o48like", 2, 1.0), ("o640like", 3, 1.4)])
+def test_outblock_with_currents_uses_intpol(built, case, irefra, amp):
+    """IREFRA = 2, 3: OUTBLOCK's output spectrum is INTPOL's, on the absolute frequency axis (outblock.F90:168-169, intpol.F90:96-271:
+    k_intpol, then the CUR instance of k_outblock); SEPWISW / WEFLUX keep FL1.  Currents up to 1.4 m/s so that bins leave the grid at
+    both ends and directions flip (negative absolute frequency)."""
+    from common import synthetic_currents
+    g, o, f, fl = make_oracle(case, irefra=irefra)
+    _, o0, _, _ = make_oracle(case, irefra=irefra)
+    _, s, w = make_gpu(case, irefra=irefra)
+    u, v = synthetic_currents(g, amp=amp)
+    o.set_field("UCUR", u); o.set_field("VCUR", v)
+    w.set_field("ucur", u); w.set_field("vcur", v)
+    for _ in range(3):
+        assert o.step() == 0 and o0.step() == 0 and w.step() == 0
+    w.synchronize()
+    b = o.outbs(OUT_ITG, OUT_ICE, OUT_SEA)
+    a = w.outbs(OUT_ITG, OUT_ICE, OUT_SEA)
+    worst = compare_bout(a, b[:, w.own])
+    assert max(worst.values()) < 1e-7
+    b0 = o0.outbs(OUT_ITG, OUT_ICE, OUT_SEA)               # no current: INTPOL is (nearly) the identity, the mean period differs
+    i3 = OUT_ITG.index(3)
+    ok = (b[i3] != ZMISS) & (b0[i3] != ZMISS)
+    assert np.abs(b[i3][ok] - b0[i3][ok]).max() > 1e-3 * np.abs(b0[i3][ok]).max()
+
+
 @pytest.mark.parametrize("case,extra", [("o48like", {}), ("o48_iphys0", {}), ("o640like", {}), ("o320like", dict(lmaskice=0))])
 def test_outblock_and_norms_match_oracle(built, case, extra):
     g, o, f, s, w = both(case, **extra)

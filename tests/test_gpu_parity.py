@@ -301,8 +301,6 @@ def test_current_refraction_bit_exact(built, irefra):
         assert o.step() == 0 and w.step() == 0
     w.synchronize()
     check_state(w, o)
-    with pytest.raises(L.EcwamError):                   # OUTBLOCK with currents needs INTPOL: rejected, not silently wrong
-        w.outbs([1], [1], [1])
 
 
 @pytest.mark.parametrize("irefra,dlf", [(2, 225.0), (3, 150.0), (3, 112.5)])
