@@ -236,6 +236,7 @@ static int fill_dev_const(const ecwam_b200_params& p, const ecwam_b200_tables& t
   c.lwnemotauoc = p.lwnemotauoc ? 1 : 0; c.lwnemocoustk = p.lwnemocoustk ? 1 : 0;
   c.nemo_send = ((p.lwnemocousend && p.lwcou) || !p.lwcou) ? 1 : 0;     // stokestrn.F90:76-78
   c.ROWATER = 1.0 / t.rowaterm1;
+  c.lwnemocouwrs = p.lwnemocouwrs ? 1 : 0; c.lwnemocouibr = p.lwnemocouibr ? 1 : 0; c.zalpwrs = p.zalpwrs; c.zibrw_thrsh = p.zibrw_thrsh;
   {   // SDICE3, IMODEL = 2: ALP = (2*CDICE*CITH**1.25*FR(M)**4.5)*ALPFAC with CDICE = 0.1274*(ZPI/SQRT(G))**4.5 (sdice3.F90:123-129)
     const double cdice = 0.1274 * std::pow(t.zpi / std::sqrt(t.g), 4.5);
     for (int m = 0; m < p.nfre && m < EW_MAXF; ++m) c.fr45[m] = 2. * cdice * std::pow(t.fr[m], 4.5);
@@ -695,16 +696,18 @@ int ecwam_b200_bind_fields(ecwam_b200_handle h, const ecwam_b200_fields* dev) {
 }
 
 static int upload_nemo_dev(H* h) {
-  if (!h->par.lwnemocou && !h->par.lwnemocoustrn) return 0;
+  if (!h->par.lwnemocou && !h->par.lwnemocoustrn && !h->par.lwnemocouwrs && !h->par.lwnemocouibr) return 0;
   NemoDev nd;
   nd.f = h->nemo; nd.nemo_on = (h->par.lwnemocou && h->nemo_bound) ? 1 : 0; nd.strn_on = h->par.lwnemocoustrn ? 1 : 0;
+  nd.wrs_on = h->par.lwnemocouwrs ? 1 : 0; nd.ibr_on = (h->par.lwnemocouibr && h->nemo_bound && h->nemo.ibrmem) ? 1 : 0;
   return h->nemo_dev.upload(std::vector<NemoDev>(1, nd), h->st);
 }
 
 int ecwam_b200_bind_nemo(ecwam_b200_handle h, const ecwam_b200_nemo_fields* dev) {
   if (!h || !dev) EW_FAIL(ECWAM_B200_EINVAL, "null argument");
   const void* const* pp = (const void* const*)dev;
-  for (size_t i = 0; i < sizeof(*dev) / sizeof(void*); ++i) if (!pp[i]) EW_FAIL(ECWAM_B200_EINVAL, "bind_nemo: member %zu is null", i);
+  for (size_t i = 0; i + 1 < sizeof(*dev) / sizeof(void*); ++i) if (!pp[i]) EW_FAIL(ECWAM_B200_EINVAL, "bind_nemo: member %zu is null", i);
+  if (h->par.lwnemocouibr && !dev->ibrmem) EW_FAIL(ECWAM_B200_EINVAL, "bind_nemo: LWNEMOCOUIBR needs IBRMEM");
   h->nemo = *dev;
   h->nemo_bound = true;
   return upload_nemo_dev(h);
@@ -935,7 +938,8 @@ static int implsch_range(H* h, int ichnk0, int nchnk, bool from_fl3) {
   if (ichnk0 < 1 || nchnk < 1 || ichnk0 + nchnk - 1 > h->par.nchnk) EW_FAIL(ECWAM_B200_EINVAL, "chunk range out of bounds");
   int rc = ensure_const(h);
   if (rc) return rc;
-  if (h->par.lwnemocou && !h->nemo_bound) EW_FAIL(ECWAM_B200_ESTATE, "IMPLSCH: LWNEMOCOU needs the WAVE2OCEAN fields (ecwam_b200_bind_nemo)");
+  if ((h->par.lwnemocou || h->par.lwnemocouibr) && !h->nemo_bound)
+    EW_FAIL(ECWAM_B200_ESTATE, "IMPLSCH: LWNEMOCOU / LWNEMOCOUIBR need the NEMO coupling fields (ecwam_b200_bind_nemo)");
   if (h->par.lwnemocoustrn && (!h->dev.strnms || !h->dev.cithick)) EW_FAIL(ECWAM_B200_ESTATE, "IMPLSCH: LWNEMOCOUSTRN needs STRNMS and CITHICK bound");
   if (h->par.licerun && (h->par.lciwa & 5) && !h->dev.cithick) EW_FAIL(ECWAM_B200_ESTATE, "IMPLSCH: LCIWA1 / LCIWA3 need CITHICK bound");
   ImplDev d = make_impl(h, from_fl3);

@@ -66,8 +66,10 @@ struct DevConst {
   int lciwa1, lciwa2, lciwa_any, pad_ice;   // lciwa_any: LCIWA1 or LCIWA2 or LCIWA3 (WNFLUXES' sea-ice constants, wnfluxes.F90:150-158)
   double zalpfacb, cdicwa;                  // YOWICE ZALPFACB, CDICWA
   int lwnemotauoc, lwnemocoustk, nemo_send, pad_nemo;   // YOWCOUP; nemo_send = (LWNEMOCOUSEND and LWCOU) or not LWCOU (stokestrn.F90:76-78)
-  double ROWATER, pad16;                    // 1 / ROWATERM1 (AKI_ICE); pad16: sizeof(DevConst) stays a multiple of 16 -- the constants that follow
-                                            // c_dc (c_exp) keep their alignment, and with it k_point's code as measured
+  double ROWATER, zalpwrs;                  // 1 / ROWATERM1 (AKI_ICE); YOWICE ZALPWRS
+  double zibrw_thrsh;                       // YOWICE ZIBRW_THRSH
+  int lwnemocouwrs, lwnemocouibr;           // YOWCOUP.  NOTE: sizeof(DevConst) must stay a multiple of 16 (static_assert in implsch.cu): the
+                                            // constants that follow c_dc (c_exp) keep their alignment, and with it k_point's code as measured
 };
 // rows of the gravity-capillary table ImplDev::gc [GC_NT][NWAV_GC] (YOWFRED *_GC, initgc.F90)
 enum { GC_XK = 0, GC_OMEGA, GC_CM, GC_C2OSQRTVG, GC_XKMSQRTVGOC2, GC_OM3GMKM, GC_OMXKM3, GC_DELKCC_NS, GC_DELKCC_OMXKM3, GC_DELKCC,

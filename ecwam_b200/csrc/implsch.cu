@@ -23,7 +23,7 @@ int upload_dev_const(const DevConst& h, cudaStream_t st) {
 // scalar scratch slots [slot][npts]
 enum {
   S_EMEAN = 0, S_FMEAN, S_F1MEAN, S_AKMEAN, S_XKMEAN,   // FKMEAN (first call)
-  S_XSTR, S_YSTR, S_F1DCOS3, S_F1DCOS2, S_PHIWA,         // STRESSO partial sums / TAU_PHI_HF inputs
+  S_XSTR, S_YSTR, S_F1DCOS3, S_F1DCOS2, S_PHIWA,         // S_XSTR / S_YSTR: XSTRESSICE / YSTRESSICE of LWNEMOCOUWRS (k_ice -> k_nemo); PHIWA
   S_UORBT, S_AORB, S_SIGN, S_TEMP2, S_PTURB, S_PVISC,    // SINPUT_ARD swell-dissipation scalars, WSIGSTAR
   S_SDS,                                                  // SDIWBK
   S_PHILF, S_XSTROC, S_YSTROC,                            // WNFLUXES sums
@@ -3360,6 +3360,78 @@ __global__ void __launch_bounds__(128) k_ice(ImplDev d, long long p0, long long 
       d.ice2[(size_t)m * n + p] = ci * ((c_dc.cdicwa * (wk * wk) * 4.0 * c_dc.zalpfacb) * d.f.cgroup[o3]);
     }
   }
+  if (!d.nemo) return;
+  const NemoDev nd = *d.nemo;
+  // LWNEMOCOUIBR (icebreak_modify_attenuation.F90:82-94): where the ice is broken (IBRMEM <= ZIBRW_THRSH) SDICE3's ALPFAC is 1/ZALPFACX
+  // instead of ZALPFACX: k_point put the ZALPFACX coefficient on SBOTTOM's plane, the difference is added here.
+  double alpfac = c_dc.zalpfacx;
+  if (nd.ibr_on && nd.f.ibrmem[p] <= c_dc.zibrw_thrsh) alpfac = 1.0 / c_dc.zalpfacx;
+  const double cith125 = (c_dc.lciwa3 && cith > 0.0) ? pow(cith, 1.25) : 0.0;
+  if (c_dc.licerun && c_dc.lciwa3 && alpfac != c_dc.zalpfacx)
+    for (int m = 0; m < F; ++m)
+      d.tbg[((size_t)TQ_SBO * F + m) * n + p] += -ci * ((c_dc.fr45[m] * cith125) * (alpfac - c_dc.zalpfacx)) * d.f.cgroup[idx3(d, p, m)];
+  // LWNEMOCOUWRS (wnfluxes.F90:178-196): the wave radiative stress on the sea ice, from SLICE = FL1 * FLDICE / max(1 - DELT5 FLDICE, 1) of
+  // the LAST attenuation term that is on (SLICE is INTENT(OUT) of SDICE1, 2, 3 in turn: sdice.F90:99-112), summed over all frequencies.
+  // FL1 is the spectrum IMPLSCH works on (depth-limited, floored: sinflx.F90:126-129), still in place before the sweep.
+  if (nd.wrs_on) {
+    const int A = c_dc.A;
+    const long long c = p / d.P;
+    const int i = (int)(p - c * d.P);
+    const size_t kstr = (size_t)d.P;
+    const double* hi = d.f.fl1 + (size_t)i + (size_t)d.P * A * F * (size_t)c;
+    const double* lo = hi;
+    int mlo = 0;
+    if (d.lo_on) { const int il = (p < d.nloc) ? i : 0; lo = d.fl_lo + (size_t)il + (size_t)d.P * A * d.lo_F * (size_t)c; mlo = d.Fr; }
+    const double fac = d.scr[S_FAC * n + p];
+    double snw, csw;
+    sincos(d.f.wdwave[p], &snw, &csw);
+    const double flmc = (1. - 0.9 * dmin(ci, 0.99)) * c_dc.flmin;
+    const double delt5 = c_dc.ximp * c_dc.delt, eps1000 = c_dc.EPSMIN * 1000.0;
+    const bool any = c_dc.licerun && c_dc.lciwa_any;
+    // SDICE1's ALP per frequency is needed again when it is the last term: recompute as above
+    double xsi = 0.0, ysi = 0.0;
+    for (int m = 0; m < F; ++m) {
+      const size_t o3 = idx3(d, p, m);
+      const double cg = d.f.cgroup[o3], wk = d.f.wavnum[o3];
+      double fld_m = 0.0;        // FLDICE of a term that does not depend on the bin
+      if (any && c_dc.lciwa3) fld_m = -((c_dc.fr45[m] * cith125) * alpfac) * cg;
+      else if (any && !c_dc.lciwa2 && c_dc.lciwa1 && d.ice1 && cith > 0.0) {
+        const int NT = d.ice_nt, NH = d.ice_nh;
+        const double* tabw = d.ice1 + (size_t)NT * NH;
+        int ih = (int)floor((cith - d.ice_hmin) / d.ice_dh + 1);
+        ih = max(1, min(ih, NH));
+        const int ih1 = max(1, min(ih + 1, NH));
+        const double wh1 = dmax(dmin(1.0, (cith - (d.ice_hmin + (ih - 1) * d.ice_dh)) / d.ice_dh), 0.0), wh = 1.0 - wh1;
+        const double wt1 = tabw[m], wt = 1.0 - wt1;
+        const int it = (int)tabw[F + m], it1 = (int)tabw[2 * F + m];
+        const double cc = wt * (wh * d.ice1[it + NT * (ih - 1)] + wh1 * d.ice1[it + NT * (ih1 - 1)]) +
+                          wt1 * (wh * d.ice1[it1 + NT * (ih - 1)] + wh1 * d.ice1[it1 + NT * (ih1 - 1)]);
+        // mean floe size as in the LCIWA1 block above
+        const double CIFRGL = 0.955, CIDMIN = 20.0, CIFRGMT = 2.0, A0 = 200.0, C0 = 300.0;
+        const int maxicm = (int)(log(A0 / CIDMIN) / log(CIFRGMT));
+        const double cidmax = A0 + C0 * ci;
+        const int icm = min((int)(log(cidmax / CIDMIN) / log(CIFRGMT)), maxicm);
+        double sn = 0.0, sd = 0.0, x = 1.0, fi = 1.0;
+        for (int j = 0; j <= icm; ++j) { sn = sn + x * cidmax / fi; sd = sd + x; x = x * (CIFRGMT * CIFRGMT * CIFRGL); fi = fi * CIFRGMT; }
+        fld_m = -(exp(cc) * (1.0 / (sn / sd)) * c_dc.zalpfacb) * cg;
+      }
+      const bool perbin = any && !c_dc.lciwa3 && c_dc.lciwa2;
+      const double c2 = (c_dc.cdicwa * (wk * wk) * 4.0 * c_dc.zalpfacb) * cg;
+      double sx = 0.0, sy = 0.0;
+      for (int k = 0; k < A; ++k) {
+        double f = dmax(__ldg((m < mlo ? lo : hi) + ((size_t)m * A + k) * kstr) * fac, c_dc.EPSMIN);
+        if (m == F - 1) f = dmax(f, flmc * sq(dmax(0.0, c_dc.COSTH[k] * csw + c_dc.SINTH[k] * snw)));
+        const double fld = perbin ? -c2 * sqrt(dmax(c_dc.EPSMIN, f * c_dc.DFIM[m])) : fld_m;
+        const double sl = dmin((f * fld) / dmax(1.0 - delt5 * fld, 1.0), -eps1000);
+        if (k == 0) { sx = c_dc.SINTH[0] * sl; sy = c_dc.COSTH[0] * sl; }
+        else { sx = sx + c_dc.SINTH[k] * sl; sy = sy + c_dc.COSTH[k] * sl; }
+      }
+      const double cinv = d.f.cinv[o3];
+      xsi = xsi + c_dc.zalpwrs * sx * cinv * c_dc.RHOWG_DFIM[m];
+      ysi = ysi + c_dc.zalpwrs * sy * cinv * c_dc.RHOWG_DFIM[m];
+    }
+    d.scr[S_XSTR * n + p] = xsi; d.scr[S_YSTR * n + p] = ysi;
+  }
 }
 
 // =========================================================================================================
@@ -3415,6 +3487,7 @@ __global__ void __launch_bounds__(128) k_nemo(ImplDev d, long long p0, long long
     }
     d.f.strnms[p] = strn;
   }
+  if (nd.wrs_on) { d.f.tauicx[p] = -d.scr[S_XSTR * n + p]; d.f.tauicy[p] = -d.scr[S_YSTR * n + p]; }   // flipped: positive stress on the ice (wnfluxes.F90:266-271)
   if (!nd.nemo_on) return;
   const ecwam_b200_nemo_fields& o = nd.f;
   {   // WNFLUXES
@@ -3484,7 +3557,7 @@ int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage
     } else if (d.iphys == 1) { k_point<true, 1, false><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<true, 2, false><<<nb, KP_NTH, smp, st>>>(d, p0, np); }
     else { k_point<false, 1, false><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<false, 2, false><<<nb, KP_NTH, smp, st>>>(d, p0, np); }
     if (d.isnonlin != 0) k_enh<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(d, p0, np);
-    if (d.ice1 || d.ice2) k_ice<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(d, p0, np);
+    if (d.ice1 || d.ice2 || d.nemo) k_ice<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(d, p0, np);
   } else return ECWAM_B200_EINVAL;
   return 0;
 }

@@ -75,6 +75,7 @@ void launch_pad(const PropDev& d, double* fl, int flF, int m0, int m1, cudaStrea
 struct NemoDev {
   ecwam_b200_nemo_fields f;   // the WAVE2OCEAN fields (valid when nemo_on)
   int nemo_on, strn_on;       // LWNEMOCOU (fields bound); LWNEMOCOUSTRN (CIMSSTRN fills STRNMS)
+  int wrs_on, ibr_on;         // LWNEMOCOUWRS (k_ice forms the radiative stress, k_nemo stores it); LWNEMOCOUIBR (k_ice, needs f.ibrmem)
 };
 struct ImplDev {
   int P, A, F, Fr, nchnk;

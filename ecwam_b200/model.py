@@ -37,7 +37,7 @@ def default_params(**kw) -> L.Params:
                  lwvflx_snl=1, lwcouast=0, icode_wnd=3, ifrelfmax=0, nproma=32, nchnk=0, idelt=900.0, idelpro=900.0,
                  delpro_lf=900.0, ximp=1.0, rnu=1.5e-5, rnum=0.11 * 1.5e-5, wspmin=1.0, cithrsh=0.3, cithrsh_tail=0.3,
                  ciblock=0.0, flmin=1e-5, bathymax=998.999, llcflcuroff=1, zalpfacx=1.0, zalpfacb=1.0, cdicwa=0.01, lwnemotauoc=0, lwnemocoustk=0,
-                 lwnemocoustrn=0, lwnemocousend=1, lwcou=0)
+                 lwnemocoustrn=0, lwnemocousend=1, lwcou=0, lwnemocouwrs=0, lwnemocouibr=0, zalpwrs=1.0, zibrw_thrsh=0.5)
     for k, v in kw.items():
         if not hasattr(p, k):
             raise KeyError(k)
@@ -203,7 +203,7 @@ class WamIntgr:
         self.t["mij"] = torch.full((Cn, P), F, dtype=torch.int32, device=dev)
         self.t["ciwa"].fill_(1.0)
         self.bind()
-        if self.par.lwnemocou:      # WAVE2OCEAN fields of the NEMO coupling (accumulators start at 0)
+        if self.par.lwnemocou or self.par.lwnemocouibr:      # WAVE2OCEAN fields of the NEMO coupling (accumulators start at 0) + IBRMEM
             nf = L.NemoFields()
             for n, _ in L.NemoFields._fields_:
                 self.t[n] = torch.zeros((Cn, P), dtype=torch.float64, device=dev)

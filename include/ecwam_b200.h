@@ -56,7 +56,7 @@ typedef struct ecwam_b200_params {
   int lciwa;       /* YOWICE bit mask: 1 LCIWA1 (SDICE1, needs ecwam_b200_tables cideac), 2 LCIWA2 (SDICE2), 4 LCIWA3 (SDICE3), 8 LCISCAL */
   int lwflux;      /* YOWCOUP LWFLUX                                                    */
   int lwfluxout;   /* YOWCOUP LWFLUXOUT (userin.F90:470 sets it .TRUE.)                 */
-  int lwnemocou;   /* YOWCOUP LWNEMOCOU (needs ecwam_b200_bind_nemo; LWNEMOCOUWRS / LWNEMOCOUIBR are not built) */
+  int lwnemocou;   /* YOWCOUP LWNEMOCOU (needs ecwam_b200_bind_nemo)                   */
   int lwvflx_snl;  /* YOWCOUP LWVFLX_SNL                                                */
   int lwcouast;    /* YOWCOUP LWCOUAST                                                  */
   int icode_wnd;   /* YOWWNDG ICODE (3 = 10 m wind, only)                               */
@@ -84,6 +84,11 @@ typedef struct ecwam_b200_params {
   int lwnemocoustrn; /* YOWCOUP LWNEMOCOUSTRN: CIMSSTRN fills STRNMS (and NEMOSTRN with LWNEMOCOU) (stokestrn.F90:70-74, 87) */
   int lwnemocousend; /* YOWCOUP LWNEMOCOUSEND (read with LWCOU only, stokestrn.F90:76-78)                             */
   int lwcou;         /* YOWCOUP LWCOU (only used in that condition)                                                 */
+  int lwnemocouwrs;  /* YOWCOUP LWNEMOCOUWRS: TAUICX/Y = wave radiative stress on the sea ice from SDICE's SLICE (wnfluxes.F90:178-196, 266-271) */
+  int lwnemocouibr;  /* YOWCOUP LWNEMOCOUIBR: SDICE3's ALPFAC = 1/ZALPFACX where IBRMEM <= ZIBRW_THRSH (icebreak_modify_attenuation.F90:82-94);
+                        needs ecwam_b200_nemo_fields.ibrmem */
+  double zalpwrs;    /* YOWICE ZALPWRS (mpuserin.F90:784: 1)                                                        */
+  double zibrw_thrsh;/* YOWICE ZIBRW_THRSH (mpuserin.F90:786: 0.5)                                                  */
 } ecwam_b200_params;
 
 /* ---------------------------------------------------------------------------------------------------
@@ -374,6 +379,7 @@ typedef struct ecwam_b200_nemo_fields {
   double* nemotauicy;
   double* nemowswave;
   double* nemophif;
+  const double* ibrmem;   /* OCEAN2WAVE: IBRMEM, the ice break-up memory (read with LWNEMOCOUIBR; may be NULL otherwise) */
 } ecwam_b200_nemo_fields;
 int ecwam_b200_bind_nemo(ecwam_b200_handle h, const ecwam_b200_nemo_fields* dev);
 

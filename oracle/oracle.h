@@ -91,6 +91,8 @@ struct Config {
   int llcflcuroff = 1;  // YOWSTAT LLCFLCUROFF (mpuserin.F90:575): retry without current refraction where the CFL check failed
   // YOWCOUP NEMO coupling (with lwnemocou): LWNEMOTAUOC, LWNEMOCOUSTK, LWNEMOCOUSTRN, LWNEMOCOUSEND (yowcoup.F90:24-33)
   int lwnemotauoc = 0, lwnemocoustk = 0, lwnemocoustrn = 0, lwnemocousend = 1;
+  int lwnemocouwrs = 0, lwnemocouibr = 0;     // YOWCOUP LWNEMOCOUWRS (radiative stress on the ice), LWNEMOCOUIBR (ice break-up memory)
+  double zalpwrs = 1.0, zibrw_thrsh = 0.5;   // YOWICE ZALPWRS, ZIBRW_THRSH (mpuserin.F90:784-786)
 };
 
 // ---------------------------------------------------------------------------

@@ -29,6 +29,7 @@ class Config(C.Structure):
         ("deptha", C.c_double), ("nproma", C.c_int), ("npr", C.c_int), ("ll1d", C.c_int),
         ("store_all_weights", C.c_int), ("nthreads", C.c_int), ("llcflcuroff", C.c_int),
         ("lwnemotauoc", C.c_int), ("lwnemocoustk", C.c_int), ("lwnemocoustrn", C.c_int), ("lwnemocousend", C.c_int),
+        ("lwnemocouwrs", C.c_int), ("lwnemocouibr", C.c_int), ("zalpwrs", C.c_double), ("zibrw_thrsh", C.c_double),
     ]
 
 
@@ -39,7 +40,8 @@ def default_config(**kw) -> Config:
                lwvflx_snl=1, lwcouast=0, lwcou=0, icode=3, idelt=900.0, idelpro=900.0, delpro_lf=900.0, ifrelfmax=0,
                ximp=1.0, rnu=1.5e-5, rnum=0.11 * 1.5e-5, wspmin=1.0, cithrsh=0.3, cithrsh_tail=0.3, ciblock=0.0,
                flmin=1e-5, zalpfacx=1.0, zalpfacb=1.0, cdicwa=0.01, bathymax=998.999, deptha=2.0, nproma=32, npr=1, ll1d=0,
-               store_all_weights=0, nthreads=1, llcflcuroff=1, lwnemotauoc=0, lwnemocoustk=0, lwnemocoustrn=0, lwnemocousend=1)
+               store_all_weights=0, nthreads=1, llcflcuroff=1, lwnemotauoc=0, lwnemocoustk=0, lwnemocoustrn=0, lwnemocousend=1, lwnemocouwrs=0,
+               lwnemocouibr=0, zalpwrs=1.0, zibrw_thrsh=0.5)
     for k, v in kw.items():
         if not hasattr(c, k):
             raise KeyError(k)

@@ -23,7 +23,7 @@ static ArrD* field2d(Fields& f, const std::string& n) {
       {"TAUOCXD", &Fields::TAUOCXD}, {"TAUOCYD", &Fields::TAUOCYD}, {"TAUOC", &Fields::TAUOC},
       {"TAUICX", &Fields::TAUICX}, {"TAUICY", &Fields::TAUICY}, {"PHIOCD", &Fields::PHIOCD},
       {"PHIEPS", &Fields::PHIEPS}, {"PHIAW", &Fields::PHIAW},
-      {"NSWH", &Fields::NSWH}, {"NMWP", &Fields::NMWP}, {"NPHIEPS", &Fields::NPHIEPS}, {"NTAUOC", &Fields::NTAUOC},
+      {"IBRMEM", &Fields::IBRMEM}, {"NSWH", &Fields::NSWH}, {"NMWP", &Fields::NMWP}, {"NPHIEPS", &Fields::NPHIEPS}, {"NTAUOC", &Fields::NTAUOC},
       {"NEMOTAUX", &Fields::NEMOTAUX}, {"NEMOTAUY", &Fields::NEMOTAUY}, {"NEMOTAUICX", &Fields::NEMOTAUICX},
       {"NEMOTAUICY", &Fields::NEMOTAUICY}, {"NEMOWSWAVE", &Fields::NEMOWSWAVE}, {"NEMOPHIF", &Fields::NEMOPHIF},
       {"NEMOUSTOKES", &Fields::NEMOUSTOKES}, {"NEMOVSTOKES", &Fields::NEMOVSTOKES}, {"NEMOSTRN", &Fields::NEMOSTRN}};

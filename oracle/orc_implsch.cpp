@@ -1075,7 +1075,7 @@ void SBOTTOM(const Ctx& x, V3 FL1, V3 FLD, V3 SL, V2 WAVNUM, V1 DEPTH) {
 struct NemoFlux { V1 NPHIEPS, NTAUOC, NSWH, NMWP, NEMOTAUX, NEMOTAUY, NEMOTAUICX, NEMOTAUICY, NEMOWSWAVE, NEMOPHIF; };
 void WNFLUXES(const Ctx& x, I1 MIJ, V2 RHOWGDFTH, V2 CINV, V3 SSURF, V1 CICOVER, V1 PHIWA, V1 EM, V1 F1, V1 WSWAVE,
               V1 WDWAVE, V1 USTRA, V1 VSTRA, V1 UFRIC, V1 AIRD, V1 TAUXD, V1 TAUYD, V1 TAUOCXD, V1 TAUOCYD, V1 TAUOC,
-              V1 TAUICX, V1 TAUICY, V1 PHIOCD, V1 PHIEPS, V1 PHIAW, const NemoFlux* NE = nullptr) {
+              V1 TAUICX, V1 TAUICY, V1 PHIOCD, V1 PHIEPS, V1 PHIAW, const NemoFlux* NE = nullptr, const V3* SLICE = nullptr) {
   (void)MIJ;
   const Tables& t = x.t;
   const Config& c = x.c;
@@ -1132,6 +1132,22 @@ void WNFLUXES(const Ctx& x, I1 MIJ, V2 RHOWGDFTH, V2 CINV, V3 SSURF, V1 CICOVER,
     TAUOC(IJ) = std::min(std::max(TAUO / TAU, t.TAUOCMIN), t.TAUOCMAX);
   }
   for (int IJ = KIJS; IJ <= KIJL; ++IJ) { TAUICX(IJ) = 0.0; TAUICY(IJ) = 0.0; }
+  if (c.lwnemocouwrs && SLICE) {   // wave radiative stress on the sea ice (wnfluxes.F90:178-196, 266-271): integrated up to FR(NFRE)
+    const double EPSMIN1000 = t.EPSMIN * 1000.0;
+    std::vector<double> XSI(n, 0.0), YSI(n, 0.0), SX(n), SY(n);
+    for (int M = 1; M <= NFRE; ++M) {
+      for (int IJ = KIJS; IJ <= KIJL; ++IJ) { SX[IJ] = t.SINTH(1) * std::min((*SLICE)(IJ, 1, M), -EPSMIN1000); SY[IJ] = t.COSTH(1) * std::min((*SLICE)(IJ, 1, M), -EPSMIN1000); }
+      for (int K = 2; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+        SX[IJ] = SX[IJ] + t.SINTH(K) * std::min((*SLICE)(IJ, K, M), -EPSMIN1000);
+        SY[IJ] = SY[IJ] + t.COSTH(K) * std::min((*SLICE)(IJ, K, M), -EPSMIN1000);
+      }
+      for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+        XSI[IJ] = XSI[IJ] + c.zalpwrs * SX[IJ] * CINV(IJ, M) * t.RHOWG_DFIM(M);
+        YSI[IJ] = YSI[IJ] + c.zalpwrs * SY[IJ] * CINV(IJ, M) * t.RHOWG_DFIM(M);
+      }
+    }
+    for (int IJ = KIJS; IJ <= KIJL; ++IJ) { TAUICX(IJ) = -XSI[IJ]; TAUICY(IJ) = -YSI[IJ]; }
+  }
   if (c.lwcouast)
     for (int IJ = KIJS; IJ <= KIJL; ++IJ)
       if (USTRA(IJ) != 0.0 || VSTRA(IJ) != 0.0) {
@@ -1315,12 +1331,15 @@ void HALPHAP(const Ctx& x, V2 WAVNUM, V2 COSWDIF, V3 FL1, V1 HALP) {
 }
 
 // sdice.F90:99-112 with sdice1.F90:102-187, sdice2.F90:97-121, sdice3.F90:107-147
-void SDICE(const Ctx& x, V3 FL1, V3 FLD, V3 SL, V2 WAVNUM, V2 CGROUP, V1 CICOVER, V1 CITHICK) {
+void SDICE(const Ctx& x, V3 FL1, V3 FLD, V3 SL, V2 WAVNUM, V2 CGROUP, V1 CICOVER, V1 CITHICK, const double* ALPFAC /*1-based, null: ZALPFACX*/,
+           V3* SLICEO /*null: not kept*/) {
+  const double DELT5 = x.c.ximp * x.c.idelt;
   const Tables& t = x.t;
   const Config& c = x.c;
   const int KIJS = x.KIJS, KIJL = x.KIJL, NANG = x.NANG, NFRE = x.NFRE;
   // SDICE (sdice.F90:99-112): type 1 scattering, type 2 under-ice friction, type 3 viscous friction, in this order.  SLICE (the
-  // attenuation's own source function) only feeds the LWNEMOCOUWRS radiative stress of WNFLUXES (wnfluxes.F90:178-196): not kept.
+  // attenuation's own source function, INTENT(OUT) of every term: the last one that is on wins) feeds the LWNEMOCOUWRS radiative
+  // stress of WNFLUXES (wnfluxes.F90:178-196).
   if (c.lciwa1) {    // SDICE1 (sdice1.F90:102-187)
     const double CIFRGL = 0.955, CIDMIN = 20.0, CIFRGMT = 2.0, A = 200.0, Cc = 300.0;
     const int MAXICM = (int)(std::log(A / CIDMIN) / std::log(CIFRGMT));
@@ -1366,6 +1385,7 @@ void SDICE(const Ctx& x, V3 FL1, V3 FLD, V3 SL, V2 WAVNUM, V2 CGROUP, V1 CICOVER
       const double SLICE = FL1(IJ, K, M) * FLDICE;
       SL(IJ, K, M) = SL(IJ, K, M) + CICOVER(IJ) * SLICE;
       FLD(IJ, K, M) = FLD(IJ, K, M) + CICOVER(IJ) * FLDICE;
+      if (SLICEO) (*SLICEO)(IJ, K, M) = SLICE / std::max((1.0 - DELT5 * FLDICE), 1.0);
     }
   }
   if (c.lciwa2) {    // SDICE2 (sdice2.F90:97-121)
@@ -1377,15 +1397,17 @@ void SDICE(const Ctx& x, V3 FL1, V3 FLD, V3 SL, V2 WAVNUM, V2 CGROUP, V1 CICOVER
       const double SLICE = FL1(IJ, K, M) * FLDICE;
       SL(IJ, K, M) = SL(IJ, K, M) + CICOVER(IJ) * SLICE;
       FLD(IJ, K, M) = FLD(IJ, K, M) + CICOVER(IJ) * FLDICE;
+      if (SLICEO) (*SLICEO)(IJ, K, M) = SLICE / std::max((1.0 - DELT5 * FLDICE), 1.0);
     }
   }
   if (c.lciwa3) {    // SDICE3 (sdice3.F90:107-147), IMODEL = 2 (Jie Yu 2022), ALPFAC = ZALPFACX (no ice-breakup coupling)
         const double CDICE = 0.1274 * std::pow(t.ZPI / std::sqrt(t.G), 4.5);
     for (int M = 1; M <= NFRE; ++M) for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
-      const double ALP = (2. * CDICE * std::pow(CITHICK(IJ), 1.25) * std::pow(t.FR(M), 4.5)) * c.zalpfacx;
+      const double ALP = (2. * CDICE * std::pow(CITHICK(IJ), 1.25) * std::pow(t.FR(M), 4.5)) * (ALPFAC ? ALPFAC[IJ] : c.zalpfacx);
       const double TEMP = -CICOVER(IJ) * ALP * CGROUP(IJ, M);
       SL(IJ, K, M) = SL(IJ, K, M) + FL1(IJ, K, M) * TEMP;
       FLD(IJ, K, M) = FLD(IJ, K, M) + TEMP;
+      if (SLICEO) { const double FLDICE = -ALP * CGROUP(IJ, M); (*SLICEO)(IJ, K, M) = (FL1(IJ, K, M) * FLDICE) / std::max((1.0 - DELT5 * FLDICE), 1.0); }
     }
   }
 }
@@ -1411,6 +1433,8 @@ void implsch_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int IC
   const size_t n3 = (size_t)P * NANG * NFRE;
   std::vector<double> sFLD(n3), sSL(n3), sSPOS(n3), sSSOURCE(n3, 0.0);
   V3 FLD{sFLD.data(), P, NANG}, SL{sSL.data(), P, NANG}, SPOS{sSPOS.data(), P, NANG}, SSOURCE{sSSOURCE.data(), P, NANG};
+  std::vector<double> sSLICE(c.lwnemocouwrs ? n3 : 0, 0.0);     // implsch.F90:205-213: zero unless an SDICE term fills it
+  V3 SLICE{sSLICE.data(), P, NANG};
   std::vector<double> sFLM((size_t)P * NANG), sCOSWDIF((size_t)P * NANG), sSINWDIF2((size_t)P * NANG), sTEMP((size_t)P * NFRE), sRHOWGDFTH((size_t)P * NFRE);
   V2 FLM{sFLM.data(), P}, COSWDIF{sCOSWDIF.data(), P}, SINWDIF2{sSINWDIF2.data(), P}, TEMP{sTEMP.data(), P}, RHOWGDFTH{sRHOWGDFTH.data(), P};
   L1 lRAORW(P), lEMEAN(P), lFMEAN(P), lHALP(P), lEMEANWS(P), lFMEANWS(P), lUSFM(P), lF1MEAN(P), lAKMEAN(P), lXKMEAN(P), lPHIWA(P), lRNFAC(P);
@@ -1469,7 +1493,10 @@ void implsch_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int IC
         SL(IJ, K, M) = BETA * SL(IJ, K, M);
         FLD(IJ, K, M) = BETA * FLD(IJ, K, M);
       }
-    if (c.lciwa1 || c.lciwa2 || c.lciwa3) SDICE(x, FL1, FLD, SL, WAVNUM, CGROUP, CICOVER, s1(f.CITHICK));
+    // ICEBREAK_MODIFY_ATTENUATION (icebreak_modify_attenuation.F90:82-94, LWNEMOCOUIBR): broken ice attenuates 1/ZALPFACX instead of ZALPFACX
+    std::vector<double> ALPFAC(KIJL + 1, c.zalpfacx);
+    if (c.lwnemocouibr) { V1 IBRMEM = s1(f.IBRMEM); for (int IJ = KIJS; IJ <= KIJL; ++IJ) if (IBRMEM(IJ) <= c.zibrw_thrsh) ALPFAC[IJ] = 1.0 / c.zalpfacx; }
+    if (c.lciwa1 || c.lciwa2 || c.lciwa3) SDICE(x, FL1, FLD, SL, WAVNUM, CGROUP, CICOVER, s1(f.CITHICK), ALPFAC.data(), c.lwnemocouwrs ? &SLICE : nullptr);
   }
   SBOTTOM(x, FL1, FLD, SL, WAVNUM, DEPTH);
   // ---- 2.4 new spectra (implsch.F90:352-395)
@@ -1494,7 +1521,7 @@ void implsch_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int IC
               s1(f.NEMOWSWAVE), s1(f.NEMOPHIF)};
   if (LCFLX)
     WNFLUXES(x, MIJ, RHOWGDFTH, CINV, SSOURCE, CICOVER, PHIWA, EMEAN, F1MEAN, WSWAVE, WDWAVE, USTRA, VSTRA, UFRIC, AIRD,
-             TAUXD, TAUYD, TAUOCXD, TAUOCYD, TAUOC, TAUICX, TAUICY, PHIOCD, PHIEPS, PHIAW, &NE);
+             TAUXD, TAUYD, TAUOCXD, TAUOCYD, TAUOC, TAUICX, TAUICY, PHIOCD, PHIEPS, PHIAW, &NE, &SLICE);
   // ---- 2.5 tail
   FKMEAN(x, FL1, WAVNUM, EMEAN, FMEAN, F1MEAN, AKMEAN, XKMEAN);
   FEMEANWS(x, FL1, XLLWS, FMEANWS, lEMEANWS.v.data());
@@ -1576,7 +1603,7 @@ void term_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int ICHNK
     FKMEAN(x, FL1, WAVNUM, lEM.view(), lFM.view(), lF1.view(), lAK.view(), lXK.view());
     SDIWBK(x, FL1, FLD, SL, DEPTH, EMAXDPT, lEM.view(), lF1.view());
   } else if (which == 5) {
-    SDICE(x, FL1, FLD, SL, WAVNUM, CGROUP, s1(f.CICOVER), s1(f.CITHICK));
+    SDICE(x, FL1, FLD, SL, WAVNUM, CGROUP, s1(f.CICOVER), s1(f.CITHICK), nullptr, nullptr);
   } else throw std::runtime_error("term_chunk: unknown term");
 }
 

@@ -390,6 +390,31 @@ def test_nemo_coupling_fields(built, case, kw):
         assert o.get_field("STRNMS").max() > 0
 
 
+@pytest.mark.parametrize("case,lciwa,ibr", [("o48like", 4, 1), ("o640like", 3, 0), ("o48_iphys0", 1, 0), ("o320like", 7, 1), ("o48like", 0, 0)])
+def test_radiative_stress_on_the_ice_and_break_up_memory(built, case, lciwa, ibr):
+    """LWNEMOCOUWRS (wnfluxes.F90:178-196, 266-271): TAUICX / TAUICY from the SLICE of the last attenuation term that is on (k_ice forms the
+    sums on the spectrum IMPLSCH works on, k_nemo stores and accumulates them), and LWNEMOCOUIBR (icebreak_modify_attenuation.F90:82-94):
+    SDICE3 with ALPFAC = 1 / ZALPFACX where IBRMEM says the ice is broken."""
+    okw = dict(lwnemocou=1, lwnemocouwrs=1, lwnemocouibr=ibr, lmaskice=0, zalpfacx=0.6, zalpwrs=0.8)
+    g, o, f, fl = make_oracle(case, lciwa1=lciwa & 1, lciwa2=(lciwa >> 1) & 1, lciwa3=(lciwa >> 2) & 1, **okw)
+    _, s, w = make_gpu(case, lciwa=lciwa, **okw)
+    n = f["CICOVER"].size
+    cith = np.where(f["CICOVER"] > 0, 0.3 + 1.5 * f["CICOVER"], 0.0)
+    ibrmem = ((np.arange(n) * 7) % 5 < 2) * 1.0            # 1 = solid, 0 = broken
+    o.set_field("CITHICK", cith); o.set_field("IBRMEM", ibrmem)
+    w.set_field("cithick", cith); w.set_field("ibrmem", ibrmem)
+    for _ in range(3):
+        assert o.step() == 0 and w.step() == 0
+    w.synchronize()
+    check_state(w, o)
+    for nm in ("TAUICX", "TAUICY", "NEMOTAUICX", "NEMOTAUICY"):
+        a, b = w.get_field(nm), o.get_field(nm)[w.own]
+        # without an attenuation term SLICE = 0 and the sums are rounding noise of -1000 EPSMIN sum(sin th): compare on a physical scale
+        assert np.abs(a - b).max() <= RTOL_FIELD * max(np.abs(b).max(), 1e-12), nm
+    if lciwa:
+        assert np.abs(o.get_field("TAUICX")).max() > 1e-6
+
+
 def test_current_cfl_fallback(built):
     """LLCFLCUROFF (ctuwdrv.F90:101-121): with a long propagation step and strong current shear the direction / frequency
     weights of the current refraction leave [0,1] at a few points; the second CTUW call switches the current refraction off at

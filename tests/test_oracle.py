@@ -1101,3 +1101,40 @@ def test_nemo_coupling_fields_against_numpy(built, case, tauoc):
     got = o.get_field("STRNMS")
     assert (got[cith > 0] > 0).any() and (got[cith == 0] == 0).all()
     np.testing.assert_allclose(got, strn, rtol=2e-5, atol=1e-30, err_msg="STRNMS")      # 6 x the solver's own 1e-6 (k enters as k^6)
+
+
+def test_radiative_stress_on_the_ice_against_numpy(built):
+    """LWNEMOCOUWRS + LWNEMOCOUIBR with SDICE3 on an all-ocean grid (no depth limitation: the spectrum IMPLSCH works on is the
+    propagated one with its floors): TAUICX / TAUICY = -ZALPWRS sum_m sum_k (sin, cos)(th_k) min(SLICE, -1000 EPSMIN) CINV RHOWG_DFIM with
+    SLICE = F FLDICE / max(1 - XIMP DELT FLDICE, 1), FLDICE = -2 CDICE h^1.25 f^4.5 ALPFAC CG, ALPFAC = 1/ZALPFACX on broken ice."""
+    kw = dict(lwnemocou=1, lwnemocouwrs=1, lwnemocouibr=1, lciwa3=1, lmaskice=0, zalpfacx=0.6, zalpwrs=0.8)
+    g, o, f, fl = make_oracle("aqua", **kw)
+    ci, wd = f["CICOVER"], f["WDWAVE"]
+    n = ci.size
+    cith = np.where(ci > 0, 0.3 + 1.5 * ci, 0.0)
+    ibrmem = ((np.arange(n) * 7) % 5 < 2) * 1.0
+    o.set_field("CITHICK", cith); o.set_field("IBRMEM", ibrmem)
+    assert o.step() == 0
+    assert o.propag() == 0
+    F1 = o.get_fl1()                                   # what the second IMPLSCH starts from
+    o.implsch()
+    NF, A, N = F1.shape
+    fr, th = o.table("FR"), o.table("TH")
+    cg, cinv = o.get_field3("CGROUP"), o.get_field3("CINV")
+    EPSMIN, G, ZPI, ROWATER = 0.1e-32, 9.806, 2 * np.pi, 1000.0
+    F = np.maximum(F1, EPSMIN)
+    flmc = (1.0 - 0.9 * np.minimum(ci, 0.99)) * o.cfg.flmin
+    flm = flmc[None, :] * np.maximum(0.0, np.cos(th[:, None] - wd[None, :])) ** 2
+    F[-1] = np.maximum(F[-1], flm)
+    alpfac = np.where(ibrmem <= 0.5, 1.0 / 0.6, 0.6)
+    cdice = 0.1274 * (ZPI / np.sqrt(G)) ** 4.5
+    fldice = -(2.0 * cdice * cith[None, :] ** 1.25 * fr[:, None] ** 4.5) * alpfac[None, :] * cg
+    slice_ = np.minimum(F * fldice[:, None, :] / np.maximum(1.0 - o.cfg.ximp * o.cfg.idelt * fldice[:, None, :], 1.0), -1000.0 * EPSMIN)
+    delth = ZPI / A
+    rdf = ROWATER * G * delth * np.log(fr[1] / fr[0]) * fr
+    rdf[0] *= 0.5; rdf[-1] *= 0.5
+    tx = 0.8 * ((slice_ * np.sin(th)[None, :, None]).sum(axis=1) * cinv * rdf[:, None]).sum(axis=0)
+    ty = 0.8 * ((slice_ * np.cos(th)[None, :, None]).sum(axis=1) * cinv * rdf[:, None]).sum(axis=0)
+    assert np.abs(tx).max() > 1e-4 and (ibrmem[ci > 0] <= 0.5).any() and (ibrmem[ci > 0] > 0.5).any()
+    np.testing.assert_allclose(o.get_field("TAUICX"), -tx, rtol=1e-10, atol=1e-14 * np.abs(tx).max())
+    np.testing.assert_allclose(o.get_field("TAUICY"), -ty, rtol=1e-10, atol=1e-14 * np.abs(ty).max())
