@@ -219,7 +219,7 @@ static int fill_dev_const(const ecwam_b200_params& p, const ecwam_b200_tables& t
   if ((p.lciwa & 1) && (t.nict < 2 || t.nich < 2 || !t.cideac || !(t.dtic > 0.0) || !(t.dhic > 0.0)))
     EW_FAIL(ECWAM_B200_EINVAL, "LCIWA1 (SDICE1) needs the CIDEAC table (ecwam_b200_tables: nict, nich, ticmin, hicmin, dtic, dhic, cideac)");
   if (p.lciwa & ~15) EW_FAIL(ECWAM_B200_EINVAL, "lciwa: unknown bits");
-  if (p.icode_wnd != 3) EW_FAIL(ECWAM_B200_EINVAL, "only ICODE_WND=3 (10 m wind forcing) is implemented");
+  if (p.icode_wnd < 1 || p.icode_wnd > 3) EW_FAIL(ECWAM_B200_EINVAL, "ICODE_WND must be 1, 2 (friction velocity / stress forcing) or 3 (10 m wind)");
 
   if (p.iphys != 0 && p.iphys != 1) EW_FAIL(ECWAM_B200_EINVAL, "IPHYS must be 0 or 1");
   if (t.mlsthg > EW_MAXMC || t.mlsthg < 1 || t.mfrstlw > 1) EW_FAIL(ECWAM_B200_EINVAL, "bad MLSTHG/MFRSTLW");
@@ -921,7 +921,7 @@ static ImplDev make_impl(H* h, bool from_fl3) {
   for (int kh = 0; kh < 2; ++kh) for (int q = 0; q < 4; ++q) d.dsb[kh][q] = h->dsh[kh][q] * 64;
   d.halo_r = h->halo_r; d.halo_c = h->halo_c;
   d.iphys = h->par.iphys; d.nsdsnth = h->nsdsnth;
-  d.cy49 = (h->par.llgcbz0 || h->par.llnormagam) ? 1 : 0;
+  d.cy49 = ((h->par.llgcbz0 || h->par.llnormagam) ? 1 : 0) | (h->par.icode_wnd != 3 ? 2 : 0);
   d.gc = h->gctab.p;
   d.sweep_ok = h->dc.sweep_ok;
   d.ssource_pre = (h->dc.lcflx && !h->par.lwvflx_snl) ? 1 : 0;
@@ -1095,11 +1095,24 @@ int ecwam_b200_wamintgr(ecwam_b200_handle h) {
 int ecwam_b200_newwind(ecwam_b200_handle h, const ecwam_b200_forcing_next* next) {
   if (!h || !next) EW_FAIL(ECWAM_B200_EINVAL, "null argument");
   if (!h->bound) EW_FAIL(ECWAM_B200_ESTATE, "fields not bound");
-  if (h->par.icode_wnd != 3) EW_FAIL(ECWAM_B200_EINVAL, "NEWWIND: only ICODE_WND = 3 (10 m wind speed) is built");
+  if (h->par.icode_wnd != 3) EW_FAIL(ECWAM_B200_EINVAL, "NEWWIND: with ICODE_WND = 1, 2 the forcing is the friction velocity: use ecwam_b200_newwind_ustar");
   const void* const* pp = (const void* const*)next;
   for (size_t i = 0; i < sizeof(*next) / sizeof(void*); ++i) if (!pp[i]) EW_FAIL(ECWAM_B200_EINVAL, "NEWWIND: FF_NEXT member %zu is null", i);
   ScopedTimer t(h, "newwind");
   launch_newwind((long long)h->par.nproma * h->par.nchnk, h->dev, *next, h->dc.ACD, h->dc.BCD, h->dc.EPSMIN, h->st);
+  h->nlaunch++;
+  EW_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int ecwam_b200_newwind_ustar(ecwam_b200_handle h, const ecwam_b200_forcing_next* next, const double* ufric_next) {
+  if (!h || !next || !ufric_next) EW_FAIL(ECWAM_B200_EINVAL, "null argument");
+  if (!h->bound) EW_FAIL(ECWAM_B200_ESTATE, "fields not bound");
+  if (h->par.icode_wnd == 3) EW_FAIL(ECWAM_B200_EINVAL, "NEWWIND: ICODE_WND = 3 takes the 10 m wind: use ecwam_b200_newwind");
+  if (!next->wdwave || !next->aird || !next->wstar || !next->cicover || !next->cithick || !next->ustra || !next->vstra)
+    EW_FAIL(ECWAM_B200_EINVAL, "NEWWIND: a FF_NEXT member is null");
+  ScopedTimer t(h, "newwind");
+  launch_newwind_ustar((long long)h->par.nproma * h->par.nchnk, h->dev, *next, ufric_next, h->dc.ALPHA, h->st);
   h->nlaunch++;
   EW_CUDA_CHECK(cudaGetLastError());
   return 0;

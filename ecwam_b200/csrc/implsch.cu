@@ -746,7 +746,20 @@ __device__ __forceinline__ void sinput_point(const PointSrc& S, const ImplDev& d
 #else
 #define KP_BOUNDS(PH) __launch_bounds__(KP_NTH, KP_MINB)
 #endif
-template <bool ARD, int PH, bool CY>
+// Z0WAVE + the logarithmic profile (z0wave.F90:68-93, airsea.F90:102-120): AIRSEA of the first SINFLX call when the forcing is the
+// friction velocity (ICODE_WND = 1, 2); US stays as it is, U10 (WSWAVE) is derived and stored for the second call's TAUT_Z0.
+__device__ __forceinline__ double z0wave_u10(double us, double tauw, double utop, double& z0, double& z0b, double& chrnck) {
+  const double alphaog = (c_dc.llcapchnk ? chnkmin(utop) : c_dc.ALPHA) * c_dc.GM1;
+  const double ust2 = us * us, ust3 = us * us * us;
+  const double arg = dmax(ust2 - tauw, c_dc.EPS1);
+  z0 = alphaog * ust3 / sqrt(arg);
+  z0b = alphaog * ust2;
+  chrnck = c_dc.G * z0 / ust2;
+  return dmax((1.0 / c_dc.XKAPPA) * us * (log(c_dc.XNLEV) - log(z0)), c_dc.wspmin);
+}
+
+// USF (only with PH = 1): the ICODE_WND = 1, 2 instance -- AIRSEA of the first SINFLX call is Z0WAVE instead of TAUT_Z0
+template <bool ARD, int PH, bool CY, bool USF = false>
 __global__ void KP_BOUNDS(PH) k_point(ImplDev d, long long p0, long long np) {
   extern __shared__ double smem[];
   long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -835,9 +848,12 @@ __global__ void KP_BOUNDS(PH) k_point(ImplDev d, long long p0, long long np) {
         }
         fac_known = true;
         if (valid) s[S_HALP * n + p] = halp;
-        taut_z0_gc(d.gc, 0, halp, wswave, wdwave, tauw, tauwdir, rnfac, ustar, z0, z0b, ch);
-      } else taut_z0(0, wswave, wdwave, tauw, tauwdir, ustar, z0, z0b, ch);
-    } else taut_z0(0, wswave, wdwave, tauw, tauwdir, ustar, z0, z0b, ch);
+        if (USF) { const double u10 = z0wave_u10(ustar, tauw, wswave, z0, z0b, ch); if (valid) d.f.wswave[p] = u10; }
+        else taut_z0_gc(d.gc, 0, halp, wswave, wdwave, tauw, tauwdir, rnfac, ustar, z0, z0b, ch);
+      } else if (USF) { const double u10 = z0wave_u10(ustar, tauw, wswave, z0, z0b, ch); if (valid) d.f.wswave[p] = u10; }
+      else taut_z0(0, wswave, wdwave, tauw, tauwdir, ustar, z0, z0b, ch);
+    } else if (USF) { const double u10 = z0wave_u10(ustar, tauw, wswave, z0, z0b, ch); if (valid) d.f.wswave[p] = u10; }
+    else taut_z0(0, wswave, wdwave, tauw, tauwdir, ustar, z0, z0b, ch);
     // SDEPTHLIM (sdepthlim.F90:50-82) needs the total energy of the incoming spectrum before anything else can be formed.
     // Instead of a separate pass over FL1, the first SINPUT pass is run with the limiting factor 1 (exact wherever the
     // spectrum is not depth-limited, i.e. almost everywhere) and sums that energy on the side; only the lanes that turn
@@ -3551,7 +3567,24 @@ int launch_implsch_stage(const ImplDev& d, long long p0, long long np, int stage
       attr_p = true;
     }
     const unsigned nb = (unsigned)((np + KP_NTH - 1) / KP_NTH);
-    if (d.cy49) {
+    const bool cy49 = (d.cy49 & 1) != 0;
+    if (d.cy49 & 2) {   // ICODE_WND = 1, 2: the first SINFLX call's AIRSEA is Z0WAVE
+      static bool attr_u = false;
+      if (!attr_u) {
+        const void* ku[4] = {(const void*)k_point<true, 1, false, true>, (const void*)k_point<false, 1, false, true>,
+                             (const void*)k_point<true, 1, true, true>, (const void*)k_point<false, 1, true, true>};
+        for (int i = 0; i < 4; ++i) {
+          EW_CUDA_CHECK(cudaFuncSetAttribute(ku[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+          EW_CUDA_CHECK(cudaFuncSetAttribute(ku[i], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        }
+        attr_u = true;
+      }
+      if (cy49) {
+        if (d.iphys == 1) { k_point<true, 1, true, true><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<true, 2, true><<<nb, KP_NTH, smp, st>>>(d, p0, np); }
+        else { k_point<false, 1, true, true><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<false, 2, true><<<nb, KP_NTH, smp, st>>>(d, p0, np); }
+      } else if (d.iphys == 1) { k_point<true, 1, false, true><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<true, 2, false><<<nb, KP_NTH, smp, st>>>(d, p0, np); }
+      else { k_point<false, 1, false, true><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<false, 2, false><<<nb, KP_NTH, smp, st>>>(d, p0, np); }
+    } else if (cy49) {
       if (d.iphys == 1) { k_point<true, 1, true><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<true, 2, true><<<nb, KP_NTH, smp, st>>>(d, p0, np); }
       else { k_point<false, 1, true><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<false, 2, true><<<nb, KP_NTH, smp, st>>>(d, p0, np); }
     } else if (d.iphys == 1) { k_point<true, 1, false><<<nb, KP_NTH, smp, st>>>(d, p0, np); k_point<true, 2, false><<<nb, KP_NTH, smp, st>>>(d, p0, np); }

@@ -94,7 +94,8 @@ struct ImplDev {
                            // k_stencil's shared-memory planes (shift * 8 points * 8 B)
   int iphys, nsdsnth;      // copies of the host-side switches the launcher needs
   int halo_r, halo_c;      // direction halo of the shared-memory spectrum rows / interaction planes of k_stencil
-  int cy49;                // LLGCBZ0 or LLNORMAGAM is on: k_point runs its gravity-capillary / renormalised-growth instance
+  int cy49;                // launcher flags.  bit 0: LLGCBZ0 or LLNORMAGAM is on (k_point runs its gravity-capillary / renormalised-growth
+                           // instance); bit 1: ICODE_WND = 1, 2 (phase 1 runs the Z0WAVE instance).  Not read by the kernels.
   const double* gc;        // [GC_NT][NWAV_GC] gravity-capillary tables (device), read by that instance only
   int sweep_ok;            // the DIA tables have the separable structure k_sweep relies on (DevConst::NLW)
   int ssource_pre;         // LCFLX and not LWVFLX_SNL: WNFLUXES takes SL before SNONLIN (only k_stencil / k_stencil_dp carry that branch)
@@ -144,6 +145,9 @@ struct OutDev {
 int upload_out_const(const OutConst& h, cudaStream_t st);
 void launch_newwind(long long npts, const ecwam_b200_fields& f, const ecwam_b200_forcing_next& nx, double acd, double bcd, double epsmin,
                     cudaStream_t st);
+// ICODE_WND = 1, 2 (newwind.F90:141-150): FF_NEXT%UFRIC instead of FF_NEXT%WSWAVE, first-guess TAUW from the Charnock parameter
+void launch_newwind_ustar(long long npts, const ecwam_b200_fields& f, const ecwam_b200_forcing_next& nx, const double* ufric_next, double alpha,
+                          cudaStream_t st);
 struct GetwndArgs {
   long long npts;
   int nx, lcorrel, licerun, lmaskice;

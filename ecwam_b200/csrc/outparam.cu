@@ -38,6 +38,19 @@ __global__ void k_newwind(long long n, ecwam_b200_fields f, ecwam_b200_forcing_n
   f.cithick[p] = nx.cithick[p]; f.ustra[p] = nx.ustra[p]; f.vstra[p] = nx.vstra[p];
 }
 
+// NEWWIND with the friction velocity as forcing (newwind.F90:141-161, ICODE_WND = 1, 2)
+__global__ void k_newwind_ustar(long long n, ecwam_b200_fields f, ecwam_b200_forcing_next nx, const double* __restrict__ ufric_next, double alpha) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const double USTMIN_RESET_TAUW = 0.08;   // yowwind.F90:20
+  const double us = ufric_next[p];
+  f.ufric[p] = us;
+  const double q = alpha / f.chrnck[p];
+  f.tauw[p] = us < USTMIN_RESET_TAUW ? 0.0 : us * us * (1.0 - q * q);
+  f.wdwave[p] = nx.wdwave[p]; f.aird[p] = nx.aird[p]; f.wstar[p] = nx.wstar[p]; f.cicover[p] = nx.cicover[p];
+  f.cithick[p] = nx.cithick[p]; f.ustra[p] = nx.ustra[p]; f.vstra[p] = nx.vstra[p];
+}
+
 // GETWND's blocking step: WAMWND (wamwnd.F90:120-300, ICODE_WND = 3) + MICEP (micep.F90:84-240, uncoupled) per grid point
 __global__ void k_getwnd(GetwndArgs a, ecwam_b200_fieldg g, ecwam_b200_getwnd_opts o, const int* __restrict__ ifromij,
                          const int* __restrict__ jfromij, ecwam_b200_forcing_next nx) {
@@ -507,6 +520,11 @@ __global__ void __launch_bounds__(32) k_norm_seq(const double* zg /*[ncol][niblo
 }
 }  // namespace
 
+void launch_newwind_ustar(long long npts, const ecwam_b200_fields& f, const ecwam_b200_forcing_next& nx, const double* ufric_next, double alpha,
+                          cudaStream_t st) {
+  if (npts <= 0) return;
+  k_newwind_ustar<<<(unsigned)((npts + 255) / 256), 256, 0, st>>>(npts, f, nx, ufric_next, alpha);
+}
 void launch_newwind(long long npts, const ecwam_b200_fields& f, const ecwam_b200_forcing_next& nx, double acd, double bcd, double epsmin,
                     cudaStream_t st) {
   if (npts <= 0) return;

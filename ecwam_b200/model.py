@@ -381,12 +381,20 @@ class WamIntgr:
         """NEWWIND (newwind.F90:105-167): FF_NOW <- FF_NEXT on the device; nxt maps field names to global arrays."""
         torch = self.torch
         keep, fn = [], L.ForcingNext()
+        usf = self.par.icode_wnd != 3          # the friction velocity is the forcing (nxt["UFRIC"]); FF_NEXT%WSWAVE is not read
         for n in self.NEXT_FIELDS:
+            if usf and n == "wswave":
+                continue
             v = nxt[n] if n in nxt else nxt[n.upper()]
             t = torch.from_numpy(np.ascontiguousarray(np.asarray(v, dtype=np.float64)[self.src])).to(self.device)
             keep.append(t)
             setattr(fn, n, C.cast(t.data_ptr(), C.POINTER(C.c_double)))
-        L.check(self.lib.ecwam_b200_newwind(self.h, C.byref(fn)), "newwind")
+        if usf:
+            us = torch.from_numpy(np.ascontiguousarray(np.asarray(nxt["UFRIC"], dtype=np.float64)[self.src])).to(self.device)
+            keep.append(us)
+            L.check(self.lib.ecwam_b200_newwind_ustar(self.h, C.byref(fn), C.c_void_p(us.data_ptr())), "newwind_ustar")
+        else:
+            L.check(self.lib.ecwam_b200_newwind(self.h, C.byref(fn)), "newwind")
         self.synchronize()      # `keep` may be released once the kernel has read it
 
     def _outsel(self, itg, icemask, seamask, zmiss, llsource):

@@ -59,7 +59,7 @@ typedef struct ecwam_b200_params {
   int lwnemocou;   /* YOWCOUP LWNEMOCOU (needs ecwam_b200_bind_nemo)                   */
   int lwvflx_snl;  /* YOWCOUP LWVFLX_SNL                                                */
   int lwcouast;    /* YOWCOUP LWCOUAST                                                  */
-  int icode_wnd;   /* YOWWNDG ICODE (3 = 10 m wind, only)                               */
+  int icode_wnd;   /* YOWWNDG ICODE: 3 = 10 m wind; 1, 2 = friction velocity / stress (UFRIC is the forcing) */
   int ifrelfmax;   /* YOWSTAT IFRELFMAX (fast-wave sub-stepping, O1280)                 */
   int nproma;      /* YOWPARAM NPROMA_WAM                                               */
   int nchnk;       /* YOWPARAM NCHNK                                                    */
@@ -473,6 +473,11 @@ typedef struct ecwam_b200_forcing_next {
  * low-wind cap on the first-guess wave stress TAUW).  The date bookkeeping (CDATEWH, INCDATE) stays with the caller:
  * call this when NEWWIND's `CDATE >= CDATEWH` test holds.                                                   */
 int ecwam_b200_newwind(ecwam_b200_handle h, const ecwam_b200_forcing_next* next);
+/* The same with the friction velocity as forcing (ICODE_WND = 1, 2; newwind.F90:141-150): FF_NOW%UFRIC <- ufric_next (DEVICE,
+ * (NPROMA, NCHNK)), first-guess TAUW = UFRIC**2 (1 - (ALPHA/CHRNCK)**2), 0 below USTMIN_RESET_TAUW; next->wswave is not read (may be
+ * NULL).  IMPLSCH then derives Z0 and U10 with Z0WAVE in the first SINFLX call (airsea.F90:102-120) -- a branch the reference's own
+ * GPU build removes (`!$loki remove`); the forcing readers WAMWND / GETWND stay ICODE_WND = 3 only.                                  */
+int ecwam_b200_newwind_ustar(ecwam_b200_handle h, const ecwam_b200_forcing_next* next, const double* ufric_next);
 
 /* GETWND's blocking step (src/ecwam/getwnd.F90:196-212): WAMWND (wamwnd.F90:120-300, ICODE_WND = 3) + MICEP
  * (micep.F90:84-240, uncoupled) turn the forcing fields on the forcing grid into the FF_NEXT members that NEWWIND

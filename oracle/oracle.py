@@ -242,8 +242,9 @@ class Oracle:
     NEXT_FIELDS = ("WSWAVE", "WDWAVE", "AIRD", "WSTAR", "CICOVER", "CITHICK", "USTRA", "VSTRA")
 
     def newwind(self, nxt: dict):
-        """NEWWIND (newwind.F90:105-167, ICODE_WND=3): FF_NOW <- FF_NEXT; nxt maps the 8 field names to global arrays."""
-        arrs = [np.ascontiguousarray(nxt[k], dtype=np.float64) for k in self.NEXT_FIELDS]
+        """NEWWIND (newwind.F90:105-167): FF_NOW <- FF_NEXT; nxt maps the 8 field names to global arrays (with ICODE_WND = 1, 2 the
+        friction velocity nxt["UFRIC"] takes the place of WSWAVE)."""
+        arrs = [np.ascontiguousarray(nxt["UFRIC" if (k == "WSWAVE" and self.cfg.icode != 3) else k], dtype=np.float64) for k in self.NEXT_FIELDS]
         ptrs = (C.c_void_p * 8)(*[a.ctypes.data for a in arrs])
         if self.lib.orc_newwind(self.h, ptrs) != 0:
             raise RuntimeError("orc_newwind failed")

@@ -1459,7 +1459,7 @@ void implsch_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int IC
   for (int ICALL = 1; ICALL <= NCALL; ++ICALL) {
     int IUSFG, ICODE_WND;
     if (ICALL == 1) { IUSFG = 0; ICODE_WND = c.icode; } else { IUSFG = 1; ICODE_WND = 3; }
-    if (ICODE_WND != 3) throw std::runtime_error("AIRSEA: only ICODE_WND=3 restated");
+    if (ICODE_WND != 3 && ICODE_WND != 1 && ICODE_WND != 2) throw std::runtime_error("AIRSEA: INVALID VALUE OF ICODE_WND");
     if (ICALL == 1) {
       for (int K = 1; K <= NANG; ++K) for (int IJ = KIJS; IJ <= KIJL; ++IJ) FL1(IJ, K, NFRE) = std::max(FL1(IJ, K, NFRE), FLM(IJ, K));
       if (c.llgcbz0) HALPHAP(x, WAVNUM, COSWDIF, FL1, HALP);
@@ -1467,7 +1467,22 @@ void implsch_chunk(const Config& c, const Tables& t, Fields& f, int KIJL, int IC
     }
     for (int IJ = KIJS; IJ <= KIJL; ++IJ)   // sinflx.F90:117-121
       RNFAC(IJ) = (c.llnormagam && c.llcapchnk) ? 1.0 + t.DTHRN_A * (1.0 + std::tanh(WSWAVE(IJ) - t.DTHRN_U)) : 1.0;
-    TAUT_Z0(x, IUSFG, HALP, WSWAVE, WDWAVE, TAUW, TAUWDIR, RNFAC, UFRIC, Z0M, Z0B, CHRNCK);
+    if (ICODE_WND == 3) TAUT_Z0(x, IUSFG, HALP, WSWAVE, WDWAVE, TAUW, TAUWDIR, RNFAC, UFRIC, Z0M, Z0B, CHRNCK);
+    else {   // the friction velocity is the forcing (airsea.F90:102-120): Z0WAVE (z0wave.F90:68-93), then U10 from the logarithmic profile
+      for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+        const double ALPHAOG = (c.llcapchnk ? CHNKMIN(t, WSWAVE(IJ)) : t.ALPHA) * t.GM1;
+        const double UST2 = UFRIC(IJ) * UFRIC(IJ), UST3 = UFRIC(IJ) * UFRIC(IJ) * UFRIC(IJ);
+        const double ARG = std::max(UST2 - TAUW(IJ), t.EPS1);
+        Z0M(IJ) = ALPHAOG * UST3 / std::sqrt(ARG);
+        Z0B(IJ) = ALPHAOG * UST2;
+        CHRNCK(IJ) = t.G * Z0M(IJ) / UST2;
+      }
+      const double XKAPPAD = 1.0 / t.XKAPPA, XLOGLEV = std::log(t.XNLEV);
+      for (int IJ = KIJS; IJ <= KIJL; ++IJ) {
+        WSWAVE(IJ) = XKAPPAD * UFRIC(IJ) * (XLOGLEV - std::log(Z0M(IJ)));
+        WSWAVE(IJ) = std::max(WSWAVE(IJ), c.wspmin);
+      }
+    }
     int NGST; bool LLPHIWA, LLSNEG;
     if (ICALL < NCALL) { NGST = 1; LLPHIWA = false; LLSNEG = false; } else { NGST = 2; LLPHIWA = true; LLSNEG = true; }
     if (c.iphys == 0) SINPUT_JAN(x, NGST, LLSNEG, FL1, WAVNUM, CINV, XK2CG, WSWAVE, UFRIC, Z0M, COSWDIF, SINWDIF2, RAORW, WSTAR, RNFAC, FLD, SL, SPOS, XLLWS);

@@ -300,7 +300,16 @@ void newwind(Model& m, int ir, const Fields& nx) {
   const double WSPMIN_RESET_TAUW = 4.0;   // yowwind.F90:19
   const double WGHT = 1.0 / std::max(WSPMIN_RESET_TAUW, t.EPSMIN);
   const RankDecomp& r = m.ranks[ir];
+  const double USTMIN_RESET_TAUW = 0.08;  // yowwind.F90:20
   for (int ICHNK = 1; ICHNK <= r.NCHNK; ++ICHNK) {
+    if (m.cfg.icode != 3) {   // newwind.F90:141-150: the forcing is the friction velocity (handed over in nx.WSWAVE's place)
+      for (int IJ = 1; IJ <= r.NPROMA; ++IJ) {
+        f.UFRIC(IJ, ICHNK) = nx.WSWAVE.d[(IJ - 1) + (size_t)r.NPROMA * (ICHNK - 1)];
+        const double q = t.ALPHA / f.CHRNCK(IJ, ICHNK);
+        f.TAUW(IJ, ICHNK) = f.UFRIC(IJ, ICHNK) * f.UFRIC(IJ, ICHNK) * (1.0 - q * q);
+        if (f.UFRIC(IJ, ICHNK) < USTMIN_RESET_TAUW) f.TAUW(IJ, ICHNK) = 0.0;
+      }
+    } else
     for (int IJ = 1; IJ <= r.NPROMA; ++IJ) {
       f.WSWAVE(IJ, ICHNK) = nx.WSWAVE.d[(IJ - 1) + (size_t)r.NPROMA * (ICHNK - 1)];
       if (f.WSWAVE(IJ, ICHNK) < WSPMIN_RESET_TAUW) {

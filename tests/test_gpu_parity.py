@@ -415,6 +415,41 @@ def test_radiative_stress_on_the_ice_and_break_up_memory(built, case, lciwa, ibr
         assert np.abs(o.get_field("TAUICX")).max() > 1e-6
 
 
+@pytest.mark.parametrize("case,icode,extra", [("o48like", 1, {}), ("o640like", 2, {}), ("o48_iphys0", 1, {}),
+                                              ("o48_cy49r1", 1, {})])
+def test_friction_velocity_forcing(built, case, icode, extra):
+    """ICODE_WND = 1, 2 (airsea.F90:102-120, z0wave.F90:68-93, newwind.F90:141-150): the friction velocity is the forcing -- the first
+    SINFLX call derives Z0 from Z0WAVE and U10 from the logarithmic profile (the USF instance of k_point phase 1, which stores WSWAVE),
+    the second call is TAUT_Z0 on that U10; NEWWIND takes FF_NEXT%UFRIC and resets TAUW from the Charnock parameter."""
+    from common import next_forcing
+    g, o, f, fl = make_oracle(case, icode=icode, **extra)
+    _, s, w = make_gpu(case, icode_wnd=icode, **extra)
+    us = np.sqrt(8.0e-4 + 8.0e-5 * f["WSWAVE"]) * f["WSWAVE"]
+    init = dict(UFRIC=us, TAUW=0.4 * us * us, TAUWDIR=f["WDWAVE"], CHRNCK=np.full_like(us, 0.018))
+    for k, v in init.items():
+        o.set_field(k, v)
+        w.set_field(k.lower(), v)
+    for _ in range(2):
+        assert o.step() == 0 and w.step() == 0
+    w.synchronize()
+    check_state(w, o)
+    assert relerr(w.get_field("wswave"), o.get_field("WSWAVE")[w.own]) <= RTOL_FIELD
+    assert relerr(o.get_field("WSWAVE"), f["WSWAVE"]) > 1e-3          # IMPLSCH rewrote U10
+    nxt = next_forcing(f)
+    nxt["UFRIC"] = np.maximum(0.05, 1.3 * us * ((np.arange(us.size) * 13) % 7) / 6.0)      # some below USTMIN_RESET_TAUW
+    o.newwind(nxt); w.newwind(nxt)
+    for nm in ("UFRIC", "WDWAVE", "CICOVER"):
+        np.testing.assert_array_equal(w.get_field(nm.lower()), o.get_field(nm)[w.own], err_msg=nm)
+    # TAUW = u*^2 (1 - (ALPHA/CHRNCK)^2) cancels where the Charnock parameter sits at ALPHA: compare on the scale of u*^2
+    assert np.abs(w.get_field("tauw") - o.get_field("TAUW")[w.own]).max() <= 1e-12 * (nxt["UFRIC"] ** 2).max()
+    assert (o.get_field("TAUW") == 0).any()
+    for _ in range(2):
+        assert o.step() == 0 and w.step() == 0
+    w.synchronize()
+    check_state(w, o)
+    assert relerr(w.get_field("wswave"), o.get_field("WSWAVE")[w.own]) <= RTOL_FIELD
+
+
 def test_current_cfl_fallback(built):
     """LLCFLCUROFF (ctuwdrv.F90:101-121): with a long propagation step and strong current shear the direction / frequency
     weights of the current refraction leave [0,1] at a few points; the second CTUW call switches the current refraction off at
@@ -531,7 +566,7 @@ def test_cfl_violation_is_reported(built):
 def test_unsupported_switches_are_rejected(built):
     from ecwam_b200 import synth
     g = synth.make_grid(8, "aqua")
-    for kw in (dict(irefra=4), dict(isnonlin=3), dict(lciwa=16), dict(icode_wnd=1)):
+    for kw in (dict(irefra=4), dict(isnonlin=3), dict(lciwa=16), dict(icode_wnd=4)):
         s = M.WamSetup(g, nproc=1, **kw)
         with pytest.raises(L.EcwamError):
             M.WamIntgr(s, 0)

@@ -1138,3 +1138,29 @@ def test_radiative_stress_on_the_ice_against_numpy(built):
     assert np.abs(tx).max() > 1e-4 and (ibrmem[ci > 0] <= 0.5).any() and (ibrmem[ci > 0] > 0.5).any()
     np.testing.assert_allclose(o.get_field("TAUICX"), -tx, rtol=1e-10, atol=1e-14 * np.abs(tx).max())
     np.testing.assert_allclose(o.get_field("TAUICY"), -ty, rtol=1e-10, atol=1e-14 * np.abs(ty).max())
+
+
+def test_friction_velocity_forcing_against_numpy(built):
+    """ICODE_WND = 1 (airsea.F90:102-120, z0wave.F90:68-93): with u* as the forcing the first SINFLX call sets
+    Z0 = alpha(U10_old)/g u*^3 / sqrt(max(u*^2 - tau_w, eps)) and U10 = max(u*/kappa ln(10 / Z0), WSPMIN); NEWWIND's u* branch
+    (newwind.F90:141-150) resets TAUW = u*^2 (1 - (ALPHA / CHARNOCK)^2), 0 below 0.08 m/s."""
+    from common import next_forcing
+    g, o, f, fl = make_oracle("o48like", icode=1)
+    u10_old = f["WSWAVE"]
+    us = np.sqrt(8.0e-4 + 8.0e-5 * u10_old) * u10_old
+    tauw = 0.4 * us * us
+    for k, v in dict(UFRIC=us, TAUW=tauw, TAUWDIR=f["WDWAVE"], CHRNCK=np.full_like(us, 0.018)).items():
+        o.set_field(k, v)
+    o.implsch()
+    alpha, alphamin, chnkmin_u = (o.table(k)[0] for k in ("ALPHA", "ALPHAMIN", "CHNKMIN_U"))
+    chnk = alphamin + (alpha - alphamin) * 0.5 * (1.0 - np.tanh(u10_old - chnkmin_u))
+    z0 = chnk * 0.101978381 * us ** 3 / np.sqrt(np.maximum(us ** 2 - tauw, 1e-5))
+    u10 = np.maximum(us / 0.4 * (np.log(10.0) - np.log(z0)), o.cfg.wspmin)
+    np.testing.assert_allclose(o.get_field("WSWAVE"), u10, rtol=1e-13)
+    nxt = next_forcing(f)
+    nxt["UFRIC"] = np.maximum(0.05, 1.3 * us * ((np.arange(us.size) * 13) % 7) / 6.0)
+    ch = o.get_field("CHRNCK")
+    o.newwind(nxt)
+    ref = np.where(nxt["UFRIC"] < 0.08, 0.0, nxt["UFRIC"] ** 2 * (1.0 - (alpha / ch) ** 2))
+    np.testing.assert_allclose(o.get_field("TAUW"), ref, rtol=1e-14)
+    np.testing.assert_array_equal(o.get_field("UFRIC"), nxt["UFRIC"])
