@@ -84,6 +84,7 @@ long orc_get_table(void* h, const char* name, double* out, long cap) {
       {"XK_GC", &t.XK_GC}, {"OMEGA_GC", &t.OMEGA_GC}, {"CM_GC", &t.CM_GC}, {"C2OSQRTVG_GC", &t.C2OSQRTVG_GC},
       {"XKMSQRTVGOC2_GC", &t.XKMSQRTVGOC2_GC}, {"OM3GMKM_GC", &t.OM3GMKM_GC}, {"OMXKM3_GC", &t.OMXKM3_GC},
       {"DELKCC_GC_NS", &t.DELKCC_GC_NS}, {"DELKCC_OMXKM3_GC", &t.DELKCC_OMXKM3_GC}, {"CIDEAC", &t.CIDEAC},
+      {"DFIMFR2", &t.DFIMFR2}, {"XKM_GC", &t.XKM_GC}, {"DELKCC_GC", &t.DELKCC_GC}, {"GOM", &t.GOM}, {"FRM5", &t.FRM5},
       {"ZDELLO", &m->grid.ZDELLO}, {"COSPH", &m->grid.COSPH}, {"SINPH", &m->grid.SINPH}, {"DELLAM", &m->grid.DELLAM}};
   auto it = mp.find(n);
   if (it != mp.end()) return copy_out(it->second->d, out, cap);
@@ -95,7 +96,19 @@ long orc_get_table(void* h, const char* name, double* out, long cap) {
       {"ACDLIN", t.ACDLIN}, {"BCDLIN", t.BCDLIN}, {"BMAXOKAP", t.BMAXOKAP}, {"GAMNCONST", t.GAMNCONST}, {"RN1_RN", t.RN1_RN},
       {"DTHRN_A", t.DTHRN_A}, {"DTHRN_U", t.DTHRN_U}, {"ANG_GC_A", t.ANG_GC_A}, {"ANG_GC_B", t.ANG_GC_B}, {"ANG_GC_C", t.ANG_GC_C},
       {"SQRTGOSURFT", t.SQRTGOSURFT}, {"NWAV_GC", (double)t.NWAV_GC}, {"Z0RAT", t.Z0RAT}, {"Z0TUBMAX", t.Z0TUBMAX},
-      {"SWELLF4", t.SWELLF4}, {"SWELLF7", t.SWELLF7}, {"CDIS", t.CDIS}, {"DELTA_SDIS", t.DELTA_SDIS}, {"CDISVIS", t.CDISVIS}};
+      {"SWELLF4", t.SWELLF4}, {"SWELLF7", t.SWELLF7}, {"CDIS", t.CDIS}, {"DELTA_SDIS", t.DELTA_SDIS}, {"CDISVIS", t.CDISVIS},
+      // every other scalar of the module state (tests/golden/make_ref_golden.py hands them to the translated reference source)
+      {"G", t.G}, {"GM1", t.GM1}, {"ROWATER", t.ROWATER}, {"ROWATERM1", t.ROWATERM1}, {"ZPI4GM1", t.ZPI4GM1}, {"ZPI4GM2", t.ZPI4GM2},
+      {"EPSMIN", t.EPSMIN}, {"EPSUS", t.EPSUS}, {"EPSU10", t.EPSU10}, {"ACD", t.ACD}, {"BCD", t.BCD}, {"CDMAX", t.CDMAX}, {"DKMAX", t.DKMAX},
+      {"TAUOCMIN", t.TAUOCMIN}, {"TAUOCMAX", t.TAUOCMAX}, {"PHIEPSMIN", t.PHIEPSMIN}, {"PHIEPSMAX", t.PHIEPSMAX}, {"WSEMEAN_MIN", t.WSEMEAN_MIN},
+      {"FRATIO", t.FRATIO}, {"WETAIL", t.WETAIL}, {"FRTAIL", t.FRTAIL}, {"WP1TAIL", t.WP1TAIL}, {"WP2TAIL", t.WP2TAIL},
+      {"XKAPPA", t.XKAPPA}, {"XNLEV", t.XNLEV}, {"ZALP", t.ZALP}, {"TAILFACTOR", t.TAILFACTOR}, {"TAILFACTOR_PM", t.TAILFACTOR_PM},
+      {"SWELLF", t.SWELLF}, {"SWELLF2", t.SWELLF2}, {"SWELLF3", t.SWELLF3}, {"SWELLF5", t.SWELLF5}, {"SWELLF6", t.SWELLF6},
+      {"SWELLF7M1", t.SWELLF7M1}, {"ABMIN", t.ABMIN}, {"ABMAX", t.ABMAX}, {"SDSBR", t.SDSBR}, {"SSDSC2", t.SSDSC2}, {"SSDSC3", t.SSDSC3},
+      {"SSDSC4", t.SSDSC4}, {"SSDSC5", t.SSDSC5}, {"SSDSC6", t.SSDSC6}, {"MICHE", t.MICHE}, {"SSDSBRF1", t.SSDSBRF1}, {"BRKPBCOEF", t.BRKPBCOEF},
+      {"ISDSDTH", (double)t.ISDSDTH}, {"ISB", (double)t.ISB}, {"IPSAT", (double)t.IPSAT}, {"EGRCRV", t.EGRCRV}, {"AFCRV", t.AFCRV}, {"BFCRV", t.BFCRV},
+      {"SURFT", t.SURFT}, {"IAB", (double)t.IAB}, {"EPS1", t.EPS1}, {"JTOT_TAUHF", (double)t.JTOT_TAUHF},
+      {"TICMIN", t.TICMIN}, {"HICMIN", t.HICMIN}, {"DTIC", t.DTIC}, {"DHIC", t.DHIC}, {"NICT", (double)t.NICT}, {"NICH", (double)t.NICH}};
   auto is = sc.find(n);
   if (is != sc.end()) { if (cap < 1) return -1; out[0] = is->second; return 1; }
   return 0;

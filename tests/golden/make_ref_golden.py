@@ -1,0 +1,234 @@
+"""Golden vectors from the REFERENCE'S OWN SOURCE (run in the build container only: needs /root/reference).
+
+`f90run.Translator` turns src/ecwam/implsch.F90 and the 43 routines below it into Python statement by statement and executes them
+on a handful of grid points of a synthetic case; the outputs go to tests/golden/ref_implsch_<case>.npz.  tests/test_reference_golden.py
+then checks the oracle (and, on a GPU, the CUDA path) against those files.  What is NOT taken from the reference source: the values of the
+module variables (tables of YOWFRED / YOWINDN / ..., read from the oracle, whose table builders are checked bit for bit against the
+product's independent host builders) and the inputs (the synthetic state of tests/common.py after two steps + PROPAG_WAM).
+
+usage: python tests/golden/make_ref_golden.py [case ...]
+"""
+import os
+import re
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, HERE); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
+
+from f90run import REF, FArr, FInt, Translator  # noqa: E402
+
+FILES = ("implsch sdepthlim semean fkmean sinflx airsea taut_z0 z0wave chnkmin sinput sinput_ard sinput_jan wsigstar femeanws frcutindex "
+         "stresso tau_phi_hf omegagc ns_gc stress_gc halphap femean meansqs_lf sdissip sdissip_ard sdissip_jan snonlin transf transf_snl "
+         "peak_ang sdiwbk sbottom sdice sdice1 sdice2 sdice3 icebreak_modify_attenuation wnfluxes imphftail setice stokestrn stokesdrift "
+         "cimsstrn aki_ice").split()
+MODULES = "yowfred yowpcons yowphys yowice yowcoup yowaltas yowshal yowtabl yowwind yowcurr yowparam yowstat yowindn yowcout".split()
+
+# IMPLSCH's dummy arguments (implsch.F90:10-23) and what they are
+ARGS3 = ("FL1", "XLLWS")
+ARGS2 = ("WAVNUM", "CGROUP", "CIWA", "CINV", "XK2CG", "STOKFAC")
+ARGS1_IN = ("EMAXDPT", "DEPTH", "IBRMEM", "AIRD", "WDWAVE", "CICOVER", "WSWAVE", "WSTAR", "USTRA", "VSTRA", "UFRIC", "TAUW", "TAUWDIR", "Z0M",
+            "Z0B", "CHRNCK", "CITHICK")
+NEMO = ("NEMOUSTOKES", "NEMOVSTOKES", "NEMOSTRN", "NPHIEPS", "NTAUOC", "NSWH", "NMWP", "NEMOTAUX", "NEMOTAUY", "NEMOTAUICX", "NEMOTAUICY",
+        "NEMOWSWAVE", "NEMOPHIF")
+ARGS1_OUT = ("WSEMEAN", "WSFMEAN", "USTOKES", "VSTOKES", "STRNMS", "TAUXD", "TAUYD", "TAUOCXD", "TAUOCYD", "TAUOC", "TAUICX", "TAUICY", "PHIOCD",
+             "PHIEPS", "PHIAW")
+OUT_CHECK = ("UFRIC", "TAUW", "TAUWDIR", "Z0M", "Z0B", "CHRNCK", "WSWAVE") + ARGS1_OUT + NEMO
+
+
+def module_parameters():
+    """PARAMETER constants of the YOW* modules, evaluated from their declarations (yowfred.F90: FRIC, WP2TAIL, ...)."""
+    from f90run import RUNTIME, _logical_lines, _split_top
+    ns = dict(RUNTIME)
+    ns.update(JWRB=8, JWRU=8, JWIM=4, JWRO=8, JPHOOK=8)
+    tr = Translator([])
+    dummy = type("R", (), dict(arrays=set(), stmtfun=set(), name="MODULE"))()
+    out = {}
+    for m in MODULES:
+        p = os.path.join(REF, m + ".F90")
+        if not os.path.exists(p):
+            continue
+        for ln in _logical_lines(p, [REF]):
+            mm = re.match(r"^(REAL|INTEGER|LOGICAL)\s*(\((?:[^()]|\([^()]*\))*\))?\s*(.*?)::\s*(.*)$", ln)
+            if not mm or "PARAMETER" not in mm.group(3) or "DIMENSION" in mm.group(3):
+                continue
+            for ent in _split_top(mm.group(4)):
+                em = re.match(r"^(\w+)\s*=\s*(.*)$", ent)
+                if not em:
+                    continue
+                try:
+                    v = eval(tr.expr(dummy, em.group(2)), ns)
+                except Exception:
+                    continue
+                ns[em.group(1)] = v
+                out[em.group(1)] = v
+    return out
+
+
+def namespace(o, cfg_extra):
+    """Module variables for the translated routines: constants from the module sources, tables from the oracle, switches from its Config."""
+    c = o.cfg
+    ns = module_parameters()
+    I = lambda v: FInt(int(v))
+    F = lambda n: float(o.table(n)[0])
+    for n in ("G GM1 ZPI ROWATER ROWATERM1 ZPI4GM1 ZPI4GM2 EPSMIN EPSUS EPSU10 ACD BCD CDMAX DKMAX TAUOCMIN TAUOCMAX PHIEPSMIN PHIEPSMAX "
+              "WSEMEAN_MIN FRATIO WETAIL FRTAIL WP1TAIL WP2TAIL DELTH FLOGSPRDM1 XKAPPA XNLEV ZALP TAILFACTOR TAILFACTOR_PM SWELLF SWELLF2 "
+              "SWELLF3 SWELLF4 SWELLF5 SWELLF6 SWELLF7 SWELLF7M1 ABMIN ABMAX SDSBR SSDSC2 SSDSC3 SSDSC4 SSDSC5 SSDSC6 MICHE SSDSBRF1 BRKPBCOEF "
+              "EGRCRV AFCRV BFCRV SURFT EPS1 TICMIN HICMIN DTIC DHIC X0TAUHF BETAMAXOXKAPPA2 TAUWSHELTER ALPHA ALPHAMIN ALPHAMAX ALPHAPMAX "
+              "CHNKMIN_U ACDLIN BCDLIN BMAXOKAP GAMNCONST RN1_RN DTHRN_A DTHRN_U ANG_GC_A ANG_GC_B ANG_GC_C SQRTGOSURFT Z0RAT Z0TUBMAX CDIS "
+              "DELTA_SDIS CDISVIS DAL1 DAL2").split():
+        ns[n] = F(n)
+    for n in "ISDSDTH ISB IPSAT IAB JTOT_TAUHF NICT NICH NWAV_GC".split():
+        ns[n] = I(F(n))
+    for n in "NSDSNTH MFRSTLW MLSTHG KFRH NFRE_ODD".split():
+        ns[n] = I(o.itable(n)[0])
+    ns.update(NANG=I(c.nang), NFRE=I(c.nfre), NFRE_RED=I(c.nfre_red), IPHYS=I(c.iphys), ISNONLIN=I(c.isnonlin), IDAMPING=I(c.idamping),
+              ICODE=I(c.icode), ICODE_CPL=I(c.icode), IDELT=I(int(c.idelt)), XIMP=float(c.ximp), RNU=float(c.rnu), RNUM=float(c.rnum), WSPMIN=float(c.wspmin),
+              CITHRSH=float(c.cithrsh), CITHRSH_TAIL=float(c.cithrsh_tail), CIBLOCK=float(c.ciblock), FLMIN=float(c.flmin), BATHYMAX=float(c.bathymax),
+              ZALPFACX=float(c.zalpfacx), ZALPFACB=float(c.zalpfacb), CDICWA=float(c.cdicwa), ZALPWRS=float(c.zalpwrs), ZIBRW_THRSH=float(c.zibrw_thrsh),
+              LBIWBK=bool(c.lbiwbk), LICERUN=bool(c.licerun), LMASKICE=bool(c.lmaskice), LWAMRSETCI=bool(c.lwamrsetci), LCIWA1=bool(c.lciwa1),
+              LCIWA2=bool(c.lciwa2), LCIWA3=bool(c.lciwa3), LCISCAL=bool(c.lciscal), LLGCBZ0=bool(c.llgcbz0), LLNORMAGAM=bool(c.llnormagam),
+              LLCAPCHNK=bool(c.llcapchnk), LLUNSTR=False, LWCOU=bool(c.lwcou), LWCOUAST=bool(c.lwcouast), LWFLUX=bool(c.lwflux),
+              LWFLUXOUT=bool(c.lwfluxout), LWNEMOCOU=bool(c.lwnemocou), LWNEMOCOUIBR=bool(c.lwnemocouibr), LWNEMOCOUSEND=bool(c.lwnemocousend),
+              LWNEMOCOUSTK=bool(c.lwnemocoustk), LWNEMOCOUSTRN=bool(c.lwnemocoustrn), LWNEMOCOUWRS=bool(c.lwnemocouwrs),
+              LWNEMOTAUOC=bool(c.lwnemotauoc), LWVFLX_SNL=bool(c.lwvflx_snl), LHOOK=False)
+    ns.update(cfg_extra)
+    A, NF = int(c.nang), int(c.nfre)
+    for n in "FR DFIM DFIMOFR DFIMFR DFIMFR2 ZPIFR FR5 COFRM4 FLMAX RHOWG_DFIM DFIM_SIM".split():
+        ns[n] = FArr.of(o.table(n)[:NF])
+    for n in "TH COSTH SINTH".split():
+        ns[n] = FArr.of(o.table(n)[:A])
+    ns["SWELLFT"] = FArr.of(o.table("SWELLFT"))
+    ns["WTAUHF"] = FArr.of(o.table("WTAUHF"))
+    ns["CIDEAC"] = FArr.of(o.table("CIDEAC").reshape((int(ns["NICT"]), int(ns["NICH"])), order="F"))
+    ng = int(ns["NWAV_GC"])
+    if ng > 0:
+        for n in "XK_GC XKM_GC OMEGA_GC CM_GC C2OSQRTVG_GC XKMSQRTVGOC2_GC OM3GMKM_GC OMXKM3_GC DELKCC_GC_NS DELKCC_OMXKM3_GC DELKCC_GC".split():
+            ns[n] = FArr.of(o.table(n)[:ng])
+    if c.iphys == 1:
+        ns2 = 2 * int(ns["NSDSNTH"]) + 1
+        ns["INDICESSAT"] = FArr.of(o.itable("INDICESSAT").reshape((A, ns2), order="F"))
+        ns["SATWEIGHTS"] = FArr.of(o.table("SATWEIGHTS").reshape((A, ns2), order="F"))
+    else:    # SDISSIP_ARD is translated with the rest of the tree but never called: its tables only have to exist
+        ns["INDICESSAT"] = FArr.of(np.ones((A, 1), dtype=np.int64)); ns["SATWEIGHTS"] = FArr.of(np.zeros((A, 1)))
+    lo, hi = int(ns["MFRSTLW"]), int(ns["MLSTHG"])
+    for n in "IKP IKP1 IKM IKM1".split():
+        ns[n] = FArr.of(o.itable(n), lb=[lo])
+    for n in "AF11 FKLAP FKLAP1 FKLAM FKLAM1".split():
+        ns[n] = FArr.of(o.table(n), lb=[lo])
+    for n in "K1W K2W K11W K21W".split():
+        ns[n] = FArr.of(o.itable(n).reshape((A, 2), order="F"))
+    ns["INLCOEF"] = FArr.of(o.itable("INLCOEF").reshape((5, hi), order="F"))
+    ns["RNLCOEF"] = FArr.of(o.table("RNLCOEF").reshape((25, hi), order="F"))
+    return ns
+
+
+def shelf(g):
+    """a 3 - 80 m shelf in the northern half: depth-limited points (SDEPTHLIM, SDIWBK), finite-depth DIA scaling, bottom friction"""
+    n = g.depth.size
+    g.depth[n // 2:] = 3.0 + 77.0 * ((np.arange(n - n // 2) * 29) % 97) / 96.0
+
+
+def prepare(case, kw, steps, hook):
+    """The state IMPLSCH starts from: `steps` WAMINTGR steps of the synthetic case + PROPAG_WAM (shared with tests/test_reference_golden.py)."""
+    from common import make_oracle
+    g, o, f, fl = make_oracle(case, grid_hook=shelf if hook else None, **kw)
+    n = g.niblo
+    ci = f["CICOVER"]
+    o.set_field("CITHICK", np.where(ci > 0, 0.3 + 1.5 * ci, 0.0))
+    o.set_field("IBRMEM", ((np.arange(n) * 7) % 5 < 2) * 1.0)
+    if kw.get("icode", 3) != 3:
+        us = np.sqrt(8.0e-4 + 8.0e-5 * f["WSWAVE"]) * f["WSWAVE"]
+        for k, v in dict(UFRIC=us, TAUW=0.4 * us * us, TAUWDIR=f["WDWAVE"], CHRNCK=np.full_like(us, 0.018)).items():
+            o.set_field(k, v)
+    for _ in range(steps):
+        assert o.step() == 0
+    assert o.propag() == 0
+    return g, o, f
+
+
+def pick_points(g, o, f, k=12):
+    """a few points of every kind: strongest / weakest wind, most ice, ice edge, shallowest, deepest, highest / lowest waves + a regular stride"""
+    n = g.niblo
+    hs = o.hs_fm()[0]
+    cand = []
+    for key, arr in (("wind", f["WSWAVE"]), ("ice", f["CICOVER"]), ("depth", -g.depth), ("hs", hs)):
+        order = np.argsort(arr)
+        cand += [int(order[-1]), int(order[-2]), int(order[0])]
+    edge = np.nonzero((f["CICOVER"] > 0.05) & (f["CICOVER"] < 0.5))[0]
+    cand += [int(x) for x in edge[:2]]
+    cand += [int(x) for x in np.linspace(5, n - 7, k).astype(int)]
+    out = []
+    for c in cand:
+        if c not in out:
+            out.append(c)
+    return np.array(sorted(out))
+
+
+def run_case(name, case, pts=None, steps=2, hook=False, **kw):
+    g, o, f = prepare(case, kw, steps, hook)
+    pts = pick_points(g, o, f) if pts is None else np.asarray(pts)
+    K = len(pts)
+    A, NF = o.cfg.nang, o.cfg.nfre
+    t0 = time.time()
+    T = Translator([x + ".F90" for x in FILES])
+    ns = T.compile(["IMPLSCH"], namespace(o, {}))
+    missing = [k for k in T.needed(["IMPLSCH"]) if k not in ns and k not in ("ENVIRONMENT", "FORCING_FIELDS", "FREQUENCY", "INTGT_PARAM_FIELDS", "WAVE2OCEAN")]
+    assert not missing, missing
+    arg = {}
+    fl1 = o.get_fl1()[:, :, pts]                       # [m, k, ij]
+    arg["FL1"] = FArr.of(np.ascontiguousarray(fl1.transpose(2, 1, 0)))
+    arg["XLLWS"] = FArr([(1, K), (1, A), (1, NF)])
+    for nm in ARGS2:
+        arg[nm] = FArr.of(np.ascontiguousarray(o.get_field3(nm)[:, pts].T))
+    for nm in ARGS1_IN + ARGS1_OUT + NEMO:
+        arg[nm] = FArr.of(o.get_field(nm)[pts])
+    arg["IOBND"] = FArr.of(np.ones(K, dtype=np.int64)); arg["IODP"] = FArr.of(np.ones(K, dtype=np.int64))
+    arg["MIJ"] = FArr.of(np.full(K, NF, dtype=np.int64))
+    inputs = {k: v.a.copy() for k, v in arg.items()}
+    order = T.routines["IMPLSCH"].args
+    ns["IMPLSCH"](*[FInt(1) if a == "KIJS" else FInt(K) if a == "KIJL" else arg[a] for a in order])
+    print("%s: the reference source ran on %d points in %.1f s" % (name, K, time.time() - t0))
+    import json
+    out = dict(case=case, pts=pts, steps=steps, hook=int(hook), kw=json.dumps(kw, sort_keys=True))
+    out["FL1"] = arg["FL1"].a.transpose(2, 1, 0); out["XLLWS"] = arg["XLLWS"].a.transpose(2, 1, 0); out["MIJ"] = arg["MIJ"].a
+    for nm in OUT_CHECK:
+        out[nm] = arg[nm].a
+    # how far the oracle is from it (printed, and asserted by the test)
+    o.implsch()
+    a, b = o.get_fl1()[:, :, pts], out["FL1"]
+    print("   FL1 max rel %.2e   MIJ equal %s   XLLWS equal %s" % (np.abs(a - b).max() / np.abs(b).max(), (o.get_field("MIJ")[pts] == out["MIJ"]).all(),
+                                                                   (o.get_xllws()[:, :, pts] == out["XLLWS"]).all()))
+    for nm in OUT_CHECK:
+        x, y = o.get_field(nm)[pts], out[nm]
+        print("   %-12s %.2e" % (nm, np.abs(x - y).max() / max(np.abs(y).max(), 1e-300)))
+    np.savez_compressed(os.path.join(HERE, "ref_implsch_%s.npz" % name), **out)
+
+
+ICE = dict(lmaskice=0, lciwa1=1, lciwa2=1, lciwa3=1, lciscal=1, zalpfacx=0.6, zalpfacb=0.8)
+CASES = {
+    "ard": dict(case="o48like"),                                               # etopo1_oper_an_fc_O48.yml physics
+    "jan": dict(case="o48_iphys0"),                                            # ..._O48_iphys_0.yml
+    "a24": dict(case="o320like"),                                              # O320 spectral setting
+    "a36_shelf": dict(case="o640like", hook=True),                             # O640 spectral setting, depth-limited points
+    "cy49r1": dict(case="o48_cy49r1"),                                         # LLGCBZ0 + LLNORMAGAM
+    "cy49r1_jan": dict(case="o48_iphys0_gc"),
+    "ice": dict(case="o48like", kw=ICE),                                       # SDICE1 + 2 + 3 + LCISCAL under the ice
+    "ice2_jan": dict(case="o48_iphys0", kw=dict(lmaskice=0, lciwa2=1)),
+    "nemo": dict(case="o48like", kw=dict(lwnemocou=1, lwnemotauoc=1, lwnemocoustk=1, lwnemocoustrn=1, lwnemocouwrs=1, lwnemocouibr=1,
+                                         lmaskice=0, lciwa3=1, zalpfacx=0.6, zalpwrs=0.8)),
+    "snl1_shelf": dict(case="o48like", hook=True, kw=dict(isnonlin=1)),
+    "snl2_shelf": dict(case="o48_iphys0", hook=True, kw=dict(isnonlin=2)),
+    "noflxsnl": dict(case="o48like", kw=dict(lwvflx_snl=0)),
+    "ustar": dict(case="o48like", kw=dict(icode=1)),
+    "lwflux": dict(case="o48like", kw=dict(lwflux=1, lwcouast=0)),
+}
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(CASES)
+    for nm in names:
+        c = CASES[nm]
+        run_case(nm, c["case"], hook=c.get("hook", False), **c.get("kw", {}))

@@ -1,0 +1,119 @@
+"""Parity against the REFERENCE'S OWN SOURCE.  tests/golden/ref_implsch_*.npz hold the outputs of src/ecwam/implsch.F90 and the 43 routines
+below it, executed statement by statement by tests/golden/f90run.py (a Fortran-subset -> Python translator; the image has no Fortran
+compiler) on 24 grid points of 14 configurations -- made in the build container by tests/golden/make_ref_golden.py, which is the only
+place that reads /root/reference.  Tolerances: spectra 1e-13 (oracle) / 1e-11 (CUDA path, whose input state is its own two steps),
+MIJ and XLLWS exact, integrated fields 1e-12 / 1e-10 of the field's maximum."""
+import glob
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import make_ref_golden as G  # noqa: E402
+
+FILES = sorted(glob.glob(os.path.join(HERE, "golden", "ref_implsch_*.npz")))
+NAMES = [os.path.basename(f)[len("ref_implsch_"):-4] for f in FILES]
+
+
+def _load(name):
+    z = np.load(os.path.join(HERE, "golden", "ref_implsch_%s.npz" % name))
+    return z, str(z["case"]), json.loads(str(z["kw"])), int(z["steps"]), bool(int(z["hook"])), z["pts"]
+
+
+def test_the_fixtures_cover_every_switch():
+    assert len(NAMES) >= 14
+    kws = [json.loads(str(np.load(f)["kw"])) for f in FILES]
+    for key in ("lciwa1", "lciwa2", "lciwa3", "lciscal", "lwnemocou", "lwnemocouwrs", "lwnemocouibr", "lwnemocoustrn", "isnonlin", "lwvflx_snl",
+                "icode", "lwflux"):
+        assert any(key in k for k in kws), key
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_matches_the_reference_source(built, name):
+    z, case, kw, steps, hook, pts = _load(name)
+    g, o, f = G.prepare(case, kw, steps, hook)
+    o.implsch()
+    a, b = o.get_fl1()[:, :, pts], z["FL1"]
+    assert np.abs(a - b).max() <= 1e-13 * np.abs(b).max()
+    big = b > 1e-8 * b.max()
+    assert (np.abs(a - b)[big] / b[big]).max() <= 1e-12
+    np.testing.assert_array_equal(o.get_xllws()[:, :, pts], z["XLLWS"])
+    np.testing.assert_array_equal(o.get_field("MIJ")[pts], z["MIJ"])
+    for nm in G.OUT_CHECK:
+        x, y = o.get_field(nm)[pts], z[nm]
+        assert np.abs(x - y).max() <= 1e-12 * max(np.abs(y).max(), 1e-30), nm
+    assert z["FL1"].max() > 1e-3 and (z["MIJ"] < o.cfg.nfre).any()            # the fixture is not trivial
+    if kw.get("lwnemocou"):
+        assert z["NSWH"].min() > 0 and np.abs(z["NEMOTAUX"]).max() > 0 and z["STRNMS"].max() > 0 and np.abs(z["TAUICX"]).max() > 1e-6
+
+
+@pytest.mark.skipif(not os.path.isdir(G.REF), reason="the reference tree exists in the build container only")
+def test_the_generator_reproduces_a_fixture(built):
+    """Runs the translator on the reference source again (4 points of the first case) and compares with the committed file bit for bit."""
+    from f90run import FArr, FInt, Translator
+    z, case, kw, steps, hook, pts = _load("ard")
+    g, o, f = G.prepare(case, kw, steps, hook)
+    sub = np.arange(0, len(pts), 6)
+    p = pts[sub]
+    T = Translator([x + ".F90" for x in G.FILES])
+    ns = T.compile(["IMPLSCH"], G.namespace(o, {}))
+    K, A, NF = len(p), o.cfg.nang, o.cfg.nfre
+    arg = {"FL1": FArr.of(np.ascontiguousarray(o.get_fl1()[:, :, p].transpose(2, 1, 0))), "XLLWS": FArr([(1, K), (1, A), (1, NF)])}
+    for nm in G.ARGS2:
+        arg[nm] = FArr.of(np.ascontiguousarray(o.get_field3(nm)[:, p].T))
+    for nm in G.ARGS1_IN + G.ARGS1_OUT + G.NEMO:
+        arg[nm] = FArr.of(o.get_field(nm)[p])
+    arg["IOBND"] = FArr.of(np.ones(K, dtype=np.int64)); arg["IODP"] = FArr.of(np.ones(K, dtype=np.int64))
+    arg["MIJ"] = FArr.of(np.full(K, NF, dtype=np.int64))
+    ns["IMPLSCH"](*[FInt(1) if a == "KIJS" else FInt(K) if a == "KIJL" else arg[a] for a in T.routines["IMPLSCH"].args])
+    np.testing.assert_array_equal(arg["FL1"].a.transpose(2, 1, 0), z["FL1"][:, :, sub])
+    np.testing.assert_array_equal(arg["MIJ"].a, z["MIJ"][sub])
+    np.testing.assert_array_equal(arg["UFRIC"].a, z["UFRIC"][sub])
+    assert len(T.routines) == 44
+
+
+GPU_KEYS = dict(icode="icode_wnd")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_cuda_path_matches_the_reference_source(built, name):
+    from common import make_gpu
+    z, case, kw, steps, hook, pts = _load(name)
+    gkw = {GPU_KEYS.get(k, k): v for k, v in kw.items() if not k.startswith("lciwa") and k != "lciscal"}
+    lciwa = (1 if kw.get("lciwa1") else 0) | (2 if kw.get("lciwa2") else 0) | (4 if kw.get("lciwa3") else 0) | (8 if kw.get("lciscal") else 0)
+    if lciwa:
+        gkw["lciwa"] = lciwa
+    g, s, w = make_gpu(case, grid_hook=G.shelf if hook else None, **gkw)
+    from ecwam_b200 import synth
+    f = synth.make_forcing(g)
+    n = g.niblo
+    ci = f["CICOVER"]
+    w.set_field("cithick", np.where(ci > 0, 0.3 + 1.5 * ci, 0.0))
+    if "ibrmem" in w.t:
+        w.set_field("ibrmem", ((np.arange(n) * 7) % 5 < 2) * 1.0)
+    if kw.get("icode", 3) != 3:
+        us = np.sqrt(8.0e-4 + 8.0e-5 * f["WSWAVE"]) * f["WSWAVE"]
+        for k, v in dict(ufric=us, tauw=0.4 * us * us, tauwdir=f["WDWAVE"], chrnck=np.full_like(us, 0.018)).items():
+            w.set_field(k, v)
+    for _ in range(steps):
+        assert w.step() == 0
+    assert w.propag() == 0
+    w.implsch()
+    w.synchronize()
+    inv = np.empty(n, dtype=np.int64)
+    inv[w.own] = np.arange(n)
+    q = inv[pts]
+    a, b = w.get_spec("fl1")[:, :, q], z["FL1"]
+    assert np.abs(a - b).max() <= 1e-11 * np.abs(b).max()
+    np.testing.assert_array_equal(w.get_spec("xllws")[:, :, q], z["XLLWS"])
+    np.testing.assert_array_equal(w.get_field("mij")[q], z["MIJ"])
+    for nm in G.OUT_CHECK:
+        if nm.lower() not in w.t:
+            continue
+        x, y = w.get_field(nm.lower())[q], z[nm]
+        assert np.abs(x - y).max() <= 1e-10 * max(np.abs(y).max(), 1e-12), nm
