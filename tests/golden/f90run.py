@@ -214,13 +214,17 @@ def F_TINY(x): return 2.2250738585072014e-308
 def F_HUGE(x): return 1.7976931348623157e308 if isinstance(x, float) else FInt(2147483647)
 def F_ATAN2(a, b): return np.arctan2(a, b) if (_isarr(a) or _isarr(b)) else math.atan2(float(a), float(b))
 def F_ALLOCATED(x): return x is not None
+def F_ICONV(v): return v if isinstance(v, int) else FInt(int(v))          # REAL -> INTEGER on assignment: truncation
+def F_RCONV(v): return float(v) if isinstance(v, int) and not isinstance(v, bool) else v     # INTEGER -> REAL on assignment
 def F_PRESENT(x): return x is not None
+def F_SIZE(x, d=None): return FInt(x.a.size if d is None else x.a.shape[int(d) - 1])
+def F_KIND(x): return FInt(8 if (isinstance(x, FArr) and x.kind is float) or isinstance(x, float) else 4)
 
 
 RUNTIME = dict(JWRB=8, JWRU=8, JWRO=8, JWIM=4, JPHOOK=8, FInt=FInt, FArr=FArr, frange=frange, fpow=fpow, np=np, math=math,
                F_MAX=F_MAX, F_MIN=F_MIN, F_SIGN=F_SIGN, F_MOD=F_MOD, F_ABS=F_ABS, F_INT=F_INT, F_NINT=F_NINT, F_FLOOR=F_FLOOR,
                F_CEILING=F_CEILING, F_REAL=F_REAL, F_MERGE=F_MERGE, F_SUM=F_SUM, F_MAXVAL=F_MAXVAL, F_MINVAL=F_MINVAL, F_EPSILON=F_EPSILON,
-               F_TINY=F_TINY, F_HUGE=F_HUGE, F_ATAN2=F_ATAN2, F_ALLOCATED=F_ALLOCATED, F_PRESENT=F_PRESENT,
+               F_TINY=F_TINY, F_HUGE=F_HUGE, F_ATAN2=F_ATAN2, F_ALLOCATED=F_ALLOCATED, F_ICONV=F_ICONV, F_RCONV=F_RCONV, F_PRESENT=F_PRESENT, F_KIND=F_KIND, F_SIZE=F_SIZE,
                F_SQRT=_fun1(math.sqrt, np.sqrt), F_EXP=_fun1(math.exp, np.exp), F_LOG=_fun1(math.log, np.log),
                F_LOG10=_fun1(math.log10, np.log10), F_TANH=_fun1(math.tanh, np.tanh), F_SINH=_fun1(math.sinh, np.sinh),
                F_COSH=_fun1(math.cosh, np.cosh), F_COS=_fun1(math.cos, np.cos), F_SIN=_fun1(math.sin, np.sin),
@@ -298,9 +302,30 @@ def _logical_lines(path, include_dirs):
         cur = (cur + " " + s) if cur else s
         if not cont:
             for part in _split_semicolon(cur):
-                out.append(part.upper() if "'" not in part and '"' not in part else part.upper())
+                part = part.upper()
+                if "'" not in part and '"' not in part:
+                    part = re.sub(r"\s*%\s*", "_", part)          # derived-type components become plain names (BLK2GLO%KXLT -> BLK2GLO_KXLT)
+                out.append(part)
             cur = ""
-    return out
+    # `IF (c) GO TO n` ... `n CONTINUE` directly in front of END DO is a CYCLE; other GO TOs are not supported
+    labels = {}
+    for i, ln in enumerate(out):
+        m = re.match(r"^(\d+)\s+CONTINUE$", ln)
+        if m:
+            labels[m.group(1)] = i
+    res = []
+    for i, ln in enumerate(out):
+        if re.match(r"^\d+\s+CONTINUE$", ln):
+            continue
+        m = re.search(r"\bGO\s*TO\s+(\d+)$", ln)
+        if m:
+            j = labels.get(m.group(1))
+            if j is not None and j + 1 < len(out) and re.match(r"^END\s*DO$", out[j + 1]):
+                ln = ln[:m.start()] + "CYCLE"
+            else:
+                ln = ln[:m.start()] + "CALL ABORT1"      # unsupported GO TO: fails if reached
+        res.append(ln)
+    return res
 
 
 def _split_semicolon(s):
@@ -341,9 +366,35 @@ _DOT = {".AND.": " and ", ".OR.": " or ", ".NOT.": " not ", ".TRUE.": " True ", 
         ".LT.": "<", ".LE.": "<=", ".GT.": ">", ".GE.": ">=", ".EQV.": "==", ".NEQV.": "!="}
 
 
+def module_registry(modules, include_dirs=(REF,)):
+    """name -> (dtype, is_array) of the variables declared in the given YOW* module files"""
+    reg = {}
+    for m in modules:
+        p = m if os.path.isabs(m) else os.path.join(REF, m + ".F90")
+        if not os.path.exists(p):
+            continue
+        for ln in _logical_lines(p, list(include_dirs)):
+            mm = re.match(r"^(REAL|INTEGER|LOGICAL)\s*(\((?:[^()]|\([^()]*\))*\))?\s*(.*?)::\s*(.*)$", ln)
+            if not mm:
+                continue
+            typ = {"REAL": float, "INTEGER": int, "LOGICAL": bool}[mm.group(1)]
+            arr_attr = "DIMENSION" in mm.group(3)
+            for ent in _split_top(mm.group(4)):
+                em = re.match(r"^(\w+)\s*(\(.*\))?", ent)
+                if em:
+                    reg[em.group(1)] = (typ, arr_attr or em.group(2) is not None)
+                    if em.group(2) is not None and ":" not in em.group(2):
+                        STATIC_DIMS[em.group(1)] = (typ, _split_top(em.group(2)[1:-1]))
+    return reg
+
+
+STATIC_DIMS = {}     # module arrays with explicit shape (WTAUHF(JTOT_TAUHF), SWELLFT(IAB)): name -> (dtype, [dim expressions])
+
+
 class Translator:
-    def __init__(self, files, include_dirs=(REF,)):
+    def __init__(self, files, include_dirs=(REF,), registry=None):
         self.routines = {}
+        self.registry = registry or {}
         for f in files:
             self._parse_file(f if os.path.isabs(f) else os.path.join(REF, f), list(include_dirs))
         self.global_arrays = set()        # module arrays (names bound to FArr in the namespace)
@@ -482,6 +533,9 @@ class Translator:
         r.outs = outs
         res = r.result if r.kind == "FUNCTION" else None
         ret = "return " + (res if res else ("(" + ", ".join(outs) + ("," if len(outs) == 1 else "") + ")" if outs else "None"))
+        used = sorted({v for lst in r.uses.values() for v in lst if re.match(r"^[A-Z_][A-Z0-9_]*$", v)} - set(r.args) - set(r.decl))
+        if used:
+            emit("global " + ", ".join(used))
         # PARAMETERs and local arrays
         for nm, d in r.decl.items():
             if d["param"] and d["init"] is not None and not d["dims"]:
@@ -518,7 +572,7 @@ class Translator:
             lines.append("    " * (ind + extra) + s)
         if re.match(r"^IF\s*\(\s*LHOOK\s*\)", ln) or re.match(r"^(WRITE|PRINT|FORMAT|CALL\s+FLUSH|CALL\s+GSTATS)\b", ln) or re.match(r"^\d+\s+FORMAT", ln):
             return
-        if re.match(r"^CONTINUE$", ln):
+        if re.match(r"^CONTINUE$", ln) or re.match(r"^INCLUDE\b", ln):
             return
         m = re.match(r"^DO\s+WHILE\s*\((.*)\)$", ln)
         if m:
@@ -576,8 +630,27 @@ class Translator:
             cond, rest = ln[m.end(): j - 1], ln[j:].strip()
             emit("if %s:" % self.expr(r, cond))
             stack.append("IF1")
+            n0 = len(lines)
             self._stmt(r, rest, None, None, stack, ret, lines)
+            if len(lines) == n0:
+                lines.append("    " * (ind + 1) + "pass")
             stack.pop()
+            return
+        m = re.match(r"^ALLOCATE\s*\((.*)\)$", ln)
+        if m:
+            for ent in _split_top(m.group(1)):
+                em = re.match(r"^(\w+)\s*\((.*)\)$", ent)
+                if not em:
+                    continue          # STAT= and the like
+                nm = em.group(1)
+                b = []
+                for x in _split_top(em.group(2)):
+                    lo, hi = (x.split(":") + [None])[:2] if ":" in x else ("1", x)
+                    b.append("(%s, %s)" % (self.expr(r, lo), self.expr(r, hi)))
+                typ = r.decl[nm]["type"] if nm in r.decl else self.registry.get(nm, (float, True))[0]
+                emit("%s = FArr([%s], %s)" % (nm, ", ".join(b), {float: "float", int: "int", bool: "bool"}[typ]))
+            return
+        if re.match(r"^DEALLOCATE\b", ln):
             return
         m = re.match(r"^CALL\s+(\w+)\s*(?:\((.*)\))?$", ln)
         if m:
@@ -621,11 +694,16 @@ class Translator:
         if r.kind == "FUNCTION" and nm == r.result and lm.group(2) is None:
             emit("%s = %s" % (nm, self.expr(r, rhs)))
             return
+        if lm.group(2) is None:      # scalar: Fortran converts to the declared type of the left-hand side
+            typ = r.decl[nm]["type"] if nm in r.decl else self.registry.get(nm, (None, False))[0]
+            conv = {int: "F_ICONV(%s)", float: "F_RCONV(%s)"}.get(typ, "%s")
+            emit("%s = %s" % (nm, conv % self.expr(r, rhs)))
+            return
         emit("%s = %s" % (self.expr(r, lhs), self.expr(r, rhs)))
 
     def compile(self, names, namespace):
         """Translate `names` (and everything they call) and exec the result in `namespace` (module variables must be in it)."""
-        self.global_arrays = {k for k, v in namespace.items() if isinstance(v, FArr)}
+        self.global_arrays = {k for k, v in namespace.items() if isinstance(v, FArr)} | {k for k, (t, a) in self.registry.items() if a}
         for n in names:
             self.translate(n)
         ns = dict(RUNTIME)

@@ -53,7 +53,7 @@ def module_parameters():
             continue
         for ln in _logical_lines(p, [REF]):
             mm = re.match(r"^(REAL|INTEGER|LOGICAL)\s*(\((?:[^()]|\([^()]*\))*\))?\s*(.*?)::\s*(.*)$", ln)
-            if not mm or "PARAMETER" not in mm.group(3) or "DIMENSION" in mm.group(3):
+            if not mm or "DIMENSION" in mm.group(3):      # PARAMETERs and initialised module variables (G = 9.806, CIRC, ...)
                 continue
             for ent in _split_top(mm.group(4)):
                 em = re.match(r"^(\w+)\s*=\s*(.*)$", ent)
@@ -208,6 +208,84 @@ def run_case(name, case, pts=None, steps=2, hook=False, **kw):
     np.savez_compressed(os.path.join(HERE, "ref_implsch_%s.npz" % name), **out)
 
 
+TABLE_FILES = "iniwcst mfredir mfr setwavphys init_x0tauhf init_sdiss_ardh inisnonlin nlweigt jafu initgc cigetdeac".split()
+TABLE_MODULES = MODULES + ["yowgridgen"]
+# name in the oracle -> kind (t = real table, i = integer table, s = scalar)
+TABLE_CHECK = dict(FR="t", DFIM="t", GOM="t", TH="t", COSTH="t", SINTH="t", X0TAUHF="s", WTAUHF="t", SATWEIGHTS="t", INDICESSAT="i", IKP="i", IKP1="i",
+                   IKM="i", IKM1="i", K1W="i", K2W="i", K11W="i", K21W="i", AF11="t", FKLAP="t", FKLAP1="t", FKLAM="t", FKLAM1="t", FRH="t",
+                   INLCOEF="i", RNLCOEF="t", FTRF="t", DAL1="s", DAL2="s", ACL1="s", ACL2="s", CL11="s", CL21="s", XK_GC="t", OMEGA_GC="t",
+                   CM_GC="t", C2OSQRTVG_GC="t", XKMSQRTVGOC2_GC="t", OM3GMKM_GC="t", OMXKM3_GC="t", DELKCC_GC_NS="t", DELKCC_OMXKM3_GC="t",
+                   CIDEAC="t", ZPI="s", R="s", BETAMAX="s", BETAMAXOXKAPPA2="s", ZALP="s", ALPHA="s", ALPHAMIN="s", ALPHAPMAX="s", CHNKMIN_U="s",
+                   TAUWSHELTER="s", TAILFACTOR="s", TAILFACTOR_PM="s", SWELLF="s", SWELLF2="s", SWELLF3="s", SWELLF4="s", SWELLF5="s", SWELLF6="s",
+                   SWELLF7="s", Z0RAT="s", Z0TUBMAX="s", CDIS="s", DELTA_SDIS="s", CDISVIS="s", SDSBR="s", SSDSC2="s", SSDSC4="s", SSDSC6="s", MICHE="s",
+                   EGRCRV="s", AFCRV="s", BFCRV="s", BMAXOKAP="s", GAMNCONST="s", RN1_RN="s", DTHRN_A="s", DTHRN_U="s", ANG_GC_A="s", ANG_GC_B="s",
+                   ANG_GC_C="s", SQRTGOSURFT="s", ZPI4GM1="s", ZPI4GM2="s", ROWATERM1="s", DELTH="s")
+
+
+def run_tables(name, **kw):
+    """The one-off table builders of the reference (INIWCST, MFREDIR, SETWAVPHYS, INIT_X0TAUHF, INIT_SDISS_ARDH, INISNONLIN + NLWEIGT +
+    JAFU, INITGC, CIGETDEAC) from their own source, for one spectral / physics setting; compared with the oracle's tables and stored."""
+    from f90run import module_registry
+    from oracle import oracle as O
+    from ecwam_b200 import synth
+    o = O.Oracle(O.default_config(**kw), synth.make_grid(8, "aqua"))
+    c = o.cfg
+    reg = module_registry(TABLE_MODULES)
+    ns = module_parameters()
+    for k, (t, a) in reg.items():
+        if k not in ns:
+            ns[k] = None
+    I = lambda v: FInt(int(v))
+    ns.update(NANG=I(c.nang), NFRE=I(c.nfre), NFRE_RED=I(c.nfre_red), NFRE_ODD=I(c.nfre - 1 + (c.nfre % 2)), IFRE1=I(c.ifre1), FR1=float(c.fr1),
+              IPHYS=I(c.iphys), ISNONLIN=I(c.isnonlin), LLGCBZ0=bool(c.llgcbz0), LLNORMAGAM=bool(c.llnormagam), LLCAPCHNK=bool(c.llcapchnk),
+              IU06=I(6), LHOOK=False, LWCOU=False, XKAPPA=float(ns.get("XKAPPA", 0.4) or 0.4), RNU=float(c.rnu), RNUM=float(c.rnum),
+              ISHALLO=I(0), IRANK=I(1))
+    from f90run import STATIC_DIMS
+    for k, (t, dims) in STATIC_DIMS.items():
+        try:
+            ns[k] = FArr([(1, int(eval(d, dict(ns)))) for d in dims], t)
+        except Exception:
+            pass
+    T = Translator([x + ".F90" for x in TABLE_FILES], registry=reg)
+    ns = T.compile(["INIWCST", "MFREDIR", "SETWAVPHYS", "INIT_X0TAUHF", "INIT_SDISS_ARDH", "INISNONLIN", "INITGC", "CIGETDEAC"], ns)
+    g = ns          # the functions' globals ARE this dict: module variables they assign land here
+    g["INIWCST"](1.0)
+    g["MFREDIR"]()
+    g["DELTH"] = g["ZPI"] / float(c.nang)          # initmdl.F90:437 (the rest of INITMDL's frequency arrays is not translated)
+    g["SETWAVPHYS"]()
+    g["INIT_X0TAUHF"]()
+    if c.iphys == 1:
+        g["INIT_SDISS_ARDH"]()
+    g["INISNONLIN"]()
+    g["INITGC"]()
+    g["CIGETDEAC"]()
+    out, worst = dict(kw=__import__("json").dumps(kw, sort_keys=True)), []
+    for nm, kind in TABLE_CHECK.items():
+        v = g.get(nm)
+        if v is None:
+            continue
+        try:
+            ref = o.itable(nm) if kind == "i" else o.table(nm)
+        except KeyError:
+            continue
+        a = np.asarray(v.a).ravel(order="F") if isinstance(v, FArr) else np.array([v])
+        if kind == "i":
+            a = a.astype(np.int64)
+        out[nm] = a
+        if a.shape != ref.shape:
+            worst.append((nm, "shape %s vs %s" % (a.shape, ref.shape)))
+            continue
+        d = float(np.abs(a - ref).max() / max(np.abs(ref).max(), 1e-300))
+        worst.append((nm, d))
+    bad = [(n, d) for n, d in worst if not isinstance(d, float) or d > 0.0]
+    print("%s: %d tables from the reference source; not bit-identical to the oracle: %s" % (name, len(worst), bad))
+    np.savez_compressed(os.path.join(HERE, "ref_tables_%s.npz" % name), **out)
+
+
+TABLE_CASES = {"a12_ard": dict(nang=12, nfre_red=25, iphys=1), "a24_ard": dict(nang=24, nfre_red=29, iphys=1), "a36_ard": dict(nang=36, nfre_red=29, iphys=1),
+               "a12_jan": dict(nang=12, nfre_red=25, iphys=0), "a12_cy49r1": dict(nang=12, nfre_red=25, iphys=1, llgcbz0=1, llnormagam=1, wspmin=0.3),
+               "a36_jan_gc": dict(nang=36, nfre_red=29, iphys=0, llgcbz0=1, llnormagam=1, wspmin=0.3)}
+
 ICE = dict(lmaskice=0, lciwa1=1, lciwa2=1, lciwa3=1, lciscal=1, zalpfacx=0.6, zalpfacb=0.8)
 CASES = {
     "ard": dict(case="o48like"),                                               # etopo1_oper_an_fc_O48.yml physics
@@ -228,7 +306,11 @@ CASES = {
 }
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(CASES)
+    names = sys.argv[1:] or (list(CASES) + ["tables"])
     for nm in names:
+        if nm == "tables":
+            for t, kw in TABLE_CASES.items():
+                run_tables(t, **kw)
+            continue
         c = CASES[nm]
         run_case(nm, c["case"], hook=c.get("hook", False), **c.get("kw", {}))

@@ -117,3 +117,45 @@ def test_cuda_path_matches_the_reference_source(built, name):
             continue
         x, y = w.get_field(nm.lower())[q], z[nm]
         assert np.abs(x - y).max() <= 1e-10 * max(np.abs(y).max(), 1e-12), nm
+
+
+TFILES = sorted(glob.glob(os.path.join(HERE, "golden", "ref_tables_*.npz")))
+
+
+@pytest.mark.parametrize("path", TFILES, ids=[os.path.basename(f)[len("ref_tables_"):-4] for f in TFILES])
+def test_tables_match_the_reference_source(built, path):
+    """The one-off tables (INIWCST, MFREDIR, SETWAVPHYS, INIT_X0TAUHF, INIT_SDISS_ARDH, INISNONLIN + NLWEIGT + JAFU, INITGC, CIGETDEAC run
+    from their own source by the translator) against the oracle's AND the product's host builders: integer tables exact, real ones
+    1e-14 (pow() against repeated multiplication)."""
+    from ecwam_b200 import model as M, synth
+    from oracle import oracle as O
+    z = np.load(path)
+    kw = json.loads(str(z["kw"]))
+    g = synth.make_grid(8, "aqua")
+    o = O.Oracle(O.default_config(**kw), g)
+    s = M.WamSetup(g, nproc=1, **kw)
+    n_checked = 0
+    for nm in z.files:
+        if nm == "kw":
+            continue
+        ref = z[nm]
+        kind = G.TABLE_CHECK[nm]
+        got = o.itable(nm) if kind == "i" else o.table(nm)
+        assert got.shape == ref.shape, nm
+        if kind == "i":
+            np.testing.assert_array_equal(got, ref, err_msg=nm)
+        else:
+            assert np.abs(got - ref).max() <= 1e-14 * max(np.abs(ref).max(), 1e-300), nm
+        n_checked += 1
+        # the product's own builder (ecwam_b200_host_tables_create), where the member exists under the same name
+        low = nm.lower()
+        if hasattr(s.tables, low):
+            v = getattr(s.tables, low)
+            if isinstance(v, (int, float)):
+                assert abs(v - float(ref[0])) <= 1e-14 * max(abs(float(ref[0])), 1e-300), "product " + nm
+            elif kind == "i":
+                np.testing.assert_array_equal(s.itable(low, ref.size), ref, err_msg="product " + nm)
+            elif nm not in ("CIDEAC",) or True:
+                p = s.table(low, ref.size)
+                assert np.abs(p - ref).max() <= 1e-14 * max(np.abs(ref).max(), 1e-300), "product " + nm
+    assert n_checked >= 80
