@@ -151,6 +151,21 @@ class FArr:
     def assign(self, val):
         self.a[...] = val.a if isinstance(val, FArr) else val
 
+    def rebase(self, lbs):
+        """the same storage seen with the callee's declared lower bounds (dummy-array bounds are local to the routine)"""
+        if list(lbs) == self.lb or len(lbs) != self.a.ndim:
+            return self
+        o = FArr.__new__(FArr)
+        o.a, o.lb, o.kind = self.a, [int(x) for x in lbs], self.kind
+        return o
+
+    def elemview(self, i):
+        """actual argument A(i) for an array dummy (sequence association, rank 1): the storage from element i on"""
+        assert self.a.ndim == 1
+        o = FArr.__new__(FArr)
+        o.a, o.lb, o.kind = self.a[int(i) - self.lb[0]:], [1], self.kind
+        return o
+
 
 def _isarr(x):
     return isinstance(x, np.ndarray)
@@ -402,8 +417,15 @@ class Translator:
     # ---- pass 1: split into routines, read declarations
     def _parse_file(self, path, incs):
         lines = _logical_lines(path, incs)
-        cur = None
+        cur, outer = None, None      # outer: the host routine while its CONTAINed procedures are read
         for ln in lines:
+            if cur is not None and ln.strip() == "CONTAINS":
+                outer, cur = cur, None
+                continue
+            if cur is None and outer is not None and re.match(r"^END\s*(SUBROUTINE|FUNCTION)\s+%s$" % outer.name, ln):
+                self.routines[outer.name] = outer
+                outer = None
+                continue
             m = re.match(r"^(?:(?:REAL|INTEGER|LOGICAL)\s*(?:\([^)]*\))?\s+)?(SUBROUTINE|FUNCTION)\s+(\w+)\s*(?:\((.*?)\))?\s*(?:RESULT\s*\((\w+)\))?$", ln)
             if m and cur is None:
                 args = [a.strip() for a in (m.group(3) or "").split(",") if a.strip()]
@@ -435,7 +457,7 @@ class Translator:
             if m:
                 r.uses[m.group(1)] = [x.strip() for x in (m.group(2) or "").split(",") if x.strip()]
                 continue
-            if re.match(r"^IMPLICIT\b", ln) or re.match(r"^(EXTERNAL|SAVE|INTRINSIC)\b", ln):
+            if re.match(r"^IMPLICIT\b", ln) or re.match(r"^(EXTERNAL|SAVE|INTRINSIC)\b", ln) or re.match(r"^TYPE\s*\(", ln):
                 continue
             m = re.match(r"^(REAL|INTEGER|LOGICAL|CHARACTER|DOUBLE\s+PRECISION)\s*(\((?:[^()]|\([^()]*\))*\))?\s*(.*?)::\s*(.*)$", ln)
             if m:
@@ -501,6 +523,9 @@ class Translator:
                     elif t in INTRINSICS:
                         out.append("F_" + t + "(")
                         closers.append(")")
+                    elif t == "OML_GET_MAX_THREADS":      # one thread
+                        out.append("FInt(1 + 0*len(")
+                        closers.append("()))")
                     else:
                         raise SyntaxError("%s: unknown function or array %s in: %s" % (r.name, t, s))
                     i += 1
@@ -536,6 +561,13 @@ class Translator:
         used = sorted({v for lst in r.uses.values() for v in lst if re.match(r"^[A-Z_][A-Z0-9_]*$", v)} - set(r.args) - set(r.decl))
         if used:
             emit("global " + ", ".join(used))
+        rebase = []
+        for nm in r.args:
+            d = r.decl.get(nm)
+            if d and d["dims"]:
+                los = [(x.split(":")[0].strip() or "1") if ":" in x else "1" for x in d["dims"]]
+                if any(lo != "1" for lo in los):
+                    rebase.append((nm, los))
         # PARAMETERs and local arrays
         for nm, d in r.decl.items():
             if d["param"] and d["init"] is not None and not d["dims"]:
@@ -554,6 +586,8 @@ class Translator:
                     b.append("(%s, %s)" % (self.expr(r, lo), self.expr(r, hi)))
                 if b is not None:
                     emit("%s = FArr([%s], %s)" % (nm, ", ".join(b), {float: "float", int: "int", bool: "bool", str: "object"}[d["type"]]))
+        for nm, los in rebase:
+            emit("if %s is not None: %s = %s.rebase([%s])" % (nm, nm, nm, ", ".join(self.expr(r, lo) for lo in los)))
         stack = []
         for ln in r.body:
             self._stmt(r, ln, emit, lambda d: None, stack, ret, lines)
@@ -573,6 +607,10 @@ class Translator:
         if re.match(r"^IF\s*\(\s*LHOOK\s*\)", ln) or re.match(r"^(WRITE|PRINT|FORMAT|CALL\s+FLUSH|CALL\s+GSTATS)\b", ln) or re.match(r"^\d+\s+FORMAT", ln):
             return
         if re.match(r"^CONTINUE$", ln) or re.match(r"^INCLUDE\b", ln):
+            return
+        m = re.match(r"^DATA\s+(\w+)\s*/(.*)/$", ln)
+        if m:      # SAVE + DATA: initialised at every call here (the routines are called once)
+            emit("%s = %s" % (m.group(1), self.expr(r, m.group(2))))
             return
         m = re.match(r"^DO\s+WHILE\s*\((.*)\)$", ln)
         if m:
@@ -660,7 +698,14 @@ class Translator:
                 raise SyntaxError("%s: CALL of %s, which is not among the translated files" % (r.name, callee))
             c = self.routines[callee]
             self.translate(callee)
-            pa = [self.expr(r, a) for a in args]
+            pa = []
+            for k, a in enumerate(args):
+                am = re.match(r"^(\w+)\s*\(([^:]*)\)$", a)
+                dummy = c.decl.get(c.args[k]) if k < len(c.args) else None
+                if am and (am.group(1) in r.arrays or am.group(1) in self.global_arrays) and dummy and dummy["dims"] and "," not in am.group(2):
+                    pa.append("%s.elemview(%s)" % (am.group(1), self.expr(r, am.group(2))))      # A(i) passed to an array dummy
+                else:
+                    pa.append(self.expr(r, a))
             outs = [pa[c.args.index(o)] for o in c.outs]
             call = "%s(%s)" % (callee, ", ".join(pa))
             if outs:

@@ -282,6 +282,89 @@ def run_tables(name, **kw):
     np.savez_compressed(os.path.join(HERE, "ref_tables_%s.npz" % name), **out)
 
 
+PROP_FILES = "ctuwupdt ctuwini ctuwdrv ctuw propags2".split()
+PROP_MODULES = MODULES + ["yowubuf", "yowmap", "yowgrid", "yowrefd", "yowmpp"]
+
+
+def run_propag(name, N=8, mask="continents", **kw):
+    """CTUWUPDT (+ CTUWINI, CTUWDRV, CTUW) and PROPAGS2 from their own source on a small one-rank grid: the CTU weights of every point,
+    direction and frequency and one advection step, compared with the oracle's stored weights / PROPAG_WAM and stored."""
+    import ctypes as C
+    from f90run import STATIC_DIMS, module_registry
+    from oracle import oracle as O
+    from ecwam_b200 import model as M, synth
+    g = synth.make_grid(N, mask)
+    c = O.default_config(store_all_weights=1, nproma=16, **kw)
+    o = O.Oracle(c, g)
+    f = synth.make_forcing(g)
+    for k, v in f.items():
+        o.set_field(k, v)
+    fl = synth.jonswap_cold_start(f["WSWAVE"], f["WDWAVE"], c.nang, 36, c.nfre_red)
+    o.set_fl1(fl)
+    n, A, FR_ = g.niblo, c.nang, c.nfre_red
+    new2ij = o.itable("NEWIJ2IJ")[1:n + 1] - 1           # original index of the point with new number IJ = 1..NIBLO
+    reg = module_registry(PROP_MODULES)
+    ns = module_parameters()
+    for k in reg:
+        ns.setdefault(k, None)
+    I = lambda v: FInt(int(v))
+    kxlt = o.itable("KXLT")[:n]
+    ixlg = o.itable("IXLG")[:n]
+    ngy = int(g.ngy)
+    ns.update(NANG=I(A), NFRE_RED=I(FR_), NGY=I(ngy), NPROC=I(1), IRANK=I(1), NPROMA_WAM=I(16), IREFRA=I(c.irefra), ICASE=I(1), IRGG=I(1), IPER=I(1),
+              IDELPRO=I(int(c.idelpro)), DELPRO_LF=float(c.delpro_lf), IFRELFMAX=I(c.ifrelfmax), LLCFLCUROFF=bool(c.llcflcuroff), LHOOK=False,
+              NULERR=I(0), IU06=I(6), ZPI=float(o.table("ZPI")[0]), R=float(o.table("R")[0]), DELTH=float(o.table("DELTH")[0]),
+              XDELLA=float(o.table("XDELLA")[0]), AMOWEP=float(g.amowep) if hasattr(g, "amowep") else 0.0, AMOSOP=float(g.amosop),
+              FR=FArr.of(o.table("FR")), COSTH=FArr.of(o.table("COSTH")[:A]), SINTH=FArr.of(o.table("SINTH")[:A]),
+              ZDELLO=FArr.of(o.table("ZDELLO")[:ngy]), COSPH=FArr.of(o.table("COSPH")[:ngy]), SINPH=FArr.of(o.table("SINPH")[:ngy]),
+              BLK2GLO_KXLT=FArr.of(kxlt.astype(np.int64)), BLK2GLO_IXLG=FArr.of(ixlg.astype(np.int64)),
+              KLAT=FArr.of(o.itable("KLAT").reshape((n, 2, 2), order="F").astype(np.int64)), KLON=FArr.of(o.itable("KLON").reshape((n, 2), order="F").astype(np.int64)),
+              KCOR=FArr.of(o.itable("KCOR").reshape((n, 4, 2), order="F").astype(np.int64)),
+              WLAT=FArr.of(o.rank_double("WLAT").reshape((n, 2), order="F")), WCOR=FArr.of(o.rank_double("WCOR").reshape((n, 4), order="F")),
+              OBSLAT=FArr.of(np.ones((n, FR_, 2))), OBSLON=FArr.of(np.ones((n, FR_, 2))), OBSCOR=FArr.of(np.ones((n, FR_, 4))))
+    ns["OML_GET_MAX_THREADS"] = lambda: FInt(1)
+    # PROENVHALO on one rank: the fields in the new numbering + the land point NSUP + 1 (proenvhalo.F90:98-106)
+    s = M.WamSetup(g, nproc=1, nang=A, nfre_red=FR_)
+    cg = o.get_field3("CGROUP")[:FR_, new2ij]                        # [m, IJ]
+    ext = lambda a, land: FArr.of(np.concatenate([a, [land]]))
+    cg_ext = FArr.of(np.concatenate([cg.T, s.land_cgroup[None, :FR_]], axis=0))
+    om = o.get_field3("OMOSNH2KD")[:FR_, new2ij]
+    om_ext = FArr.of(np.concatenate([om.T, np.zeros((1, FR_))], axis=0))
+    cosphm1 = 1.0 / o.table("COSPH")[kxlt - 1]
+    depth = g.depth[new2ij]
+    T = Translator([x + ".F90" for x in PROP_FILES], registry=reg)
+    ns = T.compile(["CTUWUPDT", "PROPAGS2"], ns)
+    t0 = time.time()
+    ns["CTUWUPDT"](I(1), I(n), I(1), I(n), None, cg_ext, om_ext, ext(cosphm1, 1.0), ext(depth, c.bathymax), ext(np.zeros(n), 0.0), ext(np.zeros(n), 0.0))
+    # PROPAGS2 on FL1_EXT (new numbering + the land slot, 0 there: propag_wam.F90:145-147)
+    f1 = np.zeros((n + 1, A, FR_))
+    f1[:n] = fl[:FR_][:, :, new2ij].transpose(2, 1, 0)
+    F1, F3 = FArr.of(f1), FArr([(1, n + 1), (1, A), (1, FR_)])
+    ns["PROPAGS2"](F1, F3, I(1), I(n), I(1), I(n), I(A), I(1), I(FR_), I(1), I(FR_))
+    print("%s: CTUWUPDT + PROPAGS2 of the reference source on %d points in %.1f s" % (name, n, time.time() - t0))
+    assert o.propag() == 0
+    out = dict(N=N, mask=mask, kw=__import__("json").dumps(kw, sort_keys=True))
+    for nm, shape in (("SUMWN", (n, A, FR_)), ("WLONN", (n, A, FR_, 2)), ("WLATN", (n, A, FR_, 2, 2)), ("WCORN", (n, A, FR_, 4, 2)), ("WKPMN", (n, A, FR_, 3))):
+        ref = ns[nm].a
+        got = o.rank_double(nm).reshape(shape, order="F")
+        out[nm] = ref
+        print("   %-6s max |oracle - reference source| = %.2e (max %.3f)" % (nm, np.abs(got - ref).max(), np.abs(ref).max()))
+    out["F3"] = F3.a[:n]
+    got = o.get_fl1()[:FR_][:, :, new2ij].transpose(2, 1, 0)
+    m0 = c.ifrelfmax if 0 < c.ifrelfmax < FR_ else 0       # the frequencies below IFRELFMAX go through further sub-steps in PROPAG_WAM
+    out["m0"] = m0
+    print("   PROPAGS2: max |oracle - reference source| = %.2e, identical: %s" % (np.abs(got - out["F3"])[:, :, m0:].max(),
+                                                                               np.array_equal(got[:, :, m0:], out["F3"][:, :, m0:])))
+    out["new2ij"] = new2ij
+    sel = np.arange(0, n, 6)             # every 6th point is kept in the fixture (size)
+    for k in ("SUMWN", "WLONN", "WLATN", "WCORN", "WKPMN", "F3"):
+        out[k] = out[k][sel]
+    out["sel"] = sel
+    np.savez_compressed(os.path.join(HERE, "ref_propag_%s.npz" % name), **out)
+
+
+PROP_CASES = {"a12": dict(N=8), "a24_fastwaves": dict(N=8, kw=dict(nang=24, nfre_red=29, ifrelfmax=5, delpro_lf=225.0, idelpro=450.0, idelt=450.0))}
+
 TABLE_CASES = {"a12_ard": dict(nang=12, nfre_red=25, iphys=1), "a24_ard": dict(nang=24, nfre_red=29, iphys=1), "a36_ard": dict(nang=36, nfre_red=29, iphys=1),
                "a12_jan": dict(nang=12, nfre_red=25, iphys=0), "a12_cy49r1": dict(nang=12, nfre_red=25, iphys=1, llgcbz0=1, llnormagam=1, wspmin=0.3),
                "a36_jan_gc": dict(nang=36, nfre_red=29, iphys=0, llgcbz0=1, llnormagam=1, wspmin=0.3)}
@@ -306,11 +389,15 @@ CASES = {
 }
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(CASES) + ["tables"])
+    names = sys.argv[1:] or (list(CASES) + ["tables", "propag"])
     for nm in names:
         if nm == "tables":
             for t, kw in TABLE_CASES.items():
                 run_tables(t, **kw)
+            continue
+        if nm == "propag":
+            for t, d in PROP_CASES.items():
+                run_propag(t, N=d.get("N", 8), **d.get("kw", {}))
             continue
         c = CASES[nm]
         run_case(nm, c["case"], hook=c.get("hook", False), **c.get("kw", {}))

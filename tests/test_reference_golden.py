@@ -159,3 +159,73 @@ def test_tables_match_the_reference_source(built, path):
                 p = s.table(low, ref.size)
                 assert np.abs(p - ref).max() <= 1e-14 * max(np.abs(ref).max(), 1e-300), "product " + nm
     assert n_checked >= 80
+
+
+PFILES = sorted(glob.glob(os.path.join(HERE, "golden", "ref_propag_*.npz")))
+
+
+def _prop_case(path):
+    from ecwam_b200 import synth
+    from oracle import oracle as O
+    z = np.load(path)
+    kw = json.loads(str(z["kw"]))
+    g = synth.make_grid(int(z["N"]), str(z["mask"]))
+    return z, kw, g
+
+
+@pytest.mark.parametrize("path", PFILES, ids=[os.path.basename(f)[len("ref_propag_"):-4] for f in PFILES])
+def test_ctu_weights_and_propags2_match_the_reference_source(built, path):
+    """CTUWUPDT + CTUWINI + CTUWDRV + CTUW + PROPAGS2 executed from their own source (every 6th point of a 323-point grid is kept in the
+    fixture): the oracle's stored weights SUMWN / WLONN / WLATN / WCORN / WKPMN and its advected spectrum are BIT-IDENTICAL."""
+    from ecwam_b200 import synth
+    from oracle import oracle as O
+    z, kw, g = _prop_case(path)
+    c = O.default_config(store_all_weights=1, nproma=16, **kw)
+    o = O.Oracle(c, g)
+    f = synth.make_forcing(g)
+    for k, v in f.items():
+        o.set_field(k, v)
+    fl = synth.jonswap_cold_start(f["WSWAVE"], f["WDWAVE"], c.nang, 36, c.nfre_red)
+    o.set_fl1(fl)
+    assert o.propag() == 0
+    n, A, FR_ = g.niblo, c.nang, c.nfre_red
+    sel, new2ij, m0 = z["sel"], z["new2ij"], int(z["m0"])
+    for nm, shape in (("SUMWN", (n, A, FR_)), ("WLONN", (n, A, FR_, 2)), ("WLATN", (n, A, FR_, 2, 2)), ("WCORN", (n, A, FR_, 4, 2)), ("WKPMN", (n, A, FR_, 3))):
+        np.testing.assert_array_equal(o.rank_double(nm).reshape(shape, order="F")[sel], z[nm], err_msg=nm)
+    got = o.get_fl1()[:FR_][:, :, new2ij].transpose(2, 1, 0)[sel]
+    np.testing.assert_array_equal(got[:, :, m0:], z["F3"][:, :, m0:])
+    assert z["WLATN"].max() > 1e-3 and z["WKPMN"].max() > 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", PFILES, ids=[os.path.basename(f)[len("ref_propag_"):-4] for f in PFILES])
+def test_cuda_propags2_matches_the_reference_source(built, monkeypatch, path):
+    """The bit-exact PROPAGS2 kernel (in-kernel CTU weights) against the reference source's advected spectrum: identical bits; the default
+    (tolerance-mode) kernel within 1e-13."""
+    from ecwam_b200 import model as M, synth
+    z, kw, g = _prop_case(path)
+    sel, new2ij, m0 = z["sel"], z["new2ij"], int(z["m0"])
+    for mode, exact in (("exact", True), (None, False)):
+        if mode:
+            monkeypatch.setenv("ECWAM_B200_PROPAG", mode)
+        else:
+            monkeypatch.delenv("ECWAM_B200_PROPAG", raising=False)
+        s = M.WamSetup(g, nproc=1, nproma=16, **kw)
+        w = M.WamIntgr(s, 0)
+        w.set_static(g.depth)
+        f = synth.make_forcing(g)
+        for k, v in f.items():
+            w.set_field(k, v)
+        fl = synth.jonswap_cold_start(f["WSWAVE"], f["WDWAVE"], w.A, 36, w.Fr)
+        w.set_fl1(fl)
+        assert w.propag() == 0
+        w.synchronize()
+        n = g.niblo
+        inv = np.empty(n, dtype=np.int64)
+        inv[w.own] = np.arange(n)
+        got = w.get_spec("fl1")[:w.Fr][:, :, inv[new2ij]].transpose(2, 1, 0)[sel]
+        if exact:
+            np.testing.assert_array_equal(got[:, :, m0:], z["F3"][:, :, m0:])
+        else:
+            assert np.abs(got - z["F3"])[:, :, m0:].max() <= 1e-13 * np.abs(z["F3"]).max()
+        w.close()
