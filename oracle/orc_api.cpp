@@ -143,7 +143,7 @@ long orc_get_rank_double(void* h, const char* name, int rank, double* out, long 
   RankDecomp& r = m->ranks[rank];
   std::string n(name);
   std::map<std::string, ArrD*> mp = {{"WLAT", &r.WLAT}, {"WCOR", &r.WCOR}, {"W8", &r.W8}, {"SUMWN", &r.SUMWN},
-                                     {"WLATN", &r.WLATN}, {"WLONN", &r.WLONN}, {"WCORN", &r.WCORN}, {"WKPMN", &r.WKPMN}};
+                                     {"WLATN", &r.WLATN}, {"WLONN", &r.WLONN}, {"WCORN", &r.WCORN}, {"WKPMN", &r.WKPMN}, {"WMPMN", &r.WMPMN}};
   auto it = mp.find(n);
   if (it != mp.end()) return copy_out(it->second->d, out, cap);
   return 0;

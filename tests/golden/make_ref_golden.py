@@ -282,7 +282,7 @@ def run_tables(name, **kw):
     np.savez_compressed(os.path.join(HERE, "ref_tables_%s.npz" % name), **out)
 
 
-PROP_FILES = "ctuwupdt ctuwini ctuwdrv ctuw propags2".split()
+PROP_FILES = "ctuwupdt ctuwini ctuwdrv ctuw propags2 propdot gradi".split()
 PROP_MODULES = MODULES + ["yowubuf", "yowmap", "yowgrid", "yowrefd", "yowmpp"]
 
 
@@ -332,10 +332,30 @@ def run_propag(name, N=8, mask="continents", **kw):
     om_ext = FArr.of(np.concatenate([om.T, np.zeros((1, FR_))], axis=0))
     cosphm1 = 1.0 / o.table("COSPH")[kxlt - 1]
     depth = g.depth[new2ij]
+    ucur, vcur = np.zeros(n), np.zeros(n)
+    if c.irefra >= 2:
+        from common import synthetic_currents
+        u0, v0 = synthetic_currents(g)
+        o.set_field("UCUR", u0); o.set_field("VCUR", v0)
+        ucur, vcur = u0[new2ij], v0[new2ij]
+    u_ext, v_ext, d_ext, c_ext = ext(ucur, 0.0), ext(vcur, 0.0), ext(depth, c.bathymax), ext(cosphm1, 1.0)
+    ns.update(NIBLO=I(n), DELPHI=float(o.table("XDELLA")[0]) * float(ns["CIRC"]) / 360.0, DELLAM=FArr.of(o.table("DELLAM")[:ngy]))
     T = Translator([x + ".F90" for x in PROP_FILES], registry=reg)
-    ns = T.compile(["CTUWUPDT", "PROPAGS2"], ns)
+    ns = T.compile(["CTUWUPDT", "PROPAGS2", "PROPDOT"], ns)
     t0 = time.time()
-    ns["CTUWUPDT"](I(1), I(n), I(1), I(n), None, cg_ext, om_ext, ext(cosphm1, 1.0), ext(depth, c.bathymax), ext(np.zeros(n), 0.0), ext(np.zeros(n), 0.0))
+    if c.irefra != 0:     # propag_wam.F90:171-216: PROPDOT (+ GRADI) on the PROENVHALO fields, before CTUWUPDT
+        land = np.array([c.bathymax])
+        lw, lo_ = np.empty(c.nfre), np.empty(c.nfre)
+        dpp = C.POINTER(C.c_double)
+        s.lib.ecwam_b200_host_depthprpt(C.byref(s.tables), c.nfre, 1, land.ctypes.data_as(dpp), lw.ctypes.data_as(dpp), None, None, None,
+                                        lo_.ctypes.data_as(dpp), None)
+        wn = o.get_field3("WAVNUM")[:FR_, new2ij]
+        wn_ext = FArr.of(np.concatenate([wn.T, lw[None, :FR_]], axis=0))
+        om_ext = FArr.of(np.concatenate([om.T, lo_[None, :FR_]], axis=0))
+        THDC, THDD, SDOT = FArr([(1, n), (1, A)]), FArr([(1, n), (1, A)]), FArr([(1, n), (1, A), (1, FR_)])
+        ns["PROPDOT"](I(1), I(n), I(1), I(n), None, wn_ext, cg_ext, om_ext, c_ext, d_ext, u_ext, v_ext, THDC, THDD, SDOT)
+        ns["THDC"], ns["THDD"], ns["SDOT"] = THDC, THDD, SDOT
+    ns["CTUWUPDT"](I(1), I(n), I(1), I(n), None, cg_ext, om_ext, c_ext, d_ext, u_ext, v_ext)
     # PROPAGS2 on FL1_EXT (new numbering + the land slot, 0 there: propag_wam.F90:145-147)
     f1 = np.zeros((n + 1, A, FR_))
     f1[:n] = fl[:FR_][:, :, new2ij].transpose(2, 1, 0)
@@ -344,7 +364,10 @@ def run_propag(name, N=8, mask="continents", **kw):
     print("%s: CTUWUPDT + PROPAGS2 of the reference source on %d points in %.1f s" % (name, n, time.time() - t0))
     assert o.propag() == 0
     out = dict(N=N, mask=mask, kw=__import__("json").dumps(kw, sort_keys=True))
-    for nm, shape in (("SUMWN", (n, A, FR_)), ("WLONN", (n, A, FR_, 2)), ("WLATN", (n, A, FR_, 2, 2)), ("WCORN", (n, A, FR_, 4, 2)), ("WKPMN", (n, A, FR_, 3))):
+    arrays = [("SUMWN", (n, A, FR_)), ("WLONN", (n, A, FR_, 2)), ("WLATN", (n, A, FR_, 2, 2)), ("WCORN", (n, A, FR_, 4, 2)), ("WKPMN", (n, A, FR_, 3))]
+    if c.irefra >= 2:
+        arrays.append(("WMPMN", (n, A, FR_, 3)))
+    for nm, shape in arrays:
         ref = ns[nm].a
         got = o.rank_double(nm).reshape(shape, order="F")
         out[nm] = ref
@@ -357,13 +380,15 @@ def run_propag(name, N=8, mask="continents", **kw):
                                                                                np.array_equal(got[:, :, m0:], out["F3"][:, :, m0:])))
     out["new2ij"] = new2ij
     sel = np.arange(0, n, 6)             # every 6th point is kept in the fixture (size)
-    for k in ("SUMWN", "WLONN", "WLATN", "WCORN", "WKPMN", "F3"):
-        out[k] = out[k][sel]
+    for k in ("SUMWN", "WLONN", "WLATN", "WCORN", "WKPMN", "WMPMN", "F3"):
+        if k in out:
+            out[k] = out[k][sel]
     out["sel"] = sel
     np.savez_compressed(os.path.join(HERE, "ref_propag_%s.npz" % name), **out)
 
 
-PROP_CASES = {"a12": dict(N=8), "a24_fastwaves": dict(N=8, kw=dict(nang=24, nfre_red=29, ifrelfmax=5, delpro_lf=225.0, idelpro=450.0, idelt=450.0))}
+PROP_CASES = {"a12": dict(N=8), "a12_irefra1": dict(N=8, kw=dict(irefra=1)), "a12_irefra3": dict(N=8, kw=dict(irefra=3)),
+              "a12_irefra2": dict(N=8, kw=dict(irefra=2)), "a24_fastwaves": dict(N=8, kw=dict(nang=24, nfre_red=29, ifrelfmax=5, delpro_lf=225.0, idelpro=450.0, idelt=450.0))}
 
 TABLE_CASES = {"a12_ard": dict(nang=12, nfre_red=25, iphys=1), "a24_ard": dict(nang=24, nfre_red=29, iphys=1), "a36_ard": dict(nang=36, nfre_red=29, iphys=1),
                "a12_jan": dict(nang=12, nfre_red=25, iphys=0), "a12_cy49r1": dict(nang=12, nfre_red=25, iphys=1, llgcbz0=1, llnormagam=1, wspmin=0.3),
@@ -395,9 +420,10 @@ if __name__ == "__main__":
             for t, kw in TABLE_CASES.items():
                 run_tables(t, **kw)
             continue
-        if nm == "propag":
+        if nm == "propag" or nm.startswith("propag:"):
             for t, d in PROP_CASES.items():
-                run_propag(t, N=d.get("N", 8), **d.get("kw", {}))
+                if nm == "propag" or t in nm.split(":")[1:]:
+                    run_propag(t, N=d.get("N", 8), **d.get("kw", {}))
             continue
         c = CASES[nm]
         run_case(nm, c["case"], hook=c.get("hook", False), **c.get("kw", {}))
