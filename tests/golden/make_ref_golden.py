@@ -387,6 +387,54 @@ def run_propag(name, N=8, mask="continents", **kw):
     np.savez_compressed(os.path.join(HERE, "ref_propag_%s.npz" % name), **out)
 
 
+def run_connect(name, N=8, mask="continents"):
+    """PROPCONNECT (propconnect.F90, 971 lines: the neighbours of every sea point on the irregular grid and their interpolation weights)
+    from its own source on a one-rank grid, compared with the oracle's KLAT / KLON / KCOR / WLAT / WCOR and stored."""
+    from f90run import module_registry
+    from oracle import oracle as O
+    from ecwam_b200 import synth
+    g = synth.make_grid(N, mask)
+    o = O.Oracle(O.default_config(nproma=16), g)
+    n, ngy = g.niblo, int(g.ngy)
+    reg = module_registry(PROP_MODULES + ["yowspec"])
+    ns = module_parameters()
+    for k in reg:
+        ns.setdefault(k, None)
+    I = lambda v: FInt(int(v))
+    ngx = int(np.max(g.nlonrgg))
+    ocean = np.zeros((ngx, ngy), dtype=bool)
+    mk = np.asarray(g.mask)
+    if mk.ndim == 1:      # flat, row by row with NLONRGG(k) entries
+        p = 0
+        for k in range(ngy):
+            ocean[: g.nlonrgg[k], k] = mk[p: p + g.nlonrgg[k]] != 0
+            p += g.nlonrgg[k]
+    else:
+        ocean[: mk.shape[1], :] = (mk != 0).T
+    ns.update(NGX=I(ngx), NGY=I(ngy), NIBLO=I(n), IPER=I(1), IRGG=I(1), IPROPAGS=I(2), LHOOK=False, XDELLA=float(o.table("XDELLA")[0]),
+              ZDELLO=FArr.of(o.table("ZDELLO")[:ngy]), NLONRGG=FArr.of(np.asarray(g.nlonrgg, dtype=np.int64)), LLOCEANMASK=FArr.of(ocean),
+              BLK2GLO_IXLG=FArr.of(o.itable("IXLG")[:n].astype(np.int64)), BLK2GLO_KXLT=FArr.of(o.itable("KXLT")[:n].astype(np.int64)),
+              IJ2NEWIJ=FArr.of(o.itable("IJ2NEWIJ")[: n + 1].astype(np.int64), lb=[0]),
+              KLAT=FArr([(1, n), (1, 2), (1, 2)], int), KLON=FArr([(1, n), (1, 2)], int), KCOR=FArr([(1, n), (1, 4), (1, 2)], int),
+              WLAT=FArr([(1, n), (1, 2)]), WCOR=FArr([(1, n), (1, 4)]), WRLAT=FArr([(1, n), (1, 2)]), WRLON=FArr([(1, n), (1, 2)]),
+              KRLAT=FArr([(1, n), (1, 2), (1, 2)], int), KRLON=FArr([(1, n), (1, 2), (1, 2)], int))
+    T = Translator(["propconnect.F90"], registry=reg)
+    ns = T.compile(["PROPCONNECT"], ns)
+    t0 = time.time()
+    ns["PROPCONNECT"](I(1), I(n), FArr.of(o.itable("NEWIJ2IJ")[1: n + 1].astype(np.int64)))
+    print("%s: PROPCONNECT of the reference source on %d points in %.1f s" % (name, n, time.time() - t0))
+    out = dict(N=N, mask=mask)
+    land = n + 1
+    for nm, shape, kind in (("KLAT", (n, 2, 2), "i"), ("KLON", (n, 2), "i"), ("KCOR", (n, 4, 2), "i"), ("WLAT", (n, 2), "d"), ("WCOR", (n, 4), "d")):
+        ref = ns[nm].a.copy()
+        got = (o.itable(nm) if kind == "i" else o.rank_double(nm)).reshape(shape, order="F")
+        if kind == "i":
+            ref = np.where(ref == 0, land, ref)         # MPDECOMP sends "no neighbour" to the land point NSUP + 1 afterwards
+        out[nm] = ref
+        print("   %-5s identical to the oracle: %s" % (nm, np.array_equal(got, ref)))
+    np.savez_compressed(os.path.join(HERE, "ref_connect_%s.npz" % name), **out)
+
+
 PROP_CASES = {"a12": dict(N=8), "a12_irefra1": dict(N=8, kw=dict(irefra=1)), "a12_irefra3": dict(N=8, kw=dict(irefra=3)),
               "a12_irefra2": dict(N=8, kw=dict(irefra=2)), "a24_fastwaves": dict(N=8, kw=dict(nang=24, nfre_red=29, ifrelfmax=5, delpro_lf=225.0, idelpro=450.0, idelt=450.0))}
 
@@ -414,11 +462,15 @@ CASES = {
 }
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(CASES) + ["tables", "propag"])
+    names = sys.argv[1:] or (list(CASES) + ["tables", "propag", "connect"])
     for nm in names:
         if nm == "tables":
             for t, kw in TABLE_CASES.items():
                 run_tables(t, **kw)
+            continue
+        if nm == "connect":
+            run_connect("continents8", 8, "continents")
+            run_connect("aqua6", 6, "aqua")
             continue
         if nm == "propag" or nm.startswith("propag:"):
             for t, d in PROP_CASES.items():

@@ -242,3 +242,25 @@ def test_cuda_propags2_matches_the_reference_source(built, monkeypatch, path):
         else:
             assert np.abs(got - z["F3"])[:, :, m0:].max() <= 1e-13 * np.abs(z["F3"]).max()
         w.close()
+
+
+CFILES = sorted(glob.glob(os.path.join(HERE, "golden", "ref_connect_*.npz")))
+
+
+@pytest.mark.parametrize("path", CFILES, ids=[os.path.basename(f)[len("ref_connect_"):-4] for f in CFILES])
+def test_grid_connectivity_matches_the_reference_source(built, path):
+    """PROPCONNECT (propconnect.F90: the 2 + 4 + 8 neighbours of every sea point on the irregular lat-lon grid and their interpolation
+    weights) executed from its own source: KLAT, KLON, KCOR, WLAT, WCOR of the oracle AND of the product's host builder are identical."""
+    from ecwam_b200 import model as M, synth
+    from oracle import oracle as O
+    z = np.load(path)
+    g = synth.make_grid(int(z["N"]), str(z["mask"]))
+    o = O.Oracle(O.default_config(nproma=16), g)
+    s = M.WamSetup(g, nproc=1, nproma=16)
+    d = s.decomp_arrays(0)
+    n = g.niblo
+    for nm, shape, kind in (("KLAT", (n, 2, 2), "i"), ("KLON", (n, 2), "i"), ("KCOR", (n, 4, 2), "i"), ("WLAT", (n, 2), "d"), ("WCOR", (n, 4), "d")):
+        got = (o.itable(nm) if kind == "i" else o.rank_double(nm)).reshape(shape, order="F")
+        np.testing.assert_array_equal(got, z[nm], err_msg="oracle " + nm)
+        np.testing.assert_array_equal(d[nm.lower()].reshape(shape, order="F"), z[nm], err_msg="product " + nm)
+    assert (z["KLAT"] == n + 1).any() and (z["KLAT"] <= n).any()          # land and sea neighbours both occur
