@@ -328,14 +328,25 @@ def _logical_lines(path, include_dirs):
         m = re.match(r"^(\d+)\s+CONTINUE$", ln)
         if m:
             labels[m.group(1)] = i
+    # a backward `GO TO n` to a label that opens the rest of the routine (AKI's iteration) is a loop: `n CONTINUE` -> LABEL_LOOP
+    back = set()
+    for i, ln in enumerate(out):
+        m = re.search(r"\bGO\s*TO\s+(\d+)$", ln)
+        if m and labels.get(m.group(1), 1 << 30) < i:
+            back.add(m.group(1))
     res = []
     for i, ln in enumerate(out):
-        if re.match(r"^\d+\s+CONTINUE$", ln):
+        m = re.match(r"^(\d+)\s+CONTINUE$", ln)
+        if m:
+            if m.group(1) in back:
+                res.append("LABEL_LOOP")
             continue
         m = re.search(r"\bGO\s*TO\s+(\d+)$", ln)
         if m:
             j = labels.get(m.group(1))
-            if j is not None and j + 1 < len(out) and re.match(r"^END\s*DO$", out[j + 1]):
+            if m.group(1) in back:
+                ln = ln[:m.start()] + "CYCLE"
+            elif j is not None and j + 1 < len(out) and re.match(r"^END\s*DO$", out[j + 1]):
                 ln = ln[:m.start()] + "CYCLE"
             else:
                 ln = ln[:m.start()] + "CALL ABORT1"      # unsupported GO TO: fails if reached
@@ -512,7 +523,7 @@ class Translator:
                 out.append("**")
             elif re.match(r"^[A-Z_]", t):
                 if nxt == "(":
-                    if t in r.arrays or t in self.global_arrays:
+                    if t in r.arrays or (t in self.global_arrays and t not in getattr(r, 'decl', {})):
                         out.append(t + "[")
                         closers.append("]")
                     elif t in r.stmtfun or t in self.routines:
@@ -593,6 +604,11 @@ class Translator:
             self._stmt(r, ln, emit, lambda d: None, stack, ret, lines)
             # indentation is tracked through the `stack` list length
             ind = 1 + len(stack)
+        while stack and stack[-1] == "LABEL_LOOP":
+            ind = 1 + len(stack)
+            emit("break")
+            stack.pop()
+        ind = 1 + len(stack)
         emit(ret)
         sig = ", ".join(a + ("=None" if r.decl.get(a, {}).get("optional") else "") for a in r.args)
         src = "def %s(%s):\n" % (name, sig) + "\n".join(lines) + "\n"
@@ -612,6 +628,8 @@ class Translator:
         if m:      # SAVE + DATA: initialised at every call here (the routines are called once)
             emit("%s = %s" % (m.group(1), self.expr(r, m.group(2))))
             return
+        if ln == "LABEL_LOOP":      # loop until the end of the routine; the backward GO TO is its `continue`
+            emit("while True:"); emit("pass", 1); stack.append("LABEL_LOOP"); return
         m = re.match(r"^DO\s+WHILE\s*\((.*)\)$", ln)
         if m:
             emit("while %s:" % self.expr(r, m.group(1))); emit("pass", 1); stack.append("DO"); return
@@ -728,16 +746,16 @@ class Translator:
         lhs, rhs = ln[:eq].strip(), ln[eq + 1:].strip()
         lm = re.match(r"^(\w+)\s*(?:\((.*)\))?$", lhs)
         nm = lm.group(1)
-        if lm.group(2) is not None and nm not in r.arrays and nm not in self.global_arrays:
+        if lm.group(2) is not None and nm not in r.arrays and not (nm in self.global_arrays and nm not in r.decl):
             # statement function
             r.stmtfun.add(nm)
             emit("def SF_%s(%s): return %s" % (nm, lm.group(2), self.expr(r, rhs)))
             return
-        if lm.group(2) is None and (nm in r.arrays or nm in self.global_arrays):
-            emit("%s.assign(%s)" % (nm, self.expr(r, rhs)))
-            return
         if r.kind == "FUNCTION" and nm == r.result and lm.group(2) is None:
             emit("%s = %s" % (nm, self.expr(r, rhs)))
+            return
+        if lm.group(2) is None and (nm in r.arrays or (nm in self.global_arrays and nm not in r.decl)):
+            emit("%s.assign(%s)" % (nm, self.expr(r, rhs)))
             return
         if lm.group(2) is None:      # scalar: Fortran converts to the declared type of the left-hand side
             typ = r.decl[nm]["type"] if nm in r.decl else self.registry.get(nm, (None, False))[0]

@@ -208,10 +208,11 @@ def run_case(name, case, pts=None, steps=2, hook=False, **kw):
     np.savez_compressed(os.path.join(HERE, "ref_implsch_%s.npz" % name), **out)
 
 
-TABLE_FILES = "iniwcst mfredir mfr setwavphys init_x0tauhf init_sdiss_ardh inisnonlin nlweigt jafu initgc cigetdeac".split()
+TABLE_FILES = "depthprpt aki iniwcst mfredir mfr setwavphys init_x0tauhf init_sdiss_ardh inisnonlin nlweigt jafu initgc cigetdeac".split()
 TABLE_MODULES = MODULES + ["yowgridgen"]
 # name in the oracle -> kind (t = real table, i = integer table, s = scalar)
-TABLE_CHECK = dict(FR="t", DFIM="t", GOM="t", TH="t", COSTH="t", SINTH="t", X0TAUHF="s", WTAUHF="t", SATWEIGHTS="t", INDICESSAT="i", IKP="i", IKP1="i",
+TABLE_CHECK = dict(DFIMOFR="t", DFIMFR="t", DFIMFR2="t", ZPIFR="t", FR5="t", COFRM4="t", FLMAX="t", RHOWG_DFIM="t", DFIM_SIM="t", FLOGSPRDM1="s",
+                   FR="t", DFIM="t", GOM="t", TH="t", COSTH="t", SINTH="t", X0TAUHF="s", WTAUHF="t", SATWEIGHTS="t", INDICESSAT="i", IKP="i", IKP1="i",
                    IKM="i", IKM1="i", K1W="i", K2W="i", K11W="i", K21W="i", AF11="t", FKLAP="t", FKLAP1="t", FKLAM="t", FKLAM1="t", FRH="t",
                    INLCOEF="i", RNLCOEF="t", FTRF="t", DAL1="s", DAL2="s", ACL1="s", ACL2="s", CL11="s", CL21="s", XK_GC="t", OMEGA_GC="t",
                    CM_GC="t", C2OSQRTVG_GC="t", XKMSQRTVGOC2_GC="t", OM3GMKM_GC="t", OMXKM3_GC="t", DELKCC_GC_NS="t", DELKCC_OMXKM3_GC="t",
@@ -247,12 +248,25 @@ def run_tables(name, **kw):
         except Exception:
             pass
     T = Translator([x + ".F90" for x in TABLE_FILES], registry=reg)
-    ns = T.compile(["INIWCST", "MFREDIR", "SETWAVPHYS", "INIT_X0TAUHF", "INIT_SDISS_ARDH", "INISNONLIN", "INITGC", "CIGETDEAC"], ns)
+    # the frequency arrays INITMDL derives inline (initmdl.F90:436-503), taken as a routine of their own
+    from f90run import Routine, _logical_lines
+    ll = _logical_lines(os.path.join(REF, "initmdl.F90"), [REF])
+    i0 = next(i for i, x in enumerate(ll) if x.replace(" ", "") == "IF(ALLOCATED(DFIMOFR))DEALLOCATE(DFIMOFR)")
+    i1 = next(i for i, x in enumerate(ll) if x.replace(" ", "") == "CALLTABU_SWELLFT")
+    fr = Routine("INITMDL_FREQ", "SUBROUTINE", [])
+    fr.result = None
+    fr.body = ll[i0:i1]
+    text = " ".join(fr.body)
+    fr.uses = {"MODULES": [k for k in reg if re.search(r"\b%s\b" % k, text)]}
+    T.routines["INITMDL_FREQ"] = fr
+    ns = T.compile(["INIWCST", "MFREDIR", "SETWAVPHYS", "INITMDL_FREQ", "INIT_X0TAUHF", "INIT_SDISS_ARDH", "INISNONLIN", "INITGC", "CIGETDEAC",
+                    "DEPTHPRPT"], ns)
     g = ns          # the functions' globals ARE this dict: module variables they assign land here
     g["INIWCST"](1.0)
     g["MFREDIR"]()
     g["DELTH"] = g["ZPI"] / float(c.nang)          # initmdl.F90:437 (the rest of INITMDL's frequency arrays is not translated)
     g["SETWAVPHYS"]()
+    g["INITMDL_FREQ"]()
     g["INIT_X0TAUHF"]()
     if c.iphys == 1:
         g["INIT_SDISS_ARDH"]()
@@ -260,6 +274,15 @@ def run_tables(name, **kw):
     g["INITGC"]()
     g["CIGETDEAC"]()
     out, worst = dict(kw=__import__("json").dumps(kw, sort_keys=True)), []
+    # DEPTHPRPT + AKI (depthprpt.F90, aki.F90): the dispersion relation at the grid's own depths
+    grid = synth.make_grid(8, "aqua")
+    dep = np.concatenate([grid.depth[::9], [1.5, 3.0, 7.0, 15.0, 40.0, 120.0, 400.0, 998.0]])
+    K, NF = dep.size, int(c.nfre)
+    dp = {k: FArr([(1, K), (1, NF)]) for k in ("WAVNUM", "CINV", "CGROUP", "XK2CG", "OMOSNH2KD", "STOKFAC")}
+    g["DEPTHPRPT"](I(1), I(K), FArr.of(dep), dp["WAVNUM"], dp["CINV"], dp["CGROUP"], dp["XK2CG"], dp["OMOSNH2KD"], dp["STOKFAC"])
+    out["DEPTH_IN"] = dep
+    for k, v in dp.items():
+        out["DP_" + k] = v.a
     for nm, kind in TABLE_CHECK.items():
         v = g.get(nm)
         if v is None:

@@ -135,8 +135,19 @@ def test_tables_match_the_reference_source(built, path):
     o = O.Oracle(O.default_config(**kw), g)
     s = M.WamSetup(g, nproc=1, **kw)
     n_checked = 0
+    # DEPTHPRPT + AKI from the reference source against the product's host routine (which test_abi_and_host.py holds bit-identical to the oracle's)
+    import ctypes as C
+    dep = np.ascontiguousarray(z["DEPTH_IN"])
+    K, NF = dep.size, 36
+    dpp = C.POINTER(C.c_double)
+    outp = {k: np.empty((NF, K)) for k in ("WAVNUM", "CINV", "CGROUP", "XK2CG", "OMOSNH2KD", "STOKFAC")}
+    assert s.lib.ecwam_b200_host_depthprpt(C.byref(s.tables), NF, K, dep.ctypes.data_as(dpp), *[outp[k].ctypes.data_as(dpp) for k in
+                                           ("WAVNUM", "CINV", "CGROUP", "XK2CG", "OMOSNH2KD", "STOKFAC")]) == 0
+    for k, v in outp.items():
+        ref = z["DP_" + k].T
+        assert np.abs(v - ref).max() <= 1e-13 * np.abs(ref).max(), "DEPTHPRPT " + k
     for nm in z.files:
-        if nm == "kw":
+        if nm == "kw" or nm.startswith("DP_") or nm == "DEPTH_IN":
             continue
         ref = z[nm]
         kind = G.TABLE_CHECK[nm]
