@@ -84,7 +84,7 @@ long orc_get_table(void* h, const char* name, double* out, long cap) {
       {"XK_GC", &t.XK_GC}, {"OMEGA_GC", &t.OMEGA_GC}, {"CM_GC", &t.CM_GC}, {"C2OSQRTVG_GC", &t.C2OSQRTVG_GC},
       {"XKMSQRTVGOC2_GC", &t.XKMSQRTVGOC2_GC}, {"OM3GMKM_GC", &t.OM3GMKM_GC}, {"OMXKM3_GC", &t.OMXKM3_GC},
       {"DELKCC_GC_NS", &t.DELKCC_GC_NS}, {"DELKCC_OMXKM3_GC", &t.DELKCC_OMXKM3_GC}, {"CIDEAC", &t.CIDEAC},
-      {"DFIMFR2", &t.DFIMFR2}, {"XKM_GC", &t.XKM_GC}, {"DELKCC_GC", &t.DELKCC_GC}, {"GOM", &t.GOM}, {"FRM5", &t.FRM5},
+      {"DFIMFR2", &t.DFIMFR2}, {"XKM_GC", &t.XKM_GC}, {"VG_GC", &t.VG_GC}, {"C_GC", &t.C_GC}, {"DELKCC_GC", &t.DELKCC_GC}, {"GOM", &t.GOM}, {"FRM5", &t.FRM5},
       {"ZDELLO", &m->grid.ZDELLO}, {"COSPH", &m->grid.COSPH}, {"SINPH", &m->grid.SINPH}, {"DELLAM", &m->grid.DELLAM}};
   auto it = mp.find(n);
   if (it != mp.end()) return copy_out(it->second->d, out, cap);

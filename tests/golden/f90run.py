@@ -133,8 +133,15 @@ class FArr:
                 out.append(j)
         return tuple(out), scalar
 
+    oob_read_zero = False      # set by a driver for a routine known to read one element outside an array with weight 0 (SEBTMEAN's FR(0))
+
     def __getitem__(self, idx):
-        ix, scalar = self._ix(idx)
+        try:
+            ix, scalar = self._ix(idx)
+        except IndexError:
+            if FArr.oob_read_zero:
+                return 0.0 if self.kind is float else FInt(0)
+            raise
         v = self.a[ix]
         if scalar:
             if self.kind is float:
@@ -150,6 +157,14 @@ class FArr:
 
     def assign(self, val):
         self.a[...] = val.a if isinstance(val, FArr) else val
+
+    @classmethod
+    def view(cls, arr):
+        """an array section passed as an actual argument: shares the storage (numpy basic slicing), lower bounds 1"""
+        o = cls.__new__(cls)
+        o.a, o.lb = arr, [1] * arr.ndim
+        o.kind = float if arr.dtype.kind == "f" else (bool if arr.dtype.kind == "b" else int)
+        return o
 
     def rebase(self, lbs):
         """the same storage seen with the callee's declared lower bounds (dummy-array bounds are local to the routine)"""
@@ -206,6 +221,8 @@ def F_SIGN(a, b):
 def F_MOD(a, b):
     if isinstance(a, int) and isinstance(b, int):
         return FInt(int(math.fmod(int(a), int(b))))
+    if _isarr(a) or _isarr(b):
+        return np.fmod(a, b)
     return math.fmod(float(a), float(b))
 
 
@@ -418,9 +435,10 @@ STATIC_DIMS = {}     # module arrays with explicit shape (WTAUHF(JTOT_TAUHF), SW
 
 
 class Translator:
-    def __init__(self, files, include_dirs=(REF,), registry=None):
+    def __init__(self, files, include_dirs=(REF,), registry=None, stubs=()):
         self.routines = {}
         self.registry = registry or {}
+        self.stubs = set(stubs)       # routines whose CALL is dropped (their results are not used by the caller's selected outputs)
         for f in files:
             self._parse_file(f if os.path.isabs(f) else os.path.join(REF, f), list(include_dirs))
         self.global_arrays = set()        # module arrays (names bound to FArr in the namespace)
@@ -463,6 +481,8 @@ class Translator:
             if in_iface:
                 if re.match(r"^END\s*INTERFACE", ln):
                     in_iface = False
+                continue
+            if re.match(r"^USE\s*,\s*INTRINSIC", ln):
                 continue
             m = re.match(r"^USE\s+(\w+)\s*(?:,\s*ONLY\s*:\s*(.*))?$", ln)
             if m:
@@ -586,6 +606,8 @@ class Translator:
         for nm, d in r.decl.items():      # Fortran leaves locals undefined; NaN makes a read-before-write visible (EPSILON(X) only asks for the kind)
             if not d["dims"] and nm not in r.args and not d["param"] and nm != getattr(r, "result", None) and d["type"] is float:
                 emit("%s = float('nan')" % nm)
+            elif not d["dims"] and nm not in r.args and not d["param"] and nm != getattr(r, "result", None) and d["type"] is bool:
+                emit("%s = False" % nm)
         for nm, d in r.decl.items():
             if d["dims"] and nm not in r.args:
                 b = []
@@ -620,6 +642,10 @@ class Translator:
 
         def emit(s, extra=0):
             lines.append("    " * (ind + extra) + s)
+        if re.search(r"\bCALL\s+IEEE_(GET|SET)_HALTING_MODE\b", ln):
+            if ln.startswith("CALL"):
+                return
+            ln = re.sub(r"CALL\s+IEEE_\w+\s*\(.*\)$", "CONTINUE", ln)
         if re.match(r"^IF\s*\(\s*LHOOK\s*\)", ln) or re.match(r"^(WRITE|PRINT|FORMAT|CALL\s+FLUSH|CALL\s+GSTATS)\b", ln) or re.match(r"^\d+\s+FORMAT", ln):
             return
         if re.match(r"^CONTINUE$", ln) or re.match(r"^INCLUDE\b", ln):
@@ -712,6 +738,9 @@ class Translator:
         if m:
             callee = m.group(1)
             args = _split_top(m.group(2)) if m.group(2) else []
+            if callee in self.stubs:
+                emit("pass")
+                return
             if callee not in self.routines:
                 raise SyntaxError("%s: CALL of %s, which is not among the translated files" % (r.name, callee))
             c = self.routines[callee]
@@ -720,7 +749,10 @@ class Translator:
             for k, a in enumerate(args):
                 am = re.match(r"^(\w+)\s*\(([^:]*)\)$", a)
                 dummy = c.decl.get(c.args[k]) if k < len(c.args) else None
-                if am and (am.group(1) in r.arrays or am.group(1) in self.global_arrays) and dummy and dummy["dims"] and "," not in am.group(2):
+                sm = re.match(r"^(\w+)\s*\((.*:.*)\)$", a)
+                if sm and (sm.group(1) in r.arrays or sm.group(1) in self.global_arrays) and dummy and dummy["dims"]:
+                    pa.append("FArr.view(%s)" % self.expr(r, a))        # array section: the callee sees it with lower bounds 1
+                elif am and (am.group(1) in r.arrays or am.group(1) in self.global_arrays) and dummy and dummy["dims"] and "," not in am.group(2):
                     pa.append("%s.elemview(%s)" % (am.group(1), self.expr(r, am.group(2))))      # A(i) passed to an array dummy
                 else:
                     pa.append(self.expr(r, a))

@@ -410,6 +410,84 @@ def run_propag(name, N=8, mask="continents", **kw):
     np.savez_compressed(os.path.join(HERE, "ref_propag_%s.npz" % name), **out)
 
 
+OUT_FILES = ("outblock femean intpol sepwisw sthq mwp1 mwp2 wdirspread peakfri scosfl outbeta weflux se10mean sebtmean meansqs meansqs_gc "
+             "meansqs_lf halphap omegagc ns_gc dominant_period cimsstrn aki_ice outsetwmask chnkmin").split()
+OUT_STUBS = ("KURTOSIS", "CAL_SECOND_ORDER_SPEC", "W_MAXH", "CTCOR", "IBRMEMOUT", "SEP3TR")      # not reached / results not selected
+
+
+def run_outblock(name, case, hook=False, **kw):
+    """OUTBLOCK (outblock.F90) and the 24 routines below it from their own source, for the 51 output parameters the product builds, on the
+    points pick_points() chooses, after two full steps; compared with the oracle's OUTBS and stored."""
+    from common import OUT_ICE, OUT_ITG, OUT_SEA
+    from f90run import module_registry
+    g, o, f = prepare(case, kw, 2, hook)
+    o.implsch()
+    if kw.get("irefra", 0) >= 2:
+        from common import synthetic_currents
+        u0, v0 = synthetic_currents(g)
+        o.set_field("UCUR", u0); o.set_field("VCUR", v0)
+    pts = pick_points(g, o, f)
+    K, A, NF = len(pts), o.cfg.nang, o.cfg.nfre
+    ns = namespace(o, {})
+    reg = module_registry(MODULES)
+    I = lambda v: FInt(int(v))
+    JP = int(ns["JPPFLAG"])
+    ipf, itob, info = np.zeros(JP, dtype=np.int64), np.zeros(JP, dtype=np.int64), np.zeros((JP, 7), dtype=np.int64)
+    for col, (itg, ice, sea) in enumerate(zip(OUT_ITG, OUT_ICE, OUT_SEA)):
+        ipf[itg - 1] = 1; itob[itg - 1] = col + 1; info[itg - 1, 5] = ice; info[itg - 1, 6] = sea
+    for ih, (tmin, tmax) in enumerate(((10, 12), (12, 14), (14, 17), (17, 21), (21, 25), (25, 30))):      # mpcrtbl.F90:371-399 (parameters 64 - 69)
+        info[63 + ih, 3] = tmin; info[63 + ih, 4] = tmax
+    ng = int(ns["NWAV_GC"])
+    ns.update(IPFGTBL=FArr.of(ipf), ITOBOUT=FArr.of(itob), IPRMINFO=FArr.of(info), NIPRMOUT=I(len(OUT_ITG)), NTRAIN=I(3), NTEWH=I(6), LSECONDORDER=False,
+              LLPARTITION=False, LLSOURCE=True, IREFRA=I(o.cfg.irefra), ZMISS=-999.0, DEG=360.0 / float(ns["ZPI"]), CLDOMAIN="g", XKMSS_CUTOFF=float(o.table("XK_GC")[ng - 1]),
+              DFIMFR_SIM=FArr.of(o.table("DFIM_SIM")[:NF] * o.table("FR")[:NF]), DFIMFR2_SIM=FArr.of(o.table("DFIM_SIM")[:NF] * o.table("FR")[:NF] ** 2),
+              VG_GC=FArr.of(o.table("VG_GC")[:ng]))
+    T = Translator([x + ".F90" for x in OUT_FILES], registry=reg, stubs=OUT_STUBS)
+    ns = T.compile(["OUTBLOCK"], ns)
+    arg = {"FL1": FArr.of(np.ascontiguousarray(o.get_fl1()[:, :, pts].transpose(2, 1, 0))),
+           "XLLWS": FArr.of(np.ascontiguousarray(o.get_xllws()[:, :, pts].transpose(2, 1, 0)))}
+    for nm in ("WAVNUM", "CINV", "CGROUP"):
+        arg[nm] = FArr.of(np.ascontiguousarray(o.get_field3(nm)[:, pts].T))
+    for nm in ("DEPTH", "UCUR", "VCUR", "IBRMEM", "USTOKES", "VSTOKES", "STRNMS", "TAUXD", "TAUYD", "TAUOCXD", "TAUOCYD", "TAUOC", "TAUICX", "TAUICY", "PHIOCD",
+               "PHIEPS", "PHIAW", "AIRD", "WDWAVE", "CICOVER", "WSWAVE", "WSTAR", "UFRIC", "TAUW", "Z0M", "Z0B", "CHRNCK", "CITHICK"):
+        arg[nm] = FArr.of(o.get_field(nm)[pts])
+    for nm in ("ALTWH", "CALTWH", "RALTCOR", "NEMOCICOVER", "NEMOCITHICK", "NEMOUCUR", "NEMOVCUR"):
+        arg[nm] = FArr.of(np.zeros(K))
+    arg["IODP"] = FArr.of(np.ones(K, dtype=np.int64))
+    arg["MIJ"] = FArr.of(o.get_field("MIJ")[pts].astype(np.int64))
+    arg["BOUT"] = FArr([(1, K), (1, len(OUT_ITG))])
+    t0 = time.time()
+    # SEBTMEAN reads FR(0) and FL1(:,:,0) for a period band that lies below the first model frequency (MCUTT = MCUTB - 1 = 0,
+    # sebtmean.F90:95,122-131): out of bounds in the reference, with weight WL = 0 -- any finite value gives EBT = EPSMIN.  The
+    # translator returns 0 for such reads in this run only.
+    FArr.oob_read_zero = True
+    try:
+        ns["OUTBLOCK"](*[FInt(1) if a == "KIJS" else FInt(K) if a == "KIJL" else arg[a] for a in T.routines["OUTBLOCK"].args])
+    finally:
+        FArr.oob_read_zero = False
+    ref = arg["BOUT"].a.T.copy()                       # [column, point]
+    got = o.outbs(OUT_ITG, OUT_ICE, OUT_SEA)[:, pts]
+    print("%s: OUTBLOCK of the reference source, %d parameters on %d points in %.1f s" % (name, len(OUT_ITG), K, time.time() - t0))
+    assert np.array_equal(ref == -999.0, got == -999.0), "missing-value pattern"
+    ok = ref != -999.0
+    bad = []
+    for i, itg in enumerate(OUT_ITG):
+        m = ok[i]
+        if not m.any():
+            continue
+        d = np.abs(got[i][m] - ref[i][m]).max() / max(np.abs(ref[i][m]).max(), 1e-300)
+        if d > 1e-12:
+            bad.append((itg, float(d)))
+    print("   parameters further than 1e-12 from the oracle:", bad)
+    import json
+    np.savez_compressed(os.path.join(HERE, "ref_outblock_%s.npz" % name), case=case, hook=int(hook), kw=json.dumps(kw, sort_keys=True), pts=pts,
+                        itg=np.array(OUT_ITG), BOUT=ref)
+
+
+OUT_CASES = {"ard": dict(case="o48like"), "jan_noicemask": dict(case="o48_iphys0", kw=dict(lmaskice=0)), "a36_shelf": dict(case="o640like", hook=True),
+             "currents": dict(case="o48like", kw=dict(irefra=3))}
+
+
 def run_connect(name, N=8, mask="continents"):
     """PROPCONNECT (propconnect.F90, 971 lines: the neighbours of every sea point on the irregular grid and their interpolation weights)
     from its own source on a one-rank grid, compared with the oracle's KLAT / KLON / KCOR / WLAT / WCOR and stored."""
@@ -485,11 +563,15 @@ CASES = {
 }
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(CASES) + ["tables", "propag", "connect"])
+    names = sys.argv[1:] or (list(CASES) + ["tables", "propag", "connect", "outblock"])
     for nm in names:
         if nm == "tables":
             for t, kw in TABLE_CASES.items():
                 run_tables(t, **kw)
+            continue
+        if nm == "outblock":
+            for t, d in OUT_CASES.items():
+                run_outblock(t, d["case"], hook=d.get("hook", False), **d.get("kw", {}))
             continue
         if nm == "connect":
             run_connect("continents8", 8, "continents")

@@ -275,3 +275,62 @@ def test_grid_connectivity_matches_the_reference_source(built, path):
         np.testing.assert_array_equal(got, z[nm], err_msg="oracle " + nm)
         np.testing.assert_array_equal(d[nm.lower()].reshape(shape, order="F"), z[nm], err_msg="product " + nm)
     assert (z["KLAT"] == n + 1).any() and (z["KLAT"] <= n).any()          # land and sea neighbours both occur
+
+
+OFILES = sorted(glob.glob(os.path.join(HERE, "golden", "ref_outblock_*.npz")))
+
+
+def _bout_close(got, ref, itgs, rtol):
+    assert np.array_equal(ref == -999.0, got == -999.0), "missing-value pattern"
+    ok = ref != -999.0
+    for i, itg in enumerate(itgs):
+        m = ok[i]
+        if m.any():
+            d = np.abs(got[i][m] - ref[i][m]).max() / max(np.abs(ref[i][m]).max(), 1e-300)
+            assert d <= rtol, "parameter %d: %g" % (itg, d)
+
+
+@pytest.mark.parametrize("path", OFILES, ids=[os.path.basename(f)[len("ref_outblock_"):-4] for f in OFILES])
+def test_outblock_matches_the_reference_source(built, path):
+    """OUTBLOCK (outblock.F90) and the 24 routines below it (FEMEAN, INTPOL, SEPWISW, STHQ, MWP1/2, WDIRSPREAD + PEAKFRI + SCOSFL, OUTBETA,
+    WEFLUX, SE10MEAN, SEBTMEAN, MEANSQS + _GC + _LF + HALPHAP, DOMINANT_PERIOD, OUTSETWMASK, ...) executed from their own source for the 51
+    parameters the product builds: the oracle's OUTBS within 1e-12 at every point and parameter, same missing-value pattern."""
+    from common import OUT_ICE, OUT_ITG, OUT_SEA
+    z = np.load(path)
+    kw, hook, pts = json.loads(str(z["kw"])), bool(int(z["hook"])), z["pts"]
+    g, o, f = G.prepare(str(z["case"]), kw, 2, hook)
+    o.implsch()
+    if kw.get("irefra", 0) >= 2:
+        from common import synthetic_currents
+        u, v = synthetic_currents(g)
+        o.set_field("UCUR", u); o.set_field("VCUR", v)
+    assert list(z["itg"]) == list(OUT_ITG)
+    _bout_close(o.outbs(OUT_ITG, OUT_ICE, OUT_SEA)[:, pts], z["BOUT"], OUT_ITG, 1e-12)
+    assert (z["BOUT"][0] > 0.1).any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", OFILES, ids=[os.path.basename(f)[len("ref_outblock_"):-4] for f in OFILES])
+def test_cuda_outblock_matches_the_reference_source(built, path):
+    from common import OUT_ICE, OUT_ITG, OUT_SEA, compare_bout, make_gpu
+    from ecwam_b200 import synth
+    z = np.load(path)
+    case, kw, hook, pts = str(z["case"]), json.loads(str(z["kw"])), bool(int(z["hook"])), z["pts"]
+    g, s, w = make_gpu(case, grid_hook=G.shelf if hook else None, **kw)
+    f = synth.make_forcing(g)
+    n = g.niblo
+    ci = f["CICOVER"]
+    w.set_field("cithick", np.where(ci > 0, 0.3 + 1.5 * ci, 0.0))
+    for _ in range(2):
+        assert w.step() == 0
+    assert w.propag() == 0
+    w.implsch()
+    if kw.get("irefra", 0) >= 2:
+        from common import synthetic_currents
+        u, v = synthetic_currents(g)
+        w.set_field("ucur", u); w.set_field("vcur", v)
+    a = w.outbs(OUT_ITG, OUT_ICE, OUT_SEA)
+    inv = np.empty(n, dtype=np.int64)
+    inv[w.own] = np.arange(n)
+    worst = compare_bout(a[:, inv[pts]], z["BOUT"])          # the tolerances of tests/test_gpu_output.py
+    assert max(worst.values()) < 1e-7
