@@ -7,11 +7,12 @@
 //
 // PINNING: the reference (Fortran + fiat + field_api + eccodes) cannot be built in this image
 // and ships no per-routine golden vectors (only end-to-end swh norms that need GRIB forcing,
-// SURVEY.md §8c).  The IMPLSCH tree of this oracle is pinned against the reference's own
-// source text, executed statement by statement through tests/golden/f90run.py (fixtures
-// tests/golden/ref_*.npz, <= 2.3e-15); the rest (PROPAG_WAM, output side) is a reviewed literal
-// restatement pinned by the invariants and numpy re-derivations in tests/ -- "parity unpinned"
-// in the strict sense for those parts.
+// SURVEY.md §8c).  This oracle is pinned against the reference's own source text, executed
+// statement by statement through tests/golden/f90run.py (fixtures tests/golden/ref_*.npz):
+// the IMPLSCH tree (<= 2.3e-15), the table builders, PROPCONNECT, CTUWUPDT / PROPDOT / GRADI /
+// PROPAGS2 for IREFRA 0-3 (bit-identical) and OUTBLOCK's 51 parameters (<= 1e-12).  MPDECOMP,
+// NEWWIND / WAMWND / MICEP and MPMINMAXAVG are a reviewed literal restatement pinned by the
+// invariants and numpy re-derivations in tests/ -- "parity unpinned" in the strict sense.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // may load this library.  The product (ecwam_b200/) never does.
