@@ -488,6 +488,58 @@ OUT_CASES = {"ard": dict(case="o48like"), "jan_noicemask": dict(case="o48_iphys0
              "currents": dict(case="o48like", kw=dict(irefra=3))}
 
 
+def run_getwnd(name, llwswave=0, llwdwave=0, lrelwind=0, irefra=0, iparamci=31, liceth=0, lmaskice=1):
+    """GETWND's blocking step -- WAMWND (wamwnd.F90, ICODE_WND = 3) + MICEP (micep.F90, uncoupled) -- from their own source on the forcing
+    fields of tests/common.py synthetic_fieldg; compared with the oracle's getwnd_points and stored."""
+    from common import synthetic_fieldg
+    from f90run import module_registry
+    from oracle import oracle as O
+    from ecwam_b200 import synth
+    g = synth.make_grid(8, "continents")
+    f, ii, jj = synthetic_fieldg(g, with_ws=bool(llwswave or llwdwave))
+    if iparamci == 139:           # the ice field is an SST [K]: ice where it is below 271.5 K
+        rng = np.random.default_rng(11)
+        f["cicover"] = 268.0 + 10.0 * rng.random(f["uwnd"].shape)
+    n = len(ii)
+    rng = np.random.default_rng(3)
+    uc, vc = rng.normal(0, 0.5, n), rng.normal(0, 0.5, n)
+    ny, nx = f["uwnd"].shape
+    reg = module_registry(MODULES + ["yowmap", "yowmpp", "yownemoflds"])
+    ns = module_parameters()
+    for k in reg:
+        ns.setdefault(k, None)
+    I = lambda v: FInt(int(v))
+    wspmin = 0.3
+    ns.update(LWCOU=False, IREFRA=I(irefra), LRELWIND=bool(lrelwind), WSPMIN=wspmin, LLWSWAVE=bool(llwswave), LLWDWAVE=bool(llwdwave),
+              ZMISS=-999.0, EPSUS=1.0e-6, G=9.806, ZPI=2.0 * float(4.0 * np.arctan(1.0)), XKAPPA=0.4, IU06=I(6), LHOOK=False,
+              CITHRSH=0.3, LICERUN=True, LMASKICE=bool(lmaskice), LICETH=bool(liceth), NGX=I(nx), NGY=I(ny), CLDOMAIN="g", IRANK=I(1), NPROC=I(1),
+              SWAMPCITH=0.0, LWNEMOCOUCIC=False, LWNEMOCOUCIT=False, LNEMOICEREST=False, HICMIN=float(ns.get("HICMIN", 0.2) or 0.2))
+    zero = np.zeros((ny, nx))
+    for k in ("uwnd", "vwnd", "aird", "wstar", "cicover", "cithick", "ustra", "vstra", "wswave", "wdwave"):
+        ns["FIELDG_" + k.upper()] = FArr.of(np.ascontiguousarray(f.get(k, zero).T))         # FIELDG%X(IX, JY)
+    ns["FIELDG_LKFR"] = FArr.of(np.zeros((nx, ny)))
+    T = Translator(["wamwnd.F90", "micep.F90"], registry=reg)
+    ns = T.compile(["WAMWND", "MICEP"], ns)
+    IF_, JF_ = FArr.of(ii.astype(np.int64)), FArr.of(jj.astype(np.int64))
+    out = {k: FArr([(1, n)]) for k in ("U10", "US", "THW", "ADS", "WSTAR", "CITH", "USTRA", "VSTRA", "CICVR")}
+    lwcur = bool(lrelwind and irefra >= 2)
+    ns["WAMWND"](I(1), I(n), IF_, JF_, I(1), I(nx), I(1), I(ny), None, FArr.of(uc), FArr.of(vc), out["U10"], out["US"], out["THW"], out["ADS"],
+                 out["WSTAR"], out["CITH"], out["USTRA"], out["VSTRA"], lwcur, I(3))
+    ns["MICEP"](I(iparamci), I(1), I(n), IF_, JF_, I(1), I(nx), I(1), I(ny), None, out["CICVR"], out["CITH"], FArr.of(np.zeros(n)), FArr.of(np.zeros(n)))
+    ref = dict(wswave=out["U10"].a, wdwave=out["THW"].a, aird=out["ADS"].a, wstar=out["WSTAR"].a, cicover=out["CICVR"].a, cithick=out["CITH"].a,
+               ustra=out["USTRA"].a, vstra=out["VSTRA"].a)
+    got = O.getwnd_points(ii, jj, f, ucur=uc, vcur=vc, llwswave=llwswave, llwdwave=llwdwave, lcorrel=int(lwcur), iparamci=iparamci, liceth=liceth,
+                          lmaskice=lmaskice, wspmin=wspmin)
+    bad = [(k, float(np.abs(got[k] - ref[k]).max())) for k in ref if not np.array_equal(got[k], ref[k])]
+    print("%s: WAMWND + MICEP of the reference source on %d points; fields not identical to the oracle: %s" % (name, n, bad))
+    np.savez_compressed(os.path.join(HERE, "ref_getwnd_%s.npz" % name), opts=np.array([llwswave, llwdwave, lrelwind, irefra, iparamci, liceth, lmaskice]),
+                        uc=uc, vc=vc, **ref)
+
+
+GETWND_CASES = {"plain": dict(), "wswave": dict(llwswave=1), "wswave_wdwave_relwind": dict(llwswave=1, llwdwave=1, lrelwind=1, irefra=3),
+                "sst_liceth": dict(iparamci=139, liceth=1), "nomask_liceth": dict(liceth=1, lmaskice=0)}
+
+
 def run_connect(name, N=8, mask="continents"):
     """PROPCONNECT (propconnect.F90, 971 lines: the neighbours of every sea point on the irregular grid and their interpolation weights)
     from its own source on a one-rank grid, compared with the oracle's KLAT / KLON / KCOR / WLAT / WCOR and stored."""
@@ -563,7 +615,7 @@ CASES = {
 }
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(CASES) + ["tables", "propag", "connect", "outblock"])
+    names = sys.argv[1:] or (list(CASES) + ["tables", "propag", "connect", "outblock", "getwnd"])
     for nm in names:
         if nm == "tables":
             for t, kw in TABLE_CASES.items():
@@ -572,6 +624,10 @@ if __name__ == "__main__":
         if nm == "outblock":
             for t, d in OUT_CASES.items():
                 run_outblock(t, d["case"], hook=d.get("hook", False), **d.get("kw", {}))
+            continue
+        if nm == "getwnd":
+            for t, d in GETWND_CASES.items():
+                run_getwnd(t, **d)
             continue
         if nm == "connect":
             run_connect("continents8", 8, "continents")

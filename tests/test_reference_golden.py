@@ -334,3 +334,47 @@ def test_cuda_outblock_matches_the_reference_source(built, path):
     inv[w.own] = np.arange(n)
     worst = compare_bout(a[:, inv[pts]], z["BOUT"])          # the tolerances of tests/test_gpu_output.py
     assert max(worst.values()) < 1e-7
+
+
+WFILES = sorted(glob.glob(os.path.join(HERE, "golden", "ref_getwnd_*.npz")))
+WNAMES = ("wswave", "wdwave", "aird", "wstar", "cicover", "cithick", "ustra", "vstra")
+
+
+def _getwnd_inputs(z):
+    from common import synthetic_fieldg
+    from ecwam_b200 import synth
+    llwswave, llwdwave, lrelwind, irefra, iparamci, liceth, lmaskice = (int(x) for x in z["opts"])
+    g = synth.make_grid(8, "continents")
+    f, ii, jj = synthetic_fieldg(g, with_ws=bool(llwswave or llwdwave))
+    if iparamci == 139:
+        f["cicover"] = 268.0 + 10.0 * np.random.default_rng(11).random(f["uwnd"].shape)
+    return g, f, ii, jj, dict(llwswave=llwswave, llwdwave=llwdwave, iparamci=iparamci, liceth=liceth), lrelwind, irefra, lmaskice
+
+
+@pytest.mark.parametrize("path", WFILES, ids=[os.path.basename(f)[len("ref_getwnd_"):-4] for f in WFILES])
+def test_getwnd_matches_the_reference_source(built, path):
+    """WAMWND (wamwnd.F90, ICODE_WND = 3: wind from components or from a previous WAM run, relative-wind correction) + MICEP (micep.F90:
+    ice fraction or SST, parametric thickness, HICMIN) executed from their own source: the oracle's FF_NEXT fields are identical."""
+    from oracle import oracle as O
+    z = np.load(path)
+    g, f, ii, jj, opts, lrelwind, irefra, lmaskice = _getwnd_inputs(z)
+    got = O.getwnd_points(ii, jj, f, ucur=z["uc"], vcur=z["vc"], lcorrel=int(lrelwind and irefra >= 2), lmaskice=lmaskice, wspmin=0.3, **opts)
+    for k in WNAMES:
+        np.testing.assert_array_equal(got[k], z[k], err_msg=k)
+    assert (z["cicover"] > 0).any() and (z["wswave"] == 0.3).any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", WFILES, ids=[os.path.basename(f)[len("ref_getwnd_"):-4] for f in WFILES])
+def test_cuda_getwnd_matches_the_reference_source(built, path):
+    from ecwam_b200 import model as M
+    z = np.load(path)
+    g, f, ii, jj, opts, lrelwind, irefra, lmaskice = _getwnd_inputs(z)
+    s = M.WamSetup(g, nproc=1, nproma=16, wspmin=0.3, irefra=irefra, lmaskice=lmaskice)
+    w = M.WamIntgr(s, 0)
+    w.set_static(g.depth)
+    w.set_field("ucur", z["uc"]); w.set_field("vcur", z["vc"])
+    out = w.getwnd(f, ii, jj, lrelwind=lrelwind, **opts)
+    for k in WNAMES:
+        a = out[k].reshape(-1)[: w.nloc].cpu().numpy()
+        np.testing.assert_allclose(a, z[k][w.own], rtol=1e-13, atol=1e-14, err_msg=k)
