@@ -361,7 +361,7 @@ def test_getwnd_matches_the_reference_source(built, path):
     got = O.getwnd_points(ii, jj, f, ucur=z["uc"], vcur=z["vc"], lcorrel=int(lrelwind and irefra >= 2), lmaskice=lmaskice, wspmin=0.3, **opts)
     for k in WNAMES:
         np.testing.assert_array_equal(got[k], z[k], err_msg=k)
-    assert (z["cicover"] > 0).any() and (z["wswave"] == 0.3).any()
+    assert (z["cicover"] > 0).any() and z["wswave"].min() >= 0.3
 
 
 @pytest.mark.gpu
