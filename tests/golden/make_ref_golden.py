@@ -540,6 +540,56 @@ GETWND_CASES = {"plain": dict(), "wswave": dict(llwswave=1), "wswave_wdwave_relw
                 "sst_liceth": dict(iparamci=139, liceth=1), "nomask_liceth": dict(liceth=1, lmaskice=0)}
 
 
+def run_newwind(name, icode=3):
+    """NEWWIND (newwind.F90:105-167) from its own source: FF_NOW <- FF_NEXT with the low-wind cap of the first-guess wave stress
+    (ICODE_WND = 3) or the friction-velocity branch (ICODE_WND = 1); compared with the oracle and stored."""
+    from common import next_forcing
+    from f90run import module_registry
+    kw = dict(icode=icode) if icode != 3 else {}
+    g, o, f = prepare("o48like", kw, 2, False)
+    n = g.niblo
+    P = 16
+    C_ = (n + P - 1) // P
+    nxt = next_forcing(f)
+    us = np.sqrt(8.0e-4 + 8.0e-5 * f["WSWAVE"]) * f["WSWAVE"]
+    nxt["UFRIC"] = np.maximum(0.05, 1.3 * us * ((np.arange(n) * 13) % 7) / 6.0)
+    nxt["WSWAVE"] = np.where(np.arange(n) % 3 == 0, 0.25 * nxt["WSWAVE"], nxt["WSWAVE"])      # some below WSPMIN_RESET_TAUW = 4 m/s
+    reg = module_registry(MODULES + ["yowgrid", "yowwndg"])
+    ns = module_parameters()
+    for k in reg:
+        ns.setdefault(k, None)
+    I = lambda v: FInt(int(v))
+    ns.update(ACD=float(o.table("ACD")[0]), BCD=float(o.table("BCD")[0]), EPSMIN=float(o.table("EPSMIN")[0]), LWCOU=False, NPROMA_WAM=I(P), NCHNK=I(C_),
+              NFRE=I(36), ALPHA=float(o.table("ALPHA")[0]), IDELWO=I(3600), IU06=I(6), CDATEWL="20200101000000", CDAWIFL="20200101000000",
+              CDATEFL="20300101000000", CDTNEXT="20200101010000", NSTORE=I(1), ICODE=I(icode), ICODE_CPL=I(icode), LHOOK=False)
+
+    def chunked(v):
+        a = np.zeros(P * C_)
+        a[:n] = v
+        return FArr.of(a.reshape((P, C_), order="F"))
+    now = ("WSWAVE", "WDWAVE", "AIRD", "WSTAR", "CICOVER", "CITHICK", "USTRA", "VSTRA", "UFRIC", "TAUW", "CHRNCK")
+    for k in now:
+        ns["FF_NOW_" + k] = chunked(o.get_field(k))
+    for k in ("WSWAVE", "WDWAVE", "AIRD", "WSTAR", "CICOVER", "CITHICK", "USTRA", "VSTRA", "UFRIC"):
+        ns["FF_NEXT_" + k] = chunked(nxt[k])
+    # the padded lanes of the last chunk divide by CHRNCK in the friction-velocity branch: give them a finite value
+    ns["FF_NOW_CHRNCK"].a[ns["FF_NOW_CHRNCK"].a == 0.0] = 0.018
+    T = Translator(["newwind.F90"], registry=reg, stubs=("INCDATE",))
+    ns = T.compile(["NEWWIND"], ns)
+    ns["NEWWIND"]("20200101010000", "20200101010000", False, None, None, None)
+    o.newwind(nxt)
+    out, bad = dict(icode=icode), []
+    for k in now:
+        ref = ns["FF_NOW_" + k].a.reshape(-1, order="F")[:n]
+        out[k] = ref
+        if not np.array_equal(o.get_field(k), ref):
+            bad.append((k, float(np.abs(o.get_field(k) - ref).max())))
+    for k in nxt:
+        out["NEXT_" + k] = nxt[k]
+    print("%s: NEWWIND of the reference source on %d points; fields not identical to the oracle: %s" % (name, n, bad))
+    np.savez_compressed(os.path.join(HERE, "ref_newwind_%s.npz" % name), **out)
+
+
 def run_connect(name, N=8, mask="continents"):
     """PROPCONNECT (propconnect.F90, 971 lines: the neighbours of every sea point on the irregular grid and their interpolation weights)
     from its own source on a one-rank grid, compared with the oracle's KLAT / KLON / KCOR / WLAT / WCOR and stored."""
@@ -615,7 +665,7 @@ CASES = {
 }
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(CASES) + ["tables", "propag", "connect", "outblock", "getwnd"])
+    names = sys.argv[1:] or (list(CASES) + ["tables", "propag", "connect", "outblock", "getwnd", "newwind"])
     for nm in names:
         if nm == "tables":
             for t, kw in TABLE_CASES.items():
@@ -624,6 +674,10 @@ if __name__ == "__main__":
         if nm == "outblock":
             for t, d in OUT_CASES.items():
                 run_outblock(t, d["case"], hook=d.get("hook", False), **d.get("kw", {}))
+            continue
+        if nm == "newwind":
+            run_newwind("u10", 3)
+            run_newwind("ustar", 1)
             continue
         if nm == "getwnd":
             for t, d in GETWND_CASES.items():

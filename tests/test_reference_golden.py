@@ -378,3 +378,48 @@ def test_cuda_getwnd_matches_the_reference_source(built, path):
     for k in WNAMES:
         a = out[k].reshape(-1)[: w.nloc].cpu().numpy()
         np.testing.assert_allclose(a, z[k][w.own], rtol=1e-13, atol=1e-14, err_msg=k)
+
+
+NFILES = sorted(glob.glob(os.path.join(HERE, "golden", "ref_newwind_*.npz")))
+NOW = ("WSWAVE", "WDWAVE", "AIRD", "WSTAR", "CICOVER", "CITHICK", "USTRA", "VSTRA", "UFRIC", "TAUW")
+
+
+@pytest.mark.parametrize("path", NFILES, ids=[os.path.basename(f)[len("ref_newwind_"):-4] for f in NFILES])
+def test_newwind_matches_the_reference_source(built, path):
+    """NEWWIND (newwind.F90:105-167) executed from its own source, the 10 m wind branch with the low-wind cap of TAUW and the
+    friction-velocity branch: the oracle's FF_NOW fields are identical."""
+    z = np.load(path)
+    icode = int(z["icode"])
+    g, o, f = G.prepare("o48like", dict(icode=icode) if icode != 3 else {}, 2, False)
+    o.newwind({k[5:]: z[k] for k in z.files if k.startswith("NEXT_")})
+    for k in NOW:
+        np.testing.assert_array_equal(o.get_field(k), z[k], err_msg=k)
+    assert (z["TAUW"] == 0).any() if icode != 3 else (z["WSWAVE"] < 4.0).any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", NFILES, ids=[os.path.basename(f)[len("ref_newwind_"):-4] for f in NFILES])
+def test_cuda_newwind_matches_the_reference_source(built, path):
+    from common import make_gpu
+    from ecwam_b200 import synth
+    z = np.load(path)
+    icode = int(z["icode"])
+    kw = dict(icode_wnd=icode) if icode != 3 else {}
+    g, s, w = make_gpu("o48like", **kw)
+    f = synth.make_forcing(g)
+    ci = f["CICOVER"]
+    w.set_field("cithick", np.where(ci > 0, 0.3 + 1.5 * ci, 0.0))
+    if icode != 3:
+        us = np.sqrt(8.0e-4 + 8.0e-5 * f["WSWAVE"]) * f["WSWAVE"]
+        for k, v in dict(ufric=us, tauw=0.4 * us * us, tauwdir=f["WDWAVE"], chrnck=np.full_like(us, 0.018)).items():
+            w.set_field(k, v)
+    for _ in range(2):
+        assert w.step() == 0
+    assert w.propag() == 0
+    w.newwind({k[5:]: z[k] for k in z.files if k.startswith("NEXT_")})
+    for k in NOW:
+        a, b = w.get_field(k.lower()), z[k][w.own]
+        if k in ("TAUW", "UFRIC", "WSWAVE"):      # products of the GPU's own two steps (1e-15 apart from the oracle's) enter TAUW / the cap
+            assert np.abs(a - b).max() <= 1e-10 * max(np.abs(b).max(), 1e-12), k
+        else:
+            np.testing.assert_array_equal(a, b, err_msg=k)
