@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "ecwam_b200.h")
 OUT = os.path.join(ROOT, "fortran", "ecwam_b200_mod.F90")
 
-STRUCTS = ["ecwam_b200_params", "ecwam_b200_tables", "ecwam_b200_decomp", "ecwam_b200_fields", "ecwam_b200_forcing_next",
+STRUCTS = ["ecwam_b200_params", "ecwam_b200_tables", "ecwam_b200_decomp", "ecwam_b200_fields", "ecwam_b200_nemo_fields", "ecwam_b200_forcing_next",
            "ecwam_b200_outsel", "ecwam_b200_fieldg", "ecwam_b200_getwnd_opts"]
 # written by hand below (assumed-size array dummies so that the reference's actual arguments can be passed as they are)
 HAND = {"ecwam_b200_implsch_f", "ecwam_b200_propag_wam_f"}
