@@ -309,7 +309,7 @@ PROP_FILES = "ctuwupdt ctuwini ctuwdrv ctuw propags2 propdot gradi".split()
 PROP_MODULES = MODULES + ["yowubuf", "yowmap", "yowgrid", "yowrefd", "yowmpp"]
 
 
-def run_propag(name, N=8, mask="continents", **kw):
+def run_propag(name, N=8, mask="continents", obs=False, **kw):
     """CTUWUPDT (+ CTUWINI, CTUWDRV, CTUW) and PROPAGS2 from their own source on a small one-rank grid: the CTU weights of every point,
     direction and frequency and one advection step, compared with the oracle's stored weights / PROPAG_WAM and stored."""
     import ctypes as C
@@ -345,6 +345,12 @@ def run_propag(name, N=8, mask="continents", **kw):
               KCOR=FArr.of(o.itable("KCOR").reshape((n, 4, 2), order="F").astype(np.int64)),
               WLAT=FArr.of(o.rank_double("WLAT").reshape((n, 2), order="F")), WCOR=FArr.of(o.rank_double("WCOR").reshape((n, 4), order="F")),
               OBSLAT=FArr.of(np.ones((n, FR_, 2))), OBSLON=FArr.of(np.ones((n, FR_, 2))), OBSCOR=FArr.of(np.ones((n, FR_, 4))))
+    if obs:      # LSUBGRID = T: synthetic obstruction coefficients (tests/test_oracle.py _obstructions), in the new numbering
+        from test_oracle import _obstructions
+        ob = _obstructions(n, FR_)
+        o.set_obstructions(*ob)
+        for nm, a in zip(("OBSLON", "OBSLAT", "OBSCOR"), ob):
+            ns[nm] = FArr.of(np.ascontiguousarray(a[:, :, new2ij].transpose(2, 1, 0)))
     ns["OML_GET_MAX_THREADS"] = lambda: FInt(1)
     # PROENVHALO on one rank: the fields in the new numbering + the land point NSUP + 1 (proenvhalo.F90:98-106)
     s = M.WamSetup(g, nproc=1, nang=A, nfre_red=FR_)
@@ -386,7 +392,7 @@ def run_propag(name, N=8, mask="continents", **kw):
     ns["PROPAGS2"](F1, F3, I(1), I(n), I(1), I(n), I(A), I(1), I(FR_), I(1), I(FR_))
     print("%s: CTUWUPDT + PROPAGS2 of the reference source on %d points in %.1f s" % (name, n, time.time() - t0))
     assert o.propag() == 0
-    out = dict(N=N, mask=mask, kw=__import__("json").dumps(kw, sort_keys=True))
+    out = dict(N=N, mask=mask, obs=int(obs), kw=__import__("json").dumps(kw, sort_keys=True))
     arrays = [("SUMWN", (n, A, FR_)), ("WLONN", (n, A, FR_, 2)), ("WLATN", (n, A, FR_, 2, 2)), ("WCORN", (n, A, FR_, 4, 2)), ("WKPMN", (n, A, FR_, 3))]
     if c.irefra >= 2:
         arrays.append(("WMPMN", (n, A, FR_, 3)))
@@ -638,7 +644,7 @@ def run_connect(name, N=8, mask="continents"):
     np.savez_compressed(os.path.join(HERE, "ref_connect_%s.npz" % name), **out)
 
 
-PROP_CASES = {"a12": dict(N=8), "a12_irefra1": dict(N=8, kw=dict(irefra=1)), "a12_irefra3": dict(N=8, kw=dict(irefra=3)),
+PROP_CASES = {"a12": dict(N=8), "a12_subgrid": dict(N=8, obs=True), "a12_subgrid_irefra3": dict(N=8, obs=True, kw=dict(irefra=3)), "a12_irefra1": dict(N=8, kw=dict(irefra=1)), "a12_irefra3": dict(N=8, kw=dict(irefra=3)),
               "a12_irefra2": dict(N=8, kw=dict(irefra=2)), "a24_fastwaves": dict(N=8, kw=dict(nang=24, nfre_red=29, ifrelfmax=5, delpro_lf=225.0, idelpro=450.0, idelt=450.0))}
 
 TABLE_CASES = {"a12_ard": dict(nang=12, nfre_red=25, iphys=1), "a24_ard": dict(nang=24, nfre_red=29, iphys=1), "a36_ard": dict(nang=36, nfre_red=29, iphys=1),
@@ -690,7 +696,7 @@ if __name__ == "__main__":
         if nm == "propag" or nm.startswith("propag:"):
             for t, d in PROP_CASES.items():
                 if nm == "propag" or t in nm.split(":")[1:]:
-                    run_propag(t, N=d.get("N", 8), **d.get("kw", {}))
+                    run_propag(t, N=d.get("N", 8), obs=d.get("obs", False), **d.get("kw", {}))
             continue
         c = CASES[nm]
         run_case(nm, c["case"], hook=c.get("hook", False), **c.get("kw", {}))

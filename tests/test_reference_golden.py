@@ -203,6 +203,9 @@ def test_ctu_weights_and_propags2_match_the_reference_source(built, path):
         from common import synthetic_currents
         u, v = synthetic_currents(g)
         o.set_field("UCUR", u); o.set_field("VCUR", v)
+    if "obs" in z.files and int(z["obs"]):      # LSUBGRID = T
+        from test_oracle import _obstructions
+        o.set_obstructions(*_obstructions(g.niblo, c.nfre_red))
     assert o.propag() == 0
     n, A, FR_ = g.niblo, c.nang, c.nfre_red
     sel, new2ij, m0 = z["sel"], z["new2ij"], int(z["m0"])
@@ -225,12 +228,17 @@ def test_cuda_propags2_matches_the_reference_source(built, monkeypatch, path):
     z, kw, g = _prop_case(path)
     sel, new2ij, m0 = z["sel"], z["new2ij"], int(z["m0"])
     cur = kw.get("irefra", 0) >= 2
-    for mode, exact in ((("exact", True),) if cur else (("exact", True), (None, False))):
+    one = cur or ("obs" in z.files and int(z["obs"]))        # currents / obstructions always run the exact kernels
+    for mode, exact in ((("exact", True),) if one else (("exact", True), (None, False))):
         if mode:
             monkeypatch.setenv("ECWAM_B200_PROPAG", mode)
         else:
             monkeypatch.delenv("ECWAM_B200_PROPAG", raising=False)
         s = M.WamSetup(g, nproc=1, nproma=16, **kw)
+        subgrid = "obs" in z.files and int(z["obs"])
+        if subgrid:
+            from test_oracle import _obstructions
+            s.set_obstructions(*_obstructions(g.niblo, s.par.nfre_red))
         w = M.WamIntgr(s, 0)
         w.set_static(g.depth)
         f = synth.make_forcing(g)
