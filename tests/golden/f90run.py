@@ -619,6 +619,8 @@ class Translator:
                     b.append("(%s, %s)" % (self.expr(r, lo), self.expr(r, hi)))
                 if b is not None:
                     emit("%s = FArr([%s], %s)" % (nm, ", ".join(b), {float: "float", int: "int", bool: "bool", str: "object"}[d["type"]]))
+                else:
+                    emit("%s = None" % nm)        # ALLOCATABLE: not allocated yet
         for nm, los in rebase:
             emit("if %s is not None: %s = %s.rebase([%s])" % (nm, nm, nm, ", ".join(self.expr(r, lo) for lo in los)))
         stack = []

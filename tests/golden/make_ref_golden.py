@@ -596,6 +596,51 @@ def run_newwind(name, icode=3):
     np.savez_compressed(os.path.join(HERE, "ref_newwind_%s.npz" % name), **out)
 
 
+def run_decomp(name, N, mask, npr, ll1d=0):
+    """The sector decomposition of MPDECOMP (mpdecomp.F90: the block between `NXFFS=1` and `DEALLOCATE(NEND1D)`, i.e. NXDECOMP x NYDECOMP
+    sectors, NSTART / NEND and the relabelling NEWIJ2IJ / IJ2NEWIJ of the sea points) executed from its own source for NPR ranks; compared
+    with the oracle's tables and stored.  (The halo lists that follow use MPL_ALLGATHERV and are not translated.)"""
+    from f90run import _logical_lines, module_registry
+    from oracle import oracle as O
+    from ecwam_b200 import synth
+    g = synth.make_grid(N, mask)
+    o = O.Oracle(O.default_config(nproma=16, npr=npr, ll1d=ll1d), g)
+    n, ngy = g.niblo, int(g.ngy)
+    reg = module_registry(PROP_MODULES + ["yowspec", "yowunpool"])
+    ns = module_parameters()
+    for k in reg:
+        ns.setdefault(k, None)
+    I = lambda v: FInt(int(v))
+    ij2new = o.itable("IJ2NEWIJ")[: n + 1]
+    ixlg0 = o.itable("IXLG")[:n][ij2new[1:] - 1]            # BLK2GLO in the ORIGINAL numbering: the state MPDECOMP starts from
+    kxlt0 = o.itable("KXLT")[:n][ij2new[1:] - 1]
+    ns.update(NGX=I(int(np.max(g.nlonrgg))), NGY=I(ngy), NIBLO=I(n), IJS=I(1), IJL=I(n), IRANK=I(1), NPROC=I(npr), LL1D=bool(ll1d), LLUNSTR=False,
+              IU06=I(6), LHOOK=False, NLONRGG=FArr.of(np.asarray(g.nlonrgg, dtype=np.int64)),
+              IPER=I(1), IRGG=I(1), AMOWEP=0.0, XDELLO=360.0 / float(np.max(g.nlonrgg)), AMOEAP=360.0 - 360.0 / float(np.max(g.nlonrgg)),
+              AMOSOP=float(g.amosop), AMONOP=float(g.amonop), XDELLA=float(o.table("XDELLA")[0]), ZDELLO=FArr.of(o.table("ZDELLO")[:ngy]),
+              BLK2GLO_IXLG=FArr.of(ixlg0.astype(np.int64)), BLK2GLO_KXLT=FArr.of(kxlt0.astype(np.int64)),
+              NEWIJ2IJ=FArr([(0, n)], int), IJ2NEWIJ=FArr([(0, n)], int))
+    T = Translator(["mpdecomp.F90"], registry=reg, stubs=("FLUSH",))
+    r = T.routines["MPDECOMP"]
+    i0 = next(i for i, x in enumerate(r.body) if x.replace(" ", "") == "NXFFS=1")
+    i1 = next(i for i, x in enumerate(r.body) if x.replace(" ", "") == "DEALLOCATE(NEND1D)")
+    # the ELSE branch of `IF (LLUNSTR)` the fragment sits in is not closed inside it
+    r.body = r.body[i0:i1 + 1]
+    ns = T.compile(["MPDECOMP"], ns)
+    ns["MPDECOMP"](I(npr), I(0), False, False)
+    out = dict(N=N, mask=mask, npr=npr, ll1d=ll1d)
+    bad = []
+    # (NEWIJ2IJ is a local of MPDECOMP; it is the inverse of the module array IJ2NEWIJ.)  BLK2GLO comes back relabelled.
+    for nm, sl in (("NSTART", slice(0, npr)), ("NEND", slice(0, npr)), ("IJ2NEWIJ", slice(1, n + 1)), ("IXLG", slice(0, n)), ("KXLT", slice(0, n))):
+        ref = ns[nm].a[sl] if nm == "IJ2NEWIJ" else ns["BLK2GLO_" + nm].a if nm in ("IXLG", "KXLT") else ns[nm].a
+        got = o.itable(nm)[sl]
+        out[nm] = np.asarray(ref, dtype=np.int64)
+        if not np.array_equal(got, ref):
+            bad.append(nm)
+    print("%s: MPDECOMP's sector decomposition of the reference source, %d points on %d ranks; tables not identical to the oracle: %s" % (name, n, npr, bad))
+    np.savez_compressed(os.path.join(HERE, "ref_decomp_%s.npz" % name), **out)
+
+
 def run_connect(name, N=8, mask="continents"):
     """PROPCONNECT (propconnect.F90, 971 lines: the neighbours of every sea point on the irregular grid and their interpolation weights)
     from its own source on a one-rank grid, compared with the oracle's KLAT / KLON / KCOR / WLAT / WCOR and stored."""
@@ -671,7 +716,7 @@ CASES = {
 }
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(CASES) + ["tables", "propag", "connect", "outblock", "getwnd", "newwind"])
+    names = sys.argv[1:] or (list(CASES) + ["tables", "propag", "connect", "outblock", "getwnd", "newwind", "decomp"])
     for nm in names:
         if nm == "tables":
             for t, kw in TABLE_CASES.items():
@@ -680,6 +725,12 @@ if __name__ == "__main__":
         if nm == "outblock":
             for t, d in OUT_CASES.items():
                 run_outblock(t, d["case"], hook=d.get("hook", False), **d.get("kw", {}))
+            continue
+        if nm == "decomp":
+            for npr in (1, 2, 3, 4, 5, 8):
+                run_decomp("continents12_npr%d" % npr, 12, "continents", npr)
+            run_decomp("aqua8_npr6", 8, "aqua", 6)
+            run_decomp("continents12_npr4_1d", 12, "continents", 4, ll1d=1)
             continue
         if nm == "newwind":
             run_newwind("u10", 3)

@@ -431,3 +431,26 @@ def test_cuda_newwind_matches_the_reference_source(built, path):
             assert np.abs(a - b).max() <= 1e-10 * max(np.abs(b).max(), 1e-12), k
         else:
             np.testing.assert_array_equal(a, b, err_msg=k)
+
+
+DFILES = sorted(glob.glob(os.path.join(HERE, "golden", "ref_decomp_*.npz")))
+
+
+@pytest.mark.parametrize("path", DFILES, ids=[os.path.basename(f)[len("ref_decomp_"):-4] for f in DFILES])
+def test_decomposition_matches_the_reference_source(built, path):
+    """MPDECOMP's sector decomposition (mpdecomp.F90: NXDECOMP x NYDECOMP sectors with staggered bands, NSTART / NEND, the relabelling
+    IJ2NEWIJ of the sea points and the relabelled BLK2GLO) executed from its own source for 1 - 8 ranks and the 1-D variant: the oracle's and
+    the product's tables are identical."""
+    from ecwam_b200 import model as M, synth
+    from oracle import oracle as O
+    z = np.load(path)
+    npr, ll1d = int(z["npr"]), int(z["ll1d"])
+    g = synth.make_grid(int(z["N"]), str(z["mask"]))
+    n = g.niblo
+    o = O.Oracle(O.default_config(nproma=16, npr=npr, ll1d=ll1d), g)
+    s = M.WamSetup(g, nproc=npr, ll1d=bool(ll1d), nproma=16)
+    np.testing.assert_array_equal(o.itable("NSTART")[:npr], z["NSTART"]); np.testing.assert_array_equal(s.nstart, z["NSTART"])
+    np.testing.assert_array_equal(o.itable("NEND")[:npr], z["NEND"]); np.testing.assert_array_equal(s.nend, z["NEND"])
+    np.testing.assert_array_equal(o.itable("IJ2NEWIJ")[1:n + 1], z["IJ2NEWIJ"]); np.testing.assert_array_equal(s.ij2new[1:n + 1], z["IJ2NEWIJ"])
+    np.testing.assert_array_equal(o.itable("KXLT")[:n], z["KXLT"]); np.testing.assert_array_equal(s.kxlt[:n], z["KXLT"])
+    np.testing.assert_array_equal(o.itable("IXLG")[:n], z["IXLG"])
