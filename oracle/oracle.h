@@ -11,10 +11,11 @@
 // statement by statement through tests/golden/f90run.py (fixtures tests/golden/ref_*.npz):
 // the IMPLSCH tree (<= 2.3e-15), the table builders, PROPCONNECT, CTUWUPDT / PROPDOT / GRADI /
 // PROPAGS2 for IREFRA 0-3 and LSUBGRID (bit-identical), OUTBLOCK's 51 parameters (<= 1e-12),
-// WAMWND + MICEP and NEWWIND (identical).  MPDECOMP, MPMINMAXAVG and TABU_SWELLFT are a reviewed
-// literal restatement pinned by the invariants, the independent second implementation in the
-// product's host builders and the numpy re-derivations in tests/ -- "parity unpinned" in the
-// strict sense for those.
+// WAMWND + MICEP and NEWWIND (identical), MPDECOMP's sector decomposition and halo lists for
+// 1-8 ranks (identical; its two MPL_ALLGATHERVs emulated).  MPMINMAXAVG and TABU_SWELLFT are a
+// reviewed literal restatement pinned by the invariants, the independent second implementation
+// in the product's host builders and the numpy re-derivations in tests/ -- "parity unpinned"
+// in the strict sense for those two.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // may load this library.  The product (ecwam_b200/) never does.

@@ -435,10 +435,11 @@ STATIC_DIMS = {}     # module arrays with explicit shape (WTAUHF(JTOT_TAUHF), SW
 
 
 class Translator:
-    def __init__(self, files, include_dirs=(REF,), registry=None, stubs=()):
+    def __init__(self, files, include_dirs=(REF,), registry=None, stubs=(), externals=()):
         self.routines = {}
         self.registry = registry or {}
         self.stubs = set(stubs)       # routines whose CALL is dropped (their results are not used by the caller's selected outputs)
+        self.externals = set(externals)   # CALLs handed to a Python callable of that name in the namespace (MPL_ALLGATHERV emulation)
         for f in files:
             self._parse_file(f if os.path.isabs(f) else os.path.join(REF, f), list(include_dirs))
         self.global_arrays = set()        # module arrays (names bound to FArr in the namespace)
@@ -742,6 +743,9 @@ class Translator:
             args = _split_top(m.group(2)) if m.group(2) else []
             if callee in self.stubs:
                 emit("pass")
+                return
+            if callee in self.externals:
+                emit("%s(%s)" % (callee, ", ".join(self.expr(r, a) for a in args)))
                 return
             if callee not in self.routines:
                 raise SyntaxError("%s: CALL of %s, which is not among the translated files" % (r.name, callee))

@@ -641,6 +641,90 @@ def run_decomp(name, N, mask, npr, ll1d=0):
     np.savez_compressed(os.path.join(HERE, "ref_decomp_%s.npz" % name), **out)
 
 
+class _GatherDone(Exception):
+    pass
+
+
+def run_halo(name, N, mask, npr):
+    """MPDECOMP from `NXFFS=1` to the end of its structured-grid branch -- the sector decomposition, PROPCONNECT for the rank, the halo points
+    it needs, the two MPL_ALLGATHERVs (emulated: every rank is run once to record what it sends, then again with the gathered arrays), the
+    send / receive lists NTOPE, NFROMPE, NIJSTART, IJTOPE and the local addressing of KLAT / KLON / KCOR -- from its own source, for every rank
+    of an NPR-rank run; compared with the oracle's per-rank tables and stored."""
+    from f90run import module_registry
+    from oracle import oracle as O
+    from ecwam_b200 import synth
+    g = synth.make_grid(N, mask)
+    o = O.Oracle(O.default_config(nproma=16, npr=npr), g)
+    n, ngy = g.niblo, int(g.ngy)
+    reg = module_registry(PROP_MODULES + ["yowspec", "yowunpool", "yowunit"])
+    I = lambda v: FInt(int(v))
+    ij2new = o.itable("IJ2NEWIJ")[: n + 1]
+    ixlg0 = o.itable("IXLG")[:n][ij2new[1:] - 1].astype(np.int64)
+    kxlt0 = o.itable("KXLT")[:n][ij2new[1:] - 1].astype(np.int64)
+    ngx = int(np.max(g.nlonrgg))
+    ocean = np.zeros((ngx, ngy), dtype=bool)
+    mk, p = np.asarray(g.mask), 0
+    for k in range(ngy):
+        ocean[: g.nlonrgg[k], k] = mk[p: p + g.nlonrgg[k]] != 0
+        p += g.nlonrgg[k]
+    T = Translator(["mpdecomp.F90", "propconnect.F90", "wam_sorti.F90", "wam_sortini.F90"], registry=reg, stubs=("FLUSH", "GSTATS"),
+                   externals=("MPL_ALLGATHERV",))
+    r = T.routines["MPDECOMP"]
+    i0 = next(i for i, x in enumerate(r.body) if x.replace(" ", "") == "NXFFS=1")
+    i1 = next(i for i, x in enumerate(r.body) if x.replace(" ", "") == "KTAG=KTAG+1")
+    r.body = r.body[i0:i1]
+    sent = {}
+
+    def run_rank(rank, gather):
+        ns = module_parameters()
+        for k in reg:
+            ns.setdefault(k, None)
+        ns.update(NGX=I(ngx), NGY=I(ngy), NIBLO=I(n), IJS=I(1), IJL=I(n), IRANK=I(rank), NPROC=I(npr), LL1D=False, LLUNSTR=False, IPROPAGS=I(2),
+                  IU06=I(6), LHOOK=False, NPROMA_WAM=I(16), KTAG=I(1), NLONRGG=FArr.of(np.asarray(g.nlonrgg, dtype=np.int64)), IPER=I(1), IRGG=I(1), AMOWEP=0.0,
+                  XDELLO=360.0 / ngx, AMOEAP=360.0 - 360.0 / ngx, AMOSOP=float(g.amosop), AMONOP=float(g.amonop), XDELLA=float(o.table("XDELLA")[0]),
+                  ZDELLO=FArr.of(o.table("ZDELLO")[:ngy]), LLOCEANMASK=FArr.of(ocean), BLK2GLO_IXLG=FArr.of(ixlg0), BLK2GLO_KXLT=FArr.of(kxlt0),
+                  NEWIJ2IJ=FArr([(0, n)], int), IJ2NEWIJ=FArr([(0, n)], int), MPL_ALLGATHERV=gather)
+        ns = T.compile(["MPDECOMP"], ns)
+        ns["IRANK"] = I(rank)
+        try:
+            ns["MPDECOMP"](I(npr), I(0), False, False)
+        except _GatherDone:
+            pass
+        return ns
+
+    for rank in range(1, npr + 1):         # pass 1: what every rank contributes to the two gathers
+        calls = []
+
+        def record(send, recv, counts, CDSTRING=None, rank=rank, calls=calls):
+            calls.append(np.array(send.a if isinstance(send, FArr) else send, copy=True))
+            if len(calls) == 2:
+                sent[rank] = calls
+                raise _GatherDone()
+        run_rank(rank, record)
+    out, bad = dict(N=N, mask=mask, npr=npr), []
+    for rank in range(1, npr + 1):         # pass 2: with the gathered arrays
+        k = [0]
+
+        def gather(send, recv, counts, CDSTRING=None, k=k):
+            data = np.concatenate([sent[q][k[0]].ravel() for q in range(1, npr + 1)])
+            recv.a.ravel()[: data.size] = data
+            k[0] += 1
+        ns = run_rank(rank, gather)
+        for nm in ("NINF", "NSUP", "NTOPEMAX", "NFROMPEMAX"):
+            ref = int(ns[nm])
+            out["%s_%d" % (nm, rank)] = ref
+            if int(o.itable(nm, rank - 1)[0]) != ref:
+                bad.append((rank, nm))
+        for nm in ("KLENBOT", "KLENTOP", "NTOPE", "NFROMPE", "NIJSTART", "IJTOPE", "KLAT", "KLON", "KCOR"):
+            ref = np.asarray(ns[nm].a).ravel(order="F").astype(np.int64)
+            got = o.itable(nm, rank - 1)
+            out["%s_%d" % (nm, rank)] = ref
+            if got.shape != ref.shape or not np.array_equal(got, ref):
+                bad.append((rank, nm))
+    print("%s: MPDECOMP's halo tables of the reference source, %d points, %d ranks; not identical to the oracle: %s" % (name, n, npr, bad))
+    np.savez_compressed(os.path.join(HERE, "ref_halo_%s.npz" % name), **out)
+
+
 def run_connect(name, N=8, mask="continents"):
     """PROPCONNECT (propconnect.F90, 971 lines: the neighbours of every sea point on the irregular grid and their interpolation weights)
     from its own source on a one-rank grid, compared with the oracle's KLAT / KLON / KCOR / WLAT / WCOR and stored."""
@@ -716,7 +800,7 @@ CASES = {
 }
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(CASES) + ["tables", "propag", "connect", "outblock", "getwnd", "newwind", "decomp"])
+    names = sys.argv[1:] or (list(CASES) + ["tables", "propag", "connect", "outblock", "getwnd", "newwind", "decomp", "halo"])
     for nm in names:
         if nm == "tables":
             for t, kw in TABLE_CASES.items():
@@ -725,6 +809,12 @@ if __name__ == "__main__":
         if nm == "outblock":
             for t, d in OUT_CASES.items():
                 run_outblock(t, d["case"], hook=d.get("hook", False), **d.get("kw", {}))
+            continue
+        if nm == "halo":
+            for npr in (2, 3, 4, 8):
+                run_halo("continents12_npr%d" % npr, 12, "continents", npr)
+            run_halo("continents16_npr6", 16, "continents", 6)
+            run_halo("aqua8_npr5", 8, "aqua", 5)
             continue
         if nm == "decomp":
             for npr in (1, 2, 3, 4, 5, 8):

@@ -454,3 +454,42 @@ def test_decomposition_matches_the_reference_source(built, path):
     np.testing.assert_array_equal(o.itable("IJ2NEWIJ")[1:n + 1], z["IJ2NEWIJ"]); np.testing.assert_array_equal(s.ij2new[1:n + 1], z["IJ2NEWIJ"])
     np.testing.assert_array_equal(o.itable("KXLT")[:n], z["KXLT"]); np.testing.assert_array_equal(s.kxlt[:n], z["KXLT"])
     np.testing.assert_array_equal(o.itable("IXLG")[:n], z["IXLG"])
+
+
+HFILES = sorted(glob.glob(os.path.join(HERE, "golden", "ref_halo_*.npz")))
+
+
+@pytest.mark.parametrize("path", HFILES, ids=[os.path.basename(f)[len("ref_halo_"):-4] for f in HFILES])
+def test_halo_lists_match_the_reference_source(built, path):
+    """The rest of MPDECOMP's structured-grid branch (mpdecomp.F90:696-1345) executed from its own source for every rank of a 2 / 3 / 4 / 8
+    rank run, the two MPL_ALLGATHERVs emulated by running all ranks twice: NINF / NSUP, KLENBOT / KLENTOP, the receive and send lists
+    NFROMPE / NTOPE / NIJSTART / IJTOPE and the local addressing of KLAT / KLON / KCOR (PROPCONNECT for the rank, halo points appended below
+    and above the own block, land -> NSUP+1) are identical in the oracle and in the product's host decomposition."""
+    from ecwam_b200 import model as M, synth
+    from oracle import oracle as O
+    z = np.load(path)
+    npr = int(z["npr"])
+    g = synth.make_grid(int(z["N"]), str(z["mask"]))
+    o = O.Oracle(O.default_config(nproma=16, npr=npr), g)
+    s = M.WamSetup(g, nproc=npr, nproma=16)
+    total_sent = total_recv = 0
+    for r in range(npr):
+        d = s.decomp_arrays(r)
+        for nm in ("NINF", "NSUP"):
+            assert int(o.itable(nm, r)[0]) == int(z["%s_%d" % (nm, r + 1)]) == d[nm.lower()], (nm, r)
+        assert int(o.itable("NTOPEMAX", r)[0]) == int(z["NTOPEMAX_%d" % (r + 1)])
+        for nm in ("KLENBOT", "KLENTOP"):
+            np.testing.assert_array_equal(o.itable(nm, r), z["%s_%d" % (nm, r + 1)], err_msg="%s rank %d" % (nm, r))
+        for nm in ("NTOPE", "NFROMPE", "NIJSTART", "KLAT", "KLON", "KCOR"):
+            ref = z["%s_%d" % (nm, r + 1)]
+            np.testing.assert_array_equal(o.itable(nm, r), ref, err_msg="oracle %s rank %d" % (nm, r))
+            np.testing.assert_array_equal(d[nm.lower()], ref, err_msg="product %s rank %d" % (nm, r))
+        ref = z["IJTOPE_%d" % (r + 1)]                      # IJTOPE(NTOPEMAX, NPROC): only the first NTOPE(ip) rows of a column are defined
+        nmax = int(z["NTOPEMAX_%d" % (r + 1)])
+        got_o, got_p = o.itable("IJTOPE", r), d["ijtope"]
+        for ip in range(npr):
+            k = int(z["NTOPE_%d" % (r + 1)][ip])
+            np.testing.assert_array_equal(got_o[ip * nmax: ip * nmax + k], ref[ip * nmax: ip * nmax + k])
+            np.testing.assert_array_equal(got_p[ip * d["ntopemax"]: ip * d["ntopemax"] + k], ref[ip * nmax: ip * nmax + k])
+        total_sent += int(z["NTOPE_%d" % (r + 1)].sum()); total_recv += int(z["NFROMPE_%d" % (r + 1)].sum())
+    assert total_sent == total_recv > 0
