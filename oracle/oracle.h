@@ -12,10 +12,10 @@
 // the IMPLSCH tree (<= 2.3e-15), the table builders, PROPCONNECT, CTUWUPDT / PROPDOT / GRADI /
 // PROPAGS2 for IREFRA 0-3 and LSUBGRID (bit-identical), OUTBLOCK's 51 parameters (<= 1e-12),
 // WAMWND + MICEP and NEWWIND (identical), MPDECOMP's sector decomposition and halo lists for
-// 1-8 ranks (identical; its two MPL_ALLGATHERVs emulated).  MPMINMAXAVG and TABU_SWELLFT are a
-// reviewed literal restatement pinned by the invariants, the independent second implementation
-// in the product's host builders and the numpy re-derivations in tests/ -- "parity unpinned"
-// in the strict sense for those two.
+// 1-8 ranks (identical; its two MPL_ALLGATHERVs emulated), MPMINMAXAVG in both flavours for
+// 1-5 ranks (identical; MPGATHERSCFLD / MPL_ALLREDUCE emulated, SUM in rank order) and
+// TABU_SWELLFT + KERKEI + KZEONE (identical).  Not executed from source: the file formats
+// (checked against scipy.io.FortranFile) and WAMINTGR's own date sequencing.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // may load this library.  The product (ecwam_b200/) never does.

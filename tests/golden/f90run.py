@@ -351,6 +351,13 @@ def _logical_lines(path, include_dirs):
         m = re.search(r"\bGO\s*TO\s+(\d+)$", ln)
         if m and labels.get(m.group(1), 1 << 30) < i:
             back.add(m.group(1))
+    # a forward `GO TO n` to a labelled executable statement (KZEONE's three branches): the routine is cut into segments at those
+    # statements; `GO TO n` outside any DO loop -> GOTOSEG n (skip to the segment), falling off a segment's end enters the next one
+    seg = {}
+    for i, ln in enumerate(out):
+        m = re.match(r"^(\d+)\s+(?!CONTINUE$|FORMAT\b)(\S.*)$", ln)
+        if m:
+            seg[m.group(1)] = i
     res = []
     for i, ln in enumerate(out):
         m = re.match(r"^(\d+)\s+CONTINUE$", ln)
@@ -358,7 +365,14 @@ def _logical_lines(path, include_dirs):
             if m.group(1) in back:
                 res.append("LABEL_LOOP")
             continue
+        m = re.match(r"^(\d+)\s+(?!FORMAT\b)(\S.*)$", ln)
+        if m and m.group(1) in seg:
+            res.append("LABEL_SEG " + m.group(1))
+            ln = m.group(2)
         m = re.search(r"\bGO\s*TO\s+(\d+)$", ln)
+        if m and seg.get(m.group(1), -1) > i:
+            res.append(ln[:m.start()] + "GOTOSEG " + m.group(1))
+            continue
         if m:
             j = labels.get(m.group(1))
             if m.group(1) in back:
@@ -439,6 +453,7 @@ class Translator:
         self.routines = {}
         self.registry = registry or {}
         self.stubs = set(stubs)       # routines whose CALL is dropped (their results are not used by the caller's selected outputs)
+        self.no_intent_outs = {}          # routine -> scalar dummies without an INTENT that it assigns (F77-style: KZEONE)
         self.externals = set(externals)   # CALLs handed to a Python callable of that name in the namespace (MPL_ALLGATHERV emulation)
         for f in files:
             self._parse_file(f if os.path.isabs(f) else os.path.join(REF, f), list(include_dirs))
@@ -586,7 +601,8 @@ class Translator:
         lines = []
         ind = 1
         emit = lambda s: lines.append("    " * ind + s)
-        outs = [a for a in r.args if a in r.decl and not r.decl[a]["dims"] and r.decl[a]["intent"] in ("OUT", "INOUT")]
+        outs = [a for a in r.args if a in r.decl and not r.decl[a]["dims"] and
+                (r.decl[a]["intent"] in ("OUT", "INOUT") or a in self.no_intent_outs.get(name, ()))]
         r.outs = outs
         res = r.result if r.kind == "FUNCTION" else None
         ret = "return " + (res if res else ("(" + ", ".join(outs) + ("," if len(outs) == 1 else "") + ")" if outs else "None"))
@@ -622,14 +638,21 @@ class Translator:
                     emit("%s = FArr([%s], %s)" % (nm, ", ".join(b), {float: "float", int: "int", bool: "bool", str: "object"}[d["type"]]))
                 else:
                     emit("%s = None" % nm)        # ALLOCATABLE: not allocated yet
+        for nm, d in r.decl.items():      # 1-D PARAMETER arrays: (/ ... /)
+            if d["dims"] and len(d["dims"]) == 1 and d["init"] and d["init"].strip().startswith("(/"):
+                items = _split_top(d["init"].strip()[2:-2])
+                emit("%s.a[:] = [%s]" % (nm, ", ".join(self.expr(r, x) for x in items)))
         for nm, los in rebase:
             emit("if %s is not None: %s = %s.rebase([%s])" % (nm, nm, nm, ", ".join(self.expr(r, lo) for lo in los)))
         stack = []
-        for ln in r.body:
+        body = r.body
+        if any(ln.startswith("LABEL_SEG ") for ln in body):
+            body = ["LABEL_SEG 0"] + list(body)
+        for ln in body:
             self._stmt(r, ln, emit, lambda d: None, stack, ret, lines)
             # indentation is tracked through the `stack` list length
             ind = 1 + len(stack)
-        while stack and stack[-1] == "LABEL_LOOP":
+        while stack and stack[-1] in ("LABEL_LOOP", "SEG"):
             ind = 1 + len(stack)
             emit("break")
             stack.pop()
@@ -657,6 +680,19 @@ class Translator:
         if m:      # SAVE + DATA: initialised at every call here (the routines are called once)
             emit("%s = %s" % (m.group(1), self.expr(r, m.group(2))))
             return
+        if ln.startswith("LABEL_SEG "):     # segments of a routine with forward GO TOs: `_pc` = 0 (running) or the label being skipped to
+            n = ln.split()[1]
+            if stack == ["SEG"]:
+                emit("break"); stack.pop()
+            if stack:
+                raise NotImplementedError("%s: label %s inside a construct" % (r.name, n))
+            if n == "0":
+                lines.append("    _pc = 0")
+            lines.append("    while _pc == 0 or _pc == %s:" % n); lines.append("        _pc = 0"); stack.append("SEG"); return
+        if ln.startswith("GOTOSEG "):
+            if "DO" in stack or "LABEL_LOOP" in stack or not stack or stack[0] != "SEG":
+                raise NotImplementedError("%s: GO TO out of a loop" % r.name)
+            emit("_pc = %s" % ln.split()[1]); emit("break"); return
         if ln == "LABEL_LOOP":      # loop until the end of the routine; the backward GO TO is its `continue`
             emit("while True:"); emit("pass", 1); stack.append("LABEL_LOOP"); return
         m = re.match(r"^DO\s+WHILE\s*\((.*)\)$", ln)
@@ -745,7 +781,11 @@ class Translator:
                 emit("pass")
                 return
             if callee in self.externals:
-                emit("%s(%s)" % (callee, ", ".join(self.expr(r, a) for a in args)))
+                pa = []
+                for a in args:
+                    km = re.match(r"^(\w+)\s*=(?!=)\s*(.*)$", a)          # keyword argument (LDREPROD=..., CDSTRING=...)
+                    pa.append("%s=%s" % (km.group(1), self.expr(r, km.group(2))) if km else self.expr(r, a))
+                emit("%s(%s)" % (callee, ", ".join(pa)))
                 return
             if callee not in self.routines:
                 raise SyntaxError("%s: CALL of %s, which is not among the translated files" % (r.name, callee))

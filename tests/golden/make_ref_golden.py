@@ -208,10 +208,10 @@ def run_case(name, case, pts=None, steps=2, hook=False, **kw):
     np.savez_compressed(os.path.join(HERE, "ref_implsch_%s.npz" % name), **out)
 
 
-TABLE_FILES = "depthprpt aki iniwcst mfredir mfr setwavphys init_x0tauhf init_sdiss_ardh inisnonlin nlweigt jafu initgc cigetdeac".split()
+TABLE_FILES = "depthprpt aki iniwcst mfredir mfr setwavphys init_x0tauhf init_sdiss_ardh inisnonlin nlweigt jafu initgc cigetdeac tabu_swellft kerkei kzeone".split()
 TABLE_MODULES = MODULES + ["yowgridgen"]
 # name in the oracle -> kind (t = real table, i = integer table, s = scalar)
-TABLE_CHECK = dict(DFIMOFR="t", DFIMFR="t", DFIMFR2="t", ZPIFR="t", FR5="t", COFRM4="t", FLMAX="t", RHOWG_DFIM="t", DFIM_SIM="t", FLOGSPRDM1="s",
+TABLE_CHECK = dict(SWELLFT="t", DFIMOFR="t", DFIMFR="t", DFIMFR2="t", ZPIFR="t", FR5="t", COFRM4="t", FLMAX="t", RHOWG_DFIM="t", DFIM_SIM="t", FLOGSPRDM1="s",
                    FR="t", DFIM="t", GOM="t", TH="t", COSTH="t", SINTH="t", X0TAUHF="s", WTAUHF="t", SATWEIGHTS="t", INDICESSAT="i", IKP="i", IKP1="i",
                    IKM="i", IKM1="i", K1W="i", K2W="i", K11W="i", K21W="i", AF11="t", FKLAP="t", FKLAP1="t", FKLAM="t", FKLAM1="t", FRH="t",
                    INLCOEF="i", RNLCOEF="t", FTRF="t", DAL1="s", DAL2="s", ACL1="s", ACL2="s", CL11="s", CL21="s", XK_GC="t", OMEGA_GC="t",
@@ -259,8 +259,10 @@ def run_tables(name, **kw):
     text = " ".join(fr.body)
     fr.uses = {"MODULES": [k for k in reg if re.search(r"\b%s\b" % k, text)]}
     T.routines["INITMDL_FREQ"] = fr
+    T.no_intent_outs["KZEONE"] = ("RE0", "IM0", "RE1", "IM1")       # F77-style dummies without INTENT
+    T.no_intent_outs["KERKEI"] = ("KER", "KEI")
     ns = T.compile(["INIWCST", "MFREDIR", "SETWAVPHYS", "INITMDL_FREQ", "INIT_X0TAUHF", "INIT_SDISS_ARDH", "INISNONLIN", "INITGC", "CIGETDEAC",
-                    "DEPTHPRPT"], ns)
+                    "DEPTHPRPT", "TABU_SWELLFT"], ns)
     g = ns          # the functions' globals ARE this dict: module variables they assign land here
     g["INIWCST"](1.0)
     g["MFREDIR"]()
@@ -273,6 +275,10 @@ def run_tables(name, **kw):
     g["INISNONLIN"]()
     g["INITGC"]()
     g["CIGETDEAC"]()
+    if name == "a12_ard":          # TABU_SWELLFT + KERKEI + KZEONE (independent of the spectral setting; 20 000 Kelvin-function evaluations): once
+        g["TABU_SWELLFT"]()
+    else:
+        g["SWELLFT"] = None
     out, worst = dict(kw=__import__("json").dumps(kw, sort_keys=True)), []
     # DEPTHPRPT + AKI (depthprpt.F90, aki.F90): the dispersion relation at the grid's own depths
     grid = synth.make_grid(8, "aqua")
@@ -725,6 +731,109 @@ def run_halo(name, N, mask, npr):
     np.savez_compressed(os.path.join(HERE, "ref_halo_%s.npz" % name), **out)
 
 
+WNORM_ITG = [1, 2, 3, 5, 11, 12, 16, 32]       # Hs, mean direction / frequency, U10, wind-sea Hs + direction, ... (some ice-masked)
+
+
+def wnorm_state(npr, ll1d=0):
+    """The oracle after one step of a cold start with some points under the ice mask, and its OUTBS columns WNORM_ITG [column, ij]."""
+    from oracle import oracle as O
+    from ecwam_b200 import synth
+    g = synth.make_grid(12, "continents")
+    o = O.Oracle(O.default_config(nang=12, nfre_red=25, nproma=16, npr=npr, ll1d=ll1d), g)
+    f = synth.make_forcing(g)
+    f["CICOVER"] = np.where(np.arange(g.niblo) % 7 == 0, 0.6, f["CICOVER"])       # some points under the ice mask -> ZMISS
+    for k, v in f.items():
+        o.set_field(k, v)
+    o.set_fl1(synth.jonswap_cold_start(f["WSWAVE"], f["WDWAVE"], 12, 36, 25))
+    assert o.step() == 0
+    return g, o, o.outbs(WNORM_ITG, [1, 1, 1, 0, 1, 1, 1, 0], [0] * len(WNORM_ITG), -999.0)
+
+
+def run_wnorm(name, npr, ll1d=0):
+    """MPMINMAXAVG (mpminmaxavg.F90) from its own source on every rank of an NPR-rank run, both flavours: LLGLOBAL = T (MPGATHERSCFLD
+    emulated: the receiving rank sees every rank's block of ZGLOBAL) and LLGLOBAL = F (MPL_ALLREDUCE emulated: SUM in rank order --
+    MPL's reproducible path --, MIN, MAX).  The columns are the oracle's OUTBS columns of a spun-up state (they contain ZMISS under the
+    ice mask); WNORM is compared with the oracle's OUTWNORM and stored together with the columns."""
+    from f90run import module_registry
+    g, o, b = wnorm_state(npr, ll1d)
+    n, NI = g.niblo, len(WNORM_ITG)
+    zmiss = -999.0
+    assert (b == zmiss).any() and (b != zmiss).any()
+    reg = module_registry(PROP_MODULES + ["yowspec", "yowcout", "yowgrid", "yowtest"])
+    I = lambda v: FInt(int(v))
+    new2ij, ij2new = o.itable("NEWIJ2IJ")[: n + 1], o.itable("IJ2NEWIJ")[: n + 1]
+    nstart, nend = o.itable("NSTART")[:npr], o.itable("NEND")[:npr]
+    T = Translator(["mpminmaxavg.F90"], registry=reg, externals=("MPGATHERSCFLD", "MPL_ALLREDUCE"))
+    bouts, chunks = [], []
+    for r in range(npr):
+        nch, nproma = int(o.itable("NCHNK", r)[0]), int(o.itable("NPROMA", r)[0])
+        kijl = o.itable("KIJL4CHNK", r)[:nch]
+        ijfrom = o.itable("IJFROMCHNK", r).reshape(nch, nproma).T        # (NPROMA, NCHNK)
+        bo = np.zeros((nproma, NI, nch))
+        for ic in range(nch):
+            for p in range(int(kijl[ic])):
+                bo[p, :, ic] = b[:, new2ij[ijfrom[p, ic]] - 1]
+        bouts.append(bo); chunks.append((nch, nproma, kijl, ijfrom))
+    wn = {}
+    for glob in (True, False):
+        partial = {}
+        for pas in (1, 2):
+            for r in range(npr):
+                nch, nproma, kijl, ijfrom = chunks[r]
+                ns = module_parameters()
+                for k in reg:
+                    ns.setdefault(k, None)
+
+                def gather(irecv, nblks, nblke, zglobal, niblo, r=r):       # MPGATHERSCFLD: the receiver gets every rank's NBLKS:NBLKE block
+                    if pas == 1:
+                        partial.setdefault(r, []).append(np.array(zglobal.a, copy=True))
+                    else:
+                        k = gather.k
+                        for q in range(npr):
+                            zglobal.a[nstart[q] - 1: nend[q]] = partial[q][k][nstart[q] - 1: nend[q]]
+                        gather.k += 1
+                gather.k = 0
+
+                def allreduce(z, op, LDREPROD=None, CDSTRING=None, r=r):
+                    if pas == 1:
+                        partial.setdefault(r, []).append(np.array(z.a, copy=True))
+                        if op == "MAX":
+                            raise _GatherDone()
+                    else:
+                        k = allreduce.k
+                        acc = partial[0][k].copy()
+                        for q in range(1, npr):
+                            acc = {"SUM": np.add, "MIN": np.minimum, "MAX": np.maximum}[op](acc, partial[q][k])
+                        z.a[:] = acc
+                        allreduce.k += 1
+                allreduce.k = 0
+                flags = np.zeros(int(ns["JPPFLAG"]), dtype=bool); itob = np.zeros(int(ns["JPPFLAG"]), dtype=np.int64)
+                for col, itg in enumerate(WNORM_ITG):
+                    flags[itg - 1] = True; itob[itg - 1] = col + 1
+                ns.update(NIBLO=I(n), IRANK=I(r + 1), NPROC=I(npr), LL1D=bool(ll1d), LLUNSTR=False, ZMISS=zmiss, IU06=I(6), LHOOK=False,
+                          NPROMA_WAM=I(nproma), NCHNK=I(nch), NIPRMOUT=I(NI), NFLAG=FArr.of(flags), ITOBOUT=FArr.of(itob),
+                          IJFROMCHNK=FArr.of(np.asarray(ijfrom, dtype=np.int64)), KIJL4CHNK=FArr.of(np.asarray(kijl, dtype=np.int64)),
+                          NBLKS=FArr.of(np.asarray(nstart, dtype=np.int64)), NBLKE=FArr.of(np.asarray(nend, dtype=np.int64)),
+                          IJ2NEWIJ=FArr.of(np.asarray(ij2new, dtype=np.int64), lb=[0]), MPGATHERSCFLD=gather, MPL_ALLREDUCE=allreduce)
+                ns = T.compile(["MPMINMAXAVG"], ns)
+                w = FArr([(1, 4), (1, NI)])
+                try:
+                    ns["MPMINMAXAVG"](glob, I(1), True, FArr.of(bouts[r]), w)
+                except _GatherDone:
+                    continue
+                if r == 0 or not glob:          # (pass 1 completes only for NPROC = 1; pass 2 overwrites it otherwise)
+                    wn[(glob, r)] = np.array(w.a, copy=True)
+    out, bad = dict(npr=npr, ll1d=ll1d, BOUT=b, ITG=np.array(WNORM_ITG), zmiss=zmiss), []
+    for glob in (True, False):
+        ref = o.outwnorm(glob)              # [column, 4]
+        for (gl, r), w in wn.items():
+            if gl == glob and not np.array_equal(w.T, ref):
+                bad.append((glob, r, float(np.abs(w.T - ref).max())))
+        out["WNORM_GLOBAL" if glob else "WNORM_LOCAL"] = wn[(glob, 0)].T
+    print("%s: MPMINMAXAVG of the reference source, %d ranks, %d columns; not identical to the oracle: %s" % (name, npr, NI, bad))
+    np.savez_compressed(os.path.join(HERE, "ref_wnorm_%s.npz" % name), **out)
+
+
 def run_connect(name, N=8, mask="continents"):
     """PROPCONNECT (propconnect.F90, 971 lines: the neighbours of every sea point on the irregular grid and their interpolation weights)
     from its own source on a one-rank grid, compared with the oracle's KLAT / KLON / KCOR / WLAT / WCOR and stored."""
@@ -800,7 +909,7 @@ CASES = {
 }
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(CASES) + ["tables", "propag", "connect", "outblock", "getwnd", "newwind", "decomp", "halo"])
+    names = sys.argv[1:] or (list(CASES) + ["tables", "propag", "connect", "outblock", "getwnd", "newwind", "decomp", "halo", "wnorm"])
     for nm in names:
         if nm == "tables":
             for t, kw in TABLE_CASES.items():
@@ -809,6 +918,11 @@ if __name__ == "__main__":
         if nm == "outblock":
             for t, d in OUT_CASES.items():
                 run_outblock(t, d["case"], hook=d.get("hook", False), **d.get("kw", {}))
+            continue
+        if nm == "wnorm":
+            for npr in (1, 2, 3, 5):
+                run_wnorm("npr%d" % npr, npr)
+            run_wnorm("npr4_1d", 4, ll1d=1)
             continue
         if nm == "halo":
             for npr in (2, 3, 4, 8):

@@ -493,3 +493,21 @@ def test_halo_lists_match_the_reference_source(built, path):
             np.testing.assert_array_equal(got_p[ip * d["ntopemax"]: ip * d["ntopemax"] + k], ref[ip * nmax: ip * nmax + k])
         total_sent += int(z["NTOPE_%d" % (r + 1)].sum()); total_recv += int(z["NFROMPE_%d" % (r + 1)].sum())
     assert total_sent == total_recv > 0
+
+
+WFILES = sorted(glob.glob(os.path.join(HERE, "golden", "ref_wnorm_*.npz")))
+
+
+@pytest.mark.parametrize("path", WFILES, ids=[os.path.basename(f)[len("ref_wnorm_"):-4] for f in WFILES])
+def test_wamnorm_matches_the_reference_source(built, path):
+    """MPMINMAXAVG (mpminmaxavg.F90:68-195) executed from its own source on every rank of a 1 / 2 / 3 / 5-rank and a 1-D 4-rank run, both
+    flavours (LLNORMWAMOUT_GLOBAL = T with MPGATHERSCFLD, = F with the three MPL_ALLREDUCEs, both emulated over the ranks): average,
+    minimum, maximum and count of 8 OUTBS columns with missing values under the ice mask are identical to the oracle's OUTWNORM."""
+    z = np.load(path)
+    g, o, b = G.wnorm_state(int(z["npr"]), int(z["ll1d"]))
+    np.testing.assert_array_equal(b, z["BOUT"])
+    count = z["WNORM_GLOBAL"][:, 3]
+    assert (count < g.niblo).any() and (count > 0).all()          # the masked columns miss points
+    np.testing.assert_array_equal(o.outwnorm(True), z["WNORM_GLOBAL"])
+    np.testing.assert_array_equal(o.outwnorm(False), z["WNORM_LOCAL"])
+    np.testing.assert_array_equal(z["WNORM_GLOBAL"][:, 1:], z["WNORM_LOCAL"][:, 1:])      # min / max / count do not depend on the flavour
