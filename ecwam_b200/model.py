@@ -140,7 +140,9 @@ class WamSetup:
 class WamClock:
     """The dates WAMODEL / WAMINTGR step through (wamodel.F90:181-185, 228-233, 283-300; wamintgr.F90:92-186), in seconds since
     the start of the run instead of CHARACTER(14) dates: CDATE, CDTPRA / CDTPRO (start / end of the running propagation step),
-    CDTIMP / CDTIMPNEXT (source-term integration), CDATEWH (date of the next forcing fields)."""
+    CDTIMP / CDTIMPNEXT (source-term integration), CDATEWH (date of the next forcing fields), CDATEWO (its value at the last
+    source-term integration, to which WAMODEL resets CDATEWH at every advection step).  tests/test_reference_golden.py replays
+    this bookkeeping against WAMODEL + WAMINTGR + NEWWIND executed from their own source."""
 
     def __init__(self, idelpro, idelt, idelwo):
         self.idelpro, self.idelt, self.idelwo = int(idelpro), int(idelt), int(idelwo)
@@ -148,7 +150,7 @@ class WamClock:
         self.cdtpra = self.cdate = 0
         self.cdtimp = 0                       # wamodel.F90:185
         self.cdtimpnext = self.idelt          # wamodel.F90:182-183
-        self.cdatewh = self.idelwo
+        self.cdatewh = self.cdatewo = self.idelwo   # CDATEWO: the forcing date as of the last source-term integration (wamintgr.F90:181)
 
 
 class WamIntgr:
@@ -457,6 +459,7 @@ class WamIntgr:
                 self.implsch()
             else:
                 self.no_source(True)
+            clk.cdatewo = clk.cdatewh                     # :181
             clk.cdtimp = clk.cdtimpnext
             clk.cdtimpnext += clk.idelt
         else:                                             # :187-195 NO SOURCE TERM CONTRIBUTION
@@ -469,6 +472,7 @@ class WamIntgr:
         clk.cdtpra = clk.cdtpro
         clk.cdtpro += clk.idelpro
         clk.cdate = clk.cdtpra
+        clk.cdatewh = clk.cdatewo                         # wamodel.F90:286 (differs from the running CDATEWH only when IDELT > IDELPRO)
         cfl, iloop = 0, 1
         while iloop == 1 or clk.cdtimpnext <= clk.cdtpro:
             cfl += self.wamintgr(clk, ff_next, llsource)

@@ -15,7 +15,8 @@
 // 1-8 ranks (identical; its two MPL_ALLGATHERVs emulated), MPMINMAXAVG in both flavours for
 // 1-5 ranks (identical; MPGATHERSCFLD / MPL_ALLREDUCE emulated, SUM in rank order) and
 // TABU_SWELLFT + KERKEI + KZEONE (identical).  Not executed from source: the file formats
-// (checked against scipy.io.FortranFile) and WAMINTGR's own date sequencing.
+// (checked against scipy.io.FortranFile).  WAMODEL's loop + WAMINTGR + NEWWIND's date sequencing
+// is executed from source too, against the product's host mirror (not part of this oracle).
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // may load this library.  The product (ecwam_b200/) never does.

@@ -453,6 +453,7 @@ class Translator:
         self.routines = {}
         self.registry = registry or {}
         self.stubs = set(stubs)       # routines whose CALL is dropped (their results are not used by the caller's selected outputs)
+        self.external_outs = {}           # external routine -> positions of the scalar arguments it returns (INCDATE: (0,))
         self.no_intent_outs = {}          # routine -> scalar dummies without an INTENT that it assigns (F77-style: KZEONE)
         self.externals = set(externals)   # CALLs handed to a Python callable of that name in the namespace (MPL_ALLGATHERV emulation)
         for f in files:
@@ -785,7 +786,8 @@ class Translator:
                 for a in args:
                     km = re.match(r"^(\w+)\s*=(?!=)\s*(.*)$", a)          # keyword argument (LDREPROD=..., CDSTRING=...)
                     pa.append("%s=%s" % (km.group(1), self.expr(r, km.group(2))) if km else self.expr(r, a))
-                emit("%s(%s)" % (callee, ", ".join(pa)))
+                outs = [pa[k] for k in self.external_outs.get(callee, ())]
+                emit("%s%s(%s)" % ((", ".join(outs) + ", = ") if outs else "", callee, ", ".join(pa)))
                 return
             if callee not in self.routines:
                 raise SyntaxError("%s: CALL of %s, which is not among the translated files" % (r.name, callee))

@@ -834,6 +834,91 @@ def run_wnorm(name, npr, ll1d=0):
     np.savez_compressed(os.path.join(HERE, "ref_wnorm_%s.npz" % name), **out)
 
 
+SEQ_CASES = {"pro900_src900_wind900": (900, 900, 900, 8, True), "pro1800_src900_wind1800": (1800, 900, 1800, 6, True),
+             "pro900_src900_wind3600": (900, 900, 3600, 10, True), "pro3600_src900_wind1800": (3600, 900, 1800, 4, True),
+             "pro3600_src1200_wind7200": (3600, 1200, 7200, 5, True), "pro900_src1800_wind1800": (900, 1800, 1800, 8, True),
+             "pro1800_src900_wind900_nosource": (1800, 900, 900, 4, False)}
+SEQ_T0 = "20200229230000"          # across the end of February of a leap year
+
+
+def run_sequence(name, idelpro, idelt, idelwo, nadv, llsource):
+    """The time stepping of the hot path from its own source: WAMODEL's initialisation of CDTIMP / CDTIMPNEXT (wamodel.F90:182-185), its
+    ADVECTION loop body (:232-233, :285-300) and WAMINTGR + NEWWIND whole (PROPAG_WAM / IMPLSCH are recorded instead of run, INCDATE is
+    Python's datetime, NEWWIND works on a 4-point block).  Stored: the order of PROPAG_WAM / new winds / IMPLSCH and the dates after
+    every WAMINTGR call, in seconds since the start."""
+    import datetime
+    from f90run import module_registry, Routine, _logical_lines
+    reg = module_registry(MODULES + ["yowgrid", "yowwndg", "yowcoup"])
+    I = lambda v: FInt(int(v))
+    fmt = "%Y%m%d%H%M%S"
+    t0 = datetime.datetime.strptime(SEQ_T0, fmt)
+    secs = lambda c: int((datetime.datetime.strptime(c, fmt) - t0).total_seconds())
+    ns = module_parameters()
+    for k in reg:
+        ns.setdefault(k, None)
+    log = []
+    src = open(os.path.join(REF, "wamintgr.F90")).read().upper()
+    for nm, idx in re.findall(r"(\w+%\w+)\s*\(([^)]*)\)", src):           # the components WAMINTGR passes on: one 4-point chunk of each
+        ns[nm.replace("%", "_")] = FArr([(1, 4)] * (idx.count(",") + 1), int if nm == "MIJ%PTR" else float)
+    for nm in re.findall(r"(\w+%\w+)", src):
+        ns.setdefault(nm.replace("%", "_"), FArr([(1, 4), (1, 1)], float))
+    for k in ("WSWAVE", "WDWAVE", "AIRD", "WSTAR", "CICOVER", "CITHICK", "USTRA", "VSTRA", "UFRIC", "TAUW", "CHRNCK"):
+        ns["FF_NOW_" + k] = FArr.of(np.full((4, 1), 0.5)); ns["FF_NEXT_" + k] = FArr.of(np.full((4, 1), 0.7))
+
+    def incdate(c, shift):
+        return ((datetime.datetime.strptime(c, fmt) + datetime.timedelta(seconds=int(shift))).strftime(fmt),)
+    ns.update(ACD=8.0e-4, BCD=8.0e-5, EPSMIN=1e-10, LWCOU=False, NPROMA_WAM=I(4), NCHNK=I(1), NFRE=I(36), NANG=I(12), ALPHA=0.0065, IDELWO=I(idelwo),
+              IDELWI=I(idelwo), IDELPRO=I(idelpro), IDELT=I(idelt), IU06=I(6), CDATEWL=SEQ_T0, CDAWIFL=SEQ_T0, CDATEFL="20300101000000",
+              CDTNEXT=SEQ_T0, NSTORE=I(1), ICODE=I(3), ICODE_CPL=I(3), LHOOK=False, LLSOURCE=bool(llsource), LWNEMOCOU=False, NEMONTAU=I(0),
+              TIME_PROPAG=0.0, TIME_PHYS=0.0, CDTPRO=SEQ_T0, CDATEWO=incdate(SEQ_T0, idelwo)[0], INCDATE=incdate,
+              PROPAG_WAM=lambda *a: log.append(("propag",)), IMPLSCH=lambda *a: log.append(("implsch",)),
+              BLK2GLO=None, WVENVI=None, WVPRPT=None, FF_NOW=None, FF_NEXT=None, INTFLDS=None, WAM2NEMO=None, MIJ=None, VARS_4D=None)
+    T = Translator(["wamintgr.F90", "newwind.F90"], registry=reg, stubs=("GSTATS",), externals=("INCDATE", "PROPAG_WAM", "IMPLSCH"))
+    T.external_outs["INCDATE"] = (0,)
+    w = T.routines["WAMINTGR"]
+    w.body = [ln for ln in w.body if "WAM_USER_CLOCK" not in ln]              # the timers
+    ll = _logical_lines(os.path.join(REF, "wamodel.F90"), [REF])
+    sq = lambda x: x.replace(" ", "")
+    i0 = next(i for i, x in enumerate(ll) if sq(x) == "CDTIMPNEXT=CDTPRO")
+    i1 = next(i for i, x in enumerate(ll) if sq(x) == "CDTPRA=CDTPRO")
+    i2 = next(i for i, x in enumerate(ll) if sq(x) == "CDATE=CDTPRA")
+    i3 = next(i for i, x in enumerate(ll) if sq(x) == "ILOOP=ILOOP+1")
+    assert sq(ll[i0 + 2]) == "CDTIMP=CDTPRO" and sq(ll[i2 + 1]) == "CDATEWH=CDATEWO" and ll[i3 - 1].startswith("CALL WAMINTGR")
+    local = ["CDATE", "CDTPRA", "CDTIMP", "CDTIMPNEXT", "CDATEWH"]            # locals of WAMODEL: kept in the namespace between the fragments
+    for nm, body in (("WAMODEL_INIT", ll[i0:i0 + 3]), ("WAMODEL_STEP", ll[i1:i1 + 2] + ll[i2:i3 + 1] + ["ENDDO"])):
+        fr = Routine(nm, "SUBROUTINE", [])
+        fr.result = None
+        fr.body = body
+        fr.uses = {"MODULES": [k for k in reg if re.search(r"\b%s\b" % k, " ".join(body))] + local + ["CDTPRO", "CDATEWO", "IDELPRO", "IDELT", "BLK2GLO", "WVENVI", "WVPRPT", "FF_NOW", "FF_NEXT", "INTFLDS", "WAM2NEMO", "MIJ", "VARS_4D"]}
+        T.routines[nm] = fr
+    for nm in local:
+        ns[nm] = SEQ_T0
+    ns = T.compile(["WAMODEL_INIT", "WAMODEL_STEP", "WAMINTGR", "NEWWIND"], ns)
+    wam, nw = ns["WAMINTGR"], ns["NEWWIND"]
+
+    def newwind(cdate, cdatewh, *a):
+        r = nw(cdate, cdatewh, *a)
+        if r[0] != cdatewh:
+            log.append(("newwind", secs(cdatewh)))
+        return r
+
+    def wamintgr(*a):
+        r = wam(*a)                     # (CDATE, CDATEWH, CDTIMP, CDTIMPNEXT)
+        log.append(("dates",) + tuple(secs(x) for x in r))
+        return r
+    ns["NEWWIND"], ns["WAMINTGR"] = newwind, wamintgr
+    ns["WAMODEL_INIT"]()
+    for _ in range(nadv):
+        ns["WAMODEL_STEP"]()
+        log.append(("step", secs(ns["CDTPRO"])))
+    code = dict(propag=1, implsch=2, newwind=3, dates=4, step=5)
+    ev = np.array([[code[e[0]]] + list(e[1:]) + [0] * (5 - len(e)) for e in log], dtype=np.int64)
+    print("%s: %d advection steps -> %d WAMINTGR calls, %d PROPAG_WAM, %d IMPLSCH, %d new winds" %
+          (name, nadv, (ev[:, 0] == 4).sum(), (ev[:, 0] == 1).sum(), (ev[:, 0] == 2).sum(), (ev[:, 0] == 3).sum()))
+    np.savez_compressed(os.path.join(HERE, "ref_sequence_%s.npz" % name), EVENTS=ev, cfg=np.array([idelpro, idelt, idelwo, nadv, int(llsource)]))
+    return ev
+
+
 def run_connect(name, N=8, mask="continents"):
     """PROPCONNECT (propconnect.F90, 971 lines: the neighbours of every sea point on the irregular grid and their interpolation weights)
     from its own source on a one-rank grid, compared with the oracle's KLAT / KLON / KCOR / WLAT / WCOR and stored."""
@@ -909,7 +994,7 @@ CASES = {
 }
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(CASES) + ["tables", "propag", "connect", "outblock", "getwnd", "newwind", "decomp", "halo", "wnorm"])
+    names = sys.argv[1:] or (list(CASES) + ["tables", "propag", "connect", "outblock", "getwnd", "newwind", "decomp", "halo", "wnorm", "sequence"])
     for nm in names:
         if nm == "tables":
             for t, kw in TABLE_CASES.items():
@@ -918,6 +1003,10 @@ if __name__ == "__main__":
         if nm == "outblock":
             for t, d in OUT_CASES.items():
                 run_outblock(t, d["case"], hook=d.get("hook", False), **d.get("kw", {}))
+            continue
+        if nm == "sequence":
+            for k, v in SEQ_CASES.items():
+                run_sequence(k, *v)
             continue
         if nm == "wnorm":
             for npr in (1, 2, 3, 5):

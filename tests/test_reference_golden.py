@@ -511,3 +511,51 @@ def test_wamnorm_matches_the_reference_source(built, path):
     np.testing.assert_array_equal(o.outwnorm(True), z["WNORM_GLOBAL"])
     np.testing.assert_array_equal(o.outwnorm(False), z["WNORM_LOCAL"])
     np.testing.assert_array_equal(z["WNORM_GLOBAL"][:, 1:], z["WNORM_LOCAL"][:, 1:])      # min / max / count do not depend on the flavour
+
+
+SFILES = sorted(glob.glob(os.path.join(HERE, "golden", "ref_sequence_*.npz")))
+
+
+class _Recorder:
+    """The time bookkeeping of ecwam_b200.model.WamIntgr (wamintgr / advection_step, unbound) around recording stand-ins of the kernels."""
+
+    def __init__(self):
+        self.log = []
+
+    def propag(self):
+        self.log.append((1, 0, 0, 0, 0)); return 0
+
+    def implsch(self):
+        self.log.append((2, 0, 0, 0, 0))
+
+    def newwind(self, t):
+        self.log.append((3, t, 0, 0, 0))
+
+    def no_source(self, off):
+        pass
+
+    def wamintgr(self, clk, ff_next=None, llsource=True):
+        from ecwam_b200 import model as M
+        r = M.WamIntgr.wamintgr(self, clk, ff_next, llsource)
+        self.log.append((4, clk.cdate, clk.cdatewh, clk.cdtimp, clk.cdtimpnext))
+        return r
+
+
+@pytest.mark.parametrize("path", SFILES, ids=[os.path.basename(f)[len("ref_sequence_"):-4] for f in SFILES])
+def test_time_stepping_matches_the_reference_source(path):
+    """WAMODEL's ADVECTION loop body + WAMINTGR + NEWWIND executed from their own source (make_ref_golden.run_sequence): the order of
+    PROPAG_WAM, new forcing and IMPLSCH and the dates CDATE / CDATEWH / CDTIMP / CDTIMPNEXT after every WAMINTGR call, for IDELPRO equal
+    to, a multiple of and a fraction of IDELT and three forcing intervals -- the product's WamClock / wamintgr / advection_step
+    bookkeeping produces the same sequence."""
+    from ecwam_b200 import model as M
+    z = np.load(path)
+    idelpro, idelt, idelwo, nadv, llsource = (int(v) for v in z["cfg"])
+    clk = M.WamClock(idelpro=idelpro, idelt=idelt, idelwo=idelwo)
+    rec = _Recorder()
+    for _ in range(nadv):
+        M.WamIntgr.advection_step(rec, clk, ff_next=lambda t: t, llsource=bool(llsource))
+        rec.log.append((5, clk.cdtpro, 0, 0, 0))
+    got, ref = np.array(rec.log, dtype=np.int64), z["EVENTS"]
+    assert got.shape == ref.shape, (got[:12], ref[:12])
+    bad = np.nonzero((got != ref).any(axis=1))[0]
+    assert bad.size == 0, (bad[0], got[max(bad[0] - 3, 0): bad[0] + 2], ref[max(bad[0] - 3, 0): bad[0] + 2])
