@@ -131,7 +131,7 @@ def main():
     if args.restart_in:          # CDATEWO of the LAW file: when the next forcing fields are due (savstress.F90:157-159)
         import datetime
         fmt = "%Y%m%d%H%M%S"
-        clk.cdatewh = int((datetime.datetime.strptime(cdatewo, fmt) - datetime.datetime.strptime(cdt, fmt)).total_seconds())
+        clk.cdatewh = clk.cdatewo = int((datetime.datetime.strptime(cdatewo, fmt) - datetime.datetime.strptime(cdt, fmt)).total_seconds())
     nadv = int(round(args.hours * 3600 / cfg["idelpro"]))
     out_every = int(round(args.output_every * 3600))
     if rank == 0:
@@ -176,7 +176,7 @@ def main():
     if args.restart_out:
         os.makedirs(args.restart_out, exist_ok=True)
         cdt, bls, law = restart_names(args.restart_out, t_start + clk.cdtpro)
-        cdatewo = restart_names(args.restart_out, t_start + clk.cdatewh)[0]
+        cdatewo = restart_names(args.restart_out, t_start + clk.cdatewo)[0]
         if rank == 0:                        # rank 0 lays the files out, then every rank writes its own points in place
             w.savspec(bls, create=True); w.savstress(law, cdt, cdatewo, create=True)
         barrier()
