@@ -6,7 +6,15 @@ then checks the oracle (and, on a GPU, the CUDA path) against those files.  What
 module variables (tables of YOWFRED / YOWINDN / ..., read from the oracle, whose table builders are checked bit for bit against the
 product's independent host builders) and the inputs (the synthetic state of tests/common.py after two steps + PROPAG_WAM).
 
-usage: python tests/golden/make_ref_golden.py [case ...]
+The other families, same method (each runner's docstring says what is run and what is emulated):
+  ref_tables_*    the one-off table builders incl. TABU_SWELLFT + KERKEI + KZEONE          ref_propag_*   CTUW + PROPAGS2, IREFRA 0-3, LSUBGRID
+  ref_connect_*   PROPCONNECT                                                              ref_outblock_* OUTBLOCK and the 24 routines below it
+  ref_getwnd_*    WAMWND + MICEP                                                           ref_newwind_*  NEWWIND's field update
+  ref_decomp_*    MPDECOMP's sector decomposition                                          ref_halo_*     MPDECOMP's halo lists (allgathers emulated)
+  ref_wnorm_*     MPMINMAXAVG, both flavours (gather / allreduce emulated)                 ref_sequence_* WAMODEL loop + WAMINTGR + NEWWIND dates
+
+usage: python tests/golden/make_ref_golden.py [<implsch case> | tables | propag[:name] | connect | outblock | getwnd | newwind | decomp | halo |
+                                               wnorm | sequence] ...        (no argument: everything)
 """
 import os
 import re

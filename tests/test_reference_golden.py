@@ -559,3 +559,12 @@ def test_time_stepping_matches_the_reference_source(path):
     assert got.shape == ref.shape, (got[:12], ref[:12])
     bad = np.nonzero((got != ref).any(axis=1))[0]
     assert bad.size == 0, (bad[0], got[max(bad[0] - 3, 0): bad[0] + 2], ref[max(bad[0] - 3, 0): bad[0] + 2])
+
+
+@pytest.mark.skipif(not os.path.isdir(G.REF), reason="the reference tree exists in the build container only")
+def test_the_generator_reproduces_the_time_stepping_fixtures(tmp_path, monkeypatch):
+    """Runs WAMODEL's loop + WAMINTGR + NEWWIND from the reference source again and compares with the committed event lists."""
+    monkeypatch.setattr(G, "HERE", str(tmp_path))
+    for name in ("pro1800_src900_wind1800", "pro900_src1800_wind1800"):
+        ev = G.run_sequence(name, *G.SEQ_CASES[name])
+        np.testing.assert_array_equal(ev, np.load(os.path.join(HERE, "golden", "ref_sequence_%s.npz" % name))["EVENTS"])
