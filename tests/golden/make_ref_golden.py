@@ -383,8 +383,10 @@ def run_propag(name, N=8, mask="continents", obs=False, **kw):
         ucur, vcur = u0[new2ij], v0[new2ij]
     u_ext, v_ext, d_ext, c_ext = ext(ucur, 0.0), ext(vcur, 0.0), ext(depth, c.bathymax), ext(cosphm1, 1.0)
     ns.update(NIBLO=I(n), DELPHI=float(o.table("XDELLA")[0]) * float(ns["CIRC"]) / 360.0, DELLAM=FArr.of(o.table("DELLAM")[:ngy]))
-    T = Translator([x + ".F90" for x in PROP_FILES], registry=reg)
-    ns = T.compile(["CTUWUPDT", "PROPAGS2", "PROPDOT"], ns)
+    T = Translator([x + ".F90" for x in PROP_FILES + ["propag_wam"]], registry=reg, stubs=("PROENVHALO", "PROPAGS", "PROPAGS1", "GSTATS"),
+                   externals=("MPEXCHNG",))
+    ns["MPEXCHNG"] = lambda *a: None            # one rank: no halo
+    ns = T.compile(["CTUWUPDT", "PROPAGS2", "PROPDOT", "PROPAG_WAM"], ns)
     t0 = time.time()
     if c.irefra != 0:     # propag_wam.F90:171-216: PROPDOT (+ GRADI) on the PROENVHALO fields, before CTUWUPDT
         land = np.array([c.bathymax])
@@ -418,6 +420,30 @@ def run_propag(name, N=8, mask="continents", obs=False, **kw):
     out["F3"] = F3.a[:n]
     got = o.get_fl1()[:FR_][:, :, new2ij].transpose(2, 1, 0)
     m0 = c.ifrelfmax if 0 < c.ifrelfmax < FR_ else 0       # the frequencies below IFRELFMAX go through further sub-steps in PROPAG_WAM
+    if m0:
+        # PROPAG_WAM whole (propag_wam.F90) with the weights built above (LUPDTWGHT = LLUPDTTD = F): chunks -> FL1_EXT, PROPAGS2, the
+        # NSTEP_LF - 1 further sub-steps of the frequencies 1..IFRELFMAX, FL3_EXT -> chunks and the padding of the last chunk
+        P = 16
+        C_ = (n + P - 1) // P
+        chunk = np.zeros((P, A, 36, C_))
+        kijl, ijfrom = np.zeros(C_, dtype=np.int64), np.zeros((P, C_), dtype=np.int64)
+        for ic in range(C_):
+            k = min(P, n - ic * P)
+            kijl[ic] = k
+            ijfrom[:k, ic] = ic * P + 1 + np.arange(k)
+            chunk[:k, :, :FR_, ic] = f1[ic * P: ic * P + k]
+        FL1 = FArr.of(chunk)
+        ns.update(NCHNK=I(C_), KIJL4CHNK=FArr.of(kijl), IJFROMCHNK=FArr.of(ijfrom), NINF=I(1), NSUP=I(n), NFRE=I(36), LLUNSTR=False, IPROPAGS=I(2),
+                  LUPDTWGHT=False, LLUPDTTD=False, LLCHKCFL=False, LLCHKCFLA=False)
+        t0 = time.time()
+        ns["PROPAG_WAM"](None, None, None, None, FL1, None, None, None, None, None)
+        whole = np.concatenate([FL1.a[:int(kijl[ic]), :, :FR_, ic] for ic in range(C_)], axis=0)
+        assert np.array_equal(whole[:, :, m0:], out["F3"][:, :, m0:])       # the frequencies above IFRELFMAX: the single PROPAGS2 call above
+        pad = FL1.a[int(kijl[-1]):, :, :FR_, -1]
+        assert np.array_equal(pad, np.broadcast_to(FL1.a[0, :, :FR_, -1], pad.shape))      # propag_wam.F90:388-398
+        out["F3"] = whole
+        m0 = 0
+        print("   PROPAG_WAM whole (%d sub-steps) in %.1f s" % (round(c.idelpro / c.delpro_lf), time.time() - t0))
     out["m0"] = m0
     print("   PROPAGS2: max |oracle - reference source| = %.2e, identical: %s" % (np.abs(got - out["F3"])[:, :, m0:].max(),
                                                                                np.array_equal(got[:, :, m0:], out["F3"][:, :, m0:])))

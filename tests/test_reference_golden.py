@@ -188,7 +188,8 @@ def _prop_case(path):
 def test_ctu_weights_and_propags2_match_the_reference_source(built, path):
     """CTUWUPDT + CTUWINI + CTUWDRV + CTUW + PROPAGS2 (and, with refraction, PROPDOT + GRADI) executed from their own source (every 6th
     point of a 323-point grid is kept in the fixture): the oracle's stored weights SUMWN / WLONN / WLATN / WCORN / WKPMN / WMPMN and its
-    advected spectrum are BIT-IDENTICAL, for IREFRA = 0, 1, 2, 3 and with the fast-wave split."""
+    advected spectrum are BIT-IDENTICAL, for IREFRA = 0, 1, 2, 3 and with the fast-wave split (there PROPAG_WAM is
+    run whole, sub-step loop and chunk copies included: all frequencies are compared)."""
     from ecwam_b200 import synth
     from oracle import oracle as O
     z, kw, g = _prop_case(path)
