@@ -381,7 +381,7 @@ def run_propag(name, N=8, mask="continents", obs=False, **kw):
         u0, v0 = synthetic_currents(g)
         o.set_field("UCUR", u0); o.set_field("VCUR", v0)
         ucur, vcur = u0[new2ij], v0[new2ij]
-    u_ext, v_ext, d_ext, c_ext = ext(ucur, 0.0), ext(vcur, 0.0), ext(depth, c.bathymax), ext(cosphm1, 1.0)
+    u_ext, v_ext, d_ext, c_ext = ext(ucur, 0.0), ext(vcur, 0.0), ext(depth, c.bathymax), ext(cosphm1, 0.0)      # the land slot: proenvhalo.F90:109-116
     ns.update(NIBLO=I(n), DELPHI=float(o.table("XDELLA")[0]) * float(ns["CIRC"]) / 360.0, DELLAM=FArr.of(o.table("DELLAM")[:ngy]))
     T = Translator([x + ".F90" for x in PROP_FILES + ["propag_wam"]], registry=reg, stubs=("PROENVHALO", "PROPAGS", "PROPAGS1", "GSTATS"),
                    externals=("MPEXCHNG",))
